@@ -1,0 +1,172 @@
+/*
+ * zkcheck.h — C-ABI of libzkcheck.so, the B200 constraint checker behind the
+ * zkevm-specs Python API.
+ *
+ * The reference (privacy-scaling-explorations/zkevm-specs @ 6058c68) has no FFI;
+ * its only seam is Python function signatures.  Each entry point below replaces
+ * the INSIDE of one of those functions' per-row loops (file:line are relative to
+ * the reference tree):
+ *
+ *   zk_check(ZK_CIRCUIT_BYTECODE) <- check_bytecode_row loop   src/zkevm_specs/bytecode_circuit.py:37-100
+ *                                                              (driver: tests/test_bytecode_circuit.py:26-47)
+ *   zk_check(ZK_CIRCUIT_STATE)    <- check_state_row loop      src/zkevm_specs/state_circuit.py:492-613
+ *                                                              (driver: tests/test_state_circuit.py:17-38)
+ *   zk_check(ZK_CIRCUIT_COPY)     <- verify_copy_table         src/zkevm_specs/copy_circuit.py:92-130
+ *   zk_check(ZK_CIRCUIT_EVM)      <- verify_steps/verify_step  src/zkevm_specs/evm_circuit/main.py:14-63
+ *   zk_upload_table / lookups     <- Tables + lookup()         src/zkevm_specs/evm_circuit/table.py:578-884
+ *   zk_set_challenge              <- the `r` / keccak_randomness arguments of the functions above
+ *
+ * Data model
+ *   cell   : one BN254-Fr element, CANONICAL (value < p), 4 little-endian uint64 limbs (32 B).
+ *   column : n_rows consecutive cells.
+ *   matrix : column-major, uint64[n_cols][n_rows][4]; a warp reading one column for 32
+ *            consecutive rows touches 1 KiB of contiguous HBM.
+ * All pointers are caller-owned HOST memory unless the name says "_device".  Nothing is
+ * retained after a call returns except the device copies owned by the context.
+ *
+ * Return codes: 0 = the call ran (results are in the output arrays); < 0 = infrastructure
+ * error (bad shape, missing table, CUDA error) — zk_last_error() has the text.
+ * A context is not thread-safe; use one context per host thread / per GPU.
+ */
+#ifndef ZKCHECK_H
+#define ZKCHECK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zk_ctx zk_ctx;
+
+/* ---- circuits (witness matrices) -------------------------------------------------- */
+enum {
+  ZK_CIRCUIT_BYTECODE = 0, /* 12 cells/row, rotation {0,+1}     bytecode_circuit.py:15-27 */
+  ZK_CIRCUIT_STATE = 1,    /* 57 cells/row, rotation {-1,0,+1}  state_circuit.py:63-96    */
+  ZK_CIRCUIT_COPY = 2,     /* 20 cells/row, rotation {0,+1,+2}  evm_circuit/table.py:472-491 */
+  ZK_CIRCUIT_EVM = 3,      /* 13 cells/step, rotation {0,+1}    evm_circuit/step.py:16-44 */
+  ZK_CIRCUIT_EXP = 4,      /* 21 cells/row, rotation {0,+1}     evm_circuit/table.py:519-535 */
+  ZK_N_CIRCUITS = 5
+};
+
+/* ---- lookup tables ---------------------------------------------------------------- */
+enum {
+  ZK_TABLE_FIXED = 0,    /* 4 cells  FixedTableRow     table.py:405-409 */
+  ZK_TABLE_BYTECODE = 1, /* 6 cells  BytecodeTableRow  table.py:438-443 (hash lo,hi,tag,index,is_code,value) */
+  ZK_TABLE_RW = 2,       /* 14 cells RWTableRow        table.py:447-457 */
+  ZK_TABLE_TX = 3,       /* 5 cells  TxTableRow        table.py:421-426 (tx_id,tag,index,value lo,hi) */
+  ZK_TABLE_BLOCK = 4,    /* 4 cells  BlockTableRow     table.py:413-417 */
+  ZK_TABLE_COPY = 5,     /* 14 cells CopyTableRow      table.py:495-507 */
+  ZK_TABLE_KECCAK = 6,   /* 5 cells  KeccakTableRow    table.py:511-515 (state_tag,input_rlc,input_len,out lo,hi) */
+  ZK_TABLE_MPT = 7,      /* 12 cells MPTTableRow       table.py:460-468 */
+  ZK_TABLE_PUSH = 8,     /* 2 cells  push table        bytecode_circuit.py:174-178 (byte, push_size) */
+  ZK_N_TABLES = 9
+};
+
+/* ---- challenges ------------------------------------------------------------------- */
+enum {
+  ZK_CHALLENGE_KECCAK = 0, /* keccak_randomness / `r` of bytecode & copy circuits */
+  ZK_CHALLENGE_LOOKUP = 1, /* RLC base used to compress table rows into hash keys;
+                              any value gives the same pass/fail (matches are confirmed
+                              exactly), it only affects bucket placement */
+  ZK_N_CHALLENGES = 2
+};
+
+/* ---- zk_check flags ---------------------------------------------------------------- */
+enum {
+  ZK_FLAG_WRAP = 1,             /* rotations wrap modulo n_rows (whole circuit resident) */
+  ZK_FLAG_EVM_FIRST_STEP = 2,   /* verify_steps(begin_with_first_step=True)  main.py:30 */
+  ZK_FLAG_EVM_LAST_STEP = 4     /* verify_steps(end_with_last_step=True): the caller has
+                                   appended the dummy EndBlock step           main.py:21-22 */
+};
+
+/* ---- error classes a constraint id maps to ------------------- */
+enum {
+  ZK_ERR_ASSERT = 0,           /* AssertionError — caught by verify_steps (main.py:45)   */
+  ZK_ERR_LOOKUP_UNSAT = 1,     /* LookupUnsatFailure      table.py:879                  */
+  ZK_ERR_LOOKUP_AMBIGUOUS = 2, /* LookupAmbiguousFailure  table.py:881                  */
+  ZK_ERR_RANGE_RAISE = 3,      /* ConstraintUnsatFailure raised (instruction.py:529-534) */
+  ZK_ERR_VALUE = 4,            /* ValueError / OverflowError from Python runtime          */
+  ZK_ERR_NOT_IMPLEMENTED = 5   /* NotImplementedError (main.py:63) or a state this build
+                                  has no gate program for                                */
+};
+
+#define ZK_PASS 0xFFFFFFFFu /* first_fail value meaning "constraint held on every row" */
+
+/* lifecycle */
+int zk_ctx_create(int device_ordinal, zk_ctx** out);
+void zk_ctx_destroy(zk_ctx* ctx);
+const char* zk_last_error(zk_ctx* ctx); /* ctx may be NULL: last create error */
+
+/* canonical Fr challenge, 4 LE limbs */
+int zk_set_challenge(zk_ctx* ctx, int which, const uint64_t r[4]);
+
+/* Witness matrix of one circuit: host uint64[n_cols][n_rows][4]; n_cols must equal the
+ * circuit's cell count (zk_circuit_cols).  Copies host->device on `stream` (a cudaStream_t
+ * passed as void*, NULL = default stream). */
+int zk_upload_columns(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                      const uint64_t* colmajor, void* stream);
+/* Same, but the matrix already lives in device memory (e.g. a torch tensor); the context
+ * borrows the pointer until the next upload/bind for this circuit. */
+int zk_bind_columns_device(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                           const uint64_t* colmajor_device);
+
+/* Optional per-row type flags that the Python objects carry outside the cells
+ * (WordOrValue.is_word, arithmetic.py:171-189): one byte per row, bit k = "word k of the
+ * row is a Word".  NULL / never called = all zero. Host pointer. */
+int zk_upload_row_flags(zk_ctx* ctx, int circuit_id, uint64_t n_rows, const uint8_t* flags,
+                        void* stream);
+
+/* Lookup table: host uint64[n_cols][n_rows][4].  Any index built on the previous contents
+ * is dropped; it is rebuilt on the device by the next zk_check that needs it. */
+int zk_upload_table(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                    const uint64_t* colmajor, void* stream);
+int zk_bind_table_device(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                         const uint64_t* colmajor_device);
+int zk_upload_table_flags(zk_ctx* ctx, int table_id, uint64_t n_rows, const uint8_t* flags,
+                          void* stream);
+
+/* Check rows [row_begin, row_end) of the resident matrix (local indices).  Without
+ * ZK_FLAG_WRAP the caller guarantees halo rows exist for the circuit's rotations.
+ * Reported rows are row_base + local index.
+ *   first_fail[n]  : per constraint id, the smallest failing row, ZK_PASS if none
+ *   fail_count[n]  : optional (may be NULL) number of failing rows per constraint
+ * n = zk_n_constraints(circuit_id).  The call enqueues on `stream`, then copies the two
+ * arrays back and synchronises the stream. */
+int zk_check(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
+             uint64_t row_base, uint32_t flags, uint32_t* first_fail, uint64_t* fail_count,
+             void* stream);
+
+/* Asynchronous form used for device-side timing and multi-GPU: enqueues the index builds
+ * and the check kernel on `stream` and leaves the result in device memory owned by the
+ * context.  zk_result_device returns that buffer (uint32 first_fail[n] followed, 8-byte
+ * aligned, by uint64 fail_count[n]) so a collective can reduce it in place; zk_fetch_result
+ * copies it to the host and synchronises. */
+int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
+                   uint64_t row_base, uint32_t flags, void* stream);
+int zk_result_device(zk_ctx* ctx, int circuit_id, uint32_t** first_fail_device,
+                     uint64_t** fail_count_device);
+int zk_fetch_result(zk_ctx* ctx, int circuit_id, uint32_t* first_fail, uint64_t* fail_count,
+                    void* stream);
+
+/* Multi-GPU: element-wise MIN of first_fail (and SUM of fail_count) across the ranks of an
+ * NCCL communicator (ncclComm_t passed as void*), on `stream`.  One small all-reduce; rows
+ * are sharded, tables replicated, so this is the only exchange. */
+int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm, void* stream);
+
+/* introspection */
+int zk_circuit_cols(int circuit_id);
+int zk_table_cols(int table_id);
+int zk_n_constraints(int circuit_id);
+/* name into buf (NUL-terminated, truncated to n); returns the ZK_ERR_* class, <0 if bad id */
+int zk_constraint_info(int circuit_id, int idx, char* buf, int n);
+/* number of kernels this context has launched since creation (bench.py: gpu_launches) */
+uint64_t zk_launch_count(zk_ctx* ctx);
+/* drop cached lookup indexes so the next zk_check rebuilds them (used by bench to time the
+ * whole path) */
+int zk_invalidate_indexes(zk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKCHECK_H */

@@ -1,0 +1,80 @@
+"""ctypes loader for the CPU oracle (oracle/_build/libzkoracle.so) — TEST SIDE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use the oracle."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+U64P = ctypes.POINTER(ctypes.c_uint64)
+U32P = ctypes.POINTER(ctypes.c_uint32)
+
+EXC_OF_CLASS = {
+    0: "AssertionError",
+    1: "LookupUnsatFailure",
+    2: "LookupAmbiguousFailure",
+    3: "ConstraintUnsatFailure",
+    4: "ValueError",
+    5: "NotImplementedError",
+}
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "_build", "libzkoracle.so")
+        srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle"))
+                if f.endswith((".c", ".h"))] + [os.path.join(ROOT, "include", "zk_constraints.h")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            build()
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def p64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(U64P)
+
+
+def limbs(v: int) -> np.ndarray:
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def from_limbs(a) -> int:
+    return sum(int(a[i]) << (64 * i) for i in range(4))
+
+
+def first_failure(first_fail: np.ndarray, classes):
+    """(row, exception name) the reference would raise first: smallest (row, id)."""
+    rows = first_fail.astype(np.int64)
+    rows[first_fail == 0xFFFFFFFF] = 1 << 40
+    r = int(rows.min())
+    if r >= (1 << 40):
+        return -1, ""
+    cid = int(np.argmax(rows == r))
+    return r, EXC_OF_CLASS[classes[cid]]
+
+
+def check_bytecode(cols, push, keccak, r, row_begin=0, row_end=None, n=22):
+    cols = np.ascontiguousarray(cols)
+    push = np.ascontiguousarray(push)
+    keccak = np.ascontiguousarray(keccak)
+    n_rows = cols.shape[1]
+    if row_end is None:
+        row_end = n_rows
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    rc = lib().orc_check_bytecode(
+        p64(cols), ctypes.c_uint64(n_rows), p64(push), ctypes.c_uint64(push.shape[1]),
+        p64(keccak), ctypes.c_uint64(keccak.shape[1]), p64(rr), ctypes.c_uint64(row_begin),
+        ctypes.c_uint64(row_end), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc
