@@ -1,0 +1,451 @@
+// api.cu — the C-ABI of libzkcheck.so (include/zkcheck.h): context, uploads, lookup-index
+// cache, kernel dispatch, result transport.  Unity build: the circuit kernels are included
+// below so the whole library is one translation unit (nvcc -gencode arch=compute_100a,
+// code=sm_100a).  No torch types cross this boundary.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zk_constraints.h"
+#include "../../include/zkcheck.h"
+#include "bytecode.cu"
+#include "circuit.cuh"
+
+using namespace zk;
+
+// ------------------------------------------------------------------ catalogue tables
+struct ConstraintInfo {
+  const char* name;
+  int cls;
+  const char* doc;
+};
+#define ZK_INFO_ENTRY(id, cls, doc) {#id, cls, doc},
+static const ConstraintInfo kBytecodeInfo[] = {ZK_BYTECODE_CONSTRAINTS(ZK_INFO_ENTRY)};
+
+static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21};
+static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
+
+static const ConstraintInfo* circuit_info(int circuit, int* n) {
+  switch (circuit) {
+    case ZK_CIRCUIT_BYTECODE: *n = BC_N_CONSTRAINTS; return kBytecodeInfo;
+    default: *n = 0; return nullptr;
+  }
+}
+
+// ------------------------------------------------------------------ context
+struct Matrix {
+  u64* dev = nullptr;
+  size_t cap_bytes = 0;
+  bool borrowed = false;
+  u64 n_rows = 0;
+  u32 n_cols = 0;
+  unsigned char* flags = nullptr;
+  size_t flags_cap = 0;
+  u64 flags_rows = 0;
+  u64 version = 0;
+};
+
+struct Index {
+  int table_id = -1;
+  u32 n_key = 0;
+  u32 key_cols[ZK_MAX_KEY];
+  u32* slots = nullptr;
+  size_t cap = 0;
+  u64 built_version = ~0ull;
+  u64 built_challenge = ~0ull;
+  IndexDev dev;
+};
+
+struct ResultBuf {
+  u32* first_fail = nullptr;  // device: u32[n] then (8B aligned) u64[n]
+  u64* fail_count = nullptr;
+  int n = 0;
+};
+
+struct zk_ctx {
+  int device = 0;
+  Matrix circ[ZK_N_CIRCUITS];
+  Matrix tab[ZK_N_TABLES];
+  Fr chal[ZK_N_CHALLENGES];
+  u64 chal_version = 0;
+  std::vector<Index*> indexes;
+  ResultBuf res[ZK_N_CIRCUITS];
+  std::string err;
+  u64 launches = 0;
+};
+
+static std::string g_create_err;
+
+#define CK(ctx, call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return -2;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+static int fail_msg(zk_ctx* ctx, const std::string& m) {
+  ctx->err = m;
+  return -1;
+}
+
+extern "C" int zk_ctx_create(int device_ordinal, zk_ctx** out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  if (device_ordinal < 0 || device_ordinal >= n) {
+    g_create_err = "bad device ordinal";
+    return -1;
+  }
+  e = cudaSetDevice(device_ordinal);
+  if (e != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return -2;
+  }
+  zk_ctx* c = new zk_ctx();
+  c->device = device_ordinal;
+  for (int i = 0; i < ZK_N_CHALLENGES; i++) c->chal[i] = fr_u64(0x10001 + i);
+  *out = c;
+  return 0;
+}
+
+static void free_matrix(Matrix& m) {
+  if (m.dev && !m.borrowed) cudaFree(m.dev);
+  if (m.flags) cudaFree(m.flags);
+  m = Matrix();
+}
+
+extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& m : ctx->circ) free_matrix(m);
+  for (auto& m : ctx->tab) free_matrix(m);
+  for (auto* ix : ctx->indexes) {
+    if (ix->slots) cudaFree(ix->slots);
+    delete ix;
+  }
+  for (auto& r : ctx->res)
+    if (r.first_fail) cudaFree(r.first_fail);
+  delete ctx;
+}
+
+extern "C" const char* zk_last_error(zk_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+static bool fr_is_canonical(const u64 r[4]) {
+  Fr a{{r[0], r[1], r[2], r[3]}}, p{{ZK_P0, ZK_P1, ZK_P2, ZK_P3}};
+  return fr_lt(a, p);
+}
+
+extern "C" int zk_set_challenge(zk_ctx* ctx, int which, const uint64_t r[4]) {
+  if (which < 0 || which >= ZK_N_CHALLENGES) return fail_msg(ctx, "bad challenge id");
+  if (!fr_is_canonical((const u64*)r)) return fail_msg(ctx, "challenge is not canonical (>= p)");
+  ctx->chal[which] = Fr{{r[0], r[1], r[2], r[3]}};
+  if (which == ZK_CHALLENGE_LOOKUP) ctx->chal_version++;
+  return 0;
+}
+
+static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const u64* host,
+                        const u64* device, cudaStream_t st) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  m.version++;
+  if (device) {
+    if (m.dev && !m.borrowed) cudaFree(m.dev);
+    m.dev = const_cast<u64*>(device);
+    m.borrowed = true;
+    m.cap_bytes = 0;
+  } else {
+    size_t bytes = (size_t)n_rows * n_cols * 32;
+    if (m.borrowed) {
+      m.dev = nullptr;
+      m.borrowed = false;
+      m.cap_bytes = 0;
+    }
+    if (bytes > m.cap_bytes) {
+      if (m.dev) cudaFree(m.dev);
+      m.dev = nullptr;
+      CK(ctx, cudaMalloc(&m.dev, bytes ? bytes : 32));
+      m.cap_bytes = bytes;
+    }
+    if (bytes) CK(ctx, cudaMemcpyAsync(m.dev, host, bytes, cudaMemcpyHostToDevice, st));
+  }
+  m.n_rows = n_rows;
+  m.n_cols = n_cols;
+  m.flags_rows = 0;  // flags belong to the previous contents
+  return 0;
+}
+
+static int store_flags(zk_ctx* ctx, Matrix& m, u64 n_rows, const uint8_t* flags, cudaStream_t st) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (n_rows != m.n_rows) return fail_msg(ctx, "flags row count differs from the matrix");
+  if (!flags) {
+    m.flags_rows = 0;
+    return 0;
+  }
+  if (n_rows > m.flags_cap) {
+    if (m.flags) cudaFree(m.flags);
+    m.flags = nullptr;
+    CK(ctx, cudaMalloc(&m.flags, n_rows ? n_rows : 1));
+    m.flags_cap = n_rows;
+  }
+  CK(ctx, cudaMemcpyAsync(m.flags, flags, n_rows, cudaMemcpyHostToDevice, st));
+  m.flags_rows = n_rows;
+  return 0;
+}
+
+extern "C" int zk_upload_columns(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                                 const uint64_t* colmajor, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  if ((int)n_cols != kCircuitCols[circuit_id]) return fail_msg(ctx, "wrong column count for circuit");
+  if (n_rows >= 0xFFFFFFFFull) return fail_msg(ctx, "too many rows (row ids are uint32)");
+  return store_matrix(ctx, ctx->circ[circuit_id], n_rows, n_cols, (const u64*)colmajor, nullptr,
+                      (cudaStream_t)stream);
+}
+extern "C" int zk_bind_columns_device(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                                      const uint64_t* dev) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  if ((int)n_cols != kCircuitCols[circuit_id]) return fail_msg(ctx, "wrong column count for circuit");
+  if (n_rows >= 0xFFFFFFFFull) return fail_msg(ctx, "too many rows (row ids are uint32)");
+  return store_matrix(ctx, ctx->circ[circuit_id], n_rows, n_cols, nullptr, (const u64*)dev, 0);
+}
+extern "C" int zk_upload_row_flags(zk_ctx* ctx, int circuit_id, uint64_t n_rows,
+                                   const uint8_t* flags, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  return store_flags(ctx, ctx->circ[circuit_id], n_rows, flags, (cudaStream_t)stream);
+}
+extern "C" int zk_upload_table(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                               const uint64_t* colmajor, void* stream) {
+  if (table_id < 0 || table_id >= ZK_N_TABLES) return fail_msg(ctx, "bad table id");
+  if ((int)n_cols != kTableCols[table_id]) return fail_msg(ctx, "wrong column count for table");
+  if (n_rows >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
+  return store_matrix(ctx, ctx->tab[table_id], n_rows, n_cols, (const u64*)colmajor, nullptr,
+                      (cudaStream_t)stream);
+}
+extern "C" int zk_bind_table_device(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                                    const uint64_t* dev) {
+  if (table_id < 0 || table_id >= ZK_N_TABLES) return fail_msg(ctx, "bad table id");
+  if ((int)n_cols != kTableCols[table_id]) return fail_msg(ctx, "wrong column count for table");
+  if (n_rows >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
+  return store_matrix(ctx, ctx->tab[table_id], n_rows, n_cols, nullptr, (const u64*)dev, 0);
+}
+extern "C" int zk_upload_table_flags(zk_ctx* ctx, int table_id, uint64_t n_rows,
+                                     const uint8_t* flags, void* stream) {
+  if (table_id < 0 || table_id >= ZK_N_TABLES) return fail_msg(ctx, "bad table id");
+  return store_flags(ctx, ctx->tab[table_id], n_rows, flags, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ lookup index cache
+static TableDev table_dev(const zk_ctx* ctx, int table_id) {
+  const Matrix& m = ctx->tab[table_id];
+  TableDev t;
+  t.cells = m.dev;
+  t.n_rows = m.dev ? m.n_rows : 0;
+  t.n_cols = m.n_cols ? m.n_cols : kTableCols[table_id];
+  t.flags = (m.flags_rows == m.n_rows && m.n_rows) ? m.flags : nullptr;
+  return t;
+}
+
+// Returns the device descriptor of the index of `table_id` on `key_cols`, building it on
+// `st` if the table or the lookup challenge changed since the last build.
+static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_key, cudaStream_t st,
+                        IndexDev* out) {
+  if (n_key == 0 || n_key > ZK_MAX_KEY) return fail_msg(ctx, "bad key width");
+  Index* ix = nullptr;
+  for (auto* c : ctx->indexes)
+    if (c->table_id == table_id && c->n_key == n_key && !memcmp(c->key_cols, key_cols, 4 * n_key)) ix = c;
+  if (!ix) {
+    ix = new Index();
+    ix->table_id = table_id;
+    ix->n_key = n_key;
+    memcpy(ix->key_cols, key_cols, 4 * n_key);
+    ctx->indexes.push_back(ix);
+  }
+  const Matrix& m = ctx->tab[table_id];
+  if (ix->built_version == m.version && ix->built_challenge == ctx->chal_version) {
+    ix->dev.tab = table_dev(ctx, table_id);  // flags may have been (re)uploaded
+    *out = ix->dev;
+    return 0;
+  }
+  TableDev t = table_dev(ctx, table_id);
+  size_t cap = 64;
+  while (cap < 2 * t.n_rows) cap <<= 1;
+  if (cap > ix->cap) {
+    if (ix->slots) cudaFree(ix->slots);
+    ix->slots = nullptr;
+    CK(ctx, cudaMalloc(&ix->slots, cap * sizeof(u32)));
+    ix->cap = cap;
+  }
+  IndexDev& d = ix->dev;
+  d.tab = t;
+  d.slots = ix->slots;
+  d.mask = (u32)(cap - 1);
+  d.n_key = n_key;
+  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_LOOKUP]);
+  Fr acc = fr_to_mont(fr_u64(1));
+  for (u32 j = 0; j < ZK_MAX_KEY; j++) {
+    d.key_cols[j] = j < n_key ? key_cols[j] : 0;
+    d.pw[j] = acc;  // r^j in Montgomery form
+    acc = fr_montmul(acc, r_mont);
+  }
+  CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u32), st));
+  if (t.n_rows) {
+    k_index_build<<<(unsigned)((t.n_rows + 255) / 256), 256, 0, st>>>(d);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+  }
+  ix->built_version = m.version;
+  ix->built_challenge = ctx->chal_version;
+  *out = d;
+  return 0;
+}
+
+extern "C" int zk_invalidate_indexes(zk_ctx* ctx) {
+  for (auto* ix : ctx->indexes) ix->built_version = ~0ull;
+  return 0;
+}
+
+// ------------------------------------------------------------------ results
+static int ensure_result(zk_ctx* ctx, int circuit, ResultDev* out, cudaStream_t st) {
+  int n = 0;
+  circuit_info(circuit, &n);
+  if (n == 0) return fail_msg(ctx, "circuit has no gate program in this build");
+  ResultBuf& r = ctx->res[circuit];
+  if (!r.first_fail) {
+    size_t off = ((size_t)n * 4 + 7) & ~(size_t)7;
+    void* p = nullptr;
+    CK(ctx, cudaMalloc(&p, off + (size_t)n * 8));
+    r.first_fail = (u32*)p;
+    r.fail_count = (u64*)((char*)p + off);
+    r.n = n;
+  }
+  CK(ctx, cudaMemsetAsync(r.first_fail, 0xFF, (size_t)n * 4, st));
+  CK(ctx, cudaMemsetAsync(r.fail_count, 0, (size_t)n * 8, st));
+  out->first_fail = r.first_fail;
+  out->fail_count = r.fail_count;
+  return 0;
+}
+
+static WitnessDev witness_dev(const Matrix& m) {
+  WitnessDev w;
+  w.cells = m.dev;
+  w.n_rows = m.n_rows;
+  w.flags = (m.flags_rows == m.n_rows && m.n_rows) ? m.flags : nullptr;
+  return w;
+}
+
+// ------------------------------------------------------------------ dispatch
+static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
+  const u32 pk[2] = {0, 1}, kk[5] = {0, 1, 2, 3, 4};
+  IndexDev push_ix, kec_ix;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_PUSH, pk, 2, st, &push_ix))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 5, st, &kec_ix))) return rc;
+  const u64 n = rg.row_end - rg.row_begin;
+  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
+  k_check_bytecode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      witness_dev(ctx->circ[ZK_CIRCUIT_BYTECODE]), rg, push_ix, kec_ix, r_mont, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
+                              uint64_t row_base, uint32_t flags, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Matrix& m = ctx->circ[circuit_id];
+  if (!m.dev && m.n_rows) return fail_msg(ctx, "no witness uploaded for circuit");
+  if (row_begin > row_end || row_end > m.n_rows) return fail_msg(ctx, "row range outside the resident matrix");
+  ResultDev res;
+  int rc = ensure_result(ctx, circuit_id, &res, st);
+  if (rc) return rc;
+  if (row_begin == row_end) return 0;
+  CheckRange rg{row_begin, row_end, row_base, flags};
+  switch (circuit_id) {
+    case ZK_CIRCUIT_BYTECODE: return check_bytecode(ctx, rg, res, st);
+    default: return fail_msg(ctx, "circuit has no gate program in this build");
+  }
+}
+
+extern "C" int zk_result_device(zk_ctx* ctx, int circuit_id, uint32_t** ff, uint64_t** fc) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  ResultBuf& r = ctx->res[circuit_id];
+  if (!r.first_fail) return fail_msg(ctx, "no result yet");
+  if (ff) *ff = r.first_fail;
+  if (fc) *fc = (uint64_t*)r.fail_count;
+  return 0;
+}
+
+extern "C" int zk_fetch_result(zk_ctx* ctx, int circuit_id, uint32_t* first_fail,
+                               uint64_t* fail_count, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ResultBuf& r = ctx->res[circuit_id];
+  if (!r.first_fail) return fail_msg(ctx, "no result yet");
+  if (first_fail)
+    CK(ctx, cudaMemcpyAsync(first_fail, r.first_fail, (size_t)r.n * 4, cudaMemcpyDeviceToHost, st));
+  if (fail_count)
+    CK(ctx, cudaMemcpyAsync(fail_count, r.fail_count, (size_t)r.n * 8, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int zk_check(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
+                        uint64_t row_base, uint32_t flags, uint32_t* first_fail,
+                        uint64_t* fail_count, void* stream) {
+  int rc = zk_check_async(ctx, circuit_id, row_begin, row_end, row_base, flags, stream);
+  if (rc) return rc;
+  return zk_fetch_result(ctx, circuit_id, first_fail, fail_count, stream);
+}
+
+// ------------------------------------------------------------------ multi-GPU
+// NCCL is bound at run time (dlopen) so that libzkcheck.so has no link-time dependency on a
+// particular libnccl; the caller owns the communicator.
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+extern "C" int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  ResultBuf& r = ctx->res[circuit_id];
+  if (!r.first_fail) return fail_msg(ctx, "no result yet");
+  static nccl_allreduce_fn fn = nullptr;
+  if (!fn) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail_msg(ctx, std::string("cannot load NCCL: ") + dlerror());
+    fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+    if (!fn) return fail_msg(ctx, "ncclAllReduce not found");
+  }
+  // ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0, ncclMin = 4 (nccl.h)
+  int e = fn(r.first_fail, r.first_fail, (size_t)r.n, 3, 4, nccl_comm, (cudaStream_t)stream);
+  if (e) return fail_msg(ctx, "ncclAllReduce(min) failed");
+  e = fn(r.fail_count, r.fail_count, (size_t)r.n, 5, 0, nccl_comm, (cudaStream_t)stream);
+  if (e) return fail_msg(ctx, "ncclAllReduce(sum) failed");
+  return 0;
+}
+
+// ------------------------------------------------------------------ introspection
+extern "C" int zk_circuit_cols(int c) { return (c >= 0 && c < ZK_N_CIRCUITS) ? kCircuitCols[c] : -1; }
+extern "C" int zk_table_cols(int t) { return (t >= 0 && t < ZK_N_TABLES) ? kTableCols[t] : -1; }
+extern "C" int zk_n_constraints(int circuit) {
+  int n = 0;
+  circuit_info(circuit, &n);
+  return n;
+}
+extern "C" int zk_constraint_info(int circuit, int idx, char* buf, int n) {
+  int cnt = 0;
+  const ConstraintInfo* info = circuit_info(circuit, &cnt);
+  if (!info || idx < 0 || idx >= cnt) return -1;
+  if (buf && n > 0) snprintf(buf, n, "%s: %s", info[idx].name, info[idx].doc);
+  return info[idx].cls;
+}
+extern "C" uint64_t zk_launch_count(zk_ctx* ctx) { return ctx->launches; }

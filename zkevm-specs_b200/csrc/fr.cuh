@@ -1,0 +1,157 @@
+// fr.cuh — BN254 scalar-field cells on the device (sm_100a).
+//
+// Device-side counterpart of the reference's FQ (src/zkevm_specs/util/arithmetic.py:41-63,
+// arithmetic in py_ecc.bn128.FQ).  A cell is 4 little-endian uint64 limbs holding the
+// CANONICAL value (< p); witness matrices stay canonical in HBM because most reference
+// checks compare the integer `.n` (ranges, `FQ == int`, `<`).  Montgomery form is used
+// only inside true Fr x Fr products: montmul(a, bR) = a*b mod p, so keeping the constant
+// operand (challenge powers, 2^-128, ...) in Montgomery form costs one multiply per product
+// and no conversions.
+#pragma once
+#include <stdint.h>
+
+namespace zk {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+struct Fr {
+  u64 l[4];
+};
+
+#define ZK_P0 0x43e1f593f0000001ull
+#define ZK_P1 0x2833e84879b97091ull
+#define ZK_P2 0xb85045b68181585dull
+#define ZK_P3 0x30644e72e131a029ull
+#define ZK_N0 0xc2e1f593efffffffull  // -p^-1 mod 2^64
+// R^2 mod p, R = 2^256
+#define ZK_R2_0 0x1bb8e645ae216da7ull
+#define ZK_R2_1 0x53fe3ab1e35c59e3ull
+#define ZK_R2_2 0x8c49833d53bb8085ull
+#define ZK_R2_3 0x0216d0b17f4e44a5ull
+
+// One 256-bit load per cell: LDG.E.256 on sm_100a; a warp reading 32 consecutive rows of a
+// column moves 1 KiB in one instruction.  .nc: witness/table cells are read-only.
+__device__ __forceinline__ Fr ld_cell(const u64* p) {
+  Fr r;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.l[0]), "=l"(r.l[1]), "=l"(r.l[2]), "=l"(r.l[3])
+               : "l"(p));
+  return r;
+}
+
+__host__ __device__ __forceinline__ Fr fr_u64(u64 v) { return Fr{{v, 0, 0, 0}}; }
+__host__ __device__ __forceinline__ Fr fr_u128(u64 lo, u64 hi) { return Fr{{lo, hi, 0, 0}}; }
+__host__ __device__ __forceinline__ bool fr_eq(const Fr& a, const Fr& b) {
+  return ((a.l[0] ^ b.l[0]) | (a.l[1] ^ b.l[1]) | (a.l[2] ^ b.l[2]) | (a.l[3] ^ b.l[3])) == 0;
+}
+__host__ __device__ __forceinline__ bool fr_is_zero(const Fr& a) {
+  return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0;
+}
+// FQ == int (py_ecc compares .n with the raw int)
+__host__ __device__ __forceinline__ bool fr_eq_u64(const Fr& a, u64 v) {
+  return a.l[0] == v && (a.l[1] | a.l[2] | a.l[3]) == 0;
+}
+// .n fits in 64 / 128 bits
+__host__ __device__ __forceinline__ bool fr_fits64(const Fr& a) { return (a.l[1] | a.l[2] | a.l[3]) == 0; }
+__host__ __device__ __forceinline__ bool fr_fits128(const Fr& a) { return (a.l[2] | a.l[3]) == 0; }
+// integer compare of .n
+__host__ __device__ __forceinline__ bool fr_lt(const Fr& a, const Fr& b) {
+  if (a.l[3] != b.l[3]) return a.l[3] < b.l[3];
+  if (a.l[2] != b.l[2]) return a.l[2] < b.l[2];
+  if (a.l[1] != b.l[1]) return a.l[1] < b.l[1];
+  return a.l[0] < b.l[0];
+}
+
+__host__ __device__ __forceinline__ u64 adc64(u64 a, u64 b, u64& c) {
+  unsigned __int128 t = (unsigned __int128)a + b + c;
+  c = (u64)(t >> 64);
+  return (u64)t;
+}
+__host__ __device__ __forceinline__ u64 sbb64(u64 a, u64 b, u64& br) {
+  unsigned __int128 t = (unsigned __int128)a - b - br;
+  br = (u64)(t >> 64) & 1;
+  return (u64)t;
+}
+__host__ __device__ __forceinline__ Fr fr_sub_p_if_ge(const Fr& s) {
+  Fr d;
+  u64 br = 0;
+  d.l[0] = sbb64(s.l[0], ZK_P0, br);
+  d.l[1] = sbb64(s.l[1], ZK_P1, br);
+  d.l[2] = sbb64(s.l[2], ZK_P2, br);
+  d.l[3] = sbb64(s.l[3], ZK_P3, br);
+  return br ? s : d;
+}
+// (a + b) mod p for canonical a, b  (a+b < 2p < 2^255: no carry out)
+__host__ __device__ __forceinline__ Fr fr_add(const Fr& a, const Fr& b) {
+  Fr s;
+  u64 c = 0;
+  s.l[0] = adc64(a.l[0], b.l[0], c);
+  s.l[1] = adc64(a.l[1], b.l[1], c);
+  s.l[2] = adc64(a.l[2], b.l[2], c);
+  s.l[3] = adc64(a.l[3], b.l[3], c);
+  return fr_sub_p_if_ge(s);
+}
+__host__ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) {
+  Fr d;
+  u64 br = 0;
+  d.l[0] = sbb64(a.l[0], b.l[0], br);
+  d.l[1] = sbb64(a.l[1], b.l[1], br);
+  d.l[2] = sbb64(a.l[2], b.l[2], br);
+  d.l[3] = sbb64(a.l[3], b.l[3], br);
+  if (br) {
+    u64 c = 0;
+    d.l[0] = adc64(d.l[0], ZK_P0, c);
+    d.l[1] = adc64(d.l[1], ZK_P1, c);
+    d.l[2] = adc64(d.l[2], ZK_P2, c);
+    d.l[3] = adc64(d.l[3], ZK_P3, c);
+  }
+  return d;
+}
+__host__ __device__ __forceinline__ Fr fr_add_u64(const Fr& a, u64 v) { return fr_add(a, fr_u64(v)); }
+__host__ __device__ __forceinline__ Fr fr_sub_u64(const Fr& a, u64 v) { return fr_sub(a, fr_u64(v)); }
+
+// Montgomery product a*b*2^-256 mod p (CIOS, 4x64-bit limbs; result canonical).
+__host__ __device__ __forceinline__ Fr fr_montmul(const Fr& a, const Fr& b) {
+  const u64 P[4] = {ZK_P0, ZK_P1, ZK_P2, ZK_P3};
+  u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const u64 bi = b.l[i];
+    unsigned __int128 x;
+    u64 c;
+    x = (unsigned __int128)a.l[0] * bi + t0; t0 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)a.l[1] * bi + t1 + c; t1 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)a.l[2] * bi + t2 + c; t2 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)a.l[3] * bi + t3 + c; t3 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)t4 + c; t4 = (u64)x;
+    u64 t5 = (u64)(x >> 64);
+    const u64 m = t0 * ZK_N0;
+    x = (unsigned __int128)m * P[0] + t0; c = (u64)(x >> 64);
+    x = (unsigned __int128)m * P[1] + t1 + c; t0 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)m * P[2] + t2 + c; t1 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)m * P[3] + t3 + c; t2 = (u64)x; c = (u64)(x >> 64);
+    x = (unsigned __int128)t4 + c; t3 = (u64)x; t4 = t5 + (u64)(x >> 64);
+  }
+  Fr r{{t0, t1, t2, t3}};
+  // p < 2^254 and inputs < p  =>  result < 2p, t4 == 0
+  return fr_sub_p_if_ge(r);
+}
+__host__ __device__ __forceinline__ Fr fr_to_mont(const Fr& a) {
+  return fr_montmul(a, Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});
+}
+// canonical product of two canonical cells
+__host__ __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
+  return fr_montmul(fr_to_mont(a), b);
+}
+// a (canonical, fits 64 bits) times small constant-free u64, exact integer if it fits,
+// else mod p: used for cheap "x * 256^k"-style terms
+__host__ __device__ __forceinline__ Fr fr_shl_small(u64 v, int bits) {  // v * 2^bits, bits<192, as integer (< p guaranteed by caller)
+  Fr r{{0, 0, 0, 0}};
+  int w = bits >> 6, s = bits & 63;
+  r.l[w] = v << s;
+  if (s && w + 1 < 4) r.l[w + 1] = v >> (64 - s);
+  return r;
+}
+
+}  // namespace zk

@@ -1,0 +1,135 @@
+// lookup.cuh — exact table lookups on the device.
+//
+// Replaces lookup()/TableRow.match (src/zkevm_specs/evm_circuit/table.py:864-884, 389-401):
+// the reference scans a Python set linearly and counts rows whose queried (non-None)
+// columns equal the query; 0 matches => LookupUnsatFailure, >1 => LookupAmbiguousFailure.
+// That scan is >99 % of the reference's EVM/copy time.
+//
+// Here every (table, queried-column set) gets an open-addressing hash index built on the
+// device.  The hash of a row is the random linear combination  h = sum_j cell_j * r^j  over
+// Fr (r = ZK_CHALLENGE_LOOKUP, powers kept in Montgomery form so each term is one montmul);
+// the low bits of the canonical h pick the bucket.  A probe recomputes h for the query,
+// walks the bucket run, and CONFIRMS each candidate by comparing the queried cells exactly,
+// so pass/fail never depends on r; it also counts distinct matching rows so ambiguity is
+// reported exactly like the reference (rows identical in every column count once, the
+// table being a set).
+#pragma once
+#include "fr.cuh"
+
+namespace zk {
+
+#define ZK_MAX_KEY 12
+#define ZK_EMPTY_SLOT 0xFFFFFFFFu
+
+struct TableDev {
+  const u64* cells;  // [n_cols][n_rows][4]
+  u64 n_rows;
+  u32 n_cols;
+  const unsigned char* flags;  // optional per-row type flags (may be null)
+};
+
+struct IndexDev {
+  TableDev tab;
+  u32* slots;  // capacity = mask+1 row ids, ZK_EMPTY_SLOT = free
+  u32 mask;
+  u32 n_key;
+  u32 key_cols[ZK_MAX_KEY];
+  Fr pw[ZK_MAX_KEY];  // r^j * 2^256 mod p (Montgomery form); pw[0] unused (r^0 = 1)
+};
+
+__device__ __forceinline__ const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
+  return t.cells + ((u64)col * t.n_rows + row) * 4;
+}
+__device__ __forceinline__ Fr table_cell(const TableDev& t, u32 col, u64 row) {
+  return ld_cell(cell_ptr(t, col, row));
+}
+
+// bucket from the canonical RLC value
+__device__ __forceinline__ u32 rlc_bucket(const Fr& h, u32 mask) {
+  u64 x = h.l[0] ^ (h.l[1] * 0x9E3779B97F4A7C15ull);
+  x ^= x >> 29;
+  return (u32)x & mask;
+}
+
+// h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
+template <int NK>
+__device__ __forceinline__ Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
+  Fr h = key[0];
+#pragma unroll
+  for (int j = 1; j < NK; j++) h = fr_add(h, fr_montmul(key[j], ix.pw[j]));
+  return h;
+}
+
+// One thread per table row: compress the queried columns and claim a slot.
+__global__ void __launch_bounds__(256) k_index_build(IndexDev ix) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= ix.tab.n_rows) return;
+  Fr h = table_cell(ix.tab, ix.key_cols[0], row);
+  for (u32 j = 1; j < ix.n_key; j++)
+    h = fr_add(h, fr_montmul(table_cell(ix.tab, ix.key_cols[j], row), ix.pw[j]));
+  u32 b = rlc_bucket(h, ix.mask);
+  for (;;) {
+    const u32 old = atomicCAS(&ix.slots[b], ZK_EMPTY_SLOT, (u32)row);
+    if (old == ZK_EMPTY_SLOT) break;
+    b = (b + 1) & ix.mask;
+  }
+}
+
+__device__ __forceinline__ bool rows_identical(const TableDev& t, u32 a, u32 b) {
+  for (u32 c = 0; c < t.n_cols; c++)
+    if (!fr_eq(table_cell(t, c, a), table_cell(t, c, b))) return false;
+  return true;
+}
+
+// Walk the bucket run starting at the bucket of h.  Returns the number of distinct matching
+// rows, capped at 2; *row = the first match.
+template <int NK>
+__device__ __forceinline__ int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK],
+                                            u32* row) {
+  int found = 0;
+  u32 first = 0;
+  u32 b = rlc_bucket(h, ix.mask);
+  for (;;) {
+    const u32 cand = __ldg(&ix.slots[b]);
+    if (cand == ZK_EMPTY_SLOT) break;
+    bool eq = true;
+#pragma unroll
+    for (int j = 0; j < NK; j++) {
+      if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
+    }
+    if (eq) {
+      if (found == 0) {
+        first = cand;
+        found = 1;
+      } else if (!rows_identical(ix.tab, first, cand)) {
+        found = 2;
+        break;
+      }
+    }
+    b = (b + 1) & ix.mask;
+  }
+  *row = first;
+  return found;
+}
+
+template <int NK>
+__device__ __forceinline__ int lookup(const IndexDev& ix, const Fr (&key)[NK], u32* row) {
+  if (ix.tab.n_rows == 0) return 0;
+  return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row);
+}
+
+// ---- result recording -------------------------------------------------------------------
+struct ResultDev {
+  u32* first_fail;  // [n_constraints]
+  u64* fail_count;  // [n_constraints]
+};
+__device__ __forceinline__ void fail(const ResultDev& r, int id, u64 row) {
+  atomicMin(&r.first_fail[id], (u32)row);
+  atomicAdd(&r.fail_count[id], 1ull);
+}
+#define ZK_REQUIRE(res, id, row, cond) \
+  do {                                 \
+    if (!(cond)) fail((res), (id), (row)); \
+  } while (0)
+
+}  // namespace zk

@@ -1,0 +1,253 @@
+"""ctypes binding of libzkcheck.so (the C-ABI in include/zkcheck.h) and its nvcc build.
+
+The product has NO CPU fallback: if the library cannot be built/loaded, or no CUDA device is
+present when a check is requested, these functions raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libzkcheck.so")
+
+# ids of include/zkcheck.h
+CIRCUIT_BYTECODE, CIRCUIT_STATE, CIRCUIT_COPY, CIRCUIT_EVM, CIRCUIT_EXP = range(5)
+(TABLE_FIXED, TABLE_BYTECODE, TABLE_RW, TABLE_TX, TABLE_BLOCK, TABLE_COPY, TABLE_KECCAK, TABLE_MPT,
+ TABLE_PUSH) = range(9)
+CHALLENGE_KECCAK, CHALLENGE_LOOKUP = 0, 1
+FLAG_WRAP, FLAG_EVM_FIRST_STEP, FLAG_EVM_LAST_STEP = 1, 2, 4
+ERR_ASSERT, ERR_LOOKUP_UNSAT, ERR_LOOKUP_AMBIGUOUS, ERR_RANGE_RAISE, ERR_VALUE, ERR_NOT_IMPLEMENTED = range(6)
+PASS = 0xFFFFFFFF
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _sources():
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out += [os.path.join(ROOT, "include", f) for f in ("zkcheck.h", "zk_constraints.h")]
+    return out
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/api.cu (unity build) for sm_100a into libzkcheck.so, in-tree."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libzkcheck.so (no CPU fallback exists)")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "api.cu"), "-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_LIB: Optional[ctypes.CDLL] = None
+_U64P = ctypes.POINTER(ctypes.c_uint64)
+_U32P = ctypes.POINTER(ctypes.c_uint32)
+_U8P = ctypes.POINTER(ctypes.c_uint8)
+
+EXPORTS = [
+    "zk_ctx_create", "zk_ctx_destroy", "zk_last_error", "zk_set_challenge", "zk_upload_columns",
+    "zk_bind_columns_device", "zk_upload_row_flags", "zk_upload_table", "zk_bind_table_device",
+    "zk_upload_table_flags", "zk_check", "zk_check_async", "zk_result_device", "zk_fetch_result",
+    "zk_allreduce_results", "zk_circuit_cols", "zk_table_cols", "zk_n_constraints",
+    "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes",
+]
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        if is_stale():
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+        L.zk_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+        L.zk_ctx_destroy.argtypes = [vp]
+        L.zk_ctx_destroy.restype = None
+        L.zk_last_error.argtypes = [vp]
+        L.zk_last_error.restype = ctypes.c_char_p
+        L.zk_set_challenge.argtypes = [vp, i32, _U64P]
+        L.zk_upload_columns.argtypes = [vp, i32, u64, u32, vp, vp]
+        L.zk_bind_columns_device.argtypes = [vp, i32, u64, u32, vp]
+        L.zk_upload_row_flags.argtypes = [vp, i32, u64, vp, vp]
+        L.zk_upload_table.argtypes = [vp, i32, u64, u32, vp, vp]
+        L.zk_bind_table_device.argtypes = [vp, i32, u64, u32, vp]
+        L.zk_upload_table_flags.argtypes = [vp, i32, u64, vp, vp]
+        L.zk_check.argtypes = [vp, i32, u64, u64, u64, u32, _U32P, _U64P, vp]
+        L.zk_check_async.argtypes = [vp, i32, u64, u64, u64, u32, vp]
+        L.zk_result_device.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+        L.zk_fetch_result.argtypes = [vp, i32, _U32P, _U64P, vp]
+        L.zk_allreduce_results.argtypes = [vp, i32, vp, vp]
+        L.zk_circuit_cols.argtypes = [i32]
+        L.zk_table_cols.argtypes = [i32]
+        L.zk_n_constraints.argtypes = [i32]
+        L.zk_constraint_info.argtypes = [i32, i32, ctypes.c_char_p, i32]
+        L.zk_launch_count.argtypes = [vp]
+        L.zk_launch_count.restype = u64
+        L.zk_invalidate_indexes.argtypes = [vp]
+        _LIB = L
+    return _LIB
+
+
+def constraint_catalogue(circuit_id: int):
+    """[(name+doc, error class)] for a circuit, from the library itself."""
+    L = lib()
+    out = []
+    buf = ctypes.create_string_buffer(256)
+    for i in range(L.zk_n_constraints(circuit_id)):
+        cls = L.zk_constraint_info(circuit_id, i, buf, 256)
+        out.append((buf.value.decode(), cls))
+    return out
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _host_ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One zk_ctx: owns the device copies of witness matrices, tables and lookup indexes."""
+
+    def __init__(self, device: int = 0) -> None:
+        self._L = lib()
+        h = ctypes.c_void_p()
+        rc = self._L.zk_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise NativeError(f"zk_ctx_create failed: {self._L.zk_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.zk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _ck(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise NativeError(f"{what}: {self._L.zk_last_error(self._h).decode()} (rc={rc})")
+
+    @staticmethod
+    def _matrix(a) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        assert a.ndim == 3 and a.shape[2] == 4, "matrix must be uint64[n_cols][n_rows][4]"
+        return a
+
+    def set_challenge(self, which: int, value: int) -> None:
+        limbs = (ctypes.c_uint64 * 4)(*[(int(value) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)])
+        self._ck(self._L.zk_set_challenge(self._h, which, limbs), "zk_set_challenge")
+
+    def upload_columns(self, circuit_id: int, matrix, flags=None, stream: int = 0) -> None:
+        m = self._matrix(matrix)
+        self._ck(self._L.zk_upload_columns(self._h, circuit_id, m.shape[1], m.shape[0], _host_ptr(m),
+                                           ctypes.c_void_p(stream)), "zk_upload_columns")
+        if flags is not None:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._ck(self._L.zk_upload_row_flags(self._h, circuit_id, f.shape[0], _host_ptr(f),
+                                                 ctypes.c_void_p(stream)), "zk_upload_row_flags")
+
+    def bind_columns_device(self, circuit_id: int, n_rows: int, n_cols: int, dev_ptr: int) -> None:
+        self._ck(self._L.zk_bind_columns_device(self._h, circuit_id, n_rows, n_cols,
+                                                ctypes.c_void_p(dev_ptr)), "zk_bind_columns_device")
+
+    def upload_table(self, table_id: int, matrix, flags=None, stream: int = 0) -> None:
+        m = self._matrix(matrix)
+        self._ck(self._L.zk_upload_table(self._h, table_id, m.shape[1], m.shape[0], _host_ptr(m),
+                                         ctypes.c_void_p(stream)), "zk_upload_table")
+        if flags is not None:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._ck(self._L.zk_upload_table_flags(self._h, table_id, f.shape[0], _host_ptr(f),
+                                                   ctypes.c_void_p(stream)), "zk_upload_table_flags")
+
+    def bind_table_device(self, table_id: int, n_rows: int, n_cols: int, dev_ptr: int) -> None:
+        self._ck(self._L.zk_bind_table_device(self._h, table_id, n_rows, n_cols,
+                                              ctypes.c_void_p(dev_ptr)), "zk_bind_table_device")
+
+    def n_constraints(self, circuit_id: int) -> int:
+        return self._L.zk_n_constraints(circuit_id)
+
+    def check(self, circuit_id: int, row_begin: int, row_end: int, row_base: int = 0,
+              flags: int = FLAG_WRAP, stream: int = 0):
+        n = self.n_constraints(circuit_id)
+        ff = np.empty(n, dtype=np.uint32)
+        fc = np.empty(n, dtype=np.uint64)
+        self._ck(self._L.zk_check(self._h, circuit_id, row_begin, row_end, row_base, flags,
+                                  ff.ctypes.data_as(_U32P), fc.ctypes.data_as(_U64P),
+                                  ctypes.c_void_p(stream)), "zk_check")
+        return ff, fc
+
+    def check_async(self, circuit_id: int, row_begin: int, row_end: int, row_base: int = 0,
+                    flags: int = FLAG_WRAP, stream: int = 0) -> None:
+        self._ck(self._L.zk_check_async(self._h, circuit_id, row_begin, row_end, row_base, flags,
+                                        ctypes.c_void_p(stream)), "zk_check_async")
+
+    def fetch_result(self, circuit_id: int, stream: int = 0):
+        n = self.n_constraints(circuit_id)
+        ff = np.empty(n, dtype=np.uint32)
+        fc = np.empty(n, dtype=np.uint64)
+        self._ck(self._L.zk_fetch_result(self._h, circuit_id, ff.ctypes.data_as(_U32P),
+                                         fc.ctypes.data_as(_U64P), ctypes.c_void_p(stream)),
+                 "zk_fetch_result")
+        return ff, fc
+
+    def result_device_ptrs(self, circuit_id: int):
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        self._ck(self._L.zk_result_device(self._h, circuit_id, ctypes.byref(a), ctypes.byref(b)),
+                 "zk_result_device")
+        return a.value, b.value
+
+    def invalidate_indexes(self) -> None:
+        self._L.zk_invalidate_indexes(self._h)
+
+    def launch_count(self) -> int:
+        return int(self._L.zk_launch_count(self._h))
+
+
+_DEFAULT: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Context(device)
+    return _DEFAULT[device]
+
+
+def first_failure(first_fail: np.ndarray, circuit_id: int):
+    """(row, constraint id, error class) of the failure the reference would hit first:
+    smallest row, then smallest id (ids follow the reference's program order)."""
+    bad = np.nonzero(first_fail != PASS)[0]
+    if len(bad) == 0:
+        return None
+    rows = first_fail[bad].astype(np.int64)
+    k = int(bad[np.argmin(rows)])  # argmin returns the first (smallest id) among equal rows
+    cat = constraint_catalogue(circuit_id)
+    return int(first_fail[k]), k, cat[k][1], cat[k][0]
