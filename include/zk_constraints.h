@@ -47,4 +47,111 @@
 
 enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTRAINTS };
 
+/* ---------------- EVM circuit: src/zkevm_specs/evm_circuit/main.py:47-63 and the gadgets ----
+ * One step runs: the common prologue, exactly one gadget block, and (for same-context
+ * opcodes) the shared epilogue EV_SC_*; ids inside each block follow program order. */
+#define ZK_EVM_PUSH_BYTE(X, i)                                                              \
+  X(EV_PUSH_B##i##_UNSAT, ZKE_UNSAT, "push.py:25-27 byte " #i ": bytecode lookup (is_code=0) unsat")  \
+  X(EV_PUSH_B##i##_AMBIG, ZKE_AMBIG, "push.py:25-27 byte " #i ": bytecode lookup ambiguous")          \
+  X(EV_PUSH_B##i##_EQ, ZKE_ASSERT, "push.py:25-27 byte " #i ": pushed byte == bytecode byte")        \
+  X(EV_PUSH_B##i##_ZERO, ZKE_ASSERT, "push.py:29 byte " #i ": unpushed/padding byte == 0")
+
+#define ZK_EVM_CONSTRAINTS(X)                                                               \
+  X(EV_FIRST_STATE, ZKE_ASSERT, "main.py:48-52 first step state in {BeginTx,EndBlock}")     \
+  X(EV_FIRST_RWC, ZKE_ASSERT, "main.py:53 first step rw_counter==1")                        \
+  X(EV_LAST_STATE, ZKE_ASSERT, "main.py:55-56 last step state==EndBlock")                   \
+  X(EV_TRANS_FROM_ENDTX, ZKE_ASSERT, "instruction.py:193-194 EndTx -> BeginTx|EndBlock")    \
+  X(EV_TRANS_FROM_ENDBLOCK, ZKE_ASSERT, "instruction.py:195-196 EndBlock -> EndBlock")      \
+  X(EV_TRANS_TO_BEGINTX, ZKE_ASSERT, "instruction.py:199-200 -> BeginTx only from EndTx")   \
+  X(EV_TRANS_TO_ENDTX, ZKE_ASSERT, "instruction.py:201-202 -> EndTx only from halting|BeginTx") \
+  X(EV_TRANS_TO_ENDBLOCK, ZKE_ASSERT, "instruction.py:203-204 -> EndBlock only from EndTx|EndBlock") \
+  X(EV_NOT_IMPLEMENTED, ZKE_NOTIMPL, "main.py:60-63 state has no gadget in the reference")  \
+  X(EV_UNSUPPORTED_STATE, ZKE_NOTIMPL, "this build has no gate program for the state")      \
+  X(EV_OP_UNSAT, ZKE_UNSAT, "instruction.py:784-790 opcode_lookup: bytecode lookup unsat")  \
+  X(EV_OP_AMBIG, ZKE_AMBIG, "instruction.py:784-790 opcode_lookup: bytecode lookup ambiguous") \
+  /* ADD / SUB: execution/add_sub.py:5-24 */                                                \
+  X(EV_ADD_A_UNSAT, ZKE_UNSAT, "add_sub.py:10 stack_pop a unsat")                           \
+  X(EV_ADD_A_AMBIG, ZKE_AMBIG, "add_sub.py:10 stack_pop a ambiguous")                       \
+  X(EV_ADD_B_UNSAT, ZKE_UNSAT, "add_sub.py:11 stack_pop b unsat")                           \
+  X(EV_ADD_B_AMBIG, ZKE_AMBIG, "add_sub.py:11 stack_pop b ambiguous")                       \
+  X(EV_ADD_C_UNSAT, ZKE_UNSAT, "add_sub.py:12 stack_push c unsat")                          \
+  X(EV_ADD_C_AMBIG, ZKE_AMBIG, "add_sub.py:12 stack_push c ambiguous")                      \
+  X(EV_ADD_SUM, ZKE_ASSERT, "add_sub.py:14-17 add_words([is_sub?c:a, b]) == (is_sub?a:c)")   \
+  /* MUL / DIV / MOD: execution/mul_div_mod.py:6-71 */                                      \
+  X(EV_MUL_POP1_UNSAT, ZKE_UNSAT, "mul_div_mod.py:18 stack_pop unsat")                      \
+  X(EV_MUL_POP1_AMBIG, ZKE_AMBIG, "mul_div_mod.py:18 stack_pop ambiguous")                  \
+  X(EV_MUL_POP2_UNSAT, ZKE_UNSAT, "mul_div_mod.py:19 stack_pop unsat")                      \
+  X(EV_MUL_POP2_AMBIG, ZKE_AMBIG, "mul_div_mod.py:19 stack_pop ambiguous")                  \
+  X(EV_MUL_PUSH_UNSAT, ZKE_UNSAT, "mul_div_mod.py:20 stack_push unsat")                     \
+  X(EV_MUL_PUSH_AMBIG, ZKE_AMBIG, "mul_div_mod.py:20 stack_push ambiguous")                 \
+  X(EV_MUL_WITNESS_DOMAIN, ZKE_NOTIMPL, "DIV/MOD witness assignment with a stack word half >= 2^128: outside the supported witness domain (DESIGN.md)") \
+  X(EV_MUL_WITNESS_NEG, ZKE_VALUE, "mul_div_mod.py:32,41 Word(negative int) -> OverflowError") \
+  X(EV_MUL_TO64, ZKE_VALUE, "instruction.py:604-605 to_64s(): half of a or b >= 2^128 -> OverflowError") \
+  X(EV_MUL_CARRY_LO, ZKE_RANGE, "instruction.py:626 range_check(carry_lo, 9)")              \
+  X(EV_MUL_CARRY_HI, ZKE_RANGE, "instruction.py:627 range_check(carry_hi, 9)")              \
+  X(EV_MUL_SELECT, ZKE_ASSERT, "mul_div_mod.py:47-54 select_word bool / Word range asserts") \
+  X(EV_MUL_PUSH_EQ, ZKE_ASSERT, "mul_div_mod.py:49-54 push == d*is_mul + a*is_div*(1-b0) + c*is_mod*(1-b0)") \
+  X(EV_MUL_C_ZERO, ZKE_ASSERT, "mul_div_mod.py:57 is_mul * sum(bytes(c)) == 0")             \
+  X(EV_MUL_REM_LT, ZKE_ASSERT, "mul_div_mod.py:60-61 remainder < divisor unless divisor==0") \
+  X(EV_MUL_OVERFLOW, ZKE_ASSERT, "mul_div_mod.py:64 (1-is_mul)*overflow == 0")              \
+  /* PUSH: execution/push.py:6-33 */                                                        \
+  X(EV_PUSH_LEN_UNSAT, ZKE_UNSAT, "push.py:9 bytecode_length lookup unsat")                 \
+  X(EV_PUSH_LEN_AMBIG, ZKE_AMBIG, "push.py:9 bytecode_length lookup ambiguous")             \
+  X(EV_PUSH_CMP_RANGE, ZKE_ASSERT, "push.py:11 compare(): operand exceeds 8 bytes (instruction.py:449-450)") \
+  X(EV_PUSH_RW_UNSAT, ZKE_UNSAT, "push.py:14 stack_push unsat")                             \
+  X(EV_PUSH_RW_AMBIG, ZKE_AMBIG, "push.py:14 stack_push ambiguous")                         \
+  X(EV_PUSH_VALUE_BYTES, ZKE_VALUE, "push.py:15 to_le_bytes(): half >= 2^128 -> OverflowError") \
+  ZK_EVM_PUSH_BYTE(X, 0)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 1)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 2)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 3)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 4)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 5)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 6)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 7)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 8)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 9)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 10)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 11)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 12)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 13)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 14)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 15)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 16)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 17)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 18)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 19)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 20)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 21)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 22)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 23)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 24)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 25)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 26)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 27)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 28)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 29)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 30)                                                              \
+  ZK_EVM_PUSH_BYTE(X, 31)                                                              \
+  /* POP: execution/pop.py:4-14 */                                                          \
+  X(EV_POP_RW_UNSAT, ZKE_UNSAT, "pop.py:7 stack_pop unsat")                                 \
+  X(EV_POP_RW_AMBIG, ZKE_AMBIG, "pop.py:7 stack_pop ambiguous")                             \
+  /* shared epilogue: step_state_transition_in_same_context, instruction.py:365-394 */      \
+  X(EV_SC_RESP_OPCODE, ZKE_UNSAT, "instruction.py:376,779-782 ResponsibleOpcode fixed lookup") \
+  X(EV_SC_OPCODE_VALUE, ZKE_VALUE, "instruction.py:378 Opcode(opcode.n): not a valid opcode -> ValueError") \
+  X(EV_SC_GAS_RANGE, ZKE_RANGE, "instruction.py:379,529-534 gas_left - gas_cost fits 8 bytes") \
+  X(EV_SC_RWC, ZKE_ASSERT, "instruction.py:381-394 rw_counter transition")                  \
+  X(EV_SC_PC, ZKE_ASSERT, "instruction.py:381-394 program_counter transition")              \
+  X(EV_SC_SP, ZKE_ASSERT, "instruction.py:381-394 stack_pointer transition")                \
+  X(EV_SC_GAS, ZKE_ASSERT, "instruction.py:381-394 gas_left transition")                    \
+  X(EV_SC_MEM, ZKE_ASSERT, "instruction.py:381-394 memory_word_size transition")            \
+  X(EV_SC_REV, ZKE_ASSERT, "instruction.py:381-394 reversible_write_counter transition")    \
+  X(EV_SC_LOG, ZKE_ASSERT, "instruction.py:381-394 log_id transition")                      \
+  X(EV_SC_CALL_ID, ZKE_ASSERT, "instruction.py:381-394 call_id same")                       \
+  X(EV_SC_IS_ROOT, ZKE_ASSERT, "instruction.py:381-394 is_root same")                       \
+  X(EV_SC_IS_CREATE, ZKE_ASSERT, "instruction.py:381-394 is_create same")                   \
+  X(EV_SC_CODE_HASH, ZKE_ASSERT, "instruction.py:381-394 code_hash same")
+
+enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

@@ -162,6 +162,12 @@ int zk_n_constraints(int circuit_id);
 int zk_constraint_info(int circuit_id, int idx, char* buf, int n);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 uint64_t zk_launch_count(zk_ctx* ctx);
+/* Device-side timing of the two phases of a check (lookup-index builds, then the circuit
+ * kernel), measured with CUDA events recorded on the SAME stream the kernels are launched on.
+ * zk_enable_timing(ctx, 1) makes every zk_check_async record events; zk_last_timing returns
+ * the durations of the most recent check after synchronising its events (milliseconds). */
+int zk_enable_timing(zk_ctx* ctx, int on);
+int zk_last_timing(zk_ctx* ctx, float* index_build_ms, float* check_kernel_ms);
 /* drop cached lookup indexes so the next zk_check rebuilds them (used by bench to time the
  * whole path) */
 int zk_invalidate_indexes(zk_ctx* ctx);

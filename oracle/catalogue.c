@@ -1,0 +1,17 @@
+/* oracle/catalogue.c — TEST INFRASTRUCTURE: constraint counts and error classes as the
+ * oracle sees them (from include/zk_constraints.h). */
+#include "../include/zk_constraints.h"
+#define CLS(id, cls, doc) cls,
+static const int kBytecode[] = {ZK_BYTECODE_CONSTRAINTS(CLS)};
+static const int kEvm[] = {ZK_EVM_CONSTRAINTS(CLS)};
+int orc_n_constraints(int circuit) {
+  switch (circuit) {
+    case 0: return BC_N_CONSTRAINTS;
+    case 3: return EV_N_CONSTRAINTS;
+    default: return 0;
+  }
+}
+int orc_constraint_class(int circuit, int idx) {
+  if (idx < 0 || idx >= orc_n_constraints(circuit)) return -1;
+  return circuit == 0 ? kBytecode[idx] : kEvm[idx];
+}

@@ -1,0 +1,341 @@
+/*
+ * oracle/evm.c — TEST INFRASTRUCTURE (CPU oracle). Never linked into the product.
+ *
+ * Restates verify_step and the hot gadgets of the reference's EVM circuit over the
+ * column-major matrices of include/zkcheck.h:
+ *   verify_steps / verify_step                  src/zkevm_specs/evm_circuit/main.py:14-63
+ *   constrain_execution_state_transition        evm_circuit/instruction.py:189-204
+ *   step_state_transition_in_same_context       evm_circuit/instruction.py:365-394, 206-264
+ *   opcode_lookup / rw_lookup / stack_pop,push  evm_circuit/instruction.py:784-790, 792-824, 915-926
+ *   add_sub                                     evm_circuit/execution/add_sub.py:5-24
+ *   mul_div_mod (+ mul_add_words, compare_word) evm_circuit/execution/mul_div_mod.py:6-71,
+ *                                               instruction.py:599-632, 447-463
+ *   push                                        evm_circuit/execution/push.py:6-33
+ *   pop                                         evm_circuit/execution/pop.py:4-14
+ * Step = 13 cells in the order of StepState (evm_circuit/step.py:16-44), code_hash as lo,hi.
+ * Pinned by tests/golden/evm.npz (verdicts of the reference's own verify_steps).
+ */
+#include "common.h"
+#include "../include/zk_evm_spec.h"
+
+enum { S_STATE, S_RWC, S_CALL_ID, S_IS_ROOT, S_IS_CREATE, S_HASH_LO, S_HASH_HI, S_PC, S_SP, S_GAS,
+       S_MEM, S_REV, S_LOG, EVM_COLS };
+/* bytecode table cells */
+enum { B_HASH_LO, B_HASH_HI, B_TAG, B_INDEX, B_ISCODE, B_VALUE };
+/* rw table cells */
+enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, R_VAL_HI, R_PREV_LO,
+       R_PREV_HI, R_AUX_LO, R_AUX_HI };
+
+static const int8_t ES_HALTS[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;
+static const int8_t ES_IMPL[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
+static const int16_t OPCODE_GAS[256] = ZK_OPCODE_GAS_INIT;
+
+/* 2^-128 mod p */
+static const fr_t INV_2_128 = {{0x18ee753c76f9dc6full, 0x54ad7e14a329e70full, 0x2b16366f4f7684dfull,
+                                0x133100d71fdf3579ull}};
+
+typedef struct {
+  const uint64_t* steps; uint64_t n_steps;
+  orc_index bytecode_ix, rw_ix, fixed_ix;
+  orc_result* res;
+} evm_env;
+
+typedef struct { fr_t lo, hi; } word_t;
+
+static int bytecode_lookup(evm_env* e, fr_t hlo, fr_t hhi, uint64_t tag, fr_t index, uint64_t is_code,
+                           fr_t* value) {
+  fr_t key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
+  uint32_t row; int n = orc_lookup(&e->bytecode_ix, key, &row);
+  if (n == 1) *value = fr_load(ORC_CELL(e->bytecode_ix.cells, e->bytecode_ix.n_rows, B_VALUE, row));
+  return n;
+}
+static int rw_lookup(evm_env* e, fr_t rwc, uint64_t rw, uint64_t tag, fr_t id, fr_t addr, word_t* value) {
+  fr_t key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
+  uint32_t row; int n = orc_lookup(&e->rw_ix, key, &row);
+  if (n == 1) {
+    value->lo = fr_load(ORC_CELL(e->rw_ix.cells, e->rw_ix.n_rows, R_VAL_LO, row));
+    value->hi = fr_load(ORC_CELL(e->rw_ix.cells, e->rw_ix.n_rows, R_VAL_HI, row));
+  }
+  return n;
+}
+/* A step stops at its FIRST failing constraint (the reference raises there), so at most one
+ * id is recorded per step. */
+#define CHECK(id, cond) do { if (!(cond)) { orc_fail(e->res, (id), row); return; } } while (0)
+/* report a lookup outcome; returns 1 if exactly one row matched */
+static int need1(evm_env* e, int n, int id_unsat, uint64_t row) {
+  if (n == 0) orc_fail(e->res, id_unsat, row);
+  if (n >= 2) orc_fail(e->res, id_unsat + 1, row);
+  return n == 1;
+}
+
+/* ---- 256/512-bit integer helpers for the witness assignment of mul_div_mod.py:23-41 ---- */
+typedef struct { uint64_t l[8]; } u512;
+static void mul256(const uint64_t a[4], const uint64_t b[4], u512* out) {
+  memset(out, 0, sizeof *out);
+  for (int i = 0; i < 4; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) {
+      u128 x = (u128)a[i] * b[j] + out->l[i + j] + c; out->l[i + j] = (uint64_t)x; c = (uint64_t)(x >> 64);
+    }
+    out->l[i + 4] = c;
+  }
+}
+static int cmp256(const uint64_t a[4], const uint64_t b[4]) {
+  for (int i = 3; i >= 0; i--) { if (a[i] < b[i]) return -1; if (a[i] > b[i]) return 1; }
+  return 0;
+}
+static void sub256(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+  uint64_t br = 0; for (int i = 0; i < 4; i++) out[i] = sbb(a[i], b[i], &br);
+}
+/* q = n / d (d != 0), schoolbook shift-subtract */
+static void div256(const uint64_t n[4], const uint64_t d[4], uint64_t q[4]) {
+  uint64_t r[4] = {0, 0, 0, 0}; memset(q, 0, 32);
+  for (int bit = 255; bit >= 0; bit--) {
+    uint64_t top = r[3] >> 63;
+    for (int i = 3; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 63);
+    r[0] = (r[0] << 1) | ((n[bit / 64] >> (bit % 64)) & 1);
+    if (top || cmp256(r, d) >= 0) { sub256(r, d, r); q[bit / 64] |= 1ull << (bit % 64); }
+  }
+}
+static void word_to_u256(word_t w, uint64_t out[4]) { out[0] = w.lo.l[0]; out[1] = w.lo.l[1]; out[2] = w.hi.l[0]; out[3] = w.hi.l[1]; }
+static word_t u256_to_word(const uint64_t v[4]) { word_t w = {fr_u128(v[0], v[1]), fr_u128(v[2], v[3])}; return w; }
+static int word_in_domain(word_t w) { return fr_fits_bits(w.lo, 128) && fr_fits_bits(w.hi, 128); }
+
+/* shared epilogue: instruction.py:365-394 */
+static void same_context(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint64_t d_rwc, fr_t d_pc,
+                         fr_t d_sp) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+#define CUR(c) fr_load(ORC_CELL(S, n, c, i))
+#define NXT(c) fr_load(ORC_CELL(S, n, c, j))
+  fr_t key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), CUR(S_STATE), opcode, fr_u64(0)};
+  CHECK(EV_SC_RESP_OPCODE, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  int gas_cost = -1;
+  if (fr_fits_bits(opcode, 8)) gas_cost = OPCODE_GAS[opcode.l[0]];
+  if (gas_cost < 0) { orc_fail(e->res, EV_SC_OPCODE_VALUE, row); return; }
+  fr_t gas_after = fr_sub(CUR(S_GAS), fr_u64((uint64_t)gas_cost));
+  CHECK(EV_SC_GAS_RANGE, fr_fits_bits(gas_after, 64));
+  CHECK(EV_SC_RWC, fr_eq(NXT(S_RWC), fr_add(CUR(S_RWC), fr_u64(d_rwc))));
+  CHECK(EV_SC_PC, fr_eq(NXT(S_PC), fr_add(CUR(S_PC), d_pc)));
+  CHECK(EV_SC_SP, fr_eq(NXT(S_SP), fr_add(CUR(S_SP), d_sp)));
+  CHECK(EV_SC_GAS, fr_eq(NXT(S_GAS), gas_after));
+  CHECK(EV_SC_MEM, fr_eq(NXT(S_MEM), CUR(S_MEM)));
+  CHECK(EV_SC_REV, fr_eq(NXT(S_REV), CUR(S_REV)));
+  CHECK(EV_SC_LOG, fr_eq(NXT(S_LOG), CUR(S_LOG)));
+  CHECK(EV_SC_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
+  CHECK(EV_SC_IS_ROOT, fr_eq(NXT(S_IS_ROOT), CUR(S_IS_ROOT)));
+  CHECK(EV_SC_IS_CREATE, fr_eq(NXT(S_IS_CREATE), CUR(S_IS_CREATE)));
+  CHECK(EV_SC_CODE_HASH,
+          fr_eq(NXT(S_HASH_LO), CUR(S_HASH_LO)) && fr_eq(NXT(S_HASH_HI), CUR(S_HASH_HI)));
+}
+
+/* add_words on two words, carry dropped (util/arithmetic.py:236-242) */
+static word_t add_words2(word_t x, word_t y) {
+  fr_t slo = fr_add(x.lo, y.lo);
+  fr_t carry_lo = fr_u128(slo.l[2], slo.l[3]);
+  fr_t shi = fr_add(fr_add(x.hi, y.hi), carry_lo);
+  word_t r = {fr_u128(slo.l[0], slo.l[1]), fr_u128(shi.l[0], shi.l[1])};
+  return r;
+}
+static int word_eq(word_t a, word_t b) { return fr_eq(a.lo, b.lo) && fr_eq(a.hi, b.hi); }
+
+static void gadget_add(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const int is_sub = fr_eq_u64(opcode, 3);
+  word_t a, b, c;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_ADD_A_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(1)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &b),
+             EV_ADD_B_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &c),
+             EV_ADD_C_UNSAT, row)) return;
+  CHECK(EV_ADD_SUM, word_eq(add_words2(is_sub ? c : a, b), is_sub ? a : c));
+  same_context(e, i, row, opcode, 3, fr_u64(1), fr_u64(1));
+}
+
+/* Word((sel*lo, sel*hi)) with the constructor's < 2^128 assertion (arithmetic.py:110-114) */
+static int word_select(word_t w, fr_t sel, word_t* out) {
+  out->lo = fr_mul(sel, w.lo); out->hi = fr_mul(sel, w.hi);
+  return word_in_domain(*out);
+}
+
+static void gadget_mul(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const fr_t one = fr_u64(1);
+  /* mul_div_mod.py:14-16 */
+  const fr_t is_mul = fr_mul(fr_mul(fr_sub(fr_u64(4), opcode), fr_sub(fr_u64(6), opcode)), fr_inv(fr_u64(8)));
+  const fr_t is_div = fr_mul(fr_mul(fr_sub(opcode, fr_u64(2)), fr_sub(fr_u64(6), opcode)), fr_inv(fr_u64(4)));
+  const fr_t is_mod = fr_mul(fr_mul(fr_sub(opcode, fr_u64(2)), fr_sub(opcode, fr_u64(4))), fr_inv(fr_u64(8)));
+  word_t pop1, pop2, push;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &pop2),
+             EV_MUL_POP2_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &push),
+             EV_MUL_PUSH_UNSAT, row)) return;
+  const int in_domain = word_in_domain(pop1) && word_in_domain(pop2) && word_in_domain(push);
+  /* witness assignment by branch, mul_div_mod.py:23-41 (Python int arithmetic) */
+  word_t a, b, c, d;
+  const word_t zero = {fr_u64(0), fr_u64(0)};
+  if (fr_eq_u64(is_mul, 1)) { a = pop1; b = pop2; c = zero; d = push; }
+  else if (!in_domain) { orc_fail(e->res, EV_MUL_WITNESS_DOMAIN, row); return; } /* needs > 512-bit ints */
+  else if (fr_eq_u64(is_div, 1)) {
+    d = pop1; b = pop2; a = push;
+    uint64_t dv[4], bv[4], av[4], cv[4]; u512 prod;
+    word_to_u256(d, dv); word_to_u256(b, bv); word_to_u256(a, av);
+    mul256(bv, av, &prod);
+    if (prod.l[4] | prod.l[5] | prod.l[6] | prod.l[7] || cmp256(prod.l, dv) > 0) {
+      orc_fail(e->res, EV_MUL_WITNESS_NEG, row); return; /* Word(negative) */
+    }
+    sub256(dv, prod.l, cv); c = u256_to_word(cv);
+  } else {
+    d = pop1; b = pop2;
+    uint64_t dv[4], bv[4], cv[4], qv[4], tv[4];
+    word_to_u256(d, dv); word_to_u256(b, bv);
+    if ((bv[0] | bv[1] | bv[2] | bv[3]) == 0) { c = d; a = zero; }
+    else {
+      c = push; word_to_u256(c, cv);
+      if (cmp256(dv, cv) < 0) { orc_fail(e->res, EV_MUL_WITNESS_NEG, row); return; } /* floor div < 0 */
+      sub256(dv, cv, tv); div256(tv, bv, qv); a = u256_to_word(qv);
+    }
+  }
+  const fr_t divisor_is_zero = fr_u64(fr_is_zero(fr_add(b.lo, b.hi)));
+  /* mul_add_words, instruction.py:599-632 */
+  CHECK(EV_MUL_TO64, word_in_domain(a) && word_in_domain(b));
+  fr_t a64[4] = {fr_u64(a.lo.l[0]), fr_u64(a.lo.l[1]), fr_u64(a.hi.l[0]), fr_u64(a.hi.l[1])};
+  fr_t b64[4] = {fr_u64(b.lo.l[0]), fr_u64(b.lo.l[1]), fr_u64(b.hi.l[0]), fr_u64(b.hi.l[1])};
+#define M(x, y) fr_mul(a64[x], b64[y])
+  const fr_t t0 = M(0, 0);
+  const fr_t t1 = fr_add(M(0, 1), M(1, 0));
+  const fr_t t2 = fr_add(fr_add(M(0, 2), M(1, 1)), M(2, 0));
+  const fr_t t3 = fr_add(fr_add(fr_add(M(0, 3), M(1, 2)), M(2, 1)), M(3, 0));
+  const fr_t two64 = {{0, 1, 0, 0}};
+  const fr_t carry_lo = fr_mul(fr_sub(fr_add(fr_add(t0, fr_mul(t1, two64)), c.lo), d.lo), INV_2_128);
+  const fr_t carry_hi =
+      fr_mul(fr_sub(fr_add(fr_add(fr_add(t2, fr_mul(t3, two64)), c.hi), carry_lo), d.hi), INV_2_128);
+  fr_t overflow = carry_hi;
+  overflow = fr_add(overflow, M(1, 3)); overflow = fr_add(overflow, M(2, 2));
+  overflow = fr_add(overflow, M(3, 1)); overflow = fr_add(overflow, M(2, 3));
+  overflow = fr_add(overflow, M(3, 2)); overflow = fr_add(overflow, M(3, 3));
+#undef M
+  if (!fr_fits_bits(carry_lo, 72)) { orc_fail(e->res, EV_MUL_CARRY_LO, row); return; }
+  if (!fr_fits_bits(carry_hi, 72)) { orc_fail(e->res, EV_MUL_CARRY_HI, row); return; }
+  /* the two constrain_equal of instruction.py:629-630 hold by construction of the carries */
+  /* mul_div_mod.py:47-54 */
+  if (!(fr_eq_u64(is_mul, 0) || fr_eq_u64(is_mul, 1))) { orc_fail(e->res, EV_MUL_SELECT, row); return; }
+  /* pop1 == select_word(is_mul, a, d) and pop2 == b hold by the assignment above */
+  word_t t_d, t_a, t_c, sum;
+  const fr_t nz = fr_sub(one, divisor_is_zero);
+  if (!word_select(d, is_mul, &t_d) || !word_select(a, fr_mul(is_div, nz), &t_a)) {
+    orc_fail(e->res, EV_MUL_SELECT, row); return;
+  }
+  if (!word_select(c, fr_mul(is_mod, nz), &t_c)) { orc_fail(e->res, EV_MUL_SELECT, row); return; }
+  sum.lo = fr_add(t_d.lo, t_a.lo); sum.hi = fr_add(t_d.hi, t_a.hi);
+  if (!word_in_domain(sum)) { orc_fail(e->res, EV_MUL_SELECT, row); return; }
+  sum.lo = fr_add(sum.lo, t_c.lo); sum.hi = fr_add(sum.hi, t_c.hi);
+  if (!word_in_domain(sum)) { orc_fail(e->res, EV_MUL_SELECT, row); return; }
+  CHECK(EV_MUL_PUSH_EQ, word_eq(push, sum));
+  /* :57  is_mul * sum(c.to_le_bytes()) == 0 */
+  uint64_t byte_sum = 0;
+  for (int k = 0; k < 2; k++) for (int s = 0; s < 64; s += 8) {
+    byte_sum += (c.lo.l[k] >> s) & 0xFF; byte_sum += (c.hi.l[k] >> s) & 0xFF;
+  }
+  CHECK(EV_MUL_C_ZERO, fr_is_zero(fr_mul(is_mul, fr_u64(byte_sum))));
+  /* :60-61 compare_word(c, b) */
+  const int hi_lt = fr_cmp(c.hi, b.hi) < 0, hi_eq = fr_eq(c.hi, b.hi), lo_lt = fr_cmp(c.lo, b.lo) < 0;
+  const fr_t lt = fr_u64((uint64_t)(hi_lt + hi_eq * lo_lt));
+  CHECK(EV_MUL_REM_LT,
+          fr_is_zero(fr_mul(fr_mul(fr_sub(one, is_mul), nz), fr_sub(one, lt))));
+  CHECK(EV_MUL_OVERFLOW, fr_is_zero(fr_mul(fr_sub(one, is_mul), overflow)));
+  same_context(e, i, row, opcode, 3, one, one);
+}
+
+static void gadget_push(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), pc = CUR(S_PC);
+  const fr_t hlo = CUR(S_HASH_LO), hhi = CUR(S_HASH_HI);
+  const fr_t num_pushed = fr_sub(opcode, fr_u64(0x5f));
+  fr_t code_length;
+  if (!need1(e, bytecode_lookup(e, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_PUSH_LEN_UNSAT, row)) return;
+  const fr_t left = fr_sub(fr_sub(code_length, pc), fr_u64(1));
+  if (!fr_fits_bits(left, 64) || !fr_fits_bits(num_pushed, 64)) { orc_fail(e->res, EV_PUSH_CMP_RANGE, row); return; }
+  const int oob = left.l[0] < num_pushed.l[0];
+  const fr_t num_padding = oob ? fr_sub(num_pushed, left) : fr_u64(0);
+  word_t value;
+  if (!need1(e, rw_lookup(e, rwc, 1, ZK_TARGET_Stack, call_id, fr_sub(sp, fr_u64(1)), &value),
+             EV_PUSH_RW_UNSAT, row)) return;
+  if (!word_in_domain(value)) { orc_fail(e->res, EV_PUSH_VALUE_BYTES, row); return; }
+  for (int idx = 0; idx < 32; idx++) {
+    const uint64_t byte = idx < 16 ? (value.lo.l[idx / 8] >> (8 * (idx % 8))) & 0xFF
+                                   : (value.hi.l[(idx - 16) / 8] >> (8 * (idx % 8))) & 0xFF;
+    /* continuous_selectors: FQ(i < value.n) on the full integer (instruction.py:413-414) */
+    const int is_pushed = fr_cmp(fr_u64((uint64_t)idx), num_pushed) < 0;
+    const int is_padding = fr_cmp(fr_u64((uint64_t)idx), num_padding) < 0;
+    const int base = EV_PUSH_B0_UNSAT + 4 * idx;
+    if (is_pushed && !is_padding) {
+      fr_t got;
+      const fr_t index = fr_sub(fr_add(pc, num_pushed), fr_u64((uint64_t)idx));
+      if (!need1(e, bytecode_lookup(e, hlo, hhi, 2, index, 0, &got), base, row)) return;
+      if (!fr_eq_u64(got, byte)) { orc_fail(e->res, base + 2, row); return; }
+    } else if (byte != 0) { orc_fail(e->res, base + 3, row); return; }
+  }
+  same_context(e, i, row, opcode, 1, fr_add(fr_u64(1), num_pushed), fr_neg(fr_u64(1)));
+}
+
+static void gadget_pop(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  word_t y;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &y), EV_POP_RW_UNSAT, row))
+    return;
+  same_context(e, i, row, opcode, 1, fr_u64(1), fr_u64(1));
+}
+
+static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
+
+static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+  const fr_t cs = CUR(S_STATE), ns = NXT(S_STATE);
+  const int is_first = (flags & 2) && row == 0;
+  const int is_last = (flags & 4) && i == n - 2;
+  if (is_first) {
+    CHECK(EV_FIRST_STATE, state_is(cs, ZK_ES_BeginTx) || state_is(cs, ZK_ES_EndBlock));
+    CHECK(EV_FIRST_RWC, fr_eq_u64(CUR(S_RWC), 1));
+  }
+  if (is_last) CHECK(EV_LAST_STATE, state_is(cs, ZK_ES_EndBlock));
+  else {
+    const int c_halts = fr_fits_bits(cs, 16) && cs.l[0] < ZK_ES_COUNT && ES_HALTS[cs.l[0]];
+    if (state_is(cs, ZK_ES_EndTx))
+      CHECK(EV_TRANS_FROM_ENDTX, state_is(ns, ZK_ES_BeginTx) || state_is(ns, ZK_ES_EndBlock));
+    else if (state_is(cs, ZK_ES_EndBlock))
+      CHECK(EV_TRANS_FROM_ENDBLOCK, state_is(ns, ZK_ES_EndBlock));
+    if (state_is(ns, ZK_ES_BeginTx)) CHECK(EV_TRANS_TO_BEGINTX, state_is(cs, ZK_ES_EndTx));
+    else if (state_is(ns, ZK_ES_EndTx)) CHECK(EV_TRANS_TO_ENDTX, c_halts || state_is(cs, ZK_ES_BeginTx));
+    else if (state_is(ns, ZK_ES_EndBlock))
+      CHECK(EV_TRANS_TO_ENDBLOCK, state_is(cs, ZK_ES_EndTx) || state_is(cs, ZK_ES_EndBlock));
+  }
+  CHECK(EV_NOT_IMPLEMENTED, fr_fits_bits(cs, 16) && cs.l[0] < ZK_ES_COUNT && ES_IMPL[cs.l[0]]);
+  const uint64_t st = cs.l[0];
+  CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP);
+  fr_t opcode;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
+    return;
+  if (st == ZK_ES_ADD) gadget_add(e, i, row, opcode);
+  else if (st == ZK_ES_MUL) gadget_mul(e, i, row, opcode);
+  else if (st == ZK_ES_PUSH) gadget_push(e, i, row, opcode);
+  else gadget_pop(e, i, row, opcode);
+}
+
+int orc_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
+                  const uint64_t* rw_tab, uint64_t n_rw, const uint64_t* fixed_tab, uint64_t n_fixed,
+                  uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                  uint32_t* first_fail, uint64_t* fail_count) {
+  orc_result res; orc_result_init(&res, first_fail, fail_count, EV_N_CONSTRAINTS);
+  if (row_end + 1 > n_steps && row_end > row_begin) return -1;
+  evm_env env; env.steps = steps; env.n_steps = n_steps; env.res = &res;
+  const uint32_t bk[5] = {0, 1, 2, 3, 4}, rk[5] = {0, 1, 2, 3, 4}, fk[4] = {0, 1, 2, 3};
+  orc_index_build(&env.bytecode_ix, bytecode_tab, n_bytecode, 6, bk, 5);
+  orc_index_build(&env.rw_ix, rw_tab, n_rw, 14, rk, 5);
+  orc_index_build(&env.fixed_ix, fixed_tab, n_fixed, 4, fk, 4);
+  for (uint64_t i = row_begin; i < row_end; i++) verify_step(&env, i, row_base + i, flags);
+  orc_index_free(&env.bytecode_ix); orc_index_free(&env.rw_ix); orc_index_free(&env.fixed_ix);
+  return 0;
+}

@@ -1,0 +1,84 @@
+// tests/emu/zk_emu.cu — TEST INFRASTRUCTURE: runs the product's gate programs (the same
+// __host__ __device__ functions the CUDA kernels call) serially on the CPU, so that kernel
+// logic can be diffed against the oracle locally before spending a GPU call.  Never shipped,
+// never used by the product (which has no CPU path); built by tests/emu_lib.py with
+// `nvcc -x cu` host compilation only.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../zkevm-specs_b200/csrc/bytecode.cu"
+#include "../../zkevm-specs_b200/csrc/evm.cu"
+
+using namespace zk;
+
+static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32* key_cols, u32 n_key,
+                            const Fr& challenge, std::vector<u32>& slots) {
+  IndexDev d;
+  d.tab.cells = cells;
+  d.tab.n_rows = n_rows;
+  d.tab.n_cols = n_cols;
+  d.tab.flags = nullptr;
+  size_t cap = 64;
+  while (cap < 2 * n_rows) cap <<= 1;
+  slots.assign(cap, ZK_EMPTY_SLOT);
+  d.slots = slots.data();
+  d.mask = (u32)(cap - 1);
+  d.n_key = n_key;
+  const Fr r_mont = fr_to_mont(challenge);
+  Fr acc = fr_to_mont(fr_u64(1));
+  for (u32 j = 0; j < ZK_MAX_KEY; j++) {
+    d.key_cols[j] = j < n_key ? key_cols[j] : 0;
+    d.pw[j] = acc;
+    acc = fr_montmul(acc, r_mont);
+  }
+  for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
+  return d;
+}
+
+static void init_result(ResultDev& res, uint32_t* ff, uint64_t* fc, int n) {
+  for (int i = 0; i < n; i++) { ff[i] = 0xFFFFFFFFu; fc[i] = 0; }
+  res.first_fail = ff;
+  res.fail_count = (u64*)fc;
+}
+
+extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode, uint64_t n_bytecode,
+                             const uint64_t* rw, uint64_t n_rw, const uint64_t* fixed, uint64_t n_fixed,
+                             uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                             const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
+  std::vector<u32> s1, s2, s3;
+  EvmTables t;
+  t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
+  t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
+  t.fixed = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, s3);
+  WitnessDev w{(const u64*)steps, n_steps, nullptr};
+  ResultDev res;
+  init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
+  for (u64 i = row_begin; i < row_end; i++) {
+    StepCtx s{w, t, res, i, i + 1, row_base + i};
+    verify_step(s, flags);
+  }
+  return 0;
+}
+
+extern "C" int emu_check_bytecode(const uint64_t* cols, uint64_t n_rows, const uint64_t* push, uint64_t n_push,
+                                  const uint64_t* keccak, uint64_t n_keccak, const uint64_t r[4],
+                                  uint64_t row_begin, uint64_t row_end, uint32_t flags,
+                                  const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 pk[2] = {0, 1}, kk[5] = {0, 1, 2, 3, 4};
+  std::vector<u32> s1, s2;
+  IndexDev push_ix = build_index((const u64*)push, n_push, 2, pk, 2, ch, s1);
+  IndexDev kec_ix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s2);
+  WitnessDev w{(const u64*)cols, n_rows, nullptr};
+  CheckRange rg{row_begin, row_end, 0, flags};
+  ResultDev res;
+  init_result(res, first_fail, fail_count, BC_N_CONSTRAINTS);
+  const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
+  for (u64 i = row_begin; i < row_end; i++) check_bytecode_row(w, rg, push_ix, kec_ix, r_mont, res, i);
+  return 0;
+}

@@ -1,0 +1,66 @@
+"""TEST INFRASTRUCTURE: CPU emulation of the product's gate programs (tests/emu/zk_emu.cu) —
+the very __host__ __device__ functions the CUDA kernels call, run serially.  Lets the CPU
+suite diff kernel logic against the oracle without a GPU.  The product never uses this."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "zk_emu.cu")
+OUT = os.path.join(ROOT, "tests", "emu", "_build", "libzkemu.so")
+_LIB = None
+U64P = ctypes.POINTER(ctypes.c_uint64)
+U32P = ctypes.POINTER(ctypes.c_uint32)
+CHALLENGE = np.array([0x1234567, 0x89ABCDEF, 0x13579BDF, 0x02468ACE], dtype=np.uint64)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        csrc = os.path.join(ROOT, "zkevm-specs_b200", "csrc")
+        deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)] + [
+            os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+        if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+            os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+                            "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC], check=True)
+        _LIB = ctypes.CDLL(OUT)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(U64P)
+
+
+def check_evm(steps, bytecode, rw, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None, challenge=None):
+    steps, bytecode, rw, fixed = [np.ascontiguousarray(a) for a in (steps, bytecode, rw, fixed)]
+    n = n or 256
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    if row_end is None:
+        row_end = steps.shape[1] - 1
+    rc = lib().emu_check_evm(_p(steps), c(steps.shape[1]), _p(bytecode), c(bytecode.shape[1]), _p(rw),
+                             c(rw.shape[1]), _p(fixed), c(fixed.shape[1]), c(row_begin), c(row_end), c(row_base),
+                             ctypes.c_uint32(flags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc
+
+
+def check_bytecode(cols, push, keccak, r, row_begin=0, row_end=None, flags=1, n=22, challenge=None):
+    cols, push, keccak = [np.ascontiguousarray(a) for a in (cols, push, keccak)]
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    if row_end is None:
+        row_end = cols.shape[1]
+    rc = lib().emu_check_bytecode(_p(cols), c(cols.shape[1]), _p(push), c(push.shape[1]), _p(keccak),
+                                  c(keccak.shape[1]), _p(rr), c(row_begin), c(row_end), ctypes.c_uint32(flags),
+                                  _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

@@ -177,6 +177,205 @@ def bytecode_cases():
     print(f"bytecode: {len(cases)} witnesses, {n_all} vectors ({n_fail} failing)")
 
 
+# --------------------------------------------------------------------------- evm
+def evm_cases():
+    """cfg2-style straight-line traces `PUSH32 b, PUSH32 a, OP, POP` (+ final STOP as the last
+    `next`), verified by the reference's verify_step loop (main.py:34-46), plus seeded
+    corruptions of step cells, rw-table cells and bytecode-table cells."""
+    import copy
+
+    from zkevm_specs.evm_circuit import (Bytecode, ExecutionState, Opcode, RWDictionary, StepState,
+                                         Tables, Block, RWTableRow, BytecodeTableRow)
+    from zkevm_specs.evm_circuit.instruction import Instruction
+    from zkevm_specs.evm_circuit.main import verify_step
+    from zkevm_specs.util import FQ, Word, WordOrValue
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from zkevm_specs_b200.evm_circuit.table import fixed_table_matrix
+
+    # our arithmetic fixed-table generator must reproduce the reference's set exactly
+    ours = fixed_table_matrix()
+    ours_set = set(tuple(sum(int(ours[c, i, k]) << (64 * k) for k in range(4)) for c in range(4))
+                   for i in range(ours.shape[1]))
+    ref_set = set((n_of(r.tag), n_of(r.value0), n_of(r.value1), n_of(r.value2)) for r in Tables.fixed_table)
+    assert ours_set == ref_set and len(ours_set) == ours.shape[1], "fixed table mismatch"
+    print("fixed table: ours == reference,", len(ref_set), "rows")
+
+    M256 = (1 << 256) - 1
+    NASTY = [(0, 0), (1, 0), (0, 1), (255, 256), (260, 513), (65535, 65536), (M256, M256 - 1),
+             (M256 - 1, M256), (M256, 0), (0, M256), (1 << 128, (1 << 128) - 1), (7, 3), (M256, 2)]
+
+    def build_trace(ops, rng):
+        """returns (steps, bytecode_rows, rw_rows)"""
+        bc = Bytecode()
+        groups = []
+        for op in ops:
+            if rng.random() < 0.5:
+                a, b = rng.choice(NASTY)
+            elif rng.random() < 0.5:
+                a, b = rng.randrange(1 << 64), rng.randrange(1, 1 << 64)
+            else:
+                a, b = rng.randrange(1 << 256), rng.randrange(1 << 256)
+            bc.push32(b).push32(a)
+            getattr(bc, op.lower())()
+            bc.pop()
+            groups.append((op, a, b))
+        bc.stop()
+        code_hash = Word(bc.hash())
+        rw = RWDictionary(1)
+        steps = []
+        pc, sp, gas = 0, 1024, 3 * 2 * len(ops) + 5 * len(ops) + 2 * len(ops) + 40
+        call_id = 1
+
+        def step(state):
+            steps.append(StepState(execution_state=state, rw_counter=rw.rw_counter, call_id=call_id,
+                                   is_root=True, is_create=False, code_hash=code_hash,
+                                   program_counter=pc, stack_pointer=sp, gas_left=gas))
+
+        for op, a, b in groups:
+            step(ExecutionState.PUSH); rw.stack_write(call_id, sp - 1, Word(b)); pc += 33; sp -= 1; gas -= 3
+            step(ExecutionState.PUSH); rw.stack_write(call_id, sp - 1, Word(a)); pc += 33; sp -= 1; gas -= 3
+            if op == "ADD":
+                c, st, g = (a + b) & M256, ExecutionState.ADD, 3
+            elif op == "SUB":
+                c, st, g = (a - b) & M256, ExecutionState.ADD, 3
+            elif op == "MUL":
+                c, st, g = (a * b) & M256, ExecutionState.MUL, 5
+            elif op == "DIV":
+                c, st, g = (0 if b == 0 else a // b), ExecutionState.MUL, 5
+            else:
+                c, st, g = (0 if b == 0 else a % b), ExecutionState.MUL, 5
+            step(st)
+            rw.stack_read(call_id, sp, Word(a)); rw.stack_read(call_id, sp + 1, Word(b))
+            rw.stack_write(call_id, sp + 1, Word(c)); pc += 1; sp += 1; gas -= g
+            step(ExecutionState.POP); rw.stack_read(call_id, sp, Word(c)); pc += 1; sp += 1; gas -= 2
+        step(ExecutionState.STOP)
+        return steps, list(bc.table_assignments()), list(rw.rws)
+
+    def step_ints(s):
+        return [int(s.execution_state), n_of(s.rw_counter), n_of(s.call_id), int(s.is_root), int(s.is_create),
+                n_of(s.code_hash.lo), n_of(s.code_hash.hi), n_of(s.program_counter), n_of(s.stack_pointer),
+                n_of(s.gas_left), n_of(s.memory_word_size), n_of(s.reversible_write_counter), n_of(s.log_id)]
+
+    def bc_ints(r):
+        return [n_of(r.bytecode_hash.lo), n_of(r.bytecode_hash.hi), n_of(r.field_tag), n_of(r.index),
+                n_of(r.is_code), n_of(r.value)]
+
+    def rw_ints(r):
+        return [n_of(r.rw_counter), n_of(r.rw), n_of(r.key0), n_of(r.id), n_of(r.address), n_of(r.field_tag),
+                n_of(r.storage_key.lo), n_of(r.storage_key.hi), n_of(r.value.lo), n_of(r.value.hi),
+                n_of(r.value_prev.lo), n_of(r.value_prev.hi), n_of(r.aux0.lo), n_of(r.aux0.hi)]
+
+    def step_from_ints(v):
+        s = StepState(execution_state=ExecutionState(v[0]), rw_counter=0)
+        s.rw_counter, s.call_id = FQ(v[1]), FQ(v[2])
+        s.is_root, s.is_create = v[3], v[4]  # ints: the reference wraps ints with FQ() (instruction.py:233)
+        s.code_hash = Word((FQ(v[5]), FQ(v[6])), check=False)
+        s.program_counter, s.stack_pointer, s.gas_left = FQ(v[7]), FQ(v[8]), FQ(v[9])
+        s.memory_word_size, s.reversible_write_counter, s.log_id = FQ(v[10]), FQ(v[11]), FQ(v[12])
+        return s
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def rw_from_ints(v):
+        return RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
+                          WordOrValue(W(v[8], v[9])), WordOrValue(W(v[10], v[11])), W(v[12], v[13]))
+
+    def bc_from_ints(v):
+        return BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]))
+
+    def run(step_rows, bc_rows, rw_rows, first=False, last=False):
+        steps = [step_from_ints(v) for v in step_rows]
+        tables = Tables(block_table=set(Block().table_assignments()), tx_table=set(), withdrawal_table=set(),
+                        bytecode_table=set(bc_from_ints(v) for v in bc_rows),
+                        rw_table=set(rw_from_ints(v) for v in rw_rows))
+        for idx, (curr, nxt) in enumerate(zip(steps, steps[1:])):
+            try:
+                verify_step(Instruction(tables=tables, curr=curr, next=nxt,
+                                        is_first_step=first and idx == 0,
+                                        is_last_step=last and idx == len(steps) - 2))
+            except Exception as e:  # noqa: BLE001
+                return idx, type(e).__name__
+        return -1, ""
+
+    valid_states = [int(s) for s in ExecutionState]
+    rng = random.Random(2)
+    traces = {
+        "add_sub": ["ADD", "SUB", "ADD"],
+        "mul_div_mod": ["MUL", "DIV", "MOD"],
+        "mixed5": ["ADD", "SUB", "MUL", "DIV", "MOD"],
+        "divmod_nasty": ["DIV", "MOD", "DIV", "MOD"],
+    }
+    out = {"names": np.array(list(traces.keys()))}
+    tot = nfail = 0
+    for name, ops in traces.items():
+        steps, bcs, rws = build_trace(ops, rng)
+        S = [step_ints(s) for s in steps]
+        B = [bc_ints(r) for r in bcs]
+        R = [rw_ints(r) for r in rws]
+        assert run(S, B, R) == (-1, ""), (name, run(S, B, R))
+        muts = [(0, -1, -1, 0, -1, "")]
+        n_mut = 70
+        for k in range(n_mut):
+            which = rng.choice([0, 0, 0, 1, 1, 2])
+            S2, B2, R2 = [list(x) for x in S], [list(x) for x in B], [list(x) for x in R]
+            if which == 0:
+                i, c = rng.randrange(len(S)), rng.randrange(13)
+                old = S[i][c]
+                if c == 0:
+                    v = rng.choice([x for x in valid_states if x != old] if rng.random() < 0.5 else
+                                   [int(ExecutionState.ADD), int(ExecutionState.MUL), int(ExecutionState.PUSH),
+                                    int(ExecutionState.POP), int(ExecutionState.STOP), int(ExecutionState.EndTx),
+                                    int(ExecutionState.BeginTx), int(ExecutionState.EndBlock)])
+                    if v == old:
+                        continue
+                elif c in (3, 4):
+                    v = 1 - old
+                else:
+                    v = corrupt_value(rng, old)
+                S2[i][c] = v
+            elif which == 1:
+                i, c = rng.randrange(len(R)), rng.randrange(14)
+                v = corrupt_value(rng, R[i][c])
+                R2[i][c] = v
+            else:
+                i = rng.randrange(len(B)) if rng.random() < 0.5 else rng.choice(
+                    [0, 1, 34, 67, 68, 69, len(B) - 1])
+                i = min(i, len(B) - 1)
+                c = rng.randrange(6)
+                v = corrupt_value(rng, B[i][c])
+                B2[i][c] = v
+            fr_, ex_ = run(S2, B2, R2)
+            muts.append((which, i, c, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        # duplicate-row ambiguity: add a second rw row equal on the queried key, different value
+        for i in (0, 2, 5):
+            if i < len(R):
+                dup = list(R[i]); dup[8] = (dup[8] + 1) % (1 << 128)
+                fr_, ex_ = run(S, B, R + [dup])
+                muts.append((3, i, 8, dup[8], fr_, ex_))
+        dupb = list(B[1]); dupb[5] = (dupb[5] + 1) % 256
+        fr_, ex_ = run(S, B + [dupb], R)
+        muts.append((4, 1, 5, dupb[5], fr_, ex_))
+        # first / last step flags
+        fr_, ex_ = run(S, B, R, first=True)
+        muts.append((5, 0, 0, 0, fr_, ex_))
+        out[f"{name}/steps"] = to_matrix(S)
+        out[f"{name}/bytecode"] = to_matrix(B)
+        out[f"{name}/rw"] = to_matrix(R)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, len(S), "steps", len(B), "bytecode rows", len(R), "rw rows", len(muts), "vectors")
+    np.savez_compressed(os.path.join(HERE, "evm.npz"), **out)
+    print(f"evm: {tot} corruptions, {nfail} failing")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}

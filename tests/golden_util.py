@@ -23,3 +23,30 @@ def bytecode_vectors():
                 cols = base.copy()
                 cols[c, i, :] = z[f"{name}/mut_val"][k]
             yield name, k, cols, push, kk, r, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def evm_vectors():
+    """yield (case, k, steps, bytecode, rw, flags, expected_row, expected_exc)"""
+    z = np.load(os.path.join(GOLDEN, "evm.npz"))
+    for name in z["names"]:
+        name = str(name)
+        S, B, R = z[f"{name}/steps"], z[f"{name}/bytecode"], z[f"{name}/rw"]
+        for k in range(len(z[f"{name}/mut_kind"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            val = z[f"{name}/mut_val"][k]
+            s, b, r, flags = S, B, R, 0
+            if kind == 0 and i >= 0:
+                s = S.copy(); s[c, i, :] = val
+            elif kind == 1:
+                r = R.copy(); r[c, i, :] = val
+            elif kind == 2:
+                b = B.copy(); b[c, i, :] = val
+            elif kind == 3:  # duplicated rw row with one cell changed (lookup ambiguity)
+                extra = R[:, i : i + 1, :].copy(); extra[c, 0, :] = val
+                r = np.ascontiguousarray(np.concatenate([R, extra], axis=1))
+            elif kind == 4:
+                extra = B[:, i : i + 1, :].copy(); extra[c, 0, :] = val
+                b = np.ascontiguousarray(np.concatenate([B, extra], axis=1))
+            elif kind == 5:
+                flags = 2  # ZK_FLAG_EVM_FIRST_STEP
+            yield name, k, s, b, r, flags, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

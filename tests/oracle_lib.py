@@ -78,3 +78,26 @@ def check_bytecode(cols, push, keccak, r, row_begin=0, row_end=None, n=22):
         ctypes.c_uint64(row_end), ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_evm(steps, bytecode, rw, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None):
+    steps, bytecode, rw, fixed = [np.ascontiguousarray(a) for a in (steps, bytecode, rw, fixed)]
+    if n is None:
+        n = lib().orc_n_constraints(3)
+    n_steps = steps.shape[1]
+    if row_end is None:
+        row_end = n_steps - 1
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    rc = lib().orc_check_evm(p64(steps), c(n_steps), p64(bytecode), c(bytecode.shape[1]), p64(rw),
+                             c(rw.shape[1]), p64(fixed), c(fixed.shape[1]), c(row_begin), c(row_end),
+                             c(row_base), ctypes.c_uint32(flags), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc
+
+
+def constraint_classes(circuit_id):
+    L = lib()
+    n = L.orc_n_constraints(circuit_id)
+    return [L.orc_constraint_class(circuit_id, i) for i in range(n)]

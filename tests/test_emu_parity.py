@@ -1,0 +1,55 @@
+"""CPU-side diff of the product's gate programs (run through tests/emu, the same
+__host__ __device__ code the CUDA kernels execute) against the oracle and the reference
+goldens.  This is a pre-GPU safety net; the -m gpu tests repeat it through the real kernels."""
+import numpy as np
+
+import emu_lib
+import golden_util
+import oracle_lib
+from zkevm_specs_b200 import synth
+from zkevm_specs_b200.evm_circuit.table import fixed_table_matrix
+
+
+def test_emu_bytecode_equals_oracle_on_goldens():
+    for name, k, cols, push, kec, r, exp_row, exp_exc in golden_util.bytecode_vectors():
+        ff, fc = emu_lib.check_bytecode(cols, push, kec, r)
+        off, ofc = oracle_lib.check_bytecode(cols, push, kec, r)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}]"
+
+
+def test_emu_evm_equals_oracle_on_goldens():
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    for name, k, s, b, r, flags, exp_row, exp_exc in golden_util.evm_vectors():
+        ff, fc = emu_lib.check_evm(s, b, r, fixed, flags=flags, n=n)
+        off, ofc = oracle_lib.check_evm(s, b, r, fixed, flags=flags)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}]"
+
+
+def test_emu_evm_synthetic_and_fuzz_equals_oracle():
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    w = synth.evm_trace(200, seed=2)
+    S, B, R = w["steps"], w["bytecode"], w["rw"]
+    ff, fc = emu_lib.check_evm(S, B, R, fixed, n=n)
+    assert (ff == 0xFFFFFFFF).all(), [(int(i), int(ff[i])) for i in np.nonzero(ff != 0xFFFFFFFF)[0]]
+    rng = np.random.default_rng(5)
+    P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    for t in range(150):
+        s, b, r = S, B, R
+        kind = t % 5
+        if kind == 0:
+            r = R.copy(); r[8 + rng.integers(2), rng.integers(R.shape[1]), rng.integers(2)] ^= np.uint64(1 << int(rng.integers(64)))
+        elif kind == 1:
+            s = S.copy(); s[int(rng.integers(1, 13)), rng.integers(S.shape[1]), 0] += np.uint64(1 + rng.integers(3))
+        elif kind == 2:
+            b = B.copy(); b[int(rng.integers(2, 6)), 1 + rng.integers(B.shape[1] - 1), 0] ^= np.uint64(1 << int(rng.integers(8)))
+        elif kind == 3:  # a random field element somewhere in the rw table
+            r = R.copy()
+            v = int(rng.integers(0, 1 << 62)) ** 4 % P
+            r[int(rng.integers(0, 10)), rng.integers(R.shape[1]), :] = [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+        else:  # swap the execution state of a step for another hot state
+            s = S.copy(); s[0, rng.integers(S.shape[1] - 1), 0] = np.uint64(rng.choice([5, 6, 40, 50]))
+        ff, fc = emu_lib.check_evm(s, b, r, fixed, n=n)
+        off, ofc = oracle_lib.check_evm(s, b, r, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (t, kind, ff[ff != off], off[ff != off], np.nonzero(ff != off))

@@ -13,6 +13,7 @@
 #include "../../include/zk_constraints.h"
 #include "../../include/zkcheck.h"
 #include "bytecode.cu"
+#include "evm.cu"
 #include "circuit.cuh"
 
 using namespace zk;
@@ -25,6 +26,7 @@ struct ConstraintInfo {
 };
 #define ZK_INFO_ENTRY(id, cls, doc) {#id, cls, doc},
 static const ConstraintInfo kBytecodeInfo[] = {ZK_BYTECODE_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kEvmInfo[] = {ZK_EVM_CONSTRAINTS(ZK_INFO_ENTRY)};
 
 static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21};
 static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
@@ -32,6 +34,7 @@ static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
 static const ConstraintInfo* circuit_info(int circuit, int* n) {
   switch (circuit) {
     case ZK_CIRCUIT_BYTECODE: *n = BC_N_CONSTRAINTS; return kBytecodeInfo;
+    case ZK_CIRCUIT_EVM: *n = EV_N_CONSTRAINTS; return kEvmInfo;
     default: *n = 0; return nullptr;
   }
 }
@@ -76,7 +79,11 @@ struct zk_ctx {
   ResultBuf res[ZK_N_CIRCUITS];
   std::string err;
   u64 launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // start, after index builds, after check kernel
+  cudaStream_t ev_mid_stream = nullptr;
 };
+static int mark_indexes_ready(zk_ctx* ctx);
 
 static std::string g_create_err;
 
@@ -134,6 +141,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   }
   for (auto& r : ctx->res)
     if (r.first_fail) cudaFree(r.first_fail);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -349,10 +358,28 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   int rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_PUSH, pk, 2, st, &push_ix))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 5, st, &kec_ix))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
   k_check_bytecode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
       witness_dev(ctx->circ[ZK_CIRCUIT_BYTECODE]), rg, push_ix, kec_ix, r_mont, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
+  const Matrix& m = ctx->circ[ZK_CIRCUIT_EVM];
+  if (rg.row_end + 1 > m.n_rows) return fail_msg(ctx, "EVM steps [b,e) need step e resident (rotation +1)");
+  const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
+  EvmTables t;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_FIXED, k4, 4, st, &t.fixed))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
+  const u64 n = rg.row_end - rg.row_begin;
+  k_check_evm<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(witness_dev(m), rg, t, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
   return 0;
@@ -371,10 +398,37 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
   if (rc) return rc;
   if (row_begin == row_end) return 0;
   CheckRange rg{row_begin, row_end, row_base, flags};
+  ctx->ev_mid_stream = st;
+  if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], st));
   switch (circuit_id) {
-    case ZK_CIRCUIT_BYTECODE: return check_bytecode(ctx, rg, res, st);
+    case ZK_CIRCUIT_BYTECODE: rc = check_bytecode(ctx, rg, res, st); break;
+    case ZK_CIRCUIT_EVM: rc = check_evm(ctx, rg, res, st); break;
     default: return fail_msg(ctx, "circuit has no gate program in this build");
   }
+  if (rc) return rc;
+  if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], st));
+  return 0;
+}
+
+// called by the per-circuit dispatchers between the index builds and the circuit kernel
+static int mark_indexes_ready(zk_ctx* ctx) {
+  if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[1], ctx->ev_mid_stream));
+  return 0;
+}
+
+extern "C" int zk_enable_timing(zk_ctx* ctx, int on) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (on && !ctx->ev[0])
+    for (auto& e : ctx->ev) CK(ctx, cudaEventCreate(&e));
+  ctx->timing = on != 0;
+  return 0;
+}
+extern "C" int zk_last_timing(zk_ctx* ctx, float* index_ms, float* check_ms) {
+  if (!ctx->timing) return fail_msg(ctx, "timing not enabled");
+  CK(ctx, cudaEventSynchronize(ctx->ev[2]));
+  if (index_ms) CK(ctx, cudaEventElapsedTime(index_ms, ctx->ev[0], ctx->ev[1]));
+  if (check_ms) CK(ctx, cudaEventElapsedTime(check_ms, ctx->ev[1], ctx->ev[2]));
+  return 0;
 }
 
 extern "C" int zk_result_device(zk_ctx* ctx, int circuit_id, uint32_t** ff, uint64_t** fc) {

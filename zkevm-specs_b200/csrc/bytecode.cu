@@ -23,11 +23,8 @@ enum { C_QFIRST, C_QLAST, C_HASH_LO, C_HASH_HI, C_TAG, C_INDEX, C_VALUE, C_ISCOD
 #define EMPTY_HI0 0x927e7db2dcc703c0ull
 #define EMPTY_HI1 0xc5d2460186f7233cull
 
-__global__ void __launch_bounds__(256)
-k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix, Fr r_mont,
-                 ResultDev res) {
-  const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rg.row_end) return;
+ZK_HD void check_bytecode_row(const WitnessDev& w, const CheckRange& rg, const IndexDev& push_ix,
+                              const IndexDev& kec_ix, const Fr& r_mont, const ResultDev& res, u64 i) {
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 j = rot_fwd(w, i, 1, wrap);
   const u64 row = rg.row_base + i;
@@ -94,6 +91,13 @@ k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix,
     ZK_REQUIRE(res, BC_LAST_LEN0, row, fr_is_zero(len));
     ZK_REQUIRE(res, BC_LAST_EMPTY_HASH, row, hash_empty);
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix, Fr r_mont,
+                 ResultDev res) {
+  const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rg.row_end) check_bytecode_row(w, rg, push_ix, kec_ix, r_mont, res, i);
 }
 
 }  // namespace zk

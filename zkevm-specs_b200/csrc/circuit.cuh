@@ -16,17 +16,17 @@ struct CheckRange {
   u32 flags;               // ZK_FLAG_*
 };
 
-__device__ __forceinline__ Fr wcell(const WitnessDev& w, u32 col, u64 row) {
+ZK_HD Fr wcell(const WitnessDev& w, u32 col, u64 row) {
   return ld_cell(w.cells + ((u64)col * w.n_rows + row) * 4);
 }
 // rotation by +k / -k: wraps modulo n_rows when the whole circuit is resident, otherwise the
 // caller supplied halo rows (include/zkcheck.h)
-__device__ __forceinline__ u64 rot_fwd(const WitnessDev& w, u64 row, u32 k, bool wrap) {
+ZK_HD u64 rot_fwd(const WitnessDev& w, u64 row, u32 k, bool wrap) {
   u64 j = row + k;
   if (j >= w.n_rows) j = wrap ? j % w.n_rows : w.n_rows - 1;
   return j;
 }
-__device__ __forceinline__ u64 rot_back(const WitnessDev& w, u64 row, bool wrap) {
+ZK_HD u64 rot_back(const WitnessDev& w, u64 row, bool wrap) {
   return row ? row - 1 : (wrap ? w.n_rows - 1 : 0);
 }
 

@@ -1,0 +1,426 @@
+// evm.cu — EVM-circuit step checker (one thread per execution step).
+//
+// Replaces the loop body of verify_steps / verify_step
+// (src/zkevm_specs/evm_circuit/main.py:14-63): state-transition legality
+// (instruction.py:189-204), one gadget per execution state, and the shared epilogue
+// step_state_transition_in_same_context (instruction.py:365-394, 206-264).  Gate programs in
+// this build: ADD/SUB (execution/add_sub.py:5-24), MUL/DIV/MOD (mul_div_mod.py:6-71 with
+// mul_add_words instruction.py:599-632 and compare_word :453-463), PUSH (push.py:6-33),
+// POP (pop.py:4-14).  Every lookup() of the reference (table.py:864-884, a linear scan over
+// a Python set) is a probe of a device hash index (lookup.cuh).
+//
+// Step = 13 cells in the order of StepState (evm_circuit/step.py:16-44), code_hash as
+// (lo, hi); rotation {0,+1}.  Algorithmic bytes per step: 13 x 32 B = 416 B, plus the
+// table rows it touches, counted once per table row (rw 448 B, bytecode 192 B).
+// A step stops at its first failing constraint (the reference raises there), so at most one
+// constraint id is recorded per step.
+#include "circuit.cuh"
+#include "../../include/zk_constraints.h"
+#include "../../include/zk_evm_spec.h"
+#include "../../include/zkcheck.h"
+
+namespace zk {
+
+enum { S_STATE, S_RWC, S_CALL_ID, S_IS_ROOT, S_IS_CREATE, S_HASH_LO, S_HASH_HI, S_PC, S_SP, S_GAS,
+       S_MEM, S_REV, S_LOG };
+enum { B_HASH_LO, B_HASH_HI, B_TAG, B_INDEX, B_ISCODE, B_VALUE };
+enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, R_VAL_HI };
+
+__constant__ signed char c_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;
+__constant__ signed char c_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
+__constant__ short c_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
+static const signed char h_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;  // host copies: tests/emu only
+static const signed char h_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
+static const short h_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
+#ifdef __CUDA_ARCH__
+#define ES_HALTS(i) c_es_halts[i]
+#define ES_IMPL(i) c_es_impl[i]
+#define OPCODE_GAS(i) c_opcode_gas[i]
+#else
+#define ES_HALTS(i) h_es_halts[i]
+#define ES_IMPL(i) h_es_impl[i]
+#define OPCODE_GAS(i) h_opcode_gas[i]
+#endif
+
+// constants in Montgomery form: montmul(x, C*2^256) == x*C mod p
+#define ZK_MONT_INV8 Fr{{0x0ull, 0x0ull, 0x0ull, 0x2000000000000000ull}}
+#define ZK_MONT_INV4 Fr{{0xbc1e0a6c0fffffffull, 0xd7cc17b786468f6eull, 0x47afba497e7ea7a2ull, 0x0f9bb18d1ece5fd6ull}}
+#define ZK_MONT_INV2_128 Fr{{0x0ull, 0x0ull, 0x1ull, 0x0ull}}
+
+struct Word2 {
+  Fr lo, hi;
+};
+ZK_HD bool word_in_domain(const Word2& w) { return fr_fits128(w.lo) && fr_fits128(w.hi); }
+ZK_HD bool word_eq(const Word2& a, const Word2& b) {
+  return fr_eq(a.lo, b.lo) && fr_eq(a.hi, b.hi);
+}
+
+struct EvmTables {
+  IndexDev bytecode;  // key (hash_lo, hash_hi, tag, index, is_code)
+  IndexDev rw;        // key (rw_counter, rw, tag, id, address)
+  IndexDev fixed;     // key (tag, v0, v1, v2)
+};
+
+// per-thread view of one step
+struct StepCtx {
+  const WitnessDev& w;
+  const EvmTables& t;
+  const ResultDev& res;
+  u64 i, j, row;
+  ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
+  ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
+};
+
+#define EV_CHECK(id, cond)      \
+  do {                          \
+    if (!(cond)) {              \
+      fail(s.res, (id), s.row); \
+      return;                   \
+    }                           \
+  } while (0)
+
+// lookup outcome -> failure id (unsat, or the next id = ambiguous); true iff exactly one row
+ZK_HD bool need1(const StepCtx& s, int n, int id_unsat) {
+  if (n == 1) return true;
+  fail(s.res, n == 0 ? id_unsat : id_unsat + 1, s.row);
+  return false;
+}
+
+ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 tag,
+                                               const Fr& index, u64 is_code, Fr* value) {
+  Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
+  u32 r;
+  const int n = lookup<5>(s.t.bytecode, key, &r);
+  if (n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
+  return n;
+}
+ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& id,
+                                         const Fr& addr, Word2* value) {
+  Fr key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
+  u32 r;
+  const int n = lookup<5>(s.t.rw, key, &r);
+  if (n == 1) {
+    value->lo = table_cell(s.t.rw.tab, R_VAL_LO, r);
+    value->hi = table_cell(s.t.rw.tab, R_VAL_HI, r);
+  }
+  return n;
+}
+
+// step_state_transition_in_same_context, instruction.py:365-394
+ZK_HD_NOINLINE void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc,
+                                          const Fr& d_sp) {
+  Fr key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), s.cur(S_STATE), opcode, fr_u64(0)};
+  u32 r;
+  EV_CHECK(EV_SC_RESP_OPCODE, lookup<4>(s.t.fixed, key, &r) >= 1);
+  int gas_cost = -1;
+  if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
+  EV_CHECK(EV_SC_OPCODE_VALUE, gas_cost >= 0);
+  const Fr gas_after = fr_sub_u64(s.cur(S_GAS), (u64)gas_cost);
+  EV_CHECK(EV_SC_GAS_RANGE, fr_fits64(gas_after));
+  EV_CHECK(EV_SC_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(s.cur(S_RWC), d_rwc)));
+  EV_CHECK(EV_SC_PC, fr_eq(s.nxt(S_PC), fr_add(s.cur(S_PC), d_pc)));
+  EV_CHECK(EV_SC_SP, fr_eq(s.nxt(S_SP), fr_add(s.cur(S_SP), d_sp)));
+  EV_CHECK(EV_SC_GAS, fr_eq(s.nxt(S_GAS), gas_after));
+  EV_CHECK(EV_SC_MEM, fr_eq(s.nxt(S_MEM), s.cur(S_MEM)));
+  EV_CHECK(EV_SC_REV, fr_eq(s.nxt(S_REV), s.cur(S_REV)));
+  EV_CHECK(EV_SC_LOG, fr_eq(s.nxt(S_LOG), s.cur(S_LOG)));
+  EV_CHECK(EV_SC_CALL_ID, fr_eq(s.nxt(S_CALL_ID), s.cur(S_CALL_ID)));
+  EV_CHECK(EV_SC_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), s.cur(S_IS_ROOT)));
+  EV_CHECK(EV_SC_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), s.cur(S_IS_CREATE)));
+  EV_CHECK(EV_SC_CODE_HASH,
+           fr_eq(s.nxt(S_HASH_LO), s.cur(S_HASH_LO)) && fr_eq(s.nxt(S_HASH_HI), s.cur(S_HASH_HI)));
+}
+
+// add_words([x, y]) with the final carry dropped (util/arithmetic.py:236-242)
+ZK_HD Word2 add_words2(const Word2& x, const Word2& y) {
+  const Fr slo = fr_add(x.lo, y.lo);
+  const Fr shi = fr_add(fr_add(x.hi, y.hi), fr_u128(slo.l[2], slo.l[3]));
+  return Word2{fr_u128(slo.l[0], slo.l[1]), fr_u128(shi.l[0], shi.l[1])};
+}
+
+ZK_HD_NOINLINE void gadget_add(const StepCtx& s, const Fr& opcode) {
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Fr sp1 = fr_add_u64(sp, 1);
+  const bool is_sub = fr_eq_u64(opcode, 3);
+  Word2 a, b, c;
+  if (!need1(s, rw_lookup(s, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_ADD_A_UNSAT)) return;
+  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &b), EV_ADD_B_UNSAT)) return;
+  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &c), EV_ADD_C_UNSAT)) return;
+  EV_CHECK(EV_ADD_SUM, word_eq(add_words2(is_sub ? c : a, b), is_sub ? a : c));
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+
+// ---- 256/512-bit integer helpers for the witness assignment of mul_div_mod.py:23-41 ----
+ZK_HD void word_to_u256(const Word2& w, u64 o[4]) {
+  o[0] = w.lo.l[0]; o[1] = w.lo.l[1]; o[2] = w.hi.l[0]; o[3] = w.hi.l[1];
+}
+ZK_HD Word2 u256_to_word(const u64 v[4]) {
+  return Word2{fr_u128(v[0], v[1]), fr_u128(v[2], v[3])};
+}
+ZK_HD int cmp256(const u64 a[4], const u64 b[4]) {
+#pragma unroll
+  for (int k = 3; k >= 0; k--) {
+    if (a[k] < b[k]) return -1;
+    if (a[k] > b[k]) return 1;
+  }
+  return 0;
+}
+ZK_HD void sub256(const u64 a[4], const u64 b[4], u64 o[4]) {
+  u64 br = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = sbb64(a[k], b[k], br);
+}
+// true iff b*a > d as integers (i.e. d - b*a < 0)
+ZK_HD bool mul256_exceeds(const u64 a[4], const u64 b[4], const u64 d[4], u64 prod_lo[4]) {
+  u64 t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    u64 c = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+      unsigned __int128 v = (unsigned __int128)a[x] * b[y] + t[x + y] + c;
+      t[x + y] = (u64)v;
+      c = (u64)(v >> 64);
+    }
+    t[x + 4] = c;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) prod_lo[k] = t[k];
+  return (t[4] | t[5] | t[6] | t[7]) != 0 || cmp256(prod_lo, d) > 0;
+}
+// q = n / d for d != 0 (shift-subtract; only MOD steps pay for it)
+ZK_HD_NOINLINE void div256(const u64 n[4], const u64 d[4], u64 q[4]) {
+  u64 r[4] = {0, 0, 0, 0};
+  q[0] = q[1] = q[2] = q[3] = 0;
+  for (int bit = 255; bit >= 0; bit--) {
+    const u64 top = r[3] >> 63;
+    r[3] = (r[3] << 1) | (r[2] >> 63);
+    r[2] = (r[2] << 1) | (r[1] >> 63);
+    r[1] = (r[1] << 1) | (r[0] >> 63);
+    r[0] = (r[0] << 1) | ((n[bit >> 6] >> (bit & 63)) & 1);
+    if (top || cmp256(r, d) >= 0) {
+      sub256(r, d, r);
+      q[bit >> 6] |= 1ull << (bit & 63);
+    }
+  }
+}
+
+// exact small unsigned integers (< 2^196) as Fr: sums of 64x64-bit limb products, optionally
+// shifted left by one limb (the "* 2^64" of mul_add_words)
+ZK_HD void acc_add_mul(Fr& acc, u64 a, u64 b, int shift_limbs) {
+  const unsigned __int128 v = (unsigned __int128)a * b;
+  u64 c = 0;
+  const u64 lo = (u64)v, hi = (u64)(v >> 64);
+  if (shift_limbs == 0) {
+    acc.l[0] = adc64(acc.l[0], lo, c);
+    acc.l[1] = adc64(acc.l[1], hi, c);
+    acc.l[2] = adc64(acc.l[2], 0, c);
+    acc.l[3] += c;
+  } else {
+    acc.l[1] = adc64(acc.l[1], lo, c);
+    acc.l[2] = adc64(acc.l[2], hi, c);
+    acc.l[3] += c;
+  }
+}
+
+// Word((sel*lo, sel*hi)) with the constructor's < 2^128 assertion (arithmetic.py:110-114)
+ZK_HD bool word_select(const Word2& w, const Fr& sel, Word2* out) {
+  if (fr_is_zero(sel)) {
+    out->lo = out->hi = fr_u64(0);
+    return true;
+  }
+  if (fr_eq_u64(sel, 1)) {
+    *out = w;
+    return word_in_domain(w);
+  }
+  const Fr sm = fr_to_mont(sel);
+  out->lo = fr_montmul(sm, w.lo);
+  out->hi = fr_montmul(sm, w.hi);
+  return word_in_domain(*out);
+}
+
+ZK_HD_NOINLINE void gadget_mul(const StepCtx& s, const Fr& opcode) {
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Fr sp1 = fr_add_u64(sp, 1);
+  const Fr one = fr_u64(1);
+  // mul_div_mod.py:14-16 (Lagrange selectors over the field)
+  Fr is_mul, is_div, is_mod;
+  if (fr_eq_u64(opcode, 2)) { is_mul = one; is_div = fr_u64(0); is_mod = fr_u64(0); }
+  else if (fr_eq_u64(opcode, 4)) { is_mul = fr_u64(0); is_div = one; is_mod = fr_u64(0); }
+  else if (fr_eq_u64(opcode, 6)) { is_mul = fr_u64(0); is_div = fr_u64(0); is_mod = one; }
+  else {
+    const Fr o2 = fr_sub(opcode, fr_u64(2)), o4 = fr_sub(opcode, fr_u64(4));
+    const Fr f4 = fr_sub(fr_u64(4), opcode), f6 = fr_sub(fr_u64(6), opcode);
+    is_mul = fr_montmul(fr_mul(f4, f6), ZK_MONT_INV8);
+    is_div = fr_montmul(fr_mul(o2, f6), ZK_MONT_INV4);
+    is_mod = fr_montmul(fr_mul(o2, o4), ZK_MONT_INV8);
+  }
+  Word2 pop1, pop2, push;
+  if (!need1(s, rw_lookup(s, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT)) return;
+  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &pop2), EV_MUL_POP2_UNSAT)) return;
+  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &push), EV_MUL_PUSH_UNSAT)) return;
+  const bool in_domain = word_in_domain(pop1) && word_in_domain(pop2) && word_in_domain(push);
+  // witness assignment by branch, mul_div_mod.py:23-41 (Python int arithmetic)
+  Word2 a, b, c, d;
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  if (fr_eq_u64(is_mul, 1)) {
+    a = pop1; b = pop2; c = zero; d = push;
+  } else {
+    EV_CHECK(EV_MUL_WITNESS_DOMAIN, in_domain);  // would need > 512-bit integers
+    d = pop1; b = pop2;
+    u64 dv[4], bv[4];
+    word_to_u256(d, dv);
+    word_to_u256(b, bv);
+    if (fr_eq_u64(is_div, 1)) {
+      a = push;
+      u64 av[4], pl[4], cv[4];
+      word_to_u256(a, av);
+      EV_CHECK(EV_MUL_WITNESS_NEG, !mul256_exceeds(av, bv, dv, pl));  // Word(d - b*a) with d < b*a
+      sub256(dv, pl, cv);
+      c = u256_to_word(cv);
+    } else if ((bv[0] | bv[1] | bv[2] | bv[3]) == 0) {
+      c = d; a = zero;
+    } else {
+      c = push;
+      u64 cv[4], tv[4], qv[4];
+      word_to_u256(c, cv);
+      EV_CHECK(EV_MUL_WITNESS_NEG, cmp256(dv, cv) >= 0);  // (d - c) // b < 0
+      sub256(dv, cv, tv);
+      div256(tv, bv, qv);
+      a = u256_to_word(qv);
+    }
+  }
+  const bool b_zero = fr_is_zero(fr_add(b.lo, b.hi));  // is_zero_word: field sum of the halves
+  // mul_add_words, instruction.py:599-632
+  EV_CHECK(EV_MUL_TO64, word_in_domain(a) && word_in_domain(b));
+  const u64 a0 = a.lo.l[0], a1 = a.lo.l[1], a2 = a.hi.l[0], a3 = a.hi.l[1];
+  const u64 b0 = b.lo.l[0], b1 = b.lo.l[1], b2 = b.hi.l[0], b3 = b.hi.l[1];
+  // t0 + t1*2^64 and t2 + t3*2^64 as exact integers (< 2^195 < p)
+  Fr lo_part = fr_u64(0), hi_part = fr_u64(0), ovf = fr_u64(0);
+  acc_add_mul(lo_part, a0, b0, 0);
+  acc_add_mul(lo_part, a0, b1, 1);
+  acc_add_mul(lo_part, a1, b0, 1);
+  acc_add_mul(hi_part, a0, b2, 0);
+  acc_add_mul(hi_part, a1, b1, 0);
+  acc_add_mul(hi_part, a2, b0, 0);
+  acc_add_mul(hi_part, a0, b3, 1);
+  acc_add_mul(hi_part, a1, b2, 1);
+  acc_add_mul(hi_part, a2, b1, 1);
+  acc_add_mul(hi_part, a3, b0, 1);
+  acc_add_mul(ovf, a1, b3, 0);
+  acc_add_mul(ovf, a2, b2, 0);
+  acc_add_mul(ovf, a3, b1, 0);
+  acc_add_mul(ovf, a2, b3, 0);
+  acc_add_mul(ovf, a3, b2, 0);
+  acc_add_mul(ovf, a3, b3, 0);
+  const Fr x_lo = fr_add(lo_part, c.lo);
+  const Fr carry_lo = fr_montmul(fr_sub(x_lo, d.lo), ZK_MONT_INV2_128);
+  const Fr x_hi = fr_add(fr_add(hi_part, c.hi), carry_lo);
+  const Fr carry_hi = fr_montmul(fr_sub(x_hi, d.hi), ZK_MONT_INV2_128);
+  const Fr overflow = fr_add(carry_hi, ovf);
+  EV_CHECK(EV_MUL_CARRY_LO, fr_fits128(carry_lo) && (carry_lo.l[1] >> 8) == 0);  // range_check(.., 9)
+  EV_CHECK(EV_MUL_CARRY_HI, fr_fits128(carry_hi) && (carry_hi.l[1] >> 8) == 0);
+  // the two constrain_equal of instruction.py:629-630 hold by construction of the carries
+  // mul_div_mod.py:47-54: select_word's bool assert, then Word range asserts of select / +
+  const bool mul0 = fr_is_zero(is_mul), mul1 = fr_eq_u64(is_mul, 1);
+  EV_CHECK(EV_MUL_SELECT, mul0 || mul1);
+  Word2 t_d, t_a, t_c, sum;
+  const Fr sel_a = b_zero ? fr_u64(0) : is_div, sel_c = b_zero ? fr_u64(0) : is_mod;
+  EV_CHECK(EV_MUL_SELECT, word_select(d, is_mul, &t_d) && word_select(a, sel_a, &t_a));
+  EV_CHECK(EV_MUL_SELECT, word_select(c, sel_c, &t_c));
+  sum.lo = fr_add(t_d.lo, t_a.lo);
+  sum.hi = fr_add(t_d.hi, t_a.hi);
+  EV_CHECK(EV_MUL_SELECT, word_in_domain(sum));
+  sum.lo = fr_add(sum.lo, t_c.lo);
+  sum.hi = fr_add(sum.hi, t_c.hi);
+  EV_CHECK(EV_MUL_SELECT, word_in_domain(sum));
+  EV_CHECK(EV_MUL_PUSH_EQ, word_eq(push, sum));
+  // :57  is_mul * sum(c.to_le_bytes()) == 0  (is_mul is 0/1 here; byte sum < p)
+  EV_CHECK(EV_MUL_C_ZERO, mul0 || (fr_is_zero(c.lo) && fr_is_zero(c.hi)));
+  // :60-61  (1-is_mul)*(1-b0)*(1-lt) == 0 with lt = compare_word(c, b)
+  const bool lt = fr_lt(c.hi, b.hi) || (fr_eq(c.hi, b.hi) && fr_lt(c.lo, b.lo));
+  EV_CHECK(EV_MUL_REM_LT, mul1 || b_zero || lt);
+  EV_CHECK(EV_MUL_OVERFLOW, mul1 || fr_is_zero(overflow));
+  same_context(s, opcode, 3, one, one);
+}
+
+ZK_HD_NOINLINE void gadget_push(const StepCtx& s, const Fr& opcode) {
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP), pc = s.cur(S_PC);
+  const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI);
+  const Fr num_pushed = fr_sub_u64(opcode, 0x5f);
+  Fr code_length;
+  if (!need1(s, bytecode_lookup(s, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_PUSH_LEN_UNSAT)) return;
+  const Fr left = fr_sub_u64(fr_sub(code_length, pc), 1);
+  EV_CHECK(EV_PUSH_CMP_RANGE, fr_fits64(left) && fr_fits64(num_pushed));
+  const u64 n_push = num_pushed.l[0];
+  const u64 n_pad = left.l[0] < n_push ? n_push - left.l[0] : 0;
+  Word2 value;
+  if (!need1(s, rw_lookup(s, rwc, 1, ZK_TARGET_Stack, call_id, fr_sub_u64(sp, 1), &value), EV_PUSH_RW_UNSAT)) return;
+  EV_CHECK(EV_PUSH_VALUE_BYTES, word_in_domain(value));
+  Fr index = fr_add(pc, num_pushed);  // pc + num_pushed - idx
+  for (int idx = 0; idx < 32; idx++) {
+    const u64 limb = idx < 16 ? value.lo.l[idx >> 3] : value.hi.l[(idx - 16) >> 3];
+    const u64 byte = (limb >> (8 * (idx & 7))) & 0xFF;
+    const int base = EV_PUSH_B0_UNSAT + 4 * idx;
+    if ((u64)idx < n_push && (u64)idx >= n_pad) {
+      Fr got;
+      if (!need1(s, bytecode_lookup(s, hlo, hhi, 2, index, 0, &got), base)) return;
+      EV_CHECK(base + 2, fr_eq_u64(got, byte));
+    } else {
+      EV_CHECK(base + 3, byte == 0);
+    }
+    index = fr_sub_u64(index, 1);
+  }
+  same_context(s, opcode, 1, fr_add_u64(num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+
+ZK_HD_NOINLINE void gadget_pop(const StepCtx& s, const Fr& opcode) {
+  Word2 y;
+  if (!need1(s, rw_lookup(s, s.cur(S_RWC), 0, ZK_TARGET_Stack, s.cur(S_CALL_ID), s.cur(S_SP), &y), EV_POP_RW_UNSAT))
+    return;
+  same_context(s, opcode, 1, fr_u64(1), fr_u64(1));
+}
+
+ZK_HD void verify_step(const StepCtx& s, u32 flags) {
+  const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
+  const bool is_first = (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0;
+  const bool is_last = (flags & ZK_FLAG_EVM_LAST_STEP) && s.i == s.w.n_rows - 2;
+  const bool cs_small = fr_fits64(cs) && cs.l[0] < ZK_ES_COUNT;
+  if (is_first) {
+    EV_CHECK(EV_FIRST_STATE, fr_eq_u64(cs, ZK_ES_BeginTx) || fr_eq_u64(cs, ZK_ES_EndBlock));
+    EV_CHECK(EV_FIRST_RWC, fr_eq_u64(s.cur(S_RWC), 1));
+  }
+  if (is_last) {
+    EV_CHECK(EV_LAST_STATE, fr_eq_u64(cs, ZK_ES_EndBlock));
+  } else {
+    if (fr_eq_u64(cs, ZK_ES_EndTx))
+      EV_CHECK(EV_TRANS_FROM_ENDTX, fr_eq_u64(ns, ZK_ES_BeginTx) || fr_eq_u64(ns, ZK_ES_EndBlock));
+    else if (fr_eq_u64(cs, ZK_ES_EndBlock))
+      EV_CHECK(EV_TRANS_FROM_ENDBLOCK, fr_eq_u64(ns, ZK_ES_EndBlock));
+    if (fr_eq_u64(ns, ZK_ES_BeginTx))
+      EV_CHECK(EV_TRANS_TO_BEGINTX, fr_eq_u64(cs, ZK_ES_EndTx));
+    else if (fr_eq_u64(ns, ZK_ES_EndTx))
+      EV_CHECK(EV_TRANS_TO_ENDTX, (cs_small && ES_HALTS(cs.l[0])) || fr_eq_u64(cs, ZK_ES_BeginTx));
+    else if (fr_eq_u64(ns, ZK_ES_EndBlock))
+      EV_CHECK(EV_TRANS_TO_ENDBLOCK, fr_eq_u64(cs, ZK_ES_EndTx) || fr_eq_u64(cs, ZK_ES_EndBlock));
+  }
+  EV_CHECK(EV_NOT_IMPLEMENTED, cs_small && ES_IMPL(cs.l[0]));
+  const u64 st = cs.l[0];
+  EV_CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP);
+  Fr opcode;
+  if (!need1(s, bytecode_lookup(s, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, &opcode), EV_OP_UNSAT))
+    return;
+  if (st == ZK_ES_ADD) gadget_add(s, opcode);
+  else if (st == ZK_ES_MUL) gadget_mul(s, opcode);
+  else if (st == ZK_ES_PUSH) gadget_push(s, opcode);
+  else gadget_pop(s, opcode);
+}
+
+__global__ void __launch_bounds__(128) k_check_evm(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res) {
+  const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rg.row_end) return;
+  StepCtx s{w, t, res, i, i + 1, rg.row_base + i};
+  verify_step(s, rg.flags);
+}
+
+}  // namespace zk

@@ -32,12 +32,50 @@ struct Fr {
 
 // One 256-bit load per cell: LDG.E.256 on sm_100a; a warp reading 32 consecutive rows of a
 // column moves 1 KiB in one instruction.  .nc: witness/table cells are read-only.
-__device__ __forceinline__ Fr ld_cell(const u64* p) {
+// (The host branch exists only so that tests/emu can run the SAME gate programs on the CPU
+// for local debugging before a GPU call; the product never executes it.)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_HD_NOINLINE __host__ __device__ __noinline__
+ZK_HD Fr ld_cell(const u64* p) {
   Fr r;
+#ifdef __CUDA_ARCH__
   asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(r.l[0]), "=l"(r.l[1]), "=l"(r.l[2]), "=l"(r.l[3])
                : "l"(p));
+#else
+  r.l[0] = p[0]; r.l[1] = p[1]; r.l[2] = p[2]; r.l[3] = p[3];
+#endif
   return r;
+}
+ZK_HD u32 ld_u32(const u32* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+ZK_HD u32 atomic_cas_u32(u32* p, u32 expect, u32 val) {
+#ifdef __CUDA_ARCH__
+  return atomicCAS(p, expect, val);
+#else
+  const u32 old = *p;
+  if (old == expect) *p = val;
+  return old;
+#endif
+}
+ZK_HD void atomic_min_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+ZK_HD void atomic_add_u64(u64* p, u64 v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
 }
 
 __host__ __device__ __forceinline__ Fr fr_u64(u64 v) { return Fr{{v, 0, 0, 0}}; }

@@ -37,15 +37,15 @@ struct IndexDev {
   Fr pw[ZK_MAX_KEY];  // r^j * 2^256 mod p (Montgomery form); pw[0] unused (r^0 = 1)
 };
 
-__device__ __forceinline__ const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
+ZK_HD const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
   return t.cells + ((u64)col * t.n_rows + row) * 4;
 }
-__device__ __forceinline__ Fr table_cell(const TableDev& t, u32 col, u64 row) {
+ZK_HD Fr table_cell(const TableDev& t, u32 col, u64 row) {
   return ld_cell(cell_ptr(t, col, row));
 }
 
 // bucket from the canonical RLC value
-__device__ __forceinline__ u32 rlc_bucket(const Fr& h, u32 mask) {
+ZK_HD u32 rlc_bucket(const Fr& h, u32 mask) {
   u64 x = h.l[0] ^ (h.l[1] * 0x9E3779B97F4A7C15ull);
   x ^= x >> 29;
   return (u32)x & mask;
@@ -53,7 +53,7 @@ __device__ __forceinline__ u32 rlc_bucket(const Fr& h, u32 mask) {
 
 // h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
 template <int NK>
-__device__ __forceinline__ Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
+ZK_HD Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
   Fr h = key[0];
 #pragma unroll
   for (int j = 1; j < NK; j++) h = fr_add(h, fr_montmul(key[j], ix.pw[j]));
@@ -61,21 +61,23 @@ __device__ __forceinline__ Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
 }
 
 // One thread per table row: compress the queried columns and claim a slot.
-__global__ void __launch_bounds__(256) k_index_build(IndexDev ix) {
-  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= ix.tab.n_rows) return;
+ZK_HD void index_insert_row(const IndexDev& ix, u64 row) {
   Fr h = table_cell(ix.tab, ix.key_cols[0], row);
   for (u32 j = 1; j < ix.n_key; j++)
     h = fr_add(h, fr_montmul(table_cell(ix.tab, ix.key_cols[j], row), ix.pw[j]));
   u32 b = rlc_bucket(h, ix.mask);
   for (;;) {
-    const u32 old = atomicCAS(&ix.slots[b], ZK_EMPTY_SLOT, (u32)row);
+    const u32 old = atomic_cas_u32(&ix.slots[b], ZK_EMPTY_SLOT, (u32)row);
     if (old == ZK_EMPTY_SLOT) break;
     b = (b + 1) & ix.mask;
   }
 }
+__global__ void __launch_bounds__(256) k_index_build(IndexDev ix) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < ix.tab.n_rows) index_insert_row(ix, row);
+}
 
-__device__ __forceinline__ bool rows_identical(const TableDev& t, u32 a, u32 b) {
+ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
   for (u32 c = 0; c < t.n_cols; c++)
     if (!fr_eq(table_cell(t, c, a), table_cell(t, c, b))) return false;
   return true;
@@ -84,13 +86,13 @@ __device__ __forceinline__ bool rows_identical(const TableDev& t, u32 a, u32 b) 
 // Walk the bucket run starting at the bucket of h.  Returns the number of distinct matching
 // rows, capped at 2; *row = the first match.
 template <int NK>
-__device__ __forceinline__ int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK],
+ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK],
                                             u32* row) {
   int found = 0;
   u32 first = 0;
   u32 b = rlc_bucket(h, ix.mask);
   for (;;) {
-    const u32 cand = __ldg(&ix.slots[b]);
+    const u32 cand = ld_u32(&ix.slots[b]);
     if (cand == ZK_EMPTY_SLOT) break;
     bool eq = true;
 #pragma unroll
@@ -113,7 +115,7 @@ __device__ __forceinline__ int probe_hashed(const IndexDev& ix, const Fr& h, con
 }
 
 template <int NK>
-__device__ __forceinline__ int lookup(const IndexDev& ix, const Fr (&key)[NK], u32* row) {
+ZK_HD int lookup(const IndexDev& ix, const Fr (&key)[NK], u32* row) {
   if (ix.tab.n_rows == 0) return 0;
   return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row);
 }
@@ -123,9 +125,9 @@ struct ResultDev {
   u32* first_fail;  // [n_constraints]
   u64* fail_count;  // [n_constraints]
 };
-__device__ __forceinline__ void fail(const ResultDev& r, int id, u64 row) {
-  atomicMin(&r.first_fail[id], (u32)row);
-  atomicAdd(&r.fail_count[id], 1ull);
+ZK_HD void fail(const ResultDev& r, int id, u64 row) {
+  atomic_min_u32(&r.first_fail[id], (u32)row);
+  atomic_add_u64(&r.fail_count[id], 1ull);
 }
 #define ZK_REQUIRE(res, id, row, cond) \
   do {                                 \

@@ -1,0 +1,106 @@
+"""verify_steps — the reference's EVM-circuit entry point (evm_circuit/main.py:14-44), with
+the per-step loop running on the device.
+
+The reference builds one `Instruction` per (curr, next) pair in Python and stops at the first
+AssertionError; other exception types propagate.  Here all steps are packed into a 13-cell
+matrix, the tables into cell matrices, ONE zk_check(ZK_CIRCUIT_EVM) evaluates every step, and
+the smallest failing (step, constraint) is turned back into the exception class the reference
+would have raised first."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .. import native, packing
+from ..util.arithmetic import FQ
+from .spec import ExecutionState
+from .step import StepState
+from .table import LookupAmbiguousFailure, LookupUnsatFailure, Tables, fixed_table_matrix
+
+
+class ConstraintUnsatFailure(Exception):
+    def __init__(self, message: str) -> None:
+        self.message = message
+        super().__init__(message)
+
+
+DUMMY_STEP_STATE = StepState(ExecutionState.EndBlock, rw_counter=-1)
+
+
+def step_row(s: StepState) -> List[int]:
+    c = packing.cell_int
+    return [int(s.execution_state), c(s.rw_counter), c(s.call_id), int(s.is_root), int(s.is_create),
+            c(s.code_hash.lo), c(s.code_hash.hi), c(s.program_counter), c(s.stack_pointer), c(s.gas_left),
+            c(s.memory_word_size), c(s.reversible_write_counter), c(s.log_id)]
+
+
+def pack_steps(steps: List[StepState]) -> np.ndarray:
+    return packing.matrix_from_ints([step_row(s) for s in steps], 13)
+
+
+def upload_tables(ctx: native.Context, tables: Tables) -> None:
+    """Python row sets -> cell matrices -> device (tables are replicated per GPU)."""
+    ctx.upload_table(native.TABLE_BYTECODE, packing.pack(tables.bytecode_table, packing.bytecode_table_row, 6))
+    rws = list(tables.rw_table)
+    ctx.upload_table(native.TABLE_RW, packing.pack(rws, packing.rw_table_row, 14),
+                     flags=np.array([packing.rw_table_flags(r) for r in rws], dtype=np.uint8))
+    upload_fixed_table(ctx)
+
+
+def upload_fixed_table(ctx: native.Context) -> None:
+    if not getattr(ctx, "_fixed_uploaded", False):
+        ctx.upload_table(native.TABLE_FIXED, fixed_table_matrix())
+        ctx._fixed_uploaded = True
+
+
+def raise_first_failure(first_fail: np.ndarray, circuit_id: int, what: str) -> None:
+    hit = native.first_failure(first_fail, circuit_id)
+    if hit is None:
+        return
+    row, cid, cls, name = hit
+    msg = f"{what} {row}: {name}"
+    if cls == native.ERR_ASSERT:
+        raise AssertionError(msg)
+    if cls == native.ERR_LOOKUP_UNSAT:
+        raise LookupUnsatFailure(name, msg)
+    if cls == native.ERR_LOOKUP_AMBIGUOUS:
+        raise LookupAmbiguousFailure(name, msg)
+    if cls == native.ERR_RANGE_RAISE:
+        raise ConstraintUnsatFailure(msg)
+    if cls == native.ERR_VALUE:
+        raise ValueError(msg)
+    raise NotImplementedError(msg)
+
+
+def check_steps(ctx: native.Context, steps_matrix: np.ndarray, begin_with_first_step: bool = False,
+                end_with_last_step: bool = False):
+    """steps already packed (and tables already uploaded): returns (first_fail, fail_count)."""
+    ctx.upload_columns(native.CIRCUIT_EVM, steps_matrix)
+    flags = (native.FLAG_EVM_FIRST_STEP if begin_with_first_step else 0) | (
+        native.FLAG_EVM_LAST_STEP if end_with_last_step else 0)
+    n = steps_matrix.shape[1]
+    return ctx.check(native.CIRCUIT_EVM, 0, max(n - 1, 0), 0, flags)
+
+
+def verify_steps(tables: Tables, steps: List[StepState], begin_with_first_step: bool = False,
+                 end_with_last_step: bool = False, success: bool = True,
+                 ctx: Optional[native.Context] = None) -> None:
+    """Reference signature and error convention (main.py:14-44): mutates `steps` when
+    end_with_last_step; an AssertionError-class failure is re-raised when success=True and
+    required when success=False; every other failure class propagates."""
+    if end_with_last_step:
+        steps.append(DUMMY_STEP_STATE)
+    ctx = ctx or native.default_context()
+    upload_tables(ctx, tables)
+    ff, _ = check_steps(ctx, pack_steps(steps), begin_with_first_step, end_with_last_step)
+    exception = None
+    try:
+        raise_first_failure(ff, native.CIRCUIT_EVM, "step")
+    except AssertionError as e:
+        exception = e
+    if success:
+        if exception:
+            raise exception
+    else:
+        assert exception is not None

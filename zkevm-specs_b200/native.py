@@ -71,7 +71,8 @@ EXPORTS = [
     "zk_bind_columns_device", "zk_upload_row_flags", "zk_upload_table", "zk_bind_table_device",
     "zk_upload_table_flags", "zk_check", "zk_check_async", "zk_result_device", "zk_fetch_result",
     "zk_allreduce_results", "zk_circuit_cols", "zk_table_cols", "zk_n_constraints",
-    "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes",
+    "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
+    "zk_last_timing",
 ]
 
 
@@ -106,6 +107,8 @@ def lib() -> ctypes.CDLL:
         L.zk_launch_count.argtypes = [vp]
         L.zk_launch_count.restype = u64
         L.zk_invalidate_indexes.argtypes = [vp]
+        L.zk_enable_timing.argtypes = [vp, i32]
+        L.zk_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         _LIB = L
     return _LIB
 
@@ -227,6 +230,23 @@ class Context:
 
     def invalidate_indexes(self) -> None:
         self._L.zk_invalidate_indexes(self._h)
+
+    def enable_timing(self, on: bool = True) -> None:
+        self._ck(self._L.zk_enable_timing(self._h, int(on)), "zk_enable_timing")
+
+    def last_timing(self):
+        """(index build ms, check kernel ms) of the most recent check, device-timed"""
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._ck(self._L.zk_last_timing(self._h, ctypes.byref(a), ctypes.byref(b)), "zk_last_timing")
+        return a.value, b.value
+
+    def upload_columns_ptr(self, circuit_id: int, n_rows: int, n_cols: int, host_ptr: int, stream: int = 0) -> None:
+        self._ck(self._L.zk_upload_columns(self._h, circuit_id, n_rows, n_cols, ctypes.c_void_p(host_ptr),
+                                           ctypes.c_void_p(stream)), "zk_upload_columns")
+
+    def upload_table_ptr(self, table_id: int, n_rows: int, n_cols: int, host_ptr: int, stream: int = 0) -> None:
+        self._ck(self._L.zk_upload_table(self._h, table_id, n_rows, n_cols, ctypes.c_void_p(host_ptr),
+                                         ctypes.c_void_p(stream)), "zk_upload_table")
 
     def launch_count(self) -> int:
         return int(self._L.zk_launch_count(self._h))

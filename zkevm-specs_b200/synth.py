@@ -1,0 +1,145 @@
+"""Seeded synthetic witnesses as cell matrices (numpy), for parity tests at scale and bench.py.
+
+They follow the witness rules of the reference's own builders (the small cases are checked
+against the reference / oracle in tests) but skip the Python row objects: 2^20 steps would
+need tens of millions of FQ objects.
+
+evm_trace: BASELINE cfg2 — straight-line groups `PUSH32 b, PUSH32 a, OP, POP` with OP cycling
+ADD, SUB, MUL, DIV, MOD and a final STOP step (recipe validated on the reference at 20 groups,
+SURVEY.md §8d).  One contract holds the whole trace; its code_hash is a seeded 256-bit tag,
+not a real keccak (the EVM circuit never recomputes the hash, it only matches it against the
+bytecode table)."""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from .evm_circuit.spec import ExecutionState, Target
+
+M256 = (1 << 256) - 1
+NASTY_AB_VALUES = (
+    (0, 0), (1, 0), (0, 1), (1, 1), (255, 0), (0, 255), (255, 255), (256, 0), (0, 256), (256, 256),
+    (260, 513), (65535, 0), (0, 65535), (65535, 65535), (65536, 0), (0, 65536), (65536, 65536),
+    (M256, M256 - 1), (M256 - 1, M256), (M256, 0), (0, M256),
+)  # the reference's edge operands, tests/common.py:23-45
+OPS = ("ADD", "SUB", "MUL", "DIV", "MOD")
+OPCODE = {"ADD": 0x01, "SUB": 0x03, "MUL": 0x02, "DIV": 0x04, "MOD": 0x06}
+GAS = {"ADD": 3, "SUB": 3, "MUL": 5, "DIV": 5, "MOD": 5}
+
+
+def ints_to_cells(vals) -> np.ndarray:
+    """list of python ints (< 2^256) -> uint64[n][4]"""
+    buf = b"".join(int(v).to_bytes(32, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u8").reshape(-1, 4).copy()
+
+
+def _operands(n: int, rng: np.random.Generator):
+    kind = rng.integers(0, 4, n)
+    raw = rng.integers(0, 1 << 63, (n, 2, 5), dtype=np.int64).astype(object)
+    a, b = [], []
+    nasty = rng.integers(0, len(NASTY_AB_VALUES), n)
+    for i in range(n):
+        k = kind[i]
+        if k < 2:  # uniform 256-bit
+            x = (raw[i, 0, 0] | raw[i, 0, 1] << 63 | raw[i, 0, 2] << 126 | raw[i, 0, 3] << 189 | raw[i, 0, 4] << 252) & M256
+            y = (raw[i, 1, 0] | raw[i, 1, 1] << 63 | raw[i, 1, 2] << 126 | raw[i, 1, 3] << 189 | raw[i, 1, 4] << 252) & M256
+        elif k == 2:  # 64-bit
+            x, y = int(raw[i, 0, 0]) | (int(raw[i, 0, 1]) & 1) << 63, int(raw[i, 1, 0]) | (int(raw[i, 1, 1]) & 1) << 63
+        else:
+            x, y = NASTY_AB_VALUES[nasty[i]]
+        a.append(int(x))
+        b.append(int(y))
+    return a, b
+
+
+def evm_trace(n_groups: int, seed: int = 2, call_id: int = 1) -> Dict[str, np.ndarray]:
+    """returns matrices: steps [13][4g+1][4], bytecode [6][68g+2][4], rw [14][6g][4]"""
+    rng = np.random.default_rng(seed)
+    g = n_groups
+    a, b = _operands(g, rng)
+    ops = [OPS[i % 5] for i in range(g)]
+    c = []
+    for op, x, y in zip(ops, a, b):
+        if op == "ADD":
+            c.append((x + y) & M256)
+        elif op == "SUB":
+            c.append((x - y) & M256)
+        elif op == "MUL":
+            c.append((x * y) & M256)
+        elif op == "DIV":
+            c.append(0 if y == 0 else x // y)
+        else:
+            c.append(0 if y == 0 else x % y)
+    A, B, C = ints_to_cells(a), ints_to_cells(b), ints_to_cells(c)  # [g][4] limbs of the 256-bit values
+    code_hash = int.from_bytes(rng.bytes(32), "little")
+    h_lo, h_hi = code_hash & ((1 << 128) - 1), code_hash >> 128
+
+    # ---- bytecode table: header + 68 bytes per group + STOP ---------------------------------
+    code = np.zeros((g, 68), dtype=np.uint8)
+    code[:, 0] = 0x7F
+    code[:, 1:33] = np.ascontiguousarray(B).view(np.uint8).reshape(g, 32)[:, ::-1]  # big-endian push data
+    code[:, 33] = 0x7F
+    code[:, 34:66] = np.ascontiguousarray(A).view(np.uint8).reshape(g, 32)[:, ::-1]
+    code[:, 66] = np.array([OPCODE[o] for o in ops], dtype=np.uint8)
+    code[:, 67] = 0x50
+    is_code = np.zeros((g, 68), dtype=np.uint8)
+    is_code[:, [0, 33, 66, 67]] = 1
+    code_len = 68 * g + 1
+    nb = code_len + 1
+    bytecode = np.zeros((6, nb, 4), dtype=np.uint64)
+    bytecode[0, :, 0] = h_lo & 0xFFFFFFFFFFFFFFFF
+    bytecode[0, :, 1] = h_lo >> 64
+    bytecode[1, :, 0] = h_hi & 0xFFFFFFFFFFFFFFFF
+    bytecode[1, :, 1] = h_hi >> 64
+    bytecode[2, 0, 0] = 1  # Header: index 0, is_code 0, value = length
+    bytecode[5, 0, 0] = code_len
+    bytecode[2, 1:, 0] = 2
+    bytecode[3, 1:, 0] = np.arange(code_len, dtype=np.uint64)
+    bytecode[4, 1:-1, 0] = is_code.reshape(-1)
+    bytecode[5, 1:-1, 0] = code.reshape(-1)
+    bytecode[4, -1, 0] = 1  # STOP
+    bytecode[5, -1, 0] = 0x00
+
+    # ---- rw table: 6 stack rows per group ------------------------------------------------
+    nr = 6 * g
+    rw = np.zeros((14, nr, 4), dtype=np.uint64)
+    rw[0, :, 0] = np.arange(1, nr + 1, dtype=np.uint64)
+    rw[1, :, 0] = np.tile(np.array([1, 1, 0, 0, 1, 0], dtype=np.uint64), g)
+    rw[2, :, 0] = int(Target.Stack)
+    rw[3, :, 0] = call_id
+    rw[4, :, 0] = np.tile(np.array([1023, 1022, 1022, 1023, 1023, 1023], dtype=np.uint64), g)
+    vals = np.stack([B, A, A, B, C, C], axis=1).reshape(nr, 4)  # [nr][4] limbs of each 256-bit value
+    rw[8, :, 0], rw[8, :, 1] = vals[:, 0], vals[:, 1]  # value.lo
+    rw[9, :, 0], rw[9, :, 1] = vals[:, 2], vals[:, 3]  # value.hi
+
+    # ---- steps: PUSH, PUSH, OP, POP per group + STOP --------------------------------------
+    ns = 4 * g + 1
+    steps = np.zeros((13, ns, 4), dtype=np.uint64)
+    op_state = np.array([int(ExecutionState.ADD) if o in ("ADD", "SUB") else int(ExecutionState.MUL) for o in ops],
+                        dtype=np.uint64)
+    st = np.empty((g, 4), dtype=np.uint64)
+    st[:, 0] = st[:, 1] = int(ExecutionState.PUSH)
+    st[:, 2] = op_state
+    st[:, 3] = int(ExecutionState.POP)
+    steps[0, :-1, 0] = st.reshape(-1)
+    steps[0, -1, 0] = int(ExecutionState.STOP)
+    grp = np.arange(g, dtype=np.uint64)
+    rwc = np.stack([6 * grp + 1, 6 * grp + 2, 6 * grp + 3, 6 * grp + 6], axis=1)
+    steps[1, :-1, 0] = rwc.reshape(-1)
+    steps[1, -1, 0] = 6 * g + 1
+    steps[2, :, 0] = call_id
+    steps[3, :, 0] = 1  # is_root
+    steps[5, :, 0], steps[5, :, 1] = h_lo & 0xFFFFFFFFFFFFFFFF, h_lo >> 64
+    steps[6, :, 0], steps[6, :, 1] = h_hi & 0xFFFFFFFFFFFFFFFF, h_hi >> 64
+    pc = np.stack([68 * grp, 68 * grp + 33, 68 * grp + 66, 68 * grp + 67], axis=1)
+    steps[7, :-1, 0] = pc.reshape(-1)
+    steps[7, -1, 0] = 68 * g
+    steps[8, :-1, 0] = np.tile(np.array([1024, 1023, 1022, 1023], dtype=np.uint64), g)
+    steps[8, -1, 0] = 1024
+    gas_op = np.array([GAS[o] for o in ops], dtype=np.uint64)
+    cost = np.stack([np.full(g, 3, np.uint64), np.full(g, 3, np.uint64), gas_op, np.full(g, 2, np.uint64)], axis=1).reshape(-1)
+    total = int(cost.sum())
+    spent_before = np.concatenate([[0], np.cumsum(cost)]).astype(np.uint64)
+    steps[9, :, 0] = np.uint64(total + 7) - spent_before
+    return {"steps": steps, "bytecode": bytecode, "rw": rw, "n_steps": ns - 1}
