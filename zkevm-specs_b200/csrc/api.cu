@@ -119,7 +119,9 @@ extern "C" int zk_ctx_create(int device_ordinal, zk_ctx** out) {
   }
   zk_ctx* c = new zk_ctx();
   c->device = device_ordinal;
-  for (int i = 0; i < ZK_N_CHALLENGES; i++) c->chal[i] = fr_u64(0x10001 + i);
+  // defaults: fixed 253-bit constants (callers normally draw their own after fixing the witness)
+  c->chal[ZK_CHALLENGE_KECCAK] = Fr{{0x9b97f4a7c15f39ccull, 0x0d6e8feb86659fd9ull, 0x3c2b2ae3d27d4eb4ull, 0x1165667b19e3779full}};
+  c->chal[ZK_CHALLENGE_LOOKUP] = Fr{{0x2545f4914f6cdd1dull, 0x5851f42d4c957f2dull, 0x14057b7ef767814full, 0x0fe3a95bd3a1c8e7ull}};
   *out = c;
   return 0;
 }

@@ -44,10 +44,16 @@ ZK_HD Fr table_cell(const TableDev& t, u32 col, u64 row) {
   return ld_cell(cell_ptr(t, col, row));
 }
 
-// bucket from the canonical RLC value
+// bucket from the canonical RLC value: fold the four limbs and finish with a 64-bit mixer, so
+// that even a weak challenge (small r) spreads structured keys over the table
 ZK_HD u32 rlc_bucket(const Fr& h, u32 mask) {
-  u64 x = h.l[0] ^ (h.l[1] * 0x9E3779B97F4A7C15ull);
-  x ^= x >> 29;
+  u64 x = h.l[0] ^ (h.l[1] * 0x9E3779B97F4A7C15ull) ^ (h.l[2] * 0xC2B2AE3D27D4EB4Full) ^
+          (h.l[3] * 0x165667B19E3779F9ull);
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
   return (u32)x & mask;
 }
 

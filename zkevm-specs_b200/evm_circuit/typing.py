@@ -87,32 +87,28 @@ class Bytecode:
 
 
 class Block:
-    """Block context (reference typing.py Block): only what the hot-path tests read."""
+    """Block context rows (reference typing.py:70-136); the hot-path gadgets never read them,
+    the class exists so that `Tables(block_table=set(Block().table_assignments()), ...)` reads
+    like the reference's tests."""
 
     def __init__(self, coinbase: int = 0x10, gas_limit: int = int(15e6), number: int = 0,
-                 timestamp: int = 0, difficulty: int = 0x200000, base_fee: int = int(1e9),
-                 chain_id: int = 0x01, history_hashes: Sequence[int] = ()) -> None:
+                 timestamp: int = 0, prev_randao: int = 0, base_fee: int = int(1e9), chainid: int = 0x01,
+                 withdrawal_root: int = 0, history_hashes: Sequence[int] = ()) -> None:
         assert len(history_hashes) <= min(256, number)
         self.coinbase, self.gas_limit, self.number, self.timestamp = coinbase, gas_limit, number, timestamp
-        self.difficulty, self.base_fee, self.chain_id = difficulty, base_fee, chain_id
+        self.prev_randao, self.base_fee, self.chainid = prev_randao, base_fee, chainid
+        self.withdrawal_root = withdrawal_root
         self.history_hashes = list(history_hashes)
 
     def table_assignments(self) -> List[BlockTableRow]:
         T = BlockContextFieldTag
-        value = lambda v: WordOrValue(FQ(v))  # noqa: E731
-        word = lambda v: WordOrValue(Word(v))  # noqa: E731
-        rows = [
-            BlockTableRow(FQ(T.Coinbase), FQ(0), word(self.coinbase)),
-            BlockTableRow(FQ(T.GasLimit), FQ(0), value(self.gas_limit)),
-            BlockTableRow(FQ(T.Number), FQ(0), value(self.number)),
-            BlockTableRow(FQ(T.Timestamp), FQ(0), value(self.timestamp)),
-            BlockTableRow(FQ(T.Difficulty), FQ(0), word(self.difficulty)),
-            BlockTableRow(FQ(T.BaseFee), FQ(0), word(self.base_fee)),
-            BlockTableRow(FQ(T.ChainId), FQ(0), value(self.chain_id)),
-        ]
-        first = self.number - len(self.history_hashes)
-        rows += [BlockTableRow(FQ(T.HistoryHash), FQ(first + i), word(h))
-                 for i, h in enumerate(self.history_hashes)]
+        fields = [(T.Coinbase, self.coinbase, True), (T.GasLimit, self.gas_limit, False),
+                  (T.Number, self.number, False), (T.Timestamp, self.timestamp, False),
+                  (T.PrevRandao, self.prev_randao, True), (T.BaseFee, self.base_fee, True),
+                  (T.ChainId, self.chainid, False), (T.WithdrawalRoot, self.withdrawal_root, False)]
+        rows = [BlockTableRow(FQ(t), FQ(0), WordOrValue(Word(v) if is_word else FQ(v))) for t, v, is_word in fields]
+        for back, h in enumerate(reversed(self.history_hashes)):
+            rows.append(BlockTableRow(FQ(T.HistoryHash), FQ(self.number - back - 1), WordOrValue(Word(h))))
         return rows
 
 
