@@ -15,7 +15,7 @@
 using namespace zk;
 
 static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32* key_cols, u32 n_key,
-                            const Fr& challenge, std::vector<u32>& slots) {
+                            const Fr& challenge, std::vector<u64>& slots) {
   IndexDev d;
   d.tab.cells = cells;
   d.tab.n_rows = n_rows;
@@ -32,6 +32,7 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   for (u32 j = 0; j < ZK_MAX_KEY; j++) {
     d.key_cols[j] = j < n_key ? key_cols[j] : 0;
     d.pw[j] = acc;
+    d.pwc[j] = fr_montmul(acc, fr_u64(1));
     acc = fr_montmul(acc, r_mont);
   }
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
@@ -50,7 +51,7 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
                              const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
-  std::vector<u32> s1, s2, s3;
+  std::vector<u64> s1, s2, s3;
   EvmTables t;
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
@@ -59,7 +60,7 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true};
     verify_step(s, flags);
   }
   return 0;
@@ -71,7 +72,7 @@ extern "C" int emu_check_bytecode(const uint64_t* cols, uint64_t n_rows, const u
                                   const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 pk[2] = {0, 1}, kk[5] = {0, 1, 2, 3, 4};
-  std::vector<u32> s1, s2;
+  std::vector<u64> s1, s2;
   IndexDev push_ix = build_index((const u64*)push, n_push, 2, pk, 2, ch, s1);
   IndexDev kec_ix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s2);
   WitnessDev w{(const u64*)cols, n_rows, nullptr};

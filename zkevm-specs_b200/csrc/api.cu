@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -56,7 +57,7 @@ struct Index {
   int table_id = -1;
   u32 n_key = 0;
   u32 key_cols[ZK_MAX_KEY];
-  u32* slots = nullptr;
+  u64* slots = nullptr;
   size_t cap = 0;
   u64 built_version = ~0ull;
   u64 built_challenge = ~0ull;
@@ -79,6 +80,9 @@ struct zk_ctx {
   ResultBuf res[ZK_N_CIRCUITS];
   std::string err;
   u64 launches = 0;
+  int sm_count = 148;
+  u32* evm_lists = nullptr;  // [G_COUNT][cap] step indices + [G_COUNT] counters
+  size_t evm_lists_cap = 0;
   bool timing = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // start, after index builds, after check kernel
   cudaStream_t ev_mid_stream = nullptr;
@@ -119,6 +123,7 @@ extern "C" int zk_ctx_create(int device_ordinal, zk_ctx** out) {
   }
   zk_ctx* c = new zk_ctx();
   c->device = device_ordinal;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
   // defaults: fixed 253-bit constants (callers normally draw their own after fixing the witness)
   c->chal[ZK_CHALLENGE_KECCAK] = Fr{{0x9b97f4a7c15f39ccull, 0x0d6e8feb86659fd9ull, 0x3c2b2ae3d27d4eb4ull, 0x1165667b19e3779full}};
   c->chal[ZK_CHALLENGE_LOOKUP] = Fr{{0x2545f4914f6cdd1dull, 0x5851f42d4c957f2dull, 0x14057b7ef767814full, 0x0fe3a95bd3a1c8e7ull}};
@@ -145,6 +150,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (r.first_fail) cudaFree(r.first_fail);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->evm_lists) cudaFree(ctx->evm_lists);
   delete ctx;
 }
 
@@ -292,7 +298,7 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   if (cap > ix->cap) {
     if (ix->slots) cudaFree(ix->slots);
     ix->slots = nullptr;
-    CK(ctx, cudaMalloc(&ix->slots, cap * sizeof(u32)));
+    CK(ctx, cudaMalloc(&ix->slots, cap * sizeof(u64)));
     ix->cap = cap;
   }
   IndexDev& d = ix->dev;
@@ -304,10 +310,11 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   Fr acc = fr_to_mont(fr_u64(1));
   for (u32 j = 0; j < ZK_MAX_KEY; j++) {
     d.key_cols[j] = j < n_key ? key_cols[j] : 0;
-    d.pw[j] = acc;  // r^j in Montgomery form
+    d.pw[j] = acc;                            // r^j in Montgomery form
+    d.pwc[j] = fr_montmul(acc, fr_u64(1));  // r^j canonical
     acc = fr_montmul(acc, r_mont);
   }
-  CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u32), st));
+  CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u64), st));
   if (t.n_rows) {
     k_index_build<<<(unsigned)((t.n_rows + 255) / 256), 256, 0, st>>>(d);
     ctx->launches++;
@@ -381,8 +388,29 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   if ((rc = ensure_index(ctx, ZK_TABLE_FIXED, k4, 4, st, &t.fixed))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  k_check_evm<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(witness_dev(m), rg, t, res);
-  ctx->launches++;
+  // per-gadget step lists (bucket by execution state), then one kernel per gate program
+  if (n > ctx->evm_lists_cap) {
+    if (ctx->evm_lists) cudaFree(ctx->evm_lists);
+    ctx->evm_lists = nullptr;
+    CK(ctx, cudaMalloc(&ctx->evm_lists, (G_COUNT * n + G_COUNT) * sizeof(u32)));
+    ctx->evm_lists_cap = n;
+  }
+  EvmLists lists;
+  lists.cap = (u32)ctx->evm_lists_cap;
+  lists.idx = ctx->evm_lists;
+  lists.count = ctx->evm_lists + (size_t)G_COUNT * ctx->evm_lists_cap;
+  CK(ctx, cudaMemsetAsync(lists.count, 0, G_COUNT * sizeof(u32), st));
+  const WitnessDev wd = witness_dev(m);
+  k_evm_classify<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wd, rg, t, res, lists);
+  // persistent grids sized in multiples of the SM count; each walks its list with a grid stride
+  const unsigned full = (unsigned)((n + 127) / 128);
+  const unsigned grid_t = std::min<unsigned>(full, (unsigned)ctx->sm_count * 8);
+  const unsigned grid_w = std::min<unsigned>((unsigned)((n * 32 + 127) / 128), (unsigned)ctx->sm_count * 12);
+  k_evm_push<<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_ADD><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_MUL><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_POP><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  ctx->launches += 5;
   CK(ctx, cudaGetLastError());
   return 0;
 }

@@ -67,35 +67,46 @@ struct StepCtx {
   const EvmTables& t;
   const ResultDev& res;
   u64 i, j, row;
+  bool record;  // warp-cooperative gadgets evaluate in every lane but only one lane records
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
   ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
 };
 
-#define EV_CHECK(id, cond)      \
-  do {                          \
-    if (!(cond)) {              \
-      fail(s.res, (id), s.row); \
-      return;                   \
-    }                           \
+ZK_HD void step_fail(const StepCtx& s, int id) {
+  if (s.record) fail(s.res, id, s.row);
+}
+#define EV_CHECK(id, cond) \
+  do {                     \
+    if (!(cond)) {         \
+      step_fail(s, (id));  \
+      return;              \
+    }                      \
+  } while (0)
+#define EV_CHECK_RET(id, cond, ret) \
+  do {                              \
+    if (!(cond)) {                  \
+      step_fail(s, (id));           \
+      return ret;                   \
+    }                               \
   } while (0)
 
 // lookup outcome -> failure id (unsat, or the next id = ambiguous); true iff exactly one row
 ZK_HD bool need1(const StepCtx& s, int n, int id_unsat) {
   if (n == 1) return true;
-  fail(s.res, n == 0 ? id_unsat : id_unsat + 1, s.row);
+  step_fail(s, n == 0 ? id_unsat : id_unsat + 1);
   return false;
 }
 
-ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 tag,
-                                               const Fr& index, u64 is_code, Fr* value) {
+ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 tag, const Fr& index,
+                          u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   u32 r;
   const int n = lookup<5>(s.t.bytecode, key, &r);
   if (n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
   return n;
 }
-ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& id,
-                                         const Fr& addr, Word2* value) {
+ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
+                    Word2* value) {
   Fr key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
   u32 r;
   const int n = lookup<5>(s.t.rw, key, &r);
@@ -106,9 +117,51 @@ ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& 
   return n;
 }
 
+// ---- prologue: verify_step before the gadget (main.py:47-63, instruction.py:189-204) --------
+enum { G_ADD, G_MUL, G_PUSH, G_POP, G_COUNT };
+// returns the gadget that must run for this step, or -1 if the step already failed
+ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
+  const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
+  const bool is_first = (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0;
+  const bool is_last = (flags & ZK_FLAG_EVM_LAST_STEP) && s.i == s.w.n_rows - 2;
+  const bool cs_small = fr_fits64(cs) && cs.l[0] < ZK_ES_COUNT;
+  if (is_first) {
+    EV_CHECK_RET(EV_FIRST_STATE, fr_eq_u64(cs, ZK_ES_BeginTx) || fr_eq_u64(cs, ZK_ES_EndBlock), -1);
+    EV_CHECK_RET(EV_FIRST_RWC, fr_eq_u64(s.cur(S_RWC), 1), -1);
+  }
+  if (is_last) {
+    EV_CHECK_RET(EV_LAST_STATE, fr_eq_u64(cs, ZK_ES_EndBlock), -1);
+  } else {
+    if (fr_eq_u64(cs, ZK_ES_EndTx))
+      EV_CHECK_RET(EV_TRANS_FROM_ENDTX, fr_eq_u64(ns, ZK_ES_BeginTx) || fr_eq_u64(ns, ZK_ES_EndBlock), -1);
+    else if (fr_eq_u64(cs, ZK_ES_EndBlock))
+      EV_CHECK_RET(EV_TRANS_FROM_ENDBLOCK, fr_eq_u64(ns, ZK_ES_EndBlock), -1);
+    if (fr_eq_u64(ns, ZK_ES_BeginTx))
+      EV_CHECK_RET(EV_TRANS_TO_BEGINTX, fr_eq_u64(cs, ZK_ES_EndTx), -1);
+    else if (fr_eq_u64(ns, ZK_ES_EndTx))
+      EV_CHECK_RET(EV_TRANS_TO_ENDTX, (cs_small && ES_HALTS(cs.l[0])) || fr_eq_u64(cs, ZK_ES_BeginTx), -1);
+    else if (fr_eq_u64(ns, ZK_ES_EndBlock))
+      EV_CHECK_RET(EV_TRANS_TO_ENDBLOCK, fr_eq_u64(cs, ZK_ES_EndTx) || fr_eq_u64(cs, ZK_ES_EndBlock), -1);
+  }
+  EV_CHECK_RET(EV_NOT_IMPLEMENTED, cs_small && ES_IMPL(cs.l[0]), -1);
+  switch (cs.l[0]) {
+    case ZK_ES_ADD: return G_ADD;
+    case ZK_ES_MUL: return G_MUL;
+    case ZK_ES_PUSH: return G_PUSH;
+    case ZK_ES_POP: return G_POP;
+    default: break;
+  }
+  step_fail(s, EV_UNSUPPORTED_STATE);
+  return -1;
+}
+
+// opcode_lookup(True) at the start of every hot gadget (instruction.py:784-790)
+ZK_HD bool opcode_lookup(const StepCtx& s, Fr* opcode) {
+  return need1(s, bytecode_lookup(s, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, opcode), EV_OP_UNSAT);
+}
+
 // step_state_transition_in_same_context, instruction.py:365-394
-ZK_HD_NOINLINE void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc,
-                                          const Fr& d_sp) {
+ZK_HD void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
   Fr key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), s.cur(S_STATE), opcode, fr_u64(0)};
   u32 r;
   EV_CHECK(EV_SC_RESP_OPCODE, lookup<4>(s.t.fixed, key, &r) >= 1);
@@ -138,7 +191,9 @@ ZK_HD Word2 add_words2(const Word2& x, const Word2& y) {
   return Word2{fr_u128(slo.l[0], slo.l[1]), fr_u128(shi.l[0], shi.l[1])};
 }
 
-ZK_HD_NOINLINE void gadget_add(const StepCtx& s, const Fr& opcode) {
+ZK_HD void gadget_add(const StepCtx& s) {
+  Fr opcode;
+  if (!opcode_lookup(s, &opcode)) return;
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Fr sp1 = fr_add_u64(sp, 1);
   const bool is_sub = fr_eq_u64(opcode, 3);
@@ -239,7 +294,9 @@ ZK_HD bool word_select(const Word2& w, const Fr& sel, Word2* out) {
   return word_in_domain(*out);
 }
 
-ZK_HD_NOINLINE void gadget_mul(const StepCtx& s, const Fr& opcode) {
+ZK_HD void gadget_mul(const StepCtx& s) {
+  Fr opcode;
+  if (!opcode_lookup(s, &opcode)) return;
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Fr sp1 = fr_add_u64(sp, 1);
   const Fr one = fr_u64(1);
@@ -344,83 +401,186 @@ ZK_HD_NOINLINE void gadget_mul(const StepCtx& s, const Fr& opcode) {
   same_context(s, opcode, 3, one, one);
 }
 
-ZK_HD_NOINLINE void gadget_push(const StepCtx& s, const Fr& opcode) {
-  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP), pc = s.cur(S_PC);
-  const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI);
-  const Fr num_pushed = fr_sub_u64(opcode, 0x5f);
-  Fr code_length;
-  if (!need1(s, bytecode_lookup(s, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_PUSH_LEN_UNSAT)) return;
-  const Fr left = fr_sub_u64(fr_sub(code_length, pc), 1);
-  EV_CHECK(EV_PUSH_CMP_RANGE, fr_fits64(left) && fr_fits64(num_pushed));
-  const u64 n_push = num_pushed.l[0];
-  const u64 n_pad = left.l[0] < n_push ? n_push - left.l[0] : 0;
+// ---- PUSH (execution/push.py:6-33), written as lane functions: on the device one WARP checks
+// one PUSH step — lane L owns pushed byte L (its bytecode lookup + equality), so the 32 table
+// rows of a PUSH32 are fetched as coalesced 1 KiB column segments; tests/emu runs the same lane
+// functions serially.
+struct PushCommon {
+  Fr hlo, hhi, pc, opcode, num_pushed;
+  u64 n_push, n_pad;
   Word2 value;
-  if (!need1(s, rw_lookup(s, rwc, 1, ZK_TARGET_Stack, call_id, fr_sub_u64(sp, 1), &value), EV_PUSH_RW_UNSAT)) return;
-  EV_CHECK(EV_PUSH_VALUE_BYTES, word_in_domain(value));
-  Fr index = fr_add(pc, num_pushed);  // pc + num_pushed - idx
-  for (int idx = 0; idx < 32; idx++) {
-    const u64 limb = idx < 16 ? value.lo.l[idx >> 3] : value.hi.l[(idx - 16) >> 3];
-    const u64 byte = (limb >> (8 * (idx & 7))) & 0xFF;
-    const int base = EV_PUSH_B0_UNSAT + 4 * idx;
-    if ((u64)idx < n_push && (u64)idx >= n_pad) {
-      Fr got;
-      if (!need1(s, bytecode_lookup(s, hlo, hhi, 2, index, 0, &got), base)) return;
-      EV_CHECK(base + 2, fr_eq_u64(got, byte));
-    } else {
-      EV_CHECK(base + 3, byte == 0);
-    }
-    index = fr_sub_u64(index, 1);
+};
+// program order up to the byte loop: opcode lookup, bytecode_length lookup, compare() range
+// asserts, stack_push lookup, to_le_bytes(); false if the step failed (recorded if s.record)
+ZK_HD bool push_prepare(const StepCtx& s, int n_op, const Fr& opcode, int n_len, const Fr& code_length,
+                        int n_rw, const Word2& value, PushCommon* c) {
+  if (!need1(s, n_op, EV_OP_UNSAT)) return false;
+  if (!need1(s, n_len, EV_PUSH_LEN_UNSAT)) return false;
+  c->opcode = opcode;
+  c->num_pushed = fr_sub_u64(opcode, 0x5f);
+  const Fr left = fr_sub_u64(fr_sub(code_length, c->pc), 1);
+  EV_CHECK_RET(EV_PUSH_CMP_RANGE, fr_fits64(left) && fr_fits64(c->num_pushed), false);
+  c->n_push = c->num_pushed.l[0];
+  c->n_pad = left.l[0] < c->n_push ? c->n_push - left.l[0] : 0;
+  if (!need1(s, n_rw, EV_PUSH_RW_UNSAT)) return false;
+  EV_CHECK_RET(EV_PUSH_VALUE_BYTES, word_in_domain(value), false);
+  c->value = value;
+  return true;
+}
+// byte idx of the pushed word: returns the failing constraint id, or -1
+ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx) {
+  const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
+  const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
+  const u64 limb = idx < 16 ? lo_limb : hi_limb;
+  const u64 byte = (limb >> (8 * (idx & 7))) & 0xFF;
+  const int base = EV_PUSH_B0_UNSAT + 4 * idx;
+  if ((u64)idx < c.n_push && (u64)idx >= c.n_pad) {
+    Fr got;
+    const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
+    const int n = bytecode_lookup(s, c.hlo, c.hhi, 2, index, 0, &got);
+    if (n != 1) return n == 0 ? base : base + 1;
+    return fr_eq_u64(got, byte) ? -1 : base + 2;
   }
-  same_context(s, opcode, 1, fr_add_u64(num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+  return byte == 0 ? -1 : base + 3;
+}
+ZK_HD void push_epilogue(const StepCtx& s, const PushCommon& c) {
+  same_context(s, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+// serial form (tests/emu, and any caller without a warp)
+ZK_HD void gadget_push(const StepCtx& s) {
+  PushCommon c;
+  c.hlo = s.cur(S_HASH_LO);
+  c.hhi = s.cur(S_HASH_HI);
+  c.pc = s.cur(S_PC);
+  Fr opcode = fr_u64(0), code_length = fr_u64(0);
+  Word2 value{fr_u64(0), fr_u64(0)};
+  const int n_op = bytecode_lookup(s, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup(s, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  const int n_rw = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
+  if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
+  for (int idx = 0; idx < 32; idx++) {
+    const int fid = push_byte(s, c, idx);
+    if (fid >= 0) {
+      step_fail(s, fid);
+      return;
+    }
+  }
+  push_epilogue(s, c);
 }
 
-ZK_HD_NOINLINE void gadget_pop(const StepCtx& s, const Fr& opcode) {
+ZK_HD void gadget_pop(const StepCtx& s) {
+  Fr opcode;
+  if (!opcode_lookup(s, &opcode)) return;
   Word2 y;
   if (!need1(s, rw_lookup(s, s.cur(S_RWC), 0, ZK_TARGET_Stack, s.cur(S_CALL_ID), s.cur(S_SP), &y), EV_POP_RW_UNSAT))
     return;
   same_context(s, opcode, 1, fr_u64(1), fr_u64(1));
 }
 
+// whole step on one thread (tests/emu)
 ZK_HD void verify_step(const StepCtx& s, u32 flags) {
-  const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
-  const bool is_first = (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0;
-  const bool is_last = (flags & ZK_FLAG_EVM_LAST_STEP) && s.i == s.w.n_rows - 2;
-  const bool cs_small = fr_fits64(cs) && cs.l[0] < ZK_ES_COUNT;
-  if (is_first) {
-    EV_CHECK(EV_FIRST_STATE, fr_eq_u64(cs, ZK_ES_BeginTx) || fr_eq_u64(cs, ZK_ES_EndBlock));
-    EV_CHECK(EV_FIRST_RWC, fr_eq_u64(s.cur(S_RWC), 1));
+  switch (step_prologue(s, flags)) {
+    case G_ADD: gadget_add(s); break;
+    case G_MUL: gadget_mul(s); break;
+    case G_PUSH: gadget_push(s); break;
+    case G_POP: gadget_pop(s); break;
+    default: break;
   }
-  if (is_last) {
-    EV_CHECK(EV_LAST_STATE, fr_eq_u64(cs, ZK_ES_EndBlock));
-  } else {
-    if (fr_eq_u64(cs, ZK_ES_EndTx))
-      EV_CHECK(EV_TRANS_FROM_ENDTX, fr_eq_u64(ns, ZK_ES_BeginTx) || fr_eq_u64(ns, ZK_ES_EndBlock));
-    else if (fr_eq_u64(cs, ZK_ES_EndBlock))
-      EV_CHECK(EV_TRANS_FROM_ENDBLOCK, fr_eq_u64(ns, ZK_ES_EndBlock));
-    if (fr_eq_u64(ns, ZK_ES_BeginTx))
-      EV_CHECK(EV_TRANS_TO_BEGINTX, fr_eq_u64(cs, ZK_ES_EndTx));
-    else if (fr_eq_u64(ns, ZK_ES_EndTx))
-      EV_CHECK(EV_TRANS_TO_ENDTX, (cs_small && ES_HALTS(cs.l[0])) || fr_eq_u64(cs, ZK_ES_BeginTx));
-    else if (fr_eq_u64(ns, ZK_ES_EndBlock))
-      EV_CHECK(EV_TRANS_TO_ENDBLOCK, fr_eq_u64(cs, ZK_ES_EndTx) || fr_eq_u64(cs, ZK_ES_EndBlock));
-  }
-  EV_CHECK(EV_NOT_IMPLEMENTED, cs_small && ES_IMPL(cs.l[0]));
-  const u64 st = cs.l[0];
-  EV_CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP);
-  Fr opcode;
-  if (!need1(s, bytecode_lookup(s, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, &opcode), EV_OP_UNSAT))
-    return;
-  if (st == ZK_ES_ADD) gadget_add(s, opcode);
-  else if (st == ZK_ES_MUL) gadget_mul(s, opcode);
-  else if (st == ZK_ES_PUSH) gadget_push(s, opcode);
-  else gadget_pop(s, opcode);
 }
 
-__global__ void __launch_bounds__(128) k_check_evm(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res) {
+// ======================================================================================
+// kernels
+// ======================================================================================
+// Steps are bucketed by execution state first (the reference dispatches one Python gadget per
+// step, execution/__init__.py:86-171): k_evm_classify runs the cheap prologue of every step and
+// appends its index to the list of its gadget; then one kernel per gadget runs a single
+// straight-line gate program, so warps do not diverge across gadgets.
+struct EvmLists {
+  u32* idx;    // [G_COUNT][cap] local step indices
+  u32* count;  // [G_COUNT]
+  u32 cap;
+};
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                      EvmLists lists) {
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rg.row_end) return;
-  StepCtx s{w, t, res, i, i + 1, rg.row_base + i};
-  verify_step(s, rg.flags);
+  int g = -1;
+  if (i < rg.row_end) {
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true};
+    g = step_prologue(s, rg.flags);
+  }
+  // warp-aggregated append: one atomicAdd per (warp, gadget)
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < G_COUNT; k++) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, g == k);
+    if (m == 0) continue;
+    u32 base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&lists.count[k], (u32)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (g == k) lists.idx[(u64)k * lists.cap + base + __popc(m & ((1u << lane) - 1))] = (u32)(i - rg.row_begin);
+  }
 }
+
+// one thread per step for the gadgets whose work is a handful of independent lookups
+template <int G>
+__global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                    EvmLists lists) {
+  const u32 n = lists.count[G];
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const u64 i = rg.row_begin + lists.idx[(u64)G * lists.cap + k];
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true};
+    if (G == G_ADD) gadget_add(s);
+    else if (G == G_MUL) gadget_mul(s);
+    else gadget_pop(s);
+  }
+}
+
+__device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
+  Fr r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src);
+  return r;
+}
+
+// one warp per PUSH step
+__global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                  EvmLists lists) {
+  const u32 n = lists.count[G_PUSH];
+  const int lane = threadIdx.x & 31;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0};
+    PushCommon c;
+    c.hlo = s.cur(S_HASH_LO);
+    c.hhi = s.cur(S_HASH_HI);
+    c.pc = s.cur(S_PC);
+    // round 1: lane 0 opcode, lane 1 bytecode length, lane 2 the stack_push row
+    int n_hit = 0;
+    Fr v = fr_u64(0);
+    Word2 val{fr_u64(0), fr_u64(0)};
+    if (lane < 2) {
+      n_hit = bytecode_lookup(s, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0), lane == 0 ? 1 : 0, &v);
+    } else if (lane == 2) {
+      n_hit = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &val);
+    }
+    const int n_op = __shfl_sync(0xFFFFFFFFu, n_hit, 0), n_len = __shfl_sync(0xFFFFFFFFu, n_hit, 1);
+    const int n_rw = __shfl_sync(0xFFFFFFFFu, n_hit, 2);
+    const Fr opcode = shfl_fr(v, 0), code_length = shfl_fr(v, 1);
+    Word2 value{shfl_fr(val.lo, 2), shfl_fr(val.hi, 2)};
+    if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) continue;  // warp-uniform
+    // round 2: lane L checks pushed byte L; the first failing byte in program order wins
+    const int fid = push_byte(s, c, lane);
+    const unsigned bad = __ballot_sync(0xFFFFFFFFu, fid >= 0);
+    if (bad) {
+      if (lane == __ffs(bad) - 1) fail(res, fid, s.row);
+      continue;
+    }
+    if (lane == 0) push_epilogue(s, c);
+  }
+}
+#endif  // __CUDACC__
 
 }  // namespace zk

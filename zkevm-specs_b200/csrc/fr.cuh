@@ -54,12 +54,28 @@ ZK_HD u32 ld_u32(const u32* p) {
   return *p;
 #endif
 }
-ZK_HD u32 atomic_cas_u32(u32* p, u32 expect, u32 val) {
+ZK_HD u64 ld_u64(const u64* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+ZK_HD u64 atomic_cas_u64(u64* p, u64 expect, u64 val) {
 #ifdef __CUDA_ARCH__
   return atomicCAS(p, expect, val);
 #else
-  const u32 old = *p;
+  const u64 old = *p;
   if (old == expect) *p = val;
+  return old;
+#endif
+}
+ZK_HD u32 atomic_add_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, v);
+#else
+  const u32 old = *p;
+  *p += v;
   return old;
 #endif
 }

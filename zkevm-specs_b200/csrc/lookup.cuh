@@ -19,7 +19,7 @@
 namespace zk {
 
 #define ZK_MAX_KEY 12
-#define ZK_EMPTY_SLOT 0xFFFFFFFFu
+#define ZK_EMPTY_SLOT 0xFFFFFFFFFFFFFFFFull  // a slot is (fingerprint32 << 32) | row32
 
 struct TableDev {
   const u64* cells;  // [n_cols][n_rows][4]
@@ -30,11 +30,12 @@ struct TableDev {
 
 struct IndexDev {
   TableDev tab;
-  u32* slots;  // capacity = mask+1 row ids, ZK_EMPTY_SLOT = free
+  u64* slots;  // capacity = mask+1 slots, ZK_EMPTY_SLOT = free
   u32 mask;
   u32 n_key;
   u32 key_cols[ZK_MAX_KEY];
-  Fr pw[ZK_MAX_KEY];  // r^j * 2^256 mod p (Montgomery form); pw[0] unused (r^0 = 1)
+  Fr pw[ZK_MAX_KEY];   // r^j * 2^256 mod p (Montgomery form): montmul(cell, pw[j]) = cell * r^j
+  Fr pwc[ZK_MAX_KEY];  // r^j canonical, for terms whose cell is a known small constant
 };
 
 ZK_HD const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
@@ -44,9 +45,9 @@ ZK_HD Fr table_cell(const TableDev& t, u32 col, u64 row) {
   return ld_cell(cell_ptr(t, col, row));
 }
 
-// bucket from the canonical RLC value: fold the four limbs and finish with a 64-bit mixer, so
-// that even a weak challenge (small r) spreads structured keys over the table
-ZK_HD u32 rlc_bucket(const Fr& h, u32 mask) {
+// 64-bit mix of the canonical RLC value: low bits pick the bucket, high 32 bits are the
+// fingerprint stored in the slot (so a probe only touches table rows whose fingerprint matches)
+ZK_HD u64 rlc_mix(const Fr& h) {
   u64 x = h.l[0] ^ (h.l[1] * 0x9E3779B97F4A7C15ull) ^ (h.l[2] * 0xC2B2AE3D27D4EB4Full) ^
           (h.l[3] * 0x165667B19E3779F9ull);
   x ^= x >> 32;
@@ -54,26 +55,34 @@ ZK_HD u32 rlc_bucket(const Fr& h, u32 mask) {
   x ^= x >> 32;
   x *= 0xD6E8FEB86659FD93ull;
   x ^= x >> 32;
-  return (u32)x & mask;
+  return x;
 }
 
+// one RLC term cell * r^j, with shortcuts for the constant-like cells (0, 1) that tags, flags
+// and selectors mostly are
+ZK_HD Fr rlc_term(const IndexDev& ix, const Fr& cell, int j) {
+  if (fr_is_zero(cell)) return cell;
+  if (fr_eq_u64(cell, 1)) return ix.pwc[j];
+  return fr_montmul(cell, ix.pw[j]);
+}
 // h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
 template <int NK>
 ZK_HD Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
   Fr h = key[0];
 #pragma unroll
-  for (int j = 1; j < NK; j++) h = fr_add(h, fr_montmul(key[j], ix.pw[j]));
+  for (int j = 1; j < NK; j++) h = fr_add(h, rlc_term(ix, key[j], j));
   return h;
 }
 
 // One thread per table row: compress the queried columns and claim a slot.
 ZK_HD void index_insert_row(const IndexDev& ix, u64 row) {
   Fr h = table_cell(ix.tab, ix.key_cols[0], row);
-  for (u32 j = 1; j < ix.n_key; j++)
-    h = fr_add(h, fr_montmul(table_cell(ix.tab, ix.key_cols[j], row), ix.pw[j]));
-  u32 b = rlc_bucket(h, ix.mask);
+  for (u32 j = 1; j < ix.n_key; j++) h = fr_add(h, rlc_term(ix, table_cell(ix.tab, ix.key_cols[j], row), (int)j));
+  const u64 mix = rlc_mix(h);
+  const u64 entry = (mix & 0xFFFFFFFF00000000ull) | (u64)(u32)row;
+  u32 b = (u32)mix & ix.mask;
   for (;;) {
-    const u32 old = atomic_cas_u32(&ix.slots[b], ZK_EMPTY_SLOT, (u32)row);
+    const u64 old = atomic_cas_u64(&ix.slots[b], ZK_EMPTY_SLOT, entry);
     if (old == ZK_EMPTY_SLOT) break;
     b = (b + 1) & ix.mask;
   }
@@ -92,26 +101,30 @@ ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
 // Walk the bucket run starting at the bucket of h.  Returns the number of distinct matching
 // rows, capped at 2; *row = the first match.
 template <int NK>
-ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK],
-                                            u32* row) {
+ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32* row) {
   int found = 0;
   u32 first = 0;
-  u32 b = rlc_bucket(h, ix.mask);
+  const u64 mix = rlc_mix(h);
+  const u32 fp = (u32)(mix >> 32);
+  u32 b = (u32)mix & ix.mask;
   for (;;) {
-    const u32 cand = ld_u32(&ix.slots[b]);
-    if (cand == ZK_EMPTY_SLOT) break;
-    bool eq = true;
+    const u64 slot = ld_u64(&ix.slots[b]);
+    if (slot == ZK_EMPTY_SLOT) break;
+    if ((u32)(slot >> 32) == fp) {
+      const u32 cand = (u32)slot;
+      bool eq = true;
 #pragma unroll
-    for (int j = 0; j < NK; j++) {
-      if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
-    }
-    if (eq) {
-      if (found == 0) {
-        first = cand;
-        found = 1;
-      } else if (!rows_identical(ix.tab, first, cand)) {
-        found = 2;
-        break;
+      for (int j = 0; j < NK; j++) {
+        if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
+      }
+      if (eq) {
+        if (found == 0) {
+          first = cand;
+          found = 1;
+        } else if (!rows_identical(ix.tab, first, cand)) {
+          found = 2;
+          break;
+        }
       }
     }
     b = (b + 1) & ix.mask;
