@@ -33,6 +33,7 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
     d.key_cols[j] = j < n_key ? key_cols[j] : 0;
     d.pw[j] = acc;
     d.pwc[j] = fr_montmul(acc, fr_u64(1));
+    d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);
     acc = fr_montmul(acc, r_mont);
   }
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);

@@ -312,6 +312,7 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     d.key_cols[j] = j < n_key ? key_cols[j] : 0;
     d.pw[j] = acc;                            // r^j in Montgomery form
     d.pwc[j] = fr_montmul(acc, fr_u64(1));  // r^j canonical
+    d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);  // r^j * 2^64 mod p
     acc = fr_montmul(acc, r_mont);
   }
   CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u64), st));

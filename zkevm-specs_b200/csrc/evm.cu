@@ -105,6 +105,24 @@ ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 ta
   if (n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
   return n;
 }
+// same lookup with the step-constant part of the key hash (hash_lo + hash_hi * r) hoisted: a PUSH
+// step probes the bytecode table up to 34 times with the same code hash
+ZK_HD Fr bytecode_hash0(const StepCtx& s, const Fr& hlo, const Fr& hhi) {
+  return fr_add(hlo, rlc_term(s.t.bytecode, hhi, 1));
+}
+ZK_HD int bytecode_lookup_h(const StepCtx& s, const Fr& h0, const Fr& hlo, const Fr& hhi, u64 tag,
+                            const Fr& index, u64 is_code, Fr* value) {
+  Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
+  const IndexDev& ix = s.t.bytecode;
+  if (ix.tab.n_rows == 0) return 0;
+  Fr h = fr_add(h0, rlc_term(ix, key[2], 2));
+  h = fr_add(h, rlc_term(ix, key[3], 3));
+  h = fr_add(h, rlc_term(ix, key[4], 4));
+  u32 r;
+  const int n = probe_hashed<5>(ix, h, key, &r);
+  if (n == 1) *value = table_cell(ix.tab, B_VALUE, r);
+  return n;
+}
 ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
                     Word2* value) {
   Fr key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
@@ -243,20 +261,51 @@ ZK_HD bool mul256_exceeds(const u64 a[4], const u64 b[4], const u64 d[4], u64 pr
   for (int k = 0; k < 4; k++) prod_lo[k] = t[k];
   return (t[4] | t[5] | t[6] | t[7]) != 0 || cmp256(prod_lo, d) > 0;
 }
-// q = n / d for d != 0 (shift-subtract; only MOD steps pay for it)
-ZK_HD_NOINLINE void div256(const u64 n[4], const u64 d[4], u64 q[4]) {
-  u64 r[4] = {0, 0, 0, 0};
+ZK_HD int bitlen256(const u64 v[4]) {
+#ifdef __CUDA_ARCH__
+#define ZK_CLZ64(x) __clzll((long long)(x))
+#else
+#define ZK_CLZ64(x) __builtin_clzll(x)
+#endif
+  if (v[3]) return 256 - ZK_CLZ64(v[3]);
+  if (v[2]) return 192 - ZK_CLZ64(v[2]);
+  if (v[1]) return 128 - ZK_CLZ64(v[1]);
+  if (v[0]) return 64 - ZK_CLZ64(v[0]);
+  return 0;
+}
+// q = n / d for d != 0: shift-subtract over the bit-length difference only, all in registers
+// (static limb indices); only MOD steps pay for it
+ZK_HD void div256(const u64 n[4], const u64 d[4], u64 q[4]) {
   q[0] = q[1] = q[2] = q[3] = 0;
-  for (int bit = 255; bit >= 0; bit--) {
-    const u64 top = r[3] >> 63;
-    r[3] = (r[3] << 1) | (r[2] >> 63);
-    r[2] = (r[2] << 1) | (r[1] >> 63);
-    r[1] = (r[1] << 1) | (r[0] >> 63);
-    r[0] = (r[0] << 1) | ((n[bit >> 6] >> (bit & 63)) & 1);
-    if (top || cmp256(r, d) >= 0) {
-      sub256(r, d, r);
-      q[bit >> 6] |= 1ull << (bit & 63);
-    }
+  const int shift = bitlen256(n) - bitlen256(d);
+  if (shift < 0) return;
+  // ds = d << shift
+  u64 w0 = d[0], w1 = d[1], w2 = d[2], w3 = d[3];
+  const int ws = shift >> 6, bs = shift & 63;
+  if (ws == 1) { w3 = w2; w2 = w1; w1 = w0; w0 = 0; }
+  else if (ws == 2) { w3 = w1; w2 = w0; w1 = 0; w0 = 0; }
+  else if (ws == 3) { w3 = w0; w2 = 0; w1 = 0; w0 = 0; }
+  if (bs) {
+    w3 = (w3 << bs) | (w2 >> (64 - bs));
+    w2 = (w2 << bs) | (w1 >> (64 - bs));
+    w1 = (w1 << bs) | (w0 >> (64 - bs));
+    w0 = w0 << bs;
+  }
+  u64 r0 = n[0], r1 = n[1], r2 = n[2], r3 = n[3];
+  for (int k = shift; k >= 0; k--) {
+    // r >= ds ?
+    u64 br = 0;
+    const u64 t0 = sbb64(r0, w0, br), t1 = sbb64(r1, w1, br), t2 = sbb64(r2, w2, br), t3 = sbb64(r3, w3, br);
+    const u64 bit = br ? 0 : 1;
+    if (bit) { r0 = t0; r1 = t1; r2 = t2; r3 = t3; }
+    q[3] = (q[3] << 1) | (q[2] >> 63);
+    q[2] = (q[2] << 1) | (q[1] >> 63);
+    q[1] = (q[1] << 1) | (q[0] >> 63);
+    q[0] = (q[0] << 1) | bit;
+    w0 = (w0 >> 1) | (w1 << 63);
+    w1 = (w1 >> 1) | (w2 << 63);
+    w2 = (w2 >> 1) | (w3 << 63);
+    w3 >>= 1;
   }
 }
 
@@ -406,7 +455,7 @@ ZK_HD void gadget_mul(const StepCtx& s) {
 // rows of a PUSH32 are fetched as coalesced 1 KiB column segments; tests/emu runs the same lane
 // functions serially.
 struct PushCommon {
-  Fr hlo, hhi, pc, opcode, num_pushed;
+  Fr hlo, hhi, h0, pc, opcode, num_pushed;
   u64 n_push, n_pad;
   Word2 value;
 };
@@ -437,7 +486,7 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx) {
   if ((u64)idx < c.n_push && (u64)idx >= c.n_pad) {
     Fr got;
     const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
-    const int n = bytecode_lookup(s, c.hlo, c.hhi, 2, index, 0, &got);
+    const int n = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 2, index, 0, &got);
     if (n != 1) return n == 0 ? base : base + 1;
     return fr_eq_u64(got, byte) ? -1 : base + 2;
   }
@@ -452,10 +501,11 @@ ZK_HD void gadget_push(const StepCtx& s) {
   c.hlo = s.cur(S_HASH_LO);
   c.hhi = s.cur(S_HASH_HI);
   c.pc = s.cur(S_PC);
+  c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
   Fr opcode = fr_u64(0), code_length = fr_u64(0);
   Word2 value{fr_u64(0), fr_u64(0)};
-  const int n_op = bytecode_lookup(s, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
-  const int n_len = bytecode_lookup(s, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  const int n_op = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
   const int n_rw = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
   if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
   for (int idx = 0; idx < 32; idx++) {
@@ -557,12 +607,13 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
+    c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
     // round 1: lane 0 opcode, lane 1 bytecode length, lane 2 the stack_push row
     int n_hit = 0;
     Fr v = fr_u64(0);
     Word2 val{fr_u64(0), fr_u64(0)};
     if (lane < 2) {
-      n_hit = bytecode_lookup(s, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0), lane == 0 ? 1 : 0, &v);
+      n_hit = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0), lane == 0 ? 1 : 0, &v);
     } else if (lane == 2) {
       n_hit = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &val);
     }

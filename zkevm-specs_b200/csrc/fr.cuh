@@ -29,6 +29,8 @@ struct Fr {
 #define ZK_R2_1 0x53fe3ab1e35c59e3ull
 #define ZK_R2_2 0x8c49833d53bb8085ull
 #define ZK_R2_3 0x0216d0b17f4e44a5ull
+// 2^64 in Montgomery form (2^64 * 2^256 mod p)
+#define ZK_MONT_TWO64 Fr{{0xb4c6edf97c5fb586ull, 0x708c8d50bfeb93beull, 0x9ffd1de404f7e0efull, 0x215b02ac9a392866ull}}
 
 // One 256-bit load per cell: LDG.E.256 on sm_100a; a warp reading 32 consecutive rows of a
 // column moves 1 KiB in one instruction.  .nc: witness/table cells are read-only.
@@ -127,27 +129,66 @@ __host__ __device__ __forceinline__ u64 sbb64(u64 a, u64 b, u64& br) {
   br = (u64)(t >> 64) & 1;
   return (u64)t;
 }
+// s - p if s >= p (s < 2^255)
 __host__ __device__ __forceinline__ Fr fr_sub_p_if_ge(const Fr& s) {
   Fr d;
+#ifdef __CUDA_ARCH__
+  u64 br;
+  asm("sub.cc.u64 %0, %5, %9;\n\t"
+      "subc.cc.u64 %1, %6, %10;\n\t"
+      "subc.cc.u64 %2, %7, %11;\n\t"
+      "subc.cc.u64 %3, %8, %12;\n\t"
+      "subc.u64 %4, 0, 0;"
+      : "=l"(d.l[0]), "=l"(d.l[1]), "=l"(d.l[2]), "=l"(d.l[3]), "=l"(br)
+      : "l"(s.l[0]), "l"(s.l[1]), "l"(s.l[2]), "l"(s.l[3]), "l"(ZK_P0), "l"(ZK_P1), "l"(ZK_P2), "l"(ZK_P3));
+  return br ? s : d;
+#else
   u64 br = 0;
   d.l[0] = sbb64(s.l[0], ZK_P0, br);
   d.l[1] = sbb64(s.l[1], ZK_P1, br);
   d.l[2] = sbb64(s.l[2], ZK_P2, br);
   d.l[3] = sbb64(s.l[3], ZK_P3, br);
   return br ? s : d;
+#endif
 }
 // (a + b) mod p for canonical a, b  (a+b < 2p < 2^255: no carry out)
 __host__ __device__ __forceinline__ Fr fr_add(const Fr& a, const Fr& b) {
   Fr s;
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u64 %0, %4, %8;\n\t"
+      "addc.cc.u64 %1, %5, %9;\n\t"
+      "addc.cc.u64 %2, %6, %10;\n\t"
+      "addc.u64 %3, %7, %11;"
+      : "=l"(s.l[0]), "=l"(s.l[1]), "=l"(s.l[2]), "=l"(s.l[3])
+      : "l"(a.l[0]), "l"(a.l[1]), "l"(a.l[2]), "l"(a.l[3]), "l"(b.l[0]), "l"(b.l[1]), "l"(b.l[2]), "l"(b.l[3]));
+#else
   u64 c = 0;
   s.l[0] = adc64(a.l[0], b.l[0], c);
   s.l[1] = adc64(a.l[1], b.l[1], c);
   s.l[2] = adc64(a.l[2], b.l[2], c);
   s.l[3] = adc64(a.l[3], b.l[3], c);
+#endif
   return fr_sub_p_if_ge(s);
 }
 __host__ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) {
   Fr d;
+#ifdef __CUDA_ARCH__
+  u64 br;
+  asm("sub.cc.u64 %0, %5, %9;\n\t"
+      "subc.cc.u64 %1, %6, %10;\n\t"
+      "subc.cc.u64 %2, %7, %11;\n\t"
+      "subc.cc.u64 %3, %8, %12;\n\t"
+      "subc.u64 %4, 0, 0;"
+      : "=l"(d.l[0]), "=l"(d.l[1]), "=l"(d.l[2]), "=l"(d.l[3]), "=l"(br)
+      : "l"(a.l[0]), "l"(a.l[1]), "l"(a.l[2]), "l"(a.l[3]), "l"(b.l[0]), "l"(b.l[1]), "l"(b.l[2]), "l"(b.l[3]));
+  // br is all-ones on borrow: add back p & br
+  asm("add.cc.u64 %0, %0, %4;\n\t"
+      "addc.cc.u64 %1, %1, %5;\n\t"
+      "addc.cc.u64 %2, %2, %6;\n\t"
+      "addc.u64 %3, %3, %7;"
+      : "+l"(d.l[0]), "+l"(d.l[1]), "+l"(d.l[2]), "+l"(d.l[3])
+      : "l"(ZK_P0 & br), "l"(ZK_P1 & br), "l"(ZK_P2 & br), "l"(ZK_P3 & br));
+#else
   u64 br = 0;
   d.l[0] = sbb64(a.l[0], b.l[0], br);
   d.l[1] = sbb64(a.l[1], b.l[1], br);
@@ -160,6 +201,7 @@ __host__ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) {
     d.l[2] = adc64(d.l[2], ZK_P2, c);
     d.l[3] = adc64(d.l[3], ZK_P3, c);
   }
+#endif
   return d;
 }
 __host__ __device__ __forceinline__ Fr fr_add_u64(const Fr& a, u64 v) { return fr_add(a, fr_u64(v)); }
@@ -190,6 +232,24 @@ __host__ __device__ __forceinline__ Fr fr_montmul(const Fr& a, const Fr& b) {
   Fr r{{t0, t1, t2, t3}};
   // p < 2^254 and inputs < p  =>  result < 2p, t4 == 0
   return fr_sub_p_if_ge(r);
+}
+// One-limb Montgomery product: v * b * 2^-64 mod p for a 64-bit v (canonical result).  With
+// b = C * 2^64 mod p this is v * C mod p at a quarter of the cost of fr_montmul — most lookup
+// key cells (tags, counters, indices, addresses) fit one limb.
+__host__ __device__ __forceinline__ Fr fr_montmul1(u64 v, const Fr& b) {
+  unsigned __int128 x;
+  u64 c, t0, t1, t2, t3, t4;
+  x = (unsigned __int128)v * b.l[0]; t0 = (u64)x; c = (u64)(x >> 64);
+  x = (unsigned __int128)v * b.l[1] + c; t1 = (u64)x; c = (u64)(x >> 64);
+  x = (unsigned __int128)v * b.l[2] + c; t2 = (u64)x; c = (u64)(x >> 64);
+  x = (unsigned __int128)v * b.l[3] + c; t3 = (u64)x; t4 = (u64)(x >> 64);
+  const u64 m = t0 * ZK_N0;
+  x = (unsigned __int128)m * ZK_P0 + t0; c = (u64)(x >> 64);
+  x = (unsigned __int128)m * ZK_P1 + t1 + c; t0 = (u64)x; c = (u64)(x >> 64);
+  x = (unsigned __int128)m * ZK_P2 + t2 + c; t1 = (u64)x; c = (u64)(x >> 64);
+  x = (unsigned __int128)m * ZK_P3 + t3 + c; t2 = (u64)x; c = (u64)(x >> 64);
+  t3 = t4 + c;  // (v*b + m*p) / 2^64 < 2p < 2^255
+  return fr_sub_p_if_ge(Fr{{t0, t1, t2, t3}});
 }
 __host__ __device__ __forceinline__ Fr fr_to_mont(const Fr& a) {
   return fr_montmul(a, Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});

@@ -35,7 +35,8 @@ struct IndexDev {
   u32 n_key;
   u32 key_cols[ZK_MAX_KEY];
   Fr pw[ZK_MAX_KEY];   // r^j * 2^256 mod p (Montgomery form): montmul(cell, pw[j]) = cell * r^j
-  Fr pwc[ZK_MAX_KEY];  // r^j canonical, for terms whose cell is a known small constant
+  Fr pwc[ZK_MAX_KEY];  // r^j canonical, for terms whose cell is 1
+  Fr pw1[ZK_MAX_KEY];  // r^j * 2^64 mod p: fr_montmul1(v, pw1[j]) = v * r^j for one-limb cells
 };
 
 ZK_HD const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
@@ -62,7 +63,7 @@ ZK_HD u64 rlc_mix(const Fr& h) {
 // and selectors mostly are
 ZK_HD Fr rlc_term(const IndexDev& ix, const Fr& cell, int j) {
   if (fr_is_zero(cell)) return cell;
-  if (fr_eq_u64(cell, 1)) return ix.pwc[j];
+  if (fr_fits64(cell)) return cell.l[0] == 1 ? ix.pwc[j] : fr_montmul1(cell.l[0], ix.pw1[j]);
   return fr_montmul(cell, ix.pw[j]);
 }
 // h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
