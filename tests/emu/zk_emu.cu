@@ -57,11 +57,14 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
   t.fixed = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, s3);
+  std::vector<u32> bitmap(ZK_RESP_BITMAP_WORDS, 0);
+  for (u64 r = 0; r < n_fixed; r++) resp_bitmap_row(t.fixed.tab, bitmap.data(), r);
+  t.resp_bitmap = bitmap.data();
   WitnessDev w{(const u64*)steps, n_steps, nullptr};
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i, true};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap};
     verify_step(s, flags);
   }
   return 0;

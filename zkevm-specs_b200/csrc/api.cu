@@ -81,6 +81,8 @@ struct zk_ctx {
   std::string err;
   u64 launches = 0;
   int sm_count = 148;
+  u32* resp_bitmap = nullptr;  // ResponsibleOpcode bitmap of the fixed table (8 KiB)
+  u64 resp_bitmap_version = ~0ull;
   u32* evm_lists = nullptr;  // [G_COUNT][cap] step indices + [G_COUNT] counters
   size_t evm_lists_cap = 0;
   bool timing = false;
@@ -151,6 +153,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   if (ctx->evm_lists) cudaFree(ctx->evm_lists);
+  if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
   delete ctx;
 }
 
@@ -387,11 +390,22 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_FIXED, k4, 4, st, &t.fixed))) return rc;
+  if (!ctx->resp_bitmap) CK(ctx, cudaMalloc(&ctx->resp_bitmap, ZK_RESP_BITMAP_WORDS * sizeof(u32)));
+  if (ctx->resp_bitmap_version != ctx->tab[ZK_TABLE_FIXED].version) {
+    CK(ctx, cudaMemsetAsync(ctx->resp_bitmap, 0, ZK_RESP_BITMAP_WORDS * sizeof(u32), st));
+    if (t.fixed.tab.n_rows) {
+      k_fixed_resp_bitmap<<<(unsigned)((t.fixed.tab.n_rows + 255) / 256), 256, 0, st>>>(t.fixed.tab, ctx->resp_bitmap);
+      ctx->launches++;
+    }
+    ctx->resp_bitmap_version = ctx->tab[ZK_TABLE_FIXED].version;
+  }
+  t.resp_bitmap = ctx->resp_bitmap;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
   // per-gadget step lists (bucket by execution state), then one kernel per gate program
   if (n > ctx->evm_lists_cap) {
     if (ctx->evm_lists) cudaFree(ctx->evm_lists);
+  if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
     ctx->evm_lists = nullptr;
     CK(ctx, cudaMalloc(&ctx->evm_lists, (G_COUNT * n + G_COUNT) * sizeof(u32)));
     ctx->evm_lists_cap = n;

@@ -30,4 +30,35 @@ ZK_HD u64 rot_back(const WitnessDev& w, u64 row, bool wrap) {
   return row ? row - 1 : (wrap ? w.n_rows - 1 : 0);
 }
 
+#ifdef __CUDACC__
+// Stage a small read-only table into shared memory with ONE bulk asynchronous copy
+// (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) completing on an mbarrier.  Called by every
+// thread of the block; returns when the bytes are visible to all of them.  `bytes` must be a
+// multiple of 16 and both addresses 16-byte aligned.
+__device__ __forceinline__ void stage_to_smem(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar) {
+  const u32 bar_a = (u32)__cvta_generic_to_shared(bar);
+  const u32 dst_a = (u32)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+        "l"(gmem_src), "r"(bytes), "r"(bar_a)
+        : "memory");
+  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "ZK_STAGE_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@!p bra ZK_STAGE_WAIT;\n\t"
+      "}" ::"r"(bar_a)
+      : "memory");
+}
+#endif
+
 }  // namespace zk

@@ -59,7 +59,33 @@ struct EvmTables {
   IndexDev bytecode;  // key (hash_lo, hash_hi, tag, index, is_code)
   IndexDev rw;        // key (rw_counter, rw, tag, id, address)
   IndexDev fixed;     // key (tag, v0, v1, v2)
+  // ResponsibleOpcode rows of the fixed table (tag 13, aux 0) with state, opcode < 256 as a
+  // 64 Kbit bitmap: bit (state << 8 | opcode).  Built from the uploaded fixed table
+  // (k_fixed_resp_bitmap) and staged into shared memory by every EVM kernel.
+  const u32* resp_bitmap;
 };
+#define ZK_RESP_BITMAP_WORDS 2048
+
+// one thread per fixed-table row
+ZK_HD void resp_bitmap_row(const TableDev& fixed, u32* bitmap, u64 row) {
+  const Fr tag = table_cell(fixed, 0, row), st = table_cell(fixed, 1, row);
+  const Fr op = table_cell(fixed, 2, row), aux = table_cell(fixed, 3, row);
+  if (fr_eq_u64(tag, ZK_FIXED_ResponsibleOpcode) && fr_is_zero(aux) && fr_fits64(st) && st.l[0] < 256 &&
+      fr_fits64(op) && op.l[0] < 256) {
+    const u32 bit = (u32)(st.l[0] << 8 | op.l[0]);
+#ifdef __CUDA_ARCH__
+    atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+#else
+    bitmap[bit >> 5] |= 1u << (bit & 31);
+#endif
+  }
+}
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256) k_fixed_resp_bitmap(TableDev fixed, u32* bitmap) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < fixed.n_rows) resp_bitmap_row(fixed, bitmap, row);
+}
+#endif
 
 // per-thread view of one step
 struct StepCtx {
@@ -67,7 +93,8 @@ struct StepCtx {
   const EvmTables& t;
   const ResultDev& res;
   u64 i, j, row;
-  bool record;  // warp-cooperative gadgets evaluate in every lane but only one lane records
+  bool record;      // warp-cooperative gadgets evaluate in every lane but only one lane records
+  const u32* resp;  // ResponsibleOpcode bitmap (shared memory on the device)
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
   ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
 };
@@ -178,11 +205,20 @@ ZK_HD bool opcode_lookup(const StepCtx& s, Fr* opcode) {
   return need1(s, bytecode_lookup(s, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, opcode), EV_OP_UNSAT);
 }
 
+// responsible_opcode_lookup (instruction.py:779-782): fixed_table contains (13, state, opcode, 0)
+ZK_HD bool responsible_opcode(const StepCtx& s, const Fr& state, const Fr& opcode) {
+  if (fr_fits64(state) && state.l[0] < 256 && fr_fits64(opcode) && opcode.l[0] < 256) {
+    const u32 bit = (u32)(state.l[0] << 8 | opcode.l[0]);
+    return (s.resp[bit >> 5] >> (bit & 31)) & 1;
+  }
+  Fr key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), state, opcode, fr_u64(0)};
+  u32 r;
+  return lookup<4>(s.t.fixed, key, &r) >= 1;  // out-of-range query: exact probe of the hash index
+}
+
 // step_state_transition_in_same_context, instruction.py:365-394
 ZK_HD void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
-  Fr key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), s.cur(S_STATE), opcode, fr_u64(0)};
-  u32 r;
-  EV_CHECK(EV_SC_RESP_OPCODE, lookup<4>(s.t.fixed, key, &r) >= 1);
+  EV_CHECK(EV_SC_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
   int gas_cost = -1;
   if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
   EV_CHECK(EV_SC_OPCODE_VALUE, gas_cost >= 0);
@@ -495,6 +531,38 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx) {
 ZK_HD void push_epilogue(const StepCtx& s, const PushCommon& c) {
   same_context(s, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
 }
+// The shared epilogue spread over a warp: lane c < 13 loads cell c of the current and next
+// step and evaluates the transition constraint of that cell; returns the id of its failing
+// constraint or INT_MAX.  Ids are in program order, so the warp minimum is the first failure.
+ZK_HD int same_context_lane(const StepCtx& s, int lane, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
+  const int kNone = 0x7FFFFFFF;
+  if (lane >= 13) return kNone;
+  const Fr cur = s.cur((u32)lane), nxt = s.nxt((u32)lane);
+  int gas_cost = -1;
+  if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
+  switch (lane) {
+    case S_STATE:
+      if (!responsible_opcode(s, cur, opcode)) return EV_SC_RESP_OPCODE;
+      return gas_cost >= 0 ? kNone : EV_SC_OPCODE_VALUE;
+    case S_GAS: {
+      if (gas_cost < 0) return kNone;  // reported by lane S_STATE with a smaller id
+      const Fr gas_after = fr_sub_u64(cur, (u64)gas_cost);
+      if (!fr_fits64(gas_after)) return EV_SC_GAS_RANGE;
+      return fr_eq(nxt, gas_after) ? kNone : EV_SC_GAS;
+    }
+    case S_RWC: return fr_eq(nxt, fr_add_u64(cur, d_rwc)) ? kNone : EV_SC_RWC;
+    case S_PC: return fr_eq(nxt, fr_add(cur, d_pc)) ? kNone : EV_SC_PC;
+    case S_SP: return fr_eq(nxt, fr_add(cur, d_sp)) ? kNone : EV_SC_SP;
+    case S_MEM: return fr_eq(nxt, cur) ? kNone : EV_SC_MEM;
+    case S_REV: return fr_eq(nxt, cur) ? kNone : EV_SC_REV;
+    case S_LOG: return fr_eq(nxt, cur) ? kNone : EV_SC_LOG;
+    case S_CALL_ID: return fr_eq(nxt, cur) ? kNone : EV_SC_CALL_ID;
+    case S_IS_ROOT: return fr_eq(nxt, cur) ? kNone : EV_SC_IS_ROOT;
+    case S_IS_CREATE: return fr_eq(nxt, cur) ? kNone : EV_SC_IS_CREATE;
+    default: return fr_eq(nxt, cur) ? kNone : EV_SC_CODE_HASH;  // S_HASH_LO, S_HASH_HI
+  }
+}
+
 // serial form (tests/emu, and any caller without a warp)
 ZK_HD void gadget_push(const StepCtx& s) {
   PushCommon c;
@@ -557,7 +625,7 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr};
     g = step_prologue(s, rg.flags);
   }
   // warp-aggregated append: one atomicAdd per (warp, gadget)
@@ -577,10 +645,13 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
 template <int G>
 __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                     EvmLists lists) {
+  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
+  __shared__ alignas(8) u64 s_bar;
+  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   const u32 n = lists.count[G];
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const u64 i = rg.row_begin + lists.idx[(u64)G * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp};
     if (G == G_ADD) gadget_add(s);
     else if (G == G_MUL) gadget_mul(s);
     else gadget_pop(s);
@@ -597,12 +668,15 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
 // one warp per PUSH step
 __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                   EvmLists lists) {
+  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
+  __shared__ alignas(8) u64 s_bar;
+  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   const u32 n = lists.count[G_PUSH];
   const int lane = threadIdx.x & 31;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
@@ -629,7 +703,9 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
       if (lane == __ffs(bad) - 1) fail(res, fid, s.row);
       continue;
     }
-    if (lane == 0) push_epilogue(s, c);
+    const int eid = same_context_lane(s, lane, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+    const int first = __reduce_min_sync(0xFFFFFFFFu, eid);
+    if (first != 0x7FFFFFFF && lane == 0) fail(res, first, s.row);
   }
 }
 #endif  // __CUDACC__

@@ -108,28 +108,45 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
   const u64 mix = rlc_mix(h);
   const u32 fp = (u32)(mix >> 32);
   u32 b = (u32)mix & ix.mask;
-  for (;;) {
-    const u64 slot = ld_u64(&ix.slots[b]);
-    if (slot == ZK_EMPTY_SLOT) break;
-    if ((u32)(slot >> 32) == fp) {
-      const u32 cand = (u32)slot;
-      bool eq = true;
+  // Lanes finish their bucket runs after different numbers of slots.  The loop runs until every
+  // lane of the group that entered together is done (warp-uniform trip count), so the group
+  // leaves the loop CONVERGED; a plain data-dependent `break` left each lane running the rest
+  // of its gate program alone (measured: 1-2 active threads per instruction).
+#ifdef __CUDA_ARCH__
+  const unsigned grp = __activemask();
+#define ZK_GROUP_ANY(p) __any_sync(grp, (p))
+#else
+#define ZK_GROUP_ANY(p) (p)
+#endif
+  bool done = false;
+  while (ZK_GROUP_ANY(!done)) {
+    if (!done) {
+      const u64 slot = ld_u64(&ix.slots[b]);
+      if (slot == ZK_EMPTY_SLOT) {
+        done = true;
+      } else {
+        if ((u32)(slot >> 32) == fp) {
+          const u32 cand = (u32)slot;
+          bool eq = true;
 #pragma unroll
-      for (int j = 0; j < NK; j++) {
-        if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
-      }
-      if (eq) {
-        if (found == 0) {
-          first = cand;
-          found = 1;
-        } else if (!rows_identical(ix.tab, first, cand)) {
-          found = 2;
-          break;
+          for (int j = 0; j < NK; j++) {
+            if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
+          }
+          if (eq) {
+            if (found == 0) {
+              first = cand;
+              found = 1;
+            } else if (!rows_identical(ix.tab, first, cand)) {
+              found = 2;
+              done = true;
+            }
+          }
         }
+        b = (b + 1) & ix.mask;
       }
     }
-    b = (b + 1) & ix.mask;
   }
+#undef ZK_GROUP_ANY
   *row = first;
   return found;
 }
