@@ -64,7 +64,7 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u};
     verify_step(s, flags);
   }
   return 0;

@@ -95,6 +95,7 @@ struct StepCtx {
   u64 i, j, row;
   bool record;      // warp-cooperative gadgets evaluate in every lane but only one lane records
   const u32* resp;  // ResponsibleOpcode bitmap (shared memory on the device)
+  unsigned mask;    // lanes that run this gate program together (warp-synchronous lookups)
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
   ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
 };
@@ -118,18 +119,21 @@ ZK_HD void step_fail(const StepCtx& s, int id) {
   } while (0)
 
 // lookup outcome -> failure id (unsat, or the next id = ambiguous); true iff exactly one row
-ZK_HD bool need1(const StepCtx& s, int n, int id_unsat) {
+ZK_HD bool need1(const StepCtx& s, bool live, int n, int id_unsat) {
+  if (!live) return false;
   if (n == 1) return true;
   step_fail(s, n == 0 ? id_unsat : id_unsat + 1);
   return false;
 }
 
-ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 tag, const Fr& index,
+// Lookups are warp-synchronous (lookup.cuh): every lane of s.mask calls them in the same order;
+// `live` is false for lanes with nothing to look up (no step, or the step already failed).
+ZK_HD int bytecode_lookup(const StepCtx& s, bool live, const Fr& hlo, const Fr& hhi, u64 tag, const Fr& index,
                           u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   u32 r;
-  const int n = lookup<5>(s.t.bytecode, key, &r);
-  if (n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
+  const int n = lookup_sync<5>(s.t.bytecode, key, &r, s.mask, live);
+  if (live && n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
   return n;
 }
 // same lookup with the step-constant part of the key hash (hash_lo + hash_hi * r) hoisted: a PUSH
@@ -137,7 +141,7 @@ ZK_HD int bytecode_lookup(const StepCtx& s, const Fr& hlo, const Fr& hhi, u64 ta
 ZK_HD Fr bytecode_hash0(const StepCtx& s, const Fr& hlo, const Fr& hhi) {
   return fr_add(hlo, rlc_term(s.t.bytecode, hhi, 1));
 }
-ZK_HD int bytecode_lookup_h(const StepCtx& s, const Fr& h0, const Fr& hlo, const Fr& hhi, u64 tag,
+ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u64 tag,
                             const Fr& index, u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   const IndexDev& ix = s.t.bytecode;
@@ -146,16 +150,16 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, const Fr& h0, const Fr& hlo, const
   h = fr_add(h, rlc_term(ix, key[3], 3));
   h = fr_add(h, rlc_term(ix, key[4], 4));
   u32 r;
-  const int n = probe_hashed<5>(ix, h, key, &r);
-  if (n == 1) *value = table_cell(ix.tab, B_VALUE, r);
+  const int n = probe_hashed<5>(ix, h, key, &r, s.mask, live);
+  if (live && n == 1) *value = table_cell(ix.tab, B_VALUE, r);
   return n;
 }
-ZK_HD int rw_lookup(const StepCtx& s, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
+ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
                     Word2* value) {
   Fr key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
   u32 r;
-  const int n = lookup<5>(s.t.rw, key, &r);
-  if (n == 1) {
+  const int n = lookup_sync<5>(s.t.rw, key, &r, s.mask, live);
+  if (live && n == 1) {
     value->lo = table_cell(s.t.rw.tab, R_VAL_LO, r);
     value->hi = table_cell(s.t.rw.tab, R_VAL_HI, r);
   }
@@ -201,8 +205,9 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
 }
 
 // opcode_lookup(True) at the start of every hot gadget (instruction.py:784-790)
-ZK_HD bool opcode_lookup(const StepCtx& s, Fr* opcode) {
-  return need1(s, bytecode_lookup(s, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, opcode), EV_OP_UNSAT);
+ZK_HD bool opcode_lookup(const StepCtx& s, bool live, Fr* opcode) {
+  return need1(s, live, bytecode_lookup(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, s.cur(S_PC), 1, opcode),
+               EV_OP_UNSAT);
 }
 
 // responsible_opcode_lookup (instruction.py:779-782): fixed_table contains (13, state, opcode, 0)
@@ -245,16 +250,18 @@ ZK_HD Word2 add_words2(const Word2& x, const Word2& y) {
   return Word2{fr_u128(slo.l[0], slo.l[1]), fr_u128(shi.l[0], shi.l[1])};
 }
 
-ZK_HD void gadget_add(const StepCtx& s) {
-  Fr opcode;
-  if (!opcode_lookup(s, &opcode)) return;
+ZK_HD void gadget_add(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Fr sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero, c = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_ADD_A_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &b), EV_ADD_B_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &c), EV_ADD_C_UNSAT);
+  if (!live) return;  // past the last lookup: plain early exits from here on
   const bool is_sub = fr_eq_u64(opcode, 3);
-  Word2 a, b, c;
-  if (!need1(s, rw_lookup(s, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_ADD_A_UNSAT)) return;
-  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &b), EV_ADD_B_UNSAT)) return;
-  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &c), EV_ADD_C_UNSAT)) return;
   EV_CHECK(EV_ADD_SUM, word_eq(add_words2(is_sub ? c : a, b), is_sub ? a : c));
   same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
@@ -379,9 +386,9 @@ ZK_HD bool word_select(const Word2& w, const Fr& sel, Word2* out) {
   return word_in_domain(*out);
 }
 
-ZK_HD void gadget_mul(const StepCtx& s) {
-  Fr opcode;
-  if (!opcode_lookup(s, &opcode)) return;
+ZK_HD void gadget_mul(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Fr sp1 = fr_add_u64(sp, 1);
   const Fr one = fr_u64(1);
@@ -397,14 +404,15 @@ ZK_HD void gadget_mul(const StepCtx& s) {
     is_div = fr_montmul(fr_mul(o2, f6), ZK_MONT_INV4);
     is_mod = fr_montmul(fr_mul(o2, o4), ZK_MONT_INV8);
   }
-  Word2 pop1, pop2, push;
-  if (!need1(s, rw_lookup(s, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT)) return;
-  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &pop2), EV_MUL_POP2_UNSAT)) return;
-  if (!need1(s, rw_lookup(s, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &push), EV_MUL_PUSH_UNSAT)) return;
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 pop1 = zero, pop2 = zero, push = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &pop2), EV_MUL_POP2_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &push), EV_MUL_PUSH_UNSAT);
+  if (!live) return;  // past the last lookup: plain early exits from here on
   const bool in_domain = word_in_domain(pop1) && word_in_domain(pop2) && word_in_domain(push);
   // witness assignment by branch, mul_div_mod.py:23-41 (Python int arithmetic)
   Word2 a, b, c, d;
-  const Word2 zero{fr_u64(0), fr_u64(0)};
   if (fr_eq_u64(is_mul, 1)) {
     a = pop1; b = pop2; c = zero; d = push;
   } else {
@@ -499,30 +507,32 @@ struct PushCommon {
 // asserts, stack_push lookup, to_le_bytes(); false if the step failed (recorded if s.record)
 ZK_HD bool push_prepare(const StepCtx& s, int n_op, const Fr& opcode, int n_len, const Fr& code_length,
                         int n_rw, const Word2& value, PushCommon* c) {
-  if (!need1(s, n_op, EV_OP_UNSAT)) return false;
-  if (!need1(s, n_len, EV_PUSH_LEN_UNSAT)) return false;
+  if (!need1(s, true, n_op, EV_OP_UNSAT)) return false;
+  if (!need1(s, true, n_len, EV_PUSH_LEN_UNSAT)) return false;
   c->opcode = opcode;
   c->num_pushed = fr_sub_u64(opcode, 0x5f);
   const Fr left = fr_sub_u64(fr_sub(code_length, c->pc), 1);
   EV_CHECK_RET(EV_PUSH_CMP_RANGE, fr_fits64(left) && fr_fits64(c->num_pushed), false);
   c->n_push = c->num_pushed.l[0];
   c->n_pad = left.l[0] < c->n_push ? c->n_push - left.l[0] : 0;
-  if (!need1(s, n_rw, EV_PUSH_RW_UNSAT)) return false;
+  if (!need1(s, true, n_rw, EV_PUSH_RW_UNSAT)) return false;
   EV_CHECK_RET(EV_PUSH_VALUE_BYTES, word_in_domain(value), false);
   c->value = value;
   return true;
 }
-// byte idx of the pushed word: returns the failing constraint id, or -1
+// byte idx of the pushed word: returns the failing constraint id, or -1.  Warp-synchronous: every
+// lane of s.mask calls it (the lookup inside is skipped with live = false where no byte is pushed)
 ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx) {
   const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
   const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
   const u64 limb = idx < 16 ? lo_limb : hi_limb;
   const u64 byte = (limb >> (8 * (idx & 7))) & 0xFF;
   const int base = EV_PUSH_B0_UNSAT + 4 * idx;
-  if ((u64)idx < c.n_push && (u64)idx >= c.n_pad) {
-    Fr got;
-    const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
-    const int n = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 2, index, 0, &got);
+  const bool pushed = (u64)idx < c.n_push && (u64)idx >= c.n_pad;
+  Fr got = fr_u64(0);
+  const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
+  const int n = bytecode_lookup_h(s, pushed, c.h0, c.hlo, c.hhi, 2, index, 0, &got);
+  if (pushed) {
     if (n != 1) return n == 0 ? base : base + 1;
     return fr_eq_u64(got, byte) ? -1 : base + 2;
   }
@@ -563,8 +573,8 @@ ZK_HD int same_context_lane(const StepCtx& s, int lane, const Fr& opcode, u64 d_
   }
 }
 
-// serial form (tests/emu, and any caller without a warp)
-ZK_HD void gadget_push(const StepCtx& s) {
+// serial form (tests/emu, and any caller without a warp): s.mask names the calling thread only
+ZK_HD void gadget_push(const StepCtx& s, bool live) {
   PushCommon c;
   c.hlo = s.cur(S_HASH_LO);
   c.hhi = s.cur(S_HASH_HI);
@@ -572,9 +582,10 @@ ZK_HD void gadget_push(const StepCtx& s) {
   c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
   Fr opcode = fr_u64(0), code_length = fr_u64(0);
   Word2 value{fr_u64(0), fr_u64(0)};
-  const int n_op = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
-  const int n_len = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
-  const int n_rw = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
+  const int n_op = bytecode_lookup_h(s, live, c.h0, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup_h(s, live, c.h0, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  const int n_rw = rw_lookup(s, live, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
+  if (!live) return;
   if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
   for (int idx = 0; idx < 32; idx++) {
     const int fid = push_byte(s, c, idx);
@@ -586,22 +597,23 @@ ZK_HD void gadget_push(const StepCtx& s) {
   push_epilogue(s, c);
 }
 
-ZK_HD void gadget_pop(const StepCtx& s) {
-  Fr opcode;
-  if (!opcode_lookup(s, &opcode)) return;
-  Word2 y;
-  if (!need1(s, rw_lookup(s, s.cur(S_RWC), 0, ZK_TARGET_Stack, s.cur(S_CALL_ID), s.cur(S_SP), &y), EV_POP_RW_UNSAT))
-    return;
+ZK_HD void gadget_pop(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  Word2 y{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, rw_lookup(s, live, s.cur(S_RWC), 0, ZK_TARGET_Stack, s.cur(S_CALL_ID), s.cur(S_SP), &y),
+               EV_POP_RW_UNSAT);
+  if (!live) return;
   same_context(s, opcode, 1, fr_u64(1), fr_u64(1));
 }
 
 // whole step on one thread (tests/emu)
 ZK_HD void verify_step(const StepCtx& s, u32 flags) {
   switch (step_prologue(s, flags)) {
-    case G_ADD: gadget_add(s); break;
-    case G_MUL: gadget_mul(s); break;
-    case G_PUSH: gadget_push(s); break;
-    case G_POP: gadget_pop(s); break;
+    case G_ADD: gadget_add(s, true); break;
+    case G_MUL: gadget_mul(s, true); break;
+    case G_PUSH: gadget_push(s, true); break;
+    case G_POP: gadget_pop(s, true); break;
     default: break;
   }
 }
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0};
     g = step_prologue(s, rg.flags);
   }
   // warp-aggregated append: one atomicAdd per (warp, gadget)
@@ -648,13 +660,19 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+  // every lane of a warp runs the same number of rounds and calls the (warp-synchronous) lookups
+  // together; lanes without a step in the last round run with live = false
   const u32 n = lists.count[G];
-  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const u64 i = rg.row_begin + lists.idx[(u64)G * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp};
-    if (G == G_ADD) gadget_add(s);
-    else if (G == G_MUL) gadget_mul(s);
-    else gadget_pop(s);
+  const u32 stride = gridDim.x * blockDim.x;
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (u32 first = 0; first < n; first += stride) {
+    const u32 k = first + tid;
+    const bool live = k < n;
+    const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu};
+    if (G == G_ADD) gadget_add(s, live);
+    else if (G == G_MUL) gadget_mul(s, live);
+    else gadget_pop(s, live);
   }
 }
 
@@ -676,21 +694,21 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp, 0xFFFFFFFFu};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
     c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
-    // round 1: lane 0 opcode, lane 1 bytecode length, lane 2 the stack_push row
-    int n_hit = 0;
+    // round 1: lane 0 opcode, lane 1 bytecode length (one warp-wide bytecode probe), then lane 2
+    // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
     Word2 val{fr_u64(0), fr_u64(0)};
-    if (lane < 2) {
-      n_hit = bytecode_lookup_h(s, c.h0, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0), lane == 0 ? 1 : 0, &v);
-    } else if (lane == 2) {
-      n_hit = rw_lookup(s, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &val);
-    }
+    int n_hit = bytecode_lookup_h(s, lane < 2, c.h0, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0),
+                                  lane == 0 ? 1 : 0, &v);
+    const int n_hit_rw = rw_lookup(s, lane == 2, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID),
+                                   fr_sub_u64(s.cur(S_SP), 1), &val);
+    if (lane == 2) n_hit = n_hit_rw;
     const int n_op = __shfl_sync(0xFFFFFFFFu, n_hit, 0), n_len = __shfl_sync(0xFFFFFFFFu, n_hit, 1);
     const int n_rw = __shfl_sync(0xFFFFFFFFu, n_hit, 2);
     const Fr opcode = shfl_fr(v, 0), code_length = shfl_fr(v, 1);

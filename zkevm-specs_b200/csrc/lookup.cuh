@@ -101,24 +101,27 @@ ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
 
 // Walk the bucket run starting at the bucket of h.  Returns the number of distinct matching
 // rows, capped at 2; *row = the first match.
+//
+// WARP-SYNCHRONOUS form: every lane named in `mask` must call it together (lanes with nothing
+// to look up pass active = false).  Lanes finish their bucket runs after different numbers of
+// slots; the loop runs until every lane of the mask is done (warp-uniform trip count), so the
+// warp leaves the loop CONVERGED.  With a plain data-dependent `break` each lane ran the rest
+// of its gate program alone (measured: 1-2 active threads per instruction, profiles/r01_v4).
 template <int NK>
-ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32* row) {
+ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32* row, unsigned mask,
+                       bool active) {
   int found = 0;
   u32 first = 0;
   const u64 mix = rlc_mix(h);
   const u32 fp = (u32)(mix >> 32);
   u32 b = (u32)mix & ix.mask;
-  // Lanes finish their bucket runs after different numbers of slots.  The loop runs until every
-  // lane of the group that entered together is done (warp-uniform trip count), so the group
-  // leaves the loop CONVERGED; a plain data-dependent `break` left each lane running the rest
-  // of its gate program alone (measured: 1-2 active threads per instruction).
 #ifdef __CUDA_ARCH__
-  const unsigned grp = __activemask();
-#define ZK_GROUP_ANY(p) __any_sync(grp, (p))
+#define ZK_GROUP_ANY(p) __any_sync(mask, (p))
 #else
 #define ZK_GROUP_ANY(p) (p)
+  (void)mask;
 #endif
-  bool done = false;
+  bool done = !active;
   while (ZK_GROUP_ANY(!done)) {
     if (!done) {
       const u64 slot = ld_u64(&ix.slots[b]);
@@ -151,10 +154,22 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
   return found;
 }
 
+// warp-synchronous lookup (see probe_hashed)
+template <int NK>
+ZK_HD int lookup_sync(const IndexDev& ix, const Fr (&key)[NK], u32* row, unsigned mask, bool active) {
+  if (ix.tab.n_rows == 0) return 0;  // uniform: the table is the same for every lane
+  return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row, mask, active);
+}
+// single-thread lookup: the calling thread is its own group
 template <int NK>
 ZK_HD int lookup(const IndexDev& ix, const Fr (&key)[NK], u32* row) {
   if (ix.tab.n_rows == 0) return 0;
-  return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row);
+#ifdef __CUDA_ARCH__
+  const unsigned self = 1u << (threadIdx.x & 31);
+#else
+  const unsigned self = 1u;
+#endif
+  return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row, self, true);
 }
 
 // ---- result recording -------------------------------------------------------------------
