@@ -405,7 +405,6 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   // per-gadget step lists (bucket by execution state), then one kernel per gate program
   if (n > ctx->evm_lists_cap) {
     if (ctx->evm_lists) cudaFree(ctx->evm_lists);
-  if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
     ctx->evm_lists = nullptr;
     CK(ctx, cudaMalloc(&ctx->evm_lists, (G_COUNT * n + G_COUNT) * sizeof(u32)));
     ctx->evm_lists_cap = n;
