@@ -63,8 +63,10 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   WitnessDev w{(const u64*)steps, n_steps, nullptr};
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
+  Fr stack_pre[2];
+  stack_key_pre(t.rw, stack_pre);
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u, stack_pre};
     verify_step(s, flags);
   }
   return 0;

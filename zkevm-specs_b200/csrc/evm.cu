@@ -96,6 +96,7 @@ struct StepCtx {
   bool record;      // warp-cooperative gadgets evaluate in every lane but only one lane records
   const u32* resp;  // ResponsibleOpcode bitmap (shared memory on the device)
   unsigned mask;    // lanes that run this gate program together (warp-synchronous lookups)
+  const Fr* stack_pre;  // [2]: rw * r + Target.Stack * r^2 for rw = Read, Write (constant key terms)
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
   ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
 };
@@ -154,11 +155,27 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, const Fr&
   if (live && n == 1) *value = table_cell(ix.tab, B_VALUE, r);
   return n;
 }
+// constant terms of a stack lookup's key hash, computed once per thread
+ZK_HD void stack_key_pre(const IndexDev& rw_ix, Fr out[2]) {
+  const Fr tag_term = rlc_term(rw_ix, fr_u64(ZK_TARGET_Stack), 2);
+  out[0] = tag_term;
+  out[1] = fr_add(rw_ix.pwc[1], tag_term);
+}
 ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
                     Word2* value) {
   Fr key[5] = {rwc, fr_u64(rw), fr_u64(tag), id, addr};
   u32 r;
-  const int n = lookup_sync<5>(s.t.rw, key, &r, s.mask, live);
+  int n = 0;
+  const IndexDev& ix = s.t.rw;
+  if (ix.tab.n_rows != 0) {
+    Fr h;
+    if (tag == ZK_TARGET_Stack && s.stack_pre) {
+      h = fr_add(fr_add(rwc, s.stack_pre[rw & 1]), fr_add(rlc_term(ix, id, 3), rlc_term(ix, addr, 4)));
+    } else {
+      h = rlc_key<5>(ix, key);
+    }
+    n = probe_hashed<5>(ix, h, key, &r, s.mask, live);
+  }
   if (live && n == 1) {
     value->lo = table_cell(s.t.rw.tab, R_VAL_LO, r);
     value->hi = table_cell(s.t.rw.tab, R_VAL_HI, r);
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr};
     g = step_prologue(s, rg.flags);
   }
   // warp-aggregated append: one atomicAdd per (warp, gadget)
@@ -662,6 +679,8 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   // every lane of a warp runs the same number of rounds and calls the (warp-synchronous) lookups
   // together; lanes without a step in the last round run with live = false
+  Fr stack_pre[2];
+  stack_key_pre(t.rw, stack_pre);
   const u32 n = lists.count[G];
   const u32 stride = gridDim.x * blockDim.x;
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -669,7 +688,7 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     const u32 k = first + tid;
     const bool live = k < n;
     const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
@@ -689,17 +708,28 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+  Fr stack_pre[2];
+  stack_key_pre(t.rw, stack_pre);
+  Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // h0 of the last code hash seen
+  bool have_h0 = false;
   const u32 n = lists.count[G_PUSH];
   const int lane = threadIdx.x & 31;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp, 0xFFFFFFFFu};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp, 0xFFFFFFFFu, stack_pre};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
-    c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
+    // consecutive steps of a warp almost always run the same contract: reuse hash_lo + hash_hi*r
+    if (!(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi))) {
+      last_hlo = c.hlo;
+      last_hhi = c.hhi;
+      last_h0 = bytecode_hash0(s, c.hlo, c.hhi);
+      have_h0 = true;
+    }
+    c.h0 = last_h0;
     // round 1: lane 0 opcode, lane 1 bytecode length (one warp-wide bytecode probe), then lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);

@@ -63,7 +63,11 @@ ZK_HD u64 rlc_mix(const Fr& h) {
 // and selectors mostly are
 ZK_HD Fr rlc_term(const IndexDev& ix, const Fr& cell, int j) {
   if (fr_is_zero(cell)) return cell;
-  if (fr_fits64(cell)) return cell.l[0] == 1 ? ix.pwc[j] : fr_montmul1(cell.l[0], ix.pw1[j]);
+  if (fr_fits64(cell)) {
+    if (cell.l[0] == 1) return ix.pwc[j];
+    if (cell.l[0] == 2) return fr_add(ix.pwc[j], ix.pwc[j]);
+    return fr_montmul1(cell.l[0], ix.pw1[j]);
+  }
   return fr_montmul(cell, ix.pw[j]);
 }
 // h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
