@@ -154,4 +154,56 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 
+/* ---------------- copy circuit: src/zkevm_specs/copy_circuit.py:23-130 ----------------------
+ * Every gate is `cond * expr == 0` over Fr (util/constraint_system.py:27-46); a row stops at its
+ * first failure. */
+#define ZK_COPY_CONSTRAINTS(X)                                                             \
+  X(CP_BOOL_FIRST, ZKE_ASSERT, "copy_circuit.py:24 is_first boolean")                       \
+  X(CP_BOOL_LAST, ZKE_ASSERT, "copy_circuit.py:25 is_last boolean")                         \
+  X(CP_FIRST_NEEDS_STEP, ZKE_ASSERT, "copy_circuit.py:27 (1-q_step)*is_first==0")           \
+  X(CP_LAST_NOT_STEP, ZKE_ASSERT, "copy_circuit.py:29 q_step*is_last==0")                   \
+  X(CP_IS_MEMORY, ZKE_ASSERT, "copy_circuit.py:30 is_memory==(tag==Memory)")                \
+  X(CP_IS_BYTECODE, ZKE_ASSERT, "copy_circuit.py:31 is_bytecode==(tag==Bytecode)")          \
+  X(CP_IS_TX_CALLDATA, ZKE_ASSERT, "copy_circuit.py:32 is_tx_calldata==(tag==TxCalldata)")  \
+  X(CP_IS_TX_LOG, ZKE_ASSERT, "copy_circuit.py:33 is_tx_log==(tag==TxLog)")                 \
+  X(CP_IS_RLC_ACC, ZKE_ASSERT, "copy_circuit.py:34 is_rlc_acc==(tag==RlcAcc)")              \
+  X(CP_ID_SAME, ZKE_ASSERT, "copy_circuit.py:40 id==rows[2].id unless last two rows")       \
+  X(CP_TAG_SAME, ZKE_ASSERT, "copy_circuit.py:41 tag==rows[2].tag")                         \
+  X(CP_ADDR_INC, ZKE_ASSERT, "copy_circuit.py:42 addr+1==rows[2].addr")                     \
+  X(CP_SRC_END_SAME, ZKE_ASSERT, "copy_circuit.py:43 src_addr_end==rows[2].src_addr_end")   \
+  X(CP_RWC, ZKE_ASSERT, "copy_circuit.py:49 rw_counter+rw_diff==next.rw_counter")           \
+  X(CP_RWC_INC_LEFT, ZKE_ASSERT, "copy_circuit.py:50 rwc_inc_left-rw_diff==next.rwc_inc_left") \
+  X(CP_RLC_ACC_SAME, ZKE_ASSERT, "copy_circuit.py:52 rlc_acc==next.rlc_acc")                \
+  X(CP_RWC_INC_LAST, ZKE_ASSERT, "copy_circuit.py:55 last row: rwc_inc_left==rw_diff")      \
+  X(CP_RLC_LAST, ZKE_ASSERT, "copy_circuit.py:59 last RlcAcc row: rlc_acc==value")          \
+  X(CP_BYTES_LEFT_LAST, ZKE_ASSERT, "copy_circuit.py:65 bytes_left==1 at the last step")    \
+  X(CP_BYTES_LEFT_DEC, ZKE_ASSERT, "copy_circuit.py:67 bytes_left==rows[2].bytes_left+1")   \
+  X(CP_PAD_VALUE0, ZKE_ASSERT, "copy_circuit.py:69 is_pad*value==0")                        \
+  X(CP_LT_RANGE, ZKE_ASSERT, "copy_circuit.py:18-19 lt(): addr / src_addr_end exceed 5 bytes") \
+  X(CP_IS_PAD, ZKE_ASSERT, "copy_circuit.py:76-78 is_pad==1-(addr<src_addr_end)")           \
+  X(CP_NEXT_NOT_PAD, ZKE_ASSERT, "copy_circuit.py:80 write row is never padding")           \
+  X(CP_RW_VALUE_EQ, ZKE_ASSERT, "copy_circuit.py:83 read value==write value unless RlcAcc")  \
+  X(CP_FIRST_VALUE_EQ, ZKE_ASSERT, "copy_circuit.py:86 first step: read value==write value") \
+  X(CP_RLC_STEP, ZKE_ASSERT, "copy_circuit.py:89 rows[2].value==value*r+rows[1].value")     \
+  X(CP_MEM_ID_TYPE, ZKE_ASSERT, "copy_circuit.py:109 id.value(): id is a Word")             \
+  X(CP_MEM_UNSAT, ZKE_UNSAT, "copy_circuit.py:108-110 rw_table memory lookup unsat")        \
+  X(CP_MEM_AMBIG, ZKE_AMBIG, "copy_circuit.py:108-110 rw_table memory lookup ambiguous")    \
+  X(CP_MEM_VALUE_TYPE, ZKE_ASSERT, "copy_circuit.py:110 .value.value(): table value is a Word") \
+  X(CP_MEM_VALUE, ZKE_ASSERT, "copy_circuit.py:111 memory byte==row.value")                 \
+  X(CP_BC_UNSAT, ZKE_UNSAT, "copy_circuit.py:113-115 bytecode_table lookup unsat")          \
+  X(CP_BC_AMBIG, ZKE_AMBIG, "copy_circuit.py:113-115 bytecode_table lookup ambiguous")      \
+  X(CP_BC_VALUE, ZKE_ASSERT, "copy_circuit.py:116 bytecode byte==row.value")                \
+  X(CP_TX_ID_TYPE, ZKE_ASSERT, "copy_circuit.py:119 id.value(): id is a Word")              \
+  X(CP_TX_UNSAT, ZKE_UNSAT, "copy_circuit.py:118-120 tx_table calldata lookup unsat")       \
+  X(CP_TX_AMBIG, ZKE_AMBIG, "copy_circuit.py:118-120 tx_table calldata lookup ambiguous")   \
+  X(CP_TX_VALUE_TYPE, ZKE_ASSERT, "copy_circuit.py:120 .value.value(): table value is a Word") \
+  X(CP_TX_VALUE, ZKE_ASSERT, "copy_circuit.py:121 calldata byte==row.value")                \
+  X(CP_LOG_ID_TYPE, ZKE_ASSERT, "copy_circuit.py:127 id.value(): id is a Word")             \
+  X(CP_LOG_UNSAT, ZKE_UNSAT, "copy_circuit.py:123-129 rw_table tx-log lookup unsat")        \
+  X(CP_LOG_AMBIG, ZKE_AMBIG, "copy_circuit.py:123-129 rw_table tx-log lookup ambiguous")    \
+  X(CP_LOG_VALUE_TYPE, ZKE_ASSERT, "copy_circuit.py:129 .value.value(): table value is a Word") \
+  X(CP_LOG_VALUE, ZKE_ASSERT, "copy_circuit.py:130 log byte==row.value")
+
+enum zk_copy_constraint { ZK_COPY_CONSTRAINTS(ZK_ENUM_ENTRY) CP_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../zkevm-specs_b200/csrc/bytecode.cu"
+#include "../../zkevm-specs_b200/csrc/copy.cu"
 #include "../../zkevm-specs_b200/csrc/evm.cu"
 
 using namespace zk;
@@ -87,5 +88,28 @@ extern "C" int emu_check_bytecode(const uint64_t* cols, uint64_t n_rows, const u
   init_result(res, first_fail, fail_count, BC_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
   for (u64 i = row_begin; i < row_end; i++) check_bytecode_row(w, rg, push_ix, kec_ix, r_mont, res, i);
+  return 0;
+}
+
+extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8_t* row_flags, const uint64_t* rw,
+                              uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* bytecode, uint64_t n_bytecode,
+                              const uint64_t* tx, uint64_t n_tx, const uint8_t* tx_flags, const uint64_t r[4],
+                              uint64_t row_begin, uint64_t row_end, uint32_t flags, const uint64_t challenge[4],
+                              uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 k5[5] = {0, 1, 2, 3, 4}, k3[3] = {0, 1, 2};
+  std::vector<u64> s1, s2, s3;
+  CopyTables t;
+  t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s1);
+  t.rw.tab.flags = rw_flags;
+  t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s2);
+  t.tx = build_index((const u64*)tx, n_tx, 5, k3, 3, ch, s3);
+  t.tx.tab.flags = tx_flags;
+  WitnessDev w{(const u64*)rows, n_rows, row_flags};
+  CheckRange rg{row_begin, row_end, 0, flags};
+  ResultDev res;
+  init_result(res, first_fail, fail_count, CP_N_CONSTRAINTS);
+  const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
+  for (u64 i = row_begin; i < row_end; i++) check_copy_row(w, rg, t, r_mont, res, i, true, 1u);
   return 0;
 }

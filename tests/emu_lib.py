@@ -64,3 +64,24 @@ def check_bytecode(cols, push, keccak, r, row_begin=0, row_end=None, flags=1, n=
                                   _p(ch), ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_copy(w, r, row_begin=0, row_end=None, flags=1, challenge=None):
+    m = {k: np.ascontiguousarray(w[k]) for k in ("copy", "rw", "tx", "bytecode")}
+    f = {k: np.ascontiguousarray(w[k], dtype=np.uint8) for k in ("copy_flags", "rw_flags", "tx_flags")}
+    p8 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if len(a) else None  # noqa: E731
+    n = 64
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    n_rows = m["copy"].shape[1]
+    if row_end is None:
+        row_end = n_rows
+    rc = lib().emu_check_copy(_p(m["copy"]), c(n_rows), p8(f["copy_flags"]), _p(m["rw"]), c(m["rw"].shape[1]),
+                              p8(f["rw_flags"]), _p(m["bytecode"]), c(m["bytecode"].shape[1]), _p(m["tx"]),
+                              c(m["tx"].shape[1]), p8(f["tx_flags"]), _p(rr), c(row_begin), c(row_end),
+                              ctypes.c_uint32(flags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

@@ -376,6 +376,182 @@ def evm_cases():
     print(f"evm: {tot} corruptions, {nfail} failing")
 
 
+# --------------------------------------------------------------------------- copy
+def copy_cases():
+    """Copy-circuit events built with the reference's CopyCircuit (typing.py:996-1150) and checked
+    by the reference's verify_copy_table (copy_circuit.py:92-130); the failing row is recovered
+    by tracking the row iterator.  Corruptions: copy rows, rw / tx / bytecode table cells."""
+    from zkevm_specs import copy_circuit as cc
+    from zkevm_specs.evm_circuit import (Bytecode, Block, CopyCircuit, CopyCircuitRow, CopyDataTypeTag,
+                                         RWDictionary, RWTableRow, BytecodeTableRow, Tables, TxTableRow,
+                                         TxContextFieldTag)
+    from zkevm_specs.util import FQ, Word, WordOrValue
+
+    r = FQ(0x0FEDCBA9876543210FEDCBA9876543210FEDCBA9876543210FEDCBA987654321 % P)
+    rng = random.Random(4)
+
+    class Tracking(list):
+        def __iter__(self):
+            for idx in range(len(self)):
+                self.last = idx
+                yield list.__getitem__(self, idx)
+
+    class FakeCircuit:
+        def __init__(self, rows):
+            self.rows = Tracking(rows)
+
+        def table(self):
+            return self.rows
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wov(lo, hi, is_word):
+        return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    # ---- row <-> ints -------------------------------------------------------------------
+    def copy_ints(x):
+        return [n_of(x.q_step), n_of(x.is_first), n_of(x.is_last), n_of(x.id.lo), n_of(x.id.hi), n_of(x.tag),
+                n_of(x.addr), n_of(x.src_addr_end), n_of(x.bytes_left), n_of(x.value), n_of(x.rlc_acc),
+                n_of(x.is_code), n_of(x.is_pad), n_of(x.rw_counter), n_of(x.rwc_inc_left), n_of(x.is_memory),
+                n_of(x.is_bytecode), n_of(x.is_tx_calldata), n_of(x.is_tx_log), n_of(x.is_rlc_acc)]
+
+    def copy_from(v, flag):
+        f = [FQ(x) for x in v]
+        return CopyCircuitRow(f[0], f[1], f[2], wov(v[3], v[4], flag & 1), *f[5:])
+
+    def rw_ints(x):
+        return [n_of(x.rw_counter), n_of(x.rw), n_of(x.key0), n_of(x.id), n_of(x.address), n_of(x.field_tag),
+                n_of(x.storage_key.lo), n_of(x.storage_key.hi), n_of(x.value.lo), n_of(x.value.hi),
+                n_of(x.value_prev.lo), n_of(x.value_prev.hi), n_of(x.aux0.lo), n_of(x.aux0.hi)]
+
+    def rw_from(v, flag):
+        return RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
+                          wov(v[8], v[9], flag & 1), wov(v[10], v[11], (flag >> 1) & 1), W(v[12], v[13]))
+
+    def tx_ints(x):
+        return [n_of(x.tx_id), n_of(x.field_tag), n_of(x.call_data_index_or_zero), n_of(x.value.lo), n_of(x.value.hi)]
+
+    def tx_from(v, flag):
+        return TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], flag & 1))
+
+    def bc_ints(x):
+        return [n_of(x.bytecode_hash.lo), n_of(x.bytecode_hash.hi), n_of(x.field_tag), n_of(x.index),
+                n_of(x.is_code), n_of(x.value)]
+
+    def bc_from(v):
+        return BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]))
+
+    def run(C, CF, RW, RWF, TX, TXF, BC):
+        fake = FakeCircuit([copy_from(v, f) for v, f in zip(C, CF)])
+        tables = Tables(block_table=set(Block().table_assignments()),
+                        tx_table=set(tx_from(v, f) for v, f in zip(TX, TXF)), withdrawal_table=set(),
+                        bytecode_table=set(bc_from(v) for v in BC),
+                        rw_table=set(rw_from(v, f) for v, f in zip(RW, RWF)))
+        try:
+            cc.verify_copy_table(fake, tables, r)
+        except Exception as e:  # noqa: BLE001
+            return fake.rows.last, type(e).__name__
+        return -1, ""
+
+    def scenario(kind):
+        circ, rw = CopyCircuit(), RWDictionary(10)
+        code = Bytecode().push32(0x1234).push1(7).add().stop()
+        bc_rows = list(code.table_assignments())
+        tx_rows = []
+        if kind in ("sha3", "mix"):
+            data = {100 + k: rng.randrange(256) for k in range(6)}
+            for a, b in data.items():
+                rw.memory_write(1, a, b)
+            circ.copy(r, rw, 1, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.RlcAcc, 100, 106, 0, 6, data)
+        if kind in ("calldata", "mix"):
+            calldata = [rng.randrange(256) for _ in range(5)]
+            tx_rows = [TxTableRow(FQ(3), FQ(TxContextFieldTag.CallData), FQ(k), WordOrValue(FQ(b)))
+                       for k, b in enumerate(calldata)]
+            # 7 bytes requested from offset 1, only 4 exist -> 3 padded reads
+            circ.copy(r, rw, 3, CopyDataTypeTag.TxCalldata, 1, CopyDataTypeTag.Memory, 1, 5, 32, 7,
+                      {k: b for k, b in enumerate(calldata)})
+        if kind in ("codecopy", "mix"):
+            src = {k: (code.code[k], code.is_code[k]) for k in range(len(code.code))}
+            circ.copy(r, rw, Word(code.hash()), CopyDataTypeTag.Bytecode, 1, CopyDataTypeTag.Memory, 30,
+                      len(code.code), 64, 8, src)
+        if kind in ("log", "mix"):
+            data = {200 + k: rng.randrange(256) for k in range(4)}
+            for a, b in data.items():
+                rw.memory_write(1, a, b)
+            circ.copy(r, rw, 1, CopyDataTypeTag.Memory, 2, CopyDataTypeTag.TxLog, 200, 204, 0, 4, data, log_id=1)
+        return list(circ.table()), list(rw.rws), tx_rows, bc_rows
+
+    out = {"r": np.array(limbs(r.n), dtype=np.uint64), "names": np.array(["sha3", "calldata", "codecopy", "log", "mix"])}
+    tot = nfail = 0
+    for name in ["sha3", "calldata", "codecopy", "log", "mix"]:
+        rows, rws, txs, bcs = scenario(name)
+        C = [copy_ints(x) for x in rows]
+        CF = [int(x.id.is_word) for x in rows]
+        RW = [rw_ints(x) for x in rws]
+        RWF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
+        TX = [tx_ints(x) for x in txs]
+        TXF = [int(x.value.is_word) for x in txs]
+        BC = [bc_ints(x) for x in bcs]
+        assert run(C, CF, RW, RWF, TX, TXF, BC) == (-1, ""), (name, run(C, CF, RW, RWF, TX, TXF, BC))
+        muts = [(-1, 0, 0, 0, -1, "")]
+        for k in range(90 if name == "mix" else 45):
+            which = rng.choice([0, 0, 0, 0, 1, 1, 2, 3, 4, 5])
+            C2, CF2, RW2, RWF2, TX2, TXF2, BC2 = ([list(x) for x in C], list(CF), [list(x) for x in RW], list(RWF),
+                                                  [list(x) for x in TX], list(TXF), [list(x) for x in BC])
+            if which == 0:
+                i, c = rng.randrange(len(C)), rng.randrange(20)
+                if c == 4 and not CF[i]:
+                    continue  # a value-typed id has no hi cell in the reference (WordOrValue.hi is FQ(0))
+                v = (1 - C[i][c]) if (C[i][c] in (0, 1) and rng.random() < 0.5) else corrupt_value(rng, C[i][c])
+                C2[i][c] = v
+            elif which == 1 and RW:
+                i, c = rng.randrange(len(RW)), rng.randrange(10)
+                v = corrupt_value(rng, RW[i][c]); RW2[i][c] = v
+            elif which == 2 and TX:
+                i, c = rng.randrange(len(TX)), rng.randrange(5)
+                v = corrupt_value(rng, TX[i][c]); TX2[i][c] = v
+            elif which == 3:
+                i, c = rng.randrange(len(BC)), rng.randrange(6)
+                v = corrupt_value(rng, BC[i][c]); BC2[i][c] = v
+            elif which == 4:  # flip the is_word type flag of a copy row id
+                i, c, v = rng.randrange(len(C)), 100, 0
+                CF2[i] ^= 1
+                if not CF2[i]:
+                    C2[i][4] = 0  # Word -> value: the hi half disappears with the type
+            elif which == 5 and RW:  # flip the is_word flag of an rw value, or duplicate an rw row
+                i = rng.randrange(len(RW))
+                if rng.random() < 0.5:
+                    c, v = 101, 0
+                    RWF2[i] ^= 1
+                else:
+                    c, v = 102, (RW[i][8] + 1) % 256
+                    dup = list(RW[i]); dup[8] = v
+                    RW2.append(dup); RWF2.append(RWF[i])
+            else:
+                continue
+            fr_, ex_ = run(C2, CF2, RW2, RWF2, TX2, TXF2, BC2)
+            muts.append((which, i, c, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        out[f"{name}/copy"] = to_matrix(C)
+        out[f"{name}/copy_flags"] = np.array(CF, dtype=np.uint8)
+        out[f"{name}/rw"] = to_matrix(RW) if RW else np.zeros((14, 0, 4), dtype=np.uint64)
+        out[f"{name}/rw_flags"] = np.array(RWF, dtype=np.uint8)
+        out[f"{name}/tx"] = to_matrix(TX) if TX else np.zeros((5, 0, 4), dtype=np.uint64)
+        out[f"{name}/tx_flags"] = np.array(TXF, dtype=np.uint8)
+        out[f"{name}/bytecode"] = to_matrix(BC)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, len(C), "copy rows", len(RW), "rw", len(TX), "tx", len(BC), "bytecode", len(muts), "vectors")
+    np.savez_compressed(os.path.join(HERE, "copy.npz"), **out)
+    print(f"copy: {tot} corruptions, {nfail} failing")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}

@@ -50,3 +50,35 @@ def evm_vectors():
             elif kind == 5:
                 flags = 2  # ZK_FLAG_EVM_FIRST_STEP
             yield name, k, s, b, r, flags, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def copy_vectors():
+    """yield (case, k, dict(copy, copy_flags, rw, rw_flags, tx, tx_flags, bytecode), r, exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, "copy.npz"))
+    r = z["r"]
+    for name in z["names"]:
+        name = str(name)
+        base = {k: z[f"{name}/{k}"] for k in ("copy", "copy_flags", "rw", "rw_flags", "tx", "tx_flags", "bytecode")}
+        for k in range(len(z[f"{name}/mut_kind"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            val = z[f"{name}/mut_val"][k]
+            w = dict(base)
+            if kind == 0:
+                w["copy"] = base["copy"].copy(); w["copy"][c, i, :] = val
+            elif kind == 1:
+                w["rw"] = base["rw"].copy(); w["rw"][c, i, :] = val
+            elif kind == 2:
+                w["tx"] = base["tx"].copy(); w["tx"][c, i, :] = val
+            elif kind == 3:
+                w["bytecode"] = base["bytecode"].copy(); w["bytecode"][c, i, :] = val
+            elif kind == 4:
+                w["copy_flags"] = base["copy_flags"].copy(); w["copy_flags"][i] ^= 1
+                if not w["copy_flags"][i]:  # Word -> value: the hi half disappears with the type
+                    w["copy"] = base["copy"].copy(); w["copy"][4, i, :] = 0
+            elif kind == 5 and c == 101:
+                w["rw_flags"] = base["rw_flags"].copy(); w["rw_flags"][i] ^= 1
+            elif kind == 5 and c == 102:
+                extra = base["rw"][:, i : i + 1, :].copy(); extra[8, 0, :] = val
+                w["rw"] = np.ascontiguousarray(np.concatenate([base["rw"], extra], axis=1))
+                w["rw_flags"] = np.concatenate([base["rw_flags"], base["rw_flags"][i : i + 1]])
+            yield name, k, w, r, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

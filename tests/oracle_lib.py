@@ -101,3 +101,27 @@ def constraint_classes(circuit_id):
     L = lib()
     n = L.orc_n_constraints(circuit_id)
     return [L.orc_constraint_class(circuit_id, i) for i in range(n)]
+
+
+def _p8(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if a is not None and len(a) else None
+
+
+def check_copy(w, r, row_begin=0, row_end=None):
+    """w: dict(copy, copy_flags, rw, rw_flags, tx, tx_flags, bytecode)"""
+    m = {k: np.ascontiguousarray(w[k]) for k in ("copy", "rw", "tx", "bytecode")}
+    f = {k: np.ascontiguousarray(w[k], dtype=np.uint8) for k in ("copy_flags", "rw_flags", "tx_flags")}
+    n = lib().orc_n_constraints(2)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    n_rows = m["copy"].shape[1]
+    if row_end is None:
+        row_end = n_rows
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    rc = lib().orc_check_copy(p64(m["copy"]), c(n_rows), _p8(f["copy_flags"]), p64(m["rw"]), c(m["rw"].shape[1]),
+                              _p8(f["rw_flags"]), p64(m["bytecode"]), c(m["bytecode"].shape[1]), p64(m["tx"]),
+                              c(m["tx"].shape[1]), _p8(f["tx_flags"]), p64(rr), c(row_begin), c(row_end),
+                              ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

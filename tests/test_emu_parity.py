@@ -53,3 +53,11 @@ def test_emu_evm_synthetic_and_fuzz_equals_oracle():
         ff, fc = emu_lib.check_evm(s, b, r, fixed, n=n)
         off, ofc = oracle_lib.check_evm(s, b, r, fixed)
         assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (t, kind, ff[ff != off], off[ff != off], np.nonzero(ff != off))
+
+
+def test_emu_copy_equals_oracle_on_goldens():
+    n = oracle_lib.lib().orc_n_constraints(2)
+    for name, k, w, r, exp_row, exp_exc in golden_util.copy_vectors():
+        ff, fc = emu_lib.check_copy(w, r)
+        off, ofc = oracle_lib.check_copy(w, r)
+        assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, ff[:n][ff[:n] != off], off[ff[:n] != off])

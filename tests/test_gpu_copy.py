@@ -1,0 +1,59 @@
+"""GPU parity of the CUDA copy-circuit checker against the reference's verdicts
+(tests/golden/copy.npz), the CPU oracle's per-constraint result, and the host API."""
+import numpy as np
+import pytest
+
+import golden_util
+import oracle_lib
+from zkevm_specs_b200 import native, packing
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_check(ctx, w, r, row_begin=0, row_end=None, flags=native.FLAG_WRAP):
+    ctx.set_challenge(native.CHALLENGE_KECCAK, packing.cell_to_int(r))
+    ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+    ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+    ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"])
+    ctx.upload_columns(native.CIRCUIT_COPY, w["copy"], flags=w["copy_flags"])
+    n = w["copy"].shape[1]
+    return ctx.check(native.CIRCUIT_COPY, row_begin, n if row_end is None else row_end, 0, flags)
+
+
+def test_copy_golden_and_oracle_parity():
+    ctx = native.default_context()
+    n = 0
+    for name, k, w, r, exp_row, exp_exc in golden_util.copy_vectors():
+        ff, fc = _device_check(ctx, w, r)
+        off, ofc = oracle_lib.check_copy(w, r)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle"
+        hit = native.first_failure(ff, native.CIRCUIT_COPY)
+        got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
+        assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
+        n += 1
+    assert n > 200
+
+
+def test_verify_copy_table_host_api():
+    """SHA3-style Memory -> RlcAcc copy built with our CopyCircuit, like tests/evm/test_sha3.py:80-111"""
+    from zkevm_specs_b200.copy_circuit import verify_copy_table
+    from zkevm_specs_b200.evm_circuit import Block, CopyCircuit, CopyDataTypeTag, RWDictionary, Tables
+    from zkevm_specs_b200.util import FQ
+
+    r = FQ(0x1234567890ABCDEF)
+    data = {100 + k: (7 * k + 3) % 256 for k in range(40)}
+    rw = RWDictionary(5)
+    for a, b in data.items():
+        rw.memory_write(1, a, b)
+    cc = CopyCircuit().copy(r, rw, 1, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.RlcAcc, 100, 140, 0, 40, data)
+    tables = Tables(block_table=set(Block().table_assignments()), tx_table=set(), withdrawal_table=set(),
+                    bytecode_table=set(), rw_table=set(rw.rws), copy_circuit=cc.rows)
+    verify_copy_table(cc, tables, r)
+    assert len(tables.copy_table) == 1
+    bad = RWDictionary(5)
+    for a, b in data.items():
+        bad.memory_write(1, a, (b + (a == 117)) % 256)
+    tables_bad = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(),
+                        rw_table=set(list(bad.rws) + list(rw.rws)[40:]))
+    with pytest.raises(AssertionError):
+        verify_copy_table(cc, tables_bad, r)

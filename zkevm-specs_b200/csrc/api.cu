@@ -14,6 +14,7 @@
 #include "../../include/zk_constraints.h"
 #include "../../include/zkcheck.h"
 #include "bytecode.cu"
+#include "copy.cu"
 #include "evm.cu"
 #include "circuit.cuh"
 
@@ -28,6 +29,7 @@ struct ConstraintInfo {
 #define ZK_INFO_ENTRY(id, cls, doc) {#id, cls, doc},
 static const ConstraintInfo kBytecodeInfo[] = {ZK_BYTECODE_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kEvmInfo[] = {ZK_EVM_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kCopyInfo[] = {ZK_COPY_CONSTRAINTS(ZK_INFO_ENTRY)};
 
 static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21};
 static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
@@ -36,6 +38,7 @@ static const ConstraintInfo* circuit_info(int circuit, int* n) {
   switch (circuit) {
     case ZK_CIRCUIT_BYTECODE: *n = BC_N_CONSTRAINTS; return kBytecodeInfo;
     case ZK_CIRCUIT_EVM: *n = EV_N_CONSTRAINTS; return kEvmInfo;
+    case ZK_CIRCUIT_COPY: *n = CP_N_CONSTRAINTS; return kCopyInfo;
     default: *n = 0; return nullptr;
   }
 }
@@ -381,6 +384,26 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   return 0;
 }
 
+static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
+  const Matrix& m = ctx->circ[ZK_CIRCUIT_COPY];
+  if (!(rg.flags & ZK_FLAG_WRAP) && rg.row_end + 2 > m.n_rows)
+    return fail_msg(ctx, "copy rows [b,e) need rows e and e+1 resident (rotations +1,+2) unless ZK_FLAG_WRAP");
+  const u32 k5[5] = {0, 1, 2, 3, 4}, k3[3] = {0, 1, 2};
+  CopyTables t;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_TX, k3, 3, st, &t.tx))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
+  const u64 n = rg.row_end - rg.row_begin;
+  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
+  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
+  k_check_copy<<<grid, 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const Matrix& m = ctx->circ[ZK_CIRCUIT_EVM];
   if (rg.row_end + 1 > m.n_rows) return fail_msg(ctx, "EVM steps [b,e) need step e resident (rotation +1)");
@@ -447,6 +470,7 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
   switch (circuit_id) {
     case ZK_CIRCUIT_BYTECODE: rc = check_bytecode(ctx, rg, res, st); break;
     case ZK_CIRCUIT_EVM: rc = check_evm(ctx, rg, res, st); break;
+    case ZK_CIRCUIT_COPY: rc = check_copy(ctx, rg, res, st); break;
     default: return fail_msg(ctx, "circuit has no gate program in this build");
   }
   if (rc) return rc;

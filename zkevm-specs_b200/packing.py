@@ -99,3 +99,21 @@ def rw_table_flags(r) -> int:
 
 def pack(rows: Iterable, flatten, n_cols: int) -> np.ndarray:
     return matrix_from_ints([flatten(r) for r in rows], n_cols)
+
+
+def copy_circuit_row(r) -> List[int]:
+    return [cell_int(r.q_step), cell_int(r.is_first), cell_int(r.is_last), cell_int(r.id.lo), cell_int(r.id.hi),
+            cell_int(r.tag), cell_int(r.addr), cell_int(r.src_addr_end), cell_int(r.bytes_left), cell_int(r.value),
+            cell_int(r.rlc_acc), cell_int(r.is_code), cell_int(r.is_pad), cell_int(r.rw_counter),
+            cell_int(r.rwc_inc_left), cell_int(r.is_memory), cell_int(r.is_bytecode), cell_int(r.is_tx_calldata),
+            cell_int(r.is_tx_log), cell_int(r.is_rlc_acc)]
+
+
+def tx_table_row(r) -> List[int]:
+    return [cell_int(r.tx_id), cell_int(r.field_tag), cell_int(r.call_data_index_or_zero),
+            cell_int(r.value.lo), cell_int(r.value.hi)]
+
+
+def word_flag(x) -> int:
+    """the WordOrValue.is_word type bit (a plain Word counts as a word)"""
+    return int(bool(getattr(x, "is_word", True)))
