@@ -50,10 +50,14 @@ def test_verify_copy_table_host_api():
                     bytecode_table=set(), rw_table=set(rw.rws), copy_circuit=cc.rows)
     verify_copy_table(cc, tables, r)
     assert len(tables.copy_table) == 1
-    bad = RWDictionary(5)
-    for a, b in data.items():
-        bad.memory_write(1, a, (b + (a == 117)) % 256)
+    # corrupt the value of one memory READ row the copy circuit looks up (row 40 + 17 of the rw list)
+    import dataclasses
+
+    from zkevm_specs_b200.util import WordOrValue
+
+    rws = list(rw.rws)
+    rws[57] = dataclasses.replace(rws[57], value=WordOrValue(FQ((rws[57].value.lo.n + 1) % 256)))
     tables_bad = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(),
-                        rw_table=set(list(bad.rws) + list(rw.rws)[40:]))
+                        rw_table=set(rws))
     with pytest.raises(AssertionError):
         verify_copy_table(cc, tables_bad, r)
