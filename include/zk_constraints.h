@@ -206,4 +206,111 @@ enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 
 enum zk_copy_constraint { ZK_COPY_CONSTRAINTS(ZK_ENUM_ENTRY) CP_N_CONSTRAINTS };
 
+/* ---------------- state circuit: src/zkevm_specs/state_circuit.py:492-613, 216-488 -----------
+ * A row stops at its first failing constraint. */
+#define ZK_STATE_CONSTRAINTS(X)                                                            \
+  X(ST_TAG_RANGE, ZKE_ASSERT, "state_circuit.py:498 tag in [1,12]")                         \
+  X(ST_ID_RANGE, ZKE_ASSERT, "state_circuit.py:499 id in [0,2^28-1]")                       \
+  X(ST_FIELD_TAG_RANGE, ZKE_ASSERT, "state_circuit.py:502 field_tag in [0,24]")             \
+  X(ST_ADDR_LIMB_RANGE, ZKE_ASSERT, "state_circuit.py:505-506 address limbs are 16-bit")    \
+  X(ST_ADDR_LIMBS, ZKE_ASSERT, "state_circuit.py:507-509 address == sum limb_i 2^(16i)")    \
+  X(ST_KEY_BYTE_RANGE, ZKE_ASSERT, "state_circuit.py:512-517 (arithmetic.py:20-22) key bytes are 8-bit") \
+  X(ST_KEY_BYTES, ZKE_ASSERT, "state_circuit.py:512-517 storage_key == bytes recombined")   \
+  X(ST_IS_WRITE_BOOL, ZKE_ASSERT, "state_circuit.py:520 is_write boolean")                  \
+  X(ST_PREV_KEY_BYTES, ZKE_VALUE, "state_circuit.py:557-559 int.from_bytes(prev key bytes): a byte >= 256 -> ValueError") \
+  X(ST_WITNESS_DOMAIN, ZKE_NOTIMPL, "previous row's keys outside their nominal ranges: packed-key compare outside the supported domain (DESIGN.md)") \
+  X(ST_LEX_ORDER, ZKE_ASSERT, "state_circuit.py:552-570 pack(prev) < pack(cur) unless Start") \
+  X(ST_READ_CONSISTENCY, ZKE_ASSERT, "state_circuit.py:577-578 read of same keys returns previous value") \
+  X(ST_INITIAL_CONSISTENCY, ZKE_ASSERT, "state_circuit.py:580-581 same keys => same initial_value") \
+  X(ST_RWC_NONZERO, ZKE_ASSERT, "state_circuit.py:584-585 rw_counter != 0 unless Start")    \
+  /* Start :216-236 */                                                                      \
+  X(ST_START_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:218")                                \
+  X(ST_START_ADDR0, ZKE_ASSERT, "state_circuit.py:219")                                     \
+  X(ST_START_ID0, ZKE_ASSERT, "state_circuit.py:220")                                       \
+  X(ST_START_KEY0, ZKE_ASSERT, "state_circuit.py:221")                                      \
+  X(ST_START_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:222")                                 \
+  X(ST_START_INIT_HI0, ZKE_ASSERT, "state_circuit.py:223")                                  \
+  X(ST_START_RWC_INC, ZKE_ASSERT, "state_circuit.py:226 selector*(rwc-prev.rwc-1)==0")      \
+  X(ST_START_VALUE0, ZKE_ASSERT, "state_circuit.py:229 value.value()==0")                   \
+  X(ST_START_INIT0, ZKE_ASSERT, "state_circuit.py:232 initial_value.value()==0")            \
+  X(ST_START_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:235-236")                             \
+  /* Memory :240-266 */                                                                     \
+  X(ST_MEM_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:244")                                  \
+  X(ST_MEM_KEY0, ZKE_ASSERT, "state_circuit.py:245")                                        \
+  X(ST_MEM_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:246")                                   \
+  X(ST_MEM_INIT_HI0, ZKE_ASSERT, "state_circuit.py:247")                                    \
+  X(ST_MEM_FIRST_READ0, ZKE_ASSERT, "state_circuit.py:253-254 first access read => 0")      \
+  X(ST_MEM_ADDR_RANGE, ZKE_ASSERT, "state_circuit.py:257 address <= 2^32-1")                \
+  X(ST_MEM_VALUE_BYTE, ZKE_ASSERT, "state_circuit.py:260 value is a byte")                  \
+  X(ST_MEM_INIT0, ZKE_ASSERT, "state_circuit.py:263")                                       \
+  X(ST_MEM_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:266")                                   \
+  /* Stack :270-301 */                                                                      \
+  X(ST_STK_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:275")                                  \
+  X(ST_STK_KEY0, ZKE_ASSERT, "state_circuit.py:276")                                        \
+  X(ST_STK_FIRST_WRITE, ZKE_ASSERT, "state_circuit.py:285-286 first access is a write")     \
+  X(ST_STK_PTR_RANGE, ZKE_ASSERT, "state_circuit.py:290 stack_ptr <= 1023")                 \
+  X(ST_STK_PTR_INC, ZKE_ASSERT, "state_circuit.py:293-295 stack_ptr increases by 0 or 1")   \
+  X(ST_STK_INIT0, ZKE_ASSERT, "state_circuit.py:298")                                       \
+  X(ST_STK_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:301")                                   \
+  /* Storage :305-324 */                                                                    \
+  X(ST_STO_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:307")                                  \
+  X(ST_STO_MPT_UNSAT, ZKE_UNSAT, "state_circuit.py:313-322 MPT lookup unsat")               \
+  X(ST_STO_MPT_AMBIG, ZKE_AMBIG, "state_circuit.py:313-322 MPT lookup ambiguous")           \
+  X(ST_STO_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:324")                                   \
+  /* CallContext :328-345 */                                                                \
+  X(ST_CC_ADDR0, ZKE_ASSERT, "state_circuit.py:330")                                        \
+  X(ST_CC_KEY0, ZKE_ASSERT, "state_circuit.py:331")                                         \
+  X(ST_CC_FIELD_TAG_RANGE, ZKE_ASSERT, "state_circuit.py:334")                              \
+  X(ST_CC_FIRST_READ0, ZKE_ASSERT, "state_circuit.py:338-339")                              \
+  X(ST_CC_INIT0, ZKE_ASSERT, "state_circuit.py:342")                                        \
+  X(ST_CC_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:345")                                    \
+  /* Account :349-380 */                                                                    \
+  X(ST_ACC_FIELD_TAG_VALUE, ZKE_VALUE, "state_circuit.py:350 AccountFieldTag(field_tag.n) -> ValueError") \
+  X(ST_ACC_ID0, ZKE_ASSERT, "state_circuit.py:353")                                         \
+  X(ST_ACC_KEY0, ZKE_ASSERT, "state_circuit.py:354")                                        \
+  X(ST_ACC_NONCE_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:356")                             \
+  X(ST_ACC_NONCE_INIT_HI0, ZKE_ASSERT, "state_circuit.py:357")                              \
+  X(ST_ACC_MPT_UNSAT, ZKE_UNSAT, "state_circuit.py:368-378 MPT lookup unsat")               \
+  X(ST_ACC_MPT_AMBIG, ZKE_AMBIG, "state_circuit.py:368-378 MPT lookup ambiguous")           \
+  X(ST_ACC_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:380")                                   \
+  /* TxRefund :387-402 */                                                                   \
+  X(ST_REF_ADDR0, ZKE_ASSERT, "state_circuit.py:389")                                       \
+  X(ST_REF_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:390")                                  \
+  X(ST_REF_KEY0, ZKE_ASSERT, "state_circuit.py:391")                                        \
+  X(ST_REF_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:394")                                   \
+  X(ST_REF_INIT0, ZKE_ASSERT, "state_circuit.py:397")                                       \
+  X(ST_REF_FIRST_READ0, ZKE_ASSERT, "state_circuit.py:401-402")                             \
+  /* TxAccessListAccount :406-419 */                                                        \
+  X(ST_ALA_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:408")                                  \
+  X(ST_ALA_KEY0, ZKE_ASSERT, "state_circuit.py:409")                                        \
+  X(ST_ALA_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:410")                                   \
+  X(ST_ALA_INIT_HI0, ZKE_ASSERT, "state_circuit.py:411")                                    \
+  X(ST_ALA_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:414")                                   \
+  X(ST_ALA_FIRST_READ0, ZKE_ASSERT, "state_circuit.py:418-419")                             \
+  /* TxAccessListAccountStorage :423-435 */                                                 \
+  X(ST_ALS_FIELD_TAG0, ZKE_ASSERT, "state_circuit.py:425")                                  \
+  X(ST_ALS_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:426")                                   \
+  X(ST_ALS_INIT_HI0, ZKE_ASSERT, "state_circuit.py:427")                                    \
+  X(ST_ALS_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:430")                                   \
+  X(ST_ALS_FIRST_READ0, ZKE_ASSERT, "state_circuit.py:434-435")                             \
+  /* TxLog :439-453 */                                                                      \
+  X(ST_LOG_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:446")                                   \
+  X(ST_LOG_INIT_HI0, ZKE_ASSERT, "state_circuit.py:447")                                    \
+  X(ST_LOG_IS_WRITE, ZKE_ASSERT, "state_circuit.py:450")                                    \
+  X(ST_LOG_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:453")                                   \
+  /* TxReceipt :460-488 */                                                                  \
+  X(ST_RCP_ADDR0, ZKE_ASSERT, "state_circuit.py:465")                                       \
+  X(ST_RCP_KEY0, ZKE_ASSERT, "state_circuit.py:466")                                        \
+  X(ST_RCP_VALUE_HI0, ZKE_ASSERT, "state_circuit.py:467")                                   \
+  X(ST_RCP_INIT_HI0, ZKE_ASSERT, "state_circuit.py:468")                                    \
+  X(ST_RCP_STATUS_BOOL, ZKE_ASSERT, "state_circuit.py:471-472")                             \
+  X(ST_RCP_TXID_INC, ZKE_ASSERT, "state_circuit.py:476")                                    \
+  X(ST_RCP_GAS_INC, ZKE_ASSERT, "state_circuit.py:477-478")                                 \
+  X(ST_RCP_FIRST_TXID1, ZKE_ASSERT, "state_circuit.py:481-483")                             \
+  X(ST_RCP_TXID_RANGE, ZKE_ASSERT, "state_circuit.py:485")                                  \
+  X(ST_RCP_ROOT_SAME, ZKE_ASSERT, "state_circuit.py:488")                                   \
+  X(ST_TAG_UNREACHABLE, ZKE_VALUE, "state_circuit.py:612-613 tag 12 has no rules: ValueError")
+
+enum zk_state_constraint { ZK_STATE_CONSTRAINTS(ZK_ENUM_ENTRY) ST_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

@@ -5,9 +5,11 @@
 static const int kBytecode[] = {ZK_BYTECODE_CONSTRAINTS(CLS)};
 static const int kEvm[] = {ZK_EVM_CONSTRAINTS(CLS)};
 static const int kCopy[] = {ZK_COPY_CONSTRAINTS(CLS)};
+static const int kState[] = {ZK_STATE_CONSTRAINTS(CLS)};
 int orc_n_constraints(int circuit) {
   switch (circuit) {
     case 0: return BC_N_CONSTRAINTS;
+    case 1: return ST_N_CONSTRAINTS;
     case 2: return CP_N_CONSTRAINTS;
     case 3: return EV_N_CONSTRAINTS;
     default: return 0;
@@ -15,5 +17,5 @@ int orc_n_constraints(int circuit) {
 }
 int orc_constraint_class(int circuit, int idx) {
   if (idx < 0 || idx >= orc_n_constraints(circuit)) return -1;
-  return circuit == 0 ? kBytecode[idx] : circuit == 2 ? kCopy[idx] : kEvm[idx];
+  return circuit == 0 ? kBytecode[idx] : circuit == 1 ? kState[idx] : circuit == 2 ? kCopy[idx] : kEvm[idx];
 }

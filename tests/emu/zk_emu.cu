@@ -12,6 +12,7 @@
 #include "../../zkevm-specs_b200/csrc/bytecode.cu"
 #include "../../zkevm-specs_b200/csrc/copy.cu"
 #include "../../zkevm-specs_b200/csrc/evm.cu"
+#include "../../zkevm-specs_b200/csrc/state.cu"
 
 using namespace zk;
 
@@ -111,5 +112,20 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
   init_result(res, first_fail, fail_count, CP_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
   for (u64 i = row_begin; i < row_end; i++) check_copy_row(w, rg, t, r_mont, res, i, true, 1u);
+  return 0;
+}
+
+extern "C" int emu_check_state(const uint64_t* rows, uint64_t n_rows, const uint8_t* flags, const uint64_t* mpt,
+                               uint64_t n_mpt, uint64_t row_begin, uint64_t row_end, uint32_t cflags,
+                               const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 k12[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+  std::vector<u64> s1;
+  IndexDev ix = build_index((const u64*)mpt, n_mpt, 12, k12, 12, ch, s1);
+  WitnessDev w{(const u64*)rows, n_rows, flags};
+  CheckRange rg{row_begin, row_end, 0, cflags};
+  ResultDev res;
+  init_result(res, first_fail, fail_count, ST_N_CONSTRAINTS);
+  for (u64 i = row_begin; i < row_end; i++) check_state_row_dev(w, rg, ix, res, i, true, 1u);
   return 0;
 }

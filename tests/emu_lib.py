@@ -85,3 +85,20 @@ def check_copy(w, r, row_begin=0, row_end=None, flags=1, challenge=None):
                               ctypes.c_uint32(flags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_state(rows, flags, mpt, row_begin=0, row_end=None, cflags=1, challenge=None):
+    rows, mpt = np.ascontiguousarray(rows), np.ascontiguousarray(mpt)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n = 128
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().emu_check_state(_p(rows), c(rows.shape[1]), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                               _p(mpt), c(mpt.shape[1]), c(row_begin), c(row_end), ctypes.c_uint32(cflags), _p(ch),
+                               ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

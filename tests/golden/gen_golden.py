@@ -552,11 +552,241 @@ def copy_cases():
     print(f"copy: {tot} corruptions, {nfail} failing")
 
 
+# --------------------------------------------------------------------------- state
+def state_cases():
+    """State-circuit rows assigned by the reference (assign_state_circuit, state_circuit.py:861-889)
+    from operation lists modelled on tests/test_state_circuit.py:41-110, checked by the reference's
+    check_state_row under its own driver loop (tests/test_state_circuit.py:17-38)."""
+    import zkevm_specs.state_circuit as sc
+    from zkevm_specs.evm_circuit import (RW, AccountFieldTag, CallContextFieldTag, TxLogFieldTag,
+                                         TxReceiptFieldTag, MPTTableRow)
+    from zkevm_specs.util import FQ, Word, WordOrValue
+
+    rng = random.Random(3)
+    R_, W_ = RW.Read, RW.Write
+
+    def ops_all():
+        return [
+            sc.StartOp(rw_counter=1, rw=R_, lexicographic_ordering_selector=0),
+            sc.StartOp(rw_counter=2, rw=R_),
+            sc.StartOp(rw_counter=3, rw=R_),
+            sc.MemoryOp(rw_counter=1, rw=R_, call_id=1, mem_addr=0, value=FQ(0)),
+            sc.MemoryOp(rw_counter=2, rw=W_, call_id=1, mem_addr=0, value=FQ(42)),
+            sc.MemoryOp(rw_counter=3, rw=R_, call_id=1, mem_addr=0, value=FQ(42)),
+            sc.MemoryOp(rw_counter=40, rw=W_, call_id=1, mem_addr=7, value=FQ(255)),
+            sc.StackOp(rw_counter=4, rw=W_, call_id=1, stack_ptr=1022, value=Word(4321)),
+            sc.StackOp(rw_counter=5, rw=W_, call_id=1, stack_ptr=1023, value=Word(533)),
+            sc.StackOp(rw_counter=6, rw=R_, call_id=1, stack_ptr=1023, value=Word(533)),
+            sc.StorageOp(rw_counter=7, rw=R_, tx_id=1, addr=0x12345678, key=0x1516, value=Word(789), committed_value=Word(789)),
+            sc.StorageOp(rw_counter=8, rw=W_, tx_id=1, addr=0x12345678, key=0x4959, value=Word(38491), committed_value=Word(98765)),
+            sc.CallContextOp(rw_counter=9, rw=R_, call_id=1, field_tag=CallContextFieldTag.IsStatic, value=FQ(0)),
+            sc.CallContextOp(rw_counter=10, rw=R_, call_id=2, field_tag=CallContextFieldTag.IsStatic, value=FQ(0)),
+            sc.AccountOp(rw_counter=12, rw=W_, addr=0x12345678, field_tag=AccountFieldTag.Nonce, value=FQ(1), committed_value=FQ(0)),
+            sc.AccountOp(rw_counter=13, rw=R_, addr=0x12345678, field_tag=AccountFieldTag.Nonce, value=FQ(1), committed_value=FQ(0)),
+            sc.AccountOp(rw_counter=42, rw=R_, addr=0x12345678, field_tag=AccountFieldTag.Balance, value=Word(3), committed_value=Word(0)),
+            sc.TxRefundOp(rw_counter=14, rw=W_, tx_id=1, value=FQ(1)),
+            sc.TxRefundOp(rw_counter=15, rw=W_, tx_id=1, value=FQ(1)),
+            sc.TxAccessListAccountOp(rw_counter=16, rw=R_, tx_id=1, addr=0x12345678, value=FQ(0)),
+            sc.TxAccessListAccountOp(rw_counter=17, rw=W_, tx_id=1, addr=0x12345678, value=FQ(1)),
+            sc.TxAccessListAccountStorageOp(rw_counter=18, rw=R_, tx_id=1, addr=0x12345678, key=0x1516, value=FQ(0)),
+            sc.TxAccessListAccountStorageOp(rw_counter=19, rw=W_, tx_id=1, addr=0x12345678, key=0x1516, value=FQ(1)),
+            sc.TxLogOp(rw_counter=20, rw=W_, tx_id=1, log_id=1, field_tag=TxLogFieldTag.Address, index=0, value=FQ(124)),
+            sc.TxLogOp(rw_counter=21, rw=W_, tx_id=1, log_id=1, field_tag=TxLogFieldTag.Topic, index=0, value=Word(10)),
+            sc.TxLogOp(rw_counter=22, rw=W_, tx_id=1, log_id=1, field_tag=TxLogFieldTag.Topic, index=1, value=Word(5)),
+            sc.TxLogOp(rw_counter=25, rw=W_, tx_id=1, log_id=1, field_tag=TxLogFieldTag.Data, index=0, value=FQ(10)),
+            sc.TxLogOp(rw_counter=27, rw=W_, tx_id=1, log_id=2, field_tag=TxLogFieldTag.Address, index=0, value=FQ(255)),
+            sc.TxLogOp(rw_counter=29, rw=W_, tx_id=2, log_id=1, field_tag=TxLogFieldTag.Address, index=0, value=FQ(210)),
+            sc.TxReceiptOp(rw_counter=32, rw=R_, tx_id=1, field_tag=TxReceiptFieldTag.PostStateOrStatus, value=FQ(1)),
+            sc.TxReceiptOp(rw_counter=33, rw=R_, tx_id=1, field_tag=TxReceiptFieldTag.CumulativeGasUsed, value=FQ(200)),
+            sc.TxReceiptOp(rw_counter=34, rw=R_, tx_id=2, field_tag=TxReceiptFieldTag.PostStateOrStatus, value=FQ(1)),
+            sc.TxReceiptOp(rw_counter=35, rw=R_, tx_id=2, field_tag=TxReceiptFieldTag.CumulativeGasUsed, value=FQ(500)),
+        ]
+
+    def ops_mem_stack():
+        ops = [sc.StartOp(rw_counter=1, rw=R_, lexicographic_ordering_selector=0), sc.StartOp(rw_counter=2, rw=R_)]
+        rwc = 1
+        for call in (1, 2):
+            for a in range(6):
+                ops.append(sc.MemoryOp(rw_counter=rwc, rw=W_, call_id=call, mem_addr=a * 3, value=FQ(rng.randrange(256)))); rwc += 1
+                ops.append(sc.MemoryOp(rw_counter=rwc, rw=R_, call_id=call, mem_addr=a * 3, value=ops[-1].value.lo)); rwc += 1
+        for call in (1, 2):
+            for sp in (1021, 1022, 1023):
+                v = Word(rng.randrange(1 << 256))
+                ops.append(sc.StackOp(rw_counter=rwc, rw=W_, call_id=call, stack_ptr=sp, value=v)); rwc += 1
+                ops.append(sc.StackOp(rw_counter=rwc, rw=R_, call_id=call, stack_ptr=sp, value=v)); rwc += 1
+        return ops
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wov(lo, hi, is_word):
+        return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    def row_ints(x):
+        return ([n_of(x.rw_counter), n_of(x.is_write)] + [n_of(k) for k in x.keys[:4]] +
+                [n_of(x.keys[4].lo), n_of(x.keys[4].hi)] + [n_of(l) for l in x.key2_limbs] +
+                [n_of(b) for b in x.key45_bytes] + [n_of(x.value.lo), n_of(x.value.hi), n_of(x.initial_value.lo),
+                                                    n_of(x.initial_value.hi), n_of(x.root.lo), n_of(x.root.hi),
+                                                    n_of(x.lexicographic_ordering_selector)])
+
+    def row_from(v, flag):
+        f = [FQ(x) for x in v]
+        return sc.Row(f[0], f[1], (f[2], f[3], f[4], f[5], W(v[6], v[7])), tuple(f[8:18]), tuple(f[18:50]),
+                      wov(v[50], v[51], flag & 1), wov(v[52], v[53], (flag >> 1) & 1), W(v[54], v[55]), f[56])
+
+    def mpt_ints(x):
+        return [n_of(x.address), n_of(x.proof_type), n_of(x.storage_key.lo), n_of(x.storage_key.hi), n_of(x.root.lo),
+                n_of(x.root.hi), n_of(x.root_prev.lo), n_of(x.root_prev.hi), n_of(x.value.lo), n_of(x.value.hi),
+                n_of(x.value_prev.lo), n_of(x.value_prev.hi)]
+
+    def mpt_from(v):
+        return MPTTableRow(FQ(v[0]), FQ(v[1]), W(v[2], v[3]), W(v[4], v[5]), W(v[6], v[7]), W(v[8], v[9]), W(v[10], v[11]))
+
+    def run(S, SF, M):
+        rows = [row_from(v, f) for v, f in zip(S, SF)]
+        tables = sc.Tables(set(mpt_from(v) for v in M))
+        for idx, row in enumerate(rows):
+            try:
+                sc.check_state_row(row, rows[(idx - 1) % len(rows)], rows[(idx + 1) % len(rows)], tables)
+            except Exception as e:  # noqa: BLE001
+                return idx, type(e).__name__
+        return -1, ""
+
+    out = {"names": np.array(["all_tags", "mem_stack"])}
+    tot = nfail = 0
+    for name, ops in (("all_tags", ops_all()), ("mem_stack", ops_mem_stack())):
+        ops = sorted(ops, key=lambda o: (0 if isinstance(o, sc.StartOp) else 1, int(o.tag), int(o.id), int(o.address),
+                                         int(o.field_tag), int(o.storage_key), o.rw_counter)) if name == "mem_stack" else ops
+        rows = sc.assign_state_circuit(ops)
+        mpt = list(sc.mpt_table_from_ops(ops))
+        S = [row_ints(x) for x in rows]
+        SF = [int(x.value.is_word) | (int(x.initial_value.is_word) << 1) for x in rows]
+        M = [mpt_ints(x) for x in mpt]
+        assert run(S, SF, M) == (-1, ""), (name, run(S, SF, M))
+        muts = [(-1, 0, 0, 0, -1, "")]
+        for k in range(260 if name == "all_tags" else 120):
+            which = rng.choice([0, 0, 0, 0, 0, 0, 1, 2, 3])
+            S2, SF2, M2 = [list(x) for x in S], list(SF), [list(x) for x in M]
+            targeted = None
+            if k < 12:  # targeted corruptions for the rarely hit Python-runtime error paths
+                acc = [j for j, x in enumerate(S) if x[2] == 6]
+                targeted = [(rng.randrange(len(S)), 2, 12), (len(S) - 1, 18 + rng.randrange(32), 300),
+                            (acc[0] if acc else 0, 5, rng.choice([0, 5, 7])), (rng.randrange(len(S)), 18 + rng.randrange(32), 256)][k % 4]
+            if targeted is not None:
+                which = 0
+                i, c, v = targeted
+                S2[i][c] = v
+            elif which == 0:
+                i = rng.randrange(len(S))
+                c = rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 50, 51, 52, 53, 54, 55, 56]) if rng.random() < 0.7 else rng.randrange(57)
+                if c == 51 and not (SF[i] & 1) or c == 53 and not (SF[i] & 2):
+                    continue  # a value-typed cell has no hi half in the reference
+                old = S[i][c]
+                if c == 2:
+                    v = rng.randrange(0, 14)
+                elif c == 5:
+                    v = rng.randrange(0, 27)
+                else:
+                    v = corrupt_value(rng, old)
+                if v == old:
+                    continue
+                S2[i][c] = v
+            elif which == 1:  # flip a type flag
+                i, c, v = rng.randrange(len(S)), 100 + rng.randrange(2), 0
+                SF2[i] ^= 1 << (c - 100)
+                if not (SF2[i] >> (c - 100)) & 1:
+                    S2[i][51 if c == 100 else 53] = 0
+            elif which == 2 and M:
+                i, c = rng.randrange(len(M)), rng.randrange(12)
+                v = corrupt_value(rng, M[i][c]); M2[i][c] = v
+            elif which == 3:  # swap two adjacent rows (ordering)
+                i, c, v = rng.randrange(len(S) - 1), 200, 0
+                S2[i], S2[i + 1] = S2[i + 1], S2[i]
+                SF2[i], SF2[i + 1] = SF2[i + 1], SF2[i]
+            else:
+                continue
+            fr_, ex_ = run(S2, SF2, M2)
+            muts.append((which, i, c, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        out[f"{name}/rows"] = to_matrix(S)
+        out[f"{name}/flags"] = np.array(SF, dtype=np.uint8)
+        out[f"{name}/mpt"] = to_matrix(M) if M else np.zeros((12, 0, 4), dtype=np.uint64)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, len(S), "rows", len(M), "mpt rows", len(muts), "vectors")
+    np.savez_compressed(os.path.join(HERE, "state.npz"), **out)
+    print(f"state: {tot} corruptions, {nfail} failing")
+
+
+# --------------------------------------------------------------------------- synthetic generators
+def synth_cases():
+    """The numpy generators of zkevm-specs_b200/synth.py (used at scale by tests and bench.py) are run
+    through the REFERENCE at small sizes: the reference must accept them."""
+    import zkevm_specs.state_circuit as sc
+    from zkevm_specs.evm_circuit import (Block, BytecodeTableRow, ExecutionState, RWTableRow, StepState, Tables,
+                                         MPTTableRow)
+    from zkevm_specs.evm_circuit.main import verify_steps
+    from zkevm_specs.util import FQ, Word, WordOrValue
+
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from zkevm_specs_b200 import synth
+
+    def cell(m, c, i):
+        return sum(int(m[c, i, k]) << (64 * k) for k in range(4))
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    # EVM trace, 10 groups = 40 steps (all five ops twice)
+    w = synth.evm_trace(10, seed=2)
+    S, B, R = w["steps"], w["bytecode"], w["rw"]
+    steps = []
+    for i in range(S.shape[1]):
+        s = StepState(ExecutionState(cell(S, 0, i)), rw_counter=cell(S, 1, i), call_id=cell(S, 2, i),
+                      is_root=bool(cell(S, 3, i)), is_create=bool(cell(S, 4, i)), code_hash=W(cell(S, 5, i), cell(S, 6, i)),
+                      program_counter=cell(S, 7, i), stack_pointer=cell(S, 8, i), gas_left=cell(S, 9, i))
+        steps.append(s)
+    tables = Tables(block_table=set(Block().table_assignments()), tx_table=set(), withdrawal_table=set(),
+                    bytecode_table=set(BytecodeTableRow(W(cell(B, 0, i), cell(B, 1, i)), FQ(cell(B, 2, i)), FQ(cell(B, 3, i)),
+                                                        FQ(cell(B, 4, i)), FQ(cell(B, 5, i))) for i in range(B.shape[1])),
+                    rw_table=set(RWTableRow(FQ(cell(R, 0, i)), FQ(cell(R, 1, i)), FQ(cell(R, 2, i)), FQ(cell(R, 3, i)),
+                                            FQ(cell(R, 4, i)), FQ(0), Word(0), WordOrValue(W(cell(R, 8, i), cell(R, 9, i))))
+                                 for i in range(R.shape[1])))
+    verify_steps(tables, steps)
+    print("synth.evm_trace(10): accepted by the reference's verify_steps,", len(steps) - 1, "steps")
+
+    # state rows, 256 rows incl. Storage / Account groups with the mock MPT table
+    w = synth.state_rows(256, seed=3, n_start=16)
+    M, F, T = w["rows"], w["flags"], w["mpt"]
+
+    def wov(lo, hi, is_word):
+        return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    rows = []
+    for i in range(M.shape[1]):
+        v = [cell(M, c, i) for c in range(57)]
+        f = [FQ(x) for x in v]
+        rows.append(sc.Row(f[0], f[1], (f[2], f[3], f[4], f[5], W(v[6], v[7])), tuple(f[8:18]), tuple(f[18:50]),
+                           wov(v[50], v[51], F[i] & 1), wov(v[52], v[53], (F[i] >> 1) & 1), W(v[54], v[55]), f[56]))
+    mpt = set(MPTTableRow(FQ(cell(T, 0, i)), FQ(cell(T, 1, i)), W(cell(T, 2, i), cell(T, 3, i)), W(cell(T, 4, i), cell(T, 5, i)),
+                          W(cell(T, 6, i), cell(T, 7, i)), W(cell(T, 8, i), cell(T, 9, i)), W(cell(T, 10, i), cell(T, 11, i)))
+              for i in range(T.shape[1]))
+    tb = sc.Tables(mpt)
+    for idx, row in enumerate(rows):
+        sc.check_state_row(row, rows[(idx - 1) % len(rows)], rows[(idx + 1) % len(rows)], tb)
+    print("synth.state_rows(256): accepted by the reference's check_state_row,", len(rows), "rows,", len(mpt), "mpt rows")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "fr"]:
+    for nm in ["state", "copy", "evm", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

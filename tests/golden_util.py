@@ -82,3 +82,27 @@ def copy_vectors():
                 w["rw"] = np.ascontiguousarray(np.concatenate([base["rw"], extra], axis=1))
                 w["rw_flags"] = np.concatenate([base["rw_flags"], base["rw_flags"][i : i + 1]])
             yield name, k, w, r, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def state_vectors():
+    """yield (case, k, rows, flags, mpt, exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, "state.npz"))
+    for name in z["names"]:
+        name = str(name)
+        S, F, M = z[f"{name}/rows"], z[f"{name}/flags"], z[f"{name}/mpt"]
+        for k in range(len(z[f"{name}/mut_kind"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            val = z[f"{name}/mut_val"][k]
+            s, f, m = S, F, M
+            if kind == 0:
+                s = S.copy(); s[c, i, :] = val
+            elif kind == 1:
+                f = F.copy(); f[i] ^= 1 << (c - 100)
+                if not (f[i] >> (c - 100)) & 1:
+                    s = S.copy(); s[51 if c == 100 else 53, i, :] = 0
+            elif kind == 2:
+                m = M.copy(); m[c, i, :] = val
+            elif kind == 3:
+                s = S.copy(); s[:, [i, i + 1], :] = S[:, [i + 1, i], :]
+                f = F.copy(); f[[i, i + 1]] = F[[i + 1, i]]
+            yield name, k, s, f, m, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

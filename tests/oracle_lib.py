@@ -125,3 +125,18 @@ def check_copy(w, r, row_begin=0, row_end=None):
                               ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_state(rows, flags, mpt, row_begin=0, row_end=None):
+    rows, mpt = np.ascontiguousarray(rows), np.ascontiguousarray(mpt)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n = lib().orc_n_constraints(1)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().orc_check_state(p64(rows), c(rows.shape[1]), _p8(flags), p64(mpt), c(mpt.shape[1]), c(row_begin),
+                               c(row_end), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

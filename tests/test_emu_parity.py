@@ -61,3 +61,11 @@ def test_emu_copy_equals_oracle_on_goldens():
         ff, fc = emu_lib.check_copy(w, r)
         off, ofc = oracle_lib.check_copy(w, r)
         assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, ff[:n][ff[:n] != off], off[ff[:n] != off])
+
+
+def test_emu_state_equals_oracle_on_goldens():
+    n = oracle_lib.lib().orc_n_constraints(1)
+    for name, k, s, f, m, exp_row, exp_exc in golden_util.state_vectors():
+        ff, fc = emu_lib.check_state(s, f, m)
+        off, ofc = oracle_lib.check_state(s, f, m)
+        assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, np.nonzero(ff[:n] != off), ff[:n][ff[:n] != off], off[ff[:n] != off])

@@ -16,6 +16,7 @@
 #include "bytecode.cu"
 #include "copy.cu"
 #include "evm.cu"
+#include "state.cu"
 #include "circuit.cuh"
 
 using namespace zk;
@@ -30,6 +31,7 @@ struct ConstraintInfo {
 static const ConstraintInfo kBytecodeInfo[] = {ZK_BYTECODE_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kEvmInfo[] = {ZK_EVM_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kCopyInfo[] = {ZK_COPY_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kStateInfo[] = {ZK_STATE_CONSTRAINTS(ZK_INFO_ENTRY)};
 
 static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21};
 static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
@@ -39,6 +41,7 @@ static const ConstraintInfo* circuit_info(int circuit, int* n) {
     case ZK_CIRCUIT_BYTECODE: *n = BC_N_CONSTRAINTS; return kBytecodeInfo;
     case ZK_CIRCUIT_EVM: *n = EV_N_CONSTRAINTS; return kEvmInfo;
     case ZK_CIRCUIT_COPY: *n = CP_N_CONSTRAINTS; return kCopyInfo;
+    case ZK_CIRCUIT_STATE: *n = ST_N_CONSTRAINTS; return kStateInfo;
     default: *n = 0; return nullptr;
   }
 }
@@ -384,6 +387,23 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   return 0;
 }
 
+static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
+  const Matrix& m = ctx->circ[ZK_CIRCUIT_STATE];
+  if (!(rg.flags & ZK_FLAG_WRAP) && (rg.row_begin == 0 || rg.row_end + 1 > m.n_rows))
+    return fail_msg(ctx, "state rows [b,e) need rows b-1 and e resident (rotations -1,+1) unless ZK_FLAG_WRAP");
+  const u32 k12[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+  IndexDev mpt;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_MPT, k12, 12, st, &mpt))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
+  const u64 n = rg.row_end - rg.row_begin;
+  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
+  k_check_state<<<grid, 128, 0, st>>>(witness_dev(m), rg, mpt, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const Matrix& m = ctx->circ[ZK_CIRCUIT_COPY];
   if (!(rg.flags & ZK_FLAG_WRAP) && rg.row_end + 2 > m.n_rows)
@@ -471,6 +491,7 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
     case ZK_CIRCUIT_BYTECODE: rc = check_bytecode(ctx, rg, res, st); break;
     case ZK_CIRCUIT_EVM: rc = check_evm(ctx, rg, res, st); break;
     case ZK_CIRCUIT_COPY: rc = check_copy(ctx, rg, res, st); break;
+    case ZK_CIRCUIT_STATE: rc = check_state(ctx, rg, res, st); break;
     default: return fail_msg(ctx, "circuit has no gate program in this build");
   }
   if (rc) return rc;

@@ -143,3 +143,132 @@ def evm_trace(n_groups: int, seed: int = 2, call_id: int = 1) -> Dict[str, np.nd
     spent_before = np.concatenate([[0], np.cumsum(cost)]).astype(np.uint64)
     steps[9, :, 0] = np.uint64(total + 7) - spent_before
     return {"steps": steps, "bytecode": bytecode, "rw": rw, "n_steps": ns - 1}
+
+
+def state_rows(n_rows: int, seed: int = 3, n_start: int = 1024) -> Dict[str, np.ndarray]:
+    """BASELINE cfg3 — a sorted RW-table witness for the state circuit as cell matrices:
+    `n_start` Start padding rows, then Memory ~40 %, Stack ~40 %, Storage ~5 %, CallContext ~10 %,
+    Account ~5 % (tag order of state_circuit.Tag), each key written once then read, with the
+    mock MPT table of the reference (`_mock_mpt_updates`, state_circuit.py:903-933: root starts
+    at 3, +5 per first touch of a Storage/Account key).  Returns rows [57][n][4], flags [n],
+    mpt [12][m][4]."""
+    rng = np.random.default_rng(seed)
+    n_start = min(n_start, n_rows // 2)
+    body = n_rows - n_start
+    per = 4  # accesses per key: 1 write + 3 reads
+    n_keys = body // per
+    counts = {"mem": int(n_keys * 0.40), "stack": int(n_keys * 0.40), "sto": int(n_keys * 0.05),
+              "cc": int(n_keys * 0.10)}
+    counts["acc"] = n_keys - sum(counts.values())
+    extra = body - n_keys * per  # leftover rows become extra Start rows
+    n_start += extra
+    n = n_rows
+
+    tag = np.zeros(n, np.uint64); idc = np.zeros(n, np.uint64); addr = np.zeros(n, np.uint64)
+    ft = np.zeros(n, np.uint64); key = np.zeros((n, 4), np.uint64)
+    is_write = np.zeros(n, np.uint64); val = np.zeros((n, 4), np.uint64); init = np.zeros((n, 4), np.uint64)
+    flags = np.zeros(n, np.uint8); selector = np.ones(n, np.uint64)
+    tag[:n_start] = 1
+    selector[0] = 0
+    pos = n_start
+
+    def fill(kind, nk):
+        nonlocal pos
+        if nk == 0:
+            return None
+        sl = slice(pos, pos + nk * per)
+        w = np.tile(np.array([1] + [0] * (per - 1), np.uint64), nk)
+        is_write[sl] = w
+        pos += nk * per
+        return sl
+
+    # Memory (tag 2): call_id 1.., consecutive addresses; value a byte
+    nk = counts["mem"]; sl = fill("mem", nk)
+    if sl:
+        k = np.repeat(np.arange(nk, dtype=np.uint64), per)
+        tag[sl] = 2; idc[sl] = 1 + k // np.uint64(1 << 16); addr[sl] = k % np.uint64(1 << 16)
+        val[sl, 0] = np.repeat(rng.integers(0, 256, nk, dtype=np.uint64), per)
+    # Stack (tag 3): per call 1024 slots, pointer ascending; value a 256-bit word
+    nk = counts["stack"]; sl = fill("stack", nk)
+    if sl:
+        k = np.repeat(np.arange(nk, dtype=np.uint64), per)
+        tag[sl] = 3; idc[sl] = 1 + k // np.uint64(1024); addr[sl] = k % np.uint64(1024)
+        val[sl] = np.repeat(rng.integers(0, 1 << 63, (nk, 4), dtype=np.uint64) * np.uint64(2) + np.uint64(1), per, axis=0)
+        flags[sl] |= 1
+    # Storage (tag 4): tx 1, one address, increasing keys; committed value = value
+    nk_sto = counts["sto"]; sl_sto = fill("sto", nk_sto)
+    if sl_sto:
+        k = np.repeat(np.arange(nk_sto, dtype=np.uint64), per)
+        tag[sl_sto] = 4; idc[sl_sto] = 1; addr[sl_sto] = 0x12345678
+        key[sl_sto, 0] = k + np.uint64(1); key[sl_sto, 2] = k * np.uint64(7)
+        v = np.repeat(rng.integers(1, 1 << 62, (nk_sto, 4), dtype=np.uint64), per, axis=0)
+        val[sl_sto] = v; init[sl_sto] = v
+        is_write[sl_sto] = 0  # reads of the committed value (a write would change value within the group)
+        flags[sl_sto] |= 3
+    # CallContext (tag 5): field tag 14 (IsStatic)
+    nk = counts["cc"]; sl = fill("cc", nk)
+    if sl:
+        k = np.repeat(np.arange(nk, dtype=np.uint64), per)
+        tag[sl] = 5; idc[sl] = 1 + k; ft[sl] = 14
+        val[sl, 0] = np.repeat(rng.integers(0, 2, nk, dtype=np.uint64), per)
+    # Account (tag 6): increasing addresses, field tag Balance (2); committed value = value
+    nk_acc = counts["acc"]; sl_acc = fill("acc", nk_acc)
+    if sl_acc:
+        k = np.repeat(np.arange(nk_acc, dtype=np.uint64), per)
+        tag[sl_acc] = 6; addr[sl_acc] = np.uint64(0x1000) + k; ft[sl_acc] = 2
+        v = np.repeat(rng.integers(1, 1 << 62, (nk_acc, 4), dtype=np.uint64), per, axis=0)
+        val[sl_acc] = v; init[sl_acc] = v
+        is_write[sl_acc] = 0
+        flags[sl_acc] |= 3
+    assert pos == n
+
+    # rw_counter: Start rows 1..n_start; the others any increasing counter (unique per row)
+    rwc = np.arange(1, n + 1, dtype=np.uint64)
+    # roots: MPT rows carry the root before their key's update; everything else the next one's
+    rp = np.full(n + 1, -1, np.int64)
+    groups = []
+    if sl_sto:
+        g = np.arange(nk_sto, dtype=np.int64)
+        rp[sl_sto] = np.repeat(3 + 5 * g, per)
+        groups.append((sl_sto, nk_sto, 0, 6))
+    if sl_acc:
+        g = np.arange(nk_acc, dtype=np.int64) + nk_sto
+        rp[sl_acc] = np.repeat(3 + 5 * g, per)
+        groups.append((sl_acc, nk_acc, nk_sto, 2))
+    n_upd = nk_sto + nk_acc
+    rp[n] = 3 + 5 * n_upd
+    big = np.where(rp >= 0, rp, np.int64(1) << 62)
+    nxt = np.minimum.accumulate(big[::-1])[::-1]  # next non-None root at or after k
+    root = nxt[1:].astype(np.uint64)  # row k carries roots[k + 1]
+
+    rows = np.zeros((57, n, 4), dtype=np.uint64)
+    rows[0, :, 0] = rwc; rows[1, :, 0] = is_write; rows[2, :, 0] = tag; rows[3, :, 0] = idc
+    rows[4, :, 0] = addr; rows[5, :, 0] = ft
+    rows[6, :, 0], rows[6, :, 1] = key[:, 0], key[:, 1]
+    rows[7, :, 0], rows[7, :, 1] = key[:, 2], key[:, 3]
+    for k in range(10):  # 16-bit address limbs (addresses here fit 64 bits)
+        rows[8 + k, :, 0] = (addr >> np.uint64(16 * k)) & np.uint64(0xFFFF) if k < 4 else 0
+    kb = np.ascontiguousarray(key).view(np.uint8).reshape(n, 32)
+    for b in range(32):
+        rows[18 + b, :, 0] = kb[:, b]
+    rows[50, :, 0], rows[50, :, 1] = val[:, 0], val[:, 1]
+    rows[51, :, 0], rows[51, :, 1] = val[:, 2], val[:, 3]
+    rows[52, :, 0], rows[52, :, 1] = init[:, 0], init[:, 1]
+    rows[53, :, 0], rows[53, :, 1] = init[:, 2], init[:, 3]
+    rows[54, :, 0] = root
+    rows[56, :, 0] = selector
+
+    mpt = np.zeros((12, n_upd, 4), dtype=np.uint64)
+    for sl, nk, g0, proof in groups:
+        first = np.arange(sl.start, sl.stop, per)
+        d = slice(g0, g0 + nk)
+        mpt[0, d, 0] = addr[first]; mpt[1, d, 0] = proof
+        mpt[2, d, 0], mpt[2, d, 1] = key[first, 0], key[first, 1]
+        mpt[3, d, 0], mpt[3, d, 1] = key[first, 2], key[first, 3]
+        mpt[4, d, 0] = 3 + 5 * (np.arange(nk, dtype=np.uint64) + np.uint64(g0)) + np.uint64(5)  # root
+        mpt[6, d, 0] = 3 + 5 * (np.arange(nk, dtype=np.uint64) + np.uint64(g0))  # root_prev
+        mpt[8, d, 0], mpt[8, d, 1] = val[first, 0], val[first, 1]
+        mpt[9, d, 0], mpt[9, d, 1] = val[first, 2], val[first, 3]
+        mpt[10, d, 0], mpt[10, d, 1] = init[first, 0], init[first, 1]
+        mpt[11, d, 0], mpt[11, d, 1] = init[first, 2], init[first, 3]
+    return {"rows": rows, "flags": flags, "mpt": mpt}
