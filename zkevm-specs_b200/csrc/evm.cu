@@ -539,13 +539,13 @@ ZK_HD bool push_prepare(const StepCtx& s, int n_op, const Fr& opcode, int n_len,
 }
 // byte idx of the pushed word: returns the failing constraint id, or -1.  Warp-synchronous: every
 // lane of s.mask calls it (the lookup inside is skipped with live = false where no byte is pushed)
-ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx) {
+ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx, bool live) {
   const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
   const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
   const u64 limb = idx < 16 ? lo_limb : hi_limb;
   const u64 byte = (limb >> (8 * (idx & 7))) & 0xFF;
   const int base = EV_PUSH_B0_UNSAT + 4 * idx;
-  const bool pushed = (u64)idx < c.n_push && (u64)idx >= c.n_pad;
+  const bool pushed = live && (u64)idx < c.n_push && (u64)idx >= c.n_pad;
   Fr got = fr_u64(0);
   const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
   const int n = bytecode_lookup_h(s, pushed, c.h0, c.hlo, c.hhi, 2, index, 0, &got);
@@ -605,7 +605,7 @@ ZK_HD void gadget_push(const StepCtx& s, bool live) {
   if (!live) return;
   if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
   for (int idx = 0; idx < 32; idx++) {
-    const int fid = push_byte(s, c, idx);
+    const int fid = push_byte(s, c, idx, true);
     if (fid >= 0) {
       step_fail(s, fid);
       return;
@@ -702,9 +702,20 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
   return r;
 }
 
-// one warp per PUSH step
-__global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                  EvmLists lists) {
+// half a warp per PUSH step (two steps per warp iteration): sub-lane L of a half owns pushed bytes
+// L and L+16 of its step.  Halving the lanes per step halves the warp-instructions per step and
+// doubles the steps in flight per warp; the kernel is latency-bound on ~8 dependent memory round
+// trips per step (profiles/README.md, v7), so both matter.  All 32 lanes call every
+// warp-synchronous lookup together; a half without a step (odd count) or whose step already
+// failed passes live = false.
+__device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
+  Fr r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src, 16);
+  return r;
+}
+__global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                     EvmLists lists) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
@@ -713,16 +724,21 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
   Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // h0 of the last code hash seen
   bool have_h0 = false;
   const u32 n = lists.count[G_PUSH];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
-    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, lane == 0, s_resp, 0xFFFFFFFFu, stack_pre};
+  const u32 n_pairs = (n + 1) >> 1;
+  const int kNone = 0x7FFFFFFF;
+  for (u32 kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; kp < n_pairs; kp += warps) {  // warp-uniform
+    const u32 k = 2 * kp + half;
+    const bool have = k < n;
+    bool live = have;
+    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + (have ? k : 2 * kp)];
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
-    // consecutive steps of a warp almost always run the same contract: reuse hash_lo + hash_hi*r
+    // consecutive steps of a lane almost always run the same contract: reuse hash_lo + hash_hi*r
     if (!(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi))) {
       last_hlo = c.hlo;
       last_hhi = c.hhi;
@@ -730,30 +746,37 @@ __global__ void __launch_bounds__(128) k_evm_push(WitnessDev w, CheckRange rg, E
       have_h0 = true;
     }
     c.h0 = last_h0;
-    // round 1: lane 0 opcode, lane 1 bytecode length (one warp-wide bytecode probe), then lane 2
+    // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
     Word2 val{fr_u64(0), fr_u64(0)};
-    int n_hit = bytecode_lookup_h(s, lane < 2, c.h0, c.hlo, c.hhi, lane == 0 ? 2 : 1, lane == 0 ? c.pc : fr_u64(0),
-                                  lane == 0 ? 1 : 0, &v);
-    const int n_hit_rw = rw_lookup(s, lane == 2, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID),
+    int n_hit = bytecode_lookup_h(s, live && sub < 2, c.h0, c.hlo, c.hhi, sub == 0 ? 2 : 1,
+                                  sub == 0 ? c.pc : fr_u64(0), sub == 0 ? 1 : 0, &v);
+    const int n_hit_rw = rw_lookup(s, live && sub == 2, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID),
                                    fr_sub_u64(s.cur(S_SP), 1), &val);
-    if (lane == 2) n_hit = n_hit_rw;
-    const int n_op = __shfl_sync(0xFFFFFFFFu, n_hit, 0), n_len = __shfl_sync(0xFFFFFFFFu, n_hit, 1);
-    const int n_rw = __shfl_sync(0xFFFFFFFFu, n_hit, 2);
-    const Fr opcode = shfl_fr(v, 0), code_length = shfl_fr(v, 1);
-    Word2 value{shfl_fr(val.lo, 2), shfl_fr(val.hi, 2)};
-    if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) continue;  // warp-uniform
-    // round 2: lane L checks pushed byte L; the first failing byte in program order wins
-    const int fid = push_byte(s, c, lane);
-    const unsigned bad = __ballot_sync(0xFFFFFFFFu, fid >= 0);
-    if (bad) {
-      if (lane == __ffs(bad) - 1) fail(res, fid, s.row);
-      continue;
+    if (sub == 2) n_hit = n_hit_rw;
+    const int n_op = __shfl_sync(0xFFFFFFFFu, n_hit, 0, 16), n_len = __shfl_sync(0xFFFFFFFFu, n_hit, 1, 16);
+    const int n_rw = __shfl_sync(0xFFFFFFFFu, n_hit, 2, 16);
+    const Fr opcode = shfl16_fr(v, 0), code_length = shfl16_fr(v, 1);
+    Word2 value{shfl16_fr(val.lo, 2), shfl16_fr(val.hi, 2)};
+    if (live) live = push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c);  // uniform per half
+    // round 2: pushed bytes L and L+16; the first failing byte in program order wins
+    const int fid0 = push_byte(s, c, sub, live);
+    const int fid1 = push_byte(s, c, sub + 16, live);
+    const unsigned bad0 = (__ballot_sync(0xFFFFFFFFu, live && fid0 >= 0) >> (16 * half)) & 0xFFFFu;
+    const unsigned bad1 = (__ballot_sync(0xFFFFFFFFu, live && fid1 >= 0) >> (16 * half)) & 0xFFFFu;
+    if (bad0) {
+      if (sub == __ffs(bad0) - 1) fail(res, fid0, s.row);
+      live = false;
+    } else if (bad1) {
+      if (sub == __ffs(bad1) - 1) fail(res, fid1, s.row);
+      live = false;
     }
-    const int eid = same_context_lane(s, lane, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
-    const int first = __reduce_min_sync(0xFFFFFFFFu, eid);
-    if (first != 0x7FFFFFFF && lane == 0) fail(res, first, s.row);
+    int eid = kNone;
+    if (live) eid = same_context_lane(s, sub, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) eid = min(eid, __shfl_xor_sync(0xFFFFFFFFu, eid, off, 16));
+    if (live && eid != kNone && sub == 0) fail(res, eid, s.row);
   }
 }
 #endif  // __CUDACC__
