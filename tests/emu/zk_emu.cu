@@ -38,9 +38,31 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
     d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);
     acc = fr_montmul(acc, r_mont);
   }
+  d.pos_ok = nullptr;
+  d.pos_kind = ZK_POS_NONE;
+  d.heads_slots = nullptr;
+  d.heads_mask = 0;
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
   return d;
 }
+// positional structure of a table, verified exactly like k_pos_verify does on the device
+struct PosState {
+  u32 ok = 1;
+  std::vector<u64> heads;
+};
+static void add_positional(IndexDev& d, u32 kind, PosState& st) {
+  d.pos_kind = kind;
+  st.heads.assign(1u << 10, ZK_EMPTY_SLOT);
+  d.heads_slots = st.heads.data();
+  d.heads_mask = (1u << 10) - 1;
+  st.ok = 1;
+  for (u64 r = 0; r < d.tab.n_rows; r++) {
+    if (kind == ZK_POS_DENSE) pos_verify_dense_row(d, &st.ok, r);
+    else pos_verify_run_row(d, &st.ok, r);
+  }
+  d.pos_ok = &st.ok;
+}
+extern "C" int g_emu_positional = 1;  // tests toggle this to run both lookup paths
 
 static void init_result(ResultDev& res, uint32_t* ff, uint64_t* fc, int n) {
   for (int i = 0; i < n; i++) { ff[i] = 0xFFFFFFFFu; fc[i] = 0; }
@@ -59,6 +81,11 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
   t.fixed = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, s3);
+  PosState p_bc, p_rw;
+  if (g_emu_positional) {
+    add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
+    add_positional(t.rw, ZK_POS_DENSE, p_rw);
+  }
   std::vector<u32> bitmap(ZK_RESP_BITMAP_WORDS, 0);
   for (u64 r = 0; r < n_fixed; r++) resp_bitmap_row(t.fixed.tab, bitmap.data(), r);
   t.resp_bitmap = bitmap.data();
@@ -106,6 +133,11 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s2);
   t.tx = build_index((const u64*)tx, n_tx, 5, k3, 3, ch, s3);
   t.tx.tab.flags = tx_flags;
+  PosState p_bc, p_rw;
+  if (g_emu_positional) {
+    add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
+    add_positional(t.rw, ZK_POS_DENSE, p_rw);
+  }
   WitnessDev w{(const u64*)rows, n_rows, row_flags};
   CheckRange rg{row_begin, row_end, 0, flags};
   ResultDev res;

@@ -102,3 +102,8 @@ def check_state(rows, flags, mpt, row_begin=0, row_end=None, cflags=1, challenge
                                ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def set_positional(on: bool) -> None:
+    """toggle the positional (regular-table) lookup fast paths in the emulation; off = hash index only"""
+    ctypes.c_int.in_dll(lib(), "g_emu_positional").value = int(on)

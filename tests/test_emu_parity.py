@@ -18,12 +18,17 @@ def test_emu_bytecode_equals_oracle_on_goldens():
 
 
 def test_emu_evm_equals_oracle_on_goldens():
+    """both lookup paths: positional (regular rw / bytecode tables, verified on the fly; corrupted
+    tables fall back by themselves) and hash index only"""
     fixed = fixed_table_matrix()
     n = oracle_lib.lib().orc_n_constraints(3)
     for name, k, s, b, r, flags, exp_row, exp_exc in golden_util.evm_vectors():
-        ff, fc = emu_lib.check_evm(s, b, r, fixed, flags=flags, n=n)
         off, ofc = oracle_lib.check_evm(s, b, r, fixed, flags=flags)
-        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}]"
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            ff, fc = emu_lib.check_evm(s, b, r, fixed, flags=flags, n=n)
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] positional={positional}"
+    emu_lib.set_positional(True)
 
 
 def test_emu_evm_synthetic_and_fuzz_equals_oracle():

@@ -65,6 +65,9 @@ struct Index {
   u32 key_cols[ZK_MAX_KEY];
   u64* slots = nullptr;
   size_t cap = 0;
+  u32 pos_kind = ZK_POS_NONE;
+  u32* pos_flag = nullptr;  // device flag written by k_pos_verify
+  u64* heads = nullptr;     // ZK_POS_RUNS heads index
   u64 built_version = ~0ull;
   u64 built_challenge = ~0ull;
   IndexDev dev;
@@ -152,6 +155,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   for (auto& m : ctx->tab) free_matrix(m);
   for (auto* ix : ctx->indexes) {
     if (ix->slots) cudaFree(ix->slots);
+    if (ix->pos_flag) cudaFree(ix->pos_flag);
+    if (ix->heads) cudaFree(ix->heads);
     delete ix;
   }
   for (auto& r : ctx->res)
@@ -282,8 +287,9 @@ static TableDev table_dev(const zk_ctx* ctx, int table_id) {
 
 // Returns the device descriptor of the index of `table_id` on `key_cols`, building it on
 // `st` if the table or the lookup challenge changed since the last build.
+#define ZK_HEADS_CAP (1u << 16)
 static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_key, cudaStream_t st,
-                        IndexDev* out) {
+                        IndexDev* out, u32 pos_kind = ZK_POS_NONE) {
   if (n_key == 0 || n_key > ZK_MAX_KEY) return fail_msg(ctx, "bad key width");
   Index* ix = nullptr;
   for (auto* c : ctx->indexes)
@@ -293,6 +299,11 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     ix->table_id = table_id;
     ix->n_key = n_key;
     memcpy(ix->key_cols, key_cols, 4 * n_key);
+    ix->pos_kind = pos_kind;
+    if (pos_kind != ZK_POS_NONE) {
+      CK(ctx, cudaMalloc(&ix->pos_flag, sizeof(u32)));
+      if (pos_kind == ZK_POS_RUNS) CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(u64)));
+    }
     ctx->indexes.push_back(ix);
   }
   const Matrix& m = ctx->tab[table_id];
@@ -324,11 +335,28 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);  // r^j * 2^64 mod p
     acc = fr_montmul(acc, r_mont);
   }
-  CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u64), st));
+  d.pos_ok = nullptr;
+  d.pos_kind = ix->pos_kind;
+  d.heads_slots = ix->heads;
+  d.heads_mask = ZK_HEADS_CAP - 1;
+  const unsigned grid = (unsigned)std::min<u64>((t.n_rows + 255) / 256, (u64)ctx->sm_count * 32);
+  if (t.n_rows && ix->pos_kind != ZK_POS_NONE) {
+    // verify the regular structure in one streaming pass; the flag stays 1 iff it holds
+    k_set_u32<<<1, 1, 0, st>>>(ix->pos_flag, 1u);
+    if (ix->heads) CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(u64), st));
+    k_pos_verify<<<grid, 256, 0, st>>>(d, ix->pos_flag);
+    ctx->launches += 2;
+    d.pos_ok = ix->pos_flag;
+  }
   if (t.n_rows) {
-    k_index_build<<<(unsigned)((t.n_rows + 255) / 256), 256, 0, st>>>(d);
-    ctx->launches++;
+    // generic hash index: cleared and built only if the table is not positional (both kernels
+    // return at once when the flag is set)
+    k_slots_clear<<<(unsigned)std::min<u64>((cap + 255) / 256, (u64)ctx->sm_count * 32), 256, 0, st>>>(ix->slots, cap, d.pos_ok);
+    k_index_build<<<grid, 256, 0, st>>>(d);
+    ctx->launches += 2;
     CK(ctx, cudaGetLastError());
+  } else {
+    CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u64), st));
   }
   ix->built_version = m.version;
   ix->built_challenge = ctx->chal_version;
@@ -411,8 +439,8 @@ static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStre
   const u32 k5[5] = {0, 1, 2, 3, 4}, k3[3] = {0, 1, 2};
   CopyTables t;
   int rc;
-  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw))) return rc;
-  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw, ZK_POS_DENSE))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode, ZK_POS_RUNS))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_TX, k3, 3, st, &t.tx))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
@@ -430,8 +458,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
   EvmTables t;
   int rc;
-  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode))) return rc;
-  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode, ZK_POS_RUNS))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw, ZK_POS_DENSE))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_FIXED, k4, 4, st, &t.fixed))) return rc;
   if (!ctx->resp_bitmap) CK(ctx, cudaMalloc(&ctx->resp_bitmap, ZK_RESP_BITMAP_WORDS * sizeof(u32)));
   if (ctx->resp_bitmap_version != ctx->tab[ZK_TABLE_FIXED].version) {

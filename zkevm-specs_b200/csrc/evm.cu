@@ -142,18 +142,32 @@ ZK_HD int bytecode_lookup(const StepCtx& s, bool live, const Fr& hlo, const Fr& 
 ZK_HD Fr bytecode_hash0(const StepCtx& s, const Fr& hlo, const Fr& hhi) {
   return fr_add(hlo, rlc_term(s.t.bytecode, hhi, 1));
 }
-ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u64 tag,
-                            const Fr& index, u64 is_code, Fr* value) {
+// `n_head/head`: result of the heads-index probe for this code hash (positional path), done once
+// per step by the caller
+ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_head, u32 head, const Fr& hlo,
+                            const Fr& hhi, u64 tag, const Fr& index, u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   const IndexDev& ix = s.t.bytecode;
   if (ix.tab.n_rows == 0) return 0;
-  Fr h = fr_add(h0, rlc_term(ix, key[2], 2));
-  h = fr_add(h, rlc_term(ix, key[3], 3));
-  h = fr_add(h, rlc_term(ix, key[4], 4));
-  u32 r;
-  const int n = probe_hashed<5>(ix, h, key, &r, s.mask, live);
+  u32 r = 0;
+  int n;
+  if (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS) {
+    n = pos_lookup_run(ix, key, n_head, head, &r, live);
+  } else {
+    Fr h = fr_add(h0, rlc_term(ix, key[2], 2));
+    h = fr_add(h, rlc_term(ix, key[3], 3));
+    h = fr_add(h, rlc_term(ix, key[4], 4));
+    n = probe_hashed<5>(ix, h, key, &r, s.mask, live);
+  }
   if (live && n == 1) *value = table_cell(ix.tab, B_VALUE, r);
   return n;
+}
+// heads-index probe of the step's code hash (no-op unless the bytecode table is positional)
+ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head) {
+  const IndexDev& ix = s.t.bytecode;
+  *head = 0;
+  if (ix.tab.n_rows == 0 || !(pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) return 0;
+  return heads_probe(ix, h0, hlo, hhi, head, s.mask, live);
 }
 // constant terms of a stack lookup's key hash, computed once per thread
 ZK_HD void stack_key_pre(const IndexDev& rw_ix, Fr out[2]) {
@@ -167,7 +181,9 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
   u32 r;
   int n = 0;
   const IndexDev& ix = s.t.rw;
-  if (ix.tab.n_rows != 0) {
+  if (ix.tab.n_rows != 0 && pos_enabled(ix) && ix.pos_kind == ZK_POS_DENSE) {
+    n = pos_lookup_dense<5>(ix, key, &r, live);
+  } else if (ix.tab.n_rows != 0) {
     Fr h;
     if (tag == ZK_TARGET_Stack && s.stack_pre) {
       h = fr_add(fr_add(rwc, s.stack_pre[rw & 1]), fr_add(rlc_term(ix, id, 3), rlc_term(ix, addr, 4)));
@@ -517,6 +533,8 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
 // functions serially.
 struct PushCommon {
   Fr hlo, hhi, h0, pc, opcode, num_pushed;
+  int n_head;  // heads-index probe of the code hash (positional bytecode table)
+  u32 head;
   u64 n_push, n_pad;
   Word2 value;
 };
@@ -548,7 +566,7 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx, bool live) {
   const bool pushed = live && (u64)idx < c.n_push && (u64)idx >= c.n_pad;
   Fr got = fr_u64(0);
   const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
-  const int n = bytecode_lookup_h(s, pushed, c.h0, c.hlo, c.hhi, 2, index, 0, &got);
+  const int n = bytecode_lookup_h(s, pushed, c.h0, c.n_head, c.head, c.hlo, c.hhi, 2, index, 0, &got);
   if (pushed) {
     if (n != 1) return n == 0 ? base : base + 1;
     return fr_eq_u64(got, byte) ? -1 : base + 2;
@@ -599,8 +617,9 @@ ZK_HD void gadget_push(const StepCtx& s, bool live) {
   c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
   Fr opcode = fr_u64(0), code_length = fr_u64(0);
   Word2 value{fr_u64(0), fr_u64(0)};
-  const int n_op = bytecode_lookup_h(s, live, c.h0, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
-  const int n_len = bytecode_lookup_h(s, live, c.h0, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
+  const int n_op = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
   const int n_rw = rw_lookup(s, live, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
   if (!live) return;
   if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
@@ -746,11 +765,12 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
       have_h0 = true;
     }
     c.h0 = last_h0;
+    c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
     // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
     Word2 val{fr_u64(0), fr_u64(0)};
-    int n_hit = bytecode_lookup_h(s, live && sub < 2, c.h0, c.hlo, c.hhi, sub == 0 ? 2 : 1,
+    int n_hit = bytecode_lookup_h(s, live && sub < 2, c.h0, c.n_head, c.head, c.hlo, c.hhi, sub == 0 ? 2 : 1,
                                   sub == 0 ? c.pc : fr_u64(0), sub == 0 ? 1 : 0, &v);
     const int n_hit_rw = rw_lookup(s, live && sub == 2, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID),
                                    fr_sub_u64(s.cur(S_SP), 1), &val);

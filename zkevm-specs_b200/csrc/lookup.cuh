@@ -37,7 +37,17 @@ struct IndexDev {
   Fr pw[ZK_MAX_KEY];   // r^j * 2^256 mod p (Montgomery form): montmul(cell, pw[j]) = cell * r^j
   Fr pwc[ZK_MAX_KEY];  // r^j canonical, for terms whose cell is 1
   Fr pw1[ZK_MAX_KEY];  // r^j * 2^64 mod p: fr_montmul1(v, pw1[j]) = v * r^j for one-limb cells
+  // Positional fast path (see "positional indexes" below).  pos_ok points at a device flag that the
+  // verify kernel leaves at 1 iff the table has the regular structure `pos_kind` promises; the
+  // hash index above is then not built and lookups go straight to the row.
+  const u32* pos_ok;
+  u32 pos_kind;
+  u64* heads_slots;  // ZK_POS_RUNS: hash index (same slot format) over the first row of every run
+  u32 heads_mask;
 };
+#define ZK_POS_NONE 0
+#define ZK_POS_DENSE 1  // key column 0 is a counter: cell(row) == cell(0) + row   (rw table by rw_counter)
+#define ZK_POS_RUNS 2   // bytecode table: runs [Header, Byte 0, Byte 1, ...] of one code hash each
 
 ZK_HD const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
   return t.cells + ((u64)col * t.n_rows + row) * 4;
@@ -92,10 +102,7 @@ ZK_HD void index_insert_row(const IndexDev& ix, u64 row) {
     b = (b + 1) & ix.mask;
   }
 }
-__global__ void __launch_bounds__(256) k_index_build(IndexDev ix) {
-  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row < ix.tab.n_rows) index_insert_row(ix, row);
-}
+
 
 ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
   for (u32 c = 0; c < t.n_cols; c++)
@@ -112,13 +119,13 @@ ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
 // warp leaves the loop CONVERGED.  With a plain data-dependent `break` each lane ran the rest
 // of its gate program alone (measured: 1-2 active threads per instruction, profiles/r01_v4).
 template <int NK>
-ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32* row, unsigned mask,
-                       bool active) {
+ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const Fr& h, const Fr (&key)[NK],
+                      u32* row, unsigned mask, bool active) {
   int found = 0;
   u32 first = 0;
   const u64 mix = rlc_mix(h);
   const u32 fp = (u32)(mix >> 32);
-  u32 b = (u32)mix & ix.mask;
+  u32 b = (u32)mix & slot_mask;
 #ifdef __CUDA_ARCH__
 #define ZK_GROUP_ANY(p) __any_sync(mask, (p))
 #else
@@ -128,7 +135,7 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
   bool done = !active;
   while (ZK_GROUP_ANY(!done)) {
     if (!done) {
-      const u64 slot = ld_u64(&ix.slots[b]);
+      const u64 slot = ld_u64(&slots[b]);
       if (slot == ZK_EMPTY_SLOT) {
         done = true;
       } else {
@@ -149,7 +156,7 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
             }
           }
         }
-        b = (b + 1) & ix.mask;
+        b = (b + 1) & slot_mask;
       }
     }
   }
@@ -157,24 +164,162 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
   *row = first;
   return found;
 }
+template <int NK>
+ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32* row, unsigned mask,
+                       bool active) {
+  return probe_slots<NK>(ix, ix.slots, ix.mask, h, key, row, mask, active);
+}
+
+// ---- positional indexes ---------------------------------------------------------------------
+// Witness generators emit some tables in a regular order (the rw table by rw_counter, the
+// bytecode table as one run per contract).  A streaming verify kernel checks that structure
+// exactly; if it holds, a lookup computes the only row that CAN match and confirms it cell by
+// cell — same match count as the reference's scan (0 or 1: the structure implies key
+// uniqueness) with no hash build, no slot probe and no RLC.  If it does not hold, the flag is 0
+// and every lookup takes the generic hash path, so the result never depends on the layout.
+ZK_HD bool pos_enabled(const IndexDev& ix) { return ix.pos_ok != nullptr && ld_u32(ix.pos_ok) != 0; }
+
+// ZK_POS_DENSE: candidate = key[0] - cell(0)
+template <int NK>
+ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active) {
+  if (!active) return 0;
+  const Fr base = table_cell(ix.tab, ix.key_cols[0], 0);
+  if (!fr_fits64(key[0]) || key[0].l[0] < base.l[0]) return 0;
+  const u64 cand = key[0].l[0] - base.l[0];
+  if (cand >= ix.tab.n_rows) return 0;
+#pragma unroll
+  for (int j = 1; j < NK; j++)
+    if (!fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j])) return 0;
+  *row = (u32)cand;
+  return 1;
+}
+// ZK_POS_RUNS (bytecode table, key = hash_lo, hash_hi, tag, index, is_code): `head` is the first
+// row of the run with this code hash (found through the heads index), Header row = head,
+// Byte row k = head + 1 + k
+ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32* row, bool active) {
+  if (!active || n_head != 1) return 0;
+  u64 cand;
+  if (fr_eq_u64(key[2], 1)) {
+    cand = head;
+  } else if (fr_eq_u64(key[2], 2) && fr_fits64(key[3]) && key[3].l[0] < ix.tab.n_rows) {
+    cand = (u64)head + 1 + key[3].l[0];
+    if (cand >= ix.tab.n_rows) return 0;
+  } else {
+    return 0;
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++)
+    if (!fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j])) return 0;
+  *row = (u32)cand;
+  return 1;
+}
+// heads index probe: h0 = hash_lo + hash_hi * r  (warp-synchronous like probe_hashed)
+ZK_HD int heads_probe(const IndexDev& ix, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head, unsigned mask,
+                      bool active) {
+  Fr key[2] = {hlo, hhi};
+  return probe_slots<2>(ix, ix.heads_slots, ix.heads_mask, h0, key, head, mask, active);
+}
+
+// verify kernels' row functions
+ZK_HD void pos_fail(u32* ok) {
+#ifdef __CUDA_ARCH__
+  atomicExch(ok, 0u);
+#else
+  *ok = 0;
+#endif
+}
+ZK_HD void pos_verify_dense_row(const IndexDev& ix, u32* ok, u64 row) {
+  const Fr c = table_cell(ix.tab, ix.key_cols[0], row), b = table_cell(ix.tab, ix.key_cols[0], 0);
+  if (!(fr_fits64(c) && fr_fits64(b) && b.l[0] + row >= b.l[0] && c.l[0] == b.l[0] + row)) pos_fail(ok);
+}
+ZK_HD void pos_verify_run_row(const IndexDev& ix, u32* ok, u64 row) {
+  const TableDev& t = ix.tab;
+  const Fr hlo = table_cell(t, 0, row), hhi = table_cell(t, 1, row), tag = table_cell(t, 2, row);
+  const Fr index = table_cell(t, 3, row);
+  bool head = row == 0;
+  Fr ptag = fr_u64(0), pindex = fr_u64(0);
+  if (row > 0) {
+    head = !(fr_eq(hlo, table_cell(t, 0, row - 1)) && fr_eq(hhi, table_cell(t, 1, row - 1)));
+    ptag = table_cell(t, 2, row - 1);
+    pindex = table_cell(t, 3, row - 1);
+  }
+  if (head) {
+    if (!(fr_eq_u64(tag, 1) && fr_is_zero(index))) {
+      pos_fail(ok);
+      return;
+    }
+    // register the run head; a second run with the same code hash makes keys ambiguous -> irregular
+    const Fr h0 = fr_add(hlo, rlc_term(ix, hhi, 1));
+    const u64 mix = rlc_mix(h0);
+    const u64 entry = (mix & 0xFFFFFFFF00000000ull) | (u64)(u32)row;
+    u32 b = (u32)mix & ix.heads_mask;
+    for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
+      const u64 old = atomic_cas_u64(&ix.heads_slots[b], ZK_EMPTY_SLOT, entry);
+      if (old == ZK_EMPTY_SLOT) return;
+      if ((old >> 32) == (mix >> 32)) {
+        const u32 other = (u32)old;
+        if (fr_eq(table_cell(t, 0, other), hlo) && fr_eq(table_cell(t, 1, other), hhi)) break;  // duplicate hash
+      }
+      b = (b + 1) & ix.heads_mask;
+    }
+    pos_fail(ok);  // duplicate code hash, or more runs than the heads index holds
+  } else {
+    const bool byte_row = fr_eq_u64(tag, 2);
+    const bool idx_ok = fr_eq_u64(ptag, 1) ? fr_is_zero(index)
+                                           : (fr_eq_u64(ptag, 2) && fr_fits64(pindex) && fr_fits64(index) &&
+                                              pindex.l[0] != ~0ull && index.l[0] == pindex.l[0] + 1);
+    if (!(byte_row && idx_ok)) pos_fail(ok);
+  }
+}
 
 // warp-synchronous lookup (see probe_hashed)
 template <int NK>
 ZK_HD int lookup_sync(const IndexDev& ix, const Fr (&key)[NK], u32* row, unsigned mask, bool active) {
   if (ix.tab.n_rows == 0) return 0;  // uniform: the table is the same for every lane
+  if (pos_enabled(ix)) {             // uniform: one flag per table
+    if (ix.pos_kind == ZK_POS_DENSE) return pos_lookup_dense<NK>(ix, key, row, active);
+    if constexpr (NK == 5) {
+      if (ix.pos_kind == ZK_POS_RUNS) {
+        u32 head = 0;
+        const int n_head = heads_probe(ix, fr_add(key[0], rlc_term(ix, key[1], 1)), key[0], key[1], &head, mask, active);
+        return pos_lookup_run(ix, key, n_head, head, row, active);
+      }
+    }
+  }
   return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row, mask, active);
 }
 // single-thread lookup: the calling thread is its own group
 template <int NK>
 ZK_HD int lookup(const IndexDev& ix, const Fr (&key)[NK], u32* row) {
-  if (ix.tab.n_rows == 0) return 0;
 #ifdef __CUDA_ARCH__
   const unsigned self = 1u << (threadIdx.x & 31);
 #else
   const unsigned self = 1u;
 #endif
-  return probe_hashed<NK>(ix, rlc_key<NK>(ix, key), key, row, self, true);
+  return lookup_sync<NK>(ix, key, row, self, true);
 }
+
+#ifdef __CUDACC__
+// the generic hash index is only needed when the table is NOT positional
+__global__ void __launch_bounds__(256) k_index_build(IndexDev ix) {
+  if (pos_enabled(ix)) return;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.tab.n_rows; row += stride) index_insert_row(ix, row);
+}
+__global__ void __launch_bounds__(256) k_slots_clear(u64* slots, u64 n, const u32* skip_if_set) {
+  if (skip_if_set && *skip_if_set) return;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) slots[i] = ZK_EMPTY_SLOT;
+}
+__global__ void k_set_u32(u32* p, u32 v) { *p = v; }
+__global__ void __launch_bounds__(256) k_pos_verify(IndexDev ix, u32* ok) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.tab.n_rows; row += stride) {
+    if (ix.pos_kind == ZK_POS_DENSE) pos_verify_dense_row(ix, ok, row);
+    else pos_verify_run_row(ix, ok, row);
+  }
+}
+#endif
 
 // ---- result recording -------------------------------------------------------------------
 struct ResultDev {
