@@ -97,6 +97,8 @@ struct StepCtx {
   const u32* resp;  // ResponsibleOpcode bitmap (shared memory on the device)
   unsigned mask;    // lanes that run this gate program together (warp-synchronous lookups)
   const Fr* stack_pre;  // [2]: rw * r + Target.Stack * r^2 for rw = Read, Write (constant key terms)
+  int pos_mode;  // -1: read the tables' positional flags at run time; 1: the kernel was specialised for
+                 // positional rw + bytecode tables (the caller checked both flags), hash paths compiled out
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
   ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
 };
@@ -151,7 +153,7 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   if (ix.tab.n_rows == 0) return 0;
   u32 r = 0;
   int n;
-  if (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS) {
+  if (s.pos_mode == 1 || (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) {
     n = pos_lookup_run(ix, key, n_head, head, &r, live);
   } else {
     Fr h = fr_add(h0, rlc_term(ix, key[2], 2));
@@ -166,7 +168,7 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
 ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head) {
   const IndexDev& ix = s.t.bytecode;
   *head = 0;
-  if (ix.tab.n_rows == 0 || !(pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) return 0;
+  if (s.pos_mode != 1 && (ix.tab.n_rows == 0 || !(pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS))) return 0;
   return heads_probe(ix, h0, hlo, hhi, head, s.mask, live);
 }
 // constant terms of a stack lookup's key hash, computed once per thread
@@ -181,7 +183,7 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
   u32 r;
   int n = 0;
   const IndexDev& ix = s.t.rw;
-  if (ix.tab.n_rows != 0 && pos_enabled(ix) && ix.pos_kind == ZK_POS_DENSE) {
+  if (s.pos_mode == 1 || (ix.tab.n_rows != 0 && pos_enabled(ix) && ix.pos_kind == ZK_POS_DENSE)) {
     n = pos_lookup_dense<5>(ix, key, &r, live);
   } else if (ix.tab.n_rows != 0) {
     Fr h;
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr, -1};
     g = step_prologue(s, rg.flags);
   }
   // warp-aggregated append: one atomicAdd per (warp, gadget)
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     const u32 k = first + tid;
     const bool live = k < n;
     const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, -1};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
@@ -733,14 +735,25 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src, 16);
   return r;
 }
-__global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                     EvmLists lists) {
+// POS = true: specialised for positional rw + bytecode tables (no hash code at all); it returns at
+// once unless both flags are set, and the POS = false instance returns at once if they are —
+// the host launches both, exactly one does the work.
+template <bool POS>
+__global__ void __launch_bounds__(128, POS ? 5 : 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t,
+                                                               ResultDev res, EvmLists lists) {
+  {
+    const bool both = t.rw.tab.n_rows != 0 && t.bytecode.tab.n_rows != 0 && pos_enabled(t.rw) &&
+                      pos_enabled(t.bytecode) && t.rw.pos_kind == ZK_POS_DENSE && t.bytecode.pos_kind == ZK_POS_RUNS;
+    if (both != POS) return;
+  }
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   Fr stack_pre[2];
   stack_key_pre(t.rw, stack_pre);
-  Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // h0 of the last code hash seen
+  Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // per-lane cache of the last code hash seen
+  u32 last_head = 0;
+  int last_n_head = 0;
   bool have_h0 = false;
   const u32 n = lists.count[G_PUSH];
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
@@ -752,20 +765,38 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     const bool have = k < n;
     bool live = have;
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + (have ? k : 2 * kp)];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, POS ? 1 : -1};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
-    // consecutive steps of a lane almost always run the same contract: reuse hash_lo + hash_hi*r
-    if (!(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi))) {
-      last_hlo = c.hlo;
-      last_hhi = c.hhi;
-      last_h0 = bytecode_hash0(s, c.hlo, c.hhi);
-      have_h0 = true;
+    // consecutive steps of a lane almost always run the same contract: reuse the work that depends
+    // only on the code hash (hash_lo + hash_hi*r; with positional tables, the run head itself)
+    const bool changed = !(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi));
+    if (POS) {
+      c.h0 = fr_u64(0);
+      u32 head = 0;
+      const Fr h0 = changed ? bytecode_hash0(s, c.hlo, c.hhi) : fr_u64(0);
+      const int nh = bytecode_head(s, live && changed, h0, c.hlo, c.hhi, &head);  // every lane calls (warp-sync)
+      if (changed) {
+        last_hlo = c.hlo;
+        last_hhi = c.hhi;
+        last_head = head;
+        last_n_head = live ? nh : 0;
+        have_h0 = live;
+      }
+      c.n_head = last_n_head;
+      c.head = last_head;
+    } else {
+      if (changed) {
+        last_hlo = c.hlo;
+        last_hhi = c.hhi;
+        last_h0 = bytecode_hash0(s, c.hlo, c.hhi);
+        have_h0 = true;
+      }
+      c.h0 = last_h0;
+      c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
     }
-    c.h0 = last_h0;
-    c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
     // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
