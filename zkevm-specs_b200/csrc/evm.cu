@@ -154,7 +154,10 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   u32 r = 0;
   int n;
   if (s.pos_mode == 1 || (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) {
-    n = pos_lookup_run(ix, key, n_head, head, &r, live);
+    Fr got;
+    n = pos_lookup_run(ix, key, n_head, head, &r, live, B_VALUE, &got);
+    if (live && n == 1) *value = got;
+    return n;
   } else {
     Fr h = fr_add(h0, rlc_term(ix, key[2], 2));
     h = fr_add(h, rlc_term(ix, key[3], 3));
@@ -739,7 +742,7 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
 // once unless both flags are set, and the POS = false instance returns at once if they are —
 // the host launches both, exactly one does the work.
 template <bool POS>
-__global__ void __launch_bounds__(128, POS ? 5 : 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t,
+__global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t,
                                                                ResultDev res, EvmLists lists) {
   {
     const bool both = t.rw.tab.n_rows != 0 && t.bytecode.tab.n_rows != 0 && pos_enabled(t.rw) &&

@@ -141,11 +141,14 @@ ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const
       } else {
         if ((u32)(slot >> 32) == fp) {
           const u32 cand = (u32)slot;
+          // all key cells are loaded before any compare: NK independent loads in flight instead of
+          // a chain of NK dependent round trips
+          Fr cells[NK];
+#pragma unroll
+          for (int j = 0; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
           bool eq = true;
 #pragma unroll
-          for (int j = 0; j < NK; j++) {
-            if (eq) eq = fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
-          }
+          for (int j = 0; j < NK; j++) eq = eq && fr_eq(cells[j], key[j]);
           if (eq) {
             if (found == 0) {
               first = cand;
@@ -187,31 +190,37 @@ ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bo
   if (!fr_fits64(key[0]) || key[0].l[0] < base.l[0]) return 0;
   const u64 cand = key[0].l[0] - base.l[0];
   if (cand >= ix.tab.n_rows) return 0;
+  Fr cells[NK];  // independent loads first, compares after
 #pragma unroll
-  for (int j = 1; j < NK; j++)
-    if (!fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j])) return 0;
+  for (int j = 1; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
+  bool eq = true;
+#pragma unroll
+  for (int j = 1; j < NK; j++) eq = eq && fr_eq(cells[j], key[j]);
   *row = (u32)cand;
-  return 1;
+  return eq ? 1 : 0;
 }
 // ZK_POS_RUNS (bytecode table, key = hash_lo, hash_hi, tag, index, is_code): `head` is the first
 // row of the run with this code hash (found through the heads index), Header row = head,
 // Byte row k = head + 1 + k
-ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32* row, bool active) {
-  if (!active || n_head != 1) return 0;
-  u64 cand;
-  if (fr_eq_u64(key[2], 1)) {
-    cand = head;
-  } else if (fr_eq_u64(key[2], 2) && fr_fits64(key[3]) && key[3].l[0] < ix.tab.n_rows) {
-    cand = (u64)head + 1 + key[3].l[0];
-    if (cand >= ix.tab.n_rows) return 0;
-  } else {
-    return 0;
-  }
+// Branch-free: the candidate row is clamped to a valid row and its cells are always loaded, so
+// several lookups of one thread have all their loads in flight together; `extra_col` (or -1)
+// names one more cell of the candidate row to fetch in the same batch (the looked-up value).
+ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32* row, bool active,
+                         int extra_col = -1, Fr* extra = nullptr) {
+  const bool is_hdr = fr_eq_u64(key[2], 1);
+  const bool is_byte = fr_eq_u64(key[2], 2) && fr_fits64(key[3]) && key[3].l[0] < ix.tab.n_rows;
+  u64 cand = is_hdr ? (u64)head : (u64)head + 1 + (is_byte ? key[3].l[0] : 0);
+  const bool valid = active && n_head == 1 && (is_hdr || is_byte) && cand < ix.tab.n_rows;
+  if (!valid) cand = 0;
+  Fr cells[5];
 #pragma unroll
-  for (int j = 0; j < 5; j++)
-    if (!fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j])) return 0;
+  for (int j = 0; j < 5; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
+  if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
+  bool eq = valid;
+#pragma unroll
+  for (int j = 0; j < 5; j++) eq = eq && fr_eq(cells[j], key[j]);
   *row = (u32)cand;
-  return 1;
+  return eq ? 1 : 0;
 }
 // heads index probe: h0 = hash_lo + hash_hi * r  (warp-synchronous like probe_hashed)
 ZK_HD int heads_probe(const IndexDev& ix, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head, unsigned mask,
