@@ -95,7 +95,7 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   Fr stack_pre[2];
   stack_key_pre(t.rw, stack_pre);
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u, stack_pre, -1};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u, stack_pre, nullptr, -1};
     verify_step(s, flags);
   }
   return 0;

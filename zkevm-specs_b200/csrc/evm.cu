@@ -97,6 +97,7 @@ struct StepCtx {
   const u32* resp;  // ResponsibleOpcode bitmap (shared memory on the device)
   unsigned mask;    // lanes that run this gate program together (warp-synchronous lookups)
   const Fr* stack_pre;  // [2]: rw * r + Target.Stack * r^2 for rw = Read, Write (constant key terms)
+  const u64* rw_base;  // limb 0 of rw_counter of rw-table row 0, hoisted (positional rw table), or nullptr
   int pos_mode;  // -1: read the tables' positional flags at run time; 1: the kernel was specialised for
                  // positional rw + bytecode tables (the caller checked both flags), hash paths compiled out
   ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
@@ -187,7 +188,13 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
   int n = 0;
   const IndexDev& ix = s.t.rw;
   if (s.pos_mode == 1 || (ix.tab.n_rows != 0 && pos_enabled(ix) && ix.pos_kind == ZK_POS_DENSE)) {
-    n = pos_lookup_dense<5>(ix, key, &r, live);
+    Fr lo, hi;
+    n = pos_lookup_dense<5>(ix, key, &r, live, s.rw_base, R_VAL_LO, &lo, R_VAL_HI, &hi);
+    if (live && n == 1) {
+      value->lo = lo;
+      value->hi = hi;
+    }
+    return n;
   } else if (ix.tab.n_rows != 0) {
     Fr h;
     if (tag == ZK_TARGET_Stack && s.stack_pre) {
@@ -578,16 +585,46 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx, bool live) {
   }
   return byte == 0 ? -1 : base + 3;
 }
+// pushed bytes idx and idx+16 of one step on a positional bytecode table: both candidate rows are
+// computed first and all 12 cell loads issued before any compare
+ZK_HD void push_two_bytes_pos(const StepCtx& s, const PushCommon& c, int idx, bool live, int* fid0, int* fid1) {
+  const IndexDev& ix = s.t.bytecode;
+  int fid[2];
+  bool pushed[2];
+  u64 byte[2];
+  Fr got[2];
+  int n[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int b = idx + 16 * k;
+    const u64 lo_limb = (b & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
+    const u64 hi_limb = (b & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
+    byte[k] = ((b < 16 ? lo_limb : hi_limb) >> (8 * (b & 7))) & 0xFF;
+    pushed[k] = live && (u64)b < c.n_push && (u64)b >= c.n_pad;
+    const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)b);
+    Fr key[5] = {c.hlo, c.hhi, fr_u64(2), index, fr_u64(0)};
+    u32 r;
+    n[k] = pos_lookup_run(ix, key, c.n_head, c.head, &r, pushed[k], B_VALUE, &got[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int base = EV_PUSH_B0_UNSAT + 4 * (idx + 16 * k);
+    if (pushed[k]) fid[k] = n[k] != 1 ? base : (fr_eq_u64(got[k], byte[k]) ? -1 : base + 2);  // positional: never ambiguous
+    else fid[k] = byte[k] == 0 ? -1 : base + 3;
+  }
+  *fid0 = fid[0];
+  *fid1 = fid[1];
+}
 ZK_HD void push_epilogue(const StepCtx& s, const PushCommon& c) {
   same_context(s, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
 }
 // The shared epilogue spread over a warp: lane c < 13 loads cell c of the current and next
 // step and evaluates the transition constraint of that cell; returns the id of its failing
 // constraint or INT_MAX.  Ids are in program order, so the warp minimum is the first failure.
-ZK_HD int same_context_lane(const StepCtx& s, int lane, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
+ZK_HD int same_context_lane(const StepCtx& s, int lane, const Fr& cur, const Fr& nxt, const Fr& opcode, u64 d_rwc,
+                            const Fr& d_pc, const Fr& d_sp) {
   const int kNone = 0x7FFFFFFF;
   if (lane >= 13) return kNone;
-  const Fr cur = s.cur((u32)lane), nxt = s.nxt((u32)lane);
   int gas_cost = -1;
   if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
   switch (lane) {
@@ -678,7 +715,7 @@ __global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange r
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr, -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr, nullptr, -1};
     g = step_prologue(s, rg.flags);
   }
   // warp-aggregated append: one atomicAdd per (warp, gadget)
@@ -712,7 +749,7 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     const u32 k = first + tid;
     const bool live = k < n;
     const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
@@ -758,6 +795,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
   u32 last_head = 0;
   int last_n_head = 0;
   bool have_h0 = false;
+  const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
   const u32 n = lists.count[G_PUSH];
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
@@ -768,11 +806,14 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     const bool have = k < n;
     bool live = have;
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + (have ? k : 2 * kp)];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, POS ? 1 : -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, POS ? &rw_base : nullptr,
+              POS ? 1 : -1};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
     c.pc = s.cur(S_PC);
+    // this lane's cell of the current / next step for the epilogue, fetched with the first batch
+    const Fr my_cur = s.cur((u32)(sub < 13 ? sub : 0)), my_nxt = s.nxt((u32)(sub < 13 ? sub : 0));
     // consecutive steps of a lane almost always run the same contract: reuse the work that depends
     // only on the code hash (hash_lo + hash_hi*r; with positional tables, the run head itself)
     const bool changed = !(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi));
@@ -815,8 +856,13 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     Word2 value{shfl16_fr(val.lo, 2), shfl16_fr(val.hi, 2)};
     if (live) live = push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c);  // uniform per half
     // round 2: pushed bytes L and L+16; the first failing byte in program order wins
-    const int fid0 = push_byte(s, c, sub, live);
-    const int fid1 = push_byte(s, c, sub + 16, live);
+    int fid0, fid1;
+    if (POS) {
+      push_two_bytes_pos(s, c, sub, live, &fid0, &fid1);
+    } else {
+      fid0 = push_byte(s, c, sub, live);
+      fid1 = push_byte(s, c, sub + 16, live);
+    }
     const unsigned bad0 = (__ballot_sync(0xFFFFFFFFu, live && fid0 >= 0) >> (16 * half)) & 0xFFFFu;
     const unsigned bad1 = (__ballot_sync(0xFFFFFFFFu, live && fid1 >= 0) >> (16 * half)) & 0xFFFFu;
     if (bad0) {
@@ -827,7 +873,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
       live = false;
     }
     int eid = kNone;
-    if (live) eid = same_context_lane(s, sub, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
+    if (live) eid = same_context_lane(s, sub, my_cur, my_nxt, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) eid = min(eid, __shfl_xor_sync(0xFFFFFFFFu, eid, off, 16));
     if (live && eid != kNone && sub == 0) fail(res, eid, s.row);

@@ -182,18 +182,22 @@ ZK_HD int probe_hashed(const IndexDev& ix, const Fr& h, const Fr (&key)[NK], u32
 // and every lookup takes the generic hash path, so the result never depends on the layout.
 ZK_HD bool pos_enabled(const IndexDev& ix) { return ix.pos_ok != nullptr && ld_u32(ix.pos_ok) != 0; }
 
-// ZK_POS_DENSE: candidate = key[0] - cell(0)
+// ZK_POS_DENSE: candidate = key[0] - cell(0).  Branch-free (candidate clamped, cells always
+// loaded) so that it overlaps with neighbouring lookups; `base0` = limb 0 of cell(0) of the
+// counter column, hoisted by callers that do many lookups (pass nullptr to read it here).
 template <int NK>
-ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active) {
-  if (!active) return 0;
-  const Fr base = table_cell(ix.tab, ix.key_cols[0], 0);
-  if (!fr_fits64(key[0]) || key[0].l[0] < base.l[0]) return 0;
-  const u64 cand = key[0].l[0] - base.l[0];
-  if (cand >= ix.tab.n_rows) return 0;
+ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active, const u64* base0 = nullptr,
+                           int extra_col = -1, Fr* extra = nullptr, int extra_col2 = -1, Fr* extra2 = nullptr) {
+  const u64 base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
+  const bool in_range = fr_fits64(key[0]) && key[0].l[0] >= base && key[0].l[0] - base < ix.tab.n_rows;
+  const bool valid = active && in_range;
+  const u64 cand = valid ? key[0].l[0] - base : 0;
   Fr cells[NK];  // independent loads first, compares after
 #pragma unroll
   for (int j = 1; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
-  bool eq = true;
+  if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
+  if (extra_col2 >= 0) *extra2 = table_cell(ix.tab, (u32)extra_col2, cand);
+  bool eq = valid;
 #pragma unroll
   for (int j = 1; j < NK; j++) eq = eq && fr_eq(cells[j], key[j]);
   *row = (u32)cand;
