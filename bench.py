@@ -76,8 +76,8 @@ def algorithmic_bytes(n_steps, n_rw, n_bytecode, n_constraints):
     return 32 * (n_steps * N_CELLS_STEP + n_rw * N_CELLS_RW + n_bytecode * N_CELLS_BYTECODE) + 4 * n_constraints
 
 
-def cpu_port(sample_groups: int, seed: int, threads: int):
-    """time the CPU oracle (C port of the reference algorithm) on a bounded sample"""
+def _cpu_port_worker(args):
+    sample_groups, seed = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from zkevm_specs_b200 import synth
@@ -93,17 +93,39 @@ def cpu_port(sample_groups: int, seed: int, threads: int):
     return w["n_steps"], dt
 
 
+def cpu_port(sample_groups: int, seed: int, threads: int):
+    """time the CPU oracle (C port of the reference algorithm) on a bounded sample.  threads > 1:
+    that many processes each check their own sample of the same size concurrently (the reference
+    has no parallelism of its own; rows are independent, so this is how it would use the cores);
+    returns (total rows, wall seconds of the slowest worker)"""
+    if threads <= 1:
+        return _cpu_port_worker((sample_groups, seed))
+    import multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    oracle_lib.lib()  # build once before forking
+    with mp.get_context("fork").Pool(threads) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_port_worker, [(sample_groups, seed + k) for k in range(threads)])
+        wall = time.perf_counter() - t0
+    # generation time is inside `wall`; use the max of the measured check times (they overlap)
+    return sum(r[0] for r in res), max(r[1] for r in res)
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's algorithm on the host cores.  The reference is pure
     Python and /root/reference is absent on the GPU box, so this times the C port (oracle/)."""
     if rank != 0:
         return
     sample_groups = args.ref_groups
+    cores = os.cpu_count() or 1
     for _ in range(args.warmup):
         cpu_port(min(sample_groups, 256), 2, 1)
     rows = secs = 0.0
     for _ in range(args.steps):
-        n, dt = cpu_port(sample_groups, 2, 1)
+        n, dt = cpu_port(sample_groups, 2, cores)
         rows += n
         secs += dt
     v = rows / secs
@@ -114,8 +136,8 @@ def run_reference_arm(args, rank, world):
         "data": "synthetic",
         "config": {"workload": f"evm_circuit cfg2 trace, bounded sample of {4 * sample_groups} steps per bench step "
                                "(same generator and seed as the CUDA arm)", "seed": 2},
-        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
-                         "sample": f"{4 * sample_groups} steps incl. sorted-index build of all tables, single thread"},
+        "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x {4 * sample_groups} steps each, C oracle incl. sorted-index build of all tables"},
         "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,8 +264,15 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # DRAM bytes of the same kernels from the committed `ncu --set full` capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))["dram_bytes_per_check"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_check_evm", "kernel_ms": chk, "index_build_ms": float(np.mean(idx_ms)),
+                "traffic": traffic if args.groups == (1 << 18) else None,
+                "kernel": "evm check phase: k_evm_classify + k_evm_push<positional> (~70 %) + k_evm_gadget<ADD|MUL|POP>",
+                "kernel_ms": chk, "index_build_ms": float(np.mean(idx_ms)),
                 "algorithmic_bytes": bytes_alg,
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6.65 TB/s"}
 
@@ -264,9 +293,10 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        n, dt = cpu_port(args.ref_groups, 2, 1)
-        cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
-               "sample": f"first {n} steps of the same generator (seed 2), C oracle incl. sorted-index build, single thread"}
+        cores = os.cpu_count() or 1
+        n, dt = cpu_port(args.ref_groups, 2, cores)
+        cpu = {"value": n / dt, "unit": "rows/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} processes x {n // cores} steps of the same generator, C oracle incl. sorted-index build"}
 
     if rank == 0:
         line = {

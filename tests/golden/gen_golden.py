@@ -781,6 +781,35 @@ def synth_cases():
         sc.check_state_row(row, rows[(idx - 1) % len(rows)], rows[(idx + 1) % len(rows)], tb)
     print("synth.state_rows(256): accepted by the reference's check_state_row,", len(rows), "rows,", len(mpt), "mpt rows")
 
+    # copy events: 2 SHA3-style + 2 CALLDATACOPY-style, 20 bytes each
+    from zkevm_specs import copy_circuit as cc
+    from zkevm_specs.evm_circuit import CopyCircuitRow, TxTableRow
+
+    w = synth.copy_events(4, 20, seed=4)
+    Cm, RWm, TXm = w["copy"], w["rw"], w["tx"]
+    r_int = sum(int(w["r"][k]) << (64 * k) for k in range(4))
+
+    class Fake:
+        def __init__(self, rows):
+            self.rows = rows
+
+        def table(self):
+            return self.rows
+
+    crow = []
+    for i in range(Cm.shape[1]):
+        v = [cell(Cm, c, i) for c in range(20)]
+        f = [FQ(x) for x in v]
+        crow.append(CopyCircuitRow(f[0], f[1], f[2], WordOrValue(FQ(v[3])), *f[5:]))
+    tables = Tables(block_table=set(), withdrawal_table=set(), bytecode_table=set(),
+                    tx_table=set(TxTableRow(FQ(cell(TXm, 0, i)), FQ(cell(TXm, 1, i)), FQ(cell(TXm, 2, i)),
+                                            WordOrValue(FQ(cell(TXm, 3, i)))) for i in range(TXm.shape[1])),
+                    rw_table=set(RWTableRow(FQ(cell(RWm, 0, i)), FQ(cell(RWm, 1, i)), FQ(cell(RWm, 2, i)), FQ(cell(RWm, 3, i)),
+                                            FQ(cell(RWm, 4, i)), FQ(0), Word(0), WordOrValue(FQ(cell(RWm, 8, i))))
+                                 for i in range(RWm.shape[1])))
+    cc.verify_copy_table(Fake(crow), tables, FQ(r_int))
+    print("synth.copy_events(4, 20): accepted by the reference's verify_copy_table,", len(crow), "rows")
+
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"

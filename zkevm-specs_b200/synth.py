@@ -272,3 +272,89 @@ def state_rows(n_rows: int, seed: int = 3, n_start: int = 1024) -> Dict[str, np.
         mpt[10, d, 0], mpt[10, d, 1] = init[first, 0], init[first, 1]
         mpt[11, d, 0], mpt[11, d, 1] = init[first, 2], init[first, 3]
     return {"rows": rows, "flags": flags, "mpt": mpt}
+
+
+FR_P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F6CDD1D5851F42D4C957F2D14057B7EF767814F) -> Dict[str, np.ndarray]:
+    """BASELINE cfg4 — copy-circuit witness as cell matrices: n_events/2 SHA3-style events
+    (Memory -> RlcAcc) and n_events/2 root CALLDATACOPY events (TxCalldata -> Memory whose last
+    10 % of bytes are out of bounds => padding), `length` bytes each, two rows per byte
+    (CopyCircuit.copy, evm_circuit/typing.py:1010-1091), with the rw-table memory rows and tx-table
+    calldata rows they look up.  Returns copy [20][2*n_events*length][4] (+copy_flags), rw [14][..]
+    (+rw_flags), tx [5][..] (+tx_flags), bytecode [6][0], r."""
+    rng = np.random.default_rng(seed)
+    L = length
+    n_sha = n_events // 2
+    n_cdc = n_events - n_sha
+    n_rows = 2 * n_events * L
+    C = np.zeros((20, n_rows, 4), dtype=np.uint64)
+    data = rng.integers(0, 256, (n_events, L), dtype=np.uint64)
+    i_idx = np.arange(L, dtype=np.uint64)
+    rw_rows = []
+    tx_rows = []
+    rwc = 1
+    pos = 0
+
+    def put(col, sl, vals):
+        C[col, sl, 0] = vals
+
+    for e in range(n_events):
+        is_sha = e < n_sha
+        rd = slice(pos, pos + 2 * L, 2)
+        wr = slice(pos + 1, pos + 2 * L, 2)
+        ev = slice(pos, pos + 2 * L)
+        b = data[e].copy()
+        put(0, rd, 1)  # q_step
+        C[1, pos, 0] = 1  # is_first
+        C[2, pos + 2 * L - 1, 0] = 1  # is_last
+        put(8, rd, np.uint64(L) - i_idx)  # bytes_left
+        if is_sha:
+            call_id, src = 1 + e, 64 * e
+            put(3, ev, call_id)
+            put(5, rd, 2); put(5, wr, 5)  # Memory -> RlcAcc
+            put(6, rd, np.uint64(src) + i_idx); put(6, wr, i_idx)
+            put(7, rd, src + L)
+            put(9, rd, b)
+            acc, accs = 0, []
+            for v in b.tolist():
+                acc = (acc * r + int(v)) % FR_P
+                accs.append(acc)
+            cells = ints_to_cells(accs)
+            C[9, wr, :] = cells
+            C[10, ev, :] = cells[-1]
+            put(13, rd, np.uint64(rwc) + i_idx); put(13, wr, np.uint64(rwc) + i_idx + np.uint64(1))
+            put(14, rd, np.uint64(L) - i_idx); put(14, wr, np.uint64(L) - i_idx - np.uint64(1))
+            put(15, rd, 1); put(19, wr, 1)
+            rw_rows.append(np.stack([np.uint64(rwc) + i_idx, np.zeros(L, np.uint64), np.full(L, 9, np.uint64),
+                                     np.full(L, call_id, np.uint64), np.uint64(src) + i_idx, b]))
+            rwc += L
+        else:
+            tx_id, call_id, dst = 1 + (e - n_sha), 1 + e, 32 * e
+            n_real = L - L // 10  # the last 10 % read past the end of calldata
+            b[n_real:] = 0
+            put(3, rd, tx_id); put(3, wr, call_id)
+            put(5, rd, 3); put(5, wr, 2)  # TxCalldata -> Memory
+            put(6, rd, i_idx); put(6, wr, np.uint64(dst) + i_idx)
+            put(7, rd, n_real)
+            put(9, ev, np.repeat(b, 2))
+            put(12, rd, (i_idx >= np.uint64(n_real)).astype(np.uint64))  # is_pad
+            put(13, ev, np.repeat(np.uint64(rwc) + i_idx, 2))
+            put(14, ev, np.repeat(np.uint64(L) - i_idx, 2))
+            put(17, rd, 1); put(15, wr, 1)
+            rw_rows.append(np.stack([np.uint64(rwc) + i_idx, np.ones(L, np.uint64), np.full(L, 9, np.uint64),
+                                     np.full(L, call_id, np.uint64), np.uint64(dst) + i_idx, b]))
+            tx_rows.append(np.stack([np.full(n_real, tx_id, np.uint64), np.full(n_real, 13, np.uint64),
+                                     i_idx[:n_real], b[:n_real]]))
+            rwc += L
+        pos += 2 * L
+    RWs = np.concatenate(rw_rows, axis=1) if rw_rows else np.zeros((6, 0), np.uint64)
+    rw = np.zeros((14, RWs.shape[1], 4), dtype=np.uint64)
+    rw[0, :, 0], rw[1, :, 0], rw[2, :, 0], rw[3, :, 0], rw[4, :, 0], rw[8, :, 0] = RWs
+    TXs = np.concatenate(tx_rows, axis=1) if tx_rows else np.zeros((4, 0), np.uint64)
+    tx = np.zeros((5, TXs.shape[1], 4), dtype=np.uint64)
+    tx[0, :, 0], tx[1, :, 0], tx[2, :, 0], tx[3, :, 0] = TXs
+    return {"copy": C, "copy_flags": np.zeros(n_rows, np.uint8), "rw": rw, "rw_flags": np.zeros(rw.shape[1], np.uint8),
+            "tx": tx, "tx_flags": np.zeros(tx.shape[1], np.uint8), "bytecode": np.zeros((6, 0, 4), np.uint64),
+            "r": np.array([(r >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)}
