@@ -164,7 +164,7 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) k_check_copy(WitnessDev w, CheckRange rg, CopyTables t, Fr r_mont,
+__global__ void __launch_bounds__(128, 4) k_check_copy(WitnessDev w, CheckRange rg, CopyTables t, Fr r_mont,
                                                     ResultDev res) {
   const u64 n = rg.row_end - rg.row_begin;
   const u64 stride = (u64)gridDim.x * blockDim.x;
