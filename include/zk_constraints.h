@@ -136,6 +136,55 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   /* POP: execution/pop.py:4-14 */                                                          \
   X(EV_POP_RW_UNSAT, ZKE_UNSAT, "pop.py:7 stack_pop unsat")                                 \
   X(EV_POP_RW_AMBIG, ZKE_AMBIG, "pop.py:7 stack_pop ambiguous")                             \
+  /* SHA3: execution/sha3.py:6-55 */                                                        \
+  X(EV_SHA_OFF_UNSAT, ZKE_UNSAT, "sha3.py:10 stack_pop offset unsat")                       \
+  X(EV_SHA_OFF_AMBIG, ZKE_AMBIG, "sha3.py:10 stack_pop offset ambiguous")                   \
+  X(EV_SHA_SIZE_UNSAT, ZKE_UNSAT, "sha3.py:12 stack_pop size unsat")                        \
+  X(EV_SHA_SIZE_AMBIG, ZKE_AMBIG, "sha3.py:12 stack_pop size ambiguous")                    \
+  X(EV_SHA_VAL_UNSAT, ZKE_UNSAT, "sha3.py:14 stack_push unsat")                             \
+  X(EV_SHA_VAL_AMBIG, ZKE_AMBIG, "sha3.py:14 stack_push ambiguous")                         \
+  X(EV_SHA_LEN_BYTES, ZKE_VALUE, "instruction.py:1123,481 to_le_bytes(size): half >= 2^128 -> OverflowError") \
+  X(EV_SHA_LEN_RANGE, ZKE_RANGE, "instruction.py:1123,482-483 size does not fit 5 bytes")   \
+  X(EV_SHA_OFF_BYTES, ZKE_VALUE, "instruction.py:1126,481 to_le_bytes(offset) -> OverflowError") \
+  X(EV_SHA_OFF_RANGE, ZKE_RANGE, "instruction.py:1126,482-483 offset does not fit 5 bytes") \
+  X(EV_SHA_COPY_UNSAT, ZKE_UNSAT, "sha3.py:20-30 copy_table lookup unsat")                  \
+  X(EV_SHA_COPY_AMBIG, ZKE_AMBIG, "sha3.py:20-30 copy_table lookup ambiguous")              \
+  X(EV_SHA_KECCAK_UNSAT, ZKE_UNSAT, "sha3.py:34 keccak_table lookup unsat")                 \
+  X(EV_SHA_KECCAK_AMBIG, ZKE_AMBIG, "sha3.py:34 keccak_table lookup ambiguous")             \
+  X(EV_SHA_HASH_EQ, ZKE_ASSERT, "sha3.py:35-38 keccak output == pushed word")               \
+  X(EV_SHA_MEMSIZE_RANGE, ZKE_RANGE, "instruction.py:1164-1166 memory word size does not fit 4 bytes") \
+  X(EV_SHA_MAX_RANGE, ZKE_ASSERT, "instruction.py:1167-1169,449-450 max(): operand exceeds 4 bytes") \
+  X(EV_SHA_WORDSIZE_RANGE, ZKE_RANGE, "instruction.py:1189 copy word size does not fit 4 bytes") \
+  X(EV_SHA_GASCOST_RANGE, ZKE_RANGE, "instruction.py:1191 copier gas cost does not fit 8 bytes") \
+  /* CALLDATACOPY: execution/calldatacopy.py:6-62 */                                        \
+  X(EV_CDC_MOFF_UNSAT, ZKE_UNSAT, "calldatacopy.py:9 stack_pop memory_offset unsat")        \
+  X(EV_CDC_MOFF_AMBIG, ZKE_AMBIG, "calldatacopy.py:9 stack_pop memory_offset ambiguous")    \
+  X(EV_CDC_DOFF_UNSAT, ZKE_UNSAT, "calldatacopy.py:10 stack_pop data_offset unsat")         \
+  X(EV_CDC_DOFF_AMBIG, ZKE_AMBIG, "calldatacopy.py:10 stack_pop data_offset ambiguous")     \
+  X(EV_CDC_LEN_UNSAT, ZKE_UNSAT, "calldatacopy.py:11 stack_pop length unsat")               \
+  X(EV_CDC_LEN_AMBIG, ZKE_AMBIG, "calldatacopy.py:11 stack_pop length ambiguous")           \
+  X(EV_CDC_LEN_BYTES, ZKE_VALUE, "calldatacopy.py:14 to_le_bytes(length) -> OverflowError") \
+  X(EV_CDC_LEN_RANGE, ZKE_RANGE, "calldatacopy.py:14 length does not fit 5 bytes")          \
+  X(EV_CDC_MOFF_BYTES, ZKE_VALUE, "calldatacopy.py:14 to_le_bytes(memory_offset) -> OverflowError") \
+  X(EV_CDC_MOFF_RANGE, ZKE_RANGE, "calldatacopy.py:14 memory_offset does not fit 5 bytes")  \
+  X(EV_CDC_DOFF_BYTES, ZKE_VALUE, "calldatacopy.py:15 to_le_bytes(data_offset) -> OverflowError") \
+  X(EV_CDC_DOFF_RANGE, ZKE_RANGE, "calldatacopy.py:15 data_offset does not fit 5 bytes")    \
+  X(EV_CDC_CC1_UNSAT, ZKE_UNSAT, "calldatacopy.py:18,24 call_context lookup (TxId | CallerId) unsat") \
+  X(EV_CDC_CC1_AMBIG, ZKE_AMBIG, "calldatacopy.py:18,24 call_context lookup ambiguous")     \
+  X(EV_CDC_CC1_TYPE, ZKE_ASSERT, "instruction.py:880 .value(): call-context value is a Word") \
+  X(EV_CDC_CC2_UNSAT, ZKE_UNSAT, "calldatacopy.py:19,25 call_context lookup CallDataLength unsat") \
+  X(EV_CDC_CC2_AMBIG, ZKE_AMBIG, "calldatacopy.py:19,25 call_context lookup ambiguous")     \
+  X(EV_CDC_CC2_TYPE, ZKE_ASSERT, "instruction.py:880 .value(): call-context value is a Word") \
+  X(EV_CDC_CC3_UNSAT, ZKE_UNSAT, "calldatacopy.py:28 call_context lookup CallDataOffset unsat") \
+  X(EV_CDC_CC3_AMBIG, ZKE_AMBIG, "calldatacopy.py:28 call_context lookup ambiguous")        \
+  X(EV_CDC_CC3_TYPE, ZKE_ASSERT, "instruction.py:880 .value(): call-context value is a Word") \
+  X(EV_CDC_MEMSIZE_RANGE, ZKE_RANGE, "instruction.py:1164-1166 memory word size does not fit 4 bytes") \
+  X(EV_CDC_MAX_RANGE, ZKE_ASSERT, "instruction.py:1167-1169 max(): operand exceeds 4 bytes") \
+  X(EV_CDC_WORDSIZE_RANGE, ZKE_RANGE, "instruction.py:1189 copy word size does not fit 4 bytes") \
+  X(EV_CDC_GASCOST_RANGE, ZKE_RANGE, "instruction.py:1191 copier gas cost does not fit 8 bytes") \
+  X(EV_CDC_SELECT_BOOL, ZKE_ASSERT, "calldatacopy.py:37-39 select(): is_root is not boolean") \
+  X(EV_CDC_COPY_UNSAT, ZKE_UNSAT, "calldatacopy.py:41-51 copy_table lookup unsat")          \
+  X(EV_CDC_COPY_AMBIG, ZKE_AMBIG, "calldatacopy.py:41-51 copy_table lookup ambiguous")      \
   /* shared epilogue: step_state_transition_in_same_context, instruction.py:365-394 */      \
   X(EV_SC_RESP_OPCODE, ZKE_UNSAT, "instruction.py:376,779-782 ResponsibleOpcode fixed lookup") \
   X(EV_SC_OPCODE_VALUE, ZKE_VALUE, "instruction.py:378 Opcode(opcode.n): not a valid opcode -> ValueError") \

@@ -36,7 +36,8 @@ static const fr_t INV_2_128 = {{0x18ee753c76f9dc6full, 0x54ad7e14a329e70full, 0x
 
 typedef struct {
   const uint64_t* steps; uint64_t n_steps;
-  orc_index bytecode_ix, rw_ix, fixed_ix;
+  orc_index bytecode_ix, rw_ix, fixed_ix, copy_ix, keccak_ix;
+  const uint8_t* rw_flags; /* bit0: value.is_word */
   orc_result* res;
 } evm_env;
 
@@ -102,8 +103,16 @@ static word_t u256_to_word(const uint64_t v[4]) { word_t w = {fr_u128(v[0], v[1]
 static int word_in_domain(word_t w) { return fr_fits_bits(w.lo, 128) && fr_fits_bits(w.hi, 128); }
 
 /* shared epilogue: instruction.py:365-394 */
+/* general form: rw_counter delta is a field element, memory_word_size either stays or moves To a
+ * value, and a dynamic gas cost is added to the opcode's constant cost */
+static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                           int mem_to, fr_t mem_value, fr_t dyn_gas);
 static void same_context(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint64_t d_rwc, fr_t d_pc,
                          fr_t d_sp) {
+  same_context_x(e, i, row, opcode, fr_u64(d_rwc), d_pc, d_sp, 0, fr_u64(0), fr_u64(0));
+}
+static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                           int mem_to, fr_t mem_value, fr_t dyn_gas) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
 #define CUR(c) fr_load(ORC_CELL(S, n, c, i))
 #define NXT(c) fr_load(ORC_CELL(S, n, c, j))
@@ -112,13 +121,13 @@ static void same_context(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint
   int gas_cost = -1;
   if (fr_fits_bits(opcode, 8)) gas_cost = OPCODE_GAS[opcode.l[0]];
   if (gas_cost < 0) { orc_fail(e->res, EV_SC_OPCODE_VALUE, row); return; }
-  fr_t gas_after = fr_sub(CUR(S_GAS), fr_u64((uint64_t)gas_cost));
+  fr_t gas_after = fr_sub(CUR(S_GAS), fr_add(fr_u64((uint64_t)gas_cost), dyn_gas));
   CHECK(EV_SC_GAS_RANGE, fr_fits_bits(gas_after, 64));
-  CHECK(EV_SC_RWC, fr_eq(NXT(S_RWC), fr_add(CUR(S_RWC), fr_u64(d_rwc))));
+  CHECK(EV_SC_RWC, fr_eq(NXT(S_RWC), fr_add(CUR(S_RWC), d_rwc)));
   CHECK(EV_SC_PC, fr_eq(NXT(S_PC), fr_add(CUR(S_PC), d_pc)));
   CHECK(EV_SC_SP, fr_eq(NXT(S_SP), fr_add(CUR(S_SP), d_sp)));
   CHECK(EV_SC_GAS, fr_eq(NXT(S_GAS), gas_after));
-  CHECK(EV_SC_MEM, fr_eq(NXT(S_MEM), CUR(S_MEM)));
+  CHECK(EV_SC_MEM, fr_eq(NXT(S_MEM), mem_to ? mem_value : CUR(S_MEM)));
   CHECK(EV_SC_REV, fr_eq(NXT(S_REV), CUR(S_REV)));
   CHECK(EV_SC_LOG, fr_eq(NXT(S_LOG), CUR(S_LOG)));
   CHECK(EV_SC_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
@@ -289,6 +298,135 @@ static void gadget_pop(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   same_context(e, i, row, opcode, 1, fr_u64(1), fr_u64(1));
 }
 
+
+/* ---- helpers of the copy gadgets ------------------------------------------------------------ */
+/* word_to_fq(word, 5): 0 ok, 1 -> to_le_bytes OverflowError, 2 -> ConstraintUnsatFailure
+ * (instruction.py:480-484) */
+static int word_to_fq5(word_t w, fr_t* out) {
+  if (!word_in_domain(w)) return 1;
+  if ((w.lo.l[0] >> 40) || w.lo.l[1] || w.hi.l[0] || w.hi.l[1]) return 2;
+  *out = fr_u64(w.lo.l[0]);
+  return 0;
+}
+/* memory_gas_cost(size) for size < 2^32: size^2 // 512 + 3 size (instruction.py:1129-1136) */
+static uint64_t memory_gas_cost(uint64_t size) { return size * size / 512 + 3 * size; }
+/* memory_expansion_dynamic_length + memory_copier_gas_cost (instruction.py:1157-1192); returns the
+ * failing id offset 0..3 (+1) or 0; ids are base_id + {MEMSIZE, MAX, WORDSIZE, GASCOST} */
+static int copier_gas(evm_env* e, uint64_t i, uint64_t offset, uint64_t length, uint64_t per_word,
+                      fr_t* next_mem, fr_t* gas) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const uint64_t cd_size = (offset + length + 31) / 32; /* offset, length < 2^40 */
+  if (cd_size >> 32) return 1;
+  const fr_t cur = CUR(S_MEM);
+  if (!fr_fits_bits(cur, 32)) return 2;
+  const uint64_t nxt = cur.l[0] < cd_size ? cd_size : cur.l[0];
+  const uint64_t expansion = memory_gas_cost(nxt) - memory_gas_cost(cur.l[0]);
+  const uint64_t words = (length + 31) / 32;
+  if (words >> 32) return 3;
+  const u128 g = (u128)words * per_word + expansion;
+  if (g >> 64) return 4;
+  *next_mem = fr_u64(nxt); *gas = fr_u64((uint64_t)g);
+  return 0;
+}
+static int copy_lookup(evm_env* e, fr_t src_id, uint64_t src_tag, fr_t dst_id, uint64_t dst_tag, fr_t src_addr,
+                       fr_t src_end, fr_t dst_addr, fr_t length, fr_t rwc, fr_t* rwc_inc, fr_t* rlc_acc) {
+  /* copy-table cells: is_first, src_id lo/hi, src_tag, dst_id lo/hi, dst_tag, src_addr, src_addr_end,
+   * dst_addr, length, rlc_acc, rw_counter, rwc_inc; ids are values here (hi = 0) */
+  fr_t key[11] = {src_id, fr_u64(0), fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end,
+                  dst_addr, length, rwc};
+  uint32_t row; const int n = orc_lookup(&e->copy_ix, key, &row);
+  if (n == 1) {
+    *rlc_acc = fr_load(ORC_CELL(e->copy_ix.cells, e->copy_ix.n_rows, 11, row));
+    *rwc_inc = fr_load(ORC_CELL(e->copy_ix.cells, e->copy_ix.n_rows, 13, row));
+  }
+  return n;
+}
+
+static void gadget_sha3(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t off_w, size_w, val_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &off_w), EV_SHA_OFF_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &size_w), EV_SHA_SIZE_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &val_w), EV_SHA_VAL_UNSAT, row)) return;
+  fr_t length, offset = fr_u64(0);
+  int rc = word_to_fq5(size_w, &length);
+  if (rc) { orc_fail(e->res, rc == 1 ? EV_SHA_LEN_BYTES : EV_SHA_LEN_RANGE, row); return; }
+  if (!fr_is_zero(length)) {
+    rc = word_to_fq5(off_w, &offset);
+    if (rc) { orc_fail(e->res, rc == 1 ? EV_SHA_OFF_BYTES : EV_SHA_OFF_RANGE, row); return; }
+  }
+  fr_t rwc_inc = fr_u64(0), rlc_acc = fr_u64(0);
+  if (!fr_is_zero(length)) {
+    if (!need1(e, copy_lookup(e, call_id, ZK_COPY_Memory, call_id, ZK_COPY_RlcAcc, offset, fr_add(offset, length),
+                              fr_u64(0), length, fr_add(rwc, fr_u64(3)), &rwc_inc, &rlc_acc), EV_SHA_COPY_UNSAT, row)) return;
+  }
+  { /* keccak_lookup(length, rlc_acc): key (state_tag=2, input_rlc, input_len) */
+    fr_t key[3] = {fr_u64(2), rlc_acc, length};
+    uint32_t hit; const int nk = orc_lookup(&e->keccak_ix, key, &hit);
+    if (!need1(e, nk, EV_SHA_KECCAK_UNSAT, row)) return;
+    CHECK(EV_SHA_HASH_EQ, fr_eq(fr_load(ORC_CELL(e->keccak_ix.cells, e->keccak_ix.n_rows, 3, hit)), val_w.lo) &&
+                              fr_eq(fr_load(ORC_CELL(e->keccak_ix.cells, e->keccak_ix.n_rows, 4, hit)), val_w.hi));
+  }
+  fr_t next_mem, gas;
+  rc = copier_gas(e, i, offset.l[0], length.l[0], ZK_GAS_COST_COPY_SHA3, &next_mem, &gas);
+  if (rc) { orc_fail(e->res, EV_SHA_MEMSIZE_RANGE + rc - 1, row); return; }
+  same_context_x(e, i, row, opcode, fr_add(fr_u64(3), rwc_inc), one, one, 1, next_mem, gas);
+}
+
+/* call_context_lookup(field_tag) at rw_counter + k: rw row (Read, CallContext, call_id, address = tag) */
+static int call_context(evm_env* e, fr_t rwc, fr_t call_id, uint64_t field_tag, fr_t* value, int* is_word) {
+  fr_t key[5] = {rwc, fr_u64(0), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
+  uint32_t r; const int n = orc_lookup(&e->rw_ix, key, &r);
+  if (n == 1) {
+    *value = fr_load(ORC_CELL(e->rw_ix.cells, e->rw_ix.n_rows, R_VAL_LO, r));
+    *is_word = e->rw_flags ? (e->rw_flags[r] & 1) : 0;
+  }
+  return n;
+}
+
+static void gadget_calldatacopy(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t moff_w, doff_w, len_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &moff_w), EV_CDC_MOFF_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &doff_w), EV_CDC_DOFF_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(2)), &len_w), EV_CDC_LEN_UNSAT, row)) return;
+  fr_t length, moff = fr_u64(0), doff;
+  int rc = word_to_fq5(len_w, &length);
+  if (rc) { orc_fail(e->res, rc == 1 ? EV_CDC_LEN_BYTES : EV_CDC_LEN_RANGE, row); return; }
+  if (!fr_is_zero(length)) {
+    rc = word_to_fq5(moff_w, &moff);
+    if (rc) { orc_fail(e->res, rc == 1 ? EV_CDC_MOFF_BYTES : EV_CDC_MOFF_RANGE, row); return; }
+  }
+  rc = word_to_fq5(doff_w, &doff);
+  if (rc) { orc_fail(e->res, rc == 1 ? EV_CDC_DOFF_BYTES : EV_CDC_DOFF_RANGE, row); return; }
+  const fr_t is_root = CUR(S_IS_ROOT);
+  const int root = !fr_is_zero(is_root); /* Python truthiness of the is_root attribute */
+  fr_t src_id, cd_len, cd_off = fr_u64(0);
+  int w;
+  uint64_t k = 3;
+  if (!need1(e, call_context(e, fr_add(rwc, fr_u64(k)), call_id, root ? ZK_CC_TxId : ZK_CC_CallerId, &src_id, &w), EV_CDC_CC1_UNSAT, row)) return;
+  CHECK(EV_CDC_CC1_TYPE, !w); k++;
+  if (!need1(e, call_context(e, fr_add(rwc, fr_u64(k)), call_id, ZK_CC_CallDataLength, &cd_len, &w), EV_CDC_CC2_UNSAT, row)) return;
+  CHECK(EV_CDC_CC2_TYPE, !w); k++;
+  if (!root) {
+    if (!need1(e, call_context(e, fr_add(rwc, fr_u64(k)), call_id, ZK_CC_CallDataOffset, &cd_off, &w), EV_CDC_CC3_UNSAT, row)) return;
+    CHECK(EV_CDC_CC3_TYPE, !w); k++;
+  }
+  fr_t next_mem, gas;
+  rc = copier_gas(e, i, moff.l[0], length.l[0], ZK_GAS_COST_COPY, &next_mem, &gas);
+  if (rc) { orc_fail(e->res, EV_CDC_MEMSIZE_RANGE + rc - 1, row); return; }
+  CHECK(EV_CDC_SELECT_BOOL, fr_eq_u64(is_root, 0) || fr_eq_u64(is_root, 1));
+  fr_t rwc_inc = fr_u64(0), unused;
+  if (!fr_is_zero(length)) {
+    if (!need1(e, copy_lookup(e, src_id, root ? ZK_COPY_TxCalldata : ZK_COPY_Memory, call_id, ZK_COPY_Memory,
+                              fr_add(cd_off, doff), fr_add(cd_off, cd_len), moff, length, fr_add(rwc, fr_u64(k)),
+                              &rwc_inc, &unused), EV_CDC_COPY_UNSAT, row)) return;
+  }
+  same_context_x(e, i, row, opcode, fr_add(fr_u64(k), rwc_inc), one, fr_u64(3), 1, next_mem, gas);
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -314,20 +452,36 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   }
   CHECK(EV_NOT_IMPLEMENTED, fr_fits_bits(cs, 16) && cs.l[0] < ZK_ES_COUNT && ES_IMPL[cs.l[0]]);
   const uint64_t st = cs.l[0];
-  CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP);
+  CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP ||
+                                  st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY);
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
     return;
   if (st == ZK_ES_ADD) gadget_add(e, i, row, opcode);
   else if (st == ZK_ES_MUL) gadget_mul(e, i, row, opcode);
   else if (st == ZK_ES_PUSH) gadget_push(e, i, row, opcode);
+  else if (st == ZK_ES_SHA3) gadget_sha3(e, i, row, opcode);
+  else if (st == ZK_ES_CALLDATACOPY) gadget_calldatacopy(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 
+int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
+                    const uint64_t* rw_tab, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed_tab,
+                    uint64_t n_fixed, const uint64_t* copy_tab, uint64_t n_copy, const uint64_t* keccak_tab,
+                    uint64_t n_keccak, uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                    uint32_t* first_fail, uint64_t* fail_count);
 int orc_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
                   const uint64_t* rw_tab, uint64_t n_rw, const uint64_t* fixed_tab, uint64_t n_fixed,
                   uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
                   uint32_t* first_fail, uint64_t* fail_count) {
+  return orc_check_evm_x(steps, n_steps, bytecode_tab, n_bytecode, rw_tab, n_rw, 0, fixed_tab, n_fixed, 0, 0, 0, 0,
+                         row_begin, row_end, row_base, flags, first_fail, fail_count);
+}
+int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
+                    const uint64_t* rw_tab, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed_tab,
+                    uint64_t n_fixed, const uint64_t* copy_tab, uint64_t n_copy, const uint64_t* keccak_tab,
+                    uint64_t n_keccak, uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                    uint32_t* first_fail, uint64_t* fail_count) {
   orc_result res; orc_result_init(&res, first_fail, fail_count, EV_N_CONSTRAINTS);
   if (row_end + 1 > n_steps && row_end > row_begin) return -1;
   evm_env env; env.steps = steps; env.n_steps = n_steps; env.res = &res;
@@ -335,7 +489,12 @@ int orc_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytec
   orc_index_build(&env.bytecode_ix, bytecode_tab, n_bytecode, 6, bk, 5);
   orc_index_build(&env.rw_ix, rw_tab, n_rw, 14, rk, 5);
   orc_index_build(&env.fixed_ix, fixed_tab, n_fixed, 4, fk, 4);
+  const uint32_t ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
+  orc_index_build(&env.copy_ix, copy_tab, n_copy, 14, ck, 11);
+  orc_index_build(&env.keccak_ix, keccak_tab, n_keccak, 5, kk, 3);
+  env.rw_flags = rw_flags;
   for (uint64_t i = row_begin; i < row_end; i++) verify_step(&env, i, row_base + i, flags);
   orc_index_free(&env.bytecode_ix); orc_index_free(&env.rw_ix); orc_index_free(&env.fixed_ix);
+  orc_index_free(&env.copy_ix); orc_index_free(&env.keccak_ix);
   return 0;
 }

@@ -70,10 +70,23 @@ static void init_result(ResultDev& res, uint32_t* ff, uint64_t* fc, int n) {
   res.fail_count = (u64*)fc;
 }
 
+extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode, uint64_t n_bytecode,
+                               const uint64_t* rw, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed,
+                               uint64_t n_fixed, const uint64_t* copy, uint64_t n_copy, const uint64_t* keccak,
+                               uint64_t n_keccak, uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                               const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count);
 extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode, uint64_t n_bytecode,
                              const uint64_t* rw, uint64_t n_rw, const uint64_t* fixed, uint64_t n_fixed,
                              uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
                              const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  return emu_check_evm_x(steps, n_steps, bytecode, n_bytecode, rw, n_rw, nullptr, fixed, n_fixed, nullptr, 0, nullptr, 0,
+                         row_begin, row_end, row_base, flags, challenge, first_fail, fail_count);
+}
+extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode, uint64_t n_bytecode,
+                               const uint64_t* rw, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed,
+                               uint64_t n_fixed, const uint64_t* copy, uint64_t n_copy, const uint64_t* keccak,
+                               uint64_t n_keccak, uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
+                               const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
   std::vector<u64> s1, s2, s3;
@@ -81,6 +94,11 @@ extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
   t.fixed = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, s3);
+  t.rw.tab.flags = rw_flags;
+  const u32 ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
+  std::vector<u64> s4, s5;
+  t.copy = build_index((const u64*)copy, n_copy, 14, ck, 11, ch, s4);
+  t.keccak = build_index((const u64*)keccak, n_keccak, 5, kk, 3, ch, s5);
   PosState p_bc, p_rw;
   if (g_emu_positional) {
     add_positional(t.bytecode, ZK_POS_RUNS, p_bc);

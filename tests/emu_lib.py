@@ -107,3 +107,22 @@ def check_state(rows, flags, mpt, row_begin=0, row_end=None, cflags=1, challenge
 def set_positional(on: bool) -> None:
     """toggle the positional (regular-table) lookup fast paths in the emulation; off = hash index only"""
     ctypes.c_int.in_dll(lib(), "g_emu_positional").value = int(on)
+
+
+def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=256, challenge=None):
+    m = {k: np.ascontiguousarray(w[k]) for k in ("steps", "bytecode", "rw", "copy", "keccak")}
+    fixed = np.ascontiguousarray(fixed)
+    rwf = np.ascontiguousarray(w["rw_flags"], dtype=np.uint8)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    if row_end is None:
+        row_end = m["steps"].shape[1] - 1
+    p8 = rwf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if len(rwf) else None
+    rc = lib().emu_check_evm_x(_p(m["steps"]), c(m["steps"].shape[1]), _p(m["bytecode"]), c(m["bytecode"].shape[1]),
+                               _p(m["rw"]), c(m["rw"].shape[1]), p8, _p(fixed), c(fixed.shape[1]), _p(m["copy"]),
+                               c(m["copy"].shape[1]), _p(m["keccak"]), c(m["keccak"].shape[1]), c(row_begin), c(row_end),
+                               c(row_base), ctypes.c_uint32(flags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

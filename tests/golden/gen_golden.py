@@ -811,11 +811,190 @@ def synth_cases():
     print("synth.copy_events(4, 20): accepted by the reference's verify_copy_table,", len(crow), "rows")
 
 
+# --------------------------------------------------------------------------- evm2: SHA3 / CALLDATACOPY
+def evm2_cases():
+    """SHA3 and CALLDATACOPY steps built like the reference's tests (tests/evm/test_sha3.py:35-141,
+    tests/evm/test_calldatacopy.py:42-164) with their copy-table and keccak-table rows, verified by the
+    reference's verify_step; corruptions of step cells, rw rows (+ type flags), copy-table and
+    keccak-table cells."""
+    from zkevm_specs.evm_circuit import (Block, Bytecode, CallContextFieldTag, CopyCircuit, CopyDataTypeTag,
+                                         CopyTableRow, ExecutionState, KeccakCircuit, KeccakTableRow, Opcode,
+                                         RWDictionary, RWTableRow, BytecodeTableRow, StepState, Tables)
+    from zkevm_specs.evm_circuit.instruction import Instruction
+    from zkevm_specs.evm_circuit.main import verify_step
+    from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
+
+    r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
+    rng = random.Random(5)
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wov(lo, hi, is_word):
+        return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    def mws(a):
+        return (a + 31) // 32
+
+    def mem_exp(cur, addr):
+        nxt = max(mws(addr), cur)
+        return nxt, (nxt - cur) * 3 + (nxt * nxt // 512 - cur * cur // 512)
+
+    def sha3_case(offset, length):
+        mem = bytes(rng.randrange(256) for _ in range(offset + length))
+        src = {i: mem[i] for i in range(offset, offset + length)}
+        bc = Bytecode().push(offset, n_bytes=32).push(length, n_bytes=32).sha3().stop()
+        h = Word(bc.hash())
+        out = Word(int.from_bytes(keccak256(mem[offset:offset + length]), "big"))
+        nxt, exp = mem_exp(mws(offset + length), offset + length)
+        gas = Opcode.SHA3.constant_gas_cost() + exp + mws(length) * GAS_COST_COPY_SHA3
+        rw = (RWDictionary(1).stack_write(1, 1023, Word(length)).stack_write(1, 1022, Word(offset))
+              .stack_read(1, 1022, Word(offset)).stack_read(1, 1023, Word(length)).stack_write(1, 1023, out))
+        cc = CopyCircuit().copy(r, rw, 1, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.RlcAcc, offset, offset + length,
+                                FQ.zero(), length, src)
+        kc = KeccakCircuit().add(mem[offset:offset + length], r)
+        steps = [StepState(ExecutionState.SHA3, rw_counter=3, call_id=1, is_root=True, code_hash=h, program_counter=66,
+                           stack_pointer=1022, memory_word_size=nxt, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, code_hash=h,
+                           program_counter=67, stack_pointer=1023, memory_word_size=nxt, gas_left=0)]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), copy_circuit=cc.rows, keccak_table=kc.rows)
+        return steps, list(bc.table_assignments()), list(rw.rws), list(t.copy_table), list(kc.rows)
+
+    def cdc_case(cd_len, data_off, mem_off, length, from_tx, cd_off):
+        bc = Bytecode().calldatacopy(mem_off, data_off, length)
+        h = Word(bc.hash())
+        call_data = bytes(rng.randrange(256) for _ in range(cd_len))
+        cur = mws(0 if from_tx else cd_off + cd_len)
+        nxt, exp = mem_exp(cur, mem_off + length if length else 0)
+        gas = Opcode.CALLDATACOPY.constant_gas_cost() + exp + mws(length) * GAS_COST_COPY
+        rw = (RWDictionary(1).stack_read(1, 1021, Word(mem_off)).stack_read(1, 1022, Word(data_off))
+              .stack_read(1, 1023, Word(length)))
+        if from_tx:
+            rw.call_context_read(1, CallContextFieldTag.TxId, 13).call_context_read(1, CallContextFieldTag.CallDataLength, cd_len)
+        else:
+            (rw.call_context_read(1, CallContextFieldTag.CallerId, 0).call_context_read(1, CallContextFieldTag.CallDataLength, cd_len)
+             .call_context_read(1, CallContextFieldTag.CallDataOffset, cd_off))
+        src = {cd_off + i: call_data[i] for i in range(data_off, min(data_off + length, len(call_data)))}
+        cc = CopyCircuit().copy(r, rw, 13 if from_tx else 0, CopyDataTypeTag.TxCalldata if from_tx else CopyDataTypeTag.Memory,
+                                1, CopyDataTypeTag.Memory, data_off + cd_off, cd_len + cd_off, mem_off, length, src)
+        steps = [StepState(ExecutionState.CALLDATACOPY, rw_counter=1, call_id=1, is_root=from_tx, code_hash=h,
+                           program_counter=99, stack_pointer=1021, memory_word_size=cur, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=from_tx, code_hash=h,
+                           program_counter=100, stack_pointer=1024, memory_word_size=nxt, gas_left=0)]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return steps, list(bc.table_assignments()), list(rw.rws), list(t.copy_table), []
+
+    def step_ints(s):
+        return [int(s.execution_state), n_of(s.rw_counter), n_of(s.call_id), int(s.is_root), int(s.is_create),
+                n_of(s.code_hash.lo), n_of(s.code_hash.hi), n_of(s.program_counter), n_of(s.stack_pointer),
+                n_of(s.gas_left), n_of(s.memory_word_size), n_of(s.reversible_write_counter), n_of(s.log_id)]
+
+    def step_from(v):
+        s = StepState(ExecutionState(v[0]), rw_counter=0)
+        s.rw_counter, s.call_id, s.is_root, s.is_create = FQ(v[1]), FQ(v[2]), v[3], v[4]
+        s.code_hash = W(v[5], v[6])
+        s.program_counter, s.stack_pointer, s.gas_left = FQ(v[7]), FQ(v[8]), FQ(v[9])
+        s.memory_word_size, s.reversible_write_counter, s.log_id = FQ(v[10]), FQ(v[11]), FQ(v[12])
+        return s
+
+    def bc_ints(x):
+        return [n_of(x.bytecode_hash.lo), n_of(x.bytecode_hash.hi), n_of(x.field_tag), n_of(x.index), n_of(x.is_code), n_of(x.value)]
+
+    def rw_ints(x):
+        return [n_of(x.rw_counter), n_of(x.rw), n_of(x.key0), n_of(x.id), n_of(x.address), n_of(x.field_tag),
+                n_of(x.storage_key.lo), n_of(x.storage_key.hi), n_of(x.value.lo), n_of(x.value.hi),
+                n_of(x.value_prev.lo), n_of(x.value_prev.hi), n_of(x.aux0.lo), n_of(x.aux0.hi)]
+
+    def copy_ints(x):
+        return [n_of(x.is_first), n_of(x.src_id.lo), n_of(x.src_id.hi), n_of(x.src_tag), n_of(x.dst_id.lo), n_of(x.dst_id.hi),
+                n_of(x.dst_tag), n_of(x.src_addr), n_of(x.src_addr_end), n_of(x.dst_addr), n_of(x.length), n_of(x.rlc_acc),
+                n_of(x.rw_counter), n_of(x.rwc_inc)]
+
+    def kec_ints(x):
+        return [n_of(x.state_tag), n_of(x.input_rlc), n_of(x.input_len), n_of(x.output.lo), n_of(x.output.hi)]
+
+    def run(S, B, R, RF, C, K):
+        steps = [step_from(v) for v in S]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(),
+                   bytecode_table=set(BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5])) for v in B),
+                   rw_table=set(RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
+                                           wov(v[8], v[9], f & 1), wov(v[10], v[11], (f >> 1) & 1), W(v[12], v[13]))
+                                for v, f in zip(R, RF)))
+        t.copy_table = set(CopyTableRow(FQ(v[0]), WordOrValue(W(v[1], v[2])), FQ(v[3]), WordOrValue(W(v[4], v[5])), FQ(v[6]),
+                                        FQ(v[7]), FQ(v[8]), FQ(v[9]), FQ(v[10]), FQ(v[11]), FQ(v[12]), FQ(v[13])) for v in C)
+        t.keccak_table = set(KeccakTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), W(v[3], v[4])) for v in K)
+        for idx, (cur, nxt) in enumerate(zip(steps, steps[1:])):
+            try:
+                verify_step(Instruction(tables=t, curr=cur, next=nxt, is_first_step=False, is_last_step=False))
+            except Exception as e:  # noqa: BLE001
+                return idx, type(e).__name__
+        return -1, ""
+
+    scenarios = {
+        "sha3_a": sha3_case(0x20, 0x40), "sha3_b": sha3_case(0x11, 0x23), "sha3_zero": sha3_case(0x202, 0),
+        "cdc_root": cdc_case(32, 5, 0xA0, 8, True, 0), "cdc_internal": cdc_case(32, 5, 0xA0, 8, False, 0x20),
+        "cdc_oob": cdc_case(32, 5, 0xA0, 45, True, 0), "cdc_zero": cdc_case(32, 5, 0xA0, 0, False, 0x20),
+    }
+    out = {"names": np.array(list(scenarios.keys()))}
+    tot = nfail = 0
+    for name, (steps, bcs, rws, cps, kcs) in scenarios.items():
+        S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
+        RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
+        C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
+        assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
+        muts = [(-1, 0, 0, 0, -1, "")]
+        for k in range(70):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4])
+            S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
+            if which == 0:
+                i, c = rng.randrange(len(S)), rng.choice([1, 2, 3, 7, 8, 9, 10, 10, 9, 5])
+                v = (1 - S[i][c]) if c == 3 else corrupt_value(rng, S[i][c])
+                S2[i][c] = v
+            elif which == 1:
+                i, c = rng.randrange(len(R)), rng.randrange(10)
+                if c == 9 and not (RF[i] & 1):
+                    continue
+                v = corrupt_value(rng, R[i][c]); R2[i][c] = v
+            elif which == 2:
+                i, c, v = rng.randrange(len(R)), 100, 0
+                RF2[i] ^= 1
+                if not RF2[i] & 1:
+                    R2[i][9] = 0
+            elif which == 3 and C:
+                i, c = rng.randrange(len(C)), rng.randrange(14)
+                if c in (2, 5):
+                    continue
+                v = corrupt_value(rng, C[i][c]); C2[i][c] = v
+            elif which == 4 and K:
+                i, c = rng.randrange(len(K)), rng.randrange(5)
+                v = corrupt_value(rng, K[i][c]); K2[i][c] = v
+            else:
+                continue
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2)
+            muts.append((which, i, c, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        for key, rows_, ncol in (("steps", S, 13), ("bytecode", B, 6), ("rw", R, 14), ("copy", C, 14), ("keccak", K, 5)):
+            out[f"{name}/{key}"] = to_matrix(rows_) if rows_ else np.zeros((ncol, 0, 4), dtype=np.uint64)
+        out[f"{name}/rw_flags"] = np.array(RF, dtype=np.uint8)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, len(R), "rw", len(C), "copy-table rows", len(K), "keccak rows", len(muts), "vectors")
+    np.savez_compressed(os.path.join(HERE, "evm2.npz"), **out)
+    print(f"evm2: {tot} corruptions, {nfail} failing")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

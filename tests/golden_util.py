@@ -106,3 +106,28 @@ def state_vectors():
                 s = S.copy(); s[:, [i, i + 1], :] = S[:, [i + 1, i], :]
                 f = F.copy(); f[[i, i + 1]] = F[[i + 1, i]]
             yield name, k, s, f, m, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def evm2_vectors():
+    """SHA3 / CALLDATACOPY steps: yield (case, k, dict(steps, bytecode, rw, rw_flags, copy, keccak), exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, "evm2.npz"))
+    for name in z["names"]:
+        name = str(name)
+        base = {k: z[f"{name}/{k}"] for k in ("steps", "bytecode", "rw", "rw_flags", "copy", "keccak")}
+        for k in range(len(z[f"{name}/mut_kind"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            val = z[f"{name}/mut_val"][k]
+            w = dict(base)
+            if kind == 0:
+                w["steps"] = base["steps"].copy(); w["steps"][c, i, :] = val
+            elif kind == 1:
+                w["rw"] = base["rw"].copy(); w["rw"][c, i, :] = val
+            elif kind == 2:
+                w["rw_flags"] = base["rw_flags"].copy(); w["rw_flags"][i] ^= 1
+                if not w["rw_flags"][i] & 1:
+                    w["rw"] = base["rw"].copy(); w["rw"][9, i, :] = 0
+            elif kind == 3:
+                w["copy"] = base["copy"].copy(); w["copy"][c, i, :] = val
+            elif kind == 4:
+                w["keccak"] = base["keccak"].copy(); w["keccak"][c, i, :] = val
+            yield name, k, w, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

@@ -140,3 +140,23 @@ def check_state(rows, flags, mpt, row_begin=0, row_end=None):
                                c(row_end), ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
+    """w: dict(steps, bytecode, rw, rw_flags, copy, keccak) — EVM steps incl. SHA3 / CALLDATACOPY"""
+    m = {k: np.ascontiguousarray(w[k]) for k in ("steps", "bytecode", "rw", "copy", "keccak")}
+    fixed = np.ascontiguousarray(fixed)
+    rwf = np.ascontiguousarray(w["rw_flags"], dtype=np.uint8)
+    n = lib().orc_n_constraints(3)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = m["steps"].shape[1] - 1
+    rc = lib().orc_check_evm_x(p64(m["steps"]), c(m["steps"].shape[1]), p64(m["bytecode"]), c(m["bytecode"].shape[1]),
+                               p64(m["rw"]), c(m["rw"].shape[1]), _p8(rwf), p64(fixed), c(fixed.shape[1]),
+                               p64(m["copy"]), c(m["copy"].shape[1]), p64(m["keccak"]), c(m["keccak"].shape[1]),
+                               c(row_begin), c(row_end), c(row_base), ctypes.c_uint32(flags),
+                               ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

@@ -74,3 +74,15 @@ def test_emu_state_equals_oracle_on_goldens():
         ff, fc = emu_lib.check_state(s, f, m)
         off, ofc = oracle_lib.check_state(s, f, m)
         assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, np.nonzero(ff[:n] != off), ff[:n][ff[:n] != off], off[ff[:n] != off])
+
+
+def test_emu_evm_sha3_calldatacopy_equals_oracle_on_goldens():
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    for name, k, w, exp_row, exp_exc in golden_util.evm2_vectors():
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            ff, fc = emu_lib.check_evm_x(w, fixed, n=n)
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, positional, np.nonzero(ff != off), ff[ff != off], off[ff != off])
+    emu_lib.set_positional(True)

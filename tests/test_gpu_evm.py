@@ -127,3 +127,78 @@ def test_verify_steps_host_api_like_reference_test_add_sub():
         verify_steps(tables(cc=Word((c.int_value() + 1) % 2**256)), steps(), success=False)
         with pytest.raises(LookupUnsatFailure):  # rw rows missing: propagates even with success=False
             verify_steps(tables(rw_start=10), steps(), success=False)
+
+
+def test_evm_sha3_calldatacopy_golden_and_oracle_parity():
+    """SHA3 / CALLDATACOPY steps (copy-table + keccak-table + call-context lookups, memory
+    expansion and copier gas): CUDA == oracle array for array, and == the reference's verdicts"""
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    n = 0
+    for name, k, w, exp_row, exp_exc in golden_util.evm2_vectors():
+        ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+        ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+        ctx.upload_table(native.TABLE_COPY, w["copy"])
+        ctx.upload_table(native.TABLE_KECCAK, w["keccak"])
+        evm_main.upload_fixed_table(ctx)
+        ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, 0)
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle"
+        hit = native.first_failure(ff, native.CIRCUIT_EVM)
+        got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
+        if got[1] == "ValueError" and exp_exc == "OverflowError":
+            got = (got[0], exp_exc)
+        assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
+        n += 1
+    assert n > 380
+    # leave the context without copy / keccak tables for the other tests
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
+
+
+def test_sha3_host_api_like_reference_test_sha3():
+    """tests/evm/test_sha3.py:35-141 on our host API: copy circuit + keccak table + SHA3 step"""
+    from zkevm_specs_b200.copy_circuit import verify_copy_table
+    from zkevm_specs_b200.evm_circuit import (Block, Bytecode, CopyCircuit, CopyDataTypeTag, ExecutionState,
+                                              KeccakCircuit, Opcode, RWDictionary, Tables)
+    from zkevm_specs_b200.evm_circuit.main import verify_steps
+    from zkevm_specs_b200.evm_circuit.step import StepState
+    from zkevm_specs_b200.util import FQ, Word, keccak256
+
+    r = FQ(0x5EED5EED5EED)
+    offset, length = 0x20, 0x40
+    mem = bytes((7 * i + 1) % 256 for i in range(offset + length))
+    src = {i: mem[i] for i in range(offset, offset + length)}
+    bc = Bytecode().push(offset, n_bytes=32).push(length, n_bytes=32).sha3().stop()
+    h = Word(bc.hash())
+    out = Word(int.from_bytes(keccak256(mem[offset:offset + length]), "big"))
+    words = (offset + length + 31) // 32
+    gas = Opcode.SHA3.constant_gas_cost() + ((length + 31) // 32) * 6
+    rw = (RWDictionary(1).stack_write(1, 1023, Word(length)).stack_write(1, 1022, Word(offset))
+          .stack_read(1, 1022, Word(offset)).stack_read(1, 1023, Word(length)).stack_write(1, 1023, out))
+    cc = CopyCircuit().copy(r, rw, 1, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.RlcAcc, offset, offset + length, 0, length, src)
+    kc = KeccakCircuit().add(mem[offset:offset + length], r)
+
+    def tables(keccak_rows):
+        return Tables(block_table=set(Block().table_assignments()), tx_table=set(), withdrawal_table=set(),
+                      bytecode_table=set(bc.table_assignments()), rw_table=set(rw.rws), copy_circuit=cc.rows,
+                      keccak_table=keccak_rows)
+
+    def steps(gas_left=gas):
+        return [StepState(ExecutionState.SHA3, rw_counter=3, call_id=1, is_root=True, code_hash=h, program_counter=66,
+                          stack_pointer=1022, memory_word_size=words, gas_left=gas_left),
+                StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, code_hash=h,
+                          program_counter=67, stack_pointer=1023, memory_word_size=words, gas_left=0)]
+
+    t = tables(kc.rows)
+    verify_copy_table(cc, t, r)
+    verify_steps(t, steps())
+    with pytest.raises(AssertionError):
+        verify_steps(t, steps(gas + 1))
+    with pytest.raises(Exception) as ei:
+        verify_steps(tables([]), steps())
+    assert type(ei.value).__name__ == "LookupUnsatFailure"
+    ctx = native.default_context()
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))

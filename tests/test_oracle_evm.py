@@ -28,3 +28,25 @@ def test_oracle_evm_matches_reference_golden():
         kinds.add(exp_exc)
     assert n > 250 and n_fail > 150 and n_unsupported < 12
     assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure"} <= kinds
+
+
+def test_oracle_evm_sha3_calldatacopy_matches_reference_golden():
+    fixed = fixed_table_matrix()
+    classes = oracle_lib.constraint_classes(3)
+    n = n_fail = n_unsupported = 0
+    kinds = set()
+    for name, k, w, exp_row, exp_exc in golden_util.evm2_vectors():
+        ff, fc = oracle_lib.check_evm_x(w, fixed)
+        row, exc = oracle_lib.first_failure(ff, classes)
+        if exc == "NotImplementedError" and exp_exc != exc:
+            assert row == exp_row
+            n_unsupported += 1
+            continue
+        if exc == "ValueError" and exp_exc == "OverflowError":
+            exc = "OverflowError"
+        assert (row, exc) == (exp_row, exp_exc), f"{name}[{k}]: oracle {(row, exc)} reference {(exp_row, exp_exc)}"
+        n += 1
+        n_fail += exp_row >= 0
+        kinds.add(exp_exc)
+    assert n > 380 and n_fail > 250 and n_unsupported == 0
+    assert {"AssertionError", "LookupUnsatFailure", "ConstraintUnsatFailure"} <= kinds

@@ -461,6 +461,11 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k5, 5, st, &t.bytecode, ZK_POS_RUNS))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_RW, k5, 5, st, &t.rw, ZK_POS_DENSE))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_FIXED, k4, 4, st, &t.fixed))) return rc;
+  {
+    const u32 ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
+    if ((rc = ensure_index(ctx, ZK_TABLE_COPY, ck, 11, st, &t.copy))) return rc;
+    if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 3, st, &t.keccak))) return rc;
+  }
   if (!ctx->resp_bitmap) CK(ctx, cudaMalloc(&ctx->resp_bitmap, ZK_RESP_BITMAP_WORDS * sizeof(u32)));
   if (ctx->resp_bitmap_version != ctx->tab[ZK_TABLE_FIXED].version) {
     CK(ctx, cudaMemsetAsync(ctx->resp_bitmap, 0, ZK_RESP_BITMAP_WORDS * sizeof(u32), st));
@@ -496,7 +501,9 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   k_evm_gadget<G_ADD><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_MUL><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_POP><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  ctx->launches += 6;
+  k_evm_gadget<G_SHA3><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_CDC><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  ctx->launches += 8;
   CK(ctx, cudaGetLastError());
   return 0;
 }

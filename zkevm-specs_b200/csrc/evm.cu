@@ -6,7 +6,7 @@
 // step_state_transition_in_same_context (instruction.py:365-394, 206-264).  Gate programs in
 // this build: ADD/SUB (execution/add_sub.py:5-24), MUL/DIV/MOD (mul_div_mod.py:6-71 with
 // mul_add_words instruction.py:599-632 and compare_word :453-463), PUSH (push.py:6-33),
-// POP (pop.py:4-14).  Every lookup() of the reference (table.py:864-884, a linear scan over
+// POP (pop.py:4-14), SHA3 (sha3.py:6-55), CALLDATACOPY (calldatacopy.py:6-62).  Every lookup() of the reference (table.py:864-884, a linear scan over
 // a Python set) is a probe of a device hash index (lookup.cuh).
 //
 // Step = 13 cells in the order of StepState (evm_circuit/step.py:16-44), code_hash as
@@ -59,6 +59,8 @@ struct EvmTables {
   IndexDev bytecode;  // key (hash_lo, hash_hi, tag, index, is_code)
   IndexDev rw;        // key (rw_counter, rw, tag, id, address)
   IndexDev fixed;     // key (tag, v0, v1, v2)
+  IndexDev copy;      // copy table, key = every queried cell of copy_lookup (table.py:760-787): cells 1..10, 12
+  IndexDev keccak;    // keccak table, key (state_tag, input_rlc, input_len)
   // ResponsibleOpcode rows of the fixed table (tag 13, aux 0) with state, opcode < 256 as a
   // 64 Kbit bitmap: bit (state << 8 | opcode).  Built from the uploaded fixed table
   // (k_fixed_resp_bitmap) and staged into shared memory by every EVM kernel.
@@ -212,7 +214,7 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
 }
 
 // ---- prologue: verify_step before the gadget (main.py:47-63, instruction.py:189-204) --------
-enum { G_ADD, G_MUL, G_PUSH, G_POP, G_COUNT };
+enum { G_ADD, G_MUL, G_PUSH, G_POP, G_SHA3, G_CDC, G_COUNT };
 // returns the gadget that must run for this step, or -1 if the step already failed
 ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
   const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
@@ -243,6 +245,8 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_MUL: return G_MUL;
     case ZK_ES_PUSH: return G_PUSH;
     case ZK_ES_POP: return G_POP;
+    case ZK_ES_SHA3: return G_SHA3;
+    case ZK_ES_CALLDATACOPY: return G_CDC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -266,19 +270,22 @@ ZK_HD bool responsible_opcode(const StepCtx& s, const Fr& state, const Fr& opcod
   return lookup<4>(s.t.fixed, key, &r) >= 1;  // out-of-range query: exact probe of the hash index
 }
 
-// step_state_transition_in_same_context, instruction.py:365-394
-ZK_HD void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
+// step_state_transition_in_same_context, instruction.py:365-394.  General form: the rw_counter
+// delta is a field element, memory_word_size either stays or moves To a value, and a dynamic gas
+// cost is added to the opcode's constant cost.
+ZK_HD void same_context_x(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
+                          bool mem_to, const Fr& mem_value, const Fr& dyn_gas) {
   EV_CHECK(EV_SC_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
   int gas_cost = -1;
   if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
   EV_CHECK(EV_SC_OPCODE_VALUE, gas_cost >= 0);
-  const Fr gas_after = fr_sub_u64(s.cur(S_GAS), (u64)gas_cost);
+  const Fr gas_after = fr_sub(s.cur(S_GAS), fr_add_u64(dyn_gas, (u64)gas_cost));
   EV_CHECK(EV_SC_GAS_RANGE, fr_fits64(gas_after));
-  EV_CHECK(EV_SC_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(s.cur(S_RWC), d_rwc)));
+  EV_CHECK(EV_SC_RWC, fr_eq(s.nxt(S_RWC), fr_add(s.cur(S_RWC), d_rwc)));
   EV_CHECK(EV_SC_PC, fr_eq(s.nxt(S_PC), fr_add(s.cur(S_PC), d_pc)));
   EV_CHECK(EV_SC_SP, fr_eq(s.nxt(S_SP), fr_add(s.cur(S_SP), d_sp)));
   EV_CHECK(EV_SC_GAS, fr_eq(s.nxt(S_GAS), gas_after));
-  EV_CHECK(EV_SC_MEM, fr_eq(s.nxt(S_MEM), s.cur(S_MEM)));
+  EV_CHECK(EV_SC_MEM, fr_eq(s.nxt(S_MEM), mem_to ? mem_value : s.cur(S_MEM)));
   EV_CHECK(EV_SC_REV, fr_eq(s.nxt(S_REV), s.cur(S_REV)));
   EV_CHECK(EV_SC_LOG, fr_eq(s.nxt(S_LOG), s.cur(S_LOG)));
   EV_CHECK(EV_SC_CALL_ID, fr_eq(s.nxt(S_CALL_ID), s.cur(S_CALL_ID)));
@@ -286,6 +293,9 @@ ZK_HD void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr&
   EV_CHECK(EV_SC_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), s.cur(S_IS_CREATE)));
   EV_CHECK(EV_SC_CODE_HASH,
            fr_eq(s.nxt(S_HASH_LO), s.cur(S_HASH_LO)) && fr_eq(s.nxt(S_HASH_HI), s.cur(S_HASH_HI)));
+}
+ZK_HD void same_context(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
+  same_context_x(s, opcode, fr_u64(d_rwc), d_pc, d_sp, false, fr_u64(0), fr_u64(0));
 }
 
 // add_words([x, y]) with the final carry dropped (util/arithmetic.py:236-242)
@@ -685,6 +695,164 @@ ZK_HD void gadget_pop(const StepCtx& s, bool live) {
   same_context(s, opcode, 1, fr_u64(1), fr_u64(1));
 }
 
+// ---- SHA3 (execution/sha3.py:6-55) and CALLDATACOPY (execution/calldatacopy.py:6-62) ----------
+// word_to_fq(word, 5) (instruction.py:480-484): 0 ok, 1 = to_le_bytes OverflowError, 2 = raise
+ZK_HD int word_to_fq5(const Word2& w, Fr* out) {
+  if (!word_in_domain(w)) return 1;
+  if ((w.lo.l[0] >> 40) || w.lo.l[1] || w.hi.l[0] || w.hi.l[1]) return 2;
+  *out = fr_u64(w.lo.l[0]);
+  return 0;
+}
+ZK_HD u64 memory_gas_cost(u64 size) { return size * size / 512 + 3 * size; }  // size < 2^32 (instruction.py:1129-1136)
+// memory_expansion_dynamic_length + memory_copier_gas_cost (instruction.py:1157-1192): 0 ok, else
+// 1 + index of the failing check in {MEMSIZE_RANGE, MAX_RANGE, WORDSIZE_RANGE, GASCOST_RANGE}
+ZK_HD int copier_gas(const StepCtx& s, u64 offset, u64 length, u64 per_word, Fr* next_mem, Fr* gas) {
+  const u64 cd_size = (offset + length + 31) / 32;  // offset, length < 2^40
+  if (cd_size >> 32) return 1;
+  const Fr cur = s.cur(S_MEM);
+  if (!(fr_fits64(cur) && (cur.l[0] >> 32) == 0)) return 2;
+  const u64 nxt = cur.l[0] < cd_size ? cd_size : cur.l[0];
+  const u64 expansion = memory_gas_cost(nxt) - memory_gas_cost(cur.l[0]);
+  const u64 words = (length + 31) / 32;
+  if (words >> 32) return 3;
+  const unsigned __int128 g = (unsigned __int128)words * per_word + expansion;
+  if ((u64)(g >> 64)) return 4;
+  *next_mem = fr_u64(nxt);
+  *gas = fr_u64((u64)g);
+  return 0;
+}
+// copy_lookup (instruction.py:1361-1386, table.py:760-787); ids are values (hi half 0)
+ZK_HD int copy_lookup(const StepCtx& s, bool live, const Fr& src_id, u64 src_tag, const Fr& dst_id, u64 dst_tag,
+                      const Fr& src_addr, const Fr& src_end, const Fr& dst_addr, const Fr& length, const Fr& rwc,
+                      Fr* rwc_inc, Fr* rlc_acc) {
+  Fr key[11] = {src_id, fr_u64(0), fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end,
+                dst_addr, length, rwc};
+  u32 r;
+  const int n = lookup_sync<11>(s.t.copy, key, &r, s.mask, live);
+  if (live && n == 1) {
+    *rlc_acc = table_cell(s.t.copy.tab, 11, r);
+    *rwc_inc = table_cell(s.t.copy.tab, 13, r);
+  }
+  return n;
+}
+// call_context_lookup: rw row (rw_counter, Read, CallContext, call_id, address = field tag)
+ZK_HD int call_context(const StepCtx& s, bool live, const Fr& rwc, const Fr& call_id, u64 field_tag, Fr* value,
+                       bool* is_word) {
+  Fr key[5] = {rwc, fr_u64(0), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
+  u32 r;
+  const int n = lookup_sync<5>(s.t.rw, key, &r, s.mask, live);
+  if (live && n == 1) {
+    *value = table_cell(s.t.rw.tab, R_VAL_LO, r);
+    *is_word = s.t.rw.tab.flags && (s.t.rw.tab.flags[r] & 1);
+  }
+  return n;
+}
+#define EV_LIVE_CHECK(id, cond)   \
+  do {                            \
+    if (live && !(cond)) {        \
+      step_fail(s, (id));         \
+      live = false;               \
+    }                             \
+  } while (0)
+
+ZK_HD void gadget_sha3(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Fr sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 off_w = zero, size_w = zero, val_w = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &off_w), EV_SHA_OFF_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &size_w), EV_SHA_SIZE_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &val_w), EV_SHA_VAL_UNSAT);
+  Fr length = fr_u64(0), offset = fr_u64(0);
+  if (live) {
+    int rc = word_to_fq5(size_w, &length);
+    EV_LIVE_CHECK(rc == 1 ? EV_SHA_LEN_BYTES : EV_SHA_LEN_RANGE, rc == 0);
+    if (live && !fr_is_zero(length)) {
+      rc = word_to_fq5(off_w, &offset);
+      EV_LIVE_CHECK(rc == 1 ? EV_SHA_OFF_BYTES : EV_SHA_OFF_RANGE, rc == 0);
+    }
+  }
+  Fr rwc_inc = fr_u64(0), rlc_acc = fr_u64(0);
+  {
+    const bool go = live && !fr_is_zero(length);
+    const int n = copy_lookup(s, go, call_id, ZK_COPY_Memory, call_id, ZK_COPY_RlcAcc, offset, fr_add(offset, length),
+                              fr_u64(0), length, fr_add_u64(rwc, 3), &rwc_inc, &rlc_acc);
+    if (go) live = need1(s, live, n, EV_SHA_COPY_UNSAT);
+  }
+  {
+    Fr key[3] = {fr_u64(2), rlc_acc, length};  // keccak_lookup(length, rlc_acc), state_tag = Finalize
+    u32 hit = 0;
+    const int n = lookup_sync<3>(s.t.keccak, key, &hit, s.mask, live);
+    live = need1(s, live, n, EV_SHA_KECCAK_UNSAT);
+    if (live)
+      EV_LIVE_CHECK(EV_SHA_HASH_EQ, fr_eq(table_cell(s.t.keccak.tab, 3, hit), val_w.lo) &&
+                                        fr_eq(table_cell(s.t.keccak.tab, 4, hit), val_w.hi));
+  }
+  if (!live) return;  // past the last lookup
+  Fr next_mem, gas;
+  const int rc = copier_gas(s, offset.l[0], length.l[0], ZK_GAS_COST_COPY_SHA3, &next_mem, &gas);
+  EV_CHECK(EV_SHA_MEMSIZE_RANGE + rc - 1, rc == 0);
+  same_context_x(s, opcode, fr_add_u64(rwc_inc, 3), fr_u64(1), fr_u64(1), true, next_mem, gas);
+}
+
+ZK_HD void gadget_calldatacopy(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 moff_w = zero, doff_w = zero, len_w = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &moff_w), EV_CDC_MOFF_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 1), &doff_w), EV_CDC_DOFF_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 2), &len_w), EV_CDC_LEN_UNSAT);
+  Fr length = fr_u64(0), moff = fr_u64(0), doff = fr_u64(0);
+  if (live) {
+    int rc = word_to_fq5(len_w, &length);
+    EV_LIVE_CHECK(rc == 1 ? EV_CDC_LEN_BYTES : EV_CDC_LEN_RANGE, rc == 0);
+    if (live && !fr_is_zero(length)) {
+      rc = word_to_fq5(moff_w, &moff);
+      EV_LIVE_CHECK(rc == 1 ? EV_CDC_MOFF_BYTES : EV_CDC_MOFF_RANGE, rc == 0);
+    }
+    if (live) {
+      rc = word_to_fq5(doff_w, &doff);
+      EV_LIVE_CHECK(rc == 1 ? EV_CDC_DOFF_BYTES : EV_CDC_DOFF_RANGE, rc == 0);
+    }
+  }
+  const Fr is_root = s.cur(S_IS_ROOT);
+  const bool root = !fr_is_zero(is_root);  // Python truthiness of StepState.is_root
+  Fr src_id = fr_u64(0), cd_len = fr_u64(0), cd_off = fr_u64(0);
+  bool w = false;
+  live = need1(s, live, call_context(s, live, fr_add_u64(rwc, 3), call_id, root ? ZK_CC_TxId : ZK_CC_CallerId, &src_id, &w), EV_CDC_CC1_UNSAT);
+  EV_LIVE_CHECK(EV_CDC_CC1_TYPE, !w);
+  live = need1(s, live, call_context(s, live, fr_add_u64(rwc, 4), call_id, ZK_CC_CallDataLength, &cd_len, &w), EV_CDC_CC2_UNSAT);
+  EV_LIVE_CHECK(EV_CDC_CC2_TYPE, !w);
+  {
+    const bool go = live && !root;
+    const int n = call_context(s, go, fr_add_u64(rwc, 5), call_id, ZK_CC_CallDataOffset, &cd_off, &w);
+    if (go) {
+      live = need1(s, live, n, EV_CDC_CC3_UNSAT);
+      EV_LIVE_CHECK(EV_CDC_CC3_TYPE, !w);
+    }
+  }
+  const u64 k = root ? 5 : 6;
+  Fr next_mem = fr_u64(0), gas = fr_u64(0);
+  if (live) {
+    const int rc = copier_gas(s, moff.l[0], length.l[0], ZK_GAS_COST_COPY, &next_mem, &gas);
+    EV_LIVE_CHECK(EV_CDC_MEMSIZE_RANGE + rc - 1, rc == 0);
+    EV_LIVE_CHECK(EV_CDC_SELECT_BOOL, fr_fits64(is_root) && is_root.l[0] <= 1);
+  }
+  Fr rwc_inc = fr_u64(0), unused = fr_u64(0);
+  {
+    const bool go = live && !fr_is_zero(length);
+    const int n = copy_lookup(s, go, src_id, root ? ZK_COPY_TxCalldata : ZK_COPY_Memory, call_id, ZK_COPY_Memory,
+                              fr_add(cd_off, doff), fr_add(cd_off, cd_len), moff, length, fr_add_u64(rwc, k), &rwc_inc, &unused);
+    if (go) live = need1(s, live, n, EV_CDC_COPY_UNSAT);
+  }
+  if (!live) return;
+  same_context_x(s, opcode, fr_add_u64(rwc_inc, k), fr_u64(1), fr_u64(3), true, next_mem, gas);
+}
+
 // whole step on one thread (tests/emu)
 ZK_HD void verify_step(const StepCtx& s, u32 flags) {
   switch (step_prologue(s, flags)) {
@@ -692,6 +860,8 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
     case G_MUL: gadget_mul(s, true); break;
     case G_PUSH: gadget_push(s, true); break;
     case G_POP: gadget_pop(s, true); break;
+    case G_SHA3: gadget_sha3(s, true); break;
+    case G_CDC: gadget_calldatacopy(s, true); break;
     default: break;
   }
 }
@@ -752,6 +922,8 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
+    else if (G == G_SHA3) gadget_sha3(s, live);
+    else if (G == G_CDC) gadget_calldatacopy(s, live);
     else gadget_pop(s, live);
   }
 }

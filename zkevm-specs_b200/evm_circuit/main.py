@@ -45,6 +45,8 @@ def upload_tables(ctx: native.Context, tables: Tables) -> None:
     rws = list(tables.rw_table)
     ctx.upload_table(native.TABLE_RW, packing.pack(rws, packing.rw_table_row, 14),
                      flags=np.array([packing.rw_table_flags(r) for r in rws], dtype=np.uint8))
+    ctx.upload_table(native.TABLE_COPY, packing.pack(tables.copy_table, packing.copy_table_row, 14))
+    ctx.upload_table(native.TABLE_KECCAK, packing.pack(tables.keccak_table, packing.keccak_table_row, 5))
     upload_fixed_table(ctx)
 
 

@@ -117,3 +117,10 @@ def tx_table_row(r) -> List[int]:
 def word_flag(x) -> int:
     """the WordOrValue.is_word type bit (a plain Word counts as a word)"""
     return int(bool(getattr(x, "is_word", True)))
+
+
+def copy_table_row(r) -> List[int]:
+    return [cell_int(r.is_first), cell_int(r.src_id.lo), cell_int(r.src_id.hi), cell_int(r.src_tag),
+            cell_int(r.dst_id.lo), cell_int(r.dst_id.hi), cell_int(r.dst_tag), cell_int(r.src_addr),
+            cell_int(r.src_addr_end), cell_int(r.dst_addr), cell_int(r.length), cell_int(r.rlc_acc),
+            cell_int(r.rw_counter), cell_int(r.rwc_inc)]
