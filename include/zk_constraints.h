@@ -362,4 +362,36 @@ enum zk_copy_constraint { ZK_COPY_CONSTRAINTS(ZK_ENUM_ENTRY) CP_N_CONSTRAINTS };
 
 enum zk_state_constraint { ZK_STATE_CONSTRAINTS(ZK_ENUM_ENTRY) ST_N_CONSTRAINTS };
 
+/* ---------------- exp circuit: src/zkevm_specs/exp_circuit.py:14-97 ------------------------
+ * Gates are cond * expr == 0 (util/constraint_system.py); the mul_add_words calls and their
+ * range checks run for EVERY row (they are not gated by cs.condition).  A row stops at its
+ * first failure. */
+#define ZK_EXP_CONSTRAINTS(X)                                                              \
+  X(XP_BASE_SAME, ZKE_ASSERT, "exp_circuit.py:18 base == next.base")                        \
+  X(XP_A_EQ_NEXT_D, ZKE_ASSERT, "exp_circuit.py:21 a == next.d")                            \
+  X(XP_ID_SAME, ZKE_ASSERT, "exp_circuit.py:23 identifier == next.identifier")              \
+  X(XP_LAST_BOOL, ZKE_ASSERT, "exp_circuit.py:28 is_step*is_last boolean")                  \
+  X(XP_R_BOOL, ZKE_ASSERT, "exp_circuit.py:30 is_step*r boolean")                           \
+  X(XP_MUL_TO64, ZKE_VALUE, "arithmetic.py:252-253 to_64s(a|b): half >= 2^128 -> OverflowError") \
+  X(XP_MUL_CARRY_LO, ZKE_RANGE, "exp_circuit.py:35 range_check(carry_lo, 9)")               \
+  X(XP_MUL_CARRY_HI, ZKE_RANGE, "exp_circuit.py:36 range_check(carry_hi, 9)")               \
+  X(XP_EXP_EQ_D, ZKE_ASSERT, "exp_circuit.py:40 exponentiation == d")                       \
+  X(XP_C_ZERO, ZKE_ASSERT, "exp_circuit.py:42 c == 0")                                      \
+  X(XP_PAR_R_WORD, ZKE_ASSERT, "exp_circuit.py:45 Word.from_lo(r): r >= 2^128")             \
+  X(XP_PAR_TO64, ZKE_VALUE, "exp_circuit.py:44-46 to_64s(q): half >= 2^128 -> OverflowError") \
+  X(XP_PAR_CARRY_LO, ZKE_RANGE, "exp_circuit.py:47 range_check(carry_lo, 9)")               \
+  X(XP_PAR_CARRY_HI, ZKE_RANGE, "exp_circuit.py:48 range_check(carry_hi, 9)")               \
+  X(XP_ODD_NEXT_LO, ZKE_ASSERT, "exp_circuit.py:59 odd: next.exponent.lo == exponent.lo - 1") \
+  X(XP_ODD_NEXT_HI, ZKE_ASSERT, "exp_circuit.py:61 odd: next.exponent.hi == exponent.hi")   \
+  X(XP_ODD_B_BASE, ZKE_ASSERT, "exp_circuit.py:63 odd: b == base")                          \
+  X(XP_EVEN_NEXT_LO, ZKE_ASSERT, "exp_circuit.py:72 even: next.exponent.lo == q.lo")        \
+  X(XP_EVEN_NEXT_HI, ZKE_ASSERT, "exp_circuit.py:73 even: next.exponent.hi == q.hi")        \
+  X(XP_EVEN_A_EQ_B, ZKE_ASSERT, "exp_circuit.py:75 even: a == b")                           \
+  X(XP_LAST_EXP_LO2, ZKE_ASSERT, "exp_circuit.py:81 last: exponent.lo == 2")                \
+  X(XP_LAST_EXP_HI0, ZKE_ASSERT, "exp_circuit.py:82 last: exponent.hi == 0")                \
+  X(XP_LAST_A_BASE, ZKE_ASSERT, "exp_circuit.py:84 last: a == base")                        \
+  X(XP_LAST_B_BASE, ZKE_ASSERT, "exp_circuit.py:86 last: b == base")
+
+enum zk_exp_constraint { ZK_EXP_CONSTRAINTS(ZK_ENUM_ENTRY) XP_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

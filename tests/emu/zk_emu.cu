@@ -12,6 +12,7 @@
 #include "../../zkevm-specs_b200/csrc/bytecode.cu"
 #include "../../zkevm-specs_b200/csrc/copy.cu"
 #include "../../zkevm-specs_b200/csrc/evm.cu"
+#include "../../zkevm-specs_b200/csrc/exp.cu"
 #include "../../zkevm-specs_b200/csrc/state.cu"
 
 using namespace zk;
@@ -177,5 +178,15 @@ extern "C" int emu_check_state(const uint64_t* rows, uint64_t n_rows, const uint
   ResultDev res;
   init_result(res, first_fail, fail_count, ST_N_CONSTRAINTS);
   for (u64 i = row_begin; i < row_end; i++) check_state_row_dev(w, rg, ix, res, i, true, 1u);
+  return 0;
+}
+
+extern "C" int emu_check_exp(const uint64_t* rows, uint64_t n_rows, uint64_t row_begin, uint64_t row_end, uint32_t cflags,
+                             uint32_t* first_fail, uint64_t* fail_count) {
+  WitnessDev w{(const u64*)rows, n_rows, nullptr};
+  CheckRange rg{row_begin, row_end, 0, cflags};
+  ResultDev res;
+  init_result(res, first_fail, fail_count, XP_N_CONSTRAINTS);
+  for (u64 i = row_begin; i < row_end; i++) check_exp_row(w, rg, res, i);
   return 0;
 }

@@ -126,3 +126,16 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=256,
                                c(row_base), ctypes.c_uint32(flags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_exp(rows, row_begin=0, row_end=None, cflags=1):
+    rows = np.ascontiguousarray(rows)
+    ff = np.zeros(64, dtype=np.uint32)
+    fc = np.zeros(64, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().emu_check_exp(_p(rows), c(rows.shape[1]), c(row_begin), c(row_end), ctypes.c_uint32(cflags),
+                             ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

@@ -990,11 +990,84 @@ def evm2_cases():
     print(f"evm2: {tot} corruptions, {nfail} failing")
 
 
+# --------------------------------------------------------------------------- exp
+def exp_cases():
+    """Exp-circuit rows built by the reference's ExpCircuit.add_event / fill_dummy_events
+    (evm_circuit/typing.py:868-994) and checked by the reference's verify_step under the loop of
+    verify_exp_circuit (exp_circuit.py:88-97)."""
+    from zkevm_specs import exp_circuit as xc
+    from zkevm_specs.evm_circuit import ExpCircuit, ExpCircuitRow
+    from zkevm_specs.util import ConstraintSystem, FQ, Word
+
+    rng = random.Random(6)
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def ints(x):
+        out = [n_of(x.q_usable), n_of(x.is_step), n_of(x.identifier), n_of(x.is_last)]
+        for wd in (x.base, x.exponent, x.exponentiation, x.a, x.b, x.c, x.d, x.q):
+            out += [n_of(wd.lo), n_of(wd.hi)]
+        return out + [n_of(x.r)]
+
+    def from_ints(v):
+        f = [FQ(x) for x in v]
+        ws = [W(v[4 + 2 * k], v[5 + 2 * k]) for k in range(8)]
+        return ExpCircuitRow(f[0], f[1], f[2], f[3], *ws, f[20])
+
+    def run(R):
+        rows = [from_ints(v) for v in R]
+        cs = ConstraintSystem()
+        for i in range(len(rows)):
+            try:
+                cs.cond = None
+                xc.verify_step(cs, [rows[i], rows[(i + 1) % len(rows)]])
+            except Exception as e:  # noqa: BLE001
+                return i, type(e).__name__
+        return -1, ""
+
+    scen = {
+        "small": [(3, 13, 7), (2, 10, 14)],
+        "big": [(rng.randrange(1 << 256), rng.randrange(2, 1 << 40), 21), ((1 << 256) - 1, 5, 28)],
+        "pow2": [(2, 255, 35), (7, 2, 42), (0, 9, 49)],
+    }
+    out = {"names": np.array(list(scen.keys()))}
+    tot = nfail = 0
+    for name, events in scen.items():
+        c = ExpCircuit(max_exp_steps=2)
+        for b, e, ident in events:
+            c.add_event(b, e, ident)
+        c.max_exp_steps = (len(c.rows) + 6) // 7 + 1
+        c.fill_dummy_events()
+        R = [ints(x) for x in c.table()]
+        assert run(R) == (-1, ""), (name, run(R))
+        muts = [(-1, 0, 0, -1, "")]
+        for k in range(120):
+            i, col = rng.randrange(len(R)), rng.randrange(1, 21)
+            old = R[i][col]
+            v = (1 - old) if (old in (0, 1) and rng.random() < 0.5) else corrupt_value(rng, old)
+            R2 = [list(x) for x in R]
+            R2[i][col] = v
+            fr_, ex_ = run(R2)
+            muts.append((i, col, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        out[f"{name}/rows"] = to_matrix(R)
+        out[f"{name}/mut_row"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[2]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[3] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[4] for m in muts])
+        print(name, len(R), "rows", len(muts), "vectors")
+    np.savez_compressed(os.path.join(HERE, "exp.npz"), **out)
+    print(f"exp: {tot} corruptions, {nfail} failing")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "exp", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -131,3 +131,17 @@ def evm2_vectors():
             elif kind == 4:
                 w["keccak"] = base["keccak"].copy(); w["keccak"][c, i, :] = val
             yield name, k, w, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def exp_vectors():
+    """yield (case, k, rows, exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, "exp.npz"))
+    for name in z["names"]:
+        name = str(name)
+        R = z[f"{name}/rows"]
+        for k in range(len(z[f"{name}/mut_row"])):
+            i, c = int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            r = R
+            if i >= 0:
+                r = R.copy(); r[c, i, :] = z[f"{name}/mut_val"][k]
+            yield name, k, r, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

@@ -160,3 +160,16 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
                                ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_exp(rows, row_begin=0, row_end=None):
+    rows = np.ascontiguousarray(rows)
+    n = lib().orc_n_constraints(4)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().orc_check_exp(p64(rows), c(rows.shape[1]), c(row_begin), c(row_end), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

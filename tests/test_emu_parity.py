@@ -86,3 +86,11 @@ def test_emu_evm_sha3_calldatacopy_equals_oracle_on_goldens():
             ff, fc = emu_lib.check_evm_x(w, fixed, n=n)
             assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, positional, np.nonzero(ff != off), ff[ff != off], off[ff != off])
     emu_lib.set_positional(True)
+
+
+def test_emu_exp_equals_oracle_on_goldens():
+    n = oracle_lib.lib().orc_n_constraints(4)
+    for name, k, r, exp_row, exp_exc in golden_util.exp_vectors():
+        ff, fc = emu_lib.check_exp(r)
+        off, ofc = oracle_lib.check_exp(r)
+        assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, np.nonzero(ff[:n] != off))

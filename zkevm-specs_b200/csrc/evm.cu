@@ -15,6 +15,7 @@
 // A step stops at its first failing constraint (the reference raises there), so at most one
 // constraint id is recorded per step.
 #include "circuit.cuh"
+#include "words.cuh"
 #include "../../include/zk_constraints.h"
 #include "../../include/zk_evm_spec.h"
 #include "../../include/zkcheck.h"
@@ -45,15 +46,6 @@ static const short h_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
 // constants in Montgomery form: montmul(x, C*2^256) == x*C mod p
 #define ZK_MONT_INV8 Fr{{0x0ull, 0x0ull, 0x0ull, 0x2000000000000000ull}}
 #define ZK_MONT_INV4 Fr{{0xbc1e0a6c0fffffffull, 0xd7cc17b786468f6eull, 0x47afba497e7ea7a2ull, 0x0f9bb18d1ece5fd6ull}}
-#define ZK_MONT_INV2_128 Fr{{0x0ull, 0x0ull, 0x1ull, 0x0ull}}
-
-struct Word2 {
-  Fr lo, hi;
-};
-ZK_HD bool word_in_domain(const Word2& w) { return fr_fits128(w.lo) && fr_fits128(w.hi); }
-ZK_HD bool word_eq(const Word2& a, const Word2& b) {
-  return fr_eq(a.lo, b.lo) && fr_eq(a.hi, b.hi);
-}
 
 struct EvmTables {
   IndexDev bytecode;  // key (hash_lo, hash_hi, tag, index, is_code)
@@ -407,24 +399,6 @@ ZK_HD void div256(const u64 n[4], const u64 d[4], u64 q[4]) {
   }
 }
 
-// exact small unsigned integers (< 2^196) as Fr: sums of 64x64-bit limb products, optionally
-// shifted left by one limb (the "* 2^64" of mul_add_words)
-ZK_HD void acc_add_mul(Fr& acc, u64 a, u64 b, int shift_limbs) {
-  const unsigned __int128 v = (unsigned __int128)a * b;
-  u64 c = 0;
-  const u64 lo = (u64)v, hi = (u64)(v >> 64);
-  if (shift_limbs == 0) {
-    acc.l[0] = adc64(acc.l[0], lo, c);
-    acc.l[1] = adc64(acc.l[1], hi, c);
-    acc.l[2] = adc64(acc.l[2], 0, c);
-    acc.l[3] += c;
-  } else {
-    acc.l[1] = adc64(acc.l[1], lo, c);
-    acc.l[2] = adc64(acc.l[2], hi, c);
-    acc.l[3] += c;
-  }
-}
-
 // Word((sel*lo, sel*hi)) with the constructor's < 2^128 assertion (arithmetic.py:110-114)
 ZK_HD bool word_select(const Word2& w, const Fr& sel, Word2* out) {
   if (fr_is_zero(sel)) {
@@ -498,33 +472,10 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
   const bool b_zero = fr_is_zero(fr_add(b.lo, b.hi));  // is_zero_word: field sum of the halves
   // mul_add_words, instruction.py:599-632
   EV_CHECK(EV_MUL_TO64, word_in_domain(a) && word_in_domain(b));
-  const u64 a0 = a.lo.l[0], a1 = a.lo.l[1], a2 = a.hi.l[0], a3 = a.hi.l[1];
-  const u64 b0 = b.lo.l[0], b1 = b.lo.l[1], b2 = b.hi.l[0], b3 = b.hi.l[1];
-  // t0 + t1*2^64 and t2 + t3*2^64 as exact integers (< 2^195 < p)
-  Fr lo_part = fr_u64(0), hi_part = fr_u64(0), ovf = fr_u64(0);
-  acc_add_mul(lo_part, a0, b0, 0);
-  acc_add_mul(lo_part, a0, b1, 1);
-  acc_add_mul(lo_part, a1, b0, 1);
-  acc_add_mul(hi_part, a0, b2, 0);
-  acc_add_mul(hi_part, a1, b1, 0);
-  acc_add_mul(hi_part, a2, b0, 0);
-  acc_add_mul(hi_part, a0, b3, 1);
-  acc_add_mul(hi_part, a1, b2, 1);
-  acc_add_mul(hi_part, a2, b1, 1);
-  acc_add_mul(hi_part, a3, b0, 1);
-  acc_add_mul(ovf, a1, b3, 0);
-  acc_add_mul(ovf, a2, b2, 0);
-  acc_add_mul(ovf, a3, b1, 0);
-  acc_add_mul(ovf, a2, b3, 0);
-  acc_add_mul(ovf, a3, b2, 0);
-  acc_add_mul(ovf, a3, b3, 0);
-  const Fr x_lo = fr_add(lo_part, c.lo);
-  const Fr carry_lo = fr_montmul(fr_sub(x_lo, d.lo), ZK_MONT_INV2_128);
-  const Fr x_hi = fr_add(fr_add(hi_part, c.hi), carry_lo);
-  const Fr carry_hi = fr_montmul(fr_sub(x_hi, d.hi), ZK_MONT_INV2_128);
-  const Fr overflow = fr_add(carry_hi, ovf);
-  EV_CHECK(EV_MUL_CARRY_LO, fr_fits128(carry_lo) && (carry_lo.l[1] >> 8) == 0);  // range_check(.., 9)
-  EV_CHECK(EV_MUL_CARRY_HI, fr_fits128(carry_hi) && (carry_hi.l[1] >> 8) == 0);
+  Fr carry_lo, carry_hi, overflow;
+  mul_add_carries(a, b, c, d, &carry_lo, &carry_hi, &overflow);
+  EV_CHECK(EV_MUL_CARRY_LO, fits_9_bytes(carry_lo));  // range_check(.., 9)
+  EV_CHECK(EV_MUL_CARRY_HI, fits_9_bytes(carry_hi));
   // the two constrain_equal of instruction.py:629-630 hold by construction of the carries
   // mul_div_mod.py:47-54: select_word's bool assert, then Word range asserts of select / +
   const bool mul0 = fr_is_zero(is_mul), mul1 = fr_eq_u64(is_mul, 1);
