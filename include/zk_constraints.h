@@ -56,6 +56,11 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_PUSH_B##i##_EQ, ZKE_ASSERT, "push.py:25-27 byte " #i ": pushed byte == bytecode byte")        \
   X(EV_PUSH_B##i##_ZERO, ZKE_ASSERT, "push.py:29 byte " #i ": unpushed/padding byte == 0")
 
+#define ZK_EVM_RESTORE_LOOKUP(X, k)                                                          \
+  X(EV_RST##k##_UNSAT, ZKE_UNSAT, "instruction.py:304-336 restore-context lookup " #k " unsat")      \
+  X(EV_RST##k##_AMBIG, ZKE_AMBIG, "instruction.py:304-336 restore-context lookup " #k " ambiguous")  \
+  X(EV_RST##k##_CHECK, ZKE_ASSERT, "instruction.py:304-336 restore-context lookup " #k ": .value() type / written value")
+
 #define ZK_EVM_CONSTRAINTS(X)                                                               \
   X(EV_FIRST_STATE, ZKE_ASSERT, "main.py:48-52 first step state in {BeginTx,EndBlock}")     \
   X(EV_FIRST_RWC, ZKE_ASSERT, "main.py:53 first step rw_counter==1")                        \
@@ -185,6 +190,46 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CDC_SELECT_BOOL, ZKE_ASSERT, "calldatacopy.py:37-39 select(): is_root is not boolean") \
   X(EV_CDC_COPY_UNSAT, ZKE_UNSAT, "calldatacopy.py:41-51 copy_table lookup unsat")          \
   X(EV_CDC_COPY_AMBIG, ZKE_AMBIG, "calldatacopy.py:41-51 copy_table lookup ambiguous")      \
+  /* STOP: execution/stop.py:7-51 */                                                        \
+  X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
+  X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \
+  X(EV_STOP_CMP_RANGE, ZKE_ASSERT, "stop.py:12-14 compare(): operand exceeds 8 bytes")      \
+  X(EV_STOP_OP_UNSAT, ZKE_UNSAT, "stop.py:18 opcode_lookup unsat")                          \
+  X(EV_STOP_OP_AMBIG, ZKE_AMBIG, "stop.py:18 opcode_lookup ambiguous")                      \
+  X(EV_STOP_RESP_OPCODE, ZKE_UNSAT, "stop.py:18 responsible_opcode_lookup")                 \
+  X(EV_STOP_CC_UNSAT, ZKE_UNSAT, "stop.py:22 call_context IsSuccess lookup unsat")          \
+  X(EV_STOP_CC_AMBIG, ZKE_AMBIG, "stop.py:22 call_context IsSuccess lookup ambiguous")      \
+  X(EV_STOP_CC_TYPE, ZKE_ASSERT, "stop.py:22 .value(): IsSuccess is a Word")                \
+  X(EV_STOP_IS_SUCCESS, ZKE_ASSERT, "stop.py:23 is_success == 1")                           \
+  X(EV_STOP_ROOT_ENDTX, ZKE_ASSERT, "stop.py:26-27 is_root == (next state is EndTx)")       \
+  X(EV_STOP_RWC, ZKE_ASSERT, "stop.py:31-34 root: rw_counter + 1")                          \
+  X(EV_STOP_CALL_ID, ZKE_ASSERT, "stop.py:31-34 root: call_id same")                        \
+  /* step_state_transition_to_restored_context, instruction.py:293-363: lookup 0 = CallerId,  \
+   * 1..8 = caller IsRoot, IsCreate, CodeHash, ProgramCounter, StackPointer, GasLeft,          \
+   * MemorySize, ReversibleWriteCounter, 9..11 = writes LastCalleeId / ReturnDataOffset / Length */ \
+  ZK_EVM_RESTORE_LOOKUP(X, 0)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 1)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 2)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 3)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 4)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 5)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 6)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 7)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 8)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 9)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 10)                                                          \
+  ZK_EVM_RESTORE_LOOKUP(X, 11)                                                          \
+  X(EV_RST_VALUE_TYPE, ZKE_ASSERT, "instruction.py:349-361 .value(): a restored field is a Word") \
+  X(EV_RST_RWC, ZKE_ASSERT, "instruction.py:348 rw_counter + delta")                        \
+  X(EV_RST_CALL_ID, ZKE_ASSERT, "instruction.py:349 call_id -> caller_id")                  \
+  X(EV_RST_IS_ROOT, ZKE_ASSERT, "instruction.py:350 is_root -> caller's")                   \
+  X(EV_RST_IS_CREATE, ZKE_ASSERT, "instruction.py:351 is_create -> caller's")               \
+  X(EV_RST_CODE_HASH, ZKE_ASSERT, "instruction.py:352 code_hash -> caller's")               \
+  X(EV_RST_PC, ZKE_ASSERT, "instruction.py:353 program_counter -> caller's")                \
+  X(EV_RST_SP, ZKE_ASSERT, "instruction.py:354 stack_pointer -> caller's")                  \
+  X(EV_RST_GAS, ZKE_ASSERT, "instruction.py:356 gas_left -> caller's + returned")           \
+  X(EV_RST_MEM, ZKE_ASSERT, "instruction.py:357 memory_word_size -> caller's")              \
+  X(EV_RST_REV, ZKE_ASSERT, "instruction.py:359-361 reversible_write_counter -> caller's + own") \
   /* shared epilogue: step_state_transition_in_same_context, instruction.py:365-394 */      \
   X(EV_SC_RESP_OPCODE, ZKE_UNSAT, "instruction.py:376,779-782 ResponsibleOpcode fixed lookup") \
   X(EV_SC_OPCODE_VALUE, ZKE_VALUE, "instruction.py:378 Opcode(opcode.n): not a valid opcode -> ValueError") \

@@ -427,6 +427,82 @@ static void gadget_calldatacopy(evm_env* e, uint64_t i, uint64_t row, fr_t opcod
   same_context_x(e, i, row, opcode, fr_add(fr_u64(k), rwc_inc), one, fr_u64(3), 1, next_mem, gas);
 }
 
+
+/* call_context_lookup_word at rw_counter, rw, call_id: value word + is_word flag */
+static int call_context_w(evm_env* e, fr_t rwc, uint64_t rw, fr_t call_id, uint64_t field_tag, word_t* value, int* is_word) {
+  fr_t key[5] = {rwc, fr_u64(rw), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
+  uint32_t r; const int n = orc_lookup(&e->rw_ix, key, &r);
+  if (n == 1) {
+    value->lo = fr_load(ORC_CELL(e->rw_ix.cells, e->rw_ix.n_rows, R_VAL_LO, r));
+    value->hi = fr_load(ORC_CELL(e->rw_ix.cells, e->rw_ix.n_rows, R_VAL_HI, r));
+    *is_word = e->rw_flags ? (e->rw_flags[r] & 1) : 0;
+  }
+  return n;
+}
+/* step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None;
+ * rw_off = rw lookups the gadget already did, add_rev = curr state halts in success */
+static void restore_context(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_off, fr_t ret_off, fr_t ret_len,
+                            fr_t gas_left, int add_rev) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+  const fr_t rwc = CUR(S_RWC);
+  static const uint64_t READ_TAGS[8] = {ZK_CC_IsRoot, ZK_CC_IsCreate, ZK_CC_CodeHash, ZK_CC_ProgramCounter,
+                                        ZK_CC_StackPointer, ZK_CC_GasLeft, ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
+  static const uint64_t WRITE_TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
+  word_t v; int w;
+  if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off)), 0, CUR(S_CALL_ID), ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT, row)) return;
+  CHECK(EV_RST0_CHECK, !w);
+  const fr_t caller_id = v.lo;
+  word_t vals[8]; int words[8];
+  for (int k = 0; k < 8; k++) {
+    if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off + 1 + k)), 0, caller_id, READ_TAGS[k], &vals[k], &words[k]),
+               EV_RST0_UNSAT + 3 * (1 + k), row)) return;
+  }
+  const fr_t expected[3] = {CUR(S_CALL_ID), ret_off, ret_len};
+  for (int k = 0; k < 3; k++) {
+    if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off + 9 + k)), 1, caller_id, WRITE_TAGS[k], &v, &w),
+               EV_RST0_UNSAT + 3 * (9 + k), row)) return;
+    CHECK(EV_RST0_UNSAT + 3 * (9 + k) + 2, !w && fr_eq(v.lo, expected[k]));
+  }
+  CHECK(EV_RST_VALUE_TYPE, !words[0] && !words[1] && !words[3] && !words[4] && !words[5] && !words[6] && !words[7]);
+  const fr_t rev = add_rev ? CUR(S_REV) : fr_u64(0);
+  CHECK(EV_RST_RWC, fr_eq(NXT(S_RWC), fr_add(rwc, fr_u64(rw_off + 12))));
+  CHECK(EV_RST_CALL_ID, fr_eq(NXT(S_CALL_ID), caller_id));
+  CHECK(EV_RST_IS_ROOT, fr_eq(NXT(S_IS_ROOT), vals[0].lo));
+  CHECK(EV_RST_IS_CREATE, fr_eq(NXT(S_IS_CREATE), vals[1].lo));
+  CHECK(EV_RST_CODE_HASH, fr_eq(NXT(S_HASH_LO), vals[2].lo) && fr_eq(NXT(S_HASH_HI), vals[2].hi));
+  CHECK(EV_RST_PC, fr_eq(NXT(S_PC), vals[3].lo));
+  CHECK(EV_RST_SP, fr_eq(NXT(S_SP), vals[4].lo));
+  CHECK(EV_RST_GAS, fr_eq(NXT(S_GAS), fr_add(vals[5].lo, gas_left)));
+  CHECK(EV_RST_MEM, fr_eq(NXT(S_MEM), vals[6].lo));
+  CHECK(EV_RST_REV, fr_eq(NXT(S_REV), fr_add(vals[7].lo, rev)));
+}
+
+static void gadget_stop(evm_env* e, uint64_t i, uint64_t row) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+  fr_t code_length;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 1, fr_u64(0), 0, &code_length), EV_STOP_LEN_UNSAT, row)) return;
+  const fr_t pc = CUR(S_PC);
+  CHECK(EV_STOP_CMP_RANGE, fr_fits_bits(code_length, 64) && fr_fits_bits(pc, 64));
+  if (code_length.l[0] > pc.l[0]) { /* lt + eq == 0 */
+    fr_t opcode;
+    if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, pc, 1, &opcode), EV_STOP_OP_UNSAT, row)) return;
+    fr_t key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), CUR(S_STATE), opcode, fr_u64(0)};
+    CHECK(EV_STOP_RESP_OPCODE, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  }
+  word_t v; int w;
+  if (!need1(e, call_context_w(e, CUR(S_RWC), 0, CUR(S_CALL_ID), ZK_CC_IsSuccess, &v, &w), EV_STOP_CC_UNSAT, row)) return;
+  CHECK(EV_STOP_CC_TYPE, !w);
+  CHECK(EV_STOP_IS_SUCCESS, fr_eq_u64(v.lo, 1));
+  const fr_t is_root = CUR(S_IS_ROOT);
+  CHECK(EV_STOP_ROOT_ENDTX, fr_eq_u64(is_root, fr_eq_u64(NXT(S_STATE), ZK_ES_EndTx) ? 1 : 0));
+  if (!fr_is_zero(is_root)) {
+    CHECK(EV_STOP_RWC, fr_eq(NXT(S_RWC), fr_add(CUR(S_RWC), fr_u64(1))));
+    CHECK(EV_STOP_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
+  } else {
+    restore_context(e, i, row, 1, fr_u64(0), fr_u64(0), CUR(S_GAS), 1);
+  }
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -453,7 +529,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   CHECK(EV_NOT_IMPLEMENTED, fr_fits_bits(cs, 16) && cs.l[0] < ZK_ES_COUNT && ES_IMPL[cs.l[0]]);
   const uint64_t st = cs.l[0];
   CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP ||
-                                  st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY);
+                                  st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY || st == ZK_ES_STOP);
+  if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
     return;

@@ -812,7 +812,7 @@ def synth_cases():
 
 
 # --------------------------------------------------------------------------- evm2: SHA3 / CALLDATACOPY
-def evm2_cases():
+def evm2_cases(part="evm2"):
     """SHA3 and CALLDATACOPY steps built like the reference's tests (tests/evm/test_sha3.py:35-141,
     tests/evm/test_calldatacopy.py:42-164) with their copy-table and keccak-table rows, verified by the
     reference's verify_step; corruptions of step cells, rw rows (+ type flags), copy-table and
@@ -825,13 +825,49 @@ def evm2_cases():
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random(5)
+    rng = random.Random(5 if part == "evm2" else 7)
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
 
     def wov(lo, hi, is_word):
         return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    def stop_case(root, with_stop, caller=(False, False, 232, 1023, 10, 3, 5)):
+        """tests/evm/test_stop.py:27-139: STOP in the root call (-> EndTx) and in an internal call
+        (restores the caller's context from 12 call-context rows)."""
+        bc = Bytecode().push(0, n_bytes=1)
+        if with_stop:
+            bc = bc.stop()
+        h = Word(bc.hash())
+        if root:
+            rw = RWDictionary(24).call_context_read(1, CallContextFieldTag.IsSuccess, 1)
+            steps = [StepState(ExecutionState.STOP, rw_counter=24, call_id=1, is_root=True, is_create=False, code_hash=h,
+                               program_counter=2, stack_pointer=1023, gas_left=0, reversible_write_counter=2),
+                     StepState(ExecutionState.EndTx, rw_counter=25, call_id=1)]
+            return steps, list(bc.table_assignments()), list(rw.rws), [], []
+        c_root, c_create, c_pc, c_sp, c_gas, c_mem, c_rev = caller
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        rw = (RWDictionary(69).call_context_read(24, CallContextFieldTag.IsSuccess, 1)
+              .call_context_read(24, CallContextFieldTag.CallerId, 1)
+              .call_context_read(1, CallContextFieldTag.IsRoot, c_root)
+              .call_context_read(1, CallContextFieldTag.IsCreate, c_create)
+              .call_context_read(1, CallContextFieldTag.CodeHash, ch)
+              .call_context_read(1, CallContextFieldTag.ProgramCounter, c_pc)
+              .call_context_read(1, CallContextFieldTag.StackPointer, c_sp)
+              .call_context_read(1, CallContextFieldTag.GasLeft, c_gas)
+              .call_context_read(1, CallContextFieldTag.MemorySize, c_mem)
+              .call_context_read(1, CallContextFieldTag.ReversibleWriteCounter, c_rev)
+              .call_context_write(1, CallContextFieldTag.LastCalleeId, 24)
+              .call_context_write(1, CallContextFieldTag.LastCalleeReturnDataOffset, 0)
+              .call_context_write(1, CallContextFieldTag.LastCalleeReturnDataLength, 0))
+        steps = [StepState(ExecutionState.STOP, rw_counter=69, call_id=24, is_root=False, is_create=False, code_hash=h,
+                           program_counter=2, stack_pointer=1023, gas_left=400, reversible_write_counter=2),
+                 StepState(ExecutionState.STOP, rw_counter=82, call_id=1, is_root=c_root, is_create=c_create, code_hash=ch,
+                           program_counter=c_pc, stack_pointer=c_sp, gas_left=c_gas + 400, memory_word_size=c_mem,
+                           reversible_write_counter=c_rev + 2)]
+        return steps, list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
     def mws(a):
         return (a + 31) // 32
@@ -932,7 +968,14 @@ def evm2_cases():
                 return idx, type(e).__name__
         return -1, ""
 
-    scenarios = {
+    if part == "evm3":
+        scenarios = {
+            "stop_root_oob": stop_case(True, False), "stop_root": stop_case(True, True),
+            "stop_internal_oob": stop_case(False, False), "stop_internal": stop_case(False, True),
+            "stop_internal_create": stop_case(False, True, (True, True, 7, 1000, 12345, 0, 0)),
+        }
+    else:
+      scenarios = {
         "sha3_a": sha3_case(0x20, 0x40), "sha3_b": sha3_case(0x11, 0x23), "sha3_zero": sha3_case(0x202, 0),
         "cdc_root": cdc_case(32, 5, 0xA0, 8, True, 0), "cdc_internal": cdc_case(32, 5, 0xA0, 8, False, 0x20),
         "cdc_oob": cdc_case(32, 5, 0xA0, 45, True, 0), "cdc_zero": cdc_case(32, 5, 0xA0, 0, False, 0x20),
@@ -945,12 +988,19 @@ def evm2_cases():
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range(70):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4])
+        for k in range(70 if part == "evm2" else 160):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
-                i, c = rng.randrange(len(S)), rng.choice([1, 2, 3, 7, 8, 9, 10, 10, 9, 5])
-                v = (1 - S[i][c]) if c == 3 else corrupt_value(rng, S[i][c])
+                cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
+                i, c = rng.randrange(len(S)), rng.choice(cols)
+                if c == 0:
+                    v = rng.choice([int(ExecutionState.EndTx), int(ExecutionState.STOP), int(ExecutionState.ADD),
+                                    int(ExecutionState.EndBlock)])
+                    if v == S[i][c]:
+                        continue
+                else:
+                    v = (1 - S[i][c]) if c in (3, 4) else corrupt_value(rng, S[i][c])
                 S2[i][c] = v
             elif which == 1:
                 i, c = rng.randrange(len(R)), rng.randrange(10)
@@ -962,6 +1012,10 @@ def evm2_cases():
                 RF2[i] ^= 1
                 if not RF2[i] & 1:
                     R2[i][9] = 0
+            elif which == 5:  # a second rw row with the same key and another value: ambiguous lookup
+                i, c = rng.randrange(len(R)), 8
+                v = corrupt_value(rng, R[i][c])
+                R2.append(list(R[i])); R2[-1][c] = v; RF2.append(RF[i])
             elif which == 3 and C:
                 i, c = rng.randrange(len(C)), rng.randrange(14)
                 if c in (2, 5):
@@ -986,8 +1040,12 @@ def evm2_cases():
         out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
         out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
         print(name, len(R), "rw", len(C), "copy-table rows", len(K), "keccak rows", len(muts), "vectors")
-    np.savez_compressed(os.path.join(HERE, "evm2.npz"), **out)
-    print(f"evm2: {tot} corruptions, {nfail} failing")
+    np.savez_compressed(os.path.join(HERE, part + ".npz"), **out)
+    print(f"{part}: {tot} corruptions, {nfail} failing")
+
+
+def evm3_cases():
+    evm2_cases("evm3")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1067,7 +1125,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "exp", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "exp", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -108,9 +108,9 @@ def state_vectors():
             yield name, k, s, f, m, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
 
 
-def evm2_vectors():
+def evm2_vectors(part="evm2"):
     """SHA3 / CALLDATACOPY steps: yield (case, k, dict(steps, bytecode, rw, rw_flags, copy, keccak), exp_row, exp_exc)"""
-    z = np.load(os.path.join(GOLDEN, "evm2.npz"))
+    z = np.load(os.path.join(GOLDEN, part + ".npz"))
     for name in z["names"]:
         name = str(name)
         base = {k: z[f"{name}/{k}"] for k in ("steps", "bytecode", "rw", "rw_flags", "copy", "keccak")}
@@ -126,11 +126,20 @@ def evm2_vectors():
                 w["rw_flags"] = base["rw_flags"].copy(); w["rw_flags"][i] ^= 1
                 if not w["rw_flags"][i] & 1:
                     w["rw"] = base["rw"].copy(); w["rw"][9, i, :] = 0
+            elif kind == 5:  # duplicate rw row i with another value
+                extra = base["rw"][:, i:i + 1, :].copy(); extra[c, 0, :] = val
+                w["rw"] = np.ascontiguousarray(np.concatenate([base["rw"], extra], axis=1))
+                w["rw_flags"] = np.concatenate([base["rw_flags"], base["rw_flags"][i:i + 1]])
             elif kind == 3:
                 w["copy"] = base["copy"].copy(); w["copy"][c, i, :] = val
             elif kind == 4:
                 w["keccak"] = base["keccak"].copy(); w["keccak"][c, i, :] = val
             yield name, k, w, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def evm3_vectors():
+    """STOP steps (root -> EndTx, internal -> restored caller context); same layout as evm2"""
+    return evm2_vectors("evm3")
 
 
 def exp_vectors():

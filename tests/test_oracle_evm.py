@@ -50,3 +50,20 @@ def test_oracle_evm_sha3_calldatacopy_matches_reference_golden():
         kinds.add(exp_exc)
     assert n > 380 and n_fail > 250 and n_unsupported == 0
     assert {"AssertionError", "LookupUnsatFailure", "ConstraintUnsatFailure"} <= kinds
+
+
+def test_oracle_evm_stop_matches_reference_golden():
+    """STOP in the root call and in an internal call (tests/evm/test_stop.py): 12 restore-context lookups"""
+    fixed = fixed_table_matrix()
+    classes = oracle_lib.constraint_classes(3)
+    n = n_fail = 0
+    kinds = set()
+    for name, k, w, exp_row, exp_exc in golden_util.evm3_vectors():
+        ff, fc = oracle_lib.check_evm_x(w, fixed)
+        row, exc = oracle_lib.first_failure(ff, classes)
+        assert (row, exc) == (exp_row, exp_exc), f"{name}[{k}]: oracle {(row, exc)} reference {(exp_row, exp_exc)}"
+        n += 1
+        n_fail += exp_row >= 0
+        kinds.add(exp_exc)
+    assert n > 550 and n_fail > 400
+    assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure"} <= kinds, kinds
