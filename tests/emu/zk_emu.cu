@@ -90,11 +90,25 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
                                const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
-  std::vector<u64> s1, s2, s3;
+  std::vector<u64> s1, s2;
   EvmTables t;
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
-  t.fixed = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, s3);
+  // the fixed table is the same array call after call: keep its index and bitmap
+  struct FixedCache { const uint64_t* p = nullptr; uint64_t n = 0, sum = 0; Fr ch; std::vector<u64> slots; IndexDev ix; std::vector<u32> bitmap; };
+  static FixedCache fxc;
+  u64 fx_sum = 0;
+  for (u64 k = 0; k < 257 && n_fixed; k++) {
+    const u64 r = (n_fixed - 1) * k / 256;
+    for (u32 c = 0; c < 4; c++) fx_sum = fx_sum * 0x9E3779B97F4A7C15ull + fixed[((u64)c * n_fixed + r) * 4];
+  }
+  if (!(fxc.p == fixed && fxc.n == n_fixed && fxc.sum == fx_sum && fr_eq(fxc.ch, ch))) {
+    fxc.ix = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, fxc.slots);
+    fxc.bitmap.assign(ZK_RESP_BITMAP_WORDS, 0);
+    for (u64 r = 0; r < n_fixed; r++) resp_bitmap_row(fxc.ix.tab, fxc.bitmap.data(), r);
+    fxc.p = fixed; fxc.n = n_fixed; fxc.sum = fx_sum; fxc.ch = ch;
+  }
+  t.fixed = fxc.ix;
   t.rw.tab.flags = rw_flags;
   const u32 ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
   std::vector<u64> s4, s5;
@@ -105,9 +119,7 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
     add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
     add_positional(t.rw, ZK_POS_DENSE, p_rw);
   }
-  std::vector<u32> bitmap(ZK_RESP_BITMAP_WORDS, 0);
-  for (u64 r = 0; r < n_fixed; r++) resp_bitmap_row(t.fixed.tab, bitmap.data(), r);
-  t.resp_bitmap = bitmap.data();
+  t.resp_bitmap = fxc.bitmap.data();
   WitnessDev w{(const u64*)steps, n_steps, nullptr};
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);

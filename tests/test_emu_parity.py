@@ -88,6 +88,19 @@ def test_emu_evm_sha3_calldatacopy_equals_oracle_on_goldens():
     emu_lib.set_positional(True)
 
 
+def test_emu_evm_stop_equals_oracle_on_goldens():
+    """STOP (root and internal call with the 12 restore-context lookups), both lookup paths"""
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    for name, k, w, exp_row, exp_exc in golden_util.evm3_vectors():
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            ff, fc = emu_lib.check_evm_x(w, fixed, n=n)
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, positional, np.nonzero(ff != off), ff[ff != off], off[ff != off])
+    emu_lib.set_positional(True)
+
+
 def test_emu_exp_equals_oracle_on_goldens():
     n = oracle_lib.lib().orc_n_constraints(4)
     for name, k, r, exp_row, exp_exc in golden_util.exp_vectors():

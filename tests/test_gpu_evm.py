@@ -157,6 +157,31 @@ def test_evm_sha3_calldatacopy_golden_and_oracle_parity():
     ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
 
 
+def test_evm_stop_golden_and_oracle_parity():
+    """STOP steps (tests/evm/test_stop.py: root call -> EndTx, internal call -> restored caller
+    context through 12 call-context lookups): CUDA == oracle array for array, == the reference"""
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    n = 0
+    for name, k, w, exp_row, exp_exc in golden_util.evm3_vectors():
+        ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+        ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+        ctx.upload_table(native.TABLE_COPY, w["copy"])
+        ctx.upload_table(native.TABLE_KECCAK, w["keccak"])
+        evm_main.upload_fixed_table(ctx)
+        ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, 0)
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle"
+        hit = native.first_failure(ff, native.CIRCUIT_EVM)
+        got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
+        assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
+        n += 1
+    assert n > 550
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
+
+
 def test_sha3_host_api_like_reference_test_sha3():
     """tests/evm/test_sha3.py:35-141 on our host API: copy circuit + keccak table + SHA3 step"""
     from zkevm_specs_b200.copy_circuit import verify_copy_table

@@ -520,7 +520,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   k_evm_gadget<G_POP><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_SHA3><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_CDC><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  ctx->launches += 8;
+  k_evm_misc<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  ctx->launches += 9;
   CK(ctx, cudaGetLastError());
   return 0;
 }

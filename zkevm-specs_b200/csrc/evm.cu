@@ -206,7 +206,9 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
 }
 
 // ---- prologue: verify_step before the gadget (main.py:47-63, instruction.py:189-204) --------
-enum { G_ADD, G_MUL, G_PUSH, G_POP, G_SHA3, G_CDC, G_COUNT };
+// G_MISC: the rare states (STOP, ...) share one list and one thread-per-step kernel that switches
+// on the state (k_evm_misc); the hot states each get a branch-uniform kernel
+enum { G_ADD, G_MUL, G_PUSH, G_POP, G_SHA3, G_CDC, G_MISC, G_COUNT };
 // returns the gadget that must run for this step, or -1 if the step already failed
 ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
   const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
@@ -239,6 +241,7 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_POP: return G_POP;
     case ZK_ES_SHA3: return G_SHA3;
     case ZK_ES_CALLDATACOPY: return G_CDC;
+    case ZK_ES_STOP: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -804,6 +807,103 @@ ZK_HD void gadget_calldatacopy(const StepCtx& s, bool live) {
   same_context_x(s, opcode, fr_add_u64(rwc_inc, k), fr_u64(1), fr_u64(3), true, next_mem, gas);
 }
 
+// ---- STOP (execution/stop.py:7-51) ------------------------------------------------------------
+// call_context_lookup_word: rw row (rw_counter, rw, CallContext, call_id, address = field tag)
+ZK_HD int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u64 rw, const Fr& call_id, u64 field_tag,
+                         Word2* value, bool* is_word) {
+  Fr key[5] = {rwc, fr_u64(rw), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
+  u32 r;
+  const int n = lookup_sync<5>(s.t.rw, key, &r, s.mask, live);
+  if (live && n == 1) {
+    value->lo = table_cell(s.t.rw.tab, R_VAL_LO, r);
+    value->hi = table_cell(s.t.rw.tab, R_VAL_HI, r);
+    *is_word = s.t.rw.tab.flags && (s.t.rw.tab.flags[r] & 1);
+  }
+  return n;
+}
+// step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None:
+// rw_off = rw lookups the gadget already did; add_rev = the current state halts in success.
+// Lookup k has ids EV_RST0_UNSAT + 3k (+1 ambiguous, +2 value type / written value).
+ZK_HD void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
+                           const Fr& gas_left, bool add_rev) {
+  const u64 READ_TAGS[8] = {ZK_CC_IsRoot,       ZK_CC_IsCreate, ZK_CC_CodeHash,   ZK_CC_ProgramCounter,
+                            ZK_CC_StackPointer, ZK_CC_GasLeft,  ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
+  const u64 WRITE_TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 v = zero;
+  bool w = false;
+  live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off), 0, call_id, ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT);
+  EV_LIVE_CHECK(EV_RST0_CHECK, !w);
+  const Fr caller_id = v.lo;
+  Word2 vals[8];
+  bool any_word = false;  // of the seven fields read through .value() (CodeHash is a word)
+  for (int k = 0; k < 8; k++) {
+    vals[k] = zero;
+    bool wk = false;
+    live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off + 1 + k), 0, caller_id, READ_TAGS[k], &vals[k], &wk),
+                 EV_RST0_UNSAT + 3 * (1 + k));
+    if (live && k != 2) any_word |= wk;
+  }
+  for (int k = 0; k < 3; k++) {
+    const Fr expected = k == 0 ? call_id : (k == 1 ? ret_off : ret_len);
+    live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off + 9 + k), 1, caller_id, WRITE_TAGS[k], &v, &w),
+                 EV_RST0_UNSAT + 3 * (9 + k));
+    EV_LIVE_CHECK(EV_RST0_UNSAT + 3 * (9 + k) + 2, !w && fr_eq(v.lo, expected));
+  }
+  if (!live) return;  // past the last lookup
+  EV_CHECK(EV_RST_VALUE_TYPE, !any_word);
+  EV_CHECK(EV_RST_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(rwc, rw_off + 12)));
+  EV_CHECK(EV_RST_CALL_ID, fr_eq(s.nxt(S_CALL_ID), caller_id));
+  EV_CHECK(EV_RST_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), vals[0].lo));
+  EV_CHECK(EV_RST_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), vals[1].lo));
+  EV_CHECK(EV_RST_CODE_HASH, fr_eq(s.nxt(S_HASH_LO), vals[2].lo) && fr_eq(s.nxt(S_HASH_HI), vals[2].hi));
+  EV_CHECK(EV_RST_PC, fr_eq(s.nxt(S_PC), vals[3].lo));
+  EV_CHECK(EV_RST_SP, fr_eq(s.nxt(S_SP), vals[4].lo));
+  EV_CHECK(EV_RST_GAS, fr_eq(s.nxt(S_GAS), fr_add(vals[5].lo, gas_left)));
+  EV_CHECK(EV_RST_MEM, fr_eq(s.nxt(S_MEM), vals[6].lo));
+  EV_CHECK(EV_RST_REV, fr_eq(s.nxt(S_REV), add_rev ? fr_add(vals[7].lo, s.cur(S_REV)) : vals[7].lo));
+}
+
+ZK_HD void gadget_stop(const StepCtx& s, bool live) {
+  const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI), pc = s.cur(S_PC);
+  Fr code_length = fr_u64(0);
+  live = need1(s, live, bytecode_lookup(s, live, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_STOP_LEN_UNSAT);
+  EV_LIVE_CHECK(EV_STOP_CMP_RANGE, fr_fits64(code_length) && fr_fits64(pc));
+  {
+    // is_within_range = 1 - lt(code_length, pc) - eq(code_length, pc)  (stop.py:12-18)
+    const bool go = live && code_length.l[0] > pc.l[0];
+    Fr opcode = fr_u64(0);
+    const int n = bytecode_lookup(s, go, hlo, hhi, 2, pc, 1, &opcode);
+    if (go) {
+      live = need1(s, live, n, EV_STOP_OP_UNSAT);
+      EV_LIVE_CHECK(EV_STOP_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
+    }
+  }
+  Word2 v{fr_u64(0), fr_u64(0)};
+  bool w = false;
+  live = need1(s, live, call_context_w(s, live, s.cur(S_RWC), 0, s.cur(S_CALL_ID), ZK_CC_IsSuccess, &v, &w), EV_STOP_CC_UNSAT);
+  EV_LIVE_CHECK(EV_STOP_CC_TYPE, !w);
+  EV_LIVE_CHECK(EV_STOP_IS_SUCCESS, fr_eq_u64(v.lo, 1));
+  const Fr is_root = s.cur(S_IS_ROOT);
+  EV_LIVE_CHECK(EV_STOP_ROOT_ENDTX, fr_eq_u64(is_root, fr_eq_u64(s.nxt(S_STATE), ZK_ES_EndTx) ? 1 : 0));
+  const bool root = !fr_is_zero(is_root);
+  if (live && root) {
+    EV_LIVE_CHECK(EV_STOP_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(s.cur(S_RWC), 1)));
+    EV_LIVE_CHECK(EV_STOP_CALL_ID, fr_eq(s.nxt(S_CALL_ID), s.cur(S_CALL_ID)));
+  }
+  restore_context(s, live && !root, 1, fr_u64(0), fr_u64(0), s.cur(S_GAS), true);
+}
+
+// the rare states: one thread per step, dispatch on the execution state
+ZK_HD void gadget_misc(const StepCtx& s, bool live) {
+  const Fr cs = s.cur(S_STATE);
+  switch (cs.l[0]) {
+    case ZK_ES_STOP: gadget_stop(s, live); break;
+    default: break;
+  }
+}
+
 // whole step on one thread (tests/emu)
 ZK_HD void verify_step(const StepCtx& s, u32 flags) {
   switch (step_prologue(s, flags)) {
@@ -813,6 +913,7 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
     case G_POP: gadget_pop(s, true); break;
     case G_SHA3: gadget_sha3(s, true); break;
     case G_CDC: gadget_calldatacopy(s, true); break;
+    case G_MISC: gadget_misc(s, true); break;
     default: break;
   }
 }
@@ -876,6 +977,22 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     else if (G == G_SHA3) gadget_sha3(s, live);
     else if (G == G_CDC) gadget_calldatacopy(s, live);
     else gadget_pop(s, live);
+  }
+}
+
+// rare states: lanes of a warp may run different gate programs, so every lookup is made
+// lane-private (mask = the lane's own bit: the probe loops need no warp agreement)
+__global__ void __launch_bounds__(128) k_evm_misc(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                  EvmLists lists) {
+  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
+  __shared__ alignas(8) u64 s_bar;
+  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+  const u32 n = lists.count[G_MISC];
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const u64 i = rg.row_begin + lists.idx[(u64)G_MISC * lists.cap + k];
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, nullptr, -1};
+    gadget_misc(s, true);
   }
 }
 
