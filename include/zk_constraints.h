@@ -190,6 +190,19 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CDC_SELECT_BOOL, ZKE_ASSERT, "calldatacopy.py:37-39 select(): is_root is not boolean") \
   X(EV_CDC_COPY_UNSAT, ZKE_UNSAT, "calldatacopy.py:41-51 copy_table lookup unsat")          \
   X(EV_CDC_COPY_AMBIG, ZKE_AMBIG, "calldatacopy.py:41-51 copy_table lookup ambiguous")      \
+  /* MEMORY (MLOAD / MSTORE / MSTORE8): execution/memory.py:7-44 */                          \
+  X(EV_MEM_ADDR_UNSAT, ZKE_UNSAT, "memory.py:10 stack_pop address unsat")                   \
+  X(EV_MEM_ADDR_AMBIG, ZKE_AMBIG, "memory.py:10 stack_pop address ambiguous")               \
+  X(EV_MEM_ADDR_BYTES, ZKE_VALUE, "memory.py:10, instruction.py:481 to_le_bytes(address) -> OverflowError") \
+  X(EV_MEM_ADDR_RANGE, ZKE_RANGE, "memory.py:10, instruction.py:482-483 address does not fit 20 bytes") \
+  X(EV_MEM_VAL_UNSAT, ZKE_UNSAT, "memory.py:17 stack_push (MLOAD) / stack_pop value unsat") \
+  X(EV_MEM_VAL_AMBIG, ZKE_AMBIG, "memory.py:17 value lookup ambiguous")                     \
+  X(EV_MEM_VAL_BYTES, ZKE_VALUE, "memory.py:18 value.to_le_bytes() -> OverflowError")       \
+  X(EV_MEM_MEMSIZE_RANGE, ZKE_RANGE, "instruction.py:1140-1142 memory size does not fit 4 bytes") \
+  X(EV_MEM_MAX_RANGE, ZKE_ASSERT, "instruction.py:1147-1149,449-450 max(): memory_word_size exceeds 4 bytes") \
+  X(EV_MEM_BYTE_UNSAT, ZKE_UNSAT, "memory.py:26,30-36 memory_lookup unsat")                 \
+  X(EV_MEM_BYTE_AMBIG, ZKE_AMBIG, "memory.py:26,30-36 memory_lookup ambiguous")             \
+  X(EV_MEM_BYTE_TYPE, ZKE_ASSERT, "instruction.py:934 .value(): memory value is a Word")    \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

@@ -126,6 +126,23 @@ int zk_bind_table_device(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_
 int zk_upload_table_flags(zk_ctx* ctx, int table_id, uint64_t n_rows, const uint8_t* flags,
                           void* stream);
 
+/* Packed columns — the compact host format of the same matrices.  The reference's cells are
+ * Python ints, most of them bytes, flags, tags and counters (table.py:405-535 row types); a
+ * packer that knows (or measures) each column's range hands column c over as n_rows
+ * little-endian unsigned integers of col_widths[c] bytes, col_widths[c] in {1,2,4,8,16,32};
+ * 0 = constant column, stored once as one 32-byte cell.  `packed` is ONE host buffer of
+ * total_bytes; column c starts at byte col_offsets[c] (a multiple of 32).  The buffer is
+ * copied host->device as it is and the kernels read the narrow columns in place (no widening
+ * pass), so both the PCIe bytes and the HBM bytes of a check shrink with the data.
+ * A 32-byte column holds canonical cells exactly as in zk_upload_columns.  Results are
+ * identical to the canonical upload of the same values (tests/test_gpu_packed.py). */
+int zk_upload_columns_packed(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                             const void* packed, uint64_t total_bytes,
+                             const uint64_t* col_offsets, const uint8_t* col_widths, void* stream);
+int zk_upload_table_packed(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                           const void* packed, uint64_t total_bytes,
+                           const uint64_t* col_offsets, const uint8_t* col_widths, void* stream);
+
 /* Check rows [row_begin, row_end) of the resident matrix (local indices).  Without
  * ZK_FLAG_WRAP the caller guarantees halo rows exist for the circuit's rotations.
  * Reported rows are row_base + local index.

@@ -503,6 +503,45 @@ static void gadget_stop(evm_env* e, uint64_t i, uint64_t row) {
   }
 }
 
+/* memory (execution/memory.py:7-44): MLOAD / MSTORE / MSTORE8.  NB the byte values are NOT
+ * constrained: `instruction.is_equal(memory_lookup(...), byte)` only computes a flag (memory.py:26,
+ * 31-36), so each of the 1 / 32 memory lookups must merely exist, be unique and hold a value. */
+static void gadget_memory(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t addr_w, val_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &addr_w), EV_MEM_ADDR_UNSAT, row)) return;
+  CHECK(EV_MEM_ADDR_BYTES, word_in_domain(addr_w));
+  CHECK(EV_MEM_ADDR_RANGE, (addr_w.hi.l[0] >> 32) == 0 && addr_w.hi.l[1] == 0); /* bytes 20..31 */
+  fr_t address = addr_w.lo; address.l[2] = addr_w.hi.l[0]; /* lo + 2^128 * hi[0:4] < 2^160 */
+  const int is_mload = fr_eq_u64(opcode, 0x51), is_mstore8 = fr_eq_u64(opcode, 0x53);
+  const int is_store = !is_mload;
+  if (is_mload) {
+    if (!need1(e, rw_lookup(e, fr_add(rwc, one), 1, ZK_TARGET_Stack, call_id, sp, &val_w), EV_MEM_VAL_UNSAT, row)) return;
+  } else {
+    if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &val_w), EV_MEM_VAL_UNSAT, row)) return;
+  }
+  CHECK(EV_MEM_VAL_BYTES, word_in_domain(val_w));
+  /* memory_expansion(offset = curr.memory_word_size, length = address + 1 + 31 * (1 - is_mstore8)):
+   * memory_size = (length + offset + 31) // 32 must fit 4 bytes (instruction.py:1138-1155) */
+  const fr_t cur_mem = CUR(S_MEM);
+  const fr_t num = fr_add(fr_add(fr_add(address, fr_u64(is_mstore8 ? 1 : 32)), cur_mem), fr_u64(31));
+  CHECK(EV_MEM_MEMSIZE_RANGE, fr_fits_bits(num, 37));
+  const uint64_t mem_size = num.l[0] >> 5;
+  CHECK(EV_MEM_MAX_RANGE, fr_fits_bits(cur_mem, 32));
+  const uint64_t nxt = cur_mem.l[0] < mem_size ? mem_size : cur_mem.l[0];
+  const fr_t gas = fr_u64(memory_gas_cost(nxt) - memory_gas_cost(cur_mem.l[0]));
+  const int n_bytes = is_mstore8 ? 1 : 32;
+  for (int k = 0; k < n_bytes; k++) {
+    fr_t key[5] = {fr_add(rwc, fr_u64(2 + k)), fr_u64(is_store ? 1 : 0), fr_u64(ZK_TARGET_Memory), call_id,
+                   fr_add(address, fr_u64(k))};
+    uint32_t r; const int m = orc_lookup(&e->rw_ix, key, &r);
+    if (!need1(e, m, EV_MEM_BYTE_UNSAT, row)) return;
+    CHECK(EV_MEM_BYTE_TYPE, !(e->rw_flags && (e->rw_flags[r] & 1)));
+  }
+  same_context_x(e, i, row, opcode, fr_u64(is_mstore8 ? 3 : 34), one, fr_u64(is_store ? 2 : 0), 1, fr_u64(nxt), gas);
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -529,7 +568,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   CHECK(EV_NOT_IMPLEMENTED, fr_fits_bits(cs, 16) && cs.l[0] < ZK_ES_COUNT && ES_IMPL[cs.l[0]]);
   const uint64_t st = cs.l[0];
   CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP ||
-                                  st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY || st == ZK_ES_STOP);
+                                  st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY || st == ZK_ES_STOP ||
+                                  st == ZK_ES_MEMORY);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
@@ -539,6 +579,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_PUSH) gadget_push(e, i, row, opcode);
   else if (st == ZK_ES_SHA3) gadget_sha3(e, i, row, opcode);
   else if (st == ZK_ES_CALLDATACOPY) gadget_calldatacopy(e, i, row, opcode);
+  else if (st == ZK_ES_MEMORY) gadget_memory(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

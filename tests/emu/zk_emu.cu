@@ -17,13 +17,83 @@
 
 using namespace zk;
 
+// tests toggle this to store every matrix in the packed format (each column at the smallest of
+// the widths 0/1/2/4/8/16/32 bytes that holds its values) instead of canonical 32-byte cells
+extern "C" int g_emu_packed = 0;
+extern "C" long long g_emu_narrow_cols = 0;  // columns stored narrower than 32 bytes so far (tests assert > 0)
+struct Store {  // owns the packed copy of a matrix
+  std::vector<unsigned char> buf;
+  u64 off[ZK_MAX_COLS];
+  unsigned char width[ZK_MAX_COLS];
+  const unsigned char* base = nullptr;
+};
+static void store_matrix(Store& st, const u64* cells, u64 n_rows, u32 n_cols, bool allow_pack = true) {
+  if (!g_emu_packed || !allow_pack || n_rows == 0) {
+    layout_canonical(st.off, st.width, n_cols, n_rows);
+    st.base = (const unsigned char*)cells;
+    return;
+  }
+  size_t total = 0;
+  for (u32 c = 0; c < n_cols; c++) {
+    const u64* col = cells + (u64)c * n_rows * 4;
+    u64 m0 = 0, m1 = 0, m23 = 0;
+    bool constant = true;
+    for (u64 r = 0; r < n_rows; r++) {
+      m0 |= col[4 * r];
+      m1 |= col[4 * r + 1];
+      m23 |= col[4 * r + 2] | col[4 * r + 3];
+      constant = constant && !memcmp(col + 4 * r, col, 32);
+    }
+    unsigned w = 32;
+    if (constant) w = 0;
+    else if (!m23 && !m1) w = m0 < 256 ? 1 : (m0 < 65536 ? 2 : (m0 < (1ull << 32) ? 4 : 8));
+    else if (!m23) w = 16;
+    st.width[c] = (unsigned char)w;
+    g_emu_narrow_cols += w < 32;
+    st.off[c] = total;
+    total += ((w ? (size_t)w * n_rows : 32) + 31) / 32 * 32;
+  }
+  st.buf.assign(total + 32, 0);
+  for (u32 c = 0; c < n_cols; c++) {
+    const u64* col = cells + (u64)c * n_rows * 4;
+    unsigned char* dst = st.buf.data() + st.off[c];
+    const unsigned w = st.width[c];
+    if (w == 0) memcpy(dst, col, 32);
+    else
+      for (u64 r = 0; r < n_rows; r++) memcpy(dst + r * w, col + 4 * r, w);  // little-endian host
+  }
+  st.base = st.buf.data();
+}
+static WitnessDev make_witness(Store& st, const u64* cells, u64 n_rows, u32 n_cols, const unsigned char* flags) {
+  store_matrix(st, cells, n_rows, n_cols);
+  WitnessDev w;
+  w.base = st.base;
+  w.n_rows = n_rows;
+  w.flags = flags;
+  for (u32 c = 0; c < ZK_MAX_COLS; c++) {
+    w.off[c] = c < n_cols ? st.off[c] : 0;
+    w.width[c] = c < n_cols ? st.width[c] : 32;
+  }
+  return w;
+}
+
+struct IndexStore {
+  std::vector<u64> slots;
+  Store st;
+};
 static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32* key_cols, u32 n_key,
-                            const Fr& challenge, std::vector<u64>& slots) {
+                            const Fr& challenge, IndexStore& own, bool allow_pack = true) {
+  std::vector<u64>& slots = own.slots;
+  store_matrix(own.st, cells, n_rows, n_cols, allow_pack);
   IndexDev d;
-  d.tab.cells = cells;
+  d.tab.base = own.st.base;
   d.tab.n_rows = n_rows;
   d.tab.n_cols = n_cols;
   d.tab.flags = nullptr;
+  for (u32 c = 0; c < ZK_MAX_TABLE_COLS; c++) {
+    d.tab.off[c] = c < n_cols ? own.st.off[c] : 0;
+    d.tab.width[c] = c < n_cols ? own.st.width[c] : 32;
+  }
   size_t cap = 64;
   while (cap < 2 * n_rows) cap <<= 1;
   slots.assign(cap, ZK_EMPTY_SLOT);
@@ -90,12 +160,12 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
                                const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
-  std::vector<u64> s1, s2;
+  IndexStore s1, s2;
   EvmTables t;
   t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
   // the fixed table is the same array call after call: keep its index and bitmap
-  struct FixedCache { const uint64_t* p = nullptr; uint64_t n = 0, sum = 0; Fr ch; std::vector<u64> slots; IndexDev ix; std::vector<u32> bitmap; };
+  struct FixedCache { const uint64_t* p = nullptr; uint64_t n = 0, sum = 0; Fr ch; IndexStore slots; IndexDev ix; std::vector<u32> bitmap; };
   static FixedCache fxc;
   u64 fx_sum = 0;
   for (u64 k = 0; k < 257 && n_fixed; k++) {
@@ -103,7 +173,7 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
     for (u32 c = 0; c < 4; c++) fx_sum = fx_sum * 0x9E3779B97F4A7C15ull + fixed[((u64)c * n_fixed + r) * 4];
   }
   if (!(fxc.p == fixed && fxc.n == n_fixed && fxc.sum == fx_sum && fr_eq(fxc.ch, ch))) {
-    fxc.ix = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, fxc.slots);
+    fxc.ix = build_index((const u64*)fixed, n_fixed, 4, k4, 4, ch, fxc.slots, false);
     fxc.bitmap.assign(ZK_RESP_BITMAP_WORDS, 0);
     for (u64 r = 0; r < n_fixed; r++) resp_bitmap_row(fxc.ix.tab, fxc.bitmap.data(), r);
     fxc.p = fixed; fxc.n = n_fixed; fxc.sum = fx_sum; fxc.ch = ch;
@@ -111,7 +181,7 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   t.fixed = fxc.ix;
   t.rw.tab.flags = rw_flags;
   const u32 ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
-  std::vector<u64> s4, s5;
+  IndexStore s4, s5;
   t.copy = build_index((const u64*)copy, n_copy, 14, ck, 11, ch, s4);
   t.keccak = build_index((const u64*)keccak, n_keccak, 5, kk, 3, ch, s5);
   PosState p_bc, p_rw;
@@ -120,7 +190,8 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
     add_positional(t.rw, ZK_POS_DENSE, p_rw);
   }
   t.resp_bitmap = fxc.bitmap.data();
-  WitnessDev w{(const u64*)steps, n_steps, nullptr};
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)steps, n_steps, 13, nullptr);
   ResultDev res;
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
   Fr stack_pre[2];
@@ -138,10 +209,11 @@ extern "C" int emu_check_bytecode(const uint64_t* cols, uint64_t n_rows, const u
                                   const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 pk[2] = {0, 1}, kk[5] = {0, 1, 2, 3, 4};
-  std::vector<u64> s1, s2;
+  IndexStore s1, s2;
   IndexDev push_ix = build_index((const u64*)push, n_push, 2, pk, 2, ch, s1);
   IndexDev kec_ix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s2);
-  WitnessDev w{(const u64*)cols, n_rows, nullptr};
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)cols, n_rows, 12, nullptr);
   CheckRange rg{row_begin, row_end, 0, flags};
   ResultDev res;
   init_result(res, first_fail, fail_count, BC_N_CONSTRAINTS);
@@ -157,7 +229,7 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
                               uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k5[5] = {0, 1, 2, 3, 4}, k3[3] = {0, 1, 2};
-  std::vector<u64> s1, s2, s3;
+  IndexStore s1, s2, s3;
   CopyTables t;
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s1);
   t.rw.tab.flags = rw_flags;
@@ -169,7 +241,8 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
     add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
     add_positional(t.rw, ZK_POS_DENSE, p_rw);
   }
-  WitnessDev w{(const u64*)rows, n_rows, row_flags};
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 20, row_flags);
   CheckRange rg{row_begin, row_end, 0, flags};
   ResultDev res;
   init_result(res, first_fail, fail_count, CP_N_CONSTRAINTS);
@@ -183,9 +256,10 @@ extern "C" int emu_check_state(const uint64_t* rows, uint64_t n_rows, const uint
                                const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
   const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
   const u32 k12[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
-  std::vector<u64> s1;
+  IndexStore s1;
   IndexDev ix = build_index((const u64*)mpt, n_mpt, 12, k12, 12, ch, s1);
-  WitnessDev w{(const u64*)rows, n_rows, flags};
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 57, flags);
   CheckRange rg{row_begin, row_end, 0, cflags};
   ResultDev res;
   init_result(res, first_fail, fail_count, ST_N_CONSTRAINTS);
@@ -195,7 +269,8 @@ extern "C" int emu_check_state(const uint64_t* rows, uint64_t n_rows, const uint
 
 extern "C" int emu_check_exp(const uint64_t* rows, uint64_t n_rows, uint64_t row_begin, uint64_t row_end, uint32_t cflags,
                              uint32_t* first_fail, uint64_t* fail_count) {
-  WitnessDev w{(const u64*)rows, n_rows, nullptr};
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 21, nullptr);
   CheckRange rg{row_begin, row_end, 0, cflags};
   ResultDev res;
   init_result(res, first_fail, fail_count, XP_N_CONSTRAINTS);

@@ -104,6 +104,15 @@ def check_state(rows, flags, mpt, row_begin=0, row_end=None, cflags=1, challenge
     return ff, fc
 
 
+def set_packed(on: bool) -> None:
+    """store every witness / table matrix in the packed narrow-column format (fr.cuh:ld_col)"""
+    ctypes.c_int.in_dll(lib(), "g_emu_packed").value = int(on)
+
+
+def narrow_cols() -> int:
+    return ctypes.c_longlong.in_dll(lib(), "g_emu_narrow_cols").value
+
+
 def set_positional(on: bool) -> None:
     """toggle the positional (regular-table) lookup fast paths in the emulation; off = hash index only"""
     ctypes.c_int.in_dll(lib(), "g_emu_positional").value = int(on)

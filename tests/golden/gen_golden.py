@@ -825,7 +825,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random(5 if part == "evm2" else 7)
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -868,6 +868,32 @@ def evm2_cases(part="evm2"):
                            program_counter=c_pc, stack_pointer=c_sp, gas_left=c_gas + 400, memory_word_size=c_mem,
                            reversible_write_counter=c_rev + 2)]
         return steps, list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
+    def memory_case(opcode, offset, value, cur_mem=0):
+        """tests/evm/test_memory.py:55-150: MLOAD / MSTORE / MSTORE8 with their 32 (1) memory rows"""
+        is_mload, is_mstore8 = opcode == Opcode.MLOAD, opcode == Opcode.MSTORE8
+        ow, vw = Word(offset), Word(value)
+        bc = (Bytecode().mload(ow).stop() if is_mload else
+              Bytecode().mstore8(ow, vw).stop() if is_mstore8 else Bytecode().mstore(ow, vw).stop())
+        h = Word(bc.hash())
+        rw = (RWDictionary(1).stack_read(1, 1022, ow).stack_write(1, 1022, vw) if is_mload else
+              RWDictionary(1).stack_read(1, 1022, ow).stack_read(1, 1023, vw))
+        data = value.to_bytes(32, "big")
+        if is_mstore8:
+            rw.memory_write(1, offset, value & 0xFF)
+        else:
+            for idx in range(32):
+                (rw.memory_read if is_mload else rw.memory_write)(1, offset + idx, data[idx])
+        # memory_expansion(offset = curr.memory_word_size, length = address + 1 + 31 * not8), as written
+        size = (offset + (1 if is_mstore8 else 32) + cur_mem + 31) // 32
+        nxt = max(cur_mem, size)
+        gas = Opcode.MLOAD.constant_gas_cost() + (nxt - cur_mem) * 3 + (nxt * nxt // 512 - cur_mem * cur_mem // 512)
+        steps = [StepState(ExecutionState.MEMORY, rw_counter=1, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=33 if is_mload else 66, stack_pointer=1022, memory_word_size=cur_mem, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=4 if is_mstore8 else 35, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=34 if is_mload else 67, stack_pointer=1022 if is_mload else 1024,
+                           memory_word_size=nxt, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
     def mws(a):
         return (a + 31) // 32
@@ -968,7 +994,13 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm3":
+    if part == "evm4":
+        scenarios = {
+            "mload_0": memory_case(Opcode.MLOAD, 0, 0xFF), "mload_1": memory_case(Opcode.MLOAD, 1, 0xFF00, 3),
+            "mstore_0": memory_case(Opcode.MSTORE, 0, 0xFF), "mstore_big": memory_case(Opcode.MSTORE, 0x1234, (1 << 255) + 77, 5),
+            "mstore8_0": memory_case(Opcode.MSTORE8, 0, 0xFFFF), "mstore8_1": memory_case(Opcode.MSTORE8, 0x21, 0xAB, 1),
+        }
+    elif part == "evm3":
         scenarios = {
             "stop_root_oob": stop_case(True, False), "stop_root": stop_case(True, True),
             "stop_internal_oob": stop_case(False, False), "stop_internal": stop_case(False, True),
@@ -988,7 +1020,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range(70 if part == "evm2" else 160):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
@@ -1046,6 +1078,10 @@ def evm2_cases(part="evm2"):
 
 def evm3_cases():
     evm2_cases("evm3")
+
+
+def evm4_cases():
+    evm2_cases("evm4")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1125,7 +1161,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "exp", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "exp", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

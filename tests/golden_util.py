@@ -154,3 +154,8 @@ def exp_vectors():
             if i >= 0:
                 r = R.copy(); r[c, i, :] = z[f"{name}/mut_val"][k]
             yield name, k, r, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def evm4_vectors():
+    """MEMORY steps (MLOAD / MSTORE / MSTORE8, tests/evm/test_memory.py); same layout as evm2"""
+    return evm2_vectors("evm4")

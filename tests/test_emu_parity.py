@@ -101,9 +101,60 @@ def test_emu_evm_stop_equals_oracle_on_goldens():
     emu_lib.set_positional(True)
 
 
+def test_emu_evm_memory_equals_oracle_on_goldens():
+    """MLOAD / MSTORE / MSTORE8, both lookup paths"""
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    for name, k, w, exp_row, exp_exc in golden_util.evm4_vectors():
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            ff, fc = emu_lib.check_evm_x(w, fixed, n=n)
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, positional, np.nonzero(ff != off), ff[ff != off], off[ff != off])
+    emu_lib.set_positional(True)
+
+
 def test_emu_exp_equals_oracle_on_goldens():
     n = oracle_lib.lib().orc_n_constraints(4)
     for name, k, r, exp_row, exp_exc in golden_util.exp_vectors():
         ff, fc = emu_lib.check_exp(r)
         off, ofc = oracle_lib.check_exp(r)
         assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, np.nonzero(ff[:n] != off))
+
+
+def test_emu_packed_columns_equal_oracle_on_every_golden_family():
+    """the packed narrow-column storage (include/zkcheck.h "packed columns", fr.cuh:ld_col): every
+    matrix stored at per-column minimal widths gives the oracle's arrays on every golden vector"""
+    fixed = fixed_table_matrix()
+    lib = oracle_lib.lib()
+    emu_lib.set_packed(True)
+    try:
+        for name, k, cols, push, kec, r, exp_row, exp_exc in golden_util.bytecode_vectors():
+            assert all(np.array_equal(a, b) for a, b in zip(emu_lib.check_bytecode(cols, push, kec, r),
+                                                            oracle_lib.check_bytecode(cols, push, kec, r))), (name, k)
+        n = lib.orc_n_constraints(3)
+        for name, k, s, b, r, flags, exp_row, exp_exc in golden_util.evm_vectors():
+            assert all(np.array_equal(a, b) for a, b in zip(emu_lib.check_evm(s, b, r, fixed, flags=flags, n=n),
+                                                            oracle_lib.check_evm(s, b, r, fixed, flags=flags))), (name, k)
+        for vectors in (golden_util.evm2_vectors, golden_util.evm3_vectors, golden_util.evm4_vectors):
+            for name, k, w, exp_row, exp_exc in vectors():
+                assert all(np.array_equal(a, b) for a, b in zip(emu_lib.check_evm_x(w, fixed, n=n),
+                                                                oracle_lib.check_evm_x(w, fixed))), (name, k)
+        n = lib.orc_n_constraints(2)
+        for name, k, w, r, exp_row, exp_exc in golden_util.copy_vectors():
+            ff, fc = emu_lib.check_copy(w, r)
+            off, ofc = oracle_lib.check_copy(w, r)
+            assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k)
+        n = lib.orc_n_constraints(1)
+        for name, k, s, f, m, exp_row, exp_exc in golden_util.state_vectors():
+            ff, fc = emu_lib.check_state(s, f, m)
+            off, ofc = oracle_lib.check_state(s, f, m)
+            assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k)
+        n = lib.orc_n_constraints(4)
+        for name, k, r, exp_row, exp_exc in golden_util.exp_vectors():
+            ff, fc = emu_lib.check_exp(r)
+            off, ofc = oracle_lib.check_exp(r)
+            assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k)
+        assert emu_lib.narrow_cols() > 10000  # the packed path really ran
+    finally:
+        emu_lib.set_packed(False)

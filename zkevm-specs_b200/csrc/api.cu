@@ -60,6 +60,8 @@ struct Matrix {
   size_t flags_cap = 0;
   u64 flags_rows = 0;
   u64 version = 0;
+  u64 off[ZK_MAX_COLS];               // byte offset of each column inside dev
+  unsigned char width[ZK_MAX_COLS];   // bytes per row of each column (fr.cuh:ld_col)
 };
 
 struct Index {
@@ -188,9 +190,24 @@ extern "C" int zk_set_challenge(zk_ctx* ctx, int which, const uint64_t r[4]) {
   return 0;
 }
 
-static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const u64* host,
-                        const u64* device, cudaStream_t st) {
+// `widths` == nullptr: canonical uint64[n_cols][n_rows][4].  Otherwise the packed format of
+// include/zkcheck.h: column c holds n_rows integers of widths[c] bytes at byte offset offs[c] of a
+// buffer of `total_bytes`; the buffer is copied as it is (one H2D copy) and read in place.
+static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const void* host,
+                        const u64* device, cudaStream_t st, const uint8_t* widths = nullptr,
+                        const uint64_t* offs = nullptr, size_t total_bytes = 0) {
   CK(ctx, cudaSetDevice(ctx->device));
+  if (n_cols > ZK_MAX_COLS) return fail_msg(ctx, "too many columns");
+  if (widths) {
+    for (u32 c = 0; c < n_cols; c++) {
+      const unsigned w = widths[c];
+      if (!(w == 0 || w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32))
+        return fail_msg(ctx, "packed column width must be 0, 1, 2, 4, 8, 16 or 32");
+      const size_t need = w ? (size_t)w * n_rows : 32;
+      if (offs[c] % 32 || offs[c] + need > total_bytes)
+        return fail_msg(ctx, "packed column offset misaligned or outside the buffer");
+    }
+  }
   m.version++;
   if (device) {
     if (m.dev && !m.borrowed) cudaFree(m.dev);
@@ -198,7 +215,7 @@ static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const u6
     m.borrowed = true;
     m.cap_bytes = 0;
   } else {
-    size_t bytes = (size_t)n_rows * n_cols * 32;
+    size_t bytes = widths ? total_bytes : (size_t)n_rows * n_cols * 32;
     if (m.borrowed) {
       m.dev = nullptr;
       m.borrowed = false;
@@ -215,6 +232,14 @@ static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const u6
   m.n_rows = n_rows;
   m.n_cols = n_cols;
   m.flags_rows = 0;  // flags belong to the previous contents
+  if (widths) {
+    for (u32 c = 0; c < n_cols; c++) {
+      m.off[c] = offs[c];
+      m.width[c] = widths[c];
+    }
+  } else {
+    layout_canonical(m.off, m.width, n_cols, n_rows);
+  }
   return 0;
 }
 
@@ -277,13 +302,38 @@ extern "C" int zk_upload_table_flags(zk_ctx* ctx, int table_id, uint64_t n_rows,
   return store_flags(ctx, ctx->tab[table_id], n_rows, flags, (cudaStream_t)stream);
 }
 
+extern "C" int zk_upload_columns_packed(zk_ctx* ctx, int circuit_id, uint64_t n_rows, uint32_t n_cols,
+                                        const void* packed, uint64_t total_bytes, const uint64_t* col_offsets,
+                                        const uint8_t* col_widths, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  if ((int)n_cols != kCircuitCols[circuit_id]) return fail_msg(ctx, "wrong column count for circuit");
+  if (n_rows >= 0xFFFFFFFFull) return fail_msg(ctx, "too many rows (row ids are uint32)");
+  if (!col_offsets || !col_widths) return fail_msg(ctx, "packed upload needs offsets and widths");
+  return store_matrix(ctx, ctx->circ[circuit_id], n_rows, n_cols, packed, nullptr, (cudaStream_t)stream, col_widths,
+                      col_offsets, (size_t)total_bytes);
+}
+extern "C" int zk_upload_table_packed(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t n_cols,
+                                      const void* packed, uint64_t total_bytes, const uint64_t* col_offsets,
+                                      const uint8_t* col_widths, void* stream) {
+  if (table_id < 0 || table_id >= ZK_N_TABLES) return fail_msg(ctx, "bad table id");
+  if ((int)n_cols != kTableCols[table_id]) return fail_msg(ctx, "wrong column count for table");
+  if (n_rows >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
+  if (!col_offsets || !col_widths) return fail_msg(ctx, "packed upload needs offsets and widths");
+  return store_matrix(ctx, ctx->tab[table_id], n_rows, n_cols, packed, nullptr, (cudaStream_t)stream, col_widths,
+                      col_offsets, (size_t)total_bytes);
+}
+
 // ------------------------------------------------------------------ lookup index cache
 static TableDev table_dev(const zk_ctx* ctx, int table_id) {
   const Matrix& m = ctx->tab[table_id];
   TableDev t;
-  t.cells = m.dev;
+  t.base = (const unsigned char*)m.dev;
   t.n_rows = m.dev ? m.n_rows : 0;
   t.n_cols = m.n_cols ? m.n_cols : kTableCols[table_id];
+  for (u32 c = 0; c < ZK_MAX_TABLE_COLS; c++) {
+    t.off[c] = c < t.n_cols && m.dev ? m.off[c] : 0;
+    t.width[c] = c < t.n_cols && m.dev ? m.width[c] : 32;
+  }
   t.flags = (m.flags_rows == m.n_rows && m.n_rows) ? m.flags : nullptr;
   return t;
 }
@@ -395,8 +445,12 @@ static int ensure_result(zk_ctx* ctx, int circuit, ResultDev* out, cudaStream_t 
 
 static WitnessDev witness_dev(const Matrix& m) {
   WitnessDev w;
-  w.cells = m.dev;
+  w.base = (const unsigned char*)m.dev;
   w.n_rows = m.n_rows;
+  for (u32 c = 0; c < ZK_MAX_COLS; c++) {
+    w.off[c] = c < m.n_cols ? m.off[c] : 0;
+    w.width[c] = c < m.n_cols ? m.width[c] : 32;
+  }
   w.flags = (m.flags_rows == m.n_rows && m.n_rows) ? m.flags : nullptr;
   return w;
 }

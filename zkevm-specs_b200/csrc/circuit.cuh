@@ -4,10 +4,13 @@
 
 namespace zk {
 
+#define ZK_MAX_COLS 64
 struct WitnessDev {
-  const u64* cells;            // [n_cols][n_rows][4]
+  const unsigned char* base;   // column c: n_rows integers of width[c] bytes at base + off[c]
   u64 n_rows;                  // resident rows (incl. halos when sharded)
   const unsigned char* flags;  // optional per-row type flags
+  u64 off[ZK_MAX_COLS];
+  unsigned char width[ZK_MAX_COLS];  // 0 (constant column), 1, 2, 4, 8, 16 or 32 (fr.cuh:ld_col)
 };
 
 struct CheckRange {
@@ -17,7 +20,7 @@ struct CheckRange {
 };
 
 ZK_HD Fr wcell(const WitnessDev& w, u32 col, u64 row) {
-  return ld_cell(w.cells + ((u64)col * w.n_rows + row) * 4);
+  return ld_col(w.base + w.off[col], w.width[col], row);
 }
 // rotation by +k / -k: wraps modulo n_rows when the whole circuit is resident, otherwise the
 // caller supplied halo rows (include/zkcheck.h)

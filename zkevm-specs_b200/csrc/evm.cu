@@ -242,6 +242,7 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_SHA3: return G_SHA3;
     case ZK_ES_CALLDATACOPY: return G_CDC;
     case ZK_ES_STOP: return G_MISC;
+    case ZK_ES_MEMORY: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -895,11 +896,61 @@ ZK_HD void gadget_stop(const StepCtx& s, bool live) {
   restore_context(s, live && !root, 1, fr_u64(0), fr_u64(0), s.cur(S_GAS), true);
 }
 
+// ---- MEMORY: MLOAD / MSTORE / MSTORE8 (execution/memory.py:7-44) -----------------------------
+// NB the byte values are NOT constrained by the reference: `instruction.is_equal(memory_lookup(..),
+// byte)` only computes a flag (memory.py:26,31-36); each of the 1 / 32 memory rows must exist, be
+// unique and hold a value (not a Word).
+ZK_HD void gadget_memory(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 addr_w = zero, val_w = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &addr_w), EV_MEM_ADDR_UNSAT);
+  EV_LIVE_CHECK(EV_MEM_ADDR_BYTES, word_in_domain(addr_w));
+  EV_LIVE_CHECK(EV_MEM_ADDR_RANGE, (addr_w.hi.l[0] >> 32) == 0 && addr_w.hi.l[1] == 0);  // bytes 20..31 zero
+  Fr address = addr_w.lo;
+  address.l[2] = addr_w.hi.l[0];  // lo + 2^128 * hi < 2^160
+  const bool is_mload = fr_eq_u64(opcode, 0x51), is_mstore8 = fr_eq_u64(opcode, 0x53);
+  const bool is_store = !is_mload;
+  // value: stack_push() at the popped slot for MLOAD, a second stack_pop() otherwise (memory.py:17)
+  live = need1(s, live,
+               rw_lookup(s, live, fr_add_u64(rwc, 1), is_mload ? 1 : 0, ZK_TARGET_Stack, call_id,
+                         is_mload ? sp : fr_add_u64(sp, 1), &val_w),
+               EV_MEM_VAL_UNSAT);
+  EV_LIVE_CHECK(EV_MEM_VAL_BYTES, word_in_domain(val_w));
+  // memory_expansion(offset = curr.memory_word_size, length = address + 1 + 31 * (1 - is_mstore8)),
+  // instruction.py:1138-1155: (length + offset + 31) // 32 must fit 4 bytes, then max() with the
+  // current size (both < 2^32)
+  const Fr cur_mem = s.cur(S_MEM);
+  const Fr num = fr_add_u64(fr_add(fr_add_u64(address, is_mstore8 ? 1 : 32), cur_mem), 31);
+  EV_LIVE_CHECK(EV_MEM_MEMSIZE_RANGE, fr_fits64(num) && (num.l[0] >> 37) == 0);
+  EV_LIVE_CHECK(EV_MEM_MAX_RANGE, fr_fits64(cur_mem) && (cur_mem.l[0] >> 32) == 0);
+  const u64 mem_size = num.l[0] >> 5;
+  const u64 nxt = cur_mem.l[0] < mem_size ? mem_size : cur_mem.l[0];
+  const int n_bytes = is_mstore8 ? 1 : 32;
+  for (int k = 0; k < 32; k++) {  // every lane runs 32 rounds (warp-synchronous lookups)
+    const bool go = live && k < n_bytes;
+    Fr key[5] = {fr_add_u64(rwc, 2 + k), fr_u64(is_store ? 1 : 0), fr_u64(ZK_TARGET_Memory), call_id,
+                 fr_add_u64(address, k)};
+    u32 r = 0;
+    const int m = lookup_sync<5>(s.t.rw, key, &r, s.mask, go);
+    if (go) {
+      live = need1(s, live, m, EV_MEM_BYTE_UNSAT);
+      EV_LIVE_CHECK(EV_MEM_BYTE_TYPE, !(s.t.rw.tab.flags && (s.t.rw.tab.flags[r] & 1)));
+    }
+  }
+  if (!live) return;
+  const Fr gas = fr_u64(memory_gas_cost(nxt) - memory_gas_cost(cur_mem.l[0]));
+  same_context_x(s, opcode, fr_u64(is_mstore8 ? 3 : 34), fr_u64(1), fr_u64(is_store ? 2 : 0), true, fr_u64(nxt), gas);
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
   switch (cs.l[0]) {
     case ZK_ES_STOP: gadget_stop(s, live); break;
+    case ZK_ES_MEMORY: gadget_memory(s, live); break;
     default: break;
   }
 }

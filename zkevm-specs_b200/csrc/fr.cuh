@@ -49,6 +49,53 @@ ZK_HD Fr ld_cell(const u64* p) {
 #endif
   return r;
 }
+// Columns are stored at their own width (include/zkcheck.h, "packed columns"): a column whose
+// values all fit w bytes is kept as n_rows little-endian w-byte integers, w in {1,2,4,8,16,32};
+// w = 0 is a constant column (one 32-byte cell).  Byte-, flag- and counter-valued columns are
+// most of every table, so a warp reading 32 consecutive rows of such a column touches 1-8
+// sectors instead of 32, and the stored tables shrink ~5x (the 17.8 M-row bytecode table of
+// the bench: 3.4 GB -> 0.70 GB).  The branch is uniform: the width is a per-column constant.
+// Device form is BRANCH-FREE (three predicated loads, one executes): with branches the compiler
+// cannot batch a thread's independent cell loads ahead of the compares, and the gate programs are
+// latency-bound on exactly that (profiles/README.md v12).  Widths <= 8 load the aligned 8-byte
+// word that contains the value (a w-byte integer at a multiple of w never straddles one; columns
+// start at multiples of 32 and are padded to 32) and shift/mask it out.
+ZK_HD Fr ld_col(const unsigned char* p, u32 width, u64 row) {
+  Fr r;
+#ifdef __CUDA_ARCH__
+  r.l[0] = r.l[1] = r.l[2] = r.l[3] = 0;
+  const u32 lw = width ? width : 32u;  // constant column: stride 0, one 32-byte cell
+  const u64 a = (u64)p + row * width;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pa, pb, pc;\n\t"
+      "setp.le.u32 pa, %5, 8;\n\t"
+      "setp.eq.u32 pb, %5, 16;\n\t"
+      "setp.eq.u32 pc, %5, 32;\n\t"
+      "@pa ld.global.nc.u64 %0, [%6];\n\t"
+      "@pb ld.global.nc.v2.u64 {%0,%1}, [%4];\n\t"
+      "@pc ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];\n\t"
+      "}"
+      : "+l"(r.l[0]), "+l"(r.l[1]), "+l"(r.l[2]), "+l"(r.l[3])
+      : "l"(a), "r"(lw), "l"(a & ~7ull));
+  const bool narrow = lw <= 8;
+  const u32 sh = narrow ? ((u32)a & 7u) * 8u : 0u;
+  const u64 m = lw >= 8 ? ~0ull : ((1ull << (8u * lw)) - 1ull);
+  r.l[0] = (r.l[0] >> sh) & m;
+#else
+  if (width == 32) return ld_cell((const u64*)p + row * 4);
+  r.l[1] = r.l[2] = r.l[3] = 0;
+  switch (width) {
+    case 1: r.l[0] = p[row]; break;
+    case 2: r.l[0] = ((const unsigned short*)p)[row]; break;
+    case 4: r.l[0] = ((const u32*)p)[row]; break;
+    case 8: r.l[0] = ((const u64*)p)[row]; break;
+    case 16: r.l[0] = ((const u64*)p)[2 * row]; r.l[1] = ((const u64*)p)[2 * row + 1]; break;
+    default: return ld_cell((const u64*)p);  // 0: constant column
+  }
+#endif
+  return r;
+}
 ZK_HD u32 ld_u32(const u32* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);

@@ -21,12 +21,22 @@ namespace zk {
 #define ZK_MAX_KEY 12
 #define ZK_EMPTY_SLOT 0xFFFFFFFFFFFFFFFFull  // a slot is (fingerprint32 << 32) | row32
 
+#define ZK_MAX_TABLE_COLS 16
 struct TableDev {
-  const u64* cells;  // [n_cols][n_rows][4]
+  const unsigned char* base;  // column c: n_rows integers of width[c] bytes at base + off[c]
   u64 n_rows;
   u32 n_cols;
   const unsigned char* flags;  // optional per-row type flags (may be null)
+  u64 off[ZK_MAX_TABLE_COLS];
+  unsigned char width[ZK_MAX_TABLE_COLS];  // 0 (constant column), 1, 2, 4, 8, 16 or 32 (fr.cuh:ld_col)
 };
+// canonical layout: uint64[n_cols][n_rows][4]
+ZK_HD void layout_canonical(u64* off, unsigned char* width, u32 n_cols, u64 n_rows) {
+  for (u32 c = 0; c < n_cols; c++) {
+    off[c] = (u64)c * n_rows * 32;
+    width[c] = 32;
+  }
+}
 
 struct IndexDev {
   TableDev tab;
@@ -49,11 +59,8 @@ struct IndexDev {
 #define ZK_POS_DENSE 1  // key column 0 is a counter: cell(row) == cell(0) + row   (rw table by rw_counter)
 #define ZK_POS_RUNS 2   // bytecode table: runs [Header, Byte 0, Byte 1, ...] of one code hash each
 
-ZK_HD const u64* cell_ptr(const TableDev& t, u32 col, u64 row) {
-  return t.cells + ((u64)col * t.n_rows + row) * 4;
-}
 ZK_HD Fr table_cell(const TableDev& t, u32 col, u64 row) {
-  return ld_cell(cell_ptr(t, col, row));
+  return ld_col(t.base + t.off[col], t.width[col], row);
 }
 
 // 64-bit mix of the canonical RLC value: low bits pick the bucket, high 32 bits are the

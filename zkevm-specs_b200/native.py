@@ -72,7 +72,7 @@ EXPORTS = [
     "zk_upload_table_flags", "zk_check", "zk_check_async", "zk_result_device", "zk_fetch_result",
     "zk_allreduce_results", "zk_circuit_cols", "zk_table_cols", "zk_n_constraints",
     "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
-    "zk_last_timing",
+    "zk_last_timing", "zk_upload_columns_packed", "zk_upload_table_packed",
 ]
 
 
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
         L.zk_upload_table.argtypes = [vp, i32, u64, u32, vp, vp]
         L.zk_bind_table_device.argtypes = [vp, i32, u64, u32, vp]
         L.zk_upload_table_flags.argtypes = [vp, i32, u64, vp, vp]
+        L.zk_upload_columns_packed.argtypes = [vp, i32, u64, u32, vp, u64, vp, vp, vp]
+        L.zk_upload_table_packed.argtypes = [vp, i32, u64, u32, vp, u64, vp, vp, vp]
         L.zk_check.argtypes = [vp, i32, u64, u64, u64, u32, _U32P, _U64P, vp]
         L.zk_check_async.argtypes = [vp, i32, u64, u64, u64, u32, vp]
         L.zk_result_device.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
@@ -143,6 +145,10 @@ class Context:
             raise NativeError(f"zk_ctx_create failed: {self._L.zk_last_error(None).decode()}")
         self._h = h
         self.device = device
+        # None: upload_columns / upload_table ship canonical 32-byte cells.  "min": they pack every
+        # matrix to its measured minimal column widths first and ship the packed buffer
+        # (zk_upload_*_packed); results are identical (tests/test_gpu_packed.py).
+        self.packed_uploads = None
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -171,6 +177,11 @@ class Context:
 
     def upload_columns(self, circuit_id: int, matrix, flags=None, stream: int = 0) -> None:
         m = self._matrix(matrix)
+        if self.packed_uploads == "min" and m.shape[1]:
+            from . import packing
+            self._keep = getattr(self, "_keep", {})
+            pm = self._keep[("c", circuit_id)] = packing.pack_matrix(m)  # host buffer outlives the async copy
+            return self.upload_columns_packed(circuit_id, pm, flags=flags, stream=stream)
         self._ck(self._L.zk_upload_columns(self._h, circuit_id, m.shape[1], m.shape[0], _host_ptr(m),
                                            ctypes.c_void_p(stream)), "zk_upload_columns")
         if flags is not None:
@@ -178,12 +189,37 @@ class Context:
             self._ck(self._L.zk_upload_row_flags(self._h, circuit_id, f.shape[0], _host_ptr(f),
                                                  ctypes.c_void_p(stream)), "zk_upload_row_flags")
 
+    def upload_columns_packed(self, circuit_id: int, pm, flags=None, stream: int = 0, host_ptr: int = 0) -> None:
+        """pm: packing.PackedMatrix (narrow columns in one host buffer); `host_ptr` overrides the
+        buffer address (e.g. a pinned copy of pm.buf)"""
+        self._ck(self._L.zk_upload_columns_packed(
+            self._h, circuit_id, pm.n_rows, pm.n_cols, ctypes.c_void_p(host_ptr or pm.buf.ctypes.data), pm.nbytes,
+            _host_ptr(pm.offsets), _host_ptr(pm.widths), ctypes.c_void_p(stream)), "zk_upload_columns_packed")
+        if flags is not None:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._ck(self._L.zk_upload_row_flags(self._h, circuit_id, f.shape[0], _host_ptr(f),
+                                                 ctypes.c_void_p(stream)), "zk_upload_row_flags")
+
+    def upload_table_packed(self, table_id: int, pm, flags=None, stream: int = 0, host_ptr: int = 0) -> None:
+        self._ck(self._L.zk_upload_table_packed(
+            self._h, table_id, pm.n_rows, pm.n_cols, ctypes.c_void_p(host_ptr or pm.buf.ctypes.data), pm.nbytes,
+            _host_ptr(pm.offsets), _host_ptr(pm.widths), ctypes.c_void_p(stream)), "zk_upload_table_packed")
+        if flags is not None:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._ck(self._L.zk_upload_table_flags(self._h, table_id, f.shape[0], _host_ptr(f),
+                                                   ctypes.c_void_p(stream)), "zk_upload_table_flags")
+
     def bind_columns_device(self, circuit_id: int, n_rows: int, n_cols: int, dev_ptr: int) -> None:
         self._ck(self._L.zk_bind_columns_device(self._h, circuit_id, n_rows, n_cols,
                                                 ctypes.c_void_p(dev_ptr)), "zk_bind_columns_device")
 
     def upload_table(self, table_id: int, matrix, flags=None, stream: int = 0) -> None:
         m = self._matrix(matrix)
+        if self.packed_uploads == "min" and m.shape[1]:
+            from . import packing
+            self._keep = getattr(self, "_keep", {})
+            pm = self._keep[("t", table_id)] = packing.pack_matrix(m)
+            return self.upload_table_packed(table_id, pm, flags=flags, stream=stream)
         self._ck(self._L.zk_upload_table(self._h, table_id, m.shape[1], m.shape[0], _host_ptr(m),
                                          ctypes.c_void_p(stream)), "zk_upload_table")
         if flags is not None:

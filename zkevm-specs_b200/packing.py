@@ -124,3 +124,123 @@ def copy_table_row(r) -> List[int]:
             cell_int(r.dst_id.lo), cell_int(r.dst_id.hi), cell_int(r.dst_tag), cell_int(r.src_addr),
             cell_int(r.src_addr_end), cell_int(r.dst_addr), cell_int(r.length), cell_int(r.rlc_acc),
             cell_int(r.rw_counter), cell_int(r.rwc_inc)]
+
+
+# ---------------------------------------------------------------------------------------------
+# Packed columns (include/zkcheck.h "packed columns"): each column at the smallest width that
+# holds its values.  The reference's cells are Python ints, most of them bytes, flags, tags and
+# counters (evm_circuit/table.py:405-535); shipping them as 32-byte cells wastes ~5x of both the
+# PCIe and the HBM bytes of a check.
+# ---------------------------------------------------------------------------------------------
+class PackedMatrix:
+    """ONE host buffer + per-column (offset, width) — the argument of zk_upload_*_packed.
+
+    `buf` is a uint8 array (pin it for asynchronous copies); column c holds n_rows little-endian
+    unsigned integers of widths[c] bytes at byte offsets[c] (a multiple of 32), widths[c] in
+    {1, 2, 4, 8, 16, 32}; width 0 = constant column stored once as one 32-byte cell."""
+
+    def __init__(self, buf: np.ndarray, offsets: np.ndarray, widths: np.ndarray, n_rows: int) -> None:
+        self.buf, self.offsets, self.widths, self.n_rows = buf, offsets, widths, n_rows
+
+    @property
+    def n_cols(self) -> int:
+        return len(self.widths)
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.buf.nbytes)
+
+    def column(self, c: int) -> np.ndarray:
+        """column c widened back to uint64[n_rows][4] (tests)"""
+        w, off = int(self.widths[c]), int(self.offsets[c])
+        out = np.zeros((self.n_rows, 4), dtype=np.uint64)
+        if w == 0:
+            out[:] = self.buf[off:off + 32].view(np.uint64)
+        elif w >= 8:
+            out[:, :w // 8] = self.buf[off:off + w * self.n_rows].view(np.uint64).reshape(self.n_rows, w // 8)
+        else:
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[w]
+            out[:, 0] = self.buf[off:off + w * self.n_rows].view(dt)
+        return out
+
+    def unpack(self) -> np.ndarray:
+        return np.stack([self.column(c) for c in range(self.n_cols)])
+
+
+def column_width(col: np.ndarray) -> int:
+    """smallest of 0/1/2/4/8/16/32 bytes that stores every cell of a uint64[n_rows][4] column"""
+    if col.shape[0] == 0:
+        return 32
+    if (col == col[0]).all():
+        return 0
+    if col[:, 2].any() or col[:, 3].any():
+        return 32
+    if col[:, 1].any():
+        return 16
+    m = int(col[:, 0].max())
+    return 1 if m < 1 << 8 else 2 if m < 1 << 16 else 4 if m < 1 << 32 else 8
+
+
+def _value_width(cell: np.ndarray) -> int:
+    if cell[2] or cell[3]:
+        return 32
+    if cell[1]:
+        return 16
+    m = int(cell[0])
+    return 1 if m < 1 << 8 else 2 if m < 1 << 16 else 4 if m < 1 << 32 else 8
+
+
+# Data-independent widths by column TYPE (what a packer that never looks at the values would use;
+# bench.py packs with these so that the measured bytes do not depend on the synthetic trace having
+# one contract or small counters).  Field order = the reference row types, Word = (lo, hi).
+TYPE_WIDTHS = {
+    # StepState, evm_circuit/step.py:16-44: state, rwc, call_id, is_root, is_create, code_hash lo/hi,
+    # pc, sp, gas_left, memory_word_size, reversible_write_counter, log_id
+    "evm_steps": [2, 8, 8, 1, 1, 16, 16, 8, 2, 8, 8, 8, 8],
+    # RWTableRow, evm_circuit/table.py:447-457: rw_counter, rw, key0 (tag), key1 (id), key2 (address, up
+    # to 160 bits), key3 (field tag), key4 lo/hi (storage key), value lo/hi, value_prev lo/hi, aux lo/hi
+    "rw_table": [8, 1, 1, 8, 32, 1, 16, 16, 16, 16, 16, 16, 16, 16],
+    # BytecodeTableRow, table.py:438-443: hash lo/hi, tag, index, is_code, value (a byte; the Header row
+    # holds the code length)
+    "bytecode_table": [16, 16, 1, 4, 1, 4],
+}
+
+
+def pack_matrix(matrix: np.ndarray, widths: Sequence[int] | None = None,
+                min_widths: Sequence[int] | None = None) -> PackedMatrix:
+    """uint64[n_cols][n_rows][4] -> PackedMatrix.
+    widths=None, min_widths=None : every column at its measured minimal width (0 = constant column)
+    min_widths                   : at least the given (type) width per column, wider if a value
+                                   needs it (corrupted witnesses), never a constant column
+    widths                       : exactly these; a value that does not fit is an error."""
+    m = np.ascontiguousarray(matrix, dtype=np.uint64)
+    n_cols, n_rows = m.shape[0], m.shape[1]
+    if min_widths is not None:
+        assert widths is None and len(min_widths) == n_cols
+        ws = [max(int(t), column_width(m[c]) or _value_width(m[c][0])) if n_rows else int(t)
+              for c, t in enumerate(min_widths)]
+    else:
+        ws = [column_width(m[c]) for c in range(n_cols)] if widths is None else [int(w) for w in widths]
+    offsets, total = [], 0
+    for w in ws:
+        offsets.append(total)
+        total += ((w * n_rows if w else 32) + 31) // 32 * 32
+    buf = np.zeros(max(total, 32), dtype=np.uint8)
+    for c, (w, off) in enumerate(zip(ws, offsets)):
+        col = m[c]
+        if n_rows == 0:
+            continue
+        if widths is not None:
+            assert w in (0, 1, 2, 4, 8, 16, 32), f"bad width {w}"
+            need = column_width(col[:1]) if w else column_width(col)  # w == 0 needs a constant column
+            if w:
+                need = max(column_width(col), _value_width(col[0]))
+            assert (w == 0 and need == 0) or (w and need <= w), f"column {c} does not fit {w} bytes"
+        if w == 0:
+            buf[off:off + 32] = col[0].view(np.uint8)
+        elif w >= 8:
+            buf[off:off + w * n_rows] = np.ascontiguousarray(col[:, :w // 8]).view(np.uint8).reshape(-1)
+        else:
+            dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[w]
+            buf[off:off + w * n_rows] = col[:, 0].astype(dt).view(np.uint8)
+    return PackedMatrix(buf, np.asarray(offsets, dtype=np.uint64), np.asarray(ws, dtype=np.uint8), n_rows)
