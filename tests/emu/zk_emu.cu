@@ -113,6 +113,7 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   d.pos_kind = ZK_POS_NONE;
   d.heads_slots = nullptr;
   d.heads_mask = 0;
+  d.heads_len = d.heads_list = d.heads_count = nullptr;
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
   return d;
 }
@@ -120,16 +121,25 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
 struct PosState {
   u32 ok = 1;
   std::vector<u64> heads;
+  std::vector<u32> aux;
 };
 static void add_positional(IndexDev& d, u32 kind, PosState& st) {
   d.pos_kind = kind;
   st.heads.assign(1u << 10, ZK_EMPTY_SLOT);
   d.heads_slots = st.heads.data();
   d.heads_mask = (1u << 10) - 1;
+  st.aux.assign(2 * (1u << 10) + 1, 0);
+  d.heads_len = st.aux.data();
+  d.heads_list = st.aux.data() + (1u << 10);
+  d.heads_count = st.aux.data() + 2 * (1u << 10);
   st.ok = 1;
   for (u64 r = 0; r < d.tab.n_rows; r++) {
     if (kind == ZK_POS_DENSE) pos_verify_dense_row(d, &st.ok, r);
     else pos_verify_run_row(d, &st.ok, r);
+  }
+  if (kind == ZK_POS_RUNS && d.tab.n_rows) {  // k_pos_runlen
+    const u32 count = *d.heads_count < d.heads_mask + 1 ? *d.heads_count : d.heads_mask + 1;
+    for (u32 k = 0; k <= count; k++) pos_runlen_entry(d, k, count);
   }
   d.pos_ok = &st.ok;
 }

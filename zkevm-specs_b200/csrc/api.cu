@@ -73,6 +73,7 @@ struct Index {
   u32 pos_kind = ZK_POS_NONE;
   u32* pos_flag = nullptr;  // device flag written by k_pos_verify
   u64* heads = nullptr;     // ZK_POS_RUNS heads index
+  u32* heads_aux = nullptr; // [ZK_HEADS_CAP] run lengths, [ZK_HEADS_CAP] head list, [1] count
   u64 built_version = ~0ull;
   u64 built_challenge = ~0ull;
   IndexDev dev;
@@ -162,6 +163,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (ix->slots) cudaFree(ix->slots);
     if (ix->pos_flag) cudaFree(ix->pos_flag);
     if (ix->heads) cudaFree(ix->heads);
+    if (ix->heads_aux) cudaFree(ix->heads_aux);
     delete ix;
   }
   for (auto& r : ctx->res)
@@ -355,7 +357,10 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     ix->pos_kind = pos_kind;
     if (pos_kind != ZK_POS_NONE) {
       CK(ctx, cudaMalloc(&ix->pos_flag, sizeof(u32)));
-      if (pos_kind == ZK_POS_RUNS) CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(u64)));
+      if (pos_kind == ZK_POS_RUNS) {
+        CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(u64)));
+        CK(ctx, cudaMalloc(&ix->heads_aux, (2 * ZK_HEADS_CAP + 1) * sizeof(u32)));
+      }
     }
     ctx->indexes.push_back(ix);
   }
@@ -392,13 +397,23 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   d.pos_kind = ix->pos_kind;
   d.heads_slots = ix->heads;
   d.heads_mask = ZK_HEADS_CAP - 1;
+  d.heads_len = ix->heads_aux;
+  d.heads_list = ix->heads_aux ? ix->heads_aux + ZK_HEADS_CAP : nullptr;
+  d.heads_count = ix->heads_aux ? ix->heads_aux + 2 * ZK_HEADS_CAP : nullptr;
   const unsigned grid = (unsigned)std::min<u64>((t.n_rows + 255) / 256, (u64)ctx->sm_count * 32);
   if (t.n_rows && ix->pos_kind != ZK_POS_NONE) {
     // verify the regular structure in one streaming pass; the flag stays 1 iff it holds
     k_set_u32<<<1, 1, 0, st>>>(ix->pos_flag, 1u);
-    if (ix->heads) CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(u64), st));
+    if (ix->heads) {
+      CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(u64), st));
+      CK(ctx, cudaMemsetAsync(ix->heads_aux, 0, (2 * ZK_HEADS_CAP + 1) * sizeof(u32), st));
+    }
     k_pos_verify<<<grid, 256, 0, st>>>(d, ix->pos_flag);
     ctx->launches += 2;
+    if (ix->pos_kind == ZK_POS_RUNS) {  // run lengths from the listed heads (a few thousand threads at most)
+      k_pos_runlen<<<16, 256, 0, st>>>(d);
+      ctx->launches += 1;
+    }
     d.pos_ok = ix->pos_flag;
   }
   if (t.n_rows) {

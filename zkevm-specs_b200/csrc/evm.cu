@@ -141,7 +141,7 @@ ZK_HD Fr bytecode_hash0(const StepCtx& s, const Fr& hlo, const Fr& hhi) {
 }
 // `n_head/head`: result of the heads-index probe for this code hash (positional path), done once
 // per step by the caller
-ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_head, u32 head, const Fr& hlo,
+ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_head, u32 head, u32 run_len, const Fr& hlo,
                             const Fr& hhi, u64 tag, const Fr& index, u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   const IndexDev& ix = s.t.bytecode;
@@ -150,7 +150,7 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   int n;
   if (s.pos_mode == 1 || (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) {
     Fr got;
-    n = pos_lookup_run(ix, key, n_head, head, &r, live, B_VALUE, &got);
+    n = pos_lookup_run(ix, key, n_head, head, run_len, &r, live, B_VALUE, &got);
     if (live && n == 1) *value = got;
     return n;
   } else {
@@ -163,11 +163,13 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   return n;
 }
 // heads-index probe of the step's code hash (no-op unless the bytecode table is positional)
-ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head) {
+ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head,
+                        u32* run_len) {
   const IndexDev& ix = s.t.bytecode;
   *head = 0;
+  *run_len = 0;
   if (s.pos_mode != 1 && (ix.tab.n_rows == 0 || !(pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS))) return 0;
-  return heads_probe(ix, h0, hlo, hhi, head, s.mask, live);
+  return heads_probe(ix, h0, hlo, hhi, head, run_len, s.mask, live);
 }
 // constant terms of a stack lookup's key hash, computed once per thread
 ZK_HD void stack_key_pre(const IndexDev& rw_ix, Fr out[2]) {
@@ -511,6 +513,7 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
 struct PushCommon {
   Fr hlo, hhi, h0, pc, opcode, num_pushed;
   int n_head;  // heads-index probe of the code hash (positional bytecode table)
+  u32 run_len;  // Byte rows of that contract's run
   u32 head;
   u64 n_push, n_pad;
   Word2 value;
@@ -543,7 +546,7 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx, bool live) {
   const bool pushed = live && (u64)idx < c.n_push && (u64)idx >= c.n_pad;
   Fr got = fr_u64(0);
   const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)idx);  // pc + num_pushed - idx
-  const int n = bytecode_lookup_h(s, pushed, c.h0, c.n_head, c.head, c.hlo, c.hhi, 2, index, 0, &got);
+  const int n = bytecode_lookup_h(s, pushed, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 2, index, 0, &got);
   if (pushed) {
     if (n != 1) return n == 0 ? base : base + 1;
     return fr_eq_u64(got, byte) ? -1 : base + 2;
@@ -569,7 +572,7 @@ ZK_HD void push_two_bytes_pos(const StepCtx& s, const PushCommon& c, int idx, bo
     const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)b);
     Fr key[5] = {c.hlo, c.hhi, fr_u64(2), index, fr_u64(0)};
     u32 r;
-    n[k] = pos_lookup_run(ix, key, c.n_head, c.head, &r, pushed[k], B_VALUE, &got[k]);
+    n[k] = pos_lookup_run(ix, key, c.n_head, c.head, c.run_len, &r, pushed[k], B_VALUE, &got[k]);
   }
 #pragma unroll
   for (int k = 0; k < 2; k++) {
@@ -624,9 +627,9 @@ ZK_HD void gadget_push(const StepCtx& s, bool live) {
   c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
   Fr opcode = fr_u64(0), code_length = fr_u64(0);
   Word2 value{fr_u64(0), fr_u64(0)};
-  c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
-  const int n_op = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
-  const int n_len = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
+  const int n_op = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
   const int n_rw = rw_lookup(s, live, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
   if (!live) return;
   if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
@@ -1083,7 +1086,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
   Fr stack_pre[2];
   stack_key_pre(t.rw, stack_pre);
   Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // per-lane cache of the last code hash seen
-  u32 last_head = 0;
+  u32 last_head = 0, last_len = 0;
   int last_n_head = 0;
   bool have_h0 = false;
   const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
@@ -1110,18 +1113,20 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     const bool changed = !(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi));
     if (POS) {
       c.h0 = fr_u64(0);
-      u32 head = 0;
+      u32 head = 0, rlen = 0;
       const Fr h0 = changed ? bytecode_hash0(s, c.hlo, c.hhi) : fr_u64(0);
-      const int nh = bytecode_head(s, live && changed, h0, c.hlo, c.hhi, &head);  // every lane calls (warp-sync)
+      const int nh = bytecode_head(s, live && changed, h0, c.hlo, c.hhi, &head, &rlen);  // every lane calls (warp-sync)
       if (changed) {
         last_hlo = c.hlo;
         last_hhi = c.hhi;
         last_head = head;
+        last_len = rlen;
         last_n_head = live ? nh : 0;
         have_h0 = live;
       }
       c.n_head = last_n_head;
       c.head = last_head;
+      c.run_len = last_len;
     } else {
       if (changed) {
         last_hlo = c.hlo;
@@ -1130,13 +1135,13 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
         have_h0 = true;
       }
       c.h0 = last_h0;
-      c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head);
+      c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
     }
     // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
     Word2 val{fr_u64(0), fr_u64(0)};
-    int n_hit = bytecode_lookup_h(s, live && sub < 2, c.h0, c.n_head, c.head, c.hlo, c.hhi, sub == 0 ? 2 : 1,
+    int n_hit = bytecode_lookup_h(s, live && sub < 2, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, sub == 0 ? 2 : 1,
                                   sub == 0 ? c.pc : fr_u64(0), sub == 0 ? 1 : 0, &v);
     const int n_hit_rw = rw_lookup(s, live && sub == 2, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID),
                                    fr_sub_u64(s.cur(S_SP), 1), &val);

@@ -110,6 +110,7 @@ ZK_HD u64 ld_u64(const u64* p) {
   return *p;
 #endif
 }
+ZK_HD u64 ld_volatile_u64(const u64* p) { return *(const volatile u64*)p; }  // written earlier in the same stream
 ZK_HD u64 atomic_cas_u64(u64* p, u64 expect, u64 val) {
 #ifdef __CUDA_ARCH__
   return atomicCAS(p, expect, val);

@@ -54,6 +54,9 @@ struct IndexDev {
   u32 pos_kind;
   u64* heads_slots;  // ZK_POS_RUNS: hash index (same slot format) over the first row of every run
   u32 heads_mask;
+  u32* heads_len;    // [heads_mask + 1] number of Byte rows of the run whose head sits in that slot
+  u32* heads_list;   // [heads_mask + 1] head rows in insertion order, heads_count[0] of them
+  u32* heads_count;
 };
 #define ZK_POS_NONE 0
 #define ZK_POS_DENSE 1  // key column 0 is a counter: cell(row) == cell(0) + row   (rw table by rw_counter)
@@ -127,9 +130,9 @@ ZK_HD bool rows_identical(const TableDev& t, u32 a, u32 b) {
 // of its gate program alone (measured: 1-2 active threads per instruction, profiles/r01_v4).
 template <int NK>
 ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const Fr& h, const Fr (&key)[NK],
-                      u32* row, unsigned mask, bool active) {
+                      u32* row, unsigned mask, bool active, u32* slot_out = nullptr) {
   int found = 0;
-  u32 first = 0;
+  u32 first = 0, first_slot = 0;
   const u64 mix = rlc_mix(h);
   const u32 fp = (u32)(mix >> 32);
   u32 b = (u32)mix & slot_mask;
@@ -159,6 +162,7 @@ ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const
           if (eq) {
             if (found == 0) {
               first = cand;
+              first_slot = b;
               found = 1;
             } else if (!rows_identical(ix.tab, first, cand)) {
               found = 2;
@@ -172,6 +176,7 @@ ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const
   }
 #undef ZK_GROUP_ANY
   *row = first;
+  if (slot_out) *slot_out = first_slot;
   return found;
 }
 template <int NK>
@@ -211,33 +216,36 @@ ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bo
   return eq ? 1 : 0;
 }
 // ZK_POS_RUNS (bytecode table, key = hash_lo, hash_hi, tag, index, is_code): `head` is the first
-// row of the run with this code hash (found through the heads index), Header row = head,
-// Byte row k = head + 1 + k
+// row of the run with this code hash and `len` its number of Byte rows (both from the heads index,
+// whose probe CONFIRMS the two hash cells); Header row = head, Byte row k = head + 1 + k, k < len.
+// The verify pass has pinned, for every row of a run, hash == the head's hash, tag (Header at the
+// head, Byte after it) and index == position in the run, so the only row that can match the key
+// is known and just ONE of its cells is still open: is_code.  A lookup therefore reads is_code
+// (+ the looked-up value) — 2 narrow cells instead of 6 — and its verdict equals the reference's
+// scan: 0 or 1 match, never 2 (distinct runs have distinct hashes, rows of a run distinct indices).
 // Branch-free: the candidate row is clamped to a valid row and its cells are always loaded, so
 // several lookups of one thread have all their loads in flight together; `extra_col` (or -1)
 // names one more cell of the candidate row to fetch in the same batch (the looked-up value).
-ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32* row, bool active,
+ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32 len, u32* row, bool active,
                          int extra_col = -1, Fr* extra = nullptr) {
-  const bool is_hdr = fr_eq_u64(key[2], 1);
-  const bool is_byte = fr_eq_u64(key[2], 2) && fr_fits64(key[3]) && key[3].l[0] < ix.tab.n_rows;
+  const bool is_hdr = fr_eq_u64(key[2], 1) && fr_is_zero(key[3]);
+  const bool is_byte = fr_eq_u64(key[2], 2) && fr_fits64(key[3]) && key[3].l[0] < (u64)len;
   u64 cand = is_hdr ? (u64)head : (u64)head + 1 + (is_byte ? key[3].l[0] : 0);
   const bool valid = active && n_head == 1 && (is_hdr || is_byte) && cand < ix.tab.n_rows;
   if (!valid) cand = 0;
-  Fr cells[5];
-#pragma unroll
-  for (int j = 0; j < 5; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
+  const Fr is_code = table_cell(ix.tab, ix.key_cols[4], cand);
   if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
-  bool eq = valid;
-#pragma unroll
-  for (int j = 0; j < 5; j++) eq = eq && fr_eq(cells[j], key[j]);
   *row = (u32)cand;
-  return eq ? 1 : 0;
+  return valid && fr_eq(is_code, key[4]) ? 1 : 0;
 }
 // heads index probe: h0 = hash_lo + hash_hi * r  (warp-synchronous like probe_hashed)
-ZK_HD int heads_probe(const IndexDev& ix, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head, unsigned mask,
-                      bool active) {
+ZK_HD int heads_probe(const IndexDev& ix, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head, u32* len,
+                      unsigned mask, bool active) {
   Fr key[2] = {hlo, hhi};
-  return probe_slots<2>(ix, ix.heads_slots, ix.heads_mask, h0, key, head, mask, active);
+  u32 slot = 0;
+  const int n = probe_slots<2>(ix, ix.heads_slots, ix.heads_mask, h0, key, head, mask, active, &slot);
+  *len = (active && n == 1) ? ld_u32(ix.heads_len + slot) : 0u;
+  return n;
 }
 
 // verify kernels' row functions
@@ -275,7 +283,11 @@ ZK_HD void pos_verify_run_row(const IndexDev& ix, u32* ok, u64 row) {
     u32 b = (u32)mix & ix.heads_mask;
     for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
       const u64 old = atomic_cas_u64(&ix.heads_slots[b], ZK_EMPTY_SLOT, entry);
-      if (old == ZK_EMPTY_SLOT) return;
+      if (old == ZK_EMPTY_SLOT) {
+        const u32 k = atomic_add_u32(ix.heads_count, 1u);  // k <= heads_mask: one slot per listed head
+        ix.heads_list[k & ix.heads_mask] = (u32)row;
+        return;
+      }
       if ((old >> 32) == (mix >> 32)) {
         const u32 other = (u32)old;
         if (fr_eq(table_cell(t, 0, other), hlo) && fr_eq(table_cell(t, 1, other), hhi)) break;  // duplicate hash
@@ -292,6 +304,42 @@ ZK_HD void pos_verify_run_row(const IndexDev& ix, u32* ok, u64 row) {
   }
 }
 
+// Second (tiny) pass over the listed heads: entry k < count closes the run that ends just before
+// head k, entry k == count the run that ends at the last row.  The last row of a run gives its
+// length directly (a Byte row's index is its position in the run, a Header-only run has none), and
+// the run's head is that many rows back; its slot in the heads index receives the length.
+// Only meaningful when the verify pass leaves the flag at 1 (otherwise nothing reads it).
+ZK_HD void pos_runlen_entry(const IndexDev& ix, u32 k, u32 count) {
+  const TableDev& t = ix.tab;
+  u64 end;
+  if (k < count) {
+    const u32 h = ix.heads_list[k];
+    if (h == 0) return;
+    end = (u64)h - 1;
+  } else {
+    end = t.n_rows - 1;
+  }
+  const Fr tag = table_cell(t, 2, end), index = table_cell(t, 3, end);
+  u64 len = 0;
+  if (!fr_eq_u64(tag, 1)) {
+    if (!fr_fits64(index) || index.l[0] >= end) return;  // irregular table: the flag is already 0
+    len = index.l[0] + 1;
+  }
+  const u64 head = end - len;
+  const Fr hlo = table_cell(t, 0, end), hhi = table_cell(t, 1, end);
+  const u64 mix = rlc_mix(fr_add(hlo, rlc_term(ix, hhi, 1)));
+  u32 b = (u32)mix & ix.heads_mask;
+  for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
+    const u64 slot = ld_volatile_u64(&ix.heads_slots[b]);
+    if (slot == ZK_EMPTY_SLOT) return;
+    if ((u32)slot == (u32)head) {
+      ix.heads_len[b] = (u32)len;
+      return;
+    }
+    b = (b + 1) & ix.heads_mask;
+  }
+}
+
 // warp-synchronous lookup (see probe_hashed)
 template <int NK>
 ZK_HD int lookup_sync(const IndexDev& ix, const Fr (&key)[NK], u32* row, unsigned mask, bool active) {
@@ -300,9 +348,9 @@ ZK_HD int lookup_sync(const IndexDev& ix, const Fr (&key)[NK], u32* row, unsigne
     if (ix.pos_kind == ZK_POS_DENSE) return pos_lookup_dense<NK>(ix, key, row, active);
     if constexpr (NK == 5) {
       if (ix.pos_kind == ZK_POS_RUNS) {
-        u32 head = 0;
-        const int n_head = heads_probe(ix, fr_add(key[0], rlc_term(ix, key[1], 1)), key[0], key[1], &head, mask, active);
-        return pos_lookup_run(ix, key, n_head, head, row, active);
+        u32 head = 0, len = 0;
+        const int n_head = heads_probe(ix, fr_add(key[0], rlc_term(ix, key[1], 1)), key[0], key[1], &head, &len, mask, active);
+        return pos_lookup_run(ix, key, n_head, head, len, row, active);
       }
     }
   }
@@ -332,6 +380,11 @@ __global__ void __launch_bounds__(256) k_slots_clear(u64* slots, u64 n, const u3
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) slots[i] = ZK_EMPTY_SLOT;
 }
 __global__ void k_set_u32(u32* p, u32 v) { *p = v; }
+__global__ void __launch_bounds__(256) k_pos_runlen(IndexDev ix) {
+  if (ix.tab.n_rows == 0) return;
+  const u32 count = min(*ix.heads_count, ix.heads_mask + 1);
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k <= count; k += gridDim.x * blockDim.x) pos_runlen_entry(ix, k, count);
+}
 __global__ void __launch_bounds__(256) k_pos_verify(IndexDev ix, u32* ok) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.tab.n_rows; row += stride) {
