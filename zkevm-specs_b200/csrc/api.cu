@@ -582,7 +582,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   const unsigned full = (unsigned)((n + 127) / 128);
   const unsigned grid_t = std::min<unsigned>(full, (unsigned)ctx->sm_count * 8);
   const unsigned grid_w = std::min<unsigned>((unsigned)((n * 32 + 127) / 128), (unsigned)ctx->sm_count * 12);
-  k_evm_push<true><<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_push_pos<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_push<false><<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_ADD><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_MUL><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);

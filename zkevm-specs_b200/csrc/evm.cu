@@ -643,6 +643,82 @@ ZK_HD void gadget_push(const StepCtx& s, bool live) {
   push_epilogue(s, c);
 }
 
+// ---- PUSH on positional tables, ONE THREAD per step ------------------------------------------
+// With positional rw + bytecode tables a PUSH step needs, per pushed byte, only the is_code and
+// value cells of row head + 1 + index (lookup.cuh:pos_lookup_run): 64 narrow, independent loads of
+// two columns.  One thread per step issues them back to back with no branch in between (the
+// outcome of every byte is folded into three bit masks, the first set bit in program order names
+// the failing constraint), so a warp instruction serves 32 steps instead of the 2 of the
+// half-warp kernel below.  `hc` caches the heads-index probe of the last code hash this thread saw.
+struct HeadCache {
+  Fr hlo, hhi;
+  u32 head, len;
+  int n;
+  bool have;
+};
+ZK_HD bool both_positional(const EvmTables& t) {
+  return t.rw.tab.n_rows != 0 && t.bytecode.tab.n_rows != 0 && pos_enabled(t.rw) && pos_enabled(t.bytecode) &&
+         t.rw.pos_kind == ZK_POS_DENSE && t.bytecode.pos_kind == ZK_POS_RUNS;
+}
+ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
+  PushCommon c;
+  c.hlo = s.cur(S_HASH_LO);
+  c.hhi = s.cur(S_HASH_HI);
+  c.pc = s.cur(S_PC);
+  c.h0 = fr_u64(0);
+  if (!(hc->have && fr_eq(c.hlo, hc->hlo) && fr_eq(c.hhi, hc->hhi))) {
+    hc->n = bytecode_head(s, true, bytecode_hash0(s, c.hlo, c.hhi), c.hlo, c.hhi, &hc->head, &hc->len);
+    hc->hlo = c.hlo;
+    hc->hhi = c.hhi;
+    hc->have = true;
+  }
+  c.n_head = hc->n;
+  c.head = hc->head;
+  c.run_len = hc->len;
+  Fr opcode = fr_u64(0), code_length = fr_u64(0);
+  Word2 value{fr_u64(0), fr_u64(0)};
+  const int n_op = bytecode_lookup_h(s, true, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
+  const int n_len = bytecode_lookup_h(s, true, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
+  const int n_rw = rw_lookup(s, true, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
+  if (!push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c)) return;
+  // byte idx is looked up at index = pc + num_pushed - idx (push.py:24-31); as a field element it
+  // only names a row when it is a small non-negative integer
+  const Fr top = fr_add(c.pc, c.num_pushed);
+  const bool top_ok = fr_fits64(top) && c.n_head == 1;
+  const TableDev& bt = s.t.bytecode.tab;
+  const unsigned char* p_is = bt.base + bt.off[B_ISCODE];
+  const unsigned char* p_val = bt.base + bt.off[B_VALUE];
+  const u32 w_is = bt.width[B_ISCODE], w_val = bt.width[B_VALUE];
+  const u64 first_row = (u64)c.head + 1;
+  u32 m_unsat = 0, m_neq = 0, m_pad = 0;
+#pragma unroll
+  for (int idx = 0; idx < 32; idx++) {
+    const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
+    const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
+    const u64 byte = ((idx < 16 ? lo_limb : hi_limb) >> (8 * (idx & 7))) & 0xFF;
+    const bool pushed = (u64)idx < c.n_push && (u64)idx >= c.n_pad;
+    const bool valid = pushed && top_ok && top.l[0] >= (u64)idx && top.l[0] - (u64)idx < (u64)c.run_len;
+    const u64 row = valid ? first_row + (top.l[0] - (u64)idx) : 0;
+    const Fr is_code = ld_col(p_is, w_is, row), got = ld_col(p_val, w_val, row);
+    const bool hit = valid && fr_is_zero(is_code);  // key: (hash, Byte, index, is_code = 0)
+    m_unsat |= (u32)(pushed && !hit) << idx;
+    m_neq |= (u32)(hit && !fr_eq_u64(got, byte)) << idx;
+    m_pad |= (u32)(!pushed && byte != 0) << idx;
+  }
+  const u32 any = m_unsat | m_neq | m_pad;
+  if (any) {
+#ifdef __CUDA_ARCH__
+    const int idx = __ffs(any) - 1;
+#else
+    const int idx = __builtin_ctz(any);
+#endif
+    const int base = EV_PUSH_B0_UNSAT + 4 * idx;
+    step_fail(s, ((m_unsat >> idx) & 1) ? base : (((m_neq >> idx) & 1) ? base + 2 : base + 3));
+    return;
+  }
+  push_epilogue(s, c);
+}
+
 ZK_HD void gadget_pop(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
   live = opcode_lookup(s, live, &opcode);
@@ -963,7 +1039,14 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
   switch (step_prologue(s, flags)) {
     case G_ADD: gadget_add(s, true); break;
     case G_MUL: gadget_mul(s, true); break;
-    case G_PUSH: gadget_push(s, true); break;
+    case G_PUSH:
+      if (both_positional(s.t)) {  // what k_evm_push_pos runs
+        HeadCache hc{};
+        gadget_push_pos1(s, &hc);
+      } else {
+        gadget_push(s, true);
+      }
+      break;
     case G_POP: gadget_pop(s, true); break;
     case G_SHA3: gadget_sha3(s, true); break;
     case G_CDC: gadget_calldatacopy(s, true); break;
@@ -1069,6 +1152,25 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src, 16);
   return r;
 }
+// positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1); returns at once
+// otherwise, and then k_evm_push<false> below does the work — the host launches both
+__global__ void __launch_bounds__(128) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                      EvmLists lists) {
+  if (!both_positional(t)) return;
+  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
+  __shared__ alignas(8) u64 s_bar;
+  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+  const u64 rw_base = table_cell(t.rw.tab, 0, 0).l[0];
+  HeadCache hc{};
+  const u32 n = lists.count[G_PUSH];
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, &rw_base, 1};
+    gadget_push_pos1(s, &hc);
+  }
+}
+
 // POS = true: specialised for positional rw + bytecode tables (no hash code at all); it returns at
 // once unless both flags are set, and the POS = false instance returns at once if they are —
 // the host launches both, exactly one does the work.
