@@ -33,37 +33,49 @@ N_CELLS_STEP, N_CELLS_RW, N_CELLS_BYTECODE = 13, 14, 6
 
 
 class ClockSampler(threading.Thread):
-    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+    """samples SM clock + throttle reasons through NVML while the timed region runs (NVML is
+    initialised in the constructor, before the region; one sample is taken at start and one at
+    stop so that even a 10 ms region is covered)"""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
-        self.max_mhz = None
-
-    def run(self):
+        self.max_mhz, self._nv, self._h, self._names = None, None, None, {}
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._names = {
                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
-            while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.05)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
+    def _sample(self):
+        nv = self._nv
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for bit, nm in self._names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self._sample()
+            time.sleep(0.005)
+
     def stop(self):
+        self._sample()  # still under load: the caller stops the sampler before synchronising
         self._stop_evt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
@@ -147,7 +159,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--groups", type=int, default=1 << 18, help="trace groups per GPU (4 steps each)")

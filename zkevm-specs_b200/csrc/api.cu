@@ -577,7 +577,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   lists.count = ctx->evm_lists + (size_t)G_COUNT * ctx->evm_lists_cap;
   CK(ctx, cudaMemsetAsync(lists.count, 0, G_COUNT * sizeof(u32), st));
   const WitnessDev wd = witness_dev(m);
-  k_evm_classify<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_classify<<<(unsigned)((n + 1023) / 1024), 1024, 0, st>>>(wd, rg, t, res, lists);
   // persistent grids sized in multiples of the SM count; each walks its list with a grid stride
   const unsigned full = (unsigned)((n + 127) / 128);
   const unsigned grid_t = std::min<unsigned>(full, (unsigned)ctx->sm_count * 8);
@@ -587,10 +587,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   k_evm_gadget<G_ADD><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_MUL><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_POP><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_SHA3><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_CDC><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_misc<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  ctx->launches += 9;
+  ctx->launches += 7;
   CK(ctx, cudaGetLastError());
   return 0;
 }

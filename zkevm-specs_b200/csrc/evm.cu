@@ -208,9 +208,9 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
 }
 
 // ---- prologue: verify_step before the gadget (main.py:47-63, instruction.py:189-204) --------
-// G_MISC: the rare states (STOP, ...) share one list and one thread-per-step kernel that switches
+// G_MISC: the rare states (SHA3, CALLDATACOPY, MEMORY, STOP, ...) share one list and one thread-per-step kernel that switches
 // on the state (k_evm_misc); the hot states each get a branch-uniform kernel
-enum { G_ADD, G_MUL, G_PUSH, G_POP, G_SHA3, G_CDC, G_MISC, G_COUNT };
+enum { G_ADD, G_MUL, G_PUSH, G_POP, G_MISC, G_COUNT };
 // returns the gadget that must run for this step, or -1 if the step already failed
 ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
   const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
@@ -241,8 +241,8 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_MUL: return G_MUL;
     case ZK_ES_PUSH: return G_PUSH;
     case ZK_ES_POP: return G_POP;
-    case ZK_ES_SHA3: return G_SHA3;
-    case ZK_ES_CALLDATACOPY: return G_CDC;
+    case ZK_ES_SHA3: return G_MISC;
+    case ZK_ES_CALLDATACOPY: return G_MISC;
     case ZK_ES_STOP: return G_MISC;
     case ZK_ES_MEMORY: return G_MISC;
     default: break;
@@ -1030,6 +1030,8 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   switch (cs.l[0]) {
     case ZK_ES_STOP: gadget_stop(s, live); break;
     case ZK_ES_MEMORY: gadget_memory(s, live); break;
+    case ZK_ES_SHA3: gadget_sha3(s, live); break;
+    case ZK_ES_CALLDATACOPY: gadget_calldatacopy(s, live); break;
     default: break;
   }
 }
@@ -1048,8 +1050,6 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
       }
       break;
     case G_POP: gadget_pop(s, true); break;
-    case G_SHA3: gadget_sha3(s, true); break;
-    case G_CDC: gadget_calldatacopy(s, true); break;
     case G_MISC: gadget_misc(s, true); break;
     default: break;
   }
@@ -1069,25 +1069,42 @@ struct EvmLists {
 };
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                      EvmLists lists) {
+__global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                       EvmLists lists) {
+  // Appends are aggregated per BLOCK: the list counters are a handful of addresses, and one
+  // atomicAdd per (warp, gadget) — 65 K same-address atomics at 2^20 steps — serialised in L2 and
+  // was most of this kernel's time.  Warp ballots give each lane its rank inside the warp, shared
+  // counters the warp's offset inside the block, ONE global atomicAdd per (block, gadget) the
+  // block's offset in the list.
+  __shared__ u32 s_warp[32][G_COUNT];  // per-warp counts, then exclusive offsets inside the block
+  __shared__ u32 s_base[G_COUNT];
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   int g = -1;
   if (i < rg.row_end) {
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr, nullptr, -1};
     g = step_prologue(s, rg.flags);
   }
-  // warp-aggregated append: one atomicAdd per (warp, gadget)
-  const unsigned lane = threadIdx.x & 31;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  u32 rank = 0;
 #pragma unroll
   for (int k = 0; k < G_COUNT; k++) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, g == k);
-    if (m == 0) continue;
-    u32 base = 0;
-    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&lists.count[k], (u32)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-    if (g == k) lists.idx[(u64)k * lists.cap + base + __popc(m & ((1u << lane) - 1))] = (u32)(i - rg.row_begin);
+    if (g == k) rank = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp][k] = __popc(m);
   }
+  __syncthreads();
+  if (threadIdx.x < G_COUNT) {
+    const int k = threadIdx.x;
+    u32 total = 0;
+    for (unsigned wi = 0; wi < n_warps; wi++) {
+      const u32 c = s_warp[wi][k];
+      s_warp[wi][k] = total;
+      total += c;
+    }
+    s_base[k] = total ? atomicAdd(&lists.count[k], total) : 0;
+  }
+  __syncthreads();
+  if (g >= 0) lists.idx[(u64)g * lists.cap + s_base[g] + s_warp[warp][g] + rank] = (u32)(i - rg.row_begin);
 }
 
 // one thread per step for the gadgets whose work is a handful of independent lookups
@@ -1111,8 +1128,6 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
-    else if (G == G_SHA3) gadget_sha3(s, live);
-    else if (G == G_CDC) gadget_calldatacopy(s, live);
     else gadget_pop(s, live);
   }
 }

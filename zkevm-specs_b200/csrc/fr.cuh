@@ -96,6 +96,28 @@ ZK_HD Fr ld_col(const unsigned char* p, u32 width, u64 row) {
 #endif
   return r;
 }
+// ld_col with the width known at compile time: one plain typed load (kernels that are
+// specialised for a storage layout, e.g. k_pos_verify over the type-width bytecode table)
+template <int W>
+ZK_HD Fr ld_col_c(const unsigned char* p, u64 row) {
+  Fr r;
+  r.l[0] = r.l[1] = r.l[2] = r.l[3] = 0;
+#ifdef __CUDA_ARCH__
+  if constexpr (W == 32) return ld_cell((const u64*)p + row * 4);
+  else if constexpr (W == 16) {
+    const ulonglong2 v = __ldg((const ulonglong2*)p + row);
+    r.l[0] = v.x;
+    r.l[1] = v.y;
+  } else if constexpr (W == 8) r.l[0] = __ldg((const u64*)p + row);
+  else if constexpr (W == 4) r.l[0] = __ldg((const u32*)p + row);
+  else if constexpr (W == 2) r.l[0] = __ldg((const unsigned short*)p + row);
+  else if constexpr (W == 1) r.l[0] = __ldg(p + row);
+  else return ld_cell((const u64*)p);
+  return r;
+#else
+  return ld_col(p, (u32)W, row);
+#endif
+}
 ZK_HD u32 ld_u32(const u32* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);

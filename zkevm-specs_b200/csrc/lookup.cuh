@@ -260,16 +260,33 @@ ZK_HD void pos_verify_dense_row(const IndexDev& ix, u32* ok, u64 row) {
   const Fr c = table_cell(ix.tab, ix.key_cols[0], row), b = table_cell(ix.tab, ix.key_cols[0], 0);
   if (!(fr_fits64(c) && fr_fits64(b) && b.l[0] + row >= b.l[0] && c.l[0] == b.l[0] + row)) pos_fail(ok);
 }
+struct RunCells {
+  Fr hlo, hhi, tag, index;
+};
+ZK_HD RunCells run_cells(const TableDev& t, u64 row) {
+  return RunCells{table_cell(t, 0, row), table_cell(t, 1, row), table_cell(t, 2, row), table_cell(t, 3, row)};
+}
+// same cells when the four columns' widths are compile-time constants (hash lo / hi, tag, index)
+template <int WH, int WT, int WI>
+ZK_HD RunCells run_cells_c(const TableDev& t, u64 row) {
+  return RunCells{ld_col_c<WH>(t.base + t.off[0], row), ld_col_c<WH>(t.base + t.off[1], row),
+                  ld_col_c<WT>(t.base + t.off[2], row), ld_col_c<WI>(t.base + t.off[3], row)};
+}
+ZK_HD void pos_verify_run_cells(const IndexDev& ix, u32* ok, u64 row, const RunCells& cur, const RunCells& prev);
 ZK_HD void pos_verify_run_row(const IndexDev& ix, u32* ok, u64 row) {
+  const RunCells cur = run_cells(ix.tab, row);
+  pos_verify_run_cells(ix, ok, row, cur, row > 0 ? run_cells(ix.tab, row - 1) : cur);
+}
+// `prev` = the cells of row - 1 (ignored for row 0)
+ZK_HD void pos_verify_run_cells(const IndexDev& ix, u32* ok, u64 row, const RunCells& cur, const RunCells& prev) {
   const TableDev& t = ix.tab;
-  const Fr hlo = table_cell(t, 0, row), hhi = table_cell(t, 1, row), tag = table_cell(t, 2, row);
-  const Fr index = table_cell(t, 3, row);
+  const Fr hlo = cur.hlo, hhi = cur.hhi, tag = cur.tag, index = cur.index;
   bool head = row == 0;
   Fr ptag = fr_u64(0), pindex = fr_u64(0);
   if (row > 0) {
-    head = !(fr_eq(hlo, table_cell(t, 0, row - 1)) && fr_eq(hhi, table_cell(t, 1, row - 1)));
-    ptag = table_cell(t, 2, row - 1);
-    pindex = table_cell(t, 3, row - 1);
+    head = !(fr_eq(hlo, prev.hlo) && fr_eq(hhi, prev.hhi));
+    ptag = prev.tag;
+    pindex = prev.index;
   }
   if (head) {
     if (!(fr_eq_u64(tag, 1) && fr_is_zero(index))) {
@@ -387,9 +404,22 @@ __global__ void __launch_bounds__(256) k_pos_runlen(IndexDev ix) {
 }
 __global__ void __launch_bounds__(256) k_pos_verify(IndexDev ix, u32* ok) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.tab.n_rows; row += stride) {
-    if (ix.pos_kind == ZK_POS_DENSE) pos_verify_dense_row(ix, ok, row);
-    else pos_verify_run_row(ix, ok, row);
+  if (ix.pos_kind == ZK_POS_DENSE) {
+    for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < ix.tab.n_rows; row += stride) pos_verify_dense_row(ix, ok, row);
+    return;
+  }
+  // the two layouts a bytecode table normally arrives in get plain typed loads; anything else goes
+  // through the generic per-column-width loader
+  const unsigned char* wd = ix.tab.width;
+  const u64 row0 = (u64)blockIdx.x * blockDim.x + threadIdx.x, n = ix.tab.n_rows;
+  if (wd[0] == 16 && wd[1] == 16 && wd[2] == 1 && wd[3] == 4) {  // packing.TYPE_WIDTHS["bytecode_table"]
+    for (u64 row = row0; row < n; row += stride)
+      pos_verify_run_cells(ix, ok, row, run_cells_c<16, 1, 4>(ix.tab, row), run_cells_c<16, 1, 4>(ix.tab, row ? row - 1 : 0));
+  } else if (wd[0] == 32 && wd[1] == 32 && wd[2] == 32 && wd[3] == 32) {  // canonical
+    for (u64 row = row0; row < n; row += stride)
+      pos_verify_run_cells(ix, ok, row, run_cells_c<32, 32, 32>(ix.tab, row), run_cells_c<32, 32, 32>(ix.tab, row ? row - 1 : 0));
+  } else {
+    for (u64 row = row0; row < n; row += stride) pos_verify_run_row(ix, ok, row);
   }
 }
 #endif
