@@ -143,6 +143,23 @@ int zk_upload_table_packed(zk_ctx* ctx, int table_id, uint64_t n_rows, uint32_t 
                            const void* packed, uint64_t total_bytes,
                            const uint64_t* col_offsets, const uint8_t* col_widths, void* stream);
 
+/* The bytecode table from the bytecode itself.  Replaces Bytecode.table_assignments
+ * (src/zkevm_specs/evm_circuit/typing.py:390-427) + the column packer for ZK_TABLE_BYTECODE: the
+ * reference unrolls every contract into one Header row (hash, Header, 0, 0, len) and len Byte rows
+ * (hash, Byte, i, is_code[i], code[i]) on the host; here the host ships only the code bytes, one
+ * is_code BIT per byte and one hash per contract, and the six columns are written on the device
+ * (k_bytecode_table_expand), in contract order, as a packed table [16,16,1,4,1,4].  ~1.1 bytes
+ * cross PCIe per table row instead of 192 (canonical) or 10-42 (packed).
+ *   code          : concatenated code bytes of all contracts
+ *   is_code_bits  : bit j (LSB first within a byte) = is_code of concatenated byte j
+ *                   (Bytecode.is_code, typing.py:309-386: false for PUSH data)
+ *   code_offsets  : [n_contracts + 1], contract k = bytes [code_offsets[k], code_offsets[k+1])
+ *   hashes        : [n_contracts][4] = code hash as (lo limb0, lo limb1, hi limb0, hi limb1)
+ * The result is an ordinary resident table (same lookups, same index building / verification). */
+int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contracts, const uint8_t* code,
+                                       const uint8_t* is_code_bits, const uint64_t* code_offsets,
+                                       const uint64_t* hashes, void* stream);
+
 /* Check rows [row_begin, row_end) of the resident matrix (local indices).  Without
  * ZK_FLAG_WRAP the caller guarantees halo rows exist for the circuit's rotations.
  * Reported rows are row_base + local index.

@@ -287,3 +287,10 @@ extern "C" int emu_check_exp(const uint64_t* rows, uint64_t n_rows, uint64_t row
   for (u64 i = row_begin; i < row_end; i++) check_exp_row(w, rg, res, i);
   return 0;
 }
+
+// 256-bit integer division of the MOD witness assignment (evm.cu:div256), for tests/test_emu_parity.py
+extern "C" void emu_div256(const uint64_t* n, const uint64_t* d, uint64_t* q) {
+  u64 qq[4];
+  div256((const u64*)n, (const u64*)d, qq);
+  for (int k = 0; k < 4; k++) q[k] = qq[k];
+}

@@ -158,3 +158,31 @@ def test_emu_packed_columns_equal_oracle_on_every_golden_family():
         assert emu_lib.narrow_cols() > 10000  # the packed path really ran
     finally:
         emu_lib.set_packed(False)
+
+
+def test_emu_div256_equals_python_integer_division():
+    """evm.cu:div256 (Knuth D, 64-bit digits) against Python's // on random, boundary and
+    nasty operands (tests/common.py:23-45 style values)"""
+    import ctypes
+    import random
+
+    lib = emu_lib.lib()
+    rnd = random.Random(256)
+    nasty = [1, 2, 3, 0xFF, 1 << 64, (1 << 64) - 1, (1 << 64) + 1, (1 << 128) - 1, 1 << 128, (1 << 128) + 1,
+             (1 << 192) - 1, 1 << 192, (1 << 255) - 1, 1 << 255, (1 << 256) - 1, (1 << 256) - 2, 0x8000000000000000,
+             0xFFFFFFFF, 0x100000000, (1 << 63) - 1, ((1 << 64) - 1) << 192, (1 << 255) + (1 << 63)]
+    cases = [(a, b) for a in nasty + [0] for b in nasty]
+    for _ in range(20000):
+        bits_n, bits_d = rnd.choice([256, 256, 200, 129, 128, 65, 64, 33]), rnd.choice([256, 255, 192, 129, 128, 65, 64, 63, 33, 32, 8, 1])
+        n = rnd.getrandbits(bits_n)
+        d = rnd.getrandbits(bits_d) | (1 << (bits_d - 1))
+        if rnd.random() < 0.2:  # quotient digits of all ones / estimate corrections
+            d = (d >> 64 << 64) | ((1 << 64) - 1) if bits_d > 64 else d
+        cases.append((n, d))
+    arr = ctypes.c_uint64 * 4
+    for n, d in cases:
+        q = arr()
+        lib.emu_div256(arr(*[(n >> (64 * k)) & (2**64 - 1) for k in range(4)]),
+                       arr(*[(d >> (64 * k)) & (2**64 - 1) for k in range(4)]), q)
+        got = sum(int(q[k]) << (64 * k) for k in range(4))
+        assert got == n // d, (hex(n), hex(d), hex(got), hex(n // d))

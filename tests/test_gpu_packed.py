@@ -104,3 +104,46 @@ def test_packed_abi_rejects_bad_layouts():
     with pytest.raises(native.NativeError, match="outside"):
         ctx.upload_table_packed(native.TABLE_RW, bad)
     ctx.upload_table_packed(native.TABLE_RW, pm)
+
+
+def test_bytecode_table_from_code_equals_uploaded_table():
+    """zk_upload_bytecode_table_from_code (Bytecode.table_assignments on the device) gives the same
+    table as uploading the unrolled rows: same verdict arrays as the oracle on (a) a PUSH32-heavy
+    trace with corruptions — every byte row of the table is looked up — and (b) the two-contract STOP
+    goldens (restore-to-caller context reads the caller's code hash)."""
+    import golden_util
+    from zkevm_specs_b200.evm_circuit import main as evm_main
+
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    evm_main.upload_fixed_table(ctx)
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
+    w = synth.evm_trace(2048, seed=21)
+    S, R = w["steps"].copy(), w["rw"].copy()
+    rng = np.random.default_rng(77)
+    for t in range(24):  # pushed values that no longer match the code, gas, pc
+        if t % 3 == 0:
+            R[8 + int(rng.integers(2)), int(rng.integers(R.shape[1])), int(rng.integers(2))] ^= np.uint64(1 << int(rng.integers(64)))
+        else:
+            S[9 if t % 3 == 1 else 7, int(rng.integers(1, S.shape[1] - 1)), 0] += np.uint64(1)
+    off, ofc = oracle_lib.check_evm(S, w["bytecode"], R, fixed)
+    assert (off != native.PASS).any()
+    ctx.upload_table(native.TABLE_RW, R)
+    ctx.upload_columns(native.CIRCUIT_EVM, S)
+    ctx.upload_bytecode_table_from_code(**w["bytecode_src"])
+    ff, fc = ctx.check(native.CIRCUIT_EVM, 0, S.shape[1] - 1, 0, 0)
+    assert np.array_equal(ff, off) and np.array_equal(fc, ofc)
+    n = 0
+    for name, k, v, exp_row, exp_exc in golden_util.evm3_vectors():
+        src = packing.bytecode_src_from_table(v["bytecode"])
+        if src is None or len(src["hashes"]) != 2:
+            continue
+        ctx.upload_bytecode_table_from_code(**src)
+        ctx.upload_table(native.TABLE_RW, v["rw"], flags=v["rw_flags"])
+        ctx.upload_columns(native.CIRCUIT_EVM, v["steps"])
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, v["steps"].shape[1] - 1, 0, 0)
+        off, ofc = oracle_lib.check_evm_x(v, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k)
+        n += 1
+    assert n > 400

@@ -98,6 +98,8 @@ struct zk_ctx {
   int sm_count = 148;
   u32* resp_bitmap = nullptr;  // ResponsibleOpcode bitmap of the fixed table (8 KiB)
   u64 resp_bitmap_version = ~0ull;
+  unsigned char* stage = nullptr;  // device staging (zk_upload_bytecode_table_from_code)
+  size_t stage_cap = 0;
   u32* evm_lists = nullptr;  // [G_COUNT][cap] step indices + [G_COUNT] counters
   size_t evm_lists_cap = 0;
   bool timing = false;
@@ -166,6 +168,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (ix->heads_aux) cudaFree(ix->heads_aux);
     delete ix;
   }
+  if (ctx->stage) cudaFree(ctx->stage);
   for (auto& r : ctx->res)
     if (r.first_fail) cudaFree(r.first_fail);
   for (auto& e : ctx->ev)
@@ -323,6 +326,121 @@ extern "C" int zk_upload_table_packed(zk_ctx* ctx, int table_id, uint64_t n_rows
   if (!col_offsets || !col_widths) return fail_msg(ctx, "packed upload needs offsets and widths");
   return store_matrix(ctx, ctx->tab[table_id], n_rows, n_cols, packed, nullptr, (cudaStream_t)stream, col_widths,
                       col_offsets, (size_t)total_bytes);
+}
+
+// ------------------------------------------------------------------ bytecode table from code
+// Bytecode.table_assignments (typing.py:390-427) on the device: one thread per table row finds its
+// contract (binary search over the row starts code_offsets[k] + k) and writes the six cells.
+struct BytecodeSrc {
+  const unsigned char* code;
+  const unsigned char* bits;
+  const u64* offsets;  // [n + 1]
+  const u64* hashes;   // [n][4]
+  u64 n_contracts, n_rows;
+};
+__global__ void __launch_bounds__(256) k_bytecode_table_expand(BytecodeSrc src, unsigned char* base, const u64 o_hlo,
+                                                               const u64 o_hhi, const u64 o_tag, const u64 o_idx,
+                                                               const u64 o_isc, const u64 o_val) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < src.n_rows; r += stride) {
+    u64 lo = 0, hi = src.n_contracts;  // largest k with offsets[k] + k <= r
+    while (hi - lo > 1) {
+      const u64 mid = (lo + hi) >> 1;
+      if (__ldg(src.offsets + mid) + mid <= r) lo = mid;
+      else hi = mid;
+    }
+    const u64 k = lo, start = __ldg(src.offsets + k), local = r - (start + k);
+    ulonglong2 hl, hh;
+    hl.x = __ldg(src.hashes + 4 * k);
+    hl.y = __ldg(src.hashes + 4 * k + 1);
+    hh.x = __ldg(src.hashes + 4 * k + 2);
+    hh.y = __ldg(src.hashes + 4 * k + 3);
+    ((ulonglong2*)(base + o_hlo))[r] = hl;
+    ((ulonglong2*)(base + o_hhi))[r] = hh;
+    u32 tag, index, value;
+    unsigned char is_code;
+    if (local == 0) {  // Header: (hash, Header, 0, 0, len)
+      tag = 1;
+      index = 0;
+      is_code = 0;
+      value = (u32)(__ldg(src.offsets + k + 1) - start);
+    } else {
+      const u64 j = start + local - 1;
+      tag = 2;
+      index = (u32)(local - 1);
+      is_code = (__ldg(src.bits + (j >> 3)) >> (j & 7)) & 1;
+      value = __ldg(src.code + j);
+    }
+    (base + o_tag)[r] = (unsigned char)tag;
+    ((u32*)(base + o_idx))[r] = index;
+    (base + o_isc)[r] = is_code;
+    ((u32*)(base + o_val))[r] = value;
+  }
+}
+
+extern "C" int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contracts, const uint8_t* code,
+                                                  const uint8_t* is_code_bits, const uint64_t* code_offsets,
+                                                  const uint64_t* hashes, void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_contracts == 0) return fail_msg(ctx, "no contracts");
+  if (code_offsets[0] != 0) return fail_msg(ctx, "code_offsets[0] must be 0");
+  for (u64 k = 0; k < n_contracts; k++) {
+    if (code_offsets[k + 1] < code_offsets[k]) return fail_msg(ctx, "code_offsets must be non-decreasing");
+    if (code_offsets[k + 1] - code_offsets[k] >= 0xFFFFFFFFull) return fail_msg(ctx, "contract too long");
+  }
+  const u64 total = code_offsets[n_contracts], n_rows = total + n_contracts;
+  if (n_rows >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
+  // staging: code | bits | offsets | hashes (each 32-byte aligned)
+  auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
+  const size_t s_code = 0, s_bits = up32(total), s_off = s_bits + up32((total + 7) / 8);
+  const size_t s_hash = s_off + up32((n_contracts + 1) * 8), s_total = s_hash + up32(n_contracts * 32);
+  if (s_total > ctx->stage_cap) {
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    CK(ctx, cudaMalloc(&ctx->stage, s_total));
+    ctx->stage_cap = s_total;
+  }
+  unsigned char* sg = ctx->stage;
+  if (total) {
+    CK(ctx, cudaMemcpyAsync(sg + s_code, code, total, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(sg + s_bits, is_code_bits, (total + 7) / 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(ctx, cudaMemcpyAsync(sg + s_off, code_offsets, (n_contracts + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(sg + s_hash, hashes, n_contracts * 32, cudaMemcpyHostToDevice, st));
+  // the resident table: packed layout [16, 16, 1, 4, 1, 4]
+  static const unsigned char kW[6] = {16, 16, 1, 4, 1, 4};
+  Matrix& m = ctx->tab[ZK_TABLE_BYTECODE];
+  u64 off[6], bytes = 0;
+  for (int c = 0; c < 6; c++) {
+    off[c] = bytes;
+    bytes += up32((size_t)kW[c] * n_rows);
+  }
+  if (m.borrowed) {
+    m.dev = nullptr;
+    m.borrowed = false;
+    m.cap_bytes = 0;
+  }
+  if (bytes > m.cap_bytes) {
+    if (m.dev) cudaFree(m.dev);
+    m.dev = nullptr;
+    CK(ctx, cudaMalloc(&m.dev, bytes));
+    m.cap_bytes = bytes;
+  }
+  m.version++;
+  m.n_rows = n_rows;
+  m.n_cols = 6;
+  m.flags_rows = 0;
+  for (int c = 0; c < 6; c++) {
+    m.off[c] = off[c];
+    m.width[c] = kW[c];
+  }
+  BytecodeSrc src{sg + s_code, sg + s_bits, (const u64*)(sg + s_off), (const u64*)(sg + s_hash), n_contracts, n_rows};
+  const unsigned grid = (unsigned)std::min<u64>((n_rows + 255) / 256, (u64)ctx->sm_count * 16);
+  k_bytecode_table_expand<<<grid, 256, 0, st>>>(src, (unsigned char*)m.dev, off[0], off[1], off[2], off[3], off[4], off[5]);
+  ctx->launches += 1;
+  CK(ctx, cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------ lookup index cache

@@ -369,39 +369,92 @@ ZK_HD int bitlen256(const u64 v[4]) {
   if (v[0]) return 64 - ZK_CLZ64(v[0]);
   return 0;
 }
-// q = n / d for d != 0: shift-subtract over the bit-length difference only, all in registers
-// (static limb indices); only MOD steps pay for it
+// (u1:u0) / v for a normalised v (bit 63 set) and u1 < v: two 64/32 steps (Hacker's Delight divlu)
+ZK_HD u64 div128by64(u64 u1, u64 u0, u64 v) {
+  const u64 b = 1ull << 32, vn1 = v >> 32, vn0 = v & 0xFFFFFFFFull, un1 = u0 >> 32, un0 = u0 & 0xFFFFFFFFull;
+  u64 q1 = u1 / vn1, rhat = u1 - q1 * vn1;
+  while (q1 >= b || q1 * vn0 > ((rhat << 32) | un1)) {
+    q1--;
+    rhat += vn1;
+    if (rhat >= b) break;
+  }
+  const u64 un21 = ((u1 << 32) | un1) - q1 * v;  // mod 2^64, exact
+  u64 q0 = un21 / vn1;
+  rhat = un21 - q0 * vn1;
+  while (q0 >= b || q0 * vn0 > ((rhat << 32) | un0)) {
+    q0--;
+    rhat += vn1;
+    if (rhat >= b) break;
+  }
+  return (q1 << 32) | q0;
+}
+// q = n / d for d != 0 (only MOD steps pay for it).  Knuth's algorithm D with 64-bit digits on
+// operands shifted so that the divisor's top bit is bit 255: always 4 quotient digits, static limb
+// indices, no data-dependent trip count — so the lanes of a warp stay together (the bit-serial
+// shift-subtract it replaces ran up to 256 iterations in the slowest lane: profiles/README.md v20).
 ZK_HD void div256(const u64 n[4], const u64 d[4], u64 q[4]) {
   q[0] = q[1] = q[2] = q[3] = 0;
-  const int shift = bitlen256(n) - bitlen256(d);
-  if (shift < 0) return;
-  // ds = d << shift
-  u64 w0 = d[0], w1 = d[1], w2 = d[2], w3 = d[3];
-  const int ws = shift >> 6, bs = shift & 63;
-  if (ws == 1) { w3 = w2; w2 = w1; w1 = w0; w0 = 0; }
-  else if (ws == 2) { w3 = w1; w2 = w0; w1 = 0; w0 = 0; }
-  else if (ws == 3) { w3 = w0; w2 = 0; w1 = 0; w0 = 0; }
-  if (bs) {
-    w3 = (w3 << bs) | (w2 >> (64 - bs));
-    w2 = (w2 << bs) | (w1 >> (64 - bs));
-    w1 = (w1 << bs) | (w0 >> (64 - bs));
-    w0 = w0 << bs;
+  if (cmp256(n, d) < 0) return;
+  const int sd = 256 - bitlen256(d);  // 0..255
+  const int ws = sd >> 6, bs = sd & 63;
+  // D = d << sd (top bit set), N = n << sd (8 limbs)
+  u64 t[8], dd[4];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u64 v = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+      if (ws == w && k - w >= 0 && k - w < 4) v = n[k - w];
+    t[k] = v;
   }
-  u64 r0 = n[0], r1 = n[1], r2 = n[2], r3 = n[3];
-  for (int k = shift; k >= 0; k--) {
-    // r >= ds ?
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    u64 v = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+      if (ws == w && k - w >= 0) v = d[k - w];
+    dd[k] = v;
+  }
+  u64 N[8], D[4];
+#pragma unroll
+  for (int k = 7; k >= 0; k--) N[k] = bs ? ((t[k] << bs) | (k ? t[k - 1] >> (64 - bs) : 0)) : t[k];
+#pragma unroll
+  for (int k = 3; k >= 0; k--) D[k] = bs ? ((dd[k] << bs) | (k ? dd[k - 1] >> (64 - bs) : 0)) : dd[k];
+  u64 r0 = N[4], r1 = N[5], r2 = N[6], r3 = N[7];  // running remainder < D
+#pragma unroll
+  for (int j = 3; j >= 0; j--) {
+    // (r3 r2 r1 r0 N[j]) / D: estimate from the top two digits, then multiply-subtract and add back
+    u64 qh = r3 >= D[3] ? ~0ull : div128by64(r3, r2, D[3]);
+    u64 p[5], c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned __int128 v = (unsigned __int128)qh * D[k] + c;
+      p[k] = (u64)v;
+      c = (u64)(v >> 64);
+    }
+    p[4] = c;
     u64 br = 0;
-    const u64 t0 = sbb64(r0, w0, br), t1 = sbb64(r1, w1, br), t2 = sbb64(r2, w2, br), t3 = sbb64(r3, w3, br);
-    const u64 bit = br ? 0 : 1;
-    if (bit) { r0 = t0; r1 = t1; r2 = t2; r3 = t3; }
-    q[3] = (q[3] << 1) | (q[2] >> 63);
-    q[2] = (q[2] << 1) | (q[1] >> 63);
-    q[1] = (q[1] << 1) | (q[0] >> 63);
-    q[0] = (q[0] << 1) | bit;
-    w0 = (w0 >> 1) | (w1 << 63);
-    w1 = (w1 >> 1) | (w2 << 63);
-    w2 = (w2 >> 1) | (w3 << 63);
-    w3 >>= 1;
+    u64 s0 = sbb64(N[j], p[0], br), s1 = sbb64(r0, p[1], br), s2 = sbb64(r1, p[2], br), s3 = sbb64(r2, p[3], br),
+        s4 = sbb64(r3, p[4], br);
+    bool neg = br != 0;
+#pragma unroll
+    for (int fix = 0; fix < 2; fix++) {  // the estimate is at most 2 too large
+      if (neg) {
+        u64 cy = 0;
+        s0 = adc64(s0, D[0], cy);
+        s1 = adc64(s1, D[1], cy);
+        s2 = adc64(s2, D[2], cy);
+        s3 = adc64(s3, D[3], cy);
+        s4 = adc64(s4, 0, cy);
+        qh--;
+        if (cy) neg = false;
+      }
+    }
+    q[j] = qh;
+    r0 = s0;
+    r1 = s1;
+    r2 = s2;
+    r3 = s3;
   }
 }
 

@@ -73,6 +73,7 @@ EXPORTS = [
     "zk_allreduce_results", "zk_circuit_cols", "zk_table_cols", "zk_n_constraints",
     "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
     "zk_last_timing", "zk_upload_columns_packed", "zk_upload_table_packed",
+    "zk_upload_bytecode_table_from_code",
 ]
 
 
@@ -97,6 +98,7 @@ def lib() -> ctypes.CDLL:
         L.zk_upload_table_flags.argtypes = [vp, i32, u64, vp, vp]
         L.zk_upload_columns_packed.argtypes = [vp, i32, u64, u32, vp, u64, vp, vp, vp]
         L.zk_upload_table_packed.argtypes = [vp, i32, u64, u32, vp, u64, vp, vp, vp]
+        L.zk_upload_bytecode_table_from_code.argtypes = [vp, u64, vp, vp, vp, vp, vp]
         L.zk_check.argtypes = [vp, i32, u64, u64, u64, u32, _U32P, _U64P, vp]
         L.zk_check_async.argtypes = [vp, i32, u64, u64, u64, u32, vp]
         L.zk_result_device.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
@@ -208,6 +210,24 @@ class Context:
             f = np.ascontiguousarray(flags, dtype=np.uint8)
             self._ck(self._L.zk_upload_table_flags(self._h, table_id, f.shape[0], _host_ptr(f),
                                                    ctypes.c_void_p(stream)), "zk_upload_table_flags")
+
+    def upload_bytecode_table_from_code(self, code: np.ndarray, is_code_bits: np.ndarray, code_offsets: np.ndarray,
+                                        hashes: np.ndarray, stream: int = 0, ptrs=None) -> None:
+        """Bytecode.table_assignments on the device (include/zkcheck.h): `code` uint8 (all contracts
+        concatenated), `is_code_bits` uint8 bitmap (LSB first), `code_offsets` uint64[n+1], `hashes`
+        uint64[n][4] = (lo limb0, lo limb1, hi limb0, hi limb1).  `ptrs` = optional (code, bits) host
+        addresses of pinned copies."""
+        code = np.ascontiguousarray(code, dtype=np.uint8)
+        bits = np.ascontiguousarray(is_code_bits, dtype=np.uint8)
+        offs = np.ascontiguousarray(code_offsets, dtype=np.uint64)
+        hs = np.ascontiguousarray(hashes, dtype=np.uint64)
+        assert hs.shape == (len(offs) - 1, 4) and len(bits) >= (len(code) + 7) // 8 and int(offs[-1]) == len(code)
+        self._keep = getattr(self, "_keep", {})
+        self._keep["bytecode_src"] = (code, bits, offs, hs)
+        pc, pb = ptrs if ptrs else (code.ctypes.data, bits.ctypes.data)
+        self._ck(self._L.zk_upload_bytecode_table_from_code(
+            self._h, len(offs) - 1, ctypes.c_void_p(pc), ctypes.c_void_p(pb), _host_ptr(offs), _host_ptr(hs),
+            ctypes.c_void_p(stream)), "zk_upload_bytecode_table_from_code")
 
     def bind_columns_device(self, circuit_id: int, n_rows: int, n_cols: int, dev_ptr: int) -> None:
         self._ck(self._L.zk_bind_columns_device(self._h, circuit_id, n_rows, n_cols,

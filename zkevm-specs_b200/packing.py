@@ -244,3 +244,36 @@ def pack_matrix(matrix: np.ndarray, widths: Sequence[int] | None = None,
             dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[w]
             buf[off:off + w * n_rows] = col[:, 0].astype(dt).view(np.uint8)
     return PackedMatrix(buf, np.asarray(offsets, dtype=np.uint64), np.asarray(ws, dtype=np.uint8), n_rows)
+
+
+def bytecode_src_from_table(table: np.ndarray):
+    """Inverse of Bytecode.table_assignments for a REGULAR bytecode-table matrix (runs
+    [Header, Byte 0, Byte 1, ...] per contract): returns the arguments of
+    Context.upload_bytecode_table_from_code, or None if the table is not of that form."""
+    t = np.ascontiguousarray(table, dtype=np.uint64)
+    n = t.shape[1]
+    if n == 0:
+        return None
+    small = not t[2:, :, 1:].any()
+    tag, index, is_code, value = t[2, :, 0], t[3, :, 0], t[4, :, 0], t[5, :, 0]
+    heads = np.nonzero(tag == 1)[0]
+    if not small or len(heads) == 0 or heads[0] != 0 or t[0:2, :, 2:].any():
+        return None
+    ends = np.append(heads[1:], n)
+    code, bits, offs, hashes = [], [], [0], []
+    for h, e in zip(heads, ends):
+        ln = int(e - h - 1)
+        body = slice(h + 1, e)
+        ok = (int(value[h]) == ln and int(index[h]) == 0 and int(is_code[h]) == 0 and (tag[body] == 2).all()
+              and (index[body] == np.arange(ln, dtype=np.uint64)).all() and (value[body] < 256).all()
+              and (is_code[body] < 2).all() and (t[0:2, h:e, :] == t[0:2, h:h + 1, :]).all())
+        if not ok:
+            return None
+        code.append(value[body].astype(np.uint8))
+        bits.append(is_code[body].astype(np.uint8))
+        offs.append(offs[-1] + ln)
+        hashes.append([t[0, h, 0], t[0, h, 1], t[1, h, 0], t[1, h, 1]])
+    code = np.concatenate(code) if code else np.zeros(0, dtype=np.uint8)
+    bits = np.packbits(np.concatenate(bits), bitorder="little") if len(code) else np.zeros(1, dtype=np.uint8)
+    return {"code": code, "is_code_bits": bits, "code_offsets": np.array(offs, dtype=np.uint64),
+            "hashes": np.array(hashes, dtype=np.uint64)}

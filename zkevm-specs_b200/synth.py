@@ -142,7 +142,14 @@ def evm_trace(n_groups: int, seed: int = 2, call_id: int = 1) -> Dict[str, np.nd
     total = int(cost.sum())
     spent_before = np.concatenate([[0], np.cumsum(cost)]).astype(np.uint64)
     steps[9, :, 0] = np.uint64(total + 7) - spent_before
-    return {"steps": steps, "bytecode": bytecode, "rw": rw, "n_steps": ns - 1}
+    # the same bytecode as raw bytes, for zk_upload_bytecode_table_from_code (one contract)
+    code_bytes = np.concatenate([code.reshape(-1), np.zeros(1, dtype=np.uint8)])  # ... + STOP
+    is_code_all = np.concatenate([is_code.reshape(-1), np.ones(1, dtype=np.uint8)])
+    src = {"code": code_bytes, "is_code_bits": np.packbits(is_code_all, bitorder="little"),
+           "code_offsets": np.array([0, code_len], dtype=np.uint64),
+           "hashes": np.array([[h_lo & 0xFFFFFFFFFFFFFFFF, h_lo >> 64, h_hi & 0xFFFFFFFFFFFFFFFF, h_hi >> 64]],
+                              dtype=np.uint64)}
+    return {"steps": steps, "bytecode": bytecode, "rw": rw, "n_steps": ns - 1, "bytecode_src": src}
 
 
 def state_rows(n_rows: int, seed: int = 3, n_start: int = 1024) -> Dict[str, np.ndarray]:
