@@ -702,11 +702,14 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   const unsigned grid_w = std::min<unsigned>((unsigned)((n * 32 + 127) / 128), (unsigned)ctx->sm_count * 12);
   k_evm_push_pos<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_push<false><<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_ADD><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_MUL><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_POP><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_ADD, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_MUL, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_POP, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_ADD, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_MUL, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_gadget<G_POP, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_misc<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  ctx->launches += 7;
+  ctx->launches += 10;
   CK(ctx, cudaGetLastError());
   return 0;
 }

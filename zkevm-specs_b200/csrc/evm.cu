@@ -130,6 +130,15 @@ ZK_HD int bytecode_lookup(const StepCtx& s, bool live, const Fr& hlo, const Fr& 
                           u64 is_code, Fr* value) {
   Fr key[5] = {hlo, hhi, fr_u64(tag), index, fr_u64(is_code)};
   u32 r;
+  if (s.pos_mode == 1) {  // kernel specialised for positional tables: no hash code at all
+    const IndexDev& ix = s.t.bytecode;
+    u32 head = 0, len = 0;
+    const int n_head = heads_probe(ix, fr_add(hlo, rlc_term(ix, hhi, 1)), hlo, hhi, &head, &len, s.mask, live);
+    Fr got;
+    const int n = pos_lookup_run(ix, key, n_head, head, len, &r, live, B_VALUE, &got);
+    if (live && n == 1) *value = got;
+    return n;
+  }
   const int n = lookup_sync<5>(s.t.bytecode, key, &r, s.mask, live);
   if (live && n == 1) *value = table_cell(s.t.bytecode.tab, B_VALUE, r);
   return n;
@@ -713,6 +722,36 @@ ZK_HD bool both_positional(const EvmTables& t) {
   return t.rw.tab.n_rows != 0 && t.bytecode.tab.n_rows != 0 && pos_enabled(t.rw) && pos_enabled(t.bytecode) &&
          t.rw.pos_kind == ZK_POS_DENSE && t.bytecode.pos_kind == ZK_POS_RUNS;
 }
+// the 32 byte lookups of a PUSH step as three bit masks (bit idx: lookup unsat / value differs / a
+// non-pushed byte is not zero).  WIS / WVAL = compile-time widths of the is_code / value columns, or
+// 0 for the generic loader.
+template <int WIS, int WVAL>
+ZK_HD void push_byte_masks(const TableDev& bt, const PushCommon& c, const Fr& top, bool top_ok, u32* m_unsat,
+                           u32* m_neq, u32* m_pad) {
+  const unsigned char* p_is = bt.base + bt.off[B_ISCODE];
+  const unsigned char* p_val = bt.base + bt.off[B_VALUE];
+  const u32 w_is = bt.width[B_ISCODE], w_val = bt.width[B_VALUE];
+  const u64 first_row = (u64)c.head + 1;
+  u32 mu = 0, mn = 0, mp = 0;
+#pragma unroll
+  for (int idx = 0; idx < 32; idx++) {
+    const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
+    const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
+    const u64 byte = ((idx < 16 ? lo_limb : hi_limb) >> (8 * (idx & 7))) & 0xFF;
+    const bool pushed = (u64)idx < c.n_push && (u64)idx >= c.n_pad;
+    const bool valid = pushed && top_ok && top.l[0] >= (u64)idx && top.l[0] - (u64)idx < (u64)c.run_len;
+    const u64 row = valid ? first_row + (top.l[0] - (u64)idx) : 0;
+    const Fr is_code = WIS ? ld_col_c<WIS>(p_is, row) : ld_col(p_is, w_is, row);
+    const Fr got = WVAL ? ld_col_c<WVAL>(p_val, row) : ld_col(p_val, w_val, row);
+    const bool hit = valid && fr_is_zero(is_code);  // key: (hash, Byte, index, is_code = 0)
+    mu |= (u32)(pushed && !hit) << idx;
+    mn |= (u32)(hit && !fr_eq_u64(got, byte)) << idx;
+    mp |= (u32)(!pushed && byte != 0) << idx;
+  }
+  *m_unsat = mu;
+  *m_neq = mn;
+  *m_pad = mp;
+}
 ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
   PushCommon c;
   c.hlo = s.cur(S_HASH_LO);
@@ -739,25 +778,11 @@ ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
   const Fr top = fr_add(c.pc, c.num_pushed);
   const bool top_ok = fr_fits64(top) && c.n_head == 1;
   const TableDev& bt = s.t.bytecode.tab;
-  const unsigned char* p_is = bt.base + bt.off[B_ISCODE];
-  const unsigned char* p_val = bt.base + bt.off[B_VALUE];
-  const u32 w_is = bt.width[B_ISCODE], w_val = bt.width[B_VALUE];
-  const u64 first_row = (u64)c.head + 1;
   u32 m_unsat = 0, m_neq = 0, m_pad = 0;
-#pragma unroll
-  for (int idx = 0; idx < 32; idx++) {
-    const u64 lo_limb = (idx & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
-    const u64 hi_limb = (idx & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
-    const u64 byte = ((idx < 16 ? lo_limb : hi_limb) >> (8 * (idx & 7))) & 0xFF;
-    const bool pushed = (u64)idx < c.n_push && (u64)idx >= c.n_pad;
-    const bool valid = pushed && top_ok && top.l[0] >= (u64)idx && top.l[0] - (u64)idx < (u64)c.run_len;
-    const u64 row = valid ? first_row + (top.l[0] - (u64)idx) : 0;
-    const Fr is_code = ld_col(p_is, w_is, row), got = ld_col(p_val, w_val, row);
-    const bool hit = valid && fr_is_zero(is_code);  // key: (hash, Byte, index, is_code = 0)
-    m_unsat |= (u32)(pushed && !hit) << idx;
-    m_neq |= (u32)(hit && !fr_eq_u64(got, byte)) << idx;
-    m_pad |= (u32)(!pushed && byte != 0) << idx;
-  }
+  // the layout every packer produces for these two columns (is_code 1 byte, value 4 bytes: the Header
+  // row holds the code length) gets plain typed loads; anything else the generic per-width loader
+  if (bt.width[B_ISCODE] == 1 && bt.width[B_VALUE] == 4) push_byte_masks<1, 4>(bt, c, top, top_ok, &m_unsat, &m_neq, &m_pad);
+  else push_byte_masks<0, 0>(bt, c, top, top_ok, &m_unsat, &m_neq, &m_pad);
   const u32 any = m_unsat | m_neq | m_pad;
   if (any) {
 #ifdef __CUDA_ARCH__
@@ -1160,17 +1185,18 @@ __global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange 
   if (g >= 0) lists.idx[(u64)g * lists.cap + s_base[g] + s_warp[warp][g] + rank] = (u32)(i - rg.row_begin);
 }
 
-// one thread per step for the gadgets whose work is a handful of independent lookups
-template <int G>
-__global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                    EvmLists lists) {
-  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
-  __shared__ alignas(8) u64 s_bar;
-  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+// one thread per step for the gadgets whose work is a handful of independent lookups.
+// POS = both tables positional (a uniform run-time fact): that instance is compiled with
+// pos_mode = 1, i.e. without any hash-index code — these kernels were stalling on instruction
+// fetch (profiles/README.md v20: "no instruction" 2-3 per issue), the executed path is now half as long.
+template <int G, bool POS>
+__device__ __forceinline__ void gadget_steps(const WitnessDev& w, const CheckRange& rg, const EvmTables& t,
+                                             const ResultDev& res, const EvmLists& lists, const u32* s_resp) {
   // every lane of a warp runs the same number of rounds and calls the (warp-synchronous) lookups
   // together; lanes without a step in the last round run with live = false
   Fr stack_pre[2];
-  stack_key_pre(t.rw, stack_pre);
+  if (!POS) stack_key_pre(t.rw, stack_pre);
+  const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
   const u32 n = lists.count[G];
   const u32 stride = gridDim.x * blockDim.x;
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1178,11 +1204,23 @@ __global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg,
     const u32 k = first + tid;
     const bool live = k < n;
     const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, POS ? nullptr : stack_pre,
+              POS ? &rw_base : nullptr, POS ? 1 : -1};
     if (G == G_ADD) gadget_add(s, live);
     else if (G == G_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
   }
+}
+// two instances per gadget (own register budgets); the host launches both, the one whose POS does
+// not match the tables returns at once
+template <int G, bool POS>
+__global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                    EvmLists lists) {
+  if (both_positional(t) != POS) return;
+  __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
+  __shared__ alignas(8) u64 s_bar;
+  stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
+  gadget_steps<G, POS>(w, rg, t, res, lists, s_resp);
 }
 
 // rare states: lanes of a warp may run different gate programs, so every lookup is made

@@ -194,6 +194,8 @@ class Context:
     def upload_columns_packed(self, circuit_id: int, pm, flags=None, stream: int = 0, host_ptr: int = 0) -> None:
         """pm: packing.PackedMatrix (narrow columns in one host buffer); `host_ptr` overrides the
         buffer address (e.g. a pinned copy of pm.buf)"""
+        self._keep = getattr(self, "_keep", {})
+        self._keep[("cp", circuit_id)] = pm  # the host buffer outlives the asynchronous copy
         self._ck(self._L.zk_upload_columns_packed(
             self._h, circuit_id, pm.n_rows, pm.n_cols, ctypes.c_void_p(host_ptr or pm.buf.ctypes.data), pm.nbytes,
             _host_ptr(pm.offsets), _host_ptr(pm.widths), ctypes.c_void_p(stream)), "zk_upload_columns_packed")
@@ -203,6 +205,8 @@ class Context:
                                                  ctypes.c_void_p(stream)), "zk_upload_row_flags")
 
     def upload_table_packed(self, table_id: int, pm, flags=None, stream: int = 0, host_ptr: int = 0) -> None:
+        self._keep = getattr(self, "_keep", {})
+        self._keep[("tp", table_id)] = pm
         self._ck(self._L.zk_upload_table_packed(
             self._h, table_id, pm.n_rows, pm.n_cols, ctypes.c_void_p(host_ptr or pm.buf.ctypes.data), pm.nbytes,
             _host_ptr(pm.offsets), _host_ptr(pm.widths), ctypes.c_void_p(stream)), "zk_upload_table_packed")
