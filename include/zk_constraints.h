@@ -452,4 +452,38 @@ enum zk_state_constraint { ZK_STATE_CONSTRAINTS(ZK_ENUM_ENTRY) ST_N_CONSTRAINTS 
 
 enum zk_exp_constraint { ZK_EXP_CONSTRAINTS(ZK_ENUM_ENTRY) XP_N_CONSTRAINTS };
 
+/* ---------------- tx circuit, Fr parts: src/zkevm_specs/tx_circuit.py:205-243, 253-289 --------
+ * One row per tx_index: SignVerifyChip.verify (keccak-table membership of the RLC of the 64 public
+ * key bytes, address == low 20 bytes of the hash, msg_hash == Word(msg_hash_bytes)) and the three
+ * copy constraints to the tx-table rows (:278-289).  The ECDSA check itself (tx_circuit.py:147-158)
+ * is third-party curve math (eth_keys): its verdict enters as a row flag.  The byte-copy asserts of
+ * :209-211 compare two Python copies of the same bytes, stored once here. */
+#define ZK_TX_CONSTRAINTS(X)                                                                  \
+  X(TX_BYTE_DOMAIN, ZKE_VALUE, "tx_circuit.py:170-172 a `bytes` cell is not < 256 (not representable in the reference)") \
+  X(TX_KECCAK_LOOKUP, ZKE_ASSERT, "tx_circuit.py:219-226,57-61 keccak_table.lookup(pub key RLC, 64, hash)") \
+  X(TX_ADDRESS, ZKE_ASSERT, "tx_circuit.py:229-232 address == pub_key_hash[-20:]")            \
+  X(TX_MSG_HASH, ZKE_ASSERT, "tx_circuit.py:236-239 Word(msg_hash_bytes).select(is_not_padding) == msg_hash") \
+  X(TX_ECDSA, ZKE_ASSERT, "tx_circuit.py:242,147-158 ecdsa_verify (third party; verdict supplied as row flag bit 1)") \
+  X(TX_ROW_ADDR_TYPE, ZKE_ASSERT, "tx_circuit.py:278 rows[caller].value.value(): the cell is a Word") \
+  X(TX_ROW_ADDR, ZKE_ASSERT, "tx_circuit.py:278-281 tx-table CallerAddress == chip address")  \
+  X(TX_ROW_HASH_LO, ZKE_ASSERT, "tx_circuit.py:282-285 tx-table TxSignHash.lo == msg_hash.lo") \
+  X(TX_ROW_HASH_HI, ZKE_ASSERT, "tx_circuit.py:286-289 tx-table TxSignHash.hi == msg_hash.hi")
+
+enum zk_tx_constraint { ZK_TX_CONSTRAINTS(ZK_ENUM_ENTRY) TX_N_CONSTRAINTS };
+
+/* ---------------- sig circuit, Fr parts: src/zkevm_specs/sig_circuit.py:64-104, 113-123 --------
+ * One row per signature: Row.verify.  ECDSA (util/ec.py:109-117, eth_keys) is third party: its
+ * boolean verdict enters as row flag bit 1 and is compared with the row's is_valid. */
+#define ZK_SIG_CONSTRAINTS(X)                                                                 \
+  X(SG_BYTE_DOMAIN, ZKE_VALUE, "sig_circuit.py:36-38 a `bytes` cell is not < 256 (not representable in the reference)") \
+  X(SG_SIG_R_COPY, ZKE_ASSERT, "sig_circuit.py:70 sig_r == the ECDSA chip's r")               \
+  X(SG_SIG_S_COPY, ZKE_ASSERT, "sig_circuit.py:71 sig_s == the ECDSA chip's s")               \
+  X(SG_V_BOOL, ZKE_ASSERT, "sig_circuit.py:74 sig_v in {0, 1}")                               \
+  X(SG_KECCAK_LOOKUP, ZKE_ASSERT, "sig_circuit.py:82-88 keccak_table.lookup(pub key RLC, 64, hash)") \
+  X(SG_ADDRESS, ZKE_ASSERT, "sig_circuit.py:91-94 recovered_addr == pub_key_hash[-20:]")      \
+  X(SG_MSG_HASH, ZKE_ASSERT, "sig_circuit.py:97-100 Word(msg_hash_bytes) == msg_hash")        \
+  X(SG_ECDSA_VALID, ZKE_ASSERT, "sig_circuit.py:103-104 ecdsa_chip.verify() == is_valid (third party; verdict = row flag bit 1)")
+
+enum zk_sig_constraint { ZK_SIG_CONSTRAINTS(ZK_ENUM_ENTRY) SG_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

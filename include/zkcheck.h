@@ -46,7 +46,19 @@ enum {
   ZK_CIRCUIT_COPY = 2,     /* 20 cells/row, rotation {0,+1,+2}  evm_circuit/table.py:472-491 */
   ZK_CIRCUIT_EVM = 3,      /* 13 cells/step, rotation {0,+1}    evm_circuit/step.py:16-44 */
   ZK_CIRCUIT_EXP = 4,      /* 21 cells/row, rotation {0,+1}     evm_circuit/table.py:519-535 */
-  ZK_N_CIRCUITS = 5
+  ZK_CIRCUIT_TX = 5,       /* 134 cells/row, no rotation: one row per tx_index = SignVerifyChip cells
+                              (address, 32 pub_key_x LE bytes, 32 pub_key_y LE bytes, 32 pub_key_hash
+                              bytes, msg_hash lo/hi, 32 msg_hash LE bytes) + the tx-table cells they
+                              are copy-constrained to (CallerAddress value, TxSignHash lo/hi)
+                              tx_circuit.py:160-243, 253-289; row flags bit 0 = the CallerAddress
+                              cell is a Word, bit 1 = the (third-party) ECDSA check failed;
+                              lookups: ZK_TABLE_KECCAK rows (is_enabled, input_rlc, input_len, out lo, hi) */
+  ZK_CIRCUIT_SIG = 6,      /* 21 cells/row, no rotation: sig_circuit.Row (sig_circuit.py:7-49): sig_v,
+                              recovered_addr, pub_key_x lo/hi, pub_key_y lo/hi, Word(pub_key_hash) lo/hi,
+                              msg_hash lo/hi, Word(msg_hash_bytes) lo/hi, is_valid, sig_r lo/hi, sig_s
+                              lo/hi, the ECDSA chip's r lo/hi and s lo/hi; row flags bit 1 = the
+                              (third-party) ecdsa_chip.verify() returned True; same keccak table */
+  ZK_N_CIRCUITS = 7
 };
 
 /* ---- lookup tables ---------------------------------------------------------------- */

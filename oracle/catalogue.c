@@ -7,6 +7,8 @@ static const int kEvm[] = {ZK_EVM_CONSTRAINTS(CLS)};
 static const int kCopy[] = {ZK_COPY_CONSTRAINTS(CLS)};
 static const int kState[] = {ZK_STATE_CONSTRAINTS(CLS)};
 static const int kExp[] = {ZK_EXP_CONSTRAINTS(CLS)};
+static const int kTx[] = {ZK_TX_CONSTRAINTS(CLS)};
+static const int kSig[] = {ZK_SIG_CONSTRAINTS(CLS)};
 int orc_n_constraints(int circuit) {
   switch (circuit) {
     case 0: return BC_N_CONSTRAINTS;
@@ -14,11 +16,15 @@ int orc_n_constraints(int circuit) {
     case 2: return CP_N_CONSTRAINTS;
     case 3: return EV_N_CONSTRAINTS;
     case 4: return XP_N_CONSTRAINTS;
+    case 5: return TX_N_CONSTRAINTS;
+    case 6: return SG_N_CONSTRAINTS;
     default: return 0;
   }
 }
 int orc_constraint_class(int circuit, int idx) {
   if (idx < 0 || idx >= orc_n_constraints(circuit)) return -1;
   if (circuit == 4) return kExp[idx];
+  if (circuit == 5) return kTx[idx];
+  if (circuit == 6) return kSig[idx];
   return circuit == 0 ? kBytecode[idx] : circuit == 1 ? kState[idx] : circuit == 2 ? kCopy[idx] : kEvm[idx];
 }

@@ -14,6 +14,7 @@
 #include "../../zkevm-specs_b200/csrc/evm.cu"
 #include "../../zkevm-specs_b200/csrc/exp.cu"
 #include "../../zkevm-specs_b200/csrc/state.cu"
+#include "../../zkevm-specs_b200/csrc/tx.cu"
 
 using namespace zk;
 
@@ -293,4 +294,36 @@ extern "C" void emu_div256(const uint64_t* n, const uint64_t* d, uint64_t* q) {
   u64 qq[4];
   div256((const u64*)n, (const u64*)d, qq);
   for (int k = 0; k < 4; k++) q[k] = qq[k];
+}
+
+extern "C" int emu_check_tx(const uint64_t* rows, uint64_t n_rows, const uint8_t* flags, const uint64_t* keccak,
+                            uint64_t n_keccak, const uint64_t r[4], uint64_t row_begin, uint64_t row_end,
+                            const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 kk[5] = {0, 1, 2, 3, 4};
+  IndexStore s1;
+  IndexDev kix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s1);
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 14, flags);
+  ResultDev res;
+  init_result(res, first_fail, fail_count, TX_N_CONSTRAINTS);
+  const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
+  for (u64 i = row_begin; i < row_end; i++) check_tx_row(w, kix, r_mont, res, i);
+  return 0;
+}
+
+extern "C" int emu_check_sig(const uint64_t* rows, uint64_t n_rows, const uint8_t* flags, const uint64_t* keccak,
+                             uint64_t n_keccak, const uint64_t r[4], uint64_t row_begin, uint64_t row_end,
+                             const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 kk[5] = {0, 1, 2, 3, 4};
+  IndexStore s1;
+  IndexDev kix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s1);
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 21, flags);
+  ResultDev res;
+  init_result(res, first_fail, fail_count, SG_N_CONSTRAINTS);
+  const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
+  for (u64 i = row_begin; i < row_end; i++) check_sig_row(w, kix, r_mont, res, i);
+  return 0;
 }

@@ -148,3 +148,35 @@ def check_exp(rows, row_begin=0, row_end=None, cflags=1):
                              ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_tx(rows, flags, keccak, r, row_begin=0, row_end=None, challenge=None):
+    rows, keccak = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak)]
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    ff = np.zeros(16, dtype=np.uint32)
+    fc = np.zeros(16, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().emu_check_tx(_p(rows), c(rows.shape[1]), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _p(keccak),
+                            c(keccak.shape[1]), _p(rr), c(row_begin), c(row_end), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc
+
+
+def check_sig(rows, flags, keccak, r, row_begin=0, row_end=None, challenge=None):
+    rows, keccak = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak)]
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    ff = np.zeros(16, dtype=np.uint32)
+    fc = np.zeros(16, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().emu_check_sig(_p(rows), c(rows.shape[1]), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _p(keccak),
+                             c(keccak.shape[1]), _p(rr), c(row_begin), c(row_end), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

@@ -1157,11 +1157,239 @@ def exp_cases():
     print(f"exp: {tot} corruptions, {nfail} failing")
 
 
+# --------------------------------------------------------------------------- tx circuit (Fr parts)
+def tx_cases():
+    """The reference's tx_circuit.verify_circuit (tx_circuit.py:253-289) run UNMODIFIED on witnesses
+    whose ECDSA chip is a stand-in: eth_keys (secp256k1) is a third-party dependency that is absent
+    here, so the chips are built directly from random public-key bytes and `ECDSAVerifyChip.verify`
+    is replaced by a per-chip flag.  Everything the path covers — the public-key RLC, the
+    keccak-table membership, address / msg-hash equalities, the copy constraints — is the
+    reference's own code.  Corruptions: any of the 14 cells of a tx (as the reference objects they
+    come from), the Word/value type of the CallerAddress row, the ECDSA flag, keccak-table cells."""
+    from zkevm_specs import tx_circuit as tc
+    from zkevm_specs.util import FQ, Word, WordOrValue
+    from eth_utils import keccak
+
+    r = FQ(0x0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF % P)
+    rng = random.Random(19)
+    MAX_TXS = 6
+
+    class StubECDSA:
+        def __init__(self, x_le, y_le, msg_le, ok=True):
+            self.pub_key_x_bytes, self.pub_key_y_bytes, self.msg_hash_bytes, self.ok = x_le, y_le, msg_le, ok
+
+        def verify(self, assert_msg):
+            assert self.ok, f"{assert_msg}: ecdsa_verify failed"
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wbytes(lo, hi):  # the 32 bytes whose Word is (lo, hi); None if not representable as bytes
+        if lo >= 1 << 128 or hi >= 1 << 128:
+            return None
+        return lo.to_bytes(16, "little") + hi.to_bytes(16, "little")
+
+    def base_cells():
+        cells, flags, pks = [], [], []
+        for i in range(MAX_TXS):
+            if i >= 4:  # padding txs: all zero (tx_circuit.py:273-275)
+                cells.append([0] * 14); flags.append(0); pks.append(None)
+                continue
+            pk = bytes(rng.randrange(256) for _ in range(64))  # x_be + y_be
+            x_le, y_le = bytes(reversed(pk[:32])), bytes(reversed(pk[32:]))
+            h = keccak(pk)
+            addr = int.from_bytes(h[-20:], "big")
+            msg = bytes(rng.randrange(256) for _ in range(32))  # tx sign hash, big-endian
+            msg_le = bytes(reversed(msg))
+            mw = Word(int.from_bytes(msg, "big"))
+            c = [addr, int.from_bytes(x_le[:16], "little"), int.from_bytes(x_le[16:], "little"),
+                 int.from_bytes(y_le[:16], "little"), int.from_bytes(y_le[16:], "little"),
+                 int.from_bytes(h[:16], "little"), int.from_bytes(h[16:], "little"), n_of(mw.lo), n_of(mw.hi),
+                 int.from_bytes(msg_le[:16], "little"), int.from_bytes(msg_le[16:], "little"), addr, n_of(mw.lo), n_of(mw.hi)]
+            assert (c[9], c[10]) == (c[7], c[8])
+            cells.append(c); flags.append(0); pks.append(pk)
+        return cells, flags, pks
+
+    def keccak_rows(pks):
+        kt = tc.KeccakTable()
+        for pk in pks:
+            if pk is not None:
+                kt.add(pk, r)
+        return sorted([[n_of(a), n_of(b), n_of(l), n_of(o.lo), n_of(o.hi)] for a, b, l, o in kt.table])
+
+    def run(cells, flags, K):
+        kt = tc.KeccakTable()
+        kt.table = set((FQ(v[0]), FQ(v[1]), FQ(v[2]), W(v[3], v[4])) for v in K)
+        rows, chips = [], []
+        for c, f in zip(cells, flags):
+            xb, yb, hb, mb = wbytes(c[1], c[2]), wbytes(c[3], c[4]), wbytes(c[5], c[6]), wbytes(c[9], c[10])
+            if None in (xb, yb, hb, mb):
+                return None  # not representable as `bytes` objects: no reference verdict
+            chips.append(tc.SignVerifyChip(hb, FQ(c[0]), W(c[7], c[8]), StubECDSA(xb, yb, mb, ok=not (f & 2))))
+            for tag in range(1, 13):  # TxContextFieldTag Nonce=1 .. TxSignHash=12 (CallerAddress=4)
+                if tag == 4:
+                    v = W(c[11], 0) if f & 1 else FQ(c[11])
+                elif tag == 12:
+                    v = W(c[12], c[13])
+                else:
+                    v = FQ(0)
+                rows.append(tc.Row(FQ(len(chips)), FQ(tag), FQ(0), v))
+        # verify_circuit(witness, m, ..) checks tx 0..m-1 and stops at the first failing assert (not
+        # every assert carries the tx_index in its message): grow m to find the failing tx
+        for m in range(1, MAX_TXS + 1):
+            try:
+                tc.verify_circuit(tc.Witness(rows, kt, chips), m, 0, r)
+            except Exception as e:  # noqa: BLE001
+                return m - 1, type(e).__name__
+        return -1, ""
+
+    import re
+    cells, flags, pks = base_cells()
+    K = keccak_rows(pks)
+    assert run(cells, flags, K) == (-1, "")
+    muts = [(-1, 0, 0, 0, -1, "")]
+    tot = nfail = 0
+    for k in range(420):
+        which = rng.choice([0, 0, 0, 0, 1, 2, 3, 3])
+        c2, f2, K2 = [list(x) for x in cells], list(flags), [list(x) for x in K]
+        if which == 0:
+            i, col = rng.randrange(MAX_TXS), rng.randrange(14)
+            v = corrupt_value(rng, cells[i][col]); c2[i][col] = v
+        elif which == 1:
+            i, col, v = rng.randrange(MAX_TXS), 100, 0
+            f2[i] ^= 1
+        elif which == 2:
+            i, col, v = rng.randrange(MAX_TXS), 101, 0
+            f2[i] ^= 2
+        else:
+            i, col = rng.randrange(len(K)), rng.randrange(5)
+            v = corrupt_value(rng, K[i][col]); K2[i][col] = v
+        out = run(c2, f2, K2)
+        if out is None:
+            continue
+        muts.append((which, i, col, v, out[0], out[1]))
+        tot += 1
+        nfail += out[0] >= 0
+    out = {"rows": to_matrix(cells), "flags": np.array(flags, dtype=np.uint8), "keccak": to_matrix(K),
+           "r": np.array(limbs(r.n), dtype=np.uint64),
+           "mut_kind": np.array([m[0] for m in muts], dtype=np.int64), "mut_row": np.array([m[1] for m in muts], dtype=np.int64),
+           "mut_col": np.array([m[2] for m in muts], dtype=np.int64), "mut_val": np.array([limbs(m[3]) for m in muts], dtype=np.uint64),
+           "exp_row": np.array([m[4] for m in muts], dtype=np.int64), "exp_exc": np.array([m[5] for m in muts])}
+    np.savez_compressed(os.path.join(HERE, "tx.npz"), **out)
+    print(f"tx: {tot} corruptions, {nfail} failing")
+
+
+# --------------------------------------------------------------------------- sig circuit (Fr parts)
+def sig_cases():
+    """sig_circuit.verify_circuit (sig_circuit.py:113-123) run UNMODIFIED on rows whose ECDSA chip
+    is a stand-in (eth_keys absent): chips carry random public-key / signature bytes and a verdict
+    flag returned by verify().  Corruptions: any of the 21 cells (as the reference attributes they
+    come from), the verdict flag, keccak-table cells."""
+    from zkevm_specs import sig_circuit as sc
+    from zkevm_specs.util import FQ, Word, KeccakTable
+    from eth_utils import keccak
+
+    r = FQ(0x0FEDCBA9876543210FEDCBA9876543210FEDCBA9876543210FEDCBA987654321 % P)
+    rng = random.Random(23)
+    N = 5
+
+    class LE:
+        def __init__(self, v):
+            self.le_bytes = v.to_bytes(32, "little")
+
+    class StubECDSA:
+        def __init__(self, x_le, y_le, msg_b, v, rr, ss, ok):
+            self.pub_key_x_bytes, self.pub_key_y_bytes, self.msg_hash_bytes = x_le, y_le, msg_b
+            self.sig_v, self.sig_r, self.sig_s, self.ok = LE(v), LE(rr), LE(ss), ok
+
+        def verify(self):
+            return self.ok
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wbytes(lo, hi):
+        if lo >= 1 << 128 or hi >= 1 << 128:
+            return None
+        return lo.to_bytes(16, "little") + hi.to_bytes(16, "little")
+
+    def halves(b):
+        return [int.from_bytes(b[:16], "little"), int.from_bytes(b[16:], "little")]
+
+    cells, flags, pks = [], [], []
+    for i in range(N):
+        pk = bytes(rng.randrange(256) for _ in range(64))
+        x_le, y_le = bytes(reversed(pk[:32])), bytes(reversed(pk[32:]))
+        h = keccak(pk)
+        addr = int.from_bytes(h[-20:], "big")
+        msg_b = bytes(rng.randrange(256) for _ in range(32))  # ECDSAVerifyChip.msg_hash_bytes (util/ec.py:88)
+        mw = Word(msg_b)
+        rr, ss = rng.getrandbits(256), rng.getrandbits(256)
+        ok = i != 3  # one row of an invalid signature with is_valid = False
+        cells.append([i & 1, addr, *halves(x_le), *halves(y_le), *halves(h), n_of(mw.lo), n_of(mw.hi), *halves(msg_b),
+                      int(ok), rr & ((1 << 128) - 1), rr >> 128, ss & ((1 << 128) - 1), ss >> 128,
+                      rr & ((1 << 128) - 1), rr >> 128, ss & ((1 << 128) - 1), ss >> 128])
+        flags.append(int(ok) << 1)
+        pks.append(pk)
+    kt0 = KeccakTable()
+    for pk in pks:
+        kt0.add(pk, r)
+    K = sorted([[n_of(a), n_of(b), n_of(l), n_of(o.lo), n_of(o.hi)] for a, b, l, o in kt0.table])
+
+    def run(cells, flags, K):
+        kt = KeccakTable()
+        kt.table = set((FQ(v[0]), FQ(v[1]), FQ(v[2]), W(v[3], v[4])) for v in K)
+        rows = []
+        for c, f in zip(cells, flags):
+            xb, yb, hb, mb = wbytes(c[2], c[3]), wbytes(c[4], c[5]), wbytes(c[6], c[7]), wbytes(c[10], c[11])
+            if None in (xb, yb, hb, mb) or max(c[17:21]) >= 1 << 128:
+                return None
+            chip = StubECDSA(xb, yb, mb, 0, c[17] + (c[18] << 128), c[19] + (c[20] << 128), bool(f & 2))
+            row = sc.Row(hb, FQ(c[1]), W(c[8], c[9]), chip, c[12])
+            row.sig_v, row.sig_r, row.sig_s = FQ(c[0]), W(c[13], c[14]), W(c[15], c[16])
+            rows.append(row)
+        for m in range(1, len(rows) + 1):
+            try:
+                sc.verify_circuit(sc.Witness(rows[:m], kt), r)
+            except Exception as e:  # noqa: BLE001
+                return m - 1, type(e).__name__
+        return -1, ""
+
+    assert run(cells, flags, K) == (-1, ""), run(cells, flags, K)
+    muts = [(-1, 0, 0, 0, -1, "")]
+    tot = nfail = 0
+    for k in range(420):
+        which = rng.choice([0, 0, 0, 0, 0, 2, 3, 3])
+        c2, f2, K2 = [list(x) for x in cells], list(flags), [list(x) for x in K]
+        if which == 0:
+            i, col = rng.randrange(N), rng.randrange(21)
+            v = corrupt_value(rng, cells[i][col]); c2[i][col] = v
+        elif which == 2:
+            i, col, v = rng.randrange(N), 101, 0
+            f2[i] ^= 2
+        else:
+            i, col = rng.randrange(len(K)), rng.randrange(5)
+            v = corrupt_value(rng, K[i][col]); K2[i][col] = v
+        out = run(c2, f2, K2)
+        if out is None:
+            continue
+        muts.append((which, i, col, v, out[0], out[1]))
+        tot += 1
+        nfail += out[0] >= 0
+    out = {"rows": to_matrix(cells), "flags": np.array(flags, dtype=np.uint8), "keccak": to_matrix(K),
+           "r": np.array(limbs(r.n), dtype=np.uint64),
+           "mut_kind": np.array([m[0] for m in muts], dtype=np.int64), "mut_row": np.array([m[1] for m in muts], dtype=np.int64),
+           "mut_col": np.array([m[2] for m in muts], dtype=np.int64), "mut_val": np.array([limbs(m[3]) for m in muts], dtype=np.uint64),
+           "exp_row": np.array([m[4] for m in muts], dtype=np.int64), "exp_exc": np.array([m[5] for m in muts])}
+    np.savez_compressed(os.path.join(HERE, "sig.npz"), **out)
+    print(f"sig: {tot} corruptions, {nfail} failing")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "exp", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

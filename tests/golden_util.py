@@ -159,3 +159,25 @@ def exp_vectors():
 def evm4_vectors():
     """MEMORY steps (MLOAD / MSTORE / MSTORE8, tests/evm/test_memory.py); same layout as evm2"""
     return evm2_vectors("evm4")
+
+
+def tx_vectors(part="tx"):
+    """tx (sig) circuit Fr parts: yield (k, rows[14 (21)][n][4], flags[n], keccak[5][m][4], r limbs, exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, part + ".npz"))
+    R, F, K, r = z["rows"], z["flags"], z["keccak"], z["r"]
+    for k in range(len(z["mut_kind"])):
+        kind, i, c, val = int(z["mut_kind"][k]), int(z["mut_row"][k]), int(z["mut_col"][k]), z["mut_val"][k]
+        rows, flags, kec = R, F, K
+        if kind == 0:
+            rows = R.copy(); rows[c, i, :] = val
+        elif kind == 1:
+            flags = F.copy(); flags[i] ^= 1
+        elif kind == 2:
+            flags = F.copy(); flags[i] ^= 2
+        elif kind == 3:
+            kec = K.copy(); kec[c, i, :] = val
+        yield k, rows, flags, kec, r, int(z["exp_row"][k]), str(z["exp_exc"][k])
+
+
+def sig_vectors():
+    return tx_vectors("sig")

@@ -173,3 +173,37 @@ def check_exp(rows, row_begin=0, row_end=None):
     rc = lib().orc_check_exp(p64(rows), c(rows.shape[1]), c(row_begin), c(row_end), ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_tx(rows, flags, keccak, r, row_begin=0, row_end=None):
+    """tx circuit Fr parts (oracle/tx.c): rows uint64[14][n][4], flags uint8[n], keccak uint64[5][k][4]"""
+    rows, keccak = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak)]
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n = lib().orc_n_constraints(5)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    rc = lib().orc_check_tx(p64(rows), c(rows.shape[1]), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), p64(keccak),
+                            c(keccak.shape[1]), p64(rr), c(row_begin), c(row_end), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc
+
+
+def check_sig(rows, flags, keccak, r, row_begin=0, row_end=None):
+    """sig circuit Fr parts (oracle/tx.c): rows uint64[21][n][4], flags uint8[n] (bit 1 = ecdsa verdict)"""
+    rows, keccak = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak)]
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    n = lib().orc_n_constraints(6)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rr = np.ascontiguousarray(r, dtype=np.uint64)
+    rc = lib().orc_check_sig(p64(rows), c(rows.shape[1]), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), p64(keccak),
+                             c(keccak.shape[1]), p64(rr), c(row_begin), c(row_end), ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

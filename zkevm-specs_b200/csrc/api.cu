@@ -17,6 +17,7 @@
 #include "copy.cu"
 #include "evm.cu"
 #include "exp.cu"
+#include "tx.cu"
 #include "state.cu"
 #include "circuit.cuh"
 
@@ -34,8 +35,10 @@ static const ConstraintInfo kEvmInfo[] = {ZK_EVM_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kCopyInfo[] = {ZK_COPY_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kStateInfo[] = {ZK_STATE_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kExpInfo[] = {ZK_EXP_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kTxInfo[] = {ZK_TX_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kSigInfo[] = {ZK_SIG_CONSTRAINTS(ZK_INFO_ENTRY)};
 
-static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21};
+static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21, 14, 21};
 static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
 
 static const ConstraintInfo* circuit_info(int circuit, int* n) {
@@ -45,6 +48,8 @@ static const ConstraintInfo* circuit_info(int circuit, int* n) {
     case ZK_CIRCUIT_COPY: *n = CP_N_CONSTRAINTS; return kCopyInfo;
     case ZK_CIRCUIT_STATE: *n = ST_N_CONSTRAINTS; return kStateInfo;
     case ZK_CIRCUIT_EXP: *n = XP_N_CONSTRAINTS; return kExpInfo;
+    case ZK_CIRCUIT_TX: *n = TX_N_CONSTRAINTS; return kTxInfo;
+    case ZK_CIRCUIT_SIG: *n = SG_N_CONSTRAINTS; return kSigInfo;
     default: *n = 0; return nullptr;
   }
 }
@@ -605,6 +610,22 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   return 0;
 }
 
+static int check_tx(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st, bool sig = false) {
+  const u32 kk[5] = {0, 1, 2, 3, 4};
+  IndexDev kec_ix;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 5, st, &kec_ix))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
+  const u64 n = rg.row_end - rg.row_begin;
+  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
+  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
+  if (sig) k_check_sig<<<grid, 128, 0, st>>>(witness_dev(ctx->circ[ZK_CIRCUIT_SIG]), rg, kec_ix, r_mont, res);
+  else k_check_tx<<<grid, 128, 0, st>>>(witness_dev(ctx->circ[ZK_CIRCUIT_TX]), rg, kec_ix, r_mont, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int check_exp(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const Matrix& m = ctx->circ[ZK_CIRCUIT_EXP];
   if (!(rg.flags & ZK_FLAG_WRAP) && rg.row_end + 1 > m.n_rows)
@@ -735,6 +756,8 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
     case ZK_CIRCUIT_COPY: rc = check_copy(ctx, rg, res, st); break;
     case ZK_CIRCUIT_STATE: rc = check_state(ctx, rg, res, st); break;
     case ZK_CIRCUIT_EXP: rc = check_exp(ctx, rg, res, st); break;
+    case ZK_CIRCUIT_TX: rc = check_tx(ctx, rg, res, st); break;
+    case ZK_CIRCUIT_SIG: rc = check_tx(ctx, rg, res, st, true); break;
     default: return fail_msg(ctx, "circuit has no gate program in this build");
   }
   if (rc) return rc;

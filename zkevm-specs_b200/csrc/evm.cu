@@ -1213,8 +1213,14 @@ __device__ __forceinline__ void gadget_steps(const WitnessDev& w, const CheckRan
 }
 // two instances per gadget (own register budgets); the host launches both, the one whose POS does
 // not match the tables returns at once
+#ifndef ZK_GADGET_MINBLOCKS
+#define ZK_GADGET_MINBLOCKS 1
+#endif
+#ifndef ZK_PUSH_MINBLOCKS
+#define ZK_PUSH_MINBLOCKS 1
+#endif
 template <int G, bool POS>
-__global__ void __launch_bounds__(128) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+__global__ void __launch_bounds__(128, ZK_GADGET_MINBLOCKS) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                     EvmLists lists) {
   if (both_positional(t) != POS) return;
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
@@ -1260,7 +1266,7 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
 }
 // positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1); returns at once
 // otherwise, and then k_evm_push<false> below does the work — the host launches both
-__global__ void __launch_bounds__(128) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+__global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                       EvmLists lists) {
   if (!both_positional(t)) return;
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
