@@ -203,6 +203,44 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_MEM_BYTE_UNSAT, ZKE_UNSAT, "memory.py:26,30-36 memory_lookup unsat")                 \
   X(EV_MEM_BYTE_AMBIG, ZKE_AMBIG, "memory.py:26,30-36 memory_lookup ambiguous")             \
   X(EV_MEM_BYTE_TYPE, ZKE_ASSERT, "instruction.py:934 .value(): memory value is a Word")    \
+  /* MSIZE (msize.py), GAS (gas.py), ISZERO (iszero.py), CMP = LT/GT/EQ (comparator.py), JUMP (jump.py), \
+   * JUMPI (jumpi.py) */                                                                     \
+  X(EV_MSZ_WORD, ZKE_ASSERT, "msize.py:12 Word.from_lo(memory_word_size * 32): >= 2^128")    \
+  X(EV_MSZ_PUSH_UNSAT, ZKE_UNSAT, "msize.py:12 stack_push unsat")                            \
+  X(EV_MSZ_PUSH_AMBIG, ZKE_AMBIG, "msize.py:12 stack_push ambiguous")                        \
+  X(EV_MSZ_EQ, ZKE_ASSERT, "msize.py:11-13 pushed word == memory_word_size * 32")            \
+  X(EV_GAS_OPCODE, ZKE_ASSERT, "gas.py:9 opcode == GAS")                                     \
+  X(EV_GAS_WORD, ZKE_ASSERT, "gas.py:12 Word.from_lo(gas_left - 2): >= 2^128")               \
+  X(EV_GAS_PUSH_UNSAT, ZKE_UNSAT, "gas.py:13 stack_push unsat")                              \
+  X(EV_GAS_PUSH_AMBIG, ZKE_AMBIG, "gas.py:13 stack_push ambiguous")                          \
+  X(EV_GAS_EQ, ZKE_ASSERT, "gas.py:11-14 pushed word == gas_left - 2")                       \
+  X(EV_ISZ_POP_UNSAT, ZKE_UNSAT, "iszero.py:8 stack_pop unsat")                              \
+  X(EV_ISZ_POP_AMBIG, ZKE_AMBIG, "iszero.py:8 stack_pop ambiguous")                          \
+  X(EV_ISZ_PUSH_UNSAT, ZKE_UNSAT, "iszero.py:12 stack_push unsat")                           \
+  X(EV_ISZ_PUSH_AMBIG, ZKE_AMBIG, "iszero.py:12 stack_push ambiguous")                       \
+  X(EV_ISZ_EQ, ZKE_ASSERT, "iszero.py:10-13 pushed word == is_zero_word(value)")             \
+  X(EV_CMP_A_UNSAT, ZKE_UNSAT, "comparator.py:13 stack_pop a unsat")                         \
+  X(EV_CMP_A_AMBIG, ZKE_AMBIG, "comparator.py:13 stack_pop a ambiguous")                     \
+  X(EV_CMP_B_UNSAT, ZKE_UNSAT, "comparator.py:14 stack_pop b unsat")                         \
+  X(EV_CMP_B_AMBIG, ZKE_AMBIG, "comparator.py:14 stack_pop b ambiguous")                     \
+  X(EV_CMP_C_UNSAT, ZKE_UNSAT, "comparator.py:15 stack_push c unsat")                        \
+  X(EV_CMP_C_AMBIG, ZKE_AMBIG, "comparator.py:15 stack_push c ambiguous")                    \
+  X(EV_CMP_RANGE_LO, ZKE_ASSERT, "comparator.py:24, instruction.py:449-450 compare(lo halves): operand exceeds 16 bytes") \
+  X(EV_CMP_RANGE_HI, ZKE_ASSERT, "comparator.py:27 compare(hi halves): operand exceeds 16 bytes") \
+  X(EV_CMP_EQ, ZKE_ASSERT, "comparator.py:34-37 pushed word == result")                      \
+  X(EV_JMP_OPCODE, ZKE_ASSERT, "jump.py:9 opcode == JUMP")                                   \
+  X(EV_JMP_DEST_UNSAT, ZKE_UNSAT, "jump.py:13 stack_pop dest unsat")                         \
+  X(EV_JMP_DEST_AMBIG, ZKE_AMBIG, "jump.py:13 stack_pop dest ambiguous")                     \
+  X(EV_JMP_DEST_HI, ZKE_ASSERT, "jump.py:14 dest.hi == 0")                                   \
+  X(EV_JMP_AT_UNSAT, ZKE_UNSAT, "jump.py:18 opcode_lookup_at(dest) unsat")                   \
+  X(EV_JMP_AT_AMBIG, ZKE_AMBIG, "jump.py:18 opcode_lookup_at(dest) ambiguous")               \
+  X(EV_JMP_NOT_JUMPDEST, ZKE_ASSERT, "jump.py:18 code at dest == JUMPDEST")                  \
+  X(EV_JMPI_OPCODE, ZKE_ASSERT, "jumpi.py:9 opcode == JUMPI")                                \
+  X(EV_JMPI_DEST_UNSAT, ZKE_UNSAT, "jumpi.py:13 stack_pop dest unsat")                       \
+  X(EV_JMPI_DEST_AMBIG, ZKE_AMBIG, "jumpi.py:13 stack_pop dest ambiguous")                   \
+  X(EV_JMPI_DEST_HI, ZKE_ASSERT, "jumpi.py:14 dest.hi == 0")                                 \
+  X(EV_JMPI_COND_UNSAT, ZKE_UNSAT, "jumpi.py:17 stack_pop cond unsat")                       \
+  X(EV_JMPI_COND_AMBIG, ZKE_AMBIG, "jumpi.py:17 stack_pop cond ambiguous")                   \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

@@ -542,6 +542,77 @@ static void gadget_memory(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   same_context_x(e, i, row, opcode, fr_u64(is_mstore8 ? 3 : 34), one, fr_u64(is_store ? 2 : 0), 1, fr_u64(nxt), gas);
 }
 
+/* ---- simple same-context gadgets: msize.py, gas.py, iszero.py, comparator.py, jump.py, jumpi.py ---- */
+static int word_is(word_t w, fr_t lo) { return fr_eq(w.lo, lo) && fr_is_zero(w.hi); }
+static void gadget_msize(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t v = fr_mul(CUR(S_MEM), fr_u64(32)); /* memory_word_size * N_BYTES_WORD over the field */
+  CHECK(EV_MSZ_WORD, fr_fits_bits(v, 128));
+  word_t w;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_MSZ_PUSH_UNSAT, row)) return;
+  CHECK(EV_MSZ_EQ, word_is(w, v));
+  same_context(e, i, row, opcode, 1, fr_u64(1), fr_neg(fr_u64(1)));
+}
+static void gadget_gas(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_GAS_OPCODE, fr_eq_u64(opcode, 0x5a));
+  const fr_t v = fr_sub(CUR(S_GAS), fr_u64(2)); /* Opcode.GAS.constant_gas_cost() == 2 */
+  CHECK(EV_GAS_WORD, fr_fits_bits(v, 128));
+  word_t w;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_GAS_PUSH_UNSAT, row)) return;
+  CHECK(EV_GAS_EQ, word_is(w, v));
+  same_context(e, i, row, opcode, 1, fr_u64(1), fr_neg(fr_u64(1)));
+}
+static void gadget_iszero(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  word_t v, w;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &v), EV_ISZ_POP_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(1)), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &w), EV_ISZ_PUSH_UNSAT, row)) return;
+  CHECK(EV_ISZ_EQ, word_is(w, fr_u64(fr_is_zero(fr_add(v.lo, v.hi)) ? 1 : 0))); /* is_zero_word: field sum of the halves */
+  same_context(e, i, row, opcode, 2, fr_u64(1), fr_u64(0));
+}
+static void gadget_cmp(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  const int is_eq = fr_eq_u64(opcode, 0x14), is_gt = fr_eq_u64(opcode, 0x11);
+  word_t a, b, c;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_CMP_A_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &b), EV_CMP_B_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &c), EV_CMP_C_UNSAT, row)) return;
+  const word_t aa = is_gt ? b : a, bb = is_gt ? a : b;
+  CHECK(EV_CMP_RANGE_LO, fr_fits_bits(aa.lo, 128) && fr_fits_bits(bb.lo, 128));
+  CHECK(EV_CMP_RANGE_HI, fr_fits_bits(aa.hi, 128) && fr_fits_bits(bb.hi, 128));
+  const int lt_lo = fr_cmp(aa.lo, bb.lo) < 0, eq_lo = fr_eq(aa.lo, bb.lo);
+  const int lt_hi = fr_cmp(aa.hi, bb.hi) < 0, eq_hi = fr_eq(aa.hi, bb.hi);
+  const int lt = lt_hi ? 1 : (eq_hi && lt_lo), eq = eq_lo && eq_hi;
+  CHECK(EV_CMP_EQ, word_is(c, fr_u64(is_eq ? eq : lt)));
+  same_context(e, i, row, opcode, 3, one, one);
+}
+static void gadget_jump(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_JMP_OPCODE, fr_eq_u64(opcode, 0x56));
+  word_t dest;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &dest), EV_JMP_DEST_UNSAT, row)) return;
+  CHECK(EV_JMP_DEST_HI, fr_is_zero(dest.hi));
+  fr_t at;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, dest.lo, 1, &at), EV_JMP_AT_UNSAT, row)) return;
+  CHECK(EV_JMP_NOT_JUMPDEST, fr_eq_u64(at, 0x5b));
+  /* program_counter = Transition.to(dest): next.pc == dest, i.e. delta dest - pc over the field */
+  same_context(e, i, row, opcode, 1, fr_sub(dest.lo, CUR(S_PC)), fr_u64(1));
+}
+static void gadget_jumpi(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_JMPI_OPCODE, fr_eq_u64(opcode, 0x57));
+  word_t dest, cond;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &dest), EV_JMPI_DEST_UNSAT, row)) return;
+  CHECK(EV_JMPI_DEST_HI, fr_is_zero(dest.hi));
+  if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(1)), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_add(CUR(S_SP), fr_u64(1)), &cond), EV_JMPI_COND_UNSAT, row)) return;
+  /* jumpi.py:20 `if instruction.is_zero_word(cond):` tests the truthiness of an FQ OBJECT (py_ecc's FQ
+   * defines neither __bool__ nor __len__), which is always true: the reference takes the
+   * fall-through branch (pc + 1) whatever cond is and never looks at the destination. */
+  same_context(e, i, row, opcode, 2, fr_u64(1), fr_u64(2));
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -569,7 +640,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t st = cs.l[0];
   CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP ||
                                   st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY || st == ZK_ES_STOP ||
-                                  st == ZK_ES_MEMORY);
+                                  st == ZK_ES_MEMORY || st == ZK_ES_MSIZE || st == ZK_ES_GAS || st == ZK_ES_ISZERO ||
+                                  st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
@@ -580,6 +652,12 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_SHA3) gadget_sha3(e, i, row, opcode);
   else if (st == ZK_ES_CALLDATACOPY) gadget_calldatacopy(e, i, row, opcode);
   else if (st == ZK_ES_MEMORY) gadget_memory(e, i, row, opcode);
+  else if (st == ZK_ES_MSIZE) gadget_msize(e, i, row, opcode);
+  else if (st == ZK_ES_GAS) gadget_gas(e, i, row, opcode);
+  else if (st == ZK_ES_ISZERO) gadget_iszero(e, i, row, opcode);
+  else if (st == ZK_ES_CMP) gadget_cmp(e, i, row, opcode);
+  else if (st == ZK_ES_JUMP) gadget_jump(e, i, row, opcode);
+  else if (st == ZK_ES_JUMPI) gadget_jumpi(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

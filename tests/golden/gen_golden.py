@@ -810,6 +810,24 @@ def synth_cases():
     cc.verify_copy_table(Fake(crow), tables, FQ(r_int))
     print("synth.copy_events(4, 20): accepted by the reference's verify_copy_table,", len(crow), "rows")
 
+    # bytecode circuit rows: 2^9 rows, 3 contracts + Header padding
+    import zkevm_specs.bytecode_circuit as bcc
+    from zkevm_specs.evm_circuit import KeccakTableRow
+
+    w = synth.bytecode_circuit_rows(9, 3, seed=5)
+    Bm, Km = w["rows"], w["keccak"]
+    r_int = sum(int(w["r"][k]) << (64 * k) for k in range(4))
+    brows = []
+    for i in range(Bm.shape[1]):
+        v = [cell(Bm, c, i) for c in range(12)]
+        brows.append(bcc.Row(FQ(v[0]), FQ(v[1]), W(v[2], v[3]), *[FQ(x) for x in v[4:]]))
+    push_table = bcc.assign_push_table()
+    kt = set(KeccakTableRow(FQ(cell(Km, 0, i)), FQ(cell(Km, 1, i)), FQ(cell(Km, 2, i)), W(cell(Km, 3, i), cell(Km, 4, i)))
+             for i in range(Km.shape[1]))
+    for idx, row in enumerate(brows):
+        bcc.check_bytecode_row(row, brows[(idx + 1) % len(brows)], push_table, kt, FQ(r_int))
+    print("synth.bytecode_circuit_rows(9, 3): accepted by the reference's check_bytecode_row,", len(brows), "rows")
+
 
 # --------------------------------------------------------------------------- evm2: SHA3 / CALLDATACOPY
 def evm2_cases(part="evm2"):
@@ -825,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -893,6 +911,56 @@ def evm2_cases(part="evm2"):
                  StepState(ExecutionState.STOP, rw_counter=4 if is_mstore8 else 35, call_id=1, is_root=True, is_create=False,
                            code_hash=h, program_counter=34 if is_mload else 67, stack_pointer=1022 if is_mload else 1024,
                            memory_word_size=nxt, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
+    def simple_case(kind, a=0, b=0):
+        """tests/evm/test_{msize,gas,iszero,comparator,jump,jumpi}.py: one step + STOP"""
+        A, B = Word(a), Word(b)
+        if kind == "msize":
+            bc, rw = Bytecode().msize().stop(), RWDictionary(9).stack_write(1, 1023, Word(a * 32))
+            cur = dict(program_counter=0, stack_pointer=1024, memory_word_size=a, gas_left=2)
+            nxt = dict(program_counter=1, stack_pointer=1023, memory_word_size=a, gas_left=0)
+            state = ExecutionState.MSIZE
+        elif kind == "gas":
+            bc, rw = Bytecode().gas().stop(), RWDictionary(9).stack_write(1, 1023, Word(a - 2))
+            cur = dict(program_counter=0, stack_pointer=1024, gas_left=a)
+            nxt = dict(program_counter=1, stack_pointer=1023, gas_left=a - 2)
+            state = ExecutionState.GAS
+        elif kind == "iszero":
+            bc = Bytecode().push(a, n_bytes=32).iszero().stop()
+            rw = RWDictionary(9).stack_read(1, 1023, A).stack_write(1, 1023, Word(int(a == 0)))
+            cur = dict(program_counter=33, stack_pointer=1023, gas_left=3)
+            nxt = dict(program_counter=34, stack_pointer=1023, gas_left=0)
+            state = ExecutionState.ISZERO
+        elif kind in ("lt", "gt", "eq"):
+            bc = getattr(Bytecode().push(b, n_bytes=32).push(a, n_bytes=32), kind)().stop()
+            res = {"lt": a < b, "gt": a > b, "eq": a == b}[kind]
+            rw = RWDictionary(9).stack_read(1, 1022, A).stack_read(1, 1023, B).stack_write(1, 1023, Word(int(res)))
+            cur = dict(program_counter=66, stack_pointer=1022, gas_left=3)
+            nxt = dict(program_counter=67, stack_pointer=1023, gas_left=0)
+            state = ExecutionState.CMP
+        elif kind == "jump":
+            bc = Bytecode().push(a, n_bytes=32).jump()
+            while len(bc.code) < a:
+                bc = bc.stop()
+            bc = bc.jumpdest().stop()
+            rw = RWDictionary(9).stack_read(1, 1023, A)
+            cur = dict(program_counter=33, stack_pointer=1023, gas_left=8)
+            nxt = dict(program_counter=a, stack_pointer=1024, gas_left=0)
+            state = ExecutionState.JUMP
+        else:  # jumpi: a = dest, b = cond
+            bc = Bytecode().push(b, n_bytes=32).push(a, n_bytes=32).jumpi()
+            while len(bc.code) < a:
+                bc = bc.stop()
+            bc = bc.jumpdest().stop()
+            rw = RWDictionary(9).stack_read(1, 1022, A).stack_read(1, 1023, B)
+            cur = dict(program_counter=66, stack_pointer=1022, gas_left=10)
+            nxt = dict(program_counter=67, stack_pointer=1024, gas_left=0)  # see oracle/evm.c:gadget_jumpi
+            state = ExecutionState.JUMPI
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, **cur),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, **nxt)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
     def mws(a):
@@ -994,7 +1062,17 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm4":
+    if part == "evm5":
+        big = (1 << 255) + 12345
+        scenarios = {
+            "msize_0": simple_case("msize", 0), "msize_7": simple_case("msize", 7), "gas": simple_case("gas", 1000),
+            "iszero_0": simple_case("iszero", 0), "iszero_big": simple_case("iszero", big),
+            "lt_true": simple_case("lt", 5, big), "lt_false": simple_case("lt", big, 5), "lt_hi_eq": simple_case("lt", (7 << 128) + 1, (7 << 128) + 2),
+            "gt_true": simple_case("gt", big, 5), "gt_false": simple_case("gt", 5, 5),
+            "eq_true": simple_case("eq", big, big), "eq_false": simple_case("eq", big, big + 1),
+            "jump": simple_case("jump", 40), "jumpi_zero": simple_case("jumpi", 90, 0), "jumpi_nonzero": simple_case("jumpi", 90, 40),
+        }
+    elif part == "evm4":
         scenarios = {
             "mload_0": memory_case(Opcode.MLOAD, 0, 0xFF), "mload_1": memory_case(Opcode.MLOAD, 1, 0xFF00, 3),
             "mstore_0": memory_case(Opcode.MSTORE, 0, 0xFF), "mstore_big": memory_case(Opcode.MSTORE, 0x1234, (1 << 255) + 77, 5),
@@ -1020,7 +1098,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
@@ -1082,6 +1160,10 @@ def evm3_cases():
 
 def evm4_cases():
     evm2_cases("evm4")
+
+
+def evm5_cases():
+    evm2_cases("evm5")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1389,7 +1471,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

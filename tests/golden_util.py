@@ -181,3 +181,8 @@ def tx_vectors(part="tx"):
 
 def sig_vectors():
     return tx_vectors("sig")
+
+
+def evm5_vectors():
+    """MSIZE / GAS / ISZERO / CMP / JUMP / JUMPI steps; same layout as evm2"""
+    return evm2_vectors("evm5")

@@ -183,15 +183,17 @@ def test_evm_stop_golden_and_oracle_parity():
 
 
 def test_evm_memory_golden_and_oracle_parity():
-    """MLOAD / MSTORE / MSTORE8 steps (tests/evm/test_memory.py): CUDA == oracle array for array, and
-    == the reference's verdicts on 650 vectors"""
+    """MLOAD / MSTORE / MSTORE8 steps (tests/evm/test_memory.py, 650 vectors) and MSIZE / GAS / ISZERO /
+    CMP / JUMP / JUMPI steps (909 vectors): CUDA == oracle array for array, == the reference's verdicts"""
     ctx = native.default_context()
     fixed = fixed_table_matrix()
     n = 0
     evm_main.upload_fixed_table(ctx)
     ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
-    for name, k, w, exp_row, exp_exc in golden_util.evm4_vectors():
+    import itertools
+
+    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm4_vectors(), golden_util.evm5_vectors()):
         ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
         ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
         ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
@@ -204,7 +206,7 @@ def test_evm_memory_golden_and_oracle_parity():
             got = (got[0], exp_exc)
         assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
         n += 1
-    assert n > 600
+    assert n > 1500
 
 
 def test_sha3_host_api_like_reference_test_sha3():

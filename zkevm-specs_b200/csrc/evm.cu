@@ -254,6 +254,12 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_CALLDATACOPY: return G_MISC;
     case ZK_ES_STOP: return G_MISC;
     case ZK_ES_MEMORY: return G_MISC;
+    case ZK_ES_MSIZE: return G_MISC;
+    case ZK_ES_GAS: return G_MISC;
+    case ZK_ES_ISZERO: return G_MISC;
+    case ZK_ES_CMP: return G_MISC;
+    case ZK_ES_JUMP: return G_MISC;
+    case ZK_ES_JUMPI: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1102,6 +1108,93 @@ ZK_HD void gadget_memory(const StepCtx& s, bool live) {
   same_context_x(s, opcode, fr_u64(is_mstore8 ? 3 : 34), fr_u64(1), fr_u64(is_store ? 2 : 0), true, fr_u64(nxt), gas);
 }
 
+// ---- simple same-context gadgets: msize.py, gas.py, iszero.py, comparator.py, jump.py, jumpi.py ----
+ZK_HD bool word_is(const Word2& w, const Fr& lo) { return fr_eq(w.lo, lo) && fr_is_zero(w.hi); }
+// one stack_push / stack_pop lookup at rw_counter + k
+ZK_HD int stack_at(const StepCtx& s, bool live, u64 k, u64 rw, const Fr& sp, Word2* out) {
+  return rw_lookup(s, live, fr_add_u64(s.cur(S_RWC), k), rw, ZK_TARGET_Stack, s.cur(S_CALL_ID), sp, out);
+}
+ZK_HD void gadget_msize(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr v = fr_montmul(s.cur(S_MEM), fr_to_mont(fr_u64(32)));  // memory_word_size * N_BYTES_WORD over the field
+  EV_LIVE_CHECK(EV_MSZ_WORD, fr_fits128(v));
+  Word2 w{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_MSZ_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_MSZ_EQ, word_is(w, v));
+  if (!live) return;
+  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+ZK_HD void gadget_gas(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_GAS_OPCODE, fr_eq_u64(opcode, 0x5a));
+  const Fr v = fr_sub_u64(s.cur(S_GAS), 2);  // Opcode.GAS.constant_gas_cost() == 2
+  EV_LIVE_CHECK(EV_GAS_WORD, fr_fits128(v));
+  Word2 w{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_GAS_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_GAS_EQ, word_is(w, v));
+  if (!live) return;
+  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+ZK_HD void gadget_iszero(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  Word2 v{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &v), EV_ISZ_POP_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 1, s.cur(S_SP), &w), EV_ISZ_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_ISZ_EQ, word_is(w, fr_u64(fr_is_zero(fr_add(v.lo, v.hi)) ? 1 : 0)));  // is_zero_word: field sum
+  if (!live) return;
+  same_context(s, opcode, 2, fr_u64(1), fr_u64(0));
+}
+ZK_HD void gadget_cmp(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const bool is_eq = fr_eq_u64(opcode, 0x14), is_gt = fr_eq_u64(opcode, 0x11);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero, c = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &a), EV_CMP_A_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &b), EV_CMP_B_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &c), EV_CMP_C_UNSAT);
+  const Word2 aa = is_gt ? b : a, bb = is_gt ? a : b;  // comparator.py:18 swap for GT
+  EV_LIVE_CHECK(EV_CMP_RANGE_LO, fr_fits128(aa.lo) && fr_fits128(bb.lo));
+  EV_LIVE_CHECK(EV_CMP_RANGE_HI, fr_fits128(aa.hi) && fr_fits128(bb.hi));
+  const bool lt_lo = fr_lt(aa.lo, bb.lo), eq_lo = fr_eq(aa.lo, bb.lo), lt_hi = fr_lt(aa.hi, bb.hi), eq_hi = fr_eq(aa.hi, bb.hi);
+  const bool lt = lt_hi || (eq_hi && lt_lo), eq = eq_lo && eq_hi;
+  EV_LIVE_CHECK(EV_CMP_EQ, word_is(c, fr_u64((is_eq ? eq : lt) ? 1 : 0)));
+  if (!live) return;
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+ZK_HD void gadget_jump(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_JMP_OPCODE, fr_eq_u64(opcode, 0x56));
+  Word2 dest{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &dest), EV_JMP_DEST_UNSAT);
+  EV_LIVE_CHECK(EV_JMP_DEST_HI, fr_is_zero(dest.hi));
+  Fr at = fr_u64(0);  // opcode_lookup_at(dest, True), instruction.py:789-790
+  live = need1(s, live, bytecode_lookup(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, dest.lo, 1, &at), EV_JMP_AT_UNSAT);
+  EV_LIVE_CHECK(EV_JMP_NOT_JUMPDEST, fr_eq_u64(at, 0x5b));
+  if (!live) return;
+  // program_counter = Transition.to(dest): next.pc == dest, i.e. the delta dest - pc over the field
+  same_context(s, opcode, 1, fr_sub(dest.lo, s.cur(S_PC)), fr_u64(1));
+}
+ZK_HD void gadget_jumpi(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_JMPI_OPCODE, fr_eq_u64(opcode, 0x57));
+  Word2 dest{fr_u64(0), fr_u64(0)}, cond{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &dest), EV_JMPI_DEST_UNSAT);
+  EV_LIVE_CHECK(EV_JMPI_DEST_HI, fr_is_zero(dest.hi));
+  live = need1(s, live, stack_at(s, live, 1, 0, fr_add_u64(s.cur(S_SP), 1), &cond), EV_JMPI_COND_UNSAT);
+  if (!live) return;
+  // jumpi.py:20 `if instruction.is_zero_word(cond):` tests the truthiness of an FQ OBJECT (py_ecc's FQ
+  // defines neither __bool__ nor __len__), which is always true: the reference takes the fall-through
+  // branch (pc + 1) whatever cond is and never looks at the destination.  Reproduced as written.
+  same_context(s, opcode, 2, fr_u64(1), fr_u64(2));
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1110,6 +1203,12 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_MEMORY: gadget_memory(s, live); break;
     case ZK_ES_SHA3: gadget_sha3(s, live); break;
     case ZK_ES_CALLDATACOPY: gadget_calldatacopy(s, live); break;
+    case ZK_ES_MSIZE: gadget_msize(s, live); break;
+    case ZK_ES_GAS: gadget_gas(s, live); break;
+    case ZK_ES_ISZERO: gadget_iszero(s, live); break;
+    case ZK_ES_CMP: gadget_cmp(s, live); break;
+    case ZK_ES_JUMP: gadget_jump(s, live); break;
+    case ZK_ES_JUMPI: gadget_jumpi(s, live); break;
     default: break;
   }
 }

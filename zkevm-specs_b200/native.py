@@ -80,7 +80,7 @@ EXPORTS = [
 def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
-        if is_stale():
+        if is_stale() and not os.environ.get("ZKCHECK_LIB"):  # a tuning build is used as it is
             build()
         L = ctypes.CDLL(LIB_PATH)
         vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int

@@ -18,6 +18,8 @@ import numpy as np
 from .evm_circuit.spec import ExecutionState, Target
 
 M256 = (1 << 256) - 1
+M64 = (1 << 64) - 1
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617  # BN254 Fr
 NASTY_AB_VALUES = (
     (0, 0), (1, 0), (0, 1), (1, 1), (255, 0), (0, 255), (255, 255), (256, 0), (0, 256), (256, 256),
     (260, 513), (65535, 0), (0, 65535), (65535, 65535), (65536, 0), (0, 65536), (65536, 65536),
@@ -365,3 +367,71 @@ def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F
     return {"copy": C, "copy_flags": np.zeros(n_rows, np.uint8), "rw": rw, "rw_flags": np.zeros(rw.shape[1], np.uint8),
             "tx": tx, "tx_flags": np.zeros(tx.shape[1], np.uint8), "bytecode": np.zeros((6, 0, 4), np.uint64),
             "r": np.array([(r >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)}
+
+
+def bytecode_circuit_rows(k: int, n_contracts: int = 4, seed: int = 5,
+                          r: int = 0x1D5851F42D4C957F2D14057B7EF767814F2545F4914F6CDD) -> Dict[str, np.ndarray]:
+    """BASELINE cfg5's bytecode-circuit share — 2^k rows of assign_bytecode_circuit
+    (src/zkevm_specs/bytecode_circuit.py:104-167) for `n_contracts` random contracts that fill the
+    circuit, as cell matrices: rows [12][2^k][4], push table [2][256][4], keccak table [5][n][4].
+    The value_rlc prefix (one Fr product per byte) is computed with Python ints."""
+    from .util.hash import keccak256
+
+    rng = np.random.default_rng(seed)
+    size = 1 << k
+    per = (size - 1) // n_contracts - 1  # bytes per contract; the rest is Header padding
+    rows = np.zeros((12, size, 4), dtype=np.uint64)
+    keccak_rows, at = [], 0
+    push_size = np.zeros(256, dtype=np.int64)
+    push_size[0x60:0x80] = np.arange(1, 33)
+
+    def put(col, lo, hi, vals):  # python ints / arrays of small ints
+        rows[col, lo:hi, 0] = vals
+
+    for _ in range(n_contracts):
+        code = rng.integers(0, 256, per, dtype=np.uint8)
+        h = int.from_bytes(keccak256(bytes(code)), "big")
+        # push_data_left / is_code: sequential scan over the code (get_push_size, opcode.py:427-433)
+        left = np.zeros(per, dtype=np.int64)
+        pending = 0
+        sizes = push_size[code]
+        for i in range(per):
+            left[i] = pending
+            pending = int(sizes[i]) if pending == 0 else pending - 1
+        is_code = (left == 0).astype(np.uint64)
+        acc, rlc = 0, []
+        for b in code:
+            acc = (acc * r + int(b)) % P
+            rlc.append(acc)
+        lo, hi = at, at + per + 1
+        h_lo, h_hi = h & ((1 << 128) - 1), h >> 128
+        rows[2, lo:hi, 0], rows[2, lo:hi, 1] = h_lo & M64, h_lo >> 64
+        rows[3, lo:hi, 0], rows[3, lo:hi, 1] = h_hi & M64, h_hi >> 64
+        put(4, lo, lo + 1, 1)                      # Header: value = length
+        put(6, lo, lo + 1, per)
+        put(10, lo, hi, per)
+        put(4, lo + 1, hi, 2)                      # Byte rows
+        put(5, lo + 1, hi, np.arange(per, dtype=np.uint64))
+        put(6, lo + 1, hi, code.astype(np.uint64))
+        put(7, lo + 1, hi, is_code)
+        put(8, lo + 1, hi, left.astype(np.uint64))
+        rows[9, lo + 1:hi, :] = ints_to_cells(rlc)
+        put(11, lo + 1, hi, sizes.astype(np.uint64))  # get_push_size(value) on every Byte row (:122)
+        keccak_rows.append([2, rlc[-1], per, h & ((1 << 128) - 1), h >> 128])
+        at = hi
+    # Header padding with the empty hash (bytecode_circuit.py:150-165)
+    e = int.from_bytes(keccak256(b""), "big")
+    e_lo, e_hi = e & ((1 << 128) - 1), e >> 128
+    rows[2, at:, 0], rows[2, at:, 1] = e_lo & M64, e_lo >> 64
+    rows[3, at:, 0], rows[3, at:, 1] = e_hi & M64, e_hi >> 64
+    rows[4, at:, 0] = 1
+    rows[0, 0, 0] = 1
+    rows[1, size - 1, 0] = 1
+    push = np.zeros((2, 256, 4), dtype=np.uint64)
+    push[0, :, 0] = np.arange(256)
+    push[1, :, 0] = push_size
+    kec = np.zeros((5, len(keccak_rows), 4), dtype=np.uint64)
+    for i, row in enumerate(keccak_rows):
+        for c, v in enumerate(row):
+            kec[c, i, :] = [(v >> (64 * j)) & M64 for j in range(4)]
+    return {"rows": rows, "push": push, "keccak": kec, "r": np.array([(r >> (64 * j)) & M64 for j in range(4)], dtype=np.uint64)}
