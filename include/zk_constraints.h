@@ -241,6 +241,24 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_JMPI_DEST_HI, ZKE_ASSERT, "jumpi.py:14 dest.hi == 0")                                 \
   X(EV_JMPI_COND_UNSAT, ZKE_UNSAT, "jumpi.py:17 stack_pop cond unsat")                       \
   X(EV_JMPI_COND_AMBIG, ZKE_AMBIG, "jumpi.py:17 stack_pop cond ambiguous")                   \
+  /* CALLER / CALLVALUE / CALLDATASIZE / ADDRESS / RETURNDATASIZE (caller.py, callvalue.py,          \
+   * calldatasize.py, address.py, returndatasize.py): one call-context read pushed on the stack; \
+   * CODESIZE (codesize.py): the bytecode length pushed on the stack */                         \
+  X(EV_CCP_OPCODE, ZKE_ASSERT, "caller.py:9 (and siblings) opcode == the gadget's opcode")    \
+  X(EV_CCP_CC_UNSAT, ZKE_UNSAT, "caller.py:10 call_context_lookup unsat")                     \
+  X(EV_CCP_CC_AMBIG, ZKE_AMBIG, "caller.py:10 call_context_lookup ambiguous")                 \
+  X(EV_CCP_CC_TYPE, ZKE_ASSERT, "calldatasize.py:14, instruction.py:880 .value(): the call-context value is a Word") \
+  X(EV_CCP_WORD, ZKE_ASSERT, "calldatasize.py:14 Word.from_lo(value): >= 2^128")              \
+  X(EV_CCP_PUSH_UNSAT, ZKE_UNSAT, "caller.py:15 stack_push unsat")                            \
+  X(EV_CCP_PUSH_AMBIG, ZKE_AMBIG, "caller.py:15 stack_push ambiguous")                        \
+  X(EV_CCP_EQ, ZKE_ASSERT, "caller.py:13-16 pushed word == call-context value")               \
+  X(EV_CSZ_OPCODE, ZKE_ASSERT, "codesize.py:9 opcode == CODESIZE")                            \
+  X(EV_CSZ_LEN_UNSAT, ZKE_UNSAT, "codesize.py:10 bytecode_length lookup unsat")               \
+  X(EV_CSZ_LEN_AMBIG, ZKE_AMBIG, "codesize.py:10 bytecode_length lookup ambiguous")           \
+  X(EV_CSZ_WORD, ZKE_ASSERT, "codesize.py:11 Word.from_lo(code_size): >= 2^128")              \
+  X(EV_CSZ_PUSH_UNSAT, ZKE_UNSAT, "codesize.py:11 stack_push unsat")                          \
+  X(EV_CSZ_PUSH_AMBIG, ZKE_AMBIG, "codesize.py:11 stack_push ambiguous")                      \
+  X(EV_CSZ_EQ, ZKE_ASSERT, "codesize.py:11 pushed word == code size")                         \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

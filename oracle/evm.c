@@ -613,6 +613,33 @@ static void gadget_jumpi(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   same_context(e, i, row, opcode, 2, fr_u64(1), fr_u64(2));
 }
 
+/* caller.py / callvalue.py / calldatasize.py / address.py / returndatasize.py: constrain the opcode, read
+ * one call-context field (as a Word, or as a value wrapped by Word.from_lo), push it */
+static void gadget_cc_push(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint64_t op, uint64_t field, int as_word) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_CCP_OPCODE, fr_eq_u64(opcode, op));
+  word_t v, w; int is_word;
+  if (!need1(e, call_context_w(e, CUR(S_RWC), 0, CUR(S_CALL_ID), field, &v, &is_word), EV_CCP_CC_UNSAT, row)) return;
+  if (!as_word) {
+    CHECK(EV_CCP_CC_TYPE, !is_word);
+    CHECK(EV_CCP_WORD, fr_fits_bits(v.lo, 128));
+    v.hi = fr_u64(0);
+  }
+  if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(1)), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_CCP_PUSH_UNSAT, row)) return;
+  CHECK(EV_CCP_EQ, fr_eq(w.lo, v.lo) && fr_eq(w.hi, v.hi));
+  same_context(e, i, row, opcode, 2, fr_u64(1), fr_neg(fr_u64(1)));
+}
+static void gadget_codesize(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_CSZ_OPCODE, fr_eq_u64(opcode, 0x38));
+  fr_t len; word_t w;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 1, fr_u64(0), 0, &len), EV_CSZ_LEN_UNSAT, row)) return;
+  CHECK(EV_CSZ_WORD, fr_fits_bits(len, 128));
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_CSZ_PUSH_UNSAT, row)) return;
+  CHECK(EV_CSZ_EQ, word_is(w, len));
+  same_context(e, i, row, opcode, 1, fr_u64(1), fr_neg(fr_u64(1)));
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -641,7 +668,9 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   CHECK(EV_UNSUPPORTED_STATE, st == ZK_ES_ADD || st == ZK_ES_MUL || st == ZK_ES_PUSH || st == ZK_ES_POP ||
                                   st == ZK_ES_SHA3 || st == ZK_ES_CALLDATACOPY || st == ZK_ES_STOP ||
                                   st == ZK_ES_MEMORY || st == ZK_ES_MSIZE || st == ZK_ES_GAS || st == ZK_ES_ISZERO ||
-                                  st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI);
+                                  st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI || st == ZK_ES_CALLER ||
+                                  st == ZK_ES_CALLVALUE || st == ZK_ES_CALLDATASIZE || st == ZK_ES_ADDRESS ||
+                                  st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
@@ -658,6 +687,12 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_CMP) gadget_cmp(e, i, row, opcode);
   else if (st == ZK_ES_JUMP) gadget_jump(e, i, row, opcode);
   else if (st == ZK_ES_JUMPI) gadget_jumpi(e, i, row, opcode);
+  else if (st == ZK_ES_CALLER) gadget_cc_push(e, i, row, opcode, 0x33, ZK_CC_CallerAddress, 1);
+  else if (st == ZK_ES_CALLVALUE) gadget_cc_push(e, i, row, opcode, 0x34, ZK_CC_Value, 1);
+  else if (st == ZK_ES_CALLDATASIZE) gadget_cc_push(e, i, row, opcode, 0x36, ZK_CC_CallDataLength, 0);
+  else if (st == ZK_ES_ADDRESS) gadget_cc_push(e, i, row, opcode, 0x30, ZK_CC_CalleeAddress, 1);
+  else if (st == ZK_ES_RETURNDATASIZE) gadget_cc_push(e, i, row, opcode, 0x3d, ZK_CC_LastCalleeReturnDataLength, 0);
+  else if (st == ZK_ES_CODESIZE) gadget_codesize(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

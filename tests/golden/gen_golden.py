@@ -843,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -963,6 +963,30 @@ def evm2_cases(part="evm2"):
                            code_hash=h, **nxt)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
+    def cc_push_case(kind, value):
+        """tests/evm/test_{caller,callvalue,calldatasize,address,returndatasize,codesize}.py"""
+        tag = {"caller": CallContextFieldTag.CallerAddress, "callvalue": CallContextFieldTag.Value,
+               "calldatasize": CallContextFieldTag.CallDataLength, "address": CallContextFieldTag.CalleeAddress,
+               "returndatasize": CallContextFieldTag.LastCalleeReturnDataLength}.get(kind)
+        state = {"caller": ExecutionState.CALLER, "callvalue": ExecutionState.CALLVALUE,
+                 "calldatasize": ExecutionState.CALLDATASIZE, "address": ExecutionState.ADDRESS,
+                 "returndatasize": ExecutionState.RETURNDATASIZE, "codesize": ExecutionState.CODESIZE}[kind]
+        bc = getattr(Bytecode(), kind)().stop()
+        if kind == "codesize":
+            bc = Bytecode().push(value, n_bytes=32).codesize().stop()
+            rw = RWDictionary(9).stack_write(1, 1022, Word(len(bc.code)))
+            pc, sp = 33, 1023
+        else:
+            as_word = kind in ("caller", "callvalue", "address")
+            rw = RWDictionary(9).call_context_read(1, tag, Word(value) if as_word else value).stack_write(1, 1023, Word(value))
+            pc, sp = 0, 1024
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=pc,
+                           stack_pointer=sp, gas_left=2),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=pc + 1, stack_pointer=sp - 1, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1062,7 +1086,13 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm5":
+    if part == "evm6":
+        scenarios = {
+            "caller": cc_push_case("caller", 0xCAFE0000000000000000000000000000BEEF1234), "callvalue": cc_push_case("callvalue", (1 << 200) + 5),
+            "calldatasize": cc_push_case("calldatasize", 1234), "address": cc_push_case("address", 0xABCDEF0123456789ABCDEF0123456789ABCDEF01),
+            "returndatasize": cc_push_case("returndatasize", 77), "codesize": cc_push_case("codesize", 0x1234),
+        }
+    elif part == "evm5":
         big = (1 << 255) + 12345
         scenarios = {
             "msize_0": simple_case("msize", 0), "msize_7": simple_case("msize", 7), "gas": simple_case("gas", 1000),
@@ -1098,7 +1128,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
@@ -1164,6 +1194,10 @@ def evm4_cases():
 
 def evm5_cases():
     evm2_cases("evm5")
+
+
+def evm6_cases():
+    evm2_cases("evm6")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1471,7 +1505,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

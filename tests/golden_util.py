@@ -186,3 +186,8 @@ def sig_vectors():
 def evm5_vectors():
     """MSIZE / GAS / ISZERO / CMP / JUMP / JUMPI steps; same layout as evm2"""
     return evm2_vectors("evm5")
+
+
+def evm6_vectors():
+    """CALLER / CALLVALUE / CALLDATASIZE / ADDRESS / RETURNDATASIZE / CODESIZE steps; same layout as evm2"""
+    return evm2_vectors("evm6")

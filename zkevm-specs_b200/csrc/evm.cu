@@ -260,6 +260,12 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_CMP: return G_MISC;
     case ZK_ES_JUMP: return G_MISC;
     case ZK_ES_JUMPI: return G_MISC;
+    case ZK_ES_CALLER: return G_MISC;
+    case ZK_ES_CALLVALUE: return G_MISC;
+    case ZK_ES_CALLDATASIZE: return G_MISC;
+    case ZK_ES_ADDRESS: return G_MISC;
+    case ZK_ES_RETURNDATASIZE: return G_MISC;
+    case ZK_ES_CODESIZE: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1195,6 +1201,39 @@ ZK_HD void gadget_jumpi(const StepCtx& s, bool live) {
   same_context(s, opcode, 2, fr_u64(1), fr_u64(2));
 }
 
+// caller.py / callvalue.py / calldatasize.py / address.py / returndatasize.py: constrain the opcode,
+// read one call-context field (as a Word, or as a value wrapped by Word.from_lo), push it
+ZK_HD void gadget_cc_push(const StepCtx& s, bool live, u64 op, u64 field, bool as_word) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_CCP_OPCODE, fr_eq_u64(opcode, op));
+  Word2 v{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
+  bool is_word = false;
+  live = need1(s, live, call_context_w(s, live, s.cur(S_RWC), 0, s.cur(S_CALL_ID), field, &v, &is_word), EV_CCP_CC_UNSAT);
+  if (!as_word) {
+    EV_LIVE_CHECK(EV_CCP_CC_TYPE, !is_word);
+    EV_LIVE_CHECK(EV_CCP_WORD, fr_fits128(v.lo));
+    v.hi = fr_u64(0);
+  }
+  live = need1(s, live, stack_at(s, live, 1, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_CCP_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_CCP_EQ, word_eq(w, v));
+  if (!live) return;
+  same_context(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+ZK_HD void gadget_codesize(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_CSZ_OPCODE, fr_eq_u64(opcode, 0x38));
+  Fr len = fr_u64(0);  // bytecode_length(code_hash): the Header row (instruction.py:772-777)
+  live = need1(s, live, bytecode_lookup(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 1, fr_u64(0), 0, &len), EV_CSZ_LEN_UNSAT);
+  EV_LIVE_CHECK(EV_CSZ_WORD, fr_fits128(len));
+  Word2 w{fr_u64(0), fr_u64(0)};
+  live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_CSZ_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_CSZ_EQ, word_is(w, len));
+  if (!live) return;
+  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1209,6 +1248,12 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_CMP: gadget_cmp(s, live); break;
     case ZK_ES_JUMP: gadget_jump(s, live); break;
     case ZK_ES_JUMPI: gadget_jumpi(s, live); break;
+    case ZK_ES_CALLER: gadget_cc_push(s, live, 0x33, ZK_CC_CallerAddress, true); break;
+    case ZK_ES_CALLVALUE: gadget_cc_push(s, live, 0x34, ZK_CC_Value, true); break;
+    case ZK_ES_CALLDATASIZE: gadget_cc_push(s, live, 0x36, ZK_CC_CallDataLength, false); break;
+    case ZK_ES_ADDRESS: gadget_cc_push(s, live, 0x30, ZK_CC_CalleeAddress, true); break;
+    case ZK_ES_RETURNDATASIZE: gadget_cc_push(s, live, 0x3d, ZK_CC_LastCalleeReturnDataLength, false); break;
+    case ZK_ES_CODESIZE: gadget_codesize(s, live); break;
     default: break;
   }
 }
