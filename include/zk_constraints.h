@@ -259,6 +259,33 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CSZ_PUSH_UNSAT, ZKE_UNSAT, "codesize.py:11 stack_push unsat")                          \
   X(EV_CSZ_PUSH_AMBIG, ZKE_AMBIG, "codesize.py:11 stack_push ambiguous")                      \
   X(EV_CSZ_EQ, ZKE_ASSERT, "codesize.py:11 pushed word == code size")                         \
+  /* BITWISE = AND / OR / XOR (bitwise.py), NOT (not_.py), BYTE (byte.py) */                     \
+  X(EV_BW_A_UNSAT, ZKE_UNSAT, "bitwise.py:9 stack_pop a unsat")                               \
+  X(EV_BW_A_AMBIG, ZKE_AMBIG, "bitwise.py:9 stack_pop a ambiguous")                           \
+  X(EV_BW_B_UNSAT, ZKE_UNSAT, "bitwise.py:10 stack_pop b unsat")                              \
+  X(EV_BW_B_AMBIG, ZKE_AMBIG, "bitwise.py:10 stack_pop b ambiguous")                          \
+  X(EV_BW_C_UNSAT, ZKE_UNSAT, "bitwise.py:11 stack_push c unsat")                             \
+  X(EV_BW_C_AMBIG, ZKE_AMBIG, "bitwise.py:11 stack_push c ambiguous")                         \
+  X(EV_BW_BYTES, ZKE_VALUE, "bitwise.py:13-15 to_le_bytes(): half >= 2^128 -> OverflowError") \
+  X(EV_BW_TAG, ZKE_VALUE, "bitwise.py:19 FixedTableTag(tag): not a valid tag -> ValueError")  \
+  X(EV_BW_FIXED_UNSAT, ZKE_UNSAT, "bitwise.py:19 fixed_lookup(tag, a[i], b[i], c[i]) unsat")  \
+  X(EV_BW_FIXED_AMBIG, ZKE_AMBIG, "bitwise.py:19 fixed_lookup ambiguous")                     \
+  X(EV_NOT_A_UNSAT, ZKE_UNSAT, "not_.py:9 stack_pop unsat")                                   \
+  X(EV_NOT_A_AMBIG, ZKE_AMBIG, "not_.py:9 stack_pop ambiguous")                               \
+  X(EV_NOT_A_BYTES, ZKE_VALUE, "not_.py:10 a.to_le_bytes() -> OverflowError")                 \
+  X(EV_NOT_B_UNSAT, ZKE_UNSAT, "not_.py:11 stack_push unsat")                                 \
+  X(EV_NOT_B_AMBIG, ZKE_AMBIG, "not_.py:11 stack_push ambiguous")                             \
+  X(EV_NOT_B_BYTES, ZKE_VALUE, "not_.py:12 b.to_le_bytes() -> OverflowError")                 \
+  X(EV_NOT_FIXED_UNSAT, ZKE_UNSAT, "not_.py:17 fixed_lookup(BitwiseXor, a[i], b[i], 255) unsat") \
+  X(EV_NOT_FIXED_AMBIG, ZKE_AMBIG, "not_.py:17 fixed_lookup ambiguous")                       \
+  X(EV_BYTE_A_UNSAT, ZKE_UNSAT, "byte.py:9 stack_pop index unsat")                            \
+  X(EV_BYTE_A_AMBIG, ZKE_AMBIG, "byte.py:9 stack_pop index ambiguous")                        \
+  X(EV_BYTE_B_UNSAT, ZKE_UNSAT, "byte.py:10 stack_pop value unsat")                           \
+  X(EV_BYTE_B_AMBIG, ZKE_AMBIG, "byte.py:10 stack_pop value ambiguous")                       \
+  X(EV_BYTE_C_UNSAT, ZKE_UNSAT, "byte.py:11 stack_push unsat")                                \
+  X(EV_BYTE_C_AMBIG, ZKE_AMBIG, "byte.py:11 stack_push ambiguous")                            \
+  X(EV_BYTE_BYTES, ZKE_VALUE, "byte.py:13-14 to_le_bytes() -> OverflowError")                 \
+  X(EV_BYTE_EQ, ZKE_ASSERT, "byte.py:30-33 pushed word == selected byte")                     \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

@@ -640,6 +640,57 @@ static void gadget_codesize(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   same_context(e, i, row, opcode, 1, fr_u64(1), fr_neg(fr_u64(1)));
 }
 
+/* bitwise.py / not_.py / byte.py */
+static unsigned word_byte(word_t w, int k) { /* k-th little-endian byte of a word in the 128-bit-halves domain */
+  const fr_t c = k < 16 ? w.lo : w.hi; k &= 15;
+  return (unsigned)((c.l[k >> 3] >> (8 * (k & 7))) & 0xFF);
+}
+static void gadget_bitwise(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t a, b, c;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_BW_A_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &b), EV_BW_B_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &c), EV_BW_C_UNSAT, row)) return;
+  CHECK(EV_BW_BYTES, word_in_domain(a) && word_in_domain(b) && word_in_domain(c));
+  /* tag = BitwiseAnd + (opcode.n - AND) as a Python int; FixedTableTag(tag) must exist (1..16) */
+  CHECK(EV_BW_TAG, fr_fits_bits(opcode, 8) && opcode.l[0] + 10 >= 0x16 + 1 && opcode.l[0] + 10 <= 0x16 + 16);
+  const uint64_t tag = opcode.l[0] + ZK_FIXED_BitwiseAnd - 0x16;
+  for (int k = 0; k < 32; k++) {
+    fr_t key[4] = {fr_u64(tag), fr_u64(word_byte(a, k)), fr_u64(word_byte(b, k)), fr_u64(word_byte(c, k))};
+    if (!need1(e, orc_lookup(&e->fixed_ix, key, 0), EV_BW_FIXED_UNSAT, row)) return;
+  }
+  same_context(e, i, row, opcode, 3, one, one);
+}
+static void gadget_not(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  word_t a, b;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &a), EV_NOT_A_UNSAT, row)) return;
+  CHECK(EV_NOT_A_BYTES, word_in_domain(a));
+  if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(1)), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), CUR(S_SP), &b), EV_NOT_B_UNSAT, row)) return;
+  CHECK(EV_NOT_B_BYTES, word_in_domain(b));
+  for (int k = 0; k < 32; k++) {
+    fr_t key[4] = {fr_u64(ZK_FIXED_BitwiseXor), fr_u64(word_byte(a, k)), fr_u64(word_byte(b, k)), fr_u64(255)};
+    if (!need1(e, orc_lookup(&e->fixed_ix, key, 0), EV_NOT_FIXED_UNSAT, row)) return;
+  }
+  same_context(e, i, row, opcode, 2, fr_u64(1), fr_u64(0));
+}
+static void gadget_byte(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t a, b, c;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_BYTE_A_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &b), EV_BYTE_B_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &c), EV_BYTE_C_UNSAT, row)) return;
+  CHECK(EV_BYTE_BYTES, word_in_domain(a) && word_in_domain(b));
+  unsigned msb = 0;
+  for (int k = 1; k < 32; k++) msb += word_byte(a, k);
+  const unsigned idx0 = word_byte(a, 0);
+  const unsigned sel = (msb == 0 && idx0 < 32) ? word_byte(b, 31 - (int)idx0) : 0;
+  CHECK(EV_BYTE_EQ, word_is(c, fr_u64(sel)));
+  same_context(e, i, row, opcode, 3, one, one);
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -670,7 +721,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_MEMORY || st == ZK_ES_MSIZE || st == ZK_ES_GAS || st == ZK_ES_ISZERO ||
                                   st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI || st == ZK_ES_CALLER ||
                                   st == ZK_ES_CALLVALUE || st == ZK_ES_CALLDATASIZE || st == ZK_ES_ADDRESS ||
-                                  st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE);
+                                  st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
+                                  st == ZK_ES_NOT || st == ZK_ES_BYTE);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
@@ -693,6 +745,9 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_ADDRESS) gadget_cc_push(e, i, row, opcode, 0x30, ZK_CC_CalleeAddress, 1);
   else if (st == ZK_ES_RETURNDATASIZE) gadget_cc_push(e, i, row, opcode, 0x3d, ZK_CC_LastCalleeReturnDataLength, 0);
   else if (st == ZK_ES_CODESIZE) gadget_codesize(e, i, row, opcode);
+  else if (st == ZK_ES_BITWISE) gadget_bitwise(e, i, row, opcode);
+  else if (st == ZK_ES_NOT) gadget_not(e, i, row, opcode);
+  else if (st == ZK_ES_BYTE) gadget_byte(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

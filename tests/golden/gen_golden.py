@@ -843,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -987,6 +987,30 @@ def evm2_cases(part="evm2"):
                            code_hash=h, program_counter=pc + 1, stack_pointer=sp - 1, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
+    def bit_case(kind, a, b=0):
+        """tests/evm/test_{bitwise,not,byte}.py"""
+        A, B = Word(a), Word(b)
+        if kind == "not":
+            bc = Bytecode().push(a, n_bytes=32).not_().stop()
+            rw = RWDictionary(9).stack_read(1, 1023, A).stack_write(1, 1023, Word(a ^ ((1 << 256) - 1)))
+            state, pc, sp, nsp, gas = ExecutionState.NOT, 33, 1023, 1023, 3
+        else:
+            if kind == "byte":
+                res = (b >> (8 * (31 - a))) & 0xFF if a < 32 else 0
+                state = ExecutionState.BYTE
+            else:
+                res = {"and": a & b, "or": a | b, "xor": a ^ b}[kind]
+                state = ExecutionState.BITWISE
+            bc = getattr(Bytecode().push(b, n_bytes=32).push(a, n_bytes=32), kind + ("_" if kind in ("and", "or", "not") else ""))().stop()
+            rw = RWDictionary(9).stack_read(1, 1022, A).stack_read(1, 1023, B).stack_write(1, 1023, Word(res))
+            pc, sp, nsp, gas = 66, 1022, 1023, 3
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=pc,
+                           stack_pointer=sp, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=pc + 1, stack_pointer=nsp, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1086,7 +1110,14 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm6":
+    if part == "evm7":
+        x, y = 0x0123456789ABCDEFFEDCBA98765432100F1E2D3C4B5A69788796A5B4C3D2E1F0, (1 << 255) | 0xFF00FF00FF00FF00FF00FF00FF00FF00
+        scenarios = {
+            "and": bit_case("and", x, y), "or": bit_case("or", x, y), "xor": bit_case("xor", x, y), "not": bit_case("not", x),
+            "byte_0": bit_case("byte", 0, x), "byte_31": bit_case("byte", 31, x), "byte_7": bit_case("byte", 7, y),
+            "byte_32": bit_case("byte", 32, x), "byte_big": bit_case("byte", 1 << 200, x),
+        }
+    elif part == "evm6":
         scenarios = {
             "caller": cc_push_case("caller", 0xCAFE0000000000000000000000000000BEEF1234), "callvalue": cc_push_case("callvalue", (1 << 200) + 5),
             "calldatasize": cc_push_case("calldatasize", 1234), "address": cc_push_case("address", 0xABCDEF0123456789ABCDEF0123456789ABCDEF01),
@@ -1128,7 +1159,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
@@ -1198,6 +1229,10 @@ def evm5_cases():
 
 def evm6_cases():
     evm2_cases("evm6")
+
+
+def evm7_cases():
+    evm2_cases("evm7")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1505,7 +1540,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -191,3 +191,8 @@ def evm5_vectors():
 def evm6_vectors():
     """CALLER / CALLVALUE / CALLDATASIZE / ADDRESS / RETURNDATASIZE / CODESIZE steps; same layout as evm2"""
     return evm2_vectors("evm6")
+
+
+def evm7_vectors():
+    """BITWISE (AND / OR / XOR) / NOT / BYTE steps; same layout as evm2"""
+    return evm2_vectors("evm7")

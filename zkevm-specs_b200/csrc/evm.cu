@@ -266,6 +266,9 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_ADDRESS: return G_MISC;
     case ZK_ES_RETURNDATASIZE: return G_MISC;
     case ZK_ES_CODESIZE: return G_MISC;
+    case ZK_ES_BITWISE: return G_MISC;
+    case ZK_ES_NOT: return G_MISC;
+    case ZK_ES_BYTE: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1234,6 +1237,72 @@ ZK_HD void gadget_codesize(const StepCtx& s, bool live) {
   same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
 
+// ---- BITWISE = AND / OR / XOR (bitwise.py), NOT (not_.py), BYTE (byte.py) ------------------------
+ZK_HD u64 word_byte(const Word2& w, int k) {  // k-th little-endian byte of a word in the 128-bit-halves domain
+  const Fr& c = k < 16 ? w.lo : w.hi;
+  k &= 15;
+  return (c.l[k >> 3] >> (8 * (k & 7))) & 0xFF;
+}
+// 32 fixed-table lookups (tag, a[i], b[i], c[i]); returns false after recording the first failure
+ZK_HD bool fixed_bytes32(const StepCtx& s, bool live, u64 tag, const Word2& a, const Word2& b, const Word2* c, u64 c_const,
+                         int id_unsat) {
+  for (int k = 0; k < 32; k++) {
+    Fr key[4] = {fr_u64(tag), fr_u64(word_byte(a, k)), fr_u64(word_byte(b, k)), fr_u64(c ? word_byte(*c, k) : c_const)};
+    u32 r = 0;
+    const int m = lookup_sync<4>(s.t.fixed, key, &r, s.mask, live);
+    live = need1(s, live, m, id_unsat);
+  }
+  return live;
+}
+ZK_HD void gadget_bitwise(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero, c = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &a), EV_BW_A_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &b), EV_BW_B_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &c), EV_BW_C_UNSAT);
+  EV_LIVE_CHECK(EV_BW_BYTES, word_in_domain(a) && word_in_domain(b) && word_in_domain(c));
+  // tag = BitwiseAnd + (opcode.n - AND) as a Python int; FixedTableTag(tag) must exist (1..16)
+  EV_LIVE_CHECK(EV_BW_TAG, fr_fits64(opcode) && opcode.l[0] >= 0x16 - 9 && opcode.l[0] <= 0x16 + 6);
+  const u64 tag = opcode.l[0] + ZK_FIXED_BitwiseAnd - 0x16;
+  live = fixed_bytes32(s, live, tag, a, b, &c, 0, EV_BW_FIXED_UNSAT);
+  if (!live) return;
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+ZK_HD void gadget_not(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &a), EV_NOT_A_UNSAT);
+  EV_LIVE_CHECK(EV_NOT_A_BYTES, word_in_domain(a));
+  live = need1(s, live, stack_at(s, live, 1, 1, s.cur(S_SP), &b), EV_NOT_B_UNSAT);
+  EV_LIVE_CHECK(EV_NOT_B_BYTES, word_in_domain(b));
+  live = fixed_bytes32(s, live, ZK_FIXED_BitwiseXor, a, b, nullptr, 255, EV_NOT_FIXED_UNSAT);
+  if (!live) return;
+  same_context(s, opcode, 2, fr_u64(1), fr_u64(0));
+}
+ZK_HD void gadget_byte(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero, c = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &a), EV_BYTE_A_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &b), EV_BYTE_B_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &c), EV_BYTE_C_UNSAT);
+  EV_LIVE_CHECK(EV_BYTE_BYTES, word_in_domain(a) && word_in_domain(b));
+  if (!live) return;
+  // byte.py:16-29: index bytes 1..31 all zero and index[0] < 32 select value byte 31 - index[0], else 0
+  const bool msb_zero = (a.lo.l[0] >> 8) == 0 && a.lo.l[1] == 0 && a.hi.l[0] == 0 && a.hi.l[1] == 0;
+  const u64 idx0 = a.lo.l[0] & 0xFF;
+  const u64 sel = (msb_zero && idx0 < 32) ? word_byte(b, 31 - (int)idx0) : 0;
+  EV_CHECK(EV_BYTE_EQ, word_is(c, fr_u64(sel)));
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1254,6 +1323,9 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_ADDRESS: gadget_cc_push(s, live, 0x30, ZK_CC_CalleeAddress, true); break;
     case ZK_ES_RETURNDATASIZE: gadget_cc_push(s, live, 0x3d, ZK_CC_LastCalleeReturnDataLength, false); break;
     case ZK_ES_CODESIZE: gadget_codesize(s, live); break;
+    case ZK_ES_BITWISE: gadget_bitwise(s, live); break;
+    case ZK_ES_NOT: gadget_not(s, live); break;
+    case ZK_ES_BYTE: gadget_byte(s, live); break;
     default: break;
   }
 }
