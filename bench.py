@@ -349,7 +349,7 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic if args.groups == (1 << 18) else None,
-                "kernel": "evm check phase: k_evm_classify + k_evm_push<positional> (~70 %) + k_evm_gadget<ADD|MUL|POP>",
+                "kernel": "evm check phase: k_evm_classify + k_evm_push_pos (~33 %) + k_evm_gadget<ADD|MUL|POP, POS> (MUL ~35 %) + k_evm_misc",
                 "kernel_ms": chk, "index_build_ms": float(np.mean(idx_ms)),
                 "algorithmic_bytes": bytes_alg, "stored_bytes": storage["stored_bytes"],
                 "achieved_stored_gbs": storage["stored_bytes"] / (chk / 1e3) / 1e9,
@@ -364,7 +364,7 @@ def main():
             ctx.fetch_result(native.CIRCUIT_EVM, stream)
 
         e2e_step()
-        k_e2e = max(3, min(args.steps, 5))
+        k_e2e = max(3, min(args.steps, 20))
         ms_e2e = timed(e2e_step, k_e2e)
         e2e = {"value": world * n_steps * k_e2e / (ms_e2e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": n_constraints * 12, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e}

@@ -147,3 +147,35 @@ def test_bytecode_table_from_code_equals_uploaded_table():
         assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k)
         n += 1
     assert n > 400
+
+
+def test_bytecode_table_from_code_with_duplicate_hashes_falls_back():
+    """two contracts with the SAME code hash make every bytecode lookup ambiguous: the library-built
+    table must then leave the positional path (k_heads_from_offsets clears the flag) and give the
+    oracle's verdict (LookupAmbiguousFailure ids), like the explicitly uploaded table does"""
+    from zkevm_specs_b200.evm_circuit import main as evm_main
+
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    evm_main.upload_fixed_table(ctx)
+    ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
+    ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
+    w = synth.evm_trace(32, seed=4)
+    src = w["bytecode_src"]
+    n = len(src["code"])
+    dup = {"code": np.concatenate([src["code"], src["code"]]),
+           "is_code_bits": np.packbits(np.concatenate([np.unpackbits(src["is_code_bits"], bitorder="little")[:n]] * 2), bitorder="little"),
+           "code_offsets": np.array([0, n, 2 * n], dtype=np.uint64),
+           "hashes": np.concatenate([src["hashes"], src["hashes"]])}
+    table = np.ascontiguousarray(np.concatenate([w["bytecode"], w["bytecode"]], axis=1))
+    off, ofc = oracle_lib.check_evm(w["steps"], table, w["rw"], fixed)
+    assert (off != native.PASS).any()
+    ctx.upload_table(native.TABLE_RW, w["rw"])
+    ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+    for from_code in (True, False):
+        if from_code:
+            ctx.upload_bytecode_table_from_code(**dup)
+        else:
+            ctx.upload_table(native.TABLE_BYTECODE, table)
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, 0)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), from_code

@@ -22,11 +22,23 @@ for r in rows:
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(unit, 1)
     per.setdefault(key, {})[d["Metric Name"]] = v * scale
 keys = list(per.keys())
-last_classify = max(i for i, k in enumerate(keys) if k[1].startswith("k_evm_classify"))
-prev_classify = max(i for i, k in enumerate(keys[:last_classify]) if k[1].startswith("k_evm_classify"))
-check = keys[last_classify:]
+INDEX = ("k_set_u32", "k_pos_verify", "k_pos_runlen", "k_slots_clear", "k_index_build", "k_heads_from_offsets")
+cls = [i for i, k in enumerate(keys) if k[1].startswith("k_evm_classify")]
+# the last COMPLETE check: a classify launch followed by its gate-program kernels and then index kernels again
+start = None
+for c in reversed(cls):
+    end = c + 1
+    while end < len(keys) and not keys[end][1].startswith(INDEX) and not keys[end][1].startswith("k_evm_classify"):
+        end += 1
+    if end < len(keys):
+        start = c
+        break
+check = keys[start:end]
 n_check = len(check)
-index = keys[prev_classify + n_check:last_classify]  # kernels between the previous check and this one
+i0 = start
+while i0 > 0 and keys[i0 - 1][1].startswith(INDEX):
+    i0 -= 1
+index = keys[i0:start]
 out = {"storage": sys.argv[2], "source": "ncu, " + sys.argv[1], "kernels": {}, "index_kernels": {}}
 tot = 0.0
 for k in check:

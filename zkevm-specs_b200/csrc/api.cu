@@ -65,6 +65,8 @@ struct Matrix {
   size_t flags_cap = 0;
   u64 flags_rows = 0;
   u64 version = 0;
+  const u64* src_offsets = nullptr;   // != nullptr: a bytecode table unrolled by the library from these
+  u64 src_contracts = 0;              // (device) contract offsets — regular by construction
   u64 off[ZK_MAX_COLS];               // byte offset of each column inside dev
   unsigned char width[ZK_MAX_COLS];   // bytes per row of each column (fr.cuh:ld_col)
 };
@@ -208,6 +210,7 @@ static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const vo
                         const uint64_t* offs = nullptr, size_t total_bytes = 0) {
   CK(ctx, cudaSetDevice(ctx->device));
   if (n_cols > ZK_MAX_COLS) return fail_msg(ctx, "too many columns");
+  m.src_offsets = nullptr;
   if (widths) {
     for (u32 c = 0; c < n_cols; c++) {
       const unsigned w = widths[c];
@@ -436,6 +439,8 @@ extern "C" int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contra
   m.n_rows = n_rows;
   m.n_cols = 6;
   m.flags_rows = 0;
+  m.src_offsets = (const u64*)(sg + s_off);  // valid until the next call (the staging buffer is reused)
+  m.src_contracts = n_contracts;
   for (int c = 0; c < 6; c++) {
     m.off[c] = off[c];
     m.width[c] = kW[c];
@@ -531,11 +536,18 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
       CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(u64), st));
       CK(ctx, cudaMemsetAsync(ix->heads_aux, 0, (2 * ZK_HEADS_CAP + 1) * sizeof(u32), st));
     }
-    k_pos_verify<<<grid, 256, 0, st>>>(d, ix->pos_flag);
-    ctx->launches += 2;
-    if (ix->pos_kind == ZK_POS_RUNS) {  // run lengths from the listed heads (a few thousand threads at most)
-      k_pos_runlen<<<16, 256, 0, st>>>(d);
-      ctx->launches += 1;
+    if (ix->pos_kind == ZK_POS_RUNS && m.src_offsets) {
+      // unrolled by the library: regular by construction, heads + lengths straight from the offsets
+      k_heads_from_offsets<<<(unsigned)std::min<u64>((m.src_contracts + 255) / 256, 64), 256, 0, st>>>(
+          d, ix->pos_flag, m.src_offsets, m.src_contracts);
+      ctx->launches += 2;
+    } else {
+      k_pos_verify<<<grid, 256, 0, st>>>(d, ix->pos_flag);
+      ctx->launches += 2;
+      if (ix->pos_kind == ZK_POS_RUNS) {  // run lengths from the listed heads (a few thousand threads at most)
+        k_pos_runlen<<<16, 256, 0, st>>>(d);
+        ctx->launches += 1;
+      }
     }
     d.pos_ok = ix->pos_flag;
   }

@@ -1429,11 +1429,13 @@ __device__ __forceinline__ void gadget_steps(const WitnessDev& w, const CheckRan
 }
 // two instances per gadget (own register budgets); the host launches both, the one whose POS does
 // not match the tables returns at once
+// minimum resident blocks per SM (= register caps of 168 / 128): measured sweep in
+// profiles/r01_v25_launch_bounds_sweep.json — (3, 4) cuts the check phase from 0.539 to 0.443 ms
 #ifndef ZK_GADGET_MINBLOCKS
-#define ZK_GADGET_MINBLOCKS 1
+#define ZK_GADGET_MINBLOCKS 3
 #endif
 #ifndef ZK_PUSH_MINBLOCKS
-#define ZK_PUSH_MINBLOCKS 1
+#define ZK_PUSH_MINBLOCKS 4
 #endif
 template <int G, bool POS>
 __global__ void __launch_bounds__(128, ZK_GADGET_MINBLOCKS) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,

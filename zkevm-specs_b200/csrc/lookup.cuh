@@ -260,6 +260,35 @@ ZK_HD void pos_verify_dense_row(const IndexDev& ix, u32* ok, u64 row) {
   const Fr c = table_cell(ix.tab, ix.key_cols[0], row), b = table_cell(ix.tab, ix.key_cols[0], 0);
   if (!(fr_fits64(c) && fr_fits64(b) && b.l[0] + row >= b.l[0] && c.l[0] == b.l[0] + row)) pos_fail(ok);
 }
+// Claim a slot of the heads index for the run that starts at `row` with code hash (hlo, hhi).
+// `len` != nullptr: the run length is known (table unrolled by the library) and is stored at once;
+// otherwise the head is listed for k_pos_runlen.  A duplicate hash or a full index clears the flag.
+ZK_HD void pos_fail(u32* ok);
+ZK_HD void heads_insert(const IndexDev& ix, u32* ok, u64 row, const Fr& hlo, const Fr& hhi, const u32* len) {
+  const TableDev& t = ix.tab;
+  const Fr h0 = fr_add(hlo, rlc_term(ix, hhi, 1));
+  const u64 mix = rlc_mix(h0);
+  const u64 entry = (mix & 0xFFFFFFFF00000000ull) | (u64)(u32)row;
+  u32 b = (u32)mix & ix.heads_mask;
+  for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
+    const u64 old = atomic_cas_u64(&ix.heads_slots[b], ZK_EMPTY_SLOT, entry);
+    if (old == ZK_EMPTY_SLOT) {
+      if (len) {
+        ix.heads_len[b] = *len;
+      } else {
+        const u32 k = atomic_add_u32(ix.heads_count, 1u);  // k <= heads_mask: one slot per listed head
+        ix.heads_list[k & ix.heads_mask] = (u32)row;
+      }
+      return;
+    }
+    if ((old >> 32) == (mix >> 32)) {
+      const u32 other = (u32)old;
+      if (fr_eq(table_cell(t, 0, other), hlo) && fr_eq(table_cell(t, 1, other), hhi)) break;  // duplicate hash
+    }
+    b = (b + 1) & ix.heads_mask;
+  }
+  pos_fail(ok);  // duplicate code hash, or more runs than the heads index holds
+}
 struct RunCells {
   Fr hlo, hhi, tag, index;
 };
@@ -294,24 +323,7 @@ ZK_HD void pos_verify_run_cells(const IndexDev& ix, u32* ok, u64 row, const RunC
       return;
     }
     // register the run head; a second run with the same code hash makes keys ambiguous -> irregular
-    const Fr h0 = fr_add(hlo, rlc_term(ix, hhi, 1));
-    const u64 mix = rlc_mix(h0);
-    const u64 entry = (mix & 0xFFFFFFFF00000000ull) | (u64)(u32)row;
-    u32 b = (u32)mix & ix.heads_mask;
-    for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
-      const u64 old = atomic_cas_u64(&ix.heads_slots[b], ZK_EMPTY_SLOT, entry);
-      if (old == ZK_EMPTY_SLOT) {
-        const u32 k = atomic_add_u32(ix.heads_count, 1u);  // k <= heads_mask: one slot per listed head
-        ix.heads_list[k & ix.heads_mask] = (u32)row;
-        return;
-      }
-      if ((old >> 32) == (mix >> 32)) {
-        const u32 other = (u32)old;
-        if (fr_eq(table_cell(t, 0, other), hlo) && fr_eq(table_cell(t, 1, other), hhi)) break;  // duplicate hash
-      }
-      b = (b + 1) & ix.heads_mask;
-    }
-    pos_fail(ok);  // duplicate code hash, or more runs than the heads index holds
+    heads_insert(ix, ok, row, hlo, hhi, nullptr);
   } else {
     const bool byte_row = fr_eq_u64(tag, 2);
     const bool idx_ok = fr_eq_u64(ptag, 1) ? fr_is_zero(index)
@@ -401,6 +413,21 @@ __global__ void __launch_bounds__(256) k_pos_runlen(IndexDev ix) {
   if (ix.tab.n_rows == 0) return;
   const u32 count = min(*ix.heads_count, ix.heads_mask + 1);
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k <= count; k += gridDim.x * blockDim.x) pos_runlen_entry(ix, k, count);
+}
+// A bytecode table unrolled by the library itself (zk_upload_bytecode_table_from_code) is regular
+// by construction: its heads index is filled straight from the contract offsets — one thread per
+// CONTRACT instead of a pass over every table row — and only duplicate code hashes (or more
+// contracts than the heads index holds) still clear the flag.
+__global__ void __launch_bounds__(256) k_heads_from_offsets(IndexDev ix, u32* ok, const u64* offsets, u64 n_contracts) {
+  if (n_contracts > (u64)ix.heads_mask + 1) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) pos_fail(ok);
+    return;
+  }
+  for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n_contracts; k += (u64)gridDim.x * blockDim.x) {
+    const u64 start = offsets[k], row = start + k;
+    const u32 len = (u32)(offsets[k + 1] - start);
+    heads_insert(ix, ok, row, table_cell(ix.tab, 0, row), table_cell(ix.tab, 1, row), &len);
+  }
 }
 __global__ void __launch_bounds__(256) k_pos_verify(IndexDev ix, u32* ok) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
