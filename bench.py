@@ -230,6 +230,7 @@ def main():
                       "rw": packing.pack_matrix(w["rw"], min_widths=packing.TYPE_WIDTHS["rw_table"])}
             fmt = "packed columns, data-independent type widths (packing.TYPE_WIDTHS)"
         else:
+            w["bytecode"] = None  # 3.4 GB of unrolled canonical rows: not needed on this path (8 ranks share the host)
             packed = {k: packing.pack_matrix(w[k]) for k in ("steps", "rw")}
             fmt = ("steps / rw table: packed columns, measured minimal width per column, constant columns stored "
                    "once (packing.pack_matrix default; the packing scan is host preparation, outside the timed "
