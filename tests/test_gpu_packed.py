@@ -163,11 +163,15 @@ def test_bytecode_table_from_code_with_duplicate_hashes_falls_back():
     w = synth.evm_trace(32, seed=4)
     src = w["bytecode_src"]
     n = len(src["code"])
-    dup = {"code": np.concatenate([src["code"], src["code"]]),
+    # same hash, different bytes (rows identical in EVERY column would count once: the table is a set)
+    other = src["code"] ^ np.uint8(1)
+    dup = {"code": np.concatenate([src["code"], other]),
            "is_code_bits": np.packbits(np.concatenate([np.unpackbits(src["is_code_bits"], bitorder="little")[:n]] * 2), bitorder="little"),
            "code_offsets": np.array([0, n, 2 * n], dtype=np.uint64),
            "hashes": np.concatenate([src["hashes"], src["hashes"]])}
-    table = np.ascontiguousarray(np.concatenate([w["bytecode"], w["bytecode"]], axis=1))
+    second = w["bytecode"].copy()
+    second[5, 1:, 0] = other.astype(np.uint64)
+    table = np.ascontiguousarray(np.concatenate([w["bytecode"], second], axis=1))
     off, ofc = oracle_lib.check_evm(w["steps"], table, w["rw"], fixed)
     assert (off != native.PASS).any()
     ctx.upload_table(native.TABLE_RW, w["rw"])
