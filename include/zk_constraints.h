@@ -286,6 +286,25 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_BYTE_C_AMBIG, ZKE_AMBIG, "byte.py:11 stack_push ambiguous")                            \
   X(EV_BYTE_BYTES, ZKE_VALUE, "byte.py:13-14 to_le_bytes() -> OverflowError")                 \
   X(EV_BYTE_EQ, ZKE_ASSERT, "byte.py:30-33 pushed word == selected byte")                     \
+  /* SCMP = SLT / SGT (slt_sgt.py), SIGNEXTEND (signextend.py) */                                \
+  X(EV_SCMP_A_UNSAT, ZKE_UNSAT, "slt_sgt.py:12 stack_pop a unsat")                            \
+  X(EV_SCMP_A_AMBIG, ZKE_AMBIG, "slt_sgt.py:12 stack_pop a ambiguous")                        \
+  X(EV_SCMP_B_UNSAT, ZKE_UNSAT, "slt_sgt.py:13 stack_pop b unsat")                            \
+  X(EV_SCMP_B_AMBIG, ZKE_AMBIG, "slt_sgt.py:13 stack_pop b ambiguous")                        \
+  X(EV_SCMP_C_UNSAT, ZKE_UNSAT, "slt_sgt.py:14 stack_push c unsat")                           \
+  X(EV_SCMP_C_AMBIG, ZKE_AMBIG, "slt_sgt.py:14 stack_push c ambiguous")                       \
+  X(EV_SCMP_BYTES, ZKE_VALUE, "slt_sgt.py:21-23 to_le_bytes(): half >= 2^128 -> OverflowError") \
+  X(EV_SCMP_C_MSB, ZKE_ASSERT, "slt_sgt.py:27 c8s[31] == 0")                                  \
+  X(EV_SCMP_EQ, ZKE_ASSERT, "slt_sgt.py:36-44 result == signed a < b")                        \
+  X(EV_SEXT_IDX_UNSAT, ZKE_UNSAT, "signextend.py:9 stack_pop index unsat")                    \
+  X(EV_SEXT_IDX_AMBIG, ZKE_AMBIG, "signextend.py:9 stack_pop index ambiguous")                \
+  X(EV_SEXT_VAL_UNSAT, ZKE_UNSAT, "signextend.py:10 stack_pop value unsat")                   \
+  X(EV_SEXT_VAL_AMBIG, ZKE_AMBIG, "signextend.py:10 stack_pop value ambiguous")               \
+  X(EV_SEXT_RES_UNSAT, ZKE_UNSAT, "signextend.py:11 stack_push result unsat")                 \
+  X(EV_SEXT_RES_AMBIG, ZKE_AMBIG, "signextend.py:11 stack_push result ambiguous")             \
+  X(EV_SEXT_BYTES, ZKE_VALUE, "signextend.py:13-15 to_le_bytes() -> OverflowError")           \
+  X(EV_SEXT_SIGN_UNSAT, ZKE_UNSAT, "signextend.py:44 sign_byte_lookup(selected_byte, sign_byte) unsat") \
+  X(EV_SEXT_SIGN_AMBIG, ZKE_AMBIG, "signextend.py:44 sign_byte_lookup ambiguous")             \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

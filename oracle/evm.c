@@ -691,6 +691,46 @@ static void gadget_byte(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   same_context(e, i, row, opcode, 3, one, one);
 }
 
+/* slt_sgt.py */
+static void gadget_scmp(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  const int is_sgt = fr_eq_u64(opcode, 0x13);
+  word_t a, b, c;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &a), EV_SCMP_A_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &b), EV_SCMP_B_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &c), EV_SCMP_C_UNSAT, row)) return;
+  const word_t aa = is_sgt ? b : a, bb = is_sgt ? a : b;
+  CHECK(EV_SCMP_BYTES, word_in_domain(aa) && word_in_domain(bb) && word_in_domain(c));
+  CHECK(EV_SCMP_C_MSB, word_byte(c, 31) == 0);
+  const int lt_lo = fr_cmp(aa.lo, bb.lo) < 0, lt_hi = fr_cmp(aa.hi, bb.hi) < 0, eq_hi = fr_eq(aa.hi, bb.hi);
+  const int a_lt_b = lt_hi ? 1 : (eq_hi && lt_lo);
+  const int a_neg = word_byte(aa, 31) >= 128, b_neg = word_byte(bb, 31) >= 128;
+  const int expect = (a_neg && !b_neg) ? 1 : ((b_neg && !a_neg) ? 0 : a_lt_b);
+  /* cc = the low 31 bytes of c as a field element; byte 31 is zero here, so cc == c */
+  CHECK(EV_SCMP_EQ, fr_eq(c.lo, fr_u64(expect)) && fr_is_zero(c.hi));
+  same_context(e, i, row, opcode, 3, one, one);
+}
+/* signextend.py: the byte-by-byte `is_equal` calls constrain nothing; what remains is the
+ * sign_byte_lookup of the selected byte (signextend.py:44) */
+static void gadget_signextend(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  word_t index, value, result;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &index), EV_SEXT_IDX_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &value), EV_SEXT_VAL_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &result), EV_SEXT_RES_UNSAT, row)) return;
+  CHECK(EV_SEXT_BYTES, word_in_domain(index) && word_in_domain(value) && word_in_domain(result));
+  unsigned msb = 0;
+  for (int k = 1; k < 32; k++) msb += word_byte(index, k);
+  const unsigned idx0 = word_byte(index, 0);
+  const unsigned sign_byte = idx0 < 31 ? (word_byte(value, (int)idx0) >> 7) * 0xFF : 0;
+  const unsigned selected = (idx0 < 31 && msb == 0) ? word_byte(value, (int)idx0) : 0;
+  fr_t key[4] = {fr_u64(ZK_FIXED_SignByte), fr_u64(selected), fr_u64(sign_byte), fr_u64(0)};
+  if (!need1(e, orc_lookup(&e->fixed_ix, key, 0), EV_SEXT_SIGN_UNSAT, row)) return;
+  same_context(e, i, row, opcode, 3, one, one);
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -722,7 +762,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI || st == ZK_ES_CALLER ||
                                   st == ZK_ES_CALLVALUE || st == ZK_ES_CALLDATASIZE || st == ZK_ES_ADDRESS ||
                                   st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
-                                  st == ZK_ES_NOT || st == ZK_ES_BYTE);
+                                  st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
@@ -748,6 +788,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_BITWISE) gadget_bitwise(e, i, row, opcode);
   else if (st == ZK_ES_NOT) gadget_not(e, i, row, opcode);
   else if (st == ZK_ES_BYTE) gadget_byte(e, i, row, opcode);
+  else if (st == ZK_ES_SCMP) gadget_scmp(e, i, row, opcode);
+  else if (st == ZK_ES_SIGNEXTEND) gadget_signextend(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

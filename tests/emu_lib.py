@@ -24,8 +24,12 @@ def lib():
             os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
         if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)
-            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                            "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC], check=True)
+            # host-only build with plain g++: the gate programs are __host__ __device__ functions, the
+            # kernels and other device-only declarations sit under #ifdef __CUDACC__ (20 s instead of the
+            # 5 minutes nvcc needs to also generate sm_100a code nobody runs here)
+            subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-D__host__=", "-D__device__=",
+                            "-D__forceinline__=inline", "-D__noinline__=__attribute__((noinline))", "-w",
+                            "-o", OUT, SRC], check=True)
         _LIB = ctypes.CDLL(OUT)
     return _LIB
 

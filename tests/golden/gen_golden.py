@@ -843,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1011,6 +1011,34 @@ def evm2_cases(part="evm2"):
                            code_hash=h, program_counter=pc + 1, stack_pointer=nsp, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
+    def signed_case(kind, a, b):
+        """tests/evm/test_{slt_sgt,signextend}.py"""
+        A, B = Word(a), Word(b)
+        M = (1 << 256)
+
+        def sgn(x):
+            return x - M if x >> 255 else x
+
+        if kind == "signextend":  # a = index, b = value
+            if a < 31:
+                bits = 8 * (a + 1)
+                low = b & ((1 << bits) - 1)
+                res = (low | (M - (1 << bits))) % M if (low >> (bits - 1)) & 1 else low
+            else:
+                res = b
+            state = ExecutionState.SIGNEXTEND
+        else:
+            res = int(sgn(a) < sgn(b)) if kind == "slt" else int(sgn(a) > sgn(b))
+            state = ExecutionState.SCMP
+        bc = getattr(Bytecode().push(b, n_bytes=32).push(a, n_bytes=32), kind)().stop()
+        rw = RWDictionary(9).stack_read(1, 1022, A).stack_read(1, 1023, B).stack_write(1, 1023, Word(res))
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=66,
+                           stack_pointer=1022, gas_left=5 if kind == "signextend" else 3),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=67, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1110,7 +1138,17 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm7":
+    if part == "evm8":
+        neg5, neg9, big = (1 << 256) - 5, (1 << 256) - 9, (1 << 254) + 99
+        scenarios = {
+            "slt_nn": signed_case("slt", neg9, neg5), "slt_np": signed_case("slt", neg5, 7), "slt_pn": signed_case("slt", 7, neg5),
+            "slt_pp": signed_case("slt", 7, big), "slt_eq": signed_case("slt", big, big),
+            "sgt_nn": signed_case("sgt", neg5, neg9), "sgt_np": signed_case("sgt", neg5, 7), "sgt_pn": signed_case("sgt", 7, neg5),
+            "sext_0_neg": signed_case("signextend", 0, 0x1234FF), "sext_0_pos": signed_case("signextend", 0, 0x12347F),
+            "sext_5": signed_case("signextend", 5, 0xAB80FFEEDDCC), "sext_30": signed_case("signextend", 30, big),
+            "sext_31": signed_case("signextend", 31, neg9), "sext_big": signed_case("signextend", (1 << 100) + 40, 0x80),
+        }
+    elif part == "evm7":
         x, y = 0x0123456789ABCDEFFEDCBA98765432100F1E2D3C4B5A69788796A5B4C3D2E1F0, (1 << 255) | 0xFF00FF00FF00FF00FF00FF00FF00FF00
         scenarios = {
             "and": bit_case("and", x, y), "or": bit_case("or", x, y), "xor": bit_case("xor", x, y), "not": bit_case("not", x),
@@ -1159,7 +1197,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
@@ -1233,6 +1271,10 @@ def evm6_cases():
 
 def evm7_cases():
     evm2_cases("evm7")
+
+
+def evm8_cases():
+    evm2_cases("evm8")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1540,7 +1582,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

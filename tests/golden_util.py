@@ -196,3 +196,8 @@ def evm6_vectors():
 def evm7_vectors():
     """BITWISE (AND / OR / XOR) / NOT / BYTE steps; same layout as evm2"""
     return evm2_vectors("evm7")
+
+
+def evm8_vectors():
+    """SCMP (SLT / SGT) / SIGNEXTEND steps; same layout as evm2"""
+    return evm2_vectors("evm8")

@@ -193,7 +193,7 @@ def test_evm_memory_golden_and_oracle_parity():
     ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
     import itertools
 
-    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm4_vectors(), golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors()):
+    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm4_vectors(), golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors(), golden_util.evm8_vectors()):
         ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
         ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
         ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
@@ -206,7 +206,7 @@ def test_evm_memory_golden_and_oracle_parity():
             got = (got[0], exp_exc)
         assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
         n += 1
-    assert n > 2600
+    assert n > 3400
 
 
 def test_sha3_host_api_like_reference_test_sha3():

@@ -93,11 +93,13 @@ ZK_HD void check_bytecode_row(const WitnessDev& w, const CheckRange& rg, const I
   }
 }
 
+#ifdef __CUDACC__
 __global__ void __launch_bounds__(256)
 k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix, Fr r_mont,
                  ResultDev res) {
   const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rg.row_end) check_bytecode_row(w, rg, push_ix, kec_ix, r_mont, res, i);
 }
+#endif
 
 }  // namespace zk

@@ -27,9 +27,11 @@ enum { S_STATE, S_RWC, S_CALL_ID, S_IS_ROOT, S_IS_CREATE, S_HASH_LO, S_HASH_HI, 
 enum { B_HASH_LO, B_HASH_HI, B_TAG, B_INDEX, B_ISCODE, B_VALUE };
 enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, R_VAL_HI };
 
+#ifdef __CUDACC__
 __constant__ signed char c_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;
 __constant__ signed char c_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
 __constant__ short c_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
+#endif
 static const signed char h_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;  // host copies: tests/emu only
 static const signed char h_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
 static const short h_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
@@ -269,6 +271,8 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_BITWISE: return G_MISC;
     case ZK_ES_NOT: return G_MISC;
     case ZK_ES_BYTE: return G_MISC;
+    case ZK_ES_SCMP: return G_MISC;
+    case ZK_ES_SIGNEXTEND: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1303,6 +1307,55 @@ ZK_HD void gadget_byte(const StepCtx& s, bool live) {
   same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
 
+// ---- SCMP = SLT / SGT (slt_sgt.py), SIGNEXTEND (signextend.py) -----------------------------------
+ZK_HD void gadget_scmp(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const bool is_sgt = fr_eq_u64(opcode, 0x13);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 a = zero, b = zero, c = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &a), EV_SCMP_A_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &b), EV_SCMP_B_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &c), EV_SCMP_C_UNSAT);
+  if (!live) return;
+  const Word2 aa = is_sgt ? b : a, bb = is_sgt ? a : b;  // slt_sgt.py:17-18 swap for SGT
+  EV_CHECK(EV_SCMP_BYTES, word_in_domain(aa) && word_in_domain(bb) && word_in_domain(c));
+  EV_CHECK(EV_SCMP_C_MSB, word_byte(c, 31) == 0);
+  const bool lt_lo = fr_lt(aa.lo, bb.lo), lt_hi = fr_lt(aa.hi, bb.hi), eq_hi = fr_eq(aa.hi, bb.hi);
+  const bool a_lt_b = lt_hi || (eq_hi && lt_lo);
+  const bool a_neg = word_byte(aa, 31) >= 128, b_neg = word_byte(bb, 31) >= 128;
+  const bool expect = (a_neg && !b_neg) ? true : ((b_neg && !a_neg) ? false : a_lt_b);
+  EV_CHECK(EV_SCMP_EQ, word_is(c, fr_u64(expect ? 1 : 0)));  // cc = low 31 bytes of c; byte 31 is zero here
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+// signextend.py: the byte-by-byte `is_equal` calls constrain nothing; what remains is the
+// sign_byte_lookup of the selected byte (signextend.py:44) — note that sign_byte ignores
+// is_msb_sum_zero while selected_byte does not (reproduced)
+ZK_HD void gadget_signextend(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 index = zero, value = zero, result = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &index), EV_SEXT_IDX_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &value), EV_SEXT_VAL_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &result), EV_SEXT_RES_UNSAT);
+  EV_LIVE_CHECK(EV_SEXT_BYTES, word_in_domain(index) && word_in_domain(value) && word_in_domain(result));
+  const bool msb_zero = (index.lo.l[0] >> 8) == 0 && index.lo.l[1] == 0 && index.hi.l[0] == 0 && index.hi.l[1] == 0;
+  const u64 idx0 = index.lo.l[0] & 0xFF;
+  const u64 vbyte = idx0 < 31 ? word_byte(value, (int)idx0) : 0;
+  const u64 sign_byte = (vbyte >> 7) * 0xFF, selected = msb_zero ? vbyte : 0;
+  {
+    Fr key[4] = {fr_u64(ZK_FIXED_SignByte), fr_u64(selected), fr_u64(sign_byte), fr_u64(0)};
+    u32 r = 0;
+    const int m = lookup_sync<4>(s.t.fixed, key, &r, s.mask, live);
+    live = need1(s, live, m, EV_SEXT_SIGN_UNSAT);
+  }
+  if (!live) return;
+  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1326,6 +1379,8 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_BITWISE: gadget_bitwise(s, live); break;
     case ZK_ES_NOT: gadget_not(s, live); break;
     case ZK_ES_BYTE: gadget_byte(s, live); break;
+    case ZK_ES_SCMP: gadget_scmp(s, live); break;
+    case ZK_ES_SIGNEXTEND: gadget_signextend(s, live); break;
     default: break;
   }
 }
