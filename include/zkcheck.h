@@ -214,8 +214,9 @@ uint64_t zk_launch_count(zk_ctx* ctx);
  * the durations of the most recent check after synchronising its events (milliseconds). */
 int zk_enable_timing(zk_ctx* ctx, int on);
 int zk_last_timing(zk_ctx* ctx, float* index_build_ms, float* check_kernel_ms);
-/* drop cached lookup indexes so the next zk_check rebuilds them (used by bench to time the
- * whole path) */
+/* drop the cached lookup indexes of the witness tables so the next zk_check rebuilds them (used
+ * by bench to time the whole path); the fixed table is a circuit constant (table.py:37-103,
+ * uploaded once), its index lives until the table is uploaded again */
 int zk_invalidate_indexes(zk_ctx* ctx);
 
 #ifdef __cplusplus

@@ -568,7 +568,10 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
 }
 
 extern "C" int zk_invalidate_indexes(zk_ctx* ctx) {
-  for (auto* ix : ctx->indexes) ix->built_version = ~0ull;
+  // the fixed table is a circuit constant (uploaded once): its index, like its ResponsibleOpcode
+  // bitmap, lives until the table is uploaded again
+  for (auto* ix : ctx->indexes)
+    if (ix->table_id != ZK_TABLE_FIXED) ix->built_version = ~0ull;
   return 0;
 }
 
@@ -734,7 +737,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   const unsigned grid_t = std::min<unsigned>(full, (unsigned)ctx->sm_count * 8);
   const unsigned grid_w = std::min<unsigned>((unsigned)((n * 32 + 127) / 128), (unsigned)ctx->sm_count * 12);
   k_evm_push_pos<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_push<false><<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
+  k_evm_push_hash<<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_ADD, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_MUL, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
   k_evm_gadget<G_POP, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);

@@ -634,36 +634,6 @@ ZK_HD int push_byte(const StepCtx& s, const PushCommon& c, int idx, bool live) {
   }
   return byte == 0 ? -1 : base + 3;
 }
-// pushed bytes idx and idx+16 of one step on a positional bytecode table: both candidate rows are
-// computed first and all 12 cell loads issued before any compare
-ZK_HD void push_two_bytes_pos(const StepCtx& s, const PushCommon& c, int idx, bool live, int* fid0, int* fid1) {
-  const IndexDev& ix = s.t.bytecode;
-  int fid[2];
-  bool pushed[2];
-  u64 byte[2];
-  Fr got[2];
-  int n[2];
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const int b = idx + 16 * k;
-    const u64 lo_limb = (b & 8) ? c.value.lo.l[1] : c.value.lo.l[0];
-    const u64 hi_limb = (b & 8) ? c.value.hi.l[1] : c.value.hi.l[0];
-    byte[k] = ((b < 16 ? lo_limb : hi_limb) >> (8 * (b & 7))) & 0xFF;
-    pushed[k] = live && (u64)b < c.n_push && (u64)b >= c.n_pad;
-    const Fr index = fr_sub_u64(fr_add(c.pc, c.num_pushed), (u64)b);
-    Fr key[5] = {c.hlo, c.hhi, fr_u64(2), index, fr_u64(0)};
-    u32 r;
-    n[k] = pos_lookup_run(ix, key, c.n_head, c.head, c.run_len, &r, pushed[k], B_VALUE, &got[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const int base = EV_PUSH_B0_UNSAT + 4 * (idx + 16 * k);
-    if (pushed[k]) fid[k] = n[k] != 1 ? base : (fr_eq_u64(got[k], byte[k]) ? -1 : base + 2);  // positional: never ambiguous
-    else fid[k] = byte[k] == 0 ? -1 : base + 3;
-  }
-  *fid0 = fid[0];
-  *fid1 = fid[1];
-}
 ZK_HD void push_epilogue(const StepCtx& s, const PushCommon& c) {
   same_context(s, c.opcode, 1, fr_add_u64(c.num_pushed, 1), fr_sub(fr_u64(0), fr_u64(1)));
 }
@@ -1538,7 +1508,7 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   return r;
 }
 // positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1); returns at once
-// otherwise, and then k_evm_push<false> below does the work — the host launches both
+// otherwise, and then k_evm_push_hash below does the work — the host launches both
 __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                       EvmLists lists) {
   if (!both_positional(t)) return;
@@ -1556,27 +1526,20 @@ __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(Witness
   }
 }
 
-// POS = true: specialised for positional rw + bytecode tables (no hash code at all); it returns at
-// once unless both flags are set, and the POS = false instance returns at once if they are —
-// the host launches both, exactly one does the work.
-template <bool POS>
-__global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg, EvmTables t,
-                                                               ResultDev res, EvmLists lists) {
-  {
-    const bool both = t.rw.tab.n_rows != 0 && t.bytecode.tab.n_rows != 0 && pos_enabled(t.rw) &&
-                      pos_enabled(t.bytecode) && t.rw.pos_kind == ZK_POS_DENSE && t.bytecode.pos_kind == ZK_POS_RUNS;
-    if (both != POS) return;
-  }
+// The generic path (tables not positional: k_evm_push_pos returns at once and this kernel does the
+// work; it returns at once when they are).  Half a warp per PUSH step (two steps per warp
+// iteration): sub-lane L of a half owns pushed bytes L and L+16 of its step, so the warp-synchronous
+// hash probes of a step's 34 bytecode lookups run side by side.
+__global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+                                                          EvmLists lists) {
+  if (both_positional(t)) return;
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   Fr stack_pre[2];
   stack_key_pre(t.rw, stack_pre);
   Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // per-lane cache of the last code hash seen
-  u32 last_head = 0, last_len = 0;
-  int last_n_head = 0;
   bool have_h0 = false;
-  const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
   const u32 n = lists.count[G_PUSH];
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
@@ -1587,8 +1550,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     const bool have = k < n;
     bool live = have;
     const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + (have ? k : 2 * kp)];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, POS ? &rw_base : nullptr,
-              POS ? 1 : -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
     c.hhi = s.cur(S_HASH_HI);
@@ -1598,32 +1560,15 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     // consecutive steps of a lane almost always run the same contract: reuse the work that depends
     // only on the code hash (hash_lo + hash_hi*r; with positional tables, the run head itself)
     const bool changed = !(have_h0 && fr_eq(c.hlo, last_hlo) && fr_eq(c.hhi, last_hhi));
-    if (POS) {
-      c.h0 = fr_u64(0);
-      u32 head = 0, rlen = 0;
-      const Fr h0 = changed ? bytecode_hash0(s, c.hlo, c.hhi) : fr_u64(0);
-      const int nh = bytecode_head(s, live && changed, h0, c.hlo, c.hhi, &head, &rlen);  // every lane calls (warp-sync)
-      if (changed) {
-        last_hlo = c.hlo;
-        last_hhi = c.hhi;
-        last_head = head;
-        last_len = rlen;
-        last_n_head = live ? nh : 0;
-        have_h0 = live;
-      }
-      c.n_head = last_n_head;
-      c.head = last_head;
-      c.run_len = last_len;
-    } else {
-      if (changed) {
-        last_hlo = c.hlo;
-        last_hhi = c.hhi;
-        last_h0 = bytecode_hash0(s, c.hlo, c.hhi);
-        have_h0 = true;
-      }
-      c.h0 = last_h0;
-      c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
+    if (changed) {
+      last_hlo = c.hlo;
+      last_hhi = c.hhi;
+      last_h0 = bytecode_hash0(s, c.hlo, c.hhi);
+      have_h0 = true;
     }
+    c.h0 = last_h0;
+    // (one of the two tables may still be positional: bytecode_head / the lookups below test the flags)
+    c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
     // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);
@@ -1639,13 +1584,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push(WitnessDev w, CheckRange rg
     Word2 value{shfl16_fr(val.lo, 2), shfl16_fr(val.hi, 2)};
     if (live) live = push_prepare(s, n_op, opcode, n_len, code_length, n_rw, value, &c);  // uniform per half
     // round 2: pushed bytes L and L+16; the first failing byte in program order wins
-    int fid0, fid1;
-    if (POS) {
-      push_two_bytes_pos(s, c, sub, live, &fid0, &fid1);
-    } else {
-      fid0 = push_byte(s, c, sub, live);
-      fid1 = push_byte(s, c, sub + 16, live);
-    }
+    const int fid0 = push_byte(s, c, sub, live), fid1 = push_byte(s, c, sub + 16, live);
     const unsigned bad0 = (__ballot_sync(0xFFFFFFFFu, live && fid0 >= 0) >> (16 * half)) & 0xFFFFu;
     const unsigned bad1 = (__ballot_sync(0xFFFFFFFFu, live && fid1 >= 0) >> (16 * half)) & 0xFFFFu;
     if (bad0) {
