@@ -305,6 +305,23 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_SEXT_BYTES, ZKE_VALUE, "signextend.py:13-15 to_le_bytes() -> OverflowError")           \
   X(EV_SEXT_SIGN_UNSAT, ZKE_UNSAT, "signextend.py:44 sign_byte_lookup(selected_byte, sign_byte) unsat") \
   X(EV_SEXT_SIGN_AMBIG, ZKE_AMBIG, "signextend.py:44 sign_byte_lookup ambiguous")             \
+  /* BlockCtx = COINBASE / TIMESTAMP / NUMBER / PREVRANDAO / GASLIMIT / CHAINID / BASEFEE (block_ctx.py), \
+   * ORIGIN (origin.py), GASPRICE (gasprice.py): a block-table or tx-table word pushed on the stack */ \
+  X(EV_BLK_OPCODE, ZKE_VALUE, "block_ctx.py:10-24 opcode is none of the seven: `op` unbound -> UnboundLocalError") \
+  X(EV_BLK_CTX_UNSAT, ZKE_UNSAT, "block_ctx.py:26 block_context_lookup_word unsat")           \
+  X(EV_BLK_CTX_AMBIG, ZKE_AMBIG, "block_ctx.py:26 block_context_lookup_word ambiguous")       \
+  X(EV_BLK_PUSH_UNSAT, ZKE_UNSAT, "block_ctx.py:27 stack_push unsat")                         \
+  X(EV_BLK_PUSH_AMBIG, ZKE_AMBIG, "block_ctx.py:27 stack_push ambiguous")                     \
+  X(EV_BLK_EQ, ZKE_ASSERT, "block_ctx.py:27 pushed word == block-context word")               \
+  X(EV_TXC_TXID_UNSAT, ZKE_UNSAT, "origin.py:8 / gasprice.py:8 call_context_lookup(TxId) unsat") \
+  X(EV_TXC_TXID_AMBIG, ZKE_AMBIG, "origin.py:8 call_context_lookup(TxId) ambiguous")          \
+  X(EV_TXC_TXID_TYPE, ZKE_ASSERT, "instruction.py:880 .value(): TxId is a Word")              \
+  X(EV_TXC_OPCODE, ZKE_ASSERT, "origin.py:10 / gasprice.py:10 opcode == ORIGIN / GASPRICE")   \
+  X(EV_TXC_TX_UNSAT, ZKE_UNSAT, "origin.py:11 tx_context_lookup_word unsat")                  \
+  X(EV_TXC_TX_AMBIG, ZKE_AMBIG, "origin.py:11 tx_context_lookup_word ambiguous")              \
+  X(EV_TXC_PUSH_UNSAT, ZKE_UNSAT, "origin.py:15 stack_push unsat")                            \
+  X(EV_TXC_PUSH_AMBIG, ZKE_AMBIG, "origin.py:15 stack_push ambiguous")                        \
+  X(EV_TXC_EQ, ZKE_ASSERT, "origin.py:13-16 pushed word == tx-context word")                  \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

@@ -37,6 +37,7 @@ static const fr_t INV_2_128 = {{0x18ee753c76f9dc6full, 0x54ad7e14a329e70full, 0x
 typedef struct {
   const uint64_t* steps; uint64_t n_steps;
   orc_index bytecode_ix, rw_ix, fixed_ix, copy_ix, keccak_ix;
+  orc_index tx_ix, block_ix; /* tx table key (tx_id, tag, index); block table key (tag, block_number) */
   const uint8_t* rw_flags; /* bit0: value.is_word */
   orc_result* res;
 } evm_env;
@@ -731,6 +732,48 @@ static void gadget_signextend(evm_env* e, uint64_t i, uint64_t row, fr_t opcode)
   same_context(e, i, row, opcode, 3, one, one);
 }
 
+/* block_ctx.py, origin.py, gasprice.py */
+static void gadget_blockctx(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  uint64_t tag = 0;
+  if (fr_fits_bits(opcode, 8)) switch (opcode.l[0]) {
+    case 0x41: tag = 1; break; /* COINBASE -> Coinbase */
+    case 0x42: tag = 4; break; /* TIMESTAMP */
+    case 0x43: tag = 3; break; /* NUMBER */
+    case 0x45: tag = 2; break; /* GASLIMIT */
+    case 0x44: tag = 5; break; /* PREVRANDAO */
+    case 0x48: tag = 6; break; /* BASEFEE */
+    case 0x46: tag = 7; break; /* CHAINID */
+    default: break;
+  }
+  CHECK(EV_BLK_OPCODE, tag != 0);
+  fr_t key[2] = {fr_u64(tag), fr_u64(0)};
+  uint32_t r; const int m = orc_lookup(&e->block_ix, key, &r);
+  if (!need1(e, m, EV_BLK_CTX_UNSAT, row)) return;
+  const fr_t lo = fr_load(ORC_CELL(e->block_ix.cells, e->block_ix.n_rows, 2, r)), hi = fr_load(ORC_CELL(e->block_ix.cells, e->block_ix.n_rows, 3, r));
+  word_t w;
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_BLK_PUSH_UNSAT, row)) return;
+  CHECK(EV_BLK_EQ, fr_eq(w.lo, lo) && fr_eq(w.hi, hi));
+  same_context(e, i, row, opcode, 1, fr_u64(1), fr_neg(fr_u64(1)));
+}
+static void gadget_txctx(evm_env* e, uint64_t i, uint64_t row, uint64_t op, uint64_t field) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  word_t v, w; int is_word;
+  /* the call-context lookup comes BEFORE the opcode lookup here (origin.py:8-9) */
+  if (!need1(e, call_context_w(e, CUR(S_RWC), 0, CUR(S_CALL_ID), ZK_CC_TxId, &v, &is_word), EV_TXC_TXID_UNSAT, row)) return;
+  CHECK(EV_TXC_TXID_TYPE, !is_word);
+  fr_t opcode;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row)) return;
+  CHECK(EV_TXC_OPCODE, fr_eq_u64(opcode, op));
+  fr_t key[3] = {v.lo, fr_u64(field), fr_u64(0)};
+  uint32_t r; const int m = orc_lookup(&e->tx_ix, key, &r);
+  if (!need1(e, m, EV_TXC_TX_UNSAT, row)) return;
+  const fr_t lo = fr_load(ORC_CELL(e->tx_ix.cells, e->tx_ix.n_rows, 3, r)), hi = fr_load(ORC_CELL(e->tx_ix.cells, e->tx_ix.n_rows, 4, r));
+  if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(1)), 1, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_TXC_PUSH_UNSAT, row)) return;
+  CHECK(EV_TXC_EQ, fr_eq(w.lo, lo) && fr_eq(w.hi, hi));
+  same_context(e, i, row, opcode, 2, fr_u64(1), fr_neg(fr_u64(1)));
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -762,8 +805,11 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_CMP || st == ZK_ES_JUMP || st == ZK_ES_JUMPI || st == ZK_ES_CALLER ||
                                   st == ZK_ES_CALLVALUE || st == ZK_ES_CALLDATASIZE || st == ZK_ES_ADDRESS ||
                                   st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
-                                  st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND);
+                                  st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND ||
+                                  st == ZK_ES_BlockCtx || st == ZK_ES_ORIGIN || st == ZK_ES_GASPRICE);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
+  if (st == ZK_ES_ORIGIN) { gadget_txctx(e, i, row, 0x32, ZK_TX_CallerAddress); return; }
+  if (st == ZK_ES_GASPRICE) { gadget_txctx(e, i, row, 0x3a, ZK_TX_GasPrice); return; }
   fr_t opcode;
   if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 2, CUR(S_PC), 1, &opcode), EV_OP_UNSAT, row))
     return;
@@ -790,6 +836,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_BYTE) gadget_byte(e, i, row, opcode);
   else if (st == ZK_ES_SCMP) gadget_scmp(e, i, row, opcode);
   else if (st == ZK_ES_SIGNEXTEND) gadget_signextend(e, i, row, opcode);
+  else if (st == ZK_ES_BlockCtx) gadget_blockctx(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 
@@ -804,6 +851,13 @@ int orc_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytec
                   uint32_t* first_fail, uint64_t* fail_count) {
   return orc_check_evm_x(steps, n_steps, bytecode_tab, n_bytecode, rw_tab, n_rw, 0, fixed_tab, n_fixed, 0, 0, 0, 0,
                          row_begin, row_end, row_base, flags, first_fail, fail_count);
+}
+/* tx table (5 cells: tx_id, tag, index, value lo, hi) and block table (4 cells: tag, block number, value
+ * lo, hi) of the NEXT orc_check_evm_x call on this thread (the ORIGIN / GASPRICE / BlockCtx gadgets) */
+static __thread const uint64_t* g_tx_tab; static __thread uint64_t g_n_tx;
+static __thread const uint64_t* g_block_tab; static __thread uint64_t g_n_block;
+void orc_set_evm_context_tables(const uint64_t* tx_tab, uint64_t n_tx, const uint64_t* block_tab, uint64_t n_block) {
+  g_tx_tab = tx_tab; g_n_tx = n_tx; g_block_tab = block_tab; g_n_block = n_block;
 }
 int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
                     const uint64_t* rw_tab, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed_tab,
@@ -836,9 +890,13 @@ int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* byt
   const uint32_t ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
   orc_index_build(&env.copy_ix, copy_tab, n_copy, 14, ck, 11);
   orc_index_build(&env.keccak_ix, keccak_tab, n_keccak, 5, kk, 3);
+  const uint32_t tk[3] = {0, 1, 2}, blk[2] = {0, 1};
+  orc_index_build(&env.tx_ix, g_tx_tab, g_n_tx, 5, tk, 3);
+  orc_index_build(&env.block_ix, g_block_tab, g_n_block, 4, blk, 2);
+  g_tx_tab = g_block_tab = 0; g_n_tx = g_n_block = 0;
   env.rw_flags = rw_flags;
   for (uint64_t i = row_begin; i < row_end; i++) verify_step(&env, i, row_base + i, flags);
   orc_index_free(&env.bytecode_ix); orc_index_free(&env.rw_ix); /* fixed_ix.order lives in fx_cache */
-  orc_index_free(&env.copy_ix); orc_index_free(&env.keccak_ix);
+  orc_index_free(&env.copy_ix); orc_index_free(&env.keccak_ix); orc_index_free(&env.tx_ix); orc_index_free(&env.block_ix);
   return 0;
 }

@@ -843,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1039,6 +1039,35 @@ def evm2_cases(part="evm2"):
                            code_hash=h, program_counter=67, stack_pointer=1023, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
+    def ctx_case(kind, value):
+        """tests/evm/test_{block_ctx,origin,gasprice}.py: a block-table / tx-table word pushed on the stack"""
+        from zkevm_specs.evm_circuit import BlockContextFieldTag, BlockTableRow, TxContextFieldTag, TxTableRow
+        txs, blocks = [], []
+        if kind in ("origin", "gasprice"):
+            bc = getattr(Bytecode(), kind)().stop()
+            tag = TxContextFieldTag.CallerAddress if kind == "origin" else TxContextFieldTag.GasPrice
+            rw = RWDictionary(9).call_context_read(1, CallContextFieldTag.TxId, 3).stack_write(1, 1023, Word(value))
+            txs = [TxTableRow(FQ(3), FQ(tag), FQ(0), WordOrValue(Word(value))),
+                   TxTableRow(FQ(3), FQ(TxContextFieldTag.Nonce), FQ(0), WordOrValue(FQ(7))),
+                   TxTableRow(FQ(4), FQ(tag), FQ(0), WordOrValue(Word(value + 1)))]
+            state = ExecutionState.ORIGIN if kind == "origin" else ExecutionState.GASPRICE
+        else:
+            bc = getattr(Bytecode(), kind)().stop()
+            tag = {"coinbase": BlockContextFieldTag.Coinbase, "timestamp": BlockContextFieldTag.Timestamp,
+                   "number": BlockContextFieldTag.Number, "gaslimit": BlockContextFieldTag.GasLimit,
+                   "prevrandao": BlockContextFieldTag.PrevRandao, "basefee": BlockContextFieldTag.BaseFee,
+                   "chainid": BlockContextFieldTag.ChainId}[kind]
+            rw = RWDictionary(9).stack_write(1, 1023, Word(value))
+            blocks = [BlockTableRow(FQ(tag), FQ(0), WordOrValue(Word(value))),
+                      BlockTableRow(FQ(BlockContextFieldTag.HistoryHash), FQ(5), WordOrValue(Word(99)))]
+            state = ExecutionState.BlockCtx
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=0,
+                           stack_pointer=1024, gas_left=2),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=1, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], [], txs, blocks
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1121,9 +1150,18 @@ def evm2_cases(part="evm2"):
     def kec_ints(x):
         return [n_of(x.state_tag), n_of(x.input_rlc), n_of(x.input_len), n_of(x.output.lo), n_of(x.output.hi)]
 
-    def run(S, B, R, RF, C, K):
+    def tx_ints(x):
+        return [n_of(x.tx_id), n_of(x.field_tag), n_of(x.call_data_index_or_zero), n_of(x.value.lo), n_of(x.value.hi)]
+
+    def blk_ints(x):
+        return [n_of(x.field_tag), n_of(x.block_number_or_zero), n_of(x.value.lo), n_of(x.value.hi)]
+
+    def run(S, B, R, RF, C, K, T=(), BL=()):
+        from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
-        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(),
+        t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), WordOrValue(W(v[2], v[3]))) for v in BL),
+                   tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), WordOrValue(W(v[3], v[4]))) for v in T),
+                   withdrawal_table=set(),
                    bytecode_table=set(BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5])) for v in B),
                    rw_table=set(RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
                                            wov(v[8], v[9], f & 1), wov(v[10], v[11], (f >> 1) & 1), W(v[12], v[13]))
@@ -1138,7 +1176,15 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm8":
+    if part == "evm9":
+        scenarios = {
+            "coinbase": ctx_case("coinbase", 0xC014BA5E0000000000000000000000000000BA5E), "timestamp": ctx_case("timestamp", 1700000000),
+            "number": ctx_case("number", 1234567), "gaslimit": ctx_case("gaslimit", 30_000_000),
+            "prevrandao": ctx_case("prevrandao", (1 << 255) + 42), "basefee": ctx_case("basefee", 12_000_000_000),
+            "chainid": ctx_case("chainid", 1337), "origin": ctx_case("origin", 0x0123456789ABCDEF0123456789ABCDEF01234567),
+            "gasprice": ctx_case("gasprice", (1 << 130) + 77),
+        }
+    elif part == "evm8":
         neg5, neg9, big = (1 << 256) - 5, (1 << 256) - 9, (1 << 254) + 99
         scenarios = {
             "slt_nn": signed_case("slt", neg9, neg5), "slt_np": signed_case("slt", neg5, 7), "slt_pn": signed_case("slt", 7, neg5),
@@ -1191,14 +1237,19 @@ def evm2_cases(part="evm2"):
     }
     out = {"names": np.array(list(scenarios.keys()))}
     tot = nfail = 0
-    for name, (steps, bcs, rws, cps, kcs) in scenarios.items():
+    for name, sc_ in scenarios.items():
+        steps, bcs, rws, cps, kcs = sc_[:5]
+        T = [tx_ints(x) for x in sc_[5]] if len(sc_) > 5 else []
+        BL = [blk_ints(x) for x in sc_[6]] if len(sc_) > 6 else []
         S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
         RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
-        assert run(S, B, R, RF, C, K) == (-1, ""), (name, run(S, B, R, RF, C, K))
+        assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 5])
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else
+                               [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
+            T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
                 cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
@@ -1225,6 +1276,12 @@ def evm2_cases(part="evm2"):
                 i, c = rng.randrange(len(R)), 8
                 v = corrupt_value(rng, R[i][c])
                 R2.append(list(R[i])); R2[-1][c] = v; RF2.append(RF[i])
+            elif which == 6 and T:
+                i, c = rng.randrange(len(T)), rng.randrange(5)
+                v = corrupt_value(rng, T[i][c]); T2[i][c] = v
+            elif which == 7 and BL:
+                i, c = rng.randrange(len(BL)), rng.randrange(4)
+                v = corrupt_value(rng, BL[i][c]); BL2[i][c] = v
             elif which == 3 and C:
                 i, c = rng.randrange(len(C)), rng.randrange(14)
                 if c in (2, 5):
@@ -1235,13 +1292,16 @@ def evm2_cases(part="evm2"):
                 v = corrupt_value(rng, K[i][c]); K2[i][c] = v
             else:
                 continue
-            fr_, ex_ = run(S2, B, R2, RF2, C2, K2)
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2)
             muts.append((which, i, c, v, fr_, ex_))
             tot += 1
             nfail += fr_ >= 0
         for key, rows_, ncol in (("steps", S, 13), ("bytecode", B, 6), ("rw", R, 14), ("copy", C, 14), ("keccak", K, 5)):
             out[f"{name}/{key}"] = to_matrix(rows_) if rows_ else np.zeros((ncol, 0, 4), dtype=np.uint64)
         out[f"{name}/rw_flags"] = np.array(RF, dtype=np.uint8)
+        if part == "evm9":
+            out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
+            out[f"{name}/block"] = to_matrix(BL) if BL else np.zeros((4, 0, 4), dtype=np.uint64)
         out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
         out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
         out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
@@ -1275,6 +1335,10 @@ def evm7_cases():
 
 def evm8_cases():
     evm2_cases("evm8")
+
+
+def evm9_cases():
+    evm2_cases("evm9")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1582,7 +1646,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -114,6 +114,9 @@ def evm2_vectors(part="evm2"):
     for name in z["names"]:
         name = str(name)
         base = {k: z[f"{name}/{k}"] for k in ("steps", "bytecode", "rw", "rw_flags", "copy", "keccak")}
+        for extra in ("tx", "block"):  # ORIGIN / GASPRICE / BlockCtx scenarios carry their context tables
+            if f"{name}/{extra}" in z.files:
+                base[extra] = z[f"{name}/{extra}"]
         for k in range(len(z[f"{name}/mut_kind"])):
             kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
             val = z[f"{name}/mut_val"][k]
@@ -130,6 +133,10 @@ def evm2_vectors(part="evm2"):
                 extra = base["rw"][:, i:i + 1, :].copy(); extra[c, 0, :] = val
                 w["rw"] = np.ascontiguousarray(np.concatenate([base["rw"], extra], axis=1))
                 w["rw_flags"] = np.concatenate([base["rw_flags"], base["rw_flags"][i:i + 1]])
+            elif kind == 6:
+                w["tx"] = base["tx"].copy(); w["tx"][c, i, :] = val
+            elif kind == 7:
+                w["block"] = base["block"].copy(); w["block"][c, i, :] = val
             elif kind == 3:
                 w["copy"] = base["copy"].copy(); w["copy"][c, i, :] = val
             elif kind == 4:
@@ -201,3 +208,8 @@ def evm7_vectors():
 def evm8_vectors():
     """SCMP (SLT / SGT) / SIGNEXTEND steps; same layout as evm2"""
     return evm2_vectors("evm8")
+
+
+def evm9_vectors():
+    """BlockCtx (7 opcodes) / ORIGIN / GASPRICE steps with their block / tx tables; evm2 layout + tx, block"""
+    return evm2_vectors("evm9")

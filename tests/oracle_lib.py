@@ -153,6 +153,10 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
     c = ctypes.c_uint64
     if row_end is None:
         row_end = m["steps"].shape[1] - 1
+    if w.get("tx") is not None or w.get("block") is not None:  # ORIGIN / GASPRICE / BlockCtx gadgets
+        tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
+        blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
+        lib().orc_set_evm_context_tables(p64(tx), c(tx.shape[1]), p64(blk), c(blk.shape[1]))
     rc = lib().orc_check_evm_x(p64(m["steps"]), c(m["steps"].shape[1]), p64(m["bytecode"]), c(m["bytecode"].shape[1]),
                                p64(m["rw"]), c(m["rw"].shape[1]), _p8(rwf), p64(fixed), c(fixed.shape[1]),
                                p64(m["copy"]), c(m["copy"].shape[1]), p64(m["keccak"]), c(m["keccak"].shape[1]),
