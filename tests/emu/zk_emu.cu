@@ -157,6 +157,15 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
                                uint64_t n_fixed, const uint64_t* copy, uint64_t n_copy, const uint64_t* keccak,
                                uint64_t n_keccak, uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
                                const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count);
+static const u64* g_emu_tx = nullptr;
+static const u64* g_emu_block = nullptr;
+static u64 g_emu_n_tx = 0, g_emu_n_block = 0;
+extern "C" void emu_set_evm_context_tables(const uint64_t* tx, uint64_t n_tx, const uint64_t* block, uint64_t n_block) {
+  g_emu_tx = (const u64*)tx;
+  g_emu_n_tx = n_tx;
+  g_emu_block = (const u64*)block;
+  g_emu_n_block = n_block;
+}
 extern "C" int emu_check_evm(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode, uint64_t n_bytecode,
                              const uint64_t* rw, uint64_t n_rw, const uint64_t* fixed, uint64_t n_fixed,
                              uint64_t row_begin, uint64_t row_end, uint64_t row_base, uint32_t flags,
@@ -195,6 +204,13 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   IndexStore s4, s5;
   t.copy = build_index((const u64*)copy, n_copy, 14, ck, 11, ch, s4);
   t.keccak = build_index((const u64*)keccak, n_keccak, 5, kk, 3, ch, s5);
+  // tx / block tables of the ORIGIN / GASPRICE / BlockCtx gadgets (set by emu_set_evm_context_tables)
+  const u32 tk[3] = {0, 1, 2}, bk[2] = {0, 1};
+  IndexStore s6, s7;
+  t.tx = build_index(g_emu_tx, g_emu_n_tx, 5, tk, 3, ch, s6);
+  t.block = build_index(g_emu_block, g_emu_n_block, 4, bk, 2, ch, s7);
+  g_emu_tx = g_emu_block = nullptr;
+  g_emu_n_tx = g_emu_n_block = 0;
   PosState p_bc, p_rw;
   if (g_emu_positional) {
     add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
@@ -327,3 +343,5 @@ extern "C" int emu_check_sig(const uint64_t* rows, uint64_t n_rows, const uint8_
   for (u64 i = row_begin; i < row_end; i++) check_sig_row(w, kix, r_mont, res, i);
   return 0;
 }
+
+extern "C" int emu_n_evm_constraints() { return EV_N_CONSTRAINTS; }

@@ -40,7 +40,7 @@ def _p(a):
 
 def check_evm(steps, bytecode, rw, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None, challenge=None):
     steps, bytecode, rw, fixed = [np.ascontiguousarray(a) for a in (steps, bytecode, rw, fixed)]
-    n = n or 256
+    n = n or lib().emu_n_evm_constraints()
     ff = np.zeros(n, dtype=np.uint32)
     fc = np.zeros(n, dtype=np.uint64)
     c = ctypes.c_uint64
@@ -122,7 +122,8 @@ def set_positional(on: bool) -> None:
     ctypes.c_int.in_dll(lib(), "g_emu_positional").value = int(on)
 
 
-def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=256, challenge=None):
+def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None, challenge=None):
+    n = n or lib().emu_n_evm_constraints()
     m = {k: np.ascontiguousarray(w[k]) for k in ("steps", "bytecode", "rw", "copy", "keccak")}
     fixed = np.ascontiguousarray(fixed)
     rwf = np.ascontiguousarray(w["rw_flags"], dtype=np.uint8)
@@ -133,6 +134,10 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=256,
     if row_end is None:
         row_end = m["steps"].shape[1] - 1
     p8 = rwf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if len(rwf) else None
+    if w.get("tx") is not None or w.get("block") is not None:
+        tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
+        blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
+        lib().emu_set_evm_context_tables(_p(tx), c(tx.shape[1]), _p(blk), c(blk.shape[1]))
     rc = lib().emu_check_evm_x(_p(m["steps"]), c(m["steps"].shape[1]), _p(m["bytecode"]), c(m["bytecode"].shape[1]),
                                _p(m["rw"]), c(m["rw"].shape[1]), p8, _p(fixed), c(fixed.shape[1]), _p(m["copy"]),
                                c(m["copy"].shape[1]), _p(m["keccak"]), c(m["keccak"].shape[1]), c(row_begin), c(row_end),

@@ -83,6 +83,7 @@ struct Index {
   u32* heads_aux = nullptr; // [ZK_HEADS_CAP] run lengths, [ZK_HEADS_CAP] head list, [1] count
   u64 built_version = ~0ull;
   u64 built_challenge = ~0ull;
+  bool empty_ready = false;  // the slot array is all-empty for an empty table (no per-check memset)
   IndexDev dev;
 };
 
@@ -558,9 +559,10 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     k_index_build<<<grid, 256, 0, st>>>(d);
     ctx->launches += 2;
     CK(ctx, cudaGetLastError());
-  } else {
+  } else if (!ix->empty_ready) {  // an empty table: clear the (minimum-size) slot array once
     CK(ctx, cudaMemsetAsync(ix->slots, 0xFF, cap * sizeof(u64), st));
   }
+  ix->empty_ready = t.n_rows == 0;
   ix->built_version = m.version;
   ix->built_challenge = ctx->chal_version;
   *out = d;
@@ -705,6 +707,9 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
     const u32 ck[11] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12}, kk[3] = {0, 1, 2};
     if ((rc = ensure_index(ctx, ZK_TABLE_COPY, ck, 11, st, &t.copy))) return rc;
     if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 3, st, &t.keccak))) return rc;
+    const u32 tk[3] = {0, 1, 2}, bk[2] = {0, 1};
+    if ((rc = ensure_index(ctx, ZK_TABLE_TX, tk, 3, st, &t.tx))) return rc;
+    if ((rc = ensure_index(ctx, ZK_TABLE_BLOCK, bk, 2, st, &t.block))) return rc;
   }
   if (!ctx->resp_bitmap) CK(ctx, cudaMalloc(&ctx->resp_bitmap, ZK_RESP_BITMAP_WORDS * sizeof(u32)));
   if (ctx->resp_bitmap_version != ctx->tab[ZK_TABLE_FIXED].version) {

@@ -55,6 +55,8 @@ struct EvmTables {
   IndexDev fixed;     // key (tag, v0, v1, v2)
   IndexDev copy;      // copy table, key = every queried cell of copy_lookup (table.py:760-787): cells 1..10, 12
   IndexDev keccak;    // keccak table, key (state_tag, input_rlc, input_len)
+  IndexDev tx;        // tx table (tx_id, tag, index | value lo, hi), key = the first three cells (table.py:697-705)
+  IndexDev block;     // block table (tag, block number | value lo, hi), key = the first two cells (table.py:691-695)
   // ResponsibleOpcode rows of the fixed table (tag 13, aux 0) with state, opcode < 256 as a
   // 64 Kbit bitmap: bit (state << 8 | opcode).  Built from the uploaded fixed table
   // (k_fixed_resp_bitmap) and staged into shared memory by every EVM kernel.
@@ -273,6 +275,9 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_BYTE: return G_MISC;
     case ZK_ES_SCMP: return G_MISC;
     case ZK_ES_SIGNEXTEND: return G_MISC;
+    case ZK_ES_BlockCtx: return G_MISC;
+    case ZK_ES_ORIGIN: return G_MISC;
+    case ZK_ES_GASPRICE: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1326,6 +1331,64 @@ ZK_HD void gadget_signextend(const StepCtx& s, bool live) {
   same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
 
+// ---- BlockCtx (block_ctx.py: COINBASE / TIMESTAMP / NUMBER / PREVRANDAO / GASLIMIT / CHAINID / BASEFEE),
+// ORIGIN (origin.py), GASPRICE (gasprice.py): a block-table / tx-table word pushed on the stack -----
+ZK_HD void gadget_blockctx(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  u64 tag = 0;  // BlockContextFieldTag of the opcode (block_ctx.py:10-24); none: `op` stays unbound
+  if (fr_fits64(opcode)) switch (opcode.l[0]) {
+      case 0x41: tag = 1; break;  // COINBASE -> Coinbase
+      case 0x42: tag = 4; break;  // TIMESTAMP
+      case 0x43: tag = 3; break;  // NUMBER
+      case 0x45: tag = 2; break;  // GASLIMIT
+      case 0x44: tag = 5; break;  // PREVRANDAO
+      case 0x48: tag = 6; break;  // BASEFEE
+      case 0x46: tag = 7; break;  // CHAINID
+      default: break;
+    }
+  EV_LIVE_CHECK(EV_BLK_OPCODE, tag != 0);
+  Word2 ctx{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
+  {
+    Fr key[2] = {fr_u64(tag), fr_u64(0)};
+    u32 r = 0;
+    const int m = lookup_sync<2>(s.t.block, key, &r, s.mask, live);
+    live = need1(s, live, m, EV_BLK_CTX_UNSAT);
+    if (live) {
+      ctx.lo = table_cell(s.t.block.tab, 2, r);
+      ctx.hi = table_cell(s.t.block.tab, 3, r);
+    }
+  }
+  live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_BLK_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_BLK_EQ, word_eq(w, ctx));
+  if (!live) return;
+  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+ZK_HD void gadget_txctx(const StepCtx& s, bool live, u64 op, u64 field) {
+  // the call-context lookup comes BEFORE the opcode lookup here (origin.py:8-9)
+  Word2 v{fr_u64(0), fr_u64(0)}, ctx{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
+  bool is_word = false;
+  live = need1(s, live, call_context_w(s, live, s.cur(S_RWC), 0, s.cur(S_CALL_ID), ZK_CC_TxId, &v, &is_word), EV_TXC_TXID_UNSAT);
+  EV_LIVE_CHECK(EV_TXC_TXID_TYPE, !is_word);
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  EV_LIVE_CHECK(EV_TXC_OPCODE, fr_eq_u64(opcode, op));
+  {
+    Fr key[3] = {v.lo, fr_u64(field), fr_u64(0)};
+    u32 r = 0;
+    const int m = lookup_sync<3>(s.t.tx, key, &r, s.mask, live);
+    live = need1(s, live, m, EV_TXC_TX_UNSAT);
+    if (live) {
+      ctx.lo = table_cell(s.t.tx.tab, 3, r);
+      ctx.hi = table_cell(s.t.tx.tab, 4, r);
+    }
+  }
+  live = need1(s, live, stack_at(s, live, 1, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_TXC_PUSH_UNSAT);
+  EV_LIVE_CHECK(EV_TXC_EQ, word_eq(w, ctx));
+  if (!live) return;
+  same_context(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1351,6 +1414,9 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_BYTE: gadget_byte(s, live); break;
     case ZK_ES_SCMP: gadget_scmp(s, live); break;
     case ZK_ES_SIGNEXTEND: gadget_signextend(s, live); break;
+    case ZK_ES_BlockCtx: gadget_blockctx(s, live); break;
+    case ZK_ES_ORIGIN: gadget_txctx(s, live, 0x32, ZK_TX_CallerAddress); break;
+    case ZK_ES_GASPRICE: gadget_txctx(s, live, 0x3a, ZK_TX_GasPrice); break;
     default: break;
   }
 }

@@ -47,6 +47,9 @@ def upload_tables(ctx: native.Context, tables: Tables) -> None:
                      flags=np.array([packing.rw_table_flags(r) for r in rws], dtype=np.uint8))
     ctx.upload_table(native.TABLE_COPY, packing.pack(tables.copy_table, packing.copy_table_row, 14))
     ctx.upload_table(native.TABLE_KECCAK, packing.pack(tables.keccak_table, packing.keccak_table_row, 5))
+    # tx / block tables: the ORIGIN / GASPRICE / BlockCtx gadgets (tables.tx_lookup / block_lookup, table.py:691-705)
+    ctx.upload_table(native.TABLE_TX, packing.pack(list(getattr(tables, "tx_table", ()) or ()), packing.tx_table_row, 5))
+    ctx.upload_table(native.TABLE_BLOCK, packing.pack(list(getattr(tables, "block_table", ()) or ()), packing.block_table_row, 4))
     upload_fixed_table(ctx)
 
 

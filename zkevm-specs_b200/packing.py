@@ -114,6 +114,11 @@ def tx_table_row(r) -> List[int]:
             cell_int(r.value.lo), cell_int(r.value.hi)]
 
 
+def block_table_row(r) -> List[int]:
+    """BlockTableRow (evm_circuit/table.py:413-417): field_tag, block_number_or_zero, value (lo, hi)"""
+    return [cell_int(r.field_tag), cell_int(r.block_number_or_zero), cell_int(r.value.lo), cell_int(r.value.hi)]
+
+
 def word_flag(x) -> int:
     """the WordOrValue.is_word type bit (a plain Word counts as a word)"""
     return int(bool(getattr(x, "is_word", True)))
