@@ -322,6 +322,27 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_TXC_PUSH_UNSAT, ZKE_UNSAT, "origin.py:15 stack_push unsat")                            \
   X(EV_TXC_PUSH_AMBIG, ZKE_AMBIG, "origin.py:15 stack_push ambiguous")                        \
   X(EV_TXC_EQ, ZKE_ASSERT, "origin.py:13-16 pushed word == tx-context word")                  \
+  /* SHL_SHR (shl_shr.py): push == pop2 << pop1 / pop2 >> pop1 through a division witness */       \
+  X(EV_SH_P1_UNSAT, ZKE_UNSAT, "shl_shr.py:10 stack_pop shift unsat")                         \
+  X(EV_SH_P1_AMBIG, ZKE_AMBIG, "shl_shr.py:10 stack_pop shift ambiguous")                     \
+  X(EV_SH_P2_UNSAT, ZKE_UNSAT, "shl_shr.py:11 stack_pop value unsat")                         \
+  X(EV_SH_P2_AMBIG, ZKE_AMBIG, "shl_shr.py:11 stack_pop value ambiguous")                     \
+  X(EV_SH_PUSH_UNSAT, ZKE_UNSAT, "shl_shr.py:12 stack_push unsat")                            \
+  X(EV_SH_PUSH_AMBIG, ZKE_AMBIG, "shl_shr.py:12 stack_push ambiguous")                        \
+  X(EV_SH_BYTES, ZKE_VALUE, "shl_shr.py:106 shift.to_le_bytes(): half >= 2^128 -> OverflowError") \
+  X(EV_SH_REM_WORD, ZKE_ASSERT, "shl_shr.py:117 Word(dividend - quotient * divisor): >= 2^256") \
+  X(EV_SH_REM_NEG, ZKE_VALUE, "shl_shr.py:117 Word(negative int): to_bytes -> OverflowError")  \
+  X(EV_SH_SELECT, ZKE_ASSERT, "shl_shr.py:59-66 Word.select / +: a half >= 2^128 (arithmetic.py:110-114)") \
+  X(EV_SH_POP2, ZKE_ASSERT, "shl_shr.py:59-62 pop2 == quotient*is_shl + dividend*is_shr")      \
+  X(EV_SH_PUSH_EQ, ZKE_ASSERT, "shl_shr.py:63-65 push == dividend*is_shl + quotient*is_shr*(1 - divisor_is_zero)") \
+  X(EV_SH_REM_LT, ZKE_ASSERT, "shl_shr.py:78-79 divisor != 0 => remainder < divisor")           \
+  X(EV_SH_SHL_REM0, ZKE_ASSERT, "shl_shr.py:82-83 SHL => remainder == 0")                       \
+  X(EV_SH_TO64, ZKE_VALUE, "instruction.py:604 to_64s(quotient): half >= 2^128 -> OverflowError") \
+  X(EV_SH_CARRY_LO, ZKE_RANGE, "instruction.py:626 range_check(carry_lo, 9)")                   \
+  X(EV_SH_CARRY_HI, ZKE_RANGE, "instruction.py:627 range_check(carry_hi, 9)")                   \
+  X(EV_SH_OVERFLOW, ZKE_ASSERT, "shl_shr.py:87 is_shr * overflow == 0")                         \
+  X(EV_SH_POW2_UNSAT, ZKE_UNSAT, "shl_shr.py:91 pow2_lookup(shf0, divisor) unsat")              \
+  X(EV_SH_POW2_AMBIG, ZKE_AMBIG, "shl_shr.py:91 pow2_lookup ambiguous")                         \
   /* STOP: execution/stop.py:7-51 */                                                        \
   X(EV_STOP_LEN_UNSAT, ZKE_UNSAT, "stop.py:11 bytecode_length lookup unsat")                \
   X(EV_STOP_LEN_AMBIG, ZKE_AMBIG, "stop.py:11 bytecode_length lookup ambiguous")            \

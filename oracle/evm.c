@@ -774,6 +774,123 @@ static void gadget_txctx(evm_env* e, uint64_t i, uint64_t row, uint64_t op, uint
   same_context(e, i, row, opcode, 2, fr_u64(1), fr_neg(fr_u64(1)));
 }
 
+/* ---- shl_shr.py -------------------------------------------------------------------------------- */
+/* unsigned big integers of 10 limbs (640 bits): Word.int_value() of arbitrary cells is < 2^382 and the
+ * SHR remainder witness is dividend - quotient * 2^shift with shift < 256 */
+typedef struct { uint64_t l[10]; } u640;
+static u640 word_int(word_t w) { /* lo + hi * 2^128 as an integer */
+  u640 r; memset(&r, 0, sizeof r);
+  uint64_t c = 0;
+  r.l[0] = w.lo.l[0]; r.l[1] = w.lo.l[1];
+  r.l[2] = adc(w.lo.l[2], w.hi.l[0], &c); r.l[3] = adc(w.lo.l[3], w.hi.l[1], &c);
+  r.l[4] = adc(w.hi.l[2], 0, &c); r.l[5] = adc(w.hi.l[3], 0, &c); r.l[6] = c;
+  return r;
+}
+static u640 u640_shl(u640 a, unsigned s) { /* s < 256 */
+  u640 r; memset(&r, 0, sizeof r);
+  const unsigned ws = s >> 6, bs = s & 63;
+  for (int k = 9; k >= 0; k--) {
+    uint64_t v = 0;
+    if (k >= (int)ws) {
+      v = a.l[k - ws] << bs;
+      if (bs && k - (int)ws - 1 >= 0) v |= a.l[k - ws - 1] >> (64 - bs);
+    }
+    r.l[k] = v;
+  }
+  return r;
+}
+static int u640_cmp(u640 a, u640 b) {
+  for (int k = 9; k >= 0; k--) { if (a.l[k] < b.l[k]) return -1; if (a.l[k] > b.l[k]) return 1; }
+  return 0;
+}
+static u640 u640_sub(u640 a, u640 b) {
+  u640 r; uint64_t br = 0;
+  for (int k = 0; k < 10; k++) {
+    const u128 d = (u128)a.l[k] - b.l[k] - br;
+    r.l[k] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1;
+  }
+  return r;
+}
+static void gadget_shl_shr(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  const word_t zero = {fr_u64(0), fr_u64(0)};
+  word_t pop1, pop2, push;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_SH_P1_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, one), 0, ZK_TARGET_Stack, call_id, fr_add(sp, one), &pop2), EV_SH_P2_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, one), &push), EV_SH_PUSH_UNSAT, row)) return;
+  /* gen_witness, shl_shr.py:103-129 */
+  const fr_t is_shl = fr_sub(fr_u64(0x1c), opcode); /* Opcode.SHR - opcode over the field */
+  CHECK(EV_SH_BYTES, word_in_domain(pop1));
+  const unsigned shf0 = word_byte(pop1, 0);
+  const int shf_lt256 = (pop1.lo.l[0] >> 8) == 0 && pop1.lo.l[1] == 0 && pop1.hi.l[0] == 0 && pop1.hi.l[1] == 0;
+  word_t divisor = zero; /* Word(1 << shf0) if the shift is < 256 else Word(0) */
+  if (shf_lt256) { if (shf0 < 128) divisor.lo.l[shf0 >> 6] = 1ull << (shf0 & 63); else divisor.hi.l[(shf0 - 128) >> 6] = 1ull << (shf0 & 63); }
+  word_t dividend, quotient, remainder = zero;
+  if (fr_eq_u64(is_shl, 1)) { dividend = push; quotient = pop2; }
+  else {
+    dividend = pop2; quotient = push;
+    /* remainder = Word(dividend.int_value() - quotient.int_value() * divisor.int_value()) as Python ints */
+    const u640 D = word_int(dividend);
+    u640 QS; memset(&QS, 0, sizeof QS);
+    if (shf_lt256) QS = u640_shl(word_int(quotient), shf0);
+    if (u640_cmp(D, QS) < 0) { orc_fail(e->res, EV_SH_REM_NEG, row); return; } /* Word(negative).to_bytes */
+    const u640 R = u640_sub(D, QS);
+    CHECK(EV_SH_REM_WORD, (R.l[4] | R.l[5] | R.l[6] | R.l[7] | R.l[8] | R.l[9]) == 0); /* assert value < 256**32 */
+    remainder.lo = fr_u128(R.l[0], R.l[1]); remainder.hi = fr_u128(R.l[2], R.l[3]);
+  }
+  /* check_witness, shl_shr.py:37-91 */
+  const fr_t is_shr = fr_sub(one, is_shl);
+  const int dz = fr_is_zero(fr_add(divisor.lo, divisor.hi));
+  const fr_t nz = fr_u64(dz ? 0 : 1);
+  word_t t1, t2, sum;
+  /* :59-62 pop2 == quotient.select(is_shl) + dividend.select(is_shr) */
+  CHECK(EV_SH_SELECT, word_select(quotient, is_shl, &t1) && word_select(dividend, is_shr, &t2));
+  sum.lo = fr_add(t1.lo, t2.lo); sum.hi = fr_add(t1.hi, t2.hi);
+  CHECK(EV_SH_SELECT, word_in_domain(sum));
+  CHECK(EV_SH_POP2, word_eq(pop2, sum));
+  /* :63-65 push == dividend.select(is_shl) + quotient.select(is_shr * (1 - divisor_is_zero)) */
+  CHECK(EV_SH_SELECT, word_select(dividend, is_shl, &t1) && word_select(quotient, fr_mul(is_shr, nz), &t2));
+  sum.lo = fr_add(t1.lo, t2.lo); sum.hi = fr_add(t1.hi, t2.hi);
+  CHECK(EV_SH_SELECT, word_in_domain(sum));
+  CHECK(EV_SH_PUSH_EQ, word_eq(push, sum));
+  /* :66-76 hold by construction of shf0 / divisor (shift in the bytes domain) */
+  /* :77-79 compare_word(remainder, divisor): both in the halves domain here */
+  {
+    const int hi_lt = fr_cmp(remainder.hi, divisor.hi) < 0, hi_eq = fr_eq(remainder.hi, divisor.hi);
+    const int lo_lt = fr_cmp(remainder.lo, divisor.lo) < 0;
+    CHECK(EV_SH_REM_LT, dz || (hi_lt + hi_eq * lo_lt) == 1);
+  }
+  CHECK(EV_SH_SHL_REM0, fr_is_zero(fr_mul(is_shl, fr_u64(fr_is_zero(fr_add(remainder.lo, remainder.hi)) ? 0 : 1))));
+  /* :86 mul_add_words(quotient, divisor, remainder, dividend) */
+  CHECK(EV_SH_TO64, word_in_domain(quotient));
+  {
+    const word_t a = quotient, b = divisor, c = remainder, d = dividend;
+    fr_t a64[4] = {fr_u64(a.lo.l[0]), fr_u64(a.lo.l[1]), fr_u64(a.hi.l[0]), fr_u64(a.hi.l[1])};
+    fr_t b64[4] = {fr_u64(b.lo.l[0]), fr_u64(b.lo.l[1]), fr_u64(b.hi.l[0]), fr_u64(b.hi.l[1])};
+#define M(x, y) fr_mul(a64[x], b64[y])
+    const fr_t t0 = M(0, 0), tt1 = fr_add(M(0, 1), M(1, 0));
+    const fr_t tt2 = fr_add(fr_add(M(0, 2), M(1, 1)), M(2, 0));
+    const fr_t tt3 = fr_add(fr_add(fr_add(M(0, 3), M(1, 2)), M(2, 1)), M(3, 0));
+    const fr_t two64 = {{0, 1, 0, 0}};
+    const fr_t carry_lo = fr_mul(fr_sub(fr_add(fr_add(t0, fr_mul(tt1, two64)), c.lo), d.lo), INV_2_128);
+    const fr_t carry_hi = fr_mul(fr_sub(fr_add(fr_add(fr_add(tt2, fr_mul(tt3, two64)), c.hi), carry_lo), d.hi), INV_2_128);
+    fr_t overflow = carry_hi;
+    overflow = fr_add(overflow, M(1, 3)); overflow = fr_add(overflow, M(2, 2));
+    overflow = fr_add(overflow, M(3, 1)); overflow = fr_add(overflow, M(2, 3));
+    overflow = fr_add(overflow, M(3, 2)); overflow = fr_add(overflow, M(3, 3));
+#undef M
+    if (!fr_fits_bits(carry_lo, 72)) { orc_fail(e->res, EV_SH_CARRY_LO, row); return; }
+    if (!fr_fits_bits(carry_hi, 72)) { orc_fail(e->res, EV_SH_CARRY_HI, row); return; }
+    CHECK(EV_SH_OVERFLOW, fr_is_zero(fr_mul(is_shr, overflow)));
+  }
+  if (!dz) { /* :90-91 pow2_lookup(shf0, divisor_lo, divisor_hi) */
+    fr_t key[4] = {fr_u64(ZK_FIXED_Pow2), fr_u64(shf0), divisor.lo, divisor.hi};
+    if (!need1(e, orc_lookup(&e->fixed_ix, key, 0), EV_SH_POW2_UNSAT, row)) return;
+  }
+  same_context(e, i, row, opcode, 3, one, one);
+}
+
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
@@ -806,7 +923,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_CALLVALUE || st == ZK_ES_CALLDATASIZE || st == ZK_ES_ADDRESS ||
                                   st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
                                   st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND ||
-                                  st == ZK_ES_BlockCtx || st == ZK_ES_ORIGIN || st == ZK_ES_GASPRICE);
+                                  st == ZK_ES_BlockCtx || st == ZK_ES_ORIGIN || st == ZK_ES_GASPRICE ||
+                                  st == ZK_ES_SHL_SHR);
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   if (st == ZK_ES_ORIGIN) { gadget_txctx(e, i, row, 0x32, ZK_TX_CallerAddress); return; }
   if (st == ZK_ES_GASPRICE) { gadget_txctx(e, i, row, 0x3a, ZK_TX_GasPrice); return; }
@@ -837,6 +955,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_SCMP) gadget_scmp(e, i, row, opcode);
   else if (st == ZK_ES_SIGNEXTEND) gadget_signextend(e, i, row, opcode);
   else if (st == ZK_ES_BlockCtx) gadget_blockctx(e, i, row, opcode);
+  else if (st == ZK_ES_SHL_SHR) gadget_shl_shr(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -843,7 +843,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1068,6 +1068,19 @@ def evm2_cases(part="evm2"):
                            code_hash=h, program_counter=1, stack_pointer=1023, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], [], txs, blocks
 
+    def shift_case(kind, shift, value):
+        """tests/evm/test_shl_shr.py"""
+        M = 1 << 256
+        res = ((value << shift) % M if shift < 256 else 0) if kind == "shl" else (value >> shift if shift < 256 else 0)
+        bc = getattr(Bytecode().push(value, n_bytes=32).push(shift, n_bytes=32), kind)().stop()
+        rw = RWDictionary(9).stack_read(1, 1022, Word(shift)).stack_read(1, 1023, Word(value)).stack_write(1, 1023, Word(res))
+        h = Word(bc.hash())
+        steps = [StepState(ExecutionState.SHL_SHR, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=66, stack_pointer=1022, gas_left=3),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=67, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1176,7 +1189,16 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm9":
+    if part == "evm10":
+        v = 0xFEDCBA9876543210F0E1D2C3B4A5968778695A4B3C2D1E0F0123456789ABCDEF
+        scenarios = {
+            "shl_0": shift_case("shl", 0, v), "shl_1": shift_case("shl", 1, v), "shl_64": shift_case("shl", 64, v),
+            "shl_129": shift_case("shl", 129, v), "shl_255": shift_case("shl", 255, v), "shl_256": shift_case("shl", 256, v),
+            "shl_big": shift_case("shl", (1 << 200) + 3, v),
+            "shr_0": shift_case("shr", 0, v), "shr_7": shift_case("shr", 7, v), "shr_128": shift_case("shr", 128, v),
+            "shr_200": shift_case("shr", 200, v), "shr_255": shift_case("shr", 255, v), "shr_300": shift_case("shr", 300, v),
+        }
+    elif part == "evm9":
         scenarios = {
             "coinbase": ctx_case("coinbase", 0xC014BA5E0000000000000000000000000000BA5E), "timestamp": ctx_case("timestamp", 1700000000),
             "number": ctx_case("number", 1234567), "gaslimit": ctx_case("gaslimit", 30_000_000),
@@ -1246,7 +1268,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
@@ -1339,6 +1361,10 @@ def evm8_cases():
 
 def evm9_cases():
     evm2_cases("evm9")
+
+
+def evm10_cases():
+    evm2_cases("evm10")
 
 
 # --------------------------------------------------------------------------- exp
@@ -1646,7 +1672,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -213,3 +213,8 @@ def evm8_vectors():
 def evm9_vectors():
     """BlockCtx (7 opcodes) / ORIGIN / GASPRICE steps with their block / tx tables; evm2 layout + tx, block"""
     return evm2_vectors("evm9")
+
+
+def evm10_vectors():
+    """SHL / SHR steps; same layout as evm2"""
+    return evm2_vectors("evm10")

@@ -278,6 +278,7 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
     case ZK_ES_BlockCtx: return G_MISC;
     case ZK_ES_ORIGIN: return G_MISC;
     case ZK_ES_GASPRICE: return G_MISC;
+    case ZK_ES_SHL_SHR: return G_MISC;
     default: break;
   }
   step_fail(s, EV_UNSUPPORTED_STATE);
@@ -1389,6 +1390,148 @@ ZK_HD void gadget_txctx(const StepCtx& s, bool live, u64 op, u64 field) {
   same_context(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
 
+// ---- SHL_SHR (shl_shr.py): push == pop2 << pop1 / pop2 >> pop1 through a division witness --------
+// unsigned 640-bit integers: Word.int_value() of arbitrary cells is < 2^382 and the SHR remainder
+// witness is dividend - quotient * 2^shift (shift < 256), all as Python ints in the reference
+struct U640 {
+  u64 l[10];
+};
+ZK_HD U640 word_int(const Word2& w) {  // lo + hi * 2^128 as an integer
+  U640 r;
+  for (int k = 0; k < 10; k++) r.l[k] = 0;
+  u64 c = 0;
+  r.l[0] = w.lo.l[0];
+  r.l[1] = w.lo.l[1];
+  r.l[2] = adc64(w.lo.l[2], w.hi.l[0], c);
+  r.l[3] = adc64(w.lo.l[3], w.hi.l[1], c);
+  r.l[4] = adc64(w.hi.l[2], 0, c);
+  r.l[5] = adc64(w.hi.l[3], 0, c);
+  r.l[6] = c;
+  return r;
+}
+ZK_HD U640 u640_shl(const U640& a, unsigned sh) {  // sh < 256
+  U640 r;
+  const int ws = (int)(sh >> 6);
+  const unsigned bs = sh & 63;
+  for (int k = 9; k >= 0; k--) {
+    u64 v = 0;
+    if (k >= ws) {
+      v = a.l[k - ws] << bs;
+      if (bs && k - ws - 1 >= 0) v |= a.l[k - ws - 1] >> (64 - bs);
+    }
+    r.l[k] = v;
+  }
+  return r;
+}
+ZK_HD int u640_cmp(const U640& a, const U640& b) {
+  for (int k = 9; k >= 0; k--) {
+    if (a.l[k] < b.l[k]) return -1;
+    if (a.l[k] > b.l[k]) return 1;
+  }
+  return 0;
+}
+ZK_HD U640 u640_sub(const U640& a, const U640& b) {
+  U640 r;
+  u64 br = 0;
+  for (int k = 0; k < 10; k++) r.l[k] = sbb64(a.l[k], b.l[k], br);
+  return r;
+}
+ZK_HD void gadget_shl_shr(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1), one = fr_u64(1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 pop1 = zero, pop2 = zero, push = zero;
+  live = need1(s, live, stack_at(s, live, 0, 0, sp, &pop1), EV_SH_P1_UNSAT);
+  live = need1(s, live, stack_at(s, live, 1, 0, sp1, &pop2), EV_SH_P2_UNSAT);
+  live = need1(s, live, stack_at(s, live, 2, 1, sp1, &push), EV_SH_PUSH_UNSAT);
+  // gen_witness, shl_shr.py:103-129
+  const Fr is_shl = fr_sub(fr_u64(0x1c), opcode);  // Opcode.SHR - opcode over the field
+  EV_LIVE_CHECK(EV_SH_BYTES, word_in_domain(pop1));
+  const unsigned shf0 = (unsigned)word_byte(pop1, 0);
+  const bool shf_lt256 = (pop1.lo.l[0] >> 8) == 0 && pop1.lo.l[1] == 0 && pop1.hi.l[0] == 0 && pop1.hi.l[1] == 0;
+  Word2 divisor = zero;  // Word(1 << shf0) if the shift is < 256 else Word(0)
+  if (shf_lt256) {
+    const u64 bit = 1ull << (shf0 & 63);
+    if (shf0 < 64) divisor.lo.l[0] = bit;
+    else if (shf0 < 128) divisor.lo.l[1] = bit;
+    else if (shf0 < 192) divisor.hi.l[0] = bit;
+    else divisor.hi.l[1] = bit;
+  }
+  Word2 dividend, quotient, remainder = zero;
+  if (fr_eq_u64(is_shl, 1)) {
+    dividend = push;
+    quotient = pop2;
+  } else {
+    dividend = pop2;
+    quotient = push;
+    if (live) {
+      // remainder = Word(dividend.int_value() - quotient.int_value() * divisor.int_value()) as Python ints
+      const U640 D = word_int(dividend);
+      U640 QS;
+      for (int k = 0; k < 10; k++) QS.l[k] = 0;
+      if (shf_lt256) QS = u640_shl(word_int(quotient), shf0);
+      EV_LIVE_CHECK(EV_SH_REM_NEG, u640_cmp(D, QS) >= 0);  // Word(negative).to_bytes -> OverflowError
+      if (live) {
+        const U640 R = u640_sub(D, QS);
+        EV_LIVE_CHECK(EV_SH_REM_WORD, (R.l[4] | R.l[5] | R.l[6] | R.l[7] | R.l[8] | R.l[9]) == 0);  // assert < 256**32
+        remainder.lo = fr_u128(R.l[0], R.l[1]);
+        remainder.hi = fr_u128(R.l[2], R.l[3]);
+      }
+    }
+  }
+  if (!live) {  // the pow2 lookup below is warp-synchronous: take part in it, inactive
+    Fr key[4] = {fr_u64(0), fr_u64(0), fr_u64(0), fr_u64(0)};
+    u32 r = 0;
+    lookup_sync<4>(s.t.fixed, key, &r, s.mask, false);
+    return;
+  }
+  // check_witness, shl_shr.py:37-91
+  const Fr is_shr = fr_sub(one, is_shl);
+  const bool dz = fr_is_zero(fr_add(divisor.lo, divisor.hi));
+  Word2 t1, t2, sum;
+  bool ok = word_select(quotient, is_shl, &t1) && word_select(dividend, is_shr, &t2);  // :59-62
+  sum.lo = fr_add(t1.lo, t2.lo);
+  sum.hi = fr_add(t1.hi, t2.hi);
+  int fail_id = -1;
+  if (!(ok && word_in_domain(sum))) fail_id = EV_SH_SELECT;
+  else if (!word_eq(pop2, sum)) fail_id = EV_SH_POP2;
+  if (fail_id < 0) {  // :63-65
+    ok = word_select(dividend, is_shl, &t1) && word_select(quotient, dz ? fr_u64(0) : is_shr, &t2);
+    sum.lo = fr_add(t1.lo, t2.lo);
+    sum.hi = fr_add(t1.hi, t2.hi);
+    if (!(ok && word_in_domain(sum))) fail_id = EV_SH_SELECT;
+    else if (!word_eq(push, sum)) fail_id = EV_SH_PUSH_EQ;
+  }
+  // :66-76 hold by construction of shf0 / divisor (the shift is in the bytes domain here)
+  if (fail_id < 0) {  // :77-79 compare_word(remainder, divisor), both in the halves domain
+    const bool lt = fr_lt(remainder.hi, divisor.hi) || (fr_eq(remainder.hi, divisor.hi) && fr_lt(remainder.lo, divisor.lo));
+    if (!(dz || lt)) fail_id = EV_SH_REM_LT;
+  }
+  if (fail_id < 0 && !fr_is_zero(is_shl) && !(fr_is_zero(remainder.lo) && fr_is_zero(remainder.hi))) fail_id = EV_SH_SHL_REM0;
+  if (fail_id < 0 && !word_in_domain(quotient)) fail_id = EV_SH_TO64;  // :86 mul_add_words(quotient, divisor, remainder, dividend)
+  if (fail_id < 0) {
+    Fr carry_lo, carry_hi, overflow;
+    mul_add_carries(quotient, divisor, remainder, dividend, &carry_lo, &carry_hi, &overflow);
+    if (!fits_9_bytes(carry_lo)) fail_id = EV_SH_CARRY_LO;
+    else if (!fits_9_bytes(carry_hi)) fail_id = EV_SH_CARRY_HI;
+    else if (!(fr_is_zero(is_shr) || fr_is_zero(overflow))) fail_id = EV_SH_OVERFLOW;
+  }
+  if (fail_id >= 0) {
+    step_fail(s, fail_id);
+    live = false;
+  }
+  {  // :90-91 pow2_lookup(shf0, divisor_lo, divisor_hi) when the divisor is not zero
+    const bool go = live && !dz;
+    Fr key[4] = {fr_u64(ZK_FIXED_Pow2), fr_u64(shf0), divisor.lo, divisor.hi};
+    u32 r = 0;
+    const int m = lookup_sync<4>(s.t.fixed, key, &r, s.mask, go);
+    if (go) live = need1(s, live, m, EV_SH_POW2_UNSAT);
+  }
+  if (!live) return;
+  same_context(s, opcode, 3, one, one);
+}
+
 // the rare states: one thread per step, dispatch on the execution state
 ZK_HD void gadget_misc(const StepCtx& s, bool live) {
   const Fr cs = s.cur(S_STATE);
@@ -1417,6 +1560,7 @@ ZK_HD void gadget_misc(const StepCtx& s, bool live) {
     case ZK_ES_BlockCtx: gadget_blockctx(s, live); break;
     case ZK_ES_ORIGIN: gadget_txctx(s, live, 0x32, ZK_TX_CallerAddress); break;
     case ZK_ES_GASPRICE: gadget_txctx(s, live, 0x3a, ZK_TX_GasPrice); break;
+    case ZK_ES_SHL_SHR: gadget_shl_shr(s, live); break;
     default: break;
   }
 }
