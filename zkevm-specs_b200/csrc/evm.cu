@@ -802,6 +802,26 @@ ZK_HD void gadget_pop(const StepCtx& s, bool live) {
   same_context(s, opcode, 1, fr_u64(1), fr_u64(1));
 }
 
+// Out-of-line copies of the shared lookups / epilogue for the RARE gate programs below: k_evm_misc holds
+// two dozen gate programs, and with every lookup inlined (hash path + positional path each) it took
+// ptxas 140 s to compile; the hot kernels keep the inlined forms.
+ZK_HD_NOINLINE int rw_lookup_ni(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
+                                Word2* value) {
+  return rw_lookup(s, live, rwc, rw, tag, id, addr, value);
+}
+ZK_HD_NOINLINE int bytecode_lookup_ni(const StepCtx& s, bool live, const Fr& hlo, const Fr& hhi, u64 tag, const Fr& index,
+                                      u64 is_code, Fr* value) {
+  return bytecode_lookup(s, live, hlo, hhi, tag, index, is_code, value);
+}
+ZK_HD_NOINLINE bool opcode_lookup_ni(const StepCtx& s, bool live, Fr* opcode) { return opcode_lookup(s, live, opcode); }
+ZK_HD_NOINLINE void same_context_x_ni(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
+                                      bool mem_to, const Fr& mem_value, const Fr& dyn_gas) {
+  same_context_x(s, opcode, d_rwc, d_pc, d_sp, mem_to, mem_value, dyn_gas);
+}
+ZK_HD_NOINLINE void same_context_ni(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
+  same_context_x(s, opcode, fr_u64(d_rwc), d_pc, d_sp, false, fr_u64(0), fr_u64(0));
+}
+
 // ---- SHA3 (execution/sha3.py:6-55) and CALLDATACOPY (execution/calldatacopy.py:6-62) ----------
 // word_to_fq(word, 5) (instruction.py:480-484): 0 ok, 1 = to_le_bytes OverflowError, 2 = raise
 ZK_HD int word_to_fq5(const Word2& w, Fr* out) {
@@ -813,7 +833,7 @@ ZK_HD int word_to_fq5(const Word2& w, Fr* out) {
 ZK_HD u64 memory_gas_cost(u64 size) { return size * size / 512 + 3 * size; }  // size < 2^32 (instruction.py:1129-1136)
 // memory_expansion_dynamic_length + memory_copier_gas_cost (instruction.py:1157-1192): 0 ok, else
 // 1 + index of the failing check in {MEMSIZE_RANGE, MAX_RANGE, WORDSIZE_RANGE, GASCOST_RANGE}
-ZK_HD int copier_gas(const StepCtx& s, u64 offset, u64 length, u64 per_word, Fr* next_mem, Fr* gas) {
+ZK_HD_NOINLINE int copier_gas(const StepCtx& s, u64 offset, u64 length, u64 per_word, Fr* next_mem, Fr* gas) {
   const u64 cd_size = (offset + length + 31) / 32;  // offset, length < 2^40
   if (cd_size >> 32) return 1;
   const Fr cur = s.cur(S_MEM);
@@ -829,7 +849,7 @@ ZK_HD int copier_gas(const StepCtx& s, u64 offset, u64 length, u64 per_word, Fr*
   return 0;
 }
 // copy_lookup (instruction.py:1361-1386, table.py:760-787); ids are values (hi half 0)
-ZK_HD int copy_lookup(const StepCtx& s, bool live, const Fr& src_id, u64 src_tag, const Fr& dst_id, u64 dst_tag,
+ZK_HD_NOINLINE int copy_lookup(const StepCtx& s, bool live, const Fr& src_id, u64 src_tag, const Fr& dst_id, u64 dst_tag,
                       const Fr& src_addr, const Fr& src_end, const Fr& dst_addr, const Fr& length, const Fr& rwc,
                       Fr* rwc_inc, Fr* rlc_acc) {
   Fr key[11] = {src_id, fr_u64(0), fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end,
@@ -843,7 +863,7 @@ ZK_HD int copy_lookup(const StepCtx& s, bool live, const Fr& src_id, u64 src_tag
   return n;
 }
 // call_context_lookup: rw row (rw_counter, Read, CallContext, call_id, address = field tag)
-ZK_HD int call_context(const StepCtx& s, bool live, const Fr& rwc, const Fr& call_id, u64 field_tag, Fr* value,
+ZK_HD_NOINLINE int call_context(const StepCtx& s, bool live, const Fr& rwc, const Fr& call_id, u64 field_tag, Fr* value,
                        bool* is_word) {
   Fr key[5] = {rwc, fr_u64(0), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
   u32 r;
@@ -862,16 +882,16 @@ ZK_HD int call_context(const StepCtx& s, bool live, const Fr& rwc, const Fr& cal
     }                             \
   } while (0)
 
-ZK_HD void gadget_sha3(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_sha3(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Fr sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 off_w = zero, size_w = zero, val_w = zero;
-  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &off_w), EV_SHA_OFF_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &size_w), EV_SHA_SIZE_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &val_w), EV_SHA_VAL_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &off_w), EV_SHA_OFF_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &size_w), EV_SHA_SIZE_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &val_w), EV_SHA_VAL_UNSAT);
   Fr length = fr_u64(0), offset = fr_u64(0);
   if (live) {
     int rc = word_to_fq5(size_w, &length);
@@ -901,18 +921,18 @@ ZK_HD void gadget_sha3(const StepCtx& s, bool live) {
   Fr next_mem, gas;
   const int rc = copier_gas(s, offset.l[0], length.l[0], ZK_GAS_COST_COPY_SHA3, &next_mem, &gas);
   EV_CHECK(EV_SHA_MEMSIZE_RANGE + rc - 1, rc == 0);
-  same_context_x(s, opcode, fr_add_u64(rwc_inc, 3), fr_u64(1), fr_u64(1), true, next_mem, gas);
+  same_context_x_ni(s, opcode, fr_add_u64(rwc_inc, 3), fr_u64(1), fr_u64(1), true, next_mem, gas);
 }
 
-ZK_HD void gadget_calldatacopy(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_calldatacopy(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 moff_w = zero, doff_w = zero, len_w = zero;
-  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &moff_w), EV_CDC_MOFF_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 1), &doff_w), EV_CDC_DOFF_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 2), &len_w), EV_CDC_LEN_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &moff_w), EV_CDC_MOFF_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 1), &doff_w), EV_CDC_DOFF_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, fr_add_u64(rwc, 2), 0, ZK_TARGET_Stack, call_id, fr_add_u64(sp, 2), &len_w), EV_CDC_LEN_UNSAT);
   Fr length = fr_u64(0), moff = fr_u64(0), doff = fr_u64(0);
   if (live) {
     int rc = word_to_fq5(len_w, &length);
@@ -957,12 +977,12 @@ ZK_HD void gadget_calldatacopy(const StepCtx& s, bool live) {
     if (go) live = need1(s, live, n, EV_CDC_COPY_UNSAT);
   }
   if (!live) return;
-  same_context_x(s, opcode, fr_add_u64(rwc_inc, k), fr_u64(1), fr_u64(3), true, next_mem, gas);
+  same_context_x_ni(s, opcode, fr_add_u64(rwc_inc, k), fr_u64(1), fr_u64(3), true, next_mem, gas);
 }
 
 // ---- STOP (execution/stop.py:7-51) ------------------------------------------------------------
 // call_context_lookup_word: rw row (rw_counter, rw, CallContext, call_id, address = field tag)
-ZK_HD int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u64 rw, const Fr& call_id, u64 field_tag,
+ZK_HD_NOINLINE int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u64 rw, const Fr& call_id, u64 field_tag,
                          Word2* value, bool* is_word) {
   Fr key[5] = {rwc, fr_u64(rw), fr_u64(ZK_TARGET_CallContext), call_id, fr_u64(field_tag)};
   u32 r;
@@ -977,7 +997,7 @@ ZK_HD int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u64 rw, con
 // step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None:
 // rw_off = rw lookups the gadget already did; add_rev = the current state halts in success.
 // Lookup k has ids EV_RST0_UNSAT + 3k (+1 ambiguous, +2 value type / written value).
-ZK_HD void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
+ZK_HD_NOINLINE void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
                            const Fr& gas_left, bool add_rev) {
   const u64 READ_TAGS[8] = {ZK_CC_IsRoot,       ZK_CC_IsCreate, ZK_CC_CodeHash,   ZK_CC_ProgramCounter,
                             ZK_CC_StackPointer, ZK_CC_GasLeft,  ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
@@ -1018,16 +1038,16 @@ ZK_HD void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& re
   EV_CHECK(EV_RST_REV, fr_eq(s.nxt(S_REV), add_rev ? fr_add(vals[7].lo, s.cur(S_REV)) : vals[7].lo));
 }
 
-ZK_HD void gadget_stop(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_stop(const StepCtx& s, bool live) {
   const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI), pc = s.cur(S_PC);
   Fr code_length = fr_u64(0);
-  live = need1(s, live, bytecode_lookup(s, live, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_STOP_LEN_UNSAT);
+  live = need1(s, live, bytecode_lookup_ni(s, live, hlo, hhi, 1, fr_u64(0), 0, &code_length), EV_STOP_LEN_UNSAT);
   EV_LIVE_CHECK(EV_STOP_CMP_RANGE, fr_fits64(code_length) && fr_fits64(pc));
   {
     // is_within_range = 1 - lt(code_length, pc) - eq(code_length, pc)  (stop.py:12-18)
     const bool go = live && code_length.l[0] > pc.l[0];
     Fr opcode = fr_u64(0);
-    const int n = bytecode_lookup(s, go, hlo, hhi, 2, pc, 1, &opcode);
+    const int n = bytecode_lookup_ni(s, go, hlo, hhi, 2, pc, 1, &opcode);
     if (go) {
       live = need1(s, live, n, EV_STOP_OP_UNSAT);
       EV_LIVE_CHECK(EV_STOP_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
@@ -1052,13 +1072,13 @@ ZK_HD void gadget_stop(const StepCtx& s, bool live) {
 // NB the byte values are NOT constrained by the reference: `instruction.is_equal(memory_lookup(..),
 // byte)` only computes a flag (memory.py:26,31-36); each of the 1 / 32 memory rows must exist, be
 // unique and hold a value (not a Word).
-ZK_HD void gadget_memory(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_memory(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 addr_w = zero, val_w = zero;
-  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &addr_w), EV_MEM_ADDR_UNSAT);
+  live = need1(s, live, rw_lookup_ni(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &addr_w), EV_MEM_ADDR_UNSAT);
   EV_LIVE_CHECK(EV_MEM_ADDR_BYTES, word_in_domain(addr_w));
   EV_LIVE_CHECK(EV_MEM_ADDR_RANGE, (addr_w.hi.l[0] >> 32) == 0 && addr_w.hi.l[1] == 0);  // bytes 20..31 zero
   Fr address = addr_w.lo;
@@ -1067,7 +1087,7 @@ ZK_HD void gadget_memory(const StepCtx& s, bool live) {
   const bool is_store = !is_mload;
   // value: stack_push() at the popped slot for MLOAD, a second stack_pop() otherwise (memory.py:17)
   live = need1(s, live,
-               rw_lookup(s, live, fr_add_u64(rwc, 1), is_mload ? 1 : 0, ZK_TARGET_Stack, call_id,
+               rw_lookup_ni(s, live, fr_add_u64(rwc, 1), is_mload ? 1 : 0, ZK_TARGET_Stack, call_id,
                          is_mload ? sp : fr_add_u64(sp, 1), &val_w),
                EV_MEM_VAL_UNSAT);
   EV_LIVE_CHECK(EV_MEM_VAL_BYTES, word_in_domain(val_w));
@@ -1094,29 +1114,29 @@ ZK_HD void gadget_memory(const StepCtx& s, bool live) {
   }
   if (!live) return;
   const Fr gas = fr_u64(memory_gas_cost(nxt) - memory_gas_cost(cur_mem.l[0]));
-  same_context_x(s, opcode, fr_u64(is_mstore8 ? 3 : 34), fr_u64(1), fr_u64(is_store ? 2 : 0), true, fr_u64(nxt), gas);
+  same_context_x_ni(s, opcode, fr_u64(is_mstore8 ? 3 : 34), fr_u64(1), fr_u64(is_store ? 2 : 0), true, fr_u64(nxt), gas);
 }
 
 // ---- simple same-context gadgets: msize.py, gas.py, iszero.py, comparator.py, jump.py, jumpi.py ----
 ZK_HD bool word_is(const Word2& w, const Fr& lo) { return fr_eq(w.lo, lo) && fr_is_zero(w.hi); }
 // one stack_push / stack_pop lookup at rw_counter + k
-ZK_HD int stack_at(const StepCtx& s, bool live, u64 k, u64 rw, const Fr& sp, Word2* out) {
-  return rw_lookup(s, live, fr_add_u64(s.cur(S_RWC), k), rw, ZK_TARGET_Stack, s.cur(S_CALL_ID), sp, out);
+ZK_HD_NOINLINE int stack_at(const StepCtx& s, bool live, u64 k, u64 rw, const Fr& sp, Word2* out) {
+  return rw_lookup_ni(s, live, fr_add_u64(s.cur(S_RWC), k), rw, ZK_TARGET_Stack, s.cur(S_CALL_ID), sp, out);
 }
-ZK_HD void gadget_msize(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_msize(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr v = fr_montmul(s.cur(S_MEM), fr_to_mont(fr_u64(32)));  // memory_word_size * N_BYTES_WORD over the field
   EV_LIVE_CHECK(EV_MSZ_WORD, fr_fits128(v));
   Word2 w{fr_u64(0), fr_u64(0)};
   live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_MSZ_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_MSZ_EQ, word_is(w, v));
   if (!live) return;
-  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
-ZK_HD void gadget_gas(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_gas(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_GAS_OPCODE, fr_eq_u64(opcode, 0x5a));
   const Fr v = fr_sub_u64(s.cur(S_GAS), 2);  // Opcode.GAS.constant_gas_cost() == 2
   EV_LIVE_CHECK(EV_GAS_WORD, fr_fits128(v));
@@ -1124,21 +1144,21 @@ ZK_HD void gadget_gas(const StepCtx& s, bool live) {
   live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_GAS_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_GAS_EQ, word_is(w, v));
   if (!live) return;
-  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
-ZK_HD void gadget_iszero(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_iszero(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   Word2 v{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
   live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &v), EV_ISZ_POP_UNSAT);
   live = need1(s, live, stack_at(s, live, 1, 1, s.cur(S_SP), &w), EV_ISZ_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_ISZ_EQ, word_is(w, fr_u64(fr_is_zero(fr_add(v.lo, v.hi)) ? 1 : 0)));  // is_zero_word: field sum
   if (!live) return;
-  same_context(s, opcode, 2, fr_u64(1), fr_u64(0));
+  same_context_ni(s, opcode, 2, fr_u64(1), fr_u64(0));
 }
-ZK_HD void gadget_cmp(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_cmp(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const bool is_eq = fr_eq_u64(opcode, 0x14), is_gt = fr_eq_u64(opcode, 0x11);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
@@ -1153,25 +1173,25 @@ ZK_HD void gadget_cmp(const StepCtx& s, bool live) {
   const bool lt = lt_hi || (eq_hi && lt_lo), eq = eq_lo && eq_hi;
   EV_LIVE_CHECK(EV_CMP_EQ, word_is(c, fr_u64((is_eq ? eq : lt) ? 1 : 0)));
   if (!live) return;
-  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+  same_context_ni(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
-ZK_HD void gadget_jump(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_jump(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_JMP_OPCODE, fr_eq_u64(opcode, 0x56));
   Word2 dest{fr_u64(0), fr_u64(0)};
   live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &dest), EV_JMP_DEST_UNSAT);
   EV_LIVE_CHECK(EV_JMP_DEST_HI, fr_is_zero(dest.hi));
   Fr at = fr_u64(0);  // opcode_lookup_at(dest, True), instruction.py:789-790
-  live = need1(s, live, bytecode_lookup(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, dest.lo, 1, &at), EV_JMP_AT_UNSAT);
+  live = need1(s, live, bytecode_lookup_ni(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 2, dest.lo, 1, &at), EV_JMP_AT_UNSAT);
   EV_LIVE_CHECK(EV_JMP_NOT_JUMPDEST, fr_eq_u64(at, 0x5b));
   if (!live) return;
   // program_counter = Transition.to(dest): next.pc == dest, i.e. the delta dest - pc over the field
-  same_context(s, opcode, 1, fr_sub(dest.lo, s.cur(S_PC)), fr_u64(1));
+  same_context_ni(s, opcode, 1, fr_sub(dest.lo, s.cur(S_PC)), fr_u64(1));
 }
-ZK_HD void gadget_jumpi(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_jumpi(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_JMPI_OPCODE, fr_eq_u64(opcode, 0x57));
   Word2 dest{fr_u64(0), fr_u64(0)}, cond{fr_u64(0), fr_u64(0)};
   live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &dest), EV_JMPI_DEST_UNSAT);
@@ -1181,14 +1201,14 @@ ZK_HD void gadget_jumpi(const StepCtx& s, bool live) {
   // jumpi.py:20 `if instruction.is_zero_word(cond):` tests the truthiness of an FQ OBJECT (py_ecc's FQ
   // defines neither __bool__ nor __len__), which is always true: the reference takes the fall-through
   // branch (pc + 1) whatever cond is and never looks at the destination.  Reproduced as written.
-  same_context(s, opcode, 2, fr_u64(1), fr_u64(2));
+  same_context_ni(s, opcode, 2, fr_u64(1), fr_u64(2));
 }
 
 // caller.py / callvalue.py / calldatasize.py / address.py / returndatasize.py: constrain the opcode,
 // read one call-context field (as a Word, or as a value wrapped by Word.from_lo), push it
-ZK_HD void gadget_cc_push(const StepCtx& s, bool live, u64 op, u64 field, bool as_word) {
+ZK_HD_NOINLINE void gadget_cc_push(const StepCtx& s, bool live, u64 op, u64 field, bool as_word) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_CCP_OPCODE, fr_eq_u64(opcode, op));
   Word2 v{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
   bool is_word = false;
@@ -1201,20 +1221,20 @@ ZK_HD void gadget_cc_push(const StepCtx& s, bool live, u64 op, u64 field, bool a
   live = need1(s, live, stack_at(s, live, 1, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_CCP_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_CCP_EQ, word_eq(w, v));
   if (!live) return;
-  same_context(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
-ZK_HD void gadget_codesize(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_codesize(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_CSZ_OPCODE, fr_eq_u64(opcode, 0x38));
   Fr len = fr_u64(0);  // bytecode_length(code_hash): the Header row (instruction.py:772-777)
-  live = need1(s, live, bytecode_lookup(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 1, fr_u64(0), 0, &len), EV_CSZ_LEN_UNSAT);
+  live = need1(s, live, bytecode_lookup_ni(s, live, s.cur(S_HASH_LO), s.cur(S_HASH_HI), 1, fr_u64(0), 0, &len), EV_CSZ_LEN_UNSAT);
   EV_LIVE_CHECK(EV_CSZ_WORD, fr_fits128(len));
   Word2 w{fr_u64(0), fr_u64(0)};
   live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_CSZ_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_CSZ_EQ, word_is(w, len));
   if (!live) return;
-  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
 
 // ---- BITWISE = AND / OR / XOR (bitwise.py), NOT (not_.py), BYTE (byte.py) ------------------------
@@ -1224,7 +1244,7 @@ ZK_HD u64 word_byte(const Word2& w, int k) {  // k-th little-endian byte of a wo
   return (c.l[k >> 3] >> (8 * (k & 7))) & 0xFF;
 }
 // 32 fixed-table lookups (tag, a[i], b[i], c[i]); returns false after recording the first failure
-ZK_HD bool fixed_bytes32(const StepCtx& s, bool live, u64 tag, const Word2& a, const Word2& b, const Word2* c, u64 c_const,
+ZK_HD_NOINLINE bool fixed_bytes32(const StepCtx& s, bool live, u64 tag, const Word2& a, const Word2& b, const Word2* c, u64 c_const,
                          int id_unsat) {
   for (int k = 0; k < 32; k++) {
     Fr key[4] = {fr_u64(tag), fr_u64(word_byte(a, k)), fr_u64(word_byte(b, k)), fr_u64(c ? word_byte(*c, k) : c_const)};
@@ -1234,9 +1254,9 @@ ZK_HD bool fixed_bytes32(const StepCtx& s, bool live, u64 tag, const Word2& a, c
   }
   return live;
 }
-ZK_HD void gadget_bitwise(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_bitwise(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 a = zero, b = zero, c = zero;
@@ -1249,11 +1269,11 @@ ZK_HD void gadget_bitwise(const StepCtx& s, bool live) {
   const u64 tag = opcode.l[0] + ZK_FIXED_BitwiseAnd - 0x16;
   live = fixed_bytes32(s, live, tag, a, b, &c, 0, EV_BW_FIXED_UNSAT);
   if (!live) return;
-  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+  same_context_ni(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
-ZK_HD void gadget_not(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_not(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 a = zero, b = zero;
   live = need1(s, live, stack_at(s, live, 0, 0, s.cur(S_SP), &a), EV_NOT_A_UNSAT);
@@ -1262,11 +1282,11 @@ ZK_HD void gadget_not(const StepCtx& s, bool live) {
   EV_LIVE_CHECK(EV_NOT_B_BYTES, word_in_domain(b));
   live = fixed_bytes32(s, live, ZK_FIXED_BitwiseXor, a, b, nullptr, 255, EV_NOT_FIXED_UNSAT);
   if (!live) return;
-  same_context(s, opcode, 2, fr_u64(1), fr_u64(0));
+  same_context_ni(s, opcode, 2, fr_u64(1), fr_u64(0));
 }
-ZK_HD void gadget_byte(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_byte(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 a = zero, b = zero, c = zero;
@@ -1280,13 +1300,13 @@ ZK_HD void gadget_byte(const StepCtx& s, bool live) {
   const u64 idx0 = a.lo.l[0] & 0xFF;
   const u64 sel = (msb_zero && idx0 < 32) ? word_byte(b, 31 - (int)idx0) : 0;
   EV_CHECK(EV_BYTE_EQ, word_is(c, fr_u64(sel)));
-  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+  same_context_ni(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
 
 // ---- SCMP = SLT / SGT (slt_sgt.py), SIGNEXTEND (signextend.py) -----------------------------------
-ZK_HD void gadget_scmp(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_scmp(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const bool is_sgt = fr_eq_u64(opcode, 0x13);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
@@ -1303,14 +1323,14 @@ ZK_HD void gadget_scmp(const StepCtx& s, bool live) {
   const bool a_neg = word_byte(aa, 31) >= 128, b_neg = word_byte(bb, 31) >= 128;
   const bool expect = (a_neg && !b_neg) ? true : ((b_neg && !a_neg) ? false : a_lt_b);
   EV_CHECK(EV_SCMP_EQ, word_is(c, fr_u64(expect ? 1 : 0)));  // cc = low 31 bytes of c; byte 31 is zero here
-  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+  same_context_ni(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
 // signextend.py: the byte-by-byte `is_equal` calls constrain nothing; what remains is the
 // sign_byte_lookup of the selected byte (signextend.py:44) — note that sign_byte ignores
 // is_msb_sum_zero while selected_byte does not (reproduced)
-ZK_HD void gadget_signextend(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_signextend(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 index = zero, value = zero, result = zero;
@@ -1329,14 +1349,14 @@ ZK_HD void gadget_signextend(const StepCtx& s, bool live) {
     live = need1(s, live, m, EV_SEXT_SIGN_UNSAT);
   }
   if (!live) return;
-  same_context(s, opcode, 3, fr_u64(1), fr_u64(1));
+  same_context_ni(s, opcode, 3, fr_u64(1), fr_u64(1));
 }
 
 // ---- BlockCtx (block_ctx.py: COINBASE / TIMESTAMP / NUMBER / PREVRANDAO / GASLIMIT / CHAINID / BASEFEE),
 // ORIGIN (origin.py), GASPRICE (gasprice.py): a block-table / tx-table word pushed on the stack -----
-ZK_HD void gadget_blockctx(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_blockctx(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   u64 tag = 0;  // BlockContextFieldTag of the opcode (block_ctx.py:10-24); none: `op` stays unbound
   if (fr_fits64(opcode)) switch (opcode.l[0]) {
       case 0x41: tag = 1; break;  // COINBASE -> Coinbase
@@ -1363,16 +1383,16 @@ ZK_HD void gadget_blockctx(const StepCtx& s, bool live) {
   live = need1(s, live, stack_at(s, live, 0, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_BLK_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_BLK_EQ, word_eq(w, ctx));
   if (!live) return;
-  same_context(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 1, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
-ZK_HD void gadget_txctx(const StepCtx& s, bool live, u64 op, u64 field) {
+ZK_HD_NOINLINE void gadget_txctx(const StepCtx& s, bool live, u64 op, u64 field) {
   // the call-context lookup comes BEFORE the opcode lookup here (origin.py:8-9)
   Word2 v{fr_u64(0), fr_u64(0)}, ctx{fr_u64(0), fr_u64(0)}, w{fr_u64(0), fr_u64(0)};
   bool is_word = false;
   live = need1(s, live, call_context_w(s, live, s.cur(S_RWC), 0, s.cur(S_CALL_ID), ZK_CC_TxId, &v, &is_word), EV_TXC_TXID_UNSAT);
   EV_LIVE_CHECK(EV_TXC_TXID_TYPE, !is_word);
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   EV_LIVE_CHECK(EV_TXC_OPCODE, fr_eq_u64(opcode, op));
   {
     Fr key[3] = {v.lo, fr_u64(field), fr_u64(0)};
@@ -1387,7 +1407,7 @@ ZK_HD void gadget_txctx(const StepCtx& s, bool live, u64 op, u64 field) {
   live = need1(s, live, stack_at(s, live, 1, 1, fr_sub_u64(s.cur(S_SP), 1), &w), EV_TXC_PUSH_UNSAT);
   EV_LIVE_CHECK(EV_TXC_EQ, word_eq(w, ctx));
   if (!live) return;
-  same_context(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
+  same_context_ni(s, opcode, 2, fr_u64(1), fr_sub(fr_u64(0), fr_u64(1)));
 }
 
 // ---- SHL_SHR (shl_shr.py): push == pop2 << pop1 / pop2 >> pop1 through a division witness --------
@@ -1436,9 +1456,9 @@ ZK_HD U640 u640_sub(const U640& a, const U640& b) {
   for (int k = 0; k < 10; k++) r.l[k] = sbb64(a.l[k], b.l[k], br);
   return r;
 }
-ZK_HD void gadget_shl_shr(const StepCtx& s, bool live) {
+ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
   Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
+  live = opcode_lookup_ni(s, live, &opcode);
   const Fr sp = s.cur(S_SP), sp1 = fr_add_u64(sp, 1), one = fr_u64(1);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 pop1 = zero, pop2 = zero, push = zero;
@@ -1529,7 +1549,7 @@ ZK_HD void gadget_shl_shr(const StepCtx& s, bool live) {
     if (go) live = need1(s, live, m, EV_SH_POW2_UNSAT);
   }
   if (!live) return;
-  same_context(s, opcode, 3, one, one);
+  same_context_ni(s, opcode, 3, one, one);
 }
 
 // the rare states: one thread per step, dispatch on the execution state
