@@ -1,13 +1,17 @@
-// evm.cu — EVM-circuit step checker (one thread per execution step).
+// evm.cu — EVM-circuit step checker.
 //
 // Replaces the loop body of verify_steps / verify_step
 // (src/zkevm_specs/evm_circuit/main.py:14-63): state-transition legality
-// (instruction.py:189-204), one gadget per execution state, and the shared epilogue
-// step_state_transition_in_same_context (instruction.py:365-394, 206-264).  Gate programs in
-// this build: ADD/SUB (execution/add_sub.py:5-24), MUL/DIV/MOD (mul_div_mod.py:6-71 with
-// mul_add_words instruction.py:599-632 and compare_word :453-463), PUSH (push.py:6-33),
-// POP (pop.py:4-14), SHA3 (sha3.py:6-55), CALLDATACOPY (calldatacopy.py:6-62).  Every lookup() of the reference (table.py:864-884, a linear scan over
-// a Python set) is a probe of a device hash index (lookup.cuh).
+// (instruction.py:189-204), one gate program per execution state, and the shared epilogue
+// step_state_transition_in_same_context (instruction.py:365-394, 206-264).
+// Hot gate programs (a kernel each): ADD/SUB (execution/add_sub.py:5-24), MUL/DIV/MOD
+// (mul_div_mod.py:6-71 with mul_add_words instruction.py:599-632 and compare_word :453-463), PUSH
+// (push.py:6-33), POP (pop.py:4-14).  Rare gate programs (k_evm_misc, one thread per step, out-of-line
+// lookups): SHA3, CALLDATACOPY, MEMORY, STOP with restore-to-caller-context, MSIZE, GAS, ISZERO, CMP, JUMP,
+// JUMPI, CALLER, CALLVALUE, CALLDATASIZE, ADDRESS, RETURNDATASIZE, CODESIZE, BITWISE, NOT, BYTE, SCMP,
+// SIGNEXTEND, BlockCtx, ORIGIN, GASPRICE, SHL_SHR (their execution/*.py files, cited at each program).
+// Every lookup() of the reference (table.py:864-884, a linear scan over a Python set) is either a
+// positional lookup on a verified-regular table or a probe of a device hash index (lookup.cuh).
 //
 // Step = 13 cells in the order of StepState (evm_circuit/step.py:16-44), code_hash as
 // (lo, hi); rotation {0,+1}.  Algorithmic bytes per step: 13 x 32 B = 416 B, plus the
@@ -593,10 +597,10 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
   same_context(s, opcode, 3, one, one);
 }
 
-// ---- PUSH (execution/push.py:6-33), written as lane functions: on the device one WARP checks
-// one PUSH step — lane L owns pushed byte L (its bytecode lookup + equality), so the 32 table
-// rows of a PUSH32 are fetched as coalesced 1 KiB column segments; tests/emu runs the same lane
-// functions serially.
+// ---- PUSH (execution/push.py:6-33).  Generic (hash-index) form, written as lane functions: in
+// k_evm_push_hash half a warp checks one PUSH step — sub-lane L owns pushed bytes L and L+16 (their
+// bytecode lookups + equalities); tests/emu runs the same lane functions serially.  Positional tables
+// take the thread-per-step form further down (gadget_push_pos1).
 struct PushCommon {
   Fr hlo, hhi, h0, pc, opcode, num_pushed;
   int n_head;  // heads-index probe of the code hash (positional bytecode table)
