@@ -26,7 +26,13 @@
  *
  * Return codes: 0 = the call ran (results are in the output arrays); < 0 = infrastructure
  * error (bad shape, missing table, CUDA error) — zk_last_error() has the text.
- * A context is not thread-safe; use one context per host thread / per GPU.
+ * A context is not thread-safe; use one context per host thread / per GPU, and ONE stream per
+ * context: uploads, index builds and checks are ordered only by the stream they are issued on
+ * (cached lookup indexes are built on the stream of the first check that needs them).  Callers that
+ * use several streams must order them with events themselves.
+ * Cells must be canonical (< p): the reference's FQ() reduces on construction, the Python mirror
+ * does the same before it ships a matrix; a raw caller that uploads unreduced 256-bit values gets
+ * undefined verdicts (field add/sub assume a + b < 2^255).  Challenges are validated.
  */
 #ifndef ZKCHECK_H
 #define ZKCHECK_H
@@ -46,10 +52,11 @@ enum {
   ZK_CIRCUIT_COPY = 2,     /* 20 cells/row, rotation {0,+1,+2}  evm_circuit/table.py:472-491 */
   ZK_CIRCUIT_EVM = 3,      /* 13 cells/step, rotation {0,+1}    evm_circuit/step.py:16-44 */
   ZK_CIRCUIT_EXP = 4,      /* 21 cells/row, rotation {0,+1}     evm_circuit/table.py:519-535 */
-  ZK_CIRCUIT_TX = 5,       /* 134 cells/row, no rotation: one row per tx_index = SignVerifyChip cells
-                              (address, 32 pub_key_x LE bytes, 32 pub_key_y LE bytes, 32 pub_key_hash
-                              bytes, msg_hash lo/hi, 32 msg_hash LE bytes) + the tx-table cells they
-                              are copy-constrained to (CallerAddress value, TxSignHash lo/hi)
+  ZK_CIRCUIT_TX = 5,       /* 14 cells/row, no rotation: one row per tx_index = SignVerifyChip cells
+                              (address, pub_key_x lo/hi, pub_key_y lo/hi, Word(pub_key_hash) lo/hi, msg_hash
+                              lo/hi, Word(msg_hash_bytes) lo/hi — a 32-byte field travels as the Word of its
+                              bytes) + the tx-table cells they are copy-constrained to (CallerAddress value,
+                              TxSignHash lo/hi)
                               tx_circuit.py:160-243, 253-289; row flags bit 0 = the CallerAddress
                               cell is a Word, bit 1 = the (third-party) ECDSA check failed;
                               lookups: ZK_TABLE_KECCAK rows (is_enabled, input_rlc, input_len, out lo, hi) */

@@ -112,27 +112,29 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   }
   d.pos_ok = nullptr;
   d.pos_kind = ZK_POS_NONE;
-  d.heads_slots = nullptr;
+  d.heads = nullptr;
   d.heads_mask = 0;
-  d.heads_len = d.heads_list = d.heads_count = nullptr;
+  for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;
+  d.heads_list = d.heads_count = nullptr;
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
   return d;
 }
 // positional structure of a table, verified exactly like k_pos_verify does on the device
 struct PosState {
   u32 ok = 1;
-  std::vector<u64> heads;
+  std::vector<HeadEnt> heads;
   std::vector<u32> aux;
 };
 static void add_positional(IndexDev& d, u32 kind, PosState& st) {
   d.pos_kind = kind;
-  st.heads.assign(1u << 10, ZK_EMPTY_SLOT);
-  d.heads_slots = st.heads.data();
+  HeadEnt empty;
+  memset(&empty, 0xFF, sizeof(empty));
+  st.heads.assign(1u << 10, empty);
+  d.heads = st.heads.data();
   d.heads_mask = (1u << 10) - 1;
-  st.aux.assign(2 * (1u << 10) + 1, 0);
-  d.heads_len = st.aux.data();
-  d.heads_list = st.aux.data() + (1u << 10);
-  d.heads_count = st.aux.data() + 2 * (1u << 10);
+  st.aux.assign((1u << 10) + 1, 0);
+  d.heads_list = st.aux.data();
+  d.heads_count = st.aux.data() + (1u << 10);
   st.ok = 1;
   for (u64 r = 0; r < d.tab.n_rows; r++) {
     if (kind == ZK_POS_DENSE) pos_verify_dense_row(d, &st.ok, r);
@@ -245,7 +247,7 @@ extern "C" int emu_check_bytecode(const uint64_t* cols, uint64_t n_rows, const u
   ResultDev res;
   init_result(res, first_fail, fail_count, BC_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
-  for (u64 i = row_begin; i < row_end; i++) check_bytecode_row(w, rg, push_ix, kec_ix, r_mont, res, i);
+  for (u64 i = row_begin; i < row_end; i++) check_bytecode_row<L_ANY>(w, rg, push_ix, nullptr, kec_ix, r_mont, res, i);
   return 0;
 }
 
@@ -274,7 +276,7 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
   ResultDev res;
   init_result(res, first_fail, fail_count, CP_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
-  for (u64 i = row_begin; i < row_end; i++) check_copy_row(w, rg, t, r_mont, res, i, true, 1u);
+  for (u64 i = row_begin; i < row_end; i++) check_copy_row<L_ANY>(w, rg, t, r_mont, res, i, true, 1u);
   return 0;
 }
 
@@ -290,7 +292,7 @@ extern "C" int emu_check_state(const uint64_t* rows, uint64_t n_rows, const uint
   CheckRange rg{row_begin, row_end, 0, cflags};
   ResultDev res;
   init_result(res, first_fail, fail_count, ST_N_CONSTRAINTS);
-  for (u64 i = row_begin; i < row_end; i++) check_state_row_dev(w, rg, ix, res, i, true, 1u);
+  for (u64 i = row_begin; i < row_end; i++) check_state_row_dev<L_ANY>(w, rg, ix, res, i, true, 1u);
   return 0;
 }
 
@@ -301,7 +303,7 @@ extern "C" int emu_check_exp(const uint64_t* rows, uint64_t n_rows, uint64_t row
   CheckRange rg{row_begin, row_end, 0, cflags};
   ResultDev res;
   init_result(res, first_fail, fail_count, XP_N_CONSTRAINTS);
-  for (u64 i = row_begin; i < row_end; i++) check_exp_row(w, rg, res, i);
+  for (u64 i = row_begin; i < row_end; i++) check_exp_row<L_ANY>(w, rg, res, i);
   return 0;
 }
 
@@ -324,7 +326,8 @@ extern "C" int emu_check_tx(const uint64_t* rows, uint64_t n_rows, const uint8_t
   ResultDev res;
   init_result(res, first_fail, fail_count, TX_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
-  for (u64 i = row_begin; i < row_end; i++) check_tx_row(w, kix, r_mont, res, i);
+  CheckRange rg{row_begin, row_end, 0, 0};
+  for (u64 i = row_begin; i < row_end; i++) check_tx_row(w, rg, kix, r_mont, res, i);
   return 0;
 }
 
@@ -340,7 +343,8 @@ extern "C" int emu_check_sig(const uint64_t* rows, uint64_t n_rows, const uint8_
   ResultDev res;
   init_result(res, first_fail, fail_count, SG_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
-  for (u64 i = row_begin; i < row_end; i++) check_sig_row(w, kix, r_mont, res, i);
+  CheckRange rg{row_begin, row_end, 0, 0};
+  for (u64 i = row_begin; i < row_end; i++) check_sig_row(w, rg, kix, r_mont, res, i);
   return 0;
 }
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/zk_constraints.h"
@@ -79,8 +80,8 @@ struct Index {
   size_t cap = 0;
   u32 pos_kind = ZK_POS_NONE;
   u32* pos_flag = nullptr;  // device flag written by k_pos_verify
-  u64* heads = nullptr;     // ZK_POS_RUNS heads index
-  u32* heads_aux = nullptr; // [ZK_HEADS_CAP] run lengths, [ZK_HEADS_CAP] head list, [1] count
+  HeadEnt* heads = nullptr;  // ZK_POS_RUNS heads index
+  u32* heads_aux = nullptr;  // [ZK_HEADS_CAP] head list, [1] count
   u64 built_version = ~0ull;
   u64 built_challenge = ~0ull;
   bool empty_ready = false;  // the slot array is all-empty for an empty table (no per-check memset)
@@ -108,8 +109,12 @@ struct zk_ctx {
   u64 resp_bitmap_version = ~0ull;
   unsigned char* stage = nullptr;  // device staging (zk_upload_bytecode_table_from_code)
   size_t stage_cap = 0;
-  u32* evm_lists = nullptr;  // [G_COUNT][cap] step indices + [G_COUNT] counters
-  size_t evm_lists_cap = 0;
+  unsigned char* evm_sort = nullptr;  // EvmSort arrays: bucket[cap] | sorted[cap] | hist, cursor, offs
+  size_t evm_sort_cap = 0;
+  u32* evm_hist_host = nullptr;  // pinned: histogram + positional flag read back after k_evm_classify
+  cudaEvent_t evm_hist_ev = nullptr;
+  int evm_occ[16] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
+  std::unordered_map<const void*, int> occ;  // same, row-circuit kernels (keyed by kernel)
   bool timing = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // start, after index builds, after check kernel
   cudaStream_t ev_mid_stream = nullptr;
@@ -181,7 +186,9 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (r.first_fail) cudaFree(r.first_fail);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
-  if (ctx->evm_lists) cudaFree(ctx->evm_lists);
+  if (ctx->evm_sort) cudaFree(ctx->evm_sort);
+  if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
+  if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
   if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
   delete ctx;
 }
@@ -487,8 +494,8 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     if (pos_kind != ZK_POS_NONE) {
       CK(ctx, cudaMalloc(&ix->pos_flag, sizeof(u32)));
       if (pos_kind == ZK_POS_RUNS) {
-        CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(u64)));
-        CK(ctx, cudaMalloc(&ix->heads_aux, (2 * ZK_HEADS_CAP + 1) * sizeof(u32)));
+        CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(HeadEnt)));
+        CK(ctx, cudaMalloc(&ix->heads_aux, (ZK_HEADS_CAP + 1) * sizeof(u32)));
       }
     }
     ctx->indexes.push_back(ix);
@@ -524,18 +531,18 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   }
   d.pos_ok = nullptr;
   d.pos_kind = ix->pos_kind;
-  d.heads_slots = ix->heads;
+  d.heads = ix->heads;
   d.heads_mask = ZK_HEADS_CAP - 1;
-  d.heads_len = ix->heads_aux;
-  d.heads_list = ix->heads_aux ? ix->heads_aux + ZK_HEADS_CAP : nullptr;
-  d.heads_count = ix->heads_aux ? ix->heads_aux + 2 * ZK_HEADS_CAP : nullptr;
+  for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;  // odd multipliers keyed by the challenge
+  d.heads_list = ix->heads_aux;
+  d.heads_count = ix->heads_aux ? ix->heads_aux + ZK_HEADS_CAP : nullptr;
   const unsigned grid = (unsigned)std::min<u64>((t.n_rows + 255) / 256, (u64)ctx->sm_count * 32);
   if (t.n_rows && ix->pos_kind != ZK_POS_NONE) {
     // verify the regular structure in one streaming pass; the flag stays 1 iff it holds
     k_set_u32<<<1, 1, 0, st>>>(ix->pos_flag, 1u);
     if (ix->heads) {
-      CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(u64), st));
-      CK(ctx, cudaMemsetAsync(ix->heads_aux, 0, (2 * ZK_HEADS_CAP + 1) * sizeof(u32), st));
+      CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(HeadEnt), st));
+      CK(ctx, cudaMemsetAsync(ix->heads_aux, 0, (ZK_HEADS_CAP + 1) * sizeof(u32), st));
     }
     if (ix->pos_kind == ZK_POS_RUNS && m.src_offsets) {
       // unrolled by the library: regular by construction, heads + lengths straight from the offsets
@@ -611,17 +618,39 @@ static WitnessDev witness_dev(const Matrix& m) {
 }
 
 // ------------------------------------------------------------------ dispatch
+static bool is_canonical(const Matrix& m) {
+  for (u32 c = 0; c < m.n_cols; c++)
+    if (m.width[c] != 32) return false;
+  return true;
+}
+// persistent grid: no more blocks than the device keeps resident (occupancy x SMs); threads walk the
+// rows with a grid stride
+template <class K>
+static unsigned grid_persistent(zk_ctx* ctx, K kernel, int threads, u64 n_items) {
+  const void* key = (const void*)kernel;
+  auto it = ctx->occ.find(key);
+  if (it == ctx->occ.end()) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    it = ctx->occ.emplace(key, occ).first;
+  }
+  const u64 want = (n_items + threads - 1) / threads;
+  return (unsigned)std::max<u64>(1, std::min<u64>(want, (u64)it->second * ctx->sm_count));
+}
 static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const u32 pk[2] = {0, 1}, kk[5] = {0, 1, 2, 3, 4};
   IndexDev push_ix, kec_ix;
   int rc;
-  if ((rc = ensure_index(ctx, ZK_TABLE_PUSH, pk, 2, st, &push_ix))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_PUSH, pk, 2, st, &push_ix, ZK_POS_DENSE))) return rc;
   if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 5, st, &kec_ix))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
-  k_check_bytecode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-      witness_dev(ctx->circ[ZK_CIRCUIT_BYTECODE]), rg, push_ix, kec_ix, r_mont, res);
+  const Matrix& m = ctx->circ[ZK_CIRCUIT_BYTECODE];
+  if (is_canonical(m))
+    k_check_bytecode<L_CANON><<<grid_persistent(ctx, k_check_bytecode<L_CANON>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
+  else
+    k_check_bytecode<L_ANY><<<grid_persistent(ctx, k_check_bytecode<L_ANY>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
   return 0;
@@ -650,8 +679,8 @@ static int check_exp(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   int rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
-  k_check_exp<<<grid, 128, 0, st>>>(witness_dev(m), rg, res);
+  if (is_canonical(m)) k_check_exp<L_CANON><<<grid_persistent(ctx, k_check_exp<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, res);
+  else k_check_exp<L_ANY><<<grid_persistent(ctx, k_check_exp<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
   return 0;
@@ -667,8 +696,8 @@ static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStr
   if ((rc = ensure_index(ctx, ZK_TABLE_MPT, k12, 12, st, &mpt))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
-  k_check_state<<<grid, 128, 0, st>>>(witness_dev(m), rg, mpt, res);
+  if (is_canonical(m)) k_check_state<L_CANON><<<grid_persistent(ctx, k_check_state<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, mpt, res);
+  else k_check_state<L_ANY><<<grid_persistent(ctx, k_check_state<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, mpt, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
   return 0;
@@ -686,9 +715,9 @@ static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStre
   if ((rc = ensure_index(ctx, ZK_TABLE_TX, k3, 3, st, &t.tx))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  const unsigned grid = (unsigned)std::min<u64>((n + 127) / 128, (u64)ctx->sm_count * 16);
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
-  k_check_copy<<<grid, 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
+  if (is_canonical(m)) k_check_copy<L_CANON><<<grid_persistent(ctx, k_check_copy<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
+  else k_check_copy<L_ANY><<<grid_persistent(ctx, k_check_copy<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
   return 0;
@@ -723,34 +752,82 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   t.resp_bitmap = ctx->resp_bitmap;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  // per-gadget step lists (bucket by execution state), then one kernel per gate program
-  if (n > ctx->evm_lists_cap) {
-    if (ctx->evm_lists) cudaFree(ctx->evm_lists);
-    ctx->evm_lists = nullptr;
-    CK(ctx, cudaMalloc(&ctx->evm_lists, (G_COUNT * n + G_COUNT) * sizeof(u32)));
-    ctx->evm_lists_cap = n;
+  // counting sort of the steps by execution state (k_evm_classify + k_evm_scatter), then one kernel
+  // per non-empty gate-program group
+  auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
+  if (n > ctx->evm_sort_cap) {
+    if (ctx->evm_sort) cudaFree(ctx->evm_sort);
+    ctx->evm_sort = nullptr;
+    CK(ctx, cudaMalloc(&ctx->evm_sort, up256(n) + up256(n * 4) + (3 * ZK_EVM_NB + 2) * sizeof(u32)));
+    ctx->evm_sort_cap = n;
   }
-  EvmLists lists;
-  lists.cap = (u32)ctx->evm_lists_cap;
-  lists.idx = ctx->evm_lists;
-  lists.count = ctx->evm_lists + (size_t)G_COUNT * ctx->evm_lists_cap;
-  CK(ctx, cudaMemsetAsync(lists.count, 0, G_COUNT * sizeof(u32), st));
+  if (!ctx->evm_hist_host) {
+    CK(ctx, cudaHostAlloc(&ctx->evm_hist_host, (ZK_EVM_NB + 1) * sizeof(u32), cudaHostAllocDefault));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->evm_hist_ev, cudaEventDisableTiming));
+  }
+  EvmSort so;
+  so.bucket = ctx->evm_sort;
+  so.sorted = (u32*)(ctx->evm_sort + up256(ctx->evm_sort_cap));
+  so.hist = (u32*)(ctx->evm_sort + up256(ctx->evm_sort_cap) + up256(ctx->evm_sort_cap * 4));
+  so.cursor = so.hist + ZK_EVM_NB + 1;
+  so.offs = so.cursor + ZK_EVM_NB;
+  CK(ctx, cudaMemsetAsync(so.hist, 0, (2 * ZK_EVM_NB + 1) * sizeof(u32), st));
   const WitnessDev wd = witness_dev(m);
-  k_evm_classify<<<(unsigned)((n + 1023) / 1024), 1024, 0, st>>>(wd, rg, t, res, lists);
-  // persistent grids sized in multiples of the SM count; each walks its list with a grid stride
-  const unsigned full = (unsigned)((n + 127) / 128);
-  const unsigned grid_t = std::min<unsigned>(full, (unsigned)ctx->sm_count * 8);
-  const unsigned grid_w = std::min<unsigned>((unsigned)((n * 32 + 127) / 128), (unsigned)ctx->sm_count * 12);
-  k_evm_push_pos<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_push_hash<<<grid_w, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_ADD, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_MUL, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_POP, true><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_ADD, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_MUL, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_gadget<G_POP, false><<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  k_evm_misc<<<grid_t, 128, 0, st>>>(wd, rg, t, res, lists);
-  ctx->launches += 10;
+  const unsigned sort_grid = (unsigned)((n + 1023) / 1024);
+  k_evm_classify<<<sort_grid, 1024, 0, st>>>(wd, rg, t, res, so);
+  CK(ctx, cudaMemcpyAsync(ctx->evm_hist_host, so.hist, (ZK_EVM_NB + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaEventRecord(ctx->evm_hist_ev, st));
+  k_evm_scatter<<<sort_grid, 1024, 0, st>>>(so, (u32)n);
+  ctx->launches += 2;
+  CK(ctx, cudaGetLastError());
+  // the histogram decides which groups run and how large their grids are; the device keeps working on
+  // the scatter meanwhile
+  CK(ctx, cudaEventSynchronize(ctx->evm_hist_ev));
+  const u32* hist = ctx->evm_hist_host;
+  const bool pos = hist[ZK_EVM_NB] != 0;
+  u64 group_n[KG_COUNT] = {0};
+  for (int b = 0; b < ZK_EVM_NB; b++) {
+    const int g = es_group(b);
+    if (g >= 0) group_n[g] += hist[b];
+  }
+  // persistent grids: at most the number of blocks the device keeps resident (occupancy x SMs), each
+  // thread walks its bucket with a grid stride
+  auto grid_for = [&](int slot, const void* kernel, u64 work_items, unsigned per_block) -> unsigned {
+    if (!ctx->evm_occ[slot]) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 128, 0) != cudaSuccess || occ < 1) occ = 1;
+      ctx->evm_occ[slot] = occ;
+    }
+    const u64 want = (work_items + per_block - 1) / per_block;
+    return (unsigned)std::max<u64>(1, std::min<u64>(want, (u64)ctx->evm_occ[slot] * ctx->sm_count));
+  };
+#define ZK_LAUNCH_GROUP(slot, kernel, items, per_block)                                        \
+  do {                                                                                         \
+    kernel<<<grid_for(slot, (const void*)kernel, items, per_block), 128, 0, st>>>(wd, rg, t, res, so); \
+    ctx->launches++;                                                                           \
+  } while (0)
+  if (group_n[KG_PUSH]) {
+    if (pos) ZK_LAUNCH_GROUP(0, k_evm_push_pos, group_n[KG_PUSH], 128);
+    else ZK_LAUNCH_GROUP(1, k_evm_push_hash, group_n[KG_PUSH], 8);  // half a warp per step
+  }
+  if (group_n[KG_MUL]) {
+    if (pos) ZK_LAUNCH_GROUP(2, (k_evm_gadget<KG_MUL, true>), group_n[KG_MUL], 128);
+    else ZK_LAUNCH_GROUP(3, (k_evm_gadget<KG_MUL, false>), group_n[KG_MUL], 128);
+  }
+  if (group_n[KG_ADD]) {
+    if (pos) ZK_LAUNCH_GROUP(4, (k_evm_gadget<KG_ADD, true>), group_n[KG_ADD], 128);
+    else ZK_LAUNCH_GROUP(5, (k_evm_gadget<KG_ADD, false>), group_n[KG_ADD], 128);
+  }
+  if (group_n[KG_POP]) {
+    if (pos) ZK_LAUNCH_GROUP(6, (k_evm_gadget<KG_POP, true>), group_n[KG_POP], 128);
+    else ZK_LAUNCH_GROUP(7, (k_evm_gadget<KG_POP, false>), group_n[KG_POP], 128);
+  }
+  if (group_n[KG_SIMPLE]) ZK_LAUNCH_GROUP(8, k_evm_group<KG_SIMPLE>, group_n[KG_SIMPLE], 128);
+  if (group_n[KG_BYTES32]) ZK_LAUNCH_GROUP(9, k_evm_group<KG_BYTES32>, group_n[KG_BYTES32], 128);
+  if (group_n[KG_COPY]) ZK_LAUNCH_GROUP(10, k_evm_group<KG_COPY>, group_n[KG_COPY], 128);
+  if (group_n[KG_WIDE]) ZK_LAUNCH_GROUP(11, k_evm_group<KG_WIDE>, group_n[KG_WIDE], 128);
+  if (group_n[KG_TX]) ZK_LAUNCH_GROUP(12, k_evm_group<KG_TX>, group_n[KG_TX], 128);
+#undef ZK_LAUNCH_GROUP
   CK(ctx, cudaGetLastError());
   return 0;
 }
@@ -763,6 +840,8 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
   const Matrix& m = ctx->circ[circuit_id];
   if (!m.dev && m.n_rows) return fail_msg(ctx, "no witness uploaded for circuit");
   if (row_begin > row_end || row_end > m.n_rows) return fail_msg(ctx, "row range outside the resident matrix");
+  if (row_base + row_end >= 0xFFFFFFFFull || row_base + row_end < row_base)
+    return fail_msg(ctx, "row_base + row_end must stay below 2^32 - 1 (first_fail holds uint32 rows, 0xFFFFFFFF = pass)");
   ResultDev res;
   int rc = ensure_result(ctx, circuit_id, &res, st);
   if (rc) return rc;

@@ -22,6 +22,21 @@ struct CheckRange {
 ZK_HD Fr wcell(const WitnessDev& w, u32 col, u64 row) {
   return ld_col(w.base + w.off[col], w.width[col], row);
 }
+// Storage layout a row-checker instance is compiled for.  L_CANON: every column holds canonical 32-byte
+// cells (zk_upload_columns) — a cell load is one address add + one LDG.256; L_ANY: per-column widths
+// (packed uploads) through the generic branch-free loader, ~20 more instructions per load.  The host
+// picks the instance from the resident matrix's widths; results are identical.
+enum { L_ANY = 0, L_CANON = 1 };
+template <int LAYOUT>
+ZK_HD Fr wcell_l(const WitnessDev& w, u32 col, u64 row) {
+  if (LAYOUT == L_CANON) return ld_cell((const u64*)(w.base + w.off[col]) + row * 4);
+  return ld_col(w.base + w.off[col], w.width[col], row);
+}
+template <int LAYOUT>
+ZK_HD Fr tcell_l(const TableDev& t, u32 col, u64 row) {
+  if (LAYOUT == L_CANON) return ld_cell((const u64*)(t.base + t.off[col]) + row * 4);
+  return ld_col(t.base + t.off[col], t.width[col], row);
+}
 // rotation by +k / -k: wraps modulo n_rows when the whole circuit is resident, otherwise the
 // caller supplied halo rows (include/zkcheck.h)
 ZK_HD u64 rot_fwd(const WitnessDev& w, u64 row, u32 k, bool wrap) {

@@ -43,6 +43,7 @@ ZK_HD bool table_flag(const TableDev& t, u32 row, int bit) { return t.flags && (
   } while (0)
 
 // Warp-synchronous: every lane of `mask` calls it; lanes without a row pass live = false.
+template <int LAYOUT>
 ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyTables& t, const Fr& r_mont,
                           const ResultDev& res, u64 i, bool live, unsigned mask) {
   const bool record = live;
@@ -50,14 +51,14 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
   const u64 j1 = rot_fwd(w, i, 1, wrap), j2 = rot_fwd(w, i, 2, wrap);
   const u64 row = rg.row_base + i;
   const Fr one = fr_u64(1);
-  const Fr q = wcell(w, K_QSTEP, i), is_first = wcell(w, K_FIRST, i), is_last = wcell(w, K_LAST, i);
-  const Fr tag = wcell(w, K_TAG, i), id_lo = wcell(w, K_ID_LO, i), id_hi = wcell(w, K_ID_HI, i);
-  const Fr addr = wcell(w, K_ADDR, i), src_end = wcell(w, K_SRC_END, i), bytes_left = wcell(w, K_BYTES_LEFT, i);
-  const Fr value = wcell(w, K_VALUE, i), rlc_acc = wcell(w, K_RLC_ACC, i), is_pad = wcell(w, K_IS_PAD, i);
-  const Fr rwc = wcell(w, K_RWC, i), rwc_inc = wcell(w, K_RWC_INC, i);
-  const Fr is_mem = wcell(w, K_IS_MEM, i), is_bc = wcell(w, K_IS_BC, i), is_tx = wcell(w, K_IS_TX, i);
-  const Fr is_log = wcell(w, K_IS_LOG, i), is_rlc = wcell(w, K_IS_RLC, i);
-  const Fr n_last = wcell(w, K_LAST, j1), n_value = wcell(w, K_VALUE, j1);
+  const Fr q = wcell_l<LAYOUT>(w, K_QSTEP, i), is_first = wcell_l<LAYOUT>(w, K_FIRST, i), is_last = wcell_l<LAYOUT>(w, K_LAST, i);
+  const Fr tag = wcell_l<LAYOUT>(w, K_TAG, i), id_lo = wcell_l<LAYOUT>(w, K_ID_LO, i), id_hi = wcell_l<LAYOUT>(w, K_ID_HI, i);
+  const Fr addr = wcell_l<LAYOUT>(w, K_ADDR, i), src_end = wcell_l<LAYOUT>(w, K_SRC_END, i), bytes_left = wcell_l<LAYOUT>(w, K_BYTES_LEFT, i);
+  const Fr value = wcell_l<LAYOUT>(w, K_VALUE, i), rlc_acc = wcell_l<LAYOUT>(w, K_RLC_ACC, i), is_pad = wcell_l<LAYOUT>(w, K_IS_PAD, i);
+  const Fr rwc = wcell_l<LAYOUT>(w, K_RWC, i), rwc_inc = wcell_l<LAYOUT>(w, K_RWC_INC, i);
+  const Fr is_mem = wcell_l<LAYOUT>(w, K_IS_MEM, i), is_bc = wcell_l<LAYOUT>(w, K_IS_BC, i), is_tx = wcell_l<LAYOUT>(w, K_IS_TX, i);
+  const Fr is_log = wcell_l<LAYOUT>(w, K_IS_LOG, i), is_rlc = wcell_l<LAYOUT>(w, K_IS_RLC, i);
+  const Fr n_last = wcell_l<LAYOUT>(w, K_LAST, j1), n_value = wcell_l<LAYOUT>(w, K_VALUE, j1);
   const bool q0 = fr_is_zero(q);
 
   // ---- verify_row ----
@@ -73,24 +74,24 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
   {
     // cond = 1 - (is_last + next.is_last)
     const bool off = fr_eq_u64(fr_add(is_last, n_last), 1);
-    CP_CHECK(CP_ID_SAME, off || (fr_eq(id_lo, wcell(w, K_ID_LO, j2)) && fr_eq(id_hi, wcell(w, K_ID_HI, j2))));
-    CP_CHECK(CP_TAG_SAME, off || fr_eq(tag, wcell(w, K_TAG, j2)));
-    CP_CHECK(CP_ADDR_INC, off || fr_eq(fr_add_u64(addr, 1), wcell(w, K_ADDR, j2)));
-    CP_CHECK(CP_SRC_END_SAME, off || fr_eq(src_end, wcell(w, K_SRC_END, j2)));
+    CP_CHECK(CP_ID_SAME, off || (fr_eq(id_lo, wcell_l<LAYOUT>(w, K_ID_LO, j2)) && fr_eq(id_hi, wcell_l<LAYOUT>(w, K_ID_HI, j2))));
+    CP_CHECK(CP_TAG_SAME, off || fr_eq(tag, wcell_l<LAYOUT>(w, K_TAG, j2)));
+    CP_CHECK(CP_ADDR_INC, off || fr_eq(fr_add_u64(addr, 1), wcell_l<LAYOUT>(w, K_ADDR, j2)));
+    CP_CHECK(CP_SRC_END_SAME, off || fr_eq(src_end, wcell_l<LAYOUT>(w, K_SRC_END, j2)));
   }
   const Fr rw_diff = fr_mul_sel(fr_sub(one, is_pad), fr_add(is_mem, is_log));
   {
     const bool off = fr_eq_u64(is_last, 1);  // cond = 1 - is_last
-    CP_CHECK(CP_RWC, off || fr_eq(fr_add(rwc, rw_diff), wcell(w, K_RWC, j1)));
-    CP_CHECK(CP_RWC_INC_LEFT, off || fr_eq(fr_sub(rwc_inc, rw_diff), wcell(w, K_RWC_INC, j1)));
-    CP_CHECK(CP_RLC_ACC_SAME, off || fr_eq(rlc_acc, wcell(w, K_RLC_ACC, j1)));
+    CP_CHECK(CP_RWC, off || fr_eq(fr_add(rwc, rw_diff), wcell_l<LAYOUT>(w, K_RWC, j1)));
+    CP_CHECK(CP_RWC_INC_LEFT, off || fr_eq(fr_sub(rwc_inc, rw_diff), wcell_l<LAYOUT>(w, K_RWC_INC, j1)));
+    CP_CHECK(CP_RLC_ACC_SAME, off || fr_eq(rlc_acc, wcell_l<LAYOUT>(w, K_RLC_ACC, j1)));
   }
   CP_CHECK(CP_RWC_INC_LAST, fr_is_zero(is_last) || fr_eq(rwc_inc, rw_diff));
   CP_CHECK(CP_RLC_LAST, fr_is_zero(is_last) || fr_is_zero(is_rlc) || fr_eq(rlc_acc, value));
   // ---- verify_step ----
   CP_CHECK(CP_BYTES_LEFT_LAST, q0 || fr_is_zero(n_last) || fr_eq_u64(bytes_left, 1));
   CP_CHECK(CP_BYTES_LEFT_DEC,
-           q0 || fr_eq_u64(n_last, 1) || fr_eq(bytes_left, fr_add_u64(wcell(w, K_BYTES_LEFT, j2), 1)));
+           q0 || fr_eq_u64(n_last, 1) || fr_eq(bytes_left, fr_add_u64(wcell_l<LAYOUT>(w, K_BYTES_LEFT, j2), 1)));
   CP_CHECK(CP_PAD_VALUE0, q0 || fr_is_zero(is_pad) || fr_is_zero(value));
   if (fr_is_zero(is_log)) {
     // lt(addr, src_addr_end, 5) is evaluated (and range-asserts) whatever q_step is
@@ -99,12 +100,12 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
     const Fr want_pad = fr_u64(addr.l[0] < src_end.l[0] ? 0 : 1);  // 1 - lt
     CP_CHECK(CP_IS_PAD, q0 || fr_eq(is_pad, want_pad));
   }
-  CP_CHECK(CP_NEXT_NOT_PAD, q0 || fr_is_zero(wcell(w, K_IS_PAD, j1)));
-  CP_CHECK(CP_RW_VALUE_EQ, q0 || fr_eq_u64(wcell(w, K_IS_RLC, j1), 1) || fr_eq(value, n_value));
+  CP_CHECK(CP_NEXT_NOT_PAD, q0 || fr_is_zero(wcell_l<LAYOUT>(w, K_IS_PAD, j1)));
+  CP_CHECK(CP_RW_VALUE_EQ, q0 || fr_eq_u64(wcell_l<LAYOUT>(w, K_IS_RLC, j1), 1) || fr_eq(value, n_value));
   CP_CHECK(CP_FIRST_VALUE_EQ, q0 || fr_is_zero(is_first) || fr_eq(value, n_value));
   if (live && !fr_eq_u64(q, 1) && !fr_eq_u64(is_last, 1) && !fr_is_zero(is_rlc)) {
     // next_write_value == write_value * r + next_read_value
-    CP_CHECK(CP_RLC_STEP, fr_eq(wcell(w, K_VALUE, j2), fr_add(fr_montmul(value, r_mont), n_value)));
+    CP_CHECK(CP_RLC_STEP, fr_eq(wcell_l<LAYOUT>(w, K_VALUE, j2), fr_add(fr_montmul(value, r_mont), n_value)));
   }
   // ---- table lookups (copy_circuit.py:106-130), one warp-wide probe per table use ----
   const bool id_is_word = w.flags && (w.flags[i] & 1);
@@ -126,7 +127,7 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
   }
   {
     const bool go = live && fr_eq_u64(is_bc, 1) && not_pad;
-    Fr key[5] = {id_lo, id_hi, fr_u64(2), addr, wcell(w, K_IS_CODE, i)};
+    Fr key[5] = {id_lo, id_hi, fr_u64(2), addr, wcell_l<LAYOUT>(w, K_IS_CODE, i)};
     const int n = lookup_sync<5>(t.bytecode, key, &hit, mask, go);
     if (go) {
       CP_CHECK(n == 0 ? CP_BC_UNSAT : CP_BC_AMBIG, n == 1);
@@ -164,6 +165,7 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
 }
 
 #ifdef __CUDACC__
+template <int LAYOUT>
 __global__ void __launch_bounds__(128, 4) k_check_copy(WitnessDev w, CheckRange rg, CopyTables t, Fr r_mont,
                                                     ResultDev res) {
   const u64 n = rg.row_end - rg.row_begin;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(128, 4) k_check_copy(WitnessDev w, CheckRange 
   for (u64 first = 0; first < n; first += stride) {  // warp-uniform trip count
     const u64 k = first + tid;
     const bool live = k < n;
-    check_copy_row(w, rg, t, r_mont, res, rg.row_begin + (live ? k : 0), live, 0xFFFFFFFFu);
+    check_copy_row<LAYOUT>(w, rg, t, r_mont, res, rg.row_begin + (live ? k : 0), live, 0xFFFFFFFFu);
   }
 }
 #endif

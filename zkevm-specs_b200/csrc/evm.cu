@@ -31,19 +31,39 @@ enum { S_STATE, S_RWC, S_CALL_ID, S_IS_ROOT, S_IS_CREATE, S_HASH_LO, S_HASH_HI, 
 enum { B_HASH_LO, B_HASH_HI, B_TAG, B_INDEX, B_ISCODE, B_VALUE };
 enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, R_VAL_HI };
 
+// execution states with a gate program in this build (others: EV_UNSUPPORTED_STATE)
+#define ZK_ES_BUILT_LIST(X)                                                                                            \
+  X(ZK_ES_ADD) X(ZK_ES_MUL) X(ZK_ES_PUSH) X(ZK_ES_POP) X(ZK_ES_SHA3) X(ZK_ES_CALLDATACOPY) X(ZK_ES_STOP) X(ZK_ES_MEMORY)  \
+  X(ZK_ES_MSIZE) X(ZK_ES_GAS) X(ZK_ES_ISZERO) X(ZK_ES_CMP) X(ZK_ES_JUMP) X(ZK_ES_JUMPI) X(ZK_ES_CALLER) X(ZK_ES_CALLVALUE) \
+  X(ZK_ES_CALLDATASIZE) X(ZK_ES_ADDRESS) X(ZK_ES_RETURNDATASIZE) X(ZK_ES_CODESIZE) X(ZK_ES_BITWISE) X(ZK_ES_NOT)         \
+  X(ZK_ES_BYTE) X(ZK_ES_SCMP) X(ZK_ES_SIGNEXTEND) X(ZK_ES_BlockCtx) X(ZK_ES_ORIGIN) X(ZK_ES_GASPRICE) X(ZK_ES_SHL_SHR)
+struct EsBuiltTable {
+  signed char v[ZK_ES_COUNT];
+};
+__host__ __device__ constexpr EsBuiltTable make_es_built() {
+  EsBuiltTable t{};
+#define ZK_X(id) t.v[id] = 1;
+  ZK_ES_BUILT_LIST(ZK_X)
+#undef ZK_X
+  return t;
+}
 #ifdef __CUDACC__
+__constant__ EsBuiltTable c_es_built = make_es_built();
 __constant__ signed char c_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;
 __constant__ signed char c_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
 __constant__ short c_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
 #endif
+static const EsBuiltTable h_es_built = make_es_built();
 static const signed char h_es_halts[ZK_ES_COUNT] = ZK_ES_HALTS_INIT;  // host copies: tests/emu only
 static const signed char h_es_impl[ZK_ES_COUNT] = ZK_ES_IMPLEMENTED_INIT;
 static const short h_opcode_gas[256] = ZK_OPCODE_GAS_INIT;
 #ifdef __CUDA_ARCH__
+#define ES_BUILT(i) c_es_built.v[i]
 #define ES_HALTS(i) c_es_halts[i]
 #define ES_IMPL(i) c_es_impl[i]
 #define OPCODE_GAS(i) c_opcode_gas[i]
 #else
+#define ES_BUILT(i) h_es_built.v[i]
 #define ES_HALTS(i) h_es_halts[i]
 #define ES_IMPL(i) h_es_impl[i]
 #define OPCODE_GAS(i) h_opcode_gas[i]
@@ -141,7 +161,7 @@ ZK_HD int bytecode_lookup(const StepCtx& s, bool live, const Fr& hlo, const Fr& 
   if (s.pos_mode == 1) {  // kernel specialised for positional tables: no hash code at all
     const IndexDev& ix = s.t.bytecode;
     u32 head = 0, len = 0;
-    const int n_head = heads_probe(ix, fr_add(hlo, rlc_term(ix, hhi, 1)), hlo, hhi, &head, &len, s.mask, live);
+    const int n_head = heads_probe(ix, hlo, hhi, &head, &len, s.mask, live);
     Fr got;
     const int n = pos_lookup_run(ix, key, n_head, head, len, &r, live, B_VALUE, &got);
     if (live && n == 1) *value = got;
@@ -180,13 +200,12 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   return n;
 }
 // heads-index probe of the step's code hash (no-op unless the bytecode table is positional)
-ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head,
-                        u32* run_len) {
+ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& hlo, const Fr& hhi, u32* head, u32* run_len) {
   const IndexDev& ix = s.t.bytecode;
   *head = 0;
   *run_len = 0;
   if (s.pos_mode != 1 && (ix.tab.n_rows == 0 || !(pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS))) return 0;
-  return heads_probe(ix, h0, hlo, hhi, head, run_len, s.mask, live);
+  return heads_probe(ix, hlo, hhi, head, run_len, s.mask, live);
 }
 // constant terms of a stack lookup's key hash, computed once per thread
 ZK_HD void stack_key_pre(const IndexDev& rw_ix, Fr out[2]) {
@@ -225,10 +244,13 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
 }
 
 // ---- prologue: verify_step before the gadget (main.py:47-63, instruction.py:189-204) --------
-// G_MISC: the rare states (SHA3, CALLDATACOPY, MEMORY, STOP, ...) share one list and one thread-per-step kernel that switches
-// on the state (k_evm_misc); the hot states each get a branch-uniform kernel
-enum { G_ADD, G_MUL, G_PUSH, G_POP, G_MISC, G_COUNT };
-// returns the gadget that must run for this step, or -1 if the step already failed
+// Steps are bucketed by execution state (one bucket per state; the MUL state is split three ways by an
+// opcode peek, see k_evm_classify) and each bucket is run by the kernel of its gate-program group.
+#define ZK_EVM_NB 128      // bucket ids: execution states 0..ZK_ES_COUNT-1, then
+#define ZK_BK_DIV ZK_ES_COUNT        // MUL-state steps whose opcode peeks as DIV
+#define ZK_BK_MOD (ZK_ES_COUNT + 1)  // ... as MOD (everything else stays in bucket ZK_ES_MUL)
+#define ZK_BK_NONE 0xFF              // the step already failed in the prologue
+// returns the execution state whose gate program must run for this step, or -1 if the step already failed
 ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
   const Fr cs = s.cur(S_STATE), ns = s.nxt(S_STATE);
   const bool is_first = (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0;
@@ -253,38 +275,7 @@ ZK_HD int step_prologue(const StepCtx& s, u32 flags) {
       EV_CHECK_RET(EV_TRANS_TO_ENDBLOCK, fr_eq_u64(cs, ZK_ES_EndTx) || fr_eq_u64(cs, ZK_ES_EndBlock), -1);
   }
   EV_CHECK_RET(EV_NOT_IMPLEMENTED, cs_small && ES_IMPL(cs.l[0]), -1);
-  switch (cs.l[0]) {
-    case ZK_ES_ADD: return G_ADD;
-    case ZK_ES_MUL: return G_MUL;
-    case ZK_ES_PUSH: return G_PUSH;
-    case ZK_ES_POP: return G_POP;
-    case ZK_ES_SHA3: return G_MISC;
-    case ZK_ES_CALLDATACOPY: return G_MISC;
-    case ZK_ES_STOP: return G_MISC;
-    case ZK_ES_MEMORY: return G_MISC;
-    case ZK_ES_MSIZE: return G_MISC;
-    case ZK_ES_GAS: return G_MISC;
-    case ZK_ES_ISZERO: return G_MISC;
-    case ZK_ES_CMP: return G_MISC;
-    case ZK_ES_JUMP: return G_MISC;
-    case ZK_ES_JUMPI: return G_MISC;
-    case ZK_ES_CALLER: return G_MISC;
-    case ZK_ES_CALLVALUE: return G_MISC;
-    case ZK_ES_CALLDATASIZE: return G_MISC;
-    case ZK_ES_ADDRESS: return G_MISC;
-    case ZK_ES_RETURNDATASIZE: return G_MISC;
-    case ZK_ES_CODESIZE: return G_MISC;
-    case ZK_ES_BITWISE: return G_MISC;
-    case ZK_ES_NOT: return G_MISC;
-    case ZK_ES_BYTE: return G_MISC;
-    case ZK_ES_SCMP: return G_MISC;
-    case ZK_ES_SIGNEXTEND: return G_MISC;
-    case ZK_ES_BlockCtx: return G_MISC;
-    case ZK_ES_ORIGIN: return G_MISC;
-    case ZK_ES_GASPRICE: return G_MISC;
-    case ZK_ES_SHL_SHR: return G_MISC;
-    default: break;
-  }
+  if (ES_BUILT(cs.l[0])) return (int)cs.l[0];
   step_fail(s, EV_UNSUPPORTED_STATE);
   return -1;
 }
@@ -688,7 +679,7 @@ ZK_HD void gadget_push(const StepCtx& s, bool live) {
   c.h0 = bytecode_hash0(s, c.hlo, c.hhi);
   Fr opcode = fr_u64(0), code_length = fr_u64(0);
   Word2 value{fr_u64(0), fr_u64(0)};
-  c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
+  c.n_head = bytecode_head(s, live, c.hlo, c.hhi, &c.head, &c.run_len);
   const int n_op = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 2, c.pc, 1, &opcode);
   const int n_len = bytecode_lookup_h(s, live, c.h0, c.n_head, c.head, c.run_len, c.hlo, c.hhi, 1, fr_u64(0), 0, &code_length);
   const int n_rw = rw_lookup(s, live, s.cur(S_RWC), 1, ZK_TARGET_Stack, s.cur(S_CALL_ID), fr_sub_u64(s.cur(S_SP), 1), &value);
@@ -758,7 +749,7 @@ ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
   c.pc = s.cur(S_PC);
   c.h0 = fr_u64(0);
   if (!(hc->have && fr_eq(c.hlo, hc->hlo) && fr_eq(c.hhi, hc->hhi))) {
-    hc->n = bytecode_head(s, true, bytecode_hash0(s, c.hlo, c.hhi), c.hlo, c.hhi, &hc->head, &hc->len);
+    hc->n = bytecode_head(s, true, c.hlo, c.hhi, &hc->head, &hc->len);
     hc->hlo = c.hlo;
     hc->hhi = c.hhi;
     hc->have = true;
@@ -1556,45 +1547,88 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
   same_context_ni(s, opcode, 3, one, one);
 }
 
-// the rare states: one thread per step, dispatch on the execution state
-ZK_HD void gadget_misc(const StepCtx& s, bool live) {
-  const Fr cs = s.cur(S_STATE);
-  switch (cs.l[0]) {
-    case ZK_ES_STOP: gadget_stop(s, live); break;
-    case ZK_ES_MEMORY: gadget_memory(s, live); break;
-    case ZK_ES_SHA3: gadget_sha3(s, live); break;
-    case ZK_ES_CALLDATACOPY: gadget_calldatacopy(s, live); break;
-    case ZK_ES_MSIZE: gadget_msize(s, live); break;
-    case ZK_ES_GAS: gadget_gas(s, live); break;
-    case ZK_ES_ISZERO: gadget_iszero(s, live); break;
-    case ZK_ES_CMP: gadget_cmp(s, live); break;
-    case ZK_ES_JUMP: gadget_jump(s, live); break;
-    case ZK_ES_JUMPI: gadget_jumpi(s, live); break;
-    case ZK_ES_CALLER: gadget_cc_push(s, live, 0x33, ZK_CC_CallerAddress, true); break;
-    case ZK_ES_CALLVALUE: gadget_cc_push(s, live, 0x34, ZK_CC_Value, true); break;
-    case ZK_ES_CALLDATASIZE: gadget_cc_push(s, live, 0x36, ZK_CC_CallDataLength, false); break;
-    case ZK_ES_ADDRESS: gadget_cc_push(s, live, 0x30, ZK_CC_CalleeAddress, true); break;
-    case ZK_ES_RETURNDATASIZE: gadget_cc_push(s, live, 0x3d, ZK_CC_LastCalleeReturnDataLength, false); break;
-    case ZK_ES_CODESIZE: gadget_codesize(s, live); break;
-    case ZK_ES_BITWISE: gadget_bitwise(s, live); break;
-    case ZK_ES_NOT: gadget_not(s, live); break;
-    case ZK_ES_BYTE: gadget_byte(s, live); break;
-    case ZK_ES_SCMP: gadget_scmp(s, live); break;
-    case ZK_ES_SIGNEXTEND: gadget_signextend(s, live); break;
-    case ZK_ES_BlockCtx: gadget_blockctx(s, live); break;
-    case ZK_ES_ORIGIN: gadget_txctx(s, live, 0x32, ZK_TX_CallerAddress); break;
-    case ZK_ES_GASPRICE: gadget_txctx(s, live, 0x3a, ZK_TX_GasPrice); break;
-    case ZK_ES_SHL_SHR: gadget_shl_shr(s, live); break;
-    default: break;
+// ---- gate-program groups --------------------------------------------------------------------
+// One kernel per GROUP of gate programs with similar register needs; inside a group kernel every
+// execution state has its own bucket of steps, so warps run one gate program (k_evm_classify /
+// k_evm_scatter sort the steps by state).  The host launches a group only when one of its buckets is
+// non-empty (zk_check_async reads the histogram back).
+enum { KG_ADD, KG_MUL, KG_PUSH, KG_POP, KG_SIMPLE, KG_BYTES32, KG_COPY, KG_WIDE, KG_TX, KG_COUNT };
+__host__ __device__ constexpr int es_group(int st) {
+  switch (st) {
+    case ZK_ES_ADD: return KG_ADD;
+    case ZK_ES_MUL: case ZK_BK_DIV: case ZK_BK_MOD: return KG_MUL;
+    case ZK_ES_PUSH: return KG_PUSH;
+    case ZK_ES_POP: return KG_POP;
+    case ZK_ES_MSIZE: case ZK_ES_GAS: case ZK_ES_ISZERO: case ZK_ES_CMP: case ZK_ES_JUMP: case ZK_ES_JUMPI:
+    case ZK_ES_CALLER: case ZK_ES_CALLVALUE: case ZK_ES_CALLDATASIZE: case ZK_ES_ADDRESS: case ZK_ES_RETURNDATASIZE:
+    case ZK_ES_CODESIZE: case ZK_ES_BYTE: case ZK_ES_SCMP: case ZK_ES_SIGNEXTEND: case ZK_ES_BlockCtx:
+    case ZK_ES_ORIGIN: case ZK_ES_GASPRICE: return KG_SIMPLE;
+    case ZK_ES_BITWISE: case ZK_ES_NOT: case ZK_ES_MEMORY: return KG_BYTES32;
+    case ZK_ES_SHA3: case ZK_ES_CALLDATACOPY: return KG_COPY;
+    case ZK_ES_SHL_SHR: return KG_WIDE;
+    case ZK_ES_STOP: return KG_TX;
+    default: return -1;
+  }
+}
+// the rare gate programs of one group (st = execution state; other states: nothing)
+template <int G>
+ZK_HD void run_group(const StepCtx& s, int st) {
+  if constexpr (G == KG_SIMPLE) {
+    switch (st) {
+      case ZK_ES_MSIZE: gadget_msize(s, true); break;
+      case ZK_ES_GAS: gadget_gas(s, true); break;
+      case ZK_ES_ISZERO: gadget_iszero(s, true); break;
+      case ZK_ES_CMP: gadget_cmp(s, true); break;
+      case ZK_ES_JUMP: gadget_jump(s, true); break;
+      case ZK_ES_JUMPI: gadget_jumpi(s, true); break;
+      case ZK_ES_CALLER: gadget_cc_push(s, true, 0x33, ZK_CC_CallerAddress, true); break;
+      case ZK_ES_CALLVALUE: gadget_cc_push(s, true, 0x34, ZK_CC_Value, true); break;
+      case ZK_ES_CALLDATASIZE: gadget_cc_push(s, true, 0x36, ZK_CC_CallDataLength, false); break;
+      case ZK_ES_ADDRESS: gadget_cc_push(s, true, 0x30, ZK_CC_CalleeAddress, true); break;
+      case ZK_ES_RETURNDATASIZE: gadget_cc_push(s, true, 0x3d, ZK_CC_LastCalleeReturnDataLength, false); break;
+      case ZK_ES_CODESIZE: gadget_codesize(s, true); break;
+      case ZK_ES_BYTE: gadget_byte(s, true); break;
+      case ZK_ES_SCMP: gadget_scmp(s, true); break;
+      case ZK_ES_SIGNEXTEND: gadget_signextend(s, true); break;
+      case ZK_ES_BlockCtx: gadget_blockctx(s, true); break;
+      case ZK_ES_ORIGIN: gadget_txctx(s, true, 0x32, ZK_TX_CallerAddress); break;
+      case ZK_ES_GASPRICE: gadget_txctx(s, true, 0x3a, ZK_TX_GasPrice); break;
+      default: break;
+    }
+  } else if constexpr (G == KG_BYTES32) {
+    switch (st) {
+      case ZK_ES_BITWISE: gadget_bitwise(s, true); break;
+      case ZK_ES_NOT: gadget_not(s, true); break;
+      case ZK_ES_MEMORY: gadget_memory(s, true); break;
+      default: break;
+    }
+  } else if constexpr (G == KG_COPY) {
+    switch (st) {
+      case ZK_ES_SHA3: gadget_sha3(s, true); break;
+      case ZK_ES_CALLDATACOPY: gadget_calldatacopy(s, true); break;
+      default: break;
+    }
+  } else if constexpr (G == KG_WIDE) {
+    switch (st) {
+      case ZK_ES_SHL_SHR: gadget_shl_shr(s, true); break;
+      default: break;
+    }
+  } else if constexpr (G == KG_TX) {
+    switch (st) {
+      case ZK_ES_STOP: gadget_stop(s, true); break;
+      default: break;
+    }
   }
 }
 
 // whole step on one thread (tests/emu)
 ZK_HD void verify_step(const StepCtx& s, u32 flags) {
-  switch (step_prologue(s, flags)) {
-    case G_ADD: gadget_add(s, true); break;
-    case G_MUL: gadget_mul(s, true); break;
-    case G_PUSH:
+  const int st = step_prologue(s, flags);
+  if (st < 0) return;
+  switch (es_group(st)) {
+    case KG_ADD: gadget_add(s, true); break;
+    case KG_MUL: gadget_mul(s, true); break;
+    case KG_PUSH:
       if (both_positional(s.t)) {  // what k_evm_push_pos runs
         HeadCache hc{};
         gadget_push_pos1(s, &hc);
@@ -1602,8 +1636,12 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
         gadget_push(s, true);
       }
       break;
-    case G_POP: gadget_pop(s, true); break;
-    case G_MISC: gadget_misc(s, true); break;
+    case KG_POP: gadget_pop(s, true); break;
+    case KG_SIMPLE: run_group<KG_SIMPLE>(s, st); break;
+    case KG_BYTES32: run_group<KG_BYTES32>(s, st); break;
+    case KG_COPY: run_group<KG_COPY>(s, st); break;
+    case KG_WIDE: run_group<KG_WIDE>(s, st); break;
+    case KG_TX: run_group<KG_TX>(s, st); break;
     default: break;
   }
 }
@@ -1611,83 +1649,122 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
 // ======================================================================================
 // kernels
 // ======================================================================================
-// Steps are bucketed by execution state first (the reference dispatches one Python gadget per
-// step, execution/__init__.py:86-171): k_evm_classify runs the cheap prologue of every step and
-// appends its index to the list of its gadget; then one kernel per gadget runs a single
-// straight-line gate program, so warps do not diverge across gadgets.
-struct EvmLists {
-  u32* idx;    // [G_COUNT][cap] local step indices
-  u32* count;  // [G_COUNT]
-  u32 cap;
+// The reference dispatches one Python gadget per step (execution/__init__.py:86-171).  Here the steps
+// are SORTED by execution state first — k_evm_classify runs the cheap prologue of every step, writes
+// its bucket and a histogram; k_evm_scatter turns the histogram into bucket offsets and writes the
+// step indices bucket by bucket (a counting sort, one byte + one u32 per step) — and then one kernel
+// per gate-program group walks its buckets, so the lanes of a warp run the same straight-line program.
+struct EvmSort {
+  unsigned char* bucket;  // [n] bucket of local step k (ZK_BK_NONE: it failed in the prologue)
+  u32* hist;              // [ZK_EVM_NB + 1] steps per bucket; entry ZK_EVM_NB: 1 iff rw + bytecode tables are positional
+  u32* cursor;            // [ZK_EVM_NB] scatter cursors (zeroed by the host)
+  u32* offs;              // [ZK_EVM_NB + 1] first entry of each bucket in `sorted`
+  u32* sorted;            // [n] local step indices, bucket by bucket
 };
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                       EvmLists lists) {
-  // Appends are aggregated per BLOCK: the list counters are a handful of addresses, and one
-  // atomicAdd per (warp, gadget) — 65 K same-address atomics at 2^20 steps — serialised in L2 and
-  // was most of this kernel's time.  Warp ballots give each lane its rank inside the warp, shared
-  // counters the warp's offset inside the block, ONE global atomicAdd per (block, gadget) the
-  // block's offset in the list.
-  __shared__ u32 s_warp[32][G_COUNT];  // per-warp counts, then exclusive offsets inside the block
-  __shared__ u32 s_base[G_COUNT];
-  const u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  int g = -1;
+// MUL-state steps are split three ways by an UNVERIFIED peek at their opcode (positional tables only):
+// MUL, DIV and MOD take three different witness-assignment branches (mul_div_mod.py:23-41), and a warp
+// that holds all three runs them one after the other.  The peek only chooses the bucket — the gate
+// program looks the opcode up again and decides everything itself — so a wrong peek costs time, never
+// the verdict.
+__device__ __forceinline__ int mul_bucket_peek(const StepCtx& s) {
+  u32 head = 0, len = 0;
+  const Fr pc = s.cur(S_PC);
+  if (heads_probe(s.t.bytecode, s.cur(S_HASH_LO), s.cur(S_HASH_HI), &head, &len, s.mask, true) != 1) return ZK_ES_MUL;
+  if (!(fr_fits64(pc) && pc.l[0] < (u64)len)) return ZK_ES_MUL;
+  const Fr v = table_cell(s.t.bytecode.tab, B_VALUE, (u64)head + 1 + pc.l[0]);
+  return fr_eq_u64(v, 4) ? ZK_BK_DIV : (fr_eq_u64(v, 6) ? ZK_BK_MOD : ZK_ES_MUL);
+}
+
+__global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res, EvmSort so) {
+  // histogram aggregated per BLOCK: lanes of a warp that share a bucket elect a leader (match_any),
+  // leaders add to a shared histogram, one global atomicAdd per (block, non-empty bucket)
+  __shared__ u32 s_hist[ZK_EVM_NB];
+  if (threadIdx.x < ZK_EVM_NB) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 i = rg.row_begin + k;
+  const unsigned lane = threadIdx.x & 31;
+  const bool pos = both_positional(t);
+  int b = ZK_BK_NONE;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 0, nullptr, nullptr, -1};
-    g = step_prologue(s, rg.flags);
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 1u << lane, nullptr, nullptr, -1};
+    const int st = step_prologue(s, rg.flags);
+    if (st >= 0) b = (st == ZK_ES_MUL && pos) ? mul_bucket_peek(s) : st;
+    so.bucket[k] = (unsigned char)b;
   }
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  u32 rank = 0;
+  const unsigned m = __match_any_sync(0xFFFFFFFFu, b);
+  if (b != ZK_BK_NONE && lane == (unsigned)(__ffs(m) - 1)) atomicAdd(&s_hist[b], (u32)__popc(m));
+  __syncthreads();
+  if (threadIdx.x < ZK_EVM_NB && s_hist[threadIdx.x]) atomicAdd(&so.hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) so.hist[ZK_EVM_NB] = pos ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(1024) k_evm_scatter(EvmSort so, u32 n) {
+  __shared__ u32 s_off[ZK_EVM_NB + 1], s_cnt[ZK_EVM_NB], s_base[ZK_EVM_NB], s_wsum[ZK_EVM_NB / 32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < ZK_EVM_NB) {  // exclusive scan of the histogram (4 warps)
+    const u32 c = so.hist[threadIdx.x];
+    u32 v = c;
 #pragma unroll
-  for (int k = 0; k < G_COUNT; k++) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, g == k);
-    if (g == k) rank = __popc(m & ((1u << lane) - 1));
-    if (lane == 0) s_warp[warp][k] = __popc(m);
-  }
-  __syncthreads();
-  if (threadIdx.x < G_COUNT) {
-    const int k = threadIdx.x;
-    u32 total = 0;
-    for (unsigned wi = 0; wi < n_warps; wi++) {
-      const u32 c = s_warp[wi][k];
-      s_warp[wi][k] = total;
-      total += c;
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 u = __shfl_up_sync(0xFFFFFFFFu, v, d);
+      if ((int)lane >= d) v += u;
     }
-    s_base[k] = total ? atomicAdd(&lists.count[k], total) : 0;
+    if (lane == 31) s_wsum[warp] = v;
+    s_off[threadIdx.x] = v - c;
+    s_cnt[threadIdx.x] = 0;
   }
   __syncthreads();
-  if (g >= 0) lists.idx[(u64)g * lists.cap + s_base[g] + s_warp[warp][g] + rank] = (u32)(i - rg.row_begin);
+  if (threadIdx.x < ZK_EVM_NB) {
+    u32 add = 0;
+    for (unsigned q = 0; q < warp; q++) add += s_wsum[q];
+    s_off[threadIdx.x] += add;
+    if (threadIdx.x == ZK_EVM_NB - 1) s_off[ZK_EVM_NB] = s_off[threadIdx.x] + so.hist[threadIdx.x];
+  }
+  const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = k < n ? (int)so.bucket[k] : ZK_BK_NONE;
+  const unsigned m = __match_any_sync(0xFFFFFFFFu, b);
+  const int leader = __ffs(m) - 1;
+  const u32 rank = __popc(m & ((1u << lane) - 1));
+  __syncthreads();
+  u32 wbase = 0;
+  if (b != ZK_BK_NONE && (int)lane == leader) wbase = atomicAdd(&s_cnt[b], (u32)__popc(m));
+  wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+  __syncthreads();
+  if (threadIdx.x < ZK_EVM_NB && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&so.cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (b != ZK_BK_NONE) so.sorted[s_off[b] + s_base[b] + wbase + rank] = k;
+  if (blockIdx.x == 0 && threadIdx.x <= ZK_EVM_NB) so.offs[threadIdx.x] = s_off[threadIdx.x];
 }
 
 // one thread per step for the gadgets whose work is a handful of independent lookups.
-// POS = both tables positional (a uniform run-time fact): that instance is compiled with
-// pos_mode = 1, i.e. without any hash-index code — these kernels were stalling on instruction
+// POS = both tables positional (known to the host from the read-back flag): that instance is compiled
+// with pos_mode = 1, i.e. without any hash-index code — these kernels were stalling on instruction
 // fetch (profiles/README.md v20: "no instruction" 2-3 per issue), the executed path is now half as long.
 template <int G, bool POS>
-__device__ __forceinline__ void gadget_steps(const WitnessDev& w, const CheckRange& rg, const EvmTables& t,
-                                             const ResultDev& res, const EvmLists& lists, const u32* s_resp) {
+__device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRange& rg, const EvmTables& t,
+                                             const ResultDev& res, const EvmSort& so, const u32* s_resp, int bucket,
+                                             const Fr* stack_pre, const u64& rw_base) {
   // every lane of a warp runs the same number of rounds and calls the (warp-synchronous) lookups
   // together; lanes without a step in the last round run with live = false
-  Fr stack_pre[2];
-  if (!POS) stack_key_pre(t.rw, stack_pre);
-  const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
-  const u32 n = lists.count[G];
+  const u32 n = so.hist[bucket];
+  if (n == 0) return;
+  const u32* list = so.sorted + so.offs[bucket];
   const u32 stride = gridDim.x * blockDim.x;
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
   for (u32 first = 0; first < n; first += stride) {
     const u32 k = first + tid;
     const bool live = k < n;
-    const u64 i = rg.row_begin + (live ? lists.idx[(u64)G * lists.cap + k] : lists.idx[(u64)G * lists.cap]);
+    const u64 i = rg.row_begin + list[live ? k : 0];
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, POS ? nullptr : stack_pre,
               POS ? &rw_base : nullptr, POS ? 1 : -1};
-    if (G == G_ADD) gadget_add(s, live);
-    else if (G == G_MUL) gadget_mul(s, live);
+    if (G == KG_ADD) gadget_add(s, live);
+    else if (G == KG_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
   }
 }
-// two instances per gadget (own register budgets); the host launches both, the one whose POS does
-// not match the tables returns at once
 // minimum resident blocks per SM (= register caps of 168 / 128): measured sweep in
 // profiles/r01_v25_launch_bounds_sweep.json — (3, 4) cuts the check phase from 0.539 to 0.443 ms
 #ifndef ZK_GADGET_MINBLOCKS
@@ -1698,27 +1775,46 @@ __device__ __forceinline__ void gadget_steps(const WitnessDev& w, const CheckRan
 #endif
 template <int G, bool POS>
 __global__ void __launch_bounds__(128, ZK_GADGET_MINBLOCKS) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                    EvmLists lists) {
-  if (both_positional(t) != POS) return;
+                                                    EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
-  gadget_steps<G, POS>(w, rg, t, res, lists, s_resp);
+  Fr stack_pre[2];
+  if (!POS) stack_key_pre(t.rw, stack_pre);
+  const u64 rw_base = POS ? table_cell(t.rw.tab, 0, 0).l[0] : 0;
+  if (G == KG_MUL) {  // three buckets (opcode peeks MUL / DIV / MOD), one after the other: warps stay uniform
+#pragma unroll 1
+    for (int sub = 0; sub < 3; sub++)
+      bucket_steps<G, POS>(w, rg, t, res, so, s_resp, sub == 0 ? ZK_ES_MUL : (sub == 1 ? ZK_BK_DIV : ZK_BK_MOD), stack_pre, rw_base);
+  } else {
+    bucket_steps<G, POS>(w, rg, t, res, so, s_resp, G == KG_ADD ? ZK_ES_ADD : ZK_ES_POP, stack_pre, rw_base);
+  }
 }
 
-// rare states: lanes of a warp may run different gate programs, so every lookup is made
-// lane-private (mask = the lane's own bit: the probe loops need no warp agreement)
-__global__ void __launch_bounds__(128) k_evm_misc(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                  EvmLists lists) {
+// rare groups: a thread takes one step of one bucket at a time; a warp may straddle two buckets at a
+// bucket boundary, so every lookup is lane-private (mask = the lane's own bit: the probe loops need
+// no warp agreement)
+template <int G>
+__global__ void __launch_bounds__(128) k_evm_group(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg,
+                                                   const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
+                                                   const __grid_constant__ EvmSort so) {
+  // __grid_constant__: the out-of-line lookups take these structures by reference; without it every
+  // thread first copies the 12 KB of kernel parameters to its local-memory stack
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
-  const u32 n = lists.count[G_MISC];
   const u32 stride = gridDim.x * blockDim.x;
-  for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-    const u64 i = rg.row_begin + lists.idx[(u64)G_MISC * lists.cap + k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, nullptr, -1};
-    gadget_misc(s, true);
+#pragma unroll 1
+  for (int st = 0; st < ZK_ES_COUNT; st++) {
+    if (es_group(st) != G) continue;
+    const u32 n = so.hist[st];
+    if (n == 0) continue;
+    const u32* list = so.sorted + so.offs[st];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+      const u64 i = rg.row_begin + list[k];
+      StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, nullptr, -1};
+      run_group<G>(s, st);
+    }
   }
 }
 
@@ -1728,45 +1824,39 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
   for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src);
   return r;
 }
-
-// half a warp per PUSH step (two steps per warp iteration): sub-lane L of a half owns pushed bytes
-// L and L+16 of its step.  Halving the lanes per step halves the warp-instructions per step and
-// doubles the steps in flight per warp; the kernel is latency-bound on ~8 dependent memory round
-// trips per step (profiles/README.md, v7), so both matter.  All 32 lanes call every
-// warp-synchronous lookup together; a half without a step (odd count) or whose step already
-// failed passes live = false.
 __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   Fr r;
 #pragma unroll
   for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src, 16);
   return r;
 }
-// positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1); returns at once
-// otherwise, and then k_evm_push_hash below does the work — the host launches both
+// positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1)
 __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                      EvmLists lists) {
-  if (!both_positional(t)) return;
+                                                      EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
   const u64 rw_base = table_cell(t.rw.tab, 0, 0).l[0];
   HeadCache hc{};
-  const u32 n = lists.count[G_PUSH];
+  const u32 n = so.hist[ZK_ES_PUSH];
+  const u32* list = so.sorted + so.offs[ZK_ES_PUSH];
   const u32 stride = gridDim.x * blockDim.x;
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + k];
+    const u64 i = rg.row_begin + list[k];
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, &rw_base, 1};
     gadget_push_pos1(s, &hc);
   }
 }
 
-// The generic path (tables not positional: k_evm_push_pos returns at once and this kernel does the
-// work; it returns at once when they are).  Half a warp per PUSH step (two steps per warp
+// The generic path (tables not positional).  Half a warp per PUSH step (two steps per warp
 // iteration): sub-lane L of a half owns pushed bytes L and L+16 of its step, so the warp-synchronous
-// hash probes of a step's 34 bytecode lookups run side by side.
+// hash probes of a step's 34 bytecode lookups run side by side.  Halving the lanes per step halves
+// the warp-instructions per step and doubles the steps in flight per warp; the kernel is
+// latency-bound on ~8 dependent memory round trips per step (profiles/README.md, v7).  All 32 lanes
+// call every warp-synchronous lookup together; a half without a step (odd count) or whose step
+// already failed passes live = false.
 __global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                          EvmLists lists) {
-  if (both_positional(t)) return;
+                                                          EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
@@ -1774,7 +1864,8 @@ __global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRan
   stack_key_pre(t.rw, stack_pre);
   Fr last_hlo = fr_u64(0), last_hhi = fr_u64(0), last_h0 = fr_u64(0);  // per-lane cache of the last code hash seen
   bool have_h0 = false;
-  const u32 n = lists.count[G_PUSH];
+  const u32 n = so.hist[ZK_ES_PUSH];
+  const u32* list = so.sorted + so.offs[ZK_ES_PUSH];
   const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
   const u32 warps = (gridDim.x * blockDim.x) >> 5;
   const u32 n_pairs = (n + 1) >> 1;
@@ -1783,7 +1874,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRan
     const u32 k = 2 * kp + half;
     const bool have = k < n;
     bool live = have;
-    const u64 i = rg.row_begin + lists.idx[(u64)G_PUSH * lists.cap + (have ? k : 2 * kp)];
+    const u64 i = rg.row_begin + list[have ? k : 2 * kp];
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, have && sub == 0, s_resp, 0xFFFFFFFFu, stack_pre, nullptr, -1};
     PushCommon c;
     c.hlo = s.cur(S_HASH_LO);
@@ -1802,7 +1893,7 @@ __global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRan
     }
     c.h0 = last_h0;
     // (one of the two tables may still be positional: bytecode_head / the lookups below test the flags)
-    c.n_head = bytecode_head(s, live, c.h0, c.hlo, c.hhi, &c.head, &c.run_len);
+    c.n_head = bytecode_head(s, live, c.hlo, c.hhi, &c.head, &c.run_len);
     // round 1: sub-lane 0 opcode, 1 bytecode length (one warp-wide bytecode probe), then sub-lane 2
     // the stack_push row (one warp-wide rw probe)
     Fr v = fr_u64(0);

@@ -25,7 +25,8 @@ enum { X_USABLE, X_STEP, X_ID, X_LAST, X_BASE, X_EXPONENT = 6, X_EXPN = 8, X_A =
     }                             \
   } while (0)
 
-ZK_HD Word2 wword(const WitnessDev& w, u32 col, u64 row) { return Word2{wcell(w, col, row), wcell(w, col + 1, row)}; }
+template <int LAYOUT>
+ZK_HD Word2 wword(const WitnessDev& w, u32 col, u64 row) { return Word2{wcell_l<LAYOUT>(w, col, row), wcell_l<LAYOUT>(w, col + 1, row)}; }
 // is_step * v in {0, 1}  <=>  is_step == 0, or v == 0, or the field product equals 1
 ZK_HD bool gated_bool(const Fr& gate, const Fr& v) {
   if (fr_is_zero(gate) || fr_is_zero(v)) return true;
@@ -33,20 +34,21 @@ ZK_HD bool gated_bool(const Fr& gate, const Fr& v) {
   return fr_eq_u64(fr_mul(gate, v), 1);
 }
 
+template <int LAYOUT>
 ZK_HD void check_exp_row(const WitnessDev& w, const CheckRange& rg, const ResultDev& res, u64 i) {
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 j = rot_fwd(w, i, 1, wrap);
   const u64 row = rg.row_base + i;
-  const Fr is_step = wcell(w, X_STEP, i), is_last = wcell(w, X_LAST, i), r = wcell(w, X_R, i);
-  const Word2 base = wword(w, X_BASE, i), expo = wword(w, X_EXPONENT, i), a = wword(w, X_A, i), b = wword(w, X_B, i);
-  const Word2 c = wword(w, X_C, i), d = wword(w, X_D, i), q = wword(w, X_Q, i);
-  const Word2 n_expo = wword(w, X_EXPONENT, j);
+  const Fr is_step = wcell_l<LAYOUT>(w, X_STEP, i), is_last = wcell_l<LAYOUT>(w, X_LAST, i), r = wcell_l<LAYOUT>(w, X_R, i);
+  const Word2 base = wword<LAYOUT>(w, X_BASE, i), expo = wword<LAYOUT>(w, X_EXPONENT, i), a = wword<LAYOUT>(w, X_A, i), b = wword<LAYOUT>(w, X_B, i);
+  const Word2 c = wword<LAYOUT>(w, X_C, i), d = wword<LAYOUT>(w, X_D, i), q = wword<LAYOUT>(w, X_Q, i);
+  const Word2 n_expo = wword<LAYOUT>(w, X_EXPONENT, j);
   const bool step0 = fr_is_zero(is_step), last1 = fr_eq_u64(is_last, 1), last0 = fr_is_zero(is_last);
   // cond = is_step * (1 - is_last)
   const bool off1 = step0 || last1;
-  XP_CHECK(XP_BASE_SAME, off1 || word_eq(base, wword(w, X_BASE, j)));
-  XP_CHECK(XP_A_EQ_NEXT_D, off1 || word_eq(a, wword(w, X_D, j)));
-  XP_CHECK(XP_ID_SAME, off1 || fr_eq(wcell(w, X_ID, i), wcell(w, X_ID, j)));
+  XP_CHECK(XP_BASE_SAME, off1 || word_eq(base, wword<LAYOUT>(w, X_BASE, j)));
+  XP_CHECK(XP_A_EQ_NEXT_D, off1 || word_eq(a, wword<LAYOUT>(w, X_D, j)));
+  XP_CHECK(XP_ID_SAME, off1 || fr_eq(wcell_l<LAYOUT>(w, X_ID, i), wcell_l<LAYOUT>(w, X_ID, j)));
   XP_CHECK(XP_LAST_BOOL, gated_bool(is_step, is_last));
   XP_CHECK(XP_R_BOOL, gated_bool(is_step, r));
   {
@@ -56,7 +58,7 @@ ZK_HD void check_exp_row(const WitnessDev& w, const CheckRange& rg, const Result
     XP_CHECK(XP_MUL_CARRY_LO, fits_9_bytes(clo));
     XP_CHECK(XP_MUL_CARRY_HI, fits_9_bytes(chi));
   }
-  XP_CHECK(XP_EXP_EQ_D, step0 || word_eq(wword(w, X_EXPN, i), d));
+  XP_CHECK(XP_EXP_EQ_D, step0 || word_eq(wword<LAYOUT>(w, X_EXPN, i), d));
   XP_CHECK(XP_C_ZERO, step0 || (fr_is_zero(c.lo) && fr_is_zero(c.hi)));
   {
     XP_CHECK(XP_PAR_R_WORD, fr_fits128(r));
@@ -85,10 +87,11 @@ ZK_HD void check_exp_row(const WitnessDev& w, const CheckRange& rg, const Result
 }
 
 #ifdef __CUDACC__
+template <int LAYOUT>
 __global__ void __launch_bounds__(128) k_check_exp(WitnessDev w, CheckRange rg, ResultDev res) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rg.row_end; i += stride)
-    check_exp_row(w, rg, res, i);
+    check_exp_row<LAYOUT>(w, rg, res, i);
 }
 #endif
 

@@ -38,6 +38,17 @@ ZK_HD void layout_canonical(u64* off, unsigned char* width, u32 n_cols, u64 n_ro
   }
 }
 
+// One entry of the heads index of a ZK_POS_RUNS table: the code hash of the run is stored INLINE, so a
+// probe is one memory round trip (claim word + hash, two loads of the same 64-byte line) instead of
+// "slot, then the table's hash cells".  Only runs whose hash cells fit 128 bits are indexed (others
+// clear the positional flag), so the two low limbs of each half identify the hash exactly.
+struct alignas(64) HeadEnt {
+  u64 claim;  // (fingerprint32 << 32) | head row; ZK_EMPTY_SLOT = free
+  u32 head;   // first row of the run (the Header row)
+  u32 len;    // number of Byte rows of the run
+  u64 pad[2];
+  u64 h[4];   // hash_lo limbs 0,1; hash_hi limbs 0,1
+};
 struct IndexDev {
   TableDev tab;
   u64* slots;  // capacity = mask+1 slots, ZK_EMPTY_SLOT = free
@@ -52,9 +63,9 @@ struct IndexDev {
   // hash index above is then not built and lookups go straight to the row.
   const u32* pos_ok;
   u32 pos_kind;
-  u64* heads_slots;  // ZK_POS_RUNS: hash index (same slot format) over the first row of every run
+  HeadEnt* heads;    // ZK_POS_RUNS: hash index over the first row of every run (one 64-byte entry each)
   u32 heads_mask;
-  u32* heads_len;    // [heads_mask + 1] number of Byte rows of the run whose head sits in that slot
+  u64 hk[4];         // keyed multipliers of the heads hash (odd, derived from the lookup challenge)
   u32* heads_list;   // [heads_mask + 1] head rows in insertion order, heads_count[0] of them
   u32* heads_count;
 };
@@ -238,14 +249,68 @@ ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32
   *row = (u32)cand;
   return valid && fr_eq(is_code, key[4]) ? 1 : 0;
 }
-// heads index probe: h0 = hash_lo + hash_hi * r  (warp-synchronous like probe_hashed)
-ZK_HD int heads_probe(const IndexDev& ix, const Fr& h0, const Fr& hlo, const Fr& hhi, u32* head, u32* len,
-                      unsigned mask, bool active) {
-  Fr key[2] = {hlo, hhi};
-  u32 slot = 0;
-  const int n = probe_slots<2>(ix, ix.heads_slots, ix.heads_mask, h0, key, head, mask, active, &slot);
-  *len = (active && n == 1) ? ld_u32(ix.heads_len + slot) : 0u;
-  return n;
+// keyed 64-bit hash of a code hash held as two 128-bit halves: four multiplies by odd constants drawn
+// from the lookup challenge + a finaliser (the RLC of the generic index would cost a 254-bit Montgomery
+// product per probe; this hash only picks a bucket, matches are confirmed on all 256 bits)
+ZK_HD u64 heads_mix(const IndexDev& ix, const Fr& hlo, const Fr& hhi) {
+  u64 x = hlo.l[0] * ix.hk[0] + hlo.l[1] * ix.hk[1] + hhi.l[0] * ix.hk[2] + hhi.l[1] * ix.hk[3];
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 29;
+  return x;
+}
+// 16-byte / 32-byte halves of a heads entry (written by an earlier kernel: read-only here)
+ZK_HD void ld_head_ent(const HeadEnt* e, u64* claim, u32* head, u32* len, u64 h[4]) {
+#ifdef __CUDA_ARCH__
+  u64 hl;
+  asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(*claim), "=l"(hl) : "l"(e));
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(h[0]), "=l"(h[1]), "=l"(h[2]), "=l"(h[3]) : "l"(e->h));
+  *head = (u32)hl;
+  *len = (u32)(hl >> 32);
+#else
+  *claim = e->claim;
+  *head = e->head;
+  *len = e->len;
+  for (int k = 0; k < 4; k++) h[k] = e->h[k];
+#endif
+}
+// heads index probe (warp-synchronous like probe_slots: lanes of `mask` call it together and leave
+// converged).  Run heads are unique by construction (a duplicate code hash clears the positional
+// flag), so the first confirmed entry is the only one: returns 0 or 1.
+ZK_HD int heads_probe(const IndexDev& ix, const Fr& hlo, const Fr& hhi, u32* head, u32* len, unsigned mask, bool active) {
+  const bool key_ok = fr_fits128(hlo) && fr_fits128(hhi);  // indexed hashes all fit 128-bit halves
+  const u64 mix = heads_mix(ix, hlo, hhi);
+  const u32 fp = (u32)(mix >> 32);
+  u32 b = (u32)mix & ix.heads_mask;
+  int found = 0;
+  *head = 0;
+  *len = 0;
+#ifdef __CUDA_ARCH__
+#define ZK_GROUP_ANY(p) __any_sync(mask, (p))
+#else
+#define ZK_GROUP_ANY(p) (p)
+  (void)mask;
+#endif
+  bool done = !(active && key_ok);
+  while (ZK_GROUP_ANY(!done)) {
+    if (!done) {
+      u64 claim, h[4];
+      u32 e_head, e_len;
+      ld_head_ent(&ix.heads[b], &claim, &e_head, &e_len, h);
+      if (claim == ZK_EMPTY_SLOT) {
+        done = true;
+      } else if ((u32)(claim >> 32) == fp && h[0] == hlo.l[0] && h[1] == hlo.l[1] && h[2] == hhi.l[0] && h[3] == hhi.l[1]) {
+        *head = e_head;
+        *len = e_len;
+        found = 1;
+        done = true;
+      } else {
+        b = (b + 1) & ix.heads_mask;
+      }
+    }
+  }
+#undef ZK_GROUP_ANY
+  return found;
 }
 
 // verify kernels' row functions
@@ -260,28 +325,36 @@ ZK_HD void pos_verify_dense_row(const IndexDev& ix, u32* ok, u64 row) {
   const Fr c = table_cell(ix.tab, ix.key_cols[0], row), b = table_cell(ix.tab, ix.key_cols[0], 0);
   if (!(fr_fits64(c) && fr_fits64(b) && b.l[0] + row >= b.l[0] && c.l[0] == b.l[0] + row)) pos_fail(ok);
 }
-// Claim a slot of the heads index for the run that starts at `row` with code hash (hlo, hhi).
+// Claim an entry of the heads index for the run that starts at `row` with code hash (hlo, hhi).
 // `len` != nullptr: the run length is known (table unrolled by the library) and is stored at once;
-// otherwise the head is listed for k_pos_runlen.  A duplicate hash or a full index clears the flag.
-ZK_HD void pos_fail(u32* ok);
+// otherwise the head is listed for k_pos_runlen.  A duplicate hash, a hash cell beyond 128 bits or a
+// full index clears the flag.
 ZK_HD void heads_insert(const IndexDev& ix, u32* ok, u64 row, const Fr& hlo, const Fr& hhi, const u32* len) {
   const TableDev& t = ix.tab;
-  const Fr h0 = fr_add(hlo, rlc_term(ix, hhi, 1));
-  const u64 mix = rlc_mix(h0);
+  if (!(fr_fits128(hlo) && fr_fits128(hhi))) {
+    pos_fail(ok);
+    return;
+  }
+  const u64 mix = heads_mix(ix, hlo, hhi);
   const u64 entry = (mix & 0xFFFFFFFF00000000ull) | (u64)(u32)row;
   u32 b = (u32)mix & ix.heads_mask;
   for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
-    const u64 old = atomic_cas_u64(&ix.heads_slots[b], ZK_EMPTY_SLOT, entry);
-    if (old == ZK_EMPTY_SLOT) {
-      if (len) {
-        ix.heads_len[b] = *len;
-      } else {
-        const u32 k = atomic_add_u32(ix.heads_count, 1u);  // k <= heads_mask: one slot per listed head
+    HeadEnt* e = &ix.heads[b];
+    const u64 old = atomic_cas_u64(&e->claim, ZK_EMPTY_SLOT, entry);
+    if (old == ZK_EMPTY_SLOT) {  // payload: read only by later kernels
+      e->head = (u32)row;
+      e->len = len ? *len : 0u;
+      e->h[0] = hlo.l[0];
+      e->h[1] = hlo.l[1];
+      e->h[2] = hhi.l[0];
+      e->h[3] = hhi.l[1];
+      if (!len) {
+        const u32 k = atomic_add_u32(ix.heads_count, 1u);  // k <= heads_mask: one entry per listed head
         ix.heads_list[k & ix.heads_mask] = (u32)row;
       }
       return;
     }
-    if ((old >> 32) == (mix >> 32)) {
+    if ((old >> 32) == (mix >> 32)) {  // the other claimant's payload may not be written yet: compare table cells
       const u32 other = (u32)old;
       if (fr_eq(table_cell(t, 0, other), hlo) && fr_eq(table_cell(t, 1, other), hhi)) break;  // duplicate hash
     }
@@ -356,13 +429,13 @@ ZK_HD void pos_runlen_entry(const IndexDev& ix, u32 k, u32 count) {
   }
   const u64 head = end - len;
   const Fr hlo = table_cell(t, 0, end), hhi = table_cell(t, 1, end);
-  const u64 mix = rlc_mix(fr_add(hlo, rlc_term(ix, hhi, 1)));
+  const u64 mix = heads_mix(ix, hlo, hhi);
   u32 b = (u32)mix & ix.heads_mask;
   for (u32 tries = 0; tries <= ix.heads_mask; tries++) {
-    const u64 slot = ld_volatile_u64(&ix.heads_slots[b]);
-    if (slot == ZK_EMPTY_SLOT) return;
-    if ((u32)slot == (u32)head) {
-      ix.heads_len[b] = (u32)len;
+    const u64 claim = ld_volatile_u64(&ix.heads[b].claim);
+    if (claim == ZK_EMPTY_SLOT) return;
+    if ((u32)claim == (u32)head) {
+      ix.heads[b].len = (u32)len;
       return;
     }
     b = (b + 1) & ix.heads_mask;
@@ -378,7 +451,7 @@ ZK_HD int lookup_sync(const IndexDev& ix, const Fr (&key)[NK], u32* row, unsigne
     if constexpr (NK == 5) {
       if (ix.pos_kind == ZK_POS_RUNS) {
         u32 head = 0, len = 0;
-        const int n_head = heads_probe(ix, fr_add(key[0], rlc_term(ix, key[1], 1)), key[0], key[1], &head, &len, mask, active);
+        const int n_head = heads_probe(ix, key[0], key[1], &head, &len, mask, active);
         return pos_lookup_run(ix, key, n_head, head, len, row, active);
       }
     }

@@ -41,15 +41,23 @@ ZK_HD bool u320_lt(const U320& a, const U320& b) {
   }
   return false;
 }
-// 32 byte cells -> 256-bit integer; false if a byte is >= 256
+// 32 byte cells -> 256-bit integer; false if a byte is >= 256.  Eight cells (one 64-bit limb) at a time:
+// eight independent 32-byte loads in flight, then folded, so the live registers stay bounded.
+template <int LAYOUT>
 ZK_HD bool gather_key_bytes(const WitnessDev& w, u64 row, Fr* out) {
   bool ok = true;
-  out->l[0] = out->l[1] = out->l[2] = out->l[3] = 0;
 #pragma unroll
-  for (int b = 0; b < 32; b++) {
-    const Fr c = wcell(w, T_BYTE0 + b, row);
-    ok = ok && fr_fits64(c) && c.l[0] < 256;
-    out->l[b >> 3] |= (c.l[0] & 0xFF) << (8 * (b & 7));
+  for (int q = 0; q < 4; q++) {
+    Fr c[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) c[b] = wcell_l<LAYOUT>(w, T_BYTE0 + 8 * q + b, row);
+    u64 limb = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      ok = ok && fr_fits64(c[b]) && c[b].l[0] < 256;
+      limb |= (c[b].l[0] & 0xFF) << (8 * b);
+    }
+    out->l[q] = limb;
   }
   return ok;
 }
@@ -81,17 +89,21 @@ ZK_HD bool fits_bits(const Fr& a, int bits) {  // bits in (0, 256)
   } while (0)
 
 // Warp-synchronous: every lane of `mask` calls it; lanes without a row pass live = false.
-ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const IndexDev& mpt, const ResultDev& res,
-                               u64 i, bool live, unsigned mask) {
+// `key_int` / `bytes_ok`: gather_key_bytes of row i; `p_key_int` / `p_bytes_ok`: of the previous row (the
+// kernel hands the previous row's over through shared memory instead of gathering 32 cells twice)
+template <int LAYOUT>
+ZK_HD void check_state_row_core(const WitnessDev& w, const CheckRange& rg, const IndexDev& mpt, const ResultDev& res,
+                                u64 i, bool live, unsigned mask, const Fr& key_int, bool bytes_ok, const Fr& p_key_int,
+                                bool p_bytes_ok) {
   const bool record = live;
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 ip = rot_back(w, i, wrap), in = rot_fwd(w, i, 1, wrap);
   const u64 row = rg.row_base + i;
-  const Fr rwc = wcell(w, T_RWC, i), is_write = wcell(w, T_IS_WRITE, i), tag = wcell(w, T_TAG, i);
-  const Fr id = wcell(w, T_ID, i), addr = wcell(w, T_ADDR, i), ft = wcell(w, T_FIELD_TAG, i);
-  const Fr key_lo = wcell(w, T_KEY_LO, i), key_hi = wcell(w, T_KEY_HI, i);
-  const Fr p_tag = wcell(w, T_TAG, ip), p_id = wcell(w, T_ID, ip), p_addr = wcell(w, T_ADDR, ip);
-  const Fr p_ft = wcell(w, T_FIELD_TAG, ip);
+  const Fr rwc = wcell_l<LAYOUT>(w, T_RWC, i), is_write = wcell_l<LAYOUT>(w, T_IS_WRITE, i), tag = wcell_l<LAYOUT>(w, T_TAG, i);
+  const Fr id = wcell_l<LAYOUT>(w, T_ID, i), addr = wcell_l<LAYOUT>(w, T_ADDR, i), ft = wcell_l<LAYOUT>(w, T_FIELD_TAG, i);
+  const Fr key_lo = wcell_l<LAYOUT>(w, T_KEY_LO, i), key_hi = wcell_l<LAYOUT>(w, T_KEY_HI, i);
+  const Fr p_tag = wcell_l<LAYOUT>(w, T_TAG, ip), p_id = wcell_l<LAYOUT>(w, T_ID, ip), p_addr = wcell_l<LAYOUT>(w, T_ADDR, ip);
+  const Fr p_ft = wcell_l<LAYOUT>(w, T_FIELD_TAG, ip);
 
   ST_CHECK(ST_TAG_RANGE, fr_fits64(tag) && tag.l[0] >= 1 && tag.l[0] <= 12);
   ST_CHECK(ST_ID_RANGE, fits_bits(id, 28));
@@ -101,7 +113,7 @@ ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const 
     Fr sum = fr_u64(0);
 #pragma unroll
     for (int k = 0; k < 10; k++) {
-      const Fr limb = wcell(w, T_LIMB0 + k, i);
+      const Fr limb = wcell_l<LAYOUT>(w, T_LIMB0 + k, i);
       limbs_ok = limbs_ok && fr_fits64(limb) && limb.l[0] < 65536;
       const int bit = 16 * k;
       sum.l[bit >> 6] |= (limb.l[0] & 0xFFFF) << (bit & 63);
@@ -109,65 +121,58 @@ ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const 
     ST_CHECK(ST_ADDR_LIMB_RANGE, limbs_ok);
     ST_CHECK(ST_ADDR_LIMBS, fr_eq(addr, sum));
   }
-  Fr key_int, p_key_int;
-  {
-    const bool bytes_ok = gather_key_bytes(w, i, &key_int);
-    ST_CHECK(ST_KEY_BYTE_RANGE, bytes_ok);
-    ST_CHECK(ST_KEY_BYTES, fr_eq(key_lo, fr_u128(key_int.l[0], key_int.l[1])) &&
-                               fr_eq(key_hi, fr_u128(key_int.l[2], key_int.l[3])));
-  }
+  ST_CHECK(ST_KEY_BYTE_RANGE, bytes_ok);
+  ST_CHECK(ST_KEY_BYTES, fr_eq(key_lo, fr_u128(key_int.l[0], key_int.l[1])) &&
+                             fr_eq(key_hi, fr_u128(key_int.l[2], key_int.l[3])));
   ST_CHECK(ST_IS_WRITE_BOOL, fr_fits64(is_write) && is_write.l[0] <= 1);
-  {
-    const bool p_bytes_ok = gather_key_bytes(w, ip, &p_key_int);
-    ST_CHECK(ST_PREV_KEY_BYTES, p_bytes_ok);
-  }
+  ST_CHECK(ST_PREV_KEY_BYTES, p_bytes_ok);
   const u64 t = tag.l[0];
   const bool is_start = t == ZK_ST_Start;
   if (live && !is_start) {
     ST_CHECK(ST_WITNESS_DOMAIN, fits_bits(p_tag, 4) && fits_bits(p_id, 28) && fits_bits(p_addr, 160) && fits_bits(p_ft, 16));
     if (live) {
-      const U320 a = pack_keys(p_tag, p_id, p_addr, p_ft, p_key_int, wcell(w, T_RWC, ip));
+      const U320 a = pack_keys(p_tag, p_id, p_addr, p_ft, p_key_int, wcell_l<LAYOUT>(w, T_RWC, ip));
       const U320 b = pack_keys(tag, id, addr, ft, key_int, rwc);
       ST_CHECK(ST_LEX_ORDER, u320_lt(a, b));
     }
   }
   const bool same = fr_eq(tag, p_tag) && fr_eq(id, p_id) && fr_eq(addr, p_addr) && fr_eq(ft, p_ft) &&
-                    fr_eq(key_lo, wcell(w, T_KEY_LO, ip)) && fr_eq(key_hi, wcell(w, T_KEY_HI, ip));
-  const Fr val_lo = wcell(w, T_VAL_LO, i), val_hi = wcell(w, T_VAL_HI, i);
-  const Fr init_lo = wcell(w, T_INIT_LO, i), init_hi = wcell(w, T_INIT_HI, i);
+                    fr_eq(key_lo, wcell_l<LAYOUT>(w, T_KEY_LO, ip)) && fr_eq(key_hi, wcell_l<LAYOUT>(w, T_KEY_HI, ip));
+  const Fr val_lo = wcell_l<LAYOUT>(w, T_VAL_LO, i), val_hi = wcell_l<LAYOUT>(w, T_VAL_HI, i);
+  const Fr init_lo = wcell_l<LAYOUT>(w, T_INIT_LO, i), init_hi = wcell_l<LAYOUT>(w, T_INIT_HI, i);
   const bool read = fr_is_zero(is_write);
   if (read && same)
-    ST_CHECK(ST_READ_CONSISTENCY, fr_eq(val_lo, wcell(w, T_VAL_LO, ip)) && fr_eq(val_hi, wcell(w, T_VAL_HI, ip)));
+    ST_CHECK(ST_READ_CONSISTENCY, fr_eq(val_lo, wcell_l<LAYOUT>(w, T_VAL_LO, ip)) && fr_eq(val_hi, wcell_l<LAYOUT>(w, T_VAL_HI, ip)));
   if (same)
-    ST_CHECK(ST_INITIAL_CONSISTENCY, fr_eq(init_lo, wcell(w, T_INIT_LO, ip)) && fr_eq(init_hi, wcell(w, T_INIT_HI, ip)));
+    ST_CHECK(ST_INITIAL_CONSISTENCY, fr_eq(init_lo, wcell_l<LAYOUT>(w, T_INIT_LO, ip)) && fr_eq(init_hi, wcell_l<LAYOUT>(w, T_INIT_HI, ip)));
   if (!is_start) ST_CHECK(ST_RWC_NONZERO, !fr_is_zero(rwc));
 
   const bool key0 = fr_is_zero(key_lo) && fr_is_zero(key_hi);
-  const bool root_same = fr_eq(wcell(w, T_ROOT_LO, i), wcell(w, T_ROOT_LO, ip)) &&
-                         fr_eq(wcell(w, T_ROOT_HI, i), wcell(w, T_ROOT_HI, ip));
+  const bool root_same = fr_eq(wcell_l<LAYOUT>(w, T_ROOT_LO, i), wcell_l<LAYOUT>(w, T_ROOT_LO, ip)) &&
+                         fr_eq(wcell_l<LAYOUT>(w, T_ROOT_HI, i), wcell_l<LAYOUT>(w, T_ROOT_HI, ip));
   const unsigned char fl = w.flags ? w.flags[i] : 0;
   const bool val_word = fl & 1, init_word = fl & 2;
   const bool first_read = !same && read;
   const bool val0 = fr_is_zero(val_lo) && fr_is_zero(val_hi), init0 = fr_is_zero(init_lo) && fr_is_zero(init_hi);
   const bool ft0 = fr_is_zero(ft), addr0 = fr_is_zero(addr), id0 = fr_is_zero(id);
   // keys of the next row differ? (last access of Storage / Account keys)
-  const bool next_same = fr_eq(tag, wcell(w, T_TAG, in)) && fr_eq(id, wcell(w, T_ID, in)) &&
-                         fr_eq(addr, wcell(w, T_ADDR, in)) && fr_eq(ft, wcell(w, T_FIELD_TAG, in)) &&
-                         fr_eq(key_lo, wcell(w, T_KEY_LO, in)) && fr_eq(key_hi, wcell(w, T_KEY_HI, in));
+  const bool next_same = fr_eq(tag, wcell_l<LAYOUT>(w, T_TAG, in)) && fr_eq(id, wcell_l<LAYOUT>(w, T_ID, in)) &&
+                         fr_eq(addr, wcell_l<LAYOUT>(w, T_ADDR, in)) && fr_eq(ft, wcell_l<LAYOUT>(w, T_FIELD_TAG, in)) &&
+                         fr_eq(key_lo, wcell_l<LAYOUT>(w, T_KEY_LO, in)) && fr_eq(key_hi, wcell_l<LAYOUT>(w, T_KEY_HI, in));
   bool need_mpt = false;
   u64 proof_type = 0;
   int mpt_unsat_id = ST_STO_MPT_UNSAT;
   if (live) {
     switch (t) {
       case ZK_ST_Start: {
-        const Fr sel = wcell(w, T_SELECTOR, i);
+        const Fr sel = wcell_l<LAYOUT>(w, T_SELECTOR, i);
         ST_CHECK(ST_START_FIELD_TAG0, ft0);
         ST_CHECK(ST_START_ADDR0, addr0);
         ST_CHECK(ST_START_ID0, id0);
         ST_CHECK(ST_START_KEY0, key0);
         ST_CHECK(ST_START_VALUE_HI0, fr_is_zero(val_hi));
         ST_CHECK(ST_START_INIT_HI0, fr_is_zero(init_hi));
-        ST_CHECK(ST_START_RWC_INC, fr_is_zero(sel) || fr_eq(rwc, fr_add_u64(wcell(w, T_RWC, ip), 1)));
+        ST_CHECK(ST_START_RWC_INC, fr_is_zero(sel) || fr_eq(rwc, fr_add_u64(wcell_l<LAYOUT>(w, T_RWC, ip), 1)));
         ST_CHECK(ST_START_VALUE0, !val_word && fr_is_zero(val_lo));
         ST_CHECK(ST_START_INIT0, !init_word && fr_is_zero(init_lo));
         if (!fr_is_zero(sel)) ST_CHECK(ST_START_ROOT_SAME, root_same);
@@ -273,7 +278,7 @@ ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const 
           ST_CHECK(ST_RCP_TXID_INC, fr_eq(id, fr_add_u64(p_id, 1)));
           if (fr_eq_u64(ft, ZK_RCPT_CumulativeGasUsed)) {
             const bool p_val_word = w.flags && (w.flags[ip] & 1);
-            ST_CHECK(ST_RCP_GAS_INC, !val_word && !p_val_word && fr_lt(wcell(w, T_VAL_LO, ip), val_lo));
+            ST_CHECK(ST_RCP_GAS_INC, !val_word && !p_val_word && fr_lt(wcell_l<LAYOUT>(w, T_VAL_LO, ip), val_lo));
           }
         }
         if (!tag_same) ST_CHECK(ST_RCP_FIRST_TXID1, fr_eq_u64(id, 1));
@@ -288,23 +293,64 @@ ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const 
   // MPT lookup for the last access of a Storage / Account key (warp-wide probe)
   {
     const bool go = live && need_mpt;
-    Fr key[12] = {addr, fr_u64(proof_type), key_lo, key_hi, wcell(w, T_ROOT_LO, i), wcell(w, T_ROOT_HI, i),
-                  wcell(w, T_ROOT_LO, ip), wcell(w, T_ROOT_HI, ip), val_lo, val_hi, init_lo, init_hi};
+    Fr key[12] = {addr, fr_u64(proof_type), key_lo, key_hi, wcell_l<LAYOUT>(w, T_ROOT_LO, i), wcell_l<LAYOUT>(w, T_ROOT_HI, i),
+                  wcell_l<LAYOUT>(w, T_ROOT_LO, ip), wcell_l<LAYOUT>(w, T_ROOT_HI, ip), val_lo, val_hi, init_lo, init_hi};
     u32 hit;
     const int n = lookup_sync<12>(mpt, key, &hit, mask, go);
     if (go && n != 1 && record) fail(res, n == 0 ? mpt_unsat_id : mpt_unsat_id + 1, row);
   }
 }
 
+// whole row on one thread (tests/emu, and rows the tiled kernel cannot serve from shared memory)
+template <int LAYOUT>
+ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const IndexDev& mpt, const ResultDev& res,
+                               u64 i, bool live, unsigned mask) {
+  Fr key_int, p_key_int;
+  const bool bytes_ok = gather_key_bytes<LAYOUT>(w, i, &key_int);
+  const bool p_bytes_ok = gather_key_bytes<LAYOUT>(w, rot_back(w, i, rg.flags & ZK_FLAG_WRAP), &p_key_int);
+  check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, mask, key_int, bytes_ok, p_key_int, p_bytes_ok);
+}
+
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) k_check_state(WitnessDev w, CheckRange rg, IndexDev mpt, ResultDev res) {
+// One thread per row, 128 consecutive rows per block iteration.  Every thread folds the 32 storage-key
+// byte cells of ITS row once and leaves the 256-bit integer in shared memory for its successor (the
+// ordering check packs the previous row's key too: state_circuit.py:552-570); the row before the tile is
+// folded by warp 0, one byte cell per lane.
+#define ZK_STATE_TILE 128
+template <int LAYOUT>
+__global__ void __launch_bounds__(ZK_STATE_TILE, 3) k_check_state(WitnessDev w, CheckRange rg, IndexDev mpt, ResultDev res) {
+  __shared__ u64 s_key[ZK_STATE_TILE + 1][4];
+  __shared__ unsigned char s_ok[ZK_STATE_TILE + 1];
+  const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 n = rg.row_end - rg.row_begin;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  for (u64 first = 0; first < n; first += stride) {  // warp-uniform trip count
-    const u64 k = first + tid;
+  const u64 n_tiles = (n + ZK_STATE_TILE - 1) / ZK_STATE_TILE;
+  const unsigned tid = threadIdx.x, lane = tid & 31;
+  for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
+    const u64 first = rg.row_begin + tile * ZK_STATE_TILE;
+    const u64 k = tile * ZK_STATE_TILE + tid;
     const bool live = k < n;
-    check_state_row_dev(w, rg, mpt, res, rg.row_begin + (live ? k : 0), live, 0xFFFFFFFFu);
+    const u64 i = live ? rg.row_begin + k : first;
+    Fr key_int;
+    const bool bytes_ok = gather_key_bytes<LAYOUT>(w, i, &key_int);
+#pragma unroll
+    for (int q = 0; q < 4; q++) s_key[tid + 1][q] = key_int.l[q];
+    s_ok[tid + 1] = bytes_ok;
+    if (tid < 32) {  // the row before the tile: lane b folds byte cell b
+      const Fr c = wcell_l<LAYOUT>(w, T_BYTE0 + lane, rot_back(w, first, wrap));
+      const bool okb = fr_fits64(c) && c.l[0] < 256;
+      u64 v = (c.l[0] & 0xFF) << (8 * (lane & 7));
+      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+      const unsigned all_ok = __all_sync(0xFFFFFFFFu, okb);
+      if ((lane & 7) == 0) s_key[0][lane >> 3] = v;
+      if (lane == 0) s_ok[0] = all_ok;
+    }
+    __syncthreads();
+    const Fr p_key_int{{s_key[tid][0], s_key[tid][1], s_key[tid][2], s_key[tid][3]}};
+    const bool p_bytes_ok = s_ok[tid];
+    check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, 0xFFFFFFFFu, key_int, bytes_ok, p_key_int, p_bytes_ok);
+    __syncthreads();
   }
 }
 #endif

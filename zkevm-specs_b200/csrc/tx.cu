@@ -24,12 +24,14 @@ ZK_HD u64 cell_byte(const Fr& c, int k) { return (c.l[k >> 3] >> (8 * (k & 7))) 
 #define TX_CHECK(id, cond)      \
   do {                          \
     if (!(cond)) {              \
-      fail(res, (id), i);       \
+      fail(res, (id), row);     \
       return;                   \
     }                           \
   } while (0)
 
-ZK_HD void check_tx_row(const WitnessDev& w, const IndexDev& keccak, const Fr& r_mont, const ResultDev& res, u64 i) {
+ZK_HD void check_tx_row(const WitnessDev& w, const CheckRange& rg, const IndexDev& keccak, const Fr& r_mont,
+                        const ResultDev& res, u64 i) {
+  const u64 row = rg.row_base + i;  // reported row (zkcheck.h: first_fail holds row_base + local row)
   const Fr address = wcell(w, X_ADDR, i);
   const bool np = !fr_is_zero(address);  // is_not_padding, :206
   const Fr pkx_lo = wcell(w, X_PKX_LO, i), pkx_hi = wcell(w, X_PKX_HI, i);
@@ -88,7 +90,9 @@ ZK_HD bool word_int_eq(const Fr& lo, const Fr& hi, const Fr& c_lo, const Fr& c_h
             s5 = adc64(hi.l[3], 0, c);
   return lo.l[0] == c_lo.l[0] && lo.l[1] == c_lo.l[1] && s2 == c_hi.l[0] && s3 == c_hi.l[1] && s4 == 0 && s5 == 0 && c == 0;
 }
-ZK_HD void check_sig_row(const WitnessDev& w, const IndexDev& keccak, const Fr& r_mont, const ResultDev& res, u64 i) {
+ZK_HD void check_sig_row(const WitnessDev& w, const CheckRange& rg, const IndexDev& keccak, const Fr& r_mont,
+                         const ResultDev& res, u64 i) {
+  const u64 row = rg.row_base + i;
   const Fr pkx_lo = wcell(w, Y_PKX_LO, i), pkx_hi = wcell(w, Y_PKX_HI, i);
   const Fr pky_lo = wcell(w, Y_PKY_LO, i), pky_hi = wcell(w, Y_PKY_HI, i);
   const Fr pkh_lo = wcell(w, Y_PKH_LO, i), pkh_hi = wcell(w, Y_PKH_HI, i);
@@ -129,12 +133,12 @@ ZK_HD void check_sig_row(const WitnessDev& w, const IndexDev& keccak, const Fr& 
 __global__ void __launch_bounds__(128) k_check_sig(WitnessDev w, CheckRange rg, IndexDev keccak, Fr r_mont, ResultDev res) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rg.row_end; i += stride)
-    check_sig_row(w, keccak, r_mont, res, i);
+    check_sig_row(w, rg, keccak, r_mont, res, i);
 }
 __global__ void __launch_bounds__(128) k_check_tx(WitnessDev w, CheckRange rg, IndexDev keccak, Fr r_mont, ResultDev res) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rg.row_end; i += stride)
-    check_tx_row(w, keccak, r_mont, res, i);
+    check_tx_row(w, rg, keccak, r_mont, res, i);
 }
 #endif
 

@@ -76,11 +76,10 @@ def pack_witness(witness: Witness, MAX_TXS: int):
         assert chip.pub_key_y_bytes == chip.ecdsa_chip.pub_key_y_bytes
         assert chip.msg_hash_bytes == chip.ecdsa_chip.msg_hash_bytes
         ecdsa_failed = 0
-        if c(chip.address) != 0 or True:  # the reference calls ecdsa_chip.verify for every tx (:242)
-            try:
-                chip.ecdsa_chip.verify(f"Constraints failed for tx_index = {tx_index}")
-            except AssertionError:
-                ecdsa_failed = 1
+        try:  # the reference calls ecdsa_chip.verify for every tx, padding ones included (:242)
+            chip.ecdsa_chip.verify(f"Constraints failed for tx_index = {tx_index}")
+        except AssertionError:
+            ecdsa_failed = 1
         cells.append([c(chip.address), *_word_cells(bytes(chip.pub_key_x_bytes)), *_word_cells(bytes(chip.pub_key_y_bytes)),
                       *_word_cells(bytes(chip.pub_key_hash)), c(chip.msg_hash.lo), c(chip.msg_hash.hi),
                       *_word_cells(bytes(chip.msg_hash_bytes)), c(caller.value.lo), c(sign_hash.value.lo),
