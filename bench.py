@@ -1,23 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — constraint-rows/sec of the EVM-circuit hot path on B200.
+"""bench.py — constraint-rows/sec of the zkevm-specs hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--groups G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W] [--scaling S]
 
-Workload (config.workload): BASELINE cfg2 generator scaled to the metric's 2^20 rows —
-per GPU 2^18 groups `PUSH32 b, PUSH32 a, {ADD,SUB,MUL,DIV,MOD}, POP` = 2^20 execution steps,
+Main line (the bench contract): workload `evm` = BASELINE cfg2's generator scaled to the metric's 2^20
+rows — per GPU 2^18 groups `PUSH32 b, PUSH32 a, {ADD,SUB,MUL,DIV,MOD}, POP` = 2^20 execution steps,
 17.8 M bytecode-table rows, 1.57 M rw-table rows, fixed table 224,490 rows (synthetic, seeded).
-One "step" of the bench = one pass of the whole hot path over that witness: build the lookup
-indexes of the bytecode / rw tables on the device, then check every execution step.
-  value : rows/s with all inputs resident in HBM (CUDA events on the launching stream)
-  e2e   : rows/s through the C-ABI with HOST (pinned) buffers: H2D of tables + steps, index
-          build, check, D2H of the result vector, all inside the timed region
-  roofline : algorithmic bytes of the check kernel / its device time, vs MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (a C port of the reference algorithm; the reference itself is
-          pure Python and absent on this box) on a bounded sample of the same workload
-Multi-GPU (torchrun): rows are sharded (each rank checks its own 2^20-step shard against its
-replicated tables), then ONE all-reduce(MIN) of the first-fail vector; scaling "weak".
+One "step" of the bench = one pass of the whole hot path over that witness: build the lookup indexes
+of the bytecode / rw tables on the device, then check every execution step.
+  value    : rows/s with all inputs resident in HBM (CUDA events on the launching stream)
+  e2e      : rows/s through the C-ABI with HOST (pinned) buffers: H2D of tables + steps, index build,
+             check, D2H of the result vector, all inside the timed region
+  roofline : algorithmic bytes of the check phase / its device time vs MEASURED_PEAKS.json, next to the
+             honest denominators: stored bytes (what sits in HBM) and DRAM traffic (ncu capture of THIS
+             build, profiles/, matched by source hash — null when the sources changed since the capture)
+  cpu_baseline : the CPU oracle (a C port of the reference algorithm; the reference itself is pure
+             Python and absent on this box) on a bounded sample of the same workload
+Extra objects on the same line (`--no-extras` skips them; they are not inside the main timed region):
+  typed          : the same check with data-independent column widths (packing.TYPE_WIDTHS)
+  circuits       : BASELINE cfg3 (state 2^18 rows), cfg4's copy circuit (2^20 rows) and the bytecode
+                   circuit (2^19 rows) on canonical 32-byte cells, each with its own roofline
+  strong_scaling : ONE 2^20-step witness split over the N ranks (tables replicated, step shards with
+                   a halo step, one collective) — north_star's "2^20-row witness at 1/2/4/8 B200"
+  cfg4 / cfg5    : copy circuit 2^20 rows and the super circuit (evm + state + copy + bytecode, 2^22 rows
+                   in total) row-sharded over the N ranks
+Multi-GPU (torchrun): rows are sharded, tables replicated, then ONE collective on the result vectors
+(zk_allreduce_results: NCCL all-gather + fold); main line scaling "weak" (own 2^20-step shard per rank).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -30,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_CELLS_STEP, N_CELLS_RW, N_CELLS_BYTECODE = 13, 14, 6
+DTYPE = "u64 limbs (BN254 Fr, 254-bit modular)"
 
 
 class ClockSampler(threading.Thread):
@@ -88,6 +100,27 @@ def algorithmic_bytes(n_steps, n_rw, n_bytecode, n_constraints):
     return 32 * (n_steps * N_CELLS_STEP + n_rw * N_CELLS_RW + n_bytecode * N_CELLS_BYTECODE) + 4 * n_constraints
 
 
+def source_hash() -> str:
+    """hash of the CUDA sources: ties a profiles/ capture to the build it was taken from"""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "zkevm-specs_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_capture():
+    """profiles/current_capture.json: {"source_hash", "dram_bytes_per_check", "kernels": {...}} written by
+    tools/traffic_from_ncu.py from an `ncu --set full` capture of this command; used only when its
+    source_hash matches the sources on disk"""
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "current_capture.json")))
+        return c if c.get("source_hash") == source_hash() else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _cpu_port_worker(args):
     sample_groups, seed = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -119,10 +152,8 @@ def cpu_port(sample_groups: int, seed: int, threads: int):
 
     oracle_lib.lib()  # build once before forking
     with mp.get_context("fork").Pool(threads) as pool:
-        t0 = time.perf_counter()
         res = pool.map(_cpu_port_worker, [(sample_groups, seed + k) for k in range(threads)])
-        wall = time.perf_counter() - t0
-    # generation time is inside `wall`; use the max of the measured check times (they overlap)
+    # generation time is outside; use the max of the measured check times (they overlap)
     return sum(r[0] for r in res), max(r[1] for r in res)
 
 
@@ -161,7 +192,7 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "constraint-rows/sec", "value": v, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (BN254 Fr, 254-bit modular)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic",
         "config": {"workload": f"evm_circuit ADD/SUB/MUL/DIV/MOD trace (cfg2 generator), bounded sample: {cores} x "
                                f"{4 * sample_groups} steps per bench step (same generator as the CUDA arm)", "seed": 2},
@@ -174,6 +205,184 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+class Harness:
+    """device context + timing helpers shared by every workload of one rank"""
+
+    def __init__(self, rank, world, local):
+        import torch
+        import torch.distributed as dist
+
+        from zkevm_specs_b200 import native
+
+        self.torch, self.dist, self.native = torch, dist, native
+        self.rank, self.world, self.local = rank, world, local
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        self.ctx = native.Context(local)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        if world > 1:  # the library's own communicator (zk_nccl_*): id drawn on rank 0, shipped through torch
+            box = [self.ctx.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.ctx.nccl_init(world, rank, box[0])
+        self.peak = 6650.0
+        self.peak_source = "fallback 6.65 TB/s"
+        try:
+            self.peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            self.peak_source = "MEASURED_PEAKS.json (burst copy)"
+        except Exception:  # noqa: BLE001
+            pass
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, k):
+        """device time of k calls of fn, barrier + synchronize on both sides, max over ranks (ms)"""
+        torch = self.torch
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        self.sync_all()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=f"cuda:{self.local}")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def check_pass(self, circuit):
+        ff, _ = self.ctx.fetch_result(circuit, self.stream)
+        assert (ff == self.native.PASS).all(), f"witness rejected: {self.native.first_failure(ff, circuit)}"
+
+    def phases(self, circuit, row_begin, row_end, row_base, flags, reps):
+        """(index build ms, check ms) of one check, device-timed inside the library, mean of reps"""
+        ctx = self.ctx
+        ctx.enable_timing(True)
+        idx, chk = [], []
+        for _ in range(reps):
+            ctx.invalidate_indexes()
+            ctx.check_async(circuit, row_begin, row_end, row_base, flags, self.stream)
+            a, b = ctx.last_timing()
+            idx.append(a)
+            chk.append(b)
+        ctx.enable_timing(False)
+        return float(np.mean(idx)), float(np.mean(chk))
+
+    def sharded_pass(self, circuit, row_begin, row_end, row_base, flags, reps):
+        """whole pass of one (sharded) circuit: index builds + check + the one collective; returns ms per pass,
+        max over ranks"""
+        ctx = self.ctx
+
+        def one():
+            ctx.invalidate_indexes()
+            ctx.check_async(circuit, row_begin, row_end, row_base, flags, self.stream)
+            if self.world > 1:
+                ctx.allreduce_results(circuit, self.stream)
+
+        for _ in range(3):
+            one()
+        self.check_pass(circuit)
+        return self.timed(one, reps) / reps
+
+
+def shard(n, rank, world):
+    b = n * rank // world
+    return b, n * (rank + 1) // world
+
+
+def take_rows(m, idx):
+    return np.ascontiguousarray(np.take(m, idx, axis=1))
+
+
+def roofline_of(h, chk_ms, bytes_alg, stored=None, **extra):
+    ach = bytes_alg / (chk_ms / 1e3) / 1e9
+    d = {"bound": "hbm", "achieved": ach, "peak": h.peak, "unit": "GB/s", "frac": ach / h.peak, "traffic": None,
+         "kernel_ms": chk_ms, "algorithmic_bytes": int(bytes_alg), "peak_source": h.peak_source}
+    if stored is not None:
+        d["stored_bytes"] = int(stored)
+        d["stored_frac"] = stored / (chk_ms / 1e3) / 1e9 / h.peak
+    d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# row circuits (canonical storage), optionally row-sharded over the ranks
+def bench_state(h, n_rows, reps, seed=3):
+    from zkevm_specs_b200 import synth
+    native = h.native
+    w = synth.state_rows(n_rows, seed=seed)
+    n = w["rows"].shape[1]
+    h.ctx.upload_table(native.TABLE_MPT, w["mpt"], stream=h.stream)
+    b, e = shard(n, h.rank, h.world)
+    if h.world == 1:
+        h.ctx.upload_columns(native.CIRCUIT_STATE, w["rows"], flags=w["flags"], stream=h.stream)
+        rng = (0, n, 0, native.FLAG_WRAP)
+    else:  # rows b-1 .. e (rotations -1, +1), wrapping at the ends of the circuit
+        idx = np.arange(b - 1, e + 1) % n
+        h.ctx.upload_columns(native.CIRCUIT_STATE, take_rows(w["rows"], idx), flags=w["flags"][idx], stream=h.stream)
+        rng = (1, 1 + e - b, b - 1, 0)
+    ms = h.sharded_pass(native.CIRCUIT_STATE, *rng, reps)
+    i_ms, c_ms = h.phases(native.CIRCUIT_STATE, *rng, min(reps, 10))
+    byt = 32 * ((e - b) * 57 + w["mpt"].shape[1] * 12)
+    return {"circuit": "state", "rows": n, "rows_per_gpu": e - b, "ms_per_pass": ms, "rows_per_s": n / (ms / 1e3),
+            "index_ms": i_ms, "roofline": roofline_of(h, c_ms, byt, kernel="k_check_state<L_CANON>")}
+
+
+def bench_copy(h, n_events, length, reps, seed=4):
+    from zkevm_specs_b200 import synth
+    native = h.native
+    w = synth.copy_events(n_events, length, seed=seed)
+    n = w["copy"].shape[1]
+    ctx = h.ctx
+    ctx.set_challenge(native.CHALLENGE_KECCAK, sum(int(w["r"][k]) << (64 * k) for k in range(4)))
+    ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"], stream=h.stream)
+    ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"], stream=h.stream)
+    ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"], stream=h.stream)
+    b, e = shard(n, h.rank, h.world)
+    if h.world == 1:
+        ctx.upload_columns(native.CIRCUIT_COPY, w["copy"], flags=w["copy_flags"], stream=h.stream)
+        rng = (0, n, 0, native.FLAG_WRAP)
+    else:  # rows b .. e+1 (rotations +1, +2)
+        idx = np.arange(b, e + 2) % n
+        ctx.upload_columns(native.CIRCUIT_COPY, take_rows(w["copy"], idx), flags=w["copy_flags"][idx], stream=h.stream)
+        rng = (0, e - b, b, 0)
+    ms = h.sharded_pass(native.CIRCUIT_COPY, *rng, reps)
+    i_ms, c_ms = h.phases(native.CIRCUIT_COPY, *rng, min(reps, 10))
+    byt = 32 * ((e - b) * 20 + w["rw"].shape[1] * 14 + w["tx"].shape[1] * 5)
+    return {"circuit": "copy", "rows": n, "rows_per_gpu": e - b, "rw_rows": int(w["rw"].shape[1]), "tx_rows": int(w["tx"].shape[1]),
+            "ms_per_pass": ms, "rows_per_s": n / (ms / 1e3), "index_ms": i_ms,
+            "roofline": roofline_of(h, c_ms, byt, kernel="k_check_copy<L_CANON>")}
+
+
+def bench_bytecode(h, k, reps):
+    from zkevm_specs_b200 import synth
+    native = h.native
+    w = synth.bytecode_circuit_rows(k, 8)
+    n = w["rows"].shape[1]
+    ctx = h.ctx
+    ctx.set_challenge(native.CHALLENGE_KECCAK, sum(int(w["r"][k_]) << (64 * k_) for k_ in range(4)))
+    ctx.upload_table(native.TABLE_PUSH, w["push"], stream=h.stream)
+    ctx.upload_table(native.TABLE_KECCAK, w["keccak"], stream=h.stream)
+    b, e = shard(n, h.rank, h.world)
+    if h.world == 1:
+        ctx.upload_columns(native.CIRCUIT_BYTECODE, w["rows"], stream=h.stream)
+        rng = (0, n, 0, native.FLAG_WRAP)
+    else:  # rows b .. e (rotation +1)
+        idx = np.arange(b, e + 1) % n
+        ctx.upload_columns(native.CIRCUIT_BYTECODE, take_rows(w["rows"], idx), stream=h.stream)
+        rng = (0, e - b, b, 0)
+    ms = h.sharded_pass(native.CIRCUIT_BYTECODE, *rng, reps)
+    i_ms, c_ms = h.phases(native.CIRCUIT_BYTECODE, *rng, min(reps, 10))
+    return {"circuit": "bytecode", "rows": n, "rows_per_gpu": e - b, "ms_per_pass": ms, "rows_per_s": n / (ms / 1e3),
+            "index_ms": i_ms, "roofline": roofline_of(h, c_ms, 32 * (e - b) * 12, kernel="k_check_bytecode<L_CANON>")}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +393,13 @@ def main():
     ap.add_argument("--ref-groups", type=int, default=1 << 12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip typed / circuits / strong_scaling / cfg4 / cfg5")
+    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode"], default="evm",
+                    help="evm: the bench contract's line.  state / copy / bytecode: only that row circuit (canonical "
+                         "storage; for profiling), printed as a JSON line of its own")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="main line under torchrun: weak = every rank checks its own 2^20-step witness; strong = ONE "
+                         "2^20-step witness split over the ranks")
     ap.add_argument("--storage", choices=["adaptive", "typed", "packed", "canonical"], default="adaptive",
                     help="adaptive: the packer's default — every column at its measured minimal width, constant "
                          "columns stored once (packing.pack_matrix); typed (= packed): data-independent widths by "
@@ -200,43 +416,58 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
-
-    from zkevm_specs_b200 import native, synth
-    from zkevm_specs_b200.evm_circuit.table import fixed_table_matrix
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = native.Context(local)
-    stream = torch.cuda.current_stream().cuda_stream
+    h = Harness(rank, world, local)
+    native, ctx, stream, dist = h.native, h.ctx, h.stream, h.dist
+    from zkevm_specs_b200 import packing, synth
+    from zkevm_specs_b200.evm_circuit.table import fixed_table_matrix
 
-    # ---- synthetic witness (per rank: its own row shard, own seed) -------------------------
-    w = synth.evm_trace(args.groups, seed=2 + rank)
-    n_steps = w["n_steps"]
+    if args.workload != "evm":
+        reps = max(3, min(args.steps, 20))
+        d = {"state": lambda: bench_state(h, 1 << 18, reps), "copy": lambda: bench_copy(h, 512, 1024, reps),
+             "bytecode": lambda: bench_bytecode(h, 19, reps)}[args.workload]()
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "n_gpus": world, "storage": "canonical", **d}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- synthetic witness ---------------------------------------------------------------------
+    # weak: per rank its own row shard, own seed.  strong: every rank generates the SAME 2^20-step
+    # witness (tables replicated) and uploads only its step shard + the halo step.
+    strong = args.scaling == "strong" and world > 1
+    t0 = time.perf_counter()
+    w = synth.evm_trace(args.groups, seed=2 + (0 if strong else rank))
+    gen_s = time.perf_counter() - t0
+    n_total = w["n_steps"]
+    sb, se = shard(n_total, rank, world) if strong else (0, n_total)
+    n_steps = se - sb
     fixed = fixed_table_matrix()
     n_rw, n_bc = w["rw"].shape[1], w["bytecode"].shape[1]
     n_constraints = ctx.n_constraints(native.CIRCUIT_EVM)
     ctx.upload_table(native.TABLE_FIXED, fixed, stream=stream)  # circuit constant: uploaded once
+    steps_m = w["steps"] if not strong else take_rows(w["steps"], np.arange(sb, se + 1))
+    row_base = sb if strong else rank * n_steps
     if args.storage == "packed":
         args.storage = "typed"
+    host_pack_ms = None
     if args.storage in ("adaptive", "typed"):
-        from zkevm_specs_b200 import packing
+        t0 = time.perf_counter()
         if args.storage == "typed":
-            packed = {"steps": packing.pack_matrix(w["steps"], min_widths=packing.TYPE_WIDTHS["evm_steps"]),
+            packed = {"steps": packing.pack_matrix(steps_m, min_widths=packing.TYPE_WIDTHS["evm_steps"]),
                       "bytecode": packing.pack_matrix(w["bytecode"], min_widths=packing.TYPE_WIDTHS["bytecode_table"]),
                       "rw": packing.pack_matrix(w["rw"], min_widths=packing.TYPE_WIDTHS["rw_table"])}
             fmt = "packed columns, data-independent type widths (packing.TYPE_WIDTHS)"
         else:
-            w["bytecode"] = None  # 3.4 GB of unrolled canonical rows: not needed on this path (8 ranks share the host)
-            packed = {k: packing.pack_matrix(w[k]) for k in ("steps", "rw")}
+            packed = {"steps": packing.pack_matrix(steps_m), "rw": packing.pack_matrix(w["rw"])}
             fmt = ("steps / rw table: packed columns, measured minimal width per column, constant columns stored "
                    "once (packing.pack_matrix default; the packing scan is host preparation, outside the timed "
-                   "region).  bytecode table: the raw code bytes + 1 is_code bit per byte + 1 hash per contract, "
-                   "unrolled on the device (zk_upload_bytecode_table_from_code = Bytecode.table_assignments, "
+                   "region: host_pack_ms).  bytecode table: the raw code bytes + 1 is_code bit per byte + 1 hash per "
+                   "contract, unrolled on the device (zk_upload_bytecode_table_from_code = Bytecode.table_assignments, "
                    "typing.py:390-427), inside the timed region")
+        host_pack_ms = 1e3 * (time.perf_counter() - t0)
         pinned = {k: torch.from_numpy(pm.buf).pin_memory() for k, pm in packed.items()}
         h2d_bytes = sum(pm.nbytes for pm in packed.values())
         src = None
@@ -251,7 +482,7 @@ def main():
             widths["bytecode"] = [16, 16, 1, 4, 1, 4]  # written by k_bytecode_table_expand
         storage = {"format": fmt, "widths": widths, "stored_bytes": stored}
 
-        def upload_inputs():
+        def upload_inputs(ctx=ctx, stream=stream):
             if src is not None:
                 ctx.upload_bytecode_table_from_code(src["code"], src["is_code_bits"], src["code_offsets"], src["hashes"],
                                                     stream=stream, ptrs=(pinned["code"].data_ptr(), pinned["bits"].data_ptr()))
@@ -261,102 +492,57 @@ def main():
             ctx.upload_table_packed(native.TABLE_RW, packed["rw"], stream=stream, host_ptr=pinned["rw"].data_ptr())
             ctx.upload_columns_packed(native.CIRCUIT_EVM, packed["steps"], stream=stream, host_ptr=pinned["steps"].data_ptr())
     else:
-        pinned = {k: torch.from_numpy(w[k]).pin_memory() for k in ("steps", "bytecode", "rw")}
+        pinned = {"steps": torch.from_numpy(steps_m).pin_memory(), "bytecode": torch.from_numpy(w["bytecode"]).pin_memory(),
+                  "rw": torch.from_numpy(w["rw"]).pin_memory()}
         h2d_bytes = 32 * ((n_steps + 1) * N_CELLS_STEP + n_rw * N_CELLS_RW + n_bc * N_CELLS_BYTECODE)
         storage = {"format": "canonical 32-byte cells", "stored_bytes": h2d_bytes}
 
-        def upload_inputs():
+        def upload_inputs(ctx=ctx, stream=stream):
             ctx.upload_table_ptr(native.TABLE_BYTECODE, n_bc, 6, pinned["bytecode"].data_ptr(), stream)
             ctx.upload_table_ptr(native.TABLE_RW, n_rw, 14, pinned["rw"].data_ptr(), stream)
             ctx.upload_columns_ptr(native.CIRCUIT_EVM, n_steps + 1, 13, pinned["steps"].data_ptr(), stream)
 
-    # result buffer as a torch tensor (zero-copy) for the NCCL all-reduce
-    class _Raw:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-
-    def hot_path():
+    def hot_path(ctx=ctx, stream=stream):
         """index builds + check of every step; + the one collective when sharded"""
         ctx.invalidate_indexes()
-        ctx.check_async(native.CIRCUIT_EVM, 0, n_steps, rank * n_steps, 0, stream)
+        ctx.check_async(native.CIRCUIT_EVM, 0, n_steps, row_base, 0, stream)
         if world > 1:
-            ff_ptr, _ = ctx.result_device_ptrs(native.CIRCUIT_EVM)
-            t = torch.as_tensor(_Raw(ff_ptr, n_constraints), device=f"cuda:{local}")
-            # first_fail is uint32 with 0xFFFFFFFF = pass; as int32 that is -1, so MIN over uint32
-            # == MIN over (x ^ 0x80000000) as int32
-            t ^= -0x80000000
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            t ^= -0x80000000
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, k):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            ctx.allreduce_results(native.CIRCUIT_EVM, stream)
 
     upload_inputs()
     for _ in range(args.warmup):
         hot_path()
-    ff, fc = ctx.fetch_result(native.CIRCUIT_EVM, stream)
-    assert (ff == native.PASS).all(), f"witness rejected: {native.first_failure(ff, native.CIRCUIT_EVM)}"
+    h.check_pass(native.CIRCUIT_EVM)
 
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launch_count()
-    ms = timed(hot_path, args.steps)
+    ms = h.timed(hot_path, args.steps)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
-    value = world * n_steps * args.steps / (ms / 1e3)
+    rows_per_step = n_total if strong else world * n_steps
+    value = rows_per_step * args.steps / (ms / 1e3)
 
-    # ---- roofline of the dominant kernel (k_check_evm), device-timed per launch -------------
-    ctx.enable_timing(True)
-    idx_ms, chk_ms = [], []
-    for _ in range(args.steps):
-        ctx.invalidate_indexes()
-        ctx.check_async(native.CIRCUIT_EVM, 0, n_steps, rank * n_steps, 0, stream)
-        a, b = ctx.last_timing()
-        idx_ms.append(a)
-        chk_ms.append(b)
-    ctx.enable_timing(False)
+    # ---- roofline of the check phase, device-timed per launch inside the library ----------------
+    idx_ms, chk = h.phases(native.CIRCUIT_EVM, 0, n_steps, row_base, 0, min(args.steps, 50))
     bytes_alg = algorithmic_bytes(n_steps, n_rw, n_bc, n_constraints)
-    chk = float(np.mean(chk_ms))
-    achieved = bytes_alg / (chk / 1e3) / 1e9
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:  # DRAM bytes of the same kernels from the committed `ncu --set full` capture of this command
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
-        traffic = tj["dram_bytes_per_check"] if tj.get("storage", "canonical") == args.storage else None
-    except Exception:  # noqa: BLE001
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic if args.groups == (1 << 18) else None,
-                "kernel": "evm check phase: k_evm_classify + k_evm_push_pos (~33 %) + k_evm_gadget<ADD|MUL|POP, POS> (MUL ~35 %) + k_evm_misc",
-                "kernel_ms": chk, "index_build_ms": float(np.mean(idx_ms)),
-                "algorithmic_bytes": bytes_alg, "stored_bytes": storage["stored_bytes"],
-                "achieved_stored_gbs": storage["stored_bytes"] / (chk / 1e3) / 1e9,
-                "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6.65 TB/s"}
+    cap = load_capture() if (args.groups == (1 << 18) and args.storage == "adaptive" and not strong) else None
+    roofline = roofline_of(h, chk, bytes_alg, stored=storage["stored_bytes"],
+                           kernel="evm check phase: k_evm_classify + k_evm_scatter + k_evm_push_pos + k_evm_gadget<MUL|ADD|POP, POS>",
+                           index_build_ms=idx_ms, achieved_stored_gbs=storage["stored_bytes"] / (chk / 1e3) / 1e9,
+                           note="frac uses SURVEY.md 8(d)'s canonical bytes (every cell at 32 B); the kernels read the "
+                                "narrow stored columns, so stored_frac / dram_frac are the figures that bound them — they "
+                                "are latency- / issue-bound, not byte-bound (profiles/README.md)")
+    if cap:
+        roofline["traffic"] = cap["dram_bytes_per_check"]
+        roofline["dram_frac"] = cap["dram_bytes_per_check"] / (chk / 1e3) / 1e9 / h.peak
+        roofline["ncu"] = {k: cap[k] for k in ("capture", "kernels", "kernel_ms_sum") if k in cap}
 
-    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----------------
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region --------------------
+    # Every step ships its inputs from pinned host memory, builds the indexes, checks, and reads the result
+    # vector back.  `serial`: one context, step k+1 starts when step k's result is on the host (latency of
+    # one check).  `value`: the throughput of a STREAM of checks — two contexts on two streams alternate, so
+    # step k+1's host->device copies run under step k's kernels (the copy engine never waits for the SMs).
     e2e = None
     if not args.no_e2e:
         def e2e_step():
@@ -365,10 +551,98 @@ def main():
             ctx.fetch_result(native.CIRCUIT_EVM, stream)
 
         e2e_step()
-        k_e2e = max(3, min(args.steps, 20))
-        ms_e2e = timed(e2e_step, k_e2e)
-        e2e = {"value": world * n_steps * k_e2e / (ms_e2e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": n_constraints * 12, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e}
+        k_e2e = max(4, min(args.steps, 20))
+        ms_serial = h.timed(e2e_step, k_e2e)
+        ctx2 = native.Context(local)
+        s2 = torch.cuda.Stream()
+        stream2 = s2.cuda_stream
+        ctx2.upload_table(native.TABLE_FIXED, fixed, stream=stream2)
+        if world > 1:
+            box = [ctx2.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx2.nccl_init(world, rank, box[0])
+        lanes = [(ctx, stream), (ctx2, stream2)]
+
+        def pipelined(k):
+            def run():
+                upload_inputs(*lanes[0])
+                for i in range(k):
+                    cur, nxt = lanes[i % 2], lanes[(i + 1) % 2]
+                    if i + 1 < k:
+                        upload_inputs(*nxt)  # enqueued before the (briefly host-blocking) check of `cur`
+                    hot_path(*cur)
+                    ff, _ = cur[0].fetch_result(native.CIRCUIT_EVM, cur[1])
+                    assert (ff == native.PASS).all()
+            return run
+
+        pipelined(2)()
+        torch.cuda.synchronize()
+        ms_e2e = h.timed(pipelined(k_e2e), 1)
+        if world > 1:
+            ctx2.nccl_destroy()
+        ctx2.close()
+        e2e = {"value": rows_per_step * k_e2e / (ms_e2e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": n_constraints * 12, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e,
+               "mode": "stream of checks, double-buffered: two contexts / two streams alternate, every step's H2D + "
+                       "index build + check + D2H inside the timed region",
+               "serial": {"value": rows_per_step * k_e2e / (ms_serial / 1e3), "ms_per_step": ms_serial / k_e2e,
+                          "mode": "one context, one stream: copy, then check, then read back"},
+               "host_pack_ms": host_pack_ms, "host_generate_ms": 1e3 * gen_s,
+               "note": "host_pack_ms (numpy scan of the canonical matrices into narrow columns) and host_generate_ms are "
+                       "host preparation done once, outside the timed region"}
+
+    # ---- extras ------------------------------------------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        reps = max(3, min(args.steps, 20))
+        if args.storage == "adaptive" and not strong:  # data-independent widths, same witness
+            tp = {"steps": packing.pack_matrix(w["steps"], min_widths=packing.TYPE_WIDTHS["evm_steps"]),
+                  "rw": packing.pack_matrix(w["rw"], min_widths=packing.TYPE_WIDTHS["rw_table"])}
+            ctx.upload_table_packed(native.TABLE_RW, tp["rw"], stream=stream)
+            ctx.upload_columns_packed(native.CIRCUIT_EVM, tp["steps"], stream=stream)
+            for _ in range(3):
+                hot_path()
+            h.check_pass(native.CIRCUIT_EVM)
+            t_ms = h.timed(hot_path, reps) / reps
+            ti, tc = h.phases(native.CIRCUIT_EVM, 0, n_steps, row_base, 0, reps)
+            extras["typed"] = {"value": world * n_steps / (t_ms / 1e3), "ms_per_step": t_ms, "kernel_ms": tc, "index_build_ms": ti,
+                               "stored_bytes": int(tp["steps"].nbytes + tp["rw"].nbytes + 42 * n_bc),
+                               "widths": {k: [int(x) for x in pm.widths] for k, pm in tp.items()}}
+            del tp
+        # ONE 2^20-step witness over the N ranks (at N = 1 this is the main line's workload)
+        if world > 1 and not strong:
+            ws = synth.evm_trace(args.groups, seed=2)
+            b, e = shard(ws["n_steps"], rank, world)
+            ctx.upload_bytecode_table_from_code(**ws["bytecode_src"], stream=stream)
+            ctx.upload_table_packed(native.TABLE_RW, packing.pack_matrix(ws["rw"]), stream=stream)
+            ctx.upload_columns_packed(native.CIRCUIT_EVM, packing.pack_matrix(take_rows(ws["steps"], np.arange(b, e + 1))), stream=stream)
+            s_ms = h.sharded_pass(native.CIRCUIT_EVM, 0, e - b, b, 0, reps)
+            si, sc = h.phases(native.CIRCUIT_EVM, 0, e - b, b, 0, reps)
+            extras["strong_scaling"] = {"rows": ws["n_steps"], "rows_per_gpu": e - b, "ms_per_pass": s_ms,
+                                        "rows_per_s": ws["n_steps"] / (s_ms / 1e3), "index_build_ms": si, "check_ms": sc,
+                                        "collective_and_launch_ms": s_ms - si - sc,
+                                        "bounded_by": max((("index build of the replicated tables", si), ("check kernels", sc),
+                                                           ("collective + launch gaps", s_ms - si - sc)), key=lambda x: x[1])[0]}
+            del ws
+        else:
+            extras["strong_scaling"] = {"rows": n_total, "rows_per_gpu": n_steps, "ms_per_pass": ms / args.steps,
+                                        "rows_per_s": value, "index_build_ms": idx_ms, "check_ms": chk}
+        # row circuits on canonical cells: cfg3, cfg4 (copy 2^20 rows, sharded over the ranks), bytecode 2^19
+        circuits = [bench_state(h, 1 << 18, reps), bench_copy(h, 512, 1024, reps), bench_bytecode(h, 19, reps)]
+        extras["circuits"] = circuits
+        extras["cfg4"] = {"copy_rows": circuits[1]["rows"], "rows_per_s": circuits[1]["rows_per_s"], "ms_per_pass": circuits[1]["ms_per_pass"],
+                          "sharding": f"copy rows over {world} rank(s), halos +1/+2, rw / tx tables replicated"}
+        # cfg5: super circuit = evm 2^20 + state 2^21 + copy 2^19 + bytecode 2^19 rows (2^22 in total), every circuit
+        # row-sharded over the ranks, each against its own tables (state's rw encoding differs: SURVEY.md A.2)
+        st5 = bench_state(h, 1 << 21, max(3, reps // 2))
+        cp5 = bench_copy(h, 256, 1024, reps)
+        evm_ms = extras["strong_scaling"]["ms_per_pass"]
+        tot_rows = n_total + st5["rows"] + cp5["rows"] + circuits[2]["rows"]
+        tot_ms = evm_ms + st5["ms_per_pass"] + cp5["ms_per_pass"] + circuits[2]["ms_per_pass"]
+        extras["cfg5"] = {"rows": int(tot_rows), "ms": tot_ms, "rows_per_s": tot_rows / (tot_ms / 1e3),
+                          "parts_ms": {"evm": evm_ms, "state": st5["ms_per_pass"], "copy": cp5["ms_per_pass"],
+                                       "bytecode": circuits[2]["ms_per_pass"]},
+                          "state_roofline_frac": st5["roofline"]["frac"], "copy_roofline_frac": cp5["roofline"]["frac"]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -380,18 +654,21 @@ def main():
     if rank == 0:
         line = {
             "metric": "constraint-rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64 limbs (BN254 Fr, 254-bit modular)", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": f"evm_circuit ADD/SUB/MUL/DIV/MOD trace (cfg2 generator), {n_steps} steps per GPU",
                        "steps_per_gpu": n_steps, "rw_rows": n_rw, "bytecode_rows": n_bc, "fixed_rows": int(fixed.shape[1]),
-                       "parallelism": f"row-shard x{world}, tables replicated, 1 all-reduce(min)",
+                       "parallelism": f"row-shard x{world}, tables replicated, 1 collective (zk_allreduce_results)",
                        "l2": "inputs larger than L2 (%.2f GB stored per GPU)" % (storage["stored_bytes"] / 1e9),
-                       "storage": storage,
+                       "storage": storage, "source_hash": source_hash(),
                        "timed_region": "lookup-index build of bytecode+rw tables, then step check"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            **extras,
         }
         print(json.dumps(line))
     if world > 1:
+        ctx.nccl_destroy()
         dist.destroy_process_group()
 
 

@@ -191,8 +191,10 @@ int zk_check(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
              void* stream);
 
 /* Asynchronous form used for device-side timing and multi-GPU: enqueues the index builds
- * and the check kernel on `stream` and leaves the result in device memory owned by the
- * context.  zk_result_device returns that buffer (uint32 first_fail[n] followed, 8-byte
+ * and the check kernels on `stream` and leaves the result in device memory owned by the
+ * context.  (ZK_CIRCUIT_EVM: the call waits on the host until the step-classification kernel has
+ * finished — it reads the per-state step counts back to launch only the gate-program kernels that
+ * have work — and returns with those kernels still running.)  zk_result_device returns that buffer (uint32 first_fail[n] followed, 8-byte
  * aligned, by uint64 fail_count[n]) so a collective can reduce it in place; zk_fetch_result
  * copies it to the host and synchronises. */
 int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_t row_end,
@@ -202,10 +204,18 @@ int zk_result_device(zk_ctx* ctx, int circuit_id, uint32_t** first_fail_device,
 int zk_fetch_result(zk_ctx* ctx, int circuit_id, uint32_t* first_fail, uint64_t* fail_count,
                     void* stream);
 
-/* Multi-GPU: element-wise MIN of first_fail (and SUM of fail_count) across the ranks of an
- * NCCL communicator (ncclComm_t passed as void*), on `stream`.  One small all-reduce; rows
- * are sharded, tables replicated, so this is the only exchange. */
+/* Multi-GPU: element-wise MIN of first_fail and SUM of fail_count across the ranks of an NCCL
+ * communicator (ncclComm_t passed as void*), on `stream`, in place in the context's device result
+ * buffer (read it with zk_fetch_result).  ONE collective — the ranks' result vectors (a few KB) are
+ * all-gathered and folded by a one-block kernel; rows are sharded, tables replicated, so this is the
+ * only exchange. */
 int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm, void* stream);
+/* Communicator plumbing for callers whose host language has no NCCL binding: rank 0 draws the
+ * 128-byte unique id, ships it to the other ranks by whatever means it has (MPI, a socket, gloo),
+ * every rank then joins.  NCCL itself is bound at run time (dlopen of libnccl.so.2). */
+int zk_nccl_unique_id(zk_ctx* ctx, uint8_t id[128]);
+int zk_nccl_comm_init(zk_ctx* ctx, int world_size, int rank, const uint8_t id[128], void** comm_out);
+int zk_nccl_comm_destroy(zk_ctx* ctx, void* comm);
 
 /* introspection */
 int zk_circuit_cols(int circuit_id);

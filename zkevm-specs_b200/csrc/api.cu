@@ -115,6 +115,10 @@ struct zk_ctx {
   cudaEvent_t evm_hist_ev = nullptr;
   int evm_occ[16] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
   std::unordered_map<const void*, int> occ;  // same, row-circuit kernels (keyed by kernel)
+  void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
+  size_t state_fold_cap = 0;
+  unsigned char* gather = nullptr;  // zk_allreduce_results: all-gathered result vectors
+  size_t gather_cap = 0;
   bool timing = false;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // start, after index builds, after check kernel
   cudaStream_t ev_mid_stream = nullptr;
@@ -186,6 +190,8 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (r.first_fail) cudaFree(r.first_fail);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->gather) cudaFree(ctx->gather);
+  if (ctx->state_fold) cudaFree(ctx->state_fold);
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
@@ -647,9 +653,15 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   const u64 n = rg.row_end - rg.row_begin;
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
   const Matrix& m = ctx->circ[ZK_CIRCUIT_BYTECODE];
-  if (is_canonical(m))
-    k_check_bytecode<L_CANON><<<grid_persistent(ctx, k_check_bytecode<L_CANON>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
-  else
+  if (is_canonical(m)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(ctx, cudaFuncSetAttribute(k_check_bytecode_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BcPipe::SMEM_BYTES));
+      attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((n + 127) / 128, (u64)ctx->sm_count));  // one CTA per SM
+    k_check_bytecode_tiled<<<grid, 128, BcPipe::SMEM_BYTES, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
+  } else
     k_check_bytecode<L_ANY><<<grid_persistent(ctx, k_check_bytecode<L_ANY>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
@@ -696,9 +708,23 @@ static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStr
   if ((rc = ensure_index(ctx, ZK_TABLE_MPT, k12, 12, st, &mpt))) return rc;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
-  if (is_canonical(m)) k_check_state<L_CANON><<<grid_persistent(ctx, k_check_state<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, mpt, res);
-  else k_check_state<L_ANY><<<grid_persistent(ctx, k_check_state<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, mpt, res);
-  ctx->launches++;
+  // fold pass over every resident row (halos included), then the gate program
+  if (m.n_rows * sizeof(StateFold) > ctx->state_fold_cap) {
+    if (ctx->state_fold) cudaFree(ctx->state_fold);
+    ctx->state_fold = nullptr;
+    CK(ctx, cudaMalloc(&ctx->state_fold, m.n_rows * sizeof(StateFold)));
+    ctx->state_fold_cap = m.n_rows * sizeof(StateFold);
+  }
+  StateFold* fold = (StateFold*)ctx->state_fold;
+  const WitnessDev wd = witness_dev(m);
+  if (is_canonical(m)) {
+    k_state_fold<L_CANON><<<grid_persistent(ctx, k_state_fold<L_CANON>, 256, m.n_rows), 256, 0, st>>>(wd, fold);
+    k_check_state<L_CANON><<<grid_persistent(ctx, k_check_state<L_CANON>, 128, n), 128, 0, st>>>(wd, rg, mpt, res, fold);
+  } else {
+    k_state_fold<L_ANY><<<grid_persistent(ctx, k_state_fold<L_ANY>, 256, m.n_rows), 256, 0, st>>>(wd, fold);
+    k_check_state<L_ANY><<<grid_persistent(ctx, k_check_state<L_ANY>, 128, n), 128, 0, st>>>(wd, rg, mpt, res, fold);
+  }
+  ctx->launches += 2;
   CK(ctx, cudaGetLastError());
   return 0;
 }
@@ -756,7 +782,9 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   // per non-empty gate-program group
   auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
   if (n > ctx->evm_sort_cap) {
-    if (ctx->evm_sort) cudaFree(ctx->evm_sort);
+    if (ctx->gather) cudaFree(ctx->gather);
+  if (ctx->state_fold) cudaFree(ctx->state_fold);
+  if (ctx->evm_sort) cudaFree(ctx->evm_sort);
     ctx->evm_sort = nullptr;
     CK(ctx, cudaMalloc(&ctx->evm_sort, up256(n) + up256(n * 4) + (3 * ZK_EVM_NB + 2) * sizeof(u32)));
     ctx->evm_sort_cap = n;
@@ -840,8 +868,9 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
   const Matrix& m = ctx->circ[circuit_id];
   if (!m.dev && m.n_rows) return fail_msg(ctx, "no witness uploaded for circuit");
   if (row_begin > row_end || row_end > m.n_rows) return fail_msg(ctx, "row range outside the resident matrix");
-  if (row_base + row_end >= 0xFFFFFFFFull || row_base + row_end < row_base)
-    return fail_msg(ctx, "row_base + row_end must stay below 2^32 - 1 (first_fail holds uint32 rows, 0xFFFFFFFF = pass)");
+  // reported rows are row_base + i (mod 2^64: a shard whose first resident row is a halo passes row_base = -1)
+  if (row_base + row_begin + (row_end - row_begin) >= 0xFFFFFFFFull || row_base + row_begin >= 0xFFFFFFFFull)
+    return fail_msg(ctx, "reported rows row_base + [row_begin, row_end) must stay below 2^32 - 1 (first_fail holds uint32 rows, 0xFFFFFFFF = pass)");
   ResultDev res;
   int rc = ensure_result(ctx, circuit_id, &res, st);
   if (rc) return rc;
@@ -919,25 +948,98 @@ extern "C" int zk_check(zk_ctx* ctx, int circuit_id, uint64_t row_begin, uint64_
 
 // ------------------------------------------------------------------ multi-GPU
 // NCCL is bound at run time (dlopen) so that libzkcheck.so has no link-time dependency on a
-// particular libnccl; the caller owns the communicator.
-typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+// particular libnccl; a process that already loaded one (e.g. through torch) gets that same library.
+struct Id128 {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char b[128];
+};
+struct NcclApi {
+  int (*get_unique_id)(void*) = nullptr;
+  int (*comm_init_rank)(void**, int, Id128, int) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  int (*comm_count)(void*, int*) = nullptr;
+  int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_bind(zk_ctx* ctx) {
+  if (g_nccl.ok) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail_msg(ctx, std::string("cannot load NCCL: ") + dlerror());
+  g_nccl.get_unique_id = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.comm_init_rank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.comm_destroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.comm_count = (int (*)(void*, int*))dlsym(h, "ncclCommCount");
+  g_nccl.all_gather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.comm_destroy || !g_nccl.comm_count || !g_nccl.all_gather)
+    return fail_msg(ctx, "NCCL symbols not found");
+  g_nccl.ok = true;
+  return 0;
+}
+extern "C" int zk_nccl_unique_id(zk_ctx* ctx, uint8_t id[128]) {
+  int rc = nccl_bind(ctx);
+  if (rc) return rc;
+  if (g_nccl.get_unique_id(id)) return fail_msg(ctx, "ncclGetUniqueId failed");
+  return 0;
+}
+extern "C" int zk_nccl_comm_init(zk_ctx* ctx, int world, int rank, const uint8_t id[128], void** comm) {
+  int rc = nccl_bind(ctx);
+  if (rc) return rc;
+  CK(ctx, cudaSetDevice(ctx->device));
+  Id128 u;
+  memcpy(u.b, id, 128);
+  if (g_nccl.comm_init_rank(comm, world, u, rank)) return fail_msg(ctx, "ncclCommInitRank failed");
+  return 0;
+}
+extern "C" int zk_nccl_comm_destroy(zk_ctx* ctx, void* comm) {
+  int rc = nccl_bind(ctx);
+  if (rc) return rc;
+  return g_nccl.comm_destroy(comm) ? fail_msg(ctx, "ncclCommDestroy failed") : 0;
+}
+
+// after the all-gather: first_fail = MIN over ranks, fail_count = SUM over ranks, in place
+__global__ void k_reduce_results(const unsigned char* gathered, size_t rank_bytes, size_t count_off, int world, int n,
+                                 u32* first_fail, u64* fail_count) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n) return;
+  u32 mn = 0xFFFFFFFFu;
+  u64 sum = 0;
+  for (int r = 0; r < world; r++) {
+    const unsigned char* p = gathered + (size_t)r * rank_bytes;
+    mn = min(mn, ((const u32*)p)[id]);
+    sum += ((const u64*)(p + count_off))[id];
+  }
+  first_fail[id] = mn;
+  fail_count[id] = sum;
+}
+
+// ONE collective: every rank's result vector (first_fail | fail_count, a few KB) is all-gathered, then
+// a one-block kernel folds the copies (MIN / SUM do not share a reduction op, an all-reduce would
+// need two rounds)
 extern "C" int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm, void* stream) {
   if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
   ResultBuf& r = ctx->res[circuit_id];
   if (!r.first_fail) return fail_msg(ctx, "no result yet");
-  static nccl_allreduce_fn fn = nullptr;
-  if (!fn) {
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) return fail_msg(ctx, std::string("cannot load NCCL: ") + dlerror());
-    fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
-    if (!fn) return fail_msg(ctx, "ncclAllReduce not found");
+  int rc = nccl_bind(ctx);
+  if (rc) return rc;
+  CK(ctx, cudaSetDevice(ctx->device));
+  int world = 0;
+  if (g_nccl.comm_count(nccl_comm, &world) || world < 1) return fail_msg(ctx, "ncclCommCount failed");
+  const size_t count_off = (size_t)((const char*)r.fail_count - (const char*)r.first_fail);
+  const size_t rank_bytes = count_off + (size_t)r.n * 8;
+  if (ctx->gather_cap < rank_bytes * world) {
+    if (ctx->gather) cudaFree(ctx->gather);
+  if (ctx->state_fold) cudaFree(ctx->state_fold);
+    ctx->gather = nullptr;
+    CK(ctx, cudaMalloc(&ctx->gather, rank_bytes * world));
+    ctx->gather_cap = rank_bytes * world;
   }
-  // ncclUint32 = 3, ncclUint64 = 5, ncclSum = 0, ncclMin = 4 (nccl.h)
-  int e = fn(r.first_fail, r.first_fail, (size_t)r.n, 3, 4, nccl_comm, (cudaStream_t)stream);
-  if (e) return fail_msg(ctx, "ncclAllReduce(min) failed");
-  e = fn(r.fail_count, r.fail_count, (size_t)r.n, 5, 0, nccl_comm, (cudaStream_t)stream);
-  if (e) return fail_msg(ctx, "ncclAllReduce(sum) failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  // ncclChar = 0 (nccl.h)
+  if (g_nccl.all_gather(r.first_fail, ctx->gather, rank_bytes, 0, nccl_comm, st)) return fail_msg(ctx, "ncclAllGather failed");
+  k_reduce_results<<<(r.n + 255) / 256, 256, 0, st>>>(ctx->gather, rank_bytes, count_off, world, r.n, r.first_fail, r.fail_count);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
   return 0;
 }
 

@@ -1668,10 +1668,9 @@ struct EvmSort {
 // that holds all three runs them one after the other.  The peek only chooses the bucket — the gate
 // program looks the opcode up again and decides everything itself — so a wrong peek costs time, never
 // the verdict.
-__device__ __forceinline__ int mul_bucket_peek(const StepCtx& s) {
+__device__ __forceinline__ int mul_bucket_peek(const StepCtx& s, const Fr& hlo, const Fr& hhi, const Fr& pc) {
   u32 head = 0, len = 0;
-  const Fr pc = s.cur(S_PC);
-  if (heads_probe(s.t.bytecode, s.cur(S_HASH_LO), s.cur(S_HASH_HI), &head, &len, s.mask, true) != 1) return ZK_ES_MUL;
+  if (heads_probe(s.t.bytecode, hlo, hhi, &head, &len, s.mask, true) != 1) return ZK_ES_MUL;
   if (!(fr_fits64(pc) && pc.l[0] < (u64)len)) return ZK_ES_MUL;
   const Fr v = table_cell(s.t.bytecode.tab, B_VALUE, (u64)head + 1 + pc.l[0]);
   return fr_eq_u64(v, 4) ? ZK_BK_DIV : (fr_eq_u64(v, 6) ? ZK_BK_MOD : ZK_ES_MUL);
@@ -1690,8 +1689,10 @@ __global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange 
   int b = ZK_BK_NONE;
   if (i < rg.row_end) {
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 1u << lane, nullptr, nullptr, -1};
+    // the peek's cells are fetched with the state cells (one memory round trip instead of two)
+    const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI), pc = s.cur(S_PC);
     const int st = step_prologue(s, rg.flags);
-    if (st >= 0) b = (st == ZK_ES_MUL && pos) ? mul_bucket_peek(s) : st;
+    if (st >= 0) b = (st == ZK_ES_MUL && pos) ? mul_bucket_peek(s, hlo, hhi, pc) : st;
     so.bucket[k] = (unsigned char)b;
   }
   const unsigned m = __match_any_sync(0xFFFFFFFFu, b);
@@ -1773,8 +1774,15 @@ __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRan
 #ifndef ZK_PUSH_MINBLOCKS
 #define ZK_PUSH_MINBLOCKS 4
 #endif
+#ifndef ZK_ADD_MINBLOCKS
+#define ZK_ADD_MINBLOCKS ZK_GADGET_MINBLOCKS
+#endif
+#ifndef ZK_POP_MINBLOCKS
+#define ZK_POP_MINBLOCKS ZK_GADGET_MINBLOCKS
+#endif
 template <int G, bool POS>
-__global__ void __launch_bounds__(128, ZK_GADGET_MINBLOCKS) k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
+__global__ void __launch_bounds__(128, G == KG_MUL ? ZK_GADGET_MINBLOCKS : (G == KG_ADD ? ZK_ADD_MINBLOCKS : ZK_POP_MINBLOCKS))
+k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
                                                     EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;

@@ -46,8 +46,9 @@ ZK_HD bool u320_lt(const U320& a, const U320& b) {
 template <int LAYOUT>
 ZK_HD bool gather_key_bytes(const WitnessDev& w, u64 row, Fr* out) {
   bool ok = true;
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
+  u64 l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+#pragma unroll 1
+  for (int q = 0; q < 4; q++) {  // not unrolled: the compiler would hoist all 32 loads (256 registers)
     Fr c[8];
 #pragma unroll
     for (int b = 0; b < 8; b++) c[b] = wcell_l<LAYOUT>(w, T_BYTE0 + 8 * q + b, row);
@@ -57,8 +58,15 @@ ZK_HD bool gather_key_bytes(const WitnessDev& w, u64 row, Fr* out) {
       ok = ok && fr_fits64(c[b]) && c[b].l[0] < 256;
       limb |= (c[b].l[0] & 0xFF) << (8 * b);
     }
-    out->l[q] = limb;
+    l0 = q == 0 ? limb : l0;
+    l1 = q == 1 ? limb : l1;
+    l2 = q == 2 ? limb : l2;
+    l3 = q == 3 ? limb : l3;
   }
+  out->l[0] = l0;
+  out->l[1] = l1;
+  out->l[2] = l2;
+  out->l[3] = l3;
   return ok;
 }
 // ((((tag*2^28+id)*2^160+address)*2^16+field_tag)*2^32 + key)*2^32 + rw_counter, as
@@ -89,12 +97,28 @@ ZK_HD bool fits_bits(const Fr& a, int bits) {  // bits in (0, 256)
   } while (0)
 
 // Warp-synchronous: every lane of `mask` calls it; lanes without a row pass live = false.
+// 10 address limb cells -> 160-bit integer (Sum limb_i * 2^(16 i), :507-509); false if a limb is >= 2^16
+template <int LAYOUT>
+ZK_HD bool gather_addr_limbs(const WitnessDev& w, u64 row, Fr* sum) {
+  bool ok = true;
+  Fr c[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) c[k] = wcell_l<LAYOUT>(w, T_LIMB0 + k, row);
+  *sum = fr_u64(0);
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    ok = ok && fr_fits64(c[k]) && c[k].l[0] < 65536;
+    const int bit = 16 * k;
+    sum->l[bit >> 6] |= (c[k].l[0] & 0xFFFF) << (bit & 63);
+  }
+  return ok;
+}
 // `key_int` / `bytes_ok`: gather_key_bytes of row i; `p_key_int` / `p_bytes_ok`: of the previous row (the
 // kernel hands the previous row's over through shared memory instead of gathering 32 cells twice)
 template <int LAYOUT>
 ZK_HD void check_state_row_core(const WitnessDev& w, const CheckRange& rg, const IndexDev& mpt, const ResultDev& res,
                                 u64 i, bool live, unsigned mask, const Fr& key_int, bool bytes_ok, const Fr& p_key_int,
-                                bool p_bytes_ok) {
+                                bool p_bytes_ok, const Fr& limb_sum, bool limbs_ok) {
   const bool record = live;
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 ip = rot_back(w, i, wrap), in = rot_fwd(w, i, 1, wrap);
@@ -108,19 +132,8 @@ ZK_HD void check_state_row_core(const WitnessDev& w, const CheckRange& rg, const
   ST_CHECK(ST_TAG_RANGE, fr_fits64(tag) && tag.l[0] >= 1 && tag.l[0] <= 12);
   ST_CHECK(ST_ID_RANGE, fits_bits(id, 28));
   ST_CHECK(ST_FIELD_TAG_RANGE, fr_fits64(ft) && ft.l[0] <= 24);
-  {
-    bool limbs_ok = true;
-    Fr sum = fr_u64(0);
-#pragma unroll
-    for (int k = 0; k < 10; k++) {
-      const Fr limb = wcell_l<LAYOUT>(w, T_LIMB0 + k, i);
-      limbs_ok = limbs_ok && fr_fits64(limb) && limb.l[0] < 65536;
-      const int bit = 16 * k;
-      sum.l[bit >> 6] |= (limb.l[0] & 0xFFFF) << (bit & 63);
-    }
-    ST_CHECK(ST_ADDR_LIMB_RANGE, limbs_ok);
-    ST_CHECK(ST_ADDR_LIMBS, fr_eq(addr, sum));
-  }
+  ST_CHECK(ST_ADDR_LIMB_RANGE, limbs_ok);
+  ST_CHECK(ST_ADDR_LIMBS, fr_eq(addr, limb_sum));
   ST_CHECK(ST_KEY_BYTE_RANGE, bytes_ok);
   ST_CHECK(ST_KEY_BYTES, fr_eq(key_lo, fr_u128(key_int.l[0], key_int.l[1])) &&
                              fr_eq(key_hi, fr_u128(key_int.l[2], key_int.l[3])));
@@ -301,56 +314,64 @@ ZK_HD void check_state_row_core(const WitnessDev& w, const CheckRange& rg, const
   }
 }
 
-// whole row on one thread (tests/emu, and rows the tiled kernel cannot serve from shared memory)
+// whole row on one thread (tests/emu)
 template <int LAYOUT>
 ZK_HD void check_state_row_dev(const WitnessDev& w, const CheckRange& rg, const IndexDev& mpt, const ResultDev& res,
                                u64 i, bool live, unsigned mask) {
-  Fr key_int, p_key_int;
+  Fr key_int, p_key_int, limb_sum;
   const bool bytes_ok = gather_key_bytes<LAYOUT>(w, i, &key_int);
   const bool p_bytes_ok = gather_key_bytes<LAYOUT>(w, rot_back(w, i, rg.flags & ZK_FLAG_WRAP), &p_key_int);
-  check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, mask, key_int, bytes_ok, p_key_int, p_bytes_ok);
+  const bool limbs_ok = gather_addr_limbs<LAYOUT>(w, i, &limb_sum);
+  check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, mask, key_int, bytes_ok, p_key_int, p_bytes_ok, limb_sum, limbs_ok);
 }
 
 #ifdef __CUDACC__
-// One thread per row, 128 consecutive rows per block iteration.  Every thread folds the 32 storage-key
-// byte cells of ITS row once and leaves the 256-bit integer in shared memory for its successor (the
-// ordering check packs the previous row's key too: state_circuit.py:552-570); the row before the tile is
-// folded by warp 0, one byte cell per lane.
-#define ZK_STATE_TILE 128
+// The state circuit runs as TWO kernels.  42 of a row's 57 cells are the 32 storage-key bytes and the 10
+// address limbs: range-checked, folded into a 256-bit and a 160-bit integer, and otherwise unused.
+// k_state_fold streams exactly those columns (few registers, every warp of the SM resident, eight
+// 32-byte loads in flight per thread) and leaves 64 bytes per row: the key integer, the limb sum and the
+// two range flags.  k_check_state then runs the gate program on the 15 remaining cells plus the folded
+// words of its row and of the previous row (the ordering check packs both keys, state_circuit.py:552-570).
+struct StateFold {  // one per resident row
+  u64 key[4];
+  u64 sum[3];
+  u64 flags;  // bit 0: every key byte < 256; bit 1: every address limb < 2^16
+};
 template <int LAYOUT>
-__global__ void __launch_bounds__(ZK_STATE_TILE, 3) k_check_state(WitnessDev w, CheckRange rg, IndexDev mpt, ResultDev res) {
-  __shared__ u64 s_key[ZK_STATE_TILE + 1][4];
-  __shared__ unsigned char s_ok[ZK_STATE_TILE + 1];
+__global__ void __launch_bounds__(256) k_state_fold(WitnessDev w, StateFold* out) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x; row < w.n_rows; row += stride) {
+    Fr key, sum;
+    const bool bytes_ok = gather_key_bytes<LAYOUT>(w, row, &key);
+    const bool limbs_ok = gather_addr_limbs<LAYOUT>(w, row, &sum);
+    ulonglong4 a, b;
+    a.x = key.l[0]; a.y = key.l[1]; a.z = key.l[2]; a.w = key.l[3];
+    b.x = sum.l[0]; b.y = sum.l[1]; b.z = sum.l[2]; b.w = (bytes_ok ? 1ull : 0ull) | (limbs_ok ? 2ull : 0ull);
+    ulonglong4* p = (ulonglong4*)(out + row);
+    p[0] = a;
+    p[1] = b;
+  }
+}
+#ifndef ZK_STATE_MINBLOCKS
+#define ZK_STATE_MINBLOCKS 3
+#endif
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, ZK_STATE_MINBLOCKS) k_check_state(WitnessDev w, CheckRange rg, IndexDev mpt, ResultDev res,
+                                                       const StateFold* fold) {
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 n = rg.row_end - rg.row_begin;
-  const u64 n_tiles = (n + ZK_STATE_TILE - 1) / ZK_STATE_TILE;
-  const unsigned tid = threadIdx.x, lane = tid & 31;
-  for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {  // block-uniform trip count
-    const u64 first = rg.row_begin + tile * ZK_STATE_TILE;
-    const u64 k = tile * ZK_STATE_TILE + tid;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (u64 first = 0; first < n; first += stride) {  // warp-uniform trip count (the MPT probe is warp-synchronous)
+    const u64 k = first + tid;
     const bool live = k < n;
-    const u64 i = live ? rg.row_begin + k : first;
-    Fr key_int;
-    const bool bytes_ok = gather_key_bytes<LAYOUT>(w, i, &key_int);
-#pragma unroll
-    for (int q = 0; q < 4; q++) s_key[tid + 1][q] = key_int.l[q];
-    s_ok[tid + 1] = bytes_ok;
-    if (tid < 32) {  // the row before the tile: lane b folds byte cell b
-      const Fr c = wcell_l<LAYOUT>(w, T_BYTE0 + lane, rot_back(w, first, wrap));
-      const bool okb = fr_fits64(c) && c.l[0] < 256;
-      u64 v = (c.l[0] & 0xFF) << (8 * (lane & 7));
-      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
-      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-      v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
-      const unsigned all_ok = __all_sync(0xFFFFFFFFu, okb);
-      if ((lane & 7) == 0) s_key[0][lane >> 3] = v;
-      if (lane == 0) s_ok[0] = all_ok;
-    }
-    __syncthreads();
-    const Fr p_key_int{{s_key[tid][0], s_key[tid][1], s_key[tid][2], s_key[tid][3]}};
-    const bool p_bytes_ok = s_ok[tid];
-    check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, 0xFFFFFFFFu, key_int, bytes_ok, p_key_int, p_bytes_ok);
-    __syncthreads();
+    const u64 i = rg.row_begin + (live ? k : 0);
+    const u64* f = (const u64*)(fold + i);
+    const u64* pf = (const u64*)(fold + rot_back(w, i, wrap));
+    const Fr f0 = ld_cell(f), f1 = ld_cell(f + 4), p0 = ld_cell(pf), p1 = ld_cell(pf + 4);
+    const Fr limb_sum{{f1.l[0], f1.l[1], f1.l[2], 0}};
+    check_state_row_core<LAYOUT>(w, rg, mpt, res, i, live, 0xFFFFFFFFu, f0, f1.l[3] & 1, p0, p1.l[3] & 1, limb_sum,
+                                 (f1.l[3] >> 1) & 1);
   }
 }
 #endif

@@ -73,7 +73,7 @@ EXPORTS = [
     "zk_allreduce_results", "zk_circuit_cols", "zk_table_cols", "zk_n_constraints",
     "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
     "zk_last_timing", "zk_upload_columns_packed", "zk_upload_table_packed",
-    "zk_upload_bytecode_table_from_code",
+    "zk_upload_bytecode_table_from_code", "zk_nccl_unique_id", "zk_nccl_comm_init", "zk_nccl_comm_destroy",
 ]
 
 
@@ -104,6 +104,9 @@ def lib() -> ctypes.CDLL:
         L.zk_result_device.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
         L.zk_fetch_result.argtypes = [vp, i32, _U32P, _U64P, vp]
         L.zk_allreduce_results.argtypes = [vp, i32, vp, vp]
+        L.zk_nccl_unique_id.argtypes = [vp, vp]
+        L.zk_nccl_comm_init.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
+        L.zk_nccl_comm_destroy.argtypes = [vp, vp]
         L.zk_circuit_cols.argtypes = [i32]
         L.zk_table_cols.argtypes = [i32]
         L.zk_n_constraints.argtypes = [i32]
@@ -310,6 +313,29 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.zk_launch_count(self._h))
+
+    # ---- multi-GPU: one NCCL communicator per context, results folded in place --------------
+    def nccl_unique_id(self) -> bytes:
+        """rank 0 draws the 128-byte NCCL id; ship it to the other ranks (gloo, MPI, a file, ...)"""
+        buf = (ctypes.c_uint8 * 128)()
+        self._ck(self._L.zk_nccl_unique_id(self._h, buf), "zk_nccl_unique_id")
+        return bytes(buf)
+
+    def nccl_init(self, world: int, rank: int, unique_id: bytes) -> None:
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        comm = ctypes.c_void_p()
+        self._ck(self._L.zk_nccl_comm_init(self._h, world, rank, buf, ctypes.byref(comm)), "zk_nccl_comm_init")
+        self._comm = comm
+
+    def allreduce_results(self, circuit_id: int, stream: int = 0) -> None:
+        """MIN of first_fail / SUM of fail_count over the communicator's ranks, in place on the device"""
+        self._ck(self._L.zk_allreduce_results(self._h, circuit_id, self._comm, ctypes.c_void_p(stream)),
+                 "zk_allreduce_results")
+
+    def nccl_destroy(self) -> None:
+        if getattr(self, "_comm", None):
+            self._L.zk_nccl_comm_destroy(self._h, self._comm)
+            self._comm = None
 
 
 _DEFAULT: dict = {}
