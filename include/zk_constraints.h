@@ -397,7 +397,257 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_SC_CALL_ID, ZKE_ASSERT, "instruction.py:381-394 call_id same")                       \
   X(EV_SC_IS_ROOT, ZKE_ASSERT, "instruction.py:381-394 is_root same")                       \
   X(EV_SC_IS_CREATE, ZKE_ASSERT, "instruction.py:381-394 is_create same")                   \
-  X(EV_SC_CODE_HASH, ZKE_ASSERT, "instruction.py:381-394 code_hash same")
+  X(EV_SC_CODE_HASH, ZKE_ASSERT, "instruction.py:381-394 code_hash same") \
+  X(EV_ETX_CC_TXID_UNSAT, ZKE_UNSAT, "end_tx.py:8 call_context_lookup(TxId) unsat") \
+  X(EV_ETX_CC_TXID_AMBIG, ZKE_AMBIG, "end_tx.py:8 call_context_lookup(TxId) ambiguous") \
+  X(EV_ETX_CC_TXID_TYPE, ZKE_ASSERT, "end_tx.py:8 call_context_lookup(TxId): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_CC_PERSIST_UNSAT, ZKE_UNSAT, "end_tx.py:9 call_context_lookup(IsPersistent) unsat") \
+  X(EV_ETX_CC_PERSIST_AMBIG, ZKE_AMBIG, "end_tx.py:9 call_context_lookup(IsPersistent) ambiguous") \
+  X(EV_ETX_CC_PERSIST_TYPE, ZKE_ASSERT, "end_tx.py:9 call_context_lookup(IsPersistent): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_TX_INVALID_UNSAT, ZKE_UNSAT, "end_tx.py:10 tx_context_lookup(TxInvalid) unsat") \
+  X(EV_ETX_TX_INVALID_AMBIG, ZKE_AMBIG, "end_tx.py:10 tx_context_lookup(TxInvalid) ambiguous") \
+  X(EV_ETX_TX_INVALID_TYPE, ZKE_ASSERT, "end_tx.py:10 tx_context_lookup(TxInvalid): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_TX_GAS_UNSAT, ZKE_UNSAT, "end_tx.py:13 tx_context_lookup(Gas) unsat") \
+  X(EV_ETX_TX_GAS_AMBIG, ZKE_AMBIG, "end_tx.py:13 tx_context_lookup(Gas) ambiguous") \
+  X(EV_ETX_TX_GAS_TYPE, ZKE_ASSERT, "end_tx.py:13 tx_context_lookup(Gas): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_MAXREFUND_RANGE, ZKE_RANGE, "end_tx.py:15-17 constant_divmod(gas_used, 5, 8): range_check(quotient, 8)") \
+  X(EV_ETX_REFUND_UNSAT, ZKE_UNSAT, "end_tx.py:18 tx_refund_read(tx_id) unsat") \
+  X(EV_ETX_REFUND_AMBIG, ZKE_AMBIG, "end_tx.py:18 tx_refund_read(tx_id) ambiguous") \
+  X(EV_ETX_REFUND_TYPE, ZKE_ASSERT, "end_tx.py:18 tx_refund_read(tx_id): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_MIN_RANGE, ZKE_ASSERT, "end_tx.py:19 min(max_refund, refund, 8): compare() operands < 256^8 (instruction.py:449-450)") \
+  X(EV_ETX_INVALID_REFUND0, ZKE_ASSERT, "end_tx.py:22-23 tx invalid => effective_refund == 0") \
+  X(EV_ETX_TX_GASPRICE_UNSAT, ZKE_UNSAT, "end_tx.py:26 tx_gas_price(tx_id) unsat") \
+  X(EV_ETX_TX_GASPRICE_AMBIG, ZKE_AMBIG, "end_tx.py:26 tx_gas_price(tx_id) ambiguous") \
+  X(EV_ETX_MUL1_OVERFLOW, ZKE_ASSERT, "end_tx.py:27 mul_word_by_u64: quotient_hi == 0 (instruction.py:595)") \
+  X(EV_ETX_TX_CALLER_UNSAT, ZKE_UNSAT, "end_tx.py:28-30 tx_context_lookup_word(CallerAddress) unsat") \
+  X(EV_ETX_TX_CALLER_AMBIG, ZKE_AMBIG, "end_tx.py:28-30 tx_context_lookup_word(CallerAddress) ambiguous") \
+  X(EV_ETX_CALLER_BYTES, ZKE_VALUE, "end_tx.py:31 word_to_address: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_ETX_CALLER_RANGE, ZKE_RANGE, "end_tx.py:31 word_to_address: bytes 20.. not zero (instruction.py:482-483)") \
+  X(EV_ETX_BAL_CALLER_UNSAT, ZKE_UNSAT, "end_tx.py:32 add_balance(caller): account_write_word(Balance) unsat") \
+  X(EV_ETX_BAL_CALLER_AMBIG, ZKE_AMBIG, "end_tx.py:32 add_balance(caller): account_write_word(Balance) ambiguous") \
+  X(EV_ETX_BAL1_EQ, ZKE_ASSERT, "end_tx.py:32 add_balance: balance == balance_prev + value (instruction.py:997)") \
+  X(EV_ETX_BAL1_CARRY, ZKE_ASSERT, "end_tx.py:32 add_balance: carry == 0 (instruction.py:998)") \
+  X(EV_ETX_BLK_BASEFEE_UNSAT, ZKE_UNSAT, "end_tx.py:35 block_context_lookup_word(BaseFee) unsat") \
+  X(EV_ETX_BLK_BASEFEE_AMBIG, ZKE_AMBIG, "end_tx.py:35 block_context_lookup_word(BaseFee) ambiguous") \
+  X(EV_ETX_SUBWORD_RANGE, ZKE_ASSERT, "end_tx.py:36 sub_word: Word((diff_lo, diff_hi)) halves < 2^128 (arithmetic.py:110-114)") \
+  X(EV_ETX_MUL2_OVERFLOW, ZKE_ASSERT, "end_tx.py:37 mul_word_by_u64(effective_tip, gas_used): quotient_hi == 0") \
+  X(EV_ETX_BLK_COINBASE_UNSAT, ZKE_UNSAT, "end_tx.py:38 block_context_lookup_word(Coinbase) unsat") \
+  X(EV_ETX_BLK_COINBASE_AMBIG, ZKE_AMBIG, "end_tx.py:38 block_context_lookup_word(Coinbase) ambiguous") \
+  X(EV_ETX_COINBASE_BYTES, ZKE_VALUE, "end_tx.py:39 word_to_address(coinbase): OverflowError") \
+  X(EV_ETX_COINBASE_RANGE, ZKE_RANGE, "end_tx.py:39 word_to_address(coinbase): bytes 20.. not zero") \
+  X(EV_ETX_BAL_COINBASE_UNSAT, ZKE_UNSAT, "end_tx.py:40 add_balance(coinbase) unsat") \
+  X(EV_ETX_BAL_COINBASE_AMBIG, ZKE_AMBIG, "end_tx.py:40 add_balance(coinbase) ambiguous") \
+  X(EV_ETX_BAL2_EQ, ZKE_ASSERT, "end_tx.py:40 add_balance(coinbase): balance == balance_prev + reward") \
+  X(EV_ETX_BAL2_CARRY, ZKE_ASSERT, "end_tx.py:40 add_balance(coinbase): carry == 0") \
+  X(EV_ETX_RCPT_STATUS_UNSAT, ZKE_UNSAT, "end_tx.py:45 tx_receipt_write(PostStateOrStatus) unsat") \
+  X(EV_ETX_RCPT_STATUS_AMBIG, ZKE_AMBIG, "end_tx.py:45 tx_receipt_write(PostStateOrStatus) ambiguous") \
+  X(EV_ETX_RCPT_STATUS_TYPE, ZKE_ASSERT, "end_tx.py:45 tx_receipt_write(PostStateOrStatus): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_STATUS, ZKE_ASSERT, "end_tx.py:43-46 (1 - is_tx_invalid) * is_persistent == PostStateOrStatus") \
+  X(EV_ETX_RCPT_LOG_UNSAT, ZKE_UNSAT, "end_tx.py:49 tx_receipt_write(LogLength) unsat") \
+  X(EV_ETX_RCPT_LOG_AMBIG, ZKE_AMBIG, "end_tx.py:49 tx_receipt_write(LogLength) ambiguous") \
+  X(EV_ETX_RCPT_LOG_TYPE, ZKE_ASSERT, "end_tx.py:49 tx_receipt_write(LogLength): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_LOGID, ZKE_ASSERT, "end_tx.py:50 log_id == curr.log_id") \
+  X(EV_ETX_LOGID0, ZKE_ASSERT, "end_tx.py:52-53 tx invalid => log_id == 0") \
+  X(EV_ETX_RCPT_PREVCUM_UNSAT, ZKE_UNSAT, "end_tx.py:60-62 tx_receipt_read(tx_id - 1, CumulativeGasUsed) unsat") \
+  X(EV_ETX_RCPT_PREVCUM_AMBIG, ZKE_AMBIG, "end_tx.py:60-62 tx_receipt_read(tx_id - 1, CumulativeGasUsed) ambiguous") \
+  X(EV_ETX_RCPT_PREVCUM_TYPE, ZKE_ASSERT, "end_tx.py:60-62 tx_receipt_read(tx_id - 1, CumulativeGasUsed): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_RCPT_CUM_UNSAT, ZKE_UNSAT, "end_tx.py:66 tx_receipt_write(CumulativeGasUsed) unsat") \
+  X(EV_ETX_RCPT_CUM_AMBIG, ZKE_AMBIG, "end_tx.py:66 tx_receipt_write(CumulativeGasUsed) ambiguous") \
+  X(EV_ETX_RCPT_CUM_TYPE, ZKE_ASSERT, "end_tx.py:66 tx_receipt_write(CumulativeGasUsed): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_CUMGAS, ZKE_ASSERT, "end_tx.py:64-67 previous cumulative gas + gas_used == CumulativeGasUsed") \
+  X(EV_ETX_CC_NEXT_TXID_UNSAT, ZKE_UNSAT, "end_tx.py:73-75 call_context_lookup(TxId, call_id=next.rw_counter) unsat") \
+  X(EV_ETX_CC_NEXT_TXID_AMBIG, ZKE_AMBIG, "end_tx.py:73-75 call_context_lookup(TxId, call_id=next.rw_counter) ambiguous") \
+  X(EV_ETX_CC_NEXT_TXID_TYPE, ZKE_ASSERT, "end_tx.py:73-75 call_context_lookup(TxId, call_id=next.rw_counter): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_ETX_NEXT_TXID, ZKE_ASSERT, "end_tx.py:72-77 next tx id == tx_id + 1") \
+  X(EV_ETX_RWC_BEGINTX, ZKE_ASSERT, "end_tx.py:79 rw_counter delta 10 - is_first_tx") \
+  X(EV_ETX_RWC_ENDBLOCK, ZKE_ASSERT, "end_tx.py:84-86 rw_counter delta 9 - is_first_tx") \
+  X(EV_ETX_CALLID_ENDBLOCK, ZKE_ASSERT, "end_tx.py:84-86 call_id same") \
+  X(EV_EB_TXINVALID_TYPE, ZKE_ASSERT, "end_block.py:87-92 tx_row.value.value() of a Word-typed TxInvalid row") \
+  X(EV_EB_EMPTY_VALID_TXS, ZKE_ASSERT, "end_block.py:118 empty block: total_valid_txs == 0") \
+  X(EV_EB_EMPTY_WDS, ZKE_ASSERT, "end_block.py:119 empty block: total_withdrawals == 0") \
+  X(EV_EB_CC_TXID_UNSAT, ZKE_UNSAT, "end_block.py:123 call_context_lookup(TxId) unsat") \
+  X(EV_EB_CC_TXID_AMBIG, ZKE_AMBIG, "end_block.py:123 call_context_lookup(TxId) ambiguous") \
+  X(EV_EB_CC_TXID_TYPE, ZKE_ASSERT, "end_block.py:123 call_context_lookup(TxId): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_EB_TXID_EQ, ZKE_ASSERT, "end_block.py:122-124 last tx id == total_txs") \
+  X(EV_EB_BLK_GASLIMIT_UNSAT, ZKE_UNSAT, "end_block.py:127 block_context_lookup(GasLimit) unsat") \
+  X(EV_EB_BLK_GASLIMIT_AMBIG, ZKE_AMBIG, "end_block.py:127 block_context_lookup(GasLimit) ambiguous") \
+  X(EV_EB_BLK_GASLIMIT_TYPE, ZKE_ASSERT, "end_block.py:127 block_context_lookup(GasLimit): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_EB_RCPT_CUM_UNSAT, ZKE_UNSAT, "end_block.py:128-131 tx_receipt_read(total_txs, CumulativeGasUsed) unsat") \
+  X(EV_EB_RCPT_CUM_AMBIG, ZKE_AMBIG, "end_block.py:128-131 tx_receipt_read(total_txs, CumulativeGasUsed) ambiguous") \
+  X(EV_EB_RCPT_CUM_TYPE, ZKE_ASSERT, "end_block.py:128-131 tx_receipt_read(total_txs, CumulativeGasUsed): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_EB_GAS_CMP_RANGE, ZKE_ASSERT, "end_block.py:132 compare(gas_limit, cumulative_gas, 8): operands < 256^8") \
+  X(EV_EB_GAS_LIMIT, ZKE_ASSERT, "end_block.py:133 cumulative gas <= gas limit") \
+  X(EV_EB_WD_WORD, ZKE_ASSERT, "end_block.py:142 Word(amount * 1e9) >= 2^256 (arithmetic.py:117)") \
+  X(EV_EB_WD_BAL_UNSAT, ZKE_UNSAT, "end_block.py:142 add_balance(withdrawal address) unsat") \
+  X(EV_EB_WD_BAL_AMBIG, ZKE_AMBIG, "end_block.py:142 add_balance(withdrawal address) ambiguous") \
+  X(EV_EB_WD_BAL_EQ, ZKE_ASSERT, "end_block.py:142 add_balance: balance == balance_prev + amount * 1e9") \
+  X(EV_EB_WD_BAL_CARRY, ZKE_ASSERT, "end_block.py:142 add_balance: carry == 0") \
+  X(EV_EB_TX_PAD_UNSAT, ZKE_UNSAT, "end_block.py:157-159 tx_context_lookup_word(total_txs + 1, CallerAddress) unsat") \
+  X(EV_EB_TX_PAD_AMBIG, ZKE_AMBIG, "end_block.py:157-159 tx_context_lookup_word(total_txs + 1, CallerAddress) ambiguous") \
+  X(EV_EB_TX_PAD_ZERO, ZKE_ASSERT, "end_block.py:156-161 the tx after the last one is padding (CallerAddress == 0)") \
+  X(EV_EB_START1_UNSAT, ZKE_UNSAT, "end_block.py:170 rw_table_start_lookup(1) unsat") \
+  X(EV_EB_START1_AMBIG, ZKE_AMBIG, "end_block.py:170 rw_table_start_lookup(1) ambiguous") \
+  X(EV_EB_START2_UNSAT, ZKE_UNSAT, "end_block.py:171 rw_table_start_lookup(max_rws - total_rws - total_withdrawals) unsat") \
+  X(EV_EB_START2_AMBIG, ZKE_AMBIG, "end_block.py:171 rw_table_start_lookup(max_rws - total_rws - total_withdrawals) ambiguous") \
+  X(EV_EB_RWC_SAME, ZKE_ASSERT, "end_block.py:180-183 rw_counter same") \
+  X(EV_EB_CALLID_SAME, ZKE_ASSERT, "end_block.py:180-183 call_id same") \
+  X(EV_BT_CC_TXID_UNSAT, ZKE_UNSAT, "begin_tx.py:26 call_context_lookup(TxId, call_id) unsat") \
+  X(EV_BT_CC_TXID_AMBIG, ZKE_AMBIG, "begin_tx.py:26 call_context_lookup(TxId, call_id) ambiguous") \
+  X(EV_BT_CC_TXID_TYPE, ZKE_ASSERT, "begin_tx.py:26 call_context_lookup(TxId, call_id): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_CC_REVEND_UNSAT, ZKE_UNSAT, "begin_tx.py:27 reversion_info: RwCounterEndOfReversion unsat") \
+  X(EV_BT_CC_REVEND_AMBIG, ZKE_AMBIG, "begin_tx.py:27 reversion_info: RwCounterEndOfReversion ambiguous") \
+  X(EV_BT_CC_REVEND_TYPE, ZKE_ASSERT, "begin_tx.py:27 reversion_info: RwCounterEndOfReversion: .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_CC_PERSIST_UNSAT, ZKE_UNSAT, "begin_tx.py:27 reversion_info: IsPersistent unsat") \
+  X(EV_BT_CC_PERSIST_AMBIG, ZKE_AMBIG, "begin_tx.py:27 reversion_info: IsPersistent ambiguous") \
+  X(EV_BT_CC_PERSIST_TYPE, ZKE_ASSERT, "begin_tx.py:27 reversion_info: IsPersistent: .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_CC_SUCCESS_UNSAT, ZKE_UNSAT, "begin_tx.py:29 call_context_lookup(IsSuccess) unsat") \
+  X(EV_BT_CC_SUCCESS_AMBIG, ZKE_AMBIG, "begin_tx.py:29 call_context_lookup(IsSuccess) ambiguous") \
+  X(EV_BT_CC_SUCCESS_TYPE, ZKE_ASSERT, "begin_tx.py:29 call_context_lookup(IsSuccess): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_SUCCESS_EQ, ZKE_ASSERT, "begin_tx.py:28-31 IsSuccess == is_persistent") \
+  X(EV_BT_FIRST_TXID, ZKE_ASSERT, "begin_tx.py:33-34 first step: tx_id == 1") \
+  X(EV_BT_BLK_COINBASE_UNSAT, ZKE_UNSAT, "begin_tx.py:37 block_context_lookup_word(Coinbase) unsat") \
+  X(EV_BT_BLK_COINBASE_AMBIG, ZKE_AMBIG, "begin_tx.py:37 block_context_lookup_word(Coinbase) ambiguous") \
+  X(EV_BT_COINBASE_BYTES, ZKE_VALUE, "begin_tx.py:38 word_to_address: OverflowError") \
+  X(EV_BT_COINBASE_RANGE, ZKE_RANGE, "begin_tx.py:38 word_to_address: bytes 20.. not zero") \
+  X(EV_BT_TX_CALLER_UNSAT, ZKE_UNSAT, "begin_tx.py:40-42 tx_context_lookup_word(CallerAddress) unsat") \
+  X(EV_BT_TX_CALLER_AMBIG, ZKE_AMBIG, "begin_tx.py:40-42 tx_context_lookup_word(CallerAddress) ambiguous") \
+  X(EV_BT_CALLER_BYTES, ZKE_VALUE, "begin_tx.py:43 word_to_address: OverflowError") \
+  X(EV_BT_CALLER_RANGE, ZKE_RANGE, "begin_tx.py:43 word_to_address: bytes 20.. not zero") \
+  X(EV_BT_TX_CALLEE_UNSAT, ZKE_UNSAT, "begin_tx.py:44-46 tx_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_BT_TX_CALLEE_AMBIG, ZKE_AMBIG, "begin_tx.py:44-46 tx_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_BT_CALLEE_BYTES, ZKE_VALUE, "begin_tx.py:47 word_to_address: OverflowError") \
+  X(EV_BT_CALLEE_RANGE, ZKE_RANGE, "begin_tx.py:47 word_to_address: bytes 20.. not zero") \
+  X(EV_BT_TX_ISCREATE_UNSAT, ZKE_UNSAT, "begin_tx.py:48 tx_context_lookup(IsCreate) unsat") \
+  X(EV_BT_TX_ISCREATE_AMBIG, ZKE_AMBIG, "begin_tx.py:48 tx_context_lookup(IsCreate) ambiguous") \
+  X(EV_BT_TX_ISCREATE_TYPE, ZKE_ASSERT, "begin_tx.py:48 tx_context_lookup(IsCreate): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_TX_VALUE_UNSAT, ZKE_UNSAT, "begin_tx.py:49 tx_context_lookup_word(Value) unsat") \
+  X(EV_BT_TX_VALUE_AMBIG, ZKE_AMBIG, "begin_tx.py:49 tx_context_lookup_word(Value) ambiguous") \
+  X(EV_BT_TX_CDLEN_UNSAT, ZKE_UNSAT, "begin_tx.py:50 tx_context_lookup(CallDataLength) unsat") \
+  X(EV_BT_TX_CDLEN_AMBIG, ZKE_AMBIG, "begin_tx.py:50 tx_context_lookup(CallDataLength) ambiguous") \
+  X(EV_BT_TX_CDLEN_TYPE, ZKE_ASSERT, "begin_tx.py:50 tx_context_lookup(CallDataLength): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_CALLER_NONZERO, ZKE_ASSERT, "begin_tx.py:53 CallerAddress != 0") \
+  X(EV_BT_TX_INVALID_UNSAT, ZKE_UNSAT, "begin_tx.py:63 tx_context_lookup(TxInvalid) unsat") \
+  X(EV_BT_TX_INVALID_AMBIG, ZKE_AMBIG, "begin_tx.py:63 tx_context_lookup(TxInvalid) ambiguous") \
+  X(EV_BT_TX_INVALID_TYPE, ZKE_ASSERT, "begin_tx.py:63 tx_context_lookup(TxInvalid): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_TX_NONCE_UNSAT, ZKE_UNSAT, "begin_tx.py:64 tx_context_lookup(Nonce) unsat") \
+  X(EV_BT_TX_NONCE_AMBIG, ZKE_AMBIG, "begin_tx.py:64 tx_context_lookup(Nonce) ambiguous") \
+  X(EV_BT_TX_NONCE_TYPE, ZKE_ASSERT, "begin_tx.py:64 tx_context_lookup(Nonce): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_ACC_NONCE_UNSAT, ZKE_UNSAT, "begin_tx.py:65 account_write(caller, Nonce) unsat") \
+  X(EV_BT_ACC_NONCE_AMBIG, ZKE_AMBIG, "begin_tx.py:65 account_write(caller, Nonce) ambiguous") \
+  X(EV_BT_ACC_NONCE_TYPE, ZKE_ASSERT, "begin_tx.py:65 account_write(caller, Nonce): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_ACC_NONCE_PREV_TYPE, ZKE_ASSERT, "begin_tx.py:65 account_write: value_prev.value() of a Word-typed cell") \
+  X(EV_BT_NONCE_EQ, ZKE_ASSERT, "begin_tx.py:68 nonce == nonce_prev + 1 - is_tx_invalid") \
+  X(EV_BT_TX_GAS_UNSAT, ZKE_UNSAT, "begin_tx.py:72 tx_context_lookup(Gas) unsat") \
+  X(EV_BT_TX_GAS_AMBIG, ZKE_AMBIG, "begin_tx.py:72 tx_context_lookup(Gas) ambiguous") \
+  X(EV_BT_TX_GAS_TYPE, ZKE_ASSERT, "begin_tx.py:72 tx_context_lookup(Gas): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_TX_GASPRICE_UNSAT, ZKE_UNSAT, "begin_tx.py:73 tx_gas_price unsat") \
+  X(EV_BT_TX_GASPRICE_AMBIG, ZKE_AMBIG, "begin_tx.py:73 tx_gas_price ambiguous") \
+  X(EV_BT_GASFEE_OVERFLOW, ZKE_ASSERT, "begin_tx.py:74 mul_word_by_u64(gas_price, gas): quotient_hi == 0") \
+  X(EV_BT_TX_CDGAS_UNSAT, ZKE_UNSAT, "begin_tx.py:82 tx_context_lookup(CallDataGasCost) unsat") \
+  X(EV_BT_TX_CDGAS_AMBIG, ZKE_AMBIG, "begin_tx.py:82 tx_context_lookup(CallDataGasCost) ambiguous") \
+  X(EV_BT_TX_CDGAS_TYPE, ZKE_ASSERT, "begin_tx.py:82 tx_context_lookup(CallDataGasCost): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_INITCODE_RANGE, ZKE_RANGE, "begin_tx.py:85-87 constant_divmod(len + 31, 32, 8): range_check") \
+  X(EV_BT_TX_ALGAS_UNSAT, ZKE_UNSAT, "begin_tx.py:91 tx_context_lookup(AccessListGasCost) unsat") \
+  X(EV_BT_TX_ALGAS_AMBIG, ZKE_AMBIG, "begin_tx.py:91 tx_context_lookup(AccessListGasCost) ambiguous") \
+  X(EV_BT_TX_ALGAS_TYPE, ZKE_ASSERT, "begin_tx.py:91 tx_context_lookup(AccessListGasCost): .value() of a Word-typed cell (arithmetic.py:186-189)") \
+  X(EV_BT_GAS_CMP_RANGE, ZKE_ASSERT, "begin_tx.py:96 compare(tx_gas, intrinsic, 31): operands < 256^31") \
+  X(EV_BT_AL_COINBASE_UNSAT, ZKE_UNSAT, "begin_tx.py:106-108 add_account_to_access_list(coinbase) unsat") \
+  X(EV_BT_AL_COINBASE_AMBIG, ZKE_AMBIG, "begin_tx.py:106-108 add_account_to_access_list(coinbase) ambiguous") \
+  X(EV_BT_AL_COINBASE_TYPE, ZKE_ASSERT, "begin_tx.py:106-108 access list (coinbase): value_prev.value() of a Word-typed cell") \
+  X(EV_BT_AL_COINBASE_ZERO, ZKE_ASSERT, "begin_tx.py:106-108 access list (coinbase): value_prev == 0") \
+  X(EV_BT_AL_CALLER_UNSAT, ZKE_UNSAT, "begin_tx.py:106-108 add_account_to_access_list(caller) unsat") \
+  X(EV_BT_AL_CALLER_AMBIG, ZKE_AMBIG, "begin_tx.py:106-108 add_account_to_access_list(caller) ambiguous") \
+  X(EV_BT_AL_CALLER_TYPE, ZKE_ASSERT, "begin_tx.py:106-108 access list (caller): value_prev.value() of a Word-typed cell") \
+  X(EV_BT_AL_CALLER_ZERO, ZKE_ASSERT, "begin_tx.py:106-108 access list (caller): value_prev == 0") \
+  X(EV_BT_AL_CALLEE_UNSAT, ZKE_UNSAT, "begin_tx.py:106-108 add_account_to_access_list(callee) unsat") \
+  X(EV_BT_AL_CALLEE_AMBIG, ZKE_AMBIG, "begin_tx.py:106-108 add_account_to_access_list(callee) ambiguous") \
+  X(EV_BT_AL_CALLEE_TYPE, ZKE_ASSERT, "begin_tx.py:106-108 access list (callee): value_prev.value() of a Word-typed cell") \
+  X(EV_BT_AL_CALLEE_ZERO, ZKE_ASSERT, "begin_tx.py:106-108 access list (callee): value_prev == 0") \
+  X(EV_BT_BAL_SENDER_UNSAT, ZKE_UNSAT, "begin_tx.py:111 transfer_with_gas_fee: sub_balance(sender) account_write_word unsat") \
+  X(EV_BT_BAL_SENDER_AMBIG, ZKE_AMBIG, "begin_tx.py:111 transfer_with_gas_fee: sub_balance(sender) account_write_word ambiguous") \
+  X(EV_BT_BAL_SENDER_REV_UNSAT, ZKE_UNSAT, "begin_tx.py:111 sub_balance(sender): reversion write (instruction.py:848-861) unsat") \
+  X(EV_BT_BAL_SENDER_REV_AMBIG, ZKE_AMBIG, "begin_tx.py:111 sub_balance(sender): reversion write (instruction.py:848-861) ambiguous") \
+  X(EV_BT_SENDER_EQ, ZKE_ASSERT, "begin_tx.py:111 sub_balance: balance_prev == balance + value + gas_fee (instruction.py:1011)") \
+  X(EV_BT_SENDER_CARRY, ZKE_ASSERT, "begin_tx.py:111 sub_balance: carry == 0") \
+  X(EV_BT_BAL_RECV_UNSAT, ZKE_UNSAT, "begin_tx.py:111 add_balance(receiver) account_write_word unsat") \
+  X(EV_BT_BAL_RECV_AMBIG, ZKE_AMBIG, "begin_tx.py:111 add_balance(receiver) account_write_word ambiguous") \
+  X(EV_BT_BAL_RECV_REV_UNSAT, ZKE_UNSAT, "begin_tx.py:111 add_balance(receiver): reversion write unsat") \
+  X(EV_BT_BAL_RECV_REV_AMBIG, ZKE_AMBIG, "begin_tx.py:111 add_balance(receiver): reversion write ambiguous") \
+  X(EV_BT_RECV_EQ, ZKE_ASSERT, "begin_tx.py:111 add_balance: balance == balance_prev + value") \
+  X(EV_BT_RECV_CARRY, ZKE_ASSERT, "begin_tx.py:111 add_balance: carry == 0") \
+  X(EV_BT_BALPREV_BYTES, ZKE_VALUE, "begin_tx.py:119-124 word_to_fq(sender_balance_prev, 31): OverflowError") \
+  X(EV_BT_BALPREV_RANGE, ZKE_RANGE, "begin_tx.py:119-124 word_to_fq(sender_balance_prev, 31): byte 31 not zero") \
+  X(EV_BT_VALUE_BYTES, ZKE_VALUE, "begin_tx.py:119-124 word_to_fq(tx_value, 31): OverflowError") \
+  X(EV_BT_VALUE_RANGE, ZKE_RANGE, "begin_tx.py:119-124 word_to_fq(tx_value, 31): byte 31 not zero") \
+  X(EV_BT_FEE_BYTES, ZKE_VALUE, "begin_tx.py:119-124 word_to_fq(gas_fee, 31): OverflowError") \
+  X(EV_BT_FEE_RANGE, ZKE_RANGE, "begin_tx.py:119-124 word_to_fq(gas_fee, 31): byte 31 not zero") \
+  X(EV_BT_BAL_CMP_RANGE, ZKE_ASSERT, "begin_tx.py:119-124 compare(balance_prev, value + gas_fee, 31): operands < 256^31") \
+  X(EV_BT_INVALID_FLAG, ZKE_ASSERT, "begin_tx.py:128 is_tx_invalid == invalid_tx") \
+  X(EV_BT_PERSISTENT1, ZKE_ASSERT, "begin_tx.py:133 / 234 tx is persistent") \
+  X(EV_BT_NEXT_ENDTX, ZKE_ASSERT, "begin_tx.py:136 / 237 next.execution_state == EndTx") \
+  X(EV_BT_END_RWC, ZKE_ASSERT, "begin_tx.py:137-140 / 238-241 rw_counter delta") \
+  X(EV_BT_END_CALLID, ZKE_ASSERT, "begin_tx.py:137-140 / 238-241 call_id To(call_id)") \
+  X(EV_BT_COPY1_UNSAT, ZKE_UNSAT, "begin_tx.py:148-158 copy_lookup(tx calldata -> RlcAcc) unsat") \
+  X(EV_BT_COPY1_AMBIG, ZKE_AMBIG, "begin_tx.py:148-158 copy_lookup(tx calldata -> RlcAcc) ambiguous") \
+  X(EV_BT_COPY1_RWC0, ZKE_ASSERT, "begin_tx.py:160 assert copy_rwc_inc == 0") \
+  X(EV_BT_KECCAK_UNSAT, ZKE_UNSAT, "begin_tx.py:163 keccak_lookup(call_data_length, calldata rlc) unsat") \
+  X(EV_BT_KECCAK_AMBIG, ZKE_AMBIG, "begin_tx.py:163 keccak_lookup(call_data_length, calldata rlc) ambiguous") \
+  X(EV_BT_COPY2_UNSAT, ZKE_UNSAT, "begin_tx.py:167-177 copy_lookup(tx calldata -> Bytecode) unsat") \
+  X(EV_BT_COPY2_AMBIG, ZKE_AMBIG, "begin_tx.py:167-177 copy_lookup(tx calldata -> Bytecode) ambiguous") \
+  X(EV_BT_COPY2_RWC0, ZKE_ASSERT, "begin_tx.py:178 assert copy_rwc_inc == 0") \
+  X(EV_BT_PRECOMPILE, ZKE_NOTIMPL, "begin_tx.py:225-227 callee is a precompile: raise NotImplementedError") \
+  X(EV_BT_ACC_CODEHASH_UNSAT, ZKE_UNSAT, "begin_tx.py:229 account_read_word(callee, CodeHash) unsat") \
+  X(EV_BT_ACC_CODEHASH_AMBIG, ZKE_AMBIG, "begin_tx.py:229 account_read_word(callee, CodeHash) ambiguous") \
+  X(EV_BT_CTX0_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(Depth) unsat") \
+  X(EV_BT_CTX0_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(Depth) ambiguous") \
+  X(EV_BT_CTX0_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context Depth == expected") \
+  X(EV_BT_CTX1_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallerAddress) unsat") \
+  X(EV_BT_CTX1_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallerAddress) ambiguous") \
+  X(EV_BT_CTX1_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context CallerAddress == expected") \
+  X(EV_BT_CTX2_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_BT_CTX2_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_BT_CTX2_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context CalleeAddress == expected") \
+  X(EV_BT_CTX3_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallDataOffset) unsat") \
+  X(EV_BT_CTX3_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallDataOffset) ambiguous") \
+  X(EV_BT_CTX3_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context CallDataOffset == expected") \
+  X(EV_BT_CTX4_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallDataLength) unsat") \
+  X(EV_BT_CTX4_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CallDataLength) ambiguous") \
+  X(EV_BT_CTX4_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context CallDataLength == expected") \
+  X(EV_BT_CTX5_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(Value) unsat") \
+  X(EV_BT_CTX5_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(Value) ambiguous") \
+  X(EV_BT_CTX5_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context Value == expected") \
+  X(EV_BT_CTX6_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsStatic) unsat") \
+  X(EV_BT_CTX6_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsStatic) ambiguous") \
+  X(EV_BT_CTX6_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context IsStatic == expected") \
+  X(EV_BT_CTX7_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeId) unsat") \
+  X(EV_BT_CTX7_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeId) ambiguous") \
+  X(EV_BT_CTX7_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context LastCalleeId == expected") \
+  X(EV_BT_CTX8_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeReturnDataOffset) unsat") \
+  X(EV_BT_CTX8_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeReturnDataOffset) ambiguous") \
+  X(EV_BT_CTX8_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context LastCalleeReturnDataOffset == expected") \
+  X(EV_BT_CTX9_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeReturnDataLength) unsat") \
+  X(EV_BT_CTX9_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(LastCalleeReturnDataLength) ambiguous") \
+  X(EV_BT_CTX9_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context LastCalleeReturnDataLength == expected") \
+  X(EV_BT_CTX10_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsRoot) unsat") \
+  X(EV_BT_CTX10_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsRoot) ambiguous") \
+  X(EV_BT_CTX10_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context IsRoot == expected") \
+  X(EV_BT_CTX11_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsCreate) unsat") \
+  X(EV_BT_CTX11_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(IsCreate) ambiguous") \
+  X(EV_BT_CTX11_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context IsCreate == expected") \
+  X(EV_BT_CTX12_UNSAT, ZKE_UNSAT, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CodeHash) unsat") \
+  X(EV_BT_CTX12_AMBIG, ZKE_AMBIG, "begin_tx.py:183-201 / 250-269 call_context_lookup_word(CodeHash) ambiguous") \
+  X(EV_BT_CTX12_EQ, ZKE_ASSERT, "begin_tx.py:198-201 / 266-269 call context CodeHash == expected") \
+  X(EV_BT_NC_RWC, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: RWC (instruction.py:266-290)") \
+  X(EV_BT_NC_CALL_ID, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: CALL_ID (instruction.py:266-290)") \
+  X(EV_BT_NC_IS_ROOT, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: IS_ROOT (instruction.py:266-290)") \
+  X(EV_BT_NC_IS_CREATE, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: IS_CREATE (instruction.py:266-290)") \
+  X(EV_BT_NC_CODE_HASH, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: CODE_HASH (instruction.py:266-290)") \
+  X(EV_BT_NC_GAS_LEFT, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: GAS_LEFT (instruction.py:266-290)") \
+  X(EV_BT_NC_REV, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: REV (instruction.py:266-290)") \
+  X(EV_BT_NC_LOG_ID, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: LOG_ID (instruction.py:266-290)") \
+  X(EV_BT_NC_PC, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: PC (instruction.py:266-290)") \
+  X(EV_BT_NC_SP, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: SP (instruction.py:266-290)") \
+  X(EV_BT_NC_MEM, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: MEM (instruction.py:266-290)")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

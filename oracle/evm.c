@@ -38,7 +38,10 @@ typedef struct {
   const uint64_t* steps; uint64_t n_steps;
   orc_index bytecode_ix, rw_ix, fixed_ix, copy_ix, keccak_ix;
   orc_index tx_ix, block_ix; /* tx table key (tx_id, tag, index); block table key (tag, block_number) */
-  const uint8_t* rw_flags; /* bit0: value.is_word */
+  orc_index rwc_ix;          /* rw table keyed on rw_counter alone (lookups with optional columns, evm_tx.h) */
+  const uint8_t* rw_flags; /* bit0: value.is_word, bit1: value_prev.is_word */
+  const uint8_t *tx_flags, *block_flags; /* bit0: value.is_word */
+  const uint64_t* wd_tab; uint64_t n_wd; /* withdrawal table (id, validator_id, address, amount) */
   orc_result* res;
 } evm_env;
 
@@ -892,6 +895,7 @@ static void gadget_shl_shr(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
 }
 
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
+#include "evm_tx.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -924,7 +928,10 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
                                   st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND ||
                                   st == ZK_ES_BlockCtx || st == ZK_ES_ORIGIN || st == ZK_ES_GASPRICE ||
-                                  st == ZK_ES_SHL_SHR);
+                                  st == ZK_ES_SHL_SHR || st == ZK_ES_BeginTx || st == ZK_ES_EndTx || st == ZK_ES_EndBlock);
+  if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
+  if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
+  if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
   if (st == ZK_ES_ORIGIN) { gadget_txctx(e, i, row, 0x32, ZK_TX_CallerAddress); return; }
   if (st == ZK_ES_GASPRICE) { gadget_txctx(e, i, row, 0x3a, ZK_TX_GasPrice); return; }
@@ -978,6 +985,11 @@ static __thread const uint64_t* g_block_tab; static __thread uint64_t g_n_block;
 void orc_set_evm_context_tables(const uint64_t* tx_tab, uint64_t n_tx, const uint64_t* block_tab, uint64_t n_block) {
   g_tx_tab = tx_tab; g_n_tx = n_tx; g_block_tab = block_tab; g_n_block = n_block;
 }
+/* value type flags of the tx / block tables and the withdrawal table of the NEXT call (BeginTx / EndTx / EndBlock) */
+static __thread const uint8_t *g_tx_flags, *g_block_flags; static __thread const uint64_t* g_wd_tab; static __thread uint64_t g_n_wd;
+void orc_set_evm_block_tables(const uint8_t* tx_flags, const uint8_t* block_flags, const uint64_t* wd_tab, uint64_t n_wd) {
+  g_tx_flags = tx_flags; g_block_flags = block_flags; g_wd_tab = wd_tab; g_n_wd = n_wd;
+}
 int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* bytecode_tab, uint64_t n_bytecode,
                     const uint64_t* rw_tab, uint64_t n_rw, const uint8_t* rw_flags, const uint64_t* fixed_tab,
                     uint64_t n_fixed, const uint64_t* copy_tab, uint64_t n_copy, const uint64_t* keccak_tab,
@@ -1013,9 +1025,14 @@ int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* byt
   orc_index_build(&env.tx_ix, g_tx_tab, g_n_tx, 5, tk, 3);
   orc_index_build(&env.block_ix, g_block_tab, g_n_block, 4, blk, 2);
   g_tx_tab = g_block_tab = 0; g_n_tx = g_n_block = 0;
+  const uint32_t ck0[1] = {0};
+  orc_index_build(&env.rwc_ix, rw_tab, n_rw, 14, ck0, 1);
+  env.tx_flags = g_tx_flags; env.block_flags = g_block_flags; env.wd_tab = g_wd_tab; env.n_wd = g_n_wd;
+  g_tx_flags = g_block_flags = 0; g_wd_tab = 0; g_n_wd = 0;
   env.rw_flags = rw_flags;
   for (uint64_t i = row_begin; i < row_end; i++) verify_step(&env, i, row_base + i, flags);
   orc_index_free(&env.bytecode_ix); orc_index_free(&env.rw_ix); /* fixed_ix.order lives in fx_cache */
   orc_index_free(&env.copy_ix); orc_index_free(&env.keccak_ix); orc_index_free(&env.tx_ix); orc_index_free(&env.block_ix);
+  orc_index_free(&env.rwc_ix);
   return 0;
 }

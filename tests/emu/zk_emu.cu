@@ -15,6 +15,7 @@
 #include "../../zkevm-specs_b200/csrc/exp.cu"
 #include "../../zkevm-specs_b200/csrc/state.cu"
 #include "../../zkevm-specs_b200/csrc/tx.cu"
+#include "../../zkevm-specs_b200/csrc/keccak.cuh"
 
 using namespace zk;
 
@@ -349,3 +350,16 @@ extern "C" int emu_check_sig(const uint64_t* rows, uint64_t n_rows, const uint8_
 }
 
 extern "C" int emu_n_evm_constraints() { return EV_N_CONSTRAINTS; }
+
+// Keccak-256 of the device header (csrc/keccak.cuh), for tests/test_emu_parity.py
+extern "C" void emu_keccak256(const uint8_t* msg, uint64_t len, uint8_t out[32]) {
+  u64 d[4];
+  keccak256(msg, len, d);
+  memcpy(out, d, 32);
+}
+extern "C" void emu_keccak256_word(const uint8_t* msg, uint64_t len, uint64_t lo[2], uint64_t hi[2]) {
+  u64 d[4], l[2], h[2];
+  keccak256(msg, len, d);
+  keccak_digest_to_word(d, l, h);
+  lo[0] = l[0]; lo[1] = l[1]; hi[0] = h[0]; hi[1] = h[1];
+}

@@ -1668,11 +1668,355 @@ def sig_cases():
     print(f"sig: {tot} corruptions, {nfail} failing")
 
 
+
+# --------------------------------------------------------------------------- evm11: BeginTx / EndTx / EndBlock
+def evm11_cases():
+    """BeginTx, EndTx and EndBlock steps built like the reference's tests (tests/evm/test_begin_tx.py:278-391,
+    test_end_tx.py:93-170, test_end_block.py:38-155), verified by the reference's verify_step with the first / last
+    step flags of verify_steps (main.py:14-44); corruptions of step cells, rw rows (all 14 cells + both type flags),
+    tx / block / withdrawal table cells (+ value type flags), copy- and keccak-table cells, duplicated rw rows."""
+    import rlp
+    from zkevm_specs.evm_circuit import (AccessTuple, Account, AccountFieldTag, Block, BlockTableRow, Bytecode,
+                                         BytecodeTableRow, CallContextFieldTag, CopyCircuit, CopyDataTypeTag, CopyTableRow,
+                                         ExecutionState, KeccakTableRow, RW, RWDictionary, RWTableRow, StepState, Tables,
+                                         Target, Transaction, TxReceiptFieldTag, TxTableRow, Withdrawal, WithdrawalTableRow)
+    from zkevm_specs.evm_circuit.instruction import Instruction
+    from zkevm_specs.evm_circuit.main import DUMMY_STEP_STATE, verify_step
+    from zkevm_specs.evm_circuit.typing import KeccakCircuit
+    from zkevm_specs.util import EMPTY_CODE_HASH, FQ, MAX_REFUND_QUOTIENT_OF_GAS_USED, U64, Word, WordOrValue
+    from zkevm_specs.util.hash import keccak256
+
+    rng = random.Random(23)
+    r_keccak = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def wov(lo, hi, is_word):
+        return WordOrValue(W(lo, hi)) if is_word else WordOrValue(FQ(lo))
+
+    # ---- scenario builders: (steps, bytecode rows, rw rows, copy-table rows, keccak rows, tx rows, block rows,
+    #      withdrawal rows, begin_with_first_step, end_with_last_step)
+    def end_tx_case(tx, gas_left, refund, is_last_tx, cum_gas):
+        block = Block()
+        eff = min(refund, (tx.gas - gas_left) // MAX_REFUND_QUOTIENT_OF_GAS_USED)
+        caller_prev = int(1e18) - (tx.value + tx.gas * tx.gas_price)
+        caller = caller_prev + (gas_left + eff) * tx.gas_price
+        coinbase = (tx.gas - gas_left) * (tx.gas_price - block.base_fee)
+        d = (RWDictionary(17)
+             .call_context_read(1, CallContextFieldTag.TxId, tx.id)
+             .call_context_read(1, CallContextFieldTag.IsPersistent, 1)
+             .tx_refund_read(tx.id, refund)
+             .account_write(tx.caller_address, AccountFieldTag.Balance, Word(caller), Word(caller_prev))
+             .account_write(block.coinbase, AccountFieldTag.Balance, Word(coinbase), Word(0))
+             .tx_receipt_write(tx.id, TxReceiptFieldTag.PostStateOrStatus, 1 - tx.invalid_tx)
+             .tx_receipt_write(tx.id, TxReceiptFieldTag.LogLength, 0))
+        first = tx.id == 1
+        if first:
+            d.tx_receipt_write(tx.id, TxReceiptFieldTag.CumulativeGasUsed, tx.gas - gas_left)
+        else:
+            d.tx_receipt_read(tx.id - 1, TxReceiptFieldTag.CumulativeGasUsed, cum_gas)
+            d.tx_receipt_write(tx.id, TxReceiptFieldTag.CumulativeGasUsed, tx.gas - gas_left + cum_gas)
+        if not is_last_tx:
+            d.call_context_read(27 - first, CallContextFieldTag.TxId, tx.id + 1)
+        steps = [StepState(ExecutionState.EndTx, rw_counter=17, call_id=1, is_root=True, is_create=False,
+                           code_hash=Word(EMPTY_CODE_HASH), program_counter=0, stack_pointer=1024, gas_left=gas_left,
+                           reversible_write_counter=2),
+                 StepState(ExecutionState.EndBlock if is_last_tx else ExecutionState.BeginTx,
+                           rw_counter=27 - first - is_last_tx, call_id=1 if is_last_tx else 0)]
+        return steps, [], list(d.rws), [], [], list(tx.table_assignments()), block.table_assignments(), [], False, False
+
+    def end_block_case(is_last_step, empty_block, max_txs, max_wds, cum_gas):
+        MAX_RWS = 32
+        tx = Transaction()
+        wd1, wd2 = Withdrawal(0, 99, 3, int(1e9)), Withdrawal(1, 999, 4, int(1.4e9))
+        rws, rwc = [], 1
+        if not empty_block:
+            rws += [RWTableRow(FQ(i + 1), *2 * [FQ(0)]) for i in range(21)]
+            rwc += 21
+            if is_last_step:
+                rws.append(RWTableRow(FQ(22), FQ(RW.Read), key0=FQ(Target.CallContext), id=FQ(1), address=FQ(3),
+                                      field_tag=FQ(CallContextFieldTag.TxId), value=WordOrValue(FQ(tx.id))))
+                rws.append(RWTableRow(FQ(23), FQ(RW.Read), key0=FQ(Target.TxReceipt), id=FQ(tx.id), address=FQ(0),
+                                      field_tag=FQ(TxReceiptFieldTag.CumulativeGasUsed), storage_key=Word(0),
+                                      value=WordOrValue(FQ(cum_gas))))
+            rws.append(RWTableRow(FQ(22 + is_last_step * 2), FQ(RW.Write), key0=FQ(Target.Account), address=FQ(wd1.address),
+                                  field_tag=FQ(AccountFieldTag.Balance), value=Word(int(5e18)), value_prev=Word(int(4e18))))
+            rws.append(RWTableRow(FQ(23 + is_last_step * 2), FQ(RW.Write), key0=FQ(Target.Account), address=FQ(wd2.address),
+                                  field_tag=FQ(AccountFieldTag.Balance), value=Word(int(5.5e18)), value_prev=Word(int(4.1e18))))
+        pad = [RWTableRow(FQ(i + 1), FQ(0), FQ(Target.Start)) for i in range(MAX_RWS - len(rws))]
+        n_tx = 0 if empty_block else 1
+        txs = []
+        for i in range(n_tx, max_txs):
+            txs += Transaction.padding(id=i + 1).table_fixed()
+        if not empty_block:
+            txs = list(tx.table_assignments())
+        n_wd = 0 if empty_block else 2
+        wds = []
+        for i in range(n_wd, max_wds):
+            wds += Withdrawal.padding(id=i).table_assignments()
+        if not empty_block:
+            wds += list(wd1.table_assignments()) + list(wd2.table_assignments())
+        steps = [StepState(ExecutionState.EndBlock, rw_counter=rwc, call_id=1),
+                 StepState(ExecutionState.EndBlock, rw_counter=rwc, call_id=1)]
+        return steps, [], pad + rws, [], [], txs, Block().table_assignments(), wds, False, is_last_step
+
+    RETURN_CODE, REVERT_CODE = Bytecode().return_(0, 0), Bytecode().revert(0, 0)
+
+    def initcode(is_return):
+        b = Bytecode().push(0x2222222222222222222222222222222222222222222222222222222222222222, n_bytes=32).push(0, n_bytes=1).mstore()
+        return b.return_() if is_return else b.revert()
+
+    def begin_tx_case(tx, callee, is_success):
+        block = Block()
+        valid = 1 - tx.invalid_tx
+        create = tx.callee_address is None
+        rev_end = 24
+        caller_prev = int(1e20)
+        caller = caller_prev - (tx.value + tx.gas * tx.gas_price) if valid else caller_prev
+        callee_bal = callee.balance + tx.value if valid else callee.balance
+        calldata_hash = Word(int.from_bytes(keccak256(tx.call_data), "big"))
+        code_hash = calldata_hash if create else Word(callee.code_hash())
+        caddr = int.from_bytes(keccak256(rlp.encode([tx.caller_address.to_bytes(20, "big"), tx.nonce]))[-20:], "big")
+        callee_address = caddr if create else tx.callee_address
+        d = (RWDictionary(1)
+             .call_context_read(1, CallContextFieldTag.TxId, tx.id)
+             .call_context_read(1, CallContextFieldTag.RwCounterEndOfReversion, 0 if is_success else rev_end)
+             .call_context_read(1, CallContextFieldTag.IsPersistent, is_success)
+             .call_context_read(1, CallContextFieldTag.IsSuccess, is_success)
+             .account_write(tx.caller_address, AccountFieldTag.Nonce, valid, 0)
+             .tx_access_list_account_write(tx.id, block.coinbase, True, False)
+             .tx_access_list_account_write(tx.id, tx.caller_address, True, False)
+             .tx_access_list_account_write(tx.id, callee_address, True, False)
+             .account_write(tx.caller_address, AccountFieldTag.Balance, Word(caller), Word(caller_prev),
+                            rw_counter_of_reversion=None if is_success else rev_end)
+             .account_write(callee_address, AccountFieldTag.Balance, Word(callee_bal), Word(callee.balance),
+                            rw_counter_of_reversion=None if is_success else rev_end - 1))
+        with_calldata = create and len(tx.call_data) > 0
+        is_contract = not create and callee.code_hash() != EMPTY_CODE_HASH
+        copy_rows, kec_rows = CopyCircuit().rows, KeccakCircuit().rows
+        if not create:
+            d.account_read(tx.callee_address, AccountFieldTag.CodeHash, code_hash)
+        elif len(tx.call_data) > 0:
+            src = dict((i, tx.call_data[i]) for i in range(len(tx.call_data)))
+            c1 = CopyCircuit().copy(r_keccak, d, 1, CopyDataTypeTag.TxCalldata, 1, CopyDataTypeTag.RlcAcc, FQ.zero(),
+                                    len(tx.call_data), FQ.zero(), len(tx.call_data), src)
+            bc = Bytecode(tx.call_data)
+            src2 = dict((i, (bc.code[i], bc.is_code[i])) for i in range(len(bc.code)))
+            c2 = CopyCircuit().copy(r_keccak, d, 1, CopyDataTypeTag.TxCalldata, calldata_hash, CopyDataTypeTag.Bytecode,
+                                    FQ.zero(), len(tx.call_data), FQ.zero(), len(tx.call_data), src2)
+            copy_rows = c1.rows + c2.rows
+            kec_rows = KeccakCircuit().add(tx.call_data, r_keccak).rows
+        if (with_calldata or is_contract) and valid == 1:
+            (d.call_context_read(1, CallContextFieldTag.Depth, 1)
+              .call_context_read(1, CallContextFieldTag.CallerAddress, Word(tx.caller_address))
+              .call_context_read(1, CallContextFieldTag.CalleeAddress, Word(callee_address))
+              .call_context_read(1, CallContextFieldTag.CallDataOffset, 0)
+              .call_context_read(1, CallContextFieldTag.CallDataLength, len(tx.call_data))
+              .call_context_read(1, CallContextFieldTag.Value, Word(tx.value))
+              .call_context_read(1, CallContextFieldTag.IsStatic, False)
+              .call_context_read(1, CallContextFieldTag.LastCalleeId, 0)
+              .call_context_read(1, CallContextFieldTag.LastCalleeReturnDataOffset, 0)
+              .call_context_read(1, CallContextFieldTag.LastCalleeReturnDataLength, 0)
+              .call_context_read(1, CallContextFieldTag.IsRoot, True)
+              .call_context_read(1, CallContextFieldTag.IsCreate, create)
+              .call_context_read(1, CallContextFieldTag.CodeHash, code_hash))
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(), rw_table=set(),
+                   copy_circuit=copy_rows, keccak_table=kec_rows)
+        steps = [StepState(ExecutionState.BeginTx, rw_counter=1),
+                 StepState(ExecutionState.EndTx if callee.code_hash() == EMPTY_CODE_HASH or valid == 0 else ExecutionState.PUSH,
+                           rw_counter=d.rw_counter, call_id=1, is_root=True, is_create=create, code_hash=code_hash,
+                           program_counter=0, stack_pointer=1024, gas_left=0, reversible_write_counter=2)]
+        return (steps, list(callee.code.table_assignments()), list(d.rws), list(t.copy_table), list(t.keccak_table),
+                list(tx.table_assignments()), block.table_assignments(), [], True, False)
+
+    CALLEE = 0xFF
+    EOA, RET, REV = Account(address=CALLEE), Account(address=CALLEE, code=RETURN_CODE), Account(address=CALLEE, code=REVERT_CODE)
+    scenarios = {
+        "endtx_refund": end_tx_case(Transaction(id=1, caller_address=0xFE, callee_address=CALLEE, gas=27000, gas_price=int(2e9)), 994, 4800, False, 0),
+        "endtx_capped": end_tx_case(Transaction(id=2, caller_address=0xFE, callee_address=CALLEE, gas=65000, gas_price=int(2e9)), 3952, 38400, False, 100),
+        "endtx_last": end_tx_case(Transaction(id=3, caller_address=0xFE, callee_address=CALLEE, gas=21000, gas_price=int(2e9)), 0, 0, True, 20000),
+        "endtx_invalid": end_tx_case(Transaction(id=1, caller_address=0xFE, callee_address=CALLEE, gas=60000, gas_price=int(2e9), invalid_tx=1), 60000, 0, False, 0),
+        "endtx_last_invalid": end_tx_case(Transaction(id=2, caller_address=0xFE, callee_address=CALLEE, gas=65000, gas_price=int(2e9), invalid_tx=1), 65000, 0, True, 21000),
+        "endblock_mid": end_block_case(False, False, 2, 5, 0),
+        "endblock_last": end_block_case(True, False, 2, 5, 0),
+        "endblock_last_full": end_block_case(True, False, 1, 2, 0),
+        "endblock_empty": end_block_case(True, True, 1, 5, 0),
+        "endblock_gas_ok": end_block_case(True, False, 1, 5, int(15e6)),
+        "endblock_gas_over": end_block_case(True, False, 1, 2, int(15e6) + 1),
+        "begintx_eoa": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, value=int(1e18)), EOA, True),
+        "begintx_contract": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, value=int(1e18)), RET, True),
+        "begintx_revert": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, value=int(1e18)), REV, False),
+        "begintx_calldata": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, gas=21080, call_data=bytes([1, 2, 3, 4, 0, 0, 0, 0])), RET, True),
+        "begintx_bad_nonce": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, value=int(1e18), nonce=U64(100), invalid_tx=1), EOA, True),
+        "begintx_poor": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, gas=21080, value=int(1e21), invalid_tx=1), REV, True),
+        "begintx_accesslist": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, gas=21080 + 2400 + 1900 * 2, value=int(1e17),
+                                                        access_list=[AccessTuple(address=0xFE, storage_keys=[5, 6])]), EOA, True),
+        "begintx_low_gas": begin_tx_case(Transaction(caller_address=0xFE, callee_address=CALLEE, gas=21080, value=int(1e17), invalid_tx=1,
+                                                     access_list=[AccessTuple(address=0xFE, storage_keys=[5, 6])]), EOA, True),
+        "begintx_create_empty": begin_tx_case(Transaction(caller_address=0xFE, callee_address=None, gas=53000, value=1), EOA, True),
+        "begintx_create_code": begin_tx_case(Transaction(caller_address=0xFE, callee_address=None, gas=53584, value=1, call_data=bytes(initcode(True).code)), EOA, True),
+        "begintx_create_revert": begin_tx_case(Transaction(caller_address=0xFE, callee_address=None, gas=53584, value=1, call_data=bytes(initcode(False).code)), EOA, True),
+    }
+
+    def step_ints(s):
+        return [int(s.execution_state), n_of(s.rw_counter), n_of(s.call_id), int(s.is_root), int(s.is_create),
+                n_of(s.code_hash.lo), n_of(s.code_hash.hi), n_of(s.program_counter), n_of(s.stack_pointer),
+                n_of(s.gas_left), n_of(s.memory_word_size), n_of(s.reversible_write_counter), n_of(s.log_id)]
+
+    def step_from(v):
+        s = StepState(ExecutionState(v[0]), rw_counter=0)
+        s.rw_counter, s.call_id, s.is_root, s.is_create = FQ(v[1]), FQ(v[2]), v[3], v[4]
+        s.code_hash = W(v[5], v[6])
+        s.program_counter, s.stack_pointer, s.gas_left = FQ(v[7]), FQ(v[8]), FQ(v[9])
+        s.memory_word_size, s.reversible_write_counter, s.log_id = FQ(v[10]), FQ(v[11]), FQ(v[12])
+        return s
+
+    bc_ints = lambda x: [n_of(x.bytecode_hash.lo), n_of(x.bytecode_hash.hi), n_of(x.field_tag), n_of(x.index), n_of(x.is_code), n_of(x.value)]  # noqa: E731
+    rw_ints = lambda x: [n_of(x.rw_counter), n_of(x.rw), n_of(x.key0), n_of(x.id), n_of(x.address), n_of(x.field_tag),  # noqa: E731
+                         n_of(x.storage_key.lo), n_of(x.storage_key.hi), n_of(x.value.lo), n_of(x.value.hi),
+                         n_of(x.value_prev.lo), n_of(x.value_prev.hi), n_of(x.aux0.lo), n_of(x.aux0.hi)]
+    copy_ints = lambda x: [n_of(x.is_first), n_of(x.src_id.lo), n_of(x.src_id.hi), n_of(x.src_tag), n_of(x.dst_id.lo), n_of(x.dst_id.hi),  # noqa: E731
+                           n_of(x.dst_tag), n_of(x.src_addr), n_of(x.src_addr_end), n_of(x.dst_addr), n_of(x.length), n_of(x.rlc_acc),
+                           n_of(x.rw_counter), n_of(x.rwc_inc)]
+    kec_ints = lambda x: [n_of(x.state_tag), n_of(x.input_rlc), n_of(x.input_len), n_of(x.output.lo), n_of(x.output.hi)]  # noqa: E731
+    tx_ints = lambda x: [n_of(x.tx_id), n_of(x.field_tag), n_of(x.call_data_index_or_zero), n_of(x.value.lo), n_of(x.value.hi)]  # noqa: E731
+    blk_ints = lambda x: [n_of(x.field_tag), n_of(x.block_number_or_zero), n_of(x.value.lo), n_of(x.value.hi)]  # noqa: E731
+    wd_ints = lambda x: [n_of(x.id), n_of(x.validator_id), n_of(x.address), n_of(x.amount)]  # noqa: E731
+
+    def run(S, B, R, RF, C, CF, K, T, TF, BL, BF, WD, first, last):
+        steps = [step_from(v) for v in S]
+        t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), wov(v[2], v[3], f)) for v, f in zip(BL, BF)),
+                   tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], f)) for v, f in zip(T, TF)),
+                   withdrawal_table=set(WithdrawalTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3])) for v in WD),
+                   bytecode_table=set(BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5])) for v in B),
+                   rw_table=set(RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
+                                           wov(v[8], v[9], f & 1), wov(v[10], v[11], (f >> 1) & 1), W(v[12], v[13]))
+                                for v, f in zip(R, RF)))
+        t.copy_table = set(CopyTableRow(FQ(v[0]), wov(v[1], v[2], f & 1), FQ(v[3]), wov(v[4], v[5], (f >> 1) & 1), FQ(v[6]),
+                                        FQ(v[7]), FQ(v[8]), FQ(v[9]), FQ(v[10]), FQ(v[11]), FQ(v[12]), FQ(v[13])) for v, f in zip(C, CF))
+        t.keccak_table = set(KeccakTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), W(v[3], v[4])) for v in K)
+        if last:
+            steps = steps + [DUMMY_STEP_STATE]
+        for idx, (cur, nxt) in enumerate(zip(steps, steps[1:])):
+            try:
+                verify_step(Instruction(tables=t, curr=cur, next=nxt, is_first_step=first and idx == 0,
+                                        is_last_step=last and idx == len(steps) - 2))
+            except Exception as e:  # noqa: BLE001
+                return idx, type(e).__name__
+        return -1, ""
+
+    out = {"names": np.array(list(scenarios.keys()))}
+    tot = nfail = 0
+    for name, (steps, bcs, rws, cps, kcs, txs, blks, wds, first, last) in scenarios.items():
+        S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
+        RF = [int(getattr(x.value, 'is_word', True)) | (int(getattr(x.value_prev, 'is_word', True)) << 1) for x in rws]
+        C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
+        CF = [int(x.src_id.is_word) | (int(x.dst_id.is_word) << 1) for x in cps]
+        T, BL, WD = [tx_ints(x) for x in txs], [blk_ints(x) for x in blks], [wd_ints(x) for x in wds]
+        TF, BF = [int(x.value.is_word) for x in txs], [int(x.value.is_word) for x in blks]
+        base = run(S, B, R, RF, C, CF, K, T, TF, BL, BF, WD, first, last)
+        if name == "endblock_gas_over":
+            assert base == (1, "AssertionError"), base
+        else:
+            assert base == (-1, ""), (name, base)
+        muts = [(-1, 0, 0, 0) + base]
+        for k in range(150):
+            which = rng.choice([0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 5, 6, 6, 6, 8, 7, 7, 9, 3, 4, 10])
+            S2, R2, RF2 = [list(x) for x in S], [list(x) for x in R], list(RF)
+            T2, TF2, BL2, BF2, WD2 = [list(x) for x in T], list(TF), [list(x) for x in BL], list(BF), [list(x) for x in WD]
+            C2, K2 = [list(x) for x in C], [list(x) for x in K]
+            if which == 0:
+                i, c = rng.randrange(len(S)), rng.randrange(13)
+                if c == 0:
+                    v = rng.choice([int(ExecutionState.EndTx), int(ExecutionState.BeginTx), int(ExecutionState.ADD), int(ExecutionState.EndBlock),
+                                    int(ExecutionState.STOP)])
+                    if v == S[i][c]:
+                        continue
+                else:
+                    v = (1 - S[i][c]) if c in (3, 4) else corrupt_value(rng, S[i][c])
+                S2[i][c] = v
+            elif which == 1 and R:
+                i, c = rng.randrange(len(R)), rng.randrange(14)
+                if (c == 9 and not (RF[i] & 1)) or (c == 11 and not (RF[i] & 2)):
+                    continue
+                v = corrupt_value(rng, R[i][c]); R2[i][c] = v
+            elif which == 2 and R:  # flip a value / value_prev type flag
+                i, c, v = rng.randrange(len(R)), 100 + rng.randrange(2), 0
+                bit = 1 << (c - 100)
+                RF2[i] ^= bit
+                if not RF2[i] & bit:
+                    R2[i][9 if bit == 1 else 11] = 0
+            elif which == 5 and R:  # a second rw row with the same key and another value: ambiguous lookup
+                i, c = rng.randrange(len(R)), rng.choice([8, 10])
+                v = corrupt_value(rng, R[i][c])
+                R2.append(list(R[i])); R2[-1][c] = v; RF2.append(RF[i])
+            elif which == 6 and T:
+                i, c = rng.randrange(len(T)), rng.randrange(5)
+                if c == 4 and not TF[i]:
+                    continue
+                v = corrupt_value(rng, T[i][c]); T2[i][c] = v
+            elif which == 8 and T:  # tx value type flag
+                i, c, v = rng.randrange(len(T)), 100, 0
+                TF2[i] ^= 1
+                if not TF2[i]:
+                    T2[i][4] = 0
+            elif which == 7 and BL:
+                i, c = rng.randrange(len(BL)), rng.randrange(5)
+                if c == 4:
+                    c, v = 100, 0
+                    BF2[i] ^= 1
+                    if not BF2[i]:
+                        BL2[i][3] = 0
+                elif c == 3 and not BF[i]:
+                    continue
+                else:
+                    v = corrupt_value(rng, BL[i][c]); BL2[i][c] = v
+            elif which == 9 and WD:
+                i, c = rng.randrange(len(WD)), rng.randrange(4)
+                v = corrupt_value(rng, WD[i][c])
+                if c == 0 and any(v == x[0] for x in WD):
+                    continue  # two withdrawals with one id: sorted() over a Python set leaves their order unspecified
+                WD2[i][c] = v
+            elif which == 3 and C:
+                i, c = rng.randrange(len(C)), rng.randrange(14)
+                if c in (2, 5):
+                    continue
+                v = corrupt_value(rng, C[i][c]); C2[i][c] = v
+            elif which == 4 and K:
+                i, c = rng.randrange(len(K)), rng.randrange(5)
+                v = corrupt_value(rng, K[i][c]); K2[i][c] = v
+            elif which == 10 and R:  # drop an rw row
+                i, c, v = rng.randrange(len(R)), 200, 0
+                del R2[i]; del RF2[i]
+            else:
+                continue
+            fr_, ex_ = run(S2, B, R2, RF2, C2, CF, K2, T2, TF2, BL2, BF2, WD2, first, last)
+            muts.append((which, i, c, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        for key, rows_, ncol in (("steps", S, 13), ("bytecode", B, 6), ("rw", R, 14), ("copy", C, 14), ("keccak", K, 5),
+                                 ("tx", T, 5), ("block", BL, 4), ("wd", WD, 4)):
+            out[f"{name}/{key}"] = to_matrix(rows_) if rows_ else np.zeros((ncol, 0, 4), dtype=np.uint64)
+        for key, fl in (("rw_flags", RF), ("copy_flags", CF), ("tx_flags", TF), ("block_flags", BF)):
+            out[f"{name}/{key}"] = np.array(fl, dtype=np.uint8)
+        out[f"{name}/first_last"] = np.array([int(first), int(last)], dtype=np.int64)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, len(R), "rw", len(T), "tx", len(WD), "wd", len(C), "copy", len(muts), "vectors",
+              sorted(set(m[5] for m in muts)))
+    np.savez_compressed(os.path.join(HERE, "evm11.npz"), **out)
+    print(f"evm11: {tot} corruptions, {nfail} failing")
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "exp", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -218,3 +218,63 @@ def evm9_vectors():
 def evm10_vectors():
     """SHL / SHR steps; same layout as evm2"""
     return evm2_vectors("evm10")
+
+
+def evm11_vectors():
+    """BeginTx / EndTx / EndBlock steps: yield (case, k, dict(steps, bytecode, rw, rw_flags, copy, keccak, tx, tx_flags,
+    block, block_flags, wd, flags = ZK_FLAG_EVM_* of the scenario), exp_row, exp_exc)"""
+    z = np.load(os.path.join(GOLDEN, "evm11.npz"))
+    for name in z["names"]:
+        name = str(name)
+        base = {k: z[f"{name}/{k}"] for k in ("steps", "bytecode", "rw", "rw_flags", "copy", "keccak", "tx", "tx_flags", "block",
+                                            "block_flags", "wd")}
+        first, last = [int(x) for x in z[f"{name}/first_last"]]
+        base["flags"] = (2 if first else 0) | (4 if last else 0)
+        if last:  # verify_steps(end_with_last_step=True) appends DUMMY_STEP_STATE = StepState(EndBlock, rw_counter=-1)
+            dummy = np.zeros((13, 1, 4), dtype=np.uint64)
+            dummy[0, 0, 0] = 3
+            P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+            dummy[1, 0, :] = [((P - 1) >> (64 * q)) & 0xFFFFFFFFFFFFFFFF for q in range(4)]
+            dummy[5, 0, :] = 0
+            dummy[8, 0, 0] = 1024
+            base["steps"] = np.ascontiguousarray(np.concatenate([base["steps"], dummy], axis=1))
+        for k in range(len(z[f"{name}/mut_kind"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            val = z[f"{name}/mut_val"][k]
+            w = dict(base)
+            if kind == 0:
+                w["steps"] = base["steps"].copy(); w["steps"][c, i, :] = val
+            elif kind == 1:
+                w["rw"] = base["rw"].copy(); w["rw"][c, i, :] = val
+            elif kind == 2:
+                bit = 1 << (c - 100)
+                w["rw_flags"] = base["rw_flags"].copy(); w["rw_flags"][i] ^= bit
+                if not w["rw_flags"][i] & bit:
+                    w["rw"] = base["rw"].copy(); w["rw"][9 if bit == 1 else 11, i, :] = 0
+            elif kind == 5:
+                extra = base["rw"][:, i:i + 1, :].copy(); extra[c, 0, :] = val
+                w["rw"] = np.ascontiguousarray(np.concatenate([base["rw"], extra], axis=1))
+                w["rw_flags"] = np.concatenate([base["rw_flags"], base["rw_flags"][i:i + 1]])
+            elif kind == 6:
+                w["tx"] = base["tx"].copy(); w["tx"][c, i, :] = val
+            elif kind == 8:
+                w["tx_flags"] = base["tx_flags"].copy(); w["tx_flags"][i] ^= 1
+                if not w["tx_flags"][i]:
+                    w["tx"] = base["tx"].copy(); w["tx"][4, i, :] = 0
+            elif kind == 7:
+                if c == 100:
+                    w["block_flags"] = base["block_flags"].copy(); w["block_flags"][i] ^= 1
+                    if not w["block_flags"][i]:
+                        w["block"] = base["block"].copy(); w["block"][3, i, :] = 0
+                else:
+                    w["block"] = base["block"].copy(); w["block"][c, i, :] = val
+            elif kind == 9:
+                w["wd"] = base["wd"].copy(); w["wd"][c, i, :] = val
+            elif kind == 3:
+                w["copy"] = base["copy"].copy(); w["copy"][c, i, :] = val
+            elif kind == 4:
+                w["keccak"] = base["keccak"].copy(); w["keccak"][c, i, :] = val
+            elif kind == 10:
+                keep = [q for q in range(base["rw"].shape[1]) if q != i]
+                w["rw"] = np.ascontiguousarray(base["rw"][:, keep, :]); w["rw_flags"] = base["rw_flags"][keep]
+            yield name, k, w, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])

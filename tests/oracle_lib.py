@@ -157,6 +157,15 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
         tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
         blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         lib().orc_set_evm_context_tables(p64(tx), c(tx.shape[1]), p64(blk), c(blk.shape[1]))
+    if w.get("wd") is not None or w.get("tx_flags") is not None:  # BeginTx / EndTx / EndBlock: value type flags + withdrawals
+        keep = getattr(check_evm_x, "_keep", None) or []
+        txf = np.ascontiguousarray(w.get("tx_flags") if w.get("tx_flags") is not None else np.zeros(0), dtype=np.uint8)
+        blf = np.ascontiguousarray(w.get("block_flags") if w.get("block_flags") is not None else np.zeros(0), dtype=np.uint8)
+        wd = np.ascontiguousarray(w["wd"] if w.get("wd") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
+        check_evm_x._keep = [txf, blf, wd]
+        lib().orc_set_evm_block_tables(_p8(txf), _p8(blf), p64(wd), c(wd.shape[1]))
+    if w.get("flags") is not None:
+        flags = int(w["flags"])
     rc = lib().orc_check_evm_x(p64(m["steps"]), c(m["steps"].shape[1]), p64(m["bytecode"]), c(m["bytecode"].shape[1]),
                                p64(m["rw"]), c(m["rw"].shape[1]), _p8(rwf), p64(fixed), c(fixed.shape[1]),
                                p64(m["copy"]), c(m["copy"].shape[1]), p64(m["keccak"]), c(m["keccak"].shape[1]),

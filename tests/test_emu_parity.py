@@ -188,3 +188,26 @@ def test_emu_div256_equals_python_integer_division():
                        arr(*[(d >> (64 * k)) & (2**64 - 1) for k in range(4)]), q)
         got = sum(int(q[k]) << (64 * k) for k in range(4))
         assert got == n // d, (hex(n), hex(d), hex(got), hex(n // d))
+
+
+def test_device_keccak256_matches_host_reference():
+    """csrc/keccak.cuh (run on the host through the emu build) against the Python sponge that the standard
+    vectors pin (zkevm_specs_b200.util.hash), at every length around the 136-byte rate boundaries"""
+    import ctypes
+
+    import emu_lib
+    from zkevm_specs_b200.util.hash import keccak256
+
+    L = emu_lib.lib()
+    rng = np.random.default_rng(7)
+    out = (ctypes.c_uint8 * 32)()
+    lo, hi = (ctypes.c_uint64 * 2)(), (ctypes.c_uint64 * 2)()
+    for n in list(range(0, 140)) + [271, 272, 273, 407, 408, 1000, 24576]:
+        msg = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        buf = (ctypes.c_uint8 * max(1, n)).from_buffer_copy(msg or b"\0")
+        L.emu_keccak256(buf, ctypes.c_uint64(n), out)
+        want = keccak256(msg)
+        assert bytes(out) == want, n
+        L.emu_keccak256_word(buf, ctypes.c_uint64(n), lo, hi)
+        v = int.from_bytes(want, "big")
+        assert lo[0] | (lo[1] << 64) == v & ((1 << 128) - 1) and hi[0] | (hi[1] << 64) == v >> 128

@@ -108,3 +108,25 @@ def test_oracle_evm_simple_gadgets_match_reference_golden():
         kinds.add(exp_exc)
     assert n > 4200 and n_fail > 3100
     assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure"} <= kinds, kinds
+
+
+def test_oracle_evm_begin_end_tx_end_block_match_reference_golden():
+    """BeginTx / EndTx / EndBlock (tests/evm/test_begin_tx.py, test_end_tx.py, test_end_block.py scenarios)"""
+    fixed = fixed_table_matrix()
+    classes = oracle_lib.constraint_classes(3)
+    n = n_fail = 0
+    kinds = set()
+    bad = []
+    for name, k, w, exp_row, exp_exc in golden_util.evm11_vectors():
+        ff, fc = oracle_lib.check_evm_x(w, fixed)
+        row, exc = oracle_lib.first_failure(ff, classes)
+        if exc == "ValueError" and exp_exc == "OverflowError":
+            exc = "OverflowError"
+        if (row, exc) != (exp_row, exp_exc):
+            bad.append(f"{name}[{k}]: oracle {(row, exc)} reference {(exp_row, exp_exc)}")
+        n += 1
+        n_fail += exp_row >= 0
+        kinds.add(exp_exc)
+    assert not bad, f"{len(bad)} of {n} differ: " + "; ".join(bad[:12])
+    assert n > 2500 and n_fail > 1000
+    assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure", "ConstraintUnsatFailure", "OverflowError"} <= kinds

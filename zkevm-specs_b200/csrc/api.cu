@@ -131,7 +131,7 @@ static std::string g_create_err;
   do {                                                                                 \
     cudaError_t e_ = (call);                                                           \
     if (e_ != cudaSuccess) {                                                           \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      (ctx)->err = std::string(#call) + " (api.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_); \
       return -2;                                                                       \
     }                                                                                  \
   } while (0)
@@ -653,15 +653,9 @@ static int check_bytecode(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cuda
   const u64 n = rg.row_end - rg.row_begin;
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
   const Matrix& m = ctx->circ[ZK_CIRCUIT_BYTECODE];
-  if (is_canonical(m)) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CK(ctx, cudaFuncSetAttribute(k_check_bytecode_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BcPipe::SMEM_BYTES));
-      attr_set = true;
-    }
-    const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((n + 127) / 128, (u64)ctx->sm_count));  // one CTA per SM
-    k_check_bytecode_tiled<<<grid, 128, BcPipe::SMEM_BYTES, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
-  } else
+  if (is_canonical(m))
+    k_check_bytecode<L_CANON><<<grid_persistent(ctx, k_check_bytecode<L_CANON>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
+  else
     k_check_bytecode<L_ANY><<<grid_persistent(ctx, k_check_bytecode<L_ANY>, 256, n), 256, 0, st>>>(witness_dev(m), rg, push_ix, kec_ix, r_mont, res);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
@@ -803,11 +797,18 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   const WitnessDev wd = witness_dev(m);
   const unsigned sort_grid = (unsigned)((n + 1023) / 1024);
   k_evm_classify<<<sort_grid, 1024, 0, st>>>(wd, rg, t, res, so);
+  {
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail_msg(ctx, std::string("launch of k_evm_classify: ") + cudaGetErrorString(e_));
+  }
   CK(ctx, cudaMemcpyAsync(ctx->evm_hist_host, so.hist, (ZK_EVM_NB + 1) * sizeof(u32), cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaEventRecord(ctx->evm_hist_ev, st));
   k_evm_scatter<<<sort_grid, 1024, 0, st>>>(so, (u32)n);
   ctx->launches += 2;
-  CK(ctx, cudaGetLastError());
+  {
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail_msg(ctx, std::string("launch of k_evm_scatter: ") + cudaGetErrorString(e_));
+  }
   // the histogram decides which groups run and how large their grids are; the device keeps working on
   // the scatter meanwhile
   CK(ctx, cudaEventSynchronize(ctx->evm_hist_ev));
@@ -833,6 +834,10 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   do {                                                                                         \
     kernel<<<grid_for(slot, (const void*)kernel, items, per_block), 128, 0, st>>>(wd, rg, t, res, so); \
     ctx->launches++;                                                                           \
+    {                                                                                          \
+      cudaError_t e_ = cudaGetLastError();                                                     \
+      if (e_ != cudaSuccess) return fail_msg(ctx, std::string("launch of " #kernel ": ") + cudaGetErrorString(e_)); \
+    }                                                                                          \
   } while (0)
   if (group_n[KG_PUSH]) {
     if (pos) ZK_LAUNCH_GROUP(0, k_evm_push_pos, group_n[KG_PUSH], 128);
@@ -876,6 +881,10 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
   if (rc) return rc;
   if (row_begin == row_end) return 0;
   CheckRange rg{row_begin, row_end, row_base, flags};
+  {  // an error left behind by an earlier call must not be blamed on this check's launches
+    cudaError_t stale = cudaGetLastError();
+    if (stale != cudaSuccess) return fail_msg(ctx, std::string("CUDA error pending before the check: ") + cudaGetErrorString(stale));
+  }
   ctx->ev_mid_stream = st;
   if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], st));
   switch (circuit_id) {

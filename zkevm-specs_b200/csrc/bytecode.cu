@@ -124,53 +124,6 @@ k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix,
     check_bytecode_row<LAYOUT>(w, rg, push_ix, staged ? s_push : nullptr, kec_ix, r_mont, res, i);
 }
 
-// Canonical storage: 128-row tiles of the 12 columns (+1 halo row for the rotation) streamed into shared
-// memory four tiles ahead by the bulk-copy engine; one thread per row reads its cells with LDS.  Rows
-// whose rotation leaves the matrix (the last row) take the global-memory path.
-typedef TilePipe<12, 128, 0, 1, 4> BcPipe;
-__global__ void __launch_bounds__(128)
-k_check_bytecode_tiled(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg,
-                       const __grid_constant__ IndexDev push_ix, const __grid_constant__ IndexDev kec_ix, Fr r_mont,
-                       ResultDev res) {
-  extern __shared__ __align__(128) unsigned char s_tiles[];
-  __shared__ alignas(32) u64 s_push[256 * 4];
-  __shared__ alignas(8) u64 s_bar_push;
-  __shared__ alignas(8) u64 s_full[4];
-  const bool staged = push_ix.tab.n_rows == 256 && push_ix.tab.width[1] == 32 && pos_enabled(push_ix) &&
-                      push_ix.pos_kind == ZK_POS_DENSE && fr_is_zero(table_cell(push_ix.tab, 0, 0));
-  if (staged) stage_to_smem(s_push, push_ix.tab.base + push_ix.tab.off[1], sizeof(s_push), &s_bar_push);
-  const u32 tiles0 = (u32)__cvta_generic_to_shared(s_tiles), bar0 = (u32)__cvta_generic_to_shared(s_full);
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < 4; k++) mbar_init(bar0 + 8 * k, 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  const u64 n = rg.row_end - rg.row_begin;
-  const u64 n_tiles = (n + 127) / 128;
-  const u64 my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const bool issuer = threadIdx.x < 32;
-  if (issuer)
-    for (u64 k = 0; k < 3 && k < my_tiles; k++)
-      BcPipe::issue(w, tiles0 + (u32)k * BcPipe::STAGE_BYTES, bar0 + 8 * (u32)k, rg.row_begin + (blockIdx.x + k * gridDim.x) * 128);
-  for (u64 k = 0; k < my_tiles; k++) {
-    const u32 stage = (u32)(k & 3);
-    if (issuer && k + 3 < my_tiles)  // refill the stage released at the end of iteration k - 1
-      BcPipe::issue(w, tiles0 + ((stage + 3) & 3) * BcPipe::STAGE_BYTES, bar0 + 8 * ((stage + 3) & 3),
-                    rg.row_begin + (blockIdx.x + (k + 3) * gridDim.x) * 128);
-    mbar_wait(bar0 + 8 * stage, (u32)((k >> 2) & 1));
-    const u64 r0 = rg.row_begin + (blockIdx.x + k * gridDim.x) * 128;
-    const u64 i = r0 + threadIdx.x;
-    if (i < rg.row_end) {
-      if (i + 1 < w.n_rows) {
-        TileDev t{tiles0 + stage * BcPipe::STAGE_BYTES, BcPipe::CAP, r0, w.n_rows, w.flags};
-        check_bytecode_row<L_CANON>(t, rg, push_ix, staged ? s_push : nullptr, kec_ix, r_mont, res, i);
-      } else {
-        check_bytecode_row<L_CANON>(w, rg, push_ix, staged ? s_push : nullptr, kec_ix, r_mont, res, i);
-      }
-    }
-    __syncthreads();
-  }
-}
 #endif
 
 }  // namespace zk

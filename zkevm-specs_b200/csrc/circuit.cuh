@@ -49,74 +49,10 @@ ZK_HD u64 rot_back(const WitnessDev& w, u64 row, bool wrap) {
 }
 
 #ifdef __CUDACC__
-// ---- shared-memory row tiles (canonical storage) ---------------------------------------------
-// The row checkers are latency-bound when every thread loads its cells straight from HBM: occupancy
-// is capped by the registers of the gate program, so too few loads are in flight (ncu: 17-24 % warps
-// active, 32-41 % of DRAM throughput).  For canonical matrices the columns of a block of rows are
-// instead streamed into shared memory by the bulk-copy engine (cp.async.bulk, one copy per column
-// per tile, completion on an mbarrier) several tiles ahead of the compute warps, which then read
-// their cells with LDS.  A TileDev is the view of one staged tile with the interface of WitnessDev.
-struct TileDev {
-  u32 smem;   // shared-window address of the stage buffer: column c at smem + c * cap * 32
-  u32 cap;    // rows per column segment
-  u64 row0;   // first staged row
-  u64 n_rows; // resident rows of the whole matrix (for the rotations)
-  const unsigned char* flags;
-};
-template <int LAYOUT>
-__device__ __forceinline__ Fr wcell_l(const TileDev& t, u32 col, u64 row) {
-  Fr r;
-  const u32 a = t.smem + (col * t.cap + (u32)(row - t.row0)) * 32u;
-  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(r.l[0]), "=l"(r.l[1]) : "r"(a));
-  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(r.l[2]), "=l"(r.l[3]) : "r"(a + 16u));
-  return r;
-}
-__device__ __forceinline__ u64 rot_fwd(const TileDev& t, u64 row, u32 k, bool) { return row + k; }  // tiles never serve edge rows
-__device__ __forceinline__ u64 rot_back(const TileDev& t, u64 row, bool) { return row - 1; }
-
-// NCOLS columns, R rows per tile plus PRE / POST halo rows, STAGES tiles in flight
-template <int NCOLS, int R, int PRE, int POST, int STAGES>
-struct TilePipe {
-  static constexpr int CAP = R + PRE + POST;
-  static constexpr u32 STAGE_BYTES = (u32)NCOLS * CAP * 32u;
-  static constexpr u32 SMEM_BYTES = STAGE_BYTES * STAGES;
-  // staged rows of the tile whose first checked row is r0: [lo, hi)
-  __device__ static __forceinline__ void range(u64 r0, u64 n_rows, u64* lo, u64* hi) {
-    *lo = r0 >= (u64)PRE ? r0 - PRE : 0;
-    *hi = r0 + R + POST < n_rows ? r0 + R + POST : n_rows;
-  }
-  // called by the 32 lanes of ONE warp: lane l issues the copies of columns l, l + 32, ...
-  __device__ static __forceinline__ void issue(const WitnessDev& w, u32 stage_smem, u32 bar, u64 r0) {
-    u64 lo, hi;
-    range(r0, w.n_rows, &lo, &hi);
-    const u32 bytes = (u32)(hi - lo) * 32u;
-    const unsigned lane = threadIdx.x & 31;
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * NCOLS) : "memory");
-    __syncwarp();
-    for (int c = lane; c < NCOLS; c += 32) {
-      const unsigned char* src = w.base + w.off[c] + lo * 32;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       stage_smem + (u32)c * CAP * 32u),
-                   "l"(src), "r"(bytes), "r"(bar)
-                   : "memory");
-    }
-  }
-};
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "ZK_TILE_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra ZK_TILE_WAIT;\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
+// (Two alternatives for the canonical row checkers were built and measured, then dropped — profiles/README.md,
+// r02: a 4-deep TMA tile pipeline with one 128-thread CTA per SM made the gate program itself the bound
+// (6 % warps active, issue slots 18 % busy, 0.35 of HBM vs 0.55 for direct loads); prefetch.global.L2 of
+// the thread's next row cost more issue slots than it hid latency (0.51 / 0.41 / 0.35 vs 0.55 / 0.51 / 0.43).)
 // Stage a small read-only table into shared memory with ONE bulk asynchronous copy
 // (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) completing on an mbarrier.  Called by every
 // thread of the block; returns when the bytes are visible to all of them.  `bytes` must be a
