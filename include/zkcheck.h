@@ -79,7 +79,8 @@ enum {
   ZK_TABLE_KECCAK = 6,   /* 5 cells  KeccakTableRow    table.py:511-515 (state_tag,input_rlc,input_len,out lo,hi) */
   ZK_TABLE_MPT = 7,      /* 12 cells MPTTableRow       table.py:460-468 */
   ZK_TABLE_PUSH = 8,     /* 2 cells  push table        bytecode_circuit.py:174-178 (byte, push_size) */
-  ZK_N_TABLES = 9
+  ZK_TABLE_WITHDRAWAL = 9, /* 4 cells WithdrawalTableRow table.py:429-435 (id, validator_id, address, amount) */
+  ZK_N_TABLES = 10
 };
 
 /* ---- challenges ------------------------------------------------------------------- */

@@ -113,6 +113,8 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   }
   d.pos_ok = nullptr;
   d.pos_kind = ZK_POS_NONE;
+  d.tail_key = -1;
+  d.tail_col = d.tail_val = 0;
   d.heads = nullptr;
   d.heads_mask = 0;
   for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;
@@ -122,7 +124,7 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
 }
 // positional structure of a table, verified exactly like k_pos_verify does on the device
 struct PosState {
-  u32 ok = 1;
+  u32 ok[2] = {1, 0};
   std::vector<HeadEnt> heads;
   std::vector<u32> aux;
 };
@@ -136,16 +138,23 @@ static void add_positional(IndexDev& d, u32 kind, PosState& st) {
   st.aux.assign((1u << 10) + 1, 0);
   d.heads_list = st.aux.data();
   d.heads_count = st.aux.data() + (1u << 10);
-  st.ok = 1;
+  st.ok[0] = 1;
+  st.ok[1] = (u32)d.tab.n_rows;
+  if (kind == ZK_POS_DENSE && d.tab.n_cols == 14) {  // the rw table: Start padding rows may form a tail run
+    d.tail_col = 2;
+    d.tail_val = 1;
+    for (u32 j = 0; j < d.n_key; j++)
+      if (d.key_cols[j] == 2) d.tail_key = (int)j;
+  }
   for (u64 r = 0; r < d.tab.n_rows; r++) {
-    if (kind == ZK_POS_DENSE) pos_verify_dense_row(d, &st.ok, r);
-    else pos_verify_run_row(d, &st.ok, r);
+    if (kind == ZK_POS_DENSE) pos_verify_dense_row(d, st.ok, r);
+    else pos_verify_run_row(d, st.ok, r);
   }
   if (kind == ZK_POS_RUNS && d.tab.n_rows) {  // k_pos_runlen
     const u32 count = *d.heads_count < d.heads_mask + 1 ? *d.heads_count : d.heads_mask + 1;
     for (u32 k = 0; k <= count; k++) pos_runlen_entry(d, k, count);
   }
-  d.pos_ok = &st.ok;
+  d.pos_ok = st.ok;
 }
 extern "C" int g_emu_positional = 1;  // tests toggle this to run both lookup paths
 
@@ -163,6 +172,16 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
 static const u64* g_emu_tx = nullptr;
 static const u64* g_emu_block = nullptr;
 static u64 g_emu_n_tx = 0, g_emu_n_block = 0;
+static const unsigned char *g_emu_tx_flags = nullptr, *g_emu_block_flags = nullptr;
+static const u64* g_emu_wd = nullptr;
+static u64 g_emu_n_wd = 0;
+// value type flags of the tx / block tables and the withdrawal table of the NEXT emu_check_evm_x call
+extern "C" void emu_set_evm_block_tables(const uint8_t* tx_flags, const uint8_t* block_flags, const uint64_t* wd, uint64_t n_wd) {
+  g_emu_tx_flags = tx_flags;
+  g_emu_block_flags = block_flags;
+  g_emu_wd = (const u64*)wd;
+  g_emu_n_wd = n_wd;
+}
 extern "C" void emu_set_evm_context_tables(const uint64_t* tx, uint64_t n_tx, const uint64_t* block, uint64_t n_block) {
   g_emu_tx = (const u64*)tx;
   g_emu_n_tx = n_tx;
@@ -212,14 +231,33 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   IndexStore s6, s7;
   t.tx = build_index(g_emu_tx, g_emu_n_tx, 5, tk, 3, ch, s6);
   t.block = build_index(g_emu_block, g_emu_n_block, 4, bk, 2, ch, s7);
+  t.tx.tab.flags = g_emu_tx_flags;
+  t.block.tab.flags = g_emu_block_flags;
+  const u32 wk[1] = {0};
+  IndexStore s8, s9;
+  IndexDev wd_ix = build_index(g_emu_wd, g_emu_n_wd, 4, wk, 1, ch, s8);
+  t.wd = wd_ix.tab;
+  t.rw_rwc = build_index((const u64*)rw, n_rw, 14, wk, 1, ch, s9);  // same storage choice as t.rw (same matrix)
+  t.rw_rwc.tab = t.rw.tab;
   g_emu_tx = g_emu_block = nullptr;
   g_emu_n_tx = g_emu_n_block = 0;
+  g_emu_tx_flags = g_emu_block_flags = nullptr;
+  g_emu_wd = nullptr;
+  g_emu_n_wd = 0;
   PosState p_bc, p_rw;
   if (g_emu_positional) {
     add_positional(t.bytecode, ZK_POS_RUNS, p_bc);
     add_positional(t.rw, ZK_POS_DENSE, p_rw);
   }
   t.resp_bitmap = fxc.bitmap.data();
+  BlockStats stats;  // k_evm_block_stats, serially
+  memset(&stats, 0, sizeof(stats));
+  for (u64 r = 0; r < t.tx.tab.n_rows; r++) block_stats_tx_row(t.tx, (u32)r, &stats);
+  for (u64 r = 0; r < t.wd.n_rows; r++) block_stats_wd_row(t.wd, (u32)r, &stats);
+  if (pos_enabled(t.rw) && t.rw.pos_kind == ZK_POS_DENSE) stats.max_rws = (u32)t.rw.tab.n_rows;
+  else
+    for (u64 r = 0; r < t.rw.tab.n_rows; r++) stats.max_rws += first_of_kind_ix(t.rw_rwc, (u32)r) ? 1 : 0;
+  t.stats = &stats;
   Store ws;
   WitnessDev w = make_witness(ws, (const u64*)steps, n_steps, 13, nullptr);
   ResultDev res;

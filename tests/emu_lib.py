@@ -138,6 +138,15 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None
         tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
         blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         lib().emu_set_evm_context_tables(_p(tx), c(tx.shape[1]), _p(blk), c(blk.shape[1]))
+    if w.get("wd") is not None or w.get("tx_flags") is not None:  # BeginTx / EndTx / EndBlock
+        p8_ = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if len(a) else None  # noqa: E731
+        txf = np.ascontiguousarray(w.get("tx_flags") if w.get("tx_flags") is not None else np.zeros(0), dtype=np.uint8)
+        blf = np.ascontiguousarray(w.get("block_flags") if w.get("block_flags") is not None else np.zeros(0), dtype=np.uint8)
+        wd = np.ascontiguousarray(w["wd"] if w.get("wd") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
+        check_evm_x._keep = [txf, blf, wd]
+        lib().emu_set_evm_block_tables(p8_(txf), p8_(blf), _p(wd), c(wd.shape[1]))
+    if w.get("flags") is not None:
+        flags = int(w["flags"])
     rc = lib().emu_check_evm_x(_p(m["steps"]), c(m["steps"].shape[1]), _p(m["bytecode"]), c(m["bytecode"].shape[1]),
                                _p(m["rw"]), c(m["rw"].shape[1]), p8, _p(fixed), c(fixed.shape[1]), _p(m["copy"]),
                                c(m["copy"].shape[1]), _p(m["keccak"]), c(m["keccak"].shape[1]), c(row_begin), c(row_end),

@@ -828,6 +828,33 @@ def synth_cases():
         bcc.check_bytecode_row(row, brows[(idx + 1) % len(brows)], push_table, kt, FQ(r_int))
     print("synth.bytecode_circuit_rows(9, 3): accepted by the reference's check_bytecode_row,", len(brows), "rows")
 
+    # whole-block trace: 3 transactions over 2 contracts, BeginTx .. STOP, EndTx per transaction, EndBlock last;
+    # verify_steps with begin_with_first_step and end_with_last_step (it appends the dummy step itself)
+    from zkevm_specs.evm_circuit import BlockTableRow, WithdrawalTableRow
+
+    w = synth.block_trace(3, 2, 2, seed=6)
+    S, B, R, RF, TX, TXF, BL, BF = (w[k] for k in ("steps", "bytecode", "rw", "rw_flags", "tx", "tx_flags", "block", "block_flags"))
+    steps = []
+    for i in range(w["n_steps"]):  # without the dummy step
+        s = StepState(ExecutionState(cell(S, 0, i)), rw_counter=cell(S, 1, i), call_id=cell(S, 2, i),
+                      is_root=bool(cell(S, 3, i)), is_create=bool(cell(S, 4, i)), code_hash=W(cell(S, 5, i), cell(S, 6, i)),
+                      program_counter=cell(S, 7, i), stack_pointer=cell(S, 8, i), gas_left=cell(S, 9, i),
+                      memory_word_size=cell(S, 10, i), reversible_write_counter=cell(S, 11, i), log_id=cell(S, 12, i))
+        steps.append(s)
+    tables = Tables(
+        block_table=set(BlockTableRow(FQ(cell(BL, 0, i)), FQ(cell(BL, 1, i)), wov(cell(BL, 2, i), cell(BL, 3, i), BF[i])) for i in range(BL.shape[1])),
+        tx_table=set(TxTableRow(FQ(cell(TX, 0, i)), FQ(cell(TX, 1, i)), FQ(cell(TX, 2, i)), wov(cell(TX, 3, i), cell(TX, 4, i), TXF[i])) for i in range(TX.shape[1])),
+        withdrawal_table=set(),
+        bytecode_table=set(BytecodeTableRow(W(cell(B, 0, i), cell(B, 1, i)), FQ(cell(B, 2, i)), FQ(cell(B, 3, i)),
+                                            FQ(cell(B, 4, i)), FQ(cell(B, 5, i))) for i in range(B.shape[1])),
+        rw_table=set(RWTableRow(FQ(cell(R, 0, i)), FQ(cell(R, 1, i)), FQ(cell(R, 2, i)), FQ(cell(R, 3, i)), FQ(cell(R, 4, i)), FQ(cell(R, 5, i)),
+                                W(cell(R, 6, i), cell(R, 7, i)), wov(cell(R, 8, i), cell(R, 9, i), RF[i] & 1),
+                                wov(cell(R, 10, i), cell(R, 11, i), (RF[i] >> 1) & 1), W(cell(R, 12, i), cell(R, 13, i)))
+                     for i in range(R.shape[1])))
+    verify_steps(tables, steps, begin_with_first_step=True, end_with_last_step=True)
+    print("synth.block_trace(3, 2, 2): accepted by the reference's verify_steps(begin_with_first_step, end_with_last_step),",
+          len(steps) - 1, "steps,", R.shape[1], "rw rows")
+
 
 # --------------------------------------------------------------------------- evm2: SHA3 / CALLDATACOPY
 def evm2_cases(part="evm2"):

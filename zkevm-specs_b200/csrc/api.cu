@@ -40,7 +40,7 @@ static const ConstraintInfo kTxInfo[] = {ZK_TX_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kSigInfo[] = {ZK_SIG_CONSTRAINTS(ZK_INFO_ENTRY)};
 
 static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21, 14, 21};
-static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2};
+static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2, 4};
 
 static const ConstraintInfo* circuit_info(int circuit, int* n) {
   switch (circuit) {
@@ -115,6 +115,7 @@ struct zk_ctx {
   cudaEvent_t evm_hist_ev = nullptr;
   int evm_occ[16] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
   std::unordered_map<const void*, int> occ;  // same, row-circuit kernels (keyed by kernel)
+  BlockStats* block_stats = nullptr;  // k_evm_block_stats output
   void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
   size_t state_fold_cap = 0;
   unsigned char* gather = nullptr;  // zk_allreduce_results: all-gathered result vectors
@@ -192,6 +193,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->gather) cudaFree(ctx->gather);
   if (ctx->state_fold) cudaFree(ctx->state_fold);
+  if (ctx->block_stats) cudaFree(ctx->block_stats);
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
@@ -498,7 +500,7 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
     memcpy(ix->key_cols, key_cols, 4 * n_key);
     ix->pos_kind = pos_kind;
     if (pos_kind != ZK_POS_NONE) {
-      CK(ctx, cudaMalloc(&ix->pos_flag, sizeof(u32)));
+      CK(ctx, cudaMalloc(&ix->pos_flag, 2 * sizeof(u32)));
       if (pos_kind == ZK_POS_RUNS) {
         CK(ctx, cudaMalloc(&ix->heads, ZK_HEADS_CAP * sizeof(HeadEnt)));
         CK(ctx, cudaMalloc(&ix->heads_aux, (ZK_HEADS_CAP + 1) * sizeof(u32)));
@@ -537,6 +539,15 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   }
   d.pos_ok = nullptr;
   d.pos_kind = ix->pos_kind;
+  // the rw table may end in a run of `Start` padding rows (tag column 2 == Target.Start == 1)
+  d.tail_key = -1;
+  d.tail_col = d.tail_val = 0;
+  if (table_id == ZK_TABLE_RW && ix->pos_kind == ZK_POS_DENSE) {
+    d.tail_col = 2;
+    d.tail_val = 1;
+    for (u32 j = 0; j < n_key; j++)
+      if (key_cols[j] == 2) d.tail_key = (int)j;
+  }
   d.heads = ix->heads;
   d.heads_mask = ZK_HEADS_CAP - 1;
   for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;  // odd multipliers keyed by the challenge
@@ -546,6 +557,7 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   if (t.n_rows && ix->pos_kind != ZK_POS_NONE) {
     // verify the regular structure in one streaming pass; the flag stays 1 iff it holds
     k_set_u32<<<1, 1, 0, st>>>(ix->pos_flag, 1u);
+    k_set_u32<<<1, 1, 0, st>>>(ix->pos_flag + 1, (u32)t.n_rows);
     if (ix->heads) {
       CK(ctx, cudaMemsetAsync(ix->heads, 0xFF, ZK_HEADS_CAP * sizeof(HeadEnt), st));
       CK(ctx, cudaMemsetAsync(ix->heads_aux, 0, (ZK_HEADS_CAP + 1) * sizeof(u32), st));
@@ -705,6 +717,7 @@ static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStr
   // fold pass over every resident row (halos included), then the gate program
   if (m.n_rows * sizeof(StateFold) > ctx->state_fold_cap) {
     if (ctx->state_fold) cudaFree(ctx->state_fold);
+  if (ctx->block_stats) cudaFree(ctx->block_stats);
     ctx->state_fold = nullptr;
     CK(ctx, cudaMalloc(&ctx->state_fold, m.n_rows * sizeof(StateFold)));
     ctx->state_fold_cap = m.n_rows * sizeof(StateFold);
@@ -770,6 +783,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
     ctx->resp_bitmap_version = ctx->tab[ZK_TABLE_FIXED].version;
   }
   t.resp_bitmap = ctx->resp_bitmap;
+  t.wd = table_dev(ctx, ZK_TABLE_WITHDRAWAL);
+  t.stats = nullptr;
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
   // counting sort of the steps by execution state (k_evm_classify + k_evm_scatter), then one kernel
@@ -778,6 +793,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   if (n > ctx->evm_sort_cap) {
     if (ctx->gather) cudaFree(ctx->gather);
   if (ctx->state_fold) cudaFree(ctx->state_fold);
+  if (ctx->block_stats) cudaFree(ctx->block_stats);
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
     ctx->evm_sort = nullptr;
     CK(ctx, cudaMalloc(&ctx->evm_sort, up256(n) + up256(n * 4) + (3 * ZK_EVM_NB + 2) * sizeof(u32)));
@@ -818,6 +834,22 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   for (int b = 0; b < ZK_EVM_NB; b++) {
     const int g = es_group(b);
     if (g >= 0) group_n[g] += hist[b];
+  }
+  // transaction-level steps (BeginTx / EndTx / EndBlock) look rw rows up by other column subsets: a dense rw
+  // table serves them by position, otherwise through an index on rw_counter alone, built only now that such
+  // steps are known to exist; EndBlock also needs the table-derived constants
+  const u64 n_tx_level = (u64)hist[ZK_ES_BeginTx] + hist[ZK_ES_EndTx] + hist[ZK_ES_EndBlock];
+  if (n_tx_level) {
+    const u32 k1[1] = {0};
+    if (!pos && (rc = ensure_index(ctx, ZK_TABLE_RW, k1, 1, st, &t.rw_rwc))) return rc;
+    if (hist[ZK_ES_EndBlock]) {
+      if (!ctx->block_stats) CK(ctx, cudaMalloc(&ctx->block_stats, sizeof(BlockStats)));
+      CK(ctx, cudaMemsetAsync(ctx->block_stats, 0, sizeof(BlockStats), st));
+      const u64 rows = std::max<u64>(std::max<u64>(t.tx.tab.n_rows, t.wd.n_rows), pos ? 1 : t.rw.tab.n_rows);
+      k_evm_block_stats<<<(unsigned)std::max<u64>(1, std::min<u64>((rows + 255) / 256, (u64)ctx->sm_count * 8)), 256, 0, st>>>(t, ctx->block_stats);
+      ctx->launches++;
+      t.stats = ctx->block_stats;
+    }
   }
   // persistent grids: at most the number of blocks the device keeps resident (occupancy x SMs), each
   // thread walks its bucket with a grid stride
@@ -1039,6 +1071,7 @@ extern "C" int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm
   if (ctx->gather_cap < rank_bytes * world) {
     if (ctx->gather) cudaFree(ctx->gather);
   if (ctx->state_fold) cudaFree(ctx->state_fold);
+  if (ctx->block_stats) cudaFree(ctx->block_stats);
     ctx->gather = nullptr;
     CK(ctx, cudaMalloc(&ctx->gather, rank_bytes * world));
     ctx->gather_cap = rank_bytes * world;

@@ -19,6 +19,7 @@
 // A step stops at its first failing constraint (the reference raises there), so at most one
 // constraint id is recorded per step.
 #include "circuit.cuh"
+#include "keccak.cuh"
 #include "words.cuh"
 #include "../../include/zk_constraints.h"
 #include "../../include/zk_evm_spec.h"
@@ -36,7 +37,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ADD) X(ZK_ES_MUL) X(ZK_ES_PUSH) X(ZK_ES_POP) X(ZK_ES_SHA3) X(ZK_ES_CALLDATACOPY) X(ZK_ES_STOP) X(ZK_ES_MEMORY)  \
   X(ZK_ES_MSIZE) X(ZK_ES_GAS) X(ZK_ES_ISZERO) X(ZK_ES_CMP) X(ZK_ES_JUMP) X(ZK_ES_JUMPI) X(ZK_ES_CALLER) X(ZK_ES_CALLVALUE) \
   X(ZK_ES_CALLDATASIZE) X(ZK_ES_ADDRESS) X(ZK_ES_RETURNDATASIZE) X(ZK_ES_CODESIZE) X(ZK_ES_BITWISE) X(ZK_ES_NOT)         \
-  X(ZK_ES_BYTE) X(ZK_ES_SCMP) X(ZK_ES_SIGNEXTEND) X(ZK_ES_BlockCtx) X(ZK_ES_ORIGIN) X(ZK_ES_GASPRICE) X(ZK_ES_SHL_SHR)
+  X(ZK_ES_BYTE) X(ZK_ES_SCMP) X(ZK_ES_SIGNEXTEND) X(ZK_ES_BlockCtx) X(ZK_ES_ORIGIN) X(ZK_ES_GASPRICE) X(ZK_ES_SHL_SHR)      \
+  X(ZK_ES_BeginTx) X(ZK_ES_EndTx) X(ZK_ES_EndBlock)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -81,6 +83,10 @@ struct EvmTables {
   IndexDev keccak;    // keccak table, key (state_tag, input_rlc, input_len)
   IndexDev tx;        // tx table (tx_id, tag, index | value lo, hi), key = the first three cells (table.py:697-705)
   IndexDev block;     // block table (tag, block number | value lo, hi), key = the first two cells (table.py:691-695)
+  IndexDev rw_rwc;    // rw table keyed on rw_counter alone: lookups that name other column subsets (evm_tx.cuh);
+                      // only built when a BeginTx / EndTx / EndBlock step exists and the rw table is not positional
+  TableDev wd;        // withdrawal table (id, validator_id, address, amount), table.py:429-435
+  const struct BlockStats* stats;  // table-derived constants of EndBlock (k_evm_block_stats)
   // ResponsibleOpcode rows of the fixed table (tag 13, aux 0) with state, opcode < 256 as a
   // 64 Kbit bitmap: bit (state << 8 | opcode).  Built from the uploaded fixed table
   // (k_fixed_resp_bitmap) and staged into shared memory by every EVM kernel.
@@ -1547,6 +1553,10 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
   same_context_ni(s, opcode, 3, one, one);
 }
 
+}  // namespace zk
+#include "evm_tx.cuh"
+namespace zk {
+
 // ---- gate-program groups --------------------------------------------------------------------
 // One kernel per GROUP of gate programs with similar register needs; inside a group kernel every
 // execution state has its own bucket of steps, so warps run one gate program (k_evm_classify /
@@ -1566,13 +1576,14 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_BITWISE: case ZK_ES_NOT: case ZK_ES_MEMORY: return KG_BYTES32;
     case ZK_ES_SHA3: case ZK_ES_CALLDATACOPY: return KG_COPY;
     case ZK_ES_SHL_SHR: return KG_WIDE;
-    case ZK_ES_STOP: return KG_TX;
+    case ZK_ES_STOP: case ZK_ES_BeginTx: case ZK_ES_EndTx: case ZK_ES_EndBlock: return KG_TX;
     default: return -1;
   }
 }
 // the rare gate programs of one group (st = execution state; other states: nothing)
+// `flags`: ZK_FLAG_EVM_* of the check (BeginTx / EndBlock look at the first / last step rules, main.py:47-56)
 template <int G>
-ZK_HD void run_group(const StepCtx& s, int st) {
+ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
   if constexpr (G == KG_SIMPLE) {
     switch (st) {
       case ZK_ES_MSIZE: gadget_msize(s, true); break;
@@ -1616,6 +1627,9 @@ ZK_HD void run_group(const StepCtx& s, int st) {
   } else if constexpr (G == KG_TX) {
     switch (st) {
       case ZK_ES_STOP: gadget_stop(s, true); break;
+      case ZK_ES_BeginTx: gadget_begin_tx(s, (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0); break;
+      case ZK_ES_EndTx: gadget_end_tx(s); break;
+      case ZK_ES_EndBlock: gadget_end_block(s, (flags & ZK_FLAG_EVM_LAST_STEP) && s.i == s.w.n_rows - 2); break;
       default: break;
     }
   }
@@ -1637,11 +1651,11 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
       }
       break;
     case KG_POP: gadget_pop(s, true); break;
-    case KG_SIMPLE: run_group<KG_SIMPLE>(s, st); break;
-    case KG_BYTES32: run_group<KG_BYTES32>(s, st); break;
-    case KG_COPY: run_group<KG_COPY>(s, st); break;
-    case KG_WIDE: run_group<KG_WIDE>(s, st); break;
-    case KG_TX: run_group<KG_TX>(s, st); break;
+    case KG_SIMPLE: run_group<KG_SIMPLE>(s, st, flags); break;
+    case KG_BYTES32: run_group<KG_BYTES32>(s, st, flags); break;
+    case KG_COPY: run_group<KG_COPY>(s, st, flags); break;
+    case KG_WIDE: run_group<KG_WIDE>(s, st, flags); break;
+    case KG_TX: run_group<KG_TX>(s, st, flags); break;
     default: break;
   }
 }
@@ -1662,7 +1676,57 @@ struct EvmSort {
   u32* sorted;            // [n] local step indices, bucket by bucket
 };
 
+// Table-derived constants of EndBlock (end_block.py:68-105).  The reference's tables are Python sets, so a
+// row identical in every column to an earlier one does not count.
+ZK_HD bool first_of_kind_ix(const IndexDev& ix, u32 r) {  // via the table's hash index: no identical row before r
+  const TableDev& t = ix.tab;
+  Fr h = table_cell(t, ix.key_cols[0], r);
+  for (u32 j = 1; j < ix.n_key; j++) h = fr_add(h, rlc_term(ix, table_cell(t, ix.key_cols[j], r), (int)j));
+  const u64 mix = rlc_mix(h);
+  const u32 fp = (u32)(mix >> 32);
+  u32 b = (u32)mix & ix.mask;
+  for (;;) {
+    const u64 slot = ld_u64(&ix.slots[b]);
+    if (slot == ZK_EMPTY_SLOT) return true;
+    const u32 cand = (u32)slot;
+    if ((u32)(slot >> 32) == fp && cand < r && rows_identical(t, cand, r)) return false;
+    b = (b + 1) & ix.mask;
+  }
+}
+ZK_HD void block_stats_tx_row(const IndexDev& tx, u32 r, BlockStats* out) {
+  const Fr tag = table_cell(tx.tab, 1, r);
+  const bool caller = fr_eq_u64(tag, ZK_TX_CallerAddress), invalid = fr_eq_u64(tag, ZK_TX_TxInvalid);
+  if (!(caller || invalid) || !first_of_kind_ix(tx, r)) return;
+  const Fr lo = table_cell(tx.tab, 3, r), hi = table_cell(tx.tab, 4, r);
+  if (caller) {
+    atomic_add_u32(&out->max_txs, 1);
+    if (!(fr_is_zero(lo) && fr_is_zero(hi))) atomic_add_u32(&out->total_txs, 1);
+  } else {
+    if (tx.tab.flags && (tx.tab.flags[r] & 1)) atomic_add_u32(&out->txinvalid_word, 1);
+    else if (fr_eq_u64(lo, 1)) atomic_add_u32(&out->invalid_txs, 1);
+  }
+}
+ZK_HD void block_stats_wd_row(const TableDev& wd, u32 r, BlockStats* out) {
+  for (u32 q = 0; q < r; q++)
+    if (rows_identical(wd, q, r)) return;
+  atomic_add_u32(&out->max_wds, 1);
+  if (!fr_is_zero(table_cell(wd, 3, r))) atomic_add_u32(&out->total_wds, 1);
+}
+
 #ifdef __CUDACC__
+// one thread per row of the largest of the three tables; `rw_rwc` may be unbuilt when the rw table is dense
+__global__ void __launch_bounds__(256) k_evm_block_stats(EvmTables t, BlockStats* out) {
+  const u64 stride = (u64)gridDim.x * blockDim.x, tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (u64 r = tid; r < t.tx.tab.n_rows; r += stride) block_stats_tx_row(t.tx, (u32)r, out);
+  for (u64 r = tid; r < t.wd.n_rows; r += stride) block_stats_wd_row(t.wd, (u32)r, out);
+  if (pos_enabled(t.rw) && t.rw.pos_kind == ZK_POS_DENSE) {  // distinct counters: every row is its own kind
+    if (tid == 0) out->max_rws = (u32)t.rw.tab.n_rows;
+  } else {
+    for (u64 r = tid; r < t.rw.tab.n_rows; r += stride)
+      if (first_of_kind_ix(t.rw_rwc, (u32)r)) atomic_add_u32(&out->max_rws, 1);
+  }
+}
+
 // MUL-state steps are split three ways by an UNVERIFIED peek at their opcode (positional tables only):
 // MUL, DIV and MOD take three different witness-assignment branches (mul_div_mod.py:23-41), and a warp
 // that holds all three runs them one after the other.  The peek only chooses the bucket — the gate
@@ -1821,7 +1885,7 @@ __global__ void __launch_bounds__(128) k_evm_group(const __grid_constant__ Witne
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
       const u64 i = rg.row_begin + list[k];
       StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, nullptr, -1};
-      run_group<G>(s, st);
+      run_group<G>(s, st, rg.flags);
     }
   }
 }

@@ -61,8 +61,13 @@ struct IndexDev {
   // Positional fast path (see "positional indexes" below).  pos_ok points at a device flag that the
   // verify kernel leaves at 1 iff the table has the regular structure `pos_kind` promises; the
   // hash index above is then not built and lookups go straight to the row.
-  const u32* pos_ok;
+  const u32* pos_ok;   // [0] the flag; [1] (ZK_POS_DENSE) the split row D between the dense head and the tail, see below
   u32 pos_kind;
+  // ZK_POS_DENSE with a tail: rows [0, D) are one dense counter run; rows [D, n) are a second dense run whose
+  // cell `tail_col` equals `tail_val` (and no head row's does) — the rw table's `Start` padding rows, whose
+  // rw_counters restart at 1 (end_block.py:30-38).  `tail_key` = index of tail_col in the lookup key, or -1.
+  u32 tail_col, tail_val;
+  int tail_key;
   HeadEnt* heads;    // ZK_POS_RUNS: hash index over the first row of every run (one 64-byte entry each)
   u32 heads_mask;
   u64 hk[4];         // keyed multipliers of the heads hash (odd, derived from the lookup challenge)
@@ -211,10 +216,24 @@ ZK_HD bool pos_enabled(const IndexDev& ix) { return ix.pos_ok != nullptr && ld_u
 template <int NK>
 ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active, const u64* base0 = nullptr,
                            int extra_col = -1, Fr* extra = nullptr, int extra_col2 = -1, Fr* extra2 = nullptr) {
-  const u64 base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
-  const bool in_range = fr_fits64(key[0]) && key[0].l[0] >= base && key[0].l[0] - base < ix.tab.n_rows;
+  u64 first = 0, limit = ix.tab.n_rows;  // the run that can hold the key: rows [first, first + limit)
+  u64 base;
+  if (ix.tail_key >= 0) {
+    const u64 split = ld_u32(ix.pos_ok + 1);
+    if (ix.tail_key < NK && fr_eq_u64(key[ix.tail_key < NK ? ix.tail_key : 0], ix.tail_val)) {
+      first = split;
+      limit = ix.tab.n_rows - split;
+      base = limit ? table_cell(ix.tab, ix.key_cols[0], split).l[0] : 0;
+    } else {
+      limit = split;
+      base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
+    }
+  } else {
+    base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
+  }
+  const bool in_range = fr_fits64(key[0]) && key[0].l[0] >= base && key[0].l[0] - base < limit;
   const bool valid = active && in_range;
-  const u64 cand = valid ? key[0].l[0] - base : 0;
+  const u64 cand = valid ? first + (key[0].l[0] - base) : 0;
   Fr cells[NK];  // independent loads first, compares after
 #pragma unroll
   for (int j = 1; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
@@ -321,9 +340,23 @@ ZK_HD void pos_fail(u32* ok) {
   *ok = 0;
 #endif
 }
+// ok[0] = flag, ok[1] = split row (initialised to n_rows).  Every row is checked against its predecessor:
+// inside a run the counter grows by one; the one allowed change of run is head -> tail.
 ZK_HD void pos_verify_dense_row(const IndexDev& ix, u32* ok, u64 row) {
-  const Fr c = table_cell(ix.tab, ix.key_cols[0], row), b = table_cell(ix.tab, ix.key_cols[0], 0);
-  if (!(fr_fits64(c) && fr_fits64(b) && b.l[0] + row >= b.l[0] && c.l[0] == b.l[0] + row)) pos_fail(ok);
+  const TableDev& t = ix.tab;
+  const Fr c = table_cell(t, ix.key_cols[0], row);
+  const bool tail = ix.tail_key >= 0 && fr_eq_u64(table_cell(t, ix.tail_col, row), ix.tail_val);
+  bool good = fr_fits64(c);
+  if (row == 0) {
+    if (tail) atomic_min_u32(ok + 1, 0u);
+  } else {
+    const Fr p = table_cell(t, ix.key_cols[0], row - 1);
+    const bool ptail = ix.tail_key >= 0 && fr_eq_u64(table_cell(t, ix.tail_col, row - 1), ix.tail_val);
+    if (tail == ptail) good = good && fr_fits64(p) && p.l[0] != ~0ull && c.l[0] == p.l[0] + 1;
+    else if (tail) atomic_min_u32(ok + 1, (u32)row);
+    else good = false;  // a head row after the tail
+  }
+  if (!good) pos_fail(ok);
 }
 // Claim an entry of the heads index for the run that starts at `row` with code hash (hlo, hhi).
 // `len` != nullptr: the run length is known (table unrolled by the library) and is stored at once;

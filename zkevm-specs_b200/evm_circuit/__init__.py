@@ -3,7 +3,8 @@ from .spec import (Opcode, ExecutionState, FixedTableTag, BlockContextFieldTag, 
                    BytecodeFieldTag, RW, Target, CallContextFieldTag, AccountFieldTag, TxLogFieldTag,
                    TxReceiptFieldTag, CopyDataTypeTag, MPTProofType, is_push_with_data, get_push_size)
 from .table import *  # noqa: F401,F403
-from .table import (Tables, FixedTableRow, BlockTableRow, TxTableRow, BytecodeTableRow, RWTableRow,  # noqa: F401
+from .table import (Tables, FixedTableRow, BlockTableRow, TxTableRow, WithdrawalTableRow, BytecodeTableRow, RWTableRow,  # noqa: F401
                     MPTTableRow, CopyCircuitRow, CopyTableRow, KeccakTableRow, LookupUnsatFailure,
                     LookupAmbiguousFailure)
-from .typing import Bytecode, Block, RWDictionary, KeccakCircuit, CopyCircuit  # noqa: F401
+from .typing import (AccessTuple, Account, Bytecode, Block, RWDictionary, KeccakCircuit, CopyCircuit, Transaction,  # noqa: F401
+                     Withdrawal)

@@ -48,8 +48,16 @@ def upload_tables(ctx: native.Context, tables: Tables) -> None:
     ctx.upload_table(native.TABLE_COPY, packing.pack(tables.copy_table, packing.copy_table_row, 14))
     ctx.upload_table(native.TABLE_KECCAK, packing.pack(tables.keccak_table, packing.keccak_table_row, 5))
     # tx / block tables: the ORIGIN / GASPRICE / BlockCtx gadgets (tables.tx_lookup / block_lookup, table.py:691-705)
-    ctx.upload_table(native.TABLE_TX, packing.pack(list(getattr(tables, "tx_table", ()) or ()), packing.tx_table_row, 5))
-    ctx.upload_table(native.TABLE_BLOCK, packing.pack(list(getattr(tables, "block_table", ()) or ()), packing.block_table_row, 4))
+    # (+ BeginTx / EndTx / EndBlock; the value type flags carry WordOrValue.is_word for their .value() asserts)
+    txs, blks = list(getattr(tables, "tx_table", ()) or ()), list(getattr(tables, "block_table", ()) or ())
+    ctx.upload_table(native.TABLE_TX, packing.pack(txs, packing.tx_table_row, 5),
+                     flags=np.array([packing.word_flag(r.value) for r in txs], dtype=np.uint8))
+    ctx.upload_table(native.TABLE_BLOCK, packing.pack(blks, packing.block_table_row, 4),
+                     flags=np.array([packing.word_flag(r.value) for r in blks], dtype=np.uint8))
+    wds = list(getattr(tables, "withdrawal_table", ()) or ())
+    c = packing.cell_int
+    ctx.upload_table(native.TABLE_WITHDRAWAL,
+                     packing.matrix_from_ints([[c(w.id), c(w.validator_id), c(w.address), c(w.amount)] for w in wds], 4))
     upload_fixed_table(ctx)
 
 

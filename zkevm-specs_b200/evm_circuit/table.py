@@ -53,6 +53,14 @@ class TxTableRow:
 
 
 @dataclass(frozen=True)
+class WithdrawalTableRow:
+    id: Expression
+    validator_id: Expression
+    address: Expression
+    amount: Expression
+
+
+@dataclass(frozen=True)
 class BytecodeTableRow:
     bytecode_hash: Word
     field_tag: Expression

@@ -1,5 +1,5 @@
 """Host-side witness builders with the reference's names: `Bytecode` (opcode DSL),
-`RWDictionary`, `KeccakCircuit`, `CopyCircuit`, `Block`.
+`RWDictionary`, `KeccakCircuit`, `CopyCircuit`, `Block`, `Transaction`, `Withdrawal`, `Account`.
 
 Mirrors /root/reference/src/zkevm_specs/evm_circuit/typing.py:327-427 (Bytecode), :464-845
 (RWDictionary), :848-865 (KeccakCircuit), :996-1150 (CopyCircuit).  They stay Python (SURVEY.md
@@ -7,13 +7,14 @@ Mirrors /root/reference/src/zkevm_specs/evm_circuit/typing.py:327-427 (Bytecode)
 from __future__ import annotations
 
 import dataclasses
-from typing import Dict, Iterator, List, Mapping, MutableSequence, Optional, Sequence, Tuple, Union
+from typing import Dict, Iterator, List, Mapping, MutableSequence, NamedTuple, Optional, Sequence, Tuple, Union
 
 from ..util.arithmetic import FQ, RLC, IntOrFQ, Word, WordOrValue
 from ..util.hash import keccak256
 from .spec import (RW, AccountFieldTag, BlockContextFieldTag, BytecodeFieldTag, CallContextFieldTag,
-                   CopyDataTypeTag, Opcode, Target, TxLogFieldTag, TxReceiptFieldTag, get_push_size)
-from .table import (BlockTableRow, BytecodeTableRow, CopyCircuitRow, KeccakTableRow, RWTableRow)
+                   CopyDataTypeTag, Opcode, Target, TxContextFieldTag, TxLogFieldTag, TxReceiptFieldTag, get_push_size)
+from .table import (BlockTableRow, BytecodeTableRow, CopyCircuitRow, KeccakTableRow, RWTableRow, TxTableRow,
+                    WithdrawalTableRow)
 
 
 def init_is_code(code: bytes) -> List[bool]:
@@ -112,6 +113,86 @@ class Block:
         return rows
 
 
+class AccessTuple(NamedTuple):
+    address: int
+    storage_keys: List[int]
+
+
+# gas schedule of a transaction's payload (reference util/param.py: call data per zero / non-zero byte,
+# access list per address / storage key)
+_GAS_CALLDATA_ZERO, _GAS_CALLDATA_NONZERO, _GAS_AL_ADDRESS, _GAS_AL_STORAGE = 4, 16, 2400, 1900
+
+
+class Transaction:
+    """One transaction and its tx-table rows (reference typing.py:145-281): twelve fixed fields per tx id,
+    then one CallData row per byte."""
+
+    def __init__(self, id: int = 1, nonce: int = 0, gas: int = 21000, gas_price: int = int(2e9), caller_address: int = 0xCAFE,
+                 callee_address: Optional[int] = None, value: int = 0, call_data: bytes = bytes(), invalid_tx: int = 0,
+                 access_list: Sequence[AccessTuple] = ()) -> None:
+        self.id, self.nonce, self.gas, self.gas_price = id, nonce, gas, gas_price
+        self.caller_address, self.callee_address, self.value = caller_address, callee_address, value
+        self.call_data, self.invalid_tx, self.access_list = call_data, invalid_tx, list(access_list)
+
+    @classmethod
+    def padding(cls, id: int) -> "Transaction":
+        return cls(id, 0, 0, 0, 0, 0, 0, bytes(), 0, [])
+
+    def call_data_gas_cost(self) -> int:
+        zeros = sum(1 for b in self.call_data if b == 0)
+        return zeros * _GAS_CALLDATA_ZERO + (len(self.call_data) - zeros) * _GAS_CALLDATA_NONZERO
+
+    def access_list_gas_cost(self) -> int:
+        return sum(_GAS_AL_ADDRESS + len(t.storage_keys) * _GAS_AL_STORAGE for t in self.access_list)
+
+    def table_fixed(self) -> List[TxTableRow]:
+        T = TxContextFieldTag
+        fields = [(T.Nonce, self.nonce, False), (T.Gas, self.gas, False), (T.GasPrice, self.gas_price, True),
+                  (T.CallerAddress, self.caller_address, True),
+                  (T.CalleeAddress, 0 if self.callee_address is None else self.callee_address, True),
+                  (T.IsCreate, int(self.callee_address is None), False), (T.Value, self.value, True),
+                  (T.CallDataLength, len(self.call_data), False), (T.CallDataGasCost, self.call_data_gas_cost(), False),
+                  (T.TxInvalid, self.invalid_tx, False), (T.AccessListGasCost, self.access_list_gas_cost(), False),
+                  (T.TxSignHash, 1234, False)]  # the reference's mock sign hash
+        return [TxTableRow(FQ(self.id), FQ(t), FQ(0), WordOrValue(Word(v) if is_word else FQ(v))) for t, v, is_word in fields]
+
+    def table_assignments(self) -> Iterator[TxTableRow]:
+        yield from self.table_fixed()
+        for idx, byte in enumerate(self.call_data):
+            yield TxTableRow(FQ(self.id), FQ(TxContextFieldTag.CallData), FQ(idx), WordOrValue(FQ(byte)))
+
+
+class Withdrawal:
+    """One validator withdrawal and its table row (reference typing.py:284-316); amount 0 = padding"""
+
+    def __init__(self, id: int = 0, validator_id: int = 0, address: int = 0xCAFE, amount: int = int(1e9)) -> None:
+        self.id, self.validator_id, self.address, self.amount = id, validator_id, address, amount
+
+    @classmethod
+    def padding(cls, id: int) -> "Withdrawal":
+        return cls(id, 0, 0, 0)
+
+    def table_assignments(self) -> List[WithdrawalTableRow]:
+        return [WithdrawalTableRow(FQ(self.id), FQ(self.validator_id), FQ(self.address), FQ(self.amount))]
+
+
+class Account:
+    """An account as the tests describe one (reference typing.py:433-461)"""
+
+    def __init__(self, address: int = 0, nonce: int = 0, balance: int = 0, code: Optional["Bytecode"] = None,
+                 storage: Optional[Dict[int, int]] = None) -> None:
+        self.address, self.nonce, self.balance = address, nonce, balance
+        self.code = Bytecode() if code is None else code
+        self.storage = dict() if storage is None else storage
+
+    def code_hash(self) -> int:
+        return self.code.hash()
+
+    def is_empty(self) -> bool:
+        from ..util.hash import EMPTY_CODE_HASH
+        return self.nonce == 0 and self.balance == 0 and self.code_hash() == EMPTY_CODE_HASH
+
+
 _WORD_CALL_CONTEXT = ("CallerAddress", "CalleeAddress", "Value", "CodeHash")
 
 
@@ -124,14 +205,28 @@ class RWDictionary:
         self.rws: List[RWTableRow] = []
 
     def _append(self, rw, target, id=FQ(0), address=FQ(0), field_tag=FQ(0), storage_key=None,
-                value=FQ(0), value_prev=FQ(0), aux0=None) -> "RWDictionary":
+                value=FQ(0), value_prev=FQ(0), aux0=None, rw_counter: Optional[int] = None) -> "RWDictionary":
+        """one row; `rw_counter` given = a row placed out of sequence (the reversion copy of a state write),
+        which does not advance the dictionary's counter"""
         as_fq = lambda v: FQ(v) if isinstance(v, int) else v  # noqa: E731
+        at = self.rw_counter if rw_counter is None else rw_counter
         self.rws.append(RWTableRow(
-            FQ(self.rw_counter), FQ(rw), FQ(target), as_fq(id), as_fq(address), as_fq(field_tag),
+            FQ(at), FQ(rw), FQ(target), as_fq(id), as_fq(address), as_fq(field_tag),
             Word(0) if storage_key is None else storage_key,
             WordOrValue(as_fq(value)), WordOrValue(as_fq(value_prev)),
             Word(0) if aux0 is None else aux0))
-        self.rw_counter += 1
+        if rw_counter is None:
+            self.rw_counter += 1
+        return self
+
+    def _state_write(self, target, rw_counter_of_reversion: Optional[int] = None, **cells) -> "RWDictionary":
+        """a reversible write (Target.write_with_reversion, reference typing.py:750-788): the write itself and,
+        when the call will revert, its undo row (value and value_prev swapped) at rw_counter_of_reversion"""
+        self._append(RW.Write, target, **cells)
+        if rw_counter_of_reversion is not None:
+            undo = dict(cells)
+            undo["value"], undo["value_prev"] = cells.get("value_prev", FQ(0)), cells.get("value", FQ(0))
+            self._append(RW.Write, target, rw_counter=rw_counter_of_reversion, **undo)
         return self
 
     def stack_read(self, call_id: IntOrFQ, stack_pointer: IntOrFQ, value: Word) -> "RWDictionary":
@@ -174,11 +269,55 @@ class RWDictionary:
     def tx_refund_read(self, tx_id: IntOrFQ, refund: IntOrFQ) -> "RWDictionary":
         return self._append(RW.Read, Target.TxRefund, id=FQ(tx_id), value=FQ(refund), value_prev=FQ(refund))
 
+    def tx_refund_write(self, tx_id: IntOrFQ, refund: IntOrFQ, refund_prev: IntOrFQ,
+                        rw_counter_of_reversion: Optional[int] = None) -> "RWDictionary":
+        return self._state_write(Target.TxRefund, rw_counter_of_reversion, id=FQ(tx_id), value=FQ(refund), value_prev=FQ(refund_prev))
+
+    def tx_receipt_read(self, tx_id: IntOrFQ, field_tag, value: IntOrFQ) -> "RWDictionary":
+        return self._append(RW.Read, Target.TxReceipt, id=FQ(tx_id), field_tag=FQ(field_tag), value=FQ(value))
+
+    def tx_receipt_write(self, tx_id: IntOrFQ, field_tag, value: IntOrFQ) -> "RWDictionary":
+        return self._append(RW.Write, Target.TxReceipt, id=FQ(tx_id), field_tag=FQ(field_tag), value=FQ(value))
+
+    def tx_access_list_account_write(self, tx_id: IntOrFQ, account_address: IntOrFQ, value: bool, value_prev: bool,
+                                     rw_counter_of_reversion: Optional[int] = None) -> "RWDictionary":
+        return self._state_write(Target.TxAccessListAccount, rw_counter_of_reversion, id=FQ(tx_id), address=FQ(account_address),
+                                 value=FQ(value), value_prev=FQ(value_prev))
+
+    def tx_access_list_account_read(self, tx_id: IntOrFQ, account_address: IntOrFQ, value: bool) -> "RWDictionary":
+        return self._append(RW.Read, Target.TxAccessListAccount, id=FQ(tx_id), address=FQ(account_address),
+                            value=FQ(value), value_prev=FQ(value))
+
+    def tx_access_list_account_storage_write(self, tx_id: IntOrFQ, account_address: IntOrFQ, storage_key: Word, value: bool,
+                                             value_prev: bool, rw_counter_of_reversion: Optional[int] = None) -> "RWDictionary":
+        return self._state_write(Target.TxAccessListAccountStorage, rw_counter_of_reversion, id=FQ(tx_id),
+                                 address=FQ(account_address), storage_key=storage_key, value=FQ(value), value_prev=FQ(value_prev))
+
+    def tx_access_list_account_storage_read(self, tx_id: IntOrFQ, account_address: IntOrFQ, storage_key: Word,
+                                            value: bool) -> "RWDictionary":
+        return self._append(RW.Read, Target.TxAccessListAccountStorage, id=FQ(tx_id), address=FQ(account_address),
+                            storage_key=storage_key, value=FQ(value), value_prev=FQ(value))
+
     def account_read(self, account_address: IntOrFQ, field_tag, value) -> "RWDictionary":
         if isinstance(value, int):
             value = FQ(value)
         return self._append(RW.Read, Target.Account, address=FQ(account_address), field_tag=FQ(field_tag),
                             value=value, value_prev=value)
+
+    def account_write(self, account_address: IntOrFQ, field_tag, value, value_prev,
+                      rw_counter_of_reversion: Optional[int] = None) -> "RWDictionary":
+        return self._state_write(Target.Account, rw_counter_of_reversion, address=FQ(account_address), field_tag=FQ(field_tag),
+                                 value=value, value_prev=value_prev)
+
+    def account_storage_read(self, account_address: IntOrFQ, storage_key: Word, value: Word, tx_id: IntOrFQ,
+                             value_committed: Word) -> "RWDictionary":
+        return self._append(RW.Read, Target.AccountStorage, id=tx_id, address=FQ(account_address), storage_key=storage_key,
+                            value=value, value_prev=value, aux0=value_committed)
+
+    def account_storage_write(self, account_address: IntOrFQ, storage_key: Word, value: Word, value_prev: Word, tx_id: IntOrFQ,
+                              value_committed: Word, rw_counter_of_reversion: Optional[int] = None) -> "RWDictionary":
+        return self._state_write(Target.AccountStorage, rw_counter_of_reversion, id=tx_id, address=FQ(account_address),
+                                 storage_key=storage_key, value=value, value_prev=value_prev, aux0=value_committed)
 
 
 class KeccakCircuit:

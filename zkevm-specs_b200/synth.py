@@ -435,3 +435,227 @@ def bytecode_circuit_rows(k: int, n_contracts: int = 4, seed: int = 5,
         for c, v in enumerate(row):
             kec[c, i, :] = [(v >> (64 * j)) & M64 for j in range(4)]
     return {"rows": rows, "push": push, "keccak": kec, "r": np.array([(r >> (64 * j)) & M64 for j in range(4)], dtype=np.uint64)}
+
+
+# ------------------------------------------------------------------------------------------------
+def block_trace(n_txs: int, groups_per_contract: int, n_contracts: int, seed: int = 6, n_padding: int = 8,
+                real_hashes: bool = False) -> Dict[str, np.ndarray]:
+    """A whole-block EVM trace, the shape `verify_steps(begin_with_first_step=True, end_with_last_step=True)` checks:
+
+        BeginTx, [PUSH32 b, PUSH32 a, OP, POP] x groups, STOP, EndTx     ... once per transaction
+        EndBlock                                                          (the last step; + the dummy step)
+
+    `n_contracts` contracts of `groups_per_contract` groups each (68 bytes per group + STOP); transaction t (id t + 1,
+    its own caller account) calls contract t % n_contracts with no value and no call data.  The rw table is laid out
+    head + tail: every row of the trace by rw_counter (1 ..), then `n_padding` Start padding rows (rw_counter 1 ..), the
+    layout EndBlock's two rw_table_start_lookups count (end_block.py:30-38, 168-171).  Code hashes are seeded tags
+    unless `real_hashes` (the EVM circuit only matches them against the bytecode table).
+    Returns steps [13][n+1][4] (dummy EndBlock step included), bytecode (table + source form), rw + rw_flags, tx +
+    tx_flags, block + block_flags, wd (empty), n_steps, flags = FIRST | LAST.  Validated on the reference at small
+    sizes by tests/golden/gen_golden.py synth."""
+    from .evm_circuit.spec import AccountFieldTag as AF, CallContextFieldTag as CC, TxContextFieldTag as TXF, TxReceiptFieldTag as RF
+    from .util.hash import keccak256
+
+    rng = np.random.default_rng(seed)
+    G, C, T = groups_per_contract, n_contracts, n_txs
+    code_len = 68 * G + 1
+    # ---- contracts: operands, code, hashes
+    a, b = _operands(G * C, rng)
+    ops_idx = np.arange(G * C) % 5
+    ops = [OPS[i] for i in ops_idx]
+    c_res = []
+    for op, x, y in zip(ops, a, b):
+        c_res.append((x + y) & M256 if op == "ADD" else (x - y) & M256 if op == "SUB" else (x * y) & M256 if op == "MUL"
+                     else (0 if y == 0 else x // y) if op == "DIV" else (0 if y == 0 else x % y))
+    A, B, Cv = ints_to_cells(a), ints_to_cells(b), ints_to_cells(c_res)
+    code = np.zeros((C, code_len), dtype=np.uint8)
+    grp = code[:, :-1].reshape(C, G, 68)
+    grp[:, :, 0] = 0x7F
+    grp[:, :, 1:33] = np.ascontiguousarray(B).view(np.uint8).reshape(C, G, 32)[:, :, ::-1]
+    grp[:, :, 33] = 0x7F
+    grp[:, :, 34:66] = np.ascontiguousarray(A).view(np.uint8).reshape(C, G, 32)[:, :, ::-1]
+    grp[:, :, 66] = np.array([OPCODE[o] for o in ops], dtype=np.uint8).reshape(C, G)
+    grp[:, :, 67] = 0x50
+    is_code = np.zeros((C, code_len), dtype=np.uint8)
+    ic = is_code[:, :-1].reshape(C, G, 68)
+    ic[:, :, [0, 33, 66, 67]] = 1
+    is_code[:, -1] = 1  # STOP
+    if real_hashes:
+        hashes_int = [int.from_bytes(keccak256(bytes(code[k])), "big") for k in range(C)]
+    else:
+        hashes_int = [int.from_bytes(rng.bytes(32), "little") | 1 for _ in range(C)]
+    H = ints_to_cells(hashes_int)  # [C][4]: lo limbs 0,1; hi limbs 2,3
+    # bytecode table (unrolled) and source form
+    nb = C * (code_len + 1)
+    bytecode = np.zeros((6, nb, 4), dtype=np.uint64)
+    rows_per = code_len + 1
+    hrep = np.repeat(H, rows_per, axis=0)
+    bytecode[0, :, 0], bytecode[0, :, 1] = hrep[:, 0], hrep[:, 1]
+    bytecode[1, :, 0], bytecode[1, :, 1] = hrep[:, 2], hrep[:, 3]
+    tagcol = np.full((C, rows_per), 2, dtype=np.uint64); tagcol[:, 0] = 1
+    idxcol = np.zeros((C, rows_per), dtype=np.uint64); idxcol[:, 1:] = np.arange(code_len, dtype=np.uint64)
+    iscol = np.zeros((C, rows_per), dtype=np.uint64); iscol[:, 1:] = is_code
+    valcol = np.zeros((C, rows_per), dtype=np.uint64); valcol[:, 0] = code_len; valcol[:, 1:] = code
+    bytecode[2, :, 0], bytecode[3, :, 0] = tagcol.reshape(-1), idxcol.reshape(-1)
+    bytecode[4, :, 0], bytecode[5, :, 0] = iscol.reshape(-1), valcol.reshape(-1)
+    src = {"code": code.reshape(-1).copy(), "is_code_bits": np.packbits(is_code.reshape(-1), bitorder="little"),
+           "code_offsets": (np.arange(C + 1, dtype=np.uint64) * np.uint64(code_len)),
+           "hashes": H.copy()}
+
+    # ---- per-transaction layout
+    S_TX = 4 * G + 3                       # BeginTx + body + STOP + EndTx
+    n_steps = T * S_TX + 1                  # + EndBlock
+    steps = np.zeros((13, n_steps + 1, 4), dtype=np.uint64)   # + the dummy step of end_with_last_step
+    GAS_PRICE, BASE_FEE, COINBASE, GAS_LIMIT = int(2e9), int(1e9), 0x10, 1 << 62
+    body_gas = np.array([3 + 3 + GAS[o] + 2 for o in ops], dtype=np.int64).reshape(C, G).sum(axis=1)
+    RW_TX_FIRST, RW_TX_REST = 24 + 6 * G + 1 + 9, 24 + 6 * G + 1 + 10   # rw rows of the first / another transaction
+    n_real = RW_TX_FIRST + (T - 1) * RW_TX_REST + 2 - 1                  # last EndTx has no next-tx row; EndBlock adds 2
+    nr = n_real + n_padding
+    rw = np.zeros((14, nr, 4), dtype=np.uint64)
+    rwf = np.zeros(nr, dtype=np.uint8)
+    tx = np.zeros((5, 12 * T, 4), dtype=np.uint64)
+    txf = np.zeros(12 * T, dtype=np.uint8)
+
+    def put_rw(k, rw_, tag, id=0, addr=0, ft=0, val=0, prev=0, word=False, prev_word=False):
+        rw[0, k, 0], rw[1, k, 0], rw[2, k, 0] = k + 1, rw_, tag
+        rw[3, k, :], rw[4, k, :] = limbs4(id), limbs4(addr)
+        rw[5, k, 0] = ft
+        v, p = limbs4(val), limbs4(prev)
+        rw[8, k, 0], rw[8, k, 1], rw[9, k, 0], rw[9, k, 1] = v[0], v[1], v[2], v[3]
+        rw[10, k, 0], rw[10, k, 1], rw[11, k, 0], rw[11, k, 1] = p[0], p[1], p[2], p[3]
+        rwf[k] = int(word) | (int(prev_word) << 1)
+
+    def limbs4(v):
+        return [(int(v) >> (64 * q)) & M64 for q in range(4)]
+
+    TAG = {"acl": int(Target.TxAccessListAccount), "refund": int(Target.TxRefund), "acc": int(Target.Account),
+           "cc": int(Target.CallContext), "stack": int(Target.Stack), "rcpt": int(Target.TxReceipt), "start": int(Target.Start)}
+    k = 0          # next rw row (rw_counter = k + 1)
+    cum_gas = 0
+    coinbase_bal = 0
+    grp_ar = np.arange(G, dtype=np.uint64)
+    for t in range(T):
+        tx_id, c, caller, callee = t + 1, t % C, 0xFE0000 + t, 0xC0DE0000 + (t % C)
+        gas = 21000 + int(body_gas[c]) + 777
+        h_lo = int(H[c, 0]) | (int(H[c, 1]) << 64)
+        h_hi = int(H[c, 2]) | (int(H[c, 3]) << 64)
+        code_hash = h_lo | (h_hi << 128)
+        s0 = t * S_TX
+        call_id = k + 1
+        # tx table: twelve fixed rows
+        fixed = [(TXF.Nonce, 0, 0), (TXF.Gas, gas, 0), (TXF.GasPrice, GAS_PRICE, 1), (TXF.CallerAddress, caller, 1),
+                 (TXF.CalleeAddress, callee, 1), (TXF.IsCreate, 0, 0), (TXF.Value, 0, 1), (TXF.CallDataLength, 0, 0),
+                 (TXF.CallDataGasCost, 0, 0), (TXF.TxInvalid, 0, 0), (TXF.AccessListGasCost, 0, 0), (TXF.TxSignHash, 1234, 0)]
+        for q, (tg, v, w_) in enumerate(fixed):
+            r_ = 12 * t + q
+            tx[0, r_, 0], tx[1, r_, 0] = tx_id, int(tg)
+            lv = limbs4(v)
+            tx[3, r_, 0], tx[3, r_, 1], tx[4, r_, 0], tx[4, r_, 1] = lv[0], lv[1], lv[2], lv[3]
+            txf[r_] = w_
+        # ---- BeginTx
+        steps[0, s0, 0], steps[1, s0, 0] = int(ExecutionState.BeginTx), k + 1
+        if t:  # StepState of a BeginTx after an EndTx: call_id 0 .. (the reference's tests leave the defaults)
+            pass
+        steps[8, s0, 0] = 1024
+        caller_bal = 10 ** 20
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.TxId), val=tx_id); k += 1
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.RwCounterEndOfReversion)); k += 1
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.IsPersistent), val=1); k += 1
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.IsSuccess), val=1); k += 1
+        put_rw(k, 1, TAG["acc"], 0, caller, int(AF.Nonce), val=1, prev=0); k += 1
+        for adr in (COINBASE, caller, callee):
+            put_rw(k, 1, TAG["acl"], tx_id, adr, val=1, prev=0); k += 1
+        put_rw(k, 1, TAG["acc"], 0, caller, int(AF.Balance), val=caller_bal - gas * GAS_PRICE, prev=caller_bal, word=True, prev_word=True); k += 1
+        put_rw(k, 1, TAG["acc"], 0, callee, int(AF.Balance), val=0, prev=0, word=True, prev_word=True); k += 1
+        put_rw(k, 0, TAG["acc"], 0, callee, int(AF.CodeHash), val=code_hash, prev=code_hash, word=True, prev_word=True); k += 1
+        ctx_vals = [(CC.Depth, 1, 0), (CC.CallerAddress, caller, 1), (CC.CalleeAddress, callee, 1), (CC.CallDataOffset, 0, 0),
+                    (CC.CallDataLength, 0, 0), (CC.Value, 0, 1), (CC.IsStatic, 0, 0), (CC.LastCalleeId, 0, 0),
+                    (CC.LastCalleeReturnDataOffset, 0, 0), (CC.LastCalleeReturnDataLength, 0, 0), (CC.IsRoot, 1, 0),
+                    (CC.IsCreate, 0, 0), (CC.CodeHash, code_hash, 1)]
+        for tg, v, w_ in ctx_vals:
+            put_rw(k, 0, TAG["cc"], call_id, int(tg), val=v, word=bool(w_)); k += 1
+        # ---- body: 4 G steps, 6 G stack rows (vectorised)
+        sb = s0 + 1
+        st = np.empty((G, 4), dtype=np.uint64)
+        st[:, 0] = st[:, 1] = int(ExecutionState.PUSH)
+        opsl = ops[c * G:(c + 1) * G]
+        st[:, 2] = np.array([int(ExecutionState.ADD) if o in ("ADD", "SUB") else int(ExecutionState.MUL) for o in opsl], dtype=np.uint64)
+        st[:, 3] = int(ExecutionState.POP)
+        body = slice(sb, sb + 4 * G)
+        steps[0, body, 0] = st.reshape(-1)
+        base_rwc = np.uint64(k + 1)
+        steps[1, body, 0] = (np.stack([6 * grp_ar, 6 * grp_ar + 1, 6 * grp_ar + 2, 6 * grp_ar + 5], axis=1) + base_rwc).reshape(-1)
+        steps[7, body, 0] = np.stack([68 * grp_ar, 68 * grp_ar + 33, 68 * grp_ar + 66, 68 * grp_ar + 67], axis=1).reshape(-1)
+        steps[8, body, 0] = np.tile(np.array([1024, 1023, 1022, 1023], dtype=np.uint64), G)
+        cost = np.stack([np.full(G, 3), np.full(G, 3), np.array([GAS[o] for o in opsl]), np.full(G, 2)], axis=1).reshape(-1)
+        gas_after_begin = gas - 21000
+        spent = np.concatenate([[0], np.cumsum(cost)])
+        steps[9, sb:sb + 4 * G + 1, 0] = (gas_after_begin - spent).astype(np.uint64)   # body steps + STOP
+        rs = slice(k, k + 6 * G)
+        rw[0, rs, 0] = np.arange(k + 1, k + 6 * G + 1, dtype=np.uint64)
+        rw[1, rs, 0] = np.tile(np.array([1, 1, 0, 0, 1, 0], dtype=np.uint64), G)
+        rw[2, rs, 0] = TAG["stack"]
+        rw[3, rs, 0] = call_id
+        rw[4, rs, 0] = np.tile(np.array([1023, 1022, 1022, 1023, 1023, 1023], dtype=np.uint64), G)
+        sl = slice(c * G, (c + 1) * G)
+        vals = np.stack([B[sl], A[sl], A[sl], B[sl], Cv[sl], Cv[sl]], axis=1).reshape(6 * G, 4)
+        rw[8, rs, 0], rw[8, rs, 1], rw[9, rs, 0], rw[9, rs, 1] = vals[:, 0], vals[:, 1], vals[:, 2], vals[:, 3]
+        rwf[rs] = 1
+        k += 6 * G
+        # ---- STOP (root call): IsSuccess read, next = EndTx
+        s_stop = sb + 4 * G
+        steps[0, s_stop, 0], steps[1, s_stop, 0] = int(ExecutionState.STOP), k + 1
+        steps[7, s_stop, 0], steps[8, s_stop, 0] = 68 * G, 1024
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.IsSuccess), val=1); k += 1
+        # every step of the call: call_id, is_root, code hash, reversible_write_counter 2
+        call = slice(sb, s_stop + 2)   # body, STOP and EndTx
+        steps[2, call, 0], steps[3, call, 0] = call_id, 1
+        steps[5, call, 0], steps[5, call, 1] = int(H[c, 0]), int(H[c, 1])
+        steps[6, call, 0], steps[6, call, 1] = int(H[c, 2]), int(H[c, 3])
+        steps[11, call, 0] = 2
+        # ---- EndTx
+        s_end = s_stop + 1
+        gas_left = gas_after_begin - int(cost.sum())
+        gas_used = gas - gas_left
+        steps[0, s_end, 0], steps[1, s_end, 0], steps[9, s_end, 0] = int(ExecutionState.EndTx), k + 1, gas_left
+        steps[7, s_end, 0], steps[8, s_end, 0] = 68 * G, 1024
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.TxId), val=tx_id); k += 1
+        put_rw(k, 0, TAG["cc"], call_id, int(CC.IsPersistent), val=1); k += 1
+        put_rw(k, 0, TAG["refund"], tx_id, val=0, prev=0); k += 1
+        bal = caller_bal - gas * GAS_PRICE
+        put_rw(k, 1, TAG["acc"], 0, caller, int(AF.Balance), val=bal + gas_left * GAS_PRICE, prev=bal, word=True, prev_word=True); k += 1
+        reward = gas_used * (GAS_PRICE - BASE_FEE)
+        put_rw(k, 1, TAG["acc"], 0, COINBASE, int(AF.Balance), val=coinbase_bal + reward, prev=coinbase_bal, word=True, prev_word=True); k += 1
+        coinbase_bal += reward
+        put_rw(k, 1, TAG["rcpt"], tx_id, 0, int(RF.PostStateOrStatus), val=1); k += 1
+        put_rw(k, 1, TAG["rcpt"], tx_id, 0, int(RF.LogLength), val=0); k += 1
+        if t:
+            put_rw(k, 0, TAG["rcpt"], tx_id - 1, 0, int(RF.CumulativeGasUsed), val=cum_gas); k += 1
+        cum_gas += gas_used
+        put_rw(k, 1, TAG["rcpt"], tx_id, 0, int(RF.CumulativeGasUsed), val=cum_gas); k += 1
+        if t + 1 < T:  # the next transaction's TxId, looked up with call_id = next.rw_counter
+            put_rw(k, 0, TAG["cc"], k + 2, int(CC.TxId), val=tx_id + 1); k += 1
+    # ---- EndBlock (the last step): TxId of the last call, cumulative gas of the last tx
+    s_eb = T * S_TX
+    last_call = int(steps[2, s_eb - 1, 0])
+    steps[0, s_eb, 0], steps[1, s_eb, 0], steps[2, s_eb, 0], steps[8, s_eb, 0] = int(ExecutionState.EndBlock), k + 1, last_call, 1024
+    put_rw(k, 0, TAG["cc"], last_call, int(CC.TxId), val=T); k += 1
+    put_rw(k, 0, TAG["rcpt"], T, 0, int(RF.CumulativeGasUsed), val=cum_gas); k += 1
+    assert k == n_real, (k, n_real)
+    for q in range(n_padding):  # tail: Start rows, rw_counter 1 ..
+        rw[0, n_real + q, 0], rw[2, n_real + q, 0] = q + 1, TAG["start"]
+    # dummy step appended by end_with_last_step: StepState(EndBlock, rw_counter = -1)
+    steps[0, n_steps, 0] = int(ExecutionState.EndBlock)
+    steps[1, n_steps, :] = limbs4(P - 1)
+    steps[8, n_steps, 0] = 1024
+    # block table
+    block = np.zeros((4, 8, 4), dtype=np.uint64)
+    bf = np.zeros(8, dtype=np.uint8)
+    for q, (v, w_) in enumerate([(COINBASE, 1), (GAS_LIMIT, 0), (0, 0), (0, 0), (0, 1), (BASE_FEE, 1), (1, 0), (0, 0)]):
+        block[0, q, 0] = q + 1
+        lv = limbs4(v)
+        block[2, q, 0], block[2, q, 1], block[3, q, 0], block[3, q, 1] = lv[0], lv[1], lv[2], lv[3]
+        bf[q] = w_
+    return {"steps": steps, "n_steps": n_steps, "flags": 2 | 4, "bytecode": bytecode, "bytecode_src": src, "rw": rw, "rw_flags": rwf,
+            "tx": tx, "tx_flags": txf, "block": block, "block_flags": bf, "wd": np.zeros((4, 0, 4), dtype=np.uint64),
+            "copy": np.zeros((14, 0, 4), dtype=np.uint64), "keccak": np.zeros((5, 0, 4), dtype=np.uint64)}
