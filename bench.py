@@ -22,6 +22,8 @@ Extra objects on the same line (`--no-extras` skips them; they are not inside th
                    circuit (2^19 rows) on canonical 32-byte cells, each with its own roofline
   strong_scaling : ONE 2^20-step witness split over the N ranks (tables replicated, step shards with
                    a halo step, one collective) — north_star's "2^20-row witness at 1/2/4/8 B200"
+  block_trace    : the realistic variant — ONE whole-block trace (4,096 transactions over 1,024 contracts: BeginTx ..
+                   STOP, EndTx each, EndBlock last) checked with the first / last step flags
   cfg4 / cfg5    : copy circuit 2^20 rows and the super circuit (evm + state + copy + bytecode, 2^22 rows
                    in total) row-sharded over the N ranks
 Multi-GPU (torchrun): rows are sharded, tables replicated, then ONE collective on the result vectors
@@ -383,6 +385,35 @@ def bench_bytecode(h, k, reps):
             "index_ms": i_ms, "roofline": roofline_of(h, c_ms, 32 * (e - b) * 12, kernel="k_check_bytecode<L_CANON>")}
 
 
+def bench_block(h, n_txs, groups, n_contracts, reps, seed=6):
+    """the realistic variant: ONE whole-block trace (synth.block_trace: BeginTx .. STOP, EndTx per transaction over
+    `n_contracts` contracts, EndBlock last) checked with the first / last step flags; step-sharded over the ranks"""
+    from zkevm_specs_b200 import packing, synth
+    native, ctx, stream = h.native, h.ctx, h.stream
+    t0 = time.perf_counter()
+    w = synth.block_trace(n_txs, groups, n_contracts, seed=seed)
+    gen_s = time.perf_counter() - t0
+    n = w["n_steps"]
+    b, e = shard(n, h.rank, h.world)
+    ctx.upload_bytecode_table_from_code(**w["bytecode_src"], stream=stream)
+    ctx.upload_table_packed(native.TABLE_RW, packing.pack_matrix(w["rw"]), flags=w["rw_flags"], stream=stream)
+    ctx.upload_columns_packed(native.CIRCUIT_EVM, packing.pack_matrix(take_rows(w["steps"], np.arange(b, e + 1))), stream=stream)
+    ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"], stream=stream)
+    ctx.upload_table(native.TABLE_BLOCK, w["block"], flags=w["block_flags"], stream=stream)
+    ctx.upload_table(native.TABLE_WITHDRAWAL, w["wd"], stream=stream)
+    flags = (native.FLAG_EVM_FIRST_STEP if b == 0 else 0) | (native.FLAG_EVM_LAST_STEP if e == n else 0)
+    ms = h.sharded_pass(native.CIRCUIT_EVM, 0, e - b, b, flags, reps)
+    i_ms, c_ms = h.phases(native.CIRCUIT_EVM, 0, e - b, b, flags, min(reps, 10))
+    states = np.bincount(w["steps"][0, :n, 0].astype(np.int64), minlength=64)
+    for t_, c_ in ((native.TABLE_TX, 5), (native.TABLE_BLOCK, 4)):
+        ctx.upload_table(t_, np.zeros((c_, 0, 4), dtype=np.uint64), stream=stream)
+    return {"workload": f"whole-block trace: {n_txs} transactions over {n_contracts} contracts of {68 * groups + 1} bytes, "
+                        "verify_steps(begin_with_first_step, end_with_last_step) as ONE trace",
+            "steps": n, "steps_per_gpu": e - b, "rw_rows": int(w["rw"].shape[1]), "bytecode_rows": int(w["bytecode"].shape[1]),
+            "tx_level_steps": int(states[1] + states[2] + states[3] + states[4]), "ms_per_pass": ms, "rows_per_s": n / (ms / 1e3),
+            "index_build_ms": i_ms, "check_ms": c_ms, "host_generate_s": gen_s}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,7 +425,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip typed / circuits / strong_scaling / cfg4 / cfg5")
-    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode"], default="evm",
+    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode", "block"], default="evm",
                     help="evm: the bench contract's line.  state / copy / bytecode: only that row circuit (canonical "
                          "storage; for profiling), printed as a JSON line of its own")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
@@ -426,8 +457,10 @@ def main():
 
     if args.workload != "evm":
         reps = max(3, min(args.steps, 20))
+        if args.workload == "block":
+            h.ctx.upload_table(native.TABLE_FIXED, fixed_table_matrix(), stream=stream)
         d = {"state": lambda: bench_state(h, 1 << 18, reps), "copy": lambda: bench_copy(h, 512, 1024, reps),
-             "bytecode": lambda: bench_bytecode(h, 19, reps)}[args.workload]()
+             "bytecode": lambda: bench_bytecode(h, 19, reps), "block": lambda: bench_block(h, 4096, 64, 1024, reps)}[args.workload]()
         if rank == 0:
             print(json.dumps({"workload": args.workload, "n_gpus": world, "storage": "canonical", **d}))
         if world > 1:
@@ -627,6 +660,7 @@ def main():
         else:
             extras["strong_scaling"] = {"rows": n_total, "rows_per_gpu": n_steps, "ms_per_pass": ms / args.steps,
                                         "rows_per_s": value, "index_build_ms": idx_ms, "check_ms": chk}
+        extras["block_trace"] = bench_block(h, 4096, 64, 1024, reps)
         # row circuits on canonical cells: cfg3, cfg4 (copy 2^20 rows, sharded over the ranks), bytecode 2^19
         circuits = [bench_state(h, 1 << 18, reps), bench_copy(h, 512, 1024, reps), bench_bytecode(h, 19, reps)]
         extras["circuits"] = circuits

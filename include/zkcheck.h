@@ -180,6 +180,17 @@ int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contracts, const 
                                        const uint8_t* is_code_bits, const uint64_t* code_offsets,
                                        const uint64_t* hashes, void* stream);
 
+/* Keccak-256 on the device (original 0x01 padding).  The reference hashes on the host through third-party
+ * packages (src/zkevm_specs/util/hash.py:7-10); its witness generators need one digest per contract and per
+ * copy event.  Message k = data[offsets[k] .. offsets[k+1]).
+ *   zk_keccak256_batch     : digests[k][0..3] = the 32 digest bytes of message k as four little-endian uint64 lanes
+ *   zk_assign_keccak_table : KeccakCircuit.add / assign_keccak_table (evm_circuit/typing.py:854-865,
+ *                            bytecode_circuit.py:182-186) for every message: the resident ZK_TABLE_KECCAK becomes
+ *                            n rows (2, RLC of the bytes under ZK_CHALLENGE_KECCAK, length, hash lo, hash hi),
+ *                            hashed and folded on the device; nothing but the message bytes crosses PCIe */
+int zk_keccak256_batch(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, uint64_t* digests, void* stream);
+int zk_assign_keccak_table(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, void* stream);
+
 /* Check rows [row_begin, row_end) of the resident matrix (local indices).  Without
  * ZK_FLAG_WRAP the caller guarantees halo rows exist for the circuit's rotations.
  * Reported rows are row_base + local index.

@@ -59,3 +59,36 @@ def test_bytecode_row_sharding_with_halo():
         ctx.upload_columns(native.CIRCUIT_BYTECODE, shard)
         b, _ = ctx.check(native.CIRCUIT_BYTECODE, 0, n - half, half, 0)
         assert np.array_equal(np.minimum(a, b), whole)
+
+
+def test_keccak256_and_keccak_table_on_the_device():
+    """zk_keccak256_batch / zk_assign_keccak_table (csrc/keccak.cuh, k_keccak256): digests equal the host sponge at every
+    length around the 136-byte rate, and a bytecode circuit checked against the DEVICE-built keccak table gives the same
+    arrays as against the host-built one (KeccakCircuit.add, typing.py:854-865)"""
+    from zkevm_specs_b200.evm_circuit import Bytecode
+    from zkevm_specs_b200.util import FQ
+    from zkevm_specs_b200.util.hash import keccak256
+
+    ctx = native.default_context()
+    rng = np.random.default_rng(11)
+    msgs = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in list(range(0, 140)) + [271, 272, 273, 1000, 24576, 50000]]
+    got = ctx.keccak256_batch(msgs)
+    for m, d in zip(msgs, got):
+        assert d == keccak256(m), len(m)
+    r = FQ(0x1234567ABCDEF)
+    codes = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (1, 33, 200, 3000)]
+    rows = bc.assign_bytecode_circuit(12, [bc.UnrolledBytecode(c, list(Bytecode(bytearray(c)).table_assignments())) for c in codes], r)
+    cols = bc.pack_rows(rows)
+    push = bc.pack_push_table(bc.assign_push_table())
+    kec = bc.pack_keccak_table(bc.assign_keccak_table(codes, r))
+    ff_host, fc_host = bc.check_matrices(cols, push, kec, r, ctx)
+    assert (ff_host == native.PASS).all()
+    ctx.set_challenge(native.CHALLENGE_KECCAK, r.n)
+    ctx.upload_table(native.TABLE_PUSH, push)
+    ctx.upload_columns(native.CIRCUIT_BYTECODE, cols)
+    ctx.assign_keccak_table(codes)
+    ff_dev, fc_dev = ctx.check(native.CIRCUIT_BYTECODE, 0, cols.shape[1], 0, native.FLAG_WRAP)
+    assert np.array_equal(ff_dev, ff_host) and np.array_equal(fc_dev, fc_host)
+    ctx.assign_keccak_table(codes[:-1] + [codes[-1][:-1] + b"\\x00"])  # one wrong message: the last contract's lookup fails
+    ff_bad, _ = ctx.check(native.CIRCUIT_BYTECODE, 0, cols.shape[1], 0, native.FLAG_WRAP)
+    assert (ff_bad != native.PASS).sum() == 1

@@ -251,6 +251,67 @@ def test_evm_begin_end_tx_end_block_golden_and_oracle_parity():
         ctx.upload_table(t, np.zeros((c, 0, 4), dtype=np.uint64))
 
 
+def _upload_block(ctx, w, from_code=True, packed=False):
+    from zkevm_specs_b200 import packing
+    if from_code:
+        ctx.upload_bytecode_table_from_code(**w["bytecode_src"])
+    else:
+        ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
+    if packed:
+        ctx.upload_table_packed(native.TABLE_RW, packing.pack_matrix(w["rw"]), flags=w["rw_flags"])
+        ctx.upload_columns_packed(native.CIRCUIT_EVM, packing.pack_matrix(w["steps"]))
+    else:
+        ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
+        ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
+    ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"])
+    ctx.upload_table(native.TABLE_BLOCK, w["block"], flags=w["block_flags"])
+    ctx.upload_table(native.TABLE_WITHDRAWAL, w["wd"])
+    ctx.upload_table(native.TABLE_COPY, w["copy"])
+    ctx.upload_table(native.TABLE_KECCAK, w["keccak"])
+
+
+def test_whole_block_trace_first_and_last_step_flags_match_oracle():
+    """synth.block_trace: BeginTx .. STOP, EndTx per transaction over several contracts, EndBlock last, checked as ONE
+    trace with ZK_FLAG_EVM_FIRST_STEP | ZK_FLAG_EVM_LAST_STEP (verify_steps(begin_with_first_step=True,
+    end_with_last_step=True); the generator is accepted by the reference itself, tests/golden/gen_golden.py synth):
+    passes on the device, corrupted copies equal the oracle array for array; packed storage and the
+    bytecode-table-from-code upload give the same arrays; sharded == whole"""
+    ctx = native.default_context()
+    fixed = fixed_table_matrix()
+    evm_main.upload_fixed_table(ctx)
+    w = synth.block_trace(96, 24, 16, seed=9)
+    n = w["n_steps"]
+    _upload_block(ctx, w)
+    ff, fc = ctx.check(native.CIRCUIT_EVM, 0, n, 0, w["flags"])
+    assert (ff == native.PASS).all(), native.first_failure(ff, native.CIRCUIT_EVM)
+    rng = np.random.default_rng(5)
+    for trial in range(24):
+        w2 = dict(w)
+        which = trial % 4
+        if which == 0:
+            m = w["steps"].copy(); m[int(rng.integers(1, 13)), int(rng.integers(0, n)), 0] += np.uint64(1); w2["steps"] = m
+        elif which == 1:
+            m = w["rw"].copy(); m[int(rng.choice([3, 4, 5, 8, 10])), int(rng.integers(0, m.shape[1])), 0] ^= np.uint64(1); w2["rw"] = m
+        elif which == 2:
+            m = w["tx"].copy(); m[3, int(rng.integers(0, m.shape[1])), 0] += np.uint64(1); w2["tx"] = m
+        else:
+            m = w["block"].copy(); m[2, int(rng.integers(0, m.shape[1])), 0] += np.uint64(1); w2["block"] = m
+        off, ofc = oracle_lib.check_evm_x(w2, fixed, row_end=n)
+        for packed in (False, True):
+            _upload_block(ctx, w2, from_code=packed, packed=packed)
+            ff, fc = ctx.check(native.CIRCUIT_EVM, 0, n, 0, w["flags"])
+            assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"trial {trial} packed={packed}: {_diff(ff, off)}"
+        if trial < 4:  # row-sharded: every shard sees the whole tables, its steps + one halo step
+            _upload_block(ctx, w2)
+            acc_ff, acc_fc = np.full_like(off, native.PASS), np.zeros_like(ofc)
+            for lo, hi in ((0, n // 3), (n // 3, 2 * n // 3), (2 * n // 3, n)):
+                sff, sfc = ctx.check(native.CIRCUIT_EVM, lo, hi, 0, w["flags"])
+                acc_ff, acc_fc = np.minimum(acc_ff, sff), acc_fc + sfc
+            assert np.array_equal(acc_ff, off) and np.array_equal(acc_fc, ofc)
+    for t, c in ((native.TABLE_TX, 5), (native.TABLE_BLOCK, 4)):
+        ctx.upload_table(t, np.zeros((c, 0, 4), dtype=np.uint64))
+
+
 def test_sha3_host_api_like_reference_test_sha3():
     """tests/evm/test_sha3.py:35-141 on our host API: copy circuit + keccak table + SHA3 step"""
     from zkevm_specs_b200.copy_circuit import verify_copy_table

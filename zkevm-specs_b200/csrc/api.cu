@@ -118,6 +118,8 @@ struct zk_ctx {
   BlockStats* block_stats = nullptr;  // k_evm_block_stats output
   void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
   size_t state_fold_cap = 0;
+  unsigned char* kstage = nullptr;  // zk_keccak256_batch / zk_assign_keccak_table staging
+  size_t kstage_cap = 0;
   unsigned char* gather = nullptr;  // zk_allreduce_results: all-gathered result vectors
   size_t gather_cap = 0;
   bool timing = false;
@@ -195,6 +197,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   if (ctx->state_fold) cudaFree(ctx->state_fold);
   if (ctx->block_stats) cudaFree(ctx->block_stats);
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
+  if (ctx->kstage) cudaFree(ctx->kstage);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
   if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
@@ -469,6 +472,136 @@ extern "C" int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contra
   return 0;
 }
 
+// ------------------------------------------------------------------ Keccak-256 on the device
+// The reference hashes on the host through third-party packages (util/hash.py:7-10); witness generators
+// call it once per contract / copy event (KeccakCircuit.add, typing.py:854-865; assign_keccak_table,
+// bytecode_circuit.py:182-186).  Here one BLOCK takes one message: thread 0 runs the sponge (the
+// permutation is sequential), all 128 threads fold the message into its random linear combination
+// sum d_i r^(n-1-i) by chunks — Horner inside a chunk, then a shared-memory tree of
+// (value, r^length) pairs: value = left * r^len(right) + right.
+struct KeccakJob {
+  const unsigned char* data;  // all messages concatenated
+  const u64* offsets;         // [n + 1]
+  u64 n;
+};
+__global__ void __launch_bounds__(128) k_keccak256(KeccakJob job, u64* digests /* [n][4] lanes */, unsigned char* table, u64 o_tag,
+                                                   u64 o_rlc, u64 o_len, u64 o_lo, u64 o_hi, Fr r_mont) {
+  __shared__ Fr s_val[128], s_pow[128];
+  const u64 m = blockIdx.x;
+  if (m >= job.n) return;
+  const unsigned char* msg = job.data + job.offsets[m];
+  const u64 len = job.offsets[m + 1] - job.offsets[m];
+  u64 d[4] = {0, 0, 0, 0};
+  if (threadIdx.x == 0) {
+    keccak256(msg, len, d);
+    if (digests)
+      for (int k = 0; k < 4; k++) digests[4 * m + k] = d[k];
+  }
+  if (!table) return;
+  // chunked Horner: thread t owns bytes [t * per, min(len, (t + 1) * per))
+  const u64 per = (len + 127) / 128;
+  const u64 lo = min(len, threadIdx.x * per), hi = min(len, lo + per);
+  const Fr one_m = fr_to_mont(fr_u64(1));
+  Fr acc = fr_u64(0), pw = one_m;  // acc canonical; pw = r^(chunk length) in Montgomery form
+  for (u64 i = lo; i < hi; i++) {
+    acc = fr_add_u64(fr_montmul(acc, r_mont), msg[i]);
+    pw = fr_montmul(pw, r_mont);
+    pw = fr_montmul(pw, Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});  // back to Montgomery form (montmul drops one R)
+  }
+  s_val[threadIdx.x] = acc;
+  s_pow[threadIdx.x] = pw;
+  __syncthreads();
+  for (int stride = 1; stride < 128; stride <<= 1) {  // (left, right) -> left * r^len(right) + right
+    if ((threadIdx.x & (2 * stride - 1)) == 0) {
+      const Fr lv = s_val[threadIdx.x], lp = s_pow[threadIdx.x];
+      const Fr rv = s_val[threadIdx.x + stride], rp = s_pow[threadIdx.x + stride];
+      s_val[threadIdx.x] = fr_add(fr_montmul(lv, rp), rv);
+      s_pow[threadIdx.x] = fr_montmul(fr_montmul(lp, rp), Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {  // the table row (2 = Finalize, input_rlc, input_len, Word(digest as a big-endian integer))
+    u64 wlo[2], whi[2];
+    keccak_digest_to_word(d, wlo, whi);
+    u64* c;
+    c = (u64*)(table + o_tag) + 4 * m; c[0] = 2; c[1] = c[2] = c[3] = 0;
+    c = (u64*)(table + o_rlc) + 4 * m; for (int k = 0; k < 4; k++) c[k] = s_val[0].l[k];
+    c = (u64*)(table + o_len) + 4 * m; c[0] = len; c[1] = c[2] = c[3] = 0;
+    c = (u64*)(table + o_lo) + 4 * m; c[0] = wlo[0]; c[1] = wlo[1]; c[2] = c[3] = 0;
+    c = (u64*)(table + o_hi) + 4 * m; c[0] = whi[0]; c[1] = whi[1]; c[2] = c[3] = 0;
+  }
+}
+static int keccak_stage(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, cudaStream_t st, KeccakJob* job,
+                        u64** dig_dev) {
+  if (n == 0) return fail_msg(ctx, "no messages");
+  if (offsets[0] != 0) return fail_msg(ctx, "offsets[0] must be 0");
+  for (u64 k = 0; k < n; k++)
+    if (offsets[k + 1] < offsets[k]) return fail_msg(ctx, "offsets must be non-decreasing");
+  auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
+  const size_t total = offsets[n], s_off = up32(total ? total : 1), s_dig = s_off + up32((n + 1) * 8), s_total = s_dig + n * 32;
+  if (s_total > ctx->kstage_cap) {
+    if (ctx->kstage) cudaFree(ctx->kstage);
+    ctx->kstage = nullptr;
+    CK(ctx, cudaMalloc(&ctx->kstage, s_total));
+    ctx->kstage_cap = s_total;
+  }
+  if (total) CK(ctx, cudaMemcpyAsync(ctx->kstage, data, total, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(ctx->kstage + s_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  job->data = ctx->kstage;
+  job->offsets = (const u64*)(ctx->kstage + s_off);
+  job->n = n;
+  *dig_dev = (u64*)(ctx->kstage + s_dig);
+  return 0;
+}
+extern "C" int zk_keccak256_batch(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, uint64_t* digests,
+                                  void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  KeccakJob job;
+  u64* dig = nullptr;
+  int rc = keccak_stage(ctx, n, data, offsets, st, &job, &dig);
+  if (rc) return rc;
+  k_keccak256<<<(unsigned)n, 128, 0, st>>>(job, dig, nullptr, 0, 0, 0, 0, 0, Fr{{0, 0, 0, 0}});
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  CK(ctx, cudaMemcpyAsync(digests, dig, n * 32, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+extern "C" int zk_assign_keccak_table(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
+  KeccakJob job;
+  u64* dig = nullptr;
+  int rc = keccak_stage(ctx, n, data, offsets, st, &job, &dig);
+  if (rc) return rc;
+  Matrix& m = ctx->tab[ZK_TABLE_KECCAK];
+  const size_t bytes = (size_t)n * 5 * 32;
+  if (m.borrowed) {
+    m.dev = nullptr;
+    m.borrowed = false;
+    m.cap_bytes = 0;
+  }
+  if (bytes > m.cap_bytes) {
+    if (m.dev) cudaFree(m.dev);
+    m.dev = nullptr;
+    CK(ctx, cudaMalloc(&m.dev, bytes));
+    m.cap_bytes = bytes;
+  }
+  m.version++;
+  m.n_rows = n;
+  m.n_cols = 5;
+  m.flags_rows = 0;
+  m.src_offsets = nullptr;
+  layout_canonical(m.off, m.width, 5, n);
+  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
+  k_keccak256<<<(unsigned)n, 128, 0, st>>>(job, dig, (unsigned char*)m.dev, m.off[0], m.off[1], m.off[2], m.off[3], m.off[4], r_mont);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ lookup index cache
 static TableDev table_dev(const zk_ctx* ctx, int table_id) {
   const Matrix& m = ctx->tab[table_id];
@@ -717,7 +850,6 @@ static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStr
   // fold pass over every resident row (halos included), then the gate program
   if (m.n_rows * sizeof(StateFold) > ctx->state_fold_cap) {
     if (ctx->state_fold) cudaFree(ctx->state_fold);
-  if (ctx->block_stats) cudaFree(ctx->block_stats);
     ctx->state_fold = nullptr;
     CK(ctx, cudaMalloc(&ctx->state_fold, m.n_rows * sizeof(StateFold)));
     ctx->state_fold_cap = m.n_rows * sizeof(StateFold);
@@ -791,10 +923,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   // per non-empty gate-program group
   auto up256 = [](size_t x) { return (x + 255) / 256 * 256; };
   if (n > ctx->evm_sort_cap) {
-    if (ctx->gather) cudaFree(ctx->gather);
-  if (ctx->state_fold) cudaFree(ctx->state_fold);
-  if (ctx->block_stats) cudaFree(ctx->block_stats);
-  if (ctx->evm_sort) cudaFree(ctx->evm_sort);
+    if (ctx->evm_sort) cudaFree(ctx->evm_sort);
     ctx->evm_sort = nullptr;
     CK(ctx, cudaMalloc(&ctx->evm_sort, up256(n) + up256(n * 4) + (3 * ZK_EVM_NB + 2) * sizeof(u32)));
     ctx->evm_sort_cap = n;
@@ -1070,8 +1199,6 @@ extern "C" int zk_allreduce_results(zk_ctx* ctx, int circuit_id, void* nccl_comm
   const size_t rank_bytes = count_off + (size_t)r.n * 8;
   if (ctx->gather_cap < rank_bytes * world) {
     if (ctx->gather) cudaFree(ctx->gather);
-  if (ctx->state_fold) cudaFree(ctx->state_fold);
-  if (ctx->block_stats) cudaFree(ctx->block_stats);
     ctx->gather = nullptr;
     CK(ctx, cudaMalloc(&ctx->gather, rank_bytes * world));
     ctx->gather_cap = rank_bytes * world;

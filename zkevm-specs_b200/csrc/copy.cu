@@ -166,8 +166,8 @@ ZK_HD void check_copy_row(const WitnessDev& w, const CheckRange& rg, const CopyT
 
 #ifdef __CUDACC__
 template <int LAYOUT>
-__global__ void __launch_bounds__(128, 4) k_check_copy(WitnessDev w, CheckRange rg, CopyTables t, Fr r_mont,
-                                                    ResultDev res) {
+__global__ void __launch_bounds__(128, 4) k_check_copy(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ CopyTables t, const __grid_constant__ Fr r_mont,
+             const __grid_constant__ ResultDev res) {
   const u64 n = rg.row_end - rg.row_begin;
   const u64 stride = (u64)gridDim.x * blockDim.x;
   const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;

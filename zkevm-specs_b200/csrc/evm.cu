@@ -1740,7 +1740,7 @@ __device__ __forceinline__ int mul_bucket_peek(const StepCtx& s, const Fr& hlo, 
   return fr_eq_u64(v, 4) ? ZK_BK_DIV : (fr_eq_u64(v, 6) ? ZK_BK_MOD : ZK_ES_MUL);
 }
 
-__global__ void __launch_bounds__(1024) k_evm_classify(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res, EvmSort so) {
+__global__ void __launch_bounds__(1024) k_evm_classify(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res, const __grid_constant__ EvmSort so) {
   // histogram aggregated per BLOCK: lanes of a warp that share a bucket elect a leader (match_any),
   // leaders add to a shared histogram, one global atomicAdd per (block, non-empty bucket)
   __shared__ u32 s_hist[ZK_EVM_NB];
@@ -1846,8 +1846,8 @@ __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRan
 #endif
 template <int G, bool POS>
 __global__ void __launch_bounds__(128, G == KG_MUL ? ZK_GADGET_MINBLOCKS : (G == KG_ADD ? ZK_ADD_MINBLOCKS : ZK_POP_MINBLOCKS))
-k_evm_gadget(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                    EvmSort so) {
+k_evm_gadget(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
+             const __grid_constant__ EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
@@ -1903,8 +1903,8 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   return r;
 }
 // positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1)
-__global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                      EvmSort so) {
+__global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
+               const __grid_constant__ EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);
@@ -1927,8 +1927,8 @@ __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(Witness
 // latency-bound on ~8 dependent memory round trips per step (profiles/README.md, v7).  All 32 lanes
 // call every warp-synchronous lookup together; a half without a step (odd count) or whose step
 // already failed passes live = false.
-__global__ void __launch_bounds__(128, 4) k_evm_push_hash(WitnessDev w, CheckRange rg, EvmTables t, ResultDev res,
-                                                          EvmSort so) {
+__global__ void __launch_bounds__(128, 4) k_evm_push_hash(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
+                const __grid_constant__ EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
   __shared__ alignas(8) u64 s_bar;
   stage_to_smem(s_resp, t.resp_bitmap, sizeof(s_resp), &s_bar);

@@ -74,6 +74,7 @@ EXPORTS = [
     "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
     "zk_last_timing", "zk_upload_columns_packed", "zk_upload_table_packed",
     "zk_upload_bytecode_table_from_code", "zk_nccl_unique_id", "zk_nccl_comm_init", "zk_nccl_comm_destroy",
+    "zk_keccak256_batch", "zk_assign_keccak_table",
 ]
 
 
@@ -107,6 +108,8 @@ def lib() -> ctypes.CDLL:
         L.zk_nccl_unique_id.argtypes = [vp, vp]
         L.zk_nccl_comm_init.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
         L.zk_nccl_comm_destroy.argtypes = [vp, vp]
+        L.zk_keccak256_batch.argtypes = [vp, u64, vp, vp, vp, vp]
+        L.zk_assign_keccak_table.argtypes = [vp, u64, vp, vp, vp]
         L.zk_circuit_cols.argtypes = [i32]
         L.zk_table_cols.argtypes = [i32]
         L.zk_n_constraints.argtypes = [i32]
@@ -313,6 +316,30 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.zk_launch_count(self._h))
+
+    # ---- Keccak-256 on the device ------------------------------------------------------------
+    @staticmethod
+    def _concat(messages):
+        offs = np.zeros(len(messages) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(m) for m in messages])
+        data = np.frombuffer(b"".join(bytes(m) for m in messages) or b"\0", dtype=np.uint8).copy()
+        return data, offs
+
+    def keccak256_batch(self, messages, stream: int = 0):
+        """digests of a list of byte strings, hashed on the device"""
+        data, offs = self._concat(messages)
+        out = np.zeros((len(messages), 4), dtype=np.uint64)
+        self._ck(self._L.zk_keccak256_batch(self._h, len(messages), _host_ptr(data), _host_ptr(offs), _host_ptr(out),
+                                            ctypes.c_void_p(stream)), "zk_keccak256_batch")
+        return [out[k].tobytes() for k in range(len(messages))]
+
+    def assign_keccak_table(self, messages, stream: int = 0) -> None:
+        """KeccakCircuit.add for every message, on the device: the resident keccak table becomes one row per message"""
+        data, offs = self._concat(messages)
+        self._keep = getattr(self, "_keep", {})
+        self._keep["keccak_src"] = (data, offs)
+        self._ck(self._L.zk_assign_keccak_table(self._h, len(messages), _host_ptr(data), _host_ptr(offs),
+                                                ctypes.c_void_p(stream)), "zk_assign_keccak_table")
 
     # ---- multi-GPU: one NCCL communicator per context, results folded in place --------------
     def nccl_unique_id(self) -> bytes:
