@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../zkevm-specs_b200/csrc/bytecode.cu"
@@ -102,14 +103,21 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   d.slots = slots.data();
   d.mask = (u32)(cap - 1);
   d.n_key = n_key;
-  const Fr r_mont = fr_to_mont(challenge);
-  Fr acc = fr_to_mont(fr_u64(1));
-  for (u32 j = 0; j < ZK_MAX_KEY; j++) {
-    d.key_cols[j] = j < n_key ? key_cols[j] : 0;
-    d.pw[j] = acc;
-    d.pwc[j] = fr_montmul(acc, fr_u64(1));
-    d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);
-    acc = fr_montmul(acc, r_mont);
+  {  // hash keys: a splitmix64 stream seeded by the lookup challenge (as api.cu:ensure_index)
+    const Fr& c = challenge;
+    u64 x = c.l[0] ^ (c.l[1] * 0x9E3779B97F4A7C15ull) ^ (c.l[2] * 0xC2B2AE3D27D4EB4Full) ^ (c.l[3] * 0x165667B19E3779F9ull);
+    auto next = [&x]() {
+      x += 0x9E3779B97F4A7C15ull;
+      u64 z = x;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      return z ^ (z >> 31);
+    };
+    for (int k = 0; k < 4; k++) d.hk[k] = next() | 1ull;
+    for (u32 j = 0; j < ZK_MAX_KEY; j++) {
+      d.key_cols[j] = j < n_key ? key_cols[j] : 0;
+      d.hm[j] = next() | 1ull;
+    }
   }
   d.pos_ok = nullptr;
   d.pos_kind = ZK_POS_NONE;
@@ -117,7 +125,6 @@ static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32*
   d.tail_col = d.tail_val = 0;
   d.heads = nullptr;
   d.heads_mask = 0;
-  for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;
   d.heads_list = d.heads_count = nullptr;
   for (u64 r = 0; r < n_rows; r++) index_insert_row(d, r);
   return d;
@@ -400,4 +407,18 @@ extern "C" void emu_keccak256_word(const uint8_t* msg, uint64_t len, uint64_t lo
   keccak256(msg, len, d);
   keccak_digest_to_word(d, l, h);
   lo[0] = l[0]; lo[1] = l[1]; hi[0] = h[0]; hi[1] = h[1];
+}
+
+// the keccak table's input_rlc as k_keccak256 folds it (128 chunks + pairwise tree), canonical result
+extern "C" void emu_keccak_rlc(const uint8_t* msg, uint64_t len, const uint64_t r[4], uint64_t out[4]) {
+  Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
+  Fr val[128], pw[128];
+  const u64 per = (len + 127) / 128;
+  for (u64 t = 0; t < 128; t++) {
+    const u64 lo = std::min<u64>(len, t * per), hi = std::min<u64>(len, lo + per);
+    rlc_chunk(msg, lo, hi, r_mont, val[t], pw[t]);
+  }
+  for (int stride = 1; stride < 128; stride <<= 1)
+    for (int t = 0; t < 128; t += 2 * stride) rlc_combine(val[t], pw[t], val[t + stride], pw[t + stride]);
+  for (int k = 0; k < 4; k++) out[k] = val[0].l[k];
 }

@@ -254,3 +254,13 @@ def test_device_keccak256_matches_host_reference():
         L.emu_keccak256_word(buf, ctypes.c_uint64(n), lo, hi)
         v = int.from_bytes(want, "big")
         assert lo[0] | (lo[1] << 64) == v & ((1 << 128) - 1) and hi[0] | (hi[1] << 64) == v >> 128
+        # the table's input_rlc column, folded as the kernel folds it (128 chunks + tree)
+        from zkevm_specs_b200.util import FQ
+        r = 0x1234567ABCDEF0FEDCBA987654321
+        rr = (ctypes.c_uint64 * 4)(*[(r >> (64 * k)) & (2**64 - 1) for k in range(4)])
+        o4 = (ctypes.c_uint64 * 4)()
+        L.emu_keccak_rlc(buf, ctypes.c_uint64(n), rr, o4)
+        acc = FQ(0)
+        for b in msg:
+            acc = acc * FQ(r) + FQ(b)
+        assert sum(int(o4[k]) << (64 * k) for k in range(4)) == acc.n, n

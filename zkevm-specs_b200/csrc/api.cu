@@ -501,23 +501,11 @@ __global__ void __launch_bounds__(128) k_keccak256(KeccakJob job, u64* digests /
   // chunked Horner: thread t owns bytes [t * per, min(len, (t + 1) * per))
   const u64 per = (len + 127) / 128;
   const u64 lo = min(len, threadIdx.x * per), hi = min(len, lo + per);
-  const Fr one_m = fr_to_mont(fr_u64(1));
-  Fr acc = fr_u64(0), pw = one_m;  // acc canonical; pw = r^(chunk length) in Montgomery form
-  for (u64 i = lo; i < hi; i++) {
-    acc = fr_add_u64(fr_montmul(acc, r_mont), msg[i]);
-    pw = fr_montmul(pw, r_mont);
-    pw = fr_montmul(pw, Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});  // back to Montgomery form (montmul drops one R)
-  }
-  s_val[threadIdx.x] = acc;
-  s_pow[threadIdx.x] = pw;
+  rlc_chunk(msg, lo, hi, r_mont, s_val[threadIdx.x], s_pow[threadIdx.x]);
   __syncthreads();
-  for (int stride = 1; stride < 128; stride <<= 1) {  // (left, right) -> left * r^len(right) + right
-    if ((threadIdx.x & (2 * stride - 1)) == 0) {
-      const Fr lv = s_val[threadIdx.x], lp = s_pow[threadIdx.x];
-      const Fr rv = s_val[threadIdx.x + stride], rp = s_pow[threadIdx.x + stride];
-      s_val[threadIdx.x] = fr_add(fr_montmul(lv, rp), rv);
-      s_pow[threadIdx.x] = fr_montmul(fr_montmul(lp, rp), Fr{{ZK_R2_0, ZK_R2_1, ZK_R2_2, ZK_R2_3}});
-    }
+  for (int stride = 1; stride < 128; stride <<= 1) {
+    if ((threadIdx.x & (2 * stride - 1)) == 0)
+      rlc_combine(s_val[threadIdx.x], s_pow[threadIdx.x], s_val[threadIdx.x + stride], s_pow[threadIdx.x + stride]);
     __syncthreads();
   }
   if (threadIdx.x == 0) {  // the table row (2 = Finalize, input_rlc, input_len, Word(digest as a big-endian integer))
@@ -661,14 +649,22 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   d.slots = ix->slots;
   d.mask = (u32)(cap - 1);
   d.n_key = n_key;
-  const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_LOOKUP]);
-  Fr acc = fr_to_mont(fr_u64(1));
-  for (u32 j = 0; j < ZK_MAX_KEY; j++) {
-    d.key_cols[j] = j < n_key ? key_cols[j] : 0;
-    d.pw[j] = acc;                            // r^j in Montgomery form
-    d.pwc[j] = fr_montmul(acc, fr_u64(1));  // r^j canonical
-    d.pw1[j] = fr_montmul(d.pwc[j], ZK_MONT_TWO64);  // r^j * 2^64 mod p
-    acc = fr_montmul(acc, r_mont);
+  // hash keys: a splitmix64 stream seeded by the lookup challenge
+  {
+    const Fr& c = ctx->chal[ZK_CHALLENGE_LOOKUP];
+    u64 x = c.l[0] ^ (c.l[1] * 0x9E3779B97F4A7C15ull) ^ (c.l[2] * 0xC2B2AE3D27D4EB4Full) ^ (c.l[3] * 0x165667B19E3779F9ull);
+    auto next = [&x]() {
+      x += 0x9E3779B97F4A7C15ull;
+      u64 z = x;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      return z ^ (z >> 31);
+    };
+    for (int k = 0; k < 4; k++) d.hk[k] = next() | 1ull;
+    for (u32 j = 0; j < ZK_MAX_KEY; j++) {
+      d.key_cols[j] = j < n_key ? key_cols[j] : 0;
+      d.hm[j] = next() | 1ull;
+    }
   }
   d.pos_ok = nullptr;
   d.pos_kind = ix->pos_kind;
@@ -683,7 +679,6 @@ static int ensure_index(zk_ctx* ctx, int table_id, const u32* key_cols, u32 n_ke
   }
   d.heads = ix->heads;
   d.heads_mask = ZK_HEADS_CAP - 1;
-  for (int k = 0; k < 4; k++) d.hk[k] = rlc_mix(d.pwc[1 + k]) | 1ull;  // odd multipliers keyed by the challenge
   d.heads_list = ix->heads_aux;
   d.heads_count = ix->heads_aux ? ix->heads_aux + ZK_HEADS_CAP : nullptr;
   const unsigned grid = (unsigned)std::min<u64>((t.n_rows + 255) / 256, (u64)ctx->sm_count * 32);

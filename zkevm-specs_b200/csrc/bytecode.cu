@@ -111,8 +111,8 @@ ZK_HD void check_bytecode_row(const W& w, const CheckRange& rg, const IndexDev& 
 #ifdef __CUDACC__
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
-k_check_bytecode(WitnessDev w, CheckRange rg, IndexDev push_ix, IndexDev kec_ix, Fr r_mont,
-                 ResultDev res) {
+k_check_bytecode(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ IndexDev push_ix, const __grid_constant__ IndexDev kec_ix, const __grid_constant__ Fr r_mont,
+                 const __grid_constant__ ResultDev res) {
   __shared__ alignas(32) u64 s_push[256 * 4];
   __shared__ alignas(8) u64 s_bar;
   // uniform: regular 256-row push table with a canonical push_size column -> stage it (8 KiB, UBLKCP)

@@ -217,7 +217,7 @@ ZK_HD int bytecode_head(const StepCtx& s, bool live, const Fr& hlo, const Fr& hh
 ZK_HD void stack_key_pre(const IndexDev& rw_ix, Fr out[2]) {
   const Fr tag_term = rlc_term(rw_ix, fr_u64(ZK_TARGET_Stack), 2);
   out[0] = tag_term;
-  out[1] = fr_add(rw_ix.pwc[1], tag_term);
+  out[1] = fr_add(rlc_term(rw_ix, fr_u64(1), 1), tag_term);
 }
 ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag, const Fr& id, const Fr& addr,
                     Word2* value) {

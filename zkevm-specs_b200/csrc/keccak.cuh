@@ -111,4 +111,22 @@ ZK_HD void keccak_digest_to_word(const u64 d[4], u64 lo[2], u64 hi[2]) {
   hi[1] = sw[3];
 }
 
+// The keccak table's input_rlc column, RLC(reversed(msg), r) = sum msg[i] * r^(len-1-i), folded in chunks: one chunk gives
+// (val, pow) = (Horner value of its bytes, r^(chunk length)); two adjacent chunks combine as val = l.val * r.pow + r.val.
+// val is canonical, pow and r_mont are in Montgomery form (canonical x Montgomery -> canonical; Montgomery x Montgomery
+// -> Montgomery).
+ZK_HD void rlc_chunk(const unsigned char* msg, u64 lo, u64 hi, const Fr& r_mont, Fr& val, Fr& pow) {
+  Fr acc = fr_u64(0), pw = fr_to_mont(fr_u64(1));
+  for (u64 i = lo; i < hi; i++) {
+    acc = fr_add_u64(fr_montmul(acc, r_mont), msg[i]);
+    pw = fr_montmul(pw, r_mont);
+  }
+  val = acc;
+  pow = pw;
+}
+ZK_HD void rlc_combine(Fr& lval, Fr& lpow, const Fr& rval, const Fr& rpow) {
+  lval = fr_add(fr_montmul(lval, rpow), rval);
+  lpow = fr_montmul(lpow, rpow);
+}
+
 }  // namespace zk

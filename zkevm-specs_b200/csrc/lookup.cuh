@@ -6,9 +6,8 @@
 // That scan is >99 % of the reference's EVM/copy time.
 //
 // Here every (table, queried-column set) gets an open-addressing hash index built on the
-// device.  The hash of a row is the random linear combination  h = sum_j cell_j * r^j  over
-// Fr (r = ZK_CHALLENGE_LOOKUP, powers kept in Montgomery form so each term is one montmul);
-// the low bits of the canonical h pick the bucket.  A probe recomputes h for the query,
+// device.  The hash of a row is a keyed combination of its queried cells (rlc_term below; the keys
+// come from ZK_CHALLENGE_LOOKUP); its low bits pick the bucket.  A probe recomputes h for the query,
 // walks the bucket run, and CONFIRMS each candidate by comparing the queried cells exactly,
 // so pass/fail never depends on r; it also counts distinct matching rows so ambiguity is
 // reported exactly like the reference (rows identical in every column count once, the
@@ -55,9 +54,7 @@ struct IndexDev {
   u32 mask;
   u32 n_key;
   u32 key_cols[ZK_MAX_KEY];
-  Fr pw[ZK_MAX_KEY];   // r^j * 2^256 mod p (Montgomery form): montmul(cell, pw[j]) = cell * r^j
-  Fr pwc[ZK_MAX_KEY];  // r^j canonical, for terms whose cell is 1
-  Fr pw1[ZK_MAX_KEY];  // r^j * 2^64 mod p: fr_montmul1(v, pw1[j]) = v * r^j for one-limb cells
+  u64 hm[ZK_MAX_KEY];  // odd per-position multipliers of the key hash (drawn from the lookup challenge)
   // Positional fast path (see "positional indexes" below).  pos_ok points at a device flag that the
   // verify kernel leaves at 1 iff the table has the regular structure `pos_kind` promises; the
   // hash index above is then not built and lookups go straight to the row.
@@ -95,18 +92,15 @@ ZK_HD u64 rlc_mix(const Fr& h) {
   return x;
 }
 
-// one RLC term cell * r^j, with shortcuts for the constant-like cells (0, 1) that tags, flags
-// and selectors mostly are
+// One term of the key hash.  Round 1 compressed a row into its random linear combination over Fr
+// (one 254-bit Montgomery product per wide cell, ~100-400 instructions); matches are confirmed cell by
+// cell anyway, so the hash only has to spread keys: a keyed multiply-add of the four limbs, times an odd
+// per-position constant (keys drawn from ZK_CHALLENGE_LOOKUP after the witness is fixed), ~30 instructions.
 ZK_HD Fr rlc_term(const IndexDev& ix, const Fr& cell, int j) {
-  if (fr_is_zero(cell)) return cell;
-  if (fr_fits64(cell)) {
-    if (cell.l[0] == 1) return ix.pwc[j];
-    if (cell.l[0] == 2) return fr_add(ix.pwc[j], ix.pwc[j]);
-    return fr_montmul1(cell.l[0], ix.pw1[j]);
-  }
-  return fr_montmul(cell, ix.pw[j]);
+  const u64 f = cell.l[0] * ix.hk[0] + cell.l[1] * ix.hk[1] + cell.l[2] * ix.hk[2] + cell.l[3] * ix.hk[3];
+  return fr_u64(f * ix.hm[j]);
 }
-// h = key[0] + sum_{j>=1} key[j] * r^j   (canonical)
+// h = key[0] + sum_{j>=1} term(key[j], j)
 template <int NK>
 ZK_HD Fr rlc_key(const IndexDev& ix, const Fr (&key)[NK]) {
   Fr h = key[0];

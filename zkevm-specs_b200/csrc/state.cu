@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(256) k_state_fold(WitnessDev w, StateFold* out
 #define ZK_STATE_MINBLOCKS 3
 #endif
 template <int LAYOUT>
-__global__ void __launch_bounds__(128, ZK_STATE_MINBLOCKS) k_check_state(WitnessDev w, CheckRange rg, IndexDev mpt, ResultDev res,
-                                                       const StateFold* fold) {
+__global__ void __launch_bounds__(128, ZK_STATE_MINBLOCKS) k_check_state(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ IndexDev mpt, const __grid_constant__ ResultDev res,
+              const StateFold* fold) {
   const bool wrap = rg.flags & ZK_FLAG_WRAP;
   const u64 n = rg.row_end - rg.row_begin;
   const u64 stride = (u64)gridDim.x * blockDim.x;

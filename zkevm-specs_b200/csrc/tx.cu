@@ -130,12 +130,12 @@ ZK_HD void check_sig_row(const WitnessDev& w, const CheckRange& rg, const IndexD
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(128) k_check_sig(WitnessDev w, CheckRange rg, IndexDev keccak, Fr r_mont, ResultDev res) {
+__global__ void __launch_bounds__(128) k_check_sig(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ IndexDev keccak, const __grid_constant__ Fr r_mont, const __grid_constant__ ResultDev res) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rg.row_end; i += stride)
     check_sig_row(w, rg, keccak, r_mont, res, i);
 }
-__global__ void __launch_bounds__(128) k_check_tx(WitnessDev w, CheckRange rg, IndexDev keccak, Fr r_mont, ResultDev res) {
+__global__ void __launch_bounds__(128) k_check_tx(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ IndexDev keccak, const __grid_constant__ Fr r_mont, const __grid_constant__ ResultDev res) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = rg.row_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rg.row_end; i += stride)
     check_tx_row(w, rg, keccak, r_mont, res, i);
