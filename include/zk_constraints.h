@@ -876,4 +876,41 @@ enum zk_tx_constraint { ZK_TX_CONSTRAINTS(ZK_ENUM_ENTRY) TX_N_CONSTRAINTS };
 
 enum zk_sig_constraint { ZK_SIG_CONSTRAINTS(ZK_ENUM_ENTRY) SG_N_CONSTRAINTS };
 
+/* ---------------- public-inputs circuit: src/zkevm_specs/pi_circuit.py:150-321 ------------------
+ * check_row under the loop of verify_circuit (:447-459).  Gates are `selector * polynomial == 0` with
+ * inverse witnesses; the three sections after the keccak lookup sit under Python `if selector != 0`. */
+#define ZK_PI_CONSTRAINTS(X)                                                                     \
+  X(PI_RLC_LAST, ZKE_ASSERT, "pi_circuit.py:162 rpi_bytes_keccakrlc[last] == rpi_bytes[last]")   \
+  X(PI_RLC_ACC, ZKE_ASSERT, "pi_circuit.py:165-170 rpi_bytes_keccakrlc[i] == keccak_rand * rpi_bytes_keccakrlc[i+1] + rpi_bytes[i]") \
+  X(PI_VALUE_ACC, ZKE_ASSERT, "pi_circuit.py:183-188 rpi_value_lc[i] == rpi_value_lc[i+1] * byte_pow_base + rpi_bytes[i]") \
+  X(PI_VALUE_START, ZKE_ASSERT, "pi_circuit.py:191-194 q_rpi_value_start: rpi_value_lc == rpi_bytes") \
+  X(PI_KECCAK_WORD, ZKE_ASSERT, "pi_circuit.py:201 rpi_digest_word.select(q): Word((lo, hi)) sanity check, halves < 2^128 (util/arithmetic.py:110-114)") \
+  X(PI_KECCAK_LOOKUP, ZKE_ASSERT, "pi_circuit.py:197-203,98-102 keccak_table.lookup(q, q*rlc, q*circuit_len, digest)") \
+  X(PI_CD_TXID_INV, ZKE_ASSERT, "pi_circuit.py:208 tx_id * (1 - tx_id_inv * tx_id) == 0")        \
+  X(PI_CD_VALUE_INV, ZKE_ASSERT, "pi_circuit.py:209-213 value.lo * (1 - tx_value_lo_inv * value.lo) == 0") \
+  X(PI_CD_DIFF_INV, ZKE_ASSERT, "pi_circuit.py:214-216 diff * (1 - tx_id_diff_inv * diff) == 0") \
+  X(PI_CD_DEF_TXID, ZKE_ASSERT, "pi_circuit.py:233,240-241 is_tx_id_zero * tx_id")               \
+  X(PI_CD_DEF_NEXT_TXID, ZKE_ASSERT, "pi_circuit.py:234 is_tx_id_zero * next.tx_id")             \
+  X(PI_CD_DEF_FINAL, ZKE_ASSERT, "pi_circuit.py:235 is_tx_id_zero * is_final")                   \
+  X(PI_CD_DEF_GAS, ZKE_ASSERT, "pi_circuit.py:236 is_tx_id_zero * calldata_gas_cost")            \
+  X(PI_CD_U16, ZKE_UNSAT, "pi_circuit.py:252-256 lookup(FixedU16Row, tx_id_not_equal_to_next * is_tx_id_next_nonzero * (diff - 1))") \
+  X(PI_CD_IDX_SAME, ZKE_ASSERT, "pi_circuit.py:258-260,279 same tx: next.index == index + 1")    \
+  X(PI_CD_IDX_NEXT, ZKE_ASSERT, "pi_circuit.py:261-263,280 next tx: next.index == 0")            \
+  X(PI_CD_GAS_SAME, ZKE_ASSERT, "pi_circuit.py:264-266,281 same tx: next.gas == gas + gas_cost_next") \
+  X(PI_CD_GAS_NEXT, ZKE_ASSERT, "pi_circuit.py:267-271,282 next tx: next.gas == gas_cost_next")  \
+  X(PI_CD_GAS_LAST, ZKE_ASSERT, "pi_circuit.py:272,283 padding next: next.gas == 0")             \
+  X(PI_CD_FINAL_SAME, ZKE_ASSERT, "pi_circuit.py:273,284 same tx: is_final == 0")                \
+  X(PI_CD_FINAL_NEXT, ZKE_ASSERT, "pi_circuit.py:274-276,285 next tx: is_final == 1")            \
+  X(PI_CD_START_INDEX, ZKE_ASSERT, "pi_circuit.py:291 calldata start: index == 0")               \
+  X(PI_CD_START_GAS, ZKE_ASSERT, "pi_circuit.py:292-294 calldata start: gas == gas_cost")        \
+  X(PI_TX_CDL_INV, ZKE_ASSERT, "pi_circuit.py:298 (tag - CallDataLength) * (1 - tx_id_inv * (tag - CallDataLength)) == 0") \
+  X(PI_TX_VALUE_INV, ZKE_ASSERT, "pi_circuit.py:299-303 value.lo * (1 - tx_value_lo_inv * value.lo) == 0") \
+  X(PI_TX_ZERO_COST, ZKE_ASSERT, "pi_circuit.py:311 CallDataLength == 0 => next row's CallDataGasCost == 0") \
+  X(PI_TX_GAS_LOOKUP, ZKE_UNSAT, "pi_circuit.py:312-318 lookup(TxCallDataGasCostAccRow): no row") \
+  X(PI_TX_GAS_AMBIG, ZKE_AMBIG, "pi_circuit.py:312-318 lookup(TxCallDataGasCostAccRow): more than one row") \
+  X(PI_WD_NEXT_ID, ZKE_ASSERT, "pi_circuit.py:321-322 next.withdrawal.id == withdrawal.id + 1")  \
+  X(PI_WD_AMOUNT, ZKE_ASSERT, "pi_circuit.py:323 withdrawal.amount != 0")
+
+enum zk_pi_constraint { ZK_PI_CONSTRAINTS(ZK_ENUM_ENTRY) PI_N_CONSTRAINTS };
+
 #endif /* ZK_CONSTRAINTS_H */

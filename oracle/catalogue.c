@@ -9,6 +9,7 @@ static const int kState[] = {ZK_STATE_CONSTRAINTS(CLS)};
 static const int kExp[] = {ZK_EXP_CONSTRAINTS(CLS)};
 static const int kTx[] = {ZK_TX_CONSTRAINTS(CLS)};
 static const int kSig[] = {ZK_SIG_CONSTRAINTS(CLS)};
+static const int kPi[] = {ZK_PI_CONSTRAINTS(CLS)};
 int orc_n_constraints(int circuit) {
   switch (circuit) {
     case 0: return BC_N_CONSTRAINTS;
@@ -18,6 +19,7 @@ int orc_n_constraints(int circuit) {
     case 4: return XP_N_CONSTRAINTS;
     case 5: return TX_N_CONSTRAINTS;
     case 6: return SG_N_CONSTRAINTS;
+    case 7: return PI_N_CONSTRAINTS;
     default: return 0;
   }
 }
@@ -26,5 +28,6 @@ int orc_constraint_class(int circuit, int idx) {
   if (circuit == 4) return kExp[idx];
   if (circuit == 5) return kTx[idx];
   if (circuit == 6) return kSig[idx];
+  if (circuit == 7) return kPi[idx];
   return circuit == 0 ? kBytecode[idx] : circuit == 1 ? kState[idx] : circuit == 2 ? kCopy[idx] : kEvm[idx];
 }

@@ -1467,6 +1467,159 @@ def exp_cases():
     print(f"exp: {tot} corruptions, {nfail} failing")
 
 
+# --------------------------------------------------------------------------- public-inputs circuit
+PI_COLS = 28
+
+
+def pi_row_ints(x):
+    """pi_circuit.Row -> the 28 cells of include/zkcheck.h ZK_CIRCUIT_PI"""
+    t, wd = x.tx_table, x.withdrawal_table
+    addr = wd.address
+    a_lo, a_hi = (n_of(addr.lo), n_of(addr.hi)) if hasattr(addr, "lo") else (n_of(addr), 0)
+    return [n_of(x.q_bytes_last), n_of(x.q_tx_table), n_of(x.q_tx_calldata), n_of(x.q_tx_calldata_start),
+            n_of(x.q_rpi_keccak_lookup), n_of(x.q_rpi_value_start), n_of(x.tx_id_inv), n_of(x.tx_value_lo_inv),
+            n_of(x.tx_id_diff_inv), n_of(x.calldata_gas_cost), n_of(x.is_final), n_of(x.q_withdrawal_table),
+            n_of(x.rpi_bytes), n_of(x.rpi_bytes_keccakrlc), n_of(x.rpi_value_lc), n_of(x.rpi_digest_word.lo),
+            n_of(x.rpi_digest_word.hi), n_of(x.q_rpi_byte_enable), n_of(t.tx_id), n_of(t.tag), n_of(t.index),
+            n_of(t.value.lo), n_of(t.value.hi), n_of(wd.id), n_of(wd.validator_id), a_lo, a_hi, n_of(wd.amount)]
+
+
+def pi_reference_runner():
+    """(run_rows, row_from, tables_from): evaluate the reference's check_row on cell vectors"""
+    from zkevm_specs import pi_circuit as pc
+    from zkevm_specs.util import FQ, Word, WordOrValue
+
+    def W(lo, hi):
+        return Word((FQ(lo), FQ(hi)), check=False)
+
+    def row_from(v, kt):
+        val = WordOrValue(FQ(v[21]))
+        val.hi = FQ(v[22])
+        f = [FQ(x) for x in v]
+        return pc.Row(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10], f[11], f[12], f[13], f[14],
+                      W(v[15], v[16]), f[17], kt, pc.TxTableRow(f[18], f[19], f[20], val),
+                      pc.WithdrawalTableRow(f[23], f[24], W(v[25], v[26]), f[27]))
+
+    def tables_from(K, G):
+        kt = pc.KeccakTable()
+        kt.table = set((FQ(k[0]), FQ(k[1]), FQ(k[2]), W(k[3], k[4])) for k in K)
+        gas = set(pc.TxCallDataGasCostAccRow(FQ(g[0]), FQ(g[1]), FQ(g[2])) for g in G)
+        return kt, gas
+
+    u16 = set(pc.FixedU16Row(FQ(i)) for i in range(1 << 16))
+
+    def run_rows(R, K, G, circuit_len, which):
+        """first failing row among `which` (ascending), as the loop of verify_circuit (pi_circuit.py:447-459)"""
+        kt, gas = tables_from(K, G)
+        n = len(R)
+        for i in sorted(which):
+            try:
+                pc.check_row(row_from(R[i], kt), row_from(R[(i + 1) % n], kt), gas, u16, kt, circuit_len)
+            except Exception as e:  # noqa: BLE001
+                return i, type(e).__name__
+        return -1, ""
+
+    return run_rows
+
+
+def pi_cases():
+    """Public-inputs circuit: witnesses built by the reference's public_data2witness (pi_circuit.py:839-1073) from
+    seeded random PublicData (the recipe of tests/test_public_inputs.py:66-128), checked by the reference's check_row
+    under the loop of verify_circuit; negatives are single-cell corruptions of the witness, the keccak table and the
+    calldata gas-cost table."""
+    from zkevm_specs import pi_circuit as pc
+    from zkevm_specs.util import U64, U160, U256
+
+    rng = random.Random(12)
+    run_rows = pi_reference_runner()
+
+    def rand_block():
+        r256 = lambda: U256(rng.randrange(1 << 256))  # noqa: E731
+        r64 = lambda: U64(rng.randrange(1 << 64))  # noqa: E731
+        return pc.Block(hash=r256(), parent_hash=r256(), uncle_hash=r256(), coinbase=U160(rng.randrange(1 << 160)),
+                        state_root=r256(), tx_hash=r256(), receipt_hash=r256(), bloom=rng.randbytes(256), prev_randao=r256(),
+                        number=r64(), gas_limit=r64(), gas_used=r64(), time=r64(), extra=bytes([]), mix_digest=r256(),
+                        nonce=r64(), base_fee=U256(0), withdrawals_root=r256())
+
+    def rand_tx(data):
+        return pc.Transaction(nonce=U64(rng.randrange(1 << 64)), gas_price=U256(rng.randrange(1 << 256)),
+                              gas=U64(rng.randrange(1 << 64)), from_addr=U160(rng.randrange(1 << 160)),
+                              to_addr=U160(rng.randrange(1 << 160)), value=U256(rng.randrange(1 << 256)), data=data,
+                              tx_sign_hash=U256(rng.randrange(1 << 256)))
+
+    def calldata(n):
+        return bytes(0 if rng.random() < 0.3 else rng.randrange(1, 256) for _ in range(n))
+
+    scen = {
+        # name: (MAX_TXS, MAX_CALLDATA_BYTES, MAX_WITHDRAWALS, calldata lengths of the txs, withdrawals)
+        "basic": (2, 8, 2, [5], 2),
+        "full": (3, 40, 3, [17, 0, 23], 3),
+        "one_empty": (2, 16, 2, [0], 1),
+    }
+    out = {"names": np.array(list(scen.keys()))}
+    tot = nfail = 0
+    for name, (max_txs, max_cd, max_wd, lens, n_wd) in scen.items():
+        pd = pc.PublicData(U64(rng.randrange(1, 128)), rand_block(), U256(rng.randrange(1 << 256)),
+                           [U256(rng.randrange(1 << 256)) for _ in range(256)], [rand_tx(calldata(n)) for n in lens],
+                           [pc.Withdrawal(id=k, validator_id=U64(rng.randrange(1 << 64)), address=U160(rng.randrange(1 << 160)),
+                                          amount=U64(rng.randrange(1, 1 << 64))) for k in range(n_wd)])
+        w = pc.public_data2witness(pd, max_txs, max_cd, max_wd)
+        pc.verify_circuit(w, max_txs, max_cd, max_wd)  # the reference accepts its own witness (incl. copy constraints)
+        w = pc.public_data2witness(pd, max_txs, max_cd, max_wd)  # verify_circuit consumed copy_constrains
+        R = [pi_row_ints(x) for x in w.rows]
+        K = sorted([n_of(k[0]), n_of(k[1]), n_of(k[2]), n_of(k[3].lo), n_of(k[3].hi)] for k in w.keccak_table.table)
+        G = sorted([n_of(g.tx_id), n_of(g.is_final), n_of(g.gas_cost_acc)] for g in w.calldata_gas_cost_table)
+        n = len(R)
+        assert n == w.circuit_len
+        assert run_rows(R, K, G, w.circuit_len, range(n)) == (-1, "")
+        lookups = [i for i in range(n) if R[i][4] or R[i][1]]
+        hot = 10 * max_txs + 1 + max_cd + max_wd + 2  # tx-table, calldata and withdrawal rows sit at the top
+        muts = [(0, -1, 0, 0, -1, "")]
+        for k in range(260):
+            kind = 0 if k < 200 else (1 if k < 230 else 2)
+            if kind == 0:
+                i = rng.randrange(hot) if rng.random() < 0.75 else rng.randrange(n)
+                if rng.random() < 0.05:
+                    i = n - 1 - rng.randrange(3)
+                col = rng.randrange(PI_COLS)
+                old = R[i][col]
+                v = (1 - old) if (old in (0, 1) and rng.random() < 0.5) else corrupt_value(rng, old)
+                R2 = [list(x) for x in (R[(i - 1) % n], R[i])]
+                R2[1][col] = v
+                Rm = list(R)
+                Rm[i] = R2[1]
+                fr_, ex_ = run_rows(Rm, K, G, w.circuit_len, {(i - 1) % n, i})
+            elif kind == 1:
+                i, col = rng.randrange(len(K)), rng.randrange(5)
+                v = corrupt_value(rng, K[i][col])
+                K2 = [list(x) for x in K]
+                K2[i][col] = v
+                fr_, ex_ = run_rows(R, K2, G, w.circuit_len, lookups)
+            else:
+                i, col = rng.randrange(len(G)), rng.randrange(3)
+                v = corrupt_value(rng, G[i][col])
+                G2 = [list(x) for x in G]
+                G2[i][col] = v
+                fr_, ex_ = run_rows(R, K, G2, w.circuit_len, lookups)
+            muts.append((kind, i, col, v, fr_, ex_))
+            tot += 1
+            nfail += fr_ >= 0
+        out[f"{name}/rows"] = to_matrix(R)
+        out[f"{name}/keccak"] = to_matrix(K)
+        out[f"{name}/gas"] = to_matrix(G)
+        out[f"{name}/circuit_len"] = np.array([w.circuit_len], dtype=np.int64)
+        out[f"{name}/params"] = np.array([max_txs, max_cd, max_wd], dtype=np.int64)
+        out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_row"] = np.array([m[1] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_col"] = np.array([m[2] for m in muts], dtype=np.int64)
+        out[f"{name}/mut_val"] = np.array([limbs(m[3]) for m in muts], dtype=np.uint64)
+        out[f"{name}/exp_row"] = np.array([m[4] for m in muts], dtype=np.int64)
+        out[f"{name}/exp_exc"] = np.array([m[5] for m in muts])
+        print(name, n, "rows", len(muts), "vectors", "failing", sum(1 for m in muts if m[4] >= 0))
+    np.savez_compressed(os.path.join(HERE, "pi.npz"), **out)
+    print(f"pi: {tot} corruptions, {nfail} failing")
+
+
 # --------------------------------------------------------------------------- tx circuit (Fr parts)
 def tx_cases():
     """The reference's tx_circuit.verify_circuit (tx_circuit.py:253-289) run UNMODIFIED on witnesses
@@ -2043,7 +2196,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "exp", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():
