@@ -18,8 +18,9 @@ of the bytecode / rw tables on the device, then check every execution step.
              Python and absent on this box) on a bounded sample of the same workload
 Extra objects on the same line (`--no-extras` skips them; they are not inside the main timed region):
   typed          : the same check with data-independent column widths (packing.TYPE_WIDTHS)
-  circuits       : BASELINE cfg3 (state 2^18 rows), cfg4's copy circuit (2^20 rows) and the bytecode
-                   circuit (2^19 rows) on canonical 32-byte cells, each with its own roofline
+  circuits       : BASELINE cfg3 (state 2^18 rows), cfg4's copy circuit (2^20 rows), the bytecode circuit
+                   (2^19 rows) and the public-inputs circuit (64 txs, 2^18 calldata bytes: 2.9e5 rows) on
+                   canonical 32-byte cells, each with its own roofline
   strong_scaling : ONE 2^20-step witness split over the N ranks (tables replicated, step shards with
                    a halo step, one collective) — north_star's "2^20-row witness at 1/2/4/8 B200"
   block_trace    : the realistic variant — ONE whole-block trace (4,096 transactions over 1,024 contracts: BeginTx ..
@@ -385,6 +386,36 @@ def bench_bytecode(h, k, reps):
             "index_ms": i_ms, "roofline": roofline_of(h, c_ms, 32 * (e - b) * 12, kernel="k_check_bytecode<L_CANON>")}
 
 
+def bench_pi(h, max_txs, max_calldata, max_wd, reps, seed=7):
+    """public-inputs circuit (pi_circuit.check_row): one row per raw public-input byte, row-sharded over the ranks"""
+    from zkevm_specs_b200 import pi_circuit as pc
+    from zkevm_specs_b200 import synth
+    native, ctx = h.native, h.ctx
+    t0 = time.perf_counter()
+    w = pc.public_data2witness(synth.pi_public_data(max_txs * 3 // 4, max_calldata, max_wd, seed=seed), max_txs, max_calldata, max_wd)
+    gen_s = time.perf_counter() - t0
+    n = w.cells.shape[1]
+    K, G = w.keccak_table.matrix(), w.gas_matrix()
+    ctx.set_challenge(native.CHALLENGE_PI_KECCAK, pc.keccak_rand.n)
+    ctx.set_challenge(native.CHALLENGE_PI_BYTE_BASE, pc.byte_pow_base.n)
+    ctx.set_challenge(native.PARAM_PI_CIRCUIT_LEN, w.circuit_len)
+    ctx.upload_table(native.TABLE_KECCAK, K, stream=h.stream)
+    ctx.upload_table(native.TABLE_CALLDATA_GAS, G, stream=h.stream)
+    b, e = shard(n, h.rank, h.world)
+    if h.world == 1:
+        ctx.upload_columns(native.CIRCUIT_PI, w.cells, stream=h.stream)
+        rng = (0, n, 0, native.FLAG_WRAP)
+    else:  # rows b .. e (rotation +1)
+        ctx.upload_columns(native.CIRCUIT_PI, take_rows(w.cells, np.arange(b, e + 1) % n), stream=h.stream)
+        rng = (0, e - b, b, 0)
+    ms = h.sharded_pass(native.CIRCUIT_PI, *rng, reps)
+    i_ms, c_ms = h.phases(native.CIRCUIT_PI, *rng, min(reps, 10))
+    byt = 32 * ((e - b) * 28 + K.shape[1] * 5 + G.shape[1] * 3)
+    return {"circuit": "pi", "rows": n, "rows_per_gpu": e - b, "gas_table_rows": int(G.shape[1]), "ms_per_pass": ms,
+            "rows_per_s": n / (ms / 1e3), "index_ms": i_ms, "host_generate_s": gen_s,
+            "roofline": roofline_of(h, c_ms, byt, kernel="k_check_pi<L_CANON>")}
+
+
 def bench_block(h, n_txs, groups, n_contracts, reps, seed=6):
     """the realistic variant: ONE whole-block trace (synth.block_trace: BeginTx .. STOP, EndTx per transaction over
     `n_contracts` contracts, EndBlock last) checked with the first / last step flags; step-sharded over the ranks"""
@@ -425,7 +456,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip typed / circuits / strong_scaling / cfg4 / cfg5")
-    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode", "block"], default="evm",
+    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode", "block", "pi"], default="evm",
                     help="evm: the bench contract's line.  state / copy / bytecode: only that row circuit (canonical "
                          "storage; for profiling), printed as a JSON line of its own")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
@@ -460,7 +491,7 @@ def main():
         if args.workload == "block":
             h.ctx.upload_table(native.TABLE_FIXED, fixed_table_matrix(), stream=stream)
         d = {"state": lambda: bench_state(h, 1 << 18, reps), "copy": lambda: bench_copy(h, 512, 1024, reps),
-             "bytecode": lambda: bench_bytecode(h, 19, reps), "block": lambda: bench_block(h, 4096, 64, 1024, reps)}[args.workload]()
+             "bytecode": lambda: bench_bytecode(h, 19, reps), "pi": lambda: bench_pi(h, 64, 1 << 18, 16, reps), "block": lambda: bench_block(h, 4096, 64, 1024, reps)}[args.workload]()
         if rank == 0:
             print(json.dumps({"workload": args.workload, "n_gpus": world, "storage": "canonical", **d}))
         if world > 1:
@@ -662,7 +693,8 @@ def main():
                                         "rows_per_s": value, "index_build_ms": idx_ms, "check_ms": chk}
         extras["block_trace"] = bench_block(h, 4096, 64, 1024, reps)
         # row circuits on canonical cells: cfg3, cfg4 (copy 2^20 rows, sharded over the ranks), bytecode 2^19
-        circuits = [bench_state(h, 1 << 18, reps), bench_copy(h, 512, 1024, reps), bench_bytecode(h, 19, reps)]
+        circuits = [bench_state(h, 1 << 18, reps), bench_copy(h, 512, 1024, reps), bench_bytecode(h, 19, reps),
+                    bench_pi(h, 64, 1 << 18, 16, reps)]
         extras["circuits"] = circuits
         extras["cfg4"] = {"copy_rows": circuits[1]["rows"], "rows_per_s": circuits[1]["rows_per_s"], "ms_per_pass": circuits[1]["ms_per_pass"],
                           "sharding": f"copy rows over {world} rank(s), halos +1/+2, rw / tx tables replicated"}

@@ -65,7 +65,15 @@ enum {
                               msg_hash lo/hi, Word(msg_hash_bytes) lo/hi, is_valid, sig_r lo/hi, sig_s
                               lo/hi, the ECDSA chip's r lo/hi and s lo/hi; row flags bit 1 = the
                               (third-party) ecdsa_chip.verify() returned True; same keccak table */
-  ZK_N_CIRCUITS = 7
+  ZK_CIRCUIT_PI = 7,       /* 28 cells/row, rotation {0,+1}: pi_circuit.Row (pi_circuit.py:105-133), Words as (lo, hi), the
+                              tx-table and withdrawal-table rows a Row carries flattened behind it: q_bytes_last,
+                              q_tx_table, q_tx_calldata, q_tx_calldata_start, q_rpi_keccak_lookup, q_rpi_value_start,
+                              tx_id_inv, tx_value_lo_inv, tx_id_diff_inv, calldata_gas_cost, is_final,
+                              q_withdrawal_table, rpi_bytes, rpi_bytes_keccakrlc, rpi_value_lc, rpi_digest_word lo/hi,
+                              q_rpi_byte_enable, tx (tx_id, tag, index, value lo/hi), withdrawal (id, validator_id,
+                              address lo/hi, amount); lookups: ZK_TABLE_KECCAK, ZK_TABLE_CALLDATA_GAS; parameters:
+                              ZK_CHALLENGE_PI_KECCAK, ZK_CHALLENGE_PI_BYTE_BASE, ZK_PARAM_PI_CIRCUIT_LEN */
+  ZK_N_CIRCUITS = 8
 };
 
 /* ---- lookup tables ---------------------------------------------------------------- */
@@ -80,7 +88,8 @@ enum {
   ZK_TABLE_MPT = 7,      /* 12 cells MPTTableRow       table.py:460-468 */
   ZK_TABLE_PUSH = 8,     /* 2 cells  push table        bytecode_circuit.py:174-178 (byte, push_size) */
   ZK_TABLE_WITHDRAWAL = 9, /* 4 cells WithdrawalTableRow table.py:429-435 (id, validator_id, address, amount) */
-  ZK_N_TABLES = 10
+  ZK_TABLE_CALLDATA_GAS = 10, /* 3 cells TxCallDataGasCostAccRow pi_circuit.py:66-70 (tx_id, is_final, gas_cost_acc) */
+  ZK_N_TABLES = 11
 };
 
 /* ---- challenges ------------------------------------------------------------------- */
@@ -89,7 +98,10 @@ enum {
   ZK_CHALLENGE_LOOKUP = 1, /* RLC base used to compress table rows into hash keys;
                               any value gives the same pass/fail (matches are confirmed
                               exactly), it only affects bucket placement */
-  ZK_N_CHALLENGES = 2
+  ZK_CHALLENGE_PI_KECCAK = 2,    /* pi_circuit.keccak_rand (a module global of the reference, pi_circuit.py:836) */
+  ZK_CHALLENGE_PI_BYTE_BASE = 3, /* pi_circuit.byte_pow_base (pi_circuit.py:834) */
+  ZK_PARAM_PI_CIRCUIT_LEN = 4,   /* Witness.circuit_len (pi_circuit.py:333), a circuit parameter held like a challenge */
+  ZK_N_CHALLENGES = 5
 };
 
 /* ---- zk_check flags ---------------------------------------------------------------- */

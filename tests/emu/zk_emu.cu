@@ -14,6 +14,7 @@
 #include "../../zkevm-specs_b200/csrc/copy.cu"
 #include "../../zkevm-specs_b200/csrc/evm.cu"
 #include "../../zkevm-specs_b200/csrc/exp.cu"
+#include "../../zkevm-specs_b200/csrc/pi.cu"
 #include "../../zkevm-specs_b200/csrc/state.cu"
 #include "../../zkevm-specs_b200/csrc/tx.cu"
 #include "../../zkevm-specs_b200/csrc/keccak.cuh"
@@ -350,6 +351,27 @@ extern "C" int emu_check_exp(const uint64_t* rows, uint64_t n_rows, uint64_t row
   ResultDev res;
   init_result(res, first_fail, fail_count, XP_N_CONSTRAINTS);
   for (u64 i = row_begin; i < row_end; i++) check_exp_row<L_ANY>(w, rg, res, i);
+  return 0;
+}
+
+extern "C" int emu_check_pi(const uint64_t* rows, uint64_t n_rows, const uint64_t* keccak, uint64_t n_keccak,
+                            const uint64_t* gas, uint64_t n_gas, const uint64_t keccak_rand[4], const uint64_t byte_base[4],
+                            const uint64_t circuit_len[4], uint64_t row_begin, uint64_t row_end, uint32_t cflags,
+                            const uint64_t challenge[4], uint32_t* first_fail, uint64_t* fail_count) {
+  const Fr ch{{challenge[0], challenge[1], challenge[2], challenge[3]}};
+  const u32 kk[5] = {0, 1, 2, 3, 4}, gk[3] = {0, 1, 2};
+  IndexStore s1, s2;
+  IndexDev kix = build_index((const u64*)keccak, n_keccak, 5, kk, 5, ch, s1);
+  IndexDev gix = build_index((const u64*)gas, n_gas, 3, gk, 3, ch, s2);
+  Store ws;
+  WitnessDev w = make_witness(ws, (const u64*)rows, n_rows, 28, nullptr);
+  ResultDev res;
+  init_result(res, first_fail, fail_count, PI_N_CONSTRAINTS);
+  PiParams pp{fr_to_mont(Fr{{keccak_rand[0], keccak_rand[1], keccak_rand[2], keccak_rand[3]}}),
+              fr_to_mont(Fr{{byte_base[0], byte_base[1], byte_base[2], byte_base[3]}}),
+              Fr{{circuit_len[0], circuit_len[1], circuit_len[2], circuit_len[3]}}};
+  CheckRange rg{row_begin, row_end, 0, cflags};
+  for (u64 i = row_begin; i < row_end; i++) check_pi_row<L_ANY>(w, rg, kix, gix, pp, res, i);
   return 0;
 }
 

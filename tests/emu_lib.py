@@ -198,3 +198,22 @@ def check_sig(rows, flags, keccak, r, row_begin=0, row_end=None, challenge=None)
                              c(keccak.shape[1]), _p(rr), c(row_begin), c(row_end), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+def check_pi(rows, keccak, gas, circuit_len, keccak_rand=255, byte_pow_base=255, row_begin=0, row_end=None, cflags=1, challenge=None):
+    rows, keccak, gas = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak, gas)]
+    ff = np.zeros(64, dtype=np.uint32)
+    fc = np.zeros(64, dtype=np.uint64)
+    c = ctypes.c_uint64
+    ch = CHALLENGE if challenge is None else np.ascontiguousarray(challenge, dtype=np.uint64)
+    if row_end is None:
+        row_end = rows.shape[1]
+
+    def lm(v):
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+    rc = lib().emu_check_pi(_p(rows), c(rows.shape[1]), _p(keccak), c(keccak.shape[1]), _p(gas), c(gas.shape[1]),
+                            _p(lm(keccak_rand)), _p(lm(byte_pow_base)), _p(lm(circuit_len)), c(row_begin), c(row_end),
+                            ctypes.c_uint32(cflags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
+    assert rc == 0
+    return ff, fc

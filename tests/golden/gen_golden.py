@@ -1554,7 +1554,7 @@ def pi_cases():
         # name: (MAX_TXS, MAX_CALLDATA_BYTES, MAX_WITHDRAWALS, calldata lengths of the txs, withdrawals)
         "basic": (2, 8, 2, [5], 2),
         "full": (3, 40, 3, [17, 0, 23], 3),
-        "one_empty": (2, 16, 2, [0], 1),
+        "one_empty": (2, 16, 2, [0], 2),
     }
     out = {"names": np.array(list(scen.keys()))}
     tot = nfail = 0
@@ -1607,6 +1607,19 @@ def pi_cases():
         out[f"{name}/rows"] = to_matrix(R)
         out[f"{name}/keccak"] = to_matrix(K)
         out[f"{name}/gas"] = to_matrix(G)
+        import json
+        b = pd.block
+        out[f"{name}/public_data"] = np.array(json.dumps({
+            "chain_id": int(pd.chain_id), "state_root_prev": int(pd.state_root_prev), "block_hashes": [int(h) for h in pd.block_hashes],
+            "block": {k: (getattr(b, k).hex() if isinstance(getattr(b, k), bytes) else int(getattr(b, k)))
+                      for k in ("hash", "parent_hash", "uncle_hash", "coinbase", "state_root", "tx_hash", "receipt_hash", "bloom",
+                                "prev_randao", "number", "gas_limit", "gas_used", "time", "extra", "mix_digest", "nonce", "base_fee",
+                                "withdrawals_root")},
+            "txs": [{"nonce": int(t.nonce), "gas_price": int(t.gas_price), "gas": int(t.gas), "from_addr": int(t.from_addr),
+                     "to_addr": int(t.to_addr), "value": int(t.value), "data": bytes(t.data).hex(), "tx_sign_hash": int(t.tx_sign_hash)}
+                    for t in pd.txs],
+            "withdrawals": [{"id": int(x.id), "validator_id": int(x.validator_id), "address": int(x.address), "amount": int(x.amount)}
+                            for x in pd.withdrawals]}))
         out[f"{name}/circuit_len"] = np.array([w.circuit_len], dtype=np.int64)
         out[f"{name}/params"] = np.array([max_txs, max_cd, max_wd], dtype=np.int64)
         out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)

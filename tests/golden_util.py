@@ -278,3 +278,23 @@ def evm11_vectors():
                 keep = [q for q in range(base["rw"].shape[1]) if q != i]
                 w["rw"] = np.ascontiguousarray(base["rw"][:, keep, :]); w["rw_flags"] = base["rw_flags"][keep]
             yield name, k, w, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+
+
+def pi_vectors():
+    """public-inputs circuit: yield (case, k, rows[28][n][4], keccak[5][m][4], gas[3][g][4], circuit_len, exp_row, exp_exc);
+    the yielded matrices are only valid until the next iteration (corruptions are applied in place and undone)"""
+    z = np.load(os.path.join(GOLDEN, "pi.npz"))
+    for name in z["names"]:
+        name = str(name)
+        R, K, G = z[f"{name}/rows"].copy(), z[f"{name}/keccak"].copy(), z[f"{name}/gas"].copy()
+        clen = int(z[f"{name}/circuit_len"][0])
+        for k in range(len(z[f"{name}/mut_row"])):
+            kind, i, c = int(z[f"{name}/mut_kind"][k]), int(z[f"{name}/mut_row"][k]), int(z[f"{name}/mut_col"][k])
+            tgt = (R, K, G)[kind]
+            old = None
+            if i >= 0:
+                old = tgt[c, i, :].copy()
+                tgt[c, i, :] = z[f"{name}/mut_val"][k]
+            yield name, k, R, K, G, clen, int(z[f"{name}/exp_row"][k]), str(z[f"{name}/exp_exc"][k])
+            if old is not None:
+                tgt[c, i, :] = old

@@ -220,3 +220,23 @@ def check_sig(rows, flags, keccak, r, row_begin=0, row_end=None):
                              c(keccak.shape[1]), p64(rr), c(row_begin), c(row_end), ff.ctypes.data_as(U32P), p64(fc))
     assert rc == 0
     return ff, fc
+
+
+PI_KECCAK_RAND = 255  # module globals of the reference, pi_circuit.py:834-836
+PI_BYTE_POW_BASE = 255
+
+
+def check_pi(rows, keccak, gas, circuit_len, keccak_rand=PI_KECCAK_RAND, byte_pow_base=PI_BYTE_POW_BASE, row_begin=0, row_end=None):
+    """public-inputs circuit (oracle/pi.c): rows uint64[28][n][4], keccak uint64[5][k][4], gas uint64[3][g][4]"""
+    rows, keccak, gas = [np.ascontiguousarray(a, dtype=np.uint64) for a in (rows, keccak, gas)]
+    n = lib().orc_n_constraints(7)
+    ff = np.zeros(n, dtype=np.uint32)
+    fc = np.zeros(n, dtype=np.uint64)
+    c = ctypes.c_uint64
+    if row_end is None:
+        row_end = rows.shape[1]
+    rc = lib().orc_check_pi(p64(rows), c(rows.shape[1]), p64(keccak), c(keccak.shape[1]), p64(gas), c(gas.shape[1]),
+                            p64(limbs(keccak_rand)), p64(limbs(byte_pow_base)), p64(limbs(circuit_len)), c(row_begin), c(row_end),
+                            ff.ctypes.data_as(U32P), p64(fc))
+    assert rc == 0
+    return ff, fc

@@ -167,6 +167,22 @@ def test_emu_exp_equals_oracle_on_goldens():
         assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, np.nonzero(ff[:n] != off))
 
 
+def test_emu_pi_equals_oracle_on_goldens():
+    """public-inputs circuit (783 reference vectors): canonical and packed storage"""
+    n = oracle_lib.lib().orc_n_constraints(7)
+    for packed in (False, True):
+        emu_lib.set_packed(packed)
+        try:
+            for name, k, R, K, G, clen, exp_row, exp_exc in golden_util.pi_vectors():
+                if packed and k % 4:
+                    continue
+                ff, fc = emu_lib.check_pi(R, K, G, clen)
+                off, ofc = oracle_lib.check_pi(R, K, G, clen)
+                assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k, packed, np.nonzero(ff[:n] != off))
+        finally:
+            emu_lib.set_packed(False)
+
+
 def test_emu_packed_columns_equal_oracle_on_every_golden_family():
     """the packed narrow-column storage (include/zkcheck.h "packed columns", fr.cuh:ld_col): every
     matrix stored at per-column minimal widths gives the oracle's arrays on every golden vector"""

@@ -18,6 +18,7 @@
 #include "copy.cu"
 #include "evm.cu"
 #include "exp.cu"
+#include "pi.cu"
 #include "tx.cu"
 #include "state.cu"
 #include "circuit.cuh"
@@ -38,9 +39,10 @@ static const ConstraintInfo kStateInfo[] = {ZK_STATE_CONSTRAINTS(ZK_INFO_ENTRY)}
 static const ConstraintInfo kExpInfo[] = {ZK_EXP_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kTxInfo[] = {ZK_TX_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kSigInfo[] = {ZK_SIG_CONSTRAINTS(ZK_INFO_ENTRY)};
+static const ConstraintInfo kPiInfo[] = {ZK_PI_CONSTRAINTS(ZK_INFO_ENTRY)};
 
-static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21, 14, 21};
-static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2, 4};
+static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21, 14, 21, 28};
+static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2, 4, 3};
 
 static const ConstraintInfo* circuit_info(int circuit, int* n) {
   switch (circuit) {
@@ -51,6 +53,7 @@ static const ConstraintInfo* circuit_info(int circuit, int* n) {
     case ZK_CIRCUIT_EXP: *n = XP_N_CONSTRAINTS; return kExpInfo;
     case ZK_CIRCUIT_TX: *n = TX_N_CONSTRAINTS; return kTxInfo;
     case ZK_CIRCUIT_SIG: *n = SG_N_CONSTRAINTS; return kSigInfo;
+    case ZK_CIRCUIT_PI: *n = PI_N_CONSTRAINTS; return kPiInfo;
     default: *n = 0; return nullptr;
   }
 }
@@ -832,6 +835,26 @@ static int check_exp(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   return 0;
 }
 
+static int check_pi(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
+  const Matrix& m = ctx->circ[ZK_CIRCUIT_PI];
+  if (!(rg.flags & ZK_FLAG_WRAP) && rg.row_end + 1 > m.n_rows)
+    return fail_msg(ctx, "pi rows [b,e) need row e resident (rotation +1) unless ZK_FLAG_WRAP");
+  const u32 kk[5] = {0, 1, 2, 3, 4}, gk[3] = {0, 1, 2};
+  IndexDev kec_ix, gas_ix;
+  int rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_KECCAK, kk, 5, st, &kec_ix))) return rc;
+  if ((rc = ensure_index(ctx, ZK_TABLE_CALLDATA_GAS, gk, 3, st, &gas_ix))) return rc;
+  if ((rc = mark_indexes_ready(ctx))) return rc;
+  PiParams pp{fr_to_mont(ctx->chal[ZK_CHALLENGE_PI_KECCAK]), fr_to_mont(ctx->chal[ZK_CHALLENGE_PI_BYTE_BASE]),
+              ctx->chal[ZK_PARAM_PI_CIRCUIT_LEN]};
+  const u64 n = rg.row_end - rg.row_begin;
+  if (is_canonical(m)) k_check_pi<L_CANON><<<grid_persistent(ctx, k_check_pi<L_CANON>, 256, n), 256, 0, st>>>(witness_dev(m), rg, kec_ix, gas_ix, pp, res);
+  else k_check_pi<L_ANY><<<grid_persistent(ctx, k_check_pi<L_ANY>, 256, n), 256, 0, st>>>(witness_dev(m), rg, kec_ix, gas_ix, pp, res);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int check_state(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const Matrix& m = ctx->circ[ZK_CIRCUIT_STATE];
   if (!(rg.flags & ZK_FLAG_WRAP) && (rg.row_begin == 0 || rg.row_end + 1 > m.n_rows))
@@ -1051,6 +1074,7 @@ extern "C" int zk_check_async(zk_ctx* ctx, int circuit_id, uint64_t row_begin, u
     case ZK_CIRCUIT_EXP: rc = check_exp(ctx, rg, res, st); break;
     case ZK_CIRCUIT_TX: rc = check_tx(ctx, rg, res, st); break;
     case ZK_CIRCUIT_SIG: rc = check_tx(ctx, rg, res, st, true); break;
+    case ZK_CIRCUIT_PI: rc = check_pi(ctx, rg, res, st); break;
     default: return fail_msg(ctx, "circuit has no gate program in this build");
   }
   if (rc) return rc;

@@ -659,3 +659,25 @@ def block_trace(n_txs: int, groups_per_contract: int, n_contracts: int, seed: in
     return {"steps": steps, "n_steps": n_steps, "flags": 2 | 4, "bytecode": bytecode, "bytecode_src": src, "rw": rw, "rw_flags": rwf,
             "tx": tx, "tx_flags": txf, "block": block, "block_flags": bf, "wd": np.zeros((4, 0, 4), dtype=np.uint64),
             "copy": np.zeros((14, 0, 4), dtype=np.uint64), "keccak": np.zeros((5, 0, 4), dtype=np.uint64)}
+
+
+def pi_public_data(n_txs: int, max_calldata: int, n_withdrawals: int, seed: int = 7):
+    """seeded random PublicData for the public-inputs circuit, the recipe of the reference's
+    tests/test_public_inputs.py:66-128 (rand_block / rand_tx / rand_withdrawal): `n_txs` transactions whose calldata
+    (30 % zero bytes) shares `max_calldata` bytes, `n_withdrawals` withdrawals with ids 0.. and a non-zero amount"""
+    from . import pi_circuit as pc
+
+    rng = np.random.default_rng(seed)
+    r256 = lambda: int.from_bytes(rng.bytes(32), "little")  # noqa: E731
+    r160 = lambda: int.from_bytes(rng.bytes(20), "little")  # noqa: E731
+    r64 = lambda: int(rng.integers(0, 1 << 63))  # noqa: E731
+    block = pc.Block(hash=r256(), parent_hash=r256(), uncle_hash=r256(), coinbase=r160(), state_root=r256(), tx_hash=r256(),
+                     receipt_hash=r256(), bloom=rng.bytes(256), prev_randao=r256(), number=r64(), gas_limit=r64(), gas_used=r64(),
+                     time=r64(), extra=b"", mix_digest=r256(), nonce=r64(), base_fee=0, withdrawals_root=r256())
+    txs = []
+    for _ in range(n_txs):
+        data = rng.integers(0, 256, int(rng.integers(0, max_calldata // max(1, n_txs) + 1)), dtype=np.uint8)
+        data[rng.random(len(data)) < 0.3] = 0
+        txs.append(pc.Transaction(r64(), r256(), r64(), r160(), r160(), r256(), bytes(data), r256()))
+    wds = [pc.Withdrawal(k, r64(), r160(), 1 + r64()) for k in range(n_withdrawals)]
+    return pc.PublicData(int(rng.integers(1, 128)), block, r256(), [r256() for _ in range(256)], txs, wds)
