@@ -25,6 +25,8 @@ Extra objects on the same line (`--no-extras` skips them; they are not inside th
                    a halo step, one collective) — north_star's "2^20-row witness at 1/2/4/8 B200"
   block_trace    : the realistic variant — ONE whole-block trace (4,096 transactions over 1,024 contracts: BeginTx ..
                    STOP, EndTx each, EndBlock last) checked with the first / last step flags
+  assign         : witness assignment on the device (bytecode 2^19 / state 2^18 / copy 2^20 rows from their compact host
+                   inputs) and the check of the narrow rows it leaves
   cfg4 / cfg5    : copy circuit 2^20 rows and the super circuit (evm + state + copy + bytecode, 2^22 rows
                    in total) row-sharded over the N ranks
 Multi-GPU (torchrun): rows are sharded, tables replicated, then ONE collective on the result vectors
@@ -416,6 +418,52 @@ def bench_pi(h, max_txs, max_calldata, max_wd, reps, seed=7):
             "roofline": roofline_of(h, c_ms, byt, kernel="k_check_pi<L_CANON>")}
 
 
+def bench_assign(h, reps):
+    """witness assignment on the device: per circuit, the time from the compact HOST inputs (raw code /
+    15 operation cells / copy events + bytes, pinned) to the resident witness, and the check of the narrow rows it leaves"""
+    import torch
+    from zkevm_specs_b200 import assign, packing, synth
+    native, ctx, stream = h.native, h.ctx, h.stream
+    out = {}
+
+    def timed_pair(assign_fn, circuit, n, flags):
+        for _ in range(2):
+            assign_fn()
+        a_ms = h.timed(assign_fn, reps) / reps
+        ctx.check_async(circuit, 0, n, 0, flags, stream)
+        h.check_pass(circuit)
+        i_ms, c_ms = h.phases(circuit, 0, n, 0, flags, min(reps, 10))
+        return a_ms, c_ms
+
+    b = synth.bytecode_circuit_rows(19, 8)
+    src = assign.bytecode_src(b["codes"])
+    ctx.set_challenge(native.CHALLENGE_KECCAK, b["r_int"])
+    ctx.upload_table(native.TABLE_PUSH, b["push"], stream=stream)
+    ctx.upload_table(native.TABLE_KECCAK, b["keccak"], stream=stream)
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in src.items()}
+    a_ms, c_ms = timed_pair(lambda: ctx.assign_bytecode_circuit(19, **{k: v.numpy() for k, v in pin.items()}, stream=stream),
+                            native.CIRCUIT_BYTECODE, 1 << 19, native.FLAG_WRAP)
+    out["bytecode"] = {"rows": 1 << 19, "assign_ms": a_ms, "check_narrow_ms": c_ms, "h2d_bytes": int(sum(v.nbytes for v in src.values())),
+                       "canonical_bytes": 32 * 12 << 19}
+    s = synth.state_rows(1 << 18, seed=3)
+    pm = packing.pack_matrix(assign.state_ops_from_rows(s["rows"]))
+    pm.buf = torch.from_numpy(pm.buf).pin_memory().numpy()
+    ctx.upload_table(native.TABLE_MPT, s["mpt"], stream=stream)
+    a_ms, c_ms = timed_pair(lambda: ctx.assign_state_circuit(pm, flags=s["flags"], stream=stream), native.CIRCUIT_STATE, 1 << 18,
+                            native.FLAG_WRAP)
+    out["state"] = {"rows": 1 << 18, "assign_ms": a_ms, "check_narrow_ms": c_ms, "h2d_bytes": int(pm.nbytes), "canonical_bytes": 32 * 57 << 18}
+    w = synth.copy_events(512, 1024)
+    n = w["copy"].shape[1]
+    ctx.set_challenge(native.CHALLENGE_KECCAK, w["r_int"])
+    ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"], stream=stream)
+    ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"], stream=stream)
+    ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"], stream=stream)
+    ev, data = torch.from_numpy(w["events"]).pin_memory().numpy(), torch.from_numpy(w["data"]).pin_memory().numpy()
+    a_ms, c_ms = timed_pair(lambda: ctx.assign_copy_circuit(ev, data, stream=stream), native.CIRCUIT_COPY, n, native.FLAG_WRAP)
+    out["copy"] = {"rows": n, "assign_ms": a_ms, "check_narrow_ms": c_ms, "h2d_bytes": int(ev.nbytes + data.nbytes), "canonical_bytes": 32 * 20 * n}
+    return out
+
+
 def bench_block(h, n_txs, groups, n_contracts, reps, seed=6):
     """the realistic variant: ONE whole-block trace (synth.block_trace: BeginTx .. STOP, EndTx per transaction over
     `n_contracts` contracts, EndBlock last) checked with the first / last step flags; step-sharded over the ranks"""
@@ -456,7 +504,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip typed / circuits / strong_scaling / cfg4 / cfg5")
-    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode", "block", "pi"], default="evm",
+    ap.add_argument("--workload", choices=["evm", "state", "copy", "bytecode", "block", "pi", "assign"], default="evm",
                     help="evm: the bench contract's line.  state / copy / bytecode: only that row circuit (canonical "
                          "storage; for profiling), printed as a JSON line of its own")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
@@ -491,7 +539,7 @@ def main():
         if args.workload == "block":
             h.ctx.upload_table(native.TABLE_FIXED, fixed_table_matrix(), stream=stream)
         d = {"state": lambda: bench_state(h, 1 << 18, reps), "copy": lambda: bench_copy(h, 512, 1024, reps),
-             "bytecode": lambda: bench_bytecode(h, 19, reps), "pi": lambda: bench_pi(h, 64, 1 << 18, 16, reps), "block": lambda: bench_block(h, 4096, 64, 1024, reps)}[args.workload]()
+             "bytecode": lambda: bench_bytecode(h, 19, reps), "pi": lambda: bench_pi(h, 64, 1 << 18, 16, reps), "assign": lambda: bench_assign(h, reps), "block": lambda: bench_block(h, 4096, 64, 1024, reps)}[args.workload]()
         if rank == 0:
             print(json.dumps({"workload": args.workload, "n_gpus": world, "storage": "canonical", **d}))
         if world > 1:
@@ -696,6 +744,8 @@ def main():
         circuits = [bench_state(h, 1 << 18, reps), bench_copy(h, 512, 1024, reps), bench_bytecode(h, 19, reps),
                     bench_pi(h, 64, 1 << 18, 16, reps)]
         extras["circuits"] = circuits
+        if world == 1:
+            extras["assign"] = bench_assign(h, reps)
         extras["cfg4"] = {"copy_rows": circuits[1]["rows"], "rows_per_s": circuits[1]["rows_per_s"], "ms_per_pass": circuits[1]["ms_per_pass"],
                           "sharding": f"copy rows over {world} rank(s), halos +1/+2, rw / tx tables replicated"}
         # cfg5: super circuit = evm 2^20 + state 2^21 + copy 2^19 + bytecode 2^19 rows (2^22 in total), every circuit

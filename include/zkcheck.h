@@ -203,6 +203,39 @@ int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contracts, const 
 int zk_keccak256_batch(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, uint64_t* digests, void* stream);
 int zk_assign_keccak_table(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint64_t* offsets, void* stream);
 
+/* ---- witness assignment on the device (csrc/assign.cu) ------------------------------------
+ * The reference builds circuit rows with Python object loops; these calls expand the compact data those
+ * loops start from into the resident witness matrix of a circuit, stored as narrow columns, ready for zk_check.
+ *
+ * zk_assign_bytecode_circuit = assign_bytecode_circuit (bytecode_circuit.py:104-167): 2^k rows from the raw code of
+ *   n_contracts contracts (arguments as zk_upload_bytecode_table_from_code: code bytes, one is_code bit per byte as
+ *   Bytecode.table_assignments computes it, code_offsets[n + 1], hashes[n][4] = hash lo (2 limbs), hi (2 limbs)):
+ *   Header + Byte rows of every contract in order, truncated at 2^k rows, then (EMPTY_HASH, Header) padding;
+ *   value_rlc under ZK_CHALLENGE_KECCAK.
+ * zk_assign_state_circuit = op2row of every operation (state_circuit.py:827-857): `packed_ops` holds the 15 cells
+ *   an operation brings (rw_counter, is_write, tag, id, address, field_tag, storage_key lo, hi, value lo, hi,
+ *   initial_value lo, hi, root lo, hi, lexicographic_ordering_selector) in the packed column format
+ *   (zk_upload_columns_packed); the ten 16-bit address limbs and the 32 storage-key bytes of the 57-cell row are
+ *   derived on the device.  An address beyond 160 bits is an error (the reference raises OverflowError).
+ *   row_flags as zk_upload_row_flags (may be NULL).
+ * zk_assign_copy_circuit = CopyCircuit.copy per event (evm_circuit/typing.py:1010-1147): events[n][16] =
+ *   { src_tag | src id is a Word << 8, dst_tag | dst id is a Word << 8, src_addr, src_addr_end, dst_addr, copy_length,
+ *   log_id, rw_counter before the event, src_id lo (2 limbs), hi (2 limbs), dst_id lo (2 limbs), hi (2 limbs) };
+ *   `data` = the copied byte values of all events back to back (copy_length bytes each, 0 where the source address is
+ *   at or beyond src_addr_end), is_code_bits = one bit per data byte (events that touch bytecode; may be NULL).
+ *   Two rows per byte (read row, write row) incl. rlc_acc under ZK_CHALLENGE_KECCAK, rw_counter / rwc_inc_left and
+ *   the id type flags.
+ * zk_download_columns widens the resident matrix of a circuit back to canonical cells
+ *   (colmajor_out: uint64[n_cols][zk_resident_rows][4]; flags_out: uint8[rows] or NULL) — inspection and tests. */
+int zk_assign_bytecode_circuit(zk_ctx* ctx, uint32_t k, uint64_t n_contracts, const uint8_t* code, const uint8_t* is_code_bits,
+                               const uint64_t* code_offsets, const uint64_t* hashes, void* stream);
+int zk_assign_state_circuit(zk_ctx* ctx, uint64_t n_rows, const void* packed_ops, uint64_t total_bytes,
+                            const uint64_t* col_offsets, const uint8_t* col_widths, const uint8_t* row_flags, void* stream);
+int zk_assign_copy_circuit(zk_ctx* ctx, uint64_t n_events, const uint64_t* events, const uint8_t* data,
+                           const uint8_t* is_code_bits, void* stream);
+int64_t zk_resident_rows(zk_ctx* ctx, int circuit_id);
+int zk_download_columns(zk_ctx* ctx, int circuit_id, uint64_t* colmajor_out, uint8_t* flags_out, void* stream);
+
 /* Check rows [row_begin, row_end) of the resident matrix (local indices).  Without
  * ZK_FLAG_WRAP the caller guarantees halo rows exist for the circuit's rotations.
  * Reported rows are row_base + local index.

@@ -15,6 +15,7 @@
 #include "../../zkevm-specs_b200/csrc/evm.cu"
 #include "../../zkevm-specs_b200/csrc/exp.cu"
 #include "../../zkevm-specs_b200/csrc/pi.cu"
+#include "../../zkevm-specs_b200/csrc/assign.cu"
 #include "../../zkevm-specs_b200/csrc/state.cu"
 #include "../../zkevm-specs_b200/csrc/tx.cu"
 #include "../../zkevm-specs_b200/csrc/keccak.cuh"
@@ -372,6 +373,97 @@ extern "C" int emu_check_pi(const uint64_t* rows, uint64_t n_rows, const uint64_
               Fr{{circuit_len[0], circuit_len[1], circuit_len[2], circuit_len[3]}}};
   CheckRange rg{row_begin, row_end, 0, cflags};
   for (u64 i = row_begin; i < row_end; i++) check_pi_row<L_ANY>(w, rg, kix, gix, pp, res, i);
+  return 0;
+}
+
+// ---- witness assignment (assign.cu): the per-thread bodies run serially, the narrow result is widened to canonical
+static size_t emu_up32(size_t x) { return (x + 31) / 32 * 32; }
+static void widen(const unsigned char* base, const u64* off, const unsigned char* width, u32 n_cols, u64 n_rows, uint64_t* out) {
+  for (u32 c = 0; c < n_cols; c++)
+    for (u64 r = 0; r < n_rows; r++) {
+      const Fr v = ld_col(base + off[c], width[c], r);
+      memcpy(out + ((size_t)c * n_rows + r) * 4, v.l, 32);
+    }
+}
+static std::vector<u64> emu_chunks(const u64* seg, u64 n) {
+  std::vector<u64> c(n + 1, 0);
+  for (u64 k = 0; k < n; k++) c[k + 1] = c[k] + (seg[k + 1] - seg[k] + ZK_SEG_CHUNK - 1) / ZK_SEG_CHUNK;
+  return c;
+}
+extern "C" int emu_assign_bytecode(uint32_t k, uint64_t n_contracts, const uint8_t* code, const uint8_t* bits,
+                                   const uint64_t* offsets, const uint64_t* hashes, const uint64_t r[4], uint64_t* out) {
+  const u64 n_rows = 1ull << k, total = offsets[n_contracts];
+  std::vector<u64> chunks = emu_chunks((const u64*)offsets, n_contracts);
+  BytecodeAssign a;
+  a.s = SegHorner{code, (const u64*)offsets, chunks.data(), n_contracts, chunks[n_contracts], fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}})};
+  a.bits = bits;
+  a.hashes = (const u64*)hashes;
+  a.n_rows = n_rows;
+  a.n_table_rows = total + n_contracts;
+  size_t bytes = 0;
+  for (int c = 0; c < 12; c++) {
+    a.off[c] = bytes;
+    bytes += emu_up32((size_t)kBytecodeAssignWidths[c] * n_rows);
+  }
+  std::vector<unsigned char> buf(bytes + 32, 0xAB);
+  a.base = buf.data();
+  std::vector<Fr> cv(a.s.n_chunks + 1);
+  for (u64 c = 0; c < a.s.n_chunks; c++) seg_local(a.s, cv.data(), c);
+  for (u64 q = 0; q < n_contracts; q++) seg_carry(a.s, cv.data(), nullptr, q);
+  for (u64 rr = 0; rr < n_rows; rr++) assign_bytecode_row(a, rr);
+  for (u64 c = 0; c < a.s.n_chunks; c++) assign_bytecode_rlc(a, cv.data(), c);
+  widen(buf.data(), a.off, kBytecodeAssignWidths, 12, n_rows, out);
+  return 0;
+}
+extern "C" int emu_assign_state(uint64_t n_rows, const uint64_t* ops /* [15][n][4] */, uint64_t* out /* [57][n][4] */) {
+  StateAssign a;
+  a.base = (const unsigned char*)ops;
+  a.off_addr = 4 * n_rows * 32, a.off_klo = 6 * n_rows * 32, a.off_khi = 7 * n_rows * 32;
+  a.w_addr = a.w_klo = a.w_khi = 32;
+  const size_t ls = emu_up32(2 * n_rows), bs = emu_up32(n_rows);
+  std::vector<unsigned char> buf(10 * ls + 32 * bs + 32, 0xAB);
+  a.limbs = buf.data();
+  a.kbytes = buf.data() + 10 * ls;
+  a.n_rows = n_rows, a.limb_stride = ls, a.byte_stride = bs;
+  for (u64 r = 0; r < n_rows; r++) assign_state_row(a, r);
+  for (int c = 0; c < 8; c++) memcpy(out + (size_t)c * n_rows * 4, ops + (size_t)c * n_rows * 4, n_rows * 32);
+  for (int c = 8; c < 15; c++) memcpy(out + (size_t)(42 + c) * n_rows * 4, ops + (size_t)c * n_rows * 4, n_rows * 32);
+  for (int q = 0; q < 10; q++)
+    for (u64 r = 0; r < n_rows; r++) {
+      const Fr v = ld_col(a.limbs + q * ls, 2, r);
+      memcpy(out + ((size_t)(8 + q) * n_rows + r) * 4, v.l, 32);
+    }
+  for (int q = 0; q < 32; q++)
+    for (u64 r = 0; r < n_rows; r++) {
+      const Fr v = ld_col(a.kbytes + q * bs, 1, r);
+      memcpy(out + ((size_t)(18 + q) * n_rows + r) * 4, v.l, 32);
+    }
+  return 0;
+}
+extern "C" int emu_assign_copy(uint64_t n_events, const uint64_t* events, const uint8_t* data, const uint8_t* bits,
+                               const uint64_t r[4], uint64_t* out /* [20][n][4] */, uint8_t* flags_out) {
+  std::vector<u64> seg(n_events + 1, 0);
+  for (u64 e = 0; e < n_events; e++) seg[e + 1] = seg[e] + events[16 * e + 5];
+  const u64 total = seg[n_events], n_rows = 2 * total;
+  std::vector<u64> chunks = emu_chunks(seg.data(), n_events);
+  CopyAssign a;
+  a.s = SegHorner{data, seg.data(), chunks.data(), n_events, chunks[n_events], fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}})};
+  a.ev = (const CopyEvent*)events;
+  a.bits = bits;
+  size_t bytes = 0;
+  for (int c = 0; c < 20; c++) {
+    a.off[c] = bytes;
+    bytes += emu_up32((size_t)kCopyAssignWidths[c] * n_rows);
+  }
+  std::vector<unsigned char> buf(bytes + 32, 0xAB);
+  a.base = buf.data();
+  a.flags = flags_out;
+  a.n_rows = n_rows;
+  std::vector<Fr> cv(a.s.n_chunks + 1), tot(n_events + 1);
+  for (u64 c = 0; c < a.s.n_chunks; c++) seg_local(a.s, cv.data(), c);
+  for (u64 q = 0; q < n_events; q++) seg_carry(a.s, cv.data(), tot.data(), q);
+  for (u64 c = 0; c < a.s.n_chunks; c++) assign_copy_chunk(a, cv.data(), tot.data(), c);
+  widen(buf.data(), a.off, kCopyAssignWidths, 20, n_rows, out);
   return 0;
 }
 

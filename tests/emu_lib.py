@@ -217,3 +217,42 @@ def check_pi(rows, keccak, gas, circuit_len, keccak_rand=255, byte_pow_base=255,
                             ctypes.c_uint32(cflags), _p(ch), ff.ctypes.data_as(U32P), _p(fc))
     assert rc == 0
     return ff, fc
+
+
+U8P = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _lm(v):
+    return np.array([(int(v) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def assign_bytecode(k, code, is_code_bits, code_offsets, hashes, r):
+    """csrc/assign.cu bodies run serially: uint64[12][2^k][4]"""
+    code, bits = np.ascontiguousarray(code, dtype=np.uint8), np.ascontiguousarray(is_code_bits, dtype=np.uint8)
+    offs, hs = np.ascontiguousarray(code_offsets, dtype=np.uint64), np.ascontiguousarray(hashes, dtype=np.uint64)
+    out = np.zeros((12, 1 << k, 4), dtype=np.uint64)
+    rc = lib().emu_assign_bytecode(ctypes.c_uint32(k), ctypes.c_uint64(len(offs) - 1), code.ctypes.data_as(U8P), bits.ctypes.data_as(U8P),
+                                   _p(offs), _p(hs), _p(_lm(r)), _p(out))
+    assert rc == 0
+    return out
+
+
+def assign_state(ops):
+    ops = np.ascontiguousarray(ops, dtype=np.uint64)
+    assert ops.shape[0] == 15
+    out = np.zeros((57, ops.shape[1], 4), dtype=np.uint64)
+    assert lib().emu_assign_state(ctypes.c_uint64(ops.shape[1]), _p(ops), _p(out)) == 0
+    return out
+
+
+def assign_copy(events, data, bits, r):
+    ev = np.ascontiguousarray(events, dtype=np.uint64).reshape(-1, 16)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    n = 2 * len(data)
+    out = np.zeros((20, n, 4), dtype=np.uint64)
+    fl = np.zeros(max(n, 1), dtype=np.uint8)
+    b = None if bits is None else np.ascontiguousarray(bits, dtype=np.uint8)
+    rc = lib().emu_assign_copy(ctypes.c_uint64(ev.shape[0]), _p(ev), data.ctypes.data_as(U8P),
+                               None if b is None else b.ctypes.data_as(U8P), _p(_lm(r)), _p(out), fl.ctypes.data_as(U8P))
+    assert rc == 0
+    return out, fl[:n]

@@ -19,6 +19,7 @@
 #include "evm.cu"
 #include "exp.cu"
 #include "pi.cu"
+#include "assign.cu"
 #include "tx.cu"
 #include "state.cu"
 #include "circuit.cuh"
@@ -122,6 +123,8 @@ struct zk_ctx {
   void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
   size_t state_fold_cap = 0;
   unsigned char* kstage = nullptr;  // zk_keccak256_batch / zk_assign_keccak_table staging
+  unsigned char* astage = nullptr;  // zk_assign_*: staged inputs + the segmented-scan scratch (chunk values, segment totals)
+  size_t astage_cap = 0;
   size_t kstage_cap = 0;
   unsigned char* gather = nullptr;  // zk_allreduce_results: all-gathered result vectors
   size_t gather_cap = 0;
@@ -132,6 +135,7 @@ struct zk_ctx {
 static int mark_indexes_ready(zk_ctx* ctx);
 
 static std::string g_create_err;
+static size_t up32(size_t x) { return (x + 31) / 32 * 32; }
 
 #define CK(ctx, call)                                                                  \
   do {                                                                                 \
@@ -201,6 +205,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   if (ctx->block_stats) cudaFree(ctx->block_stats);
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
   if (ctx->kstage) cudaFree(ctx->kstage);
+  if (ctx->astage) cudaFree(ctx->astage);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
   if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
@@ -422,7 +427,6 @@ extern "C" int zk_upload_bytecode_table_from_code(zk_ctx* ctx, uint64_t n_contra
   const u64 total = code_offsets[n_contracts], n_rows = total + n_contracts;
   if (n_rows >= 0x7FFFFFFFull) return fail_msg(ctx, "too many table rows");
   // staging: code | bits | offsets | hashes (each 32-byte aligned)
-  auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
   const size_t s_code = 0, s_bits = up32(total), s_off = s_bits + up32((total + 7) / 8);
   const size_t s_hash = s_off + up32((n_contracts + 1) * 8), s_total = s_hash + up32(n_contracts * 32);
   if (s_total > ctx->stage_cap) {
@@ -528,10 +532,10 @@ static int keccak_stage(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint
   if (offsets[0] != 0) return fail_msg(ctx, "offsets[0] must be 0");
   for (u64 k = 0; k < n; k++)
     if (offsets[k + 1] < offsets[k]) return fail_msg(ctx, "offsets must be non-decreasing");
-  auto up32 = [](size_t x) { return (x + 31) / 32 * 32; };
   const size_t total = offsets[n], s_off = up32(total ? total : 1), s_dig = s_off + up32((n + 1) * 8), s_total = s_dig + n * 32;
   if (s_total > ctx->kstage_cap) {
     if (ctx->kstage) cudaFree(ctx->kstage);
+  if (ctx->astage) cudaFree(ctx->astage);
     ctx->kstage = nullptr;
     CK(ctx, cudaMalloc(&ctx->kstage, s_total));
     ctx->kstage_cap = s_total;
@@ -590,6 +594,246 @@ extern "C" int zk_assign_keccak_table(zk_ctx* ctx, uint64_t n, const uint8_t* da
   k_keccak256<<<(unsigned)n, 128, 0, st>>>(job, dig, (unsigned char*)m.dev, m.off[0], m.off[1], m.off[2], m.off[3], m.off[4], r_mont);
   ctx->launches++;
   CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ witness assignment on the device (assign.cu)
+static int ensure_astage(zk_ctx* ctx, size_t need) {
+  if (need > ctx->astage_cap) {
+    if (ctx->astage) cudaFree(ctx->astage);
+    ctx->astage = nullptr;
+    CK(ctx, cudaMalloc(&ctx->astage, need));
+    ctx->astage_cap = need;
+  }
+  return 0;
+}
+// (re)allocates the resident matrix of a circuit as narrow columns of the given widths
+static int alloc_narrow(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const unsigned char* widths, size_t extra_front = 0) {
+  size_t bytes = extra_front;
+  for (u32 c = 0; c < n_cols; c++) {
+    m.off[c] = bytes;
+    m.width[c] = widths[c];
+    bytes += up32((size_t)widths[c] * n_rows);
+  }
+  if (m.borrowed) {
+    m.dev = nullptr;
+    m.borrowed = false;
+    m.cap_bytes = 0;
+  }
+  if (bytes > m.cap_bytes) {
+    if (m.dev) cudaFree(m.dev);
+    m.dev = nullptr;
+    CK(ctx, cudaMalloc(&m.dev, bytes ? bytes : 32));
+    m.cap_bytes = bytes;
+  }
+  m.version++;
+  m.n_rows = n_rows;
+  m.n_cols = n_cols;
+  m.flags_rows = 0;
+  m.src_offsets = nullptr;
+  return 0;
+}
+// chunk table of a segmented Horner scan: ceil(len / 32) chunks per segment
+static std::vector<u64> chunk_offsets(const u64* seg_off, u64 n_seg) {
+  std::vector<u64> c(n_seg + 1, 0);
+  for (u64 k = 0; k < n_seg; k++) c[k + 1] = c[k] + (seg_off[k + 1] - seg_off[k] + ZK_SEG_CHUNK - 1) / ZK_SEG_CHUNK;
+  return c;
+}
+static int run_seg_scan(zk_ctx* ctx, const SegHorner& s, Fr* chunk_val, Fr* seg_total, cudaStream_t st) {
+  if (s.n_chunks == 0) return 0;
+  k_seg_local<<<(unsigned)((s.n_chunks + 255) / 256), 256, 0, st>>>(s, chunk_val);
+  k_seg_carry<<<(unsigned)((s.n_seg + 127) / 128), 128, 0, st>>>(s, chunk_val, seg_total);
+  ctx->launches += 2;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int zk_assign_bytecode_circuit(zk_ctx* ctx, uint32_t k, uint64_t n_contracts, const uint8_t* code,
+                                          const uint8_t* is_code_bits, const uint64_t* code_offsets, const uint64_t* hashes,
+                                          void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k > 31) return fail_msg(ctx, "2^k rows: k must be <= 31 (row ids are uint32)");
+  if (n_contracts == 0) return fail_msg(ctx, "no contracts");
+  if (code_offsets[0] != 0) return fail_msg(ctx, "code_offsets[0] must be 0");
+  for (u64 c = 0; c < n_contracts; c++) {
+    if (code_offsets[c + 1] < code_offsets[c]) return fail_msg(ctx, "code_offsets must be non-decreasing");
+    if (code_offsets[c + 1] - code_offsets[c] >= 0xFFFFFFFFull) return fail_msg(ctx, "contract too long");
+  }
+  const u64 total = code_offsets[n_contracts], n_rows = 1ull << k;
+  const std::vector<u64> chunks = chunk_offsets((const u64*)code_offsets, n_contracts);
+  const u64 n_chunks = chunks[n_contracts];
+  const size_t s_code = 0, s_bits = up32(total), s_off = s_bits + up32((total + 7) / 8), s_chk = s_off + up32((n_contracts + 1) * 8);
+  const size_t s_hash = s_chk + up32((n_contracts + 1) * 8), s_val = s_hash + up32(n_contracts * 32), s_total = s_val + (n_chunks + 1) * 32;
+  int rc;
+  if ((rc = ensure_astage(ctx, s_total))) return rc;
+  unsigned char* sg = ctx->astage;
+  if (total) {
+    CK(ctx, cudaMemcpyAsync(sg + s_code, code, total, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(sg + s_bits, is_code_bits, (total + 7) / 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(ctx, cudaMemcpyAsync(sg + s_off, code_offsets, (n_contracts + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(sg + s_chk, chunks.data(), (n_contracts + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(sg + s_hash, hashes, n_contracts * 32, cudaMemcpyHostToDevice, st));
+  Matrix& m = ctx->circ[ZK_CIRCUIT_BYTECODE];
+  if ((rc = alloc_narrow(ctx, m, n_rows, 12, kBytecodeAssignWidths))) return rc;
+  BytecodeAssign a;
+  a.s = SegHorner{sg + s_code, (const u64*)(sg + s_off), (const u64*)(sg + s_chk), n_contracts, n_chunks,
+                  fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK])};
+  a.bits = sg + s_bits;
+  a.hashes = (const u64*)(sg + s_hash);
+  a.n_rows = n_rows;
+  a.n_table_rows = total + n_contracts;
+  a.base = (unsigned char*)m.dev;
+  for (int c = 0; c < 12; c++) a.off[c] = m.off[c];
+  Fr* chunk_val = (Fr*)(sg + s_val);
+  if ((rc = run_seg_scan(ctx, a.s, chunk_val, nullptr, st))) return rc;
+  k_assign_bytecode_rows<<<(unsigned)std::min<u64>((n_rows + 255) / 256, (u64)ctx->sm_count * 16), 256, 0, st>>>(a);
+  if (n_chunks) k_assign_bytecode_rlc<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(a, chunk_val);
+  ctx->launches += n_chunks ? 2 : 1;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int zk_assign_state_circuit(zk_ctx* ctx, uint64_t n_rows, const void* packed_ops, uint64_t total_bytes,
+                                       const uint64_t* col_offsets, const uint8_t* col_widths, const uint8_t* row_flags,
+                                       void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows >= 0xFFFFFFFFull) return fail_msg(ctx, "too many rows (row ids are uint32)");
+  if (!col_offsets || !col_widths) return fail_msg(ctx, "zk_assign_state_circuit needs offsets and widths of the 15 operation columns");
+  for (int c = 0; c < 15; c++) {
+    const unsigned w = col_widths[c];
+    if (!(w == 0 || w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32)) return fail_msg(ctx, "packed column width must be 0, 1, 2, 4, 8, 16 or 32");
+    if (col_offsets[c] % 32 || col_offsets[c] + (w ? (size_t)w * n_rows : 32) > total_bytes)
+      return fail_msg(ctx, "packed column offset misaligned or outside the buffer");
+  }
+  if (col_widths[4] == 32) {  // op.address.to_bytes(20, "little") raises OverflowError beyond 160 bits (state_circuit.py:832)
+    const u64* a = (const u64*)((const unsigned char*)packed_ops + col_offsets[4]);
+    for (u64 r = 0; r < n_rows; r++)
+      if ((a[4 * r + 2] >> 32) || a[4 * r + 3]) return fail_msg(ctx, "operation address does not fit 20 bytes (op2row raises OverflowError)");
+  }
+  // resident buffer: [uploaded operation columns | 10 limb columns (u16) | 32 key-byte columns (u8)]
+  Matrix& m = ctx->circ[ZK_CIRCUIT_STATE];
+  const size_t front = up32(total_bytes), limb_stride = up32(2 * n_rows), byte_stride = up32(n_rows);
+  const size_t bytes = front + 10 * limb_stride + 32 * byte_stride;
+  if (m.borrowed) {
+    m.dev = nullptr;
+    m.borrowed = false;
+    m.cap_bytes = 0;
+  }
+  if (bytes > m.cap_bytes) {
+    if (m.dev) cudaFree(m.dev);
+    m.dev = nullptr;
+    CK(ctx, cudaMalloc(&m.dev, bytes ? bytes : 32));
+    m.cap_bytes = bytes;
+  }
+  if (total_bytes) CK(ctx, cudaMemcpyAsync(m.dev, packed_ops, total_bytes, cudaMemcpyHostToDevice, st));
+  m.version++;
+  m.n_rows = n_rows;
+  m.n_cols = 57;
+  m.src_offsets = nullptr;
+  for (int c = 0; c < 8; c++) m.off[c] = col_offsets[c], m.width[c] = col_widths[c];
+  for (int q = 0; q < 10; q++) m.off[8 + q] = front + q * limb_stride, m.width[8 + q] = 2;
+  for (int q = 0; q < 32; q++) m.off[18 + q] = front + 10 * limb_stride + q * byte_stride, m.width[18 + q] = 1;
+  for (int c = 8; c < 15; c++) m.off[42 + c] = col_offsets[c], m.width[42 + c] = col_widths[c];
+  int rc;
+  if ((rc = store_flags(ctx, m, n_rows, row_flags, st))) return rc;
+  if (n_rows == 0) return 0;
+  StateAssign a;
+  a.base = (const unsigned char*)m.dev;
+  a.off_addr = col_offsets[4], a.off_klo = col_offsets[6], a.off_khi = col_offsets[7];
+  a.w_addr = col_widths[4], a.w_klo = col_widths[6], a.w_khi = col_widths[7];
+  a.limbs = (unsigned char*)m.dev + front;
+  a.kbytes = (unsigned char*)m.dev + front + 10 * limb_stride;
+  a.n_rows = n_rows, a.limb_stride = limb_stride, a.byte_stride = byte_stride;
+  k_assign_state_derive<<<(unsigned)std::min<u64>((n_rows + 255) / 256, (u64)ctx->sm_count * 16), 256, 0, st>>>(a);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int zk_assign_copy_circuit(zk_ctx* ctx, uint64_t n_events, const uint64_t* events, const uint8_t* data,
+                                      const uint8_t* is_code_bits, void* stream) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  static_assert(sizeof(CopyEvent) == 16 * sizeof(u64), "CopyEvent is 16 u64");
+  std::vector<u64> seg(n_events + 1, 0);
+  for (u64 e = 0; e < n_events; e++) seg[e + 1] = seg[e] + events[16 * e + 5];
+  const u64 total = seg[n_events], n_rows = 2 * total;
+  if (n_rows >= 0xFFFFFFFFull) return fail_msg(ctx, "too many rows (row ids are uint32)");
+  const std::vector<u64> chunks = chunk_offsets(seg.data(), n_events);
+  const u64 n_chunks = chunks[n_events];
+  const size_t s_data = 0, s_bits = up32(total), s_off = s_bits + up32((total + 7) / 8), s_chk = s_off + up32((n_events + 1) * 8);
+  const size_t s_ev = s_chk + up32((n_events + 1) * 8), s_val = s_ev + up32(n_events * sizeof(CopyEvent));
+  const size_t s_tot = s_val + (n_chunks + 1) * 32, s_total = s_tot + (n_events + 1) * 32;
+  int rc;
+  if ((rc = ensure_astage(ctx, s_total))) return rc;
+  unsigned char* sg = ctx->astage;
+  if (total) {
+    CK(ctx, cudaMemcpyAsync(sg + s_data, data, total, cudaMemcpyHostToDevice, st));
+    if (is_code_bits) CK(ctx, cudaMemcpyAsync(sg + s_bits, is_code_bits, (total + 7) / 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(ctx, cudaMemcpyAsync(sg + s_off, seg.data(), (n_events + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(ctx, cudaMemcpyAsync(sg + s_chk, chunks.data(), (n_events + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (n_events) CK(ctx, cudaMemcpyAsync(sg + s_ev, events, n_events * sizeof(CopyEvent), cudaMemcpyHostToDevice, st));
+  Matrix& m = ctx->circ[ZK_CIRCUIT_COPY];
+  if ((rc = alloc_narrow(ctx, m, n_rows, 20, kCopyAssignWidths))) return rc;
+  if (n_rows > m.flags_cap) {
+    if (m.flags) cudaFree(m.flags);
+    m.flags = nullptr;
+    CK(ctx, cudaMalloc(&m.flags, n_rows));
+    m.flags_cap = n_rows;
+  }
+  m.flags_rows = n_rows;
+  if (n_chunks == 0) return 0;
+  CopyAssign a;
+  a.s = SegHorner{sg + s_data, (const u64*)(sg + s_off), (const u64*)(sg + s_chk), n_events, n_chunks,
+                  fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK])};
+  a.ev = (const CopyEvent*)(sg + s_ev);
+  a.bits = is_code_bits ? sg + s_bits : nullptr;
+  a.base = (unsigned char*)m.dev;
+  a.flags = m.flags;
+  for (int c = 0; c < 20; c++) a.off[c] = m.off[c];
+  a.n_rows = n_rows;
+  Fr* chunk_val = (Fr*)(sg + s_val);
+  Fr* seg_total = (Fr*)(sg + s_tot);
+  if ((rc = run_seg_scan(ctx, a.s, chunk_val, seg_total, st))) return rc;
+  k_assign_copy_rows<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(a, chunk_val, seg_total);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t zk_resident_rows(zk_ctx* ctx, int circuit_id) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return -1;
+  return (int64_t)ctx->circ[circuit_id].n_rows;
+}
+
+// the resident matrix of a circuit widened back to canonical cells on the host (inspection / tests)
+extern "C" int zk_download_columns(zk_ctx* ctx, int circuit_id, uint64_t* colmajor_out, uint8_t* flags_out, void* stream) {
+  if (circuit_id < 0 || circuit_id >= ZK_N_CIRCUITS) return fail_msg(ctx, "bad circuit id");
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Matrix& m = ctx->circ[circuit_id];
+  CK(ctx, cudaStreamSynchronize(st));
+  std::vector<unsigned char> tmp;
+  for (u32 c = 0; c < m.n_cols; c++) {
+    const unsigned w = m.width[c];
+    const size_t nb = w ? (size_t)w * m.n_rows : 32;
+    tmp.resize(nb);
+    if (m.n_rows) CK(ctx, cudaMemcpy(tmp.data(), (const unsigned char*)m.dev + m.off[c], nb, cudaMemcpyDeviceToHost));
+    u64* out = (u64*)colmajor_out + (size_t)c * m.n_rows * 4;
+    for (u64 r = 0; r < m.n_rows; r++) {
+      u64 v[4] = {0, 0, 0, 0};
+      memcpy(v, tmp.data() + (w ? (size_t)w * r : 0), w ? w : 32);
+      memcpy(out + 4 * r, v, 32);
+    }
+  }
+  if (flags_out) {
+    if (m.flags_rows == m.n_rows && m.n_rows) CK(ctx, cudaMemcpy(flags_out, m.flags, m.n_rows, cudaMemcpyDeviceToHost));
+    else memset(flags_out, 0, m.n_rows);
+  }
   return 0;
 }
 

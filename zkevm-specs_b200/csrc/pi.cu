@@ -10,6 +10,7 @@
 // (next accumulator x challenge); the sections under `if selector != 0` (one row per tx field / calldata
 // byte / withdrawal) evaluate the reference's polynomials as written.  A row stops at its first failure.
 #include "circuit.cuh"
+// fr_mul_sel comes from copy.cu (this file is part of the unity build of api.cu, after copy.cu)
 #include "../../include/zk_constraints.h"
 #include "../../include/zkcheck.h"
 
@@ -92,10 +93,11 @@ ZK_HD void check_pi_row(const WitnessDev& w, const CheckRange& rg, const IndexDe
     PI_CHECK(PI_CD_DEF_FINAL, zr0 || Z(fin));
     PI_CHECK(PI_CD_DEF_GAS, zr0 || Z(cg));
     // gas_cost = 16 * is_byte_nonzero + 4 * (1 - is_byte_nonzero) = 4 + 12 * is_byte_nonzero
-    const Fr gas = fr_add(fr_u64(PI_GAS_ZERO_BYTE), M(fr_u64(PI_GAS_NONZERO_BYTE - PI_GAS_ZERO_BYTE), b_nz));
-    const Fr n_gas = fr_add(fr_u64(PI_GAS_ZERO_BYTE), M(fr_u64(PI_GAS_NONZERO_BYTE - PI_GAS_ZERO_BYTE), nb_nz));
+    // (is_byte_nonzero is 0 or 1 on every witness whose inverse cells are right: fr_mul_sel skips those products)
+    const Fr gas = fr_add(fr_u64(PI_GAS_ZERO_BYTE), fr_mul_sel(fr_u64(PI_GAS_NONZERO_BYTE - PI_GAS_ZERO_BYTE), b_nz));
+    const Fr n_gas = fr_add(fr_u64(PI_GAS_ZERO_BYTE), fr_mul_sel(fr_u64(PI_GAS_NONZERO_BYTE - PI_GAS_ZERO_BYTE), nb_nz));
     {  // :250-256 lookup(FixedU16Row): the table is the integers 0..65535
-      const Fr v = M(M(neq, n_nz), fr_sub(diff, one));
+      const Fr v = fr_mul_sel(fr_mul_sel(neq, n_nz), fr_sub(diff, one));
       PI_CHECK(PI_CD_U16, fr_fits64(v) && v.l[0] < 65536);
     }
     const bool nz0 = Z(nz), eq0 = Z(eq), diff0 = Z(diff);
@@ -117,8 +119,8 @@ ZK_HD void check_pi_row(const WitnessDev& w, const CheckRange& rg, const IndexDe
     PI_CHECK(PI_TX_VALUE_INV, Z(vlo) || fr_eq_u64(len_nz, 1));
     const Fr cdl_row = fr_sub(one, t), len_z = fr_sub(one, len_nz), cost = N(P_TX_VAL_LO);
     PI_CHECK(PI_TX_ZERO_COST, Z(cdl_row) || Z(len_z) || Z(cost));
-    const Fr qc = M(cdl_row, len_nz);
-    Fr key[3] = {M(C(P_TX_ID), qc), qc, M(cost, qc)};
+    const Fr qc = fr_mul_sel(cdl_row, len_nz);
+    Fr key[3] = {fr_mul_sel(C(P_TX_ID), qc), qc, fr_mul_sel(cost, qc)};
     u32 hit;
     const int n = lookup<3>(gas_ix, key, &hit);
     PI_CHECK(PI_TX_GAS_LOOKUP, n >= 1);

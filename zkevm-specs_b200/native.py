@@ -74,7 +74,8 @@ EXPORTS = [
     "zk_constraint_info", "zk_launch_count", "zk_invalidate_indexes", "zk_enable_timing",
     "zk_last_timing", "zk_upload_columns_packed", "zk_upload_table_packed",
     "zk_upload_bytecode_table_from_code", "zk_nccl_unique_id", "zk_nccl_comm_init", "zk_nccl_comm_destroy",
-    "zk_keccak256_batch", "zk_assign_keccak_table",
+    "zk_keccak256_batch", "zk_assign_keccak_table", "zk_assign_bytecode_circuit", "zk_assign_state_circuit",
+    "zk_assign_copy_circuit", "zk_download_columns", "zk_resident_rows",
 ]
 
 
@@ -110,6 +111,12 @@ def lib() -> ctypes.CDLL:
         L.zk_nccl_comm_destroy.argtypes = [vp, vp]
         L.zk_keccak256_batch.argtypes = [vp, u64, vp, vp, vp, vp]
         L.zk_assign_keccak_table.argtypes = [vp, u64, vp, vp, vp]
+        L.zk_assign_bytecode_circuit.argtypes = [vp, u32, u64, vp, vp, vp, vp, vp]
+        L.zk_assign_state_circuit.argtypes = [vp, u64, vp, u64, vp, vp, vp, vp]
+        L.zk_assign_copy_circuit.argtypes = [vp, u64, vp, vp, vp, vp]
+        L.zk_download_columns.argtypes = [vp, i32, vp, vp, vp]
+        L.zk_resident_rows.argtypes = [vp, i32]
+        L.zk_resident_rows.restype = ctypes.c_int64
         L.zk_circuit_cols.argtypes = [i32]
         L.zk_table_cols.argtypes = [i32]
         L.zk_n_constraints.argtypes = [i32]
@@ -238,6 +245,60 @@ class Context:
         self._ck(self._L.zk_upload_bytecode_table_from_code(
             self._h, len(offs) - 1, ctypes.c_void_p(pc), ctypes.c_void_p(pb), _host_ptr(offs), _host_ptr(hs),
             ctypes.c_void_p(stream)), "zk_upload_bytecode_table_from_code")
+
+    # ---- witness assignment on the device (include/zkcheck.h "witness assignment") ----------------
+    def assign_bytecode_circuit(self, k: int, code: np.ndarray, is_code_bits: np.ndarray, code_offsets: np.ndarray,
+                                hashes: np.ndarray, stream: int = 0) -> None:
+        """assign_bytecode_circuit (bytecode_circuit.py:104-167) on the device: the 2^k rows of ZK_CIRCUIT_BYTECODE from
+        the raw code (same arguments as upload_bytecode_table_from_code), value_rlc under CHALLENGE_KECCAK"""
+        code = np.ascontiguousarray(code, dtype=np.uint8)
+        bits = np.ascontiguousarray(is_code_bits, dtype=np.uint8)
+        offs = np.ascontiguousarray(code_offsets, dtype=np.uint64)
+        hs = np.ascontiguousarray(hashes, dtype=np.uint64)
+        assert hs.shape == (len(offs) - 1, 4) and len(bits) >= (len(code) + 7) // 8 and int(offs[-1]) == len(code)
+        self._ck(self._L.zk_assign_bytecode_circuit(self._h, k, len(offs) - 1, _host_ptr(code),
+                                                    _host_ptr(bits), _host_ptr(offs), _host_ptr(hs), ctypes.c_void_p(stream)),
+                 "zk_assign_bytecode_circuit")
+
+    def assign_state_circuit(self, ops, flags=None, stream: int = 0) -> None:
+        """op2row (state_circuit.py:827-857) on the device: `ops` = a PackedMatrix (or canonical uint64[15][n][4]) of the 15
+        operation cells (rw_counter, is_write, tag, id, address, field_tag, storage_key lo/hi, value lo/hi, initial_value
+        lo/hi, root lo/hi, selector); the address limbs and key bytes of the 57-cell row are derived on the device"""
+        from . import packing
+        pm = ops if isinstance(ops, packing.PackedMatrix) else packing.pack_matrix(self._matrix(ops), widths=[32] * 15)
+        assert pm.n_cols == 15
+        self._keep = getattr(self, "_keep", {})
+        self._keep["state_ops"] = pm
+        offs = np.ascontiguousarray(pm.offsets, dtype=np.uint64)
+        widths = np.ascontiguousarray(pm.widths, dtype=np.uint8)
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        self._ck(self._L.zk_assign_state_circuit(self._h, pm.n_rows, _host_ptr(pm.buf), pm.nbytes,
+                                                 _host_ptr(offs), _host_ptr(widths), None if fl is None else _host_ptr(fl),
+                                                 ctypes.c_void_p(stream)), "zk_assign_state_circuit")
+
+    def assign_copy_circuit(self, events: np.ndarray, data: np.ndarray, is_code_bits=None, stream: int = 0) -> None:
+        """CopyCircuit.copy (evm_circuit/typing.py:1010-1147) on the device: `events` uint64[n][16] (include/zkcheck.h), `data`
+        the copied byte values of all events (0 where the source is out of bounds), rlc_acc under CHALLENGE_KECCAK"""
+        ev = np.ascontiguousarray(events, dtype=np.uint64)
+        assert ev.ndim == 2 and ev.shape[1] == 16
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert int(ev[:, 5].sum()) == len(data)
+        bits = None if is_code_bits is None else np.ascontiguousarray(is_code_bits, dtype=np.uint8)
+        self._ck(self._L.zk_assign_copy_circuit(self._h, ev.shape[0], _host_ptr(ev), _host_ptr(data),
+                                                None if bits is None else _host_ptr(bits), ctypes.c_void_p(stream)),
+                 "zk_assign_copy_circuit")
+
+    def download_columns(self, circuit_id: int, stream: int = 0):
+        """the resident matrix of a circuit as canonical cells + its row flags: (uint64[n_cols][n_rows][4], uint8[n_rows])"""
+        n_cols, n_rows = self._L.zk_circuit_cols(circuit_id), self.resident_rows(circuit_id)
+        out = np.zeros((n_cols, n_rows, 4), dtype=np.uint64)
+        fl = np.zeros(max(n_rows, 1), dtype=np.uint8)
+        self._ck(self._L.zk_download_columns(self._h, circuit_id, _host_ptr(out), _host_ptr(fl), ctypes.c_void_p(stream)),
+                 "zk_download_columns")
+        return out, fl[:n_rows]
+
+    def resident_rows(self, circuit_id: int) -> int:
+        return int(self._L.zk_resident_rows(self._h, circuit_id))
 
     def bind_columns_device(self, circuit_id: int, n_rows: int, n_cols: int, dev_ptr: int) -> None:
         self._ck(self._L.zk_bind_columns_device(self._h, circuit_id, n_rows, n_cols,

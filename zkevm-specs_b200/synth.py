@@ -303,6 +303,7 @@ def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F
     i_idx = np.arange(L, dtype=np.uint64)
     rw_rows = []
     tx_rows = []
+    events = []  # rows of zk_assign_copy_circuit's events array (assign.copy_event)
     rwc = 1
     pos = 0
 
@@ -336,6 +337,7 @@ def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F
             put(13, rd, np.uint64(rwc) + i_idx); put(13, wr, np.uint64(rwc) + i_idx + np.uint64(1))
             put(14, rd, np.uint64(L) - i_idx); put(14, wr, np.uint64(L) - i_idx - np.uint64(1))
             put(15, rd, 1); put(19, wr, 1)
+            events.append([2, 5, src, src + L, 0, L, 0, rwc, call_id, 0, 0, 0, call_id, 0, 0, 0])
             rw_rows.append(np.stack([np.uint64(rwc) + i_idx, np.zeros(L, np.uint64), np.full(L, 9, np.uint64),
                                      np.full(L, call_id, np.uint64), np.uint64(src) + i_idx, b]))
             rwc += L
@@ -352,6 +354,8 @@ def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F
             put(13, ev, np.repeat(np.uint64(rwc) + i_idx, 2))
             put(14, ev, np.repeat(np.uint64(L) - i_idx, 2))
             put(17, rd, 1); put(15, wr, 1)
+            events.append([3, 2, 0, n_real, dst, L, 0, rwc, tx_id, 0, 0, 0, call_id, 0, 0, 0])
+            data[e] = b
             rw_rows.append(np.stack([np.uint64(rwc) + i_idx, np.ones(L, np.uint64), np.full(L, 9, np.uint64),
                                      np.full(L, call_id, np.uint64), np.uint64(dst) + i_idx, b]))
             tx_rows.append(np.stack([np.full(n_real, tx_id, np.uint64), np.full(n_real, 13, np.uint64),
@@ -366,6 +370,7 @@ def copy_events(n_events: int, length: int, seed: int = 4, r: int = 0x2545F4914F
     tx[0, :, 0], tx[1, :, 0], tx[2, :, 0], tx[3, :, 0] = TXs
     return {"copy": C, "copy_flags": np.zeros(n_rows, np.uint8), "rw": rw, "rw_flags": np.zeros(rw.shape[1], np.uint8),
             "tx": tx, "tx_flags": np.zeros(tx.shape[1], np.uint8), "bytecode": np.zeros((6, 0, 4), np.uint64),
+            "events": np.array(events, dtype=np.uint64).reshape(-1, 16), "data": data.astype(np.uint8).reshape(-1), "r_int": r,
             "r": np.array([(r >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)}
 
 
@@ -381,7 +386,7 @@ def bytecode_circuit_rows(k: int, n_contracts: int = 4, seed: int = 5,
     size = 1 << k
     per = (size - 1) // n_contracts - 1  # bytes per contract; the rest is Header padding
     rows = np.zeros((12, size, 4), dtype=np.uint64)
-    keccak_rows, at = [], 0
+    keccak_rows, at, codes = [], 0, []
     push_size = np.zeros(256, dtype=np.int64)
     push_size[0x60:0x80] = np.arange(1, 33)
 
@@ -390,6 +395,7 @@ def bytecode_circuit_rows(k: int, n_contracts: int = 4, seed: int = 5,
 
     for _ in range(n_contracts):
         code = rng.integers(0, 256, per, dtype=np.uint8)
+        codes.append(bytes(code))
         h = int.from_bytes(keccak256(bytes(code)), "big")
         # push_data_left / is_code: sequential scan over the code (get_push_size, opcode.py:427-433)
         left = np.zeros(per, dtype=np.int64)
@@ -434,7 +440,8 @@ def bytecode_circuit_rows(k: int, n_contracts: int = 4, seed: int = 5,
     for i, row in enumerate(keccak_rows):
         for c, v in enumerate(row):
             kec[c, i, :] = [(v >> (64 * j)) & M64 for j in range(4)]
-    return {"rows": rows, "push": push, "keccak": kec, "r": np.array([(r >> (64 * j)) & M64 for j in range(4)], dtype=np.uint64)}
+    return {"rows": rows, "push": push, "keccak": kec, "r": np.array([(r >> (64 * j)) & M64 for j in range(4)], dtype=np.uint64),
+            "codes": codes, "r_int": r}
 
 
 # ------------------------------------------------------------------------------------------------
