@@ -362,7 +362,7 @@ def bench_copy(h, n_events, length, reps, seed=4):
     byt = 32 * ((e - b) * 20 + w["rw"].shape[1] * 14 + w["tx"].shape[1] * 5)
     return {"circuit": "copy", "rows": n, "rows_per_gpu": e - b, "rw_rows": int(w["rw"].shape[1]), "tx_rows": int(w["tx"].shape[1]),
             "ms_per_pass": ms, "rows_per_s": n / (ms / 1e3), "index_ms": i_ms,
-            "roofline": roofline_of(h, c_ms, byt, kernel="k_check_copy<L_CANON>")}
+            "roofline": roofline_of(h, c_ms, byt, kernel="k_check_copy_small<L_CANON> (+ k_check_copy_general over deferred warps)")}
 
 
 def bench_bytecode(h, k, reps):

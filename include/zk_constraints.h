@@ -647,7 +647,47 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_BT_NC_LOG_ID, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: LOG_ID (instruction.py:266-290)") \
   X(EV_BT_NC_PC, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: PC (instruction.py:266-290)") \
   X(EV_BT_NC_SP, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: SP (instruction.py:266-290)") \
-  X(EV_BT_NC_MEM, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: MEM (instruction.py:266-290)")
+  X(EV_BT_NC_MEM, ZKE_ASSERT, "begin_tx.py:203-212 / 271-280 step_state_transition_to_new_context: MEM (instruction.py:266-290)") \
+  /* error states: the shared tail constrain_error_state (instruction.py:1426-1452); the restore-to-caller branch \
+   * reports through the EV_RST* ids */                                                                         \
+  X(EV_ERR_CC_UNSAT, ZKE_UNSAT, "instruction.py:1429 call_context_lookup(IsSuccess) unsat")                      \
+  X(EV_ERR_CC_AMBIG, ZKE_AMBIG, "instruction.py:1429 call_context_lookup(IsSuccess) ambiguous")                  \
+  X(EV_ERR_CC_TYPE, ZKE_ASSERT, "instruction.py:1429 .value(): IsSuccess is a Word")                             \
+  X(EV_ERR_IS_SUCCESS, ZKE_ASSERT, "instruction.py:1430 is_success == 0")                                        \
+  X(EV_ERR_ROOT_ENDTX, ZKE_ASSERT, "instruction.py:1433-1434 is_root == (next state is EndTx)")                  \
+  X(EV_ERR_RWC, ZKE_ASSERT, "instruction.py:1439-1442 root: rw_counter + rw lookups + reversible_write_counter + 1") \
+  X(EV_ERR_CALL_ID, ZKE_ASSERT, "instruction.py:1439-1442 root: call_id same")                                   \
+  X(EV_ESTK_RESP_OPCODE, ZKE_UNSAT, "error_stack.py:7 responsible_opcode_lookup(opcode, stack_pointer)")         \
+  X(EV_EINV_RESP_OPCODE, ZKE_UNSAT, "error_invalid_opcode.py:8 responsible_opcode_lookup(opcode)")               \
+  X(EV_EOGC_OPCODE_VALUE, ZKE_VALUE, "error_oog_constant.py:11 Opcode(opcode.n): not a valid opcode -> ValueError") \
+  X(EV_EOGC_GAS_UNSAT, ZKE_UNSAT, "error_oog_constant.py:10-12 fixed_lookup(OpcodeConstantGas, opcode, gas)")    \
+  X(EV_EOGC_CMP_RANGE, ZKE_ASSERT, "error_oog_constant.py:15-17 compare(): operand exceeds 8 bytes")             \
+  X(EV_EOGC_NOT_ENOUGH, ZKE_ASSERT, "error_oog_constant.py:18 gas_left < constant gas")                          \
+  X(EV_EJMP_OPCODE, ZKE_ASSERT, "error_invalid_jump.py:10 opcode in (JUMP, JUMPI)")                              \
+  X(EV_EJMP_LEN_UNSAT, ZKE_UNSAT, "error_invalid_jump.py:12 bytecode_length lookup unsat")                       \
+  X(EV_EJMP_LEN_AMBIG, ZKE_AMBIG, "error_invalid_jump.py:12 bytecode_length lookup ambiguous")                   \
+  X(EV_EJMP_DEST_UNSAT, ZKE_UNSAT, "error_invalid_jump.py:13 stack_pop(dest) unsat")                             \
+  X(EV_EJMP_DEST_AMBIG, ZKE_AMBIG, "error_invalid_jump.py:13 stack_pop(dest) ambiguous")                         \
+  X(EV_EJMP_COND_UNSAT, ZKE_UNSAT, "error_invalid_jump.py:16 stack_pop(condition) unsat")                        \
+  X(EV_EJMP_COND_AMBIG, ZKE_AMBIG, "error_invalid_jump.py:16 stack_pop(condition) ambiguous")                    \
+  X(EV_EJMP_COND_ZERO, ZKE_ASSERT, "error_invalid_jump.py:18 condition != 0")                                    \
+  X(EV_EJMP_DEST_DOMAIN, ZKE_VALUE, "error_invalid_jump.py:20 word_to_u64: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_EJMP_DEST_U64, ZKE_RANGE, "error_invalid_jump.py:20 word_to_u64(dest): more than 8 bytes")                \
+  X(EV_EJMP_CMP_RANGE, ZKE_ASSERT, "error_invalid_jump.py:22 compare(): code length exceeds 8 bytes")            \
+  X(EV_EJMP_AT_UNSAT, ZKE_UNSAT, "error_invalid_jump.py:26 bytecode_lookup_pair(dest) unsat")                    \
+  X(EV_EJMP_AT_AMBIG, ZKE_AMBIG, "error_invalid_jump.py:26 bytecode_lookup_pair(dest) ambiguous")                \
+  X(EV_EJMP_IS_JUMPDEST, ZKE_ASSERT, "error_invalid_jump.py:28-29 is_code * (value == JUMPDEST) == 0")           \
+  /* selfbalance.py */                                                                                          \
+  X(EV_SBAL_OPCODE, ZKE_ASSERT, "selfbalance.py:8 opcode == SELFBALANCE")                                        \
+  X(EV_SBAL_CC_UNSAT, ZKE_UNSAT, "selfbalance.py:10 call_context_lookup_word(CalleeAddress) unsat")              \
+  X(EV_SBAL_CC_AMBIG, ZKE_AMBIG, "selfbalance.py:10 call_context_lookup_word(CalleeAddress) ambiguous")          \
+  X(EV_SBAL_ADDR_DOMAIN, ZKE_VALUE, "selfbalance.py:11 word_to_address: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_SBAL_ADDR_RANGE, ZKE_RANGE, "selfbalance.py:11 word_to_address: more than 20 bytes")                      \
+  X(EV_SBAL_ACC_UNSAT, ZKE_UNSAT, "selfbalance.py:12 account_read_word(Balance) unsat")                          \
+  X(EV_SBAL_ACC_AMBIG, ZKE_AMBIG, "selfbalance.py:12 account_read_word(Balance) ambiguous")                      \
+  X(EV_SBAL_PUSH_UNSAT, ZKE_UNSAT, "selfbalance.py:13 stack_push unsat")                                         \
+  X(EV_SBAL_PUSH_AMBIG, ZKE_AMBIG, "selfbalance.py:13 stack_push ambiguous")                                     \
+  X(EV_SBAL_EQ, ZKE_ASSERT, "selfbalance.py:13 pushed word == balance")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -324,7 +324,7 @@ extern "C" int emu_check_copy(const uint64_t* rows, uint64_t n_rows, const uint8
   ResultDev res;
   init_result(res, first_fail, fail_count, CP_N_CONSTRAINTS);
   const Fr r_mont = fr_to_mont(Fr{{r[0], r[1], r[2], r[3]}});
-  for (u64 i = row_begin; i < row_end; i++) check_copy_row<L_ANY>(w, rg, t, r_mont, res, i, true, 1u);
+  for (u64 i = row_begin; i < row_end; i++) check_copy_rows<L_ANY>(w, rg, t, r_mont, res, i, true, 1u);
   return 0;
 }
 

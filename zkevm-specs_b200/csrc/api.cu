@@ -123,6 +123,8 @@ struct zk_ctx {
   void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
   size_t state_fold_cap = 0;
   unsigned char* kstage = nullptr;  // zk_keccak256_batch / zk_assign_keccak_table staging
+  u32* copy_slow = nullptr;  // copy circuit: [0] = count, [1..] = first rows of the warps deferred to the general kernel
+  size_t copy_slow_cap = 0;
   unsigned char* astage = nullptr;  // zk_assign_*: staged inputs + the segmented-scan scratch (chunk values, segment totals)
   size_t astage_cap = 0;
   size_t kstage_cap = 0;
@@ -206,6 +208,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   if (ctx->evm_sort) cudaFree(ctx->evm_sort);
   if (ctx->kstage) cudaFree(ctx->kstage);
   if (ctx->astage) cudaFree(ctx->astage);
+  if (ctx->copy_slow) cudaFree(ctx->copy_slow);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
   if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
@@ -535,7 +538,6 @@ static int keccak_stage(zk_ctx* ctx, uint64_t n, const uint8_t* data, const uint
   const size_t total = offsets[n], s_off = up32(total ? total : 1), s_dig = s_off + up32((n + 1) * 8), s_total = s_dig + n * 32;
   if (s_total > ctx->kstage_cap) {
     if (ctx->kstage) cudaFree(ctx->kstage);
-  if (ctx->astage) cudaFree(ctx->astage);
     ctx->kstage = nullptr;
     CK(ctx, cudaMalloc(&ctx->kstage, s_total));
     ctx->kstage_cap = s_total;
@@ -1143,9 +1145,25 @@ static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStre
   if ((rc = mark_indexes_ready(ctx))) return rc;
   const u64 n = rg.row_end - rg.row_begin;
   const Fr r_mont = fr_to_mont(ctx->chal[ZK_CHALLENGE_KECCAK]);
-  if (is_canonical(m)) k_check_copy<L_CANON><<<grid_persistent(ctx, k_check_copy<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
-  else k_check_copy<L_ANY><<<grid_persistent(ctx, k_check_copy<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res);
-  ctx->launches++;
+  // deferred-warp list of the small / general split (copy.cu): one u32 per 32 rows + the counter
+  const size_t need = (n / 32 + 2) * sizeof(u32);
+  if (need > ctx->copy_slow_cap) {
+    if (ctx->copy_slow) cudaFree(ctx->copy_slow);
+    ctx->copy_slow = nullptr;
+    CK(ctx, cudaMalloc(&ctx->copy_slow, need));
+    ctx->copy_slow_cap = need;
+  }
+  CK(ctx, cudaMemsetAsync(ctx->copy_slow, 0, sizeof(u32), st));
+  const CopySlowList slow{ctx->copy_slow, ctx->copy_slow + 1};
+  const unsigned g_general = (unsigned)std::min<u64>((n / 32 + 3) / 4 + 1, (u64)ctx->sm_count * 2);
+  if (is_canonical(m)) {
+    k_check_copy_small<L_CANON><<<grid_persistent(ctx, k_check_copy_small<L_CANON>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res, slow);
+    k_check_copy_general<L_CANON><<<g_general, 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res, slow);
+  } else {
+    k_check_copy_small<L_ANY><<<grid_persistent(ctx, k_check_copy_small<L_ANY>, 128, n), 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res, slow);
+    k_check_copy_general<L_ANY><<<g_general, 128, 0, st>>>(witness_dev(m), rg, t, r_mont, res, slow);
+  }
+  ctx->launches += 2;
   CK(ctx, cudaGetLastError());
   return 0;
 }

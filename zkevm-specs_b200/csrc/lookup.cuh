@@ -207,35 +207,29 @@ ZK_HD bool pos_enabled(const IndexDev& ix) { return ix.pos_ok != nullptr && ld_u
 // ZK_POS_DENSE: candidate = key[0] - cell(0).  Branch-free (candidate clamped, cells always
 // loaded) so that it overlaps with neighbouring lookups; `base0` = limb 0 of cell(0) of the
 // counter column, hoisted by callers that do many lookups (pass nullptr to read it here).
-// the tail run (keys whose tail column holds tail_val: the rw table's Start padding rows) — rare, out of line
-template <int NK>
-ZK_HD_NOINLINE int pos_lookup_dense_tail(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active) {
-  const u64 split = ld_u32(ix.pos_ok + 1), limit = ix.tab.n_rows - split;
-  if (!active || limit == 0) return 0;
-  const u64 base = table_cell(ix.tab, ix.key_cols[0], split).l[0];
-  if (!(fr_fits64(key[0]) && key[0].l[0] >= base && key[0].l[0] - base < limit)) return 0;
-  const u64 cand = split + (key[0].l[0] - base);
-  bool eq = true;
-  for (int j = 1; j < NK; j++) eq = eq && fr_eq(table_cell(ix.tab, ix.key_cols[j], cand), key[j]);
-  *row = (u32)cand;
-  return eq ? 1 : 0;
-}
+// The tail run (keys whose tail column holds tail_val: the rw table's Start padding rows, stored after the dense head)
+// is the same computation on another window of rows — base, limit and row offset switch, the loads and compares are
+// shared.  (Round 1 had the tail as an out-of-line function taking the key array by reference: that single call pinned
+// every caller's key array in local memory — 160-750 B of stack traffic per row in every kernel with a positional
+// lookup; profiles/README.md r02.)
 template <int NK>
 ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active, const u64* base0 = nullptr,
                            int extra_col = -1, Fr* extra = nullptr, int extra_col2 = -1, Fr* extra2 = nullptr) {
-  if (ix.tail_key >= 0 && ix.tail_key < NK && fr_eq_u64(key[ix.tail_key < NK ? ix.tail_key : 0], ix.tail_val)) {
-    const int n = pos_lookup_dense_tail<NK>(ix, key, row, active);
-    if (n == 1) {
-      if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, *row);
-      if (extra_col2 >= 0) *extra2 = table_cell(ix.tab, (u32)extra_col2, *row);
-    }
-    return n;
+  bool tail = false;  // key[ix.tail_key] == ix.tail_val, without indexing `key` by a run-time value
+#pragma unroll
+  for (int j = 0; j < NK; j++) {  // every cell compared unconditionally, combined without short-circuit: a conditional read
+    const bool e = fr_eq_u64(key[j], ix.tail_val);  // of key[j] is turned back into key[tail_key] by the compiler, which
+    tail |= (j == ix.tail_key) & e;                 // puts the caller's key array in local memory
   }
-  const u64 base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
-  const u64 limit = ix.tail_key >= 0 ? (u64)ld_u32(ix.pos_ok + 1) : ix.tab.n_rows;  // the dense head: rows [0, split)
+  const u64 split = ix.tail_key >= 0 ? (u64)ld_u32(ix.pos_ok + 1) : ix.tab.n_rows;  // dense head = rows [0, split)
+  const u64 offset = tail ? split : 0;
+  const u64 limit = tail ? ix.tab.n_rows - split : split;
+  u64 base;
+  if (tail) base = limit ? table_cell(ix.tab, ix.key_cols[0], split).l[0] : 0;
+  else base = base0 ? *base0 : table_cell(ix.tab, ix.key_cols[0], 0).l[0];
   const bool in_range = fr_fits64(key[0]) && key[0].l[0] >= base && key[0].l[0] - base < limit;
   const bool valid = active && in_range;
-  const u64 cand = valid ? key[0].l[0] - base : 0;
+  const u64 cand = valid ? offset + (key[0].l[0] - base) : 0;
   Fr cells[NK];  // independent loads first, compares after
 #pragma unroll
   for (int j = 1; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
