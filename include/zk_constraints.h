@@ -687,7 +687,28 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_SBAL_ACC_AMBIG, ZKE_AMBIG, "selfbalance.py:12 account_read_word(Balance) ambiguous")                      \
   X(EV_SBAL_PUSH_UNSAT, ZKE_UNSAT, "selfbalance.py:13 stack_push unsat")                                         \
   X(EV_SBAL_PUSH_AMBIG, ZKE_AMBIG, "selfbalance.py:13 stack_push ambiguous")                                     \
-  X(EV_SBAL_EQ, ZKE_ASSERT, "selfbalance.py:13 pushed word == balance")
+  X(EV_SBAL_EQ, ZKE_ASSERT, "selfbalance.py:13 pushed word == balance")                                          \
+  /* out-of-gas / out-of-bound error states (error_oog_sha3.py, error_oog_static_memory_expansion.py,            \
+   * error_oog_dynamic_memory_expansion.py, error_oog_log.py, error_oog_exp.py, error_return_data_out_of_bound.py): \
+   * one id per KIND of constraint, shared by the six gate programs (a step reports one id; its state names the file) */ \
+  X(EV_EOOG_OPCODE, ZKE_ASSERT, "error_oog_*.py / error_return_data_out_of_bound.py: the opcode is not one the state is responsible for") \
+  X(EV_EOOG_LOG_RANGE5, ZKE_UNSAT, "error_oog_log.py:12 range_lookup(opcode - LOG0, 5)")                          \
+  X(EV_EOOG_POP0_UNSAT, ZKE_UNSAT, "first stack lookup of the error state unsat")                                \
+  X(EV_EOOG_POP0_AMBIG, ZKE_AMBIG, "first stack lookup of the error state ambiguous")                            \
+  X(EV_EOOG_POP1_UNSAT, ZKE_UNSAT, "second stack lookup of the error state unsat")                               \
+  X(EV_EOOG_POP1_AMBIG, ZKE_AMBIG, "second stack lookup of the error state ambiguous")                           \
+  X(EV_EOOG_W0_DOMAIN, ZKE_VALUE, "word_to_fq / byte_size of the first word: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_EOOG_W0_RANGE, ZKE_RANGE, "word_to_fq of the first word: too many bytes (instruction.py:480-484)")        \
+  X(EV_EOOG_W1_DOMAIN, ZKE_VALUE, "word_to_fq of the second word: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_EOOG_W1_RANGE, ZKE_RANGE, "word_to_fq of the second word: too many bytes")                                \
+  X(EV_EOOG_MEMSIZE_RANGE, ZKE_RANGE, "memory_expansion[_dynamic_length]: memory size exceeds 4 bytes (instruction.py:1139-1145, 1164-1166)") \
+  X(EV_EOOG_MEM_MAX, ZKE_ASSERT, "memory_expansion[_dynamic_length]: max(): curr.memory_word_size exceeds 4 bytes") \
+  X(EV_EOOG_WORDSIZE_RANGE, ZKE_RANGE, "error_oog_sha3.py:24-26 minimum_word_size exceeds 4 bytes")              \
+  X(EV_EOOG_CC_UNSAT, ZKE_UNSAT, "error_return_data_out_of_bound.py:16-18 call_context_lookup(LastCalleeReturnDataLength) unsat") \
+  X(EV_EOOG_CC_AMBIG, ZKE_AMBIG, "error_return_data_out_of_bound.py:16-18 call_context_lookup ambiguous")        \
+  X(EV_EOOG_CC_TYPE, ZKE_ASSERT, "error_return_data_out_of_bound.py:16-18 .value(): the cell is a Word")         \
+  X(EV_EOOG_CMP_RANGE, ZKE_ASSERT, "compare(): an operand exceeds n_bytes (8: gas; 31: return data end)")        \
+  X(EV_EOOG_NOT_ENOUGH, ZKE_ASSERT, "gas_left < required gas / no out-of-bound condition holds")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

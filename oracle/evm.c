@@ -445,8 +445,8 @@ static int call_context_w(evm_env* e, fr_t rwc, uint64_t rw, fr_t call_id, uint6
 }
 /* step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None;
  * rw_off = rw lookups the gadget already did, add_rev = curr state halts in success */
-static void restore_context(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_off, fr_t ret_off, fr_t ret_len,
-                            fr_t gas_left, int add_rev) {
+static void restore_context_x(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_off, fr_t ret_off, fr_t ret_len,
+                              fr_t gas_left, int add_rev, fr_t extra_delta) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
   const fr_t rwc = CUR(S_RWC);
   static const uint64_t READ_TAGS[8] = {ZK_CC_IsRoot, ZK_CC_IsCreate, ZK_CC_CodeHash, ZK_CC_ProgramCounter,
@@ -469,7 +469,8 @@ static void restore_context(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_of
   }
   CHECK(EV_RST_VALUE_TYPE, !words[0] && !words[1] && !words[3] && !words[4] && !words[5] && !words[6] && !words[7]);
   const fr_t rev = add_rev ? CUR(S_REV) : fr_u64(0);
-  CHECK(EV_RST_RWC, fr_eq(NXT(S_RWC), fr_add(rwc, fr_u64(rw_off + 12))));
+  /* extra_delta: rw counters the step consumes without looking them up (the reverted writes of an error state) */
+  CHECK(EV_RST_RWC, fr_eq(NXT(S_RWC), fr_add(fr_add(rwc, fr_u64(rw_off + 12)), extra_delta)));
   CHECK(EV_RST_CALL_ID, fr_eq(NXT(S_CALL_ID), caller_id));
   CHECK(EV_RST_IS_ROOT, fr_eq(NXT(S_IS_ROOT), vals[0].lo));
   CHECK(EV_RST_IS_CREATE, fr_eq(NXT(S_IS_CREATE), vals[1].lo));
@@ -479,6 +480,10 @@ static void restore_context(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_of
   CHECK(EV_RST_GAS, fr_eq(NXT(S_GAS), fr_add(vals[5].lo, gas_left)));
   CHECK(EV_RST_MEM, fr_eq(NXT(S_MEM), vals[6].lo));
   CHECK(EV_RST_REV, fr_eq(NXT(S_REV), fr_add(vals[7].lo, rev)));
+}
+static void restore_context(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_off, fr_t ret_off, fr_t ret_len,
+                            fr_t gas_left, int add_rev) {
+  restore_context_x(e, i, row, rw_off, ret_off, ret_len, gas_left, add_rev, fr_u64(0));
 }
 
 static void gadget_stop(evm_env* e, uint64_t i, uint64_t row) {
@@ -896,6 +901,7 @@ static void gadget_shl_shr(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
 
 static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_tx.h"
+#include "evm_err.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -928,7 +934,11 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_RETURNDATASIZE || st == ZK_ES_CODESIZE || st == ZK_ES_BITWISE ||
                                   st == ZK_ES_NOT || st == ZK_ES_BYTE || st == ZK_ES_SCMP || st == ZK_ES_SIGNEXTEND ||
                                   st == ZK_ES_BlockCtx || st == ZK_ES_ORIGIN || st == ZK_ES_GASPRICE ||
-                                  st == ZK_ES_SHL_SHR || st == ZK_ES_BeginTx || st == ZK_ES_EndTx || st == ZK_ES_EndBlock);
+                                  st == ZK_ES_SHL_SHR || st == ZK_ES_BeginTx || st == ZK_ES_EndTx || st == ZK_ES_EndBlock ||
+                                  st == ZK_ES_ErrorStack || st == ZK_ES_ErrorInvalidOpcode || st == ZK_ES_ErrorOutOfGasConstant ||
+                                  st == ZK_ES_ErrorInvalidJump || st == ZK_ES_SELFBALANCE || st == ZK_ES_ErrorOutOfGasSHA3 ||
+                                  st == ZK_ES_ErrorOutOfGasStaticMemoryExpansion || st == ZK_ES_ErrorOutOfGasDynamicMemoryExpansion ||
+                                  st == ZK_ES_ErrorOutOfGasLOG || st == ZK_ES_ErrorOutOfGasEXP || st == ZK_ES_ErrorReturnDataOutOfBound);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -963,6 +973,17 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_SIGNEXTEND) gadget_signextend(e, i, row, opcode);
   else if (st == ZK_ES_BlockCtx) gadget_blockctx(e, i, row, opcode);
   else if (st == ZK_ES_SHL_SHR) gadget_shl_shr(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorStack) gadget_error_stack(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorInvalidOpcode) gadget_error_invalid_opcode(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasConstant) gadget_error_oog_constant(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorInvalidJump) gadget_error_invalid_jump(e, i, row, opcode);
+  else if (st == ZK_ES_SELFBALANCE) gadget_selfbalance(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasSHA3) gadget_error_oog_sha3(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasStaticMemoryExpansion) gadget_error_oog_static_memory(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) gadget_error_oog_dynamic_memory(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasLOG) gadget_error_oog_log(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasEXP) gadget_error_oog_exp(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorReturnDataOutOfBound) gadget_error_return_data_oob(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

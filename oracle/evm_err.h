@@ -1,0 +1,237 @@
+/*
+ * oracle/evm_err.h — TEST INFRASTRUCTURE (CPU oracle), included by evm.c.
+ *
+ * Restates constrain_error_state (/root/reference/src/zkevm_specs/evm_circuit/instruction.py:1426-1452) and the
+ * gadgets execution/error_stack.py, error_invalid_opcode.py, error_oog_constant.py, error_invalid_jump.py and
+ * selfbalance.py.  Pinned by tests/golden/evm12.npz.
+ */
+
+/* constrain_error_state(rw_counter_offset + curr.reversible_write_counter): `n_rw` = rw lookups the gadget did */
+static void error_state_tail(evm_env* e, uint64_t i, uint64_t row, uint64_t n_rw) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+  const fr_t rwc = CUR(S_RWC), rev = CUR(S_REV);
+  word_t v; int w;
+  if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(n_rw)), 0, CUR(S_CALL_ID), ZK_CC_IsSuccess, &v, &w), EV_ERR_CC_UNSAT, row)) return;
+  CHECK(EV_ERR_CC_TYPE, !w);
+  CHECK(EV_ERR_IS_SUCCESS, fr_is_zero(v.lo));
+  const fr_t is_root = CUR(S_IS_ROOT);
+  CHECK(EV_ERR_ROOT_ENDTX, fr_eq_u64(is_root, fr_eq_u64(NXT(S_STATE), ZK_ES_EndTx) ? 1 : 0));
+  if (!fr_is_zero(is_root)) {
+    CHECK(EV_ERR_RWC, fr_eq(NXT(S_RWC), fr_add(fr_add(rwc, fr_u64(n_rw + 1)), rev)));
+    CHECK(EV_ERR_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
+  } else {
+    restore_context_x(e, i, row, n_rw + 1, fr_u64(0), fr_u64(0), fr_u64(0), 0, rev);
+  }
+}
+
+/* error_stack.py */
+static void gadget_error_stack(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  fr_t key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), CUR(S_STATE), opcode, CUR(S_SP)};
+  CHECK(EV_ESTK_RESP_OPCODE, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  error_state_tail(e, i, row, 0);
+}
+/* error_invalid_opcode.py */
+static void gadget_error_invalid_opcode(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  fr_t key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), CUR(S_STATE), opcode, fr_u64(0)};
+  CHECK(EV_EINV_RESP_OPCODE, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  error_state_tail(e, i, row, 0);
+}
+/* error_oog_constant.py */
+static void gadget_error_oog_constant(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_EOGC_OPCODE_VALUE, fr_fits_bits(opcode, 8) && OPCODE_GAS[opcode.l[0]] >= 0);
+  const fr_t gas = fr_u64((uint64_t)OPCODE_GAS[opcode.l[0]]);
+  fr_t key[4] = {fr_u64(ZK_FIXED_OpcodeConstantGas), opcode, gas, fr_u64(0)};
+  CHECK(EV_EOGC_GAS_UNSAT, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_EOGC_CMP_RANGE, fr_fits_bits(gas_left, 64) && fr_fits_bits(gas, 64));
+  CHECK(EV_EOGC_NOT_ENOUGH, gas_left.l[0] < gas.l[0]);
+  error_state_tail(e, i, row, 0);
+}
+/* error_invalid_jump.py: NB constrain_error_state sits INSIDE `if within_range == FQ(1)` (:24-33) — a destination at
+ * or beyond the code length leaves the step's ending unconstrained */
+static void gadget_error_invalid_jump(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  CHECK(EV_EJMP_OPCODE, fr_eq_u64(opcode, 0x56) || fr_eq_u64(opcode, 0x57));
+  const int is_jumpi = fr_eq_u64(opcode, 0x57);
+  fr_t code_length;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 1, fr_u64(0), 0, &code_length), EV_EJMP_LEN_UNSAT, row)) return;
+  word_t dest, cond;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &dest), EV_EJMP_DEST_UNSAT, row)) return;
+  if (is_jumpi) {
+    if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(1)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &cond), EV_EJMP_COND_UNSAT, row)) return;
+    CHECK(EV_EJMP_COND_ZERO, !(fr_is_zero(cond.lo) && fr_is_zero(cond.hi)));
+  }
+  /* word_to_u64 = word_to_fq(word, 8) (instruction.py:480-484) */
+  CHECK(EV_EJMP_DEST_DOMAIN, word_in_domain(dest));
+  CHECK(EV_EJMP_DEST_U64, !(dest.lo.l[1] || dest.hi.l[0] || dest.hi.l[1]));
+  const uint64_t d = dest.lo.l[0];
+  CHECK(EV_EJMP_CMP_RANGE, fr_fits_bits(code_length, 64));
+  if (d < code_length.l[0]) {
+    /* bytecode_lookup_pair: key (hash, Byte, index), is_code not queried */
+    fr_t key[4] = {CUR(S_HASH_LO), CUR(S_HASH_HI), fr_u64(2), fr_u64(d)};
+    uint32_t r = 0; const int nn = orc_lookup_prefix(&e->bytecode_ix, key, 4, &r);
+    if (!need1(e, nn, EV_EJMP_AT_UNSAT, row)) return;
+    const fr_t value = fr_load(ORC_CELL(e->bytecode_ix.cells, e->bytecode_ix.n_rows, B_VALUE, r));
+    const fr_t is_code = fr_load(ORC_CELL(e->bytecode_ix.cells, e->bytecode_ix.n_rows, B_ISCODE, r));
+    /* is_code * FQ(value == JUMPDEST) == 0 */
+    CHECK(EV_EJMP_IS_JUMPDEST, fr_is_zero(is_code) || !fr_eq_u64(value, 0x5b));
+    error_state_tail(e, i, row, 1 + (uint64_t)is_jumpi);
+  }
+}
+/* selfbalance.py */
+static void gadget_selfbalance(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID);
+  CHECK(EV_SBAL_OPCODE, fr_eq_u64(opcode, 0x47));
+  uint32_t r;
+  LK(cc_lookup(e, rwc, call_id, ZK_CC_CalleeAddress, &r), EV_SBAL_CC_UNSAT);
+  const word_t callee = rw_value(e, r);
+  /* word_to_address = word_to_fq(word, 20) */
+  CHECK(EV_SBAL_ADDR_DOMAIN, word_in_domain(callee));
+  CHECK(EV_SBAL_ADDR_RANGE, !((callee.hi.l[0] >> 32) || callee.hi.l[1]));
+  fr_t address = {{callee.lo.l[0], callee.lo.l[1], callee.hi.l[0], 0}};
+  LK(account_lookup(e, fr_add(rwc, fr_u64(1)), 0, address, ZK_ACC_Balance, &r), EV_SBAL_ACC_UNSAT);
+  const word_t balance = rw_value(e, r);
+  word_t w;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(2)), 1, ZK_TARGET_Stack, call_id, fr_sub(CUR(S_SP), fr_u64(1)), &w), EV_SBAL_PUSH_UNSAT, row)) return;
+  CHECK(EV_SBAL_EQ, word_eq(w, balance));
+  same_context(e, i, row, opcode, 3, fr_u64(1), fr_neg(fr_u64(1)));
+}
+
+/* ---- out-of-gas / out-of-bound error states ------------------------------------------------------------------ */
+/* word_to_fq(word, n_bytes) for n_bytes <= 31: 0 ok, 1 -> OverflowError, 2 -> ConstraintUnsatFailure */
+static int word_to_fq_nb(word_t w, int n_bytes, fr_t* out) {
+  if (!word_in_domain(w)) return 1;
+  const uint64_t v[4] = {w.lo.l[0], w.lo.l[1], w.hi.l[0], w.hi.l[1]};
+  fr_t r = fr_u64(0);
+  for (int k = 0; k < 32; k++) {
+    const uint64_t b = (v[k >> 3] >> (8 * (k & 7))) & 0xFF;
+    if (k >= n_bytes) { if (b) return 2; } else r.l[k >> 3] |= b << (8 * (k & 7));
+  }
+  *out = r;
+  return 0;
+}
+#define W2FQ(word, nb, out, id_domain) do { const int rc_ = word_to_fq_nb((word), (nb), (out)); \
+  if (rc_) { orc_fail(e->res, rc_ == 1 ? (id_domain) : (id_domain) + 1, row); return; } } while (0)
+/* memory size in words of [offset, offset + length) and the gas of growing the memory to it (memory_expansion /
+ * memory_expansion_dynamic_length, instruction.py:1138-1177); offset, length < 2^40 */
+static int mem_expansion_gas(evm_env* e, uint64_t i, uint64_t words_needed, uint64_t* gas) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  if (words_needed >> 32) return 1;  /* range_check(memory_size, 4) */
+  const fr_t cur = CUR(S_MEM);
+  if (!fr_fits_bits(cur, 32)) return 2;  /* max(): compare asserts 4 bytes */
+  const uint64_t nxt = cur.l[0] < words_needed ? words_needed : cur.l[0];
+  *gas = memory_gas_cost(nxt) - memory_gas_cost(cur.l[0]);
+  return 0;
+}
+#define MEMGAS(words, gas) do { const int rc_ = mem_expansion_gas(e, i, (words), (gas)); \
+  if (rc_) { orc_fail(e->res, rc_ == 1 ? EV_EOOG_MEMSIZE_RANGE : EV_EOOG_MEM_MAX, row); return; } } while (0)
+/* compare(gas_left, cost, 8) == lt, then constrain_error_state */
+static void oog_finish(evm_env* e, uint64_t i, uint64_t row, u128 cost, uint64_t n_rw) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_EOOG_CMP_RANGE, fr_fits_bits(gas_left, 64) && !(cost >> 64));
+  CHECK(EV_EOOG_NOT_ENOUGH, gas_left.l[0] < (uint64_t)cost);
+  error_state_tail(e, i, row, n_rw);
+}
+#define POP(k, out, id) do { if (!need1(e, rw_lookup(e, fr_add(CUR(S_RWC), fr_u64(k)), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), \
+  fr_add(CUR(S_SP), fr_u64(k)), (out)), (id), row)) return; } while (0)
+
+/* error_oog_sha3.py */
+static void gadget_error_oog_sha3(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_EOOG_OPCODE, fr_eq_u64(opcode, 0x20));
+  word_t off_w, size_w;
+  POP(0, &off_w, EV_EOOG_POP0_UNSAT);
+  POP(1, &size_w, EV_EOOG_POP1_UNSAT);
+  fr_t length, offset = fr_u64(0);  /* memory_offset_and_length: the length first (the second word) */
+  W2FQ(size_w, 5, &length, EV_EOOG_W1_DOMAIN);
+  if (!fr_is_zero(length)) W2FQ(off_w, 5, &offset, EV_EOOG_W0_DOMAIN);
+  uint64_t expansion;
+  MEMGAS((offset.l[0] + length.l[0] + 31) / 32, &expansion);
+  const uint64_t words = (length.l[0] + 31) / 32;
+  CHECK(EV_EOOG_WORDSIZE_RANGE, !(words >> 32));
+  oog_finish(e, i, row, (u128)30 + (u128)words * 6 + expansion, 2);
+}
+/* error_oog_static_memory_expansion.py: `size = 1 if is_mstore8 else 32` tests the truthiness of an FQ object, which
+ * is always true — the reference charges the expansion of ONE byte whatever the opcode (reproduced as written) */
+static void gadget_error_oog_static_memory(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_EOOG_OPCODE, fr_eq_u64(opcode, 0x51) || fr_eq_u64(opcode, 0x52) || fr_eq_u64(opcode, 0x53));
+  word_t off_w;
+  POP(0, &off_w, EV_EOOG_POP0_UNSAT);
+  fr_t offset;
+  W2FQ(off_w, 5, &offset, EV_EOOG_W0_DOMAIN);
+  uint64_t expansion;
+  MEMGAS((offset.l[0] + 1 + 31) / 32, &expansion);
+  oog_finish(e, i, row, (u128)3 + expansion, 1);
+}
+/* error_oog_dynamic_memory_expansion.py */
+static void gadget_error_oog_dynamic_memory(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_EOOG_OPCODE, fr_eq_u64(opcode, 0xf3) || fr_eq_u64(opcode, 0xfd));
+  word_t off_w, size_w;
+  POP(0, &off_w, EV_EOOG_POP0_UNSAT);
+  POP(1, &size_w, EV_EOOG_POP1_UNSAT);
+  fr_t length, offset = fr_u64(0);
+  W2FQ(size_w, 5, &length, EV_EOOG_W1_DOMAIN);
+  if (!fr_is_zero(length)) W2FQ(off_w, 5, &offset, EV_EOOG_W0_DOMAIN);
+  uint64_t expansion;  /* memory_expansion: size 0 when length == 0 */
+  MEMGAS(fr_is_zero(length) ? 0 : (offset.l[0] + length.l[0] + 31) / 32, &expansion);
+  oog_finish(e, i, row, expansion, 2);
+}
+/* error_oog_log.py */
+static void gadget_error_oog_log(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t topics = fr_sub(opcode, fr_u64(0xa0));
+  {
+    fr_t key[4] = {fr_u64(ZK_FIXED_Range5), topics, fr_u64(0), fr_u64(0)};
+    CHECK(EV_EOOG_LOG_RANGE5, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  }
+  word_t start_w, size_w;
+  POP(0, &start_w, EV_EOOG_POP0_UNSAT);
+  fr_t mstart, msize;
+  W2FQ(start_w, 5, &mstart, EV_EOOG_W0_DOMAIN);
+  POP(1, &size_w, EV_EOOG_POP1_UNSAT);
+  W2FQ(size_w, 5, &msize, EV_EOOG_W1_DOMAIN);
+  uint64_t expansion;
+  MEMGAS((mstart.l[0] + msize.l[0] + 31) / 32, &expansion);
+  /* topics is a fixed-table value here (0..4 with the reference's table), the cost stays far below 2^64 */
+  oog_finish(e, i, row, (u128)375 + (u128)375 * topics.l[0] + (u128)8 * msize.l[0] + expansion, 2);
+}
+/* error_oog_exp.py */
+static void gadget_error_oog_exp(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  CHECK(EV_EOOG_OPCODE, fr_eq_u64(opcode, 0x0a));
+  word_t expo;  /* stack_lookup(Read, 1): the first rw lookup of the step, at stack_pointer + 1 */
+  if (!need1(e, rw_lookup(e, CUR(S_RWC), 0, ZK_TARGET_Stack, CUR(S_CALL_ID), fr_add(CUR(S_SP), fr_u64(1)), &expo), EV_EOOG_POP0_UNSAT, row)) return;
+  CHECK(EV_EOOG_W0_DOMAIN, word_in_domain(expo));
+  const uint64_t v[4] = {expo.lo.l[0], expo.lo.l[1], expo.hi.l[0], expo.hi.l[1]};
+  uint64_t size = 0;
+  for (int k = 0; k < 32; k++) if ((v[k >> 3] >> (8 * (k & 7))) & 0xFF) size = (uint64_t)k + 1;
+  oog_finish(e, i, row, (u128)50 * size + 10, 1);
+}
+/* error_return_data_out_of_bound.py */
+static void gadget_error_return_data_oob(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  CHECK(EV_EOOG_OPCODE, fr_eq_u64(opcode, 0x3e));
+  word_t off_w, len_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &off_w), EV_EOOG_POP0_UNSAT, row)) return;
+  fr_t data_offset, length;
+  W2FQ(off_w, 31, &data_offset, EV_EOOG_W0_DOMAIN);
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(1)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(2)), &len_w), EV_EOOG_POP1_UNSAT, row)) return;
+  W2FQ(len_w, 31, &length, EV_EOOG_W1_DOMAIN);
+  word_t v; int w;
+  if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(2)), 0, call_id, ZK_CC_LastCalleeReturnDataLength, &v, &w), EV_EOOG_CC_UNSAT, row)) return;
+  CHECK(EV_EOOG_CC_TYPE, !w);
+  const fr_t rdl = v.lo, end = fr_add(data_offset, length);  /* < 2^249: no reduction */
+  const int off_over = !fr_fits_bits(data_offset, 64), end_over = !fr_fits_bits(end, 64);
+  CHECK(EV_EOOG_CMP_RANGE, fr_fits_bits(rdl, 248) && fr_fits_bits(end, 248));
+  CHECK(EV_EOOG_NOT_ENOUGH, off_over || end_over || fr_cmp(rdl, end) < 0);
+  error_state_tail(e, i, row, 3);
+}

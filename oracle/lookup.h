@@ -74,4 +74,26 @@ static inline int orc_lookup(const orc_index* ix, const fr_t* key, uint32_t* row
     if (!orc_rows_identical(ix, first, ix->order[j])) return 2;
   return 1;
 }
+/* the same on the first n_prefix key columns only (the remaining key columns are not queried): the index is sorted
+ * on all its key columns, so the rows that match a prefix are contiguous */
+static inline int orc_prefix_cmp(const orc_index* ix, uint32_t row, const fr_t* key, uint32_t n_prefix) {
+  for (uint32_t k = 0; k < n_prefix; k++) {
+    int c = fr_cmp(fr_load(ORC_CELL(ix->cells, ix->n_rows, ix->key_cols[k], row)), key[k]);
+    if (c) return c;
+  }
+  return 0;
+}
+static inline int orc_lookup_prefix(const orc_index* ix, const fr_t* key, uint32_t n_prefix, uint32_t* row) {
+  uint64_t lo = 0, hi = ix->n_rows;
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) / 2;
+    if (orc_prefix_cmp(ix, ix->order[mid], key, n_prefix) < 0) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= ix->n_rows || orc_prefix_cmp(ix, ix->order[lo], key, n_prefix) != 0) return 0;
+  uint32_t first = ix->order[lo];
+  if (row) *row = first;
+  for (uint64_t j = lo + 1; j < ix->n_rows && orc_prefix_cmp(ix, ix->order[j], key, n_prefix) == 0; j++)
+    if (!orc_rows_identical(ix, first, ix->order[j])) return 2;
+  return 1;
+}
 #endif

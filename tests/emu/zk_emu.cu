@@ -248,6 +248,9 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   t.wd = wd_ix.tab;
   t.rw_rwc = build_index((const u64*)rw, n_rw, 14, wk, 1, ch, s9);  // same storage choice as t.rw (same matrix)
   t.rw_rwc.tab = t.rw.tab;
+  IndexStore s10;
+  t.bytecode4 = build_index((const u64*)bytecode, n_bytecode, 6, k4, 4, ch, s10);  // bytecode_lookup_pair (evm_err.cuh)
+  t.bytecode4.tab = t.bytecode.tab;
   g_emu_tx = g_emu_block = nullptr;
   g_emu_n_tx = g_emu_n_block = 0;
   g_emu_tx_flags = g_emu_block_flags = nullptr;

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1196,6 +1196,127 @@ def evm2_cases(part="evm2"):
     def blk_ints(x):
         return [n_of(x.field_tag), n_of(x.block_number_or_zero), n_of(x.value.lo), n_of(x.value.hi)]
 
+    def caller_ctx_rws(rw, caller_id, ch, ctx, callee_id):
+        """the 12 call-context rows of step_state_transition_to_restored_context (instruction.py:293-363)"""
+        c_root, c_create, c_pc, c_sp, c_gas, c_mem, c_rev = ctx
+        return (rw.call_context_read(callee_id, CallContextFieldTag.CallerId, caller_id)
+                .call_context_read(caller_id, CallContextFieldTag.IsRoot, c_root)
+                .call_context_read(caller_id, CallContextFieldTag.IsCreate, c_create)
+                .call_context_read(caller_id, CallContextFieldTag.CodeHash, ch)
+                .call_context_read(caller_id, CallContextFieldTag.ProgramCounter, c_pc)
+                .call_context_read(caller_id, CallContextFieldTag.StackPointer, c_sp)
+                .call_context_read(caller_id, CallContextFieldTag.GasLeft, c_gas)
+                .call_context_read(caller_id, CallContextFieldTag.MemorySize, c_mem)
+                .call_context_read(caller_id, CallContextFieldTag.ReversibleWriteCounter, c_rev)
+                .call_context_write(caller_id, CallContextFieldTag.LastCalleeId, callee_id)
+                .call_context_write(caller_id, CallContextFieldTag.LastCalleeReturnDataOffset, 0)
+                .call_context_write(caller_id, CallContextFieldTag.LastCalleeReturnDataLength, 0))
+
+    def error_case(kind, root, arg=None):
+        """tests/evm/test_error_{stack,invalid_opcode,oog_constant,invalid_jump}.py: an error state in the root call
+        (-> EndTx) or in an internal call (restores the caller's context), reversible_write_counter 2"""
+        from zkevm_specs.evm_circuit import AccountFieldTag  # noqa: F401
+        rev, pops = 2, []
+        if kind == "stack_underflow":
+            bc, state, pc, sp, gas = Bytecode().pop(), ExecutionState.ErrorStack, 0, 1024, 2
+        elif kind == "stack_overflow":
+            bc, state, pc, sp, gas = Bytecode().push1(0x10).push1(0x20), ExecutionState.ErrorStack, 2, 0, 10
+        elif kind == "invalid_opcode":
+            bc = Bytecode(bytearray(arg), [True] * len(arg)).stop()
+            state, pc, sp, gas = ExecutionState.ErrorInvalidOpcode, 0, 1024, 2
+        elif kind == "oog_constant":
+            bc, state, pc, sp, gas = Bytecode().push1(0x40), ExecutionState.ErrorOutOfGasConstant, 0, 1023, 2
+        else:  # invalid_jump: arg = (opcode name, dest, cond)
+            op, dest, cond = arg
+            bc = Bytecode().push1(0x80).push1(cond).push1(dest)
+            bc = (bc.jump() if op == "jump" else bc.jumpi()).jumpdest().stop()
+            state, pc, sp, gas, rev = ExecutionState.ErrorInvalidJump, 6, 1021, 8, 0
+            pops = [Word(dest)] + ([Word(cond)] if op == "jumpi" else [])
+        h = Word(bc.hash())
+        call_id = 1 if root else 2
+        rw = RWDictionary(24 if root else 69)
+        rwc0 = rw.rw_counter
+        for k, wd in enumerate(pops):
+            rw.stack_read(call_id, sp + k, wd)
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(state, rw_counter=rwc0, call_id=call_id, is_root=root, is_create=False, code_hash=h,
+                        program_counter=pc, stack_pointer=sp, gas_left=gas, reversible_write_counter=rev)
+        if root:
+            nxt = StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)
+            return [cur, nxt], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (True, False, 232, 1023, 10, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                        reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
+    def selfbalance_case(callee, balance):
+        """tests/evm/test_selfbalance.py"""
+        from zkevm_specs.evm_circuit import AccountFieldTag
+        bc = Bytecode().selfbalance().stop()
+        h = Word(bc.hash())
+        rw = (RWDictionary(9).call_context_read(1, CallContextFieldTag.CalleeAddress, Word(callee))
+              .account_read(callee, AccountFieldTag.Balance, Word(balance)).stack_write(1, 1023, Word(balance)))
+        steps = [StepState(ExecutionState.SELFBALANCE, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=0, stack_pointer=1024, gas_left=5),
+                 StepState(ExecutionState.STOP, rw_counter=12, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=1, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
+    def oog_case(kind, root, a=0, b=0, gas_left=0, cur_mem=0, op=None):
+        """tests/evm/test_error_oog_{sha3,static_memory_expansion,dynamic_memory_expansion,log,exp}.py and
+        test_error_return_data_out_of_bound.py: one error step, then EndTx (root) or the restored caller"""
+        rev, extra_cc = 2, []
+        if kind == "sha3":       # a = offset, b = size
+            bc, state, pc, sp = Bytecode().push32(b).push32(a).sha3().stop(), ExecutionState.ErrorOutOfGasSHA3, 66, 1022
+            pops = [(0, Word(a)), (1, Word(b))]
+        elif kind == "static":   # a = offset
+            bc = Bytecode().push32(7).push32(a)
+            bc = {Opcode.MLOAD: bc.mload, Opcode.MSTORE: bc.mstore, Opcode.MSTORE8: bc.mstore8}[op]().stop()
+            state, pc, sp, pops = ExecutionState.ErrorOutOfGasStaticMemoryExpansion, 66, 1022, [(0, Word(a))]
+        elif kind == "dynamic":  # a = offset, b = size
+            bc = Bytecode().push32(b).push32(a)
+            bc = (bc.return_() if op == Opcode.RETURN else bc.revert()).stop()
+            state, pc, sp, pops = ExecutionState.ErrorOutOfGasDynamicMemoryExpansion, 66, 1022, [(0, Word(a)), (1, Word(b))]
+        elif kind == "log":      # a = mstart, b = msize, op = LOGn
+            bc = Bytecode().push32(b).push32(a)
+            bc.code.append(int(op)); bc.is_code.append(True)
+            bc = bc.stop()
+            state, pc, sp, pops = ExecutionState.ErrorOutOfGasLOG, 66, 1022, [(0, Word(a)), (1, Word(b))]
+        elif kind == "exp":      # a = exponent
+            bc = Bytecode().push32(a).push32(3).exp().stop()
+            state, pc, sp, pops = ExecutionState.ErrorOutOfGasEXP, 66, 1022, [(1, Word(a))]
+        else:                    # return data: a = data_offset, b = length, cur_mem reused as return_data_length
+            bc = Bytecode().push32(b).push32(a).push32(32).returndatacopy().stop()
+            state, pc, sp, pops = ExecutionState.ErrorReturnDataOutOfBound, 99, 1021, [(1, Word(a)), (2, Word(b))]
+            extra_cc = [(CallContextFieldTag.LastCalleeReturnDataLength, cur_mem)]
+            cur_mem = 0
+        h = Word(bc.hash())
+        call_id = 1 if root else 2
+        rw = RWDictionary(15 if root else 40)
+        rwc0 = rw.rw_counter
+        for off, wd in pops:
+            rw.stack_read(call_id, sp + off, wd)
+        for tag, val in extra_cc:
+            rw.call_context_read(call_id, tag, val)
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(state, rw_counter=rwc0, call_id=call_id, is_root=root, is_create=False, code_hash=h, program_counter=pc,
+                        stack_pointer=sp, gas_left=gas_left, memory_word_size=cur_mem, reversible_write_counter=rev)
+        if root:
+            nxt = StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)
+            return [cur, nxt], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (False, False, 232, 1023, 77, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                        reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
     def run(S, B, R, RF, C, K, T=(), BL=()):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
@@ -1216,7 +1337,36 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm10":
+    if part == "evm13":
+        M64 = (1 << 64) - 1
+        scenarios = {
+            "sha3_root": oog_case("sha3", True, 0x20, 0x40, 40), "sha3_internal_zero": oog_case("sha3", False, 0x20, 0, 29),
+            "sha3_mem": oog_case("sha3", True, 0x100, 0x21, 50, cur_mem=2),
+            "static_mload_root": oog_case("static", True, 0x40, gas_left=5, op=Opcode.MLOAD),
+            "static_mstore_internal": oog_case("static", False, 0x1000, gas_left=300, op=Opcode.MSTORE),
+            "static_mstore8": oog_case("static", True, 0x20, gas_left=2, cur_mem=9, op=Opcode.MSTORE8),
+            "dynamic_return_root": oog_case("dynamic", True, 0x40, 0x40, 11, op=Opcode.RETURN),
+            "dynamic_revert_internal": oog_case("dynamic", False, 0x100, 0x101, 20, cur_mem=1, op=Opcode.REVERT),
+            "log0_internal": oog_case("log", False, 32, 32, 636, op=Opcode.LOG0), "log2_root": oog_case("log", True, 32, 32, 1386, op=Opcode.LOG2),
+            "log4_zero": oog_case("log", True, 0, 0, 1874, op=Opcode.LOG4),
+            "exp_0_internal": oog_case("exp", False, 0, gas_left=9), "exp_10_root": oog_case("exp", True, 10, gas_left=59),
+            "exp_max": oog_case("exp", False, (1 << 256) - 1, gas_left=1609),
+            "rdo_offset_over": oog_case("rdo", True, M64 + 1, 0, 5, cur_mem=320), "rdo_end_over": oog_case("rdo", False, M64, 1, 5, cur_mem=320),
+            "rdo_len": oog_case("rdo", True, 320, 1, 5, cur_mem=320), "rdo_big": oog_case("rdo", False, 0, M64 + 1, 5, cur_mem=320),
+        }
+    elif part == "evm12":
+        scenarios = {
+            "estk_under_root": error_case("stack_underflow", True), "estk_over_internal": error_case("stack_overflow", False),
+            "einv_0e_root": error_case("invalid_opcode", True, [0x0E]), "einv_fe_internal": error_case("invalid_opcode", False, [0xFE]),
+            "einv_many_root": error_case("invalid_opcode", True, [0x5C, 0x5D, 0x5E]),
+            "eogc_root": error_case("oog_constant", True), "eogc_internal": error_case("oog_constant", False),
+            "ejmp_jump_root": error_case("invalid_jump", True, ("jump", 5, 0x40)),
+            "ejmp_jump_oob_root": error_case("invalid_jump", True, ("jump", 20, 0x40)),
+            "ejmp_jumpi_internal": error_case("invalid_jump", False, ("jumpi", 5, 0x40)),
+            "ejmp_jump_internal_oob": error_case("invalid_jump", False, ("jump", 20, 0x40)),
+            "selfbalance_0": selfbalance_case(0, 10), "selfbalance_big": selfbalance_case(0xCAFE0000000000000000000000000000BEEF1234, (1 << 255) + 987654321),
+        }
+    elif part == "evm10":
         v = 0xFEDCBA9876543210F0E1D2C3B4A5968778695A4B3C2D1E0F0123456789ABCDEF
         scenarios = {
             "shl_0": shift_case("shl", 0, v), "shl_1": shift_case("shl", 1, v), "shl_64": shift_case("shl", 64, v),
@@ -1295,7 +1445,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
@@ -1392,6 +1542,18 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm13_cases():
+    """out-of-gas / out-of-bound error states: ErrorOutOfGasSHA3, ...StaticMemoryExpansion, ...DynamicMemoryExpansion, ...LOG,
+    ...EXP and ErrorReturnDataOutOfBound"""
+    evm2_cases("evm13")
+
+
+def evm12_cases():
+    """error states (ErrorStack, ErrorInvalidOpcode, ErrorOutOfGasConstant, ErrorInvalidJump: constrain_error_state in the
+    root call and with the restore-to-caller branch) and SELFBALANCE"""
+    evm2_cases("evm12")
 
 
 # --------------------------------------------------------------------------- exp
@@ -2209,7 +2371,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -220,6 +220,17 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm13_vectors():
+    """out-of-gas / out-of-bound error states (ErrorOutOfGasSHA3 / StaticMemoryExpansion / DynamicMemoryExpansion / LOG / EXP,
+    ErrorReturnDataOutOfBound)"""
+    return evm2_vectors("evm13")
+
+
+def evm12_vectors():
+    """error states (ErrorStack / ErrorInvalidOpcode / ErrorOutOfGasConstant / ErrorInvalidJump) and SELFBALANCE"""
+    return evm2_vectors("evm12")
+
+
 def evm11_vectors():
     """BeginTx / EndTx / EndBlock steps: yield (case, k, dict(steps, bytecode, rw, rw_flags, copy, keccak, tx, tx_flags,
     block, block_flags, wd, flags = ZK_FLAG_EVM_* of the scenario), exp_row, exp_exc)"""

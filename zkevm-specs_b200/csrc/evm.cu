@@ -38,7 +38,10 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_MSIZE) X(ZK_ES_GAS) X(ZK_ES_ISZERO) X(ZK_ES_CMP) X(ZK_ES_JUMP) X(ZK_ES_JUMPI) X(ZK_ES_CALLER) X(ZK_ES_CALLVALUE) \
   X(ZK_ES_CALLDATASIZE) X(ZK_ES_ADDRESS) X(ZK_ES_RETURNDATASIZE) X(ZK_ES_CODESIZE) X(ZK_ES_BITWISE) X(ZK_ES_NOT)         \
   X(ZK_ES_BYTE) X(ZK_ES_SCMP) X(ZK_ES_SIGNEXTEND) X(ZK_ES_BlockCtx) X(ZK_ES_ORIGIN) X(ZK_ES_GASPRICE) X(ZK_ES_SHL_SHR)      \
-  X(ZK_ES_BeginTx) X(ZK_ES_EndTx) X(ZK_ES_EndBlock)
+  X(ZK_ES_BeginTx) X(ZK_ES_EndTx) X(ZK_ES_EndBlock) X(ZK_ES_ErrorStack) X(ZK_ES_ErrorInvalidOpcode)                    \
+  X(ZK_ES_ErrorOutOfGasConstant) X(ZK_ES_ErrorInvalidJump) X(ZK_ES_SELFBALANCE) X(ZK_ES_ErrorOutOfGasSHA3)                  \
+  X(ZK_ES_ErrorOutOfGasStaticMemoryExpansion) X(ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) X(ZK_ES_ErrorOutOfGasLOG)       \
+  X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -83,6 +86,8 @@ struct EvmTables {
   IndexDev keccak;    // keccak table, key (state_tag, input_rlc, input_len)
   IndexDev tx;        // tx table (tx_id, tag, index | value lo, hi), key = the first three cells (table.py:697-705)
   IndexDev block;     // block table (tag, block number | value lo, hi), key = the first two cells (table.py:691-695)
+  IndexDev bytecode4; // bytecode table keyed on (hash lo, hi, tag, index): bytecode_lookup_pair does not name is_code; only built
+                      // when an ErrorInvalidJump step exists and the bytecode table is not positional
   IndexDev rw_rwc;    // rw table keyed on rw_counter alone: lookups that name other column subsets (evm_tx.cuh);
                       // only built when a BeginTx / EndTx / EndBlock step exists and the rw table is not positional
   TableDev wd;        // withdrawal table (id, validator_id, address, amount), table.py:429-435
@@ -998,8 +1003,9 @@ ZK_HD_NOINLINE int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u6
 // step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None:
 // rw_off = rw lookups the gadget already did; add_rev = the current state halts in success.
 // Lookup k has ids EV_RST0_UNSAT + 3k (+1 ambiguous, +2 value type / written value).
-ZK_HD_NOINLINE void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
-                           const Fr& gas_left, bool add_rev) {
+// extra_delta: rw counters the step consumes without looking them up (the reverted writes of an error state).
+ZK_HD_NOINLINE void restore_context_x(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
+                                      const Fr& gas_left, bool add_rev, const Fr& extra_delta) {
   const u64 READ_TAGS[8] = {ZK_CC_IsRoot,       ZK_CC_IsCreate, ZK_CC_CodeHash,   ZK_CC_ProgramCounter,
                             ZK_CC_StackPointer, ZK_CC_GasLeft,  ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
   const u64 WRITE_TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
@@ -1027,7 +1033,7 @@ ZK_HD_NOINLINE void restore_context(const StepCtx& s, bool live, u64 rw_off, con
   }
   if (!live) return;  // past the last lookup
   EV_CHECK(EV_RST_VALUE_TYPE, !any_word);
-  EV_CHECK(EV_RST_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(rwc, rw_off + 12)));
+  EV_CHECK(EV_RST_RWC, fr_eq(s.nxt(S_RWC), fr_add(fr_add_u64(rwc, rw_off + 12), extra_delta)));
   EV_CHECK(EV_RST_CALL_ID, fr_eq(s.nxt(S_CALL_ID), caller_id));
   EV_CHECK(EV_RST_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), vals[0].lo));
   EV_CHECK(EV_RST_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), vals[1].lo));
@@ -1037,6 +1043,10 @@ ZK_HD_NOINLINE void restore_context(const StepCtx& s, bool live, u64 rw_off, con
   EV_CHECK(EV_RST_GAS, fr_eq(s.nxt(S_GAS), fr_add(vals[5].lo, gas_left)));
   EV_CHECK(EV_RST_MEM, fr_eq(s.nxt(S_MEM), vals[6].lo));
   EV_CHECK(EV_RST_REV, fr_eq(s.nxt(S_REV), add_rev ? fr_add(vals[7].lo, s.cur(S_REV)) : vals[7].lo));
+}
+ZK_HD void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len, const Fr& gas_left,
+                          bool add_rev) {
+  restore_context_x(s, live, rw_off, ret_off, ret_len, gas_left, add_rev, fr_u64(0));
 }
 
 ZK_HD_NOINLINE void gadget_stop(const StepCtx& s, bool live) {
@@ -1555,6 +1565,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 
 }  // namespace zk
 #include "evm_tx.cuh"
+#include "evm_err.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1576,7 +1587,11 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_BITWISE: case ZK_ES_NOT: case ZK_ES_MEMORY: return KG_BYTES32;
     case ZK_ES_SHA3: case ZK_ES_CALLDATACOPY: return KG_COPY;
     case ZK_ES_SHL_SHR: return KG_WIDE;
-    case ZK_ES_STOP: case ZK_ES_BeginTx: case ZK_ES_EndTx: case ZK_ES_EndBlock: return KG_TX;
+    case ZK_ES_STOP: case ZK_ES_BeginTx: case ZK_ES_EndTx: case ZK_ES_EndBlock: case ZK_ES_ErrorStack:
+    case ZK_ES_ErrorInvalidOpcode: case ZK_ES_ErrorOutOfGasConstant: case ZK_ES_ErrorInvalidJump: case ZK_ES_SELFBALANCE:
+    case ZK_ES_ErrorOutOfGasSHA3: case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion:
+    case ZK_ES_ErrorOutOfGasLOG: case ZK_ES_ErrorOutOfGasEXP: case ZK_ES_ErrorReturnDataOutOfBound:
+      return KG_TX;
     default: return -1;
   }
 }
@@ -1630,6 +1645,17 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_BeginTx: gadget_begin_tx(s, (flags & ZK_FLAG_EVM_FIRST_STEP) && s.row == 0); break;
       case ZK_ES_EndTx: gadget_end_tx(s); break;
       case ZK_ES_EndBlock: gadget_end_block(s, (flags & ZK_FLAG_EVM_LAST_STEP) && s.i == s.w.n_rows - 2); break;
+      case ZK_ES_ErrorStack: gadget_error_stack(s); break;
+      case ZK_ES_ErrorInvalidOpcode: gadget_error_invalid_opcode(s); break;
+      case ZK_ES_ErrorOutOfGasConstant: gadget_error_oog_constant(s); break;
+      case ZK_ES_ErrorInvalidJump: gadget_error_invalid_jump(s); break;
+      case ZK_ES_SELFBALANCE: gadget_selfbalance(s); break;
+      case ZK_ES_ErrorOutOfGasSHA3: gadget_error_oog_sha3(s); break;
+      case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: gadget_error_oog_static_memory(s); break;
+      case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion: gadget_error_oog_dynamic_memory(s); break;
+      case ZK_ES_ErrorOutOfGasLOG: gadget_error_oog_log(s); break;
+      case ZK_ES_ErrorOutOfGasEXP: gadget_error_oog_exp(s); break;
+      case ZK_ES_ErrorReturnDataOutOfBound: gadget_error_return_data_oob(s); break;
       default: break;
     }
   }
