@@ -25,14 +25,17 @@ using namespace zk;
 // tests toggle this to store every matrix in the packed format (each column at the smallest of
 // the widths 0/1/2/4/8/16/32 bytes that holds its values) instead of canonical 32-byte cells
 extern "C" int g_emu_packed = 0;
-extern "C" long long g_emu_narrow_cols = 0;  // columns stored narrower than 32 bytes so far (tests assert > 0)
+extern "C" long long g_emu_narrow_cols = 0;
+extern "C" long long g_emu_narrow_runs = 0;  // EVM checks that took the narrow kernel form (StepCtx::narrow)  // columns stored narrower than 32 bytes so far (tests assert > 0)
 struct Store {  // owns the packed copy of a matrix
   std::vector<unsigned char> buf;
   u64 off[ZK_MAX_COLS];
   unsigned char width[ZK_MAX_COLS];
   const unsigned char* base = nullptr;
 };
-static void store_matrix(Store& st, const u64* cells, u64 n_rows, u32 n_cols, bool allow_pack = true) {
+// `want`: if every column fits these widths, store exactly them (the layout k_bytecode_table_expand writes)
+static void store_matrix(Store& st, const u64* cells, u64 n_rows, u32 n_cols, bool allow_pack = true,
+                         const unsigned char* want = nullptr) {
   if (!g_emu_packed || !allow_pack || n_rows == 0) {
     layout_canonical(st.off, st.width, n_cols, n_rows);
     st.base = (const unsigned char*)cells;
@@ -57,6 +60,18 @@ static void store_matrix(Store& st, const u64* cells, u64 n_rows, u32 n_cols, bo
     g_emu_narrow_cols += w < 32;
     st.off[c] = total;
     total += ((w ? (size_t)w * n_rows : 32) + 31) / 32 * 32;
+  }
+  if (want) {
+    bool fits = true;
+    for (u32 c = 0; c < n_cols; c++) fits = fits && (st.width[c] <= want[c]);
+    if (fits) {
+      total = 0;
+      for (u32 c = 0; c < n_cols; c++) {
+        st.width[c] = want[c];
+        st.off[c] = total;
+        total += ((size_t)want[c] * n_rows + 31) / 32 * 32;
+      }
+    }
   }
   st.buf.assign(total + 32, 0);
   for (u32 c = 0; c < n_cols; c++) {
@@ -87,9 +102,9 @@ struct IndexStore {
   Store st;
 };
 static IndexDev build_index(const u64* cells, u64 n_rows, u32 n_cols, const u32* key_cols, u32 n_key,
-                            const Fr& challenge, IndexStore& own, bool allow_pack = true) {
+                            const Fr& challenge, IndexStore& own, bool allow_pack = true, const unsigned char* want = nullptr) {
   std::vector<u64>& slots = own.slots;
-  store_matrix(own.st, cells, n_rows, n_cols, allow_pack);
+  store_matrix(own.st, cells, n_rows, n_cols, allow_pack, want);
   IndexDev d;
   d.tab.base = own.st.base;
   d.tab.n_rows = n_rows;
@@ -213,7 +228,8 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   const u32 k5[5] = {0, 1, 2, 3, 4}, k4[4] = {0, 1, 2, 3};
   IndexStore s1, s2;
   EvmTables t;
-  t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1);
+  static const unsigned char kFromCode[6] = {16, 16, 1, 4, 1, 4};
+  t.bytecode = build_index((const u64*)bytecode, n_bytecode, 6, k5, 5, ch, s1, true, kFromCode);
   t.rw = build_index((const u64*)rw, n_rw, 14, k5, 5, ch, s2);
   // the fixed table is the same array call after call: keep its index and bitmap
   struct FixedCache { const uint64_t* p = nullptr; uint64_t n = 0, sum = 0; Fr ch; IndexStore slots; IndexDev ix; std::vector<u32> bitmap; };
@@ -276,8 +292,21 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   init_result(res, first_fail, fail_count, EV_N_CONSTRAINTS);
   Fr stack_pre[2];
   stack_key_pre(t.rw, stack_pre);
+  // api.cu:evm_narrow — the narrow instances of the hot kernels run when the storage has these properties
+  auto narrow_col = [](const unsigned char* base, const u64* off, const unsigned char* width, u32 c) {
+    if (width[c] >= 1 && width[c] <= 8) return true;
+    if (width[c] != 0) return false;
+    const u64* cell = (const u64*)(base + off[c]);
+    return (cell[1] | cell[2] | cell[3]) == 0;
+  };
+  bool narrow = g_emu_packed && both_positional(t);
+  for (u32 c = 0; c < 13 && narrow; c++)
+    if (c != 5 && c != 6) narrow = narrow_col(w.base, w.off, w.width, c);
+  for (u32 c = 0; c < 5 && narrow; c++) narrow = narrow_col(t.rw.tab.base, t.rw.tab.off, t.rw.tab.width, c);
+  for (u32 c = 0; c < 6 && narrow; c++) narrow = t.bytecode.tab.width[c] == kFromCode[c];
+  g_emu_narrow_runs += narrow;
   for (u64 i = row_begin; i < row_end; i++) {
-    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u, stack_pre, nullptr, -1};
+    StepCtx s{w, t, res, i, i + 1, row_base + i, true, t.resp_bitmap, 1u, stack_pre, nullptr, -1, narrow ? 1 : 0};
     verify_step(s, flags);
   }
   return 0;

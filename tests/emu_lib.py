@@ -117,6 +117,11 @@ def narrow_cols() -> int:
     return ctypes.c_longlong.in_dll(lib(), "g_emu_narrow_cols").value
 
 
+def narrow_runs() -> int:
+    """EVM checks that took the narrow form of the hot gate programs (StepCtx::narrow)"""
+    return ctypes.c_longlong.in_dll(lib(), "g_emu_narrow_runs").value
+
+
 def set_positional(on: bool) -> None:
     """toggle the positional (regular-table) lookup fast paths in the emulation; off = hash index only"""
     ctypes.c_int.in_dll(lib(), "g_emu_positional").value = int(on)

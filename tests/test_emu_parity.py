@@ -217,6 +217,7 @@ def test_emu_packed_columns_equal_oracle_on_every_golden_family():
             off, ofc = oracle_lib.check_exp(r)
             assert np.array_equal(ff[:n], off) and np.array_equal(fc[:n], ofc), (name, k)
         assert emu_lib.narrow_cols() > 10000  # the packed path really ran
+        assert emu_lib.narrow_runs() > 1000  # ... and so did the narrow form of the hot gate programs
     finally:
         emu_lib.set_packed(False)
 

@@ -72,6 +72,7 @@ struct Matrix {
   u64 version = 0;
   const u64* src_offsets = nullptr;   // != nullptr: a bytecode table unrolled by the library from these
   u64 src_contracts = 0;              // (device) contract offsets — regular by construction
+  u64 narrow_mask = 0;                // bit c: column c is stored in <= 8 bytes per row, or is a constant below 2^64
   u64 off[ZK_MAX_COLS];               // byte offset of each column inside dev
   unsigned char width[ZK_MAX_COLS];   // bytes per row of each column (fr.cuh:ld_col)
 };
@@ -117,7 +118,7 @@ struct zk_ctx {
   size_t evm_sort_cap = 0;
   u32* evm_hist_host = nullptr;  // pinned: histogram + positional flag read back after k_evm_classify
   cudaEvent_t evm_hist_ev = nullptr;
-  int evm_occ[16] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
+  int evm_occ[20] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
   std::unordered_map<const void*, int> occ;  // same, row-circuit kernels (keyed by kernel)
   BlockStats* block_stats = nullptr;  // k_evm_block_stats output
   void* state_fold = nullptr;  // k_state_fold output: 64 bytes per resident state row
@@ -275,10 +276,17 @@ static int store_matrix(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const vo
   m.n_rows = n_rows;
   m.n_cols = n_cols;
   m.flags_rows = 0;  // flags belong to the previous contents
+  m.narrow_mask = 0;
   if (widths) {
     for (u32 c = 0; c < n_cols; c++) {
       m.off[c] = offs[c];
       m.width[c] = widths[c];
+      bool narrow = widths[c] >= 1 && widths[c] <= 8;
+      if (widths[c] == 0 && host) {  // constant column: narrow iff the one stored cell is below 2^64
+        const u64* cell = (const u64*)((const unsigned char*)host + offs[c]);
+        narrow = (cell[1] | cell[2] | cell[3]) == 0;
+      }
+      if (narrow) m.narrow_mask |= 1ull << c;
     }
   } else {
     layout_canonical(m.off, m.width, n_cols, n_rows);
@@ -633,6 +641,7 @@ static int alloc_narrow(zk_ctx* ctx, Matrix& m, u64 n_rows, u32 n_cols, const un
   m.n_cols = n_cols;
   m.flags_rows = 0;
   m.src_offsets = nullptr;
+  m.narrow_mask = 0;
   return 0;
 }
 // chunk table of a segmented Horner scan: ceil(len / 32) chunks per segment
@@ -1168,6 +1177,21 @@ static int check_copy(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStre
   return 0;
 }
 
+// the narrow instances of the hot EVM kernels (evm.cu StepCtx::narrow) apply when the resident step matrix, rw table
+// and bytecode table have these storage properties (every packer / the from-code upload produces them on real traces)
+static bool evm_narrow(const zk_ctx* ctx) {
+  const Matrix& sm = ctx->circ[ZK_CIRCUIT_EVM];
+  const Matrix& rw = ctx->tab[ZK_TABLE_RW];
+  const Matrix& bt = ctx->tab[ZK_TABLE_BYTECODE];
+  const u64 step_need = 0x1FFFull & ~((1ull << 5) | (1ull << 6));  // all 13 step cells but code_hash lo / hi
+  if ((sm.narrow_mask & step_need) != step_need) return false;
+  if ((rw.narrow_mask & 0x1Full) != 0x1Full) return false;  // rw_counter, rw, tag, id, address
+  static const unsigned char kW[6] = {16, 16, 1, 4, 1, 4};
+  for (int c = 0; c < 6; c++)
+    if (bt.width[c] != kW[c]) return false;
+  return bt.n_cols == 6;
+}
+
 static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStream_t st) {
   const Matrix& m = ctx->circ[ZK_CIRCUIT_EVM];
   if (rg.row_end + 1 > m.n_rows) return fail_msg(ctx, "EVM steps [b,e) need step e resident (rotation +1)");
@@ -1284,21 +1308,28 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
       if (e_ != cudaSuccess) return fail_msg(ctx, std::string("launch of " #kernel ": ") + cudaGetErrorString(e_)); \
     }                                                                                          \
   } while (0)
+  // narrow instances: positional tables AND every step column but the code hash, the rw table's key columns narrow
+  // (<= 8 bytes per row, Matrix::narrow_mask) AND the bytecode table in the layout k_bytecode_table_expand writes
+  const bool narrow = pos && evm_narrow(ctx);
   if (group_n[KG_PUSH]) {
-    if (pos) ZK_LAUNCH_GROUP(0, k_evm_push_pos, group_n[KG_PUSH], 128);
+    if (narrow) ZK_LAUNCH_GROUP(13, k_evm_push_pos<1>, group_n[KG_PUSH], 128);
+    else if (pos) ZK_LAUNCH_GROUP(0, k_evm_push_pos<0>, group_n[KG_PUSH], 128);
     else ZK_LAUNCH_GROUP(1, k_evm_push_hash, group_n[KG_PUSH], 8);  // half a warp per step
   }
   if (group_n[KG_MUL]) {
-    if (pos) ZK_LAUNCH_GROUP(2, (k_evm_gadget<KG_MUL, true>), group_n[KG_MUL], 128);
-    else ZK_LAUNCH_GROUP(3, (k_evm_gadget<KG_MUL, false>), group_n[KG_MUL], 128);
+    if (narrow) ZK_LAUNCH_GROUP(14, (k_evm_gadget<KG_MUL, 2>), group_n[KG_MUL], 128);
+    else if (pos) ZK_LAUNCH_GROUP(2, (k_evm_gadget<KG_MUL, 1>), group_n[KG_MUL], 128);
+    else ZK_LAUNCH_GROUP(3, (k_evm_gadget<KG_MUL, 0>), group_n[KG_MUL], 128);
   }
   if (group_n[KG_ADD]) {
-    if (pos) ZK_LAUNCH_GROUP(4, (k_evm_gadget<KG_ADD, true>), group_n[KG_ADD], 128);
-    else ZK_LAUNCH_GROUP(5, (k_evm_gadget<KG_ADD, false>), group_n[KG_ADD], 128);
+    if (narrow) ZK_LAUNCH_GROUP(15, (k_evm_gadget<KG_ADD, 2>), group_n[KG_ADD], 128);
+    else if (pos) ZK_LAUNCH_GROUP(4, (k_evm_gadget<KG_ADD, 1>), group_n[KG_ADD], 128);
+    else ZK_LAUNCH_GROUP(5, (k_evm_gadget<KG_ADD, 0>), group_n[KG_ADD], 128);
   }
   if (group_n[KG_POP]) {
-    if (pos) ZK_LAUNCH_GROUP(6, (k_evm_gadget<KG_POP, true>), group_n[KG_POP], 128);
-    else ZK_LAUNCH_GROUP(7, (k_evm_gadget<KG_POP, false>), group_n[KG_POP], 128);
+    if (narrow) ZK_LAUNCH_GROUP(16, (k_evm_gadget<KG_POP, 2>), group_n[KG_POP], 128);
+    else if (pos) ZK_LAUNCH_GROUP(6, (k_evm_gadget<KG_POP, 1>), group_n[KG_POP], 128);
+    else ZK_LAUNCH_GROUP(7, (k_evm_gadget<KG_POP, 0>), group_n[KG_POP], 128);
   }
   if (group_n[KG_SIMPLE]) ZK_LAUNCH_GROUP(8, k_evm_group<KG_SIMPLE>, group_n[KG_SIMPLE], 128);
   if (group_n[KG_BYTES32]) ZK_LAUNCH_GROUP(9, k_evm_group<KG_BYTES32>, group_n[KG_BYTES32], 128);

@@ -133,8 +133,17 @@ struct StepCtx {
   const u64* rw_base;  // limb 0 of rw_counter of rw-table row 0, hoisted (positional rw table), or nullptr
   int pos_mode;  // -1: read the tables' positional flags at run time; 1: the kernel was specialised for
                  // positional rw + bytecode tables (the caller checked both flags), hash paths compiled out
-  ZK_HD Fr cur(u32 c) const { return wcell(w, c, i); }
-  ZK_HD Fr nxt(u32 c) const { return wcell(w, c, j); }
+  int narrow = 0;  // 1: the kernel instance runs only when the host found (api.cu:evm_narrow) every step column but the code
+                   // hash, and the rw table's five key columns, narrow (<= 8 bytes per row) and the bytecode table in the
+                   // layout k_bytecode_table_expand writes: those cells load as one limb with literal zero upper limbs
+  ZK_HD Fr cur(u32 c) const {
+    if (narrow == 1 && c != S_HASH_LO && c != S_HASH_HI) return ld_col_narrow(w.base + w.off[c], w.width[c], i);
+    return wcell(w, c, i);
+  }
+  ZK_HD Fr nxt(u32 c) const {
+    if (narrow == 1 && c != S_HASH_LO && c != S_HASH_HI) return ld_col_narrow(w.base + w.off[c], w.width[c], j);
+    return wcell(w, c, j);
+  }
 };
 
 ZK_HD void step_fail(const StepCtx& s, int id) {
@@ -174,7 +183,8 @@ ZK_HD int bytecode_lookup(const StepCtx& s, bool live, const Fr& hlo, const Fr& 
     u32 head = 0, len = 0;
     const int n_head = heads_probe(ix, hlo, hhi, &head, &len, s.mask, live);
     Fr got;
-    const int n = pos_lookup_run(ix, key, n_head, head, len, &r, live, B_VALUE, &got);
+    const int n = s.narrow == 1 ? pos_lookup_run<true>(ix, key, n_head, head, len, &r, live, B_VALUE, &got)
+                                : pos_lookup_run<false>(ix, key, n_head, head, len, &r, live, B_VALUE, &got);
     if (live && n == 1) *value = got;
     return n;
   }
@@ -198,7 +208,8 @@ ZK_HD int bytecode_lookup_h(const StepCtx& s, bool live, const Fr& h0, int n_hea
   int n;
   if (s.pos_mode == 1 || (pos_enabled(ix) && ix.pos_kind == ZK_POS_RUNS)) {
     Fr got;
-    n = pos_lookup_run(ix, key, n_head, head, run_len, &r, live, B_VALUE, &got);
+    n = s.narrow == 1 ? pos_lookup_run<true>(ix, key, n_head, head, run_len, &r, live, B_VALUE, &got)
+                      : pos_lookup_run<false>(ix, key, n_head, head, run_len, &r, live, B_VALUE, &got);
     if (live && n == 1) *value = got;
     return n;
   } else {
@@ -232,7 +243,8 @@ ZK_HD int rw_lookup(const StepCtx& s, bool live, const Fr& rwc, u64 rw, u64 tag,
   const IndexDev& ix = s.t.rw;
   if (s.pos_mode == 1 || (ix.tab.n_rows != 0 && pos_enabled(ix) && ix.pos_kind == ZK_POS_DENSE)) {
     Fr lo, hi;
-    n = pos_lookup_dense<5>(ix, key, &r, live, s.rw_base, R_VAL_LO, &lo, R_VAL_HI, &hi);
+    n = s.narrow == 1 ? pos_lookup_dense<5, true>(ix, key, &r, live, s.rw_base, R_VAL_LO, &lo, R_VAL_HI, &hi)
+                      : pos_lookup_dense<5, false>(ix, key, &r, live, s.rw_base, R_VAL_LO, &lo, R_VAL_HI, &hi);
     if (live && n == 1) {
       value->lo = lo;
       value->hi = hi;
@@ -1834,7 +1846,8 @@ __global__ void __launch_bounds__(1024) k_evm_scatter(EvmSort so, u32 n) {
 // POS = both tables positional (known to the host from the read-back flag): that instance is compiled
 // with pos_mode = 1, i.e. without any hash-index code — these kernels were stalling on instruction
 // fetch (profiles/README.md v20: "no instruction" 2-3 per issue), the executed path is now half as long.
-template <int G, bool POS>
+// POS: 0 = hash indexes, 1 = both tables positional, 2 = positional AND narrow (StepCtx::narrow)
+template <int G, int POS>
 __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRange& rg, const EvmTables& t,
                                              const ResultDev& res, const EvmSort& so, const u32* s_resp, int bucket,
                                              const Fr* stack_pre, const u64& rw_base) {
@@ -1850,7 +1863,7 @@ __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRan
     const bool live = k < n;
     const u64 i = rg.row_begin + list[live ? k : 0];
     StepCtx s{w, t, res, i, i + 1, rg.row_base + i, live, s_resp, 0xFFFFFFFFu, POS ? nullptr : stack_pre,
-              POS ? &rw_base : nullptr, POS ? 1 : -1};
+              POS ? &rw_base : nullptr, POS ? 1 : -1, POS == 2 ? 1 : 0};
     if (G == KG_ADD) gadget_add(s, live);
     else if (G == KG_MUL) gadget_mul(s, live);
     else gadget_pop(s, live);
@@ -1870,7 +1883,7 @@ __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRan
 #ifndef ZK_POP_MINBLOCKS
 #define ZK_POP_MINBLOCKS ZK_GADGET_MINBLOCKS
 #endif
-template <int G, bool POS>
+template <int G, int POS>
 __global__ void __launch_bounds__(128, G == KG_MUL ? ZK_GADGET_MINBLOCKS : (G == KG_ADD ? ZK_ADD_MINBLOCKS : ZK_POP_MINBLOCKS))
 k_evm_gadget(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
              const __grid_constant__ EvmSort so) {
@@ -1928,7 +1941,8 @@ __device__ __forceinline__ Fr shfl16_fr(const Fr& v, int src) {
   for (int k = 0; k < 4; k++) r.l[k] = __shfl_sync(0xFFFFFFFFu, v.l[k], src, 16);
   return r;
 }
-// positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1)
+// positional rw + bytecode tables: one thread per PUSH step (gadget_push_pos1); NARROW: StepCtx::narrow
+template <int NARROW>
 __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res,
                const __grid_constant__ EvmSort so) {
   __shared__ alignas(16) u32 s_resp[ZK_RESP_BITMAP_WORDS];
@@ -1941,7 +1955,7 @@ __global__ void __launch_bounds__(128, ZK_PUSH_MINBLOCKS) k_evm_push_pos(const _
   const u32 stride = gridDim.x * blockDim.x;
   for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     const u64 i = rg.row_begin + list[k];
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, &rw_base, 1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, s_resp, 1u << (threadIdx.x & 31), nullptr, &rw_base, 1, NARROW};
     gadget_push_pos1(s, &hc);
   }
 }

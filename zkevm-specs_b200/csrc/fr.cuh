@@ -96,6 +96,30 @@ ZK_HD Fr ld_col(const unsigned char* p, u32 width, u64 row) {
 #endif
   return r;
 }
+// ld_col for a column the HOST has verified to be "narrow": stored in at most 8 bytes per row, or a constant below 2^64
+// (api.cu: Matrix::narrow_mask).  One aligned 8-byte load, shift, mask — and limbs 1..3 are literal zeros, so the
+// 4-limb compares / adds of the gate programs fold to one limb in kernels specialised for narrow step / key columns.
+ZK_HD Fr ld_col_narrow(const unsigned char* p, u32 width, u64 row) {
+  Fr r;
+  r.l[1] = r.l[2] = r.l[3] = 0;
+#ifdef __CUDA_ARCH__
+  const u64 a = (u64)p + row * width;  // width 0: the constant cell itself
+  u64 v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(a & ~7ull));
+  const u32 sh = ((u32)a & 7u) * 8u;
+  const u64 m = (width == 0 || width >= 8) ? ~0ull : ((1ull << (8u * width)) - 1ull);
+  r.l[0] = (v >> sh) & m;
+#else
+  switch (width) {
+    case 1: r.l[0] = p[row]; break;
+    case 2: r.l[0] = ((const unsigned short*)p)[row]; break;
+    case 4: r.l[0] = ((const u32*)p)[row]; break;
+    case 8: r.l[0] = ((const u64*)p)[row]; break;
+    default: r.l[0] = ((const u64*)p)[0]; break;  // 0: constant column
+  }
+#endif
+  return r;
+}
 // ld_col with the width known at compile time: one plain typed load (kernels that are
 // specialised for a storage layout, e.g. k_pos_verify over the type-width bytecode table)
 template <int W>

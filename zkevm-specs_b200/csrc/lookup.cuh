@@ -78,6 +78,12 @@ struct IndexDev {
 ZK_HD Fr table_cell(const TableDev& t, u32 col, u64 row) {
   return ld_col(t.base + t.off[col], t.width[col], row);
 }
+// NARROW: the caller's kernel was launched for tables whose key columns the host found narrow (fr.cuh:ld_col_narrow)
+template <bool NARROW>
+ZK_HD Fr table_key_cell(const TableDev& t, u32 col, u64 row) {
+  if (NARROW) return ld_col_narrow(t.base + t.off[col], t.width[col], row);
+  return ld_col(t.base + t.off[col], t.width[col], row);
+}
 
 // 64-bit mix of the canonical RLC value: low bits pick the bucket, high 32 bits are the
 // fingerprint stored in the slot (so a probe only touches table rows whose fingerprint matches)
@@ -212,7 +218,7 @@ ZK_HD bool pos_enabled(const IndexDev& ix) { return ix.pos_ok != nullptr && ld_u
 // shared.  (Round 1 had the tail as an out-of-line function taking the key array by reference: that single call pinned
 // every caller's key array in local memory — 160-750 B of stack traffic per row in every kernel with a positional
 // lookup; profiles/README.md r02.)
-template <int NK>
+template <int NK, bool NARROW = false>
 ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bool active, const u64* base0 = nullptr,
                            int extra_col = -1, Fr* extra = nullptr, int extra_col2 = -1, Fr* extra2 = nullptr) {
   bool tail = false;  // key[ix.tail_key] == ix.tail_val, without indexing `key` by a run-time value
@@ -232,7 +238,7 @@ ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bo
   const u64 cand = valid ? offset + (key[0].l[0] - base) : 0;
   Fr cells[NK];  // independent loads first, compares after
 #pragma unroll
-  for (int j = 1; j < NK; j++) cells[j] = table_cell(ix.tab, ix.key_cols[j], cand);
+  for (int j = 1; j < NK; j++) cells[j] = table_key_cell<NARROW>(ix.tab, ix.key_cols[j], cand);
   if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
   if (extra_col2 >= 0) *extra2 = table_cell(ix.tab, (u32)extra_col2, cand);
   bool eq = valid;
@@ -252,6 +258,8 @@ ZK_HD int pos_lookup_dense(const IndexDev& ix, const Fr (&key)[NK], u32* row, bo
 // Branch-free: the candidate row is clamped to a valid row and its cells are always loaded, so
 // several lookups of one thread have all their loads in flight together; `extra_col` (or -1)
 // names one more cell of the candidate row to fetch in the same batch (the looked-up value).
+// TYPED: the table has the layout k_bytecode_table_expand writes (is_code 1 byte, value 4 bytes): plain typed loads
+template <bool TYPED = false>
 ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32 head, u32 len, u32* row, bool active,
                          int extra_col = -1, Fr* extra = nullptr) {
   const bool is_hdr = fr_eq_u64(key[2], 1) && fr_is_zero(key[3]);
@@ -259,8 +267,14 @@ ZK_HD int pos_lookup_run(const IndexDev& ix, const Fr (&key)[5], int n_head, u32
   u64 cand = is_hdr ? (u64)head : (u64)head + 1 + (is_byte ? key[3].l[0] : 0);
   const bool valid = active && n_head == 1 && (is_hdr || is_byte) && cand < ix.tab.n_rows;
   if (!valid) cand = 0;
-  const Fr is_code = table_cell(ix.tab, ix.key_cols[4], cand);
-  if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
+  Fr is_code;
+  if (TYPED) {
+    is_code = ld_col_c<1>(ix.tab.base + ix.tab.off[4], cand);
+    if (extra_col >= 0) *extra = ld_col_c<4>(ix.tab.base + ix.tab.off[5], cand);  // the looked-up cell is `value`
+  } else {
+    is_code = table_cell(ix.tab, ix.key_cols[4], cand);
+    if (extra_col >= 0) *extra = table_cell(ix.tab, (u32)extra_col, cand);
+  }
   *row = (u32)cand;
   return valid && fr_eq(is_code, key[4]) ? 1 : 0;
 }
