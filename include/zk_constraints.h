@@ -708,7 +708,39 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_EOOG_CC_AMBIG, ZKE_AMBIG, "error_return_data_out_of_bound.py:16-18 call_context_lookup ambiguous")        \
   X(EV_EOOG_CC_TYPE, ZKE_ASSERT, "error_return_data_out_of_bound.py:16-18 .value(): the cell is a Word")         \
   X(EV_EOOG_CMP_RANGE, ZKE_ASSERT, "compare(): an operand exceeds n_bytes (8: gas; 31: return data end)")        \
-  X(EV_EOOG_NOT_ENOUGH, ZKE_ASSERT, "gas_left < required gas / no out-of-bound condition holds")
+  X(EV_EOOG_NOT_ENOUGH, ZKE_ASSERT, "gas_left < required gas / no out-of-bound condition holds")                  \
+  /* BALANCE / EXTCODEHASH / EXTCODESIZE (balance.py, extcodehash.py, extcodesize.py) and                         \
+   * ErrorOutOfGasAccountAccess (error_oog_account_access.py): shared ids, one per kind of constraint */         \
+  X(EV_ACC_OPCODE, ZKE_ASSERT, "balance.py:9 / extcodehash.py:9 / extcodesize.py:14 / error_oog_account_access.py:25 opcode") \
+  X(EV_ACC_POP_UNSAT, ZKE_UNSAT, "stack_pop(address) unsat")                                                     \
+  X(EV_ACC_POP_AMBIG, ZKE_AMBIG, "stack_pop(address) ambiguous")                                                 \
+  X(EV_ACC_ADDR_DOMAIN, ZKE_VALUE, "word_to_address: to_le_bytes of a half >= 2^128 -> OverflowError")           \
+  X(EV_ACC_ADDR_RANGE, ZKE_RANGE, "word_to_address: more than 20 bytes")                                         \
+  X(EV_ACC_TXID_UNSAT, ZKE_UNSAT, "call_context_lookup(TxId) unsat")                                             \
+  X(EV_ACC_TXID_AMBIG, ZKE_AMBIG, "call_context_lookup(TxId) ambiguous")                                         \
+  X(EV_ACC_TXID_TYPE, ZKE_ASSERT, "call_context_lookup(TxId).value(): the cell is a Word")                       \
+  X(EV_ACC_REVEND_UNSAT, ZKE_UNSAT, "reversion_info: call_context_lookup(RwCounterEndOfReversion) unsat")        \
+  X(EV_ACC_REVEND_AMBIG, ZKE_AMBIG, "reversion_info: RwCounterEndOfReversion ambiguous")                         \
+  X(EV_ACC_REVEND_TYPE, ZKE_ASSERT, "reversion_info: RwCounterEndOfReversion is a Word")                         \
+  X(EV_ACC_PERSIST_UNSAT, ZKE_UNSAT, "reversion_info: call_context_lookup(IsPersistent) unsat")                  \
+  X(EV_ACC_PERSIST_AMBIG, ZKE_AMBIG, "reversion_info: IsPersistent ambiguous")                                   \
+  X(EV_ACC_PERSIST_TYPE, ZKE_ASSERT, "reversion_info: IsPersistent is a Word")                                   \
+  X(EV_ACC_AL_UNSAT, ZKE_UNSAT, "add_account_to_access_list / read_account_to_access_list: rw lookup unsat (instruction.py:1044-1069)") \
+  X(EV_ACC_AL_AMBIG, ZKE_AMBIG, "add_account_to_access_list / read_account_to_access_list: rw lookup ambiguous")  \
+  X(EV_ACC_AL_REV_UNSAT, ZKE_UNSAT, "state_write: the reversion row is missing (instruction.py:848-861)")        \
+  X(EV_ACC_AL_REV_AMBIG, ZKE_AMBIG, "state_write: the reversion row is ambiguous")                               \
+  X(EV_ACC_AL_PREV_TYPE, ZKE_ASSERT, "access list row: value_prev.value(): the cell is a Word")                  \
+  X(EV_ACC_HASH_UNSAT, ZKE_UNSAT, "account_read_word(CodeHash) unsat")                                           \
+  X(EV_ACC_HASH_AMBIG, ZKE_AMBIG, "account_read_word(CodeHash) ambiguous")                                       \
+  X(EV_ACC_BAL_UNSAT, ZKE_UNSAT, "balance.py:23 account_read_word(Balance) unsat")                               \
+  X(EV_ACC_BAL_AMBIG, ZKE_AMBIG, "balance.py:23 account_read_word(Balance) ambiguous")                           \
+  X(EV_ACC_LEN_UNSAT, ZKE_UNSAT, "extcodesize.py:26 bytecode_length(code_hash) unsat")                           \
+  X(EV_ACC_LEN_AMBIG, ZKE_AMBIG, "extcodesize.py:26 bytecode_length(code_hash) ambiguous")                       \
+  X(EV_ACC_SIZE_WORD, ZKE_ASSERT, "extcodesize.py:31 Word.from_lo(code_size): code_size >= 2^128")               \
+  X(EV_ACC_PUSH_UNSAT, ZKE_UNSAT, "stack_push unsat")                                                            \
+  X(EV_ACC_PUSH_AMBIG, ZKE_AMBIG, "stack_push ambiguous")                                                        \
+  X(EV_ACC_EQ, ZKE_ASSERT, "the pushed word == balance / code hash / code size")                                 \
+  X(EV_ACC_WARM_BOOL, ZKE_ASSERT, "instruction.py:422 select(is_warm, ..): the access-list value_prev is not 0 / 1")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -115,8 +115,15 @@ static void same_context(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint
                          fr_t d_sp) {
   same_context_x(e, i, row, opcode, fr_u64(d_rwc), d_pc, d_sp, 0, fr_u64(0), fr_u64(0));
 }
+static void same_context_r(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                           int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev);
 static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
                            int mem_to, fr_t mem_value, fr_t dyn_gas) {
+  same_context_r(e, i, row, opcode, d_rwc, d_pc, d_sp, mem_to, mem_value, dyn_gas, 0);
+}
+/* + reversible_write_counter = Transition.delta(d_rev) */
+static void same_context_r(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                           int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
 #define CUR(c) fr_load(ORC_CELL(S, n, c, i))
 #define NXT(c) fr_load(ORC_CELL(S, n, c, j))
@@ -132,7 +139,7 @@ static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr
   CHECK(EV_SC_SP, fr_eq(NXT(S_SP), fr_add(CUR(S_SP), d_sp)));
   CHECK(EV_SC_GAS, fr_eq(NXT(S_GAS), gas_after));
   CHECK(EV_SC_MEM, fr_eq(NXT(S_MEM), mem_to ? mem_value : CUR(S_MEM)));
-  CHECK(EV_SC_REV, fr_eq(NXT(S_REV), CUR(S_REV)));
+  CHECK(EV_SC_REV, fr_eq(NXT(S_REV), fr_add(CUR(S_REV), fr_u64(d_rev))));
   CHECK(EV_SC_LOG, fr_eq(NXT(S_LOG), CUR(S_LOG)));
   CHECK(EV_SC_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
   CHECK(EV_SC_IS_ROOT, fr_eq(NXT(S_IS_ROOT), CUR(S_IS_ROOT)));
@@ -938,7 +945,9 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_ErrorStack || st == ZK_ES_ErrorInvalidOpcode || st == ZK_ES_ErrorOutOfGasConstant ||
                                   st == ZK_ES_ErrorInvalidJump || st == ZK_ES_SELFBALANCE || st == ZK_ES_ErrorOutOfGasSHA3 ||
                                   st == ZK_ES_ErrorOutOfGasStaticMemoryExpansion || st == ZK_ES_ErrorOutOfGasDynamicMemoryExpansion ||
-                                  st == ZK_ES_ErrorOutOfGasLOG || st == ZK_ES_ErrorOutOfGasEXP || st == ZK_ES_ErrorReturnDataOutOfBound);
+                                  st == ZK_ES_ErrorOutOfGasLOG || st == ZK_ES_ErrorOutOfGasEXP || st == ZK_ES_ErrorReturnDataOutOfBound ||
+                                  st == ZK_ES_BALANCE || st == ZK_ES_EXTCODEHASH || st == ZK_ES_EXTCODESIZE ||
+                                  st == ZK_ES_ErrorOutOfGasAccountAccess);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -984,6 +993,10 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_ErrorOutOfGasLOG) gadget_error_oog_log(e, i, row, opcode);
   else if (st == ZK_ES_ErrorOutOfGasEXP) gadget_error_oog_exp(e, i, row, opcode);
   else if (st == ZK_ES_ErrorReturnDataOutOfBound) gadget_error_return_data_oob(e, i, row, opcode);
+  else if (st == ZK_ES_BALANCE) gadget_account_access(e, i, row, opcode, 0x31);
+  else if (st == ZK_ES_EXTCODEHASH) gadget_account_access(e, i, row, opcode, 0x3f);
+  else if (st == ZK_ES_EXTCODESIZE) gadget_account_access(e, i, row, opcode, 0x3b);
+  else if (st == ZK_ES_ErrorOutOfGasAccountAccess) gadget_error_oog_account_access(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -235,3 +235,79 @@ static void gadget_error_return_data_oob(evm_env* e, uint64_t i, uint64_t row, f
   CHECK(EV_EOOG_NOT_ENOUGH, off_over || end_over || fr_cmp(rdl, end) < 0);
   error_state_tail(e, i, row, 3);
 }
+
+/* ---- BALANCE / EXTCODEHASH / EXTCODESIZE (balance.py, extcodehash.py, extcodesize.py) ------------------------------ */
+static void gadget_account_access(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint64_t op) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  CHECK(EV_ACC_OPCODE, fr_eq_u64(opcode, op));
+  word_t addr_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &addr_w), EV_ACC_POP_UNSAT, row)) return;
+  fr_t address;
+  W2FQ(addr_w, 20, &address, EV_ACC_ADDR_DOMAIN);
+  uint32_t r;
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(1)), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_TXID_UNSAT);
+  const fr_t tx_id = rw_cell(e, R_VAL_LO, r);
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(2)), call_id, ZK_CC_RwCounterEndOfReversion, &r), EV_ACC_REVEND_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_REVEND_UNSAT);
+  const fr_t rev_end = rw_cell(e, R_VAL_LO, r);
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(3)), call_id, ZK_CC_IsPersistent, &r), EV_ACC_PERSIST_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_PERSIST_UNSAT);
+  const fr_t is_persistent = rw_cell(e, R_VAL_LO, r);
+  /* add_account_to_access_list(tx_id, address, reversion_info): state_write(TxAccessListAccount, tx_id, address, value = 1) */
+  fr_t is_warm;
+  {
+    fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(4)), 1, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id; key[R_ADDR] = address; key[R_VAL_LO] = one;
+    LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR) | RWM_VAL, &r), EV_ACC_AL_UNSAT);
+    const uint32_t first = r;
+    if (fr_is_zero(is_persistent)) { uint32_t r2; LK(reversion_lookup(e, fr_sub(rev_end, CUR(S_REV)), first, &r2), EV_ACC_AL_REV_UNSAT); }
+    CHECK(EV_ACC_AL_PREV_TYPE, !rw_prev_is_word(e, first));
+    is_warm = rw_cell(e, R_PREV_LO, first);
+  }
+  LK(account_lookup(e, fr_add(rwc, fr_u64(5)), 0, address, ZK_ACC_CodeHash, &r), EV_ACC_HASH_UNSAT);
+  const word_t code_hash = rw_value(e, r);
+  const int exists = !fr_is_zero(fr_add(code_hash.lo, code_hash.hi));  /* 1 - is_zero(lo + hi) */
+  word_t expect = {fr_u64(0), fr_u64(0)};
+  uint64_t n_rw = 6, d_rev = 0;
+  if (op == 0x31) {  /* BALANCE */
+    if (exists) {
+      LK(account_lookup(e, fr_add(rwc, fr_u64(6)), 0, address, ZK_ACC_Balance, &r), EV_ACC_BAL_UNSAT);
+      expect = rw_value(e, r);
+      n_rw = 7;
+    }
+  } else if (op == 0x3f) {  /* EXTCODEHASH */
+    expect = code_hash;
+  } else {  /* EXTCODESIZE */
+    if (exists) {
+      fr_t len;
+      if (!need1(e, bytecode_lookup(e, code_hash.lo, code_hash.hi, 1, fr_u64(0), 0, &len), EV_ACC_LEN_UNSAT, row)) return;
+      CHECK(EV_ACC_SIZE_WORD, fr_fits_bits(len, 128));
+      expect.lo = len;
+    }
+    d_rev = 1;
+  }
+  word_t w;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(n_rw)), 1, ZK_TARGET_Stack, call_id, sp, &w), EV_ACC_PUSH_UNSAT, row)) return;
+  if (op == 0x3f) CHECK(EV_ACC_EQ, word_eq(expect, w)); else CHECK(EV_ACC_EQ, word_eq(expect, w));
+  CHECK(EV_ACC_WARM_BOOL, fr_eq_u64(is_warm, 0) || fr_eq_u64(is_warm, 1));
+  same_context_r(e, i, row, opcode, fr_u64(n_rw + 1), one, fr_u64(0), 0, fr_u64(0), fr_eq_u64(is_warm, 1) ? fr_u64(0) : fr_u64(2500), d_rev);
+}
+/* error_oog_account_access.py */
+static void gadget_error_oog_account_access(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID);
+  CHECK(EV_ACC_OPCODE, fr_eq_u64(opcode, 0x31) || fr_eq_u64(opcode, 0x3b) || fr_eq_u64(opcode, 0x3f));
+  word_t addr_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, CUR(S_SP), &addr_w), EV_ACC_POP_UNSAT, row)) return;
+  fr_t address;
+  W2FQ(addr_w, 20, &address, EV_ACC_ADDR_DOMAIN);
+  uint32_t r;
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(1)), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_TXID_UNSAT);
+  const fr_t tx_id = rw_cell(e, R_VAL_LO, r);
+  /* read_account_to_access_list: state_read(TxAccessListAccount, tx_id, address) */
+  fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(2)), 0, ZK_TARGET_TxAccessListAccount);
+  key[R_ID] = tx_id; key[R_ADDR] = address;
+  LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR), &r), EV_ACC_AL_UNSAT);
+  CHECK(EV_ACC_AL_PREV_TYPE, !rw_prev_is_word(e, r));
+  const fr_t is_warm = rw_cell(e, R_PREV_LO, r);
+  oog_finish(e, i, row, fr_eq_u64(is_warm, 1) ? 100 : 2600, 3);
+}

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1317,6 +1317,60 @@ def evm2_cases(part="evm2"):
                         reversible_write_counter=ctx[6])
         return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
+    def account_case(kind, address, exists, is_warm, is_persistent, balance=0, code=b"", rev0=0):
+        """tests/evm/test_{balance,extcodehash,extcodesize}.py: pop an address, add it to the tx access list (with its
+        reversion row when the call is not persistent), read the account, push the result"""
+        from zkevm_specs.evm_circuit import AccountFieldTag
+        from zkevm_specs.util import EMPTY_CODE_HASH
+        bc = {"balance": Bytecode().balance, "extcodehash": Bytecode().extcodehash, "extcodesize": Bytecode().extcodesize}[kind]().stop()
+        h = Word(bc.hash())
+        code_hash = int.from_bytes(keccak256(code), "big") if kind != "balance" else EMPTY_CODE_HASH
+        rev_end = 0 if is_persistent else 40
+        rw = (RWDictionary(1).stack_read(1, 1023, Word(address)).call_context_read(1, CallContextFieldTag.TxId, 1)
+              .call_context_read(1, CallContextFieldTag.RwCounterEndOfReversion, rev_end)
+              .call_context_read(1, CallContextFieldTag.IsPersistent, is_persistent)
+              .tx_access_list_account_write(1, address, True, is_warm, rw_counter_of_reversion=rev_end - rev0))
+        rw.account_read(address, AccountFieldTag.CodeHash, Word(code_hash if exists else 0))
+        if kind == "balance":
+            if exists:
+                rw.account_read(address, AccountFieldTag.Balance, Word(balance))
+            result = balance if exists else 0
+        elif kind == "extcodehash":
+            result = code_hash if exists else 0
+        else:
+            result = len(code) if exists else 0
+        rw.stack_write(1, 1023, Word(result))
+        state = {"balance": ExecutionState.BALANCE, "extcodehash": ExecutionState.EXTCODEHASH, "extcodesize": ExecutionState.EXTCODESIZE}[kind]
+        steps = [StepState(state, rw_counter=1, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=0,
+                           stack_pointer=1023, gas_left=100 + (not is_warm) * 2500, reversible_write_counter=rev0),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=1, stack_pointer=1023, gas_left=0,
+                           reversible_write_counter=rev0 + (1 if kind == "extcodesize" else 0))]
+        bcs = list(bc.table_assignments()) + (list(Bytecode(bytearray(code)).table_assignments()) if kind == "extcodesize" else [])
+        return steps, bcs, list(rw.rws), [], []
+
+    def oog_account_case(op, is_warm, root):
+        """tests/evm/test_error_oog_account_access.py"""
+        address = 0xCAFECAFE
+        bc = Bytecode().push32(address)
+        bc = {Opcode.BALANCE: bc.balance, Opcode.EXTCODESIZE: bc.extcodesize, Opcode.EXTCODEHASH: bc.extcodehash}[op]().stop()
+        h = Word(bc.hash())
+        call_id, rev = (1 if root else 2), 2
+        rw = RWDictionary(14).stack_read(call_id, 1023, Word(address)).call_context_read(call_id, CallContextFieldTag.TxId, 1)
+        rw.tx_access_list_account_read(1, address, is_warm)
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(ExecutionState.ErrorOutOfGasAccountAccess, rw_counter=14, call_id=call_id, is_root=root, is_create=False,
+                        code_hash=h, program_counter=33, stack_pointer=1023, gas_left=(99 if is_warm else 2599), reversible_write_counter=rev)
+        if root:
+            return [cur, StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (False, False, 232, 1023, 77, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
     def run(S, B, R, RF, C, K, T=(), BL=()):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
@@ -1337,7 +1391,21 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm13":
+    if part == "evm14":
+        A = 0xCAFE0000000000000000000000000000BEEF1234
+        scenarios = {
+            "bal_warm_missing": account_case("balance", 0x30000, False, True, True), "bal_cold_exists": account_case("balance", 0x30000, True, False, True, balance=200),
+            "bal_reverted": account_case("balance", A, True, False, False, balance=(1 << 255) + 9, rev0=3),
+            "bal_reverted_missing": account_case("balance", A, False, True, False),
+            "hash_warm": account_case("extcodehash", 0x30000, True, True, True, code=bytes([10, 40])), "hash_cold_missing": account_case("extcodehash", A, False, False, True),
+            "hash_reverted": account_case("extcodehash", A, True, False, False, code=bytes(range(50)), rev0=1),
+            "size_warm": account_case("extcodesize", 0x30000, True, True, True, code=bytes([10, 40])), "size_cold_missing": account_case("extcodesize", A, False, False, True, code=bytes([1])),
+            "size_empty_code": account_case("extcodesize", 0x30000, True, False, True, code=b""),
+            "size_reverted": account_case("extcodesize", A, True, True, False, code=bytes(range(100)), rev0=2),
+            "oog_bal_warm_root": oog_account_case(Opcode.BALANCE, True, True), "oog_size_cold_internal": oog_account_case(Opcode.EXTCODESIZE, False, False),
+            "oog_hash_cold_root": oog_account_case(Opcode.EXTCODEHASH, False, True),
+        }
+    elif part == "evm13":
         M64 = (1 << 64) - 1
         scenarios = {
             "sha3_root": oog_case("sha3", True, 0x20, 0x40, 40), "sha3_internal_zero": oog_case("sha3", False, 0x20, 0, 29),
@@ -1445,7 +1513,7 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
@@ -1542,6 +1610,12 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm14_cases():
+    """BALANCE / EXTCODEHASH / EXTCODESIZE (access-list write with its reversion row, account reads) and
+    ErrorOutOfGasAccountAccess"""
+    evm2_cases("evm14")
 
 
 def evm13_cases():
@@ -2371,7 +2445,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

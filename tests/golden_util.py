@@ -220,6 +220,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm14_vectors():
+    """BALANCE / EXTCODEHASH / EXTCODESIZE and ErrorOutOfGasAccountAccess"""
+    return evm2_vectors("evm14")
+
+
 def evm13_vectors():
     """out-of-gas / out-of-bound error states (ErrorOutOfGasSHA3 / StaticMemoryExpansion / DynamicMemoryExpansion / LOG / EXP,
     ErrorReturnDataOutOfBound)"""

@@ -41,7 +41,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_BeginTx) X(ZK_ES_EndTx) X(ZK_ES_EndBlock) X(ZK_ES_ErrorStack) X(ZK_ES_ErrorInvalidOpcode)                    \
   X(ZK_ES_ErrorOutOfGasConstant) X(ZK_ES_ErrorInvalidJump) X(ZK_ES_SELFBALANCE) X(ZK_ES_ErrorOutOfGasSHA3)                  \
   X(ZK_ES_ErrorOutOfGasStaticMemoryExpansion) X(ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) X(ZK_ES_ErrorOutOfGasLOG)       \
-  X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound)
+  X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
+  X(ZK_ES_ErrorOutOfGasAccountAccess)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -324,7 +325,7 @@ ZK_HD bool responsible_opcode(const StepCtx& s, const Fr& state, const Fr& opcod
 // delta is a field element, memory_word_size either stays or moves To a value, and a dynamic gas
 // cost is added to the opcode's constant cost.
 ZK_HD void same_context_x(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
-                          bool mem_to, const Fr& mem_value, const Fr& dyn_gas) {
+                          bool mem_to, const Fr& mem_value, const Fr& dyn_gas, u64 d_rev = 0) {
   EV_CHECK(EV_SC_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
   int gas_cost = -1;
   if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
@@ -336,7 +337,7 @@ ZK_HD void same_context_x(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, c
   EV_CHECK(EV_SC_SP, fr_eq(s.nxt(S_SP), fr_add(s.cur(S_SP), d_sp)));
   EV_CHECK(EV_SC_GAS, fr_eq(s.nxt(S_GAS), gas_after));
   EV_CHECK(EV_SC_MEM, fr_eq(s.nxt(S_MEM), mem_to ? mem_value : s.cur(S_MEM)));
-  EV_CHECK(EV_SC_REV, fr_eq(s.nxt(S_REV), s.cur(S_REV)));
+  EV_CHECK(EV_SC_REV, fr_eq(s.nxt(S_REV), d_rev ? fr_add_u64(s.cur(S_REV), d_rev) : s.cur(S_REV)));
   EV_CHECK(EV_SC_LOG, fr_eq(s.nxt(S_LOG), s.cur(S_LOG)));
   EV_CHECK(EV_SC_CALL_ID, fr_eq(s.nxt(S_CALL_ID), s.cur(S_CALL_ID)));
   EV_CHECK(EV_SC_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), s.cur(S_IS_ROOT)));
@@ -835,6 +836,11 @@ ZK_HD_NOINLINE bool opcode_lookup_ni(const StepCtx& s, bool live, Fr* opcode) { 
 ZK_HD_NOINLINE void same_context_x_ni(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
                                       bool mem_to, const Fr& mem_value, const Fr& dyn_gas) {
   same_context_x(s, opcode, d_rwc, d_pc, d_sp, mem_to, mem_value, dyn_gas);
+}
+// + reversible_write_counter = Transition.delta(d_rev)
+ZK_HD_NOINLINE void same_context_r_ni(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
+                                      const Fr& dyn_gas, u64 d_rev) {
+  same_context_x(s, opcode, d_rwc, d_pc, d_sp, false, fr_u64(0), dyn_gas, d_rev);
 }
 ZK_HD_NOINLINE void same_context_ni(const StepCtx& s, const Fr& opcode, u64 d_rwc, const Fr& d_pc, const Fr& d_sp) {
   same_context_x(s, opcode, fr_u64(d_rwc), d_pc, d_sp, false, fr_u64(0), fr_u64(0));
@@ -1603,6 +1609,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_ErrorInvalidOpcode: case ZK_ES_ErrorOutOfGasConstant: case ZK_ES_ErrorInvalidJump: case ZK_ES_SELFBALANCE:
     case ZK_ES_ErrorOutOfGasSHA3: case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion:
     case ZK_ES_ErrorOutOfGasLOG: case ZK_ES_ErrorOutOfGasEXP: case ZK_ES_ErrorReturnDataOutOfBound:
+    case ZK_ES_BALANCE: case ZK_ES_EXTCODEHASH: case ZK_ES_EXTCODESIZE: case ZK_ES_ErrorOutOfGasAccountAccess:
       return KG_TX;
     default: return -1;
   }
@@ -1668,6 +1675,10 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_ErrorOutOfGasLOG: gadget_error_oog_log(s); break;
       case ZK_ES_ErrorOutOfGasEXP: gadget_error_oog_exp(s); break;
       case ZK_ES_ErrorReturnDataOutOfBound: gadget_error_return_data_oob(s); break;
+      case ZK_ES_BALANCE: gadget_account_access(s, 0x31); break;
+      case ZK_ES_EXTCODEHASH: gadget_account_access(s, 0x3f); break;
+      case ZK_ES_EXTCODESIZE: gadget_account_access(s, 0x3b); break;
+      case ZK_ES_ErrorOutOfGasAccountAccess: gadget_error_oog_account_access(s); break;
       default: break;
     }
   }

@@ -262,4 +262,94 @@ ZK_HD_NOINLINE void gadget_error_return_data_oob(const StepCtx& s) {
   error_state_tail(s, 3);
 }
 
+// ---- BALANCE / EXTCODEHASH / EXTCODESIZE (balance.py, extcodehash.py, extcodesize.py) ------------------------------------
+// pop an address, add it to the transaction's access list (state_write: the write row and, when the call is not
+// persistent, its reversion row at rw_counter_end_of_reversion - reversible_write_counter), read the account, push.
+// EXTCODESIZE alone advances reversible_write_counter (extcodesize.py:41), as written.
+ZK_HD_NOINLINE void gadget_account_access(const StepCtx& s, u64 op) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  EV_CHECK(EV_ACC_OPCODE, fr_eq_u64(opcode, op));
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  Word2 addr_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, sp, &addr_w), EV_ACC_POP_UNSAT)) return;
+  Fr address = fr_u64(0);
+  EOOG_W2FQ(addr_w, 20, &address, EV_ACC_ADDR_DOMAIN);
+  u32 r = 0;
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 1), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_TXID_UNSAT);
+  const Fr tx_id = rw_cell(s, R_VAL_LO, r);
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 2), call_id, ZK_CC_RwCounterEndOfReversion, &r), EV_ACC_REVEND_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_REVEND_UNSAT);
+  const Fr rev_end = rw_cell(s, R_VAL_LO, r);
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 3), call_id, ZK_CC_IsPersistent, &r), EV_ACC_PERSIST_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_PERSIST_UNSAT);
+  const Fr is_persistent = rw_cell(s, R_VAL_LO, r);
+  Fr is_warm;
+  {
+    Fr key[14];
+    rw_key_init(key, fr_add_u64(rwc, 4), 1, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id;
+    key[R_ADDR] = address;
+    key[R_VAL_LO] = fr_u64(1);
+    TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR) | ZK_RWM(R_VAL_LO) | ZK_RWM(R_VAL_HI), &r), EV_ACC_AL_UNSAT);
+    const u32 first = r;
+    if (fr_is_zero(is_persistent)) {
+      u32 r2 = 0;
+      TX_LK(reversion_lookup_m(s, fr_sub(rev_end, s.cur(S_REV)), first, &r2), EV_ACC_AL_REV_UNSAT);
+    }
+    EV_CHECK(EV_ACC_AL_PREV_TYPE, !rw_flag(s, first, 1));
+    is_warm = rw_cell(s, R_PREV_LO, first);
+  }
+  TX_LK(account_lookup_m(s, fr_add_u64(rwc, 5), 0, address, ZK_ACC_CodeHash, &r), EV_ACC_HASH_UNSAT);
+  const Word2 code_hash = rw_word(s, R_VAL_LO, r);
+  const bool exists = !fr_is_zero(fr_add(code_hash.lo, code_hash.hi));  // 1 - is_zero(lo + hi) over the field
+  Word2 expect{fr_u64(0), fr_u64(0)};
+  u64 n_rw = 6, d_rev = 0;
+  if (op == 0x31) {
+    if (exists) {
+      TX_LK(account_lookup_m(s, fr_add_u64(rwc, 6), 0, address, ZK_ACC_Balance, &r), EV_ACC_BAL_UNSAT);
+      expect = rw_word(s, R_VAL_LO, r);
+      n_rw = 7;
+    }
+  } else if (op == 0x3f) {
+    expect = code_hash;
+  } else {
+    if (exists) {
+      Fr len = fr_u64(0);  // bytecode_length(code_hash): the Header row
+      if (!need1(s, true, bytecode_lookup_ni(s, true, code_hash.lo, code_hash.hi, 1, fr_u64(0), 0, &len), EV_ACC_LEN_UNSAT)) return;
+      EV_CHECK(EV_ACC_SIZE_WORD, fr_fits128(len));
+      expect.lo = len;
+    }
+    d_rev = 1;
+  }
+  Word2 w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, n_rw, 1, sp, &w), EV_ACC_PUSH_UNSAT)) return;
+  EV_CHECK(EV_ACC_EQ, word_eq(expect, w));
+  EV_CHECK(EV_ACC_WARM_BOOL, fr_eq_u64(is_warm, 0) || fr_eq_u64(is_warm, 1));
+  same_context_r_ni(s, opcode, fr_u64(n_rw + 1), fr_u64(1), fr_u64(0), fr_eq_u64(is_warm, 1) ? fr_u64(0) : fr_u64(2500), d_rev);
+}
+ZK_HD_NOINLINE void gadget_error_oog_account_access(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  EV_CHECK(EV_ACC_OPCODE, fr_eq_u64(opcode, 0x31) || fr_eq_u64(opcode, 0x3b) || fr_eq_u64(opcode, 0x3f));
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  Word2 addr_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, s.cur(S_SP), &addr_w), EV_ACC_POP_UNSAT)) return;
+  Fr address = fr_u64(0);
+  EOOG_W2FQ(addr_w, 20, &address, EV_ACC_ADDR_DOMAIN);
+  u32 r = 0;
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 1), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_TXID_UNSAT);
+  const Fr tx_id = rw_cell(s, R_VAL_LO, r);
+  Fr key[14];  // read_account_to_access_list: state_read(TxAccessListAccount, tx_id, address)
+  rw_key_init(key, fr_add_u64(rwc, 2), 0, ZK_TARGET_TxAccessListAccount);
+  key[R_ID] = tx_id;
+  key[R_ADDR] = address;
+  TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR), &r), EV_ACC_AL_UNSAT);
+  EV_CHECK(EV_ACC_AL_PREV_TYPE, !rw_flag(s, r, 1));
+  const Fr is_warm = rw_cell(s, R_PREV_LO, r);
+  oog_finish(s, fr_eq_u64(is_warm, 1) ? 100 : 2600, 0, 3);
+}
+
 }  // namespace zk
