@@ -740,7 +740,47 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_ACC_PUSH_UNSAT, ZKE_UNSAT, "stack_push unsat")                                                            \
   X(EV_ACC_PUSH_AMBIG, ZKE_AMBIG, "stack_push ambiguous")                                                        \
   X(EV_ACC_EQ, ZKE_ASSERT, "the pushed word == balance / code hash / code size")                                 \
-  X(EV_ACC_WARM_BOOL, ZKE_ASSERT, "instruction.py:422 select(is_warm, ..): the access-list value_prev is not 0 / 1")
+  X(EV_ACC_WARM_BOOL, ZKE_ASSERT, "instruction.py:422 select(is_warm, ..): the access-list value_prev is not 0 / 1") \
+  /* CODECOPY / RETURNDATACOPY / EXTCODECOPY (codecopy.py, returndatacopy.py, extcodecopy.py) and                  \
+   * ErrorOutOfGasMemoryCopy (error_oog_memory_copy.py): shared ids, one per kind of constraint */               \
+  X(EV_CPY_OPCODE, ZKE_ASSERT, "error_oog_memory_copy.py:28-30 opcode is one of the four copy opcodes")          \
+  X(EV_CPY_POP0_UNSAT, ZKE_UNSAT, "stack lookup 0 unsat")                                                        \
+  X(EV_CPY_POP0_AMBIG, ZKE_AMBIG, "stack lookup 0 ambiguous")                                                    \
+  X(EV_CPY_POP1_UNSAT, ZKE_UNSAT, "stack lookup 1 unsat")                                                        \
+  X(EV_CPY_POP1_AMBIG, ZKE_AMBIG, "stack lookup 1 ambiguous")                                                    \
+  X(EV_CPY_POP2_UNSAT, ZKE_UNSAT, "stack lookup 2 unsat")                                                        \
+  X(EV_CPY_POP2_AMBIG, ZKE_AMBIG, "stack lookup 2 ambiguous")                                                    \
+  X(EV_CPY_POP3_UNSAT, ZKE_UNSAT, "stack lookup 3 unsat")                                                        \
+  X(EV_CPY_POP3_AMBIG, ZKE_AMBIG, "stack lookup 3 ambiguous")                                                    \
+  X(EV_CPY_ADDR_DOMAIN, ZKE_VALUE, "word_to_address / word_to_fq(external address): OverflowError")              \
+  X(EV_CPY_ADDR_RANGE, ZKE_RANGE, "word_to_address (20 bytes; 5 bytes in error_oog_memory_copy.py:45): too many bytes") \
+  X(EV_CPY_SIZE_DOMAIN, ZKE_VALUE, "memory_offset_and_length: word_to_fq(size): OverflowError")                  \
+  X(EV_CPY_SIZE_RANGE, ZKE_RANGE, "memory_offset_and_length: size exceeds 5 bytes")                              \
+  X(EV_CPY_MOFF_DOMAIN, ZKE_VALUE, "memory_offset_and_length: word_to_fq(memory offset): OverflowError")         \
+  X(EV_CPY_MOFF_RANGE, ZKE_RANGE, "memory_offset_and_length: memory offset exceeds 5 bytes")                     \
+  X(EV_CPY_OFF_DOMAIN, ZKE_VALUE, "word_to_fq(code / data offset): OverflowError")                               \
+  X(EV_CPY_OFF_RANGE, ZKE_RANGE, "code offset exceeds 5 bytes (codecopy.py:16) / 8 bytes (extcodecopy.py:15, returndatacopy.py:26)") \
+  X(EV_CPY_SIZE8_DOMAIN, ZKE_VALUE, "returndatacopy.py:26 word_to_fq(size, 8): OverflowError")                   \
+  X(EV_CPY_SIZE8_RANGE, ZKE_RANGE, "returndatacopy.py:26 size exceeds 8 bytes")                                  \
+  X(EV_CPY_LEN_UNSAT, ZKE_UNSAT, "codecopy.py:18 bytecode_length(curr.code_hash) unsat")                         \
+  X(EV_CPY_LEN_AMBIG, ZKE_AMBIG, "codecopy.py:18 bytecode_length ambiguous")                                     \
+  X(EV_CPY_CC0_UNSAT, ZKE_UNSAT, "returndatacopy.py:15 call_context_lookup(LastCalleeId) unsat")                 \
+  X(EV_CPY_CC0_AMBIG, ZKE_AMBIG, "returndatacopy.py:15 LastCalleeId ambiguous")                                  \
+  X(EV_CPY_CC0_TYPE, ZKE_ASSERT, "returndatacopy.py:15 LastCalleeId is a Word")                                  \
+  X(EV_CPY_CC1_UNSAT, ZKE_UNSAT, "returndatacopy.py:16-18 call_context_lookup(LastCalleeReturnDataLength) unsat") \
+  X(EV_CPY_CC1_AMBIG, ZKE_AMBIG, "returndatacopy.py:16-18 LastCalleeReturnDataLength ambiguous")                 \
+  X(EV_CPY_CC1_TYPE, ZKE_ASSERT, "returndatacopy.py:16-18 LastCalleeReturnDataLength is a Word")                 \
+  X(EV_CPY_CC2_UNSAT, ZKE_UNSAT, "returndatacopy.py:19-21 call_context_lookup(LastCalleeReturnDataOffset) unsat") \
+  X(EV_CPY_CC2_AMBIG, ZKE_AMBIG, "returndatacopy.py:19-21 LastCalleeReturnDataOffset ambiguous")                 \
+  X(EV_CPY_CC2_TYPE, ZKE_ASSERT, "returndatacopy.py:19-21 LastCalleeReturnDataOffset is a Word")                 \
+  X(EV_CPY_OOB_RANGE, ZKE_RANGE, "returndatacopy.py:24-28 range_check(return_data_length - (offset + size), 4)") \
+  X(EV_CPY_MEMSIZE_RANGE, ZKE_RANGE, "memory_expansion_dynamic_length: memory size exceeds 4 bytes")             \
+  X(EV_CPY_MEM_MAX, ZKE_ASSERT, "memory_expansion_dynamic_length: max(): curr.memory_word_size exceeds 4 bytes") \
+  X(EV_CPY_WORDSIZE_RANGE, ZKE_RANGE, "memory_copier_gas_cost: word size exceeds 4 bytes")                       \
+  X(EV_CPY_GASCOST_RANGE, ZKE_RANGE, "memory_copier_gas_cost: gas cost exceeds 8 bytes")                         \
+  X(EV_CPY_COPY_UNSAT, ZKE_UNSAT, "copy_lookup unsat")                                                           \
+  X(EV_CPY_COPY_AMBIG, ZKE_AMBIG, "copy_lookup ambiguous")                                                       \
+  X(EV_CPY_RWC_INC, ZKE_ASSERT, "returndatacopy.py:48 copy_rwc_inc == size * 2")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -339,10 +339,22 @@ static int copier_gas(evm_env* e, uint64_t i, uint64_t offset, uint64_t length, 
   *next_mem = fr_u64(nxt); *gas = fr_u64((uint64_t)g);
   return 0;
 }
+/* copy-table cells: is_first, src_id lo/hi, src_tag, dst_id lo/hi, dst_tag, src_addr, src_addr_end,
+ * dst_addr, length, rlc_acc, rw_counter, rwc_inc; the ids are compared as Words (table.py:776-778) */
+static int copy_lookup_w(evm_env* e, fr_t src_lo, fr_t src_hi, uint64_t src_tag, fr_t dst_id, uint64_t dst_tag, fr_t src_addr,
+                         fr_t src_end, fr_t dst_addr, fr_t length, fr_t rwc, fr_t* rwc_inc, fr_t* rlc_acc) {
+  fr_t key[11] = {src_lo, src_hi, fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end,
+                  dst_addr, length, rwc};
+  uint32_t row; const int n = orc_lookup(&e->copy_ix, key, &row);
+  if (n == 1) {
+    *rlc_acc = fr_load(ORC_CELL(e->copy_ix.cells, e->copy_ix.n_rows, 11, row));
+    *rwc_inc = fr_load(ORC_CELL(e->copy_ix.cells, e->copy_ix.n_rows, 13, row));
+  }
+  return n;
+}
 static int copy_lookup(evm_env* e, fr_t src_id, uint64_t src_tag, fr_t dst_id, uint64_t dst_tag, fr_t src_addr,
                        fr_t src_end, fr_t dst_addr, fr_t length, fr_t rwc, fr_t* rwc_inc, fr_t* rlc_acc) {
-  /* copy-table cells: is_first, src_id lo/hi, src_tag, dst_id lo/hi, dst_tag, src_addr, src_addr_end,
-   * dst_addr, length, rlc_acc, rw_counter, rwc_inc; ids are values here (hi = 0) */
+  /* ids are values here (hi = 0) */
   fr_t key[11] = {src_id, fr_u64(0), fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end,
                   dst_addr, length, rwc};
   uint32_t row; const int n = orc_lookup(&e->copy_ix, key, &row);
@@ -947,7 +959,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_ErrorOutOfGasStaticMemoryExpansion || st == ZK_ES_ErrorOutOfGasDynamicMemoryExpansion ||
                                   st == ZK_ES_ErrorOutOfGasLOG || st == ZK_ES_ErrorOutOfGasEXP || st == ZK_ES_ErrorReturnDataOutOfBound ||
                                   st == ZK_ES_BALANCE || st == ZK_ES_EXTCODEHASH || st == ZK_ES_EXTCODESIZE ||
-                                  st == ZK_ES_ErrorOutOfGasAccountAccess);
+                                  st == ZK_ES_ErrorOutOfGasAccountAccess || st == ZK_ES_CODECOPY || st == ZK_ES_RETURNDATACOPY ||
+                                  st == ZK_ES_EXTCODECOPY || st == ZK_ES_ErrorOutOfGasMemoryCopy);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -997,6 +1010,10 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_EXTCODEHASH) gadget_account_access(e, i, row, opcode, 0x3f);
   else if (st == ZK_ES_EXTCODESIZE) gadget_account_access(e, i, row, opcode, 0x3b);
   else if (st == ZK_ES_ErrorOutOfGasAccountAccess) gadget_error_oog_account_access(e, i, row, opcode);
+  else if (st == ZK_ES_CODECOPY) gadget_codecopy(e, i, row, opcode);
+  else if (st == ZK_ES_RETURNDATACOPY) gadget_returndatacopy(e, i, row, opcode);
+  else if (st == ZK_ES_EXTCODECOPY) gadget_extcodecopy(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasMemoryCopy) gadget_error_oog_memory_copy(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -311,3 +311,134 @@ static void gadget_error_oog_account_access(evm_env* e, uint64_t i, uint64_t row
   const fr_t is_warm = rw_cell(e, R_PREV_LO, r);
   oog_finish(e, i, row, fr_eq_u64(is_warm, 1) ? 100 : 2600, 3);
 }
+
+/* ---- CODECOPY / RETURNDATACOPY / EXTCODECOPY (codecopy.py, returndatacopy.py, extcodecopy.py) ---------------------- */
+#define CPY_POP(k, out) POP((k), (out), EV_CPY_POP0_UNSAT + 2 * (k))
+/* memory_offset_and_length(moff_w, size_w) (instruction.py:1122-1127) */
+#define CPY_OFFLEN(moff_w, size_w, moff, size) do { W2FQ((size_w), 5, (size), EV_CPY_SIZE_DOMAIN); *(moff) = fr_u64(0); \
+  if (!fr_is_zero(*(size))) W2FQ((moff_w), 5, (moff), EV_CPY_MOFF_DOMAIN); } while (0)
+#define CPY_GAS(moff, size, next_mem, gas) do { const int rc_ = copier_gas(e, i, (moff).l[0], (size).l[0], ZK_GAS_COST_COPY, (next_mem), (gas)); \
+  if (rc_) { orc_fail(e->res, EV_CPY_MEMSIZE_RANGE + rc_ - 1, row); return; } } while (0)
+
+static void gadget_codecopy(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), one = fr_u64(1);
+  word_t moff_w, coff_w, size_w;
+  CPY_POP(0, &moff_w); CPY_POP(1, &coff_w); CPY_POP(2, &size_w);
+  fr_t moff, size, coff;
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  W2FQ(coff_w, 5, &coff, EV_CPY_OFF_DOMAIN);
+  fr_t code_size;
+  if (!need1(e, bytecode_lookup(e, CUR(S_HASH_LO), CUR(S_HASH_HI), 1, fr_u64(0), 0, &code_size), EV_CPY_LEN_UNSAT, row)) return;
+  fr_t next_mem, gas;
+  CPY_GAS(moff, size, &next_mem, &gas);
+  fr_t rwc_inc = fr_u64(0), unused;
+  if (!fr_is_zero(size)) {
+    if (!need1(e, copy_lookup_w(e, CUR(S_HASH_LO), CUR(S_HASH_HI), ZK_COPY_Bytecode, call_id, ZK_COPY_Memory, coff, code_size, moff, size,
+                                fr_add(rwc, fr_u64(3)), &rwc_inc, &unused), EV_CPY_COPY_UNSAT, row)) return;
+  }
+  same_context_x(e, i, row, opcode, fr_add(fr_u64(3), rwc_inc), one, fr_u64(3), 1, next_mem, gas);
+}
+static void gadget_returndatacopy(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), one = fr_u64(1);
+  word_t moff_w, off_w, size_w;
+  CPY_POP(0, &moff_w); CPY_POP(1, &off_w); CPY_POP(2, &size_w);
+  word_t v; int w;
+  static const uint64_t TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataLength, ZK_CC_LastCalleeReturnDataOffset};
+  fr_t cc[3];
+  for (int k = 0; k < 3; k++) {
+    if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(3 + k)), 0, call_id, TAGS[k], &v, &w), EV_CPY_CC0_UNSAT + 3 * k, row)) return;
+    CHECK(EV_CPY_CC0_UNSAT + 3 * k + 2, !w);
+    cc[k] = v.lo;
+  }
+  fr_t off8, size8;
+  W2FQ(off_w, 8, &off8, EV_CPY_OFF_DOMAIN);
+  W2FQ(size_w, 8, &size8, EV_CPY_SIZE8_DOMAIN);
+  CHECK(EV_CPY_OOB_RANGE, fr_fits_bits(fr_sub(cc[1], fr_add(off8, size8)), 32));
+  fr_t moff, size;
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  fr_t next_mem, gas;
+  CPY_GAS(moff, size, &next_mem, &gas);
+  fr_t rwc_inc = fr_u64(0), unused;
+  if (!need1(e, copy_lookup(e, cc[0], ZK_COPY_Memory, call_id, ZK_COPY_Memory, cc[2], fr_add(cc[2], size), moff, size,
+                            fr_add(rwc, fr_u64(6)), &rwc_inc, &unused), EV_CPY_COPY_UNSAT, row)) return;
+  CHECK(EV_CPY_RWC_INC, fr_eq(rwc_inc, fr_add(size, size)));
+  same_context_x(e, i, row, opcode, fr_add(fr_u64(6), rwc_inc), one, fr_u64(3), 1, next_mem, gas);
+}
+static void gadget_extcodecopy(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), one = fr_u64(1);
+  word_t addr_w, moff_w, coff_w, size_w;
+  CPY_POP(0, &addr_w);
+  fr_t address;
+  W2FQ(addr_w, 20, &address, EV_CPY_ADDR_DOMAIN);
+  CPY_POP(1, &moff_w); CPY_POP(2, &coff_w); CPY_POP(3, &size_w);
+  fr_t coff, moff, size;
+  W2FQ(coff_w, 8, &coff, EV_CPY_OFF_DOMAIN);
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  uint32_t r;
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(4)), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_TXID_UNSAT);
+  const fr_t tx_id = rw_cell(e, R_VAL_LO, r);
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(5)), call_id, ZK_CC_RwCounterEndOfReversion, &r), EV_ACC_REVEND_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_REVEND_UNSAT);
+  const fr_t rev_end = rw_cell(e, R_VAL_LO, r);
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(6)), call_id, ZK_CC_IsPersistent, &r), EV_ACC_PERSIST_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_PERSIST_UNSAT);
+  const fr_t is_persistent = rw_cell(e, R_VAL_LO, r);
+  fr_t is_warm;
+  {
+    fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(7)), 1, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id; key[R_ADDR] = address; key[R_VAL_LO] = one;
+    LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR) | RWM_VAL, &r), EV_ACC_AL_UNSAT);
+    const uint32_t first = r;
+    if (fr_is_zero(is_persistent)) { uint32_t r2; LK(reversion_lookup(e, fr_sub(rev_end, CUR(S_REV)), first, &r2), EV_ACC_AL_REV_UNSAT); }
+    CHECK(EV_ACC_AL_PREV_TYPE, !rw_prev_is_word(e, first));
+    is_warm = rw_cell(e, R_PREV_LO, first);
+  }
+  LK(account_lookup(e, fr_add(rwc, fr_u64(8)), 0, address, ZK_ACC_CodeHash, &r), EV_ACC_HASH_UNSAT);
+  const word_t code_hash = rw_value(e, r);
+  fr_t code_size = fr_u64(0);
+  if (!fr_is_zero(fr_add(code_hash.lo, code_hash.hi))) {
+    if (!need1(e, bytecode_lookup(e, code_hash.lo, code_hash.hi, 1, fr_u64(0), 0, &code_size), EV_ACC_LEN_UNSAT, row)) return;
+  }
+  fr_t next_mem, gas;
+  CPY_GAS(moff, size, &next_mem, &gas);
+  CHECK(EV_ACC_WARM_BOOL, fr_eq_u64(is_warm, 0) || fr_eq_u64(is_warm, 1));
+  if (!fr_eq_u64(is_warm, 1)) gas = fr_add(gas, fr_u64(2500));
+  fr_t rwc_inc = fr_u64(0), unused;
+  if (!fr_is_zero(size)) {
+    if (!need1(e, copy_lookup_w(e, code_hash.lo, code_hash.hi, ZK_COPY_Bytecode, call_id, ZK_COPY_Memory, coff, code_size, moff, size,
+                                fr_add(rwc, fr_u64(9)), &rwc_inc, &unused), EV_CPY_COPY_UNSAT, row)) return;
+  }
+  same_context_x(e, i, row, opcode, fr_add(fr_u64(9), rwc_inc), one, fr_u64(4), 1, next_mem, gas);
+}
+/* error_oog_memory_copy.py: the external address goes through word_to_fq(.., N_BYTES_MEMORY_ADDRESS = 5) (:45), as written */
+static void gadget_error_oog_memory_copy(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const int ext = fr_eq_u64(opcode, 0x3c);
+  CHECK(EV_CPY_OPCODE, fr_eq_u64(opcode, 0x37) || fr_eq_u64(opcode, 0x39) || ext || fr_eq_u64(opcode, 0x3e));
+  word_t addr_w = {fr_u64(0), fr_u64(0)}, moff_w, size_w;
+  uint64_t k = 0;
+  if (ext) { CPY_POP(0, &addr_w); k = 1; }
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(k)), &moff_w), EV_CPY_POP0_UNSAT + 2 * k, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k + 1)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(k + 2)), &size_w), EV_CPY_POP0_UNSAT + 2 * (k + 1), row)) return;
+  uint64_t n_rw = k + 2, constant = 3;
+  if (ext) {
+    fr_t address;
+    W2FQ(addr_w, 5, &address, EV_CPY_ADDR_DOMAIN);
+    uint32_t r;
+    LK(cc_lookup(e, fr_add(rwc, fr_u64(3)), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT); NOT_WORD(rw_val_is_word(e, r), EV_ACC_TXID_UNSAT);
+    const fr_t tx_id = rw_cell(e, R_VAL_LO, r);
+    fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(4)), 0, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id; key[R_ADDR] = address;
+    LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR), &r), EV_ACC_AL_UNSAT);
+    CHECK(EV_ACC_AL_PREV_TYPE, !rw_prev_is_word(e, r));
+    constant = fr_eq_u64(rw_cell(e, R_PREV_LO, r), 1) ? 100 : 2600;
+    n_rw = 5;
+  }
+  fr_t moff, size;
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  fr_t next_mem, gas;
+  CPY_GAS(moff, size, &next_mem, &gas);
+  oog_finish(e, i, row, (u128)constant + gas.l[0], n_rw);
+}

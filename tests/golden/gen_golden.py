@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1371,6 +1371,107 @@ def evm2_cases(part="evm2"):
                         program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
         return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
+    def codecopy_case(code_off, mem_off, length, cur_mem=0):
+        """tests/evm/test_codecopy.py: the running contract's code -> memory (padding beyond the code end)"""
+        bc = Bytecode().push32(length).push32(code_off).push32(mem_off).codecopy().stop()
+        h = Word(bc.hash())
+        nxt, exp = mem_exp(cur_mem, mem_off + length if length else 0)
+        gas = Opcode.CODECOPY.constant_gas_cost() + exp + mws(length) * GAS_COST_COPY
+        rw = RWDictionary(4).stack_read(1, 1021, Word(mem_off)).stack_read(1, 1022, Word(code_off)).stack_read(1, 1023, Word(length))
+        src = {i: (b, int(c)) for i, (b, c) in enumerate(zip(bc.code, bc.is_code))}
+        cc = CopyCircuit().copy(r, rw, h, CopyDataTypeTag.Bytecode, 1, CopyDataTypeTag.Memory, code_off, len(bc.code), mem_off, length, src)
+        steps = [StepState(ExecutionState.CODECOPY, rw_counter=4, call_id=1, is_root=True, code_hash=h, program_counter=99,
+                           stack_pointer=1021, memory_word_size=cur_mem, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, code_hash=h, program_counter=100,
+                           stack_pointer=1024, memory_word_size=nxt, gas_left=0)]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return steps, list(bc.table_assignments()), list(rw.rws), list(t.copy_table), []
+
+    def returndatacopy_case(rd_len, rd_off, data_off, mem_off, length, cur_mem=8):
+        """tests/evm/test_returndatacopy.py: the last callee's return data (its memory) -> memory"""
+        bc = Bytecode().push32(length).push32(data_off).push32(mem_off).returndatacopy().stop()
+        h = Word(bc.hash())
+        nxt, exp = mem_exp(cur_mem, mem_off + length if length else 0)
+        gas = Opcode.RETURNDATACOPY.constant_gas_cost() + exp + mws(length) * GAS_COST_COPY
+        callee = 7
+        rw = (RWDictionary(9).stack_read(1, 1021, Word(mem_off)).stack_read(1, 1022, Word(data_off)).stack_read(1, 1023, Word(length))
+              .call_context_read(1, CallContextFieldTag.LastCalleeId, callee)
+              .call_context_read(1, CallContextFieldTag.LastCalleeReturnDataLength, rd_len)
+              .call_context_read(1, CallContextFieldTag.LastCalleeReturnDataOffset, rd_off))
+        data = bytes(rng.randrange(256) for _ in range(rd_off + rd_len + 40))
+        src = {i: data[i] for i in range(len(data))}
+        cc = CopyCircuit().copy(r, rw, callee, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.Memory, rd_off, rd_off + length, mem_off, length, src)
+        steps = [StepState(ExecutionState.RETURNDATACOPY, rw_counter=9, call_id=1, is_root=True, code_hash=h, program_counter=99,
+                           stack_pointer=1021, memory_word_size=cur_mem, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, code_hash=h, program_counter=100,
+                           stack_pointer=1024, memory_word_size=nxt, gas_left=0)]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return steps, list(bc.table_assignments()), list(rw.rws), list(t.copy_table), []
+
+    def extcodecopy_case(code, exists, is_warm, is_persistent, code_off, mem_off, length, rev0=0):
+        """tests/evm/test_extcodecopy.py"""
+        from zkevm_specs.evm_circuit import AccountFieldTag
+        address = 0xCAFE0000000000000000000000000000BEEF1234
+        ext = Bytecode(bytearray(code))
+        ext_hash = ext.hash() if exists else 0
+        bc = Bytecode().push32(length).push32(code_off).push32(mem_off).push32(address).extcodecopy().stop()
+        h = Word(bc.hash())
+        nxt, exp = mem_exp(0, mem_off + length if length else 0)
+        gas = Opcode.EXTCODECOPY.constant_gas_cost() + exp + mws(length) * GAS_COST_COPY + (0 if is_warm else 2500)
+        rev_end = 0 if is_persistent else 60
+        rw = (RWDictionary(5).stack_read(1, 1020, Word(address)).stack_read(1, 1021, Word(mem_off)).stack_read(1, 1022, Word(code_off))
+              .stack_read(1, 1023, Word(length)).call_context_read(1, CallContextFieldTag.TxId, 1)
+              .call_context_read(1, CallContextFieldTag.RwCounterEndOfReversion, rev_end)
+              .call_context_read(1, CallContextFieldTag.IsPersistent, is_persistent)
+              .tx_access_list_account_write(1, address, True, is_warm, rw_counter_of_reversion=rev_end - rev0)
+              .account_read(address, AccountFieldTag.CodeHash, Word(ext_hash)))
+        src = {i: (b, int(c)) for i, (b, c) in enumerate(zip(ext.code, ext.is_code))} if exists else {}
+        cc = CopyCircuit()
+        if length:
+            cc.copy(r, rw, Word(ext_hash), CopyDataTypeTag.Bytecode, 1, CopyDataTypeTag.Memory, code_off, len(ext.code) if exists else 0,
+                    mem_off, length, src)
+        steps = [StepState(ExecutionState.EXTCODECOPY, rw_counter=5, call_id=1, is_root=True, code_hash=h, program_counter=132,
+                           stack_pointer=1020, memory_word_size=0, gas_left=gas, reversible_write_counter=rev0),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, code_hash=h, program_counter=133,
+                           stack_pointer=1024, memory_word_size=nxt, gas_left=0, reversible_write_counter=rev0)]
+        bcs = list(bc.table_assignments()) + (list(ext.table_assignments()) if exists else [])
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bcs), rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return steps, bcs, list(rw.rws), list(t.copy_table), []
+
+    def oog_copy_case(op, root, mem_off, length, is_warm=True):
+        """tests/evm/test_error_oog_memory_copy.py"""
+        ext = op == Opcode.EXTCODECOPY
+        bc = Bytecode().push32(length).push32(0).push32(mem_off)
+        if ext:
+            bc = bc.push32(0x1234)
+        bc.code.append(int(op)); bc.is_code.append(True)
+        bc = bc.stop()
+        h = Word(bc.hash())
+        call_id, rev, sp = (1 if root else 2), 2, (1020 if ext else 1021)
+        rw = RWDictionary(20)
+        k = 0
+        if ext:
+            rw.stack_read(call_id, sp, Word(0x1234)); k = 1
+        rw.stack_read(call_id, sp + k, Word(mem_off)).stack_read(call_id, sp + k + 2, Word(length))
+        if ext:
+            rw.call_context_read(call_id, CallContextFieldTag.TxId, 1).tx_access_list_account_read(1, 0x1234, is_warm)
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        nxt, exp = mem_exp(0, mem_off + length if length else 0)
+        need = ((100 if is_warm else 2600) if ext else 3) + exp + mws(length) * GAS_COST_COPY
+        cur = StepState(ExecutionState.ErrorOutOfGasMemoryCopy, rw_counter=20, call_id=call_id, is_root=root, is_create=False, code_hash=h,
+                        program_counter=132 if ext else 99, stack_pointer=sp, gas_left=need - 1, reversible_write_counter=rev)
+        if root:
+            return [cur, StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (False, False, 232, 1023, 77, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt_s = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                          program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
+        return [cur, nxt_s], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
     def run(S, B, R, RF, C, K, T=(), BL=()):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
@@ -1391,7 +1492,22 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm14":
+    if part == "evm15":
+        ext_code = bytes([0x60, 0x05, 0x7F]) + bytes(range(32)) + bytes([0x00, 0x5B, 0x01])
+        scenarios = {
+            "codecopy_single": codecopy_case(0, 0, 54), "codecopy_multi": codecopy_case(0, 0x40, 123), "codecopy_oob": codecopy_case(0x10, 0x20, 200, cur_mem=2),
+            "codecopy_zero": codecopy_case(3, 0x40, 0),
+            "rdc_basic": returndatacopy_case(64, 0, 0, 0x20, 64), "rdc_offset": returndatacopy_case(96, 0x40, 32, 0x100, 48),
+            "rdc_one": returndatacopy_case(32, 8, 0, 0x40, 1),  # (a zero-length RETURNDATACOPY cannot verify in the reference:
+                                                                 # its copy_lookup is unconditional, returndatacopy.py:36-46)
+            "ext_warm": extcodecopy_case(ext_code, True, True, True, 0, 0x20, 30), "ext_cold_oob": extcodecopy_case(ext_code, True, False, True, 10, 0, 64),
+            "ext_missing": extcodecopy_case(ext_code, False, False, True, 0, 0x40, 16), "ext_reverted": extcodecopy_case(ext_code, True, True, False, 2, 0x60, 20, rev0=1),
+            "ext_zero": extcodecopy_case(ext_code, True, False, True, 0, 0, 0),
+            "oog_cdc_root": oog_copy_case(Opcode.CALLDATACOPY, True, 0x40, 64), "oog_codecopy_internal": oog_copy_case(Opcode.CODECOPY, False, 0x100, 33),
+            "oog_rdc_root": oog_copy_case(Opcode.RETURNDATACOPY, True, 0, 0), "oog_ext_cold_root": oog_copy_case(Opcode.EXTCODECOPY, True, 0x20, 40, is_warm=False),
+            "oog_ext_warm_internal": oog_copy_case(Opcode.EXTCODECOPY, False, 0x20, 40, is_warm=True),
+        }
+    elif part == "evm14":
         A = 0xCAFE0000000000000000000000000000BEEF1234
         scenarios = {
             "bal_warm_missing": account_case("balance", 0x30000, False, True, True), "bal_cold_exists": account_case("balance", 0x30000, True, False, True, balance=200),
@@ -1513,8 +1629,8 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
@@ -1610,6 +1726,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm15_cases():
+    """CODECOPY / RETURNDATACOPY / EXTCODECOPY (copy-table lookups with Word and value ids) and ErrorOutOfGasMemoryCopy"""
+    evm2_cases("evm15")
 
 
 def evm14_cases():
@@ -2445,7 +2566,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -220,6 +220,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm15_vectors():
+    """CODECOPY / RETURNDATACOPY / EXTCODECOPY and ErrorOutOfGasMemoryCopy"""
+    return evm2_vectors("evm15")
+
+
 def evm14_vectors():
     """BALANCE / EXTCODEHASH / EXTCODESIZE and ErrorOutOfGasAccountAccess"""
     return evm2_vectors("evm14")

@@ -42,7 +42,7 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasConstant) X(ZK_ES_ErrorInvalidJump) X(ZK_ES_SELFBALANCE) X(ZK_ES_ErrorOutOfGasSHA3)                  \
   X(ZK_ES_ErrorOutOfGasStaticMemoryExpansion) X(ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) X(ZK_ES_ErrorOutOfGasLOG)       \
   X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
-  X(ZK_ES_ErrorOutOfGasAccountAccess)
+  X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -1610,6 +1610,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_ErrorOutOfGasSHA3: case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion:
     case ZK_ES_ErrorOutOfGasLOG: case ZK_ES_ErrorOutOfGasEXP: case ZK_ES_ErrorReturnDataOutOfBound:
     case ZK_ES_BALANCE: case ZK_ES_EXTCODEHASH: case ZK_ES_EXTCODESIZE: case ZK_ES_ErrorOutOfGasAccountAccess:
+    case ZK_ES_CODECOPY: case ZK_ES_RETURNDATACOPY: case ZK_ES_EXTCODECOPY: case ZK_ES_ErrorOutOfGasMemoryCopy:
       return KG_TX;
     default: return -1;
   }
@@ -1679,6 +1680,10 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_EXTCODEHASH: gadget_account_access(s, 0x3f); break;
       case ZK_ES_EXTCODESIZE: gadget_account_access(s, 0x3b); break;
       case ZK_ES_ErrorOutOfGasAccountAccess: gadget_error_oog_account_access(s); break;
+      case ZK_ES_CODECOPY: gadget_codecopy(s); break;
+      case ZK_ES_RETURNDATACOPY: gadget_returndatacopy(s); break;
+      case ZK_ES_EXTCODECOPY: gadget_extcodecopy(s); break;
+      case ZK_ES_ErrorOutOfGasMemoryCopy: gadget_error_oog_memory_copy(s); break;
       default: break;
     }
   }

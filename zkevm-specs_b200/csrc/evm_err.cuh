@@ -352,4 +352,182 @@ ZK_HD_NOINLINE void gadget_error_oog_account_access(const StepCtx& s) {
   oog_finish(s, fr_eq_u64(is_warm, 1) ? 100 : 2600, 0, 3);
 }
 
+// ---- CODECOPY / RETURNDATACOPY / EXTCODECOPY (codecopy.py, returndatacopy.py, extcodecopy.py) ----------------------------
+// copy_lookup with the source id compared as a Word (a code hash), table.py:776-778
+ZK_HD_NOINLINE int copy_lookup_w(const StepCtx& s, const Fr& src_lo, const Fr& src_hi, u64 src_tag, const Fr& dst_id, u64 dst_tag,
+                                 const Fr& src_addr, const Fr& src_end, const Fr& dst_addr, const Fr& length, const Fr& rwc,
+                                 Fr* rwc_inc) {
+  Fr key[11] = {src_lo, src_hi, fr_u64(src_tag), dst_id, fr_u64(0), fr_u64(dst_tag), src_addr, src_end, dst_addr, length, rwc};
+  u32 r = 0;
+  const int n = lookup_sync<11>(s.t.copy, key, &r, s.mask, true);
+  if (n == 1) *rwc_inc = table_cell(s.t.copy.tab, 13, r);
+  return n;
+}
+#define CPY_POP(k, out) EOOG_STACK((k), (k), (out), EV_CPY_POP0_UNSAT + 2 * (k))
+// memory_offset_and_length(moff_w, size_w): the size first, the offset only when the size is not zero
+#define CPY_OFFLEN(moff_w, size_w, moff, size)                          \
+  do {                                                                  \
+    EOOG_W2FQ((size_w), 5, (size), EV_CPY_SIZE_DOMAIN);                 \
+    *(moff) = fr_u64(0);                                                \
+    if (!fr_is_zero(*(size))) EOOG_W2FQ((moff_w), 5, (moff), EV_CPY_MOFF_DOMAIN); \
+  } while (0)
+#define CPY_GAS(moff, size, next_mem, gas)                                                        \
+  do {                                                                                            \
+    const int rc_ = copier_gas(s, (moff).l[0], (size).l[0], ZK_GAS_COST_COPY, (next_mem), (gas)); \
+    if (rc_) {                                                                                    \
+      step_fail(s, EV_CPY_MEMSIZE_RANGE + rc_ - 1);                                               \
+      return;                                                                                     \
+    }                                                                                             \
+  } while (0)
+
+ZK_HD_NOINLINE void gadget_codecopy(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI);
+  Word2 moff_w{fr_u64(0), fr_u64(0)}, coff_w{fr_u64(0), fr_u64(0)}, size_w{fr_u64(0), fr_u64(0)};
+  CPY_POP(0, &moff_w);
+  CPY_POP(1, &coff_w);
+  CPY_POP(2, &size_w);
+  Fr moff, size, coff = fr_u64(0);
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  EOOG_W2FQ(coff_w, 5, &coff, EV_CPY_OFF_DOMAIN);
+  Fr code_size = fr_u64(0);
+  if (!need1(s, true, bytecode_lookup_ni(s, true, hlo, hhi, 1, fr_u64(0), 0, &code_size), EV_CPY_LEN_UNSAT)) return;
+  Fr next_mem = fr_u64(0), gas = fr_u64(0);
+  CPY_GAS(moff, size, &next_mem, &gas);
+  Fr rwc_inc = fr_u64(0);
+  if (!fr_is_zero(size)) {
+    if (!need1(s, true, copy_lookup_w(s, hlo, hhi, ZK_COPY_Bytecode, call_id, ZK_COPY_Memory, coff, code_size, moff, size, fr_add_u64(rwc, 3), &rwc_inc),
+               EV_CPY_COPY_UNSAT)) return;
+  }
+  same_context_x_ni(s, opcode, fr_add_u64(rwc_inc, 3), fr_u64(1), fr_u64(3), true, next_mem, gas);
+}
+ZK_HD_NOINLINE void gadget_returndatacopy(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  Word2 moff_w{fr_u64(0), fr_u64(0)}, off_w{fr_u64(0), fr_u64(0)}, size_w{fr_u64(0), fr_u64(0)};
+  CPY_POP(0, &moff_w);
+  CPY_POP(1, &off_w);
+  CPY_POP(2, &size_w);
+  const u64 TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataLength, ZK_CC_LastCalleeReturnDataOffset};
+  Fr cc[3];
+  for (int k = 0; k < 3; k++) {
+    Word2 v{fr_u64(0), fr_u64(0)};
+    bool w = false;
+    if (!need1(s, true, call_context_w(s, true, fr_add_u64(rwc, 3 + k), 0, call_id, TAGS[k], &v, &w), EV_CPY_CC0_UNSAT + 3 * k)) return;
+    EV_CHECK(EV_CPY_CC0_UNSAT + 3 * k + 2, !w);
+    cc[k] = v.lo;
+  }
+  Fr off8 = fr_u64(0), size8 = fr_u64(0);
+  EOOG_W2FQ(off_w, 8, &off8, EV_CPY_OFF_DOMAIN);
+  EOOG_W2FQ(size_w, 8, &size8, EV_CPY_SIZE8_DOMAIN);
+  {  // range_check(return_data_length - (offset + size), N_BYTES_MEMORY_WORD_SIZE)
+    const Fr d = fr_sub(cc[1], fr_add(off8, size8));
+    EV_CHECK(EV_CPY_OOB_RANGE, fr_fits64(d) && (d.l[0] >> 32) == 0);
+  }
+  Fr moff, size;
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  Fr next_mem = fr_u64(0), gas = fr_u64(0);
+  CPY_GAS(moff, size, &next_mem, &gas);
+  Fr rwc_inc = fr_u64(0), unused = fr_u64(0);
+  if (!need1(s, true, copy_lookup(s, true, cc[0], ZK_COPY_Memory, call_id, ZK_COPY_Memory, cc[2], fr_add(cc[2], size), moff, size,
+                                  fr_add_u64(rwc, 6), &rwc_inc, &unused), EV_CPY_COPY_UNSAT)) return;
+  EV_CHECK(EV_CPY_RWC_INC, fr_eq(rwc_inc, fr_add(size, size)));
+  same_context_x_ni(s, opcode, fr_add_u64(rwc_inc, 6), fr_u64(1), fr_u64(3), true, next_mem, gas);
+}
+ZK_HD_NOINLINE void gadget_extcodecopy(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  Word2 addr_w{fr_u64(0), fr_u64(0)}, moff_w{fr_u64(0), fr_u64(0)}, coff_w{fr_u64(0), fr_u64(0)}, size_w{fr_u64(0), fr_u64(0)};
+  CPY_POP(0, &addr_w);
+  Fr address = fr_u64(0);
+  EOOG_W2FQ(addr_w, 20, &address, EV_CPY_ADDR_DOMAIN);
+  CPY_POP(1, &moff_w);
+  CPY_POP(2, &coff_w);
+  CPY_POP(3, &size_w);
+  Fr coff = fr_u64(0), moff, size;
+  EOOG_W2FQ(coff_w, 8, &coff, EV_CPY_OFF_DOMAIN);
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  u32 r = 0;
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 4), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_TXID_UNSAT);
+  const Fr tx_id = rw_cell(s, R_VAL_LO, r);
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 5), call_id, ZK_CC_RwCounterEndOfReversion, &r), EV_ACC_REVEND_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_REVEND_UNSAT);
+  const Fr rev_end = rw_cell(s, R_VAL_LO, r);
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 6), call_id, ZK_CC_IsPersistent, &r), EV_ACC_PERSIST_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_PERSIST_UNSAT);
+  const Fr is_persistent = rw_cell(s, R_VAL_LO, r);
+  Fr is_warm;
+  {
+    Fr key[14];
+    rw_key_init(key, fr_add_u64(rwc, 7), 1, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id;
+    key[R_ADDR] = address;
+    key[R_VAL_LO] = fr_u64(1);
+    TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR) | ZK_RWM(R_VAL_LO) | ZK_RWM(R_VAL_HI), &r), EV_ACC_AL_UNSAT);
+    const u32 first = r;
+    if (fr_is_zero(is_persistent)) {
+      u32 r2 = 0;
+      TX_LK(reversion_lookup_m(s, fr_sub(rev_end, s.cur(S_REV)), first, &r2), EV_ACC_AL_REV_UNSAT);
+    }
+    EV_CHECK(EV_ACC_AL_PREV_TYPE, !rw_flag(s, first, 1));
+    is_warm = rw_cell(s, R_PREV_LO, first);
+  }
+  TX_LK(account_lookup_m(s, fr_add_u64(rwc, 8), 0, address, ZK_ACC_CodeHash, &r), EV_ACC_HASH_UNSAT);
+  const Word2 code_hash = rw_word(s, R_VAL_LO, r);
+  Fr code_size = fr_u64(0);
+  if (!fr_is_zero(fr_add(code_hash.lo, code_hash.hi))) {
+    if (!need1(s, true, bytecode_lookup_ni(s, true, code_hash.lo, code_hash.hi, 1, fr_u64(0), 0, &code_size), EV_ACC_LEN_UNSAT)) return;
+  }
+  Fr next_mem = fr_u64(0), gas = fr_u64(0);
+  CPY_GAS(moff, size, &next_mem, &gas);
+  EV_CHECK(EV_ACC_WARM_BOOL, fr_eq_u64(is_warm, 0) || fr_eq_u64(is_warm, 1));
+  if (!fr_eq_u64(is_warm, 1)) gas = fr_add_u64(gas, 2500);
+  Fr rwc_inc = fr_u64(0);
+  if (!fr_is_zero(size)) {
+    if (!need1(s, true, copy_lookup_w(s, code_hash.lo, code_hash.hi, ZK_COPY_Bytecode, call_id, ZK_COPY_Memory, coff, code_size, moff, size,
+                                      fr_add_u64(rwc, 9), &rwc_inc), EV_CPY_COPY_UNSAT)) return;
+  }
+  same_context_x_ni(s, opcode, fr_add_u64(rwc_inc, 9), fr_u64(1), fr_u64(4), true, next_mem, gas);
+}
+// the external address goes through word_to_fq(.., N_BYTES_MEMORY_ADDRESS = 5) (error_oog_memory_copy.py:45), as written
+ZK_HD_NOINLINE void gadget_error_oog_memory_copy(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const bool ext = fr_eq_u64(opcode, 0x3c);
+  EV_CHECK(EV_CPY_OPCODE, fr_eq_u64(opcode, 0x37) || fr_eq_u64(opcode, 0x39) || ext || fr_eq_u64(opcode, 0x3e));
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  Word2 addr_w{fr_u64(0), fr_u64(0)}, moff_w{fr_u64(0), fr_u64(0)}, size_w{fr_u64(0), fr_u64(0)};
+  const u64 k = ext ? 1 : 0;
+  if (ext) CPY_POP(0, &addr_w);
+  EOOG_STACK(k, k, &moff_w, EV_CPY_POP0_UNSAT + 2 * k);
+  EOOG_STACK(k + 1, k + 2, &size_w, EV_CPY_POP0_UNSAT + 2 * (k + 1));
+  u64 n_rw = k + 2, constant = 3;
+  if (ext) {
+    Fr address = fr_u64(0);
+    EOOG_W2FQ(addr_w, 5, &address, EV_CPY_ADDR_DOMAIN);
+    u32 r = 0;
+    TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 3), call_id, ZK_CC_TxId, &r), EV_ACC_TXID_UNSAT);
+    TX_NOT_WORD(rw_flag(s, r, 0), EV_ACC_TXID_UNSAT);
+    const Fr tx_id = rw_cell(s, R_VAL_LO, r);
+    Fr key[14];
+    rw_key_init(key, fr_add_u64(rwc, 4), 0, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id;
+    key[R_ADDR] = address;
+    TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR), &r), EV_ACC_AL_UNSAT);
+    EV_CHECK(EV_ACC_AL_PREV_TYPE, !rw_flag(s, r, 1));
+    constant = fr_eq_u64(rw_cell(s, R_PREV_LO, r), 1) ? 100 : 2600;
+    n_rw = 5;
+  }
+  Fr moff, size;
+  CPY_OFFLEN(moff_w, size_w, &moff, &size);
+  Fr next_mem = fr_u64(0), gas = fr_u64(0);
+  CPY_GAS(moff, size, &next_mem, &gas);
+  const unsigned __int128 cost = (unsigned __int128)constant + gas.l[0];
+  oog_finish(s, (u64)cost, (u64)(cost >> 64), n_rw);
+}
+
 }  // namespace zk
