@@ -780,7 +780,38 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CPY_GASCOST_RANGE, ZKE_RANGE, "memory_copier_gas_cost: gas cost exceeds 8 bytes")                         \
   X(EV_CPY_COPY_UNSAT, ZKE_UNSAT, "copy_lookup unsat")                                                           \
   X(EV_CPY_COPY_AMBIG, ZKE_AMBIG, "copy_lookup ambiguous")                                                       \
-  X(EV_CPY_RWC_INC, ZKE_ASSERT, "returndatacopy.py:48 copy_rwc_inc == size * 2")
+  X(EV_CPY_RWC_INC, ZKE_ASSERT, "returndatacopy.py:48 copy_rwc_inc == size * 2")                 \
+  X(EV_AR_OPCODE, ZKE_ASSERT, "addmod.py:23 / mulmod.py:33 opcode == ADDMOD / MULMOD")            \
+  X(EV_AR_RW0_UNSAT, ZKE_UNSAT, "addmod / mulmod / sdiv_smod / sar: 1st stack lookup unsat")       \
+  X(EV_AR_RW0_AMBIG, ZKE_AMBIG, "1st stack lookup ambiguous")                                      \
+  X(EV_AR_RW1_UNSAT, ZKE_UNSAT, "2nd stack lookup unsat")                                          \
+  X(EV_AR_RW1_AMBIG, ZKE_AMBIG, "2nd stack lookup ambiguous")                                      \
+  X(EV_AR_RW2_UNSAT, ZKE_UNSAT, "3rd stack lookup unsat")                                          \
+  X(EV_AR_RW2_AMBIG, ZKE_AMBIG, "3rd stack lookup ambiguous")                                      \
+  X(EV_AR_RW3_UNSAT, ZKE_UNSAT, "4th stack lookup unsat")                                          \
+  X(EV_AR_RW3_AMBIG, ZKE_AMBIG, "4th stack lookup ambiguous")                                      \
+  X(EV_AR_WITNESS_DOMAIN, ZKE_NOTIMPL, "ADDMOD / MULMOD / SDIV / SMOD witness derivation with a stack word half >= 2^128: outside the supported witness domain (DESIGN.md)") \
+  X(EV_AR_ADDMOD_ZERO, ZKE_ASSERT, "addmod.py:60 n == 0 => pushed result == 0")                   \
+  X(EV_AR_ADDMOD_CARRY0, ZKE_RANGE, "addmod.py:47-50 mul_add_words_512: range_check(carry_0, 9), instruction.py:658") \
+  X(EV_AR_ADDMOD_CARRY1, ZKE_RANGE, "addmod.py:47-50 mul_add_words_512: range_check(carry_1, 9), instruction.py:659") \
+  X(EV_AR_MULMOD_R, ZKE_ASSERT, "mulmod.py:56 a_reduced * b == k * n + r")                         \
+  X(EV_AR_MULMOD_TO64, ZKE_VALUE, "mulmod.py:62 mul_add_words_512: to_64s(b) with a half >= 2^128 -> OverflowError (n == 0)") \
+  X(EV_AR_SDIV_REM_NEG, ZKE_VALUE, "sdiv_smod.py:100 Word(negative int) -> OverflowError")         \
+  X(EV_AR_SDIV_REM_WORD, ZKE_ASSERT, "sdiv_smod.py:102 Word(get_int_neg(negative int)) >= 2^256")  \
+  X(EV_AR_SDIV_CARRY_LO, ZKE_RANGE, "sdiv_smod.py:50 mul_add_words: range_check(carry_lo, 9)")     \
+  X(EV_AR_SDIV_CARRY_HI, ZKE_RANGE, "sdiv_smod.py:50 mul_add_words: range_check(carry_hi, 9)")     \
+  X(EV_AR_SDIV_OVERFLOW, ZKE_ASSERT, "sdiv_smod.py:52 overflow == 0")                              \
+  X(EV_AR_SDIV_REM_LT, ZKE_ASSERT, "sdiv_smod.py:55-56 |remainder| < |divisor| unless divisor == 0") \
+  X(EV_AR_SDIV_SIGN_REM, ZKE_ASSERT, "sdiv_smod.py:60-61 sign(dividend) == sign(remainder)")       \
+  X(EV_AR_SDIV_SIGN_QUOT, ZKE_ASSERT, "sdiv_smod.py:72-76 sign(dividend) == sign(divisor) ^ sign(quotient)") \
+  X(EV_AR_SAR_BYTES, ZKE_VALUE, "sar.py:57-59,156 to_le_bytes / to_64s: a half >= 2^128 -> OverflowError") \
+  X(EV_AR_SAR_RESULT, ZKE_ASSERT, "sar.py:79-82 b64s[idx] == limb of the pushed word")             \
+  X(EV_AR_SAR_SIGN_UNSAT, ZKE_UNSAT, "sar.py:142 sign_byte_lookup unsat")                          \
+  X(EV_AR_SAR_SIGN_AMBIG, ZKE_AMBIG, "sar.py:142 sign_byte_lookup ambiguous")                      \
+  X(EV_AR_SAR_POW_LO_UNSAT, ZKE_UNSAT, "sar.py:151 pow2_lookup(shf_mod64, p_lo) unsat")            \
+  X(EV_AR_SAR_POW_LO_AMBIG, ZKE_AMBIG, "sar.py:151 pow2_lookup ambiguous")                         \
+  X(EV_AR_SAR_POW_HI_UNSAT, ZKE_UNSAT, "sar.py:152 pow2_lookup(64 - shf_mod64, p_hi) unsat")       \
+  X(EV_AR_SAR_POW_HI_AMBIG, ZKE_AMBIG, "sar.py:152 pow2_lookup ambiguous")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

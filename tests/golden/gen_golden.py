@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1106,6 +1106,45 @@ def evm2_cases(part="evm2"):
                            program_counter=66, stack_pointer=1022, gas_left=3),
                  StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
                            code_hash=h, program_counter=67, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
+    def arith_case(kind, a, b, n=0, res=None):
+        """tests/evm/test_{addmod,mulmod,sdiv_smod,sar}.py (res: a pushed result other than the EVM's, for the cases the
+        reference leaves unconstrained)"""
+        M = 1 << 256
+
+        def sgn(x):
+            return x - M if x >> 255 else x
+
+        if kind in ("addmod", "mulmod"):
+            r = 0 if n == 0 else ((a + b) % n if kind == "addmod" else (a * b) % n)
+            bc = getattr(Bytecode().push32(n).push32(b).push32(a), kind)().stop()
+            rw = (RWDictionary(9).stack_read(1, 1021, Word(a)).stack_read(1, 1022, Word(b)).stack_read(1, 1023, Word(n))
+                  .stack_write(1, 1023, Word(r if res is None else res)))
+            state, pc, sp, nsp, gas = (ExecutionState.ADDMOD if kind == "addmod" else ExecutionState.MULMOD), 99, 1021, 1023, 8
+        else:
+            if kind == "sar":  # a = shift, b = value
+                r = (sgn(b) >> a) % M if a < 256 else (M - 1 if b >> 255 else 0)
+                state, gas = ExecutionState.SAR, 3
+            else:
+                sa, sb = sgn(a), sgn(b)
+                if b == 0:
+                    r = 0
+                elif kind == "sdiv":
+                    q = abs(sa) // abs(sb)
+                    r = (q if (sa < 0) == (sb < 0) else -q) % M
+                else:
+                    m = abs(sa) % abs(sb)
+                    r = (-m if sa < 0 else m) % M
+                state, gas = ExecutionState.SDIV_SMOD, 5
+            bc = getattr(Bytecode().push32(b).push32(a), kind)().stop()
+            rw = RWDictionary(9).stack_read(1, 1022, Word(a)).stack_read(1, 1023, Word(b)).stack_write(1, 1023, Word(r if res is None else res))
+            pc, sp, nsp = 66, 1022, 1023
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=pc,
+                           stack_pointer=sp, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
+                           code_hash=h, program_counter=pc + 1, stack_pointer=nsp, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
 
     def mws(a):
@@ -1492,7 +1531,26 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm15":
+    if part == "evm16":
+        MX, NEG = (1 << 256) - 1, 1 << 255
+        big1, big2, big3 = rng.randrange(1 << 256), rng.randrange(1 << 256), rng.randrange(1 << 200)
+        scenarios = {
+            "addmod_max": arith_case("addmod", MX, MX, MX), "addmod_n1": arith_case("addmod", MX, MX, 1), "addmod_n0": arith_case("addmod", MX, 1, 0),
+            "addmod_rand": arith_case("addmod", big1, big2, big3), "addmod_small": arith_case("addmod", 10, 7, 6), "addmod_wrap": arith_case("addmod", MX, 5, MX - 1),
+            "mulmod_max": arith_case("mulmod", MX, MX, MX - 4), "mulmod_n0": arith_case("mulmod", 7, 9, 0), "mulmod_rand": arith_case("mulmod", big1, big2, big3),
+            "mulmod_small": arith_case("mulmod", 10, 7, 6), "mulmod_n1": arith_case("mulmod", big2, big1, 1),
+            "sdiv_pos": arith_case("sdiv", 0xFFFFFF, 0xABC), "sdiv_neg": arith_case("sdiv", NEG + (7 << 128), 0x1234), "sdiv_m1": arith_case("sdiv", MX, 0xABCDEF),
+            "sdiv_by_m1": arith_case("sdiv", 0xABCDEF, MX), "sdiv_overflow": arith_case("sdiv", NEG, MX), "sdiv_zero": arith_case("sdiv", 0xABC, 0),
+            "sdiv_zero_any": arith_case("sdiv", 0xABC, 0, res=77), "sdiv_rand": arith_case("sdiv", big1, big3),
+            "smod_pos": arith_case("smod", 0xFFFFFF, 0xABC), "smod_neg": arith_case("smod", NEG + (7 << 128), 0x1234), "smod_by_m1": arith_case("smod", 0xABCDEF, MX),
+            "smod_overflow": arith_case("smod", NEG, MX), "smod_zero": arith_case("smod", 0xABC, 0), "smod_rand": arith_case("smod", big2, big3),
+            "smod_negneg": arith_case("smod", MX - 1000, MX - 6),
+            "sar_8": arith_case("sar", 8, 0x1234), "sar_neg17": arith_case("sar", 17, NEG + 0x5678), "sar_0": arith_case("sar", 0, NEG + 0xABCD),
+            "sar_64": arith_case("sar", 64, big1 | NEG), "sar_129": arith_case("sar", 129, NEG), "sar_255": arith_case("sar", 255, MX),
+            "sar_256": arith_case("sar", 256, NEG + 0xFFFF), "sar_265": arith_case("sar", 265, 0x12345), "sar_bigshift": arith_case("sar", NEG + 8, NEG + 0x1234),
+            "sar_rand": arith_case("sar", 77, big2), "sar_192": arith_case("sar", 192 + 5, big1 | NEG),
+        }
+    elif part == "evm15":
         ext_code = bytes([0x60, 0x05, 0x7F]) + bytes(range(32)) + bytes([0x00, 0x5B, 0x01])
         scenarios = {
             "codecopy_single": codecopy_case(0, 0, 54), "codecopy_multi": codecopy_case(0, 0x40, 123), "codecopy_oob": codecopy_case(0x10, 0x20, 200, cur_mem=2),
@@ -1629,8 +1687,8 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
@@ -1650,6 +1708,9 @@ def evm2_cases(part="evm2"):
                 if c == 9 and not (RF[i] & 1):
                     continue
                 v = corrupt_value(rng, R[i][c]); R2[i][c] = v
+            elif which == 8:  # a stack word half: the operands and results of the arithmetic gadgets
+                i, c = rng.randrange(len(R)), rng.choice([8, 8, 9])
+                v = corrupt_value(rng, R[i][c]); R2[i][c] = v; which = 1
             elif which == 2:
                 i, c, v = rng.randrange(len(R)), 100, 0
                 RF2[i] ^= 1
@@ -1726,6 +1787,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm16_cases():
+    """ADDMOD / MULMOD / SDIV_SMOD / SAR (witnesses the gadgets derive from the stack words by 256- and 512-bit division)"""
+    evm2_cases("evm16")
 
 
 def evm15_cases():
@@ -2566,7 +2632,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -220,6 +220,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm16_vectors():
+    """ADDMOD / MULMOD / SDIV_SMOD / SAR"""
+    return evm2_vectors("evm16")
+
+
 def evm15_vectors():
     """CODECOPY / RETURNDATACOPY / EXTCODECOPY and ErrorOutOfGasMemoryCopy"""
     return evm2_vectors("evm15")

@@ -93,20 +93,26 @@ def test_oracle_evm_simple_gadgets_match_reference_golden():
     and CALLER, CALLVALUE, CALLDATASIZE, ADDRESS, RETURNDATASIZE, CODESIZE (their tests/evm files)"""
     fixed = fixed_table_matrix()
     classes = oracle_lib.constraint_classes(3)
-    n = n_fail = 0
+    n = n_fail = n_unsupported = 0
     kinds = set()
     import itertools
 
-    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors(), golden_util.evm8_vectors(), golden_util.evm9_vectors(), golden_util.evm10_vectors(), golden_util.evm12_vectors(), golden_util.evm13_vectors(), golden_util.evm14_vectors(), golden_util.evm15_vectors()):
+    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors(), golden_util.evm8_vectors(), golden_util.evm9_vectors(), golden_util.evm10_vectors(), golden_util.evm12_vectors(), golden_util.evm13_vectors(), golden_util.evm14_vectors(), golden_util.evm15_vectors(), golden_util.evm16_vectors()):
         ff, fc = oracle_lib.check_evm_x(w, fixed)
         row, exc = oracle_lib.first_failure(ff, classes)
         if exc == "ValueError" and exp_exc in ("OverflowError", "UnboundLocalError"):
             exc = exp_exc  # one "Python runtime error" class (include/zkcheck.h ZK_ERR_VALUE)
+        if exc == "NotImplementedError" and exp_exc != exc:
+            # EV_AR_WITNESS_DOMAIN: ADDMOD / MULMOD / SDIV / SMOD with a stack word half >= 2^128, reported at the SAME
+            # step the reference fails on
+            assert row == exp_row, f"{name}[{k}]"
+            n_unsupported += 1
+            continue
         assert (row, exc) == (exp_row, exp_exc), f"{name}[{k}]: oracle {(row, exc)} reference {(exp_row, exp_exc)}"
         n += 1
         n_fail += exp_row >= 0
         kinds.add(exp_exc)
-    assert n > 4200 and n_fail > 3100
+    assert n > 5700 and n_fail > 4200 and n_unsupported <= 150
     assert {"AssertionError", "LookupUnsatFailure", "LookupAmbiguousFailure"} <= kinds, kinds
 
 

@@ -42,7 +42,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasConstant) X(ZK_ES_ErrorInvalidJump) X(ZK_ES_SELFBALANCE) X(ZK_ES_ErrorOutOfGasSHA3)                  \
   X(ZK_ES_ErrorOutOfGasStaticMemoryExpansion) X(ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) X(ZK_ES_ErrorOutOfGasLOG)       \
   X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
-  X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy)
+  X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
+  X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -1584,6 +1585,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 }  // namespace zk
 #include "evm_tx.cuh"
 #include "evm_err.cuh"
+#include "evm_arith.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1591,7 +1593,7 @@ namespace zk {
 // execution state has its own bucket of steps, so warps run one gate program (k_evm_classify /
 // k_evm_scatter sort the steps by state).  The host launches a group only when one of its buckets is
 // non-empty (zk_check_async reads the histogram back).
-enum { KG_ADD, KG_MUL, KG_PUSH, KG_POP, KG_SIMPLE, KG_BYTES32, KG_COPY, KG_WIDE, KG_TX, KG_COUNT };
+enum { KG_ADD, KG_MUL, KG_PUSH, KG_POP, KG_SIMPLE, KG_BYTES32, KG_COPY, KG_WIDE, KG_TX, KG_ARITH, KG_COUNT };
 __host__ __device__ constexpr int es_group(int st) {
   switch (st) {
     case ZK_ES_ADD: return KG_ADD;
@@ -1605,6 +1607,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_BITWISE: case ZK_ES_NOT: case ZK_ES_MEMORY: return KG_BYTES32;
     case ZK_ES_SHA3: case ZK_ES_CALLDATACOPY: return KG_COPY;
     case ZK_ES_SHL_SHR: return KG_WIDE;
+    case ZK_ES_ADDMOD: case ZK_ES_MULMOD: case ZK_ES_SDIV_SMOD: case ZK_ES_SAR: return KG_ARITH;
     case ZK_ES_STOP: case ZK_ES_BeginTx: case ZK_ES_EndTx: case ZK_ES_EndBlock: case ZK_ES_ErrorStack:
     case ZK_ES_ErrorInvalidOpcode: case ZK_ES_ErrorOutOfGasConstant: case ZK_ES_ErrorInvalidJump: case ZK_ES_SELFBALANCE:
     case ZK_ES_ErrorOutOfGasSHA3: case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion:
@@ -1686,6 +1689,14 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_ErrorOutOfGasMemoryCopy: gadget_error_oog_memory_copy(s); break;
       default: break;
     }
+  } else if constexpr (G == KG_ARITH) {
+    switch (st) {
+      case ZK_ES_ADDMOD: gadget_addmod_mulmod(s, false); break;
+      case ZK_ES_MULMOD: gadget_addmod_mulmod(s, true); break;
+      case ZK_ES_SDIV_SMOD: gadget_sdiv_smod(s); break;
+      case ZK_ES_SAR: gadget_sar(s); break;
+      default: break;
+    }
   }
 }
 
@@ -1710,6 +1721,7 @@ ZK_HD void verify_step(const StepCtx& s, u32 flags) {
     case KG_COPY: run_group<KG_COPY>(s, st, flags); break;
     case KG_WIDE: run_group<KG_WIDE>(s, st, flags); break;
     case KG_TX: run_group<KG_TX>(s, st, flags); break;
+    case KG_ARITH: run_group<KG_ARITH>(s, st, flags); break;
     default: break;
   }
 }
