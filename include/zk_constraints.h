@@ -811,7 +811,75 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_AR_SAR_POW_LO_UNSAT, ZKE_UNSAT, "sar.py:151 pow2_lookup(shf_mod64, p_lo) unsat")            \
   X(EV_AR_SAR_POW_LO_AMBIG, ZKE_AMBIG, "sar.py:151 pow2_lookup ambiguous")                         \
   X(EV_AR_SAR_POW_HI_UNSAT, ZKE_UNSAT, "sar.py:152 pow2_lookup(64 - shf_mod64, p_hi) unsat")       \
-  X(EV_AR_SAR_POW_HI_AMBIG, ZKE_AMBIG, "sar.py:152 pow2_lookup ambiguous")
+  X(EV_AR_SAR_POW_HI_AMBIG, ZKE_AMBIG, "sar.py:152 pow2_lookup ambiguous")                 \
+  X(EV_ST_OPCODE, ZKE_ASSERT, "storage.py:18,53 opcode == SLOAD / SSTORE")                           \
+  X(EV_ST_TXID_UNSAT, ZKE_UNSAT, "storage.py:20,55 call_context_lookup(TxId) unsat")                 \
+  X(EV_ST_TXID_AMBIG, ZKE_AMBIG, "storage.py:20,55 call_context_lookup(TxId) ambiguous")             \
+  X(EV_ST_TXID_TYPE, ZKE_ASSERT, "storage.py:20,55 call_context_lookup(TxId): .value() of a Word")   \
+  X(EV_ST_STATIC_UNSAT, ZKE_UNSAT, "storage.py:57-59 call_context_lookup(IsStatic) unsat")           \
+  X(EV_ST_STATIC_AMBIG, ZKE_AMBIG, "storage.py:57-59 call_context_lookup(IsStatic) ambiguous")       \
+  X(EV_ST_STATIC_TYPE, ZKE_ASSERT, "storage.py:57-59 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_ST_STATIC_NONZERO, ZKE_ASSERT, "storage.py:57-59 IsStatic == 0")                              \
+  X(EV_ST_REVEND_UNSAT, ZKE_UNSAT, "reversion_info: call_context_lookup(RwCounterEndOfReversion) unsat") \
+  X(EV_ST_REVEND_AMBIG, ZKE_AMBIG, "reversion_info: call_context_lookup(RwCounterEndOfReversion) ambiguous") \
+  X(EV_ST_REVEND_TYPE, ZKE_ASSERT, "reversion_info: call_context_lookup(RwCounterEndOfReversion): .value() of a Word") \
+  X(EV_ST_PERSIST_UNSAT, ZKE_UNSAT, "reversion_info: call_context_lookup(IsPersistent) unsat")       \
+  X(EV_ST_PERSIST_AMBIG, ZKE_AMBIG, "reversion_info: call_context_lookup(IsPersistent) ambiguous")   \
+  X(EV_ST_PERSIST_TYPE, ZKE_ASSERT, "reversion_info: call_context_lookup(IsPersistent): .value() of a Word") \
+  X(EV_ST_CALLEE_UNSAT, ZKE_UNSAT, "storage.py:22,62 call_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_ST_CALLEE_AMBIG, ZKE_AMBIG, "storage.py:22,62 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_ST_CALLEE_DOMAIN, ZKE_VALUE, "word_to_address: to_le_bytes of a half >= 2^128 -> OverflowError") \
+  X(EV_ST_CALLEE_RANGE, ZKE_RANGE, "word_to_address: more than 20 bytes")                            \
+  X(EV_ST_KEY_UNSAT, ZKE_UNSAT, "storage.py:25,65 stack_pop storage key unsat")                      \
+  X(EV_ST_KEY_AMBIG, ZKE_AMBIG, "storage.py:25,65 stack_pop storage key ambiguous")                  \
+  X(EV_ST_VAL_UNSAT, ZKE_UNSAT, "storage.py:66 stack_pop storage value unsat")                       \
+  X(EV_ST_VAL_AMBIG, ZKE_AMBIG, "storage.py:66 stack_pop storage value ambiguous")                   \
+  X(EV_ST_READ_UNSAT, ZKE_UNSAT, "storage.py:28 account_storage_read unsat")                         \
+  X(EV_ST_READ_AMBIG, ZKE_AMBIG, "storage.py:28 account_storage_read ambiguous")                     \
+  X(EV_ST_PUSH_UNSAT, ZKE_UNSAT, "storage.py:29 stack_push unsat")                                   \
+  X(EV_ST_PUSH_AMBIG, ZKE_AMBIG, "storage.py:29 stack_push ambiguous")                               \
+  X(EV_ST_READ_EQ, ZKE_ASSERT, "storage.py:27-30 storage value == pushed word")                      \
+  X(EV_ST_WRITE_UNSAT, ZKE_UNSAT, "storage.py:67-72 account_storage_write unsat")                    \
+  X(EV_ST_WRITE_AMBIG, ZKE_AMBIG, "storage.py:67-72 account_storage_write ambiguous")                \
+  X(EV_ST_WRITE_REV_UNSAT, ZKE_UNSAT, "storage.py:67-72 account_storage_write: reversion row unsat") \
+  X(EV_ST_WRITE_REV_AMBIG, ZKE_AMBIG, "storage.py:67-72 account_storage_write: reversion row ambiguous") \
+  X(EV_ST_WRITE_EQ, ZKE_ASSERT, "storage.py:73 popped value == written value")                       \
+  X(EV_ST_AL_UNSAT, ZKE_UNSAT, "storage.py:32-37,75-80 add_account_storage_to_access_list unsat")    \
+  X(EV_ST_AL_AMBIG, ZKE_AMBIG, "storage.py:32-37,75-80 add_account_storage_to_access_list ambiguous") \
+  X(EV_ST_AL_REV_UNSAT, ZKE_UNSAT, "add_account_storage_to_access_list: reversion row unsat")        \
+  X(EV_ST_AL_REV_AMBIG, ZKE_AMBIG, "add_account_storage_to_access_list: reversion row ambiguous")    \
+  X(EV_ST_AL_PREV_TYPE, ZKE_ASSERT, "instruction.py:1086 value_prev.value() of a Word")              \
+  X(EV_ST_REFUND_UNSAT, ZKE_UNSAT, "storage.py:82 tx_refund_write unsat")                            \
+  X(EV_ST_REFUND_AMBIG, ZKE_AMBIG, "storage.py:82 tx_refund_write ambiguous")                        \
+  X(EV_ST_REFUND_REV_UNSAT, ZKE_UNSAT, "storage.py:82 tx_refund_write: reversion row unsat")         \
+  X(EV_ST_REFUND_REV_AMBIG, ZKE_AMBIG, "storage.py:82 tx_refund_write: reversion row ambiguous")     \
+  X(EV_ST_REFUND_TYPE, ZKE_ASSERT, "instruction.py:950 value.value() of a Word")                     \
+  X(EV_ST_REFUND_PREV_TYPE, ZKE_ASSERT, "instruction.py:950 value_prev.value() of a Word")           \
+  X(EV_ST_REFUND_EQ, ZKE_ASSERT, "storage.py:125 gas_refund == the EIP-3529 rule")                   \
+  X(EV_ST_WARM_BOOL, ZKE_ASSERT, "storage.py:39,136 select(is_warm, ..): not a bool")                \
+  X(EV_CDL_OPCODE, ZKE_ASSERT, "calldataload.py:10 opcode == CALLDATALOAD")                          \
+  X(EV_CDL_POP_UNSAT, ZKE_UNSAT, "calldataload.py:13 stack_pop unsat")                               \
+  X(EV_CDL_POP_AMBIG, ZKE_AMBIG, "calldataload.py:13 stack_pop ambiguous")                           \
+  X(EV_CDL_OFF_DOMAIN, ZKE_VALUE, "calldataload.py:13 word_to_fq: a half >= 2^128 -> OverflowError") \
+  X(EV_CDL_OFF_RANGE, ZKE_RANGE, "calldataload.py:13 word_to_fq(.., 8): more than 8 bytes")          \
+  X(EV_CDL_CC0_UNSAT, ZKE_UNSAT, "calldataload.py:16,20 call_context_lookup(TxId / CallerId) unsat") \
+  X(EV_CDL_CC0_AMBIG, ZKE_AMBIG, "calldataload.py:16,20 call_context_lookup(TxId / CallerId) ambiguous") \
+  X(EV_CDL_CC0_TYPE, ZKE_ASSERT, "calldataload.py:16,20 call_context_lookup(TxId / CallerId): .value() of a Word") \
+  X(EV_CDL_CC1_UNSAT, ZKE_UNSAT, "calldataload.py:17,21 call_context_lookup(CallDataLength) unsat")  \
+  X(EV_CDL_CC1_AMBIG, ZKE_AMBIG, "calldataload.py:17,21 call_context_lookup(CallDataLength) ambiguous") \
+  X(EV_CDL_CC1_TYPE, ZKE_ASSERT, "calldataload.py:17,21 call_context_lookup(CallDataLength): .value() of a Word") \
+  X(EV_CDL_CC2_UNSAT, ZKE_UNSAT, "calldataload.py:22 call_context_lookup(CallDataOffset) unsat")     \
+  X(EV_CDL_CC2_AMBIG, ZKE_AMBIG, "calldataload.py:22 call_context_lookup(CallDataOffset) ambiguous") \
+  X(EV_CDL_CC2_TYPE, ZKE_ASSERT, "calldataload.py:22 call_context_lookup(CallDataOffset): .value() of a Word") \
+  X(EV_CDL_END_RANGE, ZKE_ASSERT, "memory_gadget.py:17 min(): addr_end exceeds 5 bytes (instruction.py:449)") \
+  X(EV_CDL_START_RANGE, ZKE_ASSERT, "memory_gadget.py:17 min(): addr_start exceeds 5 bytes (instruction.py:450)") \
+  X(EV_CDL_BYTE_UNSAT, ZKE_UNSAT, "calldataload.py:35,39 tx_calldata_lookup / memory_lookup unsat")  \
+  X(EV_CDL_BYTE_AMBIG, ZKE_AMBIG, "calldataload.py:35,39 tx_calldata_lookup / memory_lookup ambiguous") \
+  X(EV_CDL_BYTE_TYPE, ZKE_ASSERT, "calldataload.py:35,39 tx_calldata_lookup / memory_lookup: .value() of a Word") \
+  X(EV_CDL_BYTES_VALUE, ZKE_VALUE, "calldataload.py:46 bytes() of a value > 255 -> ValueError")      \
+  X(EV_CDL_PUSH_UNSAT, ZKE_UNSAT, "calldataload.py:47 stack_push unsat")                             \
+  X(EV_CDL_PUSH_AMBIG, ZKE_AMBIG, "calldataload.py:47 stack_push ambiguous")                         \
+  X(EV_CDL_EQ, ZKE_ASSERT, "calldataload.py:45-48 the 32 bytes == pushed word")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -922,6 +922,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_tx.h"
 #include "evm_err.h"
 #include "evm_arith.h"
+#include "evm_storage.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -962,7 +963,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_BALANCE || st == ZK_ES_EXTCODEHASH || st == ZK_ES_EXTCODESIZE ||
                                   st == ZK_ES_ErrorOutOfGasAccountAccess || st == ZK_ES_CODECOPY || st == ZK_ES_RETURNDATACOPY ||
                                   st == ZK_ES_EXTCODECOPY || st == ZK_ES_ErrorOutOfGasMemoryCopy || st == ZK_ES_ADDMOD ||
-                                  st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR);
+                                  st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR || st == ZK_ES_SLOAD || st == ZK_ES_SSTORE ||
+                                  st == ZK_ES_CALLDATALOAD);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1020,6 +1022,9 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_MULMOD) gadget_addmod_mulmod(e, i, row, opcode, 1);
   else if (st == ZK_ES_SDIV_SMOD) gadget_sdiv_smod(e, i, row, opcode);
   else if (st == ZK_ES_SAR) gadget_sar(e, i, row, opcode);
+  else if (st == ZK_ES_SLOAD) gadget_sload(e, i, row, opcode);
+  else if (st == ZK_ES_SSTORE) gadget_sstore(e, i, row, opcode);
+  else if (st == ZK_ES_CALLDATALOAD) gadget_calldataload(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1146,6 +1146,90 @@ def evm2_cases(part="evm2"):
                  StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False,
                            code_hash=h, program_counter=pc + 1, stack_pointer=nsp, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
+    def storage_case(kind, value=2, value_prev=0, original=0, warm=False, persistent=True, rev0=0, refund_prev=15000):
+        """tests/evm/test_sload.py, test_sstore.py"""
+        from zkevm_specs.util import COLD_SLOAD_COST, SLOAD_GAS, SSTORE_CLEARS_SCHEDULE, SSTORE_RESET_GAS, SSTORE_SET_GAS, WARM_STORAGE_READ_COST
+        callee = 0xCAFE0000000000000000000000000000BEEF1234
+        key = Word(int.from_bytes(bytes(range(32, 0, -1)), "big"))
+        rev_end = 0 if persistent else 40
+        if kind == "sload":
+            bc = Bytecode().push32(key.int_value()).sload().stop()
+            rw = (RWDictionary(9).call_context_read(1, CallContextFieldTag.TxId, 3)
+                  .call_context_read(1, CallContextFieldTag.RwCounterEndOfReversion, rev_end)
+                  .call_context_read(1, CallContextFieldTag.IsPersistent, persistent)
+                  .call_context_read(1, CallContextFieldTag.CalleeAddress, Word(callee))
+                  .stack_read(1, 1023, key).account_storage_read(callee, key, Word(value), 3, Word(original)).stack_write(1, 1023, Word(value))
+                  .tx_access_list_account_storage_write(3, callee, key, 1, 1 if warm else 0,
+                                                        rw_counter_of_reversion=None if persistent else rev_end - rev0))
+            gas, pc, sp, nsp, d_rev, state = (WARM_STORAGE_READ_COST if warm else COLD_SLOAD_COST), 33, 1023, 1023, 1, ExecutionState.SLOAD
+        else:
+            bc = Bytecode().push32(value).push32(key.int_value()).sstore().stop()
+            if value_prev == value:
+                gas = SLOAD_GAS
+            elif original == value_prev:
+                gas = SSTORE_SET_GAS if original == 0 else SSTORE_RESET_GAS
+            else:
+                gas = SLOAD_GAS
+            if not warm:
+                gas += COLD_SLOAD_COST
+            refund = refund_prev
+            if value_prev != value:
+                if original == value_prev:
+                    if original != 0 and value == 0:
+                        refund += SSTORE_CLEARS_SCHEDULE
+                else:
+                    if original != 0:
+                        if value_prev == 0:
+                            refund -= SSTORE_CLEARS_SCHEDULE
+                        if value == 0:
+                            refund += SSTORE_CLEARS_SCHEDULE
+                    if original == value:
+                        refund += (SSTORE_SET_GAS if original == 0 else SSTORE_RESET_GAS) - SLOAD_GAS
+            rw = (RWDictionary(9).call_context_read(1, CallContextFieldTag.TxId, 3).call_context_read(1, CallContextFieldTag.IsStatic, 0)
+                  .call_context_read(1, CallContextFieldTag.RwCounterEndOfReversion, rev_end)
+                  .call_context_read(1, CallContextFieldTag.IsPersistent, persistent)
+                  .call_context_read(1, CallContextFieldTag.CalleeAddress, Word(callee))
+                  .stack_read(1, 1022, key).stack_read(1, 1023, Word(value))
+                  .account_storage_write(callee, key, Word(value), Word(value_prev), 3, Word(original),
+                                         rw_counter_of_reversion=None if persistent else rev_end - rev0)
+                  .tx_access_list_account_storage_write(3, callee, key, True, warm, rw_counter_of_reversion=None if persistent else rev_end - rev0 - 1)
+                  .tx_refund_write(3, refund, refund_prev, rw_counter_of_reversion=None if persistent else rev_end - rev0 - 2))
+            pc, sp, nsp, d_rev, state = 66, 1022, 1024, 3, ExecutionState.SSTORE
+        h = Word(bc.hash())
+        steps = [StepState(state, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=pc,
+                           stack_pointer=sp, gas_left=gas, reversible_write_counter=rev0),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=pc + 1, stack_pointer=nsp, gas_left=0, reversible_write_counter=rev0 + d_rev)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], []
+
+    def calldataload_case(call_data, cd_len, offset, is_root, cd_off=0):
+        """tests/evm/test_calldataload.py: 32 bytes of the tx call data (tx table) or of the caller's memory"""
+        from zkevm_specs.evm_circuit import Transaction
+        tx = Transaction(id=1, call_data=bytes(call_data) if is_root else bytes())
+        bc = Bytecode().push32(offset).calldataload().stop()
+        h = Word(bc.hash())
+        call_id = 1 if is_root else 2
+        word = bytearray(32)
+        rw = RWDictionary(9).stack_read(call_id, 1023, Word(offset))
+        if is_root:
+            rw.call_context_read(call_id, CallContextFieldTag.TxId, 1).call_context_read(call_id, CallContextFieldTag.CallDataLength, cd_len)
+            for k in range(32):
+                if offset + k < cd_len:
+                    word[k] = call_data[offset + k]
+        else:
+            (rw.call_context_read(call_id, CallContextFieldTag.CallerId, 1).call_context_read(call_id, CallContextFieldTag.CallDataLength, cd_len)
+             .call_context_read(call_id, CallContextFieldTag.CallDataOffset, cd_off))
+            for k in range(32):
+                if offset + k < cd_len:
+                    word[k] = call_data[cd_off + offset + k]
+                    rw.memory_read(1, cd_off + offset + k, word[k])
+        rw.stack_write(call_id, 1023, Word(bytes(word)))
+        steps = [StepState(ExecutionState.CALLDATALOAD, rw_counter=9, call_id=call_id, is_root=is_root, is_create=False, code_hash=h,
+                           program_counter=33, stack_pointer=1023, gas_left=3),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=call_id, is_root=is_root, is_create=False, code_hash=h,
+                           program_counter=34, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], [], list(tx.table_assignments()), []
 
     def mws(a):
         return (a + 31) // 32
@@ -1511,11 +1595,11 @@ def evm2_cases(part="evm2"):
                           program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
         return [cur, nxt_s], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
-    def run(S, B, R, RF, C, K, T=(), BL=()):
+    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
         t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), WordOrValue(W(v[2], v[3]))) for v in BL),
-                   tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), WordOrValue(W(v[3], v[4]))) for v in T),
+                   tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], 1 if TF is None else TF[k_])) for k_, v in enumerate(T)),
                    withdrawal_table=set(),
                    bytecode_table=set(BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5])) for v in B),
                    rw_table=set(RWTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), W(v[6], v[7]),
@@ -1531,7 +1615,23 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm16":
+    if part == "evm17":
+        cd = bytes(rng.randrange(1, 256) for _ in range(80))
+        scenarios = {
+            "sload_cold": storage_case("sload"), "sload_warm": storage_case("sload", warm=True, value=(1 << 255) + 7, original=5),
+            "sload_cold_reverted": storage_case("sload", persistent=False, rev0=3), "sload_warm_reverted": storage_case("sload", warm=True, persistent=False, rev0=1),
+            "sstore_same": storage_case("sstore", value=0x1F2E3D, value_prev=0x1F2E3D, original=0x1F2E3D), "sstore_set": storage_case("sstore", 1, 0, 0, warm=True),
+            "sstore_reset": storage_case("sstore", 2, 1, 1), "sstore_clear": storage_case("sstore", 0, 1, 1, warm=True),
+            "sstore_dirty": storage_case("sstore", 3, 2, 1), "sstore_dirty_restore": storage_case("sstore", 1, 2, 1, warm=True),
+            "sstore_dirty_from_zero": storage_case("sstore", 7, 0, 1), "sstore_dirty_to_zero": storage_case("sstore", 0, 2, 1),
+            "sstore_restore_zero": storage_case("sstore", 0, 2, 0, warm=True),
+            "sstore_reverted": storage_case("sstore", 2, 1, 1, persistent=False, rev0=0), "sstore_reverted_warm": storage_case("sstore", 9, 0, 0, warm=True, persistent=False, rev0=2),
+            "cdl_root_full": calldataload_case(cd, 0x20, 0, True), "cdl_root_tail": calldataload_case(cd, 0x20, 0x1F, True),
+            "cdl_root_mid": calldataload_case(cd, 0x30, 0x10, True), "cdl_root_beyond": calldataload_case(cd, 0x20, 0x40, True),
+            "cdl_internal": calldataload_case(cd, 0x20, 0x10, False), "cdl_internal_off": calldataload_case(cd, 0x21, 0x10, False, cd_off=1),
+            "cdl_internal_full": calldataload_case(cd, 0x40, 0x08, False, cd_off=3),
+        }
+    elif part == "evm16":
         MX, NEG = (1 << 256) - 1, 1 << 255
         big1, big2, big3 = rng.randrange(1 << 256), rng.randrange(1 << 256), rng.randrange(1 << 200)
         scenarios = {
@@ -1685,12 +1785,14 @@ def evm2_cases(part="evm2"):
         S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
         RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
-        assert run(S, B, R, RF, C, K, T, BL) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL))
+        TF = [int(x.value.is_word) for x in sc_[5]] if part == "evm17" and len(sc_) > 5 else None
+        assert run(S, B, R, RF, C, K, T, BL, TF) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
+            TF2 = list(TF) if TF is not None else None
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
                 cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
@@ -1708,8 +1810,18 @@ def evm2_cases(part="evm2"):
                 if c == 9 and not (RF[i] & 1):
                     continue
                 v = corrupt_value(rng, R[i][c]); R2[i][c] = v
+            elif which == 9:  # storage key / previous value / committed value cells of an rw row
+                i, c = rng.randrange(len(R)), rng.choice([6, 7, 10, 11, 12, 13])
+                if c == 11 and not (RF[i] & 2):
+                    continue  # the high cell of a non-Word value does not exist in the reference's row
+                v = corrupt_value(rng, R[i][c]); R2[i][c] = v; which = 1
+            elif which == 6 and T and TF is not None and rng.random() < 0.25:  # the value type of a tx-table row
+                i, c, v = rng.randrange(len(T)), 100, 0
+                TF2[i] ^= 1; which = 12
             elif which == 8:  # a stack word half: the operands and results of the arithmetic gadgets
                 i, c = rng.randrange(len(R)), rng.choice([8, 8, 9])
+                if c == 9 and not (RF[i] & 1):
+                    continue
                 v = corrupt_value(rng, R[i][c]); R2[i][c] = v; which = 1
             elif which == 2:
                 i, c, v = rng.randrange(len(R)), 100, 0
@@ -1736,13 +1848,16 @@ def evm2_cases(part="evm2"):
                 v = corrupt_value(rng, K[i][c]); K2[i][c] = v
             else:
                 continue
-            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2)
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2)
             muts.append((which, i, c, v, fr_, ex_))
             tot += 1
             nfail += fr_ >= 0
         for key, rows_, ncol in (("steps", S, 13), ("bytecode", B, 6), ("rw", R, 14), ("copy", C, 14), ("keccak", K, 5)):
             out[f"{name}/{key}"] = to_matrix(rows_) if rows_ else np.zeros((ncol, 0, 4), dtype=np.uint64)
         out[f"{name}/rw_flags"] = np.array(RF, dtype=np.uint8)
+        if TF is not None:
+            out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
+            out[f"{name}/tx_flags"] = np.array(TF, dtype=np.uint8)
         if part == "evm9":
             out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
             out[f"{name}/block"] = to_matrix(BL) if BL else np.zeros((4, 0, 4), dtype=np.uint64)
@@ -1787,6 +1902,12 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm17_cases():
+    """SLOAD / SSTORE (storage reads and reversible writes keyed on the storage key, the refund rule) and CALLDATALOAD
+    (32 tx-table or memory lookups behind the buffer reader)"""
+    evm2_cases("evm17")
 
 
 def evm16_cases():
@@ -2632,7 +2753,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():
