@@ -879,7 +879,62 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CDL_BYTES_VALUE, ZKE_VALUE, "calldataload.py:46 bytes() of a value > 255 -> ValueError")      \
   X(EV_CDL_PUSH_UNSAT, ZKE_UNSAT, "calldataload.py:47 stack_push unsat")                             \
   X(EV_CDL_PUSH_AMBIG, ZKE_AMBIG, "calldataload.py:47 stack_push ambiguous")                         \
-  X(EV_CDL_EQ, ZKE_ASSERT, "calldataload.py:45-48 the 32 bytes == pushed word")
+  X(EV_CDL_EQ, ZKE_ASSERT, "calldataload.py:45-48 the 32 bytes == pushed word")                 \
+  X(EV_LOG_RANGE5, ZKE_UNSAT, "log.py:11 range_lookup(opcode - LOG0, 5)")                            \
+  X(EV_LOG_POP0_UNSAT, ZKE_UNSAT, "log.py:14 stack_pop mstart unsat")                                \
+  X(EV_LOG_POP0_AMBIG, ZKE_AMBIG, "log.py:14 stack_pop mstart ambiguous")                            \
+  X(EV_LOG_START_DOMAIN, ZKE_VALUE, "log.py:14 word_to_fq: a half >= 2^128 -> OverflowError")        \
+  X(EV_LOG_START_RANGE, ZKE_RANGE, "log.py:14 word_to_fq(.., 8): more than 8 bytes")                 \
+  X(EV_LOG_POP1_UNSAT, ZKE_UNSAT, "log.py:15 stack_pop msize unsat")                                 \
+  X(EV_LOG_POP1_AMBIG, ZKE_AMBIG, "log.py:15 stack_pop msize ambiguous")                             \
+  X(EV_LOG_SIZE_DOMAIN, ZKE_VALUE, "log.py:15 word_to_fq: a half >= 2^128 -> OverflowError")         \
+  X(EV_LOG_SIZE_RANGE, ZKE_RANGE, "log.py:15 word_to_fq(.., 8): more than 8 bytes")                  \
+  X(EV_LOG_TXID_UNSAT, ZKE_UNSAT, "log.py:18 call_context_lookup(TxId) unsat")                       \
+  X(EV_LOG_TXID_AMBIG, ZKE_AMBIG, "log.py:18 call_context_lookup(TxId) ambiguous")                   \
+  X(EV_LOG_TXID_TYPE, ZKE_ASSERT, "log.py:18 call_context_lookup(TxId): .value() of a Word")         \
+  X(EV_LOG_STATIC_UNSAT, ZKE_UNSAT, "log.py:20-22 call_context_lookup(IsStatic) unsat")              \
+  X(EV_LOG_STATIC_AMBIG, ZKE_AMBIG, "log.py:20-22 call_context_lookup(IsStatic) ambiguous")          \
+  X(EV_LOG_STATIC_TYPE, ZKE_ASSERT, "log.py:20-22 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_LOG_STATIC_NONZERO, ZKE_ASSERT, "log.py:20-22 IsStatic == 0")                                 \
+  X(EV_LOG_CALLEE_UNSAT, ZKE_UNSAT, "log.py:27 call_context_lookup_word(CalleeAddress) unsat")       \
+  X(EV_LOG_CALLEE_AMBIG, ZKE_AMBIG, "log.py:27 call_context_lookup_word(CalleeAddress) ambiguous")   \
+  X(EV_LOG_PERSIST_UNSAT, ZKE_UNSAT, "log.py:28 call_context_lookup(IsPersistent) unsat")            \
+  X(EV_LOG_PERSIST_AMBIG, ZKE_AMBIG, "log.py:28 call_context_lookup(IsPersistent) ambiguous")        \
+  X(EV_LOG_PERSIST_TYPE, ZKE_ASSERT, "log.py:28 call_context_lookup(IsPersistent): .value() of a Word") \
+  X(EV_LOG_ADDR_UNSAT, ZKE_UNSAT, "log.py:32-34 tx_log_lookup_word(Address) unsat")                  \
+  X(EV_LOG_ADDR_AMBIG, ZKE_AMBIG, "log.py:32-34 tx_log_lookup_word(Address) ambiguous")              \
+  X(EV_LOG_ADDR_EQ, ZKE_ASSERT, "log.py:30-35 callee address == the log's address")                  \
+  X(EV_LOG_TOPIC_POP_UNSAT, ZKE_UNSAT, "log.py:43 stack_pop topic unsat")                            \
+  X(EV_LOG_TOPIC_POP_AMBIG, ZKE_AMBIG, "log.py:43 stack_pop topic ambiguous")                        \
+  X(EV_LOG_TOPIC_UNSAT, ZKE_UNSAT, "log.py:47-52 tx_log_lookup_word(Topic, i) unsat")                \
+  X(EV_LOG_TOPIC_AMBIG, ZKE_AMBIG, "log.py:47-52 tx_log_lookup_word(Topic, i) ambiguous")            \
+  X(EV_LOG_TOPIC_EQ, ZKE_ASSERT, "log.py:45-53 topic == the log's topic")                            \
+  X(EV_LOG_COPY_UNSAT, ZKE_UNSAT, "log.py:65-76 copy_lookup(Memory -> TxLog) unsat")                 \
+  X(EV_LOG_COPY_AMBIG, ZKE_AMBIG, "log.py:65-76 copy_lookup(Memory -> TxLog) ambiguous")             \
+  X(EV_LOG_MEMSIZE_RANGE, ZKE_RANGE, "log.py:83 memory_expansion_dynamic_length: memory size beyond 4 bytes") \
+  X(EV_LOG_MEM_MAX, ZKE_ASSERT, "log.py:83 max(): curr.memory_word_size beyond 4 bytes")             \
+  X(EV_EWP_OPCODE, ZKE_ASSERT, "error_write_protection.py:42-55 opcode modifies state")              \
+  X(EV_EWP_STATIC_UNSAT, ZKE_UNSAT, "error_write_protection.py:59 call_context_lookup(IsStatic) unsat") \
+  X(EV_EWP_STATIC_AMBIG, ZKE_AMBIG, "error_write_protection.py:59 call_context_lookup(IsStatic) ambiguous") \
+  X(EV_EWP_STATIC_TYPE, ZKE_ASSERT, "error_write_protection.py:59 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_EWP_NOT_STATIC, ZKE_ASSERT, "error_write_protection.py:60 IsStatic == 1")                     \
+  X(EV_EWP_VALUE_UNSAT, ZKE_UNSAT, "error_write_protection.py:65 stack_lookup(Read, 2) unsat")       \
+  X(EV_EWP_VALUE_AMBIG, ZKE_AMBIG, "error_write_protection.py:65 stack_lookup(Read, 2) ambiguous")   \
+  X(EV_EWP_VALUE_ZERO, ZKE_ASSERT, "error_write_protection.py:66 CALL value != 0")                   \
+  X(EV_BH_POP_UNSAT, ZKE_UNSAT, "blockhash.py:9 stack_pop unsat")                                    \
+  X(EV_BH_POP_AMBIG, ZKE_AMBIG, "blockhash.py:9 stack_pop ambiguous")                                \
+  X(EV_BH_NUM_DOMAIN, ZKE_VALUE, "blockhash.py:9 word_to_u64: a half >= 2^128 -> OverflowError")     \
+  X(EV_BH_NUM_RANGE, ZKE_RANGE, "blockhash.py:9 word_to_u64: more than 8 bytes")                     \
+  X(EV_BH_CUR_UNSAT, ZKE_UNSAT, "blockhash.py:11 block_context_lookup(Number) unsat")                \
+  X(EV_BH_CUR_AMBIG, ZKE_AMBIG, "blockhash.py:11 block_context_lookup(Number) ambiguous")            \
+  X(EV_BH_CUR_TYPE, ZKE_ASSERT, "blockhash.py:11 block_context_lookup(Number): .value() of a Word")  \
+  X(EV_BH_PUSH_UNSAT, ZKE_UNSAT, "blockhash.py:13 stack_push unsat")                                 \
+  X(EV_BH_PUSH_AMBIG, ZKE_AMBIG, "blockhash.py:13 stack_push ambiguous")                             \
+  X(EV_BH_CMP1_RANGE, ZKE_ASSERT, "blockhash.py:16 compare(block_number, current, 8): range assert") \
+  X(EV_BH_CMP2_RANGE, ZKE_ASSERT, "blockhash.py:17 compare(current, 256 + block_number, 2): range assert") \
+  X(EV_BH_HASH_UNSAT, ZKE_UNSAT, "blockhash.py:21-24 block_context_lookup_word(HistoryHash, block_number) unsat") \
+  X(EV_BH_HASH_AMBIG, ZKE_AMBIG, "blockhash.py:21-24 block_context_lookup_word(HistoryHash, block_number) ambiguous") \
+  X(EV_BH_EQ, ZKE_ASSERT, "blockhash.py:29 pushed word == expected block hash")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -117,6 +117,8 @@ static void same_context(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, uint
 }
 static void same_context_r(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
                            int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev);
+static void same_context_rl(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                            int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev, fr_t d_log);
 static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
                            int mem_to, fr_t mem_value, fr_t dyn_gas) {
   same_context_r(e, i, row, opcode, d_rwc, d_pc, d_sp, mem_to, mem_value, dyn_gas, 0);
@@ -124,6 +126,11 @@ static void same_context_x(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr
 /* + reversible_write_counter = Transition.delta(d_rev) */
 static void same_context_r(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
                            int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev) {
+  same_context_rl(e, i, row, opcode, d_rwc, d_pc, d_sp, mem_to, mem_value, dyn_gas, d_rev, fr_u64(0));
+}
+/* + log_id = Transition.delta(d_log) */
+static void same_context_rl(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr_t d_rwc, fr_t d_pc, fr_t d_sp,
+                            int mem_to, fr_t mem_value, fr_t dyn_gas, uint64_t d_rev, fr_t d_log) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
 #define CUR(c) fr_load(ORC_CELL(S, n, c, i))
 #define NXT(c) fr_load(ORC_CELL(S, n, c, j))
@@ -140,7 +147,7 @@ static void same_context_r(evm_env* e, uint64_t i, uint64_t row, fr_t opcode, fr
   CHECK(EV_SC_GAS, fr_eq(NXT(S_GAS), gas_after));
   CHECK(EV_SC_MEM, fr_eq(NXT(S_MEM), mem_to ? mem_value : CUR(S_MEM)));
   CHECK(EV_SC_REV, fr_eq(NXT(S_REV), fr_add(CUR(S_REV), fr_u64(d_rev))));
-  CHECK(EV_SC_LOG, fr_eq(NXT(S_LOG), CUR(S_LOG)));
+  CHECK(EV_SC_LOG, fr_eq(NXT(S_LOG), fr_add(CUR(S_LOG), d_log)));
   CHECK(EV_SC_CALL_ID, fr_eq(NXT(S_CALL_ID), CUR(S_CALL_ID)));
   CHECK(EV_SC_IS_ROOT, fr_eq(NXT(S_IS_ROOT), CUR(S_IS_ROOT)));
   CHECK(EV_SC_IS_CREATE, fr_eq(NXT(S_IS_CREATE), CUR(S_IS_CREATE)));
@@ -923,6 +930,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_err.h"
 #include "evm_arith.h"
 #include "evm_storage.h"
+#include "evm_log.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -964,7 +972,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_ErrorOutOfGasAccountAccess || st == ZK_ES_CODECOPY || st == ZK_ES_RETURNDATACOPY ||
                                   st == ZK_ES_EXTCODECOPY || st == ZK_ES_ErrorOutOfGasMemoryCopy || st == ZK_ES_ADDMOD ||
                                   st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR || st == ZK_ES_SLOAD || st == ZK_ES_SSTORE ||
-                                  st == ZK_ES_CALLDATALOAD);
+                                  st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1025,6 +1033,9 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_SLOAD) gadget_sload(e, i, row, opcode);
   else if (st == ZK_ES_SSTORE) gadget_sstore(e, i, row, opcode);
   else if (st == ZK_ES_CALLDATALOAD) gadget_calldataload(e, i, row, opcode);
+  else if (st == ZK_ES_LOG) gadget_log(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorWriteProtection) gadget_error_write_protection(e, i, row, opcode);
+  else if (st == ZK_ES_BLOCKHASH) gadget_blockhash(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -143,7 +143,7 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None
         tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
         blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         lib().emu_set_evm_context_tables(_p(tx), c(tx.shape[1]), _p(blk), c(blk.shape[1]))
-    if w.get("wd") is not None or w.get("tx_flags") is not None:  # BeginTx / EndTx / EndBlock
+    if w.get("wd") is not None or w.get("tx_flags") is not None or w.get("block_flags") is not None:  # BeginTx / EndTx / EndBlock
         p8_ = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if len(a) else None  # noqa: E731
         txf = np.ascontiguousarray(w.get("tx_flags") if w.get("tx_flags") is not None else np.zeros(0), dtype=np.uint8)
         blf = np.ascontiguousarray(w.get("block_flags") if w.get("block_flags") is not None else np.zeros(0), dtype=np.uint8)

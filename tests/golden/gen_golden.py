@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1230,6 +1230,95 @@ def evm2_cases(part="evm2"):
                  StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=call_id, is_root=is_root, is_create=False, code_hash=h,
                            program_counter=34, stack_pointer=1023, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], [], list(tx.table_assignments()), []
+
+    def log_case(topics, mstart, msize, persistent, cur_mem=0, log_id=0):
+        """tests/evm/test_logs.py: LOG0..LOG4 (tx-log rows for the address and the topics, the data through the copy table)"""
+        from zkevm_specs.evm_circuit import TxLogFieldTag
+        from zkevm_specs.util.param import GAS_COST_LOG, GAS_COST_LOGDATA
+        callee = 0xCAFE0000000000000000000000000000BEEF1234
+        bc = Bytecode()
+        for t in reversed(topics):
+            bc.push32(t)
+        bc.push32(msize).push32(mstart)
+        getattr(bc, "log%d" % len(topics))()
+        bc.stop()
+        h = Word(bc.hash())
+        sp = 1024 - 2 - len(topics)
+        nxt, exp = mem_exp(cur_mem, mstart + msize)
+        if msize == 0:  # memory_expansion_dynamic_length still counts the offset (instruction.py:1164-1166)
+            nxt = max(cur_mem, mws(mstart)); exp = (nxt - cur_mem) * 3 + (nxt * nxt // 512 - cur_mem * cur_mem // 512)
+        gas = GAS_COST_LOG * (1 + len(topics)) + GAS_COST_LOGDATA * msize + exp
+        rw = (RWDictionary(9).stack_read(1, sp, Word(mstart)).stack_read(1, sp + 1, Word(msize))
+              .call_context_read(1, CallContextFieldTag.TxId, 3).call_context_read(1, CallContextFieldTag.IsStatic, 0)
+              .call_context_read(1, CallContextFieldTag.CalleeAddress, Word(callee))
+              .call_context_read(1, CallContextFieldTag.IsPersistent, persistent))
+        if persistent:
+            rw.tx_log_write(3, log_id + 1, TxLogFieldTag.Address, 0, Word(callee))
+        for k_, t in enumerate(topics):
+            rw.stack_read(1, sp + 2 + k_, Word(t))
+            if persistent:
+                rw.tx_log_write(3, log_id + 1, TxLogFieldTag.Topic, k_, Word(t))
+        cc = CopyCircuit()
+        if persistent and msize:
+            data = {mstart + k_: rng.randrange(256) for k_ in range(msize)}
+            cc.copy(r, rw, 1, CopyDataTypeTag.Memory, 3, CopyDataTypeTag.TxLog, mstart, mstart + msize, 0, msize, data, log_id=log_id + 1)
+        pc = 33 * (2 + len(topics))
+        steps = [StepState(ExecutionState.LOG, rw_counter=9, call_id=1, is_root=False, is_create=False, code_hash=h, program_counter=pc,
+                           stack_pointer=sp, memory_word_size=cur_mem, gas_left=gas, log_id=log_id),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=False, is_create=False, code_hash=h,
+                           program_counter=pc + 1, stack_pointer=1024, memory_word_size=nxt, gas_left=0, log_id=log_id + int(persistent))]
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return steps, list(bc.table_assignments()), list(rw.rws), list(t.copy_table), []
+
+    def ewp_case(op, root, value=100):
+        """tests/evm/test_error_write_protection.py: a state-modifying opcode in a static call"""
+        bc = Bytecode()
+        if op == "call":
+            bc = bc.call(0x2000, 0xFF, value, 0, 0, 0, 0)
+            state_pc, sp = 231, 1017
+        elif op == "sstore":
+            bc = bc.push32(5).push32(7).sstore(); state_pc, sp = 66, 1022
+        else:
+            bc = bc.push32(5).push32(7).log0(); state_pc, sp = 66, 1022
+        bc.stop()
+        h = Word(bc.hash())
+        call_id, rev = (1 if root else 2), 2
+        rw = RWDictionary(24 if root else 69)
+        rwc0 = rw.rw_counter
+        rw.call_context_read(call_id, CallContextFieldTag.IsStatic, 1)
+        if op == "call":
+            rw.stack_read(call_id, sp + 2, Word(value))
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(ExecutionState.ErrorWriteProtection, rw_counter=rwc0, call_id=call_id, is_root=root, is_create=False, code_hash=h,
+                        program_counter=state_pc, stack_pointer=sp, gas_left=100, reversible_write_counter=rev)
+        if root:
+            return [cur, StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (True, False, 232, 1023, 10, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                        reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
+    def blockhash_case(current, number, res=None):
+        """tests/evm/test_blockhash.py: the hash of one of the 256 previous blocks, else zero"""
+        from zkevm_specs.evm_circuit import BlockContextFieldTag, BlockTableRow
+        hashes = {n_: rng.randrange(1, 1 << 256) for n_ in range(max(0, current - 255), current)}
+        want = hashes.get(number, 0) if res is None else res
+        bc = Bytecode().push32(number).blockhash().stop()
+        h = Word(bc.hash())
+        rw = RWDictionary(9).stack_read(1, 1023, Word(number)).stack_write(1, 1023, Word(want))
+        blocks = [BlockTableRow(FQ(BlockContextFieldTag.Number), FQ(0), WordOrValue(FQ(current))),
+                  BlockTableRow(FQ(BlockContextFieldTag.Coinbase), FQ(0), WordOrValue(Word(0x77)))]
+        blocks += [BlockTableRow(FQ(BlockContextFieldTag.HistoryHash), FQ(n_), WordOrValue(Word(v_))) for n_, v_ in list(hashes.items())[-6:] + ([(number, hashes[number])] if number in hashes else [])]
+        steps = [StepState(ExecutionState.BLOCKHASH, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=33,
+                           stack_pointer=1023, gas_left=20),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=34, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], [], [], list(set(blocks))
 
     def mws(a):
         return (a + 31) // 32
@@ -1595,10 +1684,10 @@ def evm2_cases(part="evm2"):
                           program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
         return [cur, nxt_s], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
-    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None):
+    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None, BF=None):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
-        t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), WordOrValue(W(v[2], v[3]))) for v in BL),
+        t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), wov(v[2], v[3], 1 if BF is None else BF[k_])) for k_, v in enumerate(BL)),
                    tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], 1 if TF is None else TF[k_])) for k_, v in enumerate(T)),
                    withdrawal_table=set(),
                    bytecode_table=set(BytecodeTableRow(W(v[0], v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5])) for v in B),
@@ -1615,7 +1704,19 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm17":
+    if part == "evm18":
+        scenarios = {
+            "log0_empty": log_case([], 10, 0, True), "log1": log_case([0x030201], 10, 2, True), "log2": log_case([0x030201, 0x0F0E0D], 100, 20, True, cur_mem=2),
+            "log3": log_case([0x030201, 0x0F0E0D, 0x0D8F01], 180, 50, True, log_id=4), "log4": log_case([(1 << 255) + 5, 2, 3, (1 << 200) + 9], 0x40, 33, True),
+            "log0_data": log_case([], 0, 70, True, cur_mem=8), "log2_reverted": log_case([0x030201, 0x0F0E0D], 100, 20, False),
+            "log0_reverted_empty": log_case([], 5, 0, False, log_id=2), "log4_reverted": log_case([9, 8, 7, 6], 0x100, 5, False, cur_mem=1),
+            "ewp_call_root": ewp_case("call", True), "ewp_call_internal": ewp_case("call", False, value=(1 << 130)),
+            "ewp_sstore_internal": ewp_case("sstore", False), "ewp_log_root": ewp_case("log0", True),
+            "bh_prev": blockhash_case(1000, 999), "bh_oldest": blockhash_case(1000, 745), "bh_too_old": blockhash_case(1000, 744),
+            "bh_current": blockhash_case(1000, 1000), "bh_future": blockhash_case(300, 40000), "bh_genesis": blockhash_case(5, 0),
+            "bh_edge": blockhash_case(70, 65279),
+        }
+    elif part == "evm17":
         cd = bytes(rng.randrange(1, 256) for _ in range(80))
         scenarios = {
             "sload_cold": storage_case("sload"), "sload_warm": storage_case("sload", warm=True, value=(1 << 255) + 7, original=5),
@@ -1786,13 +1887,15 @@ def evm2_cases(part="evm2"):
         RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         TF = [int(x.value.is_word) for x in sc_[5]] if part == "evm17" and len(sc_) > 5 else None
-        assert run(S, B, R, RF, C, K, T, BL, TF) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF))
+        BF = [int(x.value.is_word) for x in sc_[6]] if part == "evm18" and len(sc_) > 6 else None
+        assert run(S, B, R, RF, C, K, T, BL, TF, BF) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
+            BF2 = list(BF) if BF is not None else None
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
                 cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
@@ -1818,6 +1921,9 @@ def evm2_cases(part="evm2"):
             elif which == 6 and T and TF is not None and rng.random() < 0.25:  # the value type of a tx-table row
                 i, c, v = rng.randrange(len(T)), 100, 0
                 TF2[i] ^= 1; which = 12
+            elif which == 7 and BL and BF is not None and rng.random() < 0.2:  # the value type of a block-table row
+                i, c, v = rng.randrange(len(BL)), 100, 0
+                BF2[i] ^= 1; which = 13
             elif which == 8:  # a stack word half: the operands and results of the arithmetic gadgets
                 i, c = rng.randrange(len(R)), rng.choice([8, 8, 9])
                 if c == 9 and not (RF[i] & 1):
@@ -1848,7 +1954,7 @@ def evm2_cases(part="evm2"):
                 v = corrupt_value(rng, K[i][c]); K2[i][c] = v
             else:
                 continue
-            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2)
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2, BF2)
             muts.append((which, i, c, v, fr_, ex_))
             tot += 1
             nfail += fr_ >= 0
@@ -1858,7 +1964,9 @@ def evm2_cases(part="evm2"):
         if TF is not None:
             out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
             out[f"{name}/tx_flags"] = np.array(TF, dtype=np.uint8)
-        if part == "evm9":
+        if BF is not None:
+            out[f"{name}/block_flags"] = np.array(BF, dtype=np.uint8)
+        if part in ("evm9", "evm18"):
             out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
             out[f"{name}/block"] = to_matrix(BL) if BL else np.zeros((4, 0, 4), dtype=np.uint64)
         out[f"{name}/mut_kind"] = np.array([m[0] for m in muts], dtype=np.int64)
@@ -1902,6 +2010,12 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm18_cases():
+    """LOG0..LOG4 (tx-log rows, the data through a copy-table lookup whose destination address carries the log id),
+    ErrorWriteProtection and BLOCKHASH (block-table lookups keyed on the block number)"""
+    evm2_cases("evm18")
 
 
 def evm17_cases():
@@ -2753,7 +2867,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

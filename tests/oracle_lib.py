@@ -157,7 +157,7 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
         tx = np.ascontiguousarray(w["tx"] if w.get("tx") is not None else np.zeros((5, 0, 4)), dtype=np.uint64)
         blk = np.ascontiguousarray(w["block"] if w.get("block") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         lib().orc_set_evm_context_tables(p64(tx), c(tx.shape[1]), p64(blk), c(blk.shape[1]))
-    if w.get("wd") is not None or w.get("tx_flags") is not None:  # BeginTx / EndTx / EndBlock: value type flags + withdrawals
+    if w.get("wd") is not None or w.get("tx_flags") is not None or w.get("block_flags") is not None:  # BeginTx / EndTx / EndBlock: value type flags + withdrawals
         keep = getattr(check_evm_x, "_keep", None) or []
         txf = np.ascontiguousarray(w.get("tx_flags") if w.get("tx_flags") is not None else np.zeros(0), dtype=np.uint8)
         blf = np.ascontiguousarray(w.get("block_flags") if w.get("block_flags") is not None else np.zeros(0), dtype=np.uint8)

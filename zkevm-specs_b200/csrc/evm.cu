@@ -43,7 +43,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasStaticMemoryExpansion) X(ZK_ES_ErrorOutOfGasDynamicMemoryExpansion) X(ZK_ES_ErrorOutOfGasLOG)       \
   X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
   X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
-  X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD)
+  X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
+  X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -326,7 +327,7 @@ ZK_HD bool responsible_opcode(const StepCtx& s, const Fr& state, const Fr& opcod
 // delta is a field element, memory_word_size either stays or moves To a value, and a dynamic gas
 // cost is added to the opcode's constant cost.
 ZK_HD void same_context_x(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, const Fr& d_pc, const Fr& d_sp,
-                          bool mem_to, const Fr& mem_value, const Fr& dyn_gas, u64 d_rev = 0) {
+                          bool mem_to, const Fr& mem_value, const Fr& dyn_gas, u64 d_rev = 0, const Fr* d_log = nullptr) {
   EV_CHECK(EV_SC_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
   int gas_cost = -1;
   if (fr_fits64(opcode) && opcode.l[0] < 256) gas_cost = OPCODE_GAS(opcode.l[0]);
@@ -339,7 +340,7 @@ ZK_HD void same_context_x(const StepCtx& s, const Fr& opcode, const Fr& d_rwc, c
   EV_CHECK(EV_SC_GAS, fr_eq(s.nxt(S_GAS), gas_after));
   EV_CHECK(EV_SC_MEM, fr_eq(s.nxt(S_MEM), mem_to ? mem_value : s.cur(S_MEM)));
   EV_CHECK(EV_SC_REV, fr_eq(s.nxt(S_REV), d_rev ? fr_add_u64(s.cur(S_REV), d_rev) : s.cur(S_REV)));
-  EV_CHECK(EV_SC_LOG, fr_eq(s.nxt(S_LOG), s.cur(S_LOG)));
+  EV_CHECK(EV_SC_LOG, fr_eq(s.nxt(S_LOG), d_log ? fr_add(s.cur(S_LOG), *d_log) : s.cur(S_LOG)));
   EV_CHECK(EV_SC_CALL_ID, fr_eq(s.nxt(S_CALL_ID), s.cur(S_CALL_ID)));
   EV_CHECK(EV_SC_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), s.cur(S_IS_ROOT)));
   EV_CHECK(EV_SC_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), s.cur(S_IS_CREATE)));
@@ -1587,6 +1588,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 #include "evm_err.cuh"
 #include "evm_arith.cuh"
 #include "evm_storage.cuh"
+#include "evm_log.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1615,7 +1617,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_ErrorOutOfGasLOG: case ZK_ES_ErrorOutOfGasEXP: case ZK_ES_ErrorReturnDataOutOfBound:
     case ZK_ES_BALANCE: case ZK_ES_EXTCODEHASH: case ZK_ES_EXTCODESIZE: case ZK_ES_ErrorOutOfGasAccountAccess:
     case ZK_ES_CODECOPY: case ZK_ES_RETURNDATACOPY: case ZK_ES_EXTCODECOPY: case ZK_ES_ErrorOutOfGasMemoryCopy:
-    case ZK_ES_SLOAD: case ZK_ES_SSTORE: case ZK_ES_CALLDATALOAD:
+    case ZK_ES_SLOAD: case ZK_ES_SSTORE: case ZK_ES_CALLDATALOAD: case ZK_ES_LOG: case ZK_ES_ErrorWriteProtection: case ZK_ES_BLOCKHASH:
       return KG_TX;
     default: return -1;
   }
@@ -1692,6 +1694,9 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_SLOAD: gadget_sload(s); break;
       case ZK_ES_SSTORE: gadget_sstore(s); break;
       case ZK_ES_CALLDATALOAD: gadget_calldataload(s); break;
+      case ZK_ES_LOG: gadget_log(s); break;
+      case ZK_ES_ErrorWriteProtection: gadget_error_write_protection(s); break;
+      case ZK_ES_BLOCKHASH: gadget_blockhash(s); break;
       default: break;
     }
   } else if constexpr (G == KG_ARITH) {
