@@ -934,7 +934,26 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_BH_CMP2_RANGE, ZKE_ASSERT, "blockhash.py:17 compare(current, 256 + block_number, 2): range assert") \
   X(EV_BH_HASH_UNSAT, ZKE_UNSAT, "blockhash.py:21-24 block_context_lookup_word(HistoryHash, block_number) unsat") \
   X(EV_BH_HASH_AMBIG, ZKE_AMBIG, "blockhash.py:21-24 block_context_lookup_word(HistoryHash, block_number) ambiguous") \
-  X(EV_BH_EQ, ZKE_ASSERT, "blockhash.py:29 pushed word == expected block hash")
+  X(EV_BH_EQ, ZKE_ASSERT, "blockhash.py:29 pushed word == expected block hash")                 \
+  X(EV_EXP_RW0_UNSAT, ZKE_UNSAT, "exp.py:8 stack_pop base unsat")                                    \
+  X(EV_EXP_RW0_AMBIG, ZKE_AMBIG, "exp.py:8 stack_pop base ambiguous")                                \
+  X(EV_EXP_RW1_UNSAT, ZKE_UNSAT, "exp.py:9 stack_pop exponent unsat")                                \
+  X(EV_EXP_RW1_AMBIG, ZKE_AMBIG, "exp.py:9 stack_pop exponent ambiguous")                            \
+  X(EV_EXP_RW2_UNSAT, ZKE_UNSAT, "exp.py:10 stack_push unsat")                                       \
+  X(EV_EXP_RW2_AMBIG, ZKE_AMBIG, "exp.py:10 stack_push ambiguous")                                   \
+  X(EV_EXP_ZERO_LO, ZKE_ASSERT, "exp.py:20 exponent == 0 => exponentiation lo == 1")                 \
+  X(EV_EXP_ZERO_HI, ZKE_ASSERT, "exp.py:21 exponent == 0 => exponentiation hi == 0")                 \
+  X(EV_EXP_ONE_LO, ZKE_ASSERT, "exp.py:23 exponent == 1 => exponentiation lo == base lo")            \
+  X(EV_EXP_ONE_HI, ZKE_ASSERT, "exp.py:24 exponent == 1 => exponentiation hi == base hi")            \
+  X(EV_EXP_BASE_TO64, ZKE_VALUE, "exp.py:26 base.to_64s(): a half >= 2^128 -> OverflowError")        \
+  X(EV_EXP_FIRST_UNSAT, ZKE_UNSAT, "exp.py:31 exp_lookup(identifier, single_step, base limbs, exponent) unsat") \
+  X(EV_EXP_FIRST_AMBIG, ZKE_AMBIG, "exp.py:31 exp_lookup(identifier, single_step, base limbs, exponent) ambiguous") \
+  X(EV_EXP_LAST_UNSAT, ZKE_UNSAT, "exp.py:33 exp_lookup(identifier, 1, base limbs, 2) unsat")        \
+  X(EV_EXP_LAST_AMBIG, ZKE_AMBIG, "exp.py:33 exp_lookup(identifier, 1, base limbs, 2) ambiguous")    \
+  X(EV_EXP_CARRY_LO, ZKE_RANGE, "exp.py:36 mul_add_words(base, base, 0, base^2): range_check(carry_lo, 9)") \
+  X(EV_EXP_CARRY_HI, ZKE_RANGE, "exp.py:36 mul_add_words: range_check(carry_hi, 9)")                 \
+  X(EV_EXP_RESULT, ZKE_ASSERT, "exp.py:39 looked-up exponentiation == pushed word")                  \
+  X(EV_EXP_EXPONENT_BYTES, ZKE_VALUE, "exp.py:41 byte_size(exponent): to_le_bytes of a half >= 2^128 -> OverflowError")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -38,6 +38,7 @@ typedef struct {
   const uint64_t* steps; uint64_t n_steps;
   orc_index bytecode_ix, rw_ix, fixed_ix, copy_ix, keccak_ix;
   orc_index tx_ix, block_ix; /* tx table key (tx_id, tag, index); block table key (tag, block_number) */
+  orc_index exp_ix;          /* exp table keyed on its first nine cells (exp_lookup, table.py:797-814) */
   orc_index rwc_ix;          /* rw table keyed on rw_counter alone (lookups with optional columns, evm_tx.h) */
   const uint8_t* rw_flags; /* bit0: value.is_word, bit1: value_prev.is_word */
   const uint8_t *tx_flags, *block_flags; /* bit0: value.is_word */
@@ -931,6 +932,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_arith.h"
 #include "evm_storage.h"
 #include "evm_log.h"
+#include "evm_exp.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -972,7 +974,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_ErrorOutOfGasAccountAccess || st == ZK_ES_CODECOPY || st == ZK_ES_RETURNDATACOPY ||
                                   st == ZK_ES_EXTCODECOPY || st == ZK_ES_ErrorOutOfGasMemoryCopy || st == ZK_ES_ADDMOD ||
                                   st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR || st == ZK_ES_SLOAD || st == ZK_ES_SSTORE ||
-                                  st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH);
+                                  st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH ||
+                                  st == ZK_ES_EXP);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1036,6 +1039,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_LOG) gadget_log(e, i, row, opcode);
   else if (st == ZK_ES_ErrorWriteProtection) gadget_error_write_protection(e, i, row, opcode);
   else if (st == ZK_ES_BLOCKHASH) gadget_blockhash(e, i, row, opcode);
+  else if (st == ZK_ES_EXP) gadget_exp(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 
@@ -1058,6 +1062,9 @@ static __thread const uint64_t* g_block_tab; static __thread uint64_t g_n_block;
 void orc_set_evm_context_tables(const uint64_t* tx_tab, uint64_t n_tx, const uint64_t* block_tab, uint64_t n_block) {
   g_tx_tab = tx_tab; g_n_tx = n_tx; g_block_tab = block_tab; g_n_block = n_block;
 }
+/* exp table (11 cells) of the NEXT call (EXP) */
+static __thread const uint64_t* g_exp_tab; static __thread uint64_t g_n_exp;
+void orc_set_evm_exp_table(const uint64_t* exp_tab, uint64_t n_exp) { g_exp_tab = exp_tab; g_n_exp = n_exp; }
 /* value type flags of the tx / block tables and the withdrawal table of the NEXT call (BeginTx / EndTx / EndBlock) */
 static __thread const uint8_t *g_tx_flags, *g_block_flags; static __thread const uint64_t* g_wd_tab; static __thread uint64_t g_n_wd;
 void orc_set_evm_block_tables(const uint8_t* tx_flags, const uint8_t* block_flags, const uint64_t* wd_tab, uint64_t n_wd) {
@@ -1098,6 +1105,9 @@ int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* byt
   orc_index_build(&env.tx_ix, g_tx_tab, g_n_tx, 5, tk, 3);
   orc_index_build(&env.block_ix, g_block_tab, g_n_block, 4, blk, 2);
   g_tx_tab = g_block_tab = 0; g_n_tx = g_n_block = 0;
+  const uint32_t ek[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+  orc_index_build(&env.exp_ix, g_exp_tab, g_n_exp, 11, ek, 9);
+  g_exp_tab = 0; g_n_exp = 0;
   const uint32_t ck0[1] = {0};
   orc_index_build(&env.rwc_ix, rw_tab, n_rw, 14, ck0, 1);
   env.tx_flags = g_tx_flags; env.block_flags = g_block_flags; env.wd_tab = g_wd_tab; env.n_wd = g_n_wd;
@@ -1106,6 +1116,6 @@ int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* byt
   for (uint64_t i = row_begin; i < row_end; i++) verify_step(&env, i, row_base + i, flags);
   orc_index_free(&env.bytecode_ix); orc_index_free(&env.rw_ix); /* fixed_ix.order lives in fx_cache */
   orc_index_free(&env.copy_ix); orc_index_free(&env.keccak_ix); orc_index_free(&env.tx_ix); orc_index_free(&env.block_ix);
-  orc_index_free(&env.rwc_ix);
+  orc_index_free(&env.rwc_ix); orc_index_free(&env.exp_ix);
   return 0;
 }

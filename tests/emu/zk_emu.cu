@@ -206,6 +206,13 @@ extern "C" void emu_set_evm_block_tables(const uint8_t* tx_flags, const uint8_t*
   g_emu_wd = (const u64*)wd;
   g_emu_n_wd = n_wd;
 }
+static const u64* g_emu_exp = nullptr;
+static u64 g_emu_n_exp = 0;
+// exp table (11 cells) of the NEXT emu_check_evm_x call
+extern "C" void emu_set_evm_exp_table(const uint64_t* exp, uint64_t n_exp) {
+  g_emu_exp = (const u64*)exp;
+  g_emu_n_exp = n_exp;
+}
 extern "C" void emu_set_evm_context_tables(const uint64_t* tx, uint64_t n_tx, const uint64_t* block, uint64_t n_block) {
   g_emu_tx = (const u64*)tx;
   g_emu_n_tx = n_tx;
@@ -258,6 +265,11 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   t.block = build_index(g_emu_block, g_emu_n_block, 4, bk, 2, ch, s7);
   t.tx.tab.flags = g_emu_tx_flags;
   t.block.tab.flags = g_emu_block_flags;
+  const u32 ek[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+  IndexStore s11;
+  t.exp = build_index(g_emu_exp, g_emu_n_exp, 11, ek, 9, ch, s11);
+  g_emu_exp = nullptr;
+  g_emu_n_exp = 0;
   const u32 wk[1] = {0};
   IndexStore s8, s9;
   IndexDev wd_ix = build_index(g_emu_wd, g_emu_n_wd, 4, wk, 1, ch, s8);

@@ -150,6 +150,10 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None
         wd = np.ascontiguousarray(w["wd"] if w.get("wd") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         check_evm_x._keep = [txf, blf, wd]
         lib().emu_set_evm_block_tables(p8_(txf), p8_(blf), _p(wd), c(wd.shape[1]))
+    if w.get("exp") is not None:  # EXP: the exp table
+        ex = np.ascontiguousarray(w["exp"], dtype=np.uint64)
+        check_evm_x._keep_exp = ex
+        lib().emu_set_evm_exp_table(_p(ex), c(ex.shape[1]))
     if w.get("flags") is not None:
         flags = int(w["flags"])
     rc = lib().emu_check_evm_x(_p(m["steps"]), c(m["steps"].shape[1]), _p(m["bytecode"]), c(m["bytecode"].shape[1]),

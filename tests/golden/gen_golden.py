@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1320,6 +1320,26 @@ def evm2_cases(part="evm2"):
                            program_counter=34, stack_pointer=1023, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], [], [], list(set(blocks))
 
+    def exp_case(base, exponent, res=None):
+        """tests/evm/test_exp.py: the exponentiation read from the exp table (first and last step rows of the exp circuit)"""
+        from zkevm_specs.evm_circuit import ExpCircuit
+        from zkevm_specs.util import GAS_COST_EXP_PER_BYTE, byte_size
+        want = pow(base, exponent, 1 << 256) if res is None else res
+        bc = Bytecode().push32(exponent).push32(base).exp().stop()
+        h = Word(bc.hash())
+        rw = RWDictionary(9).stack_read(1, 1022, Word(base)).stack_read(1, 1023, Word(exponent)).stack_write(1, 1023, Word(want))
+        ec = ExpCircuit(max_exp_steps=4).add_event(base, exponent, rw.rw_counter)
+        if rng.random() < 0.5:
+            ec.add_event(3, 5, 77)
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bc.table_assignments()),
+                   rw_table=set(rw.rws), exp_circuit=ec.rows)
+        gas = Opcode.EXP.constant_gas_cost() + byte_size(exponent) * GAS_COST_EXP_PER_BYTE
+        steps = [StepState(ExecutionState.EXP, rw_counter=9, call_id=1, is_root=True, is_create=False, code_hash=h, program_counter=66,
+                           stack_pointer=1022, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False, code_hash=h,
+                           program_counter=67, stack_pointer=1023, gas_left=0)]
+        return steps, list(bc.table_assignments()), list(rw.rws), [], [], [], [], list(t.exp_table)
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1684,7 +1704,11 @@ def evm2_cases(part="evm2"):
                           program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5], reversible_write_counter=ctx[6])
         return [cur, nxt_s], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
-    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None, BF=None):
+    def exp_ints(x):
+        return [n_of(x.is_step), n_of(x.identifier), n_of(x.is_last), n_of(x.base_limb0), n_of(x.base_limb1), n_of(x.base_limb2), n_of(x.base_limb3),
+                n_of(x.exponent.lo), n_of(x.exponent.hi), n_of(x.exponentiation.lo), n_of(x.exponentiation.hi)]
+
+    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None, BF=None, EX=()):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
         t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), wov(v[2], v[3], 1 if BF is None else BF[k_])) for k_, v in enumerate(BL)),
@@ -1697,6 +1721,9 @@ def evm2_cases(part="evm2"):
         t.copy_table = set(CopyTableRow(FQ(v[0]), WordOrValue(W(v[1], v[2])), FQ(v[3]), WordOrValue(W(v[4], v[5])), FQ(v[6]),
                                         FQ(v[7]), FQ(v[8]), FQ(v[9]), FQ(v[10]), FQ(v[11]), FQ(v[12]), FQ(v[13])) for v in C)
         t.keccak_table = set(KeccakTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), W(v[3], v[4])) for v in K)
+        if EX or part == "evm19":  # (Tables() defines exp_table only when it is given an exp circuit)
+            from zkevm_specs.evm_circuit.table import ExpTableRow
+            t.exp_table = set(ExpTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), FQ(v[3]), FQ(v[4]), FQ(v[5]), FQ(v[6]), W(v[7], v[8]), W(v[9], v[10])) for v in EX)
         for idx, (cur, nxt) in enumerate(zip(steps, steps[1:])):
             try:
                 verify_step(Instruction(tables=t, curr=cur, next=nxt, is_first_step=False, is_last_step=False))
@@ -1704,7 +1731,16 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm18":
+    if part == "evm19":
+        MX = (1 << 256) - 1
+        scenarios = {
+            "exp_0_0": exp_case(0, 0), "exp_0_max": exp_case(0, MX), "exp_1_max": exp_case(1, MX), "exp_cafe_0": exp_case(0xCAFE, 0),
+            "exp_max_1": exp_case(MX, 1), "exp_cafe_1": exp_case(0xCAFE, 1), "exp_2_5": exp_case(2, 5), "exp_3_101": exp_case(3, 101),
+            "exp_5_259": exp_case(5, 259), "exp_7_1023": exp_case(7, 1023), "exp_max_2": exp_case(MX, 2), "exp_max_3": exp_case(MX, 3),
+            "exp_max_max": exp_case(MX, MX), "exp_big_base": exp_case(rng.randrange(1 << 256), 6), "exp_2_256": exp_case(2, 256),
+            "exp_wide_exponent": exp_case(3, (1 << 200) + 12345),
+        }
+    elif part == "evm18":
         scenarios = {
             "log0_empty": log_case([], 10, 0, True), "log1": log_case([0x030201], 10, 2, True), "log2": log_case([0x030201, 0x0F0E0D], 100, 20, True, cur_mem=2),
             "log3": log_case([0x030201, 0x0F0E0D, 0x0D8F01], 180, 50, True, log_id=4), "log4": log_case([(1 << 255) + 5, 2, 3, (1 << 200) + 9], 0x40, 33, True),
@@ -1888,14 +1924,16 @@ def evm2_cases(part="evm2"):
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
         TF = [int(x.value.is_word) for x in sc_[5]] if part == "evm17" and len(sc_) > 5 else None
         BF = [int(x.value.is_word) for x in sc_[6]] if part == "evm18" and len(sc_) > 6 else None
-        assert run(S, B, R, RF, C, K, T, BL, TF, BF) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF))
+        EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
+        assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
             BF2 = list(BF) if BF is not None else None
+            EX2 = [list(x) for x in EX]
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
                 cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
@@ -1924,6 +1962,9 @@ def evm2_cases(part="evm2"):
             elif which == 7 and BL and BF is not None and rng.random() < 0.2:  # the value type of a block-table row
                 i, c, v = rng.randrange(len(BL)), 100, 0
                 BF2[i] ^= 1; which = 13
+            elif which == 14 and EX:  # a cell of an exp-table row
+                i, c = rng.randrange(len(EX)), rng.randrange(11)
+                v = corrupt_value(rng, EX[i][c]); EX2[i][c] = v
             elif which == 8:  # a stack word half: the operands and results of the arithmetic gadgets
                 i, c = rng.randrange(len(R)), rng.choice([8, 8, 9])
                 if c == 9 and not (RF[i] & 1):
@@ -1954,7 +1995,7 @@ def evm2_cases(part="evm2"):
                 v = corrupt_value(rng, K[i][c]); K2[i][c] = v
             else:
                 continue
-            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2, BF2)
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2, BF2, EX2)
             muts.append((which, i, c, v, fr_, ex_))
             tot += 1
             nfail += fr_ >= 0
@@ -1964,6 +2005,8 @@ def evm2_cases(part="evm2"):
         if TF is not None:
             out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
             out[f"{name}/tx_flags"] = np.array(TF, dtype=np.uint8)
+        if EX:
+            out[f"{name}/exp"] = to_matrix(EX)
         if BF is not None:
             out[f"{name}/block_flags"] = np.array(BF, dtype=np.uint8)
         if part in ("evm9", "evm18"):
@@ -2010,6 +2053,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm19_cases():
+    """EXP (exp-table lookups of the first and last step rows, base^2 through mul_add_words)"""
+    evm2_cases("evm19")
 
 
 def evm18_cases():
@@ -2867,7 +2915,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

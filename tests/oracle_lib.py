@@ -164,6 +164,10 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0):
         wd = np.ascontiguousarray(w["wd"] if w.get("wd") is not None else np.zeros((4, 0, 4)), dtype=np.uint64)
         check_evm_x._keep = [txf, blf, wd]
         lib().orc_set_evm_block_tables(_p8(txf), _p8(blf), p64(wd), c(wd.shape[1]))
+    if w.get("exp") is not None:  # EXP: the exp table
+        ex = np.ascontiguousarray(w["exp"], dtype=np.uint64)
+        check_evm_x._keep_exp = ex
+        lib().orc_set_evm_exp_table(p64(ex), c(ex.shape[1]))
     if w.get("flags") is not None:
         flags = int(w["flags"])
     rc = lib().orc_check_evm_x(p64(m["steps"]), c(m["steps"].shape[1]), p64(m["bytecode"]), c(m["bytecode"].shape[1]),

@@ -44,7 +44,7 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
   X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
   X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
-  X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH)
+  X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -89,6 +89,8 @@ struct EvmTables {
   IndexDev keccak;    // keccak table, key (state_tag, input_rlc, input_len)
   IndexDev tx;        // tx table (tx_id, tag, index | value lo, hi), key = the first three cells (table.py:697-705)
   IndexDev block;     // block table (tag, block number | value lo, hi), key = the first two cells (table.py:691-695)
+  IndexDev exp;       // exp table (is_step, identifier, is_last, base limbs 0..3, exponent lo / hi | exponentiation lo / hi), key = the
+                      // first nine cells (table.py:797-814)
   IndexDev bytecode4; // bytecode table keyed on (hash lo, hi, tag, index): bytecode_lookup_pair does not name is_code; only built
                       // when an ErrorInvalidJump step exists and the bytecode table is not positional
   IndexDev rw_rwc;    // rw table keyed on rw_counter alone: lookups that name other column subsets (evm_tx.cuh);
@@ -529,11 +531,54 @@ ZK_HD bool word_select(const Word2& w, const Fr& sel, Word2* out) {
   return word_in_domain(*out);
 }
 
-ZK_HD void gadget_mul(const StepCtx& s, bool live) {
-  Fr opcode = fr_u64(0);
-  live = opcode_lookup(s, live, &opcode);
-  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
-  const Fr sp1 = fr_add_u64(sp, 1);
+// low 256 bits of a * b
+ZK_HD void mul256_lo(const u64 a[4], const u64 b[4], u64 o[4]) {
+  u64 t[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    u64 c = 0;
+#pragma unroll
+    for (int y = 0; y + x < 4; y++) {
+      unsigned __int128 v = (unsigned __int128)a[x] * b[y] + t[x + y] + c;
+      t[x + y] = (u64)v;
+      c = (u64)(v >> 64);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = t[k];
+}
+// MUL / DIV / MOD decided as a whole for stack words in the halves domain: true iff every constraint of
+// mul_div_mod.py:23-64 holds.  In that domain the gate a * b + c == d (+ the 9-byte carries, overflow == 0 for
+// DIV / MOD), the select equation and remainder < divisor are statements about 256-bit integers:
+//   MUL  pop1 * pop2 == push (mod 2^256)
+//   DIV  push * pop2 <= pop1 and pop1 - push * pop2 < pop2       (pop2 == 0: push == 0)
+//   MOD  push < pop2, push <= pop1 and pop2 | pop1 - push         (pop2 == 0: push == 0)
+// On false the caller runs the gate program proper, which names the failing constraint.
+ZK_HD bool mul_fast_ok(u64 op, const Word2& pop1, const Word2& pop2, const Word2& push) {
+  u64 p1[4], p2[4], ps[4], pl[4];
+  word_to_u256(pop1, p1);
+  word_to_u256(pop2, p2);
+  word_to_u256(push, ps);
+  if (op == 2) {
+    mul256_lo(p1, p2, pl);
+    return cmp256(pl, ps) == 0;
+  }
+  if ((p2[0] | p2[1] | p2[2] | p2[3]) == 0) return (ps[0] | ps[1] | ps[2] | ps[3]) == 0;
+  if (op == 4) {
+    if (mul256_exceeds(ps, p2, p1, pl)) return false;
+    u64 c[4];
+    sub256(p1, pl, c);
+    return cmp256(c, p2) < 0;
+  }
+  if (cmp256(ps, p2) >= 0 || cmp256(p1, ps) < 0) return false;
+  u64 t[4], q[4];
+  sub256(p1, ps, t);
+  div256(t, p2, q);
+  if (mul256_exceeds(q, p2, t, pl)) return false;
+  return cmp256(pl, t) == 0;
+}
+// the gate program proper, after the three stack lookups; true iff no constraint failed
+ZK_HD_NOINLINE bool gadget_mul_exact(const StepCtx& s, const Fr& opcode, const Word2& pop1, const Word2& pop2, const Word2& push) {
   const Fr one = fr_u64(1);
   // mul_div_mod.py:14-16 (Lagrange selectors over the field)
   Fr is_mul, is_div, is_mod;
@@ -548,18 +593,13 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
     is_mod = fr_montmul(fr_mul(o2, o4), ZK_MONT_INV8);
   }
   const Word2 zero{fr_u64(0), fr_u64(0)};
-  Word2 pop1 = zero, pop2 = zero, push = zero;
-  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &pop2), EV_MUL_POP2_UNSAT);
-  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &push), EV_MUL_PUSH_UNSAT);
-  if (!live) return;  // past the last lookup: plain early exits from here on
   const bool in_domain = word_in_domain(pop1) && word_in_domain(pop2) && word_in_domain(push);
   // witness assignment by branch, mul_div_mod.py:23-41 (Python int arithmetic)
   Word2 a, b, c, d;
   if (fr_eq_u64(is_mul, 1)) {
     a = pop1; b = pop2; c = zero; d = push;
   } else {
-    EV_CHECK(EV_MUL_WITNESS_DOMAIN, in_domain);  // would need > 512-bit integers
+    EV_CHECK_RET(EV_MUL_WITNESS_DOMAIN, in_domain, false);  // would need > 512-bit integers
     d = pop1; b = pop2;
     u64 dv[4], bv[4];
     word_to_u256(d, dv);
@@ -568,7 +608,7 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
       a = push;
       u64 av[4], pl[4], cv[4];
       word_to_u256(a, av);
-      EV_CHECK(EV_MUL_WITNESS_NEG, !mul256_exceeds(av, bv, dv, pl));  // Word(d - b*a) with d < b*a
+      EV_CHECK_RET(EV_MUL_WITNESS_NEG, !mul256_exceeds(av, bv, dv, pl), false);  // Word(d - b*a) with d < b*a
       sub256(dv, pl, cv);
       c = u256_to_word(cv);
     } else if ((bv[0] | bv[1] | bv[2] | bv[3]) == 0) {
@@ -577,7 +617,7 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
       c = push;
       u64 cv[4], tv[4], qv[4];
       word_to_u256(c, cv);
-      EV_CHECK(EV_MUL_WITNESS_NEG, cmp256(dv, cv) >= 0);  // (d - c) // b < 0
+      EV_CHECK_RET(EV_MUL_WITNESS_NEG, cmp256(dv, cv) >= 0, false);  // (d - c) // b < 0
       sub256(dv, cv, tv);
       div256(tv, bv, qv);
       a = u256_to_word(qv);
@@ -585,32 +625,56 @@ ZK_HD void gadget_mul(const StepCtx& s, bool live) {
   }
   const bool b_zero = fr_is_zero(fr_add(b.lo, b.hi));  // is_zero_word: field sum of the halves
   // mul_add_words, instruction.py:599-632
-  EV_CHECK(EV_MUL_TO64, word_in_domain(a) && word_in_domain(b));
+  EV_CHECK_RET(EV_MUL_TO64, word_in_domain(a) && word_in_domain(b), false);
   Fr carry_lo, carry_hi, overflow;
   mul_add_carries(a, b, c, d, &carry_lo, &carry_hi, &overflow);
-  EV_CHECK(EV_MUL_CARRY_LO, fits_9_bytes(carry_lo));  // range_check(.., 9)
-  EV_CHECK(EV_MUL_CARRY_HI, fits_9_bytes(carry_hi));
+  EV_CHECK_RET(EV_MUL_CARRY_LO, fits_9_bytes(carry_lo), false);  // range_check(.., 9)
+  EV_CHECK_RET(EV_MUL_CARRY_HI, fits_9_bytes(carry_hi), false);
   // the two constrain_equal of instruction.py:629-630 hold by construction of the carries
   // mul_div_mod.py:47-54: select_word's bool assert, then Word range asserts of select / +
   const bool mul0 = fr_is_zero(is_mul), mul1 = fr_eq_u64(is_mul, 1);
-  EV_CHECK(EV_MUL_SELECT, mul0 || mul1);
+  EV_CHECK_RET(EV_MUL_SELECT, mul0 || mul1, false);
   Word2 t_d, t_a, t_c, sum;
   const Fr sel_a = b_zero ? fr_u64(0) : is_div, sel_c = b_zero ? fr_u64(0) : is_mod;
-  EV_CHECK(EV_MUL_SELECT, word_select(d, is_mul, &t_d) && word_select(a, sel_a, &t_a));
-  EV_CHECK(EV_MUL_SELECT, word_select(c, sel_c, &t_c));
+  EV_CHECK_RET(EV_MUL_SELECT, word_select(d, is_mul, &t_d) && word_select(a, sel_a, &t_a), false);
+  EV_CHECK_RET(EV_MUL_SELECT, word_select(c, sel_c, &t_c), false);
   sum.lo = fr_add(t_d.lo, t_a.lo);
   sum.hi = fr_add(t_d.hi, t_a.hi);
-  EV_CHECK(EV_MUL_SELECT, word_in_domain(sum));
+  EV_CHECK_RET(EV_MUL_SELECT, word_in_domain(sum), false);
   sum.lo = fr_add(sum.lo, t_c.lo);
   sum.hi = fr_add(sum.hi, t_c.hi);
-  EV_CHECK(EV_MUL_SELECT, word_in_domain(sum));
-  EV_CHECK(EV_MUL_PUSH_EQ, word_eq(push, sum));
+  EV_CHECK_RET(EV_MUL_SELECT, word_in_domain(sum), false);
+  EV_CHECK_RET(EV_MUL_PUSH_EQ, word_eq(push, sum), false);
   // :57  is_mul * sum(c.to_le_bytes()) == 0  (is_mul is 0/1 here; byte sum < p)
-  EV_CHECK(EV_MUL_C_ZERO, mul0 || (fr_is_zero(c.lo) && fr_is_zero(c.hi)));
+  EV_CHECK_RET(EV_MUL_C_ZERO, mul0 || (fr_is_zero(c.lo) && fr_is_zero(c.hi)), false);
   // :60-61  (1-is_mul)*(1-b0)*(1-lt) == 0 with lt = compare_word(c, b)
   const bool lt = fr_lt(c.hi, b.hi) || (fr_eq(c.hi, b.hi) && fr_lt(c.lo, b.lo));
-  EV_CHECK(EV_MUL_REM_LT, mul1 || b_zero || lt);
-  EV_CHECK(EV_MUL_OVERFLOW, mul1 || fr_is_zero(overflow));
+  EV_CHECK_RET(EV_MUL_REM_LT, mul1 || b_zero || lt, false);
+  EV_CHECK_RET(EV_MUL_OVERFLOW, mul1 || fr_is_zero(overflow), false);
+  return true;
+}
+ZK_HD void gadget_mul(const StepCtx& s, bool live) {
+  Fr opcode = fr_u64(0);
+  live = opcode_lookup(s, live, &opcode);
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const Fr sp1 = fr_add_u64(sp, 1);
+  const Fr one = fr_u64(1);
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 pop1 = zero, pop2 = zero, push = zero;
+  live = need1(s, live, rw_lookup(s, live, rwc, 0, ZK_TARGET_Stack, call_id, sp, &pop1), EV_MUL_POP1_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 1), 0, ZK_TARGET_Stack, call_id, sp1, &pop2), EV_MUL_POP2_UNSAT);
+  live = need1(s, live, rw_lookup(s, live, fr_add_u64(rwc, 2), 1, ZK_TARGET_Stack, call_id, sp1, &push), EV_MUL_PUSH_UNSAT);
+  if (!live) return;  // past the last lookup: plain early exits from here on
+  // the whole step decided at once when the words are in the halves domain and the opcode is one of the three;
+  // anything else (and every failing step) runs the gate program proper.  Copies go to the out-of-line call so
+  // that the passing path keeps its operands in registers.
+  const bool in_dom = word_in_domain(pop1) && word_in_domain(pop2) && word_in_domain(push);
+  const bool op_ok = fr_fits64(opcode) && (opcode.l[0] == 2 || opcode.l[0] == 4 || opcode.l[0] == 6);
+  if (!(in_dom && op_ok && mul_fast_ok(opcode.l[0], pop1, pop2, push))) {
+    const Fr o2 = opcode;
+    const Word2 a2 = pop1, b2 = pop2, c2 = push;
+    if (!gadget_mul_exact(s, o2, a2, b2, c2)) return;
+  }
   same_context(s, opcode, 3, one, one);
 }
 
@@ -768,6 +832,50 @@ ZK_HD void push_byte_masks(const TableDev& bt, const PushCommon& c, const Fr& to
   *m_neq = mn;
   *m_pad = mp;
 }
+ZK_HD_NOINLINE void push_byte_masks_ni(const TableDev& bt, const PushCommon& c, const Fr& top, bool top_ok, u32* m_unsat, u32* m_neq,
+                                       u32* m_pad) {
+  push_byte_masks<0, 0>(bt, c, top, top_ok, m_unsat, m_neq, m_pad);
+}
+// The same 32 lookups decided all at once for the layout every packer produces (is_code 1 byte, value 4 bytes):
+// true iff every one of them holds.  The rows of the pushed bytes are consecutive, downwards from index
+// pc + num_pushed, so the loads are one base pointer each with compile-time offsets, predicated by a bit of the
+// valid-index mask; the looked-up bytes are assembled into eight 32-bit words that must equal the pushed word
+// (which also makes the non-pushed bytes zero).  On false the caller runs push_byte_masks to name the first
+// failing constraint in program order — failing steps pay twice, passing steps ~6 instructions per byte.
+ZK_HD u32 bits_below(u32 x) { return x >= 32 ? 0xFFFFFFFFu : (1u << x) - 1u; }
+ZK_HD bool push_bytes_all_ok(const TableDev& bt, const PushCommon& c, const Fr& top, bool top_ok) {
+  const u32 n_push = c.n_push < 32 ? (u32)c.n_push : 32u, n_pad = c.n_pad < 32 ? (u32)c.n_pad : 32u;
+  const u32 pushed = n_push > n_pad ? (bits_below(n_push) & ~bits_below(n_pad)) : 0u;
+  // valid idx: idx <= top and top - idx < run_len
+  const u64 t = top.l[0];
+  const u32 v_hi = t >= 31 ? 32u : (u32)t + 1u;
+  const u64 below = t >= (u64)c.run_len ? t - (u64)c.run_len + 1 : 0;
+  const u32 v_lo = below < 32 ? (u32)below : 32u;
+  const u32 valid = top_ok ? (pushed & bits_below(v_hi) & ~bits_below(v_lo)) : 0u;
+  if (pushed & ~valid) return false;  // a pushed byte without a row
+  const u64 base_row = (u64)c.head + 1 + t;
+  const unsigned char* q_is = bt.base + bt.off[B_ISCODE] + base_row;
+  const u32* q_val = (const u32*)(bt.base + bt.off[B_VALUE]) + base_row;
+  u32 acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 is_any = 0, wide = 0;
+#pragma unroll
+  for (int idx = 0; idx < 32; idx++) {
+    if ((valid >> idx) & 1) {
+#ifdef __CUDA_ARCH__
+      const u32 ic = __ldg(q_is - idx), g = __ldg(q_val - idx);
+#else
+      const u32 ic = q_is[-idx], g = q_val[-idx];
+#endif
+      is_any |= ic;
+      wide |= g;
+      acc[idx >> 2] |= g << (8 * (idx & 3));
+    }
+  }
+  const u64 v0 = c.value.lo.l[0], v1 = c.value.lo.l[1], v2 = c.value.hi.l[0], v3 = c.value.hi.l[1];
+  const u32 diff = (acc[0] ^ (u32)v0) | (acc[1] ^ (u32)(v0 >> 32)) | (acc[2] ^ (u32)v1) | (acc[3] ^ (u32)(v1 >> 32)) |
+                   (acc[4] ^ (u32)v2) | (acc[5] ^ (u32)(v2 >> 32)) | (acc[6] ^ (u32)v3) | (acc[7] ^ (u32)(v3 >> 32));
+  return (is_any | (wide >> 8) | diff) == 0;
+}
 ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
   PushCommon c;
   c.hlo = s.cur(S_HASH_LO);
@@ -794,21 +902,27 @@ ZK_HD void gadget_push_pos1(const StepCtx& s, HeadCache* hc) {
   const Fr top = fr_add(c.pc, c.num_pushed);
   const bool top_ok = fr_fits64(top) && c.n_head == 1;
   const TableDev& bt = s.t.bytecode.tab;
-  u32 m_unsat = 0, m_neq = 0, m_pad = 0;
   // the layout every packer produces for these two columns (is_code 1 byte, value 4 bytes: the Header
-  // row holds the code length) gets plain typed loads; anything else the generic per-width loader
-  if (bt.width[B_ISCODE] == 1 && bt.width[B_VALUE] == 4) push_byte_masks<1, 4>(bt, c, top, top_ok, &m_unsat, &m_neq, &m_pad);
-  else push_byte_masks<0, 0>(bt, c, top, top_ok, &m_unsat, &m_neq, &m_pad);
-  const u32 any = m_unsat | m_neq | m_pad;
-  if (any) {
+  // row holds the code length) is decided as a whole first; a failing step, or any other layout, goes through
+  // the per-byte masks with the generic per-width loader (copies of the operands: the out-of-line call must not
+  // pin `c` in local memory on the passing path)
+  const bool typed = bt.width[B_ISCODE] == 1 && bt.width[B_VALUE] == 4;
+  if (!(typed && push_bytes_all_ok(bt, c, top, top_ok))) {
+    const PushCommon c2 = c;
+    const Fr top2 = top;
+    u32 m_unsat = 0, m_neq = 0, m_pad = 0;
+    push_byte_masks_ni(bt, c2, top2, top_ok, &m_unsat, &m_neq, &m_pad);
+    const u32 any = m_unsat | m_neq | m_pad;
+    if (any) {
 #ifdef __CUDA_ARCH__
-    const int idx = __ffs(any) - 1;
+      const int idx = __ffs(any) - 1;
 #else
-    const int idx = __builtin_ctz(any);
+      const int idx = __builtin_ctz(any);
 #endif
-    const int base = EV_PUSH_B0_UNSAT + 4 * idx;
-    step_fail(s, ((m_unsat >> idx) & 1) ? base : (((m_neq >> idx) & 1) ? base + 2 : base + 3));
-    return;
+      const int base = EV_PUSH_B0_UNSAT + 4 * idx;
+      step_fail(s, ((m_unsat >> idx) & 1) ? base : (((m_neq >> idx) & 1) ? base + 2 : base + 3));
+      return;
+    }
   }
   push_epilogue(s, c);
 }
@@ -1589,6 +1703,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 #include "evm_arith.cuh"
 #include "evm_storage.cuh"
 #include "evm_log.cuh"
+#include "evm_exp.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1610,7 +1725,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_BITWISE: case ZK_ES_NOT: case ZK_ES_MEMORY: return KG_BYTES32;
     case ZK_ES_SHA3: case ZK_ES_CALLDATACOPY: return KG_COPY;
     case ZK_ES_SHL_SHR: return KG_WIDE;
-    case ZK_ES_ADDMOD: case ZK_ES_MULMOD: case ZK_ES_SDIV_SMOD: case ZK_ES_SAR: return KG_ARITH;
+    case ZK_ES_ADDMOD: case ZK_ES_MULMOD: case ZK_ES_SDIV_SMOD: case ZK_ES_SAR: case ZK_ES_EXP: return KG_ARITH;
     case ZK_ES_STOP: case ZK_ES_BeginTx: case ZK_ES_EndTx: case ZK_ES_EndBlock: case ZK_ES_ErrorStack:
     case ZK_ES_ErrorInvalidOpcode: case ZK_ES_ErrorOutOfGasConstant: case ZK_ES_ErrorInvalidJump: case ZK_ES_SELFBALANCE:
     case ZK_ES_ErrorOutOfGasSHA3: case ZK_ES_ErrorOutOfGasStaticMemoryExpansion: case ZK_ES_ErrorOutOfGasDynamicMemoryExpansion:
@@ -1705,6 +1820,7 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_MULMOD: gadget_addmod_mulmod(s, true); break;
       case ZK_ES_SDIV_SMOD: gadget_sdiv_smod(s); break;
       case ZK_ES_SAR: gadget_sar(s); break;
+      case ZK_ES_EXP: gadget_exp(s); break;
       default: break;
     }
   }
