@@ -953,7 +953,24 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_EXP_CARRY_LO, ZKE_RANGE, "exp.py:36 mul_add_words(base, base, 0, base^2): range_check(carry_lo, 9)") \
   X(EV_EXP_CARRY_HI, ZKE_RANGE, "exp.py:36 mul_add_words: range_check(carry_hi, 9)")                 \
   X(EV_EXP_RESULT, ZKE_ASSERT, "exp.py:39 looked-up exponentiation == pushed word")                  \
-  X(EV_EXP_EXPONENT_BYTES, ZKE_VALUE, "exp.py:41 byte_size(exponent): to_le_bytes of a half >= 2^128 -> OverflowError")
+  X(EV_EXP_EXPONENT_BYTES, ZKE_VALUE, "exp.py:41 byte_size(exponent): to_le_bytes of a half >= 2^128 -> OverflowError")                 \
+  X(EV_ECS_OPCODE, ZKE_ASSERT, "error_code_store.py:20 / error_invalid_creation_code.py:15 opcode == RETURN") \
+  X(EV_ECS_IS_CREATE, ZKE_ASSERT, "error_code_store.py:23 / error_invalid_creation_code.py:18 is_create == 1") \
+  X(EV_ECS_LEN_UNSAT, ZKE_UNSAT, "error_code_store.py:26 stack_lookup(Read, 1) / error_invalid_creation_code.py:21 stack_pop unsat") \
+  X(EV_ECS_LEN_AMBIG, ZKE_AMBIG, "error_code_store.py:26 stack_lookup(Read, 1) / error_invalid_creation_code.py:21 stack_pop ambiguous") \
+  X(EV_ECS_LEN_DOMAIN, ZKE_VALUE, "word_to_fq: a half >= 2^128 -> OverflowError")                    \
+  X(EV_ECS_LEN_RANGE, ZKE_RANGE, "word_to_fq(.., 5): more than 5 bytes")                             \
+  X(EV_ECS_STATIC_UNSAT, ZKE_UNSAT, "error_code_store.py:30 call_context_lookup(IsStatic) unsat")    \
+  X(EV_ECS_STATIC_AMBIG, ZKE_AMBIG, "error_code_store.py:30 call_context_lookup(IsStatic) ambiguous") \
+  X(EV_ECS_STATIC_TYPE, ZKE_ASSERT, "error_code_store.py:30 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_ECS_STATIC_NONZERO, ZKE_ASSERT, "error_code_store.py:31 IsStatic == 0")                       \
+  X(EV_ECS_SIZE_RANGE, ZKE_ASSERT, "error_code_store.py:34 compare(MAX_CODE_SIZE, return_length, 2): range assert") \
+  X(EV_ECS_GAS_RANGE, ZKE_ASSERT, "error_code_store.py:38-40 compare(gas_left, deposit cost, 8): range assert") \
+  X(EV_ECS_NEITHER, ZKE_ASSERT, "error_code_store.py:43 neither out of gas nor over the maximum code size") \
+  X(EV_ECS_BYTE_UNSAT, ZKE_UNSAT, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset) unsat") \
+  X(EV_ECS_BYTE_AMBIG, ZKE_AMBIG, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset) ambiguous") \
+  X(EV_ECS_BYTE_TYPE, ZKE_ASSERT, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset): .value() of a Word") \
+  X(EV_ECS_FIRST_BYTE, ZKE_ASSERT, "error_invalid_creation_code.py:27 first byte == 0xEF")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -118,3 +118,42 @@ static void gadget_blockhash(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) 
   CHECK(EV_BH_EQ, word_eq(pushed, want));
   same_context(e, i, row, opcode, 2, one, fr_u64(0));
 }
+
+/* ---- error_code_store.py:14-52 (ErrorMaxCodeSizeExceeded, ErrorOutOfGasCodeStore), error_invalid_creation_code.py:11-34 ----
+ * Pinned by tests/golden/evm20.npz (700 verdicts of the reference's verify_step). */
+static void gadget_error_code_store(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  CHECK(EV_ECS_OPCODE, fr_eq_u64(opcode, 0xf3));
+  CHECK(EV_ECS_IS_CREATE, fr_eq_u64(CUR(S_IS_CREATE), 1));
+  word_t len_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &len_w), EV_ECS_LEN_UNSAT, row)) return;
+  fr_t length;
+  W2FQ(len_w, 5, &length, EV_ECS_LEN_DOMAIN);
+  fr_t is_static;
+  ST_CC(1, ZK_CC_IsStatic, &is_static, EV_ECS_STATIC_UNSAT);
+  CHECK(EV_ECS_STATIC_NONZERO, fr_is_zero(is_static));
+  CHECK(EV_ECS_SIZE_RANGE, fr_fits_bits(length, 16)); /* compare(MAX_CODE_SIZE, return_length, N_BYTES_STACK = 2) */
+  const int over = 24576 < length.l[0];
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_ECS_GAS_RANGE, fr_fits_bits(gas_left, 64)); /* compare(gas_left, 200 * length, 8) */
+  const int insufficient = gas_left.l[0] < 200 * length.l[0];
+  CHECK(EV_ECS_NEITHER, over || insufficient);
+  error_state_tail(e, i, row, 2);
+}
+static void gadget_error_invalid_creation_code(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  CHECK(EV_ECS_OPCODE, fr_eq_u64(opcode, 0xf3));
+  CHECK(EV_ECS_IS_CREATE, fr_eq_u64(CUR(S_IS_CREATE), 1));
+  word_t off_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &off_w), EV_ECS_LEN_UNSAT, row)) return;
+  fr_t offset;
+  W2FQ(off_w, 5, &offset, EV_ECS_LEN_DOMAIN);
+  fr_t key[5] = {fr_add(rwc, fr_u64(1)), fr_u64(0), fr_u64(ZK_TARGET_Memory), call_id, offset};
+  uint32_t r;
+  LK(orc_lookup(&e->rw_ix, key, &r), EV_ECS_BYTE_UNSAT);
+  NOT_WORD(rw_val_is_word(e, r), EV_ECS_BYTE_UNSAT);
+  CHECK(EV_ECS_FIRST_BYTE, fr_eq_u64(rw_cell(e, R_VAL_LO, r), 0xEF));
+  error_state_tail(e, i, row, 2);
+}

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1340,6 +1340,34 @@ def evm2_cases(part="evm2"):
                            program_counter=67, stack_pointer=1023, gas_left=0)]
         return steps, list(bc.table_assignments()), list(rw.rws), [], [], [], [], list(t.exp_table)
 
+    def code_store_case(kind, root, size=200, gas_left=39999, first_byte=0xEF):
+        """tests/evm/test_error_code_store.py, test_error_invalid_creation_code.py: RETURN from a CREATE / CREATE2 that cannot
+        store its code (too long / not enough gas for the deposit / first byte 0xEF)"""
+        bc = Bytecode().push32(size).push32(32).return_()
+        h = Word(bc.hash())
+        call_id, rev = (1 if root else 2), 2
+        rw = RWDictionary(24 if root else 69)
+        rwc0 = rw.rw_counter
+        if kind == "invalid":
+            state = ExecutionState.ErrorInvalidCreationCode
+            rw.stack_read(call_id, 1022, Word(32)).memory_read(call_id, 32, first_byte)
+        else:
+            state = ExecutionState.ErrorMaxCodeSizeExceeded if kind == "max" else ExecutionState.ErrorOutOfGasCodeStore
+            rw.stack_read(call_id, 1023, Word(size)).call_context_read(call_id, CallContextFieldTag.IsStatic, 0)
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(state, rw_counter=rwc0, call_id=call_id, is_root=root, is_create=True, code_hash=h, program_counter=66,
+                        stack_pointer=1022, gas_left=gas_left, reversible_write_counter=rev)
+        if root:
+            return [cur, StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)], list(bc.table_assignments()), list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (True, False, 232, 1023, 10, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                        reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1731,7 +1759,15 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm19":
+    if part == "evm20":
+        scenarios = {
+            "oog_store_root": code_store_case("oog", True), "oog_store_internal": code_store_case("oog", False),
+            "oog_store_max_size": code_store_case("oog", True, size=24576, gas_left=24576 * 200 - 1),
+            "max_size_root": code_store_case("max", True, size=24577, gas_left=5000000), "max_size_internal": code_store_case("max", False, size=24577, gas_left=2000000),
+            "max_size_both": code_store_case("max", True, size=60000, gas_left=100),
+            "invalid_code_root": code_store_case("invalid", True), "invalid_code_internal": code_store_case("invalid", False),
+        }
+    elif part == "evm19":
         MX = (1 << 256) - 1
         scenarios = {
             "exp_0_0": exp_case(0, 0), "exp_0_max": exp_case(0, MX), "exp_1_max": exp_case(1, MX), "exp_cafe_0": exp_case(0xCAFE, 0),
@@ -1927,7 +1963,7 @@ def evm2_cases(part="evm2"):
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
@@ -2053,6 +2089,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm20_cases():
+    """ErrorMaxCodeSizeExceeded / ErrorOutOfGasCodeStore (error_code_store.py) and ErrorInvalidCreationCode"""
+    evm2_cases("evm20")
 
 
 def evm19_cases():
@@ -2915,7 +2956,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

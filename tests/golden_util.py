@@ -226,6 +226,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm20_vectors():
+    """ErrorMaxCodeSizeExceeded / ErrorOutOfGasCodeStore / ErrorInvalidCreationCode"""
+    return evm2_vectors("evm20")
+
+
 def evm19_vectors():
     """EXP"""
     return evm2_vectors("evm19")

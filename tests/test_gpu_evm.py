@@ -129,6 +129,38 @@ def test_verify_steps_host_api_like_reference_test_add_sub():
             verify_steps(tables(rw_start=10), steps(), success=False)
 
 
+def test_verify_steps_host_api_like_reference_test_exp():
+    """the reference's tests/evm/test_exp.py:45-112 written against our host API: the exp table comes from the exp circuit's
+    rows (Tables(exp_circuit=...)), the exp circuit itself is checked by verify_exp_circuit"""
+    from zkevm_specs_b200.evm_circuit import (Block, Bytecode, ExecutionState, RWDictionary, Tables)
+    from zkevm_specs_b200.evm_circuit.main import verify_steps
+    from zkevm_specs_b200.evm_circuit.step import StepState
+    from zkevm_specs_b200.exp_circuit import ExpCircuit, verify_exp_circuit
+    from zkevm_specs_b200.util import Word
+
+    for base, exponent in [(2, 5), (3, 101), (0xCAFE, 0), ((1 << 256) - 1, 1), ((1 << 256) - 1, 3), (7, 1023)]:
+        result = pow(base, exponent, 1 << 256)
+        bytecode = Bytecode().push(exponent, n_bytes=32).push(base, n_bytes=32).exp().stop()
+        h = Word(bytecode.hash())
+        rw = RWDictionary(3).stack_read(1, 1022, Word(base)).stack_read(1, 1023, Word(exponent)).stack_write(1, 1023, Word(result))
+        exp_circuit = ExpCircuit().add_event(base, exponent, rw.rw_counter).fill_dummy_events()
+        verify_exp_circuit(exp_circuit)
+        gas = 10 + 50 * ((exponent.bit_length() + 7) // 8)
+
+        def tables(res=result):
+            rws = RWDictionary(3).stack_read(1, 1022, Word(base)).stack_read(1, 1023, Word(exponent)).stack_write(1, 1023, Word(res)).rws
+            return Tables(block_table=set(Block().table_assignments()), tx_table=set(), withdrawal_table=set(),
+                          bytecode_table=set(bytecode.table_assignments()), rw_table=set(rws), exp_circuit=exp_circuit.rows)
+
+        steps = [StepState(ExecutionState.EXP, rw_counter=3, call_id=1, is_root=True, code_hash=h, program_counter=66,
+                           stack_pointer=1022, gas_left=gas),
+                 StepState(ExecutionState.STOP, rw_counter=6, call_id=1, is_root=True, code_hash=h, program_counter=67,
+                           stack_pointer=1023, gas_left=0)]
+        verify_steps(tables(), steps)
+        with pytest.raises(AssertionError):  # wrong exponentiation on the stack
+            verify_steps(tables(res=(result + 1) % (1 << 256)), steps)
+
+
 def test_evm_sha3_calldatacopy_golden_and_oracle_parity():
     """SHA3 / CALLDATACOPY steps (copy-table + keccak-table + call-context lookups, memory
     expansion and copier gas): CUDA == oracle array for array, and == the reference's verdicts"""
@@ -194,7 +226,7 @@ def test_evm_memory_golden_and_oracle_parity():
     ctx.upload_table(native.TABLE_KECCAK, np.zeros((5, 0, 4), dtype=np.uint64))
     import itertools
 
-    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm4_vectors(), golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors(), golden_util.evm8_vectors(), golden_util.evm9_vectors(), golden_util.evm10_vectors(), golden_util.evm12_vectors(), golden_util.evm13_vectors(), golden_util.evm14_vectors(), golden_util.evm15_vectors(), golden_util.evm16_vectors(), golden_util.evm17_vectors(), golden_util.evm18_vectors(), golden_util.evm19_vectors()):
+    for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm4_vectors(), golden_util.evm5_vectors(), golden_util.evm6_vectors(), golden_util.evm7_vectors(), golden_util.evm8_vectors(), golden_util.evm9_vectors(), golden_util.evm10_vectors(), golden_util.evm12_vectors(), golden_util.evm13_vectors(), golden_util.evm14_vectors(), golden_util.evm15_vectors(), golden_util.evm16_vectors(), golden_util.evm17_vectors(), golden_util.evm18_vectors(), golden_util.evm19_vectors(), golden_util.evm20_vectors()):
         ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
         ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
         ctx.upload_table(native.TABLE_COPY, w["copy"])  # CODECOPY / RETURNDATACOPY / EXTCODECOPY scenarios carry one

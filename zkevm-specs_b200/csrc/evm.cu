@@ -44,7 +44,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasEXP) X(ZK_ES_ErrorReturnDataOutOfBound) X(ZK_ES_BALANCE) X(ZK_ES_EXTCODEHASH) X(ZK_ES_EXTCODESIZE)          \
   X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
   X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
-  X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP)
+  X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP) \
+  X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -1733,6 +1734,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_BALANCE: case ZK_ES_EXTCODEHASH: case ZK_ES_EXTCODESIZE: case ZK_ES_ErrorOutOfGasAccountAccess:
     case ZK_ES_CODECOPY: case ZK_ES_RETURNDATACOPY: case ZK_ES_EXTCODECOPY: case ZK_ES_ErrorOutOfGasMemoryCopy:
     case ZK_ES_SLOAD: case ZK_ES_SSTORE: case ZK_ES_CALLDATALOAD: case ZK_ES_LOG: case ZK_ES_ErrorWriteProtection: case ZK_ES_BLOCKHASH:
+    case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: case ZK_ES_ErrorInvalidCreationCode:
       return KG_TX;
     default: return -1;
   }
@@ -1812,6 +1814,8 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_LOG: gadget_log(s); break;
       case ZK_ES_ErrorWriteProtection: gadget_error_write_protection(s); break;
       case ZK_ES_BLOCKHASH: gadget_blockhash(s); break;
+      case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: gadget_error_code_store(s); break;
+      case ZK_ES_ErrorInvalidCreationCode: gadget_error_invalid_creation_code(s); break;
       default: break;
     }
   } else if constexpr (G == KG_ARITH) {
@@ -1932,6 +1936,8 @@ __device__ __forceinline__ int mul_bucket_peek(const StepCtx& s, const Fr& hlo, 
   return fr_eq_u64(v, 4) ? ZK_BK_DIV : (fr_eq_u64(v, 6) ? ZK_BK_MOD : ZK_ES_MUL);
 }
 
+// NARROW: StepCtx::narrow (the step cells but the code hash sit in columns of at most 8 bytes: one aligned load each)
+template <int NARROW>
 __global__ void __launch_bounds__(1024) k_evm_classify(const __grid_constant__ WitnessDev w, const __grid_constant__ CheckRange rg, const __grid_constant__ EvmTables t, const __grid_constant__ ResultDev res, const __grid_constant__ EvmSort so) {
   // histogram aggregated per BLOCK: lanes of a warp that share a bucket elect a leader (match_any),
   // leaders add to a shared histogram, one global atomicAdd per (block, non-empty bucket)
@@ -1944,7 +1950,7 @@ __global__ void __launch_bounds__(1024) k_evm_classify(const __grid_constant__ W
   const bool pos = both_positional(t);
   int b = ZK_BK_NONE;
   if (i < rg.row_end) {
-    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 1u << lane, nullptr, nullptr, -1};
+    StepCtx s{w, t, res, i, i + 1, rg.row_base + i, true, nullptr, 1u << lane, nullptr, nullptr, -1, NARROW};
     // the peek's cells are fetched with the state cells (one memory round trip instead of two)
     const Fr hlo = s.cur(S_HASH_LO), hhi = s.cur(S_HASH_HI), pc = s.cur(S_PC);
     const int st = step_prologue(s, rg.flags);

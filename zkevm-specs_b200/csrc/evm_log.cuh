@@ -129,4 +129,43 @@ ZK_HD_NOINLINE void gadget_blockhash(const StepCtx& s) {
   same_context_ni(s, opcode, 2, fr_u64(1), fr_u64(0));
 }
 
+// ---- error_code_store.py:14-52 (ErrorMaxCodeSizeExceeded, ErrorOutOfGasCodeStore), error_invalid_creation_code.py:11-34 ----
+ZK_HD_NOINLINE void gadget_error_code_store(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  EV_CHECK(EV_ECS_OPCODE, fr_eq_u64(opcode, 0xf3));
+  EV_CHECK(EV_ECS_IS_CREATE, fr_eq_u64(s.cur(S_IS_CREATE), 1));
+  Word2 len_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, fr_add_u64(s.cur(S_SP), 1), &len_w), EV_ECS_LEN_UNSAT)) return;
+  Fr length = fr_u64(0);
+  EOOG_W2FQ(len_w, 5, &length, EV_ECS_LEN_DOMAIN);
+  Fr is_static;
+  ST_CC(1, ZK_CC_IsStatic, &is_static, EV_ECS_STATIC_UNSAT);
+  EV_CHECK(EV_ECS_STATIC_NONZERO, fr_is_zero(is_static));
+  EV_CHECK(EV_ECS_SIZE_RANGE, (length.l[0] >> 16) == 0);  // compare(MAX_CODE_SIZE, return_length, N_BYTES_STACK = 2)
+  const Fr gas_left = s.cur(S_GAS);
+  EV_CHECK(EV_ECS_GAS_RANGE, fr_fits64(gas_left));  // compare(gas_left, 200 * length, 8)
+  EV_CHECK(EV_ECS_NEITHER, 24576 < length.l[0] || gas_left.l[0] < 200 * length.l[0]);
+  error_state_tail(s, 2);
+}
+ZK_HD_NOINLINE void gadget_error_invalid_creation_code(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  EV_CHECK(EV_ECS_OPCODE, fr_eq_u64(opcode, 0xf3));
+  EV_CHECK(EV_ECS_IS_CREATE, fr_eq_u64(s.cur(S_IS_CREATE), 1));
+  Word2 off_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, s.cur(S_SP), &off_w), EV_ECS_LEN_UNSAT)) return;
+  Fr offset = fr_u64(0);
+  EOOG_W2FQ(off_w, 5, &offset, EV_ECS_LEN_DOMAIN);
+  Fr key[14];
+  rw_key_init(key, fr_add_u64(s.cur(S_RWC), 1), 0, ZK_TARGET_Memory);
+  key[R_ID] = s.cur(S_CALL_ID);
+  key[R_ADDR] = offset;
+  u32 r = 0;
+  TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR), &r), EV_ECS_BYTE_UNSAT);
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_ECS_BYTE_UNSAT);
+  EV_CHECK(EV_ECS_FIRST_BYTE, fr_eq_u64(rw_cell(s, R_VAL_LO, r), 0xEF));
+  error_state_tail(s, 2);
+}
+
 }  // namespace zk

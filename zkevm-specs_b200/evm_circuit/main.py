@@ -58,7 +58,22 @@ def upload_tables(ctx: native.Context, tables: Tables) -> None:
     c = packing.cell_int
     ctx.upload_table(native.TABLE_WITHDRAWAL,
                      packing.matrix_from_ints([[c(w.id), c(w.validator_id), c(w.address), c(w.amount)] for w in wds], 4))
+    # exp table of the EXP gadget: one row per exp-circuit row (reference table.py:654-671)
+    ctx.upload_table(native.TABLE_EXP, packing.matrix_from_ints(exp_table_rows(getattr(tables, "exp_circuit", None) or ()), 11))
     upload_fixed_table(ctx)
+
+
+def exp_table_rows(exp_circuit) -> List[List[int]]:
+    """ExpTableRow cells of an exp circuit (is_step = 1, identifier, is_last, the base as four 64-bit limbs, exponent lo / hi,
+    exponentiation lo / hi), identical rows once like the reference's set"""
+    c = packing.cell_int
+    rows = set()
+    for r in exp_circuit:
+        lo, hi = c(r.base.lo), c(r.base.hi)
+        m64 = (1 << 64) - 1
+        rows.add((1, c(r.identifier), c(r.is_last), lo & m64, lo >> 64, hi & m64, hi >> 64,
+                  c(r.exponent.lo), c(r.exponent.hi), c(r.exponentiation.lo), c(r.exponentiation.hi)))
+    return [list(r) for r in sorted(rows)]
 
 
 def upload_fixed_table(ctx: native.Context) -> None:
