@@ -103,12 +103,13 @@ ZK_HD Fr ld_col_narrow(const unsigned char* p, u32 width, u64 row) {
   Fr r;
   r.l[1] = r.l[2] = r.l[3] = 0;
 #ifdef __CUDA_ARCH__
-  const u64 a = (u64)p + row * width;  // width 0: the constant cell itself
-  u64 v;
-  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(a & ~7ull));
-  const u32 sh = ((u32)a & 7u) * 8u;
-  const u64 m = (width == 0 || width >= 8) ? ~0ull : ((1ull << (8u * width)) - 1ull);
-  r.l[0] = (v >> sh) & m;
+  // rows of a resident matrix are below 2^32 (the sorted step lists and the table indexes hold 32-bit rows), so the
+  // address is one 32 x 32 -> 64-bit multiply-add; width 0 = the constant cell itself (stride 0, mask of 8 bytes)
+  const u64 a = (u64)p + (u64)(u32)row * width;
+  const u64 v = __ldg((const u64*)(a & ~7ull));
+  const u32 sh = ((u32)a & 7u) << 3;
+  const u32 w8 = width ? width : 8u;
+  r.l[0] = (v >> sh) & (~0ull >> (64u - 8u * w8));
 #else
   switch (width) {
     case 1: r.l[0] = p[row]; break;
