@@ -970,7 +970,54 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_ECS_BYTE_UNSAT, ZKE_UNSAT, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset) unsat") \
   X(EV_ECS_BYTE_AMBIG, ZKE_AMBIG, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset) ambiguous") \
   X(EV_ECS_BYTE_TYPE, ZKE_ASSERT, "error_invalid_creation_code.py:24 memory_lookup(Read, return_offset): .value() of a Word") \
-  X(EV_ECS_FIRST_BYTE, ZKE_ASSERT, "error_invalid_creation_code.py:27 first byte == 0xEF")
+  X(EV_ECS_FIRST_BYTE, ZKE_ASSERT, "error_invalid_creation_code.py:27 first byte == 0xEF")                 \
+  X(EV_RET_SUCCESS_UNSAT, ZKE_UNSAT, "return_revert.py:17 call_context_lookup(IsSuccess) unsat")     \
+  X(EV_RET_SUCCESS_AMBIG, ZKE_AMBIG, "return_revert.py:17 call_context_lookup(IsSuccess) ambiguous") \
+  X(EV_RET_SUCCESS_TYPE, ZKE_ASSERT, "return_revert.py:17 call_context_lookup(IsSuccess): .value() of a Word") \
+  X(EV_RET_SUCCESS_EQ, ZKE_ASSERT, "return_revert.py:18 is_success == is_return")                    \
+  X(EV_RET_POP0_UNSAT, ZKE_UNSAT, "return_revert.py:20 stack_pop return offset unsat")               \
+  X(EV_RET_POP0_AMBIG, ZKE_AMBIG, "return_revert.py:20 stack_pop return offset ambiguous")           \
+  X(EV_RET_POP1_UNSAT, ZKE_UNSAT, "return_revert.py:21 stack_pop return length unsat")               \
+  X(EV_RET_POP1_AMBIG, ZKE_AMBIG, "return_revert.py:21 stack_pop return length ambiguous")           \
+  X(EV_RET_OFF_DOMAIN, ZKE_VALUE, "return_revert.py:23 word_to_fq: a half >= 2^128 -> OverflowError") \
+  X(EV_RET_OFF_RANGE, ZKE_RANGE, "return_revert.py:23 word_to_fq(.., 5): more than 5 bytes")         \
+  X(EV_RET_LEN_DOMAIN, ZKE_VALUE, "return_revert.py:24 word_to_fq: a half >= 2^128 -> OverflowError") \
+  X(EV_RET_LEN_RANGE, ZKE_RANGE, "return_revert.py:24 word_to_fq(.., 5): more than 5 bytes")         \
+  X(EV_RET_CALLEE_UNSAT, ZKE_UNSAT, "return_revert.py:33-35 call_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_RET_CALLEE_AMBIG, ZKE_AMBIG, "return_revert.py:33-35 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_RET_CALLEE_DOMAIN, ZKE_VALUE, "return_revert.py:36 word_to_address: a half >= 2^128 -> OverflowError") \
+  X(EV_RET_CALLEE_RANGE, ZKE_RANGE, "return_revert.py:36 word_to_address: more than 20 bytes")       \
+  X(EV_RET_HASH_WRITE_UNSAT, ZKE_UNSAT, "return_revert.py:37-39 account_write_word(CodeHash) unsat") \
+  X(EV_RET_HASH_WRITE_AMBIG, ZKE_AMBIG, "return_revert.py:37-39 account_write_word(CodeHash) ambiguous") \
+  X(EV_RET_HASH_PREV, ZKE_ASSERT, "return_revert.py:40 previous code hash == EMPTY_HASH")            \
+  X(EV_RET_HASH_CUR, ZKE_ASSERT, "return_revert.py:41 written code hash == curr.code_hash")          \
+  X(EV_RET_MAX_CODE_SIZE, ZKE_UNSAT, "return_revert.py:44 range_lookup(return_length, MAX_CODE_SIZE)") \
+  X(EV_RET_COPY_CODE_UNSAT, ZKE_UNSAT, "return_revert.py:54-64 copy_lookup(Memory -> Bytecode) unsat") \
+  X(EV_RET_COPY_CODE_AMBIG, ZKE_AMBIG, "return_revert.py:54-64 copy_lookup(Memory -> Bytecode) ambiguous") \
+  X(EV_RET_COPY_CODE_INC, ZKE_ASSERT, "return_revert.py:65 copy_rwc_inc == copy_length")             \
+  X(EV_RET_CODE_LEN_UNSAT, ZKE_UNSAT, "return_revert.py:68 bytecode_length(code_hash) unsat")        \
+  X(EV_RET_CODE_LEN_AMBIG, ZKE_AMBIG, "return_revert.py:68 bytecode_length(code_hash) ambiguous")    \
+  X(EV_RET_CODE_LEN_EQ, ZKE_ASSERT, "return_revert.py:69 code size == copy_length")                  \
+  X(EV_RET_RDO_UNSAT, ZKE_UNSAT, "return_revert.py:76-78 call_context_lookup(ReturnDataOffset) unsat") \
+  X(EV_RET_RDO_AMBIG, ZKE_AMBIG, "return_revert.py:76-78 call_context_lookup(ReturnDataOffset) ambiguous") \
+  X(EV_RET_RDO_TYPE, ZKE_ASSERT, "return_revert.py:76-78 call_context_lookup(ReturnDataOffset): .value() of a Word") \
+  X(EV_RET_RDL_UNSAT, ZKE_UNSAT, "return_revert.py:79-81 call_context_lookup(ReturnDataLength) unsat") \
+  X(EV_RET_RDL_AMBIG, ZKE_AMBIG, "return_revert.py:79-81 call_context_lookup(ReturnDataLength) ambiguous") \
+  X(EV_RET_RDL_TYPE, ZKE_ASSERT, "return_revert.py:79-81 call_context_lookup(ReturnDataLength): .value() of a Word") \
+  X(EV_RET_MIN_RANGE, ZKE_ASSERT, "return_revert.py:82 min(): caller return length exceeds 5 bytes") \
+  X(EV_RET_COPY_UNSAT, ZKE_UNSAT, "return_revert.py:83-93 copy_lookup(Memory -> caller Memory) unsat") \
+  X(EV_RET_COPY_AMBIG, ZKE_AMBIG, "return_revert.py:83-93 copy_lookup(Memory -> caller Memory) ambiguous") \
+  X(EV_RET_COPY_INC, ZKE_ASSERT, "return_revert.py:94 copy_rwc_inc == 2 * copy_length")              \
+  X(EV_RET_ROOT_ENDTX, ZKE_ASSERT, "return_revert.py:101 is_root == (next state is EndTx)")          \
+  X(EV_RET_MEMSIZE_RANGE, ZKE_RANGE, "return_revert.py:103 memory_expansion_dynamic_length: memory size beyond 4 bytes") \
+  X(EV_RET_MEM_MAX, ZKE_ASSERT, "return_revert.py:103 max(): curr.memory_word_size beyond 4 bytes")  \
+  X(EV_RET_PERSIST_UNSAT, ZKE_UNSAT, "return_revert.py:115-117 call_context_lookup(IsPersistent) unsat") \
+  X(EV_RET_PERSIST_AMBIG, ZKE_AMBIG, "return_revert.py:115-117 call_context_lookup(IsPersistent) ambiguous") \
+  X(EV_RET_PERSIST_TYPE, ZKE_ASSERT, "return_revert.py:115-117 call_context_lookup(IsPersistent): .value() of a Word") \
+  X(EV_RET_PERSIST_EQ, ZKE_ASSERT, "return_revert.py:118 is_persistent == is_return")                \
+  X(EV_RET_RWC, ZKE_ASSERT, "return_revert.py:121-125 rw_counter delta")                             \
+  X(EV_RET_GAS, ZKE_ASSERT, "return_revert.py:121-125 gas_left to callee gas left")                  \
+  X(EV_RET_CALL_ID, ZKE_ASSERT, "return_revert.py:121-125 call_id same")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

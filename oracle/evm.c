@@ -472,32 +472,40 @@ static int call_context_w(evm_env* e, fr_t rwc, uint64_t rw, fr_t call_id, uint6
 }
 /* step_state_transition_to_restored_context (instruction.py:293-363) with caller_id = None;
  * rw_off = rw lookups the gadget already did, add_rev = curr state halts in success */
+/* lookups at rw_counter + look_off + k (k = 0..11), next rw_counter = rw_counter + delta12 + 12 (the two differ in
+ * return_revert.py's CREATE branch, whose rwc_delta forgets two lookups) */
+static void restore_context_f(evm_env* e, uint64_t i, uint64_t row, fr_t look_off, fr_t delta12, fr_t ret_off, fr_t ret_len,
+                              fr_t gas_left, int add_rev);
 static void restore_context_x(evm_env* e, uint64_t i, uint64_t row, uint64_t rw_off, fr_t ret_off, fr_t ret_len,
                               fr_t gas_left, int add_rev, fr_t extra_delta) {
+  restore_context_f(e, i, row, fr_u64(rw_off), fr_add(fr_u64(rw_off), extra_delta), ret_off, ret_len, gas_left, add_rev);
+}
+static void restore_context_f(evm_env* e, uint64_t i, uint64_t row, fr_t look_off, fr_t delta12, fr_t ret_off, fr_t ret_len,
+                              fr_t gas_left, int add_rev) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
   const fr_t rwc = CUR(S_RWC);
+  const fr_t lrwc = fr_add(rwc, look_off);
   static const uint64_t READ_TAGS[8] = {ZK_CC_IsRoot, ZK_CC_IsCreate, ZK_CC_CodeHash, ZK_CC_ProgramCounter,
                                         ZK_CC_StackPointer, ZK_CC_GasLeft, ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
   static const uint64_t WRITE_TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
   word_t v; int w;
-  if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off)), 0, CUR(S_CALL_ID), ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT, row)) return;
+  if (!need1(e, call_context_w(e, lrwc, 0, CUR(S_CALL_ID), ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT, row)) return;
   CHECK(EV_RST0_CHECK, !w);
   const fr_t caller_id = v.lo;
   word_t vals[8]; int words[8];
   for (int k = 0; k < 8; k++) {
-    if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off + 1 + k)), 0, caller_id, READ_TAGS[k], &vals[k], &words[k]),
+    if (!need1(e, call_context_w(e, fr_add(lrwc, fr_u64(1 + k)), 0, caller_id, READ_TAGS[k], &vals[k], &words[k]),
                EV_RST0_UNSAT + 3 * (1 + k), row)) return;
   }
   const fr_t expected[3] = {CUR(S_CALL_ID), ret_off, ret_len};
   for (int k = 0; k < 3; k++) {
-    if (!need1(e, call_context_w(e, fr_add(rwc, fr_u64(rw_off + 9 + k)), 1, caller_id, WRITE_TAGS[k], &v, &w),
+    if (!need1(e, call_context_w(e, fr_add(lrwc, fr_u64(9 + k)), 1, caller_id, WRITE_TAGS[k], &v, &w),
                EV_RST0_UNSAT + 3 * (9 + k), row)) return;
     CHECK(EV_RST0_UNSAT + 3 * (9 + k) + 2, !w && fr_eq(v.lo, expected[k]));
   }
   CHECK(EV_RST_VALUE_TYPE, !words[0] && !words[1] && !words[3] && !words[4] && !words[5] && !words[6] && !words[7]);
   const fr_t rev = add_rev ? CUR(S_REV) : fr_u64(0);
-  /* extra_delta: rw counters the step consumes without looking them up (the reverted writes of an error state) */
-  CHECK(EV_RST_RWC, fr_eq(NXT(S_RWC), fr_add(fr_add(rwc, fr_u64(rw_off + 12)), extra_delta)));
+  CHECK(EV_RST_RWC, fr_eq(NXT(S_RWC), fr_add(fr_add(rwc, delta12), fr_u64(12))));
   CHECK(EV_RST_CALL_ID, fr_eq(NXT(S_CALL_ID), caller_id));
   CHECK(EV_RST_IS_ROOT, fr_eq(NXT(S_IS_ROOT), vals[0].lo));
   CHECK(EV_RST_IS_CREATE, fr_eq(NXT(S_IS_CREATE), vals[1].lo));
@@ -933,6 +941,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_storage.h"
 #include "evm_log.h"
 #include "evm_exp.h"
+#include "evm_return.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -976,7 +985,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR || st == ZK_ES_SLOAD || st == ZK_ES_SSTORE ||
                                   st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH ||
                                   st == ZK_ES_EXP || st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore ||
-                                  st == ZK_ES_ErrorInvalidCreationCode);
+                                  st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1043,6 +1052,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_EXP) gadget_exp(e, i, row, opcode);
   else if (st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore) gadget_error_code_store(e, i, row, opcode);
   else if (st == ZK_ES_ErrorInvalidCreationCode) gadget_error_invalid_creation_code(e, i, row, opcode);
+  else if (st == ZK_ES_RETURN) gadget_return_revert(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1368,6 +1368,68 @@ def evm2_cases(part="evm2"):
                         reversible_write_counter=ctx[6])
         return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
+    def return_case(kind, is_return, offset, length, caller_len=10, cur_mem=2, gas=1000000):
+        """tests/evm/test_return_revert.py: RETURN / REVERT in the root call, in an internal call (return data copied to the
+        caller's memory, caller context restored) and at the end of a CREATE (memory -> deployed bytecode)"""
+        from zkevm_specs.evm_circuit import AccountFieldTag
+        from zkevm_specs.util.hash import EMPTY_CODE_HASH
+        from zkevm_specs.util.param import GAS_COST_CODE_DEPOSIT
+        bc = Bytecode().push32(0x2222222222222222222222222222222222222222222222222222222222222222).push1(4).mstore().push1(length).push1(offset)
+        bc = bc.return_() if is_return else bc.revert()
+        h = Word(bc.hash())
+        pc = 40
+        root = kind in ("root", "create_root")
+        create = kind.startswith("create")
+        callee = 1 if root else 2
+        if create:
+            length = len(bc.code)  # the deployed code is the running (init) code itself, as in the reference's test
+        rw = RWDictionary(24).call_context_read(callee, CallContextFieldTag.IsSuccess, int(is_return))
+        rw.stack_read(callee, 1022, Word(offset)).stack_read(callee, 1023, Word(length))
+        cc = CopyCircuit()
+        gas_left = gas
+        if create:
+            A = 0xFE
+            rw.call_context_read(callee, CallContextFieldTag.CalleeAddress, Word(A)).account_write(A, AccountFieldTag.CodeHash, h, Word(EMPTY_CODE_HASH))
+            src = {offset + k_: (bc.code[k_], bc.is_code[k_]) for k_ in range(length)}
+            cc.copy(r, rw, callee, CopyDataTypeTag.Memory, h, CopyDataTypeTag.Bytecode, offset, offset + length, 0, length, src)
+            gas_left -= length * GAS_COST_CODE_DEPOSIT
+        elif not root:
+            rw.call_context_read(callee, CallContextFieldTag.ReturnDataOffset, 0x40).call_context_read(callee, CallContextFieldTag.ReturnDataLength, caller_len)
+            n_copy = min(length, caller_len)
+            mem = [0] * 4 + [0x22] * 32 + [0] * 200
+            src = {k_: mem[k_] for k_ in range(offset, offset + n_copy)}
+            cc.copy(r, rw, callee, CopyDataTypeTag.Memory, 1, CopyDataTypeTag.Memory, offset, offset + length, 0x40, n_copy, src)
+        rev = 2
+        cur = StepState(ExecutionState.RETURN, rw_counter=24, call_id=callee, is_root=root, is_create=create, code_hash=h, program_counter=pc,
+                        stack_pointer=1022, gas_left=gas, memory_word_size=cur_mem, reversible_write_counter=rev)
+        bcs = list(bc.table_assignments())
+        if root:
+            rw.call_context_read(callee, CallContextFieldTag.IsPersistent, int(is_return))
+            # (the CREATE branch's two lookups are not counted in rwc_delta, return_revert.py:37-45: the next step starts 2 early)
+            nxt = StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter - (2 if create else 0), call_id=callee, gas_left=gas_left)
+        else:
+            nxt_mem, exp = mem_exp(cur_mem, offset + length)
+            if length == 0:
+                nxt_mem = max(cur_mem, mws(offset)); exp = (nxt_mem - cur_mem) * 3 + (nxt_mem * nxt_mem // 512 - cur_mem * cur_mem // 512)
+            cbc = Bytecode().call(0, 0xFF, 0, 0, 0, 0, 0).stop()
+            ch = Word(cbc.hash())
+            ctx = (True, False, 232, 1023, 77, 3, 5)
+            c_root, c_create, c_pc, c_sp, c_gas, c_mem, c_rev = ctx
+            (rw.call_context_read(callee, CallContextFieldTag.CallerId, 1).call_context_read(1, CallContextFieldTag.IsRoot, c_root)
+             .call_context_read(1, CallContextFieldTag.IsCreate, c_create).call_context_read(1, CallContextFieldTag.CodeHash, ch)
+             .call_context_read(1, CallContextFieldTag.ProgramCounter, c_pc).call_context_read(1, CallContextFieldTag.StackPointer, c_sp)
+             .call_context_read(1, CallContextFieldTag.GasLeft, c_gas).call_context_read(1, CallContextFieldTag.MemorySize, c_mem)
+             .call_context_read(1, CallContextFieldTag.ReversibleWriteCounter, c_rev)
+             .call_context_write(1, CallContextFieldTag.LastCalleeId, callee)
+             .call_context_write(1, CallContextFieldTag.LastCalleeReturnDataOffset, offset)
+             .call_context_write(1, CallContextFieldTag.LastCalleeReturnDataLength, length))
+            nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter - (2 if create else 0), call_id=1, is_root=c_root, is_create=c_create, code_hash=ch,
+                            program_counter=c_pc, stack_pointer=c_sp, gas_left=c_gas + gas_left - exp, memory_word_size=c_mem,
+                            reversible_write_counter=c_rev + rev)
+            bcs += list(cbc.table_assignments())
+        t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bcs), rw_table=set(rw.rws), copy_circuit=cc.rows)
+        return [cur, nxt], bcs, list(rw.rws), list(t.copy_table), []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1759,7 +1821,16 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm20":
+    if part == "evm21":
+        scenarios = {
+            "ret_root": return_case("root", True, 4, 10), "rev_root": return_case("root", False, 4, 10), "ret_root_expand": return_case("root", True, 4, 100),
+            "ret_internal_short": return_case("internal", True, 4, 8), "rev_internal_short": return_case("internal", False, 4, 8),
+            "ret_internal_equal": return_case("internal", True, 4, 10), "ret_internal_long": return_case("internal", True, 4, 20),
+            "rev_internal_expand": return_case("internal", False, 4, 100), "ret_internal_one": return_case("internal", True, 0, 1),  # (a zero-length return to a caller cannot verify: the copy lookup is unconditional)
+            "ret_create_root": return_case("create_root", True, 4, 0), "rev_create_root": return_case("create_root", False, 4, 0),
+            "ret_create_internal": return_case("create_internal", True, 4, 0), "rev_create_internal": return_case("create_internal", False, 4, 0),
+        }
+    elif part == "evm20":
         scenarios = {
             "oog_store_root": code_store_case("oog", True), "oog_store_internal": code_store_case("oog", False),
             "oog_store_max_size": code_store_case("oog", True, size=24576, gas_left=24576 * 200 - 1),
@@ -1963,8 +2034,8 @@ def evm2_cases(part="evm2"):
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part == "evm15" else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
@@ -2089,6 +2160,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm21_cases():
+    """RETURN / REVERT (return_revert.py): root, internal (return data copy + restored caller context) and CREATE endings"""
+    evm2_cases("evm21")
 
 
 def evm20_cases():
@@ -2956,7 +3032,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

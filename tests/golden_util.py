@@ -226,6 +226,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm21_vectors():
+    """RETURN / REVERT"""
+    return evm2_vectors("evm21")
+
+
 def evm20_vectors():
     """ErrorMaxCodeSizeExceeded / ErrorOutOfGasCodeStore / ErrorInvalidCreationCode"""
     return evm2_vectors("evm20")

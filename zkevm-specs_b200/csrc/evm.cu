@@ -45,7 +45,7 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
   X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
   X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP) \
-  X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode)
+  X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode) X(ZK_ES_RETURN)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -1139,16 +1139,19 @@ ZK_HD_NOINLINE int call_context_w(const StepCtx& s, bool live, const Fr& rwc, u6
 // rw_off = rw lookups the gadget already did; add_rev = the current state halts in success.
 // Lookup k has ids EV_RST0_UNSAT + 3k (+1 ambiguous, +2 value type / written value).
 // extra_delta: rw counters the step consumes without looking them up (the reverted writes of an error state).
-ZK_HD_NOINLINE void restore_context_x(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len,
-                                      const Fr& gas_left, bool add_rev, const Fr& extra_delta) {
+// General form: the 12 lookups sit at rw_counter + look_off + k, the next rw_counter is rw_counter + delta12 + 12 (the two
+// differ in return_revert.py's CREATE branch, whose rwc_delta forgets two lookups).
+ZK_HD_NOINLINE void restore_context_f(const StepCtx& s, bool live, const Fr& look_off, const Fr& delta12, const Fr& ret_off,
+                                      const Fr& ret_len, const Fr& gas_left, bool add_rev) {
   const u64 READ_TAGS[8] = {ZK_CC_IsRoot,       ZK_CC_IsCreate, ZK_CC_CodeHash,   ZK_CC_ProgramCounter,
                             ZK_CC_StackPointer, ZK_CC_GasLeft,  ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
   const u64 WRITE_TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
   const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  const Fr lrwc = fr_add(rwc, look_off);
   const Word2 zero{fr_u64(0), fr_u64(0)};
   Word2 v = zero;
   bool w = false;
-  live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off), 0, call_id, ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT);
+  live = need1(s, live, call_context_w(s, live, lrwc, 0, call_id, ZK_CC_CallerId, &v, &w), EV_RST0_UNSAT);
   EV_LIVE_CHECK(EV_RST0_CHECK, !w);
   const Fr caller_id = v.lo;
   Word2 vals[8];
@@ -1156,19 +1159,19 @@ ZK_HD_NOINLINE void restore_context_x(const StepCtx& s, bool live, u64 rw_off, c
   for (int k = 0; k < 8; k++) {
     vals[k] = zero;
     bool wk = false;
-    live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off + 1 + k), 0, caller_id, READ_TAGS[k], &vals[k], &wk),
+    live = need1(s, live, call_context_w(s, live, fr_add_u64(lrwc, 1 + k), 0, caller_id, READ_TAGS[k], &vals[k], &wk),
                  EV_RST0_UNSAT + 3 * (1 + k));
     if (live && k != 2) any_word |= wk;
   }
   for (int k = 0; k < 3; k++) {
     const Fr expected = k == 0 ? call_id : (k == 1 ? ret_off : ret_len);
-    live = need1(s, live, call_context_w(s, live, fr_add_u64(rwc, rw_off + 9 + k), 1, caller_id, WRITE_TAGS[k], &v, &w),
+    live = need1(s, live, call_context_w(s, live, fr_add_u64(lrwc, 9 + k), 1, caller_id, WRITE_TAGS[k], &v, &w),
                  EV_RST0_UNSAT + 3 * (9 + k));
     EV_LIVE_CHECK(EV_RST0_UNSAT + 3 * (9 + k) + 2, !w && fr_eq(v.lo, expected));
   }
   if (!live) return;  // past the last lookup
   EV_CHECK(EV_RST_VALUE_TYPE, !any_word);
-  EV_CHECK(EV_RST_RWC, fr_eq(s.nxt(S_RWC), fr_add(fr_add_u64(rwc, rw_off + 12), extra_delta)));
+  EV_CHECK(EV_RST_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(fr_add(rwc, delta12), 12)));
   EV_CHECK(EV_RST_CALL_ID, fr_eq(s.nxt(S_CALL_ID), caller_id));
   EV_CHECK(EV_RST_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), vals[0].lo));
   EV_CHECK(EV_RST_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), vals[1].lo));
@@ -1178,6 +1181,10 @@ ZK_HD_NOINLINE void restore_context_x(const StepCtx& s, bool live, u64 rw_off, c
   EV_CHECK(EV_RST_GAS, fr_eq(s.nxt(S_GAS), fr_add(vals[5].lo, gas_left)));
   EV_CHECK(EV_RST_MEM, fr_eq(s.nxt(S_MEM), vals[6].lo));
   EV_CHECK(EV_RST_REV, fr_eq(s.nxt(S_REV), add_rev ? fr_add(vals[7].lo, s.cur(S_REV)) : vals[7].lo));
+}
+ZK_HD void restore_context_x(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len, const Fr& gas_left,
+                            bool add_rev, const Fr& extra_delta) {
+  restore_context_f(s, live, fr_u64(rw_off), fr_add_u64(extra_delta, rw_off), ret_off, ret_len, gas_left, add_rev);
 }
 ZK_HD void restore_context(const StepCtx& s, bool live, u64 rw_off, const Fr& ret_off, const Fr& ret_len, const Fr& gas_left,
                           bool add_rev) {
@@ -1705,6 +1712,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 #include "evm_storage.cuh"
 #include "evm_log.cuh"
 #include "evm_exp.cuh"
+#include "evm_return.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1735,6 +1743,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_CODECOPY: case ZK_ES_RETURNDATACOPY: case ZK_ES_EXTCODECOPY: case ZK_ES_ErrorOutOfGasMemoryCopy:
     case ZK_ES_SLOAD: case ZK_ES_SSTORE: case ZK_ES_CALLDATALOAD: case ZK_ES_LOG: case ZK_ES_ErrorWriteProtection: case ZK_ES_BLOCKHASH:
     case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: case ZK_ES_ErrorInvalidCreationCode:
+    case ZK_ES_RETURN:
       return KG_TX;
     default: return -1;
   }
@@ -1816,6 +1825,7 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_BLOCKHASH: gadget_blockhash(s); break;
       case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: gadget_error_code_store(s); break;
       case ZK_ES_ErrorInvalidCreationCode: gadget_error_invalid_creation_code(s); break;
+      case ZK_ES_RETURN: gadget_return_revert(s); break;
       default: break;
     }
   } else if constexpr (G == KG_ARITH) {
@@ -2037,11 +2047,14 @@ __device__ __forceinline__ void bucket_steps(const WitnessDev& w, const CheckRan
 #ifndef ZK_PUSH_MINBLOCKS
 #define ZK_PUSH_MINBLOCKS 4
 #endif
+// ADD / SUB and POP are latency-bound on three dependent round trips (8-9 long-scoreboard stalls per issue,
+// profiles/r02_m_top_kernels_ncu_full.csv): 6 resident blocks (80 registers; POP without a spill, ADD with 216 bytes)
+// beat 3 (142 / 107 registers) by 3 % of the check phase (profiles/r02_m_launch_bound_variants.json)
 #ifndef ZK_ADD_MINBLOCKS
-#define ZK_ADD_MINBLOCKS ZK_GADGET_MINBLOCKS
+#define ZK_ADD_MINBLOCKS 6
 #endif
 #ifndef ZK_POP_MINBLOCKS
-#define ZK_POP_MINBLOCKS ZK_GADGET_MINBLOCKS
+#define ZK_POP_MINBLOCKS 6
 #endif
 template <int G, int POS>
 __global__ void __launch_bounds__(128, G == KG_MUL ? ZK_GADGET_MINBLOCKS : (G == KG_ADD ? ZK_ADD_MINBLOCKS : ZK_POP_MINBLOCKS))
