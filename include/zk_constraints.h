@@ -1017,7 +1017,53 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_RET_PERSIST_EQ, ZKE_ASSERT, "return_revert.py:118 is_persistent == is_return")                \
   X(EV_RET_RWC, ZKE_ASSERT, "return_revert.py:121-125 rw_counter delta")                             \
   X(EV_RET_GAS, ZKE_ASSERT, "return_revert.py:121-125 gas_left to callee gas left")                  \
-  X(EV_RET_CALL_ID, ZKE_ASSERT, "return_revert.py:121-125 call_id same")
+  X(EV_RET_CALL_ID, ZKE_ASSERT, "return_revert.py:121-125 call_id same")                 \
+  X(EV_EOC_OPCODE, ZKE_ASSERT, "error_oog_call.py:19 opcode is CALL / CALLCODE / DELEGATECALL / STATICCALL") \
+  X(EV_EOC_TXID_UNSAT, ZKE_UNSAT, "error_oog_call.py:21 call_context_lookup(TxId) unsat")            \
+  X(EV_EOC_TXID_AMBIG, ZKE_AMBIG, "error_oog_call.py:21 call_context_lookup(TxId) ambiguous")        \
+  X(EV_EOC_TXID_TYPE, ZKE_ASSERT, "error_oog_call.py:21 call_context_lookup(TxId): .value() of a Word") \
+  X(EV_EOC_POP0_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop gas unsat")                        \
+  X(EV_EOC_POP0_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop gas ambiguous")                    \
+  X(EV_EOC_POP1_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop callee address unsat")             \
+  X(EV_EOC_POP1_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop callee address ambiguous")         \
+  X(EV_EOC_POP2_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop value unsat")                      \
+  X(EV_EOC_POP2_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop value ambiguous")                  \
+  X(EV_EOC_POP3_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop cd_offset unsat")                  \
+  X(EV_EOC_POP3_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop cd_offset ambiguous")              \
+  X(EV_EOC_POP4_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop cd_length unsat")                  \
+  X(EV_EOC_POP4_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop cd_length ambiguous")              \
+  X(EV_EOC_POP5_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop rd_offset unsat")                  \
+  X(EV_EOC_POP5_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop rd_offset ambiguous")              \
+  X(EV_EOC_POP6_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop rd_length unsat")                  \
+  X(EV_EOC_POP6_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop rd_length ambiguous")              \
+  X(EV_EOC_PUSH_UNSAT, ZKE_UNSAT, "call_gadget.py:64 stack_push result unsat")                       \
+  X(EV_EOC_PUSH_AMBIG, ZKE_AMBIG, "call_gadget.py:64 stack_push result ambiguous")                   \
+  X(EV_EOC_RESULT_WORD, ZKE_ASSERT, "call_gadget.py:66 result == Word.from_lo(is_success)")          \
+  X(EV_EOC_RESULT_BOOL, ZKE_ASSERT, "call_gadget.py:69 is_success is a bool")                        \
+  X(EV_EOC_RESULT_ZERO, ZKE_ASSERT, "call_gadget.py:71 is_success == 0 (failed call)")               \
+  X(EV_EOC_GAS_DOMAIN, ZKE_VALUE, "call_gadget.py:73 gas: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_GAS_RANGE, ZKE_RANGE, "call_gadget.py:73 gas: more than 8 bytes")                         \
+  X(EV_EOC_CALLEE_DOMAIN, ZKE_VALUE, "call_gadget.py:85 callee address: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_CALLEE_RANGE, ZKE_RANGE, "call_gadget.py:85 callee address: more than 20 bytes")          \
+  X(EV_EOC_CDLEN_DOMAIN, ZKE_VALUE, "call_gadget.py:86 cd_length: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_CDLEN_RANGE, ZKE_RANGE, "call_gadget.py:86 cd_length: more than 5 bytes")                 \
+  X(EV_EOC_CDOFF_DOMAIN, ZKE_VALUE, "call_gadget.py:86 cd_offset: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_CDOFF_RANGE, ZKE_RANGE, "call_gadget.py:86 cd_offset: more than 5 bytes")                 \
+  X(EV_EOC_RDLEN_DOMAIN, ZKE_VALUE, "call_gadget.py:87 rd_length: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_RDLEN_RANGE, ZKE_RANGE, "call_gadget.py:87 rd_length: more than 5 bytes")                 \
+  X(EV_EOC_RDOFF_DOMAIN, ZKE_VALUE, "call_gadget.py:87 rd_offset: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOC_RDOFF_RANGE, ZKE_RANGE, "call_gadget.py:87 rd_offset: more than 5 bytes")                 \
+  X(EV_EOC_CD_MEMSIZE_RANGE, ZKE_RANGE, "call_gadget.py:92 memory_expansion_dynamic_length: call-data memory size beyond 4 bytes") \
+  X(EV_EOC_MEM_MAX, ZKE_ASSERT, "call_gadget.py:92 max(): curr.memory_word_size beyond 4 bytes")     \
+  X(EV_EOC_RD_MEMSIZE_RANGE, ZKE_RANGE, "call_gadget.py:92 memory_expansion_dynamic_length: return-data memory size beyond 4 bytes") \
+  X(EV_EOC_HASH_UNSAT, ZKE_UNSAT, "call_gadget.py:100 account_read_word(CodeHash) unsat")            \
+  X(EV_EOC_HASH_AMBIG, ZKE_AMBIG, "call_gadget.py:100 account_read_word(CodeHash) ambiguous")        \
+  X(EV_EOC_AL_UNSAT, ZKE_UNSAT, "error_oog_call.py:29 read_account_to_access_list unsat")            \
+  X(EV_EOC_AL_AMBIG, ZKE_AMBIG, "error_oog_call.py:29 read_account_to_access_list ambiguous")        \
+  X(EV_EOC_AL_PREV_TYPE, ZKE_ASSERT, "instruction.py:1069 value_prev.value() of a Word")             \
+  X(EV_EOC_WARM_BOOL, ZKE_ASSERT, "call_gadget.py:114 select(is_warm_access, ..): not a bool")       \
+  X(EV_EOC_CMP_RANGE, ZKE_ASSERT, "error_oog_call.py:35 compare(gas_left, gas_cost, 8): range assert") \
+  X(EV_EOC_NOT_ENOUGH, ZKE_ASSERT, "error_oog_call.py:36 gas_left < gas_cost")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -985,7 +985,8 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_MULMOD || st == ZK_ES_SDIV_SMOD || st == ZK_ES_SAR || st == ZK_ES_SLOAD || st == ZK_ES_SSTORE ||
                                   st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH ||
                                   st == ZK_ES_EXP || st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore ||
-                                  st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN);
+                                  st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN ||
+                                  st == ZK_ES_ErrorOutOfGasCall);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1053,6 +1054,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore) gadget_error_code_store(e, i, row, opcode);
   else if (st == ZK_ES_ErrorInvalidCreationCode) gadget_error_invalid_creation_code(e, i, row, opcode);
   else if (st == ZK_ES_RETURN) gadget_return_revert(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorOutOfGasCall) gadget_error_oog_call(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

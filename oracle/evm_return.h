@@ -95,3 +95,67 @@ static void gadget_return_revert(evm_env* e, uint64_t i, uint64_t row, fr_t opco
     restore_context_f(e, i, row, look, delta, offset, length, fr_sub(gas_left, fr_u64(expansion)), 1);
   }
 }
+
+/* ---- ErrorOutOfGasCall: error_oog_call.py:11-42 with util/call_gadget.py:39-125 (CallGadget, IS_SUCCESS_CALL = 0) ----
+ * Pinned by tests/golden/evm22.npz (890 verdicts of the reference's verify_step). */
+static void gadget_error_oog_call(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const uint64_t op = fr_fits_bits(opcode, 8) ? opcode.l[0] : 0x100;
+  CHECK(EV_EOC_OPCODE, op == 0xf1 || op == 0xf2 || op == 0xf4 || op == 0xfa);
+  const int has_value_pop = op == 0xf1 || op == 0xf2;
+  fr_t tx_id;
+  ST_CC(0, ZK_CC_TxId, &tx_id, EV_EOC_TXID_UNSAT);
+  /* CallGadget: the stack words, call_gadget.py:53-66 */
+  word_t w[8]; /* gas, callee, value, cd_offset, cd_length, rd_offset, rd_length, result */
+  const word_t zero = {fr_u64(0), fr_u64(0)};
+  uint64_t k = 1, spo = 0;
+  for (int f = 0; f < 7; f++) {
+    if (f == 2 && !has_value_pop) { w[2] = zero; continue; }
+    if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(spo)), &w[f]), EV_EOC_POP0_UNSAT + 2 * f, row)) return;
+    k++; spo++;
+  }
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(spo - 1)), &w[7]), EV_EOC_PUSH_UNSAT, row)) return;
+  k++;
+  CHECK(EV_EOC_RESULT_WORD, fr_is_zero(w[7].hi));                       /* Word.from_lo(is_success) == result */
+  CHECK(EV_EOC_RESULT_BOOL, fr_eq_u64(w[7].lo, 0) || fr_eq_u64(w[7].lo, 1));
+  CHECK(EV_EOC_RESULT_ZERO, fr_is_zero(w[7].lo));                       /* IS_SUCCESS_CALL == 0 */
+  fr_t gas, callee;
+  W2FQ(w[0], 8, &gas, EV_EOC_GAS_DOMAIN);
+  (void)gas;
+  const int has_value = has_value_pop && !fr_is_zero(fr_add(w[2].lo, w[2].hi));
+  W2FQ(w[1], 20, &callee, EV_EOC_CALLEE_DOMAIN);
+  /* memory_offset_and_length x 2: the length first, the offset only when the length is not zero */
+  fr_t cd_off = fr_u64(0), cd_len, rd_off = fr_u64(0), rd_len;
+  W2FQ(w[4], 5, &cd_len, EV_EOC_CDLEN_DOMAIN);
+  if (!fr_is_zero(cd_len)) W2FQ(w[3], 5, &cd_off, EV_EOC_CDOFF_DOMAIN);
+  W2FQ(w[6], 5, &rd_len, EV_EOC_RDLEN_DOMAIN);
+  if (!fr_is_zero(rd_len)) W2FQ(w[5], 5, &rd_off, EV_EOC_RDOFF_DOMAIN);
+  /* memory_expansion_dynamic_length(cd_offset, cd_length, rd_offset, rd_length), instruction.py:1157-1181 */
+  const uint64_t cd_words = (cd_off.l[0] + cd_len.l[0] + 31) / 32, rd_words = (rd_off.l[0] + rd_len.l[0] + 31) / 32;
+  CHECK(EV_EOC_CD_MEMSIZE_RANGE, !(cd_words >> 32));
+  const fr_t cur_mem = CUR(S_MEM);
+  CHECK(EV_EOC_MEM_MAX, fr_fits_bits(cur_mem, 32));
+  uint64_t nxt = cur_mem.l[0] < cd_words ? cd_words : cur_mem.l[0];
+  CHECK(EV_EOC_RD_MEMSIZE_RANGE, !(rd_words >> 32));
+  nxt = nxt < rd_words ? rd_words : nxt;
+  const uint64_t expansion = memory_gas_cost(nxt) - memory_gas_cost(cur_mem.l[0]);
+  uint32_t r;
+  LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 0, callee, ZK_ACC_CodeHash, &r), EV_EOC_HASH_UNSAT);
+  k++;
+  { /* read_account_to_access_list: state_read(TxAccessListAccount, tx_id, callee) */
+    fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(k)), 0, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id; key[R_ADDR] = callee;
+    LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR), &r), EV_EOC_AL_UNSAT);
+    k++;
+  }
+  CHECK(EV_EOC_AL_PREV_TYPE, !rw_prev_is_word(e, r));
+  const fr_t is_warm = rw_cell(e, R_PREV_LO, r);
+  CHECK(EV_EOC_WARM_BOOL, fr_eq_u64(is_warm, 0) || fr_eq_u64(is_warm, 1));
+  /* gas_cost(): is_success == 0 here, so the new-account term vanishes */
+  const uint64_t cost = (fr_eq_u64(is_warm, 1) ? 100 : 2600) + (has_value ? 9000 : 0) + expansion;
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_EOC_CMP_RANGE, fr_fits_bits(gas_left, 64));
+  CHECK(EV_EOC_NOT_ENOUGH, gas_left.l[0] < cost);
+  error_state_tail(e, i, row, k);
+}

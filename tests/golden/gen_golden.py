@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1430,6 +1430,44 @@ def evm2_cases(part="evm2"):
         t = Tables(block_table=set(), tx_table=set(), withdrawal_table=set(), bytecode_table=set(bcs), rw_table=set(rw.rws), copy_circuit=cc.rows)
         return [cur, nxt], bcs, list(rw.rws), list(t.copy_table), []
 
+    def oog_call_case(op, root, is_warm, gas_left, value=0, cd=(64, 320), rd=(0, 32), cur_mem=0):
+        """tests/evm/test_error_oog_call.py: CALL / CALLCODE / DELEGATECALL / STATICCALL without the gas for the call itself"""
+        from zkevm_specs.evm_circuit import AccountFieldTag
+        callee_code = Bytecode().stop()
+        A = 0xFF
+        has_value = op in ("call", "callcode")
+        bc = Bytecode()
+        if has_value:
+            bc = getattr(bc, op)(100, A, value, cd[0], cd[1], rd[0], rd[1]).stop()
+        else:
+            bc = getattr(bc, op)(100, A, cd[0], cd[1], rd[0], rd[1]).stop()
+        h = Word(bc.hash())
+        call_id, rev = (1 if root else 2), 2
+        sp = 1018 - int(has_value)
+        rw = RWDictionary(24 if root else 69)
+        rwc0 = rw.rw_counter
+        rw.call_context_read(call_id, CallContextFieldTag.TxId, 1).stack_read(call_id, sp, Word(100)).stack_read(call_id, sp + 1, Word(A))
+        if has_value:
+            rw.stack_read(call_id, 1019, Word(value))
+        (rw.stack_read(call_id, 1020, Word(cd[0])).stack_read(call_id, 1021, Word(cd[1])).stack_read(call_id, 1022, Word(rd[0]))
+         .stack_read(call_id, 1023, Word(rd[1])).stack_write(call_id, 1023, Word(0))
+         .account_read(A, AccountFieldTag.CodeHash, Word(callee_code.hash())).tx_access_list_account_read(1, A, is_warm)
+         .call_context_read(call_id, CallContextFieldTag.IsSuccess, 0))
+        cur = StepState(ExecutionState.ErrorOutOfGasCall, rw_counter=rwc0, call_id=call_id, is_root=root, is_create=False, code_hash=h,
+                        program_counter=231 if has_value else 198, stack_pointer=sp, gas_left=gas_left, memory_word_size=cur_mem,
+                        reversible_write_counter=rev)
+        bcs = list(bc.table_assignments()) + list(callee_code.table_assignments())
+        if root:
+            return [cur, StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter + rev, call_id=1, gas_left=0)], bcs, list(rw.rws), [], []
+        cbc = Bytecode().call(0, 0xFE, 0, 0, 0, 0, 0).stop()
+        ch = Word(cbc.hash())
+        ctx = (True, False, 232, 1023, 10, 3, 5)
+        caller_ctx_rws(rw, 1, ch, ctx, 2)
+        nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter + rev, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=ch,
+                        program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                        reversible_write_counter=ctx[6])
+        return [cur, nxt], bcs + list(cbc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1821,7 +1859,16 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm21":
+    if part == "evm22":
+        scenarios = {
+            "call_warm_root": oog_call_case("call", True, True, 50), "call_cold_internal": oog_call_case("call", False, False, 100),
+            "call_value_root": oog_call_case("call", True, True, 9100, value=5), "callcode_cold_root": oog_call_case("callcode", True, False, 2600),
+            "callcode_value_internal": oog_call_case("callcode", False, True, 9000, value=1 << 200),
+            "delegatecall_warm_root": oog_call_case("delegatecall", True, True, 50), "delegatecall_cold_internal": oog_call_case("delegatecall", False, False, 2000, cur_mem=20),
+            "staticcall_warm_internal": oog_call_case("staticcall", False, True, 100, cd=(0, 0), rd=(0x400, 0x40)),
+            "staticcall_cold_root": oog_call_case("staticcall", True, False, 2599, cd=(0, 0), rd=(0, 0)),
+        }
+    elif part == "evm21":
         scenarios = {
             "ret_root": return_case("root", True, 4, 10), "rev_root": return_case("root", False, 4, 10), "ret_root_expand": return_case("root", True, 4, 100),
             "ret_internal_short": return_case("internal", True, 4, 8), "rev_internal_short": return_case("internal", False, 4, 8),
@@ -2034,7 +2081,7 @@ def evm2_cases(part="evm2"):
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110}[part]):
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100}[part]):
             which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
@@ -2160,6 +2207,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm22_cases():
+    """ErrorOutOfGasCall (error_oog_call.py + util/call_gadget.py)"""
+    evm2_cases("evm22")
 
 
 def evm21_cases():
@@ -3032,7 +3084,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -226,6 +226,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm22_vectors():
+    """ErrorOutOfGasCall"""
+    return evm2_vectors("evm22")
+
+
 def evm21_vectors():
     """RETURN / REVERT"""
     return evm2_vectors("evm21")

@@ -105,4 +105,71 @@ ZK_HD_NOINLINE void gadget_return_revert(const StepCtx& s) {
   }
 }
 
+// ---- ErrorOutOfGasCall: error_oog_call.py:11-42 with util/call_gadget.py:39-125 (CallGadget, IS_SUCCESS_CALL = 0) ----
+ZK_HD_NOINLINE void gadget_error_oog_call(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), sp = s.cur(S_SP);
+  const u64 op = (fr_fits64(opcode) && opcode.l[0] < 256) ? opcode.l[0] : 0x100;
+  EV_CHECK(EV_EOC_OPCODE, op == 0xf1 || op == 0xf2 || op == 0xf4 || op == 0xfa);
+  const bool has_value_pop = op == 0xf1 || op == 0xf2;
+  Fr tx_id;
+  ST_CC(0, ZK_CC_TxId, &tx_id, EV_EOC_TXID_UNSAT);
+  // CallGadget: gas, callee, value (CALL / CALLCODE only), cd_offset, cd_length, rd_offset, rd_length, then the pushed result
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 w[8] = {zero, zero, zero, zero, zero, zero, zero, zero};
+  u64 k = 1, spo = 0;
+#pragma unroll
+  for (int f = 0; f < 7; f++) {
+    if (f == 2 && !has_value_pop) continue;
+    if (!need1(s, true, stack_at(s, true, k, 0, fr_add_u64(sp, spo), &w[f]), EV_EOC_POP0_UNSAT + 2 * f)) return;
+    k++;
+    spo++;
+  }
+  if (!need1(s, true, stack_at(s, true, k, 1, fr_add_u64(sp, spo - 1), &w[7]), EV_EOC_PUSH_UNSAT)) return;
+  k++;
+  EV_CHECK(EV_EOC_RESULT_WORD, fr_is_zero(w[7].hi));
+  EV_CHECK(EV_EOC_RESULT_BOOL, fr_eq_u64(w[7].lo, 0) || fr_eq_u64(w[7].lo, 1));
+  EV_CHECK(EV_EOC_RESULT_ZERO, fr_is_zero(w[7].lo));
+  Fr gas = fr_u64(0), callee = fr_u64(0);
+  EOOG_W2FQ(w[0], 8, &gas, EV_EOC_GAS_DOMAIN);
+  const bool has_value = has_value_pop && !fr_is_zero(fr_add(w[2].lo, w[2].hi));
+  EOOG_W2FQ(w[1], 20, &callee, EV_EOC_CALLEE_DOMAIN);
+  // memory_offset_and_length x 2: the length first, the offset only when the length is not zero
+  Fr cd_off = fr_u64(0), cd_len = fr_u64(0), rd_off = fr_u64(0), rd_len = fr_u64(0);
+  EOOG_W2FQ(w[4], 5, &cd_len, EV_EOC_CDLEN_DOMAIN);
+  if (!fr_is_zero(cd_len)) EOOG_W2FQ(w[3], 5, &cd_off, EV_EOC_CDOFF_DOMAIN);
+  EOOG_W2FQ(w[6], 5, &rd_len, EV_EOC_RDLEN_DOMAIN);
+  if (!fr_is_zero(rd_len)) EOOG_W2FQ(w[5], 5, &rd_off, EV_EOC_RDOFF_DOMAIN);
+  // memory_expansion_dynamic_length(cd_offset, cd_length, rd_offset, rd_length)
+  const u64 cd_words = (cd_off.l[0] + cd_len.l[0] + 31) / 32, rd_words = (rd_off.l[0] + rd_len.l[0] + 31) / 32;
+  EV_CHECK(EV_EOC_CD_MEMSIZE_RANGE, (cd_words >> 32) == 0);
+  const Fr cur_mem = s.cur(S_MEM);
+  EV_CHECK(EV_EOC_MEM_MAX, fr_fits64(cur_mem) && (cur_mem.l[0] >> 32) == 0);
+  EV_CHECK(EV_EOC_RD_MEMSIZE_RANGE, (rd_words >> 32) == 0);
+  u64 expansion = 0;
+  (void)mem_expansion_gas(s, cd_words > rd_words ? cd_words : rd_words, &expansion);
+  u32 r = 0;
+  TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 0, callee, ZK_ACC_CodeHash, &r), EV_EOC_HASH_UNSAT);
+  k++;
+  {  // read_account_to_access_list: state_read(TxAccessListAccount, tx_id, callee)
+    Fr key[14];
+    rw_key_init(key, fr_add_u64(rwc, k), 0, ZK_TARGET_TxAccessListAccount);
+    key[R_ID] = tx_id;
+    key[R_ADDR] = callee;
+    TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR), &r), EV_EOC_AL_UNSAT);
+    k++;
+  }
+  EV_CHECK(EV_EOC_AL_PREV_TYPE, !rw_flag(s, r, 1));
+  const Fr is_warm = rw_cell(s, R_PREV_LO, r);
+  const bool warm = fr_eq_u64(is_warm, 1);
+  EV_CHECK(EV_EOC_WARM_BOOL, warm || fr_eq_u64(is_warm, 0));
+  // gas_cost(): is_success == 0 here, so the new-account term vanishes
+  const u64 cost = (warm ? 100 : 2600) + (has_value ? 9000 : 0) + expansion;
+  const Fr gas_left = s.cur(S_GAS);
+  EV_CHECK(EV_EOC_CMP_RANGE, fr_fits64(gas_left));
+  EV_CHECK(EV_EOC_NOT_ENOUGH, gas_left.l[0] < cost);
+  error_state_tail(s, k);
+}
+
 }  // namespace zk

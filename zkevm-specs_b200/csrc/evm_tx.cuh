@@ -46,15 +46,9 @@ ZK_HD_NOINLINE int rw_lookup_m(const StepCtx& s, const Fr* key, u32 mask, u32* r
     const u64 base = table_cell(t, R_RWC, first).l[0];
     if (!(fr_fits64(key[R_RWC]) && key[R_RWC].l[0] >= base && key[R_RWC].l[0] - base < limit)) return 0;
     const u64 cand = first + (key[R_RWC].l[0] - base);
-    // every named cell is fetched before the first compare: one memory round trip per lookup instead of one per cell
-    // (the transaction-level gate programs are chains of 20-30 such lookups on a few thousand threads)
     bool ok = true;
-#pragma unroll
-    for (int c = 1; c < 14; c++) {
-      const bool named = (mask >> c) & 1;
-      const Fr v = named ? table_cell(t, c, cand) : key[c];
-      ok &= fr_eq(v, key[c]);
-    }
+    for (int c = 1; c < 14; c++)
+      if ((mask >> c) & 1) ok = ok && fr_eq(table_cell(t, c, cand), key[c]);
     *row = (u32)cand;
     return ok ? 1 : 0;
   }
