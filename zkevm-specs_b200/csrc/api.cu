@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -118,6 +119,11 @@ struct zk_ctx {
   size_t evm_sort_cap = 0;
   u32* evm_hist_host = nullptr;  // pinned: histogram + positional flag read back after k_evm_classify
   cudaEvent_t evm_hist_ev = nullptr;
+  // the transaction-level group (k_evm_group<TX>: a few thousand threads, each a chain of dependent lookups) runs on its
+  // own stream next to the hot kernels; forked after the scatter, joined before the check returns to the caller's stream
+  cudaStream_t evm_aux = nullptr;
+  cudaEvent_t evm_fork_ev = nullptr, evm_join_ev = nullptr;
+  int evm_tx_overlap = -1;  // -1 = not read yet (env ZKCHECK_TX_OVERLAP, default 1)
   int evm_occ[20] = {0};  // resident blocks per SM of the gate-program kernels (0 = not queried yet)
   std::unordered_map<const void*, int> occ;  // same, row-circuit kernels (keyed by kernel)
   BlockStats* block_stats = nullptr;  // k_evm_block_stats output
@@ -212,6 +218,9 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   if (ctx->copy_slow) cudaFree(ctx->copy_slow);
   if (ctx->evm_hist_host) cudaFreeHost(ctx->evm_hist_host);
   if (ctx->evm_hist_ev) cudaEventDestroy(ctx->evm_hist_ev);
+  if (ctx->evm_fork_ev) cudaEventDestroy(ctx->evm_fork_ev);
+  if (ctx->evm_join_ev) cudaEventDestroy(ctx->evm_join_ev);
+  if (ctx->evm_aux) cudaStreamDestroy(ctx->evm_aux);
   if (ctx->resp_bitmap) cudaFree(ctx->resp_bitmap);
   delete ctx;
 }
@@ -1310,9 +1319,10 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
     const u64 want = (work_items + per_block - 1) / per_block;
     return (unsigned)std::max<u64>(1, std::min<u64>(want, (u64)ctx->evm_occ[slot] * ctx->sm_count));
   };
-#define ZK_LAUNCH_GROUP(slot, kernel, items, per_block)                                        \
+#define ZK_LAUNCH_GROUP(slot, kernel, items, per_block) ZK_LAUNCH_GROUP_ON(st, slot, kernel, items, per_block)
+#define ZK_LAUNCH_GROUP_ON(stream_, slot, kernel, items, per_block)                            \
   do {                                                                                         \
-    kernel<<<grid_for(slot, (const void*)kernel, items, per_block), 128, 0, st>>>(wd, rg, t, res, so); \
+    kernel<<<grid_for(slot, (const void*)kernel, items, per_block), 128, 0, stream_>>>(wd, rg, t, res, so); \
     ctx->launches++;                                                                           \
     {                                                                                          \
       cudaError_t e_ = cudaGetLastError();                                                     \
@@ -1322,6 +1332,27 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   // narrow instances: positional tables AND every step column but the code hash, the rw table's key columns narrow
   // (<= 8 bytes per row, Matrix::narrow_mask) AND the bytecode table in the layout k_bytecode_table_expand writes
   const bool narrow = pos && evm_narrow(ctx);
+  // the transaction-level group first, on the auxiliary stream: its blocks take their places before the hot kernels'
+  // persistent grids fill the device, and its long per-thread chains run underneath them
+  bool tx_forked = false;
+  if (group_n[KG_TX]) {
+    if (ctx->evm_tx_overlap < 0) {
+      const char* e_ = getenv("ZKCHECK_TX_OVERLAP");
+      ctx->evm_tx_overlap = (e_ && e_[0] == '0') ? 0 : 1;
+    }
+    if (ctx->evm_tx_overlap) {
+      if (!ctx->evm_aux) {
+        CK(ctx, cudaStreamCreateWithFlags(&ctx->evm_aux, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->evm_fork_ev, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->evm_join_ev, cudaEventDisableTiming));
+      }
+      CK(ctx, cudaEventRecord(ctx->evm_fork_ev, st));
+      CK(ctx, cudaStreamWaitEvent(ctx->evm_aux, ctx->evm_fork_ev, 0));
+      ZK_LAUNCH_GROUP_ON(ctx->evm_aux, 12, k_evm_group<KG_TX>, group_n[KG_TX], 128);
+      CK(ctx, cudaEventRecord(ctx->evm_join_ev, ctx->evm_aux));
+      tx_forked = true;
+    }
+  }
   if (group_n[KG_PUSH]) {
     if (narrow) ZK_LAUNCH_GROUP(13, k_evm_push_pos<1>, group_n[KG_PUSH], 128);
     else if (pos) ZK_LAUNCH_GROUP(0, k_evm_push_pos<0>, group_n[KG_PUSH], 128);
@@ -1346,9 +1377,11 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
   if (group_n[KG_BYTES32]) ZK_LAUNCH_GROUP(9, k_evm_group<KG_BYTES32>, group_n[KG_BYTES32], 128);
   if (group_n[KG_COPY]) ZK_LAUNCH_GROUP(10, k_evm_group<KG_COPY>, group_n[KG_COPY], 128);
   if (group_n[KG_WIDE]) ZK_LAUNCH_GROUP(11, k_evm_group<KG_WIDE>, group_n[KG_WIDE], 128);
-  if (group_n[KG_TX]) ZK_LAUNCH_GROUP(12, k_evm_group<KG_TX>, group_n[KG_TX], 128);
+  if (group_n[KG_TX] && !tx_forked) ZK_LAUNCH_GROUP(12, k_evm_group<KG_TX>, group_n[KG_TX], 128);
   if (group_n[KG_ARITH]) ZK_LAUNCH_GROUP(17, k_evm_group<KG_ARITH>, group_n[KG_ARITH], 128);
+  if (tx_forked) CK(ctx, cudaStreamWaitEvent(st, ctx->evm_join_ev, 0));
 #undef ZK_LAUNCH_GROUP
+#undef ZK_LAUNCH_GROUP_ON
   CK(ctx, cudaGetLastError());
   return 0;
 }
