@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1468,6 +1468,34 @@ def evm2_cases(part="evm2"):
                         reversible_write_counter=ctx[6])
         return [cur, nxt], bcs + list(cbc.table_assignments()), list(rw.rws), [], []
 
+    def callop_case(idx):
+        """tests/evm/test_callop.py: case `idx` of the reference test's own TESTING_DATA, built with its template
+        (callop_test_template / expected are imported from the reference's test module; nothing of it is copied here)"""
+        import importlib
+        tdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm")
+        tdir = os.path.normpath(tdir)
+        for d_ in (tdir, os.path.dirname(tdir)):  # tests/evm and tests/ (common.py)
+            if d_ not in sys.path:
+                sys.path.insert(0, d_)
+        tc = importlib.import_module("test_callop")
+        opcode, callee, caller_ctx, stack, is_warm, depth, exp = tc.TESTING_DATA[idx]
+        (_, caller_bc, callee_bc, call_id, next_pc, sp, rw, precheck_ok, empty_hash) = tc.callop_test_template(
+            opcode, callee, caller_ctx, stack, is_warm, depth, False, exp)
+        h = Word(caller_bc.hash())
+        callee_h = Word(callee_bc.hash() if not callee.is_empty() else 0)
+        cur = StepState(ExecutionState.CALL_OP, rw_counter=call_id, call_id=1, is_root=True, is_create=False, code_hash=h,
+                        program_counter=next_pc - 1, stack_pointer=sp, gas_left=caller_ctx.gas_left, memory_word_size=caller_ctx.memory_word_size,
+                        reversible_write_counter=caller_ctx.reversible_write_counter)
+        if empty_hash or precheck_ok is False:
+            nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=True, is_create=False, code_hash=h,
+                            program_counter=next_pc, stack_pointer=1023, gas_left=exp.caller_gas_left, memory_word_size=exp.next_memory_size,
+                            reversible_write_counter=caller_ctx.reversible_write_counter + 3)
+        else:
+            nxt = StepState(ExecutionState.STOP if callee.code == tc.STOP_BYTECODE else ExecutionState.PUSH, rw_counter=rw.rw_counter, call_id=call_id,
+                            is_root=False, is_create=False, code_hash=callee_h, program_counter=0, stack_pointer=1024,
+                            gas_left=exp.callee_gas_left, reversible_write_counter=2)
+        return [cur, nxt], list(caller_bc.table_assignments()) + list(callee_bc.table_assignments()), list(rw.rws), [], []
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1859,7 +1887,19 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm22":
+    if part == "evm23":
+        # 36 of the reference test's 768 cases: every opcode x callee kind, both reversion settings, the four stack shapes,
+        # warm / cold, depth 1 / 1024 / 1025 (index = a mixed-radix number over the test's product order)
+        picks = []
+        for op_i in range(4):
+            for callee_i in range(4):
+                for v in range(2):
+                    ctx_i, stack_i = (op_i + callee_i + v) % 2, (op_i * 2 + callee_i + v) % 4
+                    warm_i, depth_i = (callee_i + v) % 2, (0 if v == 0 else (op_i + callee_i) % 3)
+                    picks.append((((((op_i * 4 + callee_i) * 2 + ctx_i) * 4 + stack_i) * 2 + warm_i) * 3) + depth_i)
+        picks += [5, 100, 300, 700]
+        scenarios = {"callop_%03d" % k_: callop_case(k_) for k_ in sorted(set(picks))}
+    elif part == "evm22":
         scenarios = {
             "call_warm_root": oog_call_case("call", True, True, 50), "call_cold_internal": oog_call_case("call", False, False, 100),
             "call_value_root": oog_call_case("call", True, True, 9100, value=5), "callcode_cold_root": oog_call_case("callcode", True, False, 2600),
@@ -2081,8 +2121,8 @@ def evm2_cases(part="evm2"):
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part == "evm17" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
@@ -2207,6 +2247,12 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm23_cases():
+    """CALL / CALLCODE / DELEGATECALL / STATICCALL (callop.py): callee without code or failed pre-check (stays in the caller)
+    and callee with code (new call context)"""
+    evm2_cases("evm23")
 
 
 def evm22_cases():
@@ -3084,7 +3130,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

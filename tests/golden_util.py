@@ -226,6 +226,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm23_vectors():
+    """CALL_OP"""
+    return evm2_vectors("evm23")
+
+
 def evm22_vectors():
     """ErrorOutOfGasCall"""
     return evm2_vectors("evm22")
