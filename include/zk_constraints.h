@@ -1063,7 +1063,215 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_EOC_AL_PREV_TYPE, ZKE_ASSERT, "instruction.py:1069 value_prev.value() of a Word")             \
   X(EV_EOC_WARM_BOOL, ZKE_ASSERT, "call_gadget.py:114 select(is_warm_access, ..): not a bool")       \
   X(EV_EOC_CMP_RANGE, ZKE_ASSERT, "error_oog_call.py:35 compare(gas_left, gas_cost, 8): range assert") \
-  X(EV_EOC_NOT_ENOUGH, ZKE_ASSERT, "error_oog_call.py:36 gas_left < gas_cost")
+  X(EV_EOC_NOT_ENOUGH, ZKE_ASSERT, "error_oog_call.py:36 gas_left < gas_cost")                 \
+  X(EV_CALL_RESP_OPCODE, ZKE_UNSAT, "callop.py:17 responsible_opcode_lookup(opcode)")                \
+  X(EV_CALL_TXID_UNSAT, ZKE_UNSAT, "callop.py:21 call_context_lookup(TxId) unsat")                   \
+  X(EV_CALL_TXID_AMBIG, ZKE_AMBIG, "callop.py:21 call_context_lookup(TxId) ambiguous")               \
+  X(EV_CALL_TXID_TYPE, ZKE_ASSERT, "callop.py:21 call_context_lookup(TxId): .value() of a Word")     \
+  X(EV_CALL_REVEND_UNSAT, ZKE_UNSAT, "callop.py:22 reversion_info: RwCounterEndOfReversion unsat")   \
+  X(EV_CALL_REVEND_AMBIG, ZKE_AMBIG, "callop.py:22 reversion_info: RwCounterEndOfReversion ambiguous") \
+  X(EV_CALL_REVEND_TYPE, ZKE_ASSERT, "callop.py:22 reversion_info: RwCounterEndOfReversion: .value() of a Word") \
+  X(EV_CALL_PERSIST_UNSAT, ZKE_UNSAT, "callop.py:22 reversion_info: IsPersistent unsat")             \
+  X(EV_CALL_PERSIST_AMBIG, ZKE_AMBIG, "callop.py:22 reversion_info: IsPersistent ambiguous")         \
+  X(EV_CALL_PERSIST_TYPE, ZKE_ASSERT, "callop.py:22 reversion_info: IsPersistent: .value() of a Word") \
+  X(EV_CALL_SELF_UNSAT, ZKE_UNSAT, "callop.py:23-25 call_context_lookup_word(CalleeAddress) unsat")  \
+  X(EV_CALL_SELF_AMBIG, ZKE_AMBIG, "callop.py:23-25 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_CALL_SELF_DOMAIN, ZKE_VALUE, "callop.py:26 word_to_address(current callee address): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_SELF_RANGE, ZKE_RANGE, "callop.py:26 word_to_address(current callee address): more than 20 bytes") \
+  X(EV_CALL_STATIC_UNSAT, ZKE_UNSAT, "callop.py:27 call_context_lookup(IsStatic) unsat")             \
+  X(EV_CALL_STATIC_AMBIG, ZKE_AMBIG, "callop.py:27 call_context_lookup(IsStatic) ambiguous")         \
+  X(EV_CALL_STATIC_TYPE, ZKE_ASSERT, "callop.py:27 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_CALL_DEPTH_UNSAT, ZKE_UNSAT, "callop.py:28 call_context_lookup(Depth) unsat")                 \
+  X(EV_CALL_DEPTH_AMBIG, ZKE_AMBIG, "callop.py:28 call_context_lookup(Depth) ambiguous")             \
+  X(EV_CALL_DEPTH_TYPE, ZKE_ASSERT, "callop.py:28 call_context_lookup(Depth): .value() of a Word")   \
+  X(EV_CALL_PCALLER_UNSAT, ZKE_UNSAT, "callop.py:31 call_context_lookup_word(CallerAddress) (DELEGATECALL) unsat") \
+  X(EV_CALL_PCALLER_AMBIG, ZKE_AMBIG, "callop.py:31 call_context_lookup_word(CallerAddress) (DELEGATECALL) ambiguous") \
+  X(EV_CALL_PVALUE_UNSAT, ZKE_UNSAT, "callop.py:32 call_context_lookup_word(Value) (DELEGATECALL) unsat") \
+  X(EV_CALL_PVALUE_AMBIG, ZKE_AMBIG, "callop.py:32 call_context_lookup_word(Value) (DELEGATECALL) ambiguous") \
+  X(EV_CALL_OPCODE, ZKE_ASSERT, "call_gadget.py:51 exactly one of CALL / CALLCODE / DELEGATECALL / STATICCALL") \
+  X(EV_CALL_POP0_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop gas unsat")                       \
+  X(EV_CALL_POP0_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop gas ambiguous")                   \
+  X(EV_CALL_POP1_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop callee address unsat")            \
+  X(EV_CALL_POP1_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop callee address ambiguous")        \
+  X(EV_CALL_POP2_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop value unsat")                     \
+  X(EV_CALL_POP2_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop value ambiguous")                 \
+  X(EV_CALL_POP3_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop cd_offset unsat")                 \
+  X(EV_CALL_POP3_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop cd_offset ambiguous")             \
+  X(EV_CALL_POP4_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop cd_length unsat")                 \
+  X(EV_CALL_POP4_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop cd_length ambiguous")             \
+  X(EV_CALL_POP5_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop rd_offset unsat")                 \
+  X(EV_CALL_POP5_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop rd_offset ambiguous")             \
+  X(EV_CALL_POP6_UNSAT, ZKE_UNSAT, "call_gadget.py:53-63 stack_pop rd_length unsat")                 \
+  X(EV_CALL_POP6_AMBIG, ZKE_AMBIG, "call_gadget.py:53-63 stack_pop rd_length ambiguous")             \
+  X(EV_CALL_PUSH_UNSAT, ZKE_UNSAT, "call_gadget.py:64 stack_push result unsat")                      \
+  X(EV_CALL_PUSH_AMBIG, ZKE_AMBIG, "call_gadget.py:64 stack_push result ambiguous")                  \
+  X(EV_CALL_RESULT_WORD, ZKE_ASSERT, "call_gadget.py:66 result == Word.from_lo(is_success)")         \
+  X(EV_CALL_RESULT_BOOL, ZKE_ASSERT, "call_gadget.py:69 is_success is a bool")                       \
+  X(EV_CALL_GAS_DOMAIN, ZKE_VALUE, "call_gadget.py:73 gas: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_GAS_RANGE, ZKE_RANGE, "call_gadget.py:73 gas: more than 8 bytes")                        \
+  X(EV_CALL_CALLEE_DOMAIN, ZKE_VALUE, "call_gadget.py:85 callee address: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_CALLEE_RANGE, ZKE_RANGE, "call_gadget.py:85 callee address: more than 20 bytes")         \
+  X(EV_CALL_CDLEN_DOMAIN, ZKE_VALUE, "call_gadget.py:86 cd_length: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_CDLEN_RANGE, ZKE_RANGE, "call_gadget.py:86 cd_length: more than 5 bytes")                \
+  X(EV_CALL_CDOFF_DOMAIN, ZKE_VALUE, "call_gadget.py:86 cd_offset: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_CDOFF_RANGE, ZKE_RANGE, "call_gadget.py:86 cd_offset: more than 5 bytes")                \
+  X(EV_CALL_RDLEN_DOMAIN, ZKE_VALUE, "call_gadget.py:87 rd_length: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_RDLEN_RANGE, ZKE_RANGE, "call_gadget.py:87 rd_length: more than 5 bytes")                \
+  X(EV_CALL_RDOFF_DOMAIN, ZKE_VALUE, "call_gadget.py:87 rd_offset: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_RDOFF_RANGE, ZKE_RANGE, "call_gadget.py:87 rd_offset: more than 5 bytes")                \
+  X(EV_CALL_CD_MEMSIZE_RANGE, ZKE_RANGE, "call_gadget.py:92 memory_expansion_dynamic_length: call-data memory size beyond 4 bytes") \
+  X(EV_CALL_MEM_MAX, ZKE_ASSERT, "call_gadget.py:92 max(): curr.memory_word_size beyond 4 bytes")    \
+  X(EV_CALL_RD_MEMSIZE_RANGE, ZKE_RANGE, "call_gadget.py:92 memory_expansion_dynamic_length: return-data memory size beyond 4 bytes") \
+  X(EV_CALL_HASH_UNSAT, ZKE_UNSAT, "call_gadget.py:100 account_read_word(CodeHash) unsat")           \
+  X(EV_CALL_HASH_AMBIG, ZKE_AMBIG, "call_gadget.py:100 account_read_word(CodeHash) ambiguous")       \
+  X(EV_CALL_CALLER_WORD, ZKE_ASSERT, "callop.py:51-53 select_word: a half of the parent caller address >= 2^128") \
+  X(EV_CALL_CALLER_DOMAIN, ZKE_VALUE, "callop.py:54 word_to_address(caller address): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CALL_CALLER_RANGE, ZKE_RANGE, "callop.py:54 word_to_address(caller address): more than 20 bytes") \
+  X(EV_CALL_AL_UNSAT, ZKE_UNSAT, "callop.py:57-59 add_account_to_access_list unsat")                 \
+  X(EV_CALL_AL_AMBIG, ZKE_AMBIG, "callop.py:57-59 add_account_to_access_list ambiguous")             \
+  X(EV_CALL_AL_REV_UNSAT, ZKE_UNSAT, "callop.py:57-59 add_account_to_access_list: reversion row unsat") \
+  X(EV_CALL_AL_REV_AMBIG, ZKE_AMBIG, "callop.py:57-59 add_account_to_access_list: reversion row ambiguous") \
+  X(EV_CALL_AL_PREV_TYPE, ZKE_ASSERT, "instruction.py:1057 value_prev.value() of a Word")            \
+  X(EV_CALL_VALUE_STATIC, ZKE_ASSERT, "callop.py:63 has_value * is_static == 0")                     \
+  X(EV_CALL_CREVEND_UNSAT, ZKE_UNSAT, "callop.py:66 reversion_info(callee): RwCounterEndOfReversion unsat") \
+  X(EV_CALL_CREVEND_AMBIG, ZKE_AMBIG, "callop.py:66 reversion_info(callee): RwCounterEndOfReversion ambiguous") \
+  X(EV_CALL_CREVEND_TYPE, ZKE_ASSERT, "callop.py:66 reversion_info(callee): RwCounterEndOfReversion: .value() of a Word") \
+  X(EV_CALL_CPERSIST_UNSAT, ZKE_UNSAT, "callop.py:66 reversion_info(callee): IsPersistent unsat")    \
+  X(EV_CALL_CPERSIST_AMBIG, ZKE_AMBIG, "callop.py:66 reversion_info(callee): IsPersistent ambiguous") \
+  X(EV_CALL_CPERSIST_TYPE, ZKE_ASSERT, "callop.py:66 reversion_info(callee): IsPersistent: .value() of a Word") \
+  X(EV_CALL_CPERSIST_EQ, ZKE_ASSERT, "callop.py:67-70 callee is_persistent == caller is_persistent * is_success") \
+  X(EV_CALL_CREVEND_EQ, ZKE_ASSERT, "callop.py:76-79 callee rw_counter_end_of_reversion == caller rw_counter_of_reversion()") \
+  X(EV_CALL_BAL_UNSAT, ZKE_UNSAT, "callop.py:84 account_read_word(caller, Balance) unsat")           \
+  X(EV_CALL_BAL_AMBIG, ZKE_AMBIG, "callop.py:84 account_read_word(caller, Balance) ambiguous")       \
+  X(EV_CALL_BAL_CMP_RANGE, ZKE_ASSERT, "callop.py:86 compare_word(caller_balance, value): 16-byte range assert") \
+  X(EV_CALL_DEPTH_RANGE, ZKE_ASSERT, "callop.py:87 compare(depth, 1025, 2): range assert")           \
+  X(EV_CALL_PRECHECK_SUCCESS, ZKE_ASSERT, "callop.py:91-92 pre-check failed => is_success == 0")     \
+  X(EV_CALL_SEND_UNSAT, ZKE_UNSAT, "callop.py:96 transfer: sub_balance account write unsat")         \
+  X(EV_CALL_SEND_AMBIG, ZKE_AMBIG, "callop.py:96 transfer: sub_balance account write ambiguous")     \
+  X(EV_CALL_SEND_REV_UNSAT, ZKE_UNSAT, "callop.py:96 transfer: sub_balance reversion row unsat")     \
+  X(EV_CALL_SEND_REV_AMBIG, ZKE_AMBIG, "callop.py:96 transfer: sub_balance reversion row ambiguous") \
+  X(EV_CALL_SEND_EQ, ZKE_ASSERT, "instruction.py:1011 sender balance_prev == balance + value")       \
+  X(EV_CALL_SEND_CARRY, ZKE_ASSERT, "instruction.py:1012 sender carry == 0")                         \
+  X(EV_CALL_RECV_UNSAT, ZKE_UNSAT, "callop.py:96 transfer: add_balance account write unsat")         \
+  X(EV_CALL_RECV_AMBIG, ZKE_AMBIG, "callop.py:96 transfer: add_balance account write ambiguous")     \
+  X(EV_CALL_RECV_REV_UNSAT, ZKE_UNSAT, "callop.py:96 transfer: add_balance reversion row unsat")     \
+  X(EV_CALL_RECV_REV_AMBIG, ZKE_AMBIG, "callop.py:96 transfer: add_balance reversion row ambiguous") \
+  X(EV_CALL_RECV_EQ, ZKE_ASSERT, "instruction.py:997 receiver balance == balance_prev + value")      \
+  X(EV_CALL_RECV_CARRY, ZKE_ASSERT, "instruction.py:998 receiver carry == 0")                        \
+  X(EV_CALL_CALLCODE_BALANCE, ZKE_ASSERT, "callop.py:98-99 CALLCODE succeeded => balance sufficient") \
+  X(EV_CALL_WARM_BOOL, ZKE_ASSERT, "call_gadget.py:114 select(is_warm_access, ..): not a bool")      \
+  X(EV_CALL_GAS_64TH_RANGE, ZKE_RANGE, "callop.py:110 constant_divmod(gas_available, 64, 8): quotient beyond 8 bytes (not enough gas)") \
+  X(EV_CALL_GAS_MIN_RANGE, ZKE_ASSERT, "callop.py:114 min(all_but_one_64th_gas, gas, 8): range assert") \
+  X(EV_CALL_PRECOMPILE_STATE, ZKE_ASSERT, "callop.py:121-123 callee is a precompile <=> the next state is a precompile state") \
+  X(EV_CALL_LAST0_UNSAT, ZKE_UNSAT, "callop.py:130-138 call_context_lookup(LastCalleeId, Write) unsat") \
+  X(EV_CALL_LAST0_AMBIG, ZKE_AMBIG, "callop.py:130-138 call_context_lookup(LastCalleeId, Write) ambiguous") \
+  X(EV_CALL_LAST0_TYPE, ZKE_ASSERT, "callop.py:130-138 call_context_lookup(LastCalleeId, Write): .value() of a Word") \
+  X(EV_CALL_LAST0_EQ, ZKE_ASSERT, "callop.py:135-138 LastCalleeId == 0")                             \
+  X(EV_CALL_LAST1_UNSAT, ZKE_UNSAT, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataOffset, Write) unsat") \
+  X(EV_CALL_LAST1_AMBIG, ZKE_AMBIG, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataOffset, Write) ambiguous") \
+  X(EV_CALL_LAST1_TYPE, ZKE_ASSERT, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataOffset, Write): .value() of a Word") \
+  X(EV_CALL_LAST1_EQ, ZKE_ASSERT, "callop.py:135-138 LastCalleeReturnDataOffset == 0")               \
+  X(EV_CALL_LAST2_UNSAT, ZKE_UNSAT, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataLength, Write) unsat") \
+  X(EV_CALL_LAST2_AMBIG, ZKE_AMBIG, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataLength, Write) ambiguous") \
+  X(EV_CALL_LAST2_TYPE, ZKE_ASSERT, "callop.py:130-138 call_context_lookup(LastCalleeReturnDataLength, Write): .value() of a Word") \
+  X(EV_CALL_LAST2_EQ, ZKE_ASSERT, "callop.py:135-138 LastCalleeReturnDataLength == 0")               \
+  X(EV_CALL_SAME_RWC, ZKE_ASSERT, "callop.py:140-151 stay in the caller: rw_counter delta")          \
+  X(EV_CALL_SAME_PC, ZKE_ASSERT, "callop.py:140-151 stay in the caller: program_counter + 1")        \
+  X(EV_CALL_SAME_SP, ZKE_ASSERT, "callop.py:140-151 stay in the caller: stack_pointer delta")        \
+  X(EV_CALL_SAME_GAS, ZKE_ASSERT, "callop.py:140-151 stay in the caller: gas_left delta")            \
+  X(EV_CALL_SAME_MEM, ZKE_ASSERT, "callop.py:140-151 stay in the caller: memory_word_size to next")  \
+  X(EV_CALL_SAME_REV, ZKE_ASSERT, "callop.py:140-151 stay in the caller: reversible_write_counter + 3") \
+  X(EV_CALL_SAME_CALL_ID, ZKE_ASSERT, "callop.py:140-151 stay in the caller: call_id same")          \
+  X(EV_CALL_SAME_IS_ROOT, ZKE_ASSERT, "callop.py:140-151 stay in the caller: is_root same")          \
+  X(EV_CALL_SAME_IS_CREATE, ZKE_ASSERT, "callop.py:140-151 stay in the caller: is_create same")      \
+  X(EV_CALL_SAME_CODE_HASH, ZKE_ASSERT, "callop.py:140-151 stay in the caller: code_hash same")      \
+  X(EV_CALL_PRECOMPILE, ZKE_NOTIMPL, "callop.py:158-277 call to a precompile: needs StepState.aux_data, which this build's 13-cell step layout does not carry (DESIGN.md)") \
+  X(EV_CALL_SAVE0_UNSAT, ZKE_UNSAT, "callop.py:280-297 call_context_lookup(ProgramCounter, Write) unsat") \
+  X(EV_CALL_SAVE0_AMBIG, ZKE_AMBIG, "callop.py:280-297 call_context_lookup(ProgramCounter, Write) ambiguous") \
+  X(EV_CALL_SAVE0_TYPE, ZKE_ASSERT, "callop.py:280-297 call_context_lookup(ProgramCounter, Write): .value() of a Word") \
+  X(EV_CALL_SAVE0_EQ, ZKE_ASSERT, "callop.py:294-297 saved ProgramCounter")                          \
+  X(EV_CALL_SAVE1_UNSAT, ZKE_UNSAT, "callop.py:280-297 call_context_lookup(StackPointer, Write) unsat") \
+  X(EV_CALL_SAVE1_AMBIG, ZKE_AMBIG, "callop.py:280-297 call_context_lookup(StackPointer, Write) ambiguous") \
+  X(EV_CALL_SAVE1_TYPE, ZKE_ASSERT, "callop.py:280-297 call_context_lookup(StackPointer, Write): .value() of a Word") \
+  X(EV_CALL_SAVE1_EQ, ZKE_ASSERT, "callop.py:294-297 saved StackPointer")                            \
+  X(EV_CALL_SAVE2_UNSAT, ZKE_UNSAT, "callop.py:280-297 call_context_lookup(GasLeft, Write) unsat")   \
+  X(EV_CALL_SAVE2_AMBIG, ZKE_AMBIG, "callop.py:280-297 call_context_lookup(GasLeft, Write) ambiguous") \
+  X(EV_CALL_SAVE2_TYPE, ZKE_ASSERT, "callop.py:280-297 call_context_lookup(GasLeft, Write): .value() of a Word") \
+  X(EV_CALL_SAVE2_EQ, ZKE_ASSERT, "callop.py:294-297 saved GasLeft")                                 \
+  X(EV_CALL_SAVE3_UNSAT, ZKE_UNSAT, "callop.py:280-297 call_context_lookup(MemorySize, Write) unsat") \
+  X(EV_CALL_SAVE3_AMBIG, ZKE_AMBIG, "callop.py:280-297 call_context_lookup(MemorySize, Write) ambiguous") \
+  X(EV_CALL_SAVE3_TYPE, ZKE_ASSERT, "callop.py:280-297 call_context_lookup(MemorySize, Write): .value() of a Word") \
+  X(EV_CALL_SAVE3_EQ, ZKE_ASSERT, "callop.py:294-297 saved MemorySize")                              \
+  X(EV_CALL_SAVE4_UNSAT, ZKE_UNSAT, "callop.py:280-297 call_context_lookup(ReversibleWriteCounter, Write) unsat") \
+  X(EV_CALL_SAVE4_AMBIG, ZKE_AMBIG, "callop.py:280-297 call_context_lookup(ReversibleWriteCounter, Write) ambiguous") \
+  X(EV_CALL_SAVE4_TYPE, ZKE_ASSERT, "callop.py:280-297 call_context_lookup(ReversibleWriteCounter, Write): .value() of a Word") \
+  X(EV_CALL_SAVE4_EQ, ZKE_ASSERT, "callop.py:294-297 saved ReversibleWriteCounter")                  \
+  X(EV_CALL_CTX0_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CallerId, callee) unsat") \
+  X(EV_CALL_CTX0_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CallerId, callee) ambiguous") \
+  X(EV_CALL_CTX0_EQ, ZKE_ASSERT, "callop.py:327-330 callee CallerId")                                \
+  X(EV_CALL_CTX1_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(TxId, callee) unsat") \
+  X(EV_CALL_CTX1_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(TxId, callee) ambiguous") \
+  X(EV_CALL_CTX1_EQ, ZKE_ASSERT, "callop.py:327-330 callee TxId")                                    \
+  X(EV_CALL_CTX2_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(Depth, callee) unsat") \
+  X(EV_CALL_CTX2_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(Depth, callee) ambiguous") \
+  X(EV_CALL_CTX2_EQ, ZKE_ASSERT, "callop.py:327-330 callee Depth")                                   \
+  X(EV_CALL_CTX3_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CallerAddress, callee) unsat") \
+  X(EV_CALL_CTX3_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CallerAddress, callee) ambiguous") \
+  X(EV_CALL_CTX3_EQ, ZKE_ASSERT, "callop.py:327-330 callee CallerAddress")                           \
+  X(EV_CALL_CTX4_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CalleeAddress, callee) unsat") \
+  X(EV_CALL_CTX4_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CalleeAddress, callee) ambiguous") \
+  X(EV_CALL_CTX4_EQ, ZKE_ASSERT, "callop.py:327-330 callee CalleeAddress")                           \
+  X(EV_CALL_CTX5_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CallDataOffset, callee) unsat") \
+  X(EV_CALL_CTX5_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CallDataOffset, callee) ambiguous") \
+  X(EV_CALL_CTX5_EQ, ZKE_ASSERT, "callop.py:327-330 callee CallDataOffset")                          \
+  X(EV_CALL_CTX6_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CallDataLength, callee) unsat") \
+  X(EV_CALL_CTX6_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CallDataLength, callee) ambiguous") \
+  X(EV_CALL_CTX6_EQ, ZKE_ASSERT, "callop.py:327-330 callee CallDataLength")                          \
+  X(EV_CALL_CTX7_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(ReturnDataOffset, callee) unsat") \
+  X(EV_CALL_CTX7_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(ReturnDataOffset, callee) ambiguous") \
+  X(EV_CALL_CTX7_EQ, ZKE_ASSERT, "callop.py:327-330 callee ReturnDataOffset")                        \
+  X(EV_CALL_CTX8_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(ReturnDataLength, callee) unsat") \
+  X(EV_CALL_CTX8_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(ReturnDataLength, callee) ambiguous") \
+  X(EV_CALL_CTX8_EQ, ZKE_ASSERT, "callop.py:327-330 callee ReturnDataLength")                        \
+  X(EV_CALL_CTX9_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(Value, callee) unsat") \
+  X(EV_CALL_CTX9_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(Value, callee) ambiguous") \
+  X(EV_CALL_CTX9_EQ, ZKE_ASSERT, "callop.py:327-330 callee Value")                                   \
+  X(EV_CALL_CTX10_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(IsSuccess, callee) unsat") \
+  X(EV_CALL_CTX10_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(IsSuccess, callee) ambiguous") \
+  X(EV_CALL_CTX10_EQ, ZKE_ASSERT, "callop.py:327-330 callee IsSuccess")                              \
+  X(EV_CALL_CTX11_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(IsStatic, callee) unsat") \
+  X(EV_CALL_CTX11_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(IsStatic, callee) ambiguous") \
+  X(EV_CALL_CTX11_EQ, ZKE_ASSERT, "callop.py:327-330 callee IsStatic")                               \
+  X(EV_CALL_CTX12_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(LastCalleeId, callee) unsat") \
+  X(EV_CALL_CTX12_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(LastCalleeId, callee) ambiguous") \
+  X(EV_CALL_CTX12_EQ, ZKE_ASSERT, "callop.py:327-330 callee LastCalleeId")                           \
+  X(EV_CALL_CTX13_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(LastCalleeReturnDataOffset, callee) unsat") \
+  X(EV_CALL_CTX13_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(LastCalleeReturnDataOffset, callee) ambiguous") \
+  X(EV_CALL_CTX13_EQ, ZKE_ASSERT, "callop.py:327-330 callee LastCalleeReturnDataOffset")             \
+  X(EV_CALL_CTX14_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(LastCalleeReturnDataLength, callee) unsat") \
+  X(EV_CALL_CTX14_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(LastCalleeReturnDataLength, callee) ambiguous") \
+  X(EV_CALL_CTX14_EQ, ZKE_ASSERT, "callop.py:327-330 callee LastCalleeReturnDataLength")             \
+  X(EV_CALL_CTX15_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(IsRoot, callee) unsat") \
+  X(EV_CALL_CTX15_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(IsRoot, callee) ambiguous") \
+  X(EV_CALL_CTX15_EQ, ZKE_ASSERT, "callop.py:327-330 callee IsRoot")                                 \
+  X(EV_CALL_CTX16_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(IsCreate, callee) unsat") \
+  X(EV_CALL_CTX16_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(IsCreate, callee) ambiguous") \
+  X(EV_CALL_CTX16_EQ, ZKE_ASSERT, "callop.py:327-330 callee IsCreate")                               \
+  X(EV_CALL_CTX17_UNSAT, ZKE_UNSAT, "callop.py:301-330 call_context_lookup_word(CodeHash, callee) unsat") \
+  X(EV_CALL_CTX17_AMBIG, ZKE_AMBIG, "callop.py:301-330 call_context_lookup_word(CodeHash, callee) ambiguous") \
+  X(EV_CALL_CTX17_EQ, ZKE_ASSERT, "callop.py:327-330 callee CodeHash")                               \
+  X(EV_CALL_VALUE_WORD, ZKE_ASSERT, "callop.py:313 select_word: a half of the value >= 2^128")       \
+  X(EV_CALL_NC_RWC, ZKE_ASSERT, "callop.py:335-344 new context: rw_counter delta")                   \
+  X(EV_CALL_NC_CALL_ID, ZKE_ASSERT, "callop.py:335-344 new context: call_id to the callee's")        \
+  X(EV_CALL_NC_IS_ROOT, ZKE_ASSERT, "callop.py:335-344 new context: is_root to False")               \
+  X(EV_CALL_NC_IS_CREATE, ZKE_ASSERT, "callop.py:335-344 new context: is_create to False")           \
+  X(EV_CALL_NC_CODE_HASH, ZKE_ASSERT, "callop.py:335-344 new context: code_hash to the callee's")    \
+  X(EV_CALL_NC_GAS, ZKE_ASSERT, "callop.py:335-344 new context: gas_left to the callee's")           \
+  X(EV_CALL_NC_REV, ZKE_ASSERT, "callop.py:335-344 new context: reversible_write_counter to 2")      \
+  X(EV_CALL_NC_LOG, ZKE_ASSERT, "callop.py:335-344 new context: log_id same")                        \
+  X(EV_CALL_NC_PC, ZKE_ASSERT, "callop.py:335-344 new context: program_counter to 0")                \
+  X(EV_CALL_NC_SP, ZKE_ASSERT, "callop.py:335-344 new context: stack_pointer to 1024")               \
+  X(EV_CALL_NC_MEM, ZKE_ASSERT, "callop.py:335-344 new context: memory_word_size to 0")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

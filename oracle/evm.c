@@ -942,6 +942,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_log.h"
 #include "evm_exp.h"
 #include "evm_return.h"
+#include "evm_call.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -986,7 +987,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH ||
                                   st == ZK_ES_EXP || st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore ||
                                   st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN ||
-                                  st == ZK_ES_ErrorOutOfGasCall);
+                                  st == ZK_ES_ErrorOutOfGasCall || st == ZK_ES_CALL_OP);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1055,6 +1056,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_ErrorInvalidCreationCode) gadget_error_invalid_creation_code(e, i, row, opcode);
   else if (st == ZK_ES_RETURN) gadget_return_revert(e, i, row, opcode);
   else if (st == ZK_ES_ErrorOutOfGasCall) gadget_error_oog_call(e, i, row, opcode);
+  else if (st == ZK_ES_CALL_OP) gadget_callop(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 
