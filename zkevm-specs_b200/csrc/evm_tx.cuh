@@ -524,7 +524,8 @@ ZK_HD_NOINLINE void gadget_begin_tx(const StepCtx& s, bool is_first) {
   EV_CHECK(EV_BT_GAS_CMP_RANGE, (tx_gas.l[3] >> 56) == 0 && (intrinsic.l[3] >> 56) == 0);
   const bool gas_not_enough = fr_lt(tx_gas, intrinsic);
   const Fr gas_left = gas_not_enough ? tx_gas : fr_sub(tx_gas, intrinsic);
-  const Fr contract = contract_address(caller, tx_nonce);
+  // (the reference derives it for every transaction; it can only matter, and is only used, for a creation)
+  const Fr contract = is_create ? contract_address(caller, tx_nonce) : fr_u64(0);
   const Fr callee_address = is_create ? contract : callee;
   for (int k = 0; k < 3; k++) {  // access list: coinbase, caller, callee
     Fr key[14];

@@ -153,7 +153,7 @@ ZK_HD int probe_slots(const IndexDev& ix, const u64* slots, u32 slot_mask, const
   const u32 fp = (u32)(mix >> 32);
   u32 b = (u32)mix & slot_mask;
 #ifdef __CUDA_ARCH__
-#define ZK_GROUP_ANY(p) __any_sync(mask, (p))
+#define ZK_GROUP_ANY(p) ((mask & (mask - 1)) ? __any_sync(mask, (p)) : (p))  /* a single-lane mask (lane-private lookups of the group kernels) needs no vote */
 #else
 #define ZK_GROUP_ANY(p) (p)
   (void)mask;
@@ -315,7 +315,7 @@ ZK_HD int heads_probe(const IndexDev& ix, const Fr& hlo, const Fr& hhi, u32* hea
   *head = 0;
   *len = 0;
 #ifdef __CUDA_ARCH__
-#define ZK_GROUP_ANY(p) __any_sync(mask, (p))
+#define ZK_GROUP_ANY(p) ((mask & (mask - 1)) ? __any_sync(mask, (p)) : (p))  /* a single-lane mask (lane-private lookups of the group kernels) needs no vote */
 #else
 #define ZK_GROUP_ANY(p) (p)
   (void)mask;
