@@ -1271,7 +1271,184 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CALL_NC_LOG, ZKE_ASSERT, "callop.py:335-344 new context: log_id same")                        \
   X(EV_CALL_NC_PC, ZKE_ASSERT, "callop.py:335-344 new context: program_counter to 0")                \
   X(EV_CALL_NC_SP, ZKE_ASSERT, "callop.py:335-344 new context: stack_pointer to 1024")               \
-  X(EV_CALL_NC_MEM, ZKE_ASSERT, "callop.py:335-344 new context: memory_word_size to 0")
+  X(EV_CALL_NC_MEM, ZKE_ASSERT, "callop.py:335-344 new context: memory_word_size to 0") \
+  X(EV_CR_RESP_OPCODE, ZKE_UNSAT, "create.py:24 responsible_opcode_lookup(opcode)") \
+  X(EV_CR_POP0_UNSAT, ZKE_UNSAT, "create.py:30-33 stack_pop value unsat") \
+  X(EV_CR_POP0_AMBIG, ZKE_AMBIG, "create.py:30-33 stack_pop value ambiguous") \
+  X(EV_CR_POP1_UNSAT, ZKE_UNSAT, "create.py:30-33 stack_pop offset unsat") \
+  X(EV_CR_POP1_AMBIG, ZKE_AMBIG, "create.py:30-33 stack_pop offset ambiguous") \
+  X(EV_CR_POP2_UNSAT, ZKE_UNSAT, "create.py:30-33 stack_pop size unsat") \
+  X(EV_CR_POP2_AMBIG, ZKE_AMBIG, "create.py:30-33 stack_pop size ambiguous") \
+  X(EV_CR_POP3_UNSAT, ZKE_UNSAT, "create.py:30-33 stack_pop salt (CREATE2) unsat") \
+  X(EV_CR_POP3_AMBIG, ZKE_AMBIG, "create.py:30-33 stack_pop salt (CREATE2) ambiguous") \
+  X(EV_CR_PUSH_UNSAT, ZKE_UNSAT, "create.py:34 stack_push contract address unsat") \
+  X(EV_CR_PUSH_AMBIG, ZKE_AMBIG, "create.py:34 stack_push contract address ambiguous") \
+  X(EV_CR_OFF_DOMAIN, ZKE_VALUE, "create.py:36 word_to_fq(offset, 5): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CR_OFF_RANGE, ZKE_RANGE, "create.py:36 word_to_fq(offset, 5): more than 5 bytes") \
+  X(EV_CR_SIZE_DOMAIN, ZKE_VALUE, "create.py:37 word_to_fq(size, 5): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CR_SIZE_RANGE, ZKE_RANGE, "create.py:37 word_to_fq(size, 5): more than 5 bytes") \
+  X(EV_CR_DEPTH_UNSAT, ZKE_UNSAT, "create.py:39 call_context_lookup(Depth) unsat") \
+  X(EV_CR_DEPTH_AMBIG, ZKE_AMBIG, "create.py:39 call_context_lookup(Depth) ambiguous") \
+  X(EV_CR_DEPTH_TYPE, ZKE_ASSERT, "create.py:39 call_context_lookup(Depth): .value() of a Word") \
+  X(EV_CR_TXID_UNSAT, ZKE_UNSAT, "create.py:40 call_context_lookup(TxId) unsat") \
+  X(EV_CR_TXID_AMBIG, ZKE_AMBIG, "create.py:40 call_context_lookup(TxId) ambiguous") \
+  X(EV_CR_TXID_TYPE, ZKE_ASSERT, "create.py:40 call_context_lookup(TxId): .value() of a Word") \
+  X(EV_CR_CALLER_UNSAT, ZKE_UNSAT, "create.py:41 call_context_lookup_word(CallerAddress) unsat") \
+  X(EV_CR_CALLER_AMBIG, ZKE_AMBIG, "create.py:41 call_context_lookup_word(CallerAddress) ambiguous") \
+  X(EV_CR_CALLER_DOMAIN, ZKE_VALUE, "create.py:42 word_to_address(caller address): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CR_CALLER_RANGE, ZKE_RANGE, "create.py:42 word_to_address(caller address): more than 20 bytes") \
+  X(EV_CR_NONCE_UNSAT, ZKE_UNSAT, "create.py:43 account_write(caller, Nonce) unsat") \
+  X(EV_CR_NONCE_AMBIG, ZKE_AMBIG, "create.py:43 account_write(caller, Nonce) ambiguous") \
+  X(EV_CR_NONCE_TYPE, ZKE_ASSERT, "create.py:43 account_write(caller, Nonce): .value() of a Word") \
+  X(EV_CR_NONCE_PREV_TYPE, ZKE_ASSERT, "create.py:43 account_write(caller, Nonce): value_prev.value() of a Word") \
+  X(EV_CR_BAL_UNSAT, ZKE_UNSAT, "create.py:44 account_read(caller, Balance) unsat") \
+  X(EV_CR_BAL_AMBIG, ZKE_AMBIG, "create.py:44 account_read(caller, Balance) ambiguous") \
+  X(EV_CR_BAL_TYPE, ZKE_ASSERT, "create.py:44 account_read(caller, Balance): .value() of a Word") \
+  X(EV_CR_SUCCESS_UNSAT, ZKE_UNSAT, "create.py:45 call_context_lookup(IsSuccess) unsat") \
+  X(EV_CR_SUCCESS_AMBIG, ZKE_AMBIG, "create.py:45 call_context_lookup(IsSuccess) ambiguous") \
+  X(EV_CR_SUCCESS_TYPE, ZKE_ASSERT, "create.py:45 call_context_lookup(IsSuccess): .value() of a Word") \
+  X(EV_CR_STATIC_UNSAT, ZKE_UNSAT, "create.py:46 call_context_lookup(IsStatic) unsat") \
+  X(EV_CR_STATIC_AMBIG, ZKE_AMBIG, "create.py:46 call_context_lookup(IsStatic) ambiguous") \
+  X(EV_CR_STATIC_TYPE, ZKE_ASSERT, "create.py:46 call_context_lookup(IsStatic): .value() of a Word") \
+  X(EV_CR_REVEND_UNSAT, ZKE_UNSAT, "create.py:47 reversion_info: RwCounterEndOfReversion unsat") \
+  X(EV_CR_REVEND_AMBIG, ZKE_AMBIG, "create.py:47 reversion_info: RwCounterEndOfReversion ambiguous") \
+  X(EV_CR_REVEND_TYPE, ZKE_ASSERT, "create.py:47 reversion_info: RwCounterEndOfReversion: .value() of a Word") \
+  X(EV_CR_PERSIST_UNSAT, ZKE_UNSAT, "create.py:47 reversion_info: IsPersistent unsat") \
+  X(EV_CR_PERSIST_AMBIG, ZKE_AMBIG, "create.py:47 reversion_info: IsPersistent ambiguous") \
+  X(EV_CR_PERSIST_TYPE, ZKE_ASSERT, "create.py:47 reversion_info: IsPersistent: .value() of a Word") \
+  X(EV_CR_MEMSIZE_RANGE, ZKE_RANGE, "create.py:59-62 memory_expansion: memory size beyond 4 bytes") \
+  X(EV_CR_MEM_MAX, ZKE_ASSERT, "create.py:59-62 memory_expansion: max(): curr.memory_word_size beyond 4 bytes") \
+  X(EV_CR_WORDLEN_RANGE, ZKE_RANGE, "create.py:68 constant_divmod(size + 31, 32, 4): quotient beyond 4 bytes") \
+  X(EV_CR_GAS_64TH_RANGE, ZKE_RANGE, "create.py:76 constant_divmod(gas_available, 64, 8): quotient beyond 8 bytes") \
+  X(EV_CR_GAS_MIN_RANGE, ZKE_ASSERT, "create.py:81-85 min(all_but_one_64th_gas, gas_left, 8): an operand beyond 8 bytes") \
+  X(EV_CR_DEPTH_RANGE, ZKE_ASSERT, "create.py:89 compare(depth, 1025, 2): depth beyond 2 bytes") \
+  X(EV_CR_BAL_CMP_RANGE, ZKE_ASSERT, "create.py:91 compare_word(balance, value): a half of the value >= 2^128") \
+  X(EV_CR_NONCE_RANGE, ZKE_ASSERT, "create.py:93 compare(nonce_prev, MAX_U64, 8): nonce_prev beyond 8 bytes") \
+  X(EV_CR_AUX_MISSING, ZKE_ASSERT, "create.py:107 curr.aux_data (the init code's hash): not exactly one entry for this step in the step-aux table") \
+  X(EV_CR_ADDR2_DOMAIN, ZKE_VALUE, "instruction.py:1349-1350 salt / code hash .to_bytes(32): a half makes the integer >= 2^256 -> OverflowError") \
+  X(EV_CR_AL_UNSAT, ZKE_UNSAT, "create.py:116 add_account_to_access_list(tx_id, contract_address) unsat") \
+  X(EV_CR_AL_AMBIG, ZKE_AMBIG, "create.py:116 add_account_to_access_list(tx_id, contract_address) ambiguous") \
+  X(EV_CR_AL_PREV_TYPE, ZKE_ASSERT, "instruction.py:1057 value_prev.value() of a Word") \
+  X(EV_CR_CHASH_UNSAT, ZKE_UNSAT, "create.py:120 account_read_word(contract, CodeHash) unsat") \
+  X(EV_CR_CHASH_AMBIG, ZKE_AMBIG, "create.py:120 account_read_word(contract, CodeHash) ambiguous") \
+  X(EV_CR_CNONCE_UNSAT, ZKE_UNSAT, "create.py:121 account_read(contract, Nonce) unsat") \
+  X(EV_CR_CNONCE_AMBIG, ZKE_AMBIG, "create.py:121 account_read(contract, Nonce) ambiguous") \
+  X(EV_CR_CNONCE_TYPE, ZKE_ASSERT, "create.py:121 account_read(contract, Nonce): .value() of a Word") \
+  X(EV_CR_RETURN_DOMAIN, ZKE_VALUE, "create.py:130 word_to_fq(return address word, 20): word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_CR_RETURN_RANGE, ZKE_RANGE, "create.py:130 word_to_fq(return address word, 20): more than 20 bytes") \
+  X(EV_CR_RETURN_EQ, ZKE_ASSERT, "create.py:129-132 pushed address == is_success * contract_address") \
+  X(EV_CR_CREVEND_UNSAT, ZKE_UNSAT, "create.py:135 reversion_info(callee): RwCounterEndOfReversion unsat") \
+  X(EV_CR_CREVEND_AMBIG, ZKE_AMBIG, "create.py:135 reversion_info(callee): RwCounterEndOfReversion ambiguous") \
+  X(EV_CR_CREVEND_TYPE, ZKE_ASSERT, "create.py:135 reversion_info(callee): RwCounterEndOfReversion: .value() of a Word") \
+  X(EV_CR_CPERSIST_UNSAT, ZKE_UNSAT, "create.py:135 reversion_info(callee): IsPersistent unsat") \
+  X(EV_CR_CPERSIST_AMBIG, ZKE_AMBIG, "create.py:135 reversion_info(callee): IsPersistent ambiguous") \
+  X(EV_CR_CPERSIST_TYPE, ZKE_ASSERT, "create.py:135 reversion_info(callee): IsPersistent: .value() of a Word") \
+  X(EV_CR_CPERSIST_EQ, ZKE_ASSERT, "create.py:136-139 callee is_persistent == is_persistent * is_success") \
+  X(EV_CR_SEND_UNSAT, ZKE_UNSAT, "create.py:142-144 transfer: sub_balance(caller) unsat") \
+  X(EV_CR_SEND_AMBIG, ZKE_AMBIG, "create.py:142-144 transfer: sub_balance(caller) ambiguous") \
+  X(EV_CR_SEND_REV_UNSAT, ZKE_UNSAT, "create.py:142-144 transfer: sub_balance(caller): reversion row unsat") \
+  X(EV_CR_SEND_REV_AMBIG, ZKE_AMBIG, "create.py:142-144 transfer: sub_balance(caller): reversion row ambiguous") \
+  X(EV_CR_SEND_EQ, ZKE_ASSERT, "create.py:142-144 transfer: sub_balance(caller): balance_prev / balance == add_words(..)") \
+  X(EV_CR_SEND_CARRY, ZKE_ASSERT, "create.py:142-144 transfer: sub_balance(caller): carry == 0") \
+  X(EV_CR_RECV_UNSAT, ZKE_UNSAT, "create.py:142-144 transfer: add_balance(contract) unsat") \
+  X(EV_CR_RECV_AMBIG, ZKE_AMBIG, "create.py:142-144 transfer: add_balance(contract) ambiguous") \
+  X(EV_CR_RECV_REV_UNSAT, ZKE_UNSAT, "create.py:142-144 transfer: add_balance(contract): reversion row unsat") \
+  X(EV_CR_RECV_REV_AMBIG, ZKE_AMBIG, "create.py:142-144 transfer: add_balance(contract): reversion row ambiguous") \
+  X(EV_CR_RECV_EQ, ZKE_ASSERT, "create.py:142-144 transfer: add_balance(contract): balance_prev / balance == add_words(..)") \
+  X(EV_CR_RECV_CARRY, ZKE_ASSERT, "create.py:142-144 transfer: add_balance(contract): carry == 0") \
+  X(EV_CR_NEWNONCE_UNSAT, ZKE_UNSAT, "create.py:147 account_write(contract, Nonce) unsat") \
+  X(EV_CR_NEWNONCE_AMBIG, ZKE_AMBIG, "create.py:147 account_write(contract, Nonce) ambiguous") \
+  X(EV_CR_NEWNONCE_TYPE, ZKE_ASSERT, "create.py:147 account_write(contract, Nonce): .value() of a Word") \
+  X(EV_CR_NEWNONCE_PREV_TYPE, ZKE_ASSERT, "create.py:147 account_write(contract, Nonce): value_prev.value() of a Word") \
+  X(EV_CR_NEWNONCE_EQ, ZKE_ASSERT, "create.py:148 EIP-161: the new contract's nonce == 1") \
+  X(EV_CR_COPY_UNSAT, ZKE_UNSAT, "create.py:152-162 copy_lookup(memory -> bytecode next.code_hash) unsat") \
+  X(EV_CR_COPY_AMBIG, ZKE_AMBIG, "create.py:152-162 copy_lookup(memory -> bytecode next.code_hash) ambiguous") \
+  X(EV_CR_CODE_LEN_UNSAT, ZKE_UNSAT, "create.py:166 bytecode_length(next.code_hash) unsat") \
+  X(EV_CR_CODE_LEN_AMBIG, ZKE_AMBIG, "create.py:166 bytecode_length(next.code_hash) ambiguous") \
+  X(EV_CR_CODE_LEN_EQ, ZKE_ASSERT, "create.py:167 code_size == size") \
+  X(EV_CR_SAVE0_UNSAT, ZKE_UNSAT, "create.py:170-186 call_context_lookup(ProgramCounter, Write) unsat") \
+  X(EV_CR_SAVE0_AMBIG, ZKE_AMBIG, "create.py:170-186 call_context_lookup(ProgramCounter, Write) ambiguous") \
+  X(EV_CR_SAVE0_TYPE, ZKE_ASSERT, "create.py:170-186 call_context_lookup(ProgramCounter, Write): .value() of a Word") \
+  X(EV_CR_SAVE0_EQ, ZKE_ASSERT, "create.py:183-186 saved ProgramCounter") \
+  X(EV_CR_SAVE1_UNSAT, ZKE_UNSAT, "create.py:170-186 call_context_lookup(StackPointer, Write) unsat") \
+  X(EV_CR_SAVE1_AMBIG, ZKE_AMBIG, "create.py:170-186 call_context_lookup(StackPointer, Write) ambiguous") \
+  X(EV_CR_SAVE1_TYPE, ZKE_ASSERT, "create.py:170-186 call_context_lookup(StackPointer, Write): .value() of a Word") \
+  X(EV_CR_SAVE1_EQ, ZKE_ASSERT, "create.py:183-186 saved StackPointer") \
+  X(EV_CR_SAVE2_UNSAT, ZKE_UNSAT, "create.py:170-186 call_context_lookup(GasLeft, Write) unsat") \
+  X(EV_CR_SAVE2_AMBIG, ZKE_AMBIG, "create.py:170-186 call_context_lookup(GasLeft, Write) ambiguous") \
+  X(EV_CR_SAVE2_TYPE, ZKE_ASSERT, "create.py:170-186 call_context_lookup(GasLeft, Write): .value() of a Word") \
+  X(EV_CR_SAVE2_EQ, ZKE_ASSERT, "create.py:183-186 saved GasLeft") \
+  X(EV_CR_SAVE3_UNSAT, ZKE_UNSAT, "create.py:170-186 call_context_lookup(MemorySize, Write) unsat") \
+  X(EV_CR_SAVE3_AMBIG, ZKE_AMBIG, "create.py:170-186 call_context_lookup(MemorySize, Write) ambiguous") \
+  X(EV_CR_SAVE3_TYPE, ZKE_ASSERT, "create.py:170-186 call_context_lookup(MemorySize, Write): .value() of a Word") \
+  X(EV_CR_SAVE3_EQ, ZKE_ASSERT, "create.py:183-186 saved MemorySize") \
+  X(EV_CR_SAVE4_UNSAT, ZKE_UNSAT, "create.py:170-186 call_context_lookup(ReversibleWriteCounter, Write) unsat") \
+  X(EV_CR_SAVE4_AMBIG, ZKE_AMBIG, "create.py:170-186 call_context_lookup(ReversibleWriteCounter, Write) ambiguous") \
+  X(EV_CR_SAVE4_TYPE, ZKE_ASSERT, "create.py:170-186 call_context_lookup(ReversibleWriteCounter, Write): .value() of a Word") \
+  X(EV_CR_SAVE4_EQ, ZKE_ASSERT, "create.py:183-186 saved ReversibleWriteCounter") \
+  X(EV_CR_CTX0_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(CallerId, callee) unsat") \
+  X(EV_CR_CTX0_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(CallerId, callee) ambiguous") \
+  X(EV_CR_CTX0_EQ, ZKE_ASSERT, "create.py:202-211 callee CallerId") \
+  X(EV_CR_CTX1_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(TxId, callee) unsat") \
+  X(EV_CR_CTX1_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(TxId, callee) ambiguous") \
+  X(EV_CR_CTX1_EQ, ZKE_ASSERT, "create.py:202-211 callee TxId") \
+  X(EV_CR_CTX2_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(Depth, callee) unsat") \
+  X(EV_CR_CTX2_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(Depth, callee) ambiguous") \
+  X(EV_CR_CTX2_EQ, ZKE_ASSERT, "create.py:202-211 callee Depth") \
+  X(EV_CR_CTX3_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(CallerAddress, callee) unsat") \
+  X(EV_CR_CTX3_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(CallerAddress, callee) ambiguous") \
+  X(EV_CR_CTX3_EQ, ZKE_ASSERT, "create.py:202-211 callee CallerAddress") \
+  X(EV_CR_CTX4_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(CalleeAddress, callee) unsat") \
+  X(EV_CR_CTX4_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(CalleeAddress, callee) ambiguous") \
+  X(EV_CR_CTX4_EQ, ZKE_ASSERT, "create.py:202-211 callee CalleeAddress") \
+  X(EV_CR_CTX5_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(IsSuccess, callee) unsat") \
+  X(EV_CR_CTX5_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(IsSuccess, callee) ambiguous") \
+  X(EV_CR_CTX5_EQ, ZKE_ASSERT, "create.py:202-211 callee IsSuccess") \
+  X(EV_CR_CTX6_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(IsStatic, callee) unsat") \
+  X(EV_CR_CTX6_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(IsStatic, callee) ambiguous") \
+  X(EV_CR_CTX6_EQ, ZKE_ASSERT, "create.py:202-211 callee IsStatic") \
+  X(EV_CR_CTX7_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(IsRoot, callee) unsat") \
+  X(EV_CR_CTX7_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(IsRoot, callee) ambiguous") \
+  X(EV_CR_CTX7_EQ, ZKE_ASSERT, "create.py:202-211 callee IsRoot") \
+  X(EV_CR_CTX8_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(IsCreate, callee) unsat") \
+  X(EV_CR_CTX8_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(IsCreate, callee) ambiguous") \
+  X(EV_CR_CTX8_EQ, ZKE_ASSERT, "create.py:202-211 callee IsCreate") \
+  X(EV_CR_CTX9_UNSAT, ZKE_UNSAT, "create.py:188-211 call_context_lookup_word(CodeHash, callee) unsat") \
+  X(EV_CR_CTX9_AMBIG, ZKE_AMBIG, "create.py:188-211 call_context_lookup_word(CodeHash, callee) ambiguous") \
+  X(EV_CR_CTX9_EQ, ZKE_ASSERT, "create.py:202-211 callee CodeHash") \
+  X(EV_CR_NC_RWC, ZKE_ASSERT, "create.py:213-223 new context: rw_counter delta") \
+  X(EV_CR_NC_CALL_ID, ZKE_ASSERT, "create.py:213-223 new context: call_id to the callee's") \
+  X(EV_CR_NC_IS_ROOT, ZKE_ASSERT, "create.py:213-223 new context: is_root to False") \
+  X(EV_CR_NC_IS_CREATE, ZKE_ASSERT, "create.py:213-223 new context: is_create to True") \
+  X(EV_CR_NC_GAS, ZKE_ASSERT, "create.py:213-223 new context: gas_left to the callee's") \
+  X(EV_CR_NC_REV, ZKE_ASSERT, "create.py:213-223 new context: reversible_write_counter to 3") \
+  X(EV_CR_NC_LOG, ZKE_ASSERT, "create.py:213-223 new context: log_id same") \
+  X(EV_CR_NC_PC, ZKE_ASSERT, "create.py:213-223 new context: program_counter to 0") \
+  X(EV_CR_NC_SP, ZKE_ASSERT, "create.py:213-223 new context: stack_pointer to 1024") \
+  X(EV_CR_NC_MEM, ZKE_ASSERT, "create.py:213-223 new context: memory_word_size to 0") \
+  X(EV_CR_FAIL_SUCCESS, ZKE_ASSERT, "create.py:228 pre-check failure / address collision: is_success == 0") \
+  X(EV_CR_LAST0_UNSAT, ZKE_UNSAT, "create.py:230-238 call_context_lookup(LastCalleeId, Write) unsat") \
+  X(EV_CR_LAST0_AMBIG, ZKE_AMBIG, "create.py:230-238 call_context_lookup(LastCalleeId, Write) ambiguous") \
+  X(EV_CR_LAST0_TYPE, ZKE_ASSERT, "create.py:230-238 call_context_lookup(LastCalleeId, Write): .value() of a Word") \
+  X(EV_CR_LAST0_EQ, ZKE_ASSERT, "create.py:235-238 LastCalleeId == 0") \
+  X(EV_CR_LAST1_UNSAT, ZKE_UNSAT, "create.py:230-238 call_context_lookup(LastCalleeReturnDataOffset, Write) unsat") \
+  X(EV_CR_LAST1_AMBIG, ZKE_AMBIG, "create.py:230-238 call_context_lookup(LastCalleeReturnDataOffset, Write) ambiguous") \
+  X(EV_CR_LAST1_TYPE, ZKE_ASSERT, "create.py:230-238 call_context_lookup(LastCalleeReturnDataOffset, Write): .value() of a Word") \
+  X(EV_CR_LAST1_EQ, ZKE_ASSERT, "create.py:235-238 LastCalleeReturnDataOffset == 0") \
+  X(EV_CR_LAST2_UNSAT, ZKE_UNSAT, "create.py:230-238 call_context_lookup(LastCalleeReturnDataLength, Write) unsat") \
+  X(EV_CR_LAST2_AMBIG, ZKE_AMBIG, "create.py:230-238 call_context_lookup(LastCalleeReturnDataLength, Write) ambiguous") \
+  X(EV_CR_LAST2_TYPE, ZKE_ASSERT, "create.py:230-238 call_context_lookup(LastCalleeReturnDataLength, Write): .value() of a Word") \
+  X(EV_CR_LAST2_EQ, ZKE_ASSERT, "create.py:235-238 LastCalleeReturnDataLength == 0") \
+  X(EV_CR_SAME_RWC, ZKE_ASSERT, "create.py:242-254 same context: rw_counter delta") \
+  X(EV_CR_SAME_PC, ZKE_ASSERT, "create.py:242-254 same context: program_counter + 1") \
+  X(EV_CR_SAME_SP, ZKE_ASSERT, "create.py:242-254 same context: stack_pointer + 2 (+ 1 for CREATE2)") \
+  X(EV_CR_SAME_REV, ZKE_ASSERT, "create.py:242-254 same context: reversible_write_counter + 3 iff created without init code") \
+  X(EV_CR_SAME_GAS, ZKE_ASSERT, "create.py:242-254 same context: gas_left - gas_cost") \
+  X(EV_CR_SAME_MEM, ZKE_ASSERT, "create.py:242-254 same context: memory_word_size to next_memory_size") \
+  X(EV_CR_SAME_CALL_ID, ZKE_ASSERT, "create.py:242-254 same context: call_id same") \
+  X(EV_CR_SAME_IS_ROOT, ZKE_ASSERT, "create.py:242-254 same context: is_root same") \
+  X(EV_CR_SAME_IS_CREATE, ZKE_ASSERT, "create.py:242-254 same context: is_create same") \
+  X(EV_CR_SAME_CODE_HASH, ZKE_ASSERT, "create.py:242-254 same context: code_hash same")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

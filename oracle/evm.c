@@ -39,6 +39,7 @@ typedef struct {
   orc_index bytecode_ix, rw_ix, fixed_ix, copy_ix, keccak_ix;
   orc_index tx_ix, block_ix; /* tx table key (tx_id, tag, index); block table key (tag, block_number) */
   orc_index exp_ix;          /* exp table keyed on its first nine cells (exp_lookup, table.py:797-814) */
+  const uint64_t* aux; uint64_t n_aux; /* step-aux side table: (step row, lo, hi), StepState.aux_data */
   orc_index rwc_ix;          /* rw table keyed on rw_counter alone (lookups with optional columns, evm_tx.h) */
   const uint8_t* rw_flags; /* bit0: value.is_word, bit1: value_prev.is_word */
   const uint8_t *tx_flags, *block_flags; /* bit0: value.is_word */
@@ -943,6 +944,7 @@ static int state_is(fr_t s, uint64_t v) { return fr_eq_u64(s, v); }
 #include "evm_exp.h"
 #include "evm_return.h"
 #include "evm_call.h"
+#include "evm_create.h"
 
 static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
@@ -987,7 +989,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_CALLDATALOAD || st == ZK_ES_LOG || st == ZK_ES_ErrorWriteProtection || st == ZK_ES_BLOCKHASH ||
                                   st == ZK_ES_EXP || st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore ||
                                   st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN ||
-                                  st == ZK_ES_ErrorOutOfGasCall || st == ZK_ES_CALL_OP);
+                                  st == ZK_ES_ErrorOutOfGasCall || st == ZK_ES_CALL_OP || st == ZK_ES_CREATE || st == ZK_ES_CREATE2);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1057,6 +1059,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_RETURN) gadget_return_revert(e, i, row, opcode);
   else if (st == ZK_ES_ErrorOutOfGasCall) gadget_error_oog_call(e, i, row, opcode);
   else if (st == ZK_ES_CALL_OP) gadget_callop(e, i, row, opcode);
+  else if (st == ZK_ES_CREATE || st == ZK_ES_CREATE2) gadget_create(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 
@@ -1082,6 +1085,9 @@ void orc_set_evm_context_tables(const uint64_t* tx_tab, uint64_t n_tx, const uin
 /* exp table (11 cells) of the NEXT call (EXP) */
 static __thread const uint64_t* g_exp_tab; static __thread uint64_t g_n_exp;
 void orc_set_evm_exp_table(const uint64_t* exp_tab, uint64_t n_exp) { g_exp_tab = exp_tab; g_n_exp = n_exp; }
+/* StepState.aux_data of the NEXT call: rows of (step row, lo, hi), column-major like every table (CREATE / CREATE2) */
+static __thread const uint64_t* g_aux_tab; static __thread uint64_t g_n_aux;
+void orc_set_evm_step_aux(const uint64_t* aux_tab, uint64_t n_aux) { g_aux_tab = aux_tab; g_n_aux = n_aux; }
 /* value type flags of the tx / block tables and the withdrawal table of the NEXT call (BeginTx / EndTx / EndBlock) */
 static __thread const uint8_t *g_tx_flags, *g_block_flags; static __thread const uint64_t* g_wd_tab; static __thread uint64_t g_n_wd;
 void orc_set_evm_block_tables(const uint8_t* tx_flags, const uint8_t* block_flags, const uint64_t* wd_tab, uint64_t n_wd) {
@@ -1125,6 +1131,7 @@ int orc_check_evm_x(const uint64_t* steps, uint64_t n_steps, const uint64_t* byt
   const uint32_t ek[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
   orc_index_build(&env.exp_ix, g_exp_tab, g_n_exp, 11, ek, 9);
   g_exp_tab = 0; g_n_exp = 0;
+  env.aux = g_aux_tab; env.n_aux = g_n_aux; g_aux_tab = 0; g_n_aux = 0;
   const uint32_t ck0[1] = {0};
   orc_index_build(&env.rwc_ix, rw_tab, n_rw, 14, ck0, 1);
   env.tx_flags = g_tx_flags; env.block_flags = g_block_flags; env.wd_tab = g_wd_tab; env.n_wd = g_n_wd;

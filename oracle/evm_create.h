@@ -1,0 +1,225 @@
+/* TEST INFRASTRUCTURE — CPU oracle, part of oracle/evm.c (included there).
+ * CREATE / CREATE2: evm_circuit/execution/create.py:20-254 (generate_contract_address / generate_CREAET2_contract_address
+ * instruction.py:1338-1352, transfer :1111-1120, add_account_to_access_list :1044-1057, memory_expansion :1138-1155,
+ * step_state_transition_to_new_context :266-290).  StepState.aux_data (the init code's hash, create.py:107) is not one of
+ * the 13 step cells: it comes from the step-aux side table (step row, lo, hi) set with orc_set_evm_step_aux.
+ * Reproduced as written: `instruction.is_zero(is_static)` (create.py:52) is computed and dropped, so a CREATE inside a
+ * STATICCALL is not rejected here; the caller's nonce write is not tied to nonce_prev + 1; the access-list write and both
+ * nonce writes carry no reversion row.
+ * Pinned by tests/golden/evm24.npz (verdicts of the reference's verify_step on 52 cases of its own test data).
+ */
+/* keccak(0xff ++ address (20, big endian) ++ salt (32, little endian) ++ code hash (32, little endian))[12:], instruction.py:1342-1352;
+ * returns 0 when a word does not fit 32 bytes (OverflowError in the reference) */
+static int contract_address2(fr_t address, word_t salt, word_t hash, fr_t* out) {
+  if (!word_in_domain(salt) || !word_in_domain(hash)) {
+    /* lo + (hi << 128) >= 2^256 needs hi >= 2^128, or hi == 2^128 - 1 with lo >= 2^128 carrying in */
+    const word_t ws[2] = {salt, hash};
+    for (int t = 0; t < 2; t++) {
+      if (!fr_fits_bits(ws[t].hi, 128)) return 0;
+      if (!fr_fits_bits(fr_add(ws[t].hi, fr_hi128(ws[t].lo)), 128)) return 0; /* < 2^128 + 2^126: no wrap */
+    }
+  }
+  uint8_t buf[85]; int n = 0;
+  buf[n++] = 0xff;
+  for (int k = 19; k >= 0; k--) buf[n++] = (uint8_t)(address.l[k >> 3] >> (8 * (k & 7)));
+  const word_t ws[2] = {salt, hash};
+  for (int t = 0; t < 2; t++) {
+    const fr_t hi = fr_add(ws[t].hi, fr_hi128(ws[t].lo));
+    for (int k = 0; k < 16; k++) buf[n++] = (uint8_t)(ws[t].lo.l[k >> 3] >> (8 * (k & 7)));
+    for (int k = 0; k < 16; k++) buf[n++] = (uint8_t)(hi.l[k >> 3] >> (8 * (k & 7)));
+  }
+  uint8_t h[32]; keccak256_small(buf, n, h);
+  fr_t r = fr_u64(0);
+  for (int k = 0; k < 20; k++) r.l[k >> 3] |= (uint64_t)h[31 - k] << (8 * (k & 7));
+  *out = r;
+  return 1;
+}
+
+static void gadget_create(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps; const uint64_t j = i + 1;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP), one = fr_u64(1);
+  const int is_create = fr_eq_u64(opcode, 0xf0), is_create2 = fr_eq_u64(opcode, 0xf5);
+  {
+    fr_t key[4] = {fr_u64(ZK_FIXED_ResponsibleOpcode), CUR(S_STATE), opcode, fr_u64(0)};
+    CHECK(EV_CR_RESP_OPCODE, orc_lookup(&e->fixed_ix, key, 0) >= 1);
+  }
+  const fr_t callee_call_id = rwc;
+  const word_t zero = {fr_u64(0), fr_u64(0)};
+  word_t w[5]; /* value, offset, size, salt, returned address */
+  uint64_t k = 0;
+  for (int f = 0; f < 4; f++) {
+    if (f == 3 && !is_create2) { w[3] = zero; continue; }
+    if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(k)), &w[f]), EV_CR_POP0_UNSAT + 2 * f, row)) return;
+    k++;
+  }
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(k)), 1, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(k - 1)), &w[4]), EV_CR_PUSH_UNSAT, row)) return;
+  k++;
+  fr_t offset, size;
+  W2FQ(w[1], 5, &offset, EV_CR_OFF_DOMAIN);
+  W2FQ(w[2], 5, &size, EV_CR_SIZE_DOMAIN);
+  fr_t depth, tx_id, is_success, is_static, rev_end, is_persistent;
+  uint32_t r;
+  CALL_CCV(k, 0, call_id, ZK_CC_Depth, &depth, EV_CR_DEPTH_UNSAT); k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_TxId, &tx_id, EV_CR_TXID_UNSAT); k++;
+  LK(cc_rw_lookup(e, fr_add(rwc, fr_u64(k)), 0, call_id, ZK_CC_CallerAddress, &r), EV_CR_CALLER_UNSAT); k++;
+  const word_t caller_w = rw_value(e, r);
+  fr_t caller;
+  W2FQ(caller_w, 20, &caller, EV_CR_CALLER_DOMAIN);
+  LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 1, caller, ZK_ACC_Nonce, &r), EV_CR_NONCE_UNSAT); k++;
+  NOT_WORD(rw_val_is_word(e, r), EV_CR_NONCE_UNSAT);
+  CHECK(EV_CR_NONCE_PREV_TYPE, !rw_prev_is_word(e, r));
+  const fr_t nonce = rw_cell(e, R_VAL_LO, r), nonce_prev = rw_cell(e, R_PREV_LO, r);
+  LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 0, caller, ZK_ACC_Balance, &r), EV_CR_BAL_UNSAT); k++;
+  NOT_WORD(rw_val_is_word(e, r), EV_CR_BAL_UNSAT);
+  const fr_t balance = rw_cell(e, R_VAL_LO, r);
+  CALL_CCV(k, 0, call_id, ZK_CC_IsSuccess, &is_success, EV_CR_SUCCESS_UNSAT); k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_IsStatic, &is_static, EV_CR_STATIC_UNSAT); k++;
+  (void)is_static; /* create.py:52 computes is_zero(is_static) and drops it */
+  CALL_CCV(k, 0, call_id, ZK_CC_RwCounterEndOfReversion, &rev_end, EV_CR_REVEND_UNSAT); k++;
+  (void)rev_end;
+  CALL_CCV(k, 0, call_id, ZK_CC_IsPersistent, &is_persistent, EV_CR_PERSIST_UNSAT); k++;
+  const int has_init_code = !fr_is_zero(size);
+  /* memory_expansion(offset, size) */
+  const uint64_t words = has_init_code ? (offset.l[0] + size.l[0] + 31) / 32 : 0; /* both below 2^40 */
+  CHECK(EV_CR_MEMSIZE_RANGE, !(words >> 32));
+  const fr_t cur_mem = CUR(S_MEM);
+  CHECK(EV_CR_MEM_MAX, fr_fits_bits(cur_mem, 32));
+  const uint64_t next_mem = cur_mem.l[0] < words ? words : cur_mem.l[0];
+  const uint64_t expansion = memory_gas_cost(next_mem) - memory_gas_cost(cur_mem.l[0]);
+  const uint64_t word_len = (size.l[0] + 31) / 32;
+  CHECK(EV_CR_WORDLEN_RANGE, !(word_len >> 32));
+  const fr_t gas_left = CUR(S_GAS);
+  const uint64_t gas_cost = 32000 + expansion + word_len * 2 + (is_create2 ? 6 * word_len : 0);
+  const fr_t gas_available = fr_sub(gas_left, fr_u64(gas_cost));
+  fr_t one_64th = {{(gas_available.l[0] >> 6) | (gas_available.l[1] << 58), (gas_available.l[1] >> 6) | (gas_available.l[2] << 58),
+                    (gas_available.l[2] >> 6) | (gas_available.l[3] << 58), gas_available.l[3] >> 6}};
+  CHECK(EV_CR_GAS_64TH_RANGE, fr_fits_bits(one_64th, 64));
+  const fr_t all_but = fr_sub(gas_available, one_64th);
+  fr_t callee_gas_left = all_but;
+  if (fr_fits_bits(gas_left, 64)) { /* is_u64_gas: min(all_but_one_64th_gas, gas_left, 8) */
+    CHECK(EV_CR_GAS_MIN_RANGE, fr_fits_bits(all_but, 64));
+    callee_gas_left = all_but.l[0] < gas_left.l[0] ? all_but : gas_left;
+  }
+  CHECK(EV_CR_DEPTH_RANGE, fr_fits_bits(depth, 16));
+  const word_t bal_w = {fr_u128(balance.l[0], balance.l[1]), fr_u128(balance.l[2], balance.l[3])};
+  CHECK(EV_CR_BAL_CMP_RANGE, word_in_domain(w[0]));
+  const int insufficient = fr_cmp(bal_w.hi, w[0].hi) < 0 || (fr_eq(bal_w.hi, w[0].hi) && fr_cmp(bal_w.lo, w[0].lo) < 0);
+  CHECK(EV_CR_NONCE_RANGE, fr_fits_bits(nonce_prev, 64));
+  const int precheck_ok = depth.l[0] < 1025 && !insufficient && nonce_prev.l[0] < 0xFFFFFFFFFFFFFFFFull;
+  const uint64_t sp_delta = 2 + (uint64_t)is_create2;
+  int not_collision = 0;
+  fr_t look = fr_u64(0); /* rw_counter_offset once the copy lookup's increment (a field element) is in */
+  if (precheck_ok) {
+    word_t code_hash = {fr_u128(0x7bfad8045d85a470ull, 0xe500b653ca82273bull), fr_u128(0x927e7db2dcc703c0ull, 0xc5d2460186f7233cull)};
+    const word_t empty = code_hash;
+    if (has_init_code) {
+      int hits = 0;
+      for (uint64_t a = 0; a < e->n_aux; a++) {
+        const fr_t ar = fr_load(ORC_CELL(e->aux, e->n_aux, 0, a));
+        if (fr_eq_u64(ar, row)) { hits++; code_hash.lo = fr_load(ORC_CELL(e->aux, e->n_aux, 1, a)); code_hash.hi = fr_load(ORC_CELL(e->aux, e->n_aux, 2, a)); }
+      }
+      CHECK(EV_CR_AUX_MISSING, hits == 1);
+    }
+    fr_t contract;
+    if (is_create) contract = contract_address(caller, nonce);
+    else CHECK(EV_CR_ADDR2_DOMAIN, contract_address2(caller, w[3], code_hash, &contract));
+    const word_t contract_w = {fr_u128(contract.l[0], contract.l[1]), fr_u64(contract.l[2])};
+    {
+      fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(k)), 1, ZK_TARGET_TxAccessListAccount);
+      key[R_ID] = tx_id; key[R_ADDR] = contract; key[R_VAL_LO] = one;
+      LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR) | RWM_VAL, &r), EV_CR_AL_UNSAT); k++;
+      CHECK(EV_CR_AL_PREV_TYPE, !rw_prev_is_word(e, r));
+    }
+    LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 0, contract, ZK_ACC_CodeHash, &r), EV_CR_CHASH_UNSAT); k++;
+    const word_t callee_hash = rw_value(e, r);
+    LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 0, contract, ZK_ACC_Nonce, &r), EV_CR_CNONCE_UNSAT); k++;
+    NOT_WORD(rw_val_is_word(e, r), EV_CR_CNONCE_UNSAT);
+    const fr_t callee_nonce = rw_cell(e, R_VAL_LO, r);
+    const int is_empty_hash = fr_is_zero(fr_add(fr_sub(callee_hash.lo, empty.lo), fr_sub(callee_hash.hi, empty.hi)));
+    const int is_zero_hash = fr_is_zero(fr_add(callee_hash.lo, callee_hash.hi));
+    not_collision = fr_is_zero(callee_nonce) && (is_empty_hash || is_zero_hash);
+    if (not_collision) {
+      fr_t ret;
+      W2FQ(w[4], 20, &ret, EV_CR_RETURN_DOMAIN);
+      CHECK(EV_CR_RETURN_EQ, fr_eq(ret, fr_mul(is_success, contract)));
+      fr_t callee_rev_end, callee_persistent;
+      CALL_CCV(k, 0, callee_call_id, ZK_CC_RwCounterEndOfReversion, &callee_rev_end, EV_CR_CREVEND_UNSAT); k++;
+      CALL_CCV(k, 0, callee_call_id, ZK_CC_IsPersistent, &callee_persistent, EV_CR_CPERSIST_UNSAT); k++;
+      CHECK(EV_CR_CPERSIST_EQ, fr_eq(callee_persistent, fr_mul(is_persistent, is_success)));
+      /* transfer(caller, contract, value, callee_reversion_info) */
+      if (!balance_write(e, row, fr_add(rwc, fr_u64(k)), caller, callee_persistent, callee_rev_end, EV_CR_SEND_UNSAT, &r)) return;
+      k++;
+      { word_t ws[2] = {rw_value(e, r), w[0]}; fr_t carry; const word_t sum = add_words_n(ws, 2, &carry);
+        CHECK(EV_CR_SEND_EQ, word_eq(rw_prev(e, r), sum)); CHECK(EV_CR_SEND_CARRY, fr_is_zero(carry)); }
+      if (!balance_write(e, row, fr_add(rwc, fr_u64(k)), contract, callee_persistent, fr_sub(callee_rev_end, one), EV_CR_RECV_UNSAT, &r)) return;
+      k++;
+      { word_t ws[2] = {rw_prev(e, r), w[0]}; fr_t carry; const word_t sum = add_words_n(ws, 2, &carry);
+        CHECK(EV_CR_RECV_EQ, word_eq(rw_value(e, r), sum)); CHECK(EV_CR_RECV_CARRY, fr_is_zero(carry)); }
+      LK(account_lookup(e, fr_add(rwc, fr_u64(k)), 1, contract, ZK_ACC_Nonce, &r), EV_CR_NEWNONCE_UNSAT); k++;
+      NOT_WORD(rw_val_is_word(e, r), EV_CR_NEWNONCE_UNSAT);
+      CHECK(EV_CR_NEWNONCE_PREV_TYPE, !rw_prev_is_word(e, r));
+      CHECK(EV_CR_NEWNONCE_EQ, fr_eq_u64(rw_cell(e, R_VAL_LO, r), 1));
+      if (has_init_code) {
+        const word_t next_hash = {NXT(S_HASH_LO), NXT(S_HASH_HI)};
+        fr_t inc;
+        if (!need1(e, copy_lookup_dw(e, call_id, ZK_COPY_Memory, next_hash, ZK_COPY_Bytecode, offset, fr_add(offset, size), fr_u64(0), size,
+                                     fr_add(rwc, fr_u64(k)), &inc), EV_CR_COPY_UNSAT, row)) return;
+        look = inc;
+        fr_t code_size;
+        if (!need1(e, bytecode_lookup(e, next_hash.lo, next_hash.hi, 1, fr_u64(0), 0, &code_size), EV_CR_CODE_LEN_UNSAT, row)) return;
+        CHECK(EV_CR_CODE_LEN_EQ, fr_eq(code_size, size));
+        {
+          const fr_t want[5] = {fr_add(CUR(S_PC), one), fr_add(sp, fr_u64(sp_delta)), fr_sub(fr_sub(gas_left, fr_u64(gas_cost)), callee_gas_left),
+                                fr_u64(next_mem), fr_add(CUR(S_REV), one)};
+          static const uint64_t TAGS[5] = {ZK_CC_ProgramCounter, ZK_CC_StackPointer, ZK_CC_GasLeft, ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
+          for (int t = 0; t < 5; t++) {
+            uint32_t r_; LK(cc_rw_lookup(e, fr_add(fr_add(rwc, look), fr_u64(k)), 1, call_id, TAGS[t], &r_), EV_CR_SAVE0_UNSAT + 4 * t); k++;
+            NOT_WORD(rw_val_is_word(e, r_), EV_CR_SAVE0_UNSAT + 4 * t);
+            CHECK(EV_CR_SAVE0_UNSAT + 4 * t + 3, fr_eq(rw_cell(e, R_VAL_LO, r_), want[t]));
+          }
+        }
+        {
+          const word_t want[10] = {{call_id, fr_u64(0)}, {tx_id, fr_u64(0)}, {fr_add(depth, one), fr_u64(0)}, caller_w, contract_w,
+                                   {is_success, fr_u64(0)}, zero, zero, {one, fr_u64(0)}, code_hash};
+          static const uint64_t TAGS[10] = {ZK_CC_CallerId, ZK_CC_TxId, ZK_CC_Depth, ZK_CC_CallerAddress, ZK_CC_CalleeAddress, ZK_CC_IsSuccess,
+                                            ZK_CC_IsStatic, ZK_CC_IsRoot, ZK_CC_IsCreate, ZK_CC_CodeHash};
+          for (int t = 0; t < 10; t++) {
+            LK(cc_rw_lookup(e, fr_add(fr_add(rwc, look), fr_u64(k)), 0, callee_call_id, TAGS[t], &r), EV_CR_CTX0_UNSAT + 3 * t); k++;
+            CHECK(EV_CR_CTX0_UNSAT + 3 * t + 2, word_eq(rw_value(e, r), want[t]));
+          }
+        }
+        CHECK(EV_CR_NC_RWC, fr_eq(NXT(S_RWC), fr_add(fr_add(rwc, look), fr_u64(k))));
+        CHECK(EV_CR_NC_CALL_ID, fr_eq(NXT(S_CALL_ID), callee_call_id));
+        CHECK(EV_CR_NC_IS_ROOT, fr_is_zero(NXT(S_IS_ROOT)));
+        CHECK(EV_CR_NC_IS_CREATE, fr_eq_u64(NXT(S_IS_CREATE), 1));
+        CHECK(EV_CR_NC_GAS, fr_eq(NXT(S_GAS), callee_gas_left));
+        CHECK(EV_CR_NC_REV, fr_eq_u64(NXT(S_REV), 3));
+        CHECK(EV_CR_NC_LOG, fr_eq(NXT(S_LOG), CUR(S_LOG)));
+        CHECK(EV_CR_NC_PC, fr_is_zero(NXT(S_PC)));
+        CHECK(EV_CR_NC_SP, fr_eq_u64(NXT(S_SP), 1024));
+        CHECK(EV_CR_NC_MEM, fr_is_zero(NXT(S_MEM)));
+        return;
+      }
+    }
+  }
+  /* pre-check failure, address collision, or nothing to run: stay in the caller's context */
+  if (!precheck_ok || !not_collision) CHECK(EV_CR_FAIL_SUCCESS, fr_is_zero(is_success));
+  {
+    static const uint64_t TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
+    for (int t = 0; t < 3; t++) {
+      fr_t v;
+      CALL_CCV(k, 1, call_id, TAGS[t], &v, EV_CR_LAST0_UNSAT + 4 * t); k++;
+      CHECK(EV_CR_LAST0_UNSAT + 4 * t + 3, fr_is_zero(v));
+    }
+  }
+  CHECK(EV_CR_SAME_RWC, fr_eq(NXT(S_RWC), fr_add(rwc, fr_u64(k))));
+  CHECK(EV_CR_SAME_PC, fr_eq(NXT(S_PC), fr_add(CUR(S_PC), one)));
+  CHECK(EV_CR_SAME_SP, fr_eq(NXT(S_SP), fr_add(sp, fr_u64(sp_delta))));
+  CHECK(EV_CR_SAME_REV, fr_eq(NXT(S_REV), fr_add(CUR(S_REV), fr_u64(not_collision ? 3 : 0))));
+  CHECK(EV_CR_SAME_GAS, fr_eq(NXT(S_GAS), fr_sub(gas_left, fr_u64(gas_cost))));
+  CHECK(EV_CR_SAME_MEM, fr_eq_u64(NXT(S_MEM), next_mem));
+  CHECK(EV_CR_SAME_CALL_ID, fr_eq(NXT(S_CALL_ID), call_id));
+  CHECK(EV_CR_SAME_IS_ROOT, fr_eq(NXT(S_IS_ROOT), CUR(S_IS_ROOT)));
+  CHECK(EV_CR_SAME_IS_CREATE, fr_eq(NXT(S_IS_CREATE), CUR(S_IS_CREATE)));
+  CHECK(EV_CR_SAME_CODE_HASH, fr_eq(NXT(S_HASH_LO), CUR(S_HASH_LO)) && fr_eq(NXT(S_HASH_HI), CUR(S_HASH_HI)));
+}

@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45, "evm24": 47}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1496,6 +1496,31 @@ def evm2_cases(part="evm2"):
                             gas_left=exp.callee_gas_left, reversible_write_counter=2)
         return [cur, nxt], list(caller_bc.table_assignments()) + list(callee_bc.table_assignments()), list(rw.rws), [], []
 
+    def create_case(idx):
+        """tests/evm/test_create.py: case `idx` of the reference test's own TESTING_DATA.  The test function is run with its
+        verify_steps / verify_copy_table replaced by a recorder, which yields the tables and the two steps it would have
+        verified (the step's aux_data = the init code's hash rides along as a side table keyed by the step row)"""
+        import importlib
+        tdir = os.path.normpath(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm"))
+        for d_ in (tdir, os.path.dirname(tdir)):
+            if d_ not in sys.path:
+                sys.path.insert(0, d_)
+        tc = importlib.import_module("test_create")
+        got = {}
+        keep = (tc.verify_steps, tc.verify_copy_table)
+        tc.verify_steps = lambda tables, steps, **kw: got.update(tables=tables, steps=steps)
+        tc.verify_copy_table = lambda *a, **kw: None
+        try:
+            tc.test_create_create2(*tc.TESTING_DATA[idx])
+        finally:
+            tc.verify_steps, tc.verify_copy_table = keep
+        t, steps = got["tables"], got["steps"]
+        aux = []
+        for k_, st_ in enumerate(steps):
+            if st_.aux_data is not None:
+                aux.append((k_, st_.aux_data.lo.n, st_.aux_data.hi.n))
+        return steps, list(t.bytecode_table), list(t.rw_table), list(getattr(t, "copy_table", [])), [], [], [], [], aux
+
     def mws(a):
         return (a + 31) // 32
 
@@ -1864,9 +1889,12 @@ def evm2_cases(part="evm2"):
         return [n_of(x.is_step), n_of(x.identifier), n_of(x.is_last), n_of(x.base_limb0), n_of(x.base_limb1), n_of(x.base_limb2), n_of(x.base_limb3),
                 n_of(x.exponent.lo), n_of(x.exponent.hi), n_of(x.exponentiation.lo), n_of(x.exponentiation.hi)]
 
-    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None, BF=None, EX=()):
+    def run(S, B, R, RF, C, K, T=(), BL=(), TF=None, BF=None, EX=(), AUX=()):
         from zkevm_specs.evm_circuit import BlockTableRow, TxTableRow
         steps = [step_from(v) for v in S]
+        for a_ in AUX:  # StepState.aux_data of step a_[0] (a Word)
+            if 0 <= a_[0] < len(steps):
+                steps[a_[0]].aux_data = W(a_[1], a_[2])
         t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), wov(v[2], v[3], 1 if BF is None else BF[k_])) for k_, v in enumerate(BL)),
                    tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], 1 if TF is None else TF[k_])) for k_, v in enumerate(T)),
                    withdrawal_table=set(),
@@ -1887,7 +1915,14 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm23":
+    if part == "evm24":
+        # 52 of the reference test's 1,152 cases: 3-4 of each of its 14 outcome classes (CREATE / CREATE2 x pre-check failure,
+        # address collision, creation without init code (reverting or not), creation with init code = a new call context)
+        picks = [0, 72, 75, 78, 97, 103, 106, 145, 216, 219, 222, 241, 247, 250, 297, 372, 377, 378, 397, 403, 516, 521, 522,
+                 541, 547, 575, 576, 648, 651, 654, 673, 679, 682, 721, 792, 795, 798, 817, 823, 826, 873, 948, 953, 954, 973,
+                 979, 1092, 1097, 1098, 1117, 1123, 1151]
+        scenarios = {"create_%04d" % k_: create_case(k_) for k_ in picks}
+    elif part == "evm23":
         # 36 of the reference test's 768 cases: every opcode x callee kind, both reversion settings, the four stack shapes,
         # warm / cold, depth 1 / 1024 / 1025 (index = a mixed-radix number over the test's product order)
         picks = []
@@ -2119,15 +2154,17 @@ def evm2_cases(part="evm2"):
         TF = [int(x.value.is_word) for x in sc_[5]] if part == "evm17" and len(sc_) > 5 else None
         BF = [int(x.value.is_word) for x in sc_[6]] if part == "evm18" and len(sc_) > 6 else None
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
-        assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX))
+        AUX = [list(x) for x in sc_[8]] if len(sc_) > 8 else []
+        assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70, "evm24": 60}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 3, 15] if part == "evm24" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
             BF2 = list(BF) if BF is not None else None
             EX2 = [list(x) for x in EX]
+            AUX2 = [list(x) for x in AUX]
             S2, R2, RF2, C2, K2 = [list(x) for x in S], [list(x) for x in R], list(RF), [list(x) for x in C], [list(x) for x in K]
             if which == 0:
                 cols = [1, 2, 3, 7, 8, 9, 10, 10, 9, 5] if part == "evm2" else [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 7, 7]
@@ -2156,6 +2193,9 @@ def evm2_cases(part="evm2"):
             elif which == 7 and BL and BF is not None and rng.random() < 0.2:  # the value type of a block-table row
                 i, c, v = rng.randrange(len(BL)), 100, 0
                 BF2[i] ^= 1; which = 13
+            elif which == 15 and AUX:  # the step's aux_data (the init code's hash)
+                i, c = rng.randrange(len(AUX)), rng.choice([1, 2])
+                v = corrupt_value(rng, AUX[i][c]); AUX2[i][c] = v
             elif which == 14 and EX:  # a cell of an exp-table row
                 i, c = rng.randrange(len(EX)), rng.randrange(11)
                 v = corrupt_value(rng, EX[i][c]); EX2[i][c] = v
@@ -2189,7 +2229,7 @@ def evm2_cases(part="evm2"):
                 v = corrupt_value(rng, K[i][c]); K2[i][c] = v
             else:
                 continue
-            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2, BF2, EX2)
+            fr_, ex_ = run(S2, B, R2, RF2, C2, K2, T2, BL2, TF2, BF2, EX2, AUX2)
             muts.append((which, i, c, v, fr_, ex_))
             tot += 1
             nfail += fr_ >= 0
@@ -2199,6 +2239,8 @@ def evm2_cases(part="evm2"):
         if TF is not None:
             out[f"{name}/tx"] = to_matrix(T) if T else np.zeros((5, 0, 4), dtype=np.uint64)
             out[f"{name}/tx_flags"] = np.array(TF, dtype=np.uint8)
+        if AUX:
+            out[f"{name}/aux"] = to_matrix(AUX)
         if EX:
             out[f"{name}/exp"] = to_matrix(EX)
         if BF is not None:
@@ -2247,6 +2289,12 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm24_cases():
+    """CREATE / CREATE2 (create.py): pre-check failures, address collisions, creations without and with init code (new call
+    context; StepState.aux_data = the init code's hash)"""
+    evm2_cases("evm24")
 
 
 def evm23_cases():
@@ -3130,7 +3178,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "evm24", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -114,7 +114,7 @@ def evm2_vectors(part="evm2"):
     for name in z["names"]:
         name = str(name)
         base = {k: z[f"{name}/{k}"] for k in ("steps", "bytecode", "rw", "rw_flags", "copy", "keccak")}
-        for extra in ("tx", "block", "tx_flags", "block_flags", "exp"):  # ORIGIN / GASPRICE / BlockCtx scenarios carry their context tables
+        for extra in ("tx", "block", "tx_flags", "block_flags", "exp", "aux"):  # ORIGIN / GASPRICE / BlockCtx scenarios carry their context tables
             if f"{name}/{extra}" in z.files:
                 base[extra] = z[f"{name}/{extra}"]
         for k in range(len(z[f"{name}/mut_kind"])):
@@ -141,6 +141,8 @@ def evm2_vectors(part="evm2"):
                 w["tx_flags"] = base["tx_flags"].copy(); w["tx_flags"][i] ^= 1
             elif kind == 14:
                 w["exp"] = base["exp"].copy(); w["exp"][c, i, :] = val
+            elif kind == 15:
+                w["aux"] = base["aux"].copy(); w["aux"][c, i, :] = val
             elif kind == 13:
                 w["block_flags"] = base["block_flags"].copy(); w["block_flags"][i] ^= 1
             elif kind == 3:
@@ -224,6 +226,11 @@ def evm9_vectors():
 def evm10_vectors():
     """SHL / SHR steps; same layout as evm2"""
     return evm2_vectors("evm10")
+
+
+def evm24_vectors():
+    """CREATE / CREATE2"""
+    return evm2_vectors("evm24")
 
 
 def evm23_vectors():
