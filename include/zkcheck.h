@@ -91,7 +91,9 @@ enum {
   ZK_TABLE_CALLDATA_GAS = 10, /* 3 cells TxCallDataGasCostAccRow pi_circuit.py:66-70 (tx_id, is_final, gas_cost_acc) */
   ZK_TABLE_EXP = 11,     /* 11 cells ExpTableRow     table.py:539-548 (is_step, identifier, is_last, base limbs 0..3, exponent lo,hi,
                             exponentiation lo,hi) */
-  ZK_N_TABLES = 12
+  ZK_TABLE_STEP_AUX = 12, /* 3 cells  StepState.aux_data  step.py (step row, aux lo, hi): the per-step auxiliary word CREATE / CREATE2
+                            read as the init code's hash (create.py:107); rows only for the steps that carry one */
+  ZK_N_TABLES = 13
 };
 
 /* ---- challenges ------------------------------------------------------------------- */

@@ -213,6 +213,13 @@ extern "C" void emu_set_evm_exp_table(const uint64_t* exp, uint64_t n_exp) {
   g_emu_exp = (const u64*)exp;
   g_emu_n_exp = n_exp;
 }
+static const u64* g_emu_aux = nullptr;
+static u64 g_emu_n_aux = 0;
+// step-aux side table (step row, lo, hi) of the NEXT emu_check_evm_x call
+extern "C" void emu_set_evm_step_aux(const uint64_t* aux, uint64_t n_aux) {
+  g_emu_aux = (const u64*)aux;
+  g_emu_n_aux = n_aux;
+}
 extern "C" void emu_set_evm_context_tables(const uint64_t* tx, uint64_t n_tx, const uint64_t* block, uint64_t n_block) {
   g_emu_tx = (const u64*)tx;
   g_emu_n_tx = n_tx;
@@ -270,6 +277,11 @@ extern "C" int emu_check_evm_x(const uint64_t* steps, uint64_t n_steps, const ui
   t.exp = build_index(g_emu_exp, g_emu_n_exp, 11, ek, 9, ch, s11);
   g_emu_exp = nullptr;
   g_emu_n_exp = 0;
+  const u32 ak[1] = {0};
+  IndexStore s12;
+  t.aux = build_index(g_emu_aux, g_emu_n_aux, 3, ak, 1, ch, s12);
+  g_emu_aux = nullptr;
+  g_emu_n_aux = 0;
   const u32 wk[1] = {0};
   IndexStore s8, s9;
   IndexDev wd_ix = build_index(g_emu_wd, g_emu_n_wd, 4, wk, 1, ch, s8);

@@ -154,6 +154,10 @@ def check_evm_x(w, fixed, row_begin=0, row_end=None, row_base=0, flags=0, n=None
         ex = np.ascontiguousarray(w["exp"], dtype=np.uint64)
         check_evm_x._keep_exp = ex
         lib().emu_set_evm_exp_table(_p(ex), c(ex.shape[1]))
+    if w.get("aux") is not None:  # CREATE / CREATE2: StepState.aux_data as (step row, lo, hi) rows
+        ax = np.ascontiguousarray(w["aux"], dtype=np.uint64)
+        check_evm_x._keep_aux = ax
+        lib().emu_set_evm_step_aux(_p(ax), c(ax.shape[1]))
     if w.get("flags") is not None:
         flags = int(w["flags"])
     rc = lib().emu_check_evm_x(_p(m["steps"]), c(m["steps"].shape[1]), _p(m["bytecode"]), c(m["bytecode"].shape[1]),

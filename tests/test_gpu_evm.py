@@ -231,6 +231,7 @@ def test_evm_memory_golden_and_oracle_parity():
         ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
         ctx.upload_table(native.TABLE_COPY, w["copy"])  # CODECOPY / RETURNDATACOPY / EXTCODECOPY scenarios carry one
         ctx.upload_table(native.TABLE_EXP, w["exp"] if "exp" in w else np.zeros((11, 0, 4), dtype=np.uint64))
+        ctx.upload_table(native.TABLE_STEP_AUX, w["aux"] if "aux" in w else np.zeros((3, 0, 4), dtype=np.uint64))  # CREATE / CREATE2
         if "tx_flags" in w:  # CALLDATALOAD: call-data rows are plain values
             ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"])
         else:
@@ -256,6 +257,7 @@ def test_evm_memory_golden_and_oracle_parity():
         assert got == (exp_row, exp_exc), f"{name}[{k}] cuda {got} reference {(exp_row, exp_exc)}"
         n += 1
     assert n > 9000 and n_unsupported <= 150
+    ctx.upload_table(native.TABLE_STEP_AUX, np.zeros((3, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_COPY, np.zeros((14, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_TX, np.zeros((5, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_BLOCK, np.zeros((4, 0, 4), dtype=np.uint64))

@@ -44,7 +44,7 @@ static const ConstraintInfo kSigInfo[] = {ZK_SIG_CONSTRAINTS(ZK_INFO_ENTRY)};
 static const ConstraintInfo kPiInfo[] = {ZK_PI_CONSTRAINTS(ZK_INFO_ENTRY)};
 
 static const int kCircuitCols[ZK_N_CIRCUITS] = {12, 57, 20, 13, 21, 14, 21, 28};
-static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2, 4, 3, 11};
+static const int kTableCols[ZK_N_TABLES] = {4, 6, 14, 5, 4, 14, 5, 12, 2, 4, 3, 11, 3};
 
 static const ConstraintInfo* circuit_info(int circuit, int* n) {
   switch (circuit) {
@@ -1219,6 +1219,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
     if ((rc = ensure_index(ctx, ZK_TABLE_BLOCK, bk, 2, st, &t.block))) return rc;
     const u32 ek[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
     if ((rc = ensure_index(ctx, ZK_TABLE_EXP, ek, 9, st, &t.exp))) return rc;
+    const u32 ak[1] = {0};
+    if ((rc = ensure_index(ctx, ZK_TABLE_STEP_AUX, ak, 1, st, &t.aux))) return rc;
   }
   if (!ctx->resp_bitmap) CK(ctx, cudaMalloc(&ctx->resp_bitmap, ZK_RESP_BITMAP_WORDS * sizeof(u32)));
   if (ctx->resp_bitmap_version != ctx->tab[ZK_TABLE_FIXED].version) {
@@ -1291,7 +1293,8 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
                          hist[ZK_ES_BALANCE] + hist[ZK_ES_EXTCODEHASH] + hist[ZK_ES_EXTCODESIZE] + hist[ZK_ES_ErrorOutOfGasAccountAccess] +
                          hist[ZK_ES_EXTCODECOPY] + hist[ZK_ES_ErrorOutOfGasMemoryCopy] + hist[ZK_ES_SLOAD] + hist[ZK_ES_SSTORE] +
                          hist[ZK_ES_CALLDATALOAD] + hist[ZK_ES_LOG] + hist[ZK_ES_ErrorWriteProtection] + hist[ZK_ES_ErrorMaxCodeSizeExceeded] +
-                         hist[ZK_ES_ErrorOutOfGasCodeStore] + hist[ZK_ES_ErrorInvalidCreationCode] + hist[ZK_ES_RETURN] + hist[ZK_ES_ErrorOutOfGasCall] + hist[ZK_ES_CALL_OP];
+                         hist[ZK_ES_ErrorOutOfGasCodeStore] + hist[ZK_ES_ErrorInvalidCreationCode] + hist[ZK_ES_RETURN] + hist[ZK_ES_ErrorOutOfGasCall] + hist[ZK_ES_CALL_OP] +
+                         hist[ZK_ES_CREATE] + hist[ZK_ES_CREATE2];
   if (hist[ZK_ES_ErrorInvalidJump] && !pos) {  // bytecode_lookup_pair: the index without is_code
     const u32 k4b[4] = {0, 1, 2, 3};
     if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k4b, 4, st, &t.bytecode4))) return rc;

@@ -45,7 +45,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ErrorOutOfGasAccountAccess) X(ZK_ES_CODECOPY) X(ZK_ES_RETURNDATACOPY) X(ZK_ES_EXTCODECOPY) X(ZK_ES_ErrorOutOfGasMemoryCopy) \
   X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
   X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP) \
-  X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode) X(ZK_ES_RETURN) X(ZK_ES_ErrorOutOfGasCall) X(ZK_ES_CALL_OP)
+  X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode) X(ZK_ES_RETURN) X(ZK_ES_ErrorOutOfGasCall) X(ZK_ES_CALL_OP) \
+  X(ZK_ES_CREATE) X(ZK_ES_CREATE2)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -92,6 +93,8 @@ struct EvmTables {
   IndexDev block;     // block table (tag, block number | value lo, hi), key = the first two cells (table.py:691-695)
   IndexDev exp;       // exp table (is_step, identifier, is_last, base limbs 0..3, exponent lo / hi | exponentiation lo / hi), key = the
                       // first nine cells (table.py:797-814)
+  IndexDev aux;       // step-aux side table (step row | aux_data lo, hi): StepState.aux_data of CREATE / CREATE2 (create.py:107), key =
+                      // the step's row
   IndexDev bytecode4; // bytecode table keyed on (hash lo, hi, tag, index): bytecode_lookup_pair does not name is_code; only built
                       // when an ErrorInvalidJump step exists and the bytecode table is not positional
   IndexDev rw_rwc;    // rw table keyed on rw_counter alone: lookups that name other column subsets (evm_tx.cuh);
@@ -1714,6 +1717,7 @@ ZK_HD_NOINLINE void gadget_shl_shr(const StepCtx& s, bool live) {
 #include "evm_exp.cuh"
 #include "evm_return.cuh"
 #include "evm_call.cuh"
+#include "evm_create.cuh"
 namespace zk {
 
 // ---- gate-program groups --------------------------------------------------------------------
@@ -1744,7 +1748,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_CODECOPY: case ZK_ES_RETURNDATACOPY: case ZK_ES_EXTCODECOPY: case ZK_ES_ErrorOutOfGasMemoryCopy:
     case ZK_ES_SLOAD: case ZK_ES_SSTORE: case ZK_ES_CALLDATALOAD: case ZK_ES_LOG: case ZK_ES_ErrorWriteProtection: case ZK_ES_BLOCKHASH:
     case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: case ZK_ES_ErrorInvalidCreationCode:
-    case ZK_ES_RETURN: case ZK_ES_ErrorOutOfGasCall: case ZK_ES_CALL_OP:
+    case ZK_ES_RETURN: case ZK_ES_ErrorOutOfGasCall: case ZK_ES_CALL_OP: case ZK_ES_CREATE: case ZK_ES_CREATE2:
       return KG_TX;
     default: return -1;
   }
@@ -1829,6 +1833,7 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_RETURN: gadget_return_revert(s); break;
       case ZK_ES_ErrorOutOfGasCall: gadget_error_oog_call(s); break;
       case ZK_ES_CALL_OP: gadget_callop(s); break;
+      case ZK_ES_CREATE: case ZK_ES_CREATE2: gadget_create(s); break;
       default: break;
     }
   } else if constexpr (G == KG_ARITH) {

@@ -1,0 +1,275 @@
+// Gate program of CREATE / CREATE2 (group KG_TX), part of evm.cu (included there).
+//   create   evm_circuit/execution/create.py:20-254 (generate_contract_address / generate_CREAET2_contract_address
+//            instruction.py:1338-1352, transfer :1111-1120, add_account_to_access_list :1044-1057, memory_expansion
+//            :1138-1155, step_state_transition_to_new_context :266-290)
+// StepState.aux_data (the init code's hash, create.py:107) is not one of the 13 step cells: it is looked up in the step-aux
+// side table ZK_TABLE_STEP_AUX (step row, lo, hi) by the step's row.  Three endings: pre-check failure (depth, balance,
+// nonce) or address collision -> the step stays in the caller with an empty return-data record; creation without init
+// code -> the same, after the transfer and the nonce write; creation with init code -> the memory chunk is copied into the
+// bytecode next.code_hash, the caller's state is saved, the new call's ten context cells are read back and the next step
+// starts the init code.  Reproduced as written: is_zero(is_static) (create.py:52) is computed and dropped; the caller's
+// nonce write is not tied to nonce_prev + 1; the access-list write and both nonce writes carry no reversion row.
+#pragma once
+namespace zk {
+
+// keccak(0xff ++ address (20, big endian) ++ salt (32, little endian) ++ code hash (32, little endian))[12:]; false when a
+// word's integer lo + (hi << 128) does not fit 32 bytes (OverflowError in the reference)
+ZK_HD_NOINLINE bool contract_address2(const Fr& address, const Word2& salt, const Word2& hash, Fr* out) {
+  unsigned char buf[85];
+  int n = 0;
+  buf[n++] = 0xff;
+  for (int k = 19; k >= 0; k--) buf[n++] = (unsigned char)(address.l[k >> 3] >> (8 * (k & 7)));
+#pragma unroll 1
+  for (int t = 0; t < 2; t++) {
+    const Word2& w = t == 0 ? salt : hash;
+    if ((w.hi.l[2] | w.hi.l[3]) != 0) return false;
+    const Fr hi = fr_add(w.hi, fr_u128(w.lo.l[2], w.lo.l[3]));  // < 2^128 + 2^126: no wrap
+    if ((hi.l[2] | hi.l[3]) != 0) return false;
+    for (int k = 0; k < 16; k++) buf[n++] = (unsigned char)(w.lo.l[k >> 3] >> (8 * (k & 7)));
+    for (int k = 0; k < 16; k++) buf[n++] = (unsigned char)(hi.l[k >> 3] >> (8 * (k & 7)));
+  }
+  u64 d[4];
+  keccak256(buf, (u64)n, d);
+  Fr r = fr_u64(0);
+  for (int k = 0; k < 20; k++) {
+    const int j = 31 - k;
+    r.l[k >> 3] |= ((d[j >> 3] >> (8 * (j & 7))) & 0xFF) << (8 * (k & 7));
+  }
+  *out = r;
+  return true;
+}
+
+ZK_HD_NOINLINE void gadget_create(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const bool is_create = fr_eq_u64(opcode, 0xf0), is_create2 = fr_eq_u64(opcode, 0xf5);
+  EV_CHECK(EV_CR_RESP_OPCODE, responsible_opcode(s, s.cur(S_STATE), opcode));
+  const Fr callee_call_id = rwc;
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 w[5] = {zero, zero, zero, zero, zero};  // value, offset, size, salt, returned address
+  u64 k = 0;
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    if (f == 3 && !is_create2) continue;
+    if (!need1(s, true, stack_at(s, true, k, 0, fr_add_u64(sp, k), &w[f]), EV_CR_POP0_UNSAT + 2 * f)) return;
+    k++;
+  }
+  if (!need1(s, true, stack_at(s, true, k, 1, fr_add_u64(sp, k - 1), &w[4]), EV_CR_PUSH_UNSAT)) return;
+  k++;
+  Fr offset = fr_u64(0), size = fr_u64(0);
+  EOOG_W2FQ(w[1], 5, &offset, EV_CR_OFF_DOMAIN);
+  EOOG_W2FQ(w[2], 5, &size, EV_CR_SIZE_DOMAIN);
+  Fr depth, tx_id, is_success, is_static, rev_end, is_persistent;
+  u32 r = 0;
+  CALL_CCV(k, 0, call_id, ZK_CC_Depth, &depth, EV_CR_DEPTH_UNSAT);
+  k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_TxId, &tx_id, EV_CR_TXID_UNSAT);
+  k++;
+  TX_LK(cc_rw_lookup_m(s, fr_add_u64(rwc, k), 0, call_id, ZK_CC_CallerAddress, &r), EV_CR_CALLER_UNSAT);
+  k++;
+  const Word2 caller_w = rw_word(s, R_VAL_LO, r);
+  Fr caller = fr_u64(0);
+  EOOG_W2FQ(caller_w, 20, &caller, EV_CR_CALLER_DOMAIN);
+  TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 1, caller, ZK_ACC_Nonce, &r), EV_CR_NONCE_UNSAT);
+  k++;
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_CR_NONCE_UNSAT);
+  EV_CHECK(EV_CR_NONCE_PREV_TYPE, !rw_flag(s, r, 1));
+  const Fr nonce = rw_cell(s, R_VAL_LO, r), nonce_prev = rw_cell(s, R_PREV_LO, r);
+  TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 0, caller, ZK_ACC_Balance, &r), EV_CR_BAL_UNSAT);
+  k++;
+  TX_NOT_WORD(rw_flag(s, r, 0), EV_CR_BAL_UNSAT);
+  const Fr balance = rw_cell(s, R_VAL_LO, r);
+  CALL_CCV(k, 0, call_id, ZK_CC_IsSuccess, &is_success, EV_CR_SUCCESS_UNSAT);
+  k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_IsStatic, &is_static, EV_CR_STATIC_UNSAT);  // create.py:52: read, never constrained
+  k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_RwCounterEndOfReversion, &rev_end, EV_CR_REVEND_UNSAT);
+  k++;
+  CALL_CCV(k, 0, call_id, ZK_CC_IsPersistent, &is_persistent, EV_CR_PERSIST_UNSAT);
+  k++;
+  const bool has_init_code = !fr_is_zero(size);
+  // memory_expansion(offset, size); both below 2^40
+  const u64 words = has_init_code ? (offset.l[0] + size.l[0] + 31) / 32 : 0;
+  EV_CHECK(EV_CR_MEMSIZE_RANGE, (words >> 32) == 0);
+  const Fr cur_mem = s.cur(S_MEM);
+  EV_CHECK(EV_CR_MEM_MAX, fr_fits64(cur_mem) && (cur_mem.l[0] >> 32) == 0);
+  const u64 next_mem = cur_mem.l[0] < words ? words : cur_mem.l[0];
+  const u64 expansion = memory_gas_cost(next_mem) - memory_gas_cost(cur_mem.l[0]);
+  const u64 word_len = (size.l[0] + 31) / 32;
+  EV_CHECK(EV_CR_WORDLEN_RANGE, (word_len >> 32) == 0);
+  const Fr gas_left = s.cur(S_GAS);
+  const u64 gas_cost = 32000 + expansion + word_len * 2 + (is_create2 ? 6 * word_len : 0);
+  const Fr gas_available = fr_sub(gas_left, fr_u64(gas_cost));
+  const Fr one_64th{{(gas_available.l[0] >> 6) | (gas_available.l[1] << 58), (gas_available.l[1] >> 6) | (gas_available.l[2] << 58),
+                     (gas_available.l[2] >> 6) | (gas_available.l[3] << 58), gas_available.l[3] >> 6}};
+  EV_CHECK(EV_CR_GAS_64TH_RANGE, fr_fits64(one_64th));
+  const Fr all_but = fr_sub(gas_available, one_64th);
+  Fr callee_gas_left = all_but;
+  if (fr_fits64(gas_left)) {  // is_u64_gas: min(all_but_one_64th_gas, gas_left, 8)
+    EV_CHECK(EV_CR_GAS_MIN_RANGE, fr_fits64(all_but));
+    callee_gas_left = all_but.l[0] < gas_left.l[0] ? all_but : gas_left;
+  }
+  EV_CHECK(EV_CR_DEPTH_RANGE, fr_fits64(depth) && (depth.l[0] >> 16) == 0);
+  const Word2 bal_w{fr_u128(balance.l[0], balance.l[1]), fr_u128(balance.l[2], balance.l[3])};
+  EV_CHECK(EV_CR_BAL_CMP_RANGE, word_in_domain(w[0]));
+  const bool insufficient = fr_lt(bal_w.hi, w[0].hi) || (fr_eq(bal_w.hi, w[0].hi) && fr_lt(bal_w.lo, w[0].lo));
+  EV_CHECK(EV_CR_NONCE_RANGE, fr_fits64(nonce_prev));
+  const bool precheck_ok = depth.l[0] < 1025 && !insufficient && nonce_prev.l[0] < 0xFFFFFFFFFFFFFFFFull;
+  const u64 sp_delta = 2 + (is_create2 ? 1 : 0);
+  bool not_collision = false;
+  if (precheck_ok) {
+    const Word2 empty{fr_u128(0x7bfad8045d85a470ull, 0xe500b653ca82273bull), fr_u128(0x927e7db2dcc703c0ull, 0xc5d2460186f7233cull)};
+    Word2 code_hash = empty;
+    if (has_init_code) {  // curr.aux_data
+      const Fr key[1] = {fr_u64(s.row)};
+      u32 ra = 0;
+      EV_CHECK(EV_CR_AUX_MISSING, lookup<1>(s.t.aux, key, &ra) == 1);
+      code_hash.lo = table_cell(s.t.aux.tab, 1, ra);
+      code_hash.hi = table_cell(s.t.aux.tab, 2, ra);
+    }
+    Fr contract = fr_u64(0);
+    if (is_create) contract = contract_address(caller, nonce);
+    else EV_CHECK(EV_CR_ADDR2_DOMAIN, contract_address2(caller, w[3], code_hash, &contract));
+    const Word2 contract_w{fr_u128(contract.l[0], contract.l[1]), fr_u64(contract.l[2])};
+    {
+      Fr key[14];
+      rw_key_init(key, fr_add_u64(rwc, k), 1, ZK_TARGET_TxAccessListAccount);
+      key[R_ID] = tx_id;
+      key[R_ADDR] = contract;
+      key[R_VAL_LO] = fr_u64(1);
+      TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR) | ZK_RWM(R_VAL_LO) | ZK_RWM(R_VAL_HI), &r), EV_CR_AL_UNSAT);
+      k++;
+      EV_CHECK(EV_CR_AL_PREV_TYPE, !rw_flag(s, r, 1));
+    }
+    TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 0, contract, ZK_ACC_CodeHash, &r), EV_CR_CHASH_UNSAT);
+    k++;
+    const Word2 callee_hash = rw_word(s, R_VAL_LO, r);
+    TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 0, contract, ZK_ACC_Nonce, &r), EV_CR_CNONCE_UNSAT);
+    k++;
+    TX_NOT_WORD(rw_flag(s, r, 0), EV_CR_CNONCE_UNSAT);
+    const Fr callee_nonce = rw_cell(s, R_VAL_LO, r);
+    // is_equal_word / is_zero_word: the FIELD SUM of the halves (differences) is zero
+    const bool is_empty_hash = fr_is_zero(fr_add(fr_sub(callee_hash.lo, empty.lo), fr_sub(callee_hash.hi, empty.hi)));
+    const bool is_zero_hash = fr_is_zero(fr_add(callee_hash.lo, callee_hash.hi));
+    not_collision = fr_is_zero(callee_nonce) && (is_empty_hash || is_zero_hash);
+    if (not_collision) {
+      Fr ret = fr_u64(0);
+      EOOG_W2FQ(w[4], 20, &ret, EV_CR_RETURN_DOMAIN);
+      EV_CHECK(EV_CR_RETURN_EQ, fr_eq(ret, fr_mul_sel(contract, is_success)));
+      Fr callee_rev_end, callee_persistent;
+      CALL_CCV(k, 0, callee_call_id, ZK_CC_RwCounterEndOfReversion, &callee_rev_end, EV_CR_CREVEND_UNSAT);
+      k++;
+      CALL_CCV(k, 0, callee_call_id, ZK_CC_IsPersistent, &callee_persistent, EV_CR_CPERSIST_UNSAT);
+      k++;
+      EV_CHECK(EV_CR_CPERSIST_EQ, fr_eq(callee_persistent, fr_mul_sel(is_persistent, is_success)));
+      // transfer(caller, contract, value, callee_reversion_info)
+      if (!balance_write(s, fr_add_u64(rwc, k), caller, callee_persistent, callee_rev_end, EV_CR_SEND_UNSAT, &r)) return;
+      k++;
+      {
+        const Word2 ws[2] = {rw_word(s, R_VAL_LO, r), w[0]};
+        Fr carry;
+        const Word2 sum = add_words_n(ws, 2, &carry);
+        EV_CHECK(EV_CR_SEND_EQ, word_eq(rw_word(s, R_PREV_LO, r), sum));
+        EV_CHECK(EV_CR_SEND_CARRY, fr_is_zero(carry));
+      }
+      if (!balance_write(s, fr_add_u64(rwc, k), contract, callee_persistent, fr_sub(callee_rev_end, fr_u64(1)), EV_CR_RECV_UNSAT, &r)) return;
+      k++;
+      {
+        const Word2 ws[2] = {rw_word(s, R_PREV_LO, r), w[0]};
+        Fr carry;
+        const Word2 sum = add_words_n(ws, 2, &carry);
+        EV_CHECK(EV_CR_RECV_EQ, word_eq(rw_word(s, R_VAL_LO, r), sum));
+        EV_CHECK(EV_CR_RECV_CARRY, fr_is_zero(carry));
+      }
+      TX_LK(account_lookup_m(s, fr_add_u64(rwc, k), 1, contract, ZK_ACC_Nonce, &r), EV_CR_NEWNONCE_UNSAT);
+      k++;
+      TX_NOT_WORD(rw_flag(s, r, 0), EV_CR_NEWNONCE_UNSAT);
+      EV_CHECK(EV_CR_NEWNONCE_PREV_TYPE, !rw_flag(s, r, 1));
+      EV_CHECK(EV_CR_NEWNONCE_EQ, fr_eq_u64(rw_cell(s, R_VAL_LO, r), 1));
+      if (has_init_code) {
+        const Word2 next_hash{s.nxt(S_HASH_LO), s.nxt(S_HASH_HI)};
+        Fr inc = fr_u64(0);
+        if (!need1(s, true, copy_lookup_dw(s, call_id, ZK_COPY_Memory, next_hash, ZK_COPY_Bytecode, offset, fr_add(offset, size), fr_u64(0),
+                                           size, fr_add_u64(rwc, k), &inc), EV_CR_COPY_UNSAT)) return;
+        const Fr base = fr_add(rwc, inc);  // rw_counter + the copy's increment (a field element)
+        Fr code_size = fr_u64(0);
+        if (!need1(s, true, bytecode_lookup_ni(s, true, next_hash.lo, next_hash.hi, 1, fr_u64(0), 0, &code_size), EV_CR_CODE_LEN_UNSAT)) return;
+        EV_CHECK(EV_CR_CODE_LEN_EQ, fr_eq(code_size, size));
+        {  // save the caller's state: 5 call-context writes on the current call
+          const u64 TAGS[5] = {ZK_CC_ProgramCounter, ZK_CC_StackPointer, ZK_CC_GasLeft, ZK_CC_MemorySize, ZK_CC_ReversibleWriteCounter};
+#pragma unroll 1
+          for (int t = 0; t < 5; t++) {
+            const Fr want = t == 0   ? fr_add_u64(s.cur(S_PC), 1)
+                            : t == 1 ? fr_add_u64(sp, sp_delta)
+                            : t == 2 ? fr_sub(fr_sub(gas_left, fr_u64(gas_cost)), callee_gas_left)
+                            : t == 3 ? fr_u64(next_mem)
+                                     : fr_add_u64(s.cur(S_REV), 1);
+            u32 r_ = 0;
+            TX_LK(cc_rw_lookup_m(s, fr_add_u64(base, k), 1, call_id, TAGS[t], &r_), EV_CR_SAVE0_UNSAT + 4 * t);
+            k++;
+            TX_NOT_WORD(rw_flag(s, r_, 0), EV_CR_SAVE0_UNSAT + 4 * t);
+            EV_CHECK(EV_CR_SAVE0_UNSAT + 4 * t + 3, fr_eq(rw_cell(s, R_VAL_LO, r_), want));
+          }
+        }
+        {  // the new call's context: 10 call-context reads compared as words (lo, hi)
+          const u64 TAGS[10] = {ZK_CC_CallerId, ZK_CC_TxId, ZK_CC_Depth, ZK_CC_CallerAddress, ZK_CC_CalleeAddress, ZK_CC_IsSuccess,
+                                ZK_CC_IsStatic, ZK_CC_IsRoot, ZK_CC_IsCreate, ZK_CC_CodeHash};
+#pragma unroll 1
+          for (int t = 0; t < 10; t++) {
+            Word2 want = zero;
+            switch (t) {
+              case 0: want.lo = call_id; break;
+              case 1: want.lo = tx_id; break;
+              case 2: want.lo = fr_add_u64(depth, 1); break;
+              case 3: want = caller_w; break;
+              case 4: want = contract_w; break;
+              case 5: want.lo = is_success; break;
+              case 8: want.lo = fr_u64(1); break;
+              case 9: want = code_hash; break;
+              default: break;
+            }
+            TX_LK(cc_rw_lookup_m(s, fr_add_u64(base, k), 0, callee_call_id, TAGS[t], &r), EV_CR_CTX0_UNSAT + 3 * t);
+            k++;
+            EV_CHECK(EV_CR_CTX0_UNSAT + 3 * t + 2, word_eq(rw_word(s, R_VAL_LO, r), want));
+          }
+        }
+        EV_CHECK(EV_CR_NC_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(base, k)));
+        EV_CHECK(EV_CR_NC_CALL_ID, fr_eq(s.nxt(S_CALL_ID), callee_call_id));
+        EV_CHECK(EV_CR_NC_IS_ROOT, fr_is_zero(s.nxt(S_IS_ROOT)));
+        EV_CHECK(EV_CR_NC_IS_CREATE, fr_eq_u64(s.nxt(S_IS_CREATE), 1));
+        EV_CHECK(EV_CR_NC_GAS, fr_eq(s.nxt(S_GAS), callee_gas_left));
+        EV_CHECK(EV_CR_NC_REV, fr_eq_u64(s.nxt(S_REV), 3));
+        EV_CHECK(EV_CR_NC_LOG, fr_eq(s.nxt(S_LOG), s.cur(S_LOG)));
+        EV_CHECK(EV_CR_NC_PC, fr_is_zero(s.nxt(S_PC)));
+        EV_CHECK(EV_CR_NC_SP, fr_eq_u64(s.nxt(S_SP), 1024));
+        EV_CHECK(EV_CR_NC_MEM, fr_is_zero(s.nxt(S_MEM)));
+        return;
+      }
+    }
+  }
+  // pre-check failure, address collision, or nothing to run: the step stays in the caller's context
+  if (!precheck_ok || !not_collision) EV_CHECK(EV_CR_FAIL_SUCCESS, fr_is_zero(is_success));
+  {
+    const u64 TAGS[3] = {ZK_CC_LastCalleeId, ZK_CC_LastCalleeReturnDataOffset, ZK_CC_LastCalleeReturnDataLength};
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+      Fr v;
+      CALL_CCV(k, 1, call_id, TAGS[t], &v, EV_CR_LAST0_UNSAT + 4 * t);
+      k++;
+      EV_CHECK(EV_CR_LAST0_UNSAT + 4 * t + 3, fr_is_zero(v));
+    }
+  }
+  EV_CHECK(EV_CR_SAME_RWC, fr_eq(s.nxt(S_RWC), fr_add_u64(rwc, k)));
+  EV_CHECK(EV_CR_SAME_PC, fr_eq(s.nxt(S_PC), fr_add_u64(s.cur(S_PC), 1)));
+  EV_CHECK(EV_CR_SAME_SP, fr_eq(s.nxt(S_SP), fr_add_u64(sp, sp_delta)));
+  EV_CHECK(EV_CR_SAME_REV, fr_eq(s.nxt(S_REV), fr_add_u64(s.cur(S_REV), not_collision ? 3 : 0)));
+  EV_CHECK(EV_CR_SAME_GAS, fr_eq(s.nxt(S_GAS), fr_sub(gas_left, fr_u64(gas_cost))));
+  EV_CHECK(EV_CR_SAME_MEM, fr_eq_u64(s.nxt(S_MEM), next_mem));
+  EV_CHECK(EV_CR_SAME_CALL_ID, fr_eq(s.nxt(S_CALL_ID), call_id));
+  EV_CHECK(EV_CR_SAME_IS_ROOT, fr_eq(s.nxt(S_IS_ROOT), s.cur(S_IS_ROOT)));
+  EV_CHECK(EV_CR_SAME_IS_CREATE, fr_eq(s.nxt(S_IS_CREATE), s.cur(S_IS_CREATE)));
+  EV_CHECK(EV_CR_SAME_CODE_HASH, fr_eq(s.nxt(S_HASH_LO), s.cur(S_HASH_LO)) && fr_eq(s.nxt(S_HASH_HI), s.cur(S_HASH_HI)));
+}
+
+}  // namespace zk

@@ -39,6 +39,18 @@ def pack_steps(steps: List[StepState]) -> np.ndarray:
     return packing.matrix_from_ints([step_row(s) for s in steps], 13)
 
 
+def step_aux_rows(steps: List[StepState], row_base: int = 0) -> List[List[int]]:
+    """StepState.aux_data (reference step.py:45) as the step-aux side table: one row (step row, lo, hi) per step that carries
+    a Word there (CREATE / CREATE2 read it as the init code's hash, create.py:107)"""
+    c = packing.cell_int
+    rows = []
+    for k, s in enumerate(steps):
+        a = getattr(s, "aux_data", None)
+        if a is not None and hasattr(a, "lo") and hasattr(a, "hi"):
+            rows.append([row_base + k, c(a.lo), c(a.hi)])
+    return rows
+
+
 def upload_tables(ctx: native.Context, tables: Tables) -> None:
     """Python row sets -> cell matrices -> device (tables are replicated per GPU)."""
     ctx.upload_table(native.TABLE_BYTECODE, packing.pack(tables.bytecode_table, packing.bytecode_table_row, 6))
@@ -121,6 +133,7 @@ def verify_steps(tables: Tables, steps: List[StepState], begin_with_first_step: 
         steps.append(DUMMY_STEP_STATE)
     ctx = ctx or native.default_context()
     upload_tables(ctx, tables)
+    ctx.upload_table(native.TABLE_STEP_AUX, packing.matrix_from_ints(step_aux_rows(steps), 3))
     ff, _ = check_steps(ctx, pack_steps(steps), begin_with_first_step, end_with_last_step)
     exception = None
     try:
