@@ -1448,7 +1448,52 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_CR_SAME_CALL_ID, ZKE_ASSERT, "create.py:242-254 same context: call_id same") \
   X(EV_CR_SAME_IS_ROOT, ZKE_ASSERT, "create.py:242-254 same context: is_root same") \
   X(EV_CR_SAME_IS_CREATE, ZKE_ASSERT, "create.py:242-254 same context: is_create same") \
-  X(EV_CR_SAME_CODE_HASH, ZKE_ASSERT, "create.py:242-254 same context: code_hash same")
+  X(EV_CR_SAME_CODE_HASH, ZKE_ASSERT, "create.py:242-254 same context: code_hash same") \
+  X(EV_ESS_OPCODE, ZKE_ASSERT, "error_oog_sload_sstore.py:18-19 is_sstore + is_sload == 1") \
+  X(EV_ESS_KEY_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:21 stack_pop storage key unsat") \
+  X(EV_ESS_KEY_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:21 stack_pop storage key ambiguous") \
+  X(EV_ESS_TXID_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:23 call_context_lookup(TxId) unsat") \
+  X(EV_ESS_TXID_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:23 call_context_lookup(TxId) ambiguous") \
+  X(EV_ESS_TXID_TYPE, ZKE_ASSERT, "error_oog_sload_sstore.py:23 call_context_lookup(TxId): .value() of a Word") \
+  X(EV_ESS_CALLEE_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:24 call_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_ESS_CALLEE_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:24 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_ESS_CALLEE_DOMAIN, ZKE_VALUE, "error_oog_sload_sstore.py:25 word_to_address: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_ESS_CALLEE_RANGE, ZKE_RANGE, "error_oog_sload_sstore.py:25 word_to_address: more than 20 bytes") \
+  X(EV_ESS_AL_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:26 read_account_storage_to_access_list unsat") \
+  X(EV_ESS_AL_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:26 read_account_storage_to_access_list ambiguous") \
+  X(EV_ESS_AL_TYPE, ZKE_ASSERT, "error_oog_sload_sstore.py:26 read_account_storage_to_access_list: .value() of a Word") \
+  X(EV_ESS_VAL_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:31 stack_pop value (SSTORE) unsat") \
+  X(EV_ESS_VAL_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:31 stack_pop value (SSTORE) ambiguous") \
+  X(EV_ESS_READ_UNSAT, ZKE_UNSAT, "error_oog_sload_sstore.py:32 account_storage_read (SSTORE) unsat") \
+  X(EV_ESS_READ_AMBIG, ZKE_AMBIG, "error_oog_sload_sstore.py:32 account_storage_read (SSTORE) ambiguous") \
+  X(EV_ESS_AUX_MISSING, ZKE_ASSERT, "error_oog_sload_sstore.py:33 Word(curr.aux_data): not exactly one entry for this step in the step-aux table") \
+  X(EV_ESS_AUX_RANGE, ZKE_ASSERT, "error_oog_sload_sstore.py:33 Word(curr.aux_data): the integer does not fit 32 bytes") \
+  X(EV_ESS_GAS_RANGE, ZKE_ASSERT, "error_oog_sload_sstore.py:48 compare(gas_left, gas_cost, 8): gas_left beyond 8 bytes") \
+  X(EV_ESS_SLOAD_NOT_OOG, ZKE_ASSERT, "error_oog_sload_sstore.py:50 SLOAD: gas_left < gas_cost") \
+  X(EV_ESS_SSTORE_NOT_OOG, ZKE_ASSERT, "error_oog_sload_sstore.py:53-56 SSTORE: gas_left <= 2300 or gas_left < gas_cost") \
+  X(EV_EOCR_OPCODE, ZKE_ASSERT, "error_oog_create.py:25 is_create + is_create2 == 1") \
+  X(EV_EOCR_OFF_UNSAT, ZKE_UNSAT, "error_oog_create.py:28 stack_lookup(Read, 1) offset unsat") \
+  X(EV_EOCR_OFF_AMBIG, ZKE_AMBIG, "error_oog_create.py:28 stack_lookup(Read, 1) offset ambiguous") \
+  X(EV_EOCR_SIZE_UNSAT, ZKE_UNSAT, "error_oog_create.py:29 stack_lookup(Read, 2) size unsat") \
+  X(EV_EOCR_SIZE_AMBIG, ZKE_AMBIG, "error_oog_create.py:29 stack_lookup(Read, 2) size ambiguous") \
+  X(EV_EOCR_SIZE_DOMAIN, ZKE_VALUE, "error_oog_create.py:30 memory_offset_and_length: size: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOCR_SIZE_RANGE, ZKE_RANGE, "error_oog_create.py:30 memory_offset_and_length: size: more than 5 bytes") \
+  X(EV_EOCR_OFF_DOMAIN, ZKE_VALUE, "error_oog_create.py:30 memory_offset_and_length: offset: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOCR_OFF_RANGE, ZKE_RANGE, "error_oog_create.py:30 memory_offset_and_length: offset: more than 5 bytes") \
+  X(EV_EOCR_ROOT_UNSAT, ZKE_UNSAT, "error_oog_create.py:32 call_context_lookup(IsRoot) unsat") \
+  X(EV_EOCR_ROOT_AMBIG, ZKE_AMBIG, "error_oog_create.py:32 call_context_lookup(IsRoot) ambiguous") \
+  X(EV_EOCR_ROOT_TYPE, ZKE_ASSERT, "error_oog_create.py:32 call_context_lookup(IsRoot): .value() of a Word") \
+  X(EV_EOCR_TXID_UNSAT, ZKE_UNSAT, "error_oog_create.py:36 call_context_lookup(TxId) unsat") \
+  X(EV_EOCR_TXID_AMBIG, ZKE_AMBIG, "error_oog_create.py:36 call_context_lookup(TxId) ambiguous") \
+  X(EV_EOCR_TXID_TYPE, ZKE_ASSERT, "error_oog_create.py:36 call_context_lookup(TxId): .value() of a Word") \
+  X(EV_EOCR_BYTE_UNSAT, ZKE_UNSAT, "error_oog_create.py:37 tx_calldata_lookup(tx_id, idx) unsat") \
+  X(EV_EOCR_BYTE_AMBIG, ZKE_AMBIG, "error_oog_create.py:37 tx_calldata_lookup(tx_id, idx) ambiguous") \
+  X(EV_EOCR_BYTE_TYPE, ZKE_ASSERT, "error_oog_create.py:37 tx_calldata_lookup(tx_id, idx): .value() of a Word") \
+  X(EV_EOCR_MEMSIZE_RANGE, ZKE_RANGE, "error_oog_create.py:47 memory_expansion: memory size beyond 4 bytes") \
+  X(EV_EOCR_MEM_MAX, ZKE_ASSERT, "error_oog_create.py:47 memory_expansion: max(): curr.memory_word_size beyond 4 bytes") \
+  X(EV_EOCR_WORDSIZE_RANGE, ZKE_RANGE, "error_oog_create.py:51 constant_divmod(size + 31, 32, 4): quotient beyond 4 bytes") \
+  X(EV_EOCR_GAS_RANGE, ZKE_ASSERT, "error_oog_create.py:60 compare(gas_left, gas_cost, 8): gas_left beyond 8 bytes") \
+  X(EV_EOCR_NOT_OOG, ZKE_ASSERT, "error_oog_create.py:62 insufficient_gas + is_exceed_max_initcode_size != 0")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

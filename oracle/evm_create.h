@@ -223,3 +223,109 @@ static void gadget_create(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
   CHECK(EV_CR_SAME_IS_CREATE, fr_eq(NXT(S_IS_CREATE), CUR(S_IS_CREATE)));
   CHECK(EV_CR_SAME_CODE_HASH, fr_eq(NXT(S_HASH_LO), CUR(S_HASH_LO)) && fr_eq(NXT(S_HASH_HI), CUR(S_HASH_HI)));
 }
+
+/* ---- ErrorOutOfGasSloadSstore: error_oog_sload_sstore.py:16-60 (read_account_storage_to_access_list instruction.py:1088-1097,
+ * account_storage_read :1015-1026, constrain_error_state).  StepState.aux_data is the slot's committed value as an INT
+ * (Word(aux_data) splits it), taken from the step-aux side table.
+ * Pinned by tests/golden/evm25.npz (verdicts of the reference's verify_step on all 34 cases of its own test). */
+static void gadget_error_oog_sload_sstore(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const int is_sstore = fr_eq_u64(opcode, 0x55), is_sload = fr_eq_u64(opcode, 0x54);
+  CHECK(EV_ESS_OPCODE, is_sstore + is_sload == 1);
+  word_t key_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, sp, &key_w), EV_ESS_KEY_UNSAT, row)) return;
+  fr_t tx_id, callee;
+  ST_CC(1, ZK_CC_TxId, &tx_id, EV_ESS_TXID_UNSAT);
+  uint32_t r;
+  LK(cc_lookup(e, fr_add(rwc, fr_u64(2)), call_id, ZK_CC_CalleeAddress, &r), EV_ESS_CALLEE_UNSAT);
+  W2FQ(rw_value(e, r), 20, &callee, EV_ESS_CALLEE_DOMAIN);
+  {
+    fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(3)), 0, ZK_TARGET_TxAccessListAccountStorage);
+    key[R_ID] = tx_id; key[R_ADDR] = callee; key[R_KEY_LO] = key_w.lo; key[R_KEY_HI] = key_w.hi;
+    LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR) | RWM_KEY, &r), EV_ESS_AL_UNSAT);
+    NOT_WORD(rw_val_is_word(e, r), EV_ESS_AL_UNSAT);
+  }
+  const fr_t is_warm = rw_cell(e, R_VAL_LO, r);
+  uint64_t gas_cost, n_rw = 4;
+  if (is_sload) gas_cost = fr_eq_u64(is_warm, 1) ? 100 : 2100;
+  else {
+    word_t value;
+    if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(4)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &value), EV_ESS_VAL_UNSAT, row)) return;
+    {
+      fr_t key[14]; rw_key_init(key, fr_add(rwc, fr_u64(5)), 0, ZK_TARGET_AccountStorage);
+      key[R_ID] = tx_id; key[R_ADDR] = callee; key[R_KEY_LO] = key_w.lo; key[R_KEY_HI] = key_w.hi;
+      LK(rw_lookup_m(e, key, RWM_BASE | RWM(R_ID) | RWM(R_ADDR) | RWM_KEY, &r), EV_ESS_READ_UNSAT);
+    }
+    const word_t value_prev = rw_value(e, r);
+    n_rw = 6;
+    word_t original = {fr_u64(0), fr_u64(0)};
+    int hits = 0;
+    for (uint64_t a = 0; a < e->n_aux; a++)
+      if (fr_eq_u64(fr_load(ORC_CELL(e->aux, e->n_aux, 0, a)), row)) {
+        hits++; original.lo = fr_load(ORC_CELL(e->aux, e->n_aux, 1, a)); original.hi = fr_load(ORC_CELL(e->aux, e->n_aux, 2, a));
+      }
+    CHECK(EV_ESS_AUX_MISSING, hits == 1);
+    /* Word(lo + (hi << 128)): the integer must fit 32 bytes, and is split again at bit 128 */
+    CHECK(EV_ESS_AUX_RANGE, fr_fits_bits(original.hi, 128));
+    original.hi = fr_add(original.hi, fr_hi128(original.lo)); /* < 2^128 + 2^126: no wrap */
+    original.lo = fr_lo128(original.lo);
+    CHECK(EV_ESS_AUX_RANGE, fr_fits_bits(original.hi, 128));
+    if (word_eq(value, value_prev)) gas_cost = 100;
+    else if (word_eq(value_prev, original)) gas_cost = (fr_is_zero(original.lo) && fr_is_zero(original.hi)) ? 20000 : 2900;
+    else gas_cost = 100;
+    if (fr_is_zero(is_warm)) gas_cost += 2100;
+  }
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_ESS_GAS_RANGE, fr_fits_bits(gas_left, 64));
+  const int insufficient = gas_left.l[0] < gas_cost;
+  if (is_sload) CHECK(EV_ESS_SLOAD_NOT_OOG, insufficient);
+  else CHECK(EV_ESS_SSTORE_NOT_OOG, insufficient || gas_left.l[0] <= 2300);
+  error_state_tail(e, i, row, n_rw);
+}
+
+/* ---- ErrorOutOfGasCREATE: error_oog_create.py:19-65.  In a root call the init code is priced as tx call data, one
+ * tx_calldata_lookup per byte (`for idx in range(size)`): the walk ends at the first index the tx table does not hold, so
+ * it is bounded by the table, not by `size`.
+ * Pinned by tests/golden/evm26.npz (verdicts of the reference's verify_step on all 8 cases of its own test). */
+static void gadget_error_oog_create(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const int is_create = fr_eq_u64(opcode, 0xf0), is_create2 = fr_eq_u64(opcode, 0xf5);
+  CHECK(EV_EOCR_OPCODE, is_create + is_create2 == 1);
+  word_t off_w, size_w;
+  if (!need1(e, rw_lookup(e, rwc, 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(1)), &off_w), EV_EOCR_OFF_UNSAT, row)) return;
+  if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(1)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(2)), &size_w), EV_EOCR_SIZE_UNSAT, row)) return;
+  fr_t offset = fr_u64(0), size, is_root;
+  W2FQ(size_w, 5, &size, EV_EOCR_SIZE_DOMAIN);
+  if (!fr_is_zero(size)) W2FQ(off_w, 5, &offset, EV_EOCR_OFF_DOMAIN);
+  ST_CC(2, ZK_CC_IsRoot, &is_root, EV_EOCR_ROOT_UNSAT);
+  uint64_t gas_cost, n_rw = 3;
+  if (fr_eq_u64(is_root, 1)) {
+    fr_t tx_id;
+    ST_CC(3, ZK_CC_TxId, &tx_id, EV_EOCR_TXID_UNSAT);
+    n_rw = 4;
+    uint64_t nz = 0;
+    for (uint64_t idx = 0; idx < size.l[0]; idx++) {
+      uint32_t r;
+      fr_t key[3] = {tx_id, fr_u64(ZK_TX_CallData), fr_u64(idx)};
+      LK(orc_lookup(&e->tx_ix, key, &r), EV_EOCR_BYTE_UNSAT);
+      NOT_WORD(tx_is_word(e, r), EV_EOCR_BYTE_UNSAT);
+      nz += !fr_is_zero(tx_value(e, r).lo);
+    }
+    gas_cost = 53000 + 16 * nz + 4 * (size.l[0] - nz);
+  } else {
+    uint64_t expansion;
+    const int rc_ = mem_expansion_gas(e, i, fr_is_zero(size) ? 0 : (offset.l[0] + size.l[0] + 31) / 32, &expansion);
+    if (rc_) { orc_fail(e->res, rc_ == 1 ? EV_EOCR_MEMSIZE_RANGE : EV_EOCR_MEM_MAX, row); return; }
+    gas_cost = 32000 + expansion;
+  }
+  const uint64_t word_size = (size.l[0] + 31) / 32;
+  CHECK(EV_EOCR_WORDSIZE_RANGE, !(word_size >> 32));
+  gas_cost += 2 * word_size + (is_create2 ? 6 * word_size : 0);
+  const int exceeds = 49152 < size.l[0];
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_EOCR_GAS_RANGE, fr_fits_bits(gas_left, 64));
+  CHECK(EV_EOCR_NOT_OOG, gas_left.l[0] < gas_cost || exceeds);
+  error_state_tail(e, i, row, n_rw);
+}

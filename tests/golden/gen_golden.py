@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45, "evm24": 47}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45, "evm24": 47, "evm25": 49, "evm26": 51}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1496,30 +1496,49 @@ def evm2_cases(part="evm2"):
                             gas_left=exp.callee_gas_left, reversible_write_counter=2)
         return [cur, nxt], list(caller_bc.table_assignments()) + list(callee_bc.table_assignments()), list(rw.rws), [], []
 
-    def create_case(idx):
-        """tests/evm/test_create.py: case `idx` of the reference test's own TESTING_DATA.  The test function is run with its
-        verify_steps / verify_copy_table replaced by a recorder, which yields the tables and the two steps it would have
-        verified (the step's aux_data = the init code's hash rides along as a side table keyed by the step row)"""
+    def recorded_case(module, fn, args):
+        """Run one of the reference's OWN test functions (tests/evm/<module>.py) with its verify_steps / verify_copy_table
+        replaced by a recorder: yields the tables and the steps it would have verified.  A step's aux_data (a Word: the
+        init code's hash of CREATE / CREATE2; an int: the committed value of ErrorOutOfGasSloadSstore) rides along as a
+        side table keyed by the step row"""
         import importlib
         tdir = os.path.normpath(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm"))
         for d_ in (tdir, os.path.dirname(tdir)):
             if d_ not in sys.path:
                 sys.path.insert(0, d_)
-        tc = importlib.import_module("test_create")
+        tc = importlib.import_module(module)
         got = {}
-        keep = (tc.verify_steps, tc.verify_copy_table)
+        keep = (tc.verify_steps, getattr(tc, "verify_copy_table", None))
         tc.verify_steps = lambda tables, steps, **kw: got.update(tables=tables, steps=steps)
-        tc.verify_copy_table = lambda *a, **kw: None
+        if keep[1] is not None:
+            tc.verify_copy_table = lambda *a, **kw: None
         try:
-            tc.test_create_create2(*tc.TESTING_DATA[idx])
+            getattr(tc, fn)(*args)
         finally:
-            tc.verify_steps, tc.verify_copy_table = keep
+            tc.verify_steps = keep[0]
+            if keep[1] is not None:
+                tc.verify_copy_table = keep[1]
         t, steps = got["tables"], got["steps"]
         aux = []
         for k_, st_ in enumerate(steps):
-            if st_.aux_data is not None:
-                aux.append((k_, st_.aux_data.lo.n, st_.aux_data.hi.n))
-        return steps, list(t.bytecode_table), list(t.rw_table), list(getattr(t, "copy_table", [])), [], [], [], [], aux
+            a_ = st_.aux_data
+            if isinstance(a_, int):
+                aux.append((k_, a_ & ((1 << 128) - 1), a_ >> 128))
+            elif a_ is not None:
+                aux.append((k_, a_.lo.n, a_.hi.n))
+        return (steps, list(t.bytecode_table), list(t.rw_table), list(getattr(t, "copy_table", [])), [], list(t.tx_table),
+                list(t.block_table), [], aux)
+
+    def create_case(idx):
+        """tests/evm/test_create.py: case `idx` of the reference test's own TESTING_DATA"""
+        import importlib
+        tdir = os.path.normpath(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm"))
+        for d_ in (tdir, os.path.dirname(tdir)):
+            if d_ not in sys.path:
+                sys.path.insert(0, d_)
+        data = importlib.import_module("test_create").TESTING_DATA[idx]
+        sc_ = recorded_case("test_create", "test_create_create2", data)
+        return sc_[:5] + ([], [], [], sc_[8])  # the creation gadget reads neither the tx nor the block table
 
     def mws(a):
         return (a + 31) // 32
@@ -1894,7 +1913,7 @@ def evm2_cases(part="evm2"):
         steps = [step_from(v) for v in S]
         for a_ in AUX:  # StepState.aux_data of step a_[0] (a Word)
             if 0 <= a_[0] < len(steps):
-                steps[a_[0]].aux_data = W(a_[1], a_[2])
+                steps[a_[0]].aux_data = W(a_[1], a_[2]) if part == "evm24" else a_[1] + (a_[2] << 128)
         t = Tables(block_table=set(BlockTableRow(FQ(v[0]), FQ(v[1]), wov(v[2], v[3], 1 if BF is None else BF[k_])) for k_, v in enumerate(BL)),
                    tx_table=set(TxTableRow(FQ(v[0]), FQ(v[1]), FQ(v[2]), wov(v[3], v[4], 1 if TF is None else TF[k_])) for k_, v in enumerate(T)),
                    withdrawal_table=set(),
@@ -1915,7 +1934,23 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm24":
+    if part == "evm26":
+        # every case of tests/evm/test_error_oog_create.py (two of them walk 320 bytes of tx call data)
+        import importlib
+        tdir = os.path.normpath(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm"))
+        for d_ in (tdir, os.path.dirname(tdir)):
+            if d_ not in sys.path:
+                sys.path.insert(0, d_)
+        data = importlib.import_module("test_error_oog_create").TESTING_DATA_IS_ROOT
+        scenarios = {"eocr_%d" % k_: recorded_case("test_error_oog_create", "test_error_oog_create", d_) for k_, d_ in enumerate(data)}
+    elif part == "evm25":
+        import itertools
+        # every case of tests/evm/test_error_oog_sload_store.py
+        scenarios = {"eoss_sload_%d" % int(w_): recorded_case("test_error_oog_sload_store", "test_error_oog_sload", (w_,)) for w_ in (False, True)}
+        for o_, p_, v_, w_, c_ in itertools.product((0, 1), (1, 2), (1, 2), (True, False), (True, False)):
+            scenarios["eoss_sstore_%d%d%d%d%d" % (o_, p_, v_, int(w_), int(c_))] = recorded_case(
+                "test_error_oog_sload_store", "test_error_oog_sstore", (o_, p_, v_, w_, c_))
+    elif part == "evm24":
         # 52 of the reference test's 1,152 cases: 3-4 of each of its 14 outcome classes (CREATE / CREATE2 x pre-check failure,
         # address collision, creation without init code (reverting or not), creation with init code = a new call context)
         picks = [0, 72, 75, 78, 97, 103, 106, 145, 216, 219, 222, 241, 247, 250, 297, 372, 377, 378, 397, 403, 516, 521, 522,
@@ -2151,14 +2186,14 @@ def evm2_cases(part="evm2"):
         S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
         RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
-        TF = [int(x.value.is_word) for x in sc_[5]] if part == "evm17" and len(sc_) > 5 else None
+        TF = [int(x.value.is_word) for x in sc_[5]] if part in ("evm17", "evm26") and len(sc_) > 5 else None
         BF = [int(x.value.is_word) for x in sc_[6]] if part == "evm18" and len(sc_) > 6 else None
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         AUX = [list(x) for x in sc_[8]] if len(sc_) > 8 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70, "evm24": 60}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 3, 15] if part == "evm24" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70, "evm24": 60, "evm25": 50, "evm26": 90}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 3, 15] if part == "evm24" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 9, 5, 15, 15] if part == "evm25" else [0, 0, 0, 1, 1, 1, 8, 2, 5, 6, 6, 6] if part == "evm26" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
@@ -2289,6 +2324,16 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm26_cases():
+    """ErrorOutOfGasCREATE (error_oog_create.py: the root-call branch prices the tx call data byte by byte)"""
+    evm2_cases("evm26")
+
+
+def evm25_cases():
+    """ErrorOutOfGasSloadSstore (error_oog_sload_sstore.py; StepState.aux_data = the slot's committed value, an int)"""
+    evm2_cases("evm25")
 
 
 def evm24_cases():
@@ -3178,7 +3223,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "evm24", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "evm24", "evm25", "evm26", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -228,6 +228,16 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm26_vectors():
+    """ErrorOutOfGasCREATE"""
+    return evm2_vectors("evm26")
+
+
+def evm25_vectors():
+    """ErrorOutOfGasSloadSstore"""
+    return evm2_vectors("evm25")
+
+
 def evm24_vectors():
     """CREATE / CREATE2"""
     return evm2_vectors("evm24")

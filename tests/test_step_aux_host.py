@@ -17,6 +17,8 @@ def test_step_aux_rows_one_row_per_step_with_a_word():
     assert step_aux_rows(steps) == [[0, h & ((1 << 128) - 1), h >> 128], [2, 7, 0]]
     assert step_aux_rows(steps, row_base=100)[1][0] == 102
     assert step_aux_rows([steps[1]]) == []
+    oog = StepState(execution_state=ExecutionState.ErrorOutOfGasSloadSstore, rw_counter=1, aux_data=(5 << 128) + 9)
+    assert step_aux_rows([steps[1], oog]) == [[1, 9, 5]]
 
 
 def test_table_ids_follow_the_header():

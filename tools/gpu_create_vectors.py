@@ -1,4 +1,4 @@
-"""CREATE / CREATE2 vectors (tests/golden/evm24.npz) through the C-ABI on cuda:0 against the oracle, array for array.
+"""ErrorOutOfGasCREATE, ErrorOutOfGasSloadSstore and CREATE / CREATE2 vectors (tests/golden/evm26.npz, evm25.npz, evm24.npz) through the C-ABI on cuda:0 against the oracle, array for array.
 Small enough to run under compute-sanitizer (tools/gpu_r02_w.sh)."""
 import os
 import sys
@@ -26,16 +26,22 @@ ctx.upload_table(native.TABLE_EXP, np.zeros((11, 0, 4), dtype=np.uint64))
 ctx.upload_table(native.TABLE_TX, np.zeros((5, 0, 4), dtype=np.uint64))
 ctx.upload_table(native.TABLE_BLOCK, np.zeros((4, 0, 4), dtype=np.uint64))
 n = 0
-for name, k, w, exp_row, exp_exc in golden_util.evm24_vectors():
+import itertools  # noqa: E402
+
+for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm26_vectors(), golden_util.evm25_vectors(), golden_util.evm24_vectors()):
     if n >= limit:
         break
     ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])
     ctx.upload_table(native.TABLE_RW, w["rw"], flags=w["rw_flags"])
     ctx.upload_table(native.TABLE_COPY, w["copy"])
+    if "tx_flags" in w:
+        ctx.upload_table(native.TABLE_TX, w["tx"], flags=w["tx_flags"])
+    else:
+        ctx.upload_table(native.TABLE_TX, w["tx"] if "tx" in w else np.zeros((5, 0, 4), dtype=np.uint64))
     ctx.upload_table(native.TABLE_STEP_AUX, w["aux"] if "aux" in w else np.zeros((3, 0, 4), dtype=np.uint64))
     ctx.upload_columns(native.CIRCUIT_EVM, w["steps"])
     ff, fc = ctx.check(native.CIRCUIT_EVM, 0, w["steps"].shape[1] - 1, 0, 0)
     off, ofc = oracle_lib.check_evm_x(w, fixed)
     assert np.array_equal(ff, off) and np.array_equal(fc, ofc), f"{name}[{k}] differs from oracle"
     n += 1
-print(f"create vectors ok: {n} cuda == oracle")
+print(f"step-aux vectors ok: {n} cuda == oracle")

@@ -272,4 +272,119 @@ ZK_HD_NOINLINE void gadget_create(const StepCtx& s) {
   EV_CHECK(EV_CR_SAME_CODE_HASH, fr_eq(s.nxt(S_HASH_LO), s.cur(S_HASH_LO)) && fr_eq(s.nxt(S_HASH_HI), s.cur(S_HASH_HI)));
 }
 
+// ErrorOutOfGasSloadSstore: error_oog_sload_sstore.py:16-60 (read_account_storage_to_access_list instruction.py:1088-1097,
+// account_storage_read :1015-1026, constrain_error_state).  StepState.aux_data is the slot's committed value as an INT
+// (Word(aux_data) splits it at bit 128), taken from ZK_TABLE_STEP_AUX by the step's row.
+ZK_HD_NOINLINE void gadget_error_oog_sload_sstore(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const bool is_sstore = fr_eq_u64(opcode, 0x55), is_sload = fr_eq_u64(opcode, 0x54);
+  EV_CHECK(EV_ESS_OPCODE, is_sstore || is_sload);
+  Word2 key_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, sp, &key_w), EV_ESS_KEY_UNSAT)) return;
+  Fr tx_id, callee = fr_u64(0);
+  ST_CC(1, ZK_CC_TxId, &tx_id, EV_ESS_TXID_UNSAT);
+  u32 r = 0;
+  TX_LK(cc_lookup_m(s, fr_add_u64(rwc, 2), call_id, ZK_CC_CalleeAddress, &r), EV_ESS_CALLEE_UNSAT);
+  EOOG_W2FQ(rw_word(s, R_VAL_LO, r), 20, &callee, EV_ESS_CALLEE_DOMAIN);
+  {
+    Fr key[14];
+    rw_key_init(key, fr_add_u64(rwc, 3), 0, ZK_TARGET_TxAccessListAccountStorage);
+    key[R_ID] = tx_id;
+    key[R_ADDR] = callee;
+    key[R_KEY_LO] = key_w.lo;
+    key[R_KEY_HI] = key_w.hi;
+    TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR) | ZK_RWM(R_KEY_LO) | ZK_RWM(R_KEY_HI), &r), EV_ESS_AL_UNSAT);
+    TX_NOT_WORD(rw_flag(s, r, 0), EV_ESS_AL_UNSAT);
+  }
+  const Fr is_warm = rw_cell(s, R_VAL_LO, r);
+  u64 gas_cost = 0, n_rw = 4;
+  if (is_sload) gas_cost = fr_eq_u64(is_warm, 1) ? 100 : 2100;
+  else {
+    Word2 value{fr_u64(0), fr_u64(0)};
+    if (!need1(s, true, stack_at(s, true, 4, 0, fr_add_u64(sp, 1), &value), EV_ESS_VAL_UNSAT)) return;
+    {
+      Fr key[14];
+      rw_key_init(key, fr_add_u64(rwc, 5), 0, ZK_TARGET_AccountStorage);
+      key[R_ID] = tx_id;
+      key[R_ADDR] = callee;
+      key[R_KEY_LO] = key_w.lo;
+      key[R_KEY_HI] = key_w.hi;
+      TX_LK(rw_lookup_m(s, key, ZK_RWM_BASE | ZK_RWM(R_ID) | ZK_RWM(R_ADDR) | ZK_RWM(R_KEY_LO) | ZK_RWM(R_KEY_HI), &r), EV_ESS_READ_UNSAT);
+    }
+    const Word2 value_prev = rw_word(s, R_VAL_LO, r);
+    n_rw = 6;
+    const Fr akey[1] = {fr_u64(s.row)};
+    u32 ra = 0;
+    EV_CHECK(EV_ESS_AUX_MISSING, lookup<1>(s.t.aux, akey, &ra) == 1);
+    Word2 original{table_cell(s.t.aux.tab, 1, ra), table_cell(s.t.aux.tab, 2, ra)};
+    // Word(lo + (hi << 128)): the integer must fit 32 bytes, and is split again at bit 128
+    EV_CHECK(EV_ESS_AUX_RANGE, (original.hi.l[2] | original.hi.l[3]) == 0);
+    original.hi = fr_add(original.hi, fr_u128(original.lo.l[2], original.lo.l[3]));  // < 2^128 + 2^126: no wrap
+    original.lo = fr_u128(original.lo.l[0], original.lo.l[1]);
+    EV_CHECK(EV_ESS_AUX_RANGE, (original.hi.l[2] | original.hi.l[3]) == 0);
+    if (word_eq(value, value_prev)) gas_cost = 100;
+    else if (word_eq(value_prev, original)) gas_cost = (fr_is_zero(original.lo) && fr_is_zero(original.hi)) ? 20000 : 2900;
+    else gas_cost = 100;
+    if (fr_is_zero(is_warm)) gas_cost += 2100;
+  }
+  const Fr gas_left = s.cur(S_GAS);
+  EV_CHECK(EV_ESS_GAS_RANGE, fr_fits64(gas_left));
+  const bool insufficient = gas_left.l[0] < gas_cost;
+  if (is_sload) EV_CHECK(EV_ESS_SLOAD_NOT_OOG, insufficient);
+  else EV_CHECK(EV_ESS_SSTORE_NOT_OOG, insufficient || gas_left.l[0] <= 2300);
+  error_state_tail(s, n_rw);
+}
+
+// ErrorOutOfGasCREATE: error_oog_create.py:19-65.  In a root call the init code is priced as tx call data, one
+// tx_calldata_lookup per byte (`for idx in range(size)`): the walk ends at the first index the tx table does not hold, so its
+// trip count is bounded by the table, not by `size`.
+ZK_HD_NOINLINE void gadget_error_oog_create(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const bool is_create = fr_eq_u64(opcode, 0xf0), is_create2 = fr_eq_u64(opcode, 0xf5);
+  EV_CHECK(EV_EOCR_OPCODE, is_create || is_create2);
+  Word2 off_w{fr_u64(0), fr_u64(0)}, size_w{fr_u64(0), fr_u64(0)};
+  if (!need1(s, true, stack_at(s, true, 0, 0, fr_add_u64(sp, 1), &off_w), EV_EOCR_OFF_UNSAT)) return;
+  if (!need1(s, true, stack_at(s, true, 1, 0, fr_add_u64(sp, 2), &size_w), EV_EOCR_SIZE_UNSAT)) return;
+  Fr offset = fr_u64(0), size = fr_u64(0), is_root;
+  EOOG_W2FQ(size_w, 5, &size, EV_EOCR_SIZE_DOMAIN);
+  if (!fr_is_zero(size)) EOOG_W2FQ(off_w, 5, &offset, EV_EOCR_OFF_DOMAIN);
+  ST_CC(2, ZK_CC_IsRoot, &is_root, EV_EOCR_ROOT_UNSAT);
+  u64 gas_cost = 0, n_rw = 3;
+  if (fr_eq_u64(is_root, 1)) {
+    Fr tx_id;
+    ST_CC(3, ZK_CC_TxId, &tx_id, EV_EOCR_TXID_UNSAT);
+    n_rw = 4;
+    u64 nz = 0;
+#pragma unroll 1
+    for (u64 idx = 0; idx < size.l[0]; idx++) {
+      u32 r = 0;
+      Fr key[3] = {tx_id, fr_u64(ZK_TX_CallData), fr_u64(idx)};
+      TX_LK(lookup<3>(s.t.tx, key, &r), EV_EOCR_BYTE_UNSAT);
+      TX_NOT_WORD(tx_is_word(s, r), EV_EOCR_BYTE_UNSAT);
+      nz += fr_is_zero(table_cell(s.t.tx.tab, 3, r)) ? 0 : 1;
+    }
+    gas_cost = 53000 + 16 * nz + 4 * (size.l[0] - nz);
+  } else {
+    u64 expansion = 0;
+    const int rc_ = mem_expansion_gas(s, fr_is_zero(size) ? 0 : (offset.l[0] + size.l[0] + 31) / 32, &expansion);
+    if (rc_) {
+      step_fail(s, rc_ == 1 ? EV_EOCR_MEMSIZE_RANGE : EV_EOCR_MEM_MAX);
+      return;
+    }
+    gas_cost = 32000 + expansion;
+  }
+  const u64 word_size = (size.l[0] + 31) / 32;
+  EV_CHECK(EV_EOCR_WORDSIZE_RANGE, (word_size >> 32) == 0);
+  gas_cost += 2 * word_size + (is_create2 ? 6 * word_size : 0);
+  const bool exceeds = 49152 < size.l[0];
+  const Fr gas_left = s.cur(S_GAS);
+  EV_CHECK(EV_EOCR_GAS_RANGE, fr_fits64(gas_left));
+  EV_CHECK(EV_EOCR_NOT_OOG, gas_left.l[0] < gas_cost || exceeds);
+  error_state_tail(s, n_rw);
+}
+
 }  // namespace zk

@@ -41,12 +41,15 @@ def pack_steps(steps: List[StepState]) -> np.ndarray:
 
 def step_aux_rows(steps: List[StepState], row_base: int = 0) -> List[List[int]]:
     """StepState.aux_data (reference step.py:45) as the step-aux side table: one row (step row, lo, hi) per step that carries
-    a Word there (CREATE / CREATE2 read it as the init code's hash, create.py:107)"""
+    a Word (CREATE / CREATE2 read it as the init code's hash, create.py:107) or an int (ErrorOutOfGasSloadSstore: the slot's
+    committed value, error_oog_sload_sstore.py:33) there"""
     c = packing.cell_int
     rows = []
     for k, s in enumerate(steps):
         a = getattr(s, "aux_data", None)
-        if a is not None and hasattr(a, "lo") and hasattr(a, "hi"):
+        if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 256):
+            rows.append([row_base + k, a & ((1 << 128) - 1), a >> 128])
+        elif a is not None and hasattr(a, "lo") and hasattr(a, "hi"):
             rows.append([row_base + k, c(a.lo), c(a.hi)])
     return rows
 
