@@ -1493,7 +1493,20 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_EOCR_MEM_MAX, ZKE_ASSERT, "error_oog_create.py:47 memory_expansion: max(): curr.memory_word_size beyond 4 bytes") \
   X(EV_EOCR_WORDSIZE_RANGE, ZKE_RANGE, "error_oog_create.py:51 constant_divmod(size + 31, 32, 4): quotient beyond 4 bytes") \
   X(EV_EOCR_GAS_RANGE, ZKE_ASSERT, "error_oog_create.py:60 compare(gas_left, gas_cost, 8): gas_left beyond 8 bytes") \
-  X(EV_EOCR_NOT_OOG, ZKE_ASSERT, "error_oog_create.py:62 insufficient_gas + is_exceed_max_initcode_size != 0")
+  X(EV_EOCR_NOT_OOG, ZKE_ASSERT, "error_oog_create.py:62 insufficient_gas + is_exceed_max_initcode_size != 0") \
+  X(EV_EOPC_CALLEE_UNSAT, ZKE_UNSAT, "error_oog_precompile.py:10 call_context_lookup_word(CalleeAddress) unsat") \
+  X(EV_EOPC_CALLEE_AMBIG, ZKE_AMBIG, "error_oog_precompile.py:10 call_context_lookup_word(CalleeAddress) ambiguous") \
+  X(EV_EOPC_CALLEE_DOMAIN, ZKE_VALUE, "error_oog_precompile.py:11 word_to_address: word_to_fq of a half >= 2^128 -> OverflowError") \
+  X(EV_EOPC_CALLEE_RANGE, ZKE_RANGE, "error_oog_precompile.py:11 word_to_address: more than 20 bytes") \
+  X(EV_EOPC_CDLEN_UNSAT, ZKE_UNSAT, "error_oog_precompile.py:12 call_context_lookup(CallDataLength) unsat") \
+  X(EV_EOPC_CDLEN_AMBIG, ZKE_AMBIG, "error_oog_precompile.py:12 call_context_lookup(CallDataLength) ambiguous") \
+  X(EV_EOPC_CDLEN_TYPE, ZKE_ASSERT, "error_oog_precompile.py:12 call_context_lookup(CallDataLength): .value() of a Word") \
+  X(EV_EOPC_NOT_PRECOMPILE, ZKE_ASSERT, "error_oog_precompile.py:15 the callee address is one of the nine precompiles") \
+  X(EV_EOPC_WORDSIZE_RANGE, ZKE_RANGE, "error_oog_precompile.py:27 memory_copier_gas_cost: constant_divmod(len + 31, 32, 4): quotient beyond 4 bytes") \
+  X(EV_EOPC_GAS_LEFT_RANGE, ZKE_ASSERT, "error_oog_precompile.py:30 compare(gas_left, gas_cost, 8): gas_left beyond 8 bytes") \
+  X(EV_EOPC_GAS_INT, ZKE_VALUE, "error_oog_precompile.py:19-30 every precompile but DATACOPY / BN254PAIRING: gas_cost is a Python int, compare() raises AttributeError on it") \
+  X(EV_EOPC_GAS_COST_RANGE, ZKE_ASSERT, "error_oog_precompile.py:23-24,30 compare(): gas_cost beyond 8 bytes (call-data length not a multiple of 192: the FIELD quotient is huge)") \
+  X(EV_EOPC_NOT_OOG, ZKE_ASSERT, "error_oog_precompile.py:31 gas_left < gas_cost")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -990,11 +990,13 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_EXP || st == ZK_ES_ErrorMaxCodeSizeExceeded || st == ZK_ES_ErrorOutOfGasCodeStore ||
                                   st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN ||
                                   st == ZK_ES_ErrorOutOfGasCall || st == ZK_ES_CALL_OP || st == ZK_ES_CREATE || st == ZK_ES_CREATE2 ||
-                                  st == ZK_ES_ErrorOutOfGasSloadSstore || st == ZK_ES_ErrorOutOfGasCREATE);
+                                  st == ZK_ES_ErrorOutOfGasSloadSstore || st == ZK_ES_ErrorOutOfGasCREATE ||
+                                  st == ZK_ES_ErrorOutOfGasPrecompile);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
   if (st == ZK_ES_STOP) { gadget_stop(e, i, row); return; }
+  if (st == ZK_ES_ErrorOutOfGasPrecompile) { gadget_error_oog_precompile(e, i, row); return; }
   if (st == ZK_ES_ORIGIN) { gadget_txctx(e, i, row, 0x32, ZK_TX_CallerAddress); return; }
   if (st == ZK_ES_GASPRICE) { gadget_txctx(e, i, row, 0x3a, ZK_TX_GasPrice); return; }
   fr_t opcode;

@@ -329,3 +329,43 @@ static void gadget_error_oog_create(evm_env* e, uint64_t i, uint64_t row, fr_t o
   CHECK(EV_EOCR_NOT_OOG, gas_left.l[0] < gas_cost || exceeds);
   error_state_tail(e, i, row, n_rw);
 }
+
+/* ---- ErrorOutOfGasPrecompile: execution/precompiles/error_oog_precompile.py:9-35 (no opcode lookup; the reference has no
+ * test of its own for it).  As written: only DATACOPY and BN254PAIRING can verify - for the other seven precompiles gas_cost
+ * stays a Python int and compare() raises AttributeError on it; the pairing count is a FIELD quotient len / 192.
+ * Pinned by tests/golden/evm27.npz (verdicts of the reference's verify_step). */
+static void gadget_error_oog_precompile(evm_env* e, uint64_t i, uint64_t row) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID);
+  uint32_t r;
+  LK(cc_lookup(e, rwc, call_id, ZK_CC_CalleeAddress, &r), EV_EOPC_CALLEE_UNSAT);
+  fr_t address, len;
+  W2FQ(rw_value(e, r), 20, &address, EV_EOPC_CALLEE_DOMAIN);
+  ST_CC(1, ZK_CC_CallDataLength, &len, EV_EOPC_CDLEN_UNSAT);
+  CHECK(EV_EOPC_NOT_PRECOMPILE, fr_fits_bits(address, 64) && address.l[0] >= 1 && address.l[0] <= 9);
+  const uint64_t a = address.l[0];
+  uint64_t gas_cost = 0;
+  int cost_ok = 1, cost_is_int = 0; /* cost_ok: gas_cost fits 8 bytes */
+  if (a == 8) {
+    /* 45000 + 34000 * (len / 192) over the field: below 2^64 only when 192 divides the integer len (and the sum is small) */
+    u128 rem = 0;
+    for (int k = 3; k >= 0; k--) rem = ((rem << 64) | len.l[k]) % 192;
+    if (rem != 0 || !fr_fits_bits(len, 64)) cost_ok = 0;
+    else {
+      const u128 c = (u128)45000 + (u128)34000 * (len.l[0] / 192);
+      if (c >> 64) cost_ok = 0; else gas_cost = (uint64_t)c;
+    }
+  } else if (a == 4) {
+    /* memory_copier_gas_cost(len, 0, 3): (len + 31) // 32 on the field sum, range-checked to 4 bytes */
+    const fr_t t = fr_add(len, fr_u64(31));
+    const fr_t q = {{(t.l[0] >> 5) | (t.l[1] << 59), (t.l[1] >> 5) | (t.l[2] << 59), (t.l[2] >> 5) | (t.l[3] << 59), t.l[3] >> 5}};
+    CHECK(EV_EOPC_WORDSIZE_RANGE, fr_fits_bits(q, 32));
+    gas_cost = 15 + 3 * q.l[0];
+  } else cost_is_int = 1;
+  const fr_t gas_left = CUR(S_GAS);
+  CHECK(EV_EOPC_GAS_LEFT_RANGE, fr_fits_bits(gas_left, 64));
+  CHECK(EV_EOPC_GAS_INT, !cost_is_int);
+  CHECK(EV_EOPC_GAS_COST_RANGE, cost_ok);
+  CHECK(EV_EOPC_NOT_OOG, gas_left.l[0] < gas_cost);
+  error_state_tail(e, i, row, 2);
+}

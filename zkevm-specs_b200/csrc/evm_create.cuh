@@ -387,4 +387,44 @@ ZK_HD_NOINLINE void gadget_error_oog_create(const StepCtx& s) {
   error_state_tail(s, n_rw);
 }
 
+// ErrorOutOfGasPrecompile: execution/precompiles/error_oog_precompile.py:9-35 (no opcode lookup).  As written: only DATACOPY
+// and BN254PAIRING can verify - for the other seven precompiles gas_cost stays a Python int and compare() raises
+// AttributeError on it (ZK_ERR_VALUE here); the pairing count is the FIELD quotient len / 192, below 2^64 only when 192
+// divides the integer.
+ZK_HD_NOINLINE void gadget_error_oog_precompile(const StepCtx& s) {
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID);
+  u32 r = 0;
+  TX_LK(cc_lookup_m(s, rwc, call_id, ZK_CC_CalleeAddress, &r), EV_EOPC_CALLEE_UNSAT);
+  Fr address = fr_u64(0), len;
+  EOOG_W2FQ(rw_word(s, R_VAL_LO, r), 20, &address, EV_EOPC_CALLEE_DOMAIN);
+  ST_CC(1, ZK_CC_CallDataLength, &len, EV_EOPC_CDLEN_UNSAT);
+  EV_CHECK(EV_EOPC_NOT_PRECOMPILE, fr_fits64(address) && address.l[0] >= 1 && address.l[0] <= 9);
+  const u64 a = address.l[0];
+  u64 gas_cost = 0;
+  bool cost_ok = true, cost_is_int = false;
+  if (a == 8) {
+    // 2^64 = 64 (mod 192): fold the four limbs with 64-bit arithmetic
+    u64 rem = 0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) rem = ((rem * 64) % 192 + len.l[k] % 192) % 192;
+    const u64 pairs = len.l[0] / 192;
+    if (rem != 0 || !fr_fits64(len) || pairs > (0xFFFFFFFFFFFFFFFFull - 45000) / 34000) cost_ok = false;
+    else gas_cost = 45000 + 34000 * pairs;
+  } else if (a == 4) {
+    // memory_copier_gas_cost(len, 0, 3): (len + 31) // 32 on the field sum, range-checked to 4 bytes
+    const Fr t = fr_add_u64(len, 31);
+    const Fr q{{(t.l[0] >> 5) | (t.l[1] << 59), (t.l[1] >> 5) | (t.l[2] << 59), (t.l[2] >> 5) | (t.l[3] << 59), t.l[3] >> 5}};
+    EV_CHECK(EV_EOPC_WORDSIZE_RANGE, fr_fits64(q) && (q.l[0] >> 32) == 0);
+    gas_cost = 15 + 3 * q.l[0];
+  } else {
+    cost_is_int = true;
+  }
+  const Fr gas_left = s.cur(S_GAS);
+  EV_CHECK(EV_EOPC_GAS_LEFT_RANGE, fr_fits64(gas_left));
+  EV_CHECK(EV_EOPC_GAS_INT, !cost_is_int);
+  EV_CHECK(EV_EOPC_GAS_COST_RANGE, cost_ok);
+  EV_CHECK(EV_EOPC_NOT_OOG, gas_left.l[0] < gas_cost);
+  error_state_tail(s, 2);
+}
+
 }  // namespace zk
