@@ -1506,7 +1506,41 @@ enum zk_bytecode_constraint { ZK_BYTECODE_CONSTRAINTS(ZK_ENUM_ENTRY) BC_N_CONSTR
   X(EV_EOPC_GAS_LEFT_RANGE, ZKE_ASSERT, "error_oog_precompile.py:30 compare(gas_left, gas_cost, 8): gas_left beyond 8 bytes") \
   X(EV_EOPC_GAS_INT, ZKE_VALUE, "error_oog_precompile.py:19-30 every precompile but DATACOPY / BN254PAIRING: gas_cost is a Python int, compare() raises AttributeError on it") \
   X(EV_EOPC_GAS_COST_RANGE, ZKE_ASSERT, "error_oog_precompile.py:23-24,30 compare(): gas_cost beyond 8 bytes (call-data length not a multiple of 192: the FIELD quotient is huge)") \
-  X(EV_EOPC_NOT_OOG, ZKE_ASSERT, "error_oog_precompile.py:31 gas_left < gas_cost")
+  X(EV_EOPC_NOT_OOG, ZKE_ASSERT, "error_oog_precompile.py:31 gas_left < gas_cost") \
+  X(EV_EGUO_CDLEN_UNSAT, ZKE_UNSAT, "error_gas_uint_overflow.py:100 call_context_lookup(CallDataLength) unsat") \
+  X(EV_EGUO_CDLEN_AMBIG, ZKE_AMBIG, "error_gas_uint_overflow.py:100 call_context_lookup(CallDataLength) ambiguous") \
+  X(EV_EGUO_CDLEN_TYPE, ZKE_ASSERT, "error_gas_uint_overflow.py:100 call_context_lookup(CallDataLength): .value() of a Word") \
+  X(EV_EGUO_TXID_UNSAT, ZKE_UNSAT, "error_gas_uint_overflow.py:101 call_context_lookup(TxId) unsat") \
+  X(EV_EGUO_TXID_AMBIG, ZKE_AMBIG, "error_gas_uint_overflow.py:101 call_context_lookup(TxId) ambiguous") \
+  X(EV_EGUO_TXID_TYPE, ZKE_ASSERT, "error_gas_uint_overflow.py:101 call_context_lookup(TxId): .value() of a Word") \
+  X(EV_EGUO_ROOT_UNSAT, ZKE_UNSAT, "error_gas_uint_overflow.py:102 call_context_lookup(IsRoot) unsat") \
+  X(EV_EGUO_ROOT_AMBIG, ZKE_AMBIG, "error_gas_uint_overflow.py:102 call_context_lookup(IsRoot) ambiguous") \
+  X(EV_EGUO_ROOT_TYPE, ZKE_ASSERT, "error_gas_uint_overflow.py:102 call_context_lookup(IsRoot): .value() of a Word") \
+  X(EV_EGUO_BYTE_UNSAT, ZKE_UNSAT, "error_gas_uint_overflow.py:105-108 tx_calldata_lookup(tx_id, idx) unsat") \
+  X(EV_EGUO_BYTE_AMBIG, ZKE_AMBIG, "error_gas_uint_overflow.py:105-108 tx_calldata_lookup(tx_id, idx) ambiguous") \
+  X(EV_EGUO_BYTE_TYPE, ZKE_ASSERT, "error_gas_uint_overflow.py:105-108 tx_calldata_lookup(tx_id, idx): .value() of a Word") \
+  X(EV_EGUO_CMP_RANGE, ZKE_ASSERT, "error_gas_uint_overflow.py:115-137 compare(): an operand beyond 8 bytes (the intrinsic gas itself passed 2^64)") \
+  X(EV_EGUO_OPCODE, ZKE_VALUE, "instruction.py:1198-1305 memory_size(opcode) returns None for an opcode without a memory operand -> TypeError (`if is_dynamic_gas:` tests an FQ object, always true)") \
+  X(EV_EGUO_POP0_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #0 unsat") \
+  X(EV_EGUO_POP0_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #0 ambiguous") \
+  X(EV_EGUO_POP1_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #1 unsat") \
+  X(EV_EGUO_POP1_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #1 ambiguous") \
+  X(EV_EGUO_POP2_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #2 unsat") \
+  X(EV_EGUO_POP2_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #2 ambiguous") \
+  X(EV_EGUO_POP3_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #3 unsat") \
+  X(EV_EGUO_POP3_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #3 ambiguous") \
+  X(EV_EGUO_POP4_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #4 unsat") \
+  X(EV_EGUO_POP4_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #4 ambiguous") \
+  X(EV_EGUO_POP5_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #5 unsat") \
+  X(EV_EGUO_POP5_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #5 ambiguous") \
+  X(EV_EGUO_POP6_UNSAT, ZKE_UNSAT, "instruction.py:1247-1295 memory_size: stack_pop #6 unsat") \
+  X(EV_EGUO_POP6_AMBIG, ZKE_AMBIG, "instruction.py:1247-1295 memory_size: stack_pop #6 ambiguous") \
+  X(EV_EGUO_LEN_DOMAIN, ZKE_VALUE, "instruction.py:1310 calc_mem_size64: word_to_fq(length, 31) of a half >= 2^128 -> OverflowError") \
+  X(EV_EGUO_LEN_RANGE, ZKE_RANGE, "instruction.py:1310 calc_mem_size64: word_to_fq(length, 31): more than 31 bytes") \
+  X(EV_EGUO_OFF_DOMAIN, ZKE_VALUE, "instruction.py:1321 calc_mem_size64_with_uint: word_to_fq(offset, 31) of a half >= 2^128 -> OverflowError") \
+  X(EV_EGUO_OFF_RANGE, ZKE_RANGE, "instruction.py:1321 calc_mem_size64_with_uint: word_to_fq(offset, 31): more than 31 bytes") \
+  X(EV_EGUO_OFF5_RANGE, ZKE_RANGE, "instruction.py:1325 calc_mem_size64_with_uint: word_to_fq(offset, 5): an offset below 2^64 with more than 5 bytes") \
+  X(EV_EGUO_NOT_OVERFLOW, ZKE_ASSERT, "error_gas_uint_overflow.py:160-167 one of the overflow flags is set")
 
 enum zk_evm_constraint { ZK_EVM_CONSTRAINTS(ZK_ENUM_ENTRY) EV_N_CONSTRAINTS };
 

@@ -991,7 +991,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
                                   st == ZK_ES_ErrorInvalidCreationCode || st == ZK_ES_RETURN ||
                                   st == ZK_ES_ErrorOutOfGasCall || st == ZK_ES_CALL_OP || st == ZK_ES_CREATE || st == ZK_ES_CREATE2 ||
                                   st == ZK_ES_ErrorOutOfGasSloadSstore || st == ZK_ES_ErrorOutOfGasCREATE ||
-                                  st == ZK_ES_ErrorOutOfGasPrecompile);
+                                  st == ZK_ES_ErrorOutOfGasPrecompile || st == ZK_ES_ErrorGasUintOverflow);
   if (st == ZK_ES_BeginTx) { gadget_begin_tx(e, i, row, is_first); return; }
   if (st == ZK_ES_EndTx) { gadget_end_tx(e, i, row); return; }
   if (st == ZK_ES_EndBlock) { gadget_end_block(e, i, row, is_last); return; }
@@ -1065,6 +1065,7 @@ static void verify_step(evm_env* e, uint64_t i, uint64_t row, uint32_t flags) {
   else if (st == ZK_ES_CREATE || st == ZK_ES_CREATE2) gadget_create(e, i, row, opcode);
   else if (st == ZK_ES_ErrorOutOfGasSloadSstore) gadget_error_oog_sload_sstore(e, i, row, opcode);
   else if (st == ZK_ES_ErrorOutOfGasCREATE) gadget_error_oog_create(e, i, row, opcode);
+  else if (st == ZK_ES_ErrorGasUintOverflow) gadget_error_gas_uint_overflow(e, i, row, opcode);
   else gadget_pop(e, i, row, opcode);
 }
 

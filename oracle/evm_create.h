@@ -369,3 +369,102 @@ static void gadget_error_oog_precompile(evm_env* e, uint64_t i, uint64_t row) {
   CHECK(EV_EOPC_NOT_OOG, gas_left.l[0] < gas_cost);
   error_state_tail(e, i, row, 2);
 }
+
+/* ---- ErrorGasUintOverflow: error_gas_uint_overflow.py:19-171 with instruction.memory_size :1198-1305, calc_mem_size64 /
+ * _with_uint :1309-1327, safe_mul :1329-1331, to_word_size :1333-1336.  As written: `if is_dynamic_gas:` tests an FQ object
+ * (always true), so memory_size runs for every opcode and returns None (TypeError) for one without a memory operand; an
+ * offset below 2^64 is read again with word_to_fq(.., 5) and raises beyond 5 bytes; `val.n < offset64.n` never holds over
+ * the field.  Pinned by tests/golden/evm28.npz (the cases the reference's own test runs + the three memory opcodes). */
+/* calc_mem_size64_with_uint: 0 ok (size / overflow set), else the failing constraint id */
+static int cms_uint(word_t off_w, fr_t len64, u128* size, int* overflow) {
+  *size = 0; *overflow = 0;
+  if (fr_is_zero(len64)) return 0;
+  fr_t off; int rc = word_to_fq_nb(off_w, 31, &off);
+  if (rc) return rc == 1 ? EV_EGUO_OFF_DOMAIN : EV_EGUO_OFF_RANGE;
+  if (!fr_fits_bits(off, 64)) { *overflow = 1; return 0; }
+  if (word_to_fq_nb(off_w, 5, &off)) return EV_EGUO_OFF5_RANGE;
+  *size = (u128)off.l[0] + len64.l[0];
+  return 0;
+}
+static int cms(word_t off_w, word_t len_w, u128* size, int* overflow) {
+  *size = 0; *overflow = 0;
+  fr_t len; const int rc = word_to_fq_nb(len_w, 31, &len);
+  if (rc) return rc == 1 ? EV_EGUO_LEN_DOMAIN : EV_EGUO_LEN_RANGE;
+  if (!fr_fits_bits(len, 64)) { *overflow = 1; return 0; }
+  return cms_uint(off_w, len, size, overflow);
+}
+static void gadget_error_gas_uint_overflow(evm_env* e, uint64_t i, uint64_t row, fr_t opcode) {
+  const uint64_t* S = e->steps; const uint64_t n = e->n_steps;
+  const fr_t rwc = CUR(S_RWC), call_id = CUR(S_CALL_ID), sp = CUR(S_SP);
+  const uint64_t op = fr_fits_bits(opcode, 8) ? opcode.l[0] : 0x100;
+  const int is_create = op == 0xf0 || op == 0xf5;
+  fr_t cd_len, tx_id, is_root;
+  ST_CC(0, ZK_CC_CallDataLength, &cd_len, EV_EGUO_CDLEN_UNSAT);
+  ST_CC(1, ZK_CC_TxId, &tx_id, EV_EGUO_TXID_UNSAT);
+  ST_CC(2, ZK_CC_IsRoot, &is_root, EV_EGUO_ROOT_UNSAT);
+  int calldata_of = 0, initcode_of = 0;
+  if (fr_eq_u64(is_root, 1)) {
+    const uint64_t len = fr_fits_bits(cd_len, 64) ? cd_len.l[0] : ~0ull; /* a longer walk ends at the first missing byte */
+    uint64_t nz = 0;
+    for (uint64_t idx = 0; idx < len; idx++) {
+      uint32_t r;
+      fr_t key[3] = {tx_id, fr_u64(ZK_TX_CallData), fr_u64(idx)};
+      LK(orc_lookup(&e->tx_ix, key, &r), EV_EGUO_BYTE_UNSAT);
+      NOT_WORD(tx_is_word(e, r), EV_EGUO_BYTE_UNSAT);
+      nz += !fr_is_zero(tx_value(e, r).lo);
+    }
+    if (len > 0) {
+      const u128 MAXU = ~(uint64_t)0;
+      u128 gas = is_create ? 53000 : 21000;
+      const int nz_of = (uint64_t)((MAXU - gas) / 16) < nz;
+      gas += (u128)nz * 16;
+      int z_of = 0;
+      if (!nz_of) {
+        CHECK(EV_EGUO_CMP_RANGE, gas <= MAXU);
+        const uint64_t z = len - nz;
+        z_of = (uint64_t)((MAXU - gas) / 4) < z;
+        gas += (u128)z * 4;
+      }
+      if (is_create) {
+        CHECK(EV_EGUO_CMP_RANGE, gas <= MAXU);
+        const uint64_t len_words = len / 32 + ((len % 32) ? 1 : 0);
+        initcode_of = (uint64_t)((MAXU - gas) / 2) < len_words;
+      }
+      calldata_of = nz_of + z_of;
+    }
+  }
+  /* memory_size(opcode): the pops of each opcode, then calc_mem_size64 on (offset, length) */
+  int n_pop, io = -1, il = -1, mem32 = 0, call = 0;
+  switch (op) {
+    case 0x20: case 0xf3: case 0xfd: case 0xa0: case 0xa1: case 0xa2: case 0xa3: case 0xa4: n_pop = 2; io = 0; il = 1; break;
+    case 0x37: case 0x3e: case 0x39: n_pop = 3; io = 1; il = 2; break;
+    case 0x3c: n_pop = 4; io = 2; il = 3; break;
+    case 0x51: n_pop = 1; io = 0; mem32 = 1; break;
+    case 0x52: case 0x53: n_pop = 2; io = 0; mem32 = 1; break;
+    case 0xf0: n_pop = 3; io = 1; il = 2; break;
+    case 0xf5: n_pop = 4; io = 1; il = 2; break;
+    case 0xf1: case 0xf2: n_pop = 7; call = 3; break;
+    case 0xf4: case 0xfa: n_pop = 6; call = 2; break;
+    default: orc_fail(e->res, EV_EGUO_OPCODE, row); return;
+  }
+  word_t w[7];
+  for (int k = 0; k < n_pop; k++)
+    if (!need1(e, rw_lookup(e, fr_add(rwc, fr_u64(3 + k)), 0, ZK_TARGET_Stack, call_id, fr_add(sp, fr_u64(k)), &w[k]), EV_EGUO_POP0_UNSAT + 2 * k, row)) return;
+  u128 size = 0; int mem_of = 0, id_;
+  if (call) {
+    u128 x, y; int ofx, ofy;
+    if ((id_ = cms(w[call + 2], w[call + 3], &x, &ofx))) { orc_fail(e->res, id_, row); return; }
+    if (ofx) mem_of = 1;
+    else {
+      if ((id_ = cms(w[call], w[call + 1], &y, &ofy))) { orc_fail(e->res, id_, row); return; }
+      if (ofy) mem_of = 1; else size = x > y ? x : y;
+    }
+  } else if (mem32) {
+    if ((id_ = cms_uint(w[io], fr_u64(32), &size, &mem_of))) { orc_fail(e->res, id_, row); return; }
+  } else {
+    if ((id_ = cms(w[io], w[il], &size, &mem_of))) { orc_fail(e->res, id_, row); return; }
+  }
+  const int mul_of = size > (u128)(~(uint64_t)0 - 31); /* to_word_size(size) * 32 passes 2^64 - 1 */
+  CHECK(EV_EGUO_NOT_OVERFLOW, mem_of + mul_of + calldata_of + initcode_of != 0);
+  error_state_tail(e, i, row, 3 + (uint64_t)n_pop);
+}

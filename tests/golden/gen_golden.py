@@ -870,7 +870,7 @@ def evm2_cases(part="evm2"):
     from zkevm_specs.util import FQ, Word, WordOrValue, keccak256, GAS_COST_COPY, GAS_COST_COPY_SHA3
 
     r = FQ(0x0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE0DDF00D0BADC0FFEE % P)
-    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45, "evm24": 47, "evm25": 49, "evm26": 51, "evm27": 53}[part])
+    rng = random.Random({"evm2": 5, "evm3": 7, "evm4": 9, "evm5": 11, "evm6": 13, "evm7": 15, "evm8": 17, "evm9": 19, "evm10": 21, "evm12": 23, "evm13": 25, "evm14": 27, "evm15": 29, "evm16": 31, "evm17": 33, "evm18": 35, "evm19": 37, "evm20": 39, "evm21": 41, "evm22": 43, "evm23": 45, "evm24": 47, "evm25": 49, "evm26": 51, "evm27": 53, "evm28": 55}[part])
 
     def W(lo, hi):
         return Word((FQ(lo), FQ(hi)), check=False)
@@ -1327,6 +1327,35 @@ def evm2_cases(part="evm2"):
                         reversible_write_counter=ctx[6])
         return [cur, nxt], list(bc.table_assignments()) + list(cbc.table_assignments()), list(rw.rws), [], []
 
+    def eguo_mem_case(op, offset, root=False):
+        """ErrorGasUintOverflow on MLOAD / MSTORE / MSTORE8 (error_gas_uint_overflow.py; the reference's test returns early for
+        these three): the memory offset alone overflows"""
+        from zkevm_specs.evm_circuit import Transaction
+        bc = getattr(Bytecode(), op)()
+        h = Word(bc.hash())
+        call_id = 1 if root else 2
+        tx = Transaction(id=1, call_data=bytes([0x7f]))
+        rw = RWDictionary(25)
+        rw.call_context_read(call_id, CallContextFieldTag.CallDataLength, 1)
+        rw.call_context_read(call_id, CallContextFieldTag.TxId, 1)
+        rw.call_context_read(call_id, CallContextFieldTag.IsRoot, FQ(root))
+        if op == "mload":
+            rw.stack_read(call_id, 1023, Word(offset)); sp = 1023
+        else:
+            rw.stack_read(call_id, 1022, Word(offset)).stack_read(call_id, 1023, Word(7)); sp = 1022
+        rw.call_context_read(call_id, CallContextFieldTag.IsSuccess, 0)
+        cur = StepState(ExecutionState.ErrorGasUintOverflow, rw_counter=25, call_id=call_id, is_root=root, is_create=False, code_hash=h,
+                        program_counter=0, stack_pointer=sp, gas_left=0, reversible_write_counter=0)
+        if root:
+            nxt = StepState(ExecutionState.EndTx, rw_counter=rw.rw_counter, call_id=1, gas_left=0)
+        else:
+            ctx = (False, False, 232, 1023, 100, 100, 0)
+            caller_ctx_rws(rw, 1, h, ctx, 2)
+            nxt = StepState(ExecutionState.STOP, rw_counter=rw.rw_counter, call_id=1, is_root=ctx[0], is_create=ctx[1], code_hash=h,
+                            program_counter=ctx[2], stack_pointer=ctx[3], gas_left=ctx[4], memory_word_size=ctx[5],
+                            reversible_write_counter=ctx[6])
+        return [cur, nxt], list(bc.table_assignments()), list(rw.rws), [], [], list(tx.table_assignments())
+
     def blockhash_case(current, number, res=None):
         """tests/evm/test_blockhash.py: the hash of one of the 256 previous blocks, else zero"""
         from zkevm_specs.evm_circuit import BlockContextFieldTag, BlockTableRow
@@ -1542,6 +1571,8 @@ def evm2_cases(part="evm2"):
             tc.verify_steps = keep[0]
             if keep[1] is not None:
                 tc.verify_copy_table = keep[1]
+        if not got:
+            return None  # the reference test skipped this case
         t, steps = got["tables"], got["steps"]
         aux = []
         for k_, st_ in enumerate(steps):
@@ -1958,7 +1989,28 @@ def evm2_cases(part="evm2"):
                 return idx, type(e).__name__
         return -1, ""
 
-    if part == "evm27":
+    if part == "evm28":
+        # every case of tests/evm/test_error_gas_uint_overflow.py that the test itself runs (it returns early where an
+        # overflowing call data would be needed) + the three memory opcodes it always skips
+        import importlib
+        tdir = os.path.normpath(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(sys.modules["zkevm_specs"].__file__))), "..", "tests", "evm"))
+        for d_ in (tdir, os.path.dirname(tdir)):
+            if d_ not in sys.path:
+                sys.path.insert(0, d_)
+        data = importlib.import_module("test_error_gas_uint_overflow").TESTING_DATA
+        scenarios = {}
+        for k_, d_ in enumerate(data):
+            sc_ = recorded_case("test_error_gas_uint_overflow", "test_error_gas_uint_overflow_root", d_)
+            if sc_ is not None:
+                scenarios["eguo_%03d" % k_] = sc_
+        for k_, (op_, off_, root_) in enumerate([("mload", 1 << 64, False), ("mstore", (1 << 64) + 5, False), ("mstore8", 1 << 200, False),
+                                                   ("mload", (1 << 70) + 3, True), ("mstore8", 1 << 64, True)]):
+            try:
+                scenarios["eguo_mem_%d" % k_] = eguo_mem_case(op_, off_, root_)
+                S_ = scenarios["eguo_mem_%d" % k_]
+            except Exception:
+                raise
+    elif part == "evm27":
         # only DATACOPY and BN254PAIRING can verify: for the other seven precompiles gas_cost stays a Python int and
         # compare() raises AttributeError on it (error_oog_precompile.py:19-30) - reached here through the corruptions of the
         # callee-address cell; a root call cannot end in this state (it does not count as halting, execution_state.py:364-390)
@@ -2222,14 +2274,14 @@ def evm2_cases(part="evm2"):
         S, B, R = [step_ints(x) for x in steps], [bc_ints(x) for x in bcs], [rw_ints(x) for x in rws]
         RF = [int(x.value.is_word) | (int(x.value_prev.is_word) << 1) for x in rws]
         C, K = [copy_ints(x) for x in cps], [kec_ints(x) for x in kcs]
-        TF = [int(x.value.is_word) for x in sc_[5]] if part in ("evm17", "evm26") and len(sc_) > 5 else None
+        TF = [int(x.value.is_word) for x in sc_[5]] if part in ("evm17", "evm26", "evm28") and len(sc_) > 5 else None
         BF = [int(x.value.is_word) for x in sc_[6]] if part == "evm18" and len(sc_) > 6 else None
         EX = [exp_ints(x) for x in sc_[7]] if len(sc_) > 7 else []
         AUX = [list(x) for x in sc_[8]] if len(sc_) > 8 else []
         assert run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX) == (-1, ""), (name, run(S, B, R, RF, C, K, T, BL, TF, BF, EX, AUX))
         muts = [(-1, 0, 0, 0, -1, "")]
-        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70, "evm24": 60, "evm25": 50, "evm26": 90, "evm27": 70}[part]):
-            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 3, 15] if part == "evm24" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 9, 5, 15, 15] if part == "evm25" else [0, 0, 0, 1, 1, 1, 8, 2, 5, 6, 6, 6] if part == "evm26" else [0, 0, 0, 1, 1, 1, 2, 5, 16, 16, 16, 16] if part == "evm27" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
+        for k in range({"evm2": 70, "evm3": 160, "evm4": 110, "evm5": 60, "evm6": 90, "evm7": 70, "evm8": 60, "evm9": 70, "evm10": 70, "evm12": 75, "evm13": 75, "evm14": 90, "evm15": 100, "evm16": 45, "evm17": 80, "evm18": 80, "evm19": 75, "evm20": 90, "evm21": 110, "evm22": 100, "evm23": 70, "evm24": 60, "evm25": 50, "evm26": 90, "evm27": 70, "evm28": 30}[part]):
+            which = rng.choice([0, 0, 0, 1, 1, 2, 3, 4] if part == "evm2" else [0, 0, 0, 1, 1, 1, 2, 3, 3, 5] if part in ("evm15", "evm21") else [0, 0, 1, 1, 8, 8, 8, 8, 8, 2, 5] if part == "evm16" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 3, 15] if part == "evm24" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 9, 5, 15, 15] if part == "evm25" else [0, 0, 0, 1, 1, 1, 8, 2, 5, 6, 6, 6] if part == "evm26" else [0, 0, 0, 1, 1, 1, 2, 5, 16, 16, 16, 16] if part == "evm27" else [0, 0, 1, 1, 1, 8, 8, 8, 8, 2, 5, 6] if part == "evm28" else [0, 0, 0, 1, 1, 1, 1, 8, 2, 2, 9, 5, 6] if part in ("evm17", "evm23") else [0, 0, 0, 1, 1, 1, 1, 8, 2, 3, 3, 5, 7, 7] if part == "evm18" else [0, 0, 1, 1, 8, 8, 8, 2, 5, 14, 14, 14, 14] if part == "evm19" else
                                [0, 0, 0, 1, 1, 2, 5, 6, 6, 7, 7] if part == "evm9" else [0, 0, 0, 1, 1, 1, 2, 5])
             T2, BL2 = [list(x) for x in T], [list(x) for x in BL]
             TF2 = list(TF) if TF is not None else None
@@ -2371,6 +2423,11 @@ def evm9_cases():
 
 def evm10_cases():
     evm2_cases("evm10")
+
+
+def evm28_cases():
+    """ErrorGasUintOverflow (error_gas_uint_overflow.py with instruction.memory_size / calc_mem_size64 / safe_mul / to_word_size)"""
+    evm2_cases("evm28")
 
 
 def evm27_cases():
@@ -3275,7 +3332,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     todo = {"bytecode": bytecode_cases}
     g = globals()
-    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "evm24", "evm25", "evm26", "evm27", "exp", "pi", "tx", "sig", "fr", "synth"]:
+    for nm in ["state", "copy", "evm", "evm2", "evm3", "evm4", "evm5", "evm6", "evm7", "evm8", "evm9", "evm10", "evm11", "evm12", "evm13", "evm14", "evm15", "evm16", "evm17", "evm18", "evm19", "evm20", "evm21", "evm22", "evm23", "evm24", "evm25", "evm26", "evm27", "evm28", "exp", "pi", "tx", "sig", "fr", "synth"]:
         if nm + "_cases" in g:
             todo[nm] = g[nm + "_cases"]
     for nm, fn in todo.items():

@@ -228,6 +228,11 @@ def evm10_vectors():
     return evm2_vectors("evm10")
 
 
+def evm28_vectors():
+    """ErrorGasUintOverflow"""
+    return evm2_vectors("evm28")
+
+
 def evm27_vectors():
     """ErrorOutOfGasPrecompile"""
     return evm2_vectors("evm27")

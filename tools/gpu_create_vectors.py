@@ -28,7 +28,7 @@ ctx.upload_table(native.TABLE_BLOCK, np.zeros((4, 0, 4), dtype=np.uint64))
 n = 0
 import itertools  # noqa: E402
 
-for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm27_vectors(), golden_util.evm26_vectors(), golden_util.evm25_vectors(), golden_util.evm24_vectors()):
+for name, k, w, exp_row, exp_exc in itertools.chain(golden_util.evm28_vectors(), golden_util.evm27_vectors(), golden_util.evm26_vectors(), golden_util.evm25_vectors(), golden_util.evm24_vectors()):
     if n >= limit:
         break
     ctx.upload_table(native.TABLE_BYTECODE, w["bytecode"])

@@ -1295,7 +1295,7 @@ static int check_evm(zk_ctx* ctx, const CheckRange& rg, ResultDev res, cudaStrea
                          hist[ZK_ES_CALLDATALOAD] + hist[ZK_ES_LOG] + hist[ZK_ES_ErrorWriteProtection] + hist[ZK_ES_ErrorMaxCodeSizeExceeded] +
                          hist[ZK_ES_ErrorOutOfGasCodeStore] + hist[ZK_ES_ErrorInvalidCreationCode] + hist[ZK_ES_RETURN] + hist[ZK_ES_ErrorOutOfGasCall] + hist[ZK_ES_CALL_OP] +
                          hist[ZK_ES_CREATE] + hist[ZK_ES_CREATE2] + hist[ZK_ES_ErrorOutOfGasSloadSstore] + hist[ZK_ES_ErrorOutOfGasCREATE] +
-                         hist[ZK_ES_ErrorOutOfGasPrecompile];
+                         hist[ZK_ES_ErrorOutOfGasPrecompile] + hist[ZK_ES_ErrorGasUintOverflow];
   if (hist[ZK_ES_ErrorInvalidJump] && !pos) {  // bytecode_lookup_pair: the index without is_code
     const u32 k4b[4] = {0, 1, 2, 3};
     if ((rc = ensure_index(ctx, ZK_TABLE_BYTECODE, k4b, 4, st, &t.bytecode4))) return rc;

@@ -46,7 +46,8 @@ enum { R_RWC, R_RW, R_TAG, R_ID, R_ADDR, R_FIELD, R_KEY_LO, R_KEY_HI, R_VAL_LO, 
   X(ZK_ES_ADDMOD) X(ZK_ES_MULMOD) X(ZK_ES_SDIV_SMOD) X(ZK_ES_SAR) X(ZK_ES_SLOAD) X(ZK_ES_SSTORE) X(ZK_ES_CALLDATALOAD) \
   X(ZK_ES_LOG) X(ZK_ES_ErrorWriteProtection) X(ZK_ES_BLOCKHASH) X(ZK_ES_EXP) \
   X(ZK_ES_ErrorMaxCodeSizeExceeded) X(ZK_ES_ErrorOutOfGasCodeStore) X(ZK_ES_ErrorInvalidCreationCode) X(ZK_ES_RETURN) X(ZK_ES_ErrorOutOfGasCall) X(ZK_ES_CALL_OP) \
-  X(ZK_ES_CREATE) X(ZK_ES_CREATE2) X(ZK_ES_ErrorOutOfGasSloadSstore) X(ZK_ES_ErrorOutOfGasCREATE) X(ZK_ES_ErrorOutOfGasPrecompile)
+  X(ZK_ES_CREATE) X(ZK_ES_CREATE2) X(ZK_ES_ErrorOutOfGasSloadSstore) X(ZK_ES_ErrorOutOfGasCREATE) X(ZK_ES_ErrorOutOfGasPrecompile) \
+  X(ZK_ES_ErrorGasUintOverflow)
 struct EsBuiltTable {
   signed char v[ZK_ES_COUNT];
 };
@@ -1750,6 +1751,7 @@ __host__ __device__ constexpr int es_group(int st) {
     case ZK_ES_ErrorMaxCodeSizeExceeded: case ZK_ES_ErrorOutOfGasCodeStore: case ZK_ES_ErrorInvalidCreationCode:
     case ZK_ES_RETURN: case ZK_ES_ErrorOutOfGasCall: case ZK_ES_CALL_OP: case ZK_ES_CREATE: case ZK_ES_CREATE2:
     case ZK_ES_ErrorOutOfGasSloadSstore: case ZK_ES_ErrorOutOfGasCREATE: case ZK_ES_ErrorOutOfGasPrecompile:
+    case ZK_ES_ErrorGasUintOverflow:
       return KG_TX;
     default: return -1;
   }
@@ -1838,6 +1840,7 @@ ZK_HD void run_group(const StepCtx& s, int st, u32 flags) {
       case ZK_ES_ErrorOutOfGasSloadSstore: gadget_error_oog_sload_sstore(s); break;
       case ZK_ES_ErrorOutOfGasCREATE: gadget_error_oog_create(s); break;
       case ZK_ES_ErrorOutOfGasPrecompile: gadget_error_oog_precompile(s); break;
+      case ZK_ES_ErrorGasUintOverflow: gadget_error_gas_uint_overflow(s); break;
       default: break;
     }
   } else if constexpr (G == KG_ARITH) {

@@ -427,4 +427,122 @@ ZK_HD_NOINLINE void gadget_error_oog_precompile(const StepCtx& s) {
   error_state_tail(s, 2);
 }
 
+// ErrorGasUintOverflow: error_gas_uint_overflow.py:19-171 with instruction.memory_size :1198-1305, calc_mem_size64 /
+// _with_uint :1309-1327, safe_mul :1329-1331, to_word_size :1333-1336.  As written: `if is_dynamic_gas:` tests an FQ object
+// (always true), so memory_size runs for every opcode and returns None (TypeError, ZK_ERR_VALUE) for one without a memory
+// operand; an offset below 2^64 is read again with word_to_fq(.., 5) and raises beyond 5 bytes; `val.n < offset64.n` never
+// holds over the field.  A memory size is offset (< 2^40) + length (< 2^64): 64 bits and a carry.
+struct MemSize {
+  u64 lo;
+  bool carry, overflow;
+};
+// calc_mem_size64_with_uint: 0 ok, else the failing constraint id
+ZK_HD_NOINLINE int cms_uint(const Word2& off_w, u64 len64, MemSize* m) {
+  m->lo = 0;
+  m->carry = m->overflow = false;
+  if (len64 == 0) return 0;
+  Fr off = fr_u64(0);
+  const int rc = word_to_fq_n(off_w, 31, &off);
+  if (rc) return rc == 1 ? EV_EGUO_OFF_DOMAIN : EV_EGUO_OFF_RANGE;
+  if (!fr_fits64(off)) {
+    m->overflow = true;
+    return 0;
+  }
+  if ((off.l[0] >> 40) != 0) return EV_EGUO_OFF5_RANGE;  // word_to_fq(offset, 5)
+  m->lo = off.l[0] + len64;
+  m->carry = m->lo < len64;
+  return 0;
+}
+ZK_HD_NOINLINE int cms(const Word2& off_w, const Word2& len_w, MemSize* m) {
+  m->lo = 0;
+  m->carry = m->overflow = false;
+  Fr len = fr_u64(0);
+  const int rc = word_to_fq_n(len_w, 31, &len);
+  if (rc) return rc == 1 ? EV_EGUO_LEN_DOMAIN : EV_EGUO_LEN_RANGE;
+  if (!fr_fits64(len)) {
+    m->overflow = true;
+    return 0;
+  }
+  return cms_uint(off_w, len.l[0], m);
+}
+ZK_HD_NOINLINE void gadget_error_gas_uint_overflow(const StepCtx& s) {
+  Fr opcode = fr_u64(0);
+  if (!opcode_lookup_ni(s, true, &opcode)) return;
+  const Fr rwc = s.cur(S_RWC), call_id = s.cur(S_CALL_ID), sp = s.cur(S_SP);
+  const u64 op = (fr_fits64(opcode) && opcode.l[0] < 256) ? opcode.l[0] : 0x100;
+  const bool is_create = op == 0xf0 || op == 0xf5;
+  Fr cd_len, tx_id, is_root;
+  ST_CC(0, ZK_CC_CallDataLength, &cd_len, EV_EGUO_CDLEN_UNSAT);
+  ST_CC(1, ZK_CC_TxId, &tx_id, EV_EGUO_TXID_UNSAT);
+  ST_CC(2, ZK_CC_IsRoot, &is_root, EV_EGUO_ROOT_UNSAT);
+  bool calldata_of = false, initcode_of = false;
+  if (fr_eq_u64(is_root, 1)) {
+    // the walk ends at the first byte the tx table does not hold: its trip count is bounded by the table (< 2^32 rows),
+    // so the intrinsic gas below stays far from 2^64 and plain 64-bit arithmetic is exact
+    const u64 len = fr_fits64(cd_len) ? cd_len.l[0] : ~0ull;
+    u64 nz = 0;
+#pragma unroll 1
+    for (u64 idx = 0; idx < len; idx++) {
+      u32 r = 0;
+      Fr key[3] = {tx_id, fr_u64(ZK_TX_CallData), fr_u64(idx)};
+      TX_LK(lookup<3>(s.t.tx, key, &r), EV_EGUO_BYTE_UNSAT);
+      TX_NOT_WORD(tx_is_word(s, r), EV_EGUO_BYTE_UNSAT);
+      nz += fr_is_zero(table_cell(s.t.tx.tab, 3, r)) ? 0 : 1;
+    }
+    if (len > 0) {
+      const u64 MAXU = ~0ull;
+      u64 gas = is_create ? 53000 : 21000;
+      const bool nz_of = (MAXU - gas) / 16 < nz;
+      gas += nz * 16;
+      bool z_of = false;
+      if (!nz_of) {
+        const u64 z = len - nz;
+        z_of = (MAXU - gas) / 4 < z;
+        gas += z * 4;
+      }
+      if (is_create) initcode_of = (MAXU - gas) / 2 < len / 32 + ((len % 32) ? 1 : 0);
+      calldata_of = nz_of || z_of;
+    }
+  }
+  // memory_size(opcode): the pops of each opcode, then calc_mem_size64 on (offset, length)
+  int n_pop = 0, io = 0, il = 0, call = 0;
+  bool mem32 = false;
+  switch (op) {
+    case 0x20: case 0xf3: case 0xfd: case 0xa0: case 0xa1: case 0xa2: case 0xa3: case 0xa4: n_pop = 2; io = 0; il = 1; break;
+    case 0x37: case 0x3e: case 0x39: n_pop = 3; io = 1; il = 2; break;
+    case 0x3c: n_pop = 4; io = 2; il = 3; break;
+    case 0x51: n_pop = 1; io = 0; mem32 = true; break;
+    case 0x52: case 0x53: n_pop = 2; io = 0; mem32 = true; break;
+    case 0xf0: n_pop = 3; io = 1; il = 2; break;
+    case 0xf5: n_pop = 4; io = 1; il = 2; break;
+    case 0xf1: case 0xf2: n_pop = 7; call = 3; break;
+    case 0xf4: case 0xfa: n_pop = 6; call = 2; break;
+    default: step_fail(s, EV_EGUO_OPCODE); return;
+  }
+  const Word2 zero{fr_u64(0), fr_u64(0)};
+  Word2 w[7] = {zero, zero, zero, zero, zero, zero, zero};
+#pragma unroll 1
+  for (int k = 0; k < n_pop; k++)
+    if (!need1(s, true, stack_at(s, true, 3 + (u64)k, 0, fr_add_u64(sp, (u64)k), &w[k]), EV_EGUO_POP0_UNSAT + 2 * k)) return;
+  MemSize m{0, false, false};
+  int id_ = 0;
+  if (call) {
+    MemSize x, y;
+    if ((id_ = cms(w[call + 2], w[call + 3], &x))) { step_fail(s, id_); return; }
+    if (x.overflow) m.overflow = true;
+    else {
+      if ((id_ = cms(w[call], w[call + 1], &y))) { step_fail(s, id_); return; }
+      if (y.overflow) m.overflow = true;
+      else m = (x.carry != y.carry ? x.carry : x.lo > y.lo) ? x : y;
+    }
+  } else if (mem32) {
+    if ((id_ = cms_uint(w[io], 32, &m))) { step_fail(s, id_); return; }
+  } else {
+    if ((id_ = cms(w[io], w[il], &m))) { step_fail(s, id_); return; }
+  }
+  const bool mul_of = !m.overflow && (m.carry || m.lo > ~0ull - 31);  // to_word_size(size) * 32 passes 2^64 - 1
+  EV_CHECK(EV_EGUO_NOT_OVERFLOW, m.overflow || mul_of || calldata_of || initcode_of);
+  error_state_tail(s, 3 + (u64)n_pop);
+}
+
 }  // namespace zk
